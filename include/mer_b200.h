@@ -1,0 +1,101 @@
+/* mer_b200.h — C ABI of libmer_b200.so (B200 / sm_100a only).
+ *
+ * Drop-in boundary for the MERTools hot path: the reference has no FFI; the
+ * seam a maintainer would bind is the model-object call
+ *     model(x, output_hidden_states=True).hidden_states  ->  readout
+ * in MERBench/feature_extraction/{visual/extract_vision_huggingface.py:140-144,
+ * audio/extract_audio_huggingface.py:93-100, text/extract_text_huggingface.py:222-231}
+ * and the fusion step of MERBench/main-release.py:31-66.  Every function below cites the
+ * reference lines it replaces.  INTEGRATION.md shows the ctypes stub on the reference side.
+ *
+ * Conventions: all pointers are DEVICE pointers owned by the caller unless a parameter is
+ * documented as host; `stream` is a cudaStream_t passed as void*; return 0 on success, non-zero
+ * on failure with the message available from mer_last_error().  No global state besides the
+ * per-thread error string and cached device attributes.  No CPU fallback exists.
+ */
+#ifndef MER_B200_H_
+#define MER_B200_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define MER_API __attribute__((visibility("default")))
+#else
+#define MER_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ------------------------------------------------------------------------- */
+MER_API const char* mer_last_error(void);
+MER_API int mer_abi_version(void);
+/* 0 when the current device is compute capability 10.x, non-zero (and an error string) otherwise */
+MER_API int mer_check_device(void);
+
+/* ---- GEMM (nn.Linear / Conv1d-as-GEMM / patch-embed) ---------------------------------- */
+enum { MER_EPI_GELU = 1, MER_EPI_ROUND_TF32 = 2 };
+
+typedef struct MerGemmEpilogue {
+  const float* bias; /* [N] or NULL */
+  const float* res;  /* residual rows or NULL */
+  float* out;
+  long long out_bstride; /* out row = b*out_bstride + out_row0 + m */
+  long long out_row0;
+  long long res_bstride; /* res row = b*res_bstride + res_row0 + m */
+  long long res_row0;
+  int ld_out; /* floats */
+  int ld_res;
+  int flags; /* MER_EPI_* */
+} MerGemmEpilogue;
+
+/* A[b, m, tap*K_inner + c] = base[b*a_batch_stride + (m + tap / P)*a_row_stride +
+ *                                 (tap % P)*a_phase_stride + c]        (element strides)
+ * Plain row-major A[M,K]: taps = 1, P = 1, K_inner = K, batches = 1, a_row_stride = K.
+ * Conv1d(kernel k, stride s) over time-major activations x[b, tau, c]:
+ *   taps = k, P = s, K_inner = C_in, a_phase_stride = C_in, a_row_stride = s*C_in.           */
+typedef struct MerGemmDesc {
+  const float* A;
+  const float* W; /* [N, taps*K_inner] row-major (nn.Linear layout) */
+  int rows_per_batch;
+  int a_rows_dim; /* addressable row groups per batch entry (>= rows_per_batch + (taps-1)/P) */
+  int batches;
+  int N;
+  int K_inner;
+  int taps;
+  int P;
+  long long a_phase_stride;
+  long long a_row_stride;
+  long long a_batch_stride;
+  int force_block_n; /* 0 = auto, 128 or 256 */
+  MerGemmEpilogue ep;
+} MerGemmDesc;
+
+/* tcgen05 TF32 GEMM with fused epilogue.  Replaces torch nn.Linear / nn.Conv1d calls inside
+ * HF ViTLayer / HubertEncoderLayer / BertLayer reached from the reference extractors. */
+MER_API int mer_gemm_tf32(const MerGemmDesc* desc, void* stream);
+
+/* ---- row-wise kernels ------------------------------------------------------------------ */
+enum { MER_LN_ROUND_TF32 = 1, MER_LN_ACC_INIT = 2, MER_LN_ACC_ADD = 4 };
+/* y = LayerNorm(x) * gamma + beta over the last dim (768 or 512).  Optional side buffer acc
+ * (same shape): acc = y (ACC_INIT) or acc += y (ACC_ADD) — the "sum of the last four hidden
+ * states" readout of extract_audio_huggingface.py:98 / extract_text_huggingface.py:226. */
+MER_API int mer_layernorm(const float* x, const float* gamma, const float* beta, float* y, float* acc,
+                  long long rows, int dim, float eps, int flags, void* stream);
+
+/* in-place round-to-nearest fp32 -> tf32 (weights at load time) */
+MER_API int mer_round_tf32(float* x, long long n, void* stream);
+
+/* ---- attention ------------------------------------------------------------------------- */
+/* softmax(Q K^T / 8) V per (sequence, head); head_dim 64.  qkv is [tokens, 3*heads*64] with
+ * Q | K | V column blocks, sequences packed back to back, cu_seqlens[n_seq+1] (device, int32).
+ * ctx is [tokens, heads*64].  flags: MER_EPI_ROUND_TF32 rounds ctx for the out-proj GEMM.
+ * Replaces HF eager/sdpa attention (modeling_vit.py:171-196, modeling_hubert.py:262-345). */
+MER_API int mer_attention(const float* qkv, float* ctx, const int32_t* cu_seqlens, int n_seq,
+                  int max_seqlen, int heads, int flags, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MER_B200_H_ */

@@ -1,0 +1,110 @@
+// rowwise.cu — HBM-bound row kernels: LayerNorm (+ optional "last-4 hidden states" accumulation)
+// and the fp32 -> tf32 rounding pass used on weights at load time.
+//
+// LayerNorm follows torch.nn.LayerNorm exactly (biased variance, eps inside the sqrt), one warp
+// per row, 128-bit loads/stores, the whole row kept in registers between the mean pass and the
+// variance pass (two-pass, no E[x^2]-E[x]^2 cancellation).  Algorithmic traffic: 8 bytes per
+// element (+4 per element for the accumulation buffer, +4 more when it is read back).
+// Reference ops: HF ViTLayer.layernorm_before/after (modeling_vit.py:325-340),
+// HubertEncoderLayer.layer_norm/final_layer_norm (modeling_hubert.py:372-405),
+// BertSelfOutput/BertOutput.LayerNorm.
+#include "mer_common.cuh"
+#include "mer_kernels.h"
+
+namespace {
+
+using namespace mer;
+
+template <int VEC>  // VEC float4 per lane: dim = 128 * VEC
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float* __restrict__ y, float* __restrict__ acc,
+                 long long rows, float eps, int flags) {
+  constexpr int DIM = 128 * VEC;
+  const int lane = threadIdx.x & 31;
+  const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+  long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+
+  float4 g[VEC], b[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+    b[i] = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
+  }
+  for (; row < rows; row += warps_total) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * DIM);
+    float4 v[VEC];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      v[i] = xr[lane + 32 * i];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) * (1.0f / DIM);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / DIM) + eps);
+    float4* yr = reinterpret_cast<float4*>(y + row * DIM);
+    float4* ar = acc ? reinterpret_cast<float4*>(acc + row * DIM) : nullptr;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float4 o;
+      o.x = v[i].x * rstd * g[i].x + b[i].x;
+      o.y = v[i].y * rstd * g[i].y + b[i].y;
+      o.z = v[i].z * rstd * g[i].z + b[i].z;
+      o.w = v[i].w * rstd * g[i].w + b[i].w;
+      if (ar) {
+        if (flags & MER_LN_ACC_INIT) {
+          ar[lane + 32 * i] = o;
+        } else if (flags & MER_LN_ACC_ADD) {
+          float4 a = ar[lane + 32 * i];
+          a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+          ar[lane + 32 * i] = a;
+        }
+      }
+      if (flags & MER_LN_ROUND_TF32) {
+        o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+      }
+      yr[lane + 32 * i] = o;
+    }
+  }
+}
+
+__global__ void round_tf32_kernel(float* x, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) x[i] = round_tf32(x[i]);
+}
+
+}  // namespace
+
+int mer_layernorm_launch(const float* x, const float* gamma, const float* beta, float* y,
+                         float* acc, long long rows, int dim, float eps, int flags,
+                         cudaStream_t stream) {
+  MER_REQUIRE(x && gamma && beta && y, "mer_layernorm: null operand");
+  MER_REQUIRE(dim == 768 || dim == 512, "mer_layernorm: dim %d not supported (768 or 512)", dim);
+  if (rows <= 0) return 0;
+  const int warps_per_block = 8;
+  long long blocks = (rows + warps_per_block - 1) / warps_per_block;
+  const long long max_blocks = (long long)mer_num_sms() * 16;
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (dim == 768)
+    layernorm_kernel<6><<<(int)blocks, 256, 0, stream>>>(x, gamma, beta, y, acc, rows, eps, flags);
+  else
+    layernorm_kernel<4><<<(int)blocks, 256, 0, stream>>>(x, gamma, beta, y, acc, rows, eps, flags);
+  MER_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mer_round_tf32(float* x, long long n, void* stream) {
+  if (n <= 0) return 0;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  round_tf32_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n);
+  MER_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

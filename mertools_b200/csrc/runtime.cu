@@ -1,0 +1,112 @@
+// runtime.cu — host-side plumbing of libmer_b200.so: error string, device checks, TMA descriptor
+// encoding through the driver entry point (resolved at run time so the library links without
+// libcuda and loads on a GPU-less build box), and the thin extern "C" wrappers of the kernel-level
+// entry points declared in include/mer_b200.h.
+#include <stdarg.h>
+
+#include "mer_common.cuh"
+#include "mer_kernels.h"
+
+static thread_local char g_err[1024] = "";
+
+void mer_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+int mer_make_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const void* base,
+                  const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                  CUtensorMapSwizzle swizzle) {
+  PFN_encodeTiled enc = get_encode();
+  MER_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i + 1 < rank) gstr[i] = strides_bytes[i];
+  }
+  CUresult r = enc(out, dtype, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mer_set_error(
+        "cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu %llu %llu %llu] strides "
+        "[%llu %llu %llu] box [%u %u %u %u] base %p",
+        (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+        (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+        (unsigned long long)(rank > 1 ? strides_bytes[0] : 0),
+        (unsigned long long)(rank > 2 ? strides_bytes[1] : 0),
+        (unsigned long long)(rank > 3 ? strides_bytes[2] : 0), box[0], rank > 1 ? box[1] : 0,
+        rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, base);
+    return 3;
+  }
+  return 0;
+}
+
+int mer_num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+extern "C" {
+
+const char* mer_last_error(void) { return g_err; }
+
+int mer_abi_version(void) { return 1; }
+
+int mer_check_device(void) {
+  int dev = 0, major = 0, minor = 0;
+  MER_CUDA_CHECK(cudaGetDevice(&dev));
+  MER_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  MER_CUDA_CHECK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  MER_REQUIRE(major == 10, "libmer_b200 needs an sm_100a device, found sm_%d%d", major, minor);
+  return 0;
+}
+
+int mer_gemm_tf32(const MerGemmDesc* desc, void* stream) {
+  return mer_gemm_tf32_launch(desc, static_cast<cudaStream_t>(stream));
+}
+
+int mer_layernorm(const float* x, const float* gamma, const float* beta, float* y, float* acc,
+                  long long rows, int dim, float eps, int flags, void* stream) {
+  return mer_layernorm_launch(x, gamma, beta, y, acc, rows, dim, eps, flags,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int mer_attention(const float* qkv, float* ctx, const int32_t* cu_seqlens, int n_seq,
+                  int max_seqlen, int heads, int flags, void* stream) {
+  return mer_attention_launch(qkv, ctx, cu_seqlens, n_seq, max_seqlen, heads, flags,
+                              static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,237 @@
+"""GPU probe: correctness + timing of the kernel-level entry points, with verbose diagnostics.
+
+Run on the GPU box:  timeout 300 python scripts/gpu_probe.py [section ...]
+Writes one JSON line per check to stdout (and gpurun_out/probe.jsonl).
+"""
+import json
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mertools_b200 import _lib as L  # noqa: E402
+
+OUT = None
+
+
+def emit(**kw):
+    line = json.dumps(kw)
+    print(line, flush=True)
+    if OUT:
+        OUT.write(line + "\n")
+        OUT.flush()
+
+
+def tf32(x):
+    i = x.contiguous().view(torch.int32)
+    r = (i + 0xFFF + ((i >> 13) & 1)) & ~0x1FFF
+    return r.view(torch.float32)
+
+
+def time_cuda(fn, iters=20, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def gelu(x):
+    return torch.nn.functional.gelu(x)
+
+
+def check_gemm(name, M, N, K, bias=False, use_gelu=False, res=False, rnd=False, ints=False,
+               force=0):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    if ints:
+        A = torch.randint(-3, 4, (M, K), device="cuda", generator=g).float()
+        W = torch.randint(-3, 4, (N, K), device="cuda", generator=g).float()
+    else:
+        A = tf32(torch.randn(M, K, device="cuda", generator=g))
+        W = tf32(torch.randn(N, K, device="cuda", generator=g) * 0.05)
+    b = torch.randn(N, device="cuda", generator=g) if bias else None
+    R = torch.randn(M, N, device="cuda", generator=g) if res else None
+    out = torch.full((M, N), float("nan"), device="cuda")
+    try:
+        L.gemm_tf32(A, W, out, bias=b, res=R, gelu=use_gelu, round_out=rnd, force_block_n=force)
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001
+        emit(check=name, ok=False, error=str(e)[:500])
+        return False
+    ref = A.double() @ W.double().t()
+    if bias:
+        ref = ref + b.double()
+    if use_gelu:
+        ref = gelu(ref)
+    if res:
+        ref = ref + R.double()
+    if rnd:
+        ref = tf32(ref.float()).double()
+    err = (out.double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    nan = int(torch.isnan(out).sum().item())
+    ok = nan == 0 and err <= 2e-5 * max(scale, 1.0) * (8 if rnd else 1) + (1e-3 * scale if rnd else 0)
+    info = dict(check=name, ok=bool(ok), M=M, N=N, K=K, max_err=err, ref_max=scale, nan=nan)
+    if not ok:
+        bad = ((out.double() - ref).abs() > 1e-3 * max(scale, 1.0)) | torch.isnan(out)
+        rows = bad.any(1).nonzero().flatten()[:8].tolist()
+        cols = bad.any(0).nonzero().flatten()[:8].tolist()
+        info.update(bad_frac=bad.float().mean().item(), bad_rows=rows, bad_cols=cols,
+                    sample_out=out[:2, :4].tolist(), sample_ref=ref[:2, :4].tolist())
+    emit(**info)
+    return ok
+
+
+def sec_gemm():
+    ok = True
+    ok &= check_gemm("gemm_int_1tile_k32", 128, 128, 32, ints=True)
+    ok &= check_gemm("gemm_int_1tile_k128", 128, 128, 128, ints=True)
+    ok &= check_gemm("gemm_int_n256", 128, 256, 64, ints=True, force=256)
+    ok &= check_gemm("gemm_tail_m300", 300, 256, 768)
+    ok &= check_gemm("gemm_bias_gelu", 1000, 3072, 768, bias=True, use_gelu=True, rnd=True)
+    ok &= check_gemm("gemm_bias_res", 1000, 768, 3072, bias=True, res=True)
+    ok &= check_gemm("gemm_big_256", 20000, 2304, 768, bias=True, force=256)
+    ok &= check_gemm("gemm_big_128", 20000, 768, 768, bias=True, force=128)
+    return ok
+
+
+def sec_conv():
+    """Conv1d(k=3,s=2) and (k=2,s=2) over time-major activations through the tap-aware A map."""
+    ok = True
+    for (k, s, T) in [(3, 2, 1001), (2, 2, 499), (3, 2, 15999)]:
+        B, Cin, Cout = 3, 512, 512
+        g = torch.Generator(device="cuda").manual_seed(2)
+        x = tf32(torch.randn(B, T + 2, Cin, device="cuda", generator=g))  # +2 rows of slack
+        w = tf32(torch.randn(Cout, Cin, k, device="cuda", generator=g) * 0.03)
+        Tout = (T - k) // s + 1
+        Wg = w.permute(0, 2, 1).contiguous().view(Cout, k * Cin)  # [out, tap, in]
+        out = torch.full((B, Tout, Cout), float("nan"), device="cuda")
+        try:
+            L.gemm_tf32(x, Wg, out, gelu=True, rows_per_batch=Tout, batches=B,
+                        a_rows_dim=(T + 2) // s, K_inner=Cin, taps=k, P=s,
+                        a_phase_stride=Cin, a_row_stride=s * Cin, a_batch_stride=(T + 2) * Cin,
+                        out_bstride=Tout, ld_out=Cout)
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            emit(check=f"conv_k{k}s{s}_T{T}", ok=False, error=str(e)[:500])
+            ok = False
+            continue
+        ref = torch.nn.functional.conv1d(x[:, :T].double().transpose(1, 2), w.double(), stride=s)
+        ref = gelu(ref).transpose(1, 2)
+        err = (out.double() - ref).abs().max().item()
+        good = err < 1e-4 and not torch.isnan(out).any().item()
+        emit(check=f"conv_k{k}s{s}_T{T}", ok=bool(good), max_err=err, ref_max=ref.abs().max().item())
+        ok &= good
+    return ok
+
+
+def sec_gemm_perf():
+    for (name, M, N, K, kw) in [
+        ("qkv", 403456 // 4, 2304, 768, dict(bias=True, rnd=True)),
+        ("outproj", 403456 // 4, 768, 768, dict(bias=True, res=True)),
+        ("fc1", 403456 // 4, 3072, 768, dict(bias=True, gelu=True, rnd=True)),
+        ("fc2", 403456 // 4, 768, 3072, dict(bias=True, res=True)),
+        ("fc1_full", 403456, 3072, 768, dict(bias=True, gelu=True, rnd=True)),
+    ]:
+        A = tf32(torch.randn(M, K, device="cuda"))
+        W = tf32(torch.randn(N, K, device="cuda") * 0.02)
+        b = torch.randn(N, device="cuda")
+        R = torch.randn(M, N, device="cuda") if kw.get("res") else None
+        out = torch.empty(M, N, device="cuda")
+        fn = lambda: L.gemm_tf32(A, W, out, bias=b, res=R, gelu=kw.get("gelu", False),  # noqa: E731
+                                 round_out=kw.get("rnd", False))
+        try:
+            ms = time_cuda(fn, iters=10)
+        except Exception as e:  # noqa: BLE001
+            emit(perf=name, error=str(e)[:300])
+            continue
+        torch.backends.cuda.matmul.allow_tf32 = True
+        ms_t = time_cuda(lambda: torch.matmul(A, W.t(), out=out), iters=10)
+        emit(perf=name, M=M, N=N, K=K, ms=ms, tflops=2.0 * M * N * K / ms / 1e9,
+             torch_tf32_ms=ms_t, torch_tflops=2.0 * M * N * K / ms_t / 1e9)
+        del A, W, out, R
+
+
+def sec_ln():
+    ok = True
+    for dim, eps in [(768, 1e-12), (512, 1e-5), (768, 1e-5)]:
+        rows = 5003
+        x = torch.randn(rows, dim, device="cuda") * 3 + 1
+        g = torch.randn(dim, device="cuda")
+        b = torch.randn(dim, device="cuda")
+        y = torch.empty_like(x)
+        acc = torch.zeros_like(x)
+        L.layernorm(x, g, b, y, eps=eps, acc=acc, flags=L.MER_LN_ACC_INIT)
+        L.layernorm(x, g, b, y, eps=eps, acc=acc, flags=L.MER_LN_ACC_ADD)
+        torch.cuda.synchronize()
+        ref = torch.nn.functional.layer_norm(x.double(), (dim,), g.double(), b.double(), eps)
+        e1 = (y.double() - ref).abs().max().item()
+        e2 = (acc.double() - 2 * ref).abs().max().item()
+        good = e1 < 2e-5 and e2 < 4e-5
+        emit(check=f"layernorm_{dim}", ok=bool(good), err=e1, err_acc=e2)
+        ok &= good
+    rows = 403456
+    x = torch.randn(rows, 768, device="cuda")
+    y = torch.empty_like(x)
+    g = torch.ones(768, device="cuda")
+    b = torch.zeros(768, device="cuda")
+    ms = time_cuda(lambda: L.layernorm(x, g, b, y, eps=1e-12, flags=L.MER_LN_ROUND_TF32))
+    emit(perf="layernorm_768", rows=rows, ms=ms, gbs=rows * 768 * 8 / ms / 1e6)
+    return ok
+
+
+def sec_attn():
+    ok = True
+    heads = 12
+    for lens in [[197] * 5, [249] * 3, [7, 64, 65, 1, 130, 499]]:
+        cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device="cuda")
+        tot = sum(lens)
+        qkv = tf32(torch.randn(tot, 3 * heads * 64, device="cuda") * 1.5)
+        ctx = torch.full((tot, heads * 64), float("nan"), device="cuda")
+        L.attention(qkv, ctx, cu, max(lens), heads)
+        torch.cuda.synchronize()
+        err = 0.0
+        s0 = 0
+        for n in lens:
+            q, k, v = qkv[s0:s0 + n].double().view(n, 3, heads, 64).permute(1, 2, 0, 3)
+            p = torch.softmax(q @ k.transpose(-1, -2) / 8.0, -1)
+            ref = (p @ v).permute(1, 0, 2).reshape(n, heads * 64)
+            err = max(err, (ctx[s0:s0 + n].double() - ref).abs().max().item())
+            s0 += n
+        good = err < 2e-3 and not torch.isnan(ctx).any().item()
+        emit(check=f"attention_{lens[0]}x{len(lens)}", ok=bool(good), max_err=err)
+        ok &= good
+    n_seq = 2048
+    cu = (torch.arange(n_seq + 1, device="cuda", dtype=torch.int32) * 197)
+    qkv = torch.randn(n_seq * 197, 2304, device="cuda")
+    ctx = torch.empty(n_seq * 197, 768, device="cuda")
+    ms = time_cuda(lambda: L.attention(qkv, ctx, cu, 197, heads, round_out=True), iters=5)
+    flops = n_seq * heads * 4.0 * 197 * 197 * 64
+    emit(perf="attention_vit_2048x197", ms=ms, tflops=flops / ms / 1e9)
+    return ok
+
+
+SECTIONS = dict(gemm=sec_gemm, conv=sec_conv, gemm_perf=sec_gemm_perf, ln=sec_ln, attn=sec_attn)
+
+if __name__ == "__main__":
+    os.makedirs("gpurun_out", exist_ok=True)
+    OUT = open("gpurun_out/probe.jsonl", "a")
+    L.check(L.lib().mer_check_device())
+    emit(device=torch.cuda.get_device_name(0), abi=L.lib().mer_abi_version())
+    names = sys.argv[1:] or list(SECTIONS)
+    for n in names:
+        t0 = time.time()
+        try:
+            r = SECTIONS[n]()
+        except Exception as e:  # noqa: BLE001
+            emit(section=n, crashed=str(e)[:800])
+            # a sticky CUDA error poisons the context: stop here
+            break
+        emit(section=n, ok=r, seconds=round(time.time() - t0, 1))
