@@ -95,6 +95,55 @@ MER_API int mer_round_tf32(float* x, long long n, void* stream);
 MER_API int mer_attention(const float* qkv, float* ctx, const int32_t* cu_seqlens, int n_seq,
                   int max_seqlen, int heads, int flags, void* stream);
 
+/* ---- segment reduce (readouts) ------------------------------------------------------------ */
+enum { MER_SEG_SUM = 0, MER_SEG_MEAN = 1 };
+/* out[s, :] = sum or mean of in[offsets[s] : offsets[s+1], :] (dim % 4 == 0; offsets device int32,
+ * n_seg+1 entries).  Empty segments give zeros (extract_text_huggingface.py:236-249 writes zeros
+ * for an empty sentence).  Replaces hidden_states[-1].sum(dim=1) / np.mean(axis=0)
+ * (extract_vision_huggingface.py:144,187-188; extract_audio_huggingface.py:105-108). */
+MER_API int mer_segment_reduce(const float* in, const int32_t* offsets, int n_seg, int dim, int mode,
+                               float* out, void* stream);
+
+/* ---- transformer encoder stack shared by the three modalities ----------------------------------- */
+typedef struct MerLayerWeights {
+  const float* ln1_g; /* ViT: layernorm_before | HuBERT: layer_norm | BERT: attention.output.LayerNorm */
+  const float* ln1_b;
+  const float* w_qkv; /* [2304, 768] = rows Q | K | V, tf32-rounded */
+  const float* b_qkv; /* [2304] */
+  const float* w_o;   /* [768, 768] */
+  const float* b_o;
+  const float* ln2_g; /* ViT: layernorm_after | HuBERT: final_layer_norm | BERT: output.LayerNorm */
+  const float* ln2_b;
+  const float* w_fc1; /* [3072, 768] */
+  const float* b_fc1;
+  const float* w_fc2; /* [768, 3072] */
+  const float* b_fc2;
+} MerLayerWeights;
+
+/* ---- ViT-B/16 frame encoder (visual) ------------------------------------------------------------ */
+typedef struct MerVitModel {
+  int n_layers;        /* 12 */
+  float ln_eps;        /* 1e-12 */
+  const float* patch_w;   /* [768, 768]  conv weight flattened (c, ph, pw), tf32-rounded */
+  const float* patch_b;   /* [768] */
+  const float* cls_pos0;  /* [768]  cls_token + position_embeddings[0] */
+  const float* pos_rest;  /* [196, 768] position_embeddings[1:] */
+  const MerLayerWeights* layers; /* host array of n_layers entries (device pointers inside) */
+} MerVitModel;
+
+/* bytes of caller-provided device workspace for n_frames frames */
+MER_API long long mer_vit_workspace_bytes(int n_frames);
+
+/* frames: uint8 [n_frames, 224, 224, 3] BGR (the reference's openface_face/<vid>/<vid>.npy layout).
+ * Does, on the device: BGR->RGB, x/255, (x-.5)/.5 (HF ViTImageProcessor as invoked at
+ * extract_vision_huggingface.py:137-138), the 12-layer pre-LN ViT forward (HF modeling_vit.py),
+ * and the readout hidden_states[-1].sum(dim=1) (extract_vision_huggingface.py:143-144).
+ * out_frame_feats: [n_frames, 768].  opt_hidden: NULL or [(n_layers+1), n_frames*197, 768] to
+ * receive every hidden state (parity tests). */
+MER_API int mer_vit_forward(const MerVitModel* model, const uint8_t* frames_bgr, int n_frames,
+                            void* workspace, long long workspace_bytes, float* out_frame_feats,
+                            float* opt_hidden, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

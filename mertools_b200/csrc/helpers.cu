@@ -1,0 +1,137 @@
+// helpers.cu — small HBM-bound kernels around the encoders: ViT frame preprocessing + patch
+// gather, CLS rows, and the segment reduce used by every readout.
+#include "mer_common.cuh"
+#include "mer_kernels.h"
+
+namespace {
+
+using namespace mer;
+
+// One thread = one 16-pixel row of one 16x16 patch, all 3 channels: reads 48 contiguous bytes of
+// the uint8 BGR HWC frame, writes three 64-byte runs of the patch-major GEMM operand
+//   A[(n, py, px), c*256 + i*16 + j] = ((frame[n, py*16+i, px*16+j, 2-c] * (1/255)) - 0.5) / 0.5
+// (BGR->RGB of extract_vision_huggingface.py:29-31, then HF ViTImageProcessor rescale+normalize),
+// rounded to tf32 because its only consumer is the patch-embedding GEMM.
+// Algorithmic traffic per frame: 150,528 B in + 602,112 B out.
+__global__ void __launch_bounds__(256)
+vit_patchify_kernel(const uint8_t* __restrict__ frames, float* __restrict__ a, long long total) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int i = idx & 15;               // row inside the patch
+  const long long patch = idx >> 4;     // (n*14 + py)*14 + px
+  const int px = patch % 14;
+  const long long t = patch / 14;
+  const int py = t % 14;
+  const long long n = t / 14;
+  const uint8_t* src = frames + ((n * 224 + (py * 16 + i)) * 224 + px * 16) * 3;
+  uint4 raw[3];
+  raw[0] = __ldg(reinterpret_cast<const uint4*>(src));
+  raw[1] = __ldg(reinterpret_cast<const uint4*>(src) + 1);
+  raw[2] = __ldg(reinterpret_cast<const uint4*>(src) + 2);
+  const uint8_t* b = reinterpret_cast<const uint8_t*>(raw);
+  float* dst = a + patch * 768 + i * 16;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float p = (float)b[j * 3 + (2 - c)];
+      v[j] = round_tf32((p * 0.00392156862745098f - 0.5f) / 0.5f);
+    }
+    float4* d4 = reinterpret_cast<float4*>(dst + c * 256);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) d4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+}
+
+// x[n, 0, :] = cls_token + position_embeddings[0]  (HF ViTEmbeddings, modeling_vit.py:117-124)
+__global__ void vit_cls_rows_kernel(const float* __restrict__ cls_pos0, float* __restrict__ x,
+                                    int n_frames) {
+  const int n = blockIdx.x;
+  if (n >= n_frames) return;
+  float4* dst = reinterpret_cast<float4*>(x + (long long)n * 197 * 768);
+  dst[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(cls_pos0) + threadIdx.x);
+}
+
+// out[s, :] = sum|mean over rows [offsets[s], offsets[s+1]) of in[:, dim].  One block per
+// (segment, 512-column slab); 4 row-groups of 128 threads each stride over the rows with float4
+// loads and are combined through shared memory.  Algorithmic traffic: rows*dim*4 B in.
+__global__ void __launch_bounds__(512)
+segment_reduce_kernel(const float* __restrict__ in, const int* __restrict__ offsets, int dim,
+                      int mode, float* __restrict__ out) {
+  __shared__ float4 part[4][128];
+  const int s = blockIdx.x;
+  const int col4 = blockIdx.y * 128 + (threadIdx.x & 127);  // float4 column
+  const int grp = threadIdx.x >> 7;
+  const int r0 = offsets[s], r1 = offsets[s + 1];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col4 * 4 < dim) {
+    for (int r = r0 + grp; r < r1; r += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(in + (long long)r * dim + col4 * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  part[grp][threadIdx.x & 127] = acc;
+  __syncthreads();
+  if (grp == 0 && col4 * 4 < dim) {
+    float4 a = part[0][threadIdx.x], b = part[1][threadIdx.x], c = part[2][threadIdx.x],
+           d = part[3][threadIdx.x];
+    float4 r;
+    r.x = (a.x + b.x) + (c.x + d.x);
+    r.y = (a.y + b.y) + (c.y + d.y);
+    r.z = (a.z + b.z) + (c.z + d.z);
+    r.w = (a.w + b.w) + (c.w + d.w);
+    if (mode == MER_SEG_MEAN && r1 > r0) {
+      const float inv = 1.0f / (float)(r1 - r0);
+      r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv;
+    }
+    *reinterpret_cast<float4*>(out + (long long)s * dim + col4 * 4) = r;
+  }
+}
+
+__global__ void iota_offsets_kernel(int* offsets, int n_seg, int step) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= n_seg) offsets[i] = i * step;
+}
+
+}  // namespace
+
+int mer_vit_patchify_launch(const uint8_t* frames_bgr, int n_frames, float* a_patches,
+                            cudaStream_t stream) {
+  const long long total = (long long)n_frames * 196 * 16;
+  if (total <= 0) return 0;
+  vit_patchify_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(frames_bgr, a_patches,
+                                                                           total);
+  MER_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int mer_vit_cls_rows_launch(const float* cls_pos0, float* x, int n_frames, cudaStream_t stream) {
+  if (n_frames <= 0) return 0;
+  vit_cls_rows_kernel<<<n_frames, 192, 0, stream>>>(cls_pos0, x, n_frames);
+  MER_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int mer_segment_reduce_launch(const float* in, const int* offsets, int n_seg, int dim, int mode,
+                              float* out, cudaStream_t stream) {
+  MER_REQUIRE(in && offsets && out, "mer_segment_reduce: null operand");
+  MER_REQUIRE(dim > 0 && dim % 4 == 0, "mer_segment_reduce: dim %d must be a multiple of 4", dim);
+  if (n_seg <= 0) return 0;
+  dim3 grid(n_seg, (dim + 511) / 512);
+  segment_reduce_kernel<<<grid, 512, 0, stream>>>(in, offsets, dim, mode, out);
+  MER_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int mer_iota_offsets_launch(int* offsets, int n_seg, int step, cudaStream_t stream) {
+  iota_offsets_kernel<<<(n_seg + 256) / 256, 256, 0, stream>>>(offsets, n_seg, step);
+  MER_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mer_segment_reduce(const float* in, const int32_t* offsets, int n_seg, int dim,
+                                  int mode, float* out, void* stream) {
+  return mer_segment_reduce_launch(in, offsets, n_seg, dim, mode, out,
+                                   static_cast<cudaStream_t>(stream));
+}

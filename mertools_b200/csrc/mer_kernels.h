@@ -15,3 +15,31 @@ int mer_layernorm_launch(const float* x, const float* gamma, const float* beta, 
 // attention.cu
 int mer_attention_launch(const float* qkv, float* ctx, const int* cu_seqlens, int n_seq,
                          int max_seqlen, int heads, int flags, cudaStream_t stream);
+
+// helpers.cu
+int mer_vit_patchify_launch(const uint8_t* frames_bgr, int n_frames, float* a_patches,
+                            cudaStream_t stream);
+int mer_vit_cls_rows_launch(const float* cls_pos0, float* x, int n_frames, cudaStream_t stream);
+int mer_segment_reduce_launch(const float* in, const int* offsets, int n_seg, int dim, int mode,
+                              float* out, cudaStream_t stream);
+int mer_iota_offsets_launch(int* offsets, int n_seg, int step, cudaStream_t stream);
+
+// encoder.cu — transformer stack shared by ViT (pre-LN) and HuBERT/BERT (post-LN)
+struct MerStackArgs {
+  const MerLayerWeights* layers;
+  int n_layers;
+  int pre_ln;
+  float eps;
+  long long tokens;          // total packed tokens (rows of x)
+  const int* cu_seqlens;     // device [n_seq+1]
+  int n_seq;
+  int max_seqlen;
+  float* x;                  // [tokens,768] residual stream (in/out)
+  float* xn;                 // [tokens,768] scratch (LN out / attention ctx / pre-LN sum)
+  float* qkv;                // [tokens,2304]
+  float* h;                  // [tokens,3072]
+  float* acc;                // optional [tokens,768]: sum of the last `acc_last` hidden states
+  int acc_last;
+  float* opt_hidden;         // optional [(n_layers+1), tokens, 768]
+};
+int mer_run_stack(const MerStackArgs& a, cudaStream_t stream);

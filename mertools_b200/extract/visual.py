@@ -1,0 +1,135 @@
+"""Frame-level visual feature extraction — B200 mirror of
+MERBench/feature_extraction/visual/extract_vision_huggingface.py.
+
+Same CLI flags (:67-72), same ``config.py`` keys, same output naming
+``PATH_TO_FEATURES[dataset]/<model>-<UTT|FRA>/<vid>.npy`` (:79-80,175-189) and the same helper
+names.  The per-clip python loop of the reference (:104-171, one clip per forward, CPU
+preprocessing) becomes: stage uint8 BGR frames of MANY clips in pinned memory, one H2D copy, one
+fused device forward (preprocess + ViT + token-sum) through libmer_b200.so, one D2H copy.
+"""
+from __future__ import annotations
+
+import argparse
+import math
+import os
+
+import numpy as np
+import torch
+
+from ..encoders import VitEncoder
+from . import common
+
+DINO2_LARGE = "dinov2-large"
+DINO2_GIANT = "dinov2-giant"
+DATA2VEC_VISUAL = "data2vec-vision-base-ft1k"
+
+
+def func_read_frames(face_dir, vid):
+    npy_path = os.path.join(face_dir, vid, f"{vid}.npy")
+    assert os.path.exists(npy_path), f"Error: {vid} does not have frames.npy!"
+    return np.load(npy_path)
+
+
+def resample_frames_uniform(frames, nframe=16):
+    """Uniformly sample ``nframe`` frames (reference :44-56).  Indices are floor(i * vlen / m)
+    for i < m = min(nframe, vlen), padded with the last index — computed with the same float64
+    product the reference's ``np.arange(0, vlen, vlen/m).astype(int)`` evaluates."""
+    vlen = len(frames)
+    m = min(nframe, vlen)
+    step = vlen / m
+    indices = [int(0 + i * step) for i in range(m)]
+    indices += [indices[-1]] * (nframe - len(indices))
+    return frames[indices[:nframe]]
+
+
+def split_into_batch(inputs, bsize=32):
+    return [inputs[i * bsize:(i + 1) * bsize] for i in range(math.ceil(len(inputs) / bsize))]
+
+
+class VisualExtractor:
+    """ViT frame encoder + readout over batches of clips."""
+
+    def __init__(self, state_dict, device="cuda", max_frames_per_launch=2048):
+        self.enc = VitEncoder(state_dict, device=device)
+        self.device = self.enc.device
+        self.max_frames = max_frames_per_launch
+        self._pinned = None
+
+    def _stage(self, frame_list):
+        n = sum(len(f) for f in frame_list)
+        if self._pinned is None or self._pinned.shape[0] < n:
+            self._pinned = torch.empty((n, 224, 224, 3), dtype=torch.uint8, pin_memory=True)
+        host = self._pinned[:n]
+        o = 0
+        for f in frame_list:
+            f = np.asarray(f)
+            assert f.dtype == np.uint8 and f.shape[1:] == (224, 224, 3), \
+                f"frames must be uint8 [n,224,224,3] BGR, got {f.dtype} {f.shape}"
+            host[o:o + len(f)] = torch.from_numpy(np.ascontiguousarray(f))
+            o += len(f)
+        return host
+
+    def frame_features(self, frame_list):
+        """list of [n_i,224,224,3] uint8 -> list of [n_i,768] float32 numpy (one H2D, one D2H)."""
+        lens = [len(f) for f in frame_list]
+        host = self._stage(frame_list)
+        outs = []
+        for s in range(0, len(host), self.max_frames):
+            dev = host[s:s + self.max_frames].to(self.device, non_blocking=True)
+            outs.append(self.enc.frame_features(dev))
+        feats = torch.cat(outs).cpu().numpy()
+        res, o = [], 0
+        for n in lens:
+            res.append(feats[o:o + n])
+            o += n
+        return res
+
+    def extract_clips(self, clips, feature_level="UTTERANCE", nframe=None, save_files=None):
+        """clips: list of uint8 [vlen,224,224,3] BGR arrays.  ``nframe`` resamples every clip
+        first (64 in the reference's DINOv2 branch :136, None in the data2vec branch)."""
+        if nframe is not None:
+            clips = [resample_frames_uniform(np.asarray(c), nframe) for c in clips]
+        feats = self.frame_features(clips)
+        out = []
+        for i, f in enumerate(feats):
+            sf = save_files[i] if save_files is not None else None
+            out.append(common.save_feature(sf, f.squeeze(), feature_level, 768))
+        return out
+
+
+def main(params, config=None, clips_per_launch=32):
+    """Reproduces the script body (:74-189) for the HF ViT branches."""
+    if config is None:
+        from .. import config as config  # noqa: PLW0127
+    print(f"==> Extracting {params.model_name} embeddings...")
+    model_name = params.model_name.split(".")[0]
+    face_dir = config.PATH_TO_RAW_FACE[params.dataset]
+    save_dir = os.path.join(config.PATH_TO_FEATURES[params.dataset],
+                            f"{model_name}-{params.feature_level[:3]}")
+    os.makedirs(save_dir, exist_ok=True)
+    model_dir = os.path.join(config.PATH_TO_PRETRAINED_MODELS, f"transformers/{params.model_name}")
+    assert params.gpu != -1, "mertools_b200 has no CPU path (reference: --gpu=-1 means CPU)"
+    torch.cuda.set_device(params.gpu)
+    ext = VisualExtractor(common.load_hf_state_dict(model_dir), device=f"cuda:{params.gpu}")
+    nframe = 64 if params.model_name in (DINO2_LARGE, DINO2_GIANT) else None
+    vids = os.listdir(face_dir)
+    print(f'Find total "{len(vids)}" videos.')
+    for s in range(0, len(vids), clips_per_launch):
+        chunk = vids[s:s + clips_per_launch]
+        clips = [func_read_frames(face_dir, vid) for vid in chunk]
+        files = [os.path.join(save_dir, f"{vid}.npy") for vid in chunk]
+        ext.extract_clips(clips, params.feature_level, nframe=nframe, save_files=files)
+        print(f"Processed {min(s + clips_per_launch, len(vids))}/{len(vids)} videos")
+
+
+def build_parser():
+    parser = argparse.ArgumentParser(description="Run.")
+    parser.add_argument("--dataset", type=str, default="MER2023", help="input dataset")
+    parser.add_argument("--model_name", type=str, default=None, help="name of pretrained model")
+    parser.add_argument("--feature_level", type=str, default="UTTERANCE", help="feature level [FRAME or UTTERANCE]")
+    parser.add_argument("--gpu", type=int, default=0, help="gpu id")
+    return parser
+
+
+if __name__ == "__main__":
+    main(build_parser().parse_args())

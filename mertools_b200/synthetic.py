@@ -1,0 +1,168 @@
+"""Deterministic synthetic checkpoints and inputs (there is no network: no pretrained weights).
+
+Produces HF-named ``state_dict``s (numpy, float32) for ViT-B/16, HuBERT-base and BERT/RoBERTa-base
+(SURVEY.md Appendix A), seeded with ``numpy.random.default_rng`` so that the golden-fixture
+generator (which loads them into the HF classes the reference scripts instantiate), the oracle,
+the CUDA path, bench.py and the GPU box all see bit-identical weights without shipping them.
+
+Values are drawn tensor by tensor in a fixed order; ``scale`` multiplies every matrix weight of
+the transformer layers (the "stress checkpoint" of SURVEY.md Appendix A: scale 4 gives peaky
+softmax rows, large GELU arguments and LayerNorm inputs with large means).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+VIT_CFG = dict(hidden=768, heads=12, ffn=3072, layers=12, image=224, patch=16, eps=1e-12)
+HUBERT_CFG = dict(hidden=768, heads=12, ffn=3072, layers=12, conv_dim=512,
+                  conv_kernel=(10, 3, 3, 3, 3, 2, 2), conv_stride=(5, 2, 2, 2, 2, 2, 2),
+                  pos_kernel=128, pos_groups=16, eps=1e-5)
+BERT_CFG = dict(hidden=768, heads=12, ffn=3072, layers=12, max_pos=512, type_vocab=2, eps=1e-12)
+
+
+class _Gen:
+    def __init__(self, seed):
+        self.rng = np.random.default_rng(seed)
+        self.sd = {}
+
+    def normal(self, name, shape, std):
+        self.sd[name] = (self.rng.standard_normal(shape, dtype=np.float32) * np.float32(std))
+        return self.sd[name]
+
+    def ln(self, prefix, dim):
+        self.sd[prefix + ".weight"] = (1.0 + 0.1 * self.rng.standard_normal(dim)).astype(np.float32)
+        self.sd[prefix + ".bias"] = (0.1 * self.rng.standard_normal(dim)).astype(np.float32)
+
+    def linear(self, prefix, out_dim, in_dim, std):
+        self.normal(prefix + ".weight", (out_dim, in_dim), std)
+        self.normal(prefix + ".bias", (out_dim,), 0.02)
+
+
+def vit_state_dict(seed=0, layers=12, scale=1.0):
+    """Keys of ``transformers.ViTModel(ViTConfig(num_hidden_layers=layers))`` (with pooler)."""
+    c = VIT_CFG
+    g = _Gen(seed)
+    d = c["hidden"]
+    g.normal("embeddings.cls_token", (1, 1, d), 0.02)
+    g.normal("embeddings.position_embeddings", (1, (c["image"] // c["patch"]) ** 2 + 1, d), 0.02)
+    g.normal("embeddings.patch_embeddings.projection.weight", (d, 3, c["patch"], c["patch"]), 0.02)
+    g.normal("embeddings.patch_embeddings.projection.bias", (d,), 0.02)
+    std = 0.02 * scale
+    for i in range(layers):
+        p = f"encoder.layer.{i}."
+        for n in ("query", "key", "value"):
+            g.linear(p + f"attention.attention.{n}", d, d, std)
+        g.linear(p + "attention.output.dense", d, d, std)
+        g.linear(p + "intermediate.dense", c["ffn"], d, std)
+        g.linear(p + "output.dense", d, c["ffn"], std)
+        g.ln(p + "layernorm_before", d)
+        g.ln(p + "layernorm_after", d)
+    g.ln("layernorm", d)
+    g.linear("pooler.dense", d, d, 0.02)
+    return g.sd
+
+
+def hubert_state_dict(seed=1, layers=12, scale=1.0):
+    """Keys of ``transformers.HubertModel(HubertConfig(num_hidden_layers=layers))``."""
+    c = HUBERT_CFG
+    g = _Gen(seed)
+    d, cd = c["hidden"], c["conv_dim"]
+    g.sd["masked_spec_embed"] = g.rng.random(d, dtype=np.float32)
+    cin = 1
+    for i, k in enumerate(c["conv_kernel"]):
+        g.normal(f"feature_extractor.conv_layers.{i}.conv.weight", (cd, cin, k),
+                 np.sqrt(2.0 / (cin * k)))
+        if i == 0:
+            g.ln("feature_extractor.conv_layers.0.layer_norm", cd)
+        cin = cd
+    g.ln("feature_projection.layer_norm", cd)
+    g.linear("feature_projection.projection", d, cd, 0.04)
+    pk, pg = c["pos_kernel"], c["pos_groups"]
+    g.normal("encoder.pos_conv_embed.conv.bias", (d,), 0.02)
+    v = g.normal("encoder.pos_conv_embed.conv.parametrizations.weight.original1", (d, d // pg, pk),
+                 2.0 * np.sqrt(1.0 / (pk * d)))
+    norm = np.sqrt((v.astype(np.float64) ** 2).sum(axis=(0, 1), keepdims=True))
+    g.sd["encoder.pos_conv_embed.conv.parametrizations.weight.original0"] = (
+        norm * (1.0 + 0.1 * g.rng.standard_normal(norm.shape))).astype(np.float32)
+    g.ln("encoder.layer_norm", d)
+    std = 0.02 * scale
+    for i in range(layers):
+        p = f"encoder.layers.{i}."
+        for n in ("k_proj", "v_proj", "q_proj", "out_proj"):
+            g.linear(p + f"attention.{n}", d, d, std)
+        g.ln(p + "layer_norm", d)
+        g.linear(p + "feed_forward.intermediate_dense", c["ffn"], d, std)
+        g.linear(p + "feed_forward.output_dense", d, c["ffn"], std)
+        g.ln(p + "final_layer_norm", d)
+    return g.sd
+
+
+def bert_state_dict(vocab_size, seed=2, layers=12, scale=1.0, max_pos=None, type_vocab=None):
+    """Keys of ``transformers.BertModel`` / ``RobertaModel`` (identical names)."""
+    c = BERT_CFG
+    g = _Gen(seed)
+    d = c["hidden"]
+    g.normal("embeddings.word_embeddings.weight", (vocab_size, d), 0.05)
+    g.normal("embeddings.position_embeddings.weight", (max_pos or c["max_pos"], d), 0.05)
+    g.normal("embeddings.token_type_embeddings.weight", (type_vocab or c["type_vocab"], d), 0.05)
+    g.ln("embeddings.LayerNorm", d)
+    std = 0.02 * scale
+    for i in range(layers):
+        p = f"encoder.layer.{i}."
+        for n in ("query", "key", "value"):
+            g.linear(p + f"attention.self.{n}", d, d, std)
+        g.linear(p + "attention.output.dense", d, d, std)
+        g.ln(p + "attention.output.LayerNorm", d)
+        g.linear(p + "intermediate.dense", c["ffn"], d, std)
+        g.linear(p + "output.dense", d, c["ffn"], std)
+        g.ln(p + "output.LayerNorm", d)
+    g.linear("pooler.dense", d, d, 0.02)
+    return g.sd
+
+
+def fusion_state_dict(seed=3, audio_dim=768, text_dim=768, video_dim=768, hidden=128,
+                      out1=6, out2=1):
+    """Keys of toolkit/models/attention.py:Attention (feat_type='utt'), nn.Linear-style
+    uniform(-1/sqrt(fan_in), 1/sqrt(fan_in)) init, in construction order (attention.py:21-34)."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+
+    def lin(prefix, o, i):
+        b = 1.0 / np.sqrt(i)
+        sd[prefix + ".weight"] = rng.uniform(-b, b, (o, i)).astype(np.float32)
+        sd[prefix + ".bias"] = rng.uniform(-b, b, (o,)).astype(np.float32)
+
+    def mlp(prefix, i):
+        lin(prefix + ".linear_1", hidden, i)
+        lin(prefix + ".linear_2", hidden, hidden)
+        lin(prefix + ".linear_3", hidden, hidden)
+
+    mlp("audio_encoder", audio_dim)
+    mlp("text_encoder", text_dim)
+    mlp("video_encoder", video_dim)
+    mlp("attention_mlp", hidden * 3)
+    lin("fc_att", 3, hidden)
+    lin("fc_out_1", out1, hidden)
+    lin("fc_out_2", out2, hidden)
+    return sd
+
+
+# ---- synthetic inputs ---------------------------------------------------------
+def synth_frames(n_clips, n_frames=8, size=224, seed=0):
+    """uint8 BGR face crops, [n_clips, n_frames, H, W, 3] ~ U{0..255}."""
+    rng = np.random.default_rng(1000 + seed)
+    return rng.integers(0, 256, (n_clips, n_frames, size, size, 3), dtype=np.uint8)
+
+
+def synth_waves(n_clips, n_samples=80000, seed=0):
+    """int16 waveforms round(3000 * N(0,1)) at 16 kHz, [n_clips, n_samples]."""
+    rng = np.random.default_rng(2000 + seed)
+    return np.round(3000.0 * rng.standard_normal((n_clips, n_samples))).astype(np.int16)
+
+
+def synth_fusion_features(n, dim=768, seed=0):
+    rng = np.random.default_rng(3000 + seed)
+    a, t, v = (rng.standard_normal((n, dim), dtype=np.float32) for _ in range(3))
+    emo = rng.integers(0, 6, n).astype(np.int64)
+    val = rng.uniform(-3, 3, n).astype(np.float32)
+    return a, t, v, emo, val

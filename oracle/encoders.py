@@ -1,0 +1,185 @@
+"""ORACLE (test infrastructure — never imported by the product path).
+
+CPU restatement, in plain torch fp32/fp64 tensor ops, of the three encoder forwards the
+reference extractors reach through ``transformers.AutoModel`` (an un-vendored third-party
+dependency of the reference: ``transformers==4.28.0`` pinned in MERBench/environment.yml:44; this
+image ships 5.5.0).  Each function returns the ``hidden_states`` tuple the reference scripts
+consume (``output_hidden_states=True``), i.e. 1 + num_layers tensors ``[B, T, 768]``.
+
+Pinned by tests/test_oracle.py against (a) the HF classes themselves, layer by layer, on the
+synthetic checkpoints of mertools_b200/synthetic.py and (b) the golden fixtures produced by the
+UNMODIFIED reference scripts (tests/golden/make_golden.py).  The reference holds no test or
+golden vector of its own for this path, so those two are the pin.
+
+HF = site-packages/transformers (5.5.0).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def _t(sd, name, dtype):
+    v = sd[name]
+    if not isinstance(v, torch.Tensor):
+        v = torch.from_numpy(v)
+    return v.to(dtype)
+
+
+def _linear(x, sd, prefix, dtype):
+    return F.linear(x, _t(sd, prefix + ".weight", dtype), _t(sd, prefix + ".bias", dtype))
+
+
+def _ln(x, sd, prefix, eps, dtype):
+    return F.layer_norm(x, (x.shape[-1],), _t(sd, prefix + ".weight", dtype),
+                        _t(sd, prefix + ".bias", dtype), eps)
+
+
+def _mha(q, k, v, heads):
+    """softmax(q k^T / sqrt(d)) v, no mask (HF eager_attention_forward, modeling_vit.py:171-196;
+    HubertAttention modeling_hubert.py:262-345; BertSelfAttention)."""
+    B, T, D = q.shape
+    hd = D // heads
+    q = q.view(B, T, heads, hd).transpose(1, 2)
+    k = k.view(B, T, heads, hd).transpose(1, 2)
+    v = v.view(B, T, heads, hd).transpose(1, 2)
+    p = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), dim=-1)
+    return (p @ v).transpose(1, 2).reshape(B, T, D)
+
+
+# ------------------------------------------------------------------------------------------------
+# ViT  (HF models/vit/modeling_vit.py)
+# ------------------------------------------------------------------------------------------------
+def vit_hidden_states(sd, pixel_values, layers=12, heads=12, eps=1e-12, dtype=torch.float32):
+    """``ViTModel(pixel_values, output_hidden_states=True).hidden_states``.
+
+    pixel_values [N,3,224,224].  Embeddings: patch conv k=s=16 (:151,166) -> prepend CLS ->
+    + position embeddings (:117-124).  Layers are PRE-LN (:328-346).  hidden_states[-1] is the
+    last layer's output BEFORE ViTModel.layernorm (:455), which is what the reference reads
+    (extract_vision_huggingface.py:143-144)."""
+    x = pixel_values.to(dtype)
+    w = _t(sd, "embeddings.patch_embeddings.projection.weight", dtype)
+    b = _t(sd, "embeddings.patch_embeddings.projection.bias", dtype)
+    x = F.conv2d(x, w, b, stride=w.shape[-1]).flatten(2).transpose(1, 2)  # [N,196,768]
+    cls = _t(sd, "embeddings.cls_token", dtype).expand(x.shape[0], -1, -1)
+    x = torch.cat([cls, x], dim=1) + _t(sd, "embeddings.position_embeddings", dtype)
+    hs = [x]
+    for i in range(layers):
+        p = f"encoder.layer.{i}."
+        h = _ln(x, sd, p + "layernorm_before", eps, dtype)
+        q = _linear(h, sd, p + "attention.attention.query", dtype)
+        k = _linear(h, sd, p + "attention.attention.key", dtype)
+        v = _linear(h, sd, p + "attention.attention.value", dtype)
+        a = _linear(_mha(q, k, v, heads), sd, p + "attention.output.dense", dtype)
+        x = x + a
+        h = _ln(x, sd, p + "layernorm_after", eps, dtype)
+        h = F.gelu(_linear(h, sd, p + "intermediate.dense", dtype))
+        x = x + _linear(h, sd, p + "output.dense", dtype)
+        hs.append(x)
+    return tuple(hs)
+
+
+# ------------------------------------------------------------------------------------------------
+# HuBERT  (HF models/hubert/modeling_hubert.py)
+# ------------------------------------------------------------------------------------------------
+def hubert_pos_conv_weight(sd, dtype=torch.float32):
+    """Effective weight of the weight-normed positional conv (:45-92): W = g * v / ||v||, the
+    norm taken over dims (0,1) per kernel tap (weight_norm dim=2).  Older checkpoints name the
+    parameters weight_g / weight_v."""
+    pre = "encoder.pos_conv_embed.conv."
+    if pre + "parametrizations.weight.original0" in sd:
+        g = _t(sd, pre + "parametrizations.weight.original0", torch.float64)
+        v = _t(sd, pre + "parametrizations.weight.original1", torch.float64)
+    elif pre + "weight_g" in sd:
+        g = _t(sd, pre + "weight_g", torch.float64)
+        v = _t(sd, pre + "weight_v", torch.float64)
+    else:
+        return _t(sd, pre + "weight", dtype)
+    norm = v.pow(2).sum(dim=(0, 1), keepdim=True).sqrt()
+    return (g * v / norm).to(dtype)
+
+
+def hubert_hidden_states(sd, input_values, layers=12, heads=12, eps=1e-5,
+                         conv_stride=(5, 2, 2, 2, 2, 2, 2), pos_groups=16, dtype=torch.float32):
+    """``HubertModel(input_values, output_hidden_states=True).hidden_states`` in eval mode.
+
+    input_values [B, L] (already zero-mean/unit-variance).  Feature encoder (:178-213): conv0 +
+    GroupNorm(512 groups) + GELU (:154-175), conv1..6 + GELU (:106-124), no biases.  Feature
+    projection (:216-231): LayerNorm(512) -> Linear.  Positional conv (:45-103): grouped conv
+    k=128 pad=64, drop last frame, GELU; add; encoder.layer_norm (:440-442).  POST-LN layers
+    (:372-405)."""
+    x = input_values.to(dtype)[:, None, :]
+    n_conv = len(conv_stride)
+    for i in range(n_conv):
+        w = _t(sd, f"feature_extractor.conv_layers.{i}.conv.weight", dtype)
+        x = F.conv1d(x, w, stride=conv_stride[i])
+        if i == 0:
+            x = F.group_norm(x, w.shape[0],
+                             _t(sd, "feature_extractor.conv_layers.0.layer_norm.weight", dtype),
+                             _t(sd, "feature_extractor.conv_layers.0.layer_norm.bias", dtype), 1e-5)
+        x = F.gelu(x)
+    x = x.transpose(1, 2)  # [B,T,512]
+    x = _ln(x, sd, "feature_projection.layer_norm", eps, dtype)
+    x = _linear(x, sd, "feature_projection.projection", dtype)
+    wpos = hubert_pos_conv_weight(sd, dtype)
+    pos = F.conv1d(x.transpose(1, 2), wpos, _t(sd, "encoder.pos_conv_embed.conv.bias", dtype),
+                   padding=wpos.shape[-1] // 2, groups=pos_groups)
+    if wpos.shape[-1] % 2 == 0:
+        pos = pos[:, :, :-1]
+    x = x + F.gelu(pos).transpose(1, 2)
+    x = _ln(x, sd, "encoder.layer_norm", eps, dtype)
+    hs = [x]
+    for i in range(layers):
+        p = f"encoder.layers.{i}."
+        q = _linear(x, sd, p + "attention.q_proj", dtype)
+        k = _linear(x, sd, p + "attention.k_proj", dtype)
+        v = _linear(x, sd, p + "attention.v_proj", dtype)
+        a = _linear(_mha(q, k, v, heads), sd, p + "attention.out_proj", dtype)
+        x = _ln(x + a, sd, p + "layer_norm", eps, dtype)
+        h = F.gelu(_linear(x, sd, p + "feed_forward.intermediate_dense", dtype))
+        h = _linear(h, sd, p + "feed_forward.output_dense", dtype)
+        x = _ln(x + h, sd, p + "final_layer_norm", eps, dtype)
+        hs.append(x)
+    return tuple(hs)
+
+
+def hubert_num_frames(n_samples, conv_kernel=(10, 3, 3, 3, 3, 2, 2), conv_stride=(5, 2, 2, 2, 2, 2, 2)):
+    t = n_samples
+    for k, s in zip(conv_kernel, conv_stride):
+        t = (t - k) // s + 1
+    return t
+
+
+# ------------------------------------------------------------------------------------------------
+# BERT / RoBERTa  (HF models/bert/modeling_bert.py, models/roberta/modeling_roberta.py)
+# ------------------------------------------------------------------------------------------------
+def bert_hidden_states(sd, input_ids, layers=12, heads=12, eps=1e-12, position_offset=0,
+                       dtype=torch.float32):
+    """``BertModel(input_ids, output_hidden_states=True).hidden_states`` (token_type_ids = 0, no
+    padding: the reference tokenises one sentence at a time, extract_text_huggingface.py:222).
+    RoBERTa: same graph with position ids starting at pad_token_id + 1 = 2
+    (modeling_roberta.py:157-159) -> ``position_offset=2``."""
+    ids = torch.as_tensor(input_ids, dtype=torch.long)
+    if ids.dim() == 1:
+        ids = ids[None]
+    T = ids.shape[1]
+    pos = torch.arange(T) + position_offset
+    x = (_t(sd, "embeddings.word_embeddings.weight", dtype)[ids]
+         + _t(sd, "embeddings.token_type_embeddings.weight", dtype)[0]
+         + _t(sd, "embeddings.position_embeddings.weight", dtype)[pos])
+    x = _ln(x, sd, "embeddings.LayerNorm", eps, dtype)
+    hs = [x]
+    for i in range(layers):
+        p = f"encoder.layer.{i}."
+        q = _linear(x, sd, p + "attention.self.query", dtype)
+        k = _linear(x, sd, p + "attention.self.key", dtype)
+        v = _linear(x, sd, p + "attention.self.value", dtype)
+        a = _linear(_mha(q, k, v, heads), sd, p + "attention.output.dense", dtype)
+        x = _ln(x + a, sd, p + "attention.output.LayerNorm", eps, dtype)
+        h = F.gelu(_linear(x, sd, p + "intermediate.dense", dtype))
+        h = _linear(h, sd, p + "output.dense", dtype)
+        x = _ln(x + h, sd, p + "output.LayerNorm", eps, dtype)
+        hs.append(x)
+    return tuple(hs)

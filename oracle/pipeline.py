@@ -1,0 +1,166 @@
+"""ORACLE (test infrastructure — never imported by the product path).
+
+CPU restatement of the per-clip logic of the three reference extractors, around the encoder
+restatements of oracle/encoders.py.  Every function cites the reference lines it follows
+(paths relative to MERBench/feature_extraction/ in /root/reference).  Pinned against the outputs
+of the UNMODIFIED reference scripts by tests/test_oracle.py + tests/golden/ (the reference has
+no tests of its own for this path: SURVEY.md §4).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import encoders as E
+
+
+# ------------------------------------------------------------------------------------------------
+# visual  (visual/extract_vision_huggingface.py)
+# ------------------------------------------------------------------------------------------------
+def resample_frames_uniform_indices(vlen, nframe=16):
+    """Frame indices of ``resample_frames_uniform`` (:44-56): uniform float stride, truncate to
+    int, pad with the last index, cut to nframe.  Same rule in toolkit/utils/functions.py:85-104
+    (load_video_from_npy, n_frms=8, 'uniform')."""
+    n_upd = min(nframe, vlen)
+    indices = np.arange(0, vlen, vlen / n_upd).astype(int).tolist()
+    while len(indices) < nframe:
+        indices.append(indices[-1])
+    return indices[:nframe]
+
+
+def split_into_batch(inputs, bsize=32):
+    """:58-63."""
+    return [inputs[i * bsize:(i + 1) * bsize] for i in range(math.ceil(len(inputs) / bsize))]
+
+
+def vit_preprocess(frames_bgr):
+    """``func_opencv_to_image`` (:29-31, BGR->RGB) + HF ``ViTImageProcessor`` as called at
+    :137-138 for frames that already are 224x224: rescale by 1/255 then (x - 0.5) / 0.5, fp32,
+    NCHW.  (Resize is the identity at 224x224; other sizes are outside round-1 scope.)"""
+    f = np.asarray(frames_bgr)
+    assert f.dtype == np.uint8 and f.shape[1:] == (224, 224, 3), f.shape
+    rgb = f[..., ::-1].astype(np.float32)
+    x = rgb * np.float32(1.0 / 255.0)
+    x = (x - np.float32(0.5)) / np.float32(0.5)
+    return torch.from_numpy(np.ascontiguousarray(x.transpose(0, 3, 1, 2)))
+
+
+def visual_clip_features(sd, frames_bgr, nframe=None, layers=12, feature_level="UTTERANCE",
+                         dtype=torch.float32):
+    """One clip through the DINOv2/data2vec branch (:135-145 / :125-133) and the save logic
+    (:171-189).  ``nframe=64`` reproduces the DINOv2 branch of the script (resample to 64 frames);
+    ``nframe=None`` the data2vec branch (all frames); ``nframe=8`` the 8-frame variant of
+    toolkit/utils/functions.py:79.  Returns the array the script would ``np.save``."""
+    frames = np.asarray(frames_bgr)
+    if nframe is not None:
+        frames = frames[resample_frames_uniform_indices(len(frames), nframe)]
+    inputs = vit_preprocess(frames)
+    embs = []
+    for batch in split_into_batch(inputs, 32):
+        hs = E.vit_hidden_states(sd, batch, layers=layers, dtype=dtype)
+        embs.append(torch.stack(hs)[-1].sum(dim=1))  # :143-144
+    emb = torch.cat(embs, dim=0).float().squeeze().numpy()  # :171
+    emb = np.array(emb).squeeze()
+    if feature_level == "FRAME":
+        if len(emb) == 0:
+            emb = np.zeros((1, 768))
+        elif emb.ndim == 1:
+            emb = emb[np.newaxis, :]
+        return emb
+    if len(emb) == 0:
+        return np.zeros((768,))
+    if emb.ndim == 2:
+        emb = np.mean(emb, axis=0)
+    return emb
+
+
+# ------------------------------------------------------------------------------------------------
+# audio  (audio/extract_audio_huggingface.py)
+# ------------------------------------------------------------------------------------------------
+def wav2vec2_normalize(samples):
+    """HF ``Wav2Vec2FeatureExtractor(do_normalize=True)`` as called at :94: cast the float64
+    samples of ``sf.read`` to float32 FIRST, then (x - mean) / sqrt(var + 1e-7) with numpy's
+    float32 reductions (HF feature_extraction_wav2vec2.py:78-97,205-236)."""
+    x = np.asarray(samples)
+    if x.dtype == np.float64:
+        x = x.astype(np.float32)
+    x = np.asarray(x, dtype=np.float32)
+    return (x - x.mean()) / np.sqrt(x.var() + 1e-7)
+
+
+def audio_split_into_batch(input_values, maxlen=16000 * 10):
+    """:40-50 — waveforms longer than 10 s are zero-padded to a multiple of 10 s AFTER
+    normalisation and reshaped into independent rows."""
+    if len(input_values[0]) <= maxlen:
+        return input_values
+    bs, wavlen = input_values.shape
+    assert bs == 1
+    tgt = math.ceil(wavlen / maxlen) * maxlen
+    out = torch.zeros((1, tgt))
+    out[:, :wavlen] = input_values
+    return out.view(-1, maxlen)
+
+
+def audio_clip_features(sd, samples, layers=12, feature_level="UTTERANCE", dtype=torch.float32):
+    """One wav through ``extract`` (:72-110): normalise, chunk, HuBERT, sum of the last four
+    hidden states (:98), flatten (B*T, D) (:100), UTTERANCE -> mean over axis 0 (:105-108)."""
+    iv = torch.from_numpy(wav2vec2_normalize(samples))[None]
+    iv = audio_split_into_batch(iv)
+    hs = E.hubert_hidden_states(sd, iv, layers=layers, dtype=dtype)
+    feat = torch.stack(hs)[[-4, -3, -2, -1]].sum(dim=0)
+    feat = feat.reshape(-1, feat.shape[-1]).float().squeeze().numpy()
+    if feature_level == "UTTERANCE":
+        feat = np.array(feat).squeeze()
+        if feat.ndim != 1:
+            feat = np.mean(feat, axis=0)
+    return feat
+
+
+# ------------------------------------------------------------------------------------------------
+# text  (text/extract_text_huggingface.py)
+# ------------------------------------------------------------------------------------------------
+def find_start_end_pos(tokenizer):
+    """:90-114 — probe the tokenizer with '今天天气真好' to find how many special tokens wrap a
+    sentence.  BERT/RoBERTa-style tokenizers give (1, -1)."""
+    sentence = "今天天气真好"
+    input_ids = tokenizer(sentence, return_tensors="pt")["input_ids"][0]
+    start, end = None, None
+    for start in range(0, 3, 1):
+        outputs = tokenizer.decode(input_ids[start:]).replace(" ", "")
+        if outputs == sentence:
+            return start, None
+        if outputs.startswith(sentence):
+            break
+    for end in range(-1, -3, -1):
+        outputs = tokenizer.decode(input_ids[start:end]).replace(" ", "")
+        if outputs == sentence:
+            break
+    assert tokenizer.decode(input_ids[start:end]).replace(" ", "") == sentence
+    return start, end
+
+
+def text_clip_features(sd, input_ids, start, end, layers=12, feature_level="UTTERANCE",
+                       position_offset=0, eps=1e-12, dtype=torch.float32):
+    """One sentence through :222-249: ids -> BERT -> sum of last four hidden states -> strip
+    [start:end] -> UTTERANCE mean.  ``input_ids`` empty / None reproduces the empty-sentence branch
+    (zeros, float64, :236-249)."""
+    embeddings = []
+    if input_ids is not None and len(input_ids) > 0:
+        hs = E.bert_hidden_states(sd, input_ids, layers=layers, eps=eps,
+                                  position_offset=position_offset, dtype=dtype)
+        out = torch.stack(hs)[[-4, -3, -2, -1]].sum(dim=0).float().numpy()
+        embeddings = out[0, start:end]
+    emb = np.array(embeddings).squeeze()
+    if feature_level == "FRAME":
+        if len(emb) == 0:
+            return np.zeros((1, 768))
+        if emb.ndim == 1:
+            emb = emb[np.newaxis, :]
+        return emb
+    if len(emb) == 0:
+        return np.zeros((768,))
+    if emb.ndim == 2:
+        emb = np.mean(emb, axis=0)
+    return emb

@@ -218,7 +218,19 @@ def sec_attn():
     return ok
 
 
-SECTIONS = dict(gemm=sec_gemm, conv=sec_conv, gemm_perf=sec_gemm_perf, ln=sec_ln, attn=sec_attn)
+def sec_vit():
+    from mertools_b200 import synthetic as S
+    from mertools_b200.encoders import VitEncoder
+    enc = VitEncoder(S.vit_state_dict(seed=0, layers=12), device="cuda")
+    for n in (256, 2048):
+        frames = torch.randint(0, 256, (n, 224, 224, 3), dtype=torch.uint8, device="cuda")
+        ms = time_cuda(lambda: enc.frame_features(frames), iters=3, warmup=2)
+        emit(perf=f"vit_forward_{n}frames", ms=ms, clips_per_s=n / 8 / ms * 1e3,
+             tflops=35.13e9 * n / ms / 1e9)
+    return True
+
+
+SECTIONS = dict(vit=sec_vit, gemm=sec_gemm, conv=sec_conv, gemm_perf=sec_gemm_perf, ln=sec_ln, attn=sec_attn)
 
 if __name__ == "__main__":
     os.makedirs("gpurun_out", exist_ok=True)

@@ -1,0 +1,91 @@
+"""Pin the oracle (oracle/) against the HF classes the reference extractors instantiate.
+
+CPU only.  The reference reaches its arithmetic through transformers.AutoModel; the golden-vector
+tests (test_golden.py) additionally pin the oracle to outputs of the unmodified reference scripts.
+"""
+import numpy as np
+import pytest
+import torch
+
+from mertools_b200 import synthetic as S
+from oracle import encoders as E
+from oracle import pipeline as P
+
+transformers = pytest.importorskip("transformers")
+
+
+def _load(model, sd):
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    return model.eval()
+
+
+def _maxrel(a, b):
+    return float((a - b).abs().max() / b.abs().max())
+
+
+def test_vit_oracle_matches_hf():
+    sd = S.vit_state_dict(seed=0, layers=2, scale=2.0)
+    m = _load(transformers.ViTModel(transformers.ViTConfig(num_hidden_layers=2)), sd)
+    x = P.vit_preprocess(S.synth_frames(1, 2, seed=3)[0])
+    with torch.no_grad():
+        ref = m(x, output_hidden_states=True).hidden_states
+    got = E.vit_hidden_states(sd, x, layers=2)
+    assert len(ref) == len(got) == 3
+    for r, g in zip(ref, got):
+        assert _maxrel(g, r) < 2e-5
+
+
+def test_hubert_oracle_matches_hf():
+    sd = S.hubert_state_dict(seed=1, layers=2, scale=2.0)
+    m = _load(transformers.HubertModel(transformers.HubertConfig(num_hidden_layers=2)), sd)
+    wav = S.synth_waves(2, 16000, seed=4).astype(np.float64) / 32768.0
+    iv = torch.from_numpy(np.stack([P.wav2vec2_normalize(w) for w in wav]))
+    with torch.no_grad():
+        ref = m(iv, output_hidden_states=True).hidden_states
+    got = E.hubert_hidden_states(sd, iv, layers=2)
+    assert ref[0].shape[1] == E.hubert_num_frames(16000) == 49
+    for r, g in zip(ref, got):
+        assert _maxrel(g, r) < 5e-5
+
+
+def test_wav2vec2_normalize_matches_hf():
+    fe = transformers.Wav2Vec2FeatureExtractor(do_normalize=True)
+    wav = S.synth_waves(1, 8000, seed=5)[0].astype(np.float64) / 32768.0
+    ref = fe(wav, sampling_rate=16000, return_tensors="pt").input_values[0].numpy()
+    got = P.wav2vec2_normalize(wav)
+    assert ref.dtype == got.dtype == np.float32
+    np.testing.assert_array_equal(ref, got)
+
+
+def test_bert_oracle_matches_hf():
+    sd = S.bert_state_dict(300, seed=2, layers=2, scale=2.0)
+    m = _load(transformers.BertModel(transformers.BertConfig(num_hidden_layers=2, vocab_size=300)), sd)
+    ids = torch.tensor([[5, 17, 250, 3, 99, 42, 7]])
+    with torch.no_grad():
+        ref = m(input_ids=ids, output_hidden_states=True).hidden_states
+    got = E.bert_hidden_states(sd, ids, layers=2)
+    for r, g in zip(ref, got):
+        assert _maxrel(g, r) < 2e-5
+
+
+def test_roberta_oracle_matches_hf():
+    sd = S.bert_state_dict(300, seed=2, layers=2, max_pos=514, type_vocab=1)
+    cfg = transformers.RobertaConfig(num_hidden_layers=2, vocab_size=300, max_position_embeddings=514,
+                                     type_vocab_size=1, layer_norm_eps=1e-5)
+    m = _load(transformers.RobertaModel(cfg), sd)
+    ids = torch.tensor([[0, 17, 250, 3, 99, 42, 2]])
+    with torch.no_grad():
+        ref = m(input_ids=ids, output_hidden_states=True).hidden_states
+    got = E.bert_hidden_states(sd, ids, layers=2, eps=1e-5, position_offset=2)
+    for r, g in zip(ref, got):
+        assert _maxrel(g, r) < 2e-5
+
+
+def test_vit_image_processor_matches_oracle_preprocess():
+    proc = transformers.ViTImageProcessor()
+    frames = S.synth_frames(1, 2, seed=6)[0]
+    from PIL import Image
+    pil = [Image.fromarray(np.ascontiguousarray(f[..., ::-1])) for f in frames]
+    ref = proc(images=pil, return_tensors="pt")["pixel_values"]
+    got = P.vit_preprocess(frames)
+    assert float((ref - got).abs().max()) <= 2.4e-7
