@@ -97,12 +97,12 @@ MER_API int mer_attention(const float* qkv, float* ctx, const int32_t* cu_seqlen
 
 /* ---- segment reduce (readouts) ------------------------------------------------------------ */
 enum { MER_SEG_SUM = 0, MER_SEG_MEAN = 1 };
-/* out[s, :] = sum or mean of in[offsets[s] : offsets[s+1], :] (dim % 4 == 0; offsets device int32,
- * n_seg+1 entries).  Empty segments give zeros (extract_text_huggingface.py:236-249 writes zeros
+/* out[s, :] = sum or mean of in[begins[s] : ends[s], :] (dim % 4 == 0; begins/ends device int32,
+ * n_seg entries each; for back-to-back segments pass offsets and offsets+1).  Empty segments give zeros (extract_text_huggingface.py:236-249 writes zeros
  * for an empty sentence).  Replaces hidden_states[-1].sum(dim=1) / np.mean(axis=0)
  * (extract_vision_huggingface.py:144,187-188; extract_audio_huggingface.py:105-108). */
-MER_API int mer_segment_reduce(const float* in, const int32_t* offsets, int n_seg, int dim, int mode,
-                               float* out, void* stream);
+MER_API int mer_segment_reduce(const float* in, const int32_t* begins, const int32_t* ends, int n_seg,
+                               int dim, int mode, float* out, void* stream);
 
 /* ---- transformer encoder stack shared by the three modalities ----------------------------------- */
 typedef struct MerLayerWeights {
@@ -143,6 +143,65 @@ MER_API long long mer_vit_workspace_bytes(int n_frames);
 MER_API int mer_vit_forward(const MerVitModel* model, const uint8_t* frames_bgr, int n_frames,
                             void* workspace, long long workspace_bytes, float* out_frame_feats,
                             float* opt_hidden, void* stream);
+
+/* ---- HuBERT-base audio encoder ------------------------------------------------------------------ */
+typedef struct MerHubertModel {
+  int n_layers;  /* 12 (>= 4: the readout sums the last four hidden states) */
+  float ln_eps;  /* 1e-5 */
+  const float* conv0_w;    /* [512, 10] */
+  const float* gn_g;       /* GroupNorm(512 groups) affine, [512] */
+  const float* gn_b;
+  const float* conv_w[6];  /* conv1..6, [512, k*512] laid out [out][tap][in], tf32-rounded */
+  const float* fp_ln_g;    /* feature_projection.layer_norm [512] */
+  const float* fp_ln_b;
+  const float* fp_w;       /* [768, 512] tf32-rounded */
+  const float* fp_b;
+  const float* pos_w;      /* [16][128][48][48] = [group][tap][out][in], weight-norm folded, tf32 */
+  const float* pos_b;      /* [768] */
+  const float* enc_ln_g;   /* encoder.layer_norm */
+  const float* enc_ln_b;
+  const MerLayerWeights* layers;
+} MerHubertModel;
+
+/* frames produced for n_samples input samples (conv kernels 10,3,3,3,3,2,2 / strides 5,2,2,2,2,2,2) */
+MER_API int mer_hubert_num_frames(int n_samples);
+MER_API long long mer_hubert_workspace_bytes(int batch, int n_samples);
+
+/* wave: fp32 [batch, n_samples] raw samples (every row the same length; the reference feeds one
+ * clip at a time, or 10 s rows from split_into_batch, extract_audio_huggingface.py:40-50,95).
+ * normalize != 0 applies the Wav2Vec2FeatureExtractor zero-mean/unit-variance step per row (:94).
+ * Then HubertModel forward (HF modeling_hubert.py) and the readout
+ * torch.stack(hidden_states)[[-4,-3,-2,-1]].sum(0) (:98).
+ * out_frames: NULL or [batch*T, 768] (FRAME level, :100); out_utt: NULL or [batch, 768] = mean over
+ * each row's T frames (UTTERANCE level for clips <= 10 s, :105-108). */
+MER_API int mer_hubert_forward(const MerHubertModel* model, const float* wave, int batch, int n_samples,
+                               int normalize, void* workspace, long long workspace_bytes,
+                               float* out_frames, float* out_utt, float* opt_hidden, void* stream);
+
+/* ---- BERT / RoBERTa-base text encoder ------------------------------------------------------------ */
+typedef struct MerBertModel {
+  int n_layers;
+  float ln_eps;             /* 1e-12 (BERT) / 1e-5 (roberta-base checkpoint) */
+  const float* word_emb;    /* [V, 768] */
+  const float* pos_emb;     /* [P, 768] */
+  const float* type_emb0;   /* token_type_embeddings[0], [768] */
+  const float* emb_ln_g;
+  const float* emb_ln_b;
+  const MerLayerWeights* layers;
+} MerBertModel;
+
+MER_API long long mer_bert_workspace_bytes(int tokens, int n_seq);
+
+/* Packed variable-length batch of tokenised sentences (ids from the HF tokenizer on the host, as in
+ * extract_text_huggingface.py:222).  ids/pos_ids: device int32 [tokens]; cu_seqlens: device int32
+ * [n_seq+1]; seg_begins/seg_ends: device int32 [n_seq], the token range kept by the reference's
+ * outputs[0, start:end] slice (:228-231).  out_tokens: NULL or [tokens, 768] = sum of the last four
+ * hidden states (:226); out_utt: NULL or [n_seq, 768] = mean over the kept range (:243-249). */
+MER_API int mer_bert_forward(const MerBertModel* model, const int32_t* ids, const int32_t* pos_ids,
+                             const int32_t* cu_seqlens, int n_seq, int tokens, int max_seqlen,
+                             const int32_t* seg_begins, const int32_t* seg_ends, void* workspace,
+                             long long workspace_bytes, float* out_tokens, float* out_utt,
+                             float* opt_hidden, void* stream);
 
 #ifdef __cplusplus
 }

@@ -54,7 +54,7 @@ int mer_run_stack(const MerStackArgs& a, cudaStream_t stream) {
   MER_REQUIRE(a.tokens > 0 && a.tokens < (1ll << 31), "mer_run_stack: bad token count %lld", a.tokens);
   const long long M = a.tokens;
   const size_t hs_bytes = (size_t)M * D * sizeof(float);
-  if (a.opt_hidden) MER_CUDA_CHECK(cudaMemcpyAsync(a.opt_hidden, a.x, hs_bytes, cudaMemcpyDeviceToDevice, stream));
+  if (a.opt_hidden && !a.hidden0_done) MER_CUDA_CHECK(cudaMemcpyAsync(a.opt_hidden, a.x, hs_bytes, cudaMemcpyDeviceToDevice, stream));
   for (int l = 0; l < a.n_layers; ++l) {
     const MerLayerWeights& w = a.layers[l];
     const int first_acc = a.n_layers - a.acc_last;  // hidden state index l+1 > first_acc is summed
@@ -175,7 +175,207 @@ int mer_vit_forward(const MerVitModel* m, const uint8_t* frames_bgr, int n_frame
   a.h = h;
   a.opt_hidden = opt_hidden;
   MER_TRY(mer_run_stack(a, stream));
-  MER_TRY(mer_segment_reduce_launch(x, offsets, n_frames, D, MER_SEG_SUM, out_frame_feats, stream));
+  MER_TRY(mer_segment_reduce_launch(x, offsets, offsets + 1, n_frames, D, MER_SEG_SUM, out_frame_feats, stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// HuBERT
+// ------------------------------------------------------------------------------------------------
+static const int kHubK[7] = {10, 3, 3, 3, 3, 2, 2};
+static const int kHubS[7] = {5, 2, 2, 2, 2, 2, 2};
+
+struct HubertPlan {
+  int T[7];      // frames after conv i
+  int Tpad[7];   // allocated rows per clip (even)
+  long long off_wave, off_stats, off_ping, off_pong, off_x, off_xn, off_qkv, off_h, off_acc, off_cu,
+      total;
+  long long M;
+};
+
+static HubertPlan hubert_plan(int B, int L) {
+  HubertPlan p;
+  int t = L;
+  for (int i = 0; i < 7; ++i) {
+    t = (t - kHubK[i]) / kHubS[i] + 1;
+    if (t < 0) t = 0;
+    p.T[i] = t;
+    p.Tpad[i] = (t + 1) & ~1;
+  }
+  p.M = (long long)B * p.T[6];
+  auto al = [](long long x) { return (x + 255) & ~255ll; };
+  long long o = 0;
+  p.off_wave = o;  o += al((long long)B * L * 4);
+  p.off_stats = o; o += al((long long)B * 512 * 2 * 8);
+  p.off_ping = o;  o += al((long long)B * p.Tpad[0] * 512 * 4);
+  p.off_pong = o;  o += al((long long)B * p.Tpad[1] * 512 * 4);
+  p.off_x = o;     o += al(p.M * D * 4);
+  p.off_xn = o;    o += al(p.M * D * 4);
+  p.off_qkv = o;   o += al(p.M * DQKV * 4);
+  p.off_h = o;     o += al(p.M * DFF * 4);
+  p.off_acc = o;   o += al(p.M * D * 4);
+  p.off_cu = o;    o += al(((long long)B + 1) * 4);
+  p.total = o;
+  return p;
+}
+
+int mer_hubert_num_frames(int n_samples) { return hubert_plan(1, n_samples).T[6]; }
+
+long long mer_hubert_workspace_bytes(int batch, int n_samples) {
+  return hubert_plan(batch, n_samples).total;
+}
+
+int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L, int normalize,
+                       void* workspace, long long workspace_bytes, float* out_frames, float* out_utt,
+                       float* opt_hidden, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MER_REQUIRE(m && wave && workspace, "mer_hubert_forward: null operand");
+  MER_REQUIRE(B > 0 && L > 0, "mer_hubert_forward: batch=%d n_samples=%d", B, L);
+  MER_REQUIRE(m->n_layers >= 4, "mer_hubert_forward: the last-four readout needs >= 4 layers");
+  const HubertPlan p = hubert_plan(B, L);
+  MER_REQUIRE(p.T[6] > 0, "mer_hubert_forward: %d samples give no output frame", L);
+  MER_REQUIRE(workspace_bytes >= p.total, "mer_hubert_forward: workspace %lld B < required %lld B",
+              workspace_bytes, p.total);
+  char* ws = static_cast<char*>(workspace);
+  float* wave_n = reinterpret_cast<float*>(ws + p.off_wave);
+  double* stats = reinterpret_cast<double*>(ws + p.off_stats);
+  float* ping = reinterpret_cast<float*>(ws + p.off_ping);
+  float* pong = reinterpret_cast<float*>(ws + p.off_pong);
+  float* x = reinterpret_cast<float*>(ws + p.off_x);
+  float* xn = reinterpret_cast<float*>(ws + p.off_xn);
+  float* qkv = reinterpret_cast<float*>(ws + p.off_qkv);
+  float* h = reinterpret_cast<float*>(ws + p.off_h);
+  float* acc = reinterpret_cast<float*>(ws + p.off_acc);
+  int* cu = reinterpret_cast<int*>(ws + p.off_cu);
+  const int T = p.T[6];
+  const long long M = p.M;
+
+  const float* wsrc = wave;
+  if (normalize) {
+    MER_TRY(mer_wave_normalize_launch(wave, wave_n, B, L, L, L, stream));
+    wsrc = wave_n;
+  }
+  // conv0 + GroupNorm + GELU -> ping [B, Tpad0, 512]
+  MER_TRY(mer_hubert_conv0_launch(wsrc, L, B, L, m->conv0_w, m->gn_g, m->gn_b, stats, ping,
+                                  (long long)p.Tpad[0] * 512, stream));
+  // conv1..6 as implicit GEMMs over the time-major activations
+  float* src = ping;
+  float* dst = pong;
+  for (int i = 1; i < 7; ++i) {
+    MerGemmDesc g;
+    memset(&g, 0, sizeof(g));
+    g.A = src;
+    g.W = m->conv_w[i - 1];
+    g.rows_per_batch = p.T[i];
+    g.a_rows_dim = p.Tpad[i - 1] / 2;
+    g.batches = B;
+    g.N = 512;
+    g.K_inner = 512;
+    g.taps = kHubK[i];
+    g.P = 2;
+    g.a_phase_stride = 512;
+    g.a_row_stride = 1024;
+    g.a_batch_stride = (long long)p.Tpad[i - 1] * 512;
+    g.ep.out = dst;
+    g.ep.out_bstride = (i == 6) ? p.T[6] : p.Tpad[i];  // conv6 output is packed [B*T, 512]
+    g.ep.ld_out = 512;
+    g.ep.flags = MER_EPI_GELU | (i == 6 ? 0 : MER_EPI_ROUND_TF32);
+    MER_TRY(mer_gemm_tf32_launch(&g, stream));
+    float* tmp = src;
+    src = dst;
+    dst = tmp;
+  }
+  float* feat = src;  // [M, 512]
+  // feature projection: LayerNorm(512) -> Linear 512->768  (x0 lands in the qkv buffer)
+  MER_TRY(mer_layernorm_launch(feat, m->fp_ln_g, m->fp_ln_b, feat, nullptr, M, 512, m->ln_eps,
+                               MER_LN_ROUND_TF32, stream));
+  float* x0 = qkv;
+  MER_TRY(linear(feat, m->fp_w, m->fp_b, nullptr, x0, M, D, 512, 0, stream));
+  // positional conv + GELU + residual -> xn ; encoder.layer_norm -> x
+  MER_TRY(mer_iota_offsets_launch(cu, B, T, stream));
+  MER_TRY(mer_posconv_launch(x0, m->pos_w, m->pos_b, cu, B, T, xn, stream));
+  if (opt_hidden)
+    MER_TRY(mer_layernorm_launch(xn, m->enc_ln_g, m->enc_ln_b, opt_hidden, nullptr, M, D, m->ln_eps,
+                                 0, stream));
+  MER_TRY(mer_layernorm_launch(xn, m->enc_ln_g, m->enc_ln_b, x, nullptr, M, D, m->ln_eps,
+                               MER_LN_ROUND_TF32, stream));
+  MerStackArgs a;
+  memset(&a, 0, sizeof(a));
+  a.layers = m->layers;
+  a.n_layers = m->n_layers;
+  a.pre_ln = 0;
+  a.eps = m->ln_eps;
+  a.tokens = M;
+  a.cu_seqlens = cu;
+  a.n_seq = B;
+  a.max_seqlen = T;
+  a.x = x;
+  a.xn = xn;
+  a.qkv = qkv;
+  a.h = h;
+  a.acc = acc;
+  a.acc_last = 4;
+  a.opt_hidden = opt_hidden;
+  a.hidden0_done = 1;
+  MER_TRY(mer_run_stack(a, stream));
+  if (out_frames)
+    MER_CUDA_CHECK(cudaMemcpyAsync(out_frames, acc, (size_t)M * D * 4, cudaMemcpyDeviceToDevice, stream));
+  if (out_utt)
+    MER_TRY(mer_segment_reduce_launch(acc, cu, cu + 1, B, D, MER_SEG_MEAN, out_utt, stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BERT / RoBERTa
+// ------------------------------------------------------------------------------------------------
+long long mer_bert_workspace_bytes(int tokens, int n_seq) {
+  const long long M = tokens;
+  return M * (D + D + DQKV + DFF + D) * 4 + 4096;
+}
+
+int mer_bert_forward(const MerBertModel* m, const int32_t* ids, const int32_t* pos_ids,
+                     const int32_t* cu_seqlens, int n_seq, int tokens, int max_seqlen,
+                     const int32_t* seg_begins, const int32_t* seg_ends, void* workspace,
+                     long long workspace_bytes, float* out_tokens, float* out_utt, float* opt_hidden,
+                     void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MER_REQUIRE(m && ids && pos_ids && cu_seqlens && workspace, "mer_bert_forward: null operand");
+  MER_REQUIRE(n_seq > 0 && tokens > 0 && max_seqlen > 0, "mer_bert_forward: empty batch");
+  MER_REQUIRE(m->n_layers >= 4, "mer_bert_forward: the last-four readout needs >= 4 layers");
+  MER_REQUIRE(workspace_bytes >= mer_bert_workspace_bytes(tokens, n_seq),
+              "mer_bert_forward: workspace %lld B < required %lld B", workspace_bytes,
+              mer_bert_workspace_bytes(tokens, n_seq));
+  const long long M = tokens;
+  float* x = static_cast<float*>(workspace);
+  float* xn = x + M * D;
+  float* qkv = xn + M * D;
+  float* h = qkv + M * DQKV;
+  float* acc = h + M * DFF;
+  MER_TRY(mer_bert_embed_launch(ids, pos_ids, m->word_emb, m->pos_emb, m->type_emb0, m->emb_ln_g,
+                                m->emb_ln_b, m->ln_eps, tokens, x, opt_hidden, stream));
+  MerStackArgs a;
+  memset(&a, 0, sizeof(a));
+  a.layers = m->layers;
+  a.n_layers = m->n_layers;
+  a.pre_ln = 0;
+  a.eps = m->ln_eps;
+  a.tokens = M;
+  a.cu_seqlens = cu_seqlens;
+  a.n_seq = n_seq;
+  a.max_seqlen = max_seqlen;
+  a.x = x;
+  a.xn = xn;
+  a.qkv = qkv;
+  a.h = h;
+  a.acc = acc;
+  a.acc_last = 4;
+  a.opt_hidden = opt_hidden;
+  a.hidden0_done = 1;
+  MER_TRY(mer_run_stack(a, stream));
+  if (out_tokens)
+    MER_CUDA_CHECK(cudaMemcpyAsync(out_tokens, acc, (size_t)M * D * 4, cudaMemcpyDeviceToDevice, stream));
+  if (out_utt && seg_begins && seg_ends)
+    MER_TRY(mer_segment_reduce_launch(acc, seg_begins, seg_ends, n_seq, D, MER_SEG_MEAN, out_utt, stream));
   return 0;
 }
 

@@ -57,13 +57,13 @@ __global__ void vit_cls_rows_kernel(const float* __restrict__ cls_pos0, float* _
 // (segment, 512-column slab); 4 row-groups of 128 threads each stride over the rows with float4
 // loads and are combined through shared memory.  Algorithmic traffic: rows*dim*4 B in.
 __global__ void __launch_bounds__(512)
-segment_reduce_kernel(const float* __restrict__ in, const int* __restrict__ offsets, int dim,
-                      int mode, float* __restrict__ out) {
+segment_reduce_kernel(const float* __restrict__ in, const int* __restrict__ begins,
+                      const int* __restrict__ ends, int dim, int mode, float* __restrict__ out) {
   __shared__ float4 part[4][128];
   const int s = blockIdx.x;
   const int col4 = blockIdx.y * 128 + (threadIdx.x & 127);  // float4 column
   const int grp = threadIdx.x >> 7;
-  const int r0 = offsets[s], r1 = offsets[s + 1];
+  const int r0 = begins[s], r1 = max(ends[s], begins[s]);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (col4 * 4 < dim) {
     for (int r = r0 + grp; r < r1; r += 4) {
@@ -86,6 +86,52 @@ segment_reduce_kernel(const float* __restrict__ in, const int* __restrict__ offs
       r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv;
     }
     *reinterpret_cast<float4*>(out + (long long)s * dim + col4 * 4) = r;
+  }
+}
+
+// BERT/RoBERTa embeddings (HF modeling_bert.py BertEmbeddings / modeling_roberta.py:56-122):
+// (word[id] + token_type[0]) + position[pos] -> LayerNorm -> tf32-rounded x.  One warp per token.
+__global__ void __launch_bounds__(256)
+bert_embed_ln_kernel(const int* __restrict__ ids, const int* __restrict__ pos_ids,
+                     const float* __restrict__ word, const float* __restrict__ pos,
+                     const float* __restrict__ type0, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, int tokens, float* __restrict__ out,
+                     float* __restrict__ out_exact) {
+  const int lane = threadIdx.x & 31;
+  const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tok >= tokens) return;
+  const float4* w = reinterpret_cast<const float4*>(word + (long long)ids[tok] * 768);
+  const float4* p = reinterpret_cast<const float4*>(pos + (long long)pos_ids[tok] * 768);
+  const float4* ty = reinterpret_cast<const float4*>(type0);
+  float4 v[6];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const float4 a = __ldg(w + lane + 32 * i), b = __ldg(ty + lane + 32 * i), c = __ldg(p + lane + 32 * i);
+    v[i].x = (a.x + b.x) + c.x; v[i].y = (a.y + b.y) + c.y;
+    v[i].z = (a.z + b.z) + c.z; v[i].w = (a.w + b.w) + c.w;
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / 768);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / 768) + eps);
+  float4* o = reinterpret_cast<float4*>(out + (long long)tok * 768);
+  float4* oe = out_exact ? reinterpret_cast<float4*>(out_exact + (long long)tok * 768) : nullptr;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
+    float4 r;
+    r.x = v[i].x * rstd * g.x + b.x; r.y = v[i].y * rstd * g.y + b.y;
+    r.z = v[i].z * rstd * g.z + b.z; r.w = v[i].w * rstd * g.w + b.w;
+    if (oe) oe[lane + 32 * i] = r;
+    r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w);
+    o[lane + 32 * i] = r;
   }
 }
 
@@ -113,13 +159,23 @@ int mer_vit_cls_rows_launch(const float* cls_pos0, float* x, int n_frames, cudaS
   return 0;
 }
 
-int mer_segment_reduce_launch(const float* in, const int* offsets, int n_seg, int dim, int mode,
-                              float* out, cudaStream_t stream) {
-  MER_REQUIRE(in && offsets && out, "mer_segment_reduce: null operand");
+int mer_segment_reduce_launch(const float* in, const int* begins, const int* ends, int n_seg,
+                              int dim, int mode, float* out, cudaStream_t stream) {
+  MER_REQUIRE(in && begins && ends && out, "mer_segment_reduce: null operand");
   MER_REQUIRE(dim > 0 && dim % 4 == 0, "mer_segment_reduce: dim %d must be a multiple of 4", dim);
   if (n_seg <= 0) return 0;
   dim3 grid(n_seg, (dim + 511) / 512);
-  segment_reduce_kernel<<<grid, 512, 0, stream>>>(in, offsets, dim, mode, out);
+  segment_reduce_kernel<<<grid, 512, 0, stream>>>(in, begins, ends, dim, mode, out);
+  MER_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int mer_bert_embed_launch(const int* ids, const int* pos_ids, const float* word, const float* pos,
+                          const float* type0, const float* gamma, const float* beta, float eps,
+                          int tokens, float* out, float* out_exact, cudaStream_t stream) {
+  if (tokens <= 0) return 0;
+  bert_embed_ln_kernel<<<(tokens + 7) / 8, 256, 0, stream>>>(ids, pos_ids, word, pos, type0, gamma,
+                                                            beta, eps, tokens, out, out_exact);
   MER_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -130,8 +186,8 @@ int mer_iota_offsets_launch(int* offsets, int n_seg, int step, cudaStream_t stre
   return 0;
 }
 
-extern "C" int mer_segment_reduce(const float* in, const int32_t* offsets, int n_seg, int dim,
-                                  int mode, float* out, void* stream) {
-  return mer_segment_reduce_launch(in, offsets, n_seg, dim, mode, out,
+extern "C" int mer_segment_reduce(const float* in, const int32_t* begins, const int32_t* ends,
+                                  int n_seg, int dim, int mode, float* out, void* stream) {
+  return mer_segment_reduce_launch(in, begins, ends, n_seg, dim, mode, out,
                                    static_cast<cudaStream_t>(stream));
 }

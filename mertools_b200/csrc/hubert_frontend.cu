@@ -1,0 +1,147 @@
+// hubert_frontend.cu — the HBM-bound head of the audio encoder (SURVEY.md kernel rows A0/A1):
+//
+//   wave_normalize   : HF Wav2Vec2FeatureExtractor zero-mean / unit-variance, eps 1e-7
+//                      (feature_extraction_wav2vec2.py:78-97, called at
+//                      extract_audio_huggingface.py:94)
+//   conv0_stats      : per (clip, channel) sum / sum-of-squares of Conv1d(1->512, k=10, s=5)
+//                      over time, for GroupNorm(512 groups) (modeling_hubert.py:154-175)
+//   conv0_apply      : recompute conv0, normalise, affine, exact GELU, round to tf32, write the
+//                      TIME-MAJOR activation [B, T0_pad, 512] that the conv1 implicit GEMM reads.
+//
+// The fp32 conv0 output (32.8 MB per 5 s clip) is never materialised un-normalised: the waveform
+// (320 KB per clip) is read three times instead.  Algorithmic traffic per clip:
+// 3 x 320 KB in + 15,999 x 512 x 4 B = 32.8 MB out.
+#include "mer_common.cuh"
+#include "mer_kernels.h"
+
+namespace {
+
+using namespace mer;
+
+constexpr int C0 = 512;
+constexpr int K0 = 10;
+constexpr int S0 = 5;
+
+__device__ __forceinline__ double block_sum_double(double v, double* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double r = 0.0;
+  const int nw = blockDim.x >> 5;
+  for (int i = 0; i < nw; ++i) r += sh[i];
+  __syncthreads();
+  return r;
+}
+
+// one block per clip; two passes over the waveform (mean, then variance about the mean)
+__global__ void __launch_bounds__(1024)
+wave_normalize_kernel(const float* __restrict__ in, float* __restrict__ out, int L, long long ld_in,
+                      long long ld_out) {
+  __shared__ double sh[32];
+  const float* x = in + (long long)blockIdx.x * ld_in;
+  float* y = out + (long long)blockIdx.x * ld_out;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) s += (double)x[i];
+  const double mean = block_sum_double(s, sh) / (double)L;
+  double q = 0.0;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    const double d = (double)x[i] - mean;
+    q += d * d;
+  }
+  const double var = block_sum_double(q, sh) / (double)L;
+  const float meanf = (float)mean;
+  const float denom = sqrtf((float)var + 1e-7f);
+  for (int i = threadIdx.x; i < L; i += blockDim.x) y[i] = (x[i] - meanf) / denom;
+}
+
+// grid (chunks, B); 512 threads = one channel each; each block covers TCHUNK output frames.
+constexpr int TCHUNK = 128;
+
+__global__ void __launch_bounds__(C0)
+conv0_stats_kernel(const float* __restrict__ wave, long long ld_wave, const float* __restrict__ w0,
+                   int T0, double* __restrict__ stats /*[B,512,2]*/) {
+  __shared__ float xs[TCHUNK * S0 + K0];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * TCHUNK;
+  const int nt = min(TCHUNK, T0 - t0);
+  const float* x = wave + (long long)b * ld_wave + (long long)t0 * S0;
+  const int nx = (nt - 1) * S0 + K0;
+  for (int i = threadIdx.x; i < nx; i += blockDim.x) xs[i] = x[i];
+  __syncthreads();
+  const int c = threadIdx.x;
+  float w[K0];
+#pragma unroll
+  for (int k = 0; k < K0; ++k) w[k] = __ldg(w0 + c * K0 + k);
+  float s = 0.f, q = 0.f;
+  for (int t = 0; t < nt; ++t) {
+    float y = 0.f;
+#pragma unroll
+    for (int k = 0; k < K0; ++k) y = fmaf(w[k], xs[t * S0 + k], y);
+    s += y;
+    q = fmaf(y, y, q);
+  }
+  atomicAdd(&stats[((long long)b * C0 + c) * 2 + 0], (double)s);
+  atomicAdd(&stats[((long long)b * C0 + c) * 2 + 1], (double)q);
+}
+
+__global__ void __launch_bounds__(C0)
+conv0_apply_kernel(const float* __restrict__ wave, long long ld_wave, const float* __restrict__ w0,
+                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                   const double* __restrict__ stats, int T0, long long out_bstride /*floats*/,
+                   float* __restrict__ out) {
+  __shared__ float xs[TCHUNK * S0 + K0];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * TCHUNK;
+  const int nt = min(TCHUNK, T0 - t0);
+  const float* x = wave + (long long)b * ld_wave + (long long)t0 * S0;
+  const int nx = (nt - 1) * S0 + K0;
+  for (int i = threadIdx.x; i < nx; i += blockDim.x) xs[i] = x[i];
+  __syncthreads();
+  const int c = threadIdx.x;
+  float w[K0];
+#pragma unroll
+  for (int k = 0; k < K0; ++k) w[k] = __ldg(w0 + c * K0 + k);
+  // GroupNorm with num_groups == channels: biased variance over time, eps 1e-5
+  const double sum = stats[((long long)b * C0 + c) * 2 + 0];
+  const double sq = stats[((long long)b * C0 + c) * 2 + 1];
+  const double mean_d = sum / (double)T0;
+  double var_d = sq / (double)T0 - mean_d * mean_d;
+  if (var_d < 0.0) var_d = 0.0;
+  const float mean = (float)mean_d;
+  const float rstd = (float)(1.0 / sqrt(var_d + 1e-5));
+  const float g = __ldg(gamma + c) * rstd;
+  const float bt = __ldg(beta + c);
+  float* o = out + (long long)b * out_bstride + (long long)t0 * C0 + c;
+  for (int t = 0; t < nt; ++t) {
+    float y = 0.f;
+#pragma unroll
+    for (int k = 0; k < K0; ++k) y = fmaf(w[k], xs[t * S0 + k], y);
+    o[(long long)t * C0] = round_tf32(gelu_erf((y - mean) * g + bt));
+  }
+}
+
+}  // namespace
+
+int mer_wave_normalize_launch(const float* in, float* out, int B, int L, long long ld_in,
+                              long long ld_out, cudaStream_t stream) {
+  MER_REQUIRE(in && out && B > 0 && L > 0, "mer_wave_normalize: bad arguments");
+  wave_normalize_kernel<<<B, 1024, 0, stream>>>(in, out, L, ld_in, ld_out);
+  MER_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int mer_hubert_conv0_launch(const float* wave, long long ld_wave, int B, int L, const float* w0,
+                            const float* gamma, const float* beta, double* stats, float* out,
+                            long long out_bstride, cudaStream_t stream) {
+  const int T0 = (L - K0) / S0 + 1;
+  MER_REQUIRE(T0 > 0, "mer_hubert_conv0: waveform too short (%d samples)", L);
+  MER_CUDA_CHECK(cudaMemsetAsync(stats, 0, (size_t)B * C0 * 2 * sizeof(double), stream));
+  dim3 grid((T0 + TCHUNK - 1) / TCHUNK, B);
+  conv0_stats_kernel<<<grid, C0, 0, stream>>>(wave, ld_wave, w0, T0, stats);
+  MER_CUDA_CHECK(cudaGetLastError());
+  conv0_apply_kernel<<<grid, C0, 0, stream>>>(wave, ld_wave, w0, gamma, beta, stats, T0,
+                                              out_bstride, out);
+  MER_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

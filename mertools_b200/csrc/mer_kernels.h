@@ -20,8 +20,21 @@ int mer_attention_launch(const float* qkv, float* ctx, const int* cu_seqlens, in
 int mer_vit_patchify_launch(const uint8_t* frames_bgr, int n_frames, float* a_patches,
                             cudaStream_t stream);
 int mer_vit_cls_rows_launch(const float* cls_pos0, float* x, int n_frames, cudaStream_t stream);
-int mer_segment_reduce_launch(const float* in, const int* offsets, int n_seg, int dim, int mode,
-                              float* out, cudaStream_t stream);
+int mer_segment_reduce_launch(const float* in, const int* begins, const int* ends, int n_seg,
+                              int dim, int mode, float* out, cudaStream_t stream);
+int mer_bert_embed_launch(const int* ids, const int* pos_ids, const float* word, const float* pos,
+                          const float* type0, const float* gamma, const float* beta, float eps,
+                          int tokens, float* out, float* out_exact, cudaStream_t stream);
+
+// hubert_frontend.cu
+int mer_wave_normalize_launch(const float* in, float* out, int B, int L, long long ld_in,
+                              long long ld_out, cudaStream_t stream);
+int mer_hubert_conv0_launch(const float* wave, long long ld_wave, int B, int L, const float* w0,
+                            const float* gamma, const float* beta, double* stats, float* out,
+                            long long out_bstride, cudaStream_t stream);
+// posconv.cu
+int mer_posconv_launch(const float* x0, const float* wp, const float* bias, const int* cu_seqlens,
+                       int n_seq, int max_seqlen, float* x1, cudaStream_t stream);
 int mer_iota_offsets_launch(int* offsets, int n_seg, int step, cudaStream_t stream);
 
 // encoder.cu — transformer stack shared by ViT (pre-LN) and HuBERT/BERT (post-LN)
@@ -41,5 +54,6 @@ struct MerStackArgs {
   float* acc;                // optional [tokens,768]: sum of the last `acc_last` hidden states
   int acc_last;
   float* opt_hidden;         // optional [(n_layers+1), tokens, 768]
+  int hidden0_done;          // caller already wrote opt_hidden[0] (post-LN: the un-rounded LN)
 };
 int mer_run_stack(const MerStackArgs& a, cudaStream_t stream);

@@ -88,3 +88,173 @@ class VitEncoder:
 
 
 VIT_PROBE = "encoder.layer.{i}.layernorm_before.weight"
+
+
+class MerHubertModel(C.Structure):
+    _fields_ = [("n_layers", C.c_int), ("ln_eps", C.c_float), ("conv0_w", C.c_void_p),
+                ("gn_g", C.c_void_p), ("gn_b", C.c_void_p), ("conv_w", C.c_void_p * 6),
+                ("fp_ln_g", C.c_void_p), ("fp_ln_b", C.c_void_p), ("fp_w", C.c_void_p),
+                ("fp_b", C.c_void_p), ("pos_w", C.c_void_p), ("pos_b", C.c_void_p),
+                ("enc_ln_g", C.c_void_p), ("enc_ln_b", C.c_void_p),
+                ("layers", C.POINTER(W.MerLayerWeights))]
+
+
+def fold_pos_conv_weight(sd):
+    """Effective weight of the weight-normed positional conv: g * v / ||v||_(dims 0,1)
+    (HF modeling_hubert.py:45-92; torch weight_norm dim=2), float64 math, fp32 result."""
+    pre = "encoder.pos_conv_embed.conv."
+    if pre + "parametrizations.weight.original0" in sd:
+        g, v = sd[pre + "parametrizations.weight.original0"], sd[pre + "parametrizations.weight.original1"]
+    elif pre + "weight_g" in sd:
+        g, v = sd[pre + "weight_g"], sd[pre + "weight_v"]
+    else:
+        return np.asarray(sd[pre + "weight"], dtype=np.float32)
+    v = np.asarray(v, dtype=np.float64)
+    norm = np.sqrt((v ** 2).sum(axis=(0, 1), keepdims=True))
+    return (np.asarray(g, dtype=np.float64) * v / norm).astype(np.float32)
+
+
+class HubertEncoder:
+    """HuBERT-base (HF ``HubertModel``, group-norm feature extractor, post-LN) + the reference
+    readout ``torch.stack(hidden_states)[[-4,-3,-2,-1]].sum(0)``.
+
+    Reference: MERBench/feature_extraction/audio/extract_audio_huggingface.py:93-110."""
+
+    def __init__(self, state_dict, device="cuda", ln_eps=1e-5):
+        L.check(L.lib().mer_check_device())
+        sd = W._np(state_dict)
+        self.device = torch.device(device)
+        pk = self.pk = W.Packed(self.device)
+        self.n_layers = W.count_layers(sd, "encoder.layers.{i}.layer_norm.weight")
+        m = MerHubertModel()
+        m.n_layers, m.ln_eps = self.n_layers, ln_eps
+        w0 = sd["feature_extractor.conv_layers.0.conv.weight"]
+        assert w0.shape == (512, 1, 10), f"HuBERT-base feature extractor only, conv0 {w0.shape}"
+        assert "feature_extractor.conv_layers.0.layer_norm.weight" in sd and \
+            "feature_extractor.conv_layers.1.layer_norm.weight" not in sd, \
+            "only feat_extract_norm='group' (HuBERT/wav2vec2 base) is implemented"
+        m.conv0_w = pk.keep(w0.reshape(512, 10)).data_ptr()
+        m.gn_g = pk.keep(sd["feature_extractor.conv_layers.0.layer_norm.weight"]).data_ptr()
+        m.gn_b = pk.keep(sd["feature_extractor.conv_layers.0.layer_norm.bias"]).data_ptr()
+        for i, k in enumerate((3, 3, 3, 3, 2, 2)):
+            w = sd[f"feature_extractor.conv_layers.{i + 1}.conv.weight"]
+            assert w.shape == (512, 512, k), w.shape
+            assert f"feature_extractor.conv_layers.{i + 1}.conv.bias" not in sd, "conv_bias=True unsupported"
+            m.conv_w[i] = pk.keep(np.ascontiguousarray(w.transpose(0, 2, 1)).reshape(512, k * 512),
+                                  tf32=True).data_ptr()
+        m.fp_ln_g = pk.keep(sd["feature_projection.layer_norm.weight"]).data_ptr()
+        m.fp_ln_b = pk.keep(sd["feature_projection.layer_norm.bias"]).data_ptr()
+        m.fp_w = pk.keep(sd["feature_projection.projection.weight"], tf32=True).data_ptr()
+        m.fp_b = pk.keep(sd["feature_projection.projection.bias"]).data_ptr()
+        wpos = fold_pos_conv_weight(sd)
+        assert wpos.shape == (768, 48, 128), wpos.shape
+        wp = wpos.reshape(16, 48, 48, 128).transpose(0, 3, 1, 2)  # [g][tap][out][in]
+        m.pos_w = pk.keep(np.ascontiguousarray(wp), tf32=True).data_ptr()
+        m.pos_b = pk.keep(sd["encoder.pos_conv_embed.conv.bias"]).data_ptr()
+        m.enc_ln_g = pk.keep(sd["encoder.layer_norm.weight"]).data_ptr()
+        m.enc_ln_b = pk.keep(sd["encoder.layer_norm.bias"]).data_ptr()
+        self.layers = W.pack_layers(sd, W.HUBERT_NAMES, self.n_layers, pk)
+        m.layers = self.layers
+        self.model = m
+        self.ws = _Workspace(self.device)
+        lib = L.lib()
+        lib.mer_hubert_workspace_bytes.restype = C.c_longlong
+        lib.mer_hubert_workspace_bytes.argtypes = [C.c_int, C.c_int]
+        lib.mer_hubert_num_frames.argtypes = [C.c_int]
+        self._fwd = L.declare("mer_hubert_forward", [C.POINTER(MerHubertModel), C.c_void_p, C.c_int,
+                                                     C.c_int, C.c_int, C.c_void_p, C.c_longlong,
+                                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p])
+
+    def num_frames(self, n_samples):
+        return L.lib().mer_hubert_num_frames(int(n_samples))
+
+    def forward(self, wave: torch.Tensor, normalize=True, want_frames=False, return_hidden=False):
+        """wave: fp32 CUDA [B, L] (equal-length rows).  Returns (utt [B,768], frames [B,T,768]|None
+        [, hidden [(layers+1), B, T, 768]])."""
+        assert wave.dtype == torch.float32 and wave.is_cuda and wave.dim() == 2
+        wave = wave.contiguous()
+        B, Ls = wave.shape
+        T = self.num_frames(Ls)
+        ws = self.ws.get(L.lib().mer_hubert_workspace_bytes(B, Ls))
+        utt = torch.empty(B, 768, dtype=torch.float32, device=self.device)
+        frames = torch.empty(B, T, 768, dtype=torch.float32, device=self.device) if want_frames else None
+        hidden = (torch.empty(self.n_layers + 1, B, T, 768, dtype=torch.float32, device=self.device)
+                  if return_hidden else None)
+        L.check(self._fwd(C.byref(self.model), L.ptr(wave), B, Ls, 1 if normalize else 0, L.ptr(ws),
+                          ws.numel(), L.ptr(frames), L.ptr(utt), L.ptr(hidden), L.stream_ptr()))
+        if return_hidden:
+            return utt, frames, hidden
+        return utt, frames
+
+
+class MerBertModel(C.Structure):
+    _fields_ = [("n_layers", C.c_int), ("ln_eps", C.c_float), ("word_emb", C.c_void_p),
+                ("pos_emb", C.c_void_p), ("type_emb0", C.c_void_p), ("emb_ln_g", C.c_void_p),
+                ("emb_ln_b", C.c_void_p), ("layers", C.POINTER(W.MerLayerWeights))]
+
+
+class BertEncoder:
+    """BERT / RoBERTa-base (HF ``BertModel`` / ``RobertaModel``) over a packed variable-length batch
+    + the reference readout (sum of the last four hidden states, strip specials, mean).
+
+    Reference: MERBench/feature_extraction/text/extract_text_huggingface.py:222-249."""
+
+    def __init__(self, state_dict, device="cuda", ln_eps=1e-12, position_offset=0):
+        L.check(L.lib().mer_check_device())
+        sd = W._np(state_dict)
+        self.device = torch.device(device)
+        pk = self.pk = W.Packed(self.device)
+        self.position_offset = position_offset  # 0 = BERT, 2 = RoBERTa (pad_token_id + 1)
+        self.n_layers = W.count_layers(sd, "encoder.layer.{i}.output.LayerNorm.weight")
+        m = MerBertModel()
+        m.n_layers, m.ln_eps = self.n_layers, ln_eps
+        self.word = pk.keep(sd["embeddings.word_embeddings.weight"])
+        self.pos = pk.keep(sd["embeddings.position_embeddings.weight"])
+        self.vocab_size, self.max_pos = self.word.shape[0], self.pos.shape[0]
+        m.word_emb, m.pos_emb = self.word.data_ptr(), self.pos.data_ptr()
+        m.type_emb0 = pk.keep(sd["embeddings.token_type_embeddings.weight"][0]).data_ptr()
+        m.emb_ln_g = pk.keep(sd["embeddings.LayerNorm.weight"]).data_ptr()
+        m.emb_ln_b = pk.keep(sd["embeddings.LayerNorm.bias"]).data_ptr()
+        self.layers = W.pack_layers(sd, W.BERT_NAMES, self.n_layers, pk)
+        m.layers = self.layers
+        self.model = m
+        self.ws = _Workspace(self.device)
+        lib = L.lib()
+        lib.mer_bert_workspace_bytes.restype = C.c_longlong
+        lib.mer_bert_workspace_bytes.argtypes = [C.c_int, C.c_int]
+        vp, i32 = C.c_void_p, C.c_int
+        self._fwd = L.declare("mer_bert_forward", [C.POINTER(MerBertModel), vp, vp, vp, i32, i32, i32,
+                                                   vp, vp, vp, C.c_longlong, vp, vp, vp, vp])
+
+    def forward(self, id_lists, start=1, end=-1, want_tokens=False, return_hidden=False):
+        """id_lists: list of non-empty python/numpy int sequences (one tokenised sentence each).
+        Returns (utt [n,768], tokens [sum T,768]|None [, hidden, cu_seqlens])."""
+        lens = [len(x) for x in id_lists]
+        assert all(n > 0 for n in lens), "empty sentences are handled by the caller (zeros)"
+        assert max(lens) + self.position_offset <= self.max_pos, "sentence longer than position table"
+        ids = np.concatenate([np.asarray(x, dtype=np.int64) for x in id_lists])
+        assert ids.min() >= 0 and ids.max() < self.vocab_size, "token id outside the vocabulary"
+        cu = np.zeros(len(lens) + 1, dtype=np.int32)
+        cu[1:] = np.cumsum(lens)
+        pos = np.concatenate([np.arange(n) for n in lens]).astype(np.int32) + self.position_offset
+        e = end if end is not None else 0
+        seg_b = (cu[:-1] + (start or 0)).astype(np.int32)
+        seg_e = (cu[1:] + e).astype(np.int32)
+        host = np.concatenate([ids.astype(np.int32), pos, cu, seg_b, seg_e])
+        dev = torch.from_numpy(host).pin_memory().to(self.device, non_blocking=True)
+        n_tok, n_seq = int(cu[-1]), len(lens)
+        d_ids, d_pos = dev[:n_tok], dev[n_tok:2 * n_tok]
+        d_cu = dev[2 * n_tok:2 * n_tok + n_seq + 1]
+        d_b = dev[2 * n_tok + n_seq + 1:2 * n_tok + 2 * n_seq + 1]
+        d_e = dev[2 * n_tok + 2 * n_seq + 1:]
+        ws = self.ws.get(L.lib().mer_bert_workspace_bytes(n_tok, n_seq))
+        utt = torch.empty(n_seq, 768, dtype=torch.float32, device=self.device)
+        toks = torch.empty(n_tok, 768, dtype=torch.float32, device=self.device) if want_tokens else None
+        hidden = (torch.empty(self.n_layers + 1, n_tok, 768, dtype=torch.float32, device=self.device)
+                  if return_hidden else None)
+        L.check(self._fwd(C.byref(self.model), L.ptr(d_ids), L.ptr(d_pos), L.ptr(d_cu), n_seq, n_tok,
+                          max(lens), L.ptr(d_b), L.ptr(d_e), L.ptr(ws), ws.numel(), L.ptr(toks),
+                          L.ptr(utt), L.ptr(hidden), L.stream_ptr()))
+        if return_hidden:
+            return utt, toks, hidden, cu
+        return utt, toks

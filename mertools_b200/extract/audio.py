@@ -1,0 +1,143 @@
+"""Acoustic feature extraction — B200 mirror of
+MERBench/feature_extraction/audio/extract_audio_huggingface.py (HuBERT / wav2vec2-base branch).
+
+Keeps ``extract(model_name, audio_files, save_dir, feature_level, gpu)`` (:52) and
+``split_into_batch`` (:40-50).  The per-file loop of the reference (batch = 1 clip, numpy
+normalisation on the host) becomes: raw float32 samples of many clips staged in pinned memory,
+grouped by length, one fused device pass per group (normalise + conv stack + 12 layers + readout).
+"""
+from __future__ import annotations
+
+import argparse
+import glob
+import math
+import os
+import time
+
+import numpy as np
+import torch
+
+from ..encoders import HubertEncoder
+from . import common
+
+HUBERT_BASE_CHINESE = "chinese-hubert-base"
+WAV2VEC2_BASE_CHINESE = "chinese-wav2vec2-base"
+MAXLEN = 16000 * 10
+
+
+def split_into_batch(input_values, maxlen=MAXLEN):
+    """[1, wavlen] -> [ceil(wavlen/maxlen), maxlen], zero padded (reference :40-50)."""
+    if input_values.shape[1] <= maxlen:
+        return input_values
+    assert input_values.shape[0] == 1
+    wavlen = input_values.shape[1]
+    tgt = math.ceil(wavlen / maxlen) * maxlen
+    out = torch.zeros((1, tgt), dtype=input_values.dtype, device=input_values.device)
+    out[:, :wavlen] = input_values
+    return out.view(-1, maxlen)
+
+
+class AudioExtractor:
+    def __init__(self, state_dict, device="cuda", max_rows_per_launch=128):
+        self.enc = HubertEncoder(state_dict, device=device)
+        self.device = self.enc.device
+        self.max_rows = max_rows_per_launch
+
+    def _run_rows(self, rows, normalize):
+        """rows: CUDA fp32 [R, L] -> frames [R, T, 768] (sum of the last four hidden states)."""
+        outs = []
+        for s in range(0, rows.shape[0], self.max_rows):
+            _, fr = self.enc.forward(rows[s:s + self.max_rows], normalize=normalize, want_frames=True)
+            outs.append(fr.clone())
+        return torch.cat(outs)
+
+    def extract_waves(self, waves, feature_level="UTTERANCE", save_files=None):
+        """waves: list of 1-D float arrays (what ``sf.read`` returns, 16 kHz mono).  Returns the
+        arrays the reference would ``np.save`` (:103-110)."""
+        res = [None] * len(waves)
+        short = {}
+        for i, w in enumerate(waves):
+            w = np.asarray(w)
+            assert w.ndim == 1, "mono audio only"
+            if len(w) <= MAXLEN:
+                short.setdefault(len(w), []).append(i)
+        # clips <= 10 s: batch by identical length; normalisation fused on the device
+        for n, idxs in short.items():
+            host = torch.empty((len(idxs), n), dtype=torch.float32, pin_memory=True)
+            for r, i in enumerate(idxs):
+                host[r] = torch.from_numpy(np.asarray(waves[i]).astype(np.float32))
+            fr = self._run_rows(host.to(self.device, non_blocking=True), normalize=True)
+            feats = fr.mean(dim=1).cpu().numpy() if feature_level == "UTTERANCE" else fr.cpu().numpy()
+            for r, i in enumerate(idxs):
+                res[i] = feats[r]
+        # clips > 10 s: normalise the whole waveform first, then 10 s rows (reference order :94-95)
+        for i, w in enumerate(waves):
+            if res[i] is not None:
+                continue
+            x = torch.from_numpy(np.asarray(w).astype(np.float32))[None].to(self.device)
+            x = (x - x.mean()) / torch.sqrt(x.var(unbiased=False) + 1e-7)
+            rows = split_into_batch(x)
+            fr = self._run_rows(rows.contiguous(), normalize=False).reshape(-1, 768)
+            res[i] = (fr.mean(dim=0) if feature_level == "UTTERANCE" else fr).cpu().numpy()
+        if save_files is not None:
+            for f, r in zip(save_files, res):
+                np.save(f, r)
+        return res
+
+
+def extract(model_name, audio_files, save_dir, feature_level, gpu, config=None, clips_per_launch=128):
+    """Same signature and on-disk result as the reference ``extract`` (:52-113)."""
+    import soundfile as sf
+    if config is None:
+        from .. import config as config  # noqa: PLW0127
+    start_time = time.time()
+    assert gpu != -1, "mertools_b200 has no CPU path (reference: gpu=-1 means CPU)"
+    model_file = os.path.join(config.PATH_TO_PRETRAINED_MODELS, f"transformers/{model_name}")
+    ext = AudioExtractor(common.load_hf_state_dict(model_file), device=f"cuda:{gpu}")
+    for s in range(0, len(audio_files), clips_per_launch):
+        chunk = audio_files[s:s + clips_per_launch]
+        waves = []
+        for audio_file in chunk:
+            samples, sr = sf.read(audio_file)
+            assert sr == 16000, "currently, we only test on 16k audio"
+            waves.append(samples)
+        files = [os.path.join(save_dir, os.path.basename(f)[:-4] + ".npy") for f in chunk]
+        ext.extract_waves(waves, feature_level, save_files=files)
+    print(f"Total time used: {time.time() - start_time:.1f}s.")
+
+
+def build_parser():
+    parser = argparse.ArgumentParser(description="Run.")
+    parser.add_argument("--gpu", type=int, default=0, help="index of gpu")
+    parser.add_argument("--model_name", type=str, default="chinese-hubert-base", help="feature extractor")
+    parser.add_argument("--feature_level", type=str, default="FRAME", help="FRAME or UTTERANCE")
+    parser.add_argument("--dataset", type=str, default="MER2023", help="input dataset")
+    parser.add_argument("--noise_case", type=str, default=None)
+    parser.add_argument("--tts_lang", type=str, default=None)
+    return parser
+
+
+def main(args, config=None):
+    if config is None:
+        from .. import config as config  # noqa: PLW0127
+    audio_dir = config.PATH_TO_RAW_AUDIO[args.dataset]
+    save_dir = config.PATH_TO_FEATURES[args.dataset]
+    if args.noise_case is not None:
+        audio_dir += "_" + args.noise_case
+    if args.tts_lang is not None:
+        audio_dir += "-" + f"tts{args.tts_lang[:3]}16k"
+    audio_files = glob.glob(os.path.join(audio_dir, "*.wav"))
+    print(f'Find total "{len(audio_files)}" audio files.')
+    if args.noise_case is not None:
+        dir_name = f"{args.model_name}-noise{args.noise_case}-{args.feature_level[:3]}"
+    elif args.tts_lang is not None:
+        dir_name = f"{args.model_name}-tts{args.tts_lang[:3]}-{args.feature_level[:3]}"
+    else:
+        dir_name = f"{args.model_name}-{args.feature_level[:3]}"
+    save_dir = os.path.join(save_dir, dir_name)
+    os.makedirs(save_dir, exist_ok=True)
+    extract(args.model_name, audio_files, save_dir, args.feature_level, gpu=args.gpu, config=config)
+
+
+if __name__ == "__main__":
+    main(build_parser().parse_args())
