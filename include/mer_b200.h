@@ -35,7 +35,11 @@ MER_API int mer_abi_version(void);
 MER_API int mer_check_device(void);
 
 /* ---- GEMM (nn.Linear / Conv1d-as-GEMM / patch-embed) ---------------------------------- */
-enum { MER_EPI_GELU = 1, MER_EPI_ROUND_TF32 = 2 };
+enum { MER_EPI_GELU = 1, MER_EPI_ROUND_TF32 = 2, MER_EPI_SPLIT_BF16 = 4 };
+/* Arithmetic mode of a GEMM.  TF32: operands are fp32 arrays (pre-rounded to tf32).  BF16X3: every
+ * operand row of K values is stored as K bf16 "hi" followed by K bf16 "lo" (x = hi + lo to 2^-17) in
+ * the bytes K fp32 values would occupy; three bf16 MMAs per product recover ~fp32 accuracy. */
+enum { MER_GEMM_TF32 = 0, MER_GEMM_BF16X3 = 1 };
 
 typedef struct MerGemmEpilogue {
   const float* bias; /* [N] or NULL */
@@ -47,7 +51,9 @@ typedef struct MerGemmEpilogue {
   long long res_row0;
   int ld_out; /* floats */
   int ld_res;
-  int flags; /* MER_EPI_* */
+  int flags;     /* MER_EPI_* */
+  int split_off; /* MER_EPI_SPLIT_BF16: logical columns per out row (= offset of the lo half);
+                    ld_out stays the row pitch in 4-byte slots */
 } MerGemmEpilogue;
 
 /* A[b, m, tap*K_inner + c] = base[b*a_batch_stride + (m + tap / P)*a_row_stride +
@@ -69,20 +75,26 @@ typedef struct MerGemmDesc {
   long long a_row_stride;
   long long a_batch_stride;
   int force_block_n; /* 0 = auto, 128 or 256 */
+  int mode;          /* MER_GEMM_TF32 | MER_GEMM_BF16X3; all A strides are in 4-byte slots either way */
   MerGemmEpilogue ep;
 } MerGemmDesc;
 
-/* tcgen05 TF32 GEMM with fused epilogue.  Replaces torch nn.Linear / nn.Conv1d calls inside
+/* tcgen05 GEMM with fused epilogue.  Replaces torch nn.Linear / nn.Conv1d calls inside
  * HF ViTLayer / HubertEncoderLayer / BertLayer reached from the reference extractors. */
-MER_API int mer_gemm_tf32(const MerGemmDesc* desc, void* stream);
+MER_API int mer_gemm(const MerGemmDesc* desc, void* stream);
+/* fp32 [rows, K] -> split bf16 [rows, hi(K) | lo(K)] (same byte size); used on weights at load time */
+MER_API int mer_split_bf16(const float* in, void* out, long long rows, int K, void* stream);
 
 /* ---- row-wise kernels ------------------------------------------------------------------ */
 enum { MER_LN_ROUND_TF32 = 1, MER_LN_ACC_INIT = 2, MER_LN_ACC_ADD = 4 };
-/* y = LayerNorm(x) * gamma + beta over the last dim (768 or 512).  Optional side buffer acc
+/* y = LayerNorm(x) * gamma + beta over the last dim (768 or 512).  y (fp32, tf32-rounded when
+ * MER_LN_ROUND_TF32) and y_split (bf16 hi|lo rows, the BF16X3 GEMM operand) are both optional;
+ * at least one must be given.  Optional side buffer acc
  * (same shape): acc = y (ACC_INIT) or acc += y (ACC_ADD) — the "sum of the last four hidden
  * states" readout of extract_audio_huggingface.py:98 / extract_text_huggingface.py:226. */
-MER_API int mer_layernorm(const float* x, const float* gamma, const float* beta, float* y, float* acc,
-                  long long rows, int dim, float eps, int flags, void* stream);
+MER_API int mer_layernorm(const float* x, const float* gamma, const float* beta, float* y,
+                          void* y_split, float* acc, long long rows, int dim, float eps, int flags,
+                          void* stream);
 
 /* in-place round-to-nearest fp32 -> tf32 (weights at load time) */
 MER_API int mer_round_tf32(float* x, long long n, void* stream);
@@ -90,7 +102,8 @@ MER_API int mer_round_tf32(float* x, long long n, void* stream);
 /* ---- attention ------------------------------------------------------------------------- */
 /* softmax(Q K^T / 8) V per (sequence, head); head_dim 64.  qkv is [tokens, 3*heads*64] with
  * Q | K | V column blocks, sequences packed back to back, cu_seqlens[n_seq+1] (device, int32).
- * ctx is [tokens, heads*64].  flags: MER_EPI_ROUND_TF32 rounds ctx for the out-proj GEMM.
+ * ctx is [tokens, heads*64].  flags: MER_EPI_ROUND_TF32 rounds ctx for a TF32 out-proj GEMM,
+ * MER_EPI_SPLIT_BF16 writes ctx as bf16 hi|lo rows for a BF16X3 out-proj GEMM.
  * Replaces HF eager/sdpa attention (modeling_vit.py:171-196, modeling_hubert.py:262-345). */
 MER_API int mer_attention(const float* qkv, float* ctx, const int32_t* cu_seqlens, int n_seq,
                   int max_seqlen, int heads, int flags, void* stream);
@@ -105,6 +118,8 @@ MER_API int mer_segment_reduce(const float* in, const int32_t* begins, const int
                                int dim, int mode, float* out, void* stream);
 
 /* ---- transformer encoder stack shared by the three modalities ----------------------------------- */
+/* GEMM weights (w_*) are tf32-rounded fp32 [N,K] for a MER_GEMM_TF32 stack and split bf16
+ * [N, hi(K)|lo(K)] for a MER_GEMM_BF16X3 stack (ViT: TF32; HuBERT/BERT: BF16X3). */
 typedef struct MerLayerWeights {
   const float* ln1_g; /* ViT: layernorm_before | HuBERT: layer_norm | BERT: attention.output.LayerNorm */
   const float* ln1_b;
@@ -151,10 +166,10 @@ typedef struct MerHubertModel {
   const float* conv0_w;    /* [512, 10] */
   const float* gn_g;       /* GroupNorm(512 groups) affine, [512] */
   const float* gn_b;
-  const float* conv_w[6];  /* conv1..6, [512, k*512] laid out [out][tap][in], tf32-rounded */
+  const float* conv_w[6];  /* conv1..6, [512, k*512] laid out [out][tap][in], split bf16 (BF16X3) */
   const float* fp_ln_g;    /* feature_projection.layer_norm [512] */
   const float* fp_ln_b;
-  const float* fp_w;       /* [768, 512] tf32-rounded */
+  const float* fp_w;       /* [768, 512] split bf16 (BF16X3) */
   const float* fp_b;
   const float* pos_w;      /* [16][128][48][48] = [group][tap][out][in], weight-norm folded, tf32 */
   const float* pos_b;      /* [768] */
@@ -162,6 +177,12 @@ typedef struct MerHubertModel {
   const float* enc_ln_b;
   const MerLayerWeights* layers;
 } MerHubertModel;
+
+/* per-row zero-mean / unit-variance (eps 1e-7) of HF Wav2Vec2FeatureExtractor(do_normalize=True)
+ * (feature_extraction_wav2vec2.py:78-97), as called at extract_audio_huggingface.py:94.
+ * in/out: fp32 [batch, n_samples] with row pitches ld_in / ld_out (floats). */
+MER_API int mer_wave_normalize(const float* in, float* out, int batch, int n_samples, long long ld_in,
+                               long long ld_out, void* stream);
 
 /* frames produced for n_samples input samples (conv kernels 10,3,3,3,3,2,2 / strides 5,2,2,2,2,2,2) */
 MER_API int mer_hubert_num_frames(int n_samples);
@@ -202,6 +223,51 @@ MER_API int mer_bert_forward(const MerBertModel* model, const int32_t* ids, cons
                              const int32_t* seg_begins, const int32_t* seg_ends, void* workspace,
                              long long workspace_bytes, float* out_tokens, float* out_utt,
                              float* opt_hidden, void* stream);
+
+/* ---- Attention fusion network: forward, loss, backward, Adam ------------------------------------ */
+/* toolkit/models/attention.py:8-57 (feat_type 'utt': three MLPEncoders 768->H->H->H, attention MLP
+ * 3H->H->H->H, fc_att H->3, weighted sum, heads H->out1 / H->out2), toolkit/utils/loss.py:5-28,
+ * main-release.py:50-66,205.  Parameters, gradients and Adam moments are flat fp32 buffers in the
+ * reference's state_dict order (audio_encoder.linear_1.weight, .bias, ... fc_out_2.bias). */
+typedef struct MerFusionDims {
+  int audio_dim, text_dim, video_dim; /* 768 each for the base encoders */
+  int hidden;                         /* <= 256 */
+  int out1;                           /* emotion classes (6) */
+  int out2;                           /* valence outputs (1) */
+} MerFusionDims;
+
+MER_API long long mer_fusion_param_count(const MerFusionDims* dims);
+MER_API long long mer_fusion_workspace_bytes(const MerFusionDims* dims, int max_batch);
+
+/* eval-mode forward (no dropout): features [B,hidden], emos_out [B,out1], vals_out [B,out2] —
+ * the first three members of the 4-tuple Attention.forward returns (attention.py:52-57). */
+MER_API int mer_fusion_forward(const MerFusionDims* dims, const float* params, const float* audios,
+                               const float* texts, const float* videos, int batch, void* workspace,
+                               long long workspace_bytes, float* features, float* emos_out,
+                               float* vals_out, void* stream);
+
+/* train-mode forward + CELoss + MSELoss + backward.  grads receives d(loss)/d(params) with
+ * loss = (sum CE + sum SE) * loss_inv_batch (1/batch single-GPU; 1/global_batch under data
+ * parallelism so that an all-reduce SUM of grads gives the reference's batch-mean gradient).
+ * dropout_p > 0: keep-masks come from a counter hash of (seed, *step_counter, index) unless
+ * ext_masks (HOST array of 4 device pointers: audio [B,Da], text, video, concat [B,3H]; entries may
+ * be NULL) supplies them (parity tests inject the reference's masks).
+ * loss_out: device float[3] = {CE mean, MSE mean, total}. */
+MER_API int mer_fusion_fwd_bwd(const MerFusionDims* dims, const float* params, float* grads,
+                               const float* audios, const float* texts, const float* videos,
+                               const int64_t* emos, const float* vals, int batch, float loss_inv_batch,
+                               float dropout_p, unsigned long long seed, const int* step_counter,
+                               const float* const* ext_masks, void* workspace, long long workspace_bytes,
+                               float* loss_out, float* features, float* emos_out, float* vals_out,
+                               void* stream);
+
+/* torch.optim.Adam(lr, betas, eps, weight_decay) with coupled L2, after multiplying the gradient by
+ * grad_scale and (grad_clip > 0) clamping it to [-grad_clip, grad_clip] (clip_grad_value_,
+ * main-release.py:64-65).  *step_counter (device int) is read as t-1 and incremented. */
+MER_API int mer_fusion_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                            long long n, float lr, float beta1, float beta2, float eps,
+                            float weight_decay, float grad_scale, float grad_clip, int* step_counter,
+                            void* stream);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,9 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmer_b200.so")
 
 MER_EPI_GELU = 1
 MER_EPI_ROUND_TF32 = 2
+MER_EPI_SPLIT_BF16 = 4
+MER_GEMM_TF32 = 0
+MER_GEMM_BF16X3 = 1
 MER_LN_ROUND_TF32 = 1
 MER_LN_ACC_INIT = 2
 MER_LN_ACC_ADD = 4
@@ -28,7 +31,7 @@ class MerGemmEpilogue(C.Structure):
         ("bias", C.c_void_p), ("res", C.c_void_p), ("out", C.c_void_p),
         ("out_bstride", C.c_longlong), ("out_row0", C.c_longlong),
         ("res_bstride", C.c_longlong), ("res_row0", C.c_longlong),
-        ("ld_out", C.c_int), ("ld_res", C.c_int), ("flags", C.c_int),
+        ("ld_out", C.c_int), ("ld_res", C.c_int), ("flags", C.c_int), ("split_off", C.c_int),
     ]
 
 
@@ -38,7 +41,7 @@ class MerGemmDesc(C.Structure):
         ("rows_per_batch", C.c_int), ("a_rows_dim", C.c_int), ("batches", C.c_int),
         ("N", C.c_int), ("K_inner", C.c_int), ("taps", C.c_int), ("P", C.c_int),
         ("a_phase_stride", C.c_longlong), ("a_row_stride", C.c_longlong),
-        ("a_batch_stride", C.c_longlong), ("force_block_n", C.c_int),
+        ("a_batch_stride", C.c_longlong), ("force_block_n", C.c_int), ("mode", C.c_int),
         ("ep", MerGemmEpilogue),
     ]
 
@@ -65,9 +68,10 @@ def _declare(l):
     sig = {
         "mer_abi_version": [],
         "mer_check_device": [],
-        "mer_gemm_tf32": [C.POINTER(MerGemmDesc), vp],
-        "mer_layernorm": [vp, vp, vp, vp, vp, i64, i32, f32, i32, vp],
+        "mer_gemm": [C.POINTER(MerGemmDesc), vp],
+        "mer_layernorm": [vp, vp, vp, vp, vp, vp, i64, i32, f32, i32, vp],
         "mer_round_tf32": [vp, i64, vp],
+        "mer_split_bf16": [vp, vp, i64, i32, vp],
         "mer_attention": [vp, vp, vp, i32, i32, i32, i32, vp],
     }
     for name, args in sig.items():
@@ -102,12 +106,13 @@ def stream_ptr():
 
 
 # ---- thin python wrappers of the kernel-level entry points (used by tests and the encoders) ----
-def gemm_tf32(A, W, out, *, bias=None, res=None, gelu=False, round_out=False,
-              rows_per_batch=None, batches=1, a_rows_dim=None, K_inner=None, taps=1, P=1,
-              a_phase_stride=0, a_row_stride=None, a_batch_stride=0,
-              out_bstride=0, out_row0=0, res_bstride=0, res_row0=0,
-              ld_out=None, ld_res=None, force_block_n=0):
-    """out = epilogue(A @ W.T).  A, W, out fp32 CUDA tensors; see MerGemmDesc in mer_b200.h."""
+def gemm(A, W, out, *, bias=None, res=None, gelu=False, round_out=False, split_out=False,
+         mode=MER_GEMM_TF32, rows_per_batch=None, batches=1, a_rows_dim=None, K_inner=None, taps=1, P=1,
+         a_phase_stride=0, a_row_stride=None, a_batch_stride=0,
+         out_bstride=0, out_row0=0, res_bstride=0, res_row0=0,
+         ld_out=None, ld_res=None, force_block_n=0):
+    """out = epilogue(A @ W.T).  A, W: fp32 CUDA tensors of LOGICAL shape [rows, K] / [N, K] (holding
+    tf32-rounded fp32, or split bf16 hi|lo bytes when mode is BF16X3); see MerGemmDesc in mer_b200.h."""
     N, K = W.shape
     d = MerGemmDesc()
     d.A, d.W = A.data_ptr(), W.data_ptr()
@@ -122,6 +127,7 @@ def gemm_tf32(A, W, out, *, bias=None, res=None, gelu=False, round_out=False,
     d.a_row_stride = a_row_stride if a_row_stride is not None else K
     d.a_batch_stride = a_batch_stride if batches > 1 else d.a_row_stride * d.a_rows_dim
     d.force_block_n = force_block_n
+    d.mode = mode
     d.ep.bias = bias.data_ptr() if bias is not None else None
     d.ep.res = res.data_ptr() if res is not None else None
     d.ep.out = out.data_ptr()
@@ -129,16 +135,38 @@ def gemm_tf32(A, W, out, *, bias=None, res=None, gelu=False, round_out=False,
     d.ep.res_bstride, d.ep.res_row0 = res_bstride, res_row0
     d.ep.ld_out = ld_out if ld_out is not None else N
     d.ep.ld_res = ld_res if ld_res is not None else N
-    d.ep.flags = (MER_EPI_GELU if gelu else 0) | (MER_EPI_ROUND_TF32 if round_out else 0)
-    check(lib().mer_gemm_tf32(C.byref(d), stream_ptr()))
+    d.ep.flags = ((MER_EPI_GELU if gelu else 0) | (MER_EPI_ROUND_TF32 if round_out else 0)
+                  | (MER_EPI_SPLIT_BF16 if split_out else 0))
+    d.ep.split_off = N
+    check(lib().mer_gemm(C.byref(d), stream_ptr()))
     return out
 
 
-def layernorm(x, gamma, beta, y, *, eps, acc=None, flags=0):
+gemm_tf32 = gemm
+
+
+def layernorm(x, gamma, beta, y, *, eps, y_split=None, acc=None, flags=0):
     rows = x.numel() // x.shape[-1]
-    check(lib().mer_layernorm(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(acc), rows, x.shape[-1],
-                              eps, flags, stream_ptr()))
+    check(lib().mer_layernorm(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(y_split), ptr(acc), rows,
+                              x.shape[-1], eps, flags, stream_ptr()))
     return y
+
+
+def split_bf16(x):
+    """fp32 [rows, K] CUDA tensor -> same-shape fp32-typed tensor whose bytes are bf16 hi|lo rows."""
+    import torch
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    check(lib().mer_split_bf16(ptr(x), ptr(out), x.numel() // x.shape[-1], x.shape[-1], stream_ptr()))
+    return out
+
+
+def unsplit_bf16(xs):
+    """Inverse of split_bf16 (for tests): hi + lo as fp32."""
+    import torch
+    K = xs.shape[-1]
+    b = xs.contiguous().view(torch.bfloat16).view(*xs.shape[:-1], 2 * K)
+    return b[..., :K].float() + b[..., K:].float()
 
 
 def round_tf32_(x):

@@ -49,7 +49,7 @@ __device__ __forceinline__ void cp_async_wait() {
 
 __global__ void __launch_bounds__(ATT_THREADS, 3)
 attention_kernel(const float* __restrict__ qkv, float* __restrict__ ctx,
-                 const int* __restrict__ cu_seqlens, int heads, int round_out) {
+                 const int* __restrict__ cu_seqlens, int heads, int out_mode) {
   extern __shared__ __align__(16) float smem_f[];
   float* Ks = smem_f;                  // [2][BKV][LDS]
   float* Vs = smem_f + 2 * BKV * LDS;  // [2][BKV][LDS]
@@ -216,7 +216,23 @@ attention_kernel(const float* __restrict__ qkv, float* __restrict__ ctx,
   for (int dt = 0; dt < 8; ++dt) {
     float2 a = make_float2(o[dt][0] * inv_lo, o[dt][1] * inv_lo);
     float2 b = make_float2(o[dt][2] * inv_hi, o[dt][3] * inv_hi);
-    if (round_out) {
+    if (out_mode == 2) {  // split bf16 rows [hi(ldc) | lo(ldc)] for a BF16X3 out-proj GEMM
+      const int col = h * HD + dt * 8 + 2 * t;
+      if (row_lo < len) {
+        uint16_t* o = reinterpret_cast<uint16_t*>(ctx + (long long)(start + row_lo) * ldc);
+        const float hx = bf16_round(a.x), hy = bf16_round(a.y);
+        *reinterpret_cast<uint32_t*>(o + col) = pack_bf16x2(hx, hy);
+        *reinterpret_cast<uint32_t*>(o + ldc + col) = pack_bf16x2(a.x - hx, a.y - hy);
+      }
+      if (row_hi < len) {
+        uint16_t* o = reinterpret_cast<uint16_t*>(ctx + (long long)(start + row_hi) * ldc);
+        const float hx = bf16_round(b.x), hy = bf16_round(b.y);
+        *reinterpret_cast<uint32_t*>(o + col) = pack_bf16x2(hx, hy);
+        *reinterpret_cast<uint32_t*>(o + ldc + col) = pack_bf16x2(b.x - hx, b.y - hy);
+      }
+      continue;
+    }
+    if (out_mode == 1) {
       a.x = round_tf32(a.x); a.y = round_tf32(a.y); b.x = round_tf32(b.x); b.y = round_tf32(b.y);
     }
     if (row_lo < len) *reinterpret_cast<float2*>(c_lo + dt * 8) = a;
@@ -240,7 +256,7 @@ int mer_attention_launch(const float* qkv, float* ctx, const int* cu_seqlens, in
   }
   dim3 grid((max_seqlen + BQ - 1) / BQ, heads, n_seq);
   attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(qkv, ctx, cu_seqlens, heads,
-                                                           (flags & MER_EPI_ROUND_TF32) ? 1 : 0);
+                                                           (flags & MER_EPI_SPLIT_BF16) ? 2 : ((flags & MER_EPI_ROUND_TF32) ? 1 : 0));
   MER_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

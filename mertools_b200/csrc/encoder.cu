@@ -18,7 +18,7 @@ constexpr int DQKV = 2304;
 constexpr int DFF = 3072;
 constexpr int HEADS = 12;
 
-int linear(const float* A, const float* W, const float* bias, const float* res, float* out,
+int linear(int mode, const float* A, const float* W, const float* bias, const float* res, float* out,
            long long M, int N, int K, int flags, cudaStream_t stream) {
   MerGemmDesc g;
   memset(&g, 0, sizeof(g));
@@ -40,7 +40,9 @@ int linear(const float* A, const float* W, const float* bias, const float* res, 
   g.ep.ld_out = N;
   g.ep.ld_res = N;
   g.ep.flags = flags;
-  return mer_gemm_tf32_launch(&g, stream);
+  g.ep.split_off = N;
+  g.mode = mode;
+  return mer_gemm_launch(&g, stream);
 }
 
 #define MER_TRY(expr)          \
@@ -58,38 +60,41 @@ int mer_run_stack(const MerStackArgs& a, cudaStream_t stream) {
   for (int l = 0; l < a.n_layers; ++l) {
     const MerLayerWeights& w = a.layers[l];
     const int first_acc = a.n_layers - a.acc_last;  // hidden state index l+1 > first_acc is summed
+    // operand format of the tensor-core inputs in this stack: tf32-rounded fp32, or split bf16
+    const bool split = a.mode == MER_GEMM_BF16X3;
+    const int opnd = split ? MER_EPI_SPLIT_BF16 : MER_EPI_ROUND_TF32;
     if (a.pre_ln) {
       // x = x + Wo * Attn(LN1(x));  x = x + W2 * GELU(W1 * LN2(x))
-      MER_TRY(mer_layernorm_launch(a.x, w.ln1_g, w.ln1_b, a.xn, nullptr, M, D, a.eps,
-                                   MER_LN_ROUND_TF32, stream));
-      MER_TRY(linear(a.xn, w.w_qkv, w.b_qkv, nullptr, a.qkv, M, DQKV, D, MER_EPI_ROUND_TF32, stream));
-      MER_TRY(mer_attention_launch(a.qkv, a.xn, a.cu_seqlens, a.n_seq, a.max_seqlen, HEADS,
-                                   MER_EPI_ROUND_TF32, stream));
-      MER_TRY(linear(a.xn, w.w_o, w.b_o, a.x, a.x, M, D, D, 0, stream));
-      MER_TRY(mer_layernorm_launch(a.x, w.ln2_g, w.ln2_b, a.xn, nullptr, M, D, a.eps,
-                                   MER_LN_ROUND_TF32, stream));
-      MER_TRY(linear(a.xn, w.w_fc1, w.b_fc1, nullptr, a.h, M, DFF, D,
-                     MER_EPI_GELU | MER_EPI_ROUND_TF32, stream));
-      MER_TRY(linear(a.h, w.w_fc2, w.b_fc2, a.x, a.x, M, D, DFF, 0, stream));
+      MER_TRY(mer_layernorm_launch(a.x, w.ln1_g, w.ln1_b, split ? nullptr : a.xn, split ? a.xn : nullptr,
+                                   nullptr, M, D, a.eps, MER_LN_ROUND_TF32, stream));
+      MER_TRY(linear(a.mode, a.xn, w.w_qkv, w.b_qkv, nullptr, a.qkv, M, DQKV, D, MER_EPI_ROUND_TF32, stream));
+      MER_TRY(mer_attention_launch(a.qkv, a.xn, a.cu_seqlens, a.n_seq, a.max_seqlen, HEADS, opnd, stream));
+      MER_TRY(linear(a.mode, a.xn, w.w_o, w.b_o, a.x, a.x, M, D, D, 0, stream));
+      MER_TRY(mer_layernorm_launch(a.x, w.ln2_g, w.ln2_b, split ? nullptr : a.xn, split ? a.xn : nullptr,
+                                   nullptr, M, D, a.eps, MER_LN_ROUND_TF32, stream));
+      MER_TRY(linear(a.mode, a.xn, w.w_fc1, w.b_fc1, nullptr, a.h, M, DFF, D, MER_EPI_GELU | opnd, stream));
+      MER_TRY(linear(a.mode, a.h, w.w_fc2, w.b_fc2, a.x, a.x, M, D, DFF, 0, stream));
     } else {
-      // x = LN1(x + Wo * Attn(x));  x = LN2(x + W2 * GELU(W1 * x))   (x enters tf32-rounded)
-      MER_TRY(linear(a.x, w.w_qkv, w.b_qkv, nullptr, a.qkv, M, DQKV, D, MER_EPI_ROUND_TF32, stream));
-      MER_TRY(mer_attention_launch(a.qkv, a.xn, a.cu_seqlens, a.n_seq, a.max_seqlen, HEADS,
-                                   MER_EPI_ROUND_TF32, stream));
+      // x = LN1(x + Wo * Attn(x));  x = LN2(x + W2 * GELU(W1 * x)).
+      // TF32: x itself is tf32-rounded and doubles as the GEMM operand.  BF16X3: x stays exact fp32
+      // (residual) and xs carries its split copy (GEMM operand).
+      const float* xop = split ? a.xs : a.x;
+      MER_TRY(linear(a.mode, xop, w.w_qkv, w.b_qkv, nullptr, a.qkv, M, DQKV, D, MER_EPI_ROUND_TF32, stream));
+      MER_TRY(mer_attention_launch(a.qkv, a.xn, a.cu_seqlens, a.n_seq, a.max_seqlen, HEADS, opnd, stream));
       // the pre-LN sum goes to the (now dead) qkv buffer: ctx in xn is still being read
-      MER_TRY(linear(a.xn, w.w_o, w.b_o, a.x, a.qkv, M, D, D, 0, stream));
-      MER_TRY(mer_layernorm_launch(a.qkv, w.ln1_g, w.ln1_b, a.x, nullptr, M, D, a.eps,
-                                   MER_LN_ROUND_TF32, stream));
-      MER_TRY(linear(a.x, w.w_fc1, w.b_fc1, nullptr, a.h, M, DFF, D,
-                     MER_EPI_GELU | MER_EPI_ROUND_TF32, stream));
-      MER_TRY(linear(a.h, w.w_fc2, w.b_fc2, a.x, a.xn, M, D, DFF, 0, stream));
-      int fl = MER_LN_ROUND_TF32;
+      MER_TRY(linear(a.mode, a.xn, w.w_o, w.b_o, a.x, a.qkv, M, D, D, 0, stream));
+      MER_TRY(mer_layernorm_launch(a.qkv, w.ln1_g, w.ln1_b, a.x, split ? a.xs : nullptr, nullptr, M, D,
+                                   a.eps, split ? 0 : MER_LN_ROUND_TF32, stream));
+      MER_TRY(linear(a.mode, xop, w.w_fc1, w.b_fc1, nullptr, a.h, M, DFF, D, MER_EPI_GELU | opnd, stream));
+      MER_TRY(linear(a.mode, a.h, w.w_fc2, w.b_fc2, a.x, a.xn, M, D, DFF, 0, stream));
+      int fl = split ? 0 : MER_LN_ROUND_TF32;
       float* acc = nullptr;
       if (a.acc && a.acc_last > 0 && l + 1 > first_acc) {
         acc = a.acc;
         fl |= (l + 1 == first_acc + 1) ? MER_LN_ACC_INIT : MER_LN_ACC_ADD;
       }
-      MER_TRY(mer_layernorm_launch(a.xn, w.ln2_g, w.ln2_b, a.x, acc, M, D, a.eps, fl, stream));
+      MER_TRY(mer_layernorm_launch(a.xn, w.ln2_g, w.ln2_b, a.x, split ? a.xs : nullptr, acc, M, D, a.eps,
+                                   fl, stream));
     }
     if (a.opt_hidden) {
       // post-LN: the hidden state is the un-rounded LayerNorm output; re-derive it exactly from
@@ -98,7 +103,7 @@ int mer_run_stack(const MerStackArgs& a, cudaStream_t stream) {
       if (a.pre_ln) {
         MER_CUDA_CHECK(cudaMemcpyAsync(dst, a.x, hs_bytes, cudaMemcpyDeviceToDevice, stream));
       } else {
-        MER_TRY(mer_layernorm_launch(a.xn, w.ln2_g, w.ln2_b, dst, nullptr, M, D, a.eps, 0, stream));
+        MER_TRY(mer_layernorm_launch(a.xn, w.ln2_g, w.ln2_b, dst, nullptr, nullptr, M, D, a.eps, 0, stream));
       }
     }
   }
@@ -157,13 +162,15 @@ int mer_vit_forward(const MerVitModel* m, const uint8_t* frames_bgr, int n_frame
     g.ep.out_row0 = 1;
     g.ep.ld_out = D;
     g.ep.ld_res = D;
-    MER_TRY(mer_gemm_tf32_launch(&g, stream));
+    g.mode = MER_GEMM_TF32;
+    MER_TRY(mer_gemm_launch(&g, stream));
   }
   MerStackArgs a;
   memset(&a, 0, sizeof(a));
   a.layers = m->layers;
   a.n_layers = m->n_layers;
   a.pre_ln = 1;
+  a.mode = MER_GEMM_TF32;
   a.eps = m->ln_eps;
   a.tokens = M;
   a.cu_seqlens = offsets;
@@ -188,8 +195,8 @@ static const int kHubS[7] = {5, 2, 2, 2, 2, 2, 2};
 struct HubertPlan {
   int T[7];      // frames after conv i
   int Tpad[7];   // allocated rows per clip (even)
-  long long off_wave, off_stats, off_ping, off_pong, off_x, off_xn, off_qkv, off_h, off_acc, off_cu,
-      total;
+  long long off_wave, off_stats, off_ping, off_pong, off_x, off_xs, off_xn, off_qkv, off_h, off_acc,
+      off_cu, total;
   long long M;
 };
 
@@ -210,6 +217,7 @@ static HubertPlan hubert_plan(int B, int L) {
   p.off_ping = o;  o += al((long long)B * p.Tpad[0] * 512 * 4);
   p.off_pong = o;  o += al((long long)B * p.Tpad[1] * 512 * 4);
   p.off_x = o;     o += al(p.M * D * 4);
+  p.off_xs = o;    o += al(p.M * D * 4);
   p.off_xn = o;    o += al(p.M * D * 4);
   p.off_qkv = o;   o += al(p.M * DQKV * 4);
   p.off_h = o;     o += al(p.M * DFF * 4);
@@ -242,6 +250,7 @@ int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L,
   float* ping = reinterpret_cast<float*>(ws + p.off_ping);
   float* pong = reinterpret_cast<float*>(ws + p.off_pong);
   float* x = reinterpret_cast<float*>(ws + p.off_x);
+  float* xs = reinterpret_cast<float*>(ws + p.off_xs);
   float* xn = reinterpret_cast<float*>(ws + p.off_xn);
   float* qkv = reinterpret_cast<float*>(ws + p.off_qkv);
   float* h = reinterpret_cast<float*>(ws + p.off_h);
@@ -257,7 +266,7 @@ int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L,
   }
   // conv0 + GroupNorm + GELU -> ping [B, Tpad0, 512]
   MER_TRY(mer_hubert_conv0_launch(wsrc, L, B, L, m->conv0_w, m->gn_g, m->gn_b, stats, ping,
-                                  (long long)p.Tpad[0] * 512, stream));
+                                  (long long)p.Tpad[0] * 512, /*split_out=*/1, stream));
   // conv1..6 as implicit GEMMs over the time-major activations
   float* src = ping;
   float* dst = pong;
@@ -279,37 +288,39 @@ int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L,
     g.ep.out = dst;
     g.ep.out_bstride = (i == 6) ? p.T[6] : p.Tpad[i];  // conv6 output is packed [B*T, 512]
     g.ep.ld_out = 512;
-    g.ep.flags = MER_EPI_GELU | (i == 6 ? 0 : MER_EPI_ROUND_TF32);
-    MER_TRY(mer_gemm_tf32_launch(&g, stream));
+    g.ep.flags = MER_EPI_GELU | (i == 6 ? 0 : MER_EPI_SPLIT_BF16);  // conv6 feeds a LayerNorm: fp32
+    g.ep.split_off = 512;
+    g.mode = MER_GEMM_BF16X3;
+    MER_TRY(mer_gemm_launch(&g, stream));
     float* tmp = src;
     src = dst;
     dst = tmp;
   }
   float* feat = src;  // [M, 512]
   // feature projection: LayerNorm(512) -> Linear 512->768  (x0 lands in the qkv buffer)
-  MER_TRY(mer_layernorm_launch(feat, m->fp_ln_g, m->fp_ln_b, feat, nullptr, M, 512, m->ln_eps,
-                               MER_LN_ROUND_TF32, stream));
+  MER_TRY(mer_layernorm_launch(feat, m->fp_ln_g, m->fp_ln_b, nullptr, feat, nullptr, M, 512,
+                               m->ln_eps, 0, stream));
   float* x0 = qkv;
-  MER_TRY(linear(feat, m->fp_w, m->fp_b, nullptr, x0, M, D, 512, 0, stream));
+  MER_TRY(linear(MER_GEMM_BF16X3, feat, m->fp_w, m->fp_b, nullptr, x0, M, D, 512, 0, stream));
   // positional conv + GELU + residual -> xn ; encoder.layer_norm -> x
   MER_TRY(mer_iota_offsets_launch(cu, B, T, stream));
   MER_TRY(mer_posconv_launch(x0, m->pos_w, m->pos_b, cu, B, T, xn, stream));
+  MER_TRY(mer_layernorm_launch(xn, m->enc_ln_g, m->enc_ln_b, x, xs, nullptr, M, D, m->ln_eps, 0, stream));
   if (opt_hidden)
-    MER_TRY(mer_layernorm_launch(xn, m->enc_ln_g, m->enc_ln_b, opt_hidden, nullptr, M, D, m->ln_eps,
-                                 0, stream));
-  MER_TRY(mer_layernorm_launch(xn, m->enc_ln_g, m->enc_ln_b, x, nullptr, M, D, m->ln_eps,
-                               MER_LN_ROUND_TF32, stream));
+    MER_CUDA_CHECK(cudaMemcpyAsync(opt_hidden, x, (size_t)M * D * 4, cudaMemcpyDeviceToDevice, stream));
   MerStackArgs a;
   memset(&a, 0, sizeof(a));
   a.layers = m->layers;
   a.n_layers = m->n_layers;
   a.pre_ln = 0;
+  a.mode = MER_GEMM_BF16X3;
   a.eps = m->ln_eps;
   a.tokens = M;
   a.cu_seqlens = cu;
   a.n_seq = B;
   a.max_seqlen = T;
   a.x = x;
+  a.xs = xs;
   a.xn = xn;
   a.qkv = qkv;
   a.h = h;
@@ -330,7 +341,7 @@ int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L,
 // ------------------------------------------------------------------------------------------------
 long long mer_bert_workspace_bytes(int tokens, int n_seq) {
   const long long M = tokens;
-  return M * (D + D + DQKV + DFF + D) * 4 + 4096;
+  return M * (D + D + D + DQKV + DFF + D) * 4 + 4096;
 }
 
 int mer_bert_forward(const MerBertModel* m, const int32_t* ids, const int32_t* pos_ids,
@@ -347,23 +358,28 @@ int mer_bert_forward(const MerBertModel* m, const int32_t* ids, const int32_t* p
               mer_bert_workspace_bytes(tokens, n_seq));
   const long long M = tokens;
   float* x = static_cast<float*>(workspace);
-  float* xn = x + M * D;
+  float* xs = x + M * D;
+  float* xn = xs + M * D;
   float* qkv = xn + M * D;
   float* h = qkv + M * DQKV;
   float* acc = h + M * DFF;
   MER_TRY(mer_bert_embed_launch(ids, pos_ids, m->word_emb, m->pos_emb, m->type_emb0, m->emb_ln_g,
-                                m->emb_ln_b, m->ln_eps, tokens, x, opt_hidden, stream));
+                                m->emb_ln_b, m->ln_eps, tokens, x, xs, stream));
+  if (opt_hidden)
+    MER_CUDA_CHECK(cudaMemcpyAsync(opt_hidden, x, (size_t)M * D * 4, cudaMemcpyDeviceToDevice, stream));
   MerStackArgs a;
   memset(&a, 0, sizeof(a));
   a.layers = m->layers;
   a.n_layers = m->n_layers;
   a.pre_ln = 0;
+  a.mode = MER_GEMM_BF16X3;
   a.eps = m->ln_eps;
   a.tokens = M;
   a.cu_seqlens = cu_seqlens;
   a.n_seq = n_seq;
   a.max_seqlen = max_seqlen;
   a.x = x;
+  a.xs = xs;
   a.xn = xn;
   a.qkv = qkv;
   a.h = h;

@@ -1,0 +1,535 @@
+// fusion.cu — the Attention-fusion network of MERBench/toolkit/models/attention.py:8-57 (with
+// MLPEncoder, modules/encoder.py:9-41), its loss (toolkit/utils/loss.py:5-28), the backward pass
+// and the Adam update (main-release.py:50-66,205: torch.optim.Adam(lr, weight_decay=l2), optional
+// clip_grad_value_), as explicit fp32 kernels.
+//
+// This is the tiny-kernel regime (0.48 MMAC per clip forward): everything is fp32 SIMT with a
+// FIXED summation order (no atomics -> bit-reproducible), batched across the three modality
+// encoders per launch, and the host captures the whole step in one CUDA graph.  The flat parameter
+// / gradient buffers use the reference's state_dict order so the gradient buffer is the single
+// NCCL all-reduce operand (477,962 floats at hidden 128).
+#include "mer_common.cuh"
+#include "mer_kernels.h"
+
+namespace {
+
+using namespace mer;
+
+struct LinP {          // y = relu?( (x .* mask * mscale) W^T + b )
+  const float* x; int ldx;
+  const float* mask;   // dropout keep-mask (0/1) on x, or null
+  float mscale;
+  const float* W;      // [N,K]
+  const float* b;      // [N]
+  float* y; int ldy;
+  int K, N, relu;
+};
+struct LinBatch { LinP p[3]; };
+
+constexpr int KC = 128;
+
+// grid (ceil(N/8), ceil(B/32), nprob); block 256: warp w -> output column, lane -> batch row
+__global__ void __launch_bounds__(256)
+fus_linear_fwd_kernel(const LinBatch lb, int B) {
+  __shared__ float xs[KC][33];
+  const LinP& p = lb.p[blockIdx.z];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + warp;
+  const int b0 = blockIdx.y * 32;
+  if (blockIdx.x * 8 >= p.N) return;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < p.K; k0 += KC) {
+    const int kc = min(KC, p.K - k0);
+    for (int i = threadIdx.x; i < 32 * KC; i += 256) {
+      const int r = i / KC, k = i % KC;
+      float v = 0.f;
+      if (b0 + r < B && k < kc) {
+        v = p.x[(long long)(b0 + r) * p.ldx + k0 + k];
+        if (p.mask) v *= p.mask[(long long)(b0 + r) * p.K + k0 + k] * p.mscale;
+      }
+      xs[k][r] = v;
+    }
+    __syncthreads();
+    if (n < p.N) {
+      const float* w = p.W + (long long)n * p.K + k0;
+      for (int k = 0; k < kc; ++k) acc = fmaf(xs[k][lane], __ldg(w + k), acc);
+    }
+    __syncthreads();
+  }
+  if (n < p.N && b0 + lane < B) {
+    float v = acc + p.b[n];
+    if (p.relu) v = fmaxf(v, 0.f);
+    p.y[(long long)(b0 + lane) * p.ldy + n] = v;
+  }
+}
+
+struct BwdP {
+  const float* dy; int lddy;   // grad wrt y (post-relu)
+  const float* yact; int ldy;  // y itself (relu mask source) or null
+  const float* x; int ldx;     // layer input (pre-dropout)
+  const float* mask; float mscale;
+  const float* W;
+  float* dW; float* db;        // [N,K], [N]
+  float* dx; int lddx;         // grad wrt x (null to skip)
+  int accumulate_dx;
+  int K, N;
+};
+struct BwdBatch { BwdP p[3]; };
+
+// dW[n,k] = sum_b dyeff[b,n] * xd[b,k];  db[n] = sum_b dyeff[b,n].   grid (ceil(K/256), N, nprob)
+__global__ void __launch_bounds__(256)
+fus_linear_bwd_w_kernel(const BwdBatch bb, int B) {
+  const BwdP& p = bb.p[blockIdx.z];
+  const int n = blockIdx.y;
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  if (n >= p.N || blockIdx.x * 256 >= p.K) return;
+  float acc = 0.f, accb = 0.f;
+  for (int b = 0; b < B; ++b) {
+    float g = p.dy[(long long)b * p.lddy + n];
+    if (p.yact && !(p.yact[(long long)b * p.ldy + n] > 0.f)) g = 0.f;
+    accb += g;
+    if (k < p.K) {
+      float xv = p.x[(long long)b * p.ldx + k];
+      if (p.mask) xv *= p.mask[(long long)b * p.K + k] * p.mscale;
+      acc = fmaf(g, xv, acc);
+    }
+  }
+  if (k < p.K) p.dW[(long long)n * p.K + k] = acc;
+  if (k == 0) p.db[n] = accb;
+}
+
+// dx[b,k] (+)= (sum_n dyeff[b,n] W[n,k]) * mask.   grid (ceil(K/256), B, nprob)
+__global__ void __launch_bounds__(256)
+fus_linear_bwd_x_kernel(const BwdBatch bb, int B) {
+  __shared__ float dys[256];
+  const BwdP& p = bb.p[blockIdx.z];
+  if (!p.dx || blockIdx.x * 256 >= p.K) return;
+  const int b = blockIdx.y;
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  for (int n = threadIdx.x; n < p.N; n += 256) {
+    float g = p.dy[(long long)b * p.lddy + n];
+    if (p.yact && !(p.yact[(long long)b * p.ldy + n] > 0.f)) g = 0.f;
+    dys[n] = g;
+  }
+  __syncthreads();
+  if (k >= p.K) return;
+  float acc = 0.f;
+  for (int n = 0; n < p.N; ++n) acc = fmaf(dys[n], __ldg(p.W + (long long)n * p.K + k), acc);
+  if (p.mask) acc *= p.mask[(long long)b * p.K + k] * p.mscale;
+  float* d = p.dx + (long long)b * p.lddx + k;
+  *d = p.accumulate_dx ? (*d + acc) : acc;
+}
+
+__device__ __forceinline__ float block_sum128(float v, float* sh) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  return (sh[0] + sh[1]) + (sh[2] + sh[3]);
+}
+
+struct HeadArgs {
+  const float* h3cat;  // [B,3H]  audio | text | video hidden
+  const float* a3;     // [B,H]   attention_mlp output
+  const float* w_att; const float* b_att;  // [3,H],[3]
+  const float* w_o1; const float* b_o1;    // [O1,H]
+  const float* w_o2; const float* b_o2;    // [O2,H]
+  const long long* emo; const float* val;  // labels or null (eval)
+  float* features; float* emos_out; float* vals_out;  // [B,H],[B,O1],[B,O2]
+  float* loss_terms;   // [B,2]
+  float* d_emos; float* d_vals; float* d_att; float* d_cat; float* d_a3;
+  int H, O1, O2;
+  float inv_batch;     // 1 / (batch the loss is averaged over)
+};
+
+// one block (128 threads) per sample; H <= 256
+__global__ void __launch_bounds__(128)
+fus_head_kernel(const HeadArgs a) {
+  __shared__ float sh[4];
+  __shared__ float fused[256], dfused[256];
+  __shared__ float att[3], datt[3], logits[16], dlog[16], dval[4];
+  const int b = blockIdx.x, H = a.H, tid = threadIdx.x;
+  const float* h3 = a.h3cat + (long long)b * 3 * H;
+  const float* a3 = a.a3 + (long long)b * H;
+  for (int m = 0; m < 3; ++m) {
+    float s = 0.f;
+    for (int j = tid; j < H; j += 128) s = fmaf(a.w_att[m * H + j], a3[j], s);
+    s = block_sum128(s, sh);
+    if (tid == 0) att[m] = s + a.b_att[m];
+  }
+  __syncthreads();
+  for (int j = tid; j < H; j += 128) {
+    const float f = (h3[j] * att[0] + h3[H + j] * att[1]) + h3[2 * H + j] * att[2];
+    fused[j] = f;
+    a.features[(long long)b * H + j] = f;
+  }
+  __syncthreads();
+  for (int c = 0; c < a.O1; ++c) {
+    float s = 0.f;
+    for (int j = tid; j < H; j += 128) s = fmaf(a.w_o1[c * H + j], fused[j], s);
+    s = block_sum128(s, sh);
+    if (tid == 0) { logits[c] = s + a.b_o1[c]; a.emos_out[(long long)b * a.O1 + c] = logits[c]; }
+  }
+  for (int c = 0; c < a.O2; ++c) {
+    float s = 0.f;
+    for (int j = tid; j < H; j += 128) s = fmaf(a.w_o2[c * H + j], fused[j], s);
+    s = block_sum128(s, sh);
+    if (tid == 0) { dval[c] = s + a.b_o2[c]; a.vals_out[(long long)b * a.O2 + c] = dval[c]; }
+  }
+  __syncthreads();
+  if (!a.emo) return;  // eval: forward only
+  if (tid == 0) {
+    // CELoss: NLL(log_softmax) summed / N ; MSELoss: squared error summed / N  (loss.py:11-28)
+    float mx = logits[0];
+    for (int c = 1; c < a.O1; ++c) mx = fmaxf(mx, logits[c]);
+    float se = 0.f;
+    for (int c = 0; c < a.O1; ++c) se += expf(logits[c] - mx);
+    const float lse = mx + logf(se);
+    const int tgt = (int)a.emo[b];
+    a.loss_terms[2 * b + 0] = lse - logits[tgt];
+    for (int c = 0; c < a.O1; ++c) {
+      const float sm = expf(logits[c] - lse);
+      dlog[c] = (sm - (c == tgt ? 1.f : 0.f)) * a.inv_batch;
+      a.d_emos[(long long)b * a.O1 + c] = dlog[c];
+    }
+    float mse = 0.f;
+    for (int c = 0; c < a.O2; ++c) {
+      const float d = dval[c] - a.val[(long long)b * a.O2 + c];
+      mse += d * d;
+      dval[c] = 2.f * d * a.inv_batch;
+      a.d_vals[(long long)b * a.O2 + c] = dval[c];
+    }
+    a.loss_terms[2 * b + 1] = mse;
+  }
+  __syncthreads();
+  for (int j = tid; j < H; j += 128) {
+    float s = 0.f;
+    for (int c = 0; c < a.O1; ++c) s = fmaf(a.w_o1[c * H + j], dlog[c], s);
+    for (int c = 0; c < a.O2; ++c) s = fmaf(a.w_o2[c * H + j], dval[c], s);
+    dfused[j] = s;
+  }
+  __syncthreads();
+  for (int m = 0; m < 3; ++m) {
+    float s = 0.f;
+    for (int j = tid; j < H; j += 128) s = fmaf(h3[m * H + j], dfused[j], s);
+    s = block_sum128(s, sh);
+    if (tid == 0) { datt[m] = s; a.d_att[3 * b + m] = s; }
+  }
+  __syncthreads();
+  for (int j = tid; j < H; j += 128) {
+    for (int m = 0; m < 3; ++m) a.d_cat[(long long)b * 3 * H + m * H + j] = att[m] * dfused[j];
+    a.d_a3[(long long)b * H + j] =
+        (a.w_att[j] * datt[0] + a.w_att[H + j] * datt[1]) + a.w_att[2 * H + j] * datt[2];
+  }
+}
+
+__global__ void fus_loss_reduce_kernel(const float* terms, int B, float inv_batch, float* loss_out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float ce = 0.f, mse = 0.f;
+  for (int b = 0; b < B; ++b) { ce += terms[2 * b]; mse += terms[2 * b + 1]; }
+  loss_out[0] = ce * inv_batch;
+  loss_out[1] = mse * inv_batch;
+  loss_out[2] = ce * inv_batch + mse * inv_batch;
+}
+
+// torch.optim.Adam (coupled L2) in its own operation order; step counter lives on the device so a
+// captured CUDA graph advances it on every replay.
+__global__ void __launch_bounds__(256)
+fus_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps,
+                float wd, float gscale, float clip, const int* __restrict__ step) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float t = (float)(*step + 1);
+  const float bc1 = 1.f - powf(beta1, t);
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, t));
+  float grad = g[i] * gscale;
+  if (clip > 0.f) grad = fminf(fmaxf(grad, -clip), clip);
+  const float pi = p[i];
+  grad = fmaf(wd, pi, grad);
+  const float mi = m[i] + (grad - m[i]) * (1.f - beta1);       // lerp, as torch
+  const float vi = v[i] * beta2 + (1.f - beta2) * grad * grad; // mul + addcmul
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] = pi - (lr / bc1) * (mi / denom);
+}
+__global__ void fus_step_inc_kernel(int* step) { if (threadIdx.x == 0 && blockIdx.x == 0) ++(*step); }
+
+// keep-mask (0/1 floats) from a counter hash of (seed, step, index); keep prob = 1 - p
+__global__ void __launch_bounds__(256)
+fus_dropout_mask_kernel(float* mask, long long n, float p, unsigned long long seed, const int* step) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(*step + 1) +
+                         0xD1B54A32D192ED03ull * (unsigned long long)(i + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const float u = (float)(z >> 40) * (1.0f / 16777216.0f);
+  mask[i] = u >= p ? 1.f : 0.f;
+}
+
+struct Layout {  // offsets (floats) into the flat parameter buffer, reference state_dict order
+  long long enc_w1[3], enc_b1[3], enc_w2[3], enc_b2[3], enc_w3[3], enc_b3[3];
+  long long att_w1, att_b1, att_w2, att_b2, att_w3, att_b3;
+  long long fa_w, fa_b, o1_w, o1_b, o2_w, o2_b, total;
+};
+
+Layout make_layout(const MerFusionDims& d) {
+  Layout L;
+  long long o = 0;
+  const int in[3] = {d.audio_dim, d.text_dim, d.video_dim};
+  const int H = d.hidden;
+  for (int m = 0; m < 3; ++m) {
+    L.enc_w1[m] = o; o += (long long)H * in[m];
+    L.enc_b1[m] = o; o += H;
+    L.enc_w2[m] = o; o += (long long)H * H;
+    L.enc_b2[m] = o; o += H;
+    L.enc_w3[m] = o; o += (long long)H * H;
+    L.enc_b3[m] = o; o += H;
+  }
+  L.att_w1 = o; o += (long long)H * 3 * H;
+  L.att_b1 = o; o += H;
+  L.att_w2 = o; o += (long long)H * H;
+  L.att_b2 = o; o += H;
+  L.att_w3 = o; o += (long long)H * H;
+  L.att_b3 = o; o += H;
+  L.fa_w = o; o += 3ll * H;
+  L.fa_b = o; o += 3;
+  L.o1_w = o; o += (long long)d.out1 * H;
+  L.o1_b = o; o += d.out1;
+  L.o2_w = o; o += (long long)d.out2 * H;
+  L.o2_b = o; o += d.out2;
+  L.total = o;
+  return L;
+}
+
+struct Scratch {  // activations + activation grads, floats
+  float *h1, *h2, *h3cat, *a1, *a2, *a3, *features_unused;
+  float *d_h1, *d_h2, *d_cat, *d_a1, *d_a2, *d_a3, *d_emos, *d_vals, *d_att, *loss_terms;
+  float *mask_in[3], *mask_cat;
+};
+
+long long scratch_floats(const MerFusionDims& d, int B) {
+  const long long H = d.hidden;
+  const long long in_sum = (long long)d.audio_dim + d.text_dim + d.video_dim;
+  return (long long)B * (3 * H * 2 /*h1,h2*/ + 3 * H /*h3cat*/ + 3 * H /*a1..a3*/ +
+                         3 * H * 2 /*d_h1,d_h2*/ + 3 * H /*d_cat*/ + 3 * H /*d_a*/ + d.out1 + d.out2 +
+                         3 + 2 + in_sum + 3 * H) + 64;
+}
+
+Scratch carve(const MerFusionDims& d, int B, float* base) {
+  Scratch s;
+  const long long H = d.hidden;
+  float* p = base;
+  auto take = [&](long long n) { float* r = p; p += n; return r; };
+  s.h1 = take(3 * B * H); s.h2 = take(3 * B * H); s.h3cat = take(3 * B * H);
+  s.a1 = take(B * H); s.a2 = take(B * H); s.a3 = take(B * H);
+  s.d_h1 = take(3 * B * H); s.d_h2 = take(3 * B * H); s.d_cat = take(3 * B * H);
+  s.d_a1 = take(B * H); s.d_a2 = take(B * H); s.d_a3 = take(B * H);
+  s.d_emos = take((long long)B * d.out1); s.d_vals = take((long long)B * d.out2);
+  s.d_att = take(3ll * B); s.loss_terms = take(2ll * B);
+  s.mask_in[0] = take((long long)B * d.audio_dim);
+  s.mask_in[1] = take((long long)B * d.text_dim);
+  s.mask_in[2] = take((long long)B * d.video_dim);
+  s.mask_cat = take(3 * B * H);
+  return s;
+}
+
+int check_dims(const MerFusionDims* d, int B) {
+  MER_REQUIRE(d && d->hidden > 0 && d->hidden <= 256 && d->out1 > 0 && d->out1 <= 16 &&
+                  d->out2 > 0 && d->out2 <= 4 && d->audio_dim > 0 && d->text_dim > 0 &&
+                  d->video_dim > 0,
+              "mer_fusion: unsupported dims (hidden <= 256, out1 <= 16, out2 <= 4)");
+  MER_REQUIRE(B > 0 && B <= 65535, "mer_fusion: batch %d out of range", B);
+  return 0;
+}
+
+// forward through the head; train != 0 also generates/uses dropout masks
+int run_forward(const MerFusionDims& d, const Layout& L, const float* P, const Scratch& s,
+                const float* const x[3], int B, float p_drop, const float* const ext_masks[4],
+                bool use_dropout, cudaStream_t st) {
+  const int H = d.hidden;
+  const int in[3] = {d.audio_dim, d.text_dim, d.video_dim};
+  const float mscale = use_dropout ? 1.f / (1.f - p_drop) : 1.f;
+  LinBatch lb;
+  for (int m = 0; m < 3; ++m) {
+    const float* mk = use_dropout ? (ext_masks && ext_masks[m] ? ext_masks[m] : s.mask_in[m]) : nullptr;
+    lb.p[m] = LinP{x[m], in[m], mk, mscale, P + L.enc_w1[m], P + L.enc_b1[m],
+                   s.h1 + (long long)m * B * H, H, in[m], H, 1};
+  }
+  dim3 g1((H + 7) / 8, (B + 31) / 32, 3);
+  fus_linear_fwd_kernel<<<g1, 256, 0, st>>>(lb, B);
+  for (int m = 0; m < 3; ++m)
+    lb.p[m] = LinP{s.h1 + (long long)m * B * H, H, nullptr, 1.f, P + L.enc_w2[m], P + L.enc_b2[m],
+                   s.h2 + (long long)m * B * H, H, H, H, 1};
+  fus_linear_fwd_kernel<<<g1, 256, 0, st>>>(lb, B);
+  for (int m = 0; m < 3; ++m)  // h3 written straight into the concatenated [B,3H] layout
+    lb.p[m] = LinP{s.h2 + (long long)m * B * H, H, nullptr, 1.f, P + L.enc_w3[m], P + L.enc_b3[m],
+                   s.h3cat + m * H, 3 * H, H, H, 1};
+  fus_linear_fwd_kernel<<<g1, 256, 0, st>>>(lb, B);
+  dim3 g2((H + 7) / 8, (B + 31) / 32, 1);
+  const float* mkc = use_dropout ? (ext_masks && ext_masks[3] ? ext_masks[3] : s.mask_cat) : nullptr;
+  lb.p[0] = LinP{s.h3cat, 3 * H, mkc, mscale, P + L.att_w1, P + L.att_b1, s.a1, H, 3 * H, H, 1};
+  fus_linear_fwd_kernel<<<g2, 256, 0, st>>>(lb, B);
+  lb.p[0] = LinP{s.a1, H, nullptr, 1.f, P + L.att_w2, P + L.att_b2, s.a2, H, H, H, 1};
+  fus_linear_fwd_kernel<<<g2, 256, 0, st>>>(lb, B);
+  lb.p[0] = LinP{s.a2, H, nullptr, 1.f, P + L.att_w3, P + L.att_b3, s.a3, H, H, H, 1};
+  fus_linear_fwd_kernel<<<g2, 256, 0, st>>>(lb, B);
+  MER_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+long long mer_fusion_param_count(const MerFusionDims* d) {
+  if (!d) return -1;
+  return make_layout(*d).total;
+}
+
+long long mer_fusion_workspace_bytes(const MerFusionDims* d, int max_batch) {
+  if (!d) return -1;
+  return scratch_floats(*d, max_batch) * 4;
+}
+
+int mer_fusion_forward(const MerFusionDims* d, const float* params, const float* audios,
+                       const float* texts, const float* videos, int B, void* workspace,
+                       long long workspace_bytes, float* features, float* emos_out, float* vals_out,
+                       void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (int rc = check_dims(d, B)) return rc;
+  MER_REQUIRE(params && audios && texts && videos && workspace && features && emos_out && vals_out,
+              "mer_fusion_forward: null operand");
+  MER_REQUIRE(workspace_bytes >= mer_fusion_workspace_bytes(d, B), "mer_fusion_forward: workspace too small");
+  const Layout L = make_layout(*d);
+  const Scratch s = carve(*d, B, static_cast<float*>(workspace));
+  const float* x[3] = {audios, texts, videos};
+  if (int rc = run_forward(*d, L, params, s, x, B, 0.f, nullptr, false, st)) return rc;
+  HeadArgs h;
+  memset(&h, 0, sizeof(h));
+  h.h3cat = s.h3cat; h.a3 = s.a3;
+  h.w_att = params + L.fa_w; h.b_att = params + L.fa_b;
+  h.w_o1 = params + L.o1_w; h.b_o1 = params + L.o1_b;
+  h.w_o2 = params + L.o2_w; h.b_o2 = params + L.o2_b;
+  h.features = features; h.emos_out = emos_out; h.vals_out = vals_out;
+  h.H = d->hidden; h.O1 = d->out1; h.O2 = d->out2;
+  fus_head_kernel<<<B, 128, 0, st>>>(h);
+  MER_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int mer_fusion_fwd_bwd(const MerFusionDims* d, const float* params, float* grads, const float* audios,
+                       const float* texts, const float* videos, const int64_t* emos, const float* vals,
+                       int B, float loss_inv_batch, float dropout_p, unsigned long long seed,
+                       const int* step_counter, const float* const* ext_masks, void* workspace,
+                       long long workspace_bytes, float* loss_out, float* features, float* emos_out,
+                       float* vals_out, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (int rc = check_dims(d, B)) return rc;
+  MER_REQUIRE(params && grads && audios && texts && videos && emos && vals && workspace && loss_out &&
+                  features && emos_out && vals_out && step_counter,
+              "mer_fusion_fwd_bwd: null operand");
+  MER_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "mer_fusion_fwd_bwd: dropout %f", dropout_p);
+  MER_REQUIRE(workspace_bytes >= mer_fusion_workspace_bytes(d, B), "mer_fusion_fwd_bwd: workspace too small");
+  const Layout L = make_layout(*d);
+  const Scratch s = carve(*d, B, static_cast<float*>(workspace));
+  const int H = d->hidden;
+  const int in[3] = {d->audio_dim, d->text_dim, d->video_dim};
+  const float* x[3] = {audios, texts, videos};
+  const bool drop = dropout_p > 0.f;
+  const float mscale = drop ? 1.f / (1.f - dropout_p) : 1.f;
+  const float* masks[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (drop) {
+    for (int m = 0; m < 4; ++m) {
+      if (ext_masks && ext_masks[m]) { masks[m] = ext_masks[m]; continue; }
+      float* dst = m < 3 ? s.mask_in[m] : s.mask_cat;
+      const long long n = (long long)B * (m < 3 ? in[m] : 3 * H);
+      fus_dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+          dst, n, dropout_p, seed + 0x1000ull * (m + 1), step_counter);
+      masks[m] = dst;
+    }
+  }
+  if (int rc = run_forward(*d, L, params, s, x, B, dropout_p, masks, drop, st)) return rc;
+  HeadArgs h;
+  memset(&h, 0, sizeof(h));
+  h.h3cat = s.h3cat; h.a3 = s.a3;
+  h.w_att = params + L.fa_w; h.b_att = params + L.fa_b;
+  h.w_o1 = params + L.o1_w; h.b_o1 = params + L.o1_b;
+  h.w_o2 = params + L.o2_w; h.b_o2 = params + L.o2_b;
+  h.emo = reinterpret_cast<const long long*>(emos); h.val = vals;
+  h.features = features; h.emos_out = emos_out; h.vals_out = vals_out;
+  h.loss_terms = s.loss_terms; h.d_emos = s.d_emos; h.d_vals = s.d_vals; h.d_att = s.d_att;
+  h.d_cat = s.d_cat; h.d_a3 = s.d_a3;
+  h.H = H; h.O1 = d->out1; h.O2 = d->out2; h.inv_batch = loss_inv_batch;
+  fus_head_kernel<<<B, 128, 0, st>>>(h);
+  fus_loss_reduce_kernel<<<1, 32, 0, st>>>(s.loss_terms, B, loss_inv_batch, loss_out);
+
+  float* G = grads;
+  BwdBatch bb;
+  auto launch_w = [&](int nprob, int K, int N) {
+    dim3 g((K + 255) / 256, N, nprob);
+    fus_linear_bwd_w_kernel<<<g, 256, 0, st>>>(bb, B);
+  };
+  auto launch_x = [&](int nprob, int K) {
+    dim3 g((K + 255) / 256, B, nprob);
+    fus_linear_bwd_x_kernel<<<g, 256, 0, st>>>(bb, B);
+  };
+  // heads: fc_out_1, fc_out_2 (x = fused features), fc_att (x = a3); no relu, no dx needed here
+  bb.p[0] = BwdP{s.d_emos, d->out1, nullptr, 0, features, H, nullptr, 1.f, params + L.o1_w,
+                 G + L.o1_w, G + L.o1_b, nullptr, 0, 0, H, d->out1};
+  bb.p[1] = BwdP{s.d_vals, d->out2, nullptr, 0, features, H, nullptr, 1.f, params + L.o2_w,
+                 G + L.o2_w, G + L.o2_b, nullptr, 0, 0, H, d->out2};
+  bb.p[2] = BwdP{s.d_att, 3, nullptr, 0, s.a3, H, nullptr, 1.f, params + L.fa_w, G + L.fa_w,
+                 G + L.fa_b, nullptr, 0, 0, H, 3};
+  launch_w(3, H, 16);
+  // attention_mlp: linear_3, linear_2, linear_1 (its dx is accumulated into d_cat through the mask)
+  bb.p[0] = BwdP{s.d_a3, H, s.a3, H, s.a2, H, nullptr, 1.f, params + L.att_w3, G + L.att_w3,
+                 G + L.att_b3, s.d_a2, H, 0, H, H};
+  launch_w(1, H, H); launch_x(1, H);
+  bb.p[0] = BwdP{s.d_a2, H, s.a2, H, s.a1, H, nullptr, 1.f, params + L.att_w2, G + L.att_w2,
+                 G + L.att_b2, s.d_a1, H, 0, H, H};
+  launch_w(1, H, H); launch_x(1, H);
+  bb.p[0] = BwdP{s.d_a1, H, s.a1, H, s.h3cat, 3 * H, masks[3], mscale, params + L.att_w1,
+                 G + L.att_w1, G + L.att_b1, s.d_cat, 3 * H, 1, 3 * H, H};
+  launch_w(1, 3 * H, H); launch_x(1, 3 * H);
+  // modality encoders, three at a time
+  for (int m = 0; m < 3; ++m)
+    bb.p[m] = BwdP{s.d_cat + m * H, 3 * H, s.h3cat + m * H, 3 * H, s.h2 + (long long)m * B * H, H,
+                   nullptr, 1.f, params + L.enc_w3[m], G + L.enc_w3[m], G + L.enc_b3[m],
+                   s.d_h2 + (long long)m * B * H, H, 0, H, H};
+  launch_w(3, H, H); launch_x(3, H);
+  for (int m = 0; m < 3; ++m)
+    bb.p[m] = BwdP{s.d_h2 + (long long)m * B * H, H, s.h2 + (long long)m * B * H, H,
+                   s.h1 + (long long)m * B * H, H, nullptr, 1.f, params + L.enc_w2[m],
+                   G + L.enc_w2[m], G + L.enc_b2[m], s.d_h1 + (long long)m * B * H, H, 0, H, H};
+  launch_w(3, H, H); launch_x(3, H);
+  int kmax = 0;
+  for (int m = 0; m < 3; ++m) {
+    bb.p[m] = BwdP{s.d_h1 + (long long)m * B * H, H, s.h1 + (long long)m * B * H, H, x[m], in[m],
+                   masks[m], mscale, params + L.enc_w1[m], G + L.enc_w1[m], G + L.enc_b1[m],
+                   nullptr, 0, 0, in[m], H};
+    kmax = in[m] > kmax ? in[m] : kmax;
+  }
+  launch_w(3, kmax, H);
+  MER_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int mer_fusion_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                    float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                    float grad_clip, int* step_counter, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  MER_REQUIRE(params && grads && exp_avg && exp_avg_sq && step_counter && n > 0, "mer_fusion_adam: bad operands");
+  fus_adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, lr,
+                                                              beta1, beta2, eps, weight_decay, grad_scale,
+                                                              grad_clip, step_counter);
+  fus_step_inc_kernel<<<1, 32, 0, st>>>(step_counter);
+  MER_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

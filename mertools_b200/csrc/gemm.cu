@@ -1,4 +1,4 @@
-// gemm_tf32.cu — the one GEMM every encoder layer goes through.
+// gemm.cu — the one GEMM every encoder layer goes through.
 //
 //   out[b*out_bstride + out_row0 + m, n] =
 //       round?( act( sum_k A[b, m, k] * W[n, k] + bias[n] ) + res[b*res_bstride + res_row0 + m, n] )
@@ -10,11 +10,19 @@
 // W is the nn.Linear weight as stored: [N, K] row-major == K-major B operand.
 //
 // Structure (persistent, warp-specialised, one CTA per SM):
-//   warp 0      TMA producer: A/B tiles -> 128B-swizzled smem ring (mbarrier full/empty)
-//   warp 1      MMA issuer  : tcgen05.mma.kind::tf32, UMMA 128 x BLOCK_N x 8, fp32 accum in TMEM
+//   warp 0      TMA producer: A/B tiles -> swizzled smem ring (mbarrier full/empty)
+//   warp 1      MMA issuer  : tcgen05.mma, UMMA 128 x BLOCK_N x (32 bytes of K), fp32 accum in TMEM
 //   warp 2      TMEM allocator
 //   warps 4..7  epilogue    : tcgen05.ld TMEM -> registers -> bias/GELU/residual -> st.global
 // TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Two arithmetic modes share the pipeline (both move 4 bytes per operand element):
+//   MER_GEMM_TF32   : fp32 operands (pre-rounded to tf32 by their producers), kind::tf32, 128B swizzle.
+//                     ~2.4e-4 relative error per GEMM: enough for the pre-LN ViT at 1e-3.
+//   MER_GEMM_BF16X3 : every operand stored as a bf16 (hi | lo) pair, x = hi + lo to 2^-17; three
+//                     kind::f16 MMAs per K step (hi*hi + lo*hi + hi*lo), fp32 accumulate, 64B swizzle.
+//                     ~2e-5 relative error per GEMM: what the post-LN HuBERT/BERT stacks need to stay
+//                     inside 1e-3 after 12 layers (measured: single-pass TF32 reaches 1.0e-3 after 4).
 #include "mer_common.cuh"
 #include "mer_kernels.h"
 
@@ -23,28 +31,46 @@ namespace {
 using namespace mer;
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 32;  // 32 tf32 = 128 bytes = one swizzle row
-constexpr int UMMA_K = 8;    // 32 bytes of K per tcgen05.mma
+constexpr int BLOCK_K = 32;  // K elements per stage in BOTH modes (128 B of tf32 / 64 B of bf16 per part)
 constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MODE>
 struct GemmCfg {
+  static constexpr bool kSplit = MODE == MER_GEMM_BF16X3;
+  static constexpr int kParts = kSplit ? 2 : 1;         // hi (+ lo) tiles per operand
+  static constexpr int kRowBytes = kSplit ? 64 : 128;   // bytes of K per smem row = swizzle span
+  static constexpr int kKSteps = kRowBytes / 32;        // tcgen05.mma K steps (32 B each) per stage
+  static constexpr int kSBO = 8 * kRowBytes;            // byte stride between 8-row core groups
+  static constexpr int kLayout = kSplit ? 4 : 2;        // UMMA LayoutType: SWIZZLE_64B / SWIZZLE_128B
+  static constexpr int kFmt = kSplit ? 1 : 2;           // instr-desc operand format: bf16 / tf32
   static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
-  static constexpr int kABytes = BLOCK_M * BLOCK_K * 4;
-  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 4;
+  static constexpr int kAPart = BLOCK_M * kRowBytes;
+  static constexpr int kBPart = BLOCK_N * kRowBytes;
+  static constexpr int kABytes = kAPart * kParts;
+  static constexpr int kBBytes = kBPart * kParts;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N;
   static constexpr int kBarBytes = 256;
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +align slack
 };
 
-template <int BLOCK_N>
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, int sbo_bytes, int layout) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(layout) << 61;
+  return d;
+}
+
+template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                 const __grid_constant__ CUtensorMap tmap_b, const MerGemmEpilogue ep,
-                 int rows_per_batch, int batches, int N, int K, int K_inner, int P) {
-  using Cfg = GemmCfg<BLOCK_N>;
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
+            const __grid_constant__ CUtensorMap tmap_b, const MerGemmEpilogue ep,
+            int rows_per_batch, int batches, int N, int K, int K_inner, int P) {
+  using Cfg = GemmCfg<BLOCK_N, MODE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -104,10 +130,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           const int kk = kb * BLOCK_K;
           const int tap = kk / K_inner;
-          tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kk - tap * K_inner,
-                      tap % P, mt * BLOCK_M + tap / P, b);
-          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * BLOCK_K,
-                      n_blk * BLOCK_N);
+          const int c0 = kk - tap * K_inner;
+          tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], c0, tap % P,
+                      mt * BLOCK_M + tap / P, b);
+          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kk, n_blk * BLOCK_N);
+          if (Cfg::kSplit) {  // lo halves: K_inner / K elements further along the same rows
+            tma_load_4d(smem_a + stage * Cfg::kABytes + Cfg::kAPart, &tmap_a, &full_bar[stage],
+                        K_inner + c0, tap % P, mt * BLOCK_M + tap / P, b);
+            tma_load_2d(smem_b + stage * Cfg::kBBytes + Cfg::kBPart, &tmap_b, &full_bar[stage],
+                        K + kk, n_blk * BLOCK_N);
+          }
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -118,7 +150,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(2, BLOCK_M, BLOCK_N);
+      constexpr uint32_t idesc = umma_idesc(Cfg::kFmt, BLOCK_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -130,12 +162,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
-          const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+          const uint64_t da = umma_desc(smem_u32(smem_a + stage * Cfg::kABytes), Cfg::kSBO, Cfg::kLayout);
+          const uint64_t db = umma_desc(smem_u32(smem_b + stage * Cfg::kBBytes), Cfg::kSBO, Cfg::kLayout);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance the start address by k*32 bytes inside the 128B swizzle row (>>4 => +2)
-            tc_mma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < Cfg::kKSteps; ++k) {
+            // advance the start address by k*32 bytes inside the swizzle row (>>4 => +2)
+            if (!Cfg::kSplit) {
+              tc_mma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            } else {
+              const uint64_t da_lo = da + (Cfg::kAPart >> 4);
+              const uint64_t db_lo = db + (Cfg::kBPart >> 4);
+              tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);  // hi * hi
+              tc_mma_bf16(d_tmem, da_lo + 2 * k, db + 2 * k, idesc, 1);           // lo * hi
+              tc_mma_bf16(d_tmem, da + 2 * k, db_lo + 2 * k, idesc, 1);           // hi * lo
+            }
           }
           tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (++stage == Cfg::kStages) {
@@ -157,6 +197,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint32_t aphase = 0;
     const bool do_gelu = (ep.flags & MER_EPI_GELU) != 0;
     const bool do_round = (ep.flags & MER_EPI_ROUND_TF32) != 0;
+    const bool do_split = (ep.flags & MER_EPI_SPLIT_BF16) != 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int n_blk = t % n_tiles;
       const int mb = t / n_tiles;
@@ -197,6 +238,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
               const float4 rr = *reinterpret_cast<const float4*>(res_row + n0 + j);
               v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
             }
+            if (do_split) {
+              // out row holds [hi(split_off) | lo(split_off)] bf16 in the bytes of split_off fp32 slots
+              store_split4(out_row, ep.split_off, n0 + j, v);
+              continue;
+            }
             if (do_round) {
               v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
             }
@@ -223,33 +269,35 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MODE>
 int launch_gemm(const MerGemmDesc* g, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, MODE>;
   CUtensorMap ta, tb;
+  const CUtensorMapDataType dt =
+      Cfg::kSplit ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapSwizzle sw = Cfg::kSplit ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  const uint64_t mult = Cfg::kSplit ? 2 : 1;  // bf16 elements per 4-byte operand slot
   {
-    const uint64_t dims[4] = {(uint64_t)g->K_inner, (uint64_t)g->P, (uint64_t)g->a_rows_dim,
+    // strides are given in 4-byte operand slots in both modes (a split row of K (hi|lo) pairs
+    // occupies exactly the bytes of K fp32 values)
+    const uint64_t dims[4] = {(uint64_t)g->K_inner * mult, (uint64_t)g->P, (uint64_t)g->a_rows_dim,
                               (uint64_t)g->batches};
     const uint64_t strides[3] = {(uint64_t)g->a_phase_stride * 4ull,
                                  (uint64_t)g->a_row_stride * 4ull,
                                  (uint64_t)g->a_batch_stride * 4ull};
     const uint32_t box[4] = {BLOCK_K, 1, BLOCK_M, 1};
-    if (int rc = mer_make_tmap(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g->A, dims, strides, box,
-                               CU_TENSOR_MAP_SWIZZLE_128B))
-      return rc;
+    if (int rc = mer_make_tmap(&ta, dt, 4, g->A, dims, strides, box, sw)) return rc;
   }
   {
     const int K = g->K_inner * g->taps;
-    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)g->N};
+    const uint64_t dims[2] = {(uint64_t)K * mult, (uint64_t)g->N};
     const uint64_t strides[1] = {(uint64_t)K * 4ull};
     const uint32_t box[2] = {BLOCK_K, BLOCK_N};
-    if (int rc = mer_make_tmap(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, g->W, dims, strides, box,
-                               CU_TENSOR_MAP_SWIZZLE_128B))
-      return rc;
+    if (int rc = mer_make_tmap(&tb, dt, 2, g->W, dims, strides, box, sw)) return rc;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    MER_CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32_kernel<BLOCK_N>,
+    MER_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BLOCK_N, MODE>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes));
     attr_set = true;
@@ -258,7 +306,7 @@ int launch_gemm(const MerGemmDesc* g, cudaStream_t stream) {
   const long long tiles = (long long)g->batches * m_tiles * (g->N / BLOCK_N);
   int grid = mer_num_sms();
   if (tiles < grid) grid = (int)tiles;
-  gemm_tf32_kernel<BLOCK_N><<<grid, NUM_THREADS, Cfg::kSmemBytes, stream>>>(
+  gemm_kernel<BLOCK_N, MODE><<<grid, NUM_THREADS, Cfg::kSmemBytes, stream>>>(
       ta, tb, g->ep, g->rows_per_batch, g->batches, g->N, g->K_inner * g->taps, g->K_inner, g->P);
   MER_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -266,22 +314,27 @@ int launch_gemm(const MerGemmDesc* g, cudaStream_t stream) {
 
 }  // namespace
 
-int mer_gemm_tf32_launch(const MerGemmDesc* g, cudaStream_t stream) {
-  MER_REQUIRE(g && g->A && g->W && g->ep.out, "mer_gemm_tf32: null operand");
+int mer_gemm_launch(const MerGemmDesc* g, cudaStream_t stream) {
+  MER_REQUIRE(g && g->A && g->W && g->ep.out, "mer_gemm: null operand");
+  MER_REQUIRE(g->mode == MER_GEMM_TF32 || g->mode == MER_GEMM_BF16X3, "mer_gemm: unknown mode %d", g->mode);
+  MER_REQUIRE(!(g->ep.flags & MER_EPI_SPLIT_BF16) || (g->ep.split_off > 0 && g->ep.split_off % 4 == 0),
+              "mer_gemm: split output needs split_off (logical columns, multiple of 4)");
   MER_REQUIRE(g->K_inner > 0 && g->K_inner % BLOCK_K == 0 && g->taps > 0 && g->P > 0,
-              "mer_gemm_tf32: K_inner=%d must be a positive multiple of %d (taps=%d P=%d)",
+              "mer_gemm: K_inner=%d must be a positive multiple of %d (taps=%d P=%d)",
               g->K_inner, BLOCK_K, g->taps, g->P);
-  MER_REQUIRE(g->a_rows_dim >= g->rows_per_batch, "mer_gemm_tf32: a_rows_dim < rows_per_batch");
-  MER_REQUIRE(g->N > 0 && g->N % 128 == 0, "mer_gemm_tf32: N=%d must be a multiple of 128", g->N);
-  MER_REQUIRE(g->rows_per_batch > 0 && g->batches > 0, "mer_gemm_tf32: empty problem");
+  MER_REQUIRE(g->a_rows_dim >= g->rows_per_batch, "mer_gemm: a_rows_dim < rows_per_batch");
+  MER_REQUIRE(g->N > 0 && g->N % 128 == 0, "mer_gemm: N=%d must be a multiple of 128", g->N);
+  MER_REQUIRE(g->rows_per_batch > 0 && g->batches > 0, "mer_gemm: empty problem");
   MER_REQUIRE(g->a_row_stride % 4 == 0 && g->a_batch_stride % 4 == 0 && g->a_phase_stride % 4 == 0,
-              "mer_gemm_tf32: A strides must be multiples of 16 bytes");
+              "mer_gemm: A strides must be multiples of 16 bytes");
   MER_REQUIRE(g->ep.ld_out % 4 == 0 && (g->ep.res == nullptr || g->ep.ld_res % 4 == 0),
-              "mer_gemm_tf32: out/res leading dims must be multiples of 4 floats");
+              "mer_gemm: out/res leading dims must be multiples of 4 floats");
   const int m_tiles = (g->rows_per_batch + BLOCK_M - 1) / BLOCK_M;
   const long long tiles256 = (g->N % 256 == 0) ? (long long)g->batches * m_tiles * (g->N / 256) : 0;
   // 128 x 256 tiles whenever they fill the machine; 128 x 128 for small problems / N % 256 != 0
-  if (tiles256 >= mer_num_sms() && g->force_block_n != 128) return launch_gemm<256>(g, stream);
-  if (g->force_block_n == 256 && tiles256 > 0) return launch_gemm<256>(g, stream);
-  return launch_gemm<128>(g, stream);
+  const bool wide = (tiles256 >= mer_num_sms() && g->force_block_n != 128) ||
+                    (g->force_block_n == 256 && tiles256 > 0);
+  if (g->mode == MER_GEMM_BF16X3)
+    return wide ? launch_gemm<256, MER_GEMM_BF16X3>(g, stream) : launch_gemm<128, MER_GEMM_BF16X3>(g, stream);
+  return wide ? launch_gemm<256, MER_GEMM_TF32>(g, stream) : launch_gemm<128, MER_GEMM_TF32>(g, stream);
 }

@@ -90,13 +90,14 @@ segment_reduce_kernel(const float* __restrict__ in, const int* __restrict__ begi
 }
 
 // BERT/RoBERTa embeddings (HF modeling_bert.py BertEmbeddings / modeling_roberta.py:56-122):
-// (word[id] + token_type[0]) + position[pos] -> LayerNorm -> tf32-rounded x.  One warp per token.
+// (word[id] + token_type[0]) + position[pos] -> LayerNorm -> x (fp32) and its split-bf16 copy.
+// One warp per token.
 __global__ void __launch_bounds__(256)
 bert_embed_ln_kernel(const int* __restrict__ ids, const int* __restrict__ pos_ids,
                      const float* __restrict__ word, const float* __restrict__ pos,
                      const float* __restrict__ type0, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float eps, int tokens, float* __restrict__ out,
-                     float* __restrict__ out_exact) {
+                     void* __restrict__ out_split) {
   const int lane = threadIdx.x & 31;
   const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (tok >= tokens) return;
@@ -121,7 +122,7 @@ bert_embed_ln_kernel(const int* __restrict__ ids, const int* __restrict__ pos_id
   }
   const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / 768) + eps);
   float4* o = reinterpret_cast<float4*>(out + (long long)tok * 768);
-  float4* oe = out_exact ? reinterpret_cast<float4*>(out_exact + (long long)tok * 768) : nullptr;
+  float* os = out_split ? reinterpret_cast<float*>(out_split) + (long long)tok * 768 : nullptr;
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
@@ -129,8 +130,7 @@ bert_embed_ln_kernel(const int* __restrict__ ids, const int* __restrict__ pos_id
     float4 r;
     r.x = v[i].x * rstd * g.x + b.x; r.y = v[i].y * rstd * g.y + b.y;
     r.z = v[i].z * rstd * g.z + b.z; r.w = v[i].w * rstd * g.w + b.w;
-    if (oe) oe[lane + 32 * i] = r;
-    r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w);
+    if (os) store_split4(os, 768, 4 * (lane + 32 * i), r);
     o[lane + 32 * i] = r;
   }
 }
@@ -172,10 +172,10 @@ int mer_segment_reduce_launch(const float* in, const int* begins, const int* end
 
 int mer_bert_embed_launch(const int* ids, const int* pos_ids, const float* word, const float* pos,
                           const float* type0, const float* gamma, const float* beta, float eps,
-                          int tokens, float* out, float* out_exact, cudaStream_t stream) {
+                          int tokens, float* out, void* out_split, cudaStream_t stream) {
   if (tokens <= 0) return 0;
   bert_embed_ln_kernel<<<(tokens + 7) / 8, 256, 0, stream>>>(ids, pos_ids, word, pos, type0, gamma,
-                                                            beta, eps, tokens, out, out_exact);
+                                                            beta, eps, tokens, out, out_split);
   MER_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

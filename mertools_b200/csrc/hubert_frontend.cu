@@ -5,8 +5,9 @@
 //                      extract_audio_huggingface.py:94)
 //   conv0_stats      : per (clip, channel) sum / sum-of-squares of Conv1d(1->512, k=10, s=5)
 //                      over time, for GroupNorm(512 groups) (modeling_hubert.py:154-175)
-//   conv0_apply      : recompute conv0, normalise, affine, exact GELU, round to tf32, write the
-//                      TIME-MAJOR activation [B, T0_pad, 512] that the conv1 implicit GEMM reads.
+//   conv0_apply      : recompute conv0, normalise, affine, exact GELU, write the TIME-MAJOR
+//                      activation [B, T0_pad, 512] that the conv1 implicit GEMM reads (split bf16
+//                      hi|lo rows for the BF16X3 GEMM, or tf32-rounded fp32).
 //
 // The fp32 conv0 output (32.8 MB per 5 s clip) is never materialised un-normalised: the waveform
 // (320 KB per clip) is read three times instead.  Algorithmic traffic per clip:
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(C0)
 conv0_apply_kernel(const float* __restrict__ wave, long long ld_wave, const float* __restrict__ w0,
                    const float* __restrict__ gamma, const float* __restrict__ beta,
                    const double* __restrict__ stats, int T0, long long out_bstride /*floats*/,
-                   float* __restrict__ out) {
+                   int split_out, float* __restrict__ out) {
   __shared__ float xs[TCHUNK * S0 + K0];
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * TCHUNK;
@@ -112,12 +113,14 @@ conv0_apply_kernel(const float* __restrict__ wave, long long ld_wave, const floa
   const float rstd = (float)(1.0 / sqrt(var_d + 1e-5));
   const float g = __ldg(gamma + c) * rstd;
   const float bt = __ldg(beta + c);
-  float* o = out + (long long)b * out_bstride + (long long)t0 * C0 + c;
+  float* orow = out + (long long)b * out_bstride + (long long)t0 * C0;
   for (int t = 0; t < nt; ++t) {
     float y = 0.f;
 #pragma unroll
     for (int k = 0; k < K0; ++k) y = fmaf(w[k], xs[t * S0 + k], y);
-    o[(long long)t * C0] = round_tf32(gelu_erf((y - mean) * g + bt));
+    const float v = gelu_erf((y - mean) * g + bt);
+    if (split_out) store_split1(orow + (long long)t * C0, C0, c, v);
+    else orow[(long long)t * C0 + c] = round_tf32(v);
   }
 }
 
@@ -133,7 +136,7 @@ int mer_wave_normalize_launch(const float* in, float* out, int B, int L, long lo
 
 int mer_hubert_conv0_launch(const float* wave, long long ld_wave, int B, int L, const float* w0,
                             const float* gamma, const float* beta, double* stats, float* out,
-                            long long out_bstride, cudaStream_t stream) {
+                            long long out_bstride, int split_out, cudaStream_t stream) {
   const int T0 = (L - K0) / S0 + 1;
   MER_REQUIRE(T0 > 0, "mer_hubert_conv0: waveform too short (%d samples)", L);
   MER_CUDA_CHECK(cudaMemsetAsync(stats, 0, (size_t)B * C0 * 2 * sizeof(double), stream));
@@ -141,7 +144,13 @@ int mer_hubert_conv0_launch(const float* wave, long long ld_wave, int B, int L, 
   conv0_stats_kernel<<<grid, C0, 0, stream>>>(wave, ld_wave, w0, T0, stats);
   MER_CUDA_CHECK(cudaGetLastError());
   conv0_apply_kernel<<<grid, C0, 0, stream>>>(wave, ld_wave, w0, gamma, beta, stats, T0,
-                                              out_bstride, out);
+                                              out_bstride, split_out, out);
   MER_CUDA_CHECK(cudaGetLastError());
   return 0;
+}
+
+extern "C" int mer_wave_normalize(const float* in, float* out, int batch, int n_samples,
+                                  long long ld_in, long long ld_out, void* stream) {
+  return mer_wave_normalize_launch(in, out, batch, n_samples, ld_in, ld_out,
+                                   static_cast<cudaStream_t>(stream));
 }

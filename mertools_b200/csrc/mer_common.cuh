@@ -234,6 +234,30 @@ __device__ __forceinline__ float round_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
 }
+// fp32 -> (hi, lo) bf16 pair with x = hi + lo to 2^-17 relative (operand format of MER_GEMM_BF16X3)
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {  // low half <- a, high <- b
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ float bf16_round(float x) {
+  return __uint_as_float(pack_bf16x2(x, 0.f) << 16);
+}
+// store 4 consecutive logical columns starting at `col` of a split row: hi at col, lo at K + col
+__device__ __forceinline__ void store_split4(void* row_base, int K, int col, float4 v) {
+  const float hx = bf16_round(v.x), hy = bf16_round(v.y), hz = bf16_round(v.z), hw = bf16_round(v.w);
+  uint16_t* o = reinterpret_cast<uint16_t*>(row_base);
+  *reinterpret_cast<uint2*>(o + col) = make_uint2(pack_bf16x2(hx, hy), pack_bf16x2(hz, hw));
+  *reinterpret_cast<uint2*>(o + K + col) =
+      make_uint2(pack_bf16x2(v.x - hx, v.y - hy), pack_bf16x2(v.z - hz, v.w - hw));
+}
+__device__ __forceinline__ void store_split1(void* row_base, int K, int col, float v) {
+  const float h = bf16_round(v);
+  uint16_t* o = reinterpret_cast<uint16_t*>(row_base);
+  o[col] = (uint16_t)(__float_as_uint(h) >> 16);
+  o[K + col] = (uint16_t)(pack_bf16x2(v - h, 0.f) & 0xFFFFu);
+}
+
 // exact (erf) GELU, as torch.nn.functional.gelu default
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));

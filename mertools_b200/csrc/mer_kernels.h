@@ -4,12 +4,12 @@
 #include <cuda_runtime.h>
 #include "../../include/mer_b200.h"
 
-// gemm_tf32.cu
-int mer_gemm_tf32_launch(const MerGemmDesc* g, cudaStream_t stream);
+// gemm.cu
+int mer_gemm_launch(const MerGemmDesc* g, cudaStream_t stream);
 
 // rowwise.cu
 int mer_layernorm_launch(const float* x, const float* gamma, const float* beta, float* y,
-                         float* acc, long long rows, int dim, float eps, int flags,
+                         void* y_split, float* acc, long long rows, int dim, float eps, int flags,
                          cudaStream_t stream);
 
 // attention.cu
@@ -24,14 +24,14 @@ int mer_segment_reduce_launch(const float* in, const int* begins, const int* end
                               int dim, int mode, float* out, cudaStream_t stream);
 int mer_bert_embed_launch(const int* ids, const int* pos_ids, const float* word, const float* pos,
                           const float* type0, const float* gamma, const float* beta, float eps,
-                          int tokens, float* out, float* out_exact, cudaStream_t stream);
+                          int tokens, float* out, void* out_split, cudaStream_t stream);
 
 // hubert_frontend.cu
 int mer_wave_normalize_launch(const float* in, float* out, int B, int L, long long ld_in,
                               long long ld_out, cudaStream_t stream);
 int mer_hubert_conv0_launch(const float* wave, long long ld_wave, int B, int L, const float* w0,
                             const float* gamma, const float* beta, double* stats, float* out,
-                            long long out_bstride, cudaStream_t stream);
+                            long long out_bstride, int split_out, cudaStream_t stream);
 // posconv.cu
 int mer_posconv_launch(const float* x0, const float* wp, const float* bias, const int* cu_seqlens,
                        int n_seq, int max_seqlen, float* x1, cudaStream_t stream);
@@ -42,6 +42,7 @@ struct MerStackArgs {
   const MerLayerWeights* layers;
   int n_layers;
   int pre_ln;
+  int mode;                  // MER_GEMM_TF32 | MER_GEMM_BF16X3
   float eps;
   long long tokens;          // total packed tokens (rows of x)
   const int* cu_seqlens;     // device [n_seq+1]
@@ -49,6 +50,7 @@ struct MerStackArgs {
   int max_seqlen;
   float* x;                  // [tokens,768] residual stream (in/out)
   float* xn;                 // [tokens,768] scratch (LN out / attention ctx / pre-LN sum)
+  float* xs;                 // BF16X3 only: [tokens,768] slots holding the split copy of x
   float* qkv;                // [tokens,2304]
   float* h;                  // [tokens,3072]
   float* acc;                // optional [tokens,768]: sum of the last `acc_last` hidden states

@@ -18,8 +18,8 @@ using namespace mer;
 template <int VEC>  // VEC float4 per lane: dim = 128 * VEC
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, float* __restrict__ y, float* __restrict__ acc,
-                 long long rows, float eps, int flags) {
+                 const float* __restrict__ beta, float* __restrict__ y, void* __restrict__ ys,
+                 float* __restrict__ acc, long long rows, float eps, int flags) {
   constexpr int DIM = 128 * VEC;
   const int lane = threadIdx.x & 31;
   const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
@@ -48,7 +48,8 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
       q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
     }
     const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / DIM) + eps);
-    float4* yr = reinterpret_cast<float4*>(y + row * DIM);
+    float4* yr = y ? reinterpret_cast<float4*>(y + row * DIM) : nullptr;
+    float* ysr = ys ? reinterpret_cast<float*>(ys) + row * DIM : nullptr;  // split row: DIM 4-byte slots
     float4* ar = acc ? reinterpret_cast<float4*>(acc + row * DIM) : nullptr;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
@@ -66,11 +67,28 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
           ar[lane + 32 * i] = a;
         }
       }
-      if (flags & MER_LN_ROUND_TF32) {
-        o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+      if (ysr) store_split4(ysr, DIM, 4 * (lane + 32 * i), o);
+      if (yr) {
+        if (flags & MER_LN_ROUND_TF32) {
+          o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+        }
+        yr[lane + 32 * i] = o;
       }
-      yr[lane + 32 * i] = o;
     }
+  }
+}
+
+// fp32 [rows,K] -> split bf16 [rows, hi(K)|lo(K)]
+__global__ void split_bf16_kernel(const float* __restrict__ in, void* __restrict__ out, long long rows,
+                                  int K) {
+  const long long total = rows * (K / 4);
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const long long r = i / (K / 4);
+    const int c4 = (int)(i % (K / 4));
+    const float4 v = *reinterpret_cast<const float4*>(in + r * K + c4 * 4);
+    store_split4(reinterpret_cast<float*>(out) + r * K, K, c4 * 4, v);
   }
 }
 
@@ -83,9 +101,11 @@ __global__ void round_tf32_kernel(float* x, long long n) {
 }  // namespace
 
 int mer_layernorm_launch(const float* x, const float* gamma, const float* beta, float* y,
-                         float* acc, long long rows, int dim, float eps, int flags,
+                         void* y_split, float* acc, long long rows, int dim, float eps, int flags,
                          cudaStream_t stream) {
-  MER_REQUIRE(x && gamma && beta && y, "mer_layernorm: null operand");
+  MER_REQUIRE(x && gamma && beta && (y || y_split), "mer_layernorm: null operand");
+  // y == x and y_split == x are both fine: a warp holds its whole row in registers before it
+  // writes, and a split row occupies exactly the bytes of the fp32 row it replaces.
   MER_REQUIRE(dim == 768 || dim == 512, "mer_layernorm: dim %d not supported (768 or 512)", dim);
   if (rows <= 0) return 0;
   const int warps_per_block = 8;
@@ -93,9 +113,9 @@ int mer_layernorm_launch(const float* x, const float* gamma, const float* beta, 
   const long long max_blocks = (long long)mer_num_sms() * 16;
   if (blocks > max_blocks) blocks = max_blocks;
   if (dim == 768)
-    layernorm_kernel<6><<<(int)blocks, 256, 0, stream>>>(x, gamma, beta, y, acc, rows, eps, flags);
+    layernorm_kernel<6><<<(int)blocks, 256, 0, stream>>>(x, gamma, beta, y, y_split, acc, rows, eps, flags);
   else
-    layernorm_kernel<4><<<(int)blocks, 256, 0, stream>>>(x, gamma, beta, y, acc, rows, eps, flags);
+    layernorm_kernel<4><<<(int)blocks, 256, 0, stream>>>(x, gamma, beta, y, y_split, acc, rows, eps, flags);
   MER_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -105,6 +125,16 @@ extern "C" int mer_round_tf32(float* x, long long n, void* stream) {
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
   round_tf32_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n);
+  MER_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mer_split_bf16(const float* in, void* out, long long rows, int K, void* stream) {
+  MER_REQUIRE(in && out && (const void*)in != out && K > 0 && K % 4 == 0, "mer_split_bf16: bad operands");
+  if (rows <= 0) return 0;
+  long long blocks = (rows * (K / 4) + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  split_bf16_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, rows, K);
   MER_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

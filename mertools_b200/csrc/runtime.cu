@@ -93,13 +93,13 @@ int mer_check_device(void) {
   return 0;
 }
 
-int mer_gemm_tf32(const MerGemmDesc* desc, void* stream) {
-  return mer_gemm_tf32_launch(desc, static_cast<cudaStream_t>(stream));
+int mer_gemm(const MerGemmDesc* desc, void* stream) {
+  return mer_gemm_launch(desc, static_cast<cudaStream_t>(stream));
 }
 
-int mer_layernorm(const float* x, const float* gamma, const float* beta, float* y, float* acc,
-                  long long rows, int dim, float eps, int flags, void* stream) {
-  return mer_layernorm_launch(x, gamma, beta, y, acc, rows, dim, eps, flags,
+int mer_layernorm(const float* x, const float* gamma, const float* beta, float* y, void* y_split,
+                  float* acc, long long rows, int dim, float eps, int flags, void* stream) {
+  return mer_layernorm_launch(x, gamma, beta, y, y_split, acc, rows, dim, eps, flags,
                               static_cast<cudaStream_t>(stream));
 }
 

@@ -141,10 +141,10 @@ class HubertEncoder:
             assert w.shape == (512, 512, k), w.shape
             assert f"feature_extractor.conv_layers.{i + 1}.conv.bias" not in sd, "conv_bias=True unsupported"
             m.conv_w[i] = pk.keep(np.ascontiguousarray(w.transpose(0, 2, 1)).reshape(512, k * 512),
-                                  tf32=True).data_ptr()
+                                  split=True).data_ptr()
         m.fp_ln_g = pk.keep(sd["feature_projection.layer_norm.weight"]).data_ptr()
         m.fp_ln_b = pk.keep(sd["feature_projection.layer_norm.bias"]).data_ptr()
-        m.fp_w = pk.keep(sd["feature_projection.projection.weight"], tf32=True).data_ptr()
+        m.fp_w = pk.keep(sd["feature_projection.projection.weight"], split=True).data_ptr()
         m.fp_b = pk.keep(sd["feature_projection.projection.bias"]).data_ptr()
         wpos = fold_pos_conv_weight(sd)
         assert wpos.shape == (768, 48, 128), wpos.shape
@@ -153,7 +153,7 @@ class HubertEncoder:
         m.pos_b = pk.keep(sd["encoder.pos_conv_embed.conv.bias"]).data_ptr()
         m.enc_ln_g = pk.keep(sd["encoder.layer_norm.weight"]).data_ptr()
         m.enc_ln_b = pk.keep(sd["encoder.layer_norm.bias"]).data_ptr()
-        self.layers = W.pack_layers(sd, W.HUBERT_NAMES, self.n_layers, pk)
+        self.layers = W.pack_layers(sd, W.HUBERT_NAMES, self.n_layers, pk, split=True)
         m.layers = self.layers
         self.model = m
         self.ws = _Workspace(self.device)
@@ -215,7 +215,7 @@ class BertEncoder:
         m.type_emb0 = pk.keep(sd["embeddings.token_type_embeddings.weight"][0]).data_ptr()
         m.emb_ln_g = pk.keep(sd["embeddings.LayerNorm.weight"]).data_ptr()
         m.emb_ln_b = pk.keep(sd["embeddings.LayerNorm.bias"]).data_ptr()
-        self.layers = W.pack_layers(sd, W.BERT_NAMES, self.n_layers, pk)
+        self.layers = W.pack_layers(sd, W.BERT_NAMES, self.n_layers, pk, split=True)
         m.layers = self.layers
         self.model = m
         self.ws = _Workspace(self.device)

@@ -17,6 +17,9 @@ import time
 import numpy as np
 import torch
 
+import ctypes as C
+
+from .. import _lib as L
 from ..encoders import HubertEncoder
 from . import common
 
@@ -42,6 +45,8 @@ class AudioExtractor:
         self.enc = HubertEncoder(state_dict, device=device)
         self.device = self.enc.device
         self.max_rows = max_rows_per_launch
+        self._norm = L.declare("mer_wave_normalize", [C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                                      C.c_longlong, C.c_longlong, C.c_void_p])
 
     def _run_rows(self, rows, normalize):
         """rows: CUDA fp32 [R, L] -> frames [R, T, 768] (sum of the last four hidden states)."""
@@ -75,8 +80,10 @@ class AudioExtractor:
             if res[i] is not None:
                 continue
             x = torch.from_numpy(np.asarray(w).astype(np.float32))[None].to(self.device)
-            x = (x - x.mean()) / torch.sqrt(x.var(unbiased=False) + 1e-7)
-            rows = split_into_batch(x)
+            xn = torch.empty_like(x)
+            L.check(self._norm(L.ptr(x), L.ptr(xn), 1, x.shape[1], x.shape[1], x.shape[1],
+                               L.stream_ptr()))
+            rows = split_into_batch(xn)
             fr = self._run_rows(rows.contiguous(), normalize=False).reshape(-1, 768)
             res[i] = (fr.mean(dim=0) if feature_level == "UTTERANCE" else fr).cpu().numpy()
         if save_files is not None:

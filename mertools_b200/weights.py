@@ -33,10 +33,13 @@ class Packed:
         self.device = device
         self.tensors = []
 
-    def keep(self, x, tf32=False):
+    def keep(self, x, tf32=False, split=False):
+        """tf32: round-to-nearest in place (TF32 GEMM operand); split: bf16 hi|lo rows (BF16X3)."""
         t = _dev(x, self.device)
         if tf32:
             L.round_tf32_(t)
+        if split:
+            t = L.split_bf16(t)
         self.tensors.append(t)
         return t
 
@@ -44,8 +47,10 @@ class Packed:
         return sum(t.numel() * 4 for t in self.tensors)
 
 
-def pack_layers(sd, names, n_layers, pk: Packed):
-    """names: dict role -> key template with ``{i}``; returns (ctypes array, list of dicts)."""
+def pack_layers(sd, names, n_layers, pk: Packed, split=False):
+    """names: dict role -> key template with ``{i}``.  split=False: tf32-rounded fp32 GEMM weights
+    (MER_GEMM_TF32 stack); split=True: bf16 hi|lo rows (MER_GEMM_BF16X3 stack)."""
+    kw = dict(split=True) if split else dict(tf32=True)
     arr = (MerLayerWeights * n_layers)()
     for i in range(n_layers):
         g = lambda role: sd[names[role].format(i=i)]  # noqa: E731
@@ -53,11 +58,11 @@ def pack_layers(sd, names, n_layers, pk: Packed):
         bq = np.concatenate([np.asarray(g("q_b")), np.asarray(g("k_b")), np.asarray(g("v_b"))], 0)
         ent = dict(
             ln1_g=pk.keep(g("ln1_g")), ln1_b=pk.keep(g("ln1_b")),
-            w_qkv=pk.keep(wq, tf32=True), b_qkv=pk.keep(bq),
-            w_o=pk.keep(g("o_w"), tf32=True), b_o=pk.keep(g("o_b")),
+            w_qkv=pk.keep(wq, **kw), b_qkv=pk.keep(bq),
+            w_o=pk.keep(g("o_w"), **kw), b_o=pk.keep(g("o_b")),
             ln2_g=pk.keep(g("ln2_g")), ln2_b=pk.keep(g("ln2_b")),
-            w_fc1=pk.keep(g("fc1_w"), tf32=True), b_fc1=pk.keep(g("fc1_b")),
-            w_fc2=pk.keep(g("fc2_w"), tf32=True), b_fc2=pk.keep(g("fc2_b")),
+            w_fc1=pk.keep(g("fc1_w"), **kw), b_fc1=pk.keep(g("fc1_b")),
+            w_fc2=pk.keep(g("fc2_w"), **kw), b_fc2=pk.keep(g("fc2_b")),
         )
         for k, t in ent.items():
             setattr(arr[i], k, t.data_ptr())

@@ -102,6 +102,39 @@ def sec_gemm():
     return ok
 
 
+def sec_gemm_x3():
+    """BF16X3 mode: split operands, 3 MMAs per K step, ~fp32 accuracy; also split outputs."""
+    ok = True
+    for (name, M, N, K, force) in [("x3_1tile", 128, 128, 64, 0), ("x3_tail", 300, 256, 768, 256),
+                                   ("x3_fc1", 5000, 3072, 768, 0), ("x3_fc2", 5000, 768, 3072, 0)]:
+        g = torch.Generator(device="cuda").manual_seed(7)
+        A = torch.randn(M, K, device="cuda", generator=g)
+        W = torch.randn(N, K, device="cuda", generator=g) * 0.05
+        b = torch.randn(N, device="cuda", generator=g)
+        As, Ws = L.split_bf16(A), L.split_bf16(W)
+        rt = (L.unsplit_bf16(As) - A).abs().max().item() / A.abs().max().item()
+        out = torch.full((M, N), float("nan"), device="cuda")
+        L.gemm(As, Ws, out, bias=b, mode=L.MER_GEMM_BF16X3, force_block_n=force)
+        outs = torch.full((M, N), float("nan"), device="cuda")
+        L.gemm(As, Ws, outs, bias=b, gelu=True, split_out=True, mode=L.MER_GEMM_BF16X3, force_block_n=force)
+        torch.cuda.synchronize()
+        ref = A.double() @ W.double().t() + b.double()
+        err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
+        refg = gelu(ref)
+        errs = (L.unsplit_bf16(outs).double() - refg).abs().max().item() / refg.abs().max().item()
+        good = err < 5e-5 and errs < 5e-5 and rt < 2e-5
+        emit(check=name, ok=bool(good), M=M, N=N, K=K, rel_err=err, rel_err_split_out=errs, split_roundtrip=rt)
+        ok &= good
+    M, N, K = 100864, 3072, 768
+    A = L.split_bf16(torch.randn(M, K, device="cuda"))
+    W = L.split_bf16(torch.randn(N, K, device="cuda") * 0.02)
+    b = torch.randn(N, device="cuda")
+    out = torch.empty(M, N, device="cuda")
+    ms = time_cuda(lambda: L.gemm(A, W, out, bias=b, gelu=True, split_out=True, mode=L.MER_GEMM_BF16X3), iters=10)
+    emit(perf="x3_fc1", M=M, N=N, K=K, ms=ms, tflops_useful=2.0 * M * N * K / ms / 1e9)
+    return ok
+
+
 def sec_conv():
     """Conv1d(k=3,s=2) and (k=2,s=2) over time-major activations through the tap-aware A map."""
     ok = True
@@ -230,7 +263,7 @@ def sec_vit():
     return True
 
 
-SECTIONS = dict(vit=sec_vit, gemm=sec_gemm, conv=sec_conv, gemm_perf=sec_gemm_perf, ln=sec_ln, attn=sec_attn)
+SECTIONS = dict(vit=sec_vit, gemm_x3=sec_gemm_x3, gemm=sec_gemm, conv=sec_conv, gemm_perf=sec_gemm_perf, ln=sec_ln, attn=sec_attn)
 
 if __name__ == "__main__":
     os.makedirs("gpurun_out", exist_ok=True)
