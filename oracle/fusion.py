@@ -1,0 +1,72 @@
+"""ORACLE (test infrastructure — never imported by the product path).
+
+CPU restatement (torch autograd, fp32) of the Attention fusion net, its losses and the training
+step of the reference:
+  MERBench/toolkit/models/attention.py:8-57, toolkit/models/modules/encoder.py:9-41 (MLPEncoder),
+  toolkit/utils/loss.py:5-28, main-release.py:31-66 (zero_grad, forward, loss = interloss + CE + MSE,
+  backward, optional clip_grad_value_, Adam(lr, weight_decay=l2) :205).
+Dropout masks are explicit inputs (the reference's nn.Dropout draws them from the global CPU
+generator; a CUDA run cannot reproduce that stream) so both sides use the same masks.
+Pinned against the reference's own classes by tests/golden/make_golden.py (fusion_golden.npz).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ENC = ("audio_encoder", "text_encoder", "video_encoder", "attention_mlp")
+
+
+def _mlp(sd, prefix, x, mask, p):
+    """MLPEncoder.forward (encoder.py:30-41): dropout -> 3 x (Linear + ReLU)."""
+    if mask is not None:
+        x = x * mask / (1.0 - p)
+    for l in ("linear_1", "linear_2", "linear_3"):
+        x = F.relu(F.linear(x, sd[f"{prefix}.{l}.weight"], sd[f"{prefix}.{l}.bias"]))
+    return x
+
+
+def attention_forward(sd, audios, texts, videos, masks=None, p=0.0):
+    """Attention.forward (attention.py:36-57).  masks: None (eval) or 4 keep-masks
+    [audio, text, video, concat].  Returns (features, emos_out, vals_out)."""
+    m = masks or (None, None, None, None)
+    ha = _mlp(sd, "audio_encoder", audios, m[0], p)
+    ht = _mlp(sd, "text_encoder", texts, m[1], p)
+    hv = _mlp(sd, "video_encoder", videos, m[2], p)
+    cat = torch.cat([ha, ht, hv], dim=1)
+    att = F.linear(_mlp(sd, "attention_mlp", cat, m[3], p), sd["fc_att.weight"], sd["fc_att.bias"])
+    fused = torch.matmul(torch.stack([ha, ht, hv], dim=2), att.unsqueeze(2)).squeeze(2)
+    emos = F.linear(fused, sd["fc_out_1.weight"], sd["fc_out_1.bias"])
+    vals = F.linear(fused, sd["fc_out_2.weight"], sd["fc_out_2.bias"])
+    return fused, emos, vals
+
+
+def losses(emos_out, vals_out, emos, vals):
+    """CELoss + MSELoss (loss.py:11-28)."""
+    ce = F.nll_loss(F.log_softmax(emos_out, 1), emos.long(), reduction="sum") / len(emos_out)
+    mse = F.mse_loss(vals_out.view(-1, 1), vals.view(-1, 1), reduction="sum") / len(vals_out)
+    return ce, mse
+
+
+class Trainer:
+    """State of one reference training run: parameters as leaf tensors + torch.optim.Adam."""
+
+    def __init__(self, state_dict, lr=1e-3, l2=1e-5, grad_clip=-1.0, dropout=0.0):
+        self.sd = {k: torch.tensor(np.asarray(v), dtype=torch.float32, requires_grad=True)
+                   for k, v in state_dict.items()}
+        self.opt = torch.optim.Adam(list(self.sd.values()), lr=lr, weight_decay=l2)
+        self.grad_clip, self.p = grad_clip, dropout
+
+    def step(self, a, t, v, emos, vals, masks=None):
+        """main-release.py:31-66 for one batch.  Returns (ce, mse, total, emos_out, vals_out, grads)."""
+        self.opt.zero_grad()
+        _, eo, vo = attention_forward(self.sd, a, t, v, masks, self.p)
+        ce, mse = losses(eo, vo, emos, vals)
+        loss = ce + mse
+        loss.backward()
+        grads = {k: p.grad.detach().clone() for k, p in self.sd.items()}
+        if self.grad_clip != -1:
+            torch.nn.utils.clip_grad_value_(list(self.sd.values()), self.grad_clip)
+        self.opt.step()
+        return float(ce.detach()), float(mse.detach()), float(loss.detach()), eo.detach(), vo.detach(), grads
