@@ -34,6 +34,15 @@ MER_API int mer_abi_version(void);
 /* 0 when the current device is compute capability 10.x, non-zero (and an error string) otherwise */
 MER_API int mer_check_device(void);
 
+/* cumulative number of CUDA kernels this library has launched in this process (bench.py's
+ * gpu_launches); CUDA-graph replays are not seen here and are counted by their owner */
+MER_API long long mer_launch_count(void);
+/* per-launch CUDA-event timing of the GEMM kernel (roofline in bench.py): enable(1) starts a fresh
+ * recording, enable(0) stops; collect sums duration / algorithmic FLOPs (2*M*N*K) / launches of one
+ * MER_GEMM_* mode since the last enable(1). */
+MER_API int mer_profile_enable(int on);
+MER_API int mer_profile_collect(int mode, double* total_ms, double* total_flops, int* launches);
+
 /* ---- GEMM (nn.Linear / Conv1d-as-GEMM / patch-embed) ---------------------------------- */
 enum { MER_EPI_GELU = 1, MER_EPI_ROUND_TF32 = 2, MER_EPI_SPLIT_BF16 = 4 };
 /* Arithmetic mode of a GEMM.  TF32: operands are fp32 arrays (pre-rounded to tf32).  BF16X3: every

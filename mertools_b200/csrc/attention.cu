@@ -258,5 +258,6 @@ int mer_attention_launch(const float* qkv, float* ctx, const int* cu_seqlens, in
   attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(qkv, ctx, cu_seqlens, heads,
                                                            (flags & MER_EPI_SPLIT_BF16) ? 2 : ((flags & MER_EPI_ROUND_TF32) ? 1 : 0));
   MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
   return 0;
 }

@@ -379,6 +379,7 @@ int run_forward(const MerFusionDims& d, const Layout& L, const float* P, const S
   lb.p[0] = LinP{s.a2, H, nullptr, 1.f, P + L.att_w3, P + L.att_b3, s.a3, H, H, H, 1};
   fus_linear_fwd_kernel<<<g2, 256, 0, st>>>(lb, B);
   MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(6);
   return 0;
 }
 
@@ -419,6 +420,7 @@ int mer_fusion_forward(const MerFusionDims* d, const float* params, const float*
   h.H = d->hidden; h.O1 = d->out1; h.O2 = d->out2;
   fus_head_kernel<<<B, 128, 0, st>>>(h);
   MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
   return 0;
 }
 
@@ -450,6 +452,7 @@ int mer_fusion_fwd_bwd(const MerFusionDims* d, const float* params, float* grads
       const long long n = (long long)B * (m < 3 ? in[m] : 3 * H);
       fus_dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
           dst, n, dropout_p, seed + 0x1000ull * (m + 1), step_counter);
+      mer_count_launches(1);
       masks[m] = dst;
     }
   }
@@ -467,16 +470,19 @@ int mer_fusion_fwd_bwd(const MerFusionDims* d, const float* params, float* grads
   h.H = H; h.O1 = d->out1; h.O2 = d->out2; h.inv_batch = loss_inv_batch;
   fus_head_kernel<<<B, 128, 0, st>>>(h);
   fus_loss_reduce_kernel<<<1, 32, 0, st>>>(s.loss_terms, B, loss_inv_batch, loss_out);
+  mer_count_launches(2);
 
   float* G = grads;
   BwdBatch bb;
   auto launch_w = [&](int nprob, int K, int N) {
     dim3 g((K + 255) / 256, N, nprob);
     fus_linear_bwd_w_kernel<<<g, 256, 0, st>>>(bb, B);
+    mer_count_launches(1);
   };
   auto launch_x = [&](int nprob, int K) {
     dim3 g((K + 255) / 256, B, nprob);
     fus_linear_bwd_x_kernel<<<g, 256, 0, st>>>(bb, B);
+    mer_count_launches(1);
   };
   // heads: fc_out_1, fc_out_2 (x = fused features), fc_att (x = a3); no relu, no dx needed here
   bb.p[0] = BwdP{s.d_emos, d->out1, nullptr, 0, features, H, nullptr, 1.f, params + L.o1_w,
@@ -529,6 +535,7 @@ int mer_fusion_adam(float* params, const float* grads, float* exp_avg, float* ex
                                                               grad_clip, step_counter);
   fus_step_inc_kernel<<<1, 32, 0, st>>>(step_counter);
   MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(2);
   return 0;
 }
 

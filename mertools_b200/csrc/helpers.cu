@@ -149,6 +149,7 @@ int mer_vit_patchify_launch(const uint8_t* frames_bgr, int n_frames, float* a_pa
   vit_patchify_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(frames_bgr, a_patches,
                                                                            total);
   MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
   return 0;
 }
 
@@ -156,6 +157,7 @@ int mer_vit_cls_rows_launch(const float* cls_pos0, float* x, int n_frames, cudaS
   if (n_frames <= 0) return 0;
   vit_cls_rows_kernel<<<n_frames, 192, 0, stream>>>(cls_pos0, x, n_frames);
   MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
   return 0;
 }
 
@@ -167,6 +169,7 @@ int mer_segment_reduce_launch(const float* in, const int* begins, const int* end
   dim3 grid(n_seg, (dim + 511) / 512);
   segment_reduce_kernel<<<grid, 512, 0, stream>>>(in, begins, ends, dim, mode, out);
   MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
   return 0;
 }
 
@@ -177,12 +180,14 @@ int mer_bert_embed_launch(const int* ids, const int* pos_ids, const float* word,
   bert_embed_ln_kernel<<<(tokens + 7) / 8, 256, 0, stream>>>(ids, pos_ids, word, pos, type0, gamma,
                                                             beta, eps, tokens, out, out_split);
   MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
   return 0;
 }
 
 int mer_iota_offsets_launch(int* offsets, int n_seg, int step, cudaStream_t stream) {
   iota_offsets_kernel<<<(n_seg + 256) / 256, 256, 0, stream>>>(offsets, n_seg, step);
   MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
   return 0;
 }
 

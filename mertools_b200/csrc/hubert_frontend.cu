@@ -131,6 +131,7 @@ int mer_wave_normalize_launch(const float* in, float* out, int B, int L, long lo
   MER_REQUIRE(in && out && B > 0 && L > 0, "mer_wave_normalize: bad arguments");
   wave_normalize_kernel<<<B, 1024, 0, stream>>>(in, out, L, ld_in, ld_out);
   MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
   return 0;
 }
 
@@ -146,6 +147,7 @@ int mer_hubert_conv0_launch(const float* wave, long long ld_wave, int B, int L, 
   conv0_apply_kernel<<<grid, C0, 0, stream>>>(wave, ld_wave, w0, gamma, beta, stats, T0,
                                               out_bstride, split_out, out);
   MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(2);
   return 0;
 }
 

@@ -40,6 +40,7 @@ int mer_make_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const v
                   CUtensorMapSwizzle swizzle);
 
 int mer_num_sms();
+void mer_count_launches(int n);  // cumulative count of kernels launched by this library
 
 // --------------------------------------------------------------------------------------------
 // device-side helpers

@@ -164,5 +164,6 @@ int mer_posconv_launch(const float* x0, const float* wp, const float* bias, cons
   dim3 grid((max_seqlen + BT - 1) / BT, NG, n_seq);
   posconv_kernel<<<grid, PC_THREADS, PC_SMEM, stream>>>(x0, wp, bias, cu_seqlens, x1);
   MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
   return 0;
 }

@@ -117,6 +117,7 @@ int mer_layernorm_launch(const float* x, const float* gamma, const float* beta, 
   else
     layernorm_kernel<4><<<(int)blocks, 256, 0, stream>>>(x, gamma, beta, y, y_split, acc, rows, eps, flags);
   MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
   return 0;
 }
 
@@ -126,6 +127,7 @@ extern "C" int mer_round_tf32(float* x, long long n, void* stream) {
   if (blocks > 148 * 32) blocks = 148 * 32;
   round_tf32_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n);
   MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
   return 0;
 }
 
@@ -136,5 +138,6 @@ extern "C" int mer_split_bf16(const float* in, void* out, long long rows, int K,
   if (blocks > 148 * 32) blocks = 148 * 32;
   split_bf16_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, rows, K);
   MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
   return 0;
 }

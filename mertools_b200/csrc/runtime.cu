@@ -78,7 +78,12 @@ int mer_num_sms() {
   return n;
 }
 
+static long long g_launches = 0;
+void mer_count_launches(int n) { g_launches += n; }
+
 extern "C" {
+
+long long mer_launch_count(void) { return g_launches; }
 
 const char* mer_last_error(void) { return g_err; }
 

@@ -226,6 +226,28 @@ class BertEncoder:
         self._fwd = L.declare("mer_bert_forward", [C.POINTER(MerBertModel), vp, vp, vp, i32, i32, i32,
                                                    vp, vp, vp, C.c_longlong, vp, vp, vp, vp])
 
+    def forward_packed(self, ids, seqlen, start=1, end=-1):
+        """Device fast path for n sentences of identical length: ids int32 CUDA [n, seqlen].  Position
+        ids / cu_seqlens / kept ranges are built once per (n, seqlen) on the device.
+        Returns (utt [n,768], None)."""
+        assert ids.is_cuda and ids.dtype == torch.int32 and ids.shape[1] == seqlen
+        n = ids.shape[0]
+        key = (n, seqlen, start, end)
+        if getattr(self, "_packed_key", None) != key:
+            ar = torch.arange(n + 1, dtype=torch.int32, device=self.device) * seqlen
+            pos = (torch.arange(seqlen, dtype=torch.int32, device=self.device) + self.position_offset).repeat(n)
+            self._packed = (ar, pos.contiguous(), (ar[:-1] + (start or 0)).contiguous(),
+                            (ar[1:] + (end if end is not None else 0)).contiguous())
+            self._packed_key = key
+        cu, pos, seg_b, seg_e = self._packed
+        n_tok = n * seqlen
+        ws = self.ws.get(L.lib().mer_bert_workspace_bytes(n_tok, n))
+        utt = torch.empty(n, 768, dtype=torch.float32, device=self.device)
+        L.check(self._fwd(C.byref(self.model), L.ptr(ids.contiguous()), L.ptr(pos), L.ptr(cu), n, n_tok,
+                          seqlen, L.ptr(seg_b), L.ptr(seg_e), L.ptr(ws), ws.numel(), None, L.ptr(utt),
+                          None, L.stream_ptr()))
+        return utt, None
+
     def forward(self, id_lists, start=1, end=-1, want_tokens=False, return_hidden=False):
         """id_lists: list of non-empty python/numpy int sequences (one tokenised sentence each).
         Returns (utt [n,768], tokens [sum T,768]|None [, hidden, cu_seqlens])."""

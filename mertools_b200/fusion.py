@@ -83,6 +83,8 @@ class FusionNet:
         self.ws = torch.empty(int(lib.mer_fusion_workspace_bytes(C.byref(self.dims), max_batch)),
                               dtype=torch.uint8, device=self.device)
         self.training = True
+        self.graph_launches = 0  # kernels launched through CUDA-graph replays (not seen by the library counter)
+        lib.mer_launch_count.restype = C.c_longlong
         self._graphs = {}
         self._static = None
 
@@ -197,14 +199,16 @@ class FusionNet:
             for dst, src in zip((self.params, self.exp_avg, self.exp_avg_sq, self.step_counter), saved):
                 dst.copy_(src)
             g = torch.cuda.CUDAGraph()
+            n0 = L.lib().mer_launch_count()
             with torch.cuda.graph(g):
                 self._launch_step(st["a"], st["t"], st["v"], st["emo"], st["val"], st["feats"],
                                   st["emos"], st["vals"], lr, betas, eps, weight_decay, world_size, None)
-            self._graphs[key] = (g, st)
-        g, st = self._graphs[key]
+            self._graphs[key] = (g, st, int(L.lib().mer_launch_count() - n0))
+        g, st, n_kernels = self._graphs[key]
         for k, src in (("a", a), ("t", t), ("v", v), ("emo", emo), ("val", val)):
             st[k].copy_(src, non_blocking=True)
         g.replay()
+        self.graph_launches += n_kernels
         return self.loss, st["emos"], st["vals"]
 
 
