@@ -46,8 +46,9 @@ MER_API int mer_profile_collect(int mode, double* total_ms, double* total_flops,
 /* ---- GEMM (nn.Linear / Conv1d-as-GEMM / patch-embed) ---------------------------------- */
 enum { MER_EPI_GELU = 1, MER_EPI_ROUND_TF32 = 2, MER_EPI_SPLIT_BF16 = 4 };
 /* Arithmetic mode of a GEMM.  TF32: operands are fp32 arrays (pre-rounded to tf32).  BF16X3: every
- * operand row of K values is stored as K bf16 "hi" followed by K bf16 "lo" (x = hi + lo to 2^-17) in
- * the bytes K fp32 values would occupy; three bf16 MMAs per product recover ~fp32 accuracy. */
+ * operand value x is stored as a bf16 pair (hi, lo), x = hi + lo to 2^-17; a row of K values (K % 32
+ * == 0) occupies the bytes K fp32 values would, as 128-byte groups [32 x hi | 32 x lo]; three bf16
+ * MMAs per product (hi*hi + lo*hi + hi*lo) recover ~fp32 accuracy ("split rows" below). */
 enum { MER_GEMM_TF32 = 0, MER_GEMM_BF16X3 = 1 };
 
 typedef struct MerGemmEpilogue {
@@ -61,8 +62,7 @@ typedef struct MerGemmEpilogue {
   int ld_out; /* floats */
   int ld_res;
   int flags;     /* MER_EPI_* */
-  int split_off; /* MER_EPI_SPLIT_BF16: logical columns per out row (= offset of the lo half);
-                    ld_out stays the row pitch in 4-byte slots */
+  int split_off; /* reserved (0) */
 } MerGemmEpilogue;
 
 /* A[b, m, tap*K_inner + c] = base[b*a_batch_stride + (m + tap / P)*a_row_stride +
@@ -91,7 +91,7 @@ typedef struct MerGemmDesc {
 /* tcgen05 GEMM with fused epilogue.  Replaces torch nn.Linear / nn.Conv1d calls inside
  * HF ViTLayer / HubertEncoderLayer / BertLayer reached from the reference extractors. */
 MER_API int mer_gemm(const MerGemmDesc* desc, void* stream);
-/* fp32 [rows, K] -> split bf16 [rows, hi(K) | lo(K)] (same byte size); used on weights at load time */
+/* fp32 [rows, K] -> split rows (same byte size, K % 32 == 0); used on weights at load time */
 MER_API int mer_split_bf16(const float* in, void* out, long long rows, int K, void* stream);
 
 /* ---- row-wise kernels ------------------------------------------------------------------ */
@@ -128,7 +128,7 @@ MER_API int mer_segment_reduce(const float* in, const int32_t* begins, const int
 
 /* ---- transformer encoder stack shared by the three modalities ----------------------------------- */
 /* GEMM weights (w_*) are tf32-rounded fp32 [N,K] for a MER_GEMM_TF32 stack and split bf16
- * [N, hi(K)|lo(K)] for a MER_GEMM_BF16X3 stack (ViT: TF32; HuBERT/BERT: BF16X3). */
+ * split rows for a MER_GEMM_BF16X3 stack (ViT: TF32; HuBERT/BERT: BF16X3). */
 typedef struct MerLayerWeights {
   const float* ln1_g; /* ViT: layernorm_before | HuBERT: layer_norm | BERT: attention.output.LayerNorm */
   const float* ln1_b;

@@ -153,7 +153,8 @@ def layernorm(x, gamma, beta, y, *, eps, y_split=None, acc=None, flags=0):
 
 
 def split_bf16(x):
-    """fp32 [rows, K] CUDA tensor -> same-shape fp32-typed tensor whose bytes are bf16 hi|lo rows."""
+    """fp32 [rows, K] CUDA tensor -> same-shape fp32-typed tensor whose bytes are split rows
+    (128-byte groups of 32 bf16 hi | 32 bf16 lo; see mer_b200.h)."""
     import torch
     x = x.contiguous()
     out = torch.empty_like(x)
@@ -165,8 +166,8 @@ def unsplit_bf16(xs):
     """Inverse of split_bf16 (for tests): hi + lo as fp32."""
     import torch
     K = xs.shape[-1]
-    b = xs.contiguous().view(torch.bfloat16).view(*xs.shape[:-1], 2 * K)
-    return b[..., :K].float() + b[..., K:].float()
+    b = xs.contiguous().view(torch.bfloat16).view(*xs.shape[:-1], K // 32, 2, 32).float()
+    return (b[..., 0, :] + b[..., 1, :]).reshape(*xs.shape[:-1], K)
 
 
 def round_tf32_(x):

@@ -216,20 +216,10 @@ attention_kernel(const float* __restrict__ qkv, float* __restrict__ ctx,
   for (int dt = 0; dt < 8; ++dt) {
     float2 a = make_float2(o[dt][0] * inv_lo, o[dt][1] * inv_lo);
     float2 b = make_float2(o[dt][2] * inv_hi, o[dt][3] * inv_hi);
-    if (out_mode == 2) {  // split bf16 rows [hi(ldc) | lo(ldc)] for a BF16X3 out-proj GEMM
+    if (out_mode == 2) {  // split bf16 rows for a BF16X3 out-proj GEMM
       const int col = h * HD + dt * 8 + 2 * t;
-      if (row_lo < len) {
-        uint16_t* o = reinterpret_cast<uint16_t*>(ctx + (long long)(start + row_lo) * ldc);
-        const float hx = bf16_round(a.x), hy = bf16_round(a.y);
-        *reinterpret_cast<uint32_t*>(o + col) = pack_bf16x2(hx, hy);
-        *reinterpret_cast<uint32_t*>(o + ldc + col) = pack_bf16x2(a.x - hx, a.y - hy);
-      }
-      if (row_hi < len) {
-        uint16_t* o = reinterpret_cast<uint16_t*>(ctx + (long long)(start + row_hi) * ldc);
-        const float hx = bf16_round(b.x), hy = bf16_round(b.y);
-        *reinterpret_cast<uint32_t*>(o + col) = pack_bf16x2(hx, hy);
-        *reinterpret_cast<uint32_t*>(o + ldc + col) = pack_bf16x2(b.x - hx, b.y - hy);
-      }
+      if (row_lo < len) store_split2(ctx + (long long)(start + row_lo) * ldc, col, a.x, a.y);
+      if (row_hi < len) store_split2(ctx + (long long)(start + row_hi) * ldc, col, b.x, b.y);
       continue;
     }
     if (out_mode == 1) {

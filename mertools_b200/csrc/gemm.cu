@@ -19,8 +19,9 @@
 // Two arithmetic modes share the pipeline (both move 4 bytes per operand element):
 //   MER_GEMM_TF32   : fp32 operands (pre-rounded to tf32 by their producers), kind::tf32, 128B swizzle.
 //                     ~2.4e-4 relative error per GEMM: enough for the pre-LN ViT at 1e-3.
-//   MER_GEMM_BF16X3 : every operand stored as a bf16 (hi | lo) pair, x = hi + lo to 2^-17; three
-//                     kind::f16 MMAs per K step (hi*hi + lo*hi + hi*lo), fp32 accumulate, 64B swizzle.
+//   MER_GEMM_BF16X3 : every operand stored as bf16 (hi, lo) pairs, x = hi + lo to 2^-17, in 128-byte
+//                     groups [32 hi | 32 lo] so that tiles move exactly like TF32 tiles; three
+//                     kind::f16 MMAs per 16-wide K step (hi*hi + lo*hi + hi*lo), fp32 accumulate.
 //                     ~2e-5 relative error per GEMM: what the post-LN HuBERT/BERT stacks need to stay
 //                     inside 1e-3 after 12 layers (measured: single-pass TF32 reaches 1.0e-3 after 4).
 #include <vector>
@@ -48,17 +49,13 @@ constexpr int EPI_WARP0 = 4;
 template <int BLOCK_N, int MODE>
 struct GemmCfg {
   static constexpr bool kSplit = MODE == MER_GEMM_BF16X3;
-  static constexpr int kParts = kSplit ? 2 : 1;         // hi (+ lo) tiles per operand
-  static constexpr int kRowBytes = kSplit ? 64 : 128;   // bytes of K per smem row = swizzle span
-  static constexpr int kKSteps = kRowBytes / 32;        // tcgen05.mma K steps (32 B each) per stage
+  static constexpr int kRowBytes = 128;                 // bytes of K per smem row = swizzle span
   static constexpr int kSBO = 8 * kRowBytes;            // byte stride between 8-row core groups
-  static constexpr int kLayout = kSplit ? 4 : 2;        // UMMA LayoutType: SWIZZLE_64B / SWIZZLE_128B
+  static constexpr int kLayout = 2;                     // UMMA LayoutType SWIZZLE_128B
   static constexpr int kFmt = kSplit ? 1 : 2;           // instr-desc operand format: bf16 / tf32
   static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
-  static constexpr int kAPart = BLOCK_M * kRowBytes;
-  static constexpr int kBPart = BLOCK_N * kRowBytes;
-  static constexpr int kABytes = kAPart * kParts;
-  static constexpr int kBBytes = kBPart * kParts;
+  static constexpr int kABytes = BLOCK_M * kRowBytes;
+  static constexpr int kBBytes = BLOCK_N * kRowBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N;
   static constexpr int kBarBytes = 256;
@@ -141,15 +138,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const int kk = kb * BLOCK_K;
           const int tap = kk / K_inner;
           const int c0 = kk - tap * K_inner;
-          tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], c0, tap % P,
+          constexpr int kEl = Cfg::kSplit ? 2 : 1;  // tensor-map elements per operand value
+          tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], c0 * kEl, tap % P,
                       mt * BLOCK_M + tap / P, b);
-          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kk, n_blk * BLOCK_N);
-          if (Cfg::kSplit) {  // lo halves: K_inner / K elements further along the same rows
-            tma_load_4d(smem_a + stage * Cfg::kABytes + Cfg::kAPart, &tmap_a, &full_bar[stage],
-                        K_inner + c0, tap % P, mt * BLOCK_M + tap / P, b);
-            tma_load_2d(smem_b + stage * Cfg::kBBytes + Cfg::kBPart, &tmap_b, &full_bar[stage],
-                        K + kk, n_blk * BLOCK_N);
-          }
+          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kk * kEl,
+                      n_blk * BLOCK_N);
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -174,17 +167,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           tc_fence_after();
           const uint64_t da = umma_desc(smem_u32(smem_a + stage * Cfg::kABytes), Cfg::kSBO, Cfg::kLayout);
           const uint64_t db = umma_desc(smem_u32(smem_b + stage * Cfg::kBBytes), Cfg::kSBO, Cfg::kLayout);
+          // advance the start address by 32-byte K steps inside the 128B swizzle row (>>4 => +2)
+          if (!Cfg::kSplit) {
 #pragma unroll
-          for (int k = 0; k < Cfg::kKSteps; ++k) {
-            // advance the start address by k*32 bytes inside the swizzle row (>>4 => +2)
-            if (!Cfg::kSplit) {
+            for (int k = 0; k < 4; ++k)  // 4 x 8 tf32
               tc_mma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-            } else {
-              const uint64_t da_lo = da + (Cfg::kAPart >> 4);
-              const uint64_t db_lo = db + (Cfg::kBPart >> 4);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {  // 2 x 16 bf16; hi at bytes [0,64), lo at [64,128) of the row
               tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);  // hi * hi
-              tc_mma_bf16(d_tmem, da_lo + 2 * k, db + 2 * k, idesc, 1);           // lo * hi
-              tc_mma_bf16(d_tmem, da + 2 * k, db_lo + 2 * k, idesc, 1);           // hi * lo
+              tc_mma_bf16(d_tmem, da + 4 + 2 * k, db + 2 * k, idesc, 1);          // lo * hi
+              tc_mma_bf16(d_tmem, da + 2 * k, db + 4 + 2 * k, idesc, 1);          // hi * lo
             }
           }
           tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
@@ -227,8 +220,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         uint32_t r[32];
         tmem_ld_32x32(t_row + c * 32, r);
-        tmem_ld_wait();
         const int n0 = n_blk * BLOCK_N + c * 32;
+        // residual chunk: 8 independent 16-byte loads issued before anything is stored (out may
+        // alias res, so loads placed after a store could not be hoisted by the compiler)
+        float4 rr[8];
+        if (res_row && valid) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rr[j] = *reinterpret_cast<const float4*>(res_row + n0 + 4 * j);
+        }
+        tmem_ld_wait();
         if (valid) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -245,12 +245,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
             }
             if (res_row) {
-              const float4 rr = *reinterpret_cast<const float4*>(res_row + n0 + j);
-              v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+              const float4 q = rr[j >> 2];
+              v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
             }
             if (do_split) {
-              // out row holds [hi(split_off) | lo(split_off)] bf16 in the bytes of split_off fp32 slots
-              store_split4(out_row, ep.split_off, n0 + j, v);
+              store_split4(out_row, n0 + j, v);
               continue;
             }
             if (do_round) {
@@ -285,7 +284,7 @@ int launch_gemm(const MerGemmDesc* g, cudaStream_t stream) {
   CUtensorMap ta, tb;
   const CUtensorMapDataType dt =
       Cfg::kSplit ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  const CUtensorMapSwizzle sw = Cfg::kSplit ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
   const uint64_t mult = Cfg::kSplit ? 2 : 1;  // bf16 elements per 4-byte operand slot
   {
     // strides are given in 4-byte operand slots in both modes (a split row of K (hi|lo) pairs
@@ -295,14 +294,14 @@ int launch_gemm(const MerGemmDesc* g, cudaStream_t stream) {
     const uint64_t strides[3] = {(uint64_t)g->a_phase_stride * 4ull,
                                  (uint64_t)g->a_row_stride * 4ull,
                                  (uint64_t)g->a_batch_stride * 4ull};
-    const uint32_t box[4] = {BLOCK_K, 1, BLOCK_M, 1};
+    const uint32_t box[4] = {(uint32_t)(BLOCK_K * mult), 1, BLOCK_M, 1};
     if (int rc = mer_make_tmap(&ta, dt, 4, g->A, dims, strides, box, sw)) return rc;
   }
   {
     const int K = g->K_inner * g->taps;
     const uint64_t dims[2] = {(uint64_t)K * mult, (uint64_t)g->N};
     const uint64_t strides[1] = {(uint64_t)K * 4ull};
-    const uint32_t box[2] = {BLOCK_K, BLOCK_N};
+    const uint32_t box[2] = {(uint32_t)(BLOCK_K * mult), BLOCK_N};
     if (int rc = mer_make_tmap(&tb, dt, 2, g->W, dims, strides, box, sw)) return rc;
   }
   static bool attr_set = false;
@@ -345,8 +344,7 @@ int launch_gemm(const MerGemmDesc* g, cudaStream_t stream) {
 int mer_gemm_launch(const MerGemmDesc* g, cudaStream_t stream) {
   MER_REQUIRE(g && g->A && g->W && g->ep.out, "mer_gemm: null operand");
   MER_REQUIRE(g->mode == MER_GEMM_TF32 || g->mode == MER_GEMM_BF16X3, "mer_gemm: unknown mode %d", g->mode);
-  MER_REQUIRE(!(g->ep.flags & MER_EPI_SPLIT_BF16) || (g->ep.split_off > 0 && g->ep.split_off % 4 == 0),
-              "mer_gemm: split output needs split_off (logical columns, multiple of 4)");
+
   MER_REQUIRE(g->K_inner > 0 && g->K_inner % BLOCK_K == 0 && g->taps > 0 && g->P > 0,
               "mer_gemm: K_inner=%d must be a positive multiple of %d (taps=%d P=%d)",
               g->K_inner, BLOCK_K, g->taps, g->P);

@@ -130,7 +130,7 @@ bert_embed_ln_kernel(const int* __restrict__ ids, const int* __restrict__ pos_id
     float4 r;
     r.x = v[i].x * rstd * g.x + b.x; r.y = v[i].y * rstd * g.y + b.y;
     r.z = v[i].z * rstd * g.z + b.z; r.w = v[i].w * rstd * g.w + b.w;
-    if (os) store_split4(os, 768, 4 * (lane + 32 * i), r);
+    if (os) store_split4(os, 4 * (lane + 32 * i), r);
     o[lane + 32 * i] = r;
   }
 }

@@ -235,7 +235,10 @@ __device__ __forceinline__ float round_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
 }
-// fp32 -> (hi, lo) bf16 pair with x = hi + lo to 2^-17 relative (operand format of MER_GEMM_BF16X3)
+// fp32 -> (hi, lo) bf16 pair with x = hi + lo to 2^-17 relative: operand format of MER_GEMM_BF16X3.
+// A split row of K values occupies the bytes of K fp32 values, organised in 128-byte groups of
+// 32 values: [32 x bf16 hi | 32 x bf16 lo].  One 128B-swizzled TMA row therefore carries both halves
+// of a 32-wide K block, exactly like a row of 32 fp32 values in TF32 mode.
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {  // low half <- a, high <- b
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
@@ -244,19 +247,27 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {  // low half
 __device__ __forceinline__ float bf16_round(float x) {
   return __uint_as_float(pack_bf16x2(x, 0.f) << 16);
 }
-// store 4 consecutive logical columns starting at `col` of a split row: hi at col, lo at K + col
-__device__ __forceinline__ void store_split4(void* row_base, int K, int col, float4 v) {
+// index (in bf16 units) of the hi half of logical column `col`; the lo half sits 32 further
+__device__ __forceinline__ int split_index(int col) { return ((col >> 5) << 6) + (col & 31); }
+// store 4 consecutive logical columns (col % 4 == 0) of a split row
+__device__ __forceinline__ void store_split4(void* row_base, int col, float4 v) {
   const float hx = bf16_round(v.x), hy = bf16_round(v.y), hz = bf16_round(v.z), hw = bf16_round(v.w);
-  uint16_t* o = reinterpret_cast<uint16_t*>(row_base);
-  *reinterpret_cast<uint2*>(o + col) = make_uint2(pack_bf16x2(hx, hy), pack_bf16x2(hz, hw));
-  *reinterpret_cast<uint2*>(o + K + col) =
+  uint16_t* o = reinterpret_cast<uint16_t*>(row_base) + split_index(col);
+  *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(hx, hy), pack_bf16x2(hz, hw));
+  *reinterpret_cast<uint2*>(o + 32) =
       make_uint2(pack_bf16x2(v.x - hx, v.y - hy), pack_bf16x2(v.z - hz, v.w - hw));
 }
-__device__ __forceinline__ void store_split1(void* row_base, int K, int col, float v) {
+__device__ __forceinline__ void store_split2(void* row_base, int col, float a, float b) {  // col % 2 == 0
+  const float ha = bf16_round(a), hb = bf16_round(b);
+  uint16_t* o = reinterpret_cast<uint16_t*>(row_base) + split_index(col);
+  *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(ha, hb);
+  *reinterpret_cast<uint32_t*>(o + 32) = pack_bf16x2(a - ha, b - hb);
+}
+__device__ __forceinline__ void store_split1(void* row_base, int col, float v) {
   const float h = bf16_round(v);
-  uint16_t* o = reinterpret_cast<uint16_t*>(row_base);
-  o[col] = (uint16_t)(__float_as_uint(h) >> 16);
-  o[K + col] = (uint16_t)(pack_bf16x2(v - h, 0.f) & 0xFFFFu);
+  uint16_t* o = reinterpret_cast<uint16_t*>(row_base) + split_index(col);
+  o[0] = (uint16_t)(__float_as_uint(h) >> 16);
+  o[32] = (uint16_t)(pack_bf16x2(v - h, 0.f) & 0xFFFFu);
 }
 
 // exact (erf) GELU, as torch.nn.functional.gelu default

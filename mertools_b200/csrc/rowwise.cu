@@ -67,7 +67,7 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
           ar[lane + 32 * i] = a;
         }
       }
-      if (ysr) store_split4(ysr, DIM, 4 * (lane + 32 * i), o);
+      if (ysr) store_split4(ysr, 4 * (lane + 32 * i), o);
       if (yr) {
         if (flags & MER_LN_ROUND_TF32) {
           o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
@@ -78,7 +78,7 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
   }
 }
 
-// fp32 [rows,K] -> split bf16 [rows, hi(K)|lo(K)]
+// fp32 [rows,K] -> split bf16 rows (128-byte groups of 32 hi | 32 lo), K % 32 == 0
 __global__ void split_bf16_kernel(const float* __restrict__ in, void* __restrict__ out, long long rows,
                                   int K) {
   const long long total = rows * (K / 4);
@@ -88,7 +88,7 @@ __global__ void split_bf16_kernel(const float* __restrict__ in, void* __restrict
     const long long r = i / (K / 4);
     const int c4 = (int)(i % (K / 4));
     const float4 v = *reinterpret_cast<const float4*>(in + r * K + c4 * 4);
-    store_split4(reinterpret_cast<float*>(out) + r * K, K, c4 * 4, v);
+    store_split4(reinterpret_cast<float*>(out) + r * K, c4 * 4, v);
   }
 }
 
@@ -132,7 +132,7 @@ extern "C" int mer_round_tf32(float* x, long long n, void* stream) {
 }
 
 extern "C" int mer_split_bf16(const float* in, void* out, long long rows, int K, void* stream) {
-  MER_REQUIRE(in && out && (const void*)in != out && K > 0 && K % 4 == 0, "mer_split_bf16: bad operands");
+  MER_REQUIRE(in && out && (const void*)in != out && K > 0 && K % 32 == 0, "mer_split_bf16: bad operands");
   if (rows <= 0) return 0;
   long long blocks = (rows * (K / 4) + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;

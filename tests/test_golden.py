@@ -1,0 +1,91 @@
+"""Pin the oracle to the outputs of the UNMODIFIED reference scripts (tests/golden/*.npz, produced
+by tests/golden/make_golden.py from /root/reference on seeded synthetic checkpoints and inputs).
+
+CPU only.  Integer work (frame indices, token ids, special-token offsets) is bit-exact; floating
+point within 2e-5 relative (fp32 torch on both sides; HF model code vs the oracle restatement)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from mertools_b200 import synthetic as S
+from oracle import fusion as OF
+from oracle import pipeline as P
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _rel(a, b):
+    return float(np.abs(np.asarray(a, dtype=np.float64) - b).max() / np.abs(b).max())
+
+
+def _t(sd):
+    return {k: torch.from_numpy(v) for k, v in sd.items()}
+
+
+@pytest.mark.slow
+def test_visual_oracle_matches_reference_script():
+    g = np.load(os.path.join(G, "visual_golden.npz"))
+    sd = _t(S.vit_state_dict(seed=0))
+    clips = S.synth_frames(int(g["n_clips"]), 8, seed=int(g["seed"]))
+    with torch.no_grad():
+        utt = P.visual_clip_features(sd, clips[0], nframe=int(g["nframe"]))
+        fra = P.visual_clip_features(sd, clips[1], nframe=int(g["nframe"]), feature_level="FRAME")
+    assert utt.shape == g["utt0"].shape == (768,) and utt.dtype == g["utt0"].dtype
+    assert _rel(utt, g["utt0"]) < 2e-5
+    assert fra.shape == g["fra1"].shape == (64, 768)
+    assert _rel(fra, g["fra1"]) < 2e-5
+
+
+def test_audio_oracle_matches_reference_script():
+    g = np.load(os.path.join(G, "audio_golden.npz"))
+    sd = _t(S.hubert_state_dict(seed=1))
+    for i, n in enumerate(g["lens"]):
+        w = S.synth_waves(1, int(n), seed=int(g["seed0"]) + i)[0].astype(np.float64) / 32768.0
+        with torch.no_grad():
+            utt = P.audio_clip_features(sd, w)
+            fra = P.audio_clip_features(sd, w, feature_level="FRAME")
+        assert utt.shape == (768,) and utt.dtype == g[f"utt{i}"].dtype
+        assert _rel(utt, g[f"utt{i}"]) < 5e-5, f"clip {i} ({n} samples)"
+        assert _rel(fra[::8], g[f"fra{i}"]) < 5e-5
+
+
+def test_text_oracle_and_token_ids_match_reference_script():
+    transformers = pytest.importorskip("transformers")
+    g = np.load(os.path.join(G, "text_golden.npz"))
+    tok = transformers.BertTokenizer(os.path.join(G, "text_vocab.txt"))
+    assert P.find_start_end_pos(tok) == (int(g["start"]), int(g["end"])) == (1, -1)
+    sd = _t(S.bert_state_dict(int(g["vocab_size"]), seed=2))
+    for i, s in enumerate(g["sentences"]):
+        s = str(s)
+        if s:
+            ids = tok(s)["input_ids"]
+            np.testing.assert_array_equal(np.array(ids), g[f"ids{i}"])  # bit-exact token ids
+        else:
+            ids = None
+        with torch.no_grad():
+            utt = P.text_clip_features(sd, ids, 1, -1)
+            fra = P.text_clip_features(sd, ids, 1, -1, feature_level="FRAME")
+        assert utt.shape == g[f"utt{i}"].shape and utt.dtype == g[f"utt{i}"].dtype
+        assert fra.shape == g[f"fra{i}"].shape
+        if s:
+            assert _rel(utt, g[f"utt{i}"]) < 2e-5 and _rel(fra, g[f"fra{i}"]) < 2e-5
+        else:
+            assert not utt.any() and not fra.any()
+
+
+def test_fusion_oracle_matches_reference_trainer():
+    g = np.load(os.path.join(G, "fusion_golden.npz"))
+    tr = OF.Trainer(S.fusion_state_dict(seed=3), lr=1e-3, l2=1e-5)
+    a, t, v, emo, val = S.synth_fusion_features(32, seed=7)
+    T = torch.from_numpy
+    for step, ref in enumerate(g["losses"]):
+        ce, mse, tot, eo, vo, grads = tr.step(T(a), T(t), T(v), T(emo), T(val).view(-1, 1))
+        assert abs(tot - ref) <= 1e-5 * max(1.0, abs(ref)), f"step {step}: {tot} vs {ref}"
+        if step == 0:
+            assert _rel(eo.numpy(), g["emos0"]) < 1e-5 and _rel(vo.numpy(), g["vals0"]) < 1e-5
+            assert _rel(grads["fc_att.weight"].numpy(), g["grad_fc_att_w"]) < 1e-4
+            assert _rel(grads["audio_encoder.linear_1.bias"].numpy(), g["grad_audio_l1_b"]) < 1e-4
+    assert _rel(tr.sd["fc_out_1.weight"].detach().numpy(), g["final_fc_out_1_w"]) < 1e-4
+    assert _rel(tr.sd["audio_encoder.linear_1.weight"].detach().numpy()[0], g["final_audio_l1_w_row0"]) < 1e-4

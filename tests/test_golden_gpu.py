@@ -1,0 +1,83 @@
+"""CUDA hot path vs the golden outputs of the unmodified reference scripts (tests/golden/*.npz),
+through the public extractor API.  Tolerance 1e-3 relative (north_star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from mertools_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-3
+
+
+def _rel(a, b):
+    return float(np.abs(np.asarray(a, dtype=np.float64) - b).max() / np.abs(b).max())
+
+
+def test_visual_extractor_vs_reference_golden(cuda):
+    from mertools_b200.extract.visual import VisualExtractor
+    g = np.load(os.path.join(G, "visual_golden.npz"))
+    clips = S.synth_frames(int(g["n_clips"]), 8, seed=int(g["seed"]))
+    ext = VisualExtractor(S.vit_state_dict(seed=0), device=cuda)
+    utt = ext.extract_clips(list(clips), "UTTERANCE", nframe=int(g["nframe"]))
+    fra = ext.extract_clips(list(clips), "FRAME", nframe=int(g["nframe"]))
+    for i in range(len(clips)):
+        assert utt[i].shape == g[f"utt{i}"].shape and utt[i].dtype == g[f"utt{i}"].dtype
+        assert _rel(utt[i], g[f"utt{i}"]) < TOL
+        assert fra[i].shape == g[f"fra{i}"].shape and _rel(fra[i], g[f"fra{i}"]) < TOL
+
+
+def test_audio_extractor_vs_reference_golden(cuda):
+    from mertools_b200.extract.audio import AudioExtractor
+    g = np.load(os.path.join(G, "audio_golden.npz"))
+    waves = [S.synth_waves(1, int(n), seed=int(g["seed0"]) + i)[0].astype(np.float64) / 32768.0
+             for i, n in enumerate(g["lens"])]
+    ext = AudioExtractor(S.hubert_state_dict(seed=1), device=cuda)
+    utt = ext.extract_waves(waves, "UTTERANCE")
+    fra = ext.extract_waves(waves, "FRAME")
+    for i in range(len(waves)):
+        assert utt[i].shape == (768,) and utt[i].dtype == g[f"utt{i}"].dtype
+        assert _rel(utt[i], g[f"utt{i}"]) < TOL, f"clip {i}"
+        assert _rel(fra[i][::8], g[f"fra{i}"]) < 2 * TOL, f"clip {i} frames"
+
+
+def test_text_extractor_vs_reference_golden(cuda):
+    transformers = pytest.importorskip("transformers")
+    from mertools_b200.extract.text import TextExtractor
+    g = np.load(os.path.join(G, "text_golden.npz"))
+    tok = transformers.BertTokenizer(os.path.join(G, "text_vocab.txt"))
+    ext = TextExtractor(S.bert_state_dict(int(g["vocab_size"]), seed=2), tok, device=cuda)
+    assert (ext.start, ext.end) == (int(g["start"]), int(g["end"]))
+    sents = [str(s) if str(s) else None for s in g["sentences"]]
+    for i, s in enumerate(sents):
+        if s:
+            np.testing.assert_array_equal(np.array(ext.tokenize(s)), g[f"ids{i}"])  # bit-exact ids
+    utt = ext.extract_sentences(sents, "UTTERANCE")
+    fra = ext.extract_sentences(sents, "FRAME")
+    for i, s in enumerate(sents):
+        assert utt[i].shape == g[f"utt{i}"].shape and utt[i].dtype == g[f"utt{i}"].dtype
+        assert fra[i].shape == g[f"fra{i}"].shape
+        if s:
+            assert _rel(utt[i], g[f"utt{i}"]) < TOL and _rel(fra[i], g[f"fra{i}"]) < 2 * TOL
+        else:
+            assert not utt[i].any() and not fra[i].any()
+
+
+def test_fusion_vs_reference_golden(cuda):
+    """north_star: fusion-train step matching reference loss to 1e-3 (20 Adam steps, dropout 0)."""
+    from mertools_b200.fusion import FusionNet
+    g = np.load(os.path.join(G, "fusion_golden.npz"))
+    net = FusionNet(device=cuda).load_state_dict(S.fusion_state_dict(seed=3))
+    a, t, v, emo, val = S.synth_fusion_features(32, seed=7)
+    dev = [torch.from_numpy(x).to(cuda) for x in (a, t, v, emo)] + [torch.from_numpy(val).view(-1, 1).to(cuda)]
+    for step, ref in enumerate(g["losses"]):
+        loss, eo, vo = net.train_step(*dev, lr=1e-3, weight_decay=1e-5)
+        assert abs(float(loss[2].cpu()) - ref) <= 1e-3, f"step {step}: {float(loss[2])} vs {ref}"
+        if step == 0:
+            assert _rel(eo.cpu().numpy(), g["emos0"]) < 1e-4
+            gv = net.named_views(net.grads)
+            assert _rel(gv["fc_att.weight"].cpu().numpy(), g["grad_fc_att_w"]) < 1e-3
+    assert _rel(net.named_views()["fc_out_1.weight"].cpu().numpy(), g["final_fc_out_1_w"]) < 1e-2

@@ -1,0 +1,154 @@
+"""CPU tests of the host-side logic and of the C-ABI surface (no GPU compute)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from mertools_b200 import shard
+from mertools_b200 import synthetic as S
+from oracle import pipeline as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_frame_sampling_is_bit_exact_with_the_reference_rule():
+    from mertools_b200.extract.visual import resample_frames_uniform
+    for n in (8, 16, 64):
+        for vlen in list(range(1, 400)) + [999, 1000, 1999, 4097]:
+            got = resample_frames_uniform(np.arange(vlen), n).tolist()
+            assert got == P.resample_frames_uniform_indices(vlen, n), (n, vlen)
+            assert len(got) == n and max(got) < vlen
+
+
+def test_split_into_batch_matches_reference_rule():
+    from mertools_b200.extract import audio, visual
+    x = list(range(70))
+    assert visual.split_into_batch(x, 32) == P.split_into_batch(x, 32)
+    assert [len(b) for b in visual.split_into_batch(x, 32)] == [32, 32, 6]
+    for n in (1000, 160000, 160001, 170000, 320000, 320001):
+        w = torch.arange(n, dtype=torch.float32)[None]
+        a, b = audio.split_into_batch(w), P.audio_split_into_batch(w)
+        assert a.shape == b.shape and torch.equal(a, b)
+
+
+def test_feature_file_contract(tmp_path):
+    from mertools_b200.extract.common import save_feature
+    f = str(tmp_path / "x.npy")
+    e = save_feature(f, np.ones((5, 768), np.float32), "UTTERANCE", 768)
+    assert e.shape == (768,) and np.load(f).dtype == np.float32
+    e = save_feature(f, np.ones((768,), np.float32), "FRAME", 768)
+    assert np.load(f).shape == (1, 768)
+    e = save_feature(f, [], "UTTERANCE", 768)
+    assert e.shape == (768,) and e.dtype == np.float64 and not e.any()   # np.zeros fallback of the reference
+    e = save_feature(f, [], "FRAME", 768)
+    assert e.shape == (1, 768)
+
+
+def test_config_mirror_has_the_reference_keys():
+    from mertools_b200 import config
+    for k in ("PATH_TO_RAW_AUDIO", "PATH_TO_RAW_FACE", "PATH_TO_TRANSCRIPTIONS", "PATH_TO_FEATURES",
+              "PATH_TO_LABEL"):
+        assert "MER2023" in getattr(config, k)
+    assert isinstance(config.PATH_TO_PRETRAINED_MODELS, str)
+
+
+def test_shared_library_exports_every_declared_symbol():
+    """The C ABI loads without a GPU and exports what include/mer_b200.h declares."""
+    lib_path = os.path.join(ROOT, "mertools_b200", "lib", "libmer_b200.so")
+    if not os.path.exists(lib_path):
+        import __graft_entry__
+        __graft_entry__.build()
+    dll = ctypes.CDLL(lib_path)
+    hdr = open(os.path.join(ROOT, "include", "mer_b200.h")).read()
+    names = sorted(set(re.findall(r"MER_API[^;(]*?\b(mer_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(dll, n), f"missing export {n}"
+    assert dll.mer_abi_version() == 1
+    dll.mer_last_error.restype = ctypes.c_char_p
+    assert isinstance(dll.mer_last_error(), bytes)
+
+
+def test_no_cpu_fallback_without_a_device():
+    """Without a GPU the product path must fail loudly, never fall back to the oracle/CPU."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mertools_b200 import _lib
+    rc = _lib.lib().mer_check_device()
+    assert rc != 0 and _lib.lib().mer_last_error()
+    from mertools_b200.encoders import VitEncoder
+    with pytest.raises(_lib.MerError):
+        VitEncoder(S.vit_state_dict(layers=1))
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "mertools_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(d, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports oracle"
+
+
+def test_fusion_parameter_layout_matches_reference_state_dict_order():
+    from mertools_b200.fusion import param_names, param_shapes
+    names = param_names()
+    assert names == list(S.fusion_state_dict().keys())
+    shapes = param_shapes(768, 768, 768, 128, 6, 1)
+    assert sum(int(np.prod(s)) for s in shapes.values()) == 477962
+
+
+def test_shard_helpers():
+    assert shard.shard_indices(10, 1, 4) == [1, 5, 9]
+    cover = sorted(i for r in range(8) for i in shard.shard_indices(1000, r, 8))
+    assert cover == list(range(1000))
+    sl = [shard.batch_slice(70, r, 4) for r in range(4)]
+    assert sl[0][0] == 0 and sl[-1][1] == 70 and all(a[1] == b[0] for a, b in zip(sl, sl[1:]))
+    assert sorted(h - l for l, h in sl) == [17, 17, 18, 18]
+
+
+def _dp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from oracle import fusion as OF
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    sd = S.fusion_state_dict(seed=3)
+    a, t, v, emo, val = S.synth_fusion_features(50, seed=5)
+    lo, hi = shard.batch_slice(50, rank, world)
+    T = torch.from_numpy
+    psd = {k: torch.tensor(x, requires_grad=True) for k, x in sd.items()}
+    _, eo, vo = OF.attention_forward(psd, T(a[lo:hi]), T(t[lo:hi]), T(v[lo:hi]))
+    # per-rank loss = sum of per-sample losses / GLOBAL batch (loss_inv_batch of mer_fusion_fwd_bwd)
+    ce, mse = OF.losses(eo, vo, T(emo[lo:hi]), T(val[lo:hi]).view(-1, 1))
+    ((ce + mse) * (hi - lo) / 50.0).backward()
+    flat = torch.cat([p.grad.reshape(-1) for p in psd.values()])
+    shard.allreduce_grads_(flat, world)
+    q.put((rank, flat.numpy()))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_equals_full_batch_gradient_gloo():
+    """world_size-2 gloo run of the N>1 fusion path semantics: all-reduce(SUM) of per-rank gradients
+    scaled by 1/global_batch == the reference's gradient on the concatenated batch."""
+    import torch.multiprocessing as mp
+    from oracle import fusion as OF
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    sd = S.fusion_state_dict(seed=3)
+    a, t, v, emo, val = S.synth_fusion_features(50, seed=5)
+    T = torch.from_numpy
+    tr = OF.Trainer(sd)
+    grads = tr.step(T(a), T(t), T(v), T(emo), T(val).view(-1, 1))[5]
+    full = torch.cat([grads[k].reshape(-1) for k in sd]).numpy()
+    for r in (0, 1):
+        assert np.abs(outs[r] - full).max() <= 1e-5 * np.abs(full).max()
+    assert np.array_equal(outs[0], outs[1])
