@@ -85,6 +85,7 @@ typedef struct MerGemmDesc {
   long long a_batch_stride;
   int force_block_n; /* 0 = auto, 128 or 256 */
   int mode;          /* MER_GEMM_TF32 | MER_GEMM_BF16X3; all A strides are in 4-byte slots either way */
+  int cluster;       /* 0 = auto, 1 = single CTAs, 2 = CTA pairs sharing a multicast weight tile */
   MerGemmEpilogue ep;
 } MerGemmDesc;
 

@@ -42,7 +42,7 @@ class MerGemmDesc(C.Structure):
         ("N", C.c_int), ("K_inner", C.c_int), ("taps", C.c_int), ("P", C.c_int),
         ("a_phase_stride", C.c_longlong), ("a_row_stride", C.c_longlong),
         ("a_batch_stride", C.c_longlong), ("force_block_n", C.c_int), ("mode", C.c_int),
-        ("ep", MerGemmEpilogue),
+        ("cluster", C.c_int), ("ep", MerGemmEpilogue),
     ]
 
 
@@ -110,7 +110,7 @@ def gemm(A, W, out, *, bias=None, res=None, gelu=False, round_out=False, split_o
          mode=MER_GEMM_TF32, rows_per_batch=None, batches=1, a_rows_dim=None, K_inner=None, taps=1, P=1,
          a_phase_stride=0, a_row_stride=None, a_batch_stride=0,
          out_bstride=0, out_row0=0, res_bstride=0, res_row0=0,
-         ld_out=None, ld_res=None, force_block_n=0):
+         ld_out=None, ld_res=None, force_block_n=0, cluster=0):
     """out = epilogue(A @ W.T).  A, W: fp32 CUDA tensors of LOGICAL shape [rows, K] / [N, K] (holding
     tf32-rounded fp32, or split bf16 hi|lo bytes when mode is BF16X3); see MerGemmDesc in mer_b200.h."""
     N, K = W.shape
@@ -128,6 +128,7 @@ def gemm(A, W, out, *, bias=None, res=None, gelu=False, round_out=False, split_o
     d.a_batch_stride = a_batch_stride if batches > 1 else d.a_row_stride * d.a_rows_dim
     d.force_block_n = force_block_n
     d.mode = mode
+    d.cluster = cluster
     d.ep.bias = bias.data_ptr() if bias is not None else None
     d.ep.res = res.data_ptr() if res is not None else None
     d.ep.out = out.data_ptr()

@@ -72,7 +72,10 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, int sbo_bytes,
   return d;
 }
 
-template <int BLOCK_N, int MODE>
+// CLUSTER == 2: a pair of CTAs works on two vertically adjacent 128-row tiles of the same BLOCK_N
+// column block; each loads its own A tile and HALF of the shared B tile, multicast into both CTAs'
+// shared memory (L2 -> SM traffic per CTA drops from 128+BLOCK_N to 128+BLOCK_N/2 rows per stage).
+template <int BLOCK_N, int MODE, int CLUSTER>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             const __grid_constant__ CUtensorMap tmap_b, const MerGemmEpilogue ep,
@@ -95,8 +98,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   const int m_tiles = (rows_per_batch + BLOCK_M - 1) / BLOCK_M;
   const int n_tiles = N / BLOCK_N;
-  const int num_tiles = batches * m_tiles * n_tiles;
   const int num_kb = K / BLOCK_K;
+  // work items: (row-tile group, column block); a group is CLUSTER consecutive (batch, m-tile) tiles
+  const int total_m = batches * m_tiles;
+  const int num_tiles = ((total_m + CLUSTER - 1) / CLUSTER) * n_tiles;
+  const int cta_rank = CLUSTER > 1 ? (int)cluster_ctarank() : 0;
+  const int first_tile = blockIdx.x / CLUSTER;
+  const int tile_step = gridDim.x / CLUSTER;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -105,7 +113,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], CLUSTER);  // one tcgen05.commit arrival per CTA of the cluster
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -118,7 +126,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     tmem_relinquish();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -127,9 +135,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = first_tile; t < num_tiles; t += tile_step) {
         const int n_blk = t % n_tiles;
-        const int mb = t / n_tiles;
+        const int mb = (t / n_tiles) * CLUSTER + cta_rank;  // >= total_m: padding tile (TMA zero-fills)
         const int b = mb / m_tiles;
         const int mt = mb % m_tiles;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -141,8 +149,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           constexpr int kEl = Cfg::kSplit ? 2 : 1;  // tensor-map elements per operand value
           tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], c0 * kEl, tap % P,
                       mt * BLOCK_M + tap / P, b);
-          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kk * kEl,
-                      n_blk * BLOCK_N);
+          if (CLUSTER == 1) {
+            tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kk * kEl,
+                        n_blk * BLOCK_N);
+          } else {
+            tma_load_2d_mc(smem_b + stage * Cfg::kBBytes + cta_rank * (Cfg::kBBytes / CLUSTER), &tmap_b,
+                           &full_bar[stage], kk * kEl, n_blk * BLOCK_N + cta_rank * (BLOCK_N / CLUSTER),
+                           (uint16_t)((1u << CLUSTER) - 1));
+          }
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -158,7 +172,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = first_tile; t < num_tiles; t += tile_step) {
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
@@ -180,7 +194,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
               tc_mma_bf16(d_tmem, da + 2 * k, db + 4 + 2 * k, idesc, 1);          // hi * lo
             }
           }
-          tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          // free the smem slot when these MMAs retire (in every CTA that multicasts into it)
+          if (CLUSTER == 1) tc_commit(&empty_bar[stage]);
+          else tc_commit_mc(&empty_bar[stage], (uint16_t)((1u << CLUSTER) - 1));
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -201,13 +217,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const bool do_gelu = (ep.flags & MER_EPI_GELU) != 0;
     const bool do_round = (ep.flags & MER_EPI_ROUND_TF32) != 0;
     const bool do_split = (ep.flags & MER_EPI_SPLIT_BF16) != 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = first_tile; t < num_tiles; t += tile_step) {
       const int n_blk = t % n_tiles;
-      const int mb = t / n_tiles;
+      const int mb = (t / n_tiles) * CLUSTER + cta_rank;
       const int b = mb / m_tiles;
       const int mt = mb % m_tiles;
       const int m = mt * BLOCK_M + ew * 32 + lane;  // row inside the batch entry
-      const bool valid = m < rows_per_batch;
+      const bool valid = m < rows_per_batch && mb < total_m;
       float* out_row =
           ep.out + ((long long)b * ep.out_bstride + ep.out_row0 + m) * (long long)ep.ld_out;
       const float* res_row =
@@ -271,14 +287,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 
   tc_fence_before();
-  __syncthreads();
+  // nobody leaves while a peer may still multicast into this CTA's smem / arrive on its barriers
+  if (CLUSTER > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, int CLUSTER>
 int launch_gemm(const MerGemmDesc* g, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, MODE>;
   CUtensorMap ta, tb;
@@ -301,20 +318,21 @@ int launch_gemm(const MerGemmDesc* g, cudaStream_t stream) {
     const int K = g->K_inner * g->taps;
     const uint64_t dims[2] = {(uint64_t)K * mult, (uint64_t)g->N};
     const uint64_t strides[1] = {(uint64_t)K * 4ull};
-    const uint32_t box[2] = {(uint32_t)(BLOCK_K * mult), BLOCK_N};
+    const uint32_t box[2] = {(uint32_t)(BLOCK_K * mult), BLOCK_N / CLUSTER};  // each CTA loads its share
     if (int rc = mer_make_tmap(&tb, dt, 2, g->W, dims, strides, box, sw)) return rc;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    MER_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BLOCK_N, MODE>,
+    MER_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BLOCK_N, MODE, CLUSTER>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes));
     attr_set = true;
   }
   const int m_tiles = (g->rows_per_batch + BLOCK_M - 1) / BLOCK_M;
-  const long long tiles = (long long)g->batches * m_tiles * (g->N / BLOCK_N);
-  int grid = mer_num_sms();
-  if (tiles < grid) grid = (int)tiles;
+  const long long groups = ((long long)g->batches * m_tiles + CLUSTER - 1) / CLUSTER;
+  const long long tiles = groups * (g->N / BLOCK_N);
+  int grid = (mer_num_sms() / CLUSTER) * CLUSTER;
+  if (tiles * CLUSTER < grid) grid = (int)tiles * CLUSTER;
   ProfSlot slot;
   if (g_prof_on) {
     if (!g_prof_pool.empty()) {
@@ -328,8 +346,24 @@ int launch_gemm(const MerGemmDesc* g, cudaStream_t stream) {
     slot.mode = MODE;
     MER_CUDA_CHECK(cudaEventRecord(slot.a, stream));
   }
-  gemm_kernel<BLOCK_N, MODE><<<grid, NUM_THREADS, Cfg::kSmemBytes, stream>>>(
-      ta, tb, g->ep, g->rows_per_batch, g->batches, g->N, g->K_inner * g->taps, g->K_inner, g->P);
+  {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MER_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<BLOCK_N, MODE, CLUSTER>, ta, tb, g->ep,
+                                      g->rows_per_batch, g->batches, g->N, g->K_inner * g->taps,
+                                      g->K_inner, g->P));
+  }
   MER_CUDA_CHECK(cudaGetLastError());
   mer_count_launches(1);
   if (g_prof_on) {
@@ -360,9 +394,15 @@ int mer_gemm_launch(const MerGemmDesc* g, cudaStream_t stream) {
   // 128 x 256 tiles whenever they fill the machine; 128 x 128 for small problems / N % 256 != 0
   const bool wide = (tiles256 >= mer_num_sms() && g->force_block_n != 128) ||
                     (g->force_block_n == 256 && tiles256 > 0);
-  if (g->mode == MER_GEMM_BF16X3)
-    return wide ? launch_gemm<256, MER_GEMM_BF16X3>(g, stream) : launch_gemm<128, MER_GEMM_BF16X3>(g, stream);
-  return wide ? launch_gemm<256, MER_GEMM_TF32>(g, stream) : launch_gemm<128, MER_GEMM_TF32>(g, stream);
+  // CTA pairs with a multicast B tile once there is more than a wave of 128x256 tiles
+  const bool pair = wide && g->cluster != 1 && (g->cluster == 2 || tiles256 >= 2 * mer_num_sms());
+  if (g->mode == MER_GEMM_BF16X3) {
+    if (pair) return launch_gemm<256, MER_GEMM_BF16X3, 2>(g, stream);
+    return wide ? launch_gemm<256, MER_GEMM_BF16X3, 1>(g, stream)
+                : launch_gemm<128, MER_GEMM_BF16X3, 1>(g, stream);
+  }
+  if (pair) return launch_gemm<256, MER_GEMM_TF32, 2>(g, stream);
+  return wide ? launch_gemm<256, MER_GEMM_TF32, 1>(g, stream) : launch_gemm<128, MER_GEMM_TF32, 1>(g, stream);
 }
 
 extern "C" int mer_profile_enable(int on) {

@@ -48,7 +48,7 @@ def gelu(x):
 
 
 def check_gemm(name, M, N, K, bias=False, use_gelu=False, res=False, rnd=False, ints=False,
-               force=0):
+               force=0, cluster=0):
     g = torch.Generator(device="cuda").manual_seed(1)
     if ints:
         A = torch.randint(-3, 4, (M, K), device="cuda", generator=g).float()
@@ -60,7 +60,8 @@ def check_gemm(name, M, N, K, bias=False, use_gelu=False, res=False, rnd=False, 
     R = torch.randn(M, N, device="cuda", generator=g) if res else None
     out = torch.full((M, N), float("nan"), device="cuda")
     try:
-        L.gemm_tf32(A, W, out, bias=b, res=R, gelu=use_gelu, round_out=rnd, force_block_n=force)
+        L.gemm_tf32(A, W, out, bias=b, res=R, gelu=use_gelu, round_out=rnd, force_block_n=force,
+                    cluster=cluster)
         torch.cuda.synchronize()
     except Exception as e:  # noqa: BLE001
         emit(check=name, ok=False, error=str(e)[:500])
@@ -99,6 +100,11 @@ def sec_gemm():
     ok &= check_gemm("gemm_bias_res", 1000, 768, 3072, bias=True, res=True)
     ok &= check_gemm("gemm_big_256", 20000, 2304, 768, bias=True, force=256)
     ok &= check_gemm("gemm_big_128", 20000, 768, 768, bias=True, force=128)
+    # CTA pairs with multicast weight tiles (odd and even numbers of row tiles, residual in place)
+    ok &= check_gemm("gemm_pair_int", 256, 256, 64, ints=True, force=256, cluster=2)
+    ok &= check_gemm("gemm_pair_odd_tiles", 128 * 5 + 7, 768, 768, bias=True, res=True, force=256, cluster=2)
+    ok &= check_gemm("gemm_pair_big", 40000, 2304, 768, bias=True, rnd=True, cluster=2)
+    ok &= check_gemm("gemm_pair_fc2", 40000, 768, 3072, bias=True, res=True, cluster=2)
     return ok
 
 
@@ -130,8 +136,10 @@ def sec_gemm_x3():
     W = L.split_bf16(torch.randn(N, K, device="cuda") * 0.02)
     b = torch.randn(N, device="cuda")
     out = torch.empty(M, N, device="cuda")
-    ms = time_cuda(lambda: L.gemm(A, W, out, bias=b, gelu=True, split_out=True, mode=L.MER_GEMM_BF16X3), iters=10)
-    emit(perf="x3_fc1", M=M, N=N, K=K, ms=ms, tflops_useful=2.0 * M * N * K / ms / 1e9)
+    for cl in (1, 2):
+        ms = time_cuda(lambda: L.gemm(A, W, out, bias=b, gelu=True, split_out=True, mode=L.MER_GEMM_BF16X3,
+                                      cluster=cl), iters=10)
+        emit(perf=f"x3_fc1_cluster{cl}", M=M, N=N, K=K, ms=ms, tflops_useful=2.0 * M * N * K / ms / 1e9)
     return ok
 
 
@@ -179,9 +187,13 @@ def sec_gemm_perf():
         R = torch.randn(M, N, device="cuda") if kw.get("res") else None
         out = torch.empty(M, N, device="cuda")
         fn = lambda: L.gemm_tf32(A, W, out, bias=b, res=R, gelu=kw.get("gelu", False),  # noqa: E731
-                                 round_out=kw.get("rnd", False))
+                                 round_out=kw.get("rnd", False), cluster=1)
+        fn2 = lambda: L.gemm_tf32(A, W, out, bias=b, res=R, gelu=kw.get("gelu", False),  # noqa: E731
+                                  round_out=kw.get("rnd", False), cluster=2)
         try:
             ms = time_cuda(fn, iters=10)
+            ms2 = time_cuda(fn2, iters=10)
+            emit(perf=name + "_pair", ms=ms2, tflops=2.0 * M * N * K / ms2 / 1e9)
         except Exception as e:  # noqa: BLE001
             emit(perf=name, error=str(e)[:300])
             continue
