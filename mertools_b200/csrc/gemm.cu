@@ -244,6 +244,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
           for (int j = 0; j < 8; ++j) rr[j] = *reinterpret_cast<const float4*>(res_row + n0 + 4 * j);
         }
+        // bias chunk: 8 independent loads in distinct registers (issued back to back; ncu showed the
+        // one-at-a-time form serialising the whole epilogue on long-scoreboard stalls)
+        float4 bb[8];
+        if (ep.bias) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bb[j] = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + j);
+        }
         tmem_ld_wait();
         if (valid) {
 #pragma unroll
@@ -254,8 +261,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             v.z = __uint_as_float(r[j + 2]);
             v.w = __uint_as_float(r[j + 3]);
             if (ep.bias) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
-              v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+              const float4 q = bb[j >> 2];
+              v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
             }
             if (do_gelu) {
               v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
