@@ -105,7 +105,7 @@ def device_step(models, dev_in, clips, world):
     """The hot path on device-resident inputs.  Returns the loss tensor (device)."""
     vit, hub, bert, fus = models
     frames, wave, ids, emo, val = dev_in
-    vfeat = vit.frame_features(frames).view(clips, FRAMES, 768).mean(dim=1)
+    vfeat = vit.clip_features(frames, FRAMES)
     afeat, _ = hub.forward(wave, normalize=True)
     tfeat, _ = bert.forward_packed(ids, TOKENS)
     loss, _, _ = fus.train_step(afeat, tfeat, vfeat, emo, val, lr=1e-3, weight_decay=1e-5,
@@ -173,7 +173,7 @@ def run_ours(args):
     def e2e_step():
         frames, wave, ids, emo, val = host_in
         d = [x.to(device, non_blocking=True) for x in (frames, wave, ids)]
-        vfeat = vit.frame_features(d[0]).view(clips, FRAMES, 768).mean(dim=1)
+        vfeat = vit.clip_features(d[0], FRAMES)
         afeat, _ = hub.forward(d[1], normalize=True)
         tfeat, _ = bert.forward_packed(d[2], TOKENS)
         feats = [f.cpu() for f in (afeat, tfeat, vfeat)]           # what the .npy files would hold

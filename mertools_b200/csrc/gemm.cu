@@ -13,7 +13,8 @@
 //   warp 0      TMA producer: A/B tiles -> swizzled smem ring (mbarrier full/empty)
 //   warp 1      MMA issuer  : tcgen05.mma, UMMA 128 x BLOCK_N x (32 bytes of K), fp32 accum in TMEM
 //   warp 2      TMEM allocator
-//   warps 4..7  epilogue    : tcgen05.ld TMEM -> registers -> bias/GELU/residual -> st.global
+//   warps 4..11 epilogue    : tcgen05.ld TMEM -> registers -> bias/GELU/residual -> st.global
+//                             (two warps per TMEM lane quarter, half of the columns each)
 // TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // Two arithmetic modes share the pipeline (both move 4 bytes per operand element):
@@ -43,8 +44,9 @@ using namespace mer;
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;  // K elements per stage in BOTH modes (128 B of tf32 / 64 B of bf16 per part)
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;  // 4 control warps + 8 epilogue warps
 constexpr int EPI_WARP0 = 4;
+constexpr int EPI_WARPS = 8;      // two per TMEM lane quarter, each taking half of the tile's columns
 
 template <int BLOCK_N, int MODE>
 struct GemmCfg {
@@ -117,7 +119,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -211,7 +213,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp >= EPI_WARP0) {
     // ===================== epilogue =====================
-    const int ew = warp - EPI_WARP0;  // == warp % 4: the TMEM lane quarter this warp may read
+    const int ew = (warp - EPI_WARP0) & 3;    // == warp % 4: the TMEM lane quarter this warp may read
+    const int chalf = (warp - EPI_WARP0) >> 2;  // which half of the tile's columns this warp handles
     int as = 0;
     uint32_t aphase = 0;
     const bool do_gelu = (ep.flags & MER_EPI_GELU) != 0;
@@ -233,7 +236,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(ew * 32) << 16) + as * BLOCK_N;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
+      for (int c = chalf * (BLOCK_N / 64); c < (chalf + 1) * (BLOCK_N / 64); ++c) {
         uint32_t r[32];
         tmem_ld_32x32(t_row + c * 32, r);
         const int n0 = n_blk * BLOCK_N + c * 32;

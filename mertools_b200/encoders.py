@@ -87,6 +87,25 @@ class VitEncoder:
         return out
 
 
+    def clip_features(self, frames_bgr_u8: torch.Tensor, frames_per_clip: int):
+        """UTTERANCE-level features of equal-length clips: mean over each clip's frame features
+        (np.mean(axis=0) at extract_vision_huggingface.py:187-188), on the device.  [C,768]."""
+        n = frames_bgr_u8.shape[0]
+        assert n % frames_per_clip == 0
+        c = n // frames_per_clip
+        ff = self.frame_features(frames_bgr_u8)
+        key = (c, frames_per_clip)
+        if getattr(self, "_clip_key", None) != key:
+            self._clip_off = torch.arange(c + 1, dtype=torch.int32, device=self.device) * frames_per_clip
+            self._clip_key = key
+        out = torch.empty(c, 768, dtype=torch.float32, device=self.device)
+        seg = L.declare("mer_segment_reduce", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                               C.c_int, C.c_void_p, C.c_void_p])
+        L.check(seg(L.ptr(ff), L.ptr(self._clip_off), L.ptr(self._clip_off[1:]), c, 768, 1, L.ptr(out),
+                    L.stream_ptr()))
+        return out
+
+
 VIT_PROBE = "encoder.layer.{i}.layernorm_before.weight"
 
 
