@@ -113,6 +113,11 @@ def device_step(models, dev_in, clips, world):
     return loss
 
 
+def _log(msg):
+    if os.environ.get("MER_BENCH_VERBOSE"):
+        print(f"[bench rank {os.environ.get('RANK', '0')} {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_ours(args):
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -123,6 +128,7 @@ def run_ours(args):
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+        _log("process group up")
     from mertools_b200 import _lib as L
     L.check(L.lib().mer_check_device())
     L.lib().mer_launch_count.restype = __import__("ctypes").c_longlong
@@ -130,6 +136,7 @@ def run_ours(args):
     models = build_models(device)
     host_in = make_inputs(rank, clips)
     dev_in = [x.to(device) for x in host_in]
+    _log("models and inputs ready")
 
     def barrier():
         if world > 1:
@@ -140,6 +147,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         device_step(models, dev_in, clips, world)
     barrier()
+    _log("warm-up done")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -166,22 +174,16 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_dev = float(tmax.item())
+    _log(f"device arm done: {ms_dev:.1f} ms")
 
     # ---------------- end-to-end arm (host buffers, copies timed) ----------------
     vit, hub, bert, fus = models
 
+    from mertools_b200.pipeline import TriModalPipeline
+    pipe = TriModalPipeline(vit, hub, bert, fus, frames_per_clip=FRAMES, seqlen=TOKENS, world_size=world)
+
     def e2e_step():
-        frames, wave, ids, emo, val = host_in
-        d = [x.to(device, non_blocking=True) for x in (frames, wave, ids)]
-        vfeat = vit.clip_features(d[0], FRAMES)
-        afeat, _ = hub.forward(d[1], normalize=True)
-        tfeat, _ = bert.forward_packed(d[2], TOKENS)
-        feats = [f.cpu() for f in (afeat, tfeat, vfeat)]           # what the .npy files would hold
-        fd = [f.pin_memory().to(device, non_blocking=True) for f in feats]
-        loss, _, _ = fus.train_step(fd[0], fd[1], fd[2], emo.to(device, non_blocking=True),
-                                    val.to(device, non_blocking=True), lr=1e-3, weight_decay=1e-5,
-                                    world_size=world)
-        return float(loss[2].cpu())
+        return pipe.step_host(*host_in)
 
     for _ in range(max(1, args.warmup // 2)):
         e2e_step()

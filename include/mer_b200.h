@@ -111,12 +111,14 @@ MER_API int mer_round_tf32(float* x, long long n, void* stream);
 
 /* ---- attention ------------------------------------------------------------------------- */
 /* softmax(Q K^T / 8) V per (sequence, head); head_dim 64.  qkv is [tokens, 3*heads*64] with
- * Q | K | V column blocks, sequences packed back to back, cu_seqlens[n_seq+1] (device, int32).
+ * Q | K | V column blocks, sequences packed back to back, cu_seqlens[n_seq+1] (device, int32),
+ * tokens = cu_seqlens[n_seq] (host copy, sizes the TMA descriptor).  max_seqlen <= 256 runs the
+ * tcgen05 kernel (S in TMEM, P fed to the second MMA from TMEM), longer sequences the flash-style one.
  * ctx is [tokens, heads*64].  flags: MER_EPI_ROUND_TF32 rounds ctx for a TF32 out-proj GEMM,
  * MER_EPI_SPLIT_BF16 writes ctx as bf16 hi|lo rows for a BF16X3 out-proj GEMM.
  * Replaces HF eager/sdpa attention (modeling_vit.py:171-196, modeling_hubert.py:262-345). */
 MER_API int mer_attention(const float* qkv, float* ctx, const int32_t* cu_seqlens, int n_seq,
-                  int max_seqlen, int heads, int flags, void* stream);
+                          long long tokens, int max_seqlen, int heads, int flags, void* stream);
 
 /* ---- segment reduce (readouts) ------------------------------------------------------------ */
 enum { MER_SEG_SUM = 0, MER_SEG_MEAN = 1 };

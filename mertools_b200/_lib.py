@@ -72,7 +72,7 @@ def _declare(l):
         "mer_layernorm": [vp, vp, vp, vp, vp, vp, i64, i32, f32, i32, vp],
         "mer_round_tf32": [vp, i64, vp],
         "mer_split_bf16": [vp, vp, i64, i32, vp],
-        "mer_attention": [vp, vp, vp, i32, i32, i32, i32, vp],
+        "mer_attention": [vp, vp, vp, i32, i64, i32, i32, i32, vp],
     }
     for name, args in sig.items():
         fn = getattr(l, name)
@@ -178,6 +178,6 @@ def round_tf32_(x):
 
 def attention(qkv, ctx, cu_seqlens, max_seqlen, heads, round_out=False):
     check(lib().mer_attention(ptr(qkv), ptr(ctx), ptr(cu_seqlens), cu_seqlens.numel() - 1,
-                              max_seqlen, heads, MER_EPI_ROUND_TF32 if round_out else 0,
+                              qkv.shape[0], max_seqlen, heads, MER_EPI_ROUND_TF32 if round_out else 0,
                               stream_ptr()))
     return ctx

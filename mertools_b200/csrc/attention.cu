@@ -13,6 +13,8 @@
 // inside each 8-key group (keys 2t / 2t+1 <-> k-columns t / t+4), with V rows fetched under the
 // same permutation, so no shuffles or smem round-trip are needed.
 // [round 1: legacy tensor path; the tcgen05 version is the follow-up named in DESIGN.md]
+#include <stdlib.h>
+
 #include "mer_common.cuh"
 #include "mer_kernels.h"
 
@@ -233,8 +235,12 @@ attention_kernel(const float* __restrict__ qkv, float* __restrict__ ctx,
 }  // namespace
 
 int mer_attention_launch(const float* qkv, float* ctx, const int* cu_seqlens, int n_seq,
-                         int max_seqlen, int heads, int flags, cudaStream_t stream) {
+                         long long tokens, int max_seqlen, int heads, int flags, cudaStream_t stream) {
   MER_REQUIRE(qkv && ctx && cu_seqlens, "mer_attention: null operand");
+  // sequences of up to 256 tokens (ViT 197, HuBERT 5 s = 249, most sentences): tcgen05 kernel
+  static const bool legacy = getenv("MER_ATTENTION_LEGACY") != nullptr;
+  if (!legacy && max_seqlen <= 256 && tokens > 0 && heads <= 65535)
+    return mer_attention_tc_launch(qkv, ctx, cu_seqlens, n_seq, tokens, heads, flags, stream);
   MER_REQUIRE(heads > 0 && heads <= 65535 && n_seq <= 65535, "mer_attention: bad grid (%d heads, %d seqs)",
               heads, n_seq);
   if (n_seq <= 0 || max_seqlen <= 0) return 0;

@@ -68,7 +68,7 @@ int mer_run_stack(const MerStackArgs& a, cudaStream_t stream) {
       MER_TRY(mer_layernorm_launch(a.x, w.ln1_g, w.ln1_b, split ? nullptr : a.xn, split ? a.xn : nullptr,
                                    nullptr, M, D, a.eps, MER_LN_ROUND_TF32, stream));
       MER_TRY(linear(a.mode, a.xn, w.w_qkv, w.b_qkv, nullptr, a.qkv, M, DQKV, D, MER_EPI_ROUND_TF32, stream));
-      MER_TRY(mer_attention_launch(a.qkv, a.xn, a.cu_seqlens, a.n_seq, a.max_seqlen, HEADS, opnd, stream));
+      MER_TRY(mer_attention_launch(a.qkv, a.xn, a.cu_seqlens, a.n_seq, M, a.max_seqlen, HEADS, opnd, stream));
       MER_TRY(linear(a.mode, a.xn, w.w_o, w.b_o, a.x, a.x, M, D, D, 0, stream));
       MER_TRY(mer_layernorm_launch(a.x, w.ln2_g, w.ln2_b, split ? nullptr : a.xn, split ? a.xn : nullptr,
                                    nullptr, M, D, a.eps, MER_LN_ROUND_TF32, stream));
@@ -80,7 +80,7 @@ int mer_run_stack(const MerStackArgs& a, cudaStream_t stream) {
       // (residual) and xs carries its split copy (GEMM operand).
       const float* xop = split ? a.xs : a.x;
       MER_TRY(linear(a.mode, xop, w.w_qkv, w.b_qkv, nullptr, a.qkv, M, DQKV, D, MER_EPI_ROUND_TF32, stream));
-      MER_TRY(mer_attention_launch(a.qkv, a.xn, a.cu_seqlens, a.n_seq, a.max_seqlen, HEADS, opnd, stream));
+      MER_TRY(mer_attention_launch(a.qkv, a.xn, a.cu_seqlens, a.n_seq, M, a.max_seqlen, HEADS, opnd, stream));
       // the pre-LN sum goes to the (now dead) qkv buffer: ctx in xn is still being read
       MER_TRY(linear(a.mode, a.xn, w.w_o, w.b_o, a.x, a.qkv, M, D, D, 0, stream));
       MER_TRY(mer_layernorm_launch(a.qkv, w.ln1_g, w.ln1_b, a.x, split ? a.xs : nullptr, nullptr, M, D,

@@ -14,7 +14,10 @@ int mer_layernorm_launch(const float* x, const float* gamma, const float* beta, 
 
 // attention.cu
 int mer_attention_launch(const float* qkv, float* ctx, const int* cu_seqlens, int n_seq,
-                         int max_seqlen, int heads, int flags, cudaStream_t stream);
+                         long long tokens, int max_seqlen, int heads, int flags, cudaStream_t stream);
+// attention_tc.cu (tcgen05; max_seqlen <= 256)
+int mer_attention_tc_launch(const float* qkv, float* ctx, const int* cu_seqlens, int n_seq,
+                            long long tokens, int heads, int flags, cudaStream_t stream);
 
 // helpers.cu
 int mer_vit_patchify_launch(const uint8_t* frames_bgr, int n_frames, float* a_patches,

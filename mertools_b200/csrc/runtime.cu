@@ -109,8 +109,8 @@ int mer_layernorm(const float* x, const float* gamma, const float* beta, float* 
 }
 
 int mer_attention(const float* qkv, float* ctx, const int32_t* cu_seqlens, int n_seq,
-                  int max_seqlen, int heads, int flags, void* stream) {
-  return mer_attention_launch(qkv, ctx, cu_seqlens, n_seq, max_seqlen, heads, flags,
+                  long long tokens, int max_seqlen, int heads, int flags, void* stream) {
+  return mer_attention_launch(qkv, ctx, cu_seqlens, n_seq, tokens, max_seqlen, heads, flags,
                               static_cast<cudaStream_t>(stream));
 }
 

@@ -175,7 +175,9 @@ class FusionNet:
         per batch size and replayed; inputs are copied into static buffers first."""
         B = a.shape[0]
         assert B <= self.max_batch and emo.dtype == torch.int64 and val.dtype == torch.float32
-        if not use_graph or ext_masks is not None:
+        # under data parallelism the step is launched eagerly: the NCCL all-reduce sits between the
+        # backward and the Adam kernels and is not captured (30 launches per step either way)
+        if not use_graph or ext_masks is not None or world_size > 1:
             feats, emos_out, vals_out = self._bufs(B)
             self._launch_step(a.contiguous(), t.contiguous(), v.contiguous(), emo.contiguous(),
                               val.contiguous(), feats, emos_out, vals_out, lr, betas, eps,

@@ -235,7 +235,7 @@ def sec_ln():
 def sec_attn():
     ok = True
     heads = 12
-    for lens in [[197] * 5, [249] * 3, [7, 64, 65, 1, 130, 499]]:
+    for lens in [[197] * 5, [249] * 3, [7, 64, 65, 1, 130, 499], [7, 64, 65, 1, 130, 256, 200, 128, 129], [16] * 40]:
         cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device="cuda")
         tot = sum(lens)
         qkv = tf32(torch.randn(tot, 3 * heads * 64, device="cuda") * 1.5)
