@@ -13,8 +13,9 @@
 //   warp 0      TMA producer: A/B tiles -> swizzled smem ring (mbarrier full/empty)
 //   warp 1      MMA issuer  : tcgen05.mma, UMMA 128 x BLOCK_N x (32 bytes of K), fp32 accum in TMEM
 //   warp 2      TMEM allocator
-//   warps 4..11 epilogue    : tcgen05.ld TMEM -> registers -> bias/GELU/residual -> st.global
-//                             (two warps per TMEM lane quarter, half of the columns each)
+//   warps 4..11 epilogue    : tcgen05.ld TMEM -> registers -> bias/GELU/residual -> swizzled smem
+//                             transpose -> 512-byte coalesced st.global (two warps per TMEM lane
+//                             quarter, half of the columns each)
 // TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // Two arithmetic modes share the pipeline (both move 4 bytes per operand element):
@@ -61,7 +62,8 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N;
   static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +align slack
+  static constexpr int kStagingBytes = 8 * 4096;  // one 32 x 128 B transpose buffer per epilogue warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;  // +align slack
 };
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, int sbo_bytes, int layout) {
@@ -88,7 +90,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + Cfg::kStages;
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;
@@ -213,8 +216,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp >= EPI_WARP0) {
     // ===================== epilogue =====================
-    const int ew = (warp - EPI_WARP0) & 3;    // == warp % 4: the TMEM lane quarter this warp may read
+    // Thread = accumulator row (TMEM lane).  Global traffic is re-shaped through a per-warp 32 x 128 B
+    // staging tile (XOR-swizzled 16-byte slots, conflict-free both ways) so that every warp-level
+    // load / store touches 4 rows x 128 contiguous bytes instead of 32 rows x 16 bytes.
+    const int ew = (warp - EPI_WARP0) & 3;      // == warp % 4: the TMEM lane quarter this warp may read
     const int chalf = (warp - EPI_WARP0) >> 2;  // which half of the tile's columns this warp handles
+    float* stg = reinterpret_cast<float*>(staging) + (warp - EPI_WARP0) * 1024;
+    const int sub_r = lane >> 3;  // row within a group of 4 rows (coalesced phase)
+    const int sub_c = lane & 7;   // 16-byte slot within the 128-byte row (coalesced phase)
+    auto slot = [&](int row, int j) -> float4* {
+      return reinterpret_cast<float4*>(stg + row * 32 + ((j ^ (row & 7)) << 2));
+    };
     int as = 0;
     uint32_t aphase = 0;
     const bool do_gelu = (ep.flags & MER_EPI_GELU) != 0;
@@ -225,12 +237,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int mb = (t / n_tiles) * CLUSTER + cta_rank;
       const int b = mb / m_tiles;
       const int mt = mb % m_tiles;
-      const int m = mt * BLOCK_M + ew * 32 + lane;  // row inside the batch entry
-      const bool valid = m < rows_per_batch && mb < total_m;
-      float* out_row =
-          ep.out + ((long long)b * ep.out_bstride + ep.out_row0 + m) * (long long)ep.ld_out;
-      const float* res_row =
-          ep.res ? ep.res + ((long long)b * ep.res_bstride + ep.res_row0 + m) * (long long)ep.ld_res
+      const int m0 = mt * BLOCK_M + ew * 32;  // first row (inside the batch entry) of this warp's 32
+      const int rows_left = (mb < total_m) ? rows_per_batch - m0 : 0;  // rows r < rows_left are real
+      float* out_base = ep.out + ((long long)b * ep.out_bstride + ep.out_row0 + m0) * (long long)ep.ld_out;
+      const float* res_base =
+          ep.res ? ep.res + ((long long)b * ep.res_bstride + ep.res_row0 + m0) * (long long)ep.ld_res
                  : nullptr;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
@@ -240,50 +251,71 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         uint32_t r[32];
         tmem_ld_32x32(t_row + c * 32, r);
         const int n0 = n_blk * BLOCK_N + c * 32;
-        // residual chunk: 8 independent 16-byte loads issued before anything is stored (out may
-        // alias res, so loads placed after a store could not be hoisted by the compiler)
+        // residual tile: coalesced loads (row 4i + sub_r, slot sub_c), issued before anything else
         float4 rr[8];
-        if (res_row && valid) {
+        if (res_base) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) rr[j] = *reinterpret_cast<const float4*>(res_row + n0 + 4 * j);
+          for (int i = 0; i < 8; ++i) {
+            const int row = 4 * i + sub_r;
+            rr[i] = (row < rows_left)
+                        ? *reinterpret_cast<const float4*>(res_base + (long long)row * ep.ld_res + n0 + sub_c * 4)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
-        // bias chunk: 8 independent loads in distinct registers (issued back to back; ncu showed the
-        // one-at-a-time form serialising the whole epilogue on long-scoreboard stalls)
         float4 bb[8];
         if (ep.bias) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) bb[j] = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + j);
         }
-        tmem_ld_wait();
-        if (valid) {
+        if (res_base) {  // transpose the residual tile: coalesced layout -> one row per thread
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 v;
-            v.x = __uint_as_float(r[j + 0]);
-            v.y = __uint_as_float(r[j + 1]);
-            v.z = __uint_as_float(r[j + 2]);
-            v.w = __uint_as_float(r[j + 3]);
-            if (ep.bias) {
-              const float4 q = bb[j >> 2];
-              v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
-            }
-            if (do_gelu) {
-              v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
-            }
-            if (res_row) {
-              const float4 q = rr[j >> 2];
-              v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
-            }
-            if (do_split) {
-              store_split4(out_row, n0 + j, v);
-              continue;
-            }
+          for (int i = 0; i < 8; ++i) *slot(4 * i + sub_r, sub_c) = rr[i];
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rr[j] = *slot(lane, j);
+          __syncwarp();
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 v;
+          v.x = __uint_as_float(r[4 * j + 0]);
+          v.y = __uint_as_float(r[4 * j + 1]);
+          v.z = __uint_as_float(r[4 * j + 2]);
+          v.w = __uint_as_float(r[4 * j + 3]);
+          if (ep.bias) {
+            v.x += bb[j].x; v.y += bb[j].y; v.z += bb[j].z; v.w += bb[j].w;
+          }
+          if (do_gelu) {
+            v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+          }
+          if (res_base) {
+            v.x += rr[j].x; v.y += rr[j].y; v.z += rr[j].z; v.w += rr[j].w;
+          }
+          if (do_split) {
+            // the row's 128 bytes are [32 x bf16 hi | 32 x bf16 lo]: 8 bytes of each half per j
+            const float hx = bf16_round(v.x), hy = bf16_round(v.y), hz = bf16_round(v.z), hw = bf16_round(v.w);
+            uint2* hi = reinterpret_cast<uint2*>(slot(lane, j >> 1)) + (j & 1);
+            uint2* lo = reinterpret_cast<uint2*>(slot(lane, 4 + (j >> 1))) + (j & 1);
+            *hi = make_uint2(pack_bf16x2(hx, hy), pack_bf16x2(hz, hw));
+            *lo = make_uint2(pack_bf16x2(v.x - hx, v.y - hy), pack_bf16x2(v.z - hz, v.w - hw));
+          } else {
             if (do_round) {
               v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
             }
-            *reinterpret_cast<float4*>(out_row + n0 + j) = v;
+            *slot(lane, j) = v;
           }
         }
+        __syncwarp();
+        // coalesced write-out: 4 rows x 128 contiguous bytes per warp instruction
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = 4 * i + sub_r;
+          const float4 d = *slot(row, sub_c);
+          if (row < rows_left)
+            *reinterpret_cast<float4*>(out_base + (long long)row * ep.ld_out + n0 + sub_c * 4) = d;
+        }
+        __syncwarp();
       }
       // all TMEM reads of this stage are complete (wait::ld above) -> hand it back to the MMA warp
       tc_fence_before();
