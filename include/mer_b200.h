@@ -63,6 +63,12 @@ typedef struct MerGemmEpilogue {
   int ld_res;
   int flags;     /* MER_EPI_* */
   int split_off; /* reserved (0) */
+  /* optional transposed side output: columns n >= vt_col0 are written as vt[(n - vt_col0) * vt_ld +
+   * out_row] INSTEAD of out[out_row, n] (the QKV GEMM hands V^T, keys contiguous, to the tcgen05
+   * attention kernel as a K-major operand) */
+  float* vt;
+  long long vt_ld;
+  int vt_col0;
 } MerGemmEpilogue;
 
 /* A[b, m, tap*K_inner + c] = base[b*a_batch_stride + (m + tap / P)*a_row_stride +
@@ -112,13 +118,17 @@ MER_API int mer_round_tf32(float* x, long long n, void* stream);
 /* ---- attention ------------------------------------------------------------------------- */
 /* softmax(Q K^T / 8) V per (sequence, head); head_dim 64.  qkv is [tokens, 3*heads*64] with
  * Q | K | V column blocks, sequences packed back to back, cu_seqlens[n_seq+1] (device, int32),
- * tokens = cu_seqlens[n_seq] (host copy, sizes the TMA descriptor).  max_seqlen <= 256 runs the
- * tcgen05 kernel (S in TMEM, P fed to the second MMA from TMEM), longer sequences the flash-style one.
+ * tokens = cu_seqlens[n_seq] (host copy, sizes the TMA descriptors).  vt (optional): V^T, [heads*64,
+ * vt_ld] with vt[d, token] = V[token, d] (vt_ld >= tokens, multiple of 4), as written by mer_gemm's
+ * transposed side output.  With vt and max_seqlen <= 256 the tcgen05 kernel runs (S in TMEM, P staged
+ * through smem, both MMAs on K-major operands) and the V columns of qkv are not read; otherwise the
+ * flash-style kernel.
  * ctx is [tokens, heads*64].  flags: MER_EPI_ROUND_TF32 rounds ctx for a TF32 out-proj GEMM,
  * MER_EPI_SPLIT_BF16 writes ctx as bf16 hi|lo rows for a BF16X3 out-proj GEMM.
  * Replaces HF eager/sdpa attention (modeling_vit.py:171-196, modeling_hubert.py:262-345). */
-MER_API int mer_attention(const float* qkv, float* ctx, const int32_t* cu_seqlens, int n_seq,
-                          long long tokens, int max_seqlen, int heads, int flags, void* stream);
+MER_API int mer_attention(const float* qkv, const float* vt, long long vt_ld, float* ctx,
+                          const int32_t* cu_seqlens, int n_seq, long long tokens, int max_seqlen,
+                          int heads, int flags, void* stream);
 
 /* ---- segment reduce (readouts) ------------------------------------------------------------ */
 enum { MER_SEG_SUM = 0, MER_SEG_MEAN = 1 };

@@ -32,6 +32,7 @@ class MerGemmEpilogue(C.Structure):
         ("out_bstride", C.c_longlong), ("out_row0", C.c_longlong),
         ("res_bstride", C.c_longlong), ("res_row0", C.c_longlong),
         ("ld_out", C.c_int), ("ld_res", C.c_int), ("flags", C.c_int), ("split_off", C.c_int),
+        ("vt", C.c_void_p), ("vt_ld", C.c_longlong), ("vt_col0", C.c_int),
     ]
 
 
@@ -72,7 +73,7 @@ def _declare(l):
         "mer_layernorm": [vp, vp, vp, vp, vp, vp, i64, i32, f32, i32, vp],
         "mer_round_tf32": [vp, i64, vp],
         "mer_split_bf16": [vp, vp, i64, i32, vp],
-        "mer_attention": [vp, vp, vp, i32, i64, i32, i32, i32, vp],
+        "mer_attention": [vp, vp, i64, vp, vp, i32, i64, i32, i32, i32, vp],
     }
     for name, args in sig.items():
         fn = getattr(l, name)
@@ -110,7 +111,7 @@ def gemm(A, W, out, *, bias=None, res=None, gelu=False, round_out=False, split_o
          mode=MER_GEMM_TF32, rows_per_batch=None, batches=1, a_rows_dim=None, K_inner=None, taps=1, P=1,
          a_phase_stride=0, a_row_stride=None, a_batch_stride=0,
          out_bstride=0, out_row0=0, res_bstride=0, res_row0=0,
-         ld_out=None, ld_res=None, force_block_n=0, cluster=0):
+         ld_out=None, ld_res=None, force_block_n=0, cluster=0, vt=None, vt_col0=0):
     """out = epilogue(A @ W.T).  A, W: fp32 CUDA tensors of LOGICAL shape [rows, K] / [N, K] (holding
     tf32-rounded fp32, or split bf16 hi|lo bytes when mode is BF16X3); see MerGemmDesc in mer_b200.h."""
     N, K = W.shape
@@ -139,6 +140,8 @@ def gemm(A, W, out, *, bias=None, res=None, gelu=False, round_out=False, split_o
     d.ep.flags = ((MER_EPI_GELU if gelu else 0) | (MER_EPI_ROUND_TF32 if round_out else 0)
                   | (MER_EPI_SPLIT_BF16 if split_out else 0))
     d.ep.split_off = N
+    if vt is not None:
+        d.ep.vt, d.ep.vt_ld, d.ep.vt_col0 = vt.data_ptr(), vt.shape[1], vt_col0
     check(lib().mer_gemm(C.byref(d), stream_ptr()))
     return out
 
@@ -176,8 +179,9 @@ def round_tf32_(x):
     return x
 
 
-def attention(qkv, ctx, cu_seqlens, max_seqlen, heads, round_out=False):
-    check(lib().mer_attention(ptr(qkv), ptr(ctx), ptr(cu_seqlens), cu_seqlens.numel() - 1,
-                              qkv.shape[0], max_seqlen, heads, MER_EPI_ROUND_TF32 if round_out else 0,
-                              stream_ptr()))
+def attention(qkv, ctx, cu_seqlens, max_seqlen, heads, round_out=False, vt=None):
+    """vt: optional V^T [heads*64, ld] (enables the tcgen05 kernel for max_seqlen <= 256)."""
+    check(lib().mer_attention(ptr(qkv), ptr(vt), vt.shape[1] if vt is not None else 0, ptr(ctx),
+                              ptr(cu_seqlens), cu_seqlens.numel() - 1, qkv.shape[0], max_seqlen, heads,
+                              MER_EPI_ROUND_TF32 if round_out else 0, stream_ptr()))
     return ctx

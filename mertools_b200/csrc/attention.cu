@@ -234,13 +234,19 @@ attention_kernel(const float* __restrict__ qkv, float* __restrict__ ctx,
 
 }  // namespace
 
-int mer_attention_launch(const float* qkv, float* ctx, const int* cu_seqlens, int n_seq,
-                         long long tokens, int max_seqlen, int heads, int flags, cudaStream_t stream) {
-  MER_REQUIRE(qkv && ctx && cu_seqlens, "mer_attention: null operand");
-  // sequences of up to 256 tokens (ViT 197, HuBERT 5 s = 249, most sentences): tcgen05 kernel
+bool mer_attention_uses_tc(int max_seqlen) {
   static const bool legacy = getenv("MER_ATTENTION_LEGACY") != nullptr;
-  if (!legacy && max_seqlen <= 256 && tokens > 0 && heads <= 65535)
-    return mer_attention_tc_launch(qkv, ctx, cu_seqlens, n_seq, tokens, heads, flags, stream);
+  return !legacy && max_seqlen <= 253;  // + up to 3 alignment keys must fit the 256-key S tile
+}
+
+int mer_attention_launch(const float* qkv, const float* vt, long long vt_ld, float* ctx,
+                         const int* cu_seqlens, int n_seq, long long tokens, int max_seqlen, int heads,
+                         int flags, cudaStream_t stream) {
+  MER_REQUIRE(qkv && ctx && cu_seqlens, "mer_attention: null operand");
+  // sequences of up to 256 tokens (ViT 197, HuBERT 5 s = 249, most sentences): tcgen05 kernel,
+  // which reads V^T (written by the QKV GEMM epilogue) instead of the V columns of qkv
+  if (vt && mer_attention_uses_tc(max_seqlen) && tokens > 0)
+    return mer_attention_tc_launch(qkv, vt, vt_ld, ctx, cu_seqlens, n_seq, tokens, heads, flags, stream);
   MER_REQUIRE(heads > 0 && heads <= 65535 && n_seq <= 65535, "mer_attention: bad grid (%d heads, %d seqs)",
               heads, n_seq);
   if (n_seq <= 0 || max_seqlen <= 0) return 0;

@@ -5,14 +5,19 @@
 // (HF eager/sdpa attention, modeling_vit.py:171-196, modeling_hubert.py:262-345).
 //
 // Persistent, one CTA per SM, work item = (sequence, head):
-//   warp 0      TMA producer: K, V (all keys) and the 128-row Q tiles of the item -> 128B-swizzled smem
-//   warp 1      tcgen05 issuer:  S = Q_tile K^T  (UMMA 128 x NK x 8, kind::tf32, both operands K-major
-//               in smem) into TMEM columns [0,256);  then  O = P V  with P read straight from TMEM
-//               (A operand in tensor memory) and V as an MN-major smem operand, into columns [256,320)
+//   warp 0      TMA producer: K (all keys), V^T (keys contiguous; written transposed by the QKV GEMM
+//               epilogue) and the 128-row Q tiles of the item -> 128B-swizzled smem
+//   warp 1      tcgen05 issuer:  S = Q_tile K^T  (UMMA 128 x NK x 8, kind::tf32) into TMEM columns
+//               [0,256);  then, per 64-key chunk of P staged in smem by the softmax warps,
+//               O += P_chunk V_chunk  (UMMA 128 x 64 x 8) into TMEM columns [256,320)
 //   warps 2..5  softmax + epilogue: S rows TMEM -> registers (thread = query row), max, exp2, sum,
-//               tf32-rounded P written back IN PLACE with tcgen05.st; after P V: O / sum -> ctx
-// The score matrix never leaves the SM.  Algorithmic HBM traffic per token and layer: 9 KB of qkv in,
-// 3 KB of ctx out.
+//               tf32-rounded P chunks -> swizzled smem (A operand of the second MMA); O / sum -> ctx
+// The score matrix never leaves the SM.  Algorithmic HBM traffic per token and layer: 9 KB of
+// q|k|v^T in, 3 KB of ctx out.
+// (A first version fed P to the second MMA straight from TMEM and V as an MN-major operand; both
+// gave wrong results on the device and were replaced by these two known-good K-major smem operands.)
+#include <stdlib.h>
+
 #include "mer_common.cuh"
 #include "mer_kernels.h"
 
@@ -25,10 +30,12 @@ constexpr int MAXS = 256;
 constexpr int TC_THREADS = 192;
 constexpr int CHUNK_BYTES = MAXS * 128;           // one 32-float column chunk of K or V: [256][128 B]
 constexpr int QTILE_BYTES = 2 * 128 * 128;        // one 128-row Q tile: 2 chunks x [128][128 B]
+constexpr int VT_CHUNK = HD * 128;                // V^T chunk: 64 d-rows x 32 keys (128 B)
 constexpr int SMEM_K = 0;
-constexpr int SMEM_V = 2 * CHUNK_BYTES;
+constexpr int SMEM_V = 2 * CHUNK_BYTES;           // 8 V^T chunks = 64 KB
 constexpr int SMEM_Q = 4 * CHUNK_BYTES;
-constexpr int SMEM_BAR = SMEM_Q + 2 * QTILE_BYTES;
+constexpr int SMEM_P = SMEM_Q + 2 * QTILE_BYTES;  // P chunk: 2 x [128 rows][32 keys] = 32 KB
+constexpr int SMEM_BAR = SMEM_P + 2 * 16384;
 constexpr int TC_SMEM = SMEM_BAR + 256 + 1024;
 constexpr uint32_t S_COL = 0, O_COL = 256, TMEM_COLS = 512;
 
@@ -36,39 +43,10 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) {  // SW128, SBO 
   return static_cast<uint64_t>((addr & 0x3FFFF) >> 4) | (1ull << 16) | (uint64_t(1024 >> 4) << 32) |
          (1ull << 46) | (2ull << 61);
 }
-// MN-major SW128 operand: 32-float (128 B) atoms along MN `lbo` bytes apart, 8-row K groups 1024 B apart
-__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t addr, uint32_t lbo) {
-  return static_cast<uint64_t>((addr & 0x3FFFF) >> 4) | (uint64_t(lbo >> 4) << 16) |
-         (uint64_t(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t desc_b,
-                                            uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
-      "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
-      "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() {
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, float* __restrict__ ctx,
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
+                    const __grid_constant__ CUtensorMap tmap_vt, float* __restrict__ ctx,
                     const int* __restrict__ cu_seqlens, int n_seq, int heads, int out_mode) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -76,22 +54,30 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, float* __restr
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
   uint64_t* bar_kq = bars + 0;
   uint64_t* bar_v = bars + 1;
-  uint64_t* bar_sfull = bars + 2;
-  uint64_t* bar_pfull = bars + 3;
-  uint64_t* bar_ofull = bars + 4;
-  uint64_t* bar_ofree = bars + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  // sfull / ofull exist twice, indexed by (tile counter & 1) with phase (tile counter >> 1) & 1: the
+  // producer looks back at BOTH tiles of the previous item, and a parity wait is only unambiguous
+  // when the waiter can never be two completions behind on the same barrier
+  uint64_t* bar_sfull = bars + 2;   // [2] MMA -> softmax/producer: S tile complete
+  uint64_t* bar_pready = bars + 4;  // softmax -> MMA: a P chunk sits in smem
+  uint64_t* bar_ofull = bars + 5;   // [2] MMA -> softmax/producer: O complete (all MMAs of the tile done)
+  uint64_t* bar_ofree = bars + 7;
+  uint64_t* bar_pfree = bars + 8;   // MMA -> softmax: the P chunk buffer has been consumed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = n_seq * heads;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_vt);
     mbar_init(bar_kq, 1);
     mbar_init(bar_v, 1);
-    mbar_init(bar_sfull, 1);
-    mbar_init(bar_pfull, 4);
-    mbar_init(bar_ofull, 1);
+    mbar_init(&bar_sfull[0], 1);
+    mbar_init(&bar_sfull[1], 1);
+    mbar_init(bar_pready, 4);
+    mbar_init(bar_pfree, 1);
+    mbar_init(&bar_ofull[0], 1);
+    mbar_init(&bar_ofull[1], 1);
     mbar_init(bar_ofree, 4);
     fence_mbar_init();
   }
@@ -108,52 +94,61 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, float* __restr
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t tiles_done = 0;  // tiles of all previous items of this CTA
-      bool first = true;
+      uint32_t prev_tiles = 0;  // tiles of the previous item (0 for the first)
       for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const int seq = it / heads, h = it % heads;
         const int start = cu_seqlens[seq];
         const int len = cu_seqlens[seq + 1] - start;
         const int n_mt = (len + 127) >> 7;
-        const int nb = n_mt;  // 128-row boxes of K / V actually needed
+        // TMA needs 16-byte aligned inner-dimension starts: V^T (keys contiguous) is read from the
+        // token rounded down to a multiple of 4, and K rows likewise, so both MMAs see the same key
+        // axis k' = key + shift; the (up to 3) leading keys of the previous sequence are masked
+        const int a_start = start & ~3, shift = start - a_start;
+        const int Lk = shift + len;
+        const int nb = (Lk + 127) >> 7;  // 128-row boxes of K actually needed
         // K + Q tile 0: the previous item's S MMAs (last tile) must have consumed K and Q
-        if (!first) mbar_wait(bar_sfull, (tiles_done - 1) & 1);
+        for (uint32_t tt = tiles_done - prev_tiles; tt < tiles_done; ++tt)
+          mbar_wait(&bar_sfull[tt & 1], (tt >> 1) & 1);
         mbar_expect_tx(bar_kq, (uint32_t)(2 * nb * 16384 + 2 * 16384));
         for (int c = 0; c < 2; ++c) {
           for (int b = 0; b < nb; ++b)
             tma_load_2d(smem + SMEM_K + c * CHUNK_BYTES + b * 16384, &tmap_qkv, bar_kq,
-                        heads * HD + h * HD + c * 32, start + b * 128);
+                        heads * HD + h * HD + c * 32, a_start + b * 128);
           tma_load_2d(smem + SMEM_Q + c * 16384, &tmap_qkv, bar_kq, h * HD + c * 32, start);
         }
         // V (+ Q tile 1): the previous item's P V MMAs must have consumed V
-        if (!first) mbar_wait(bar_ofull, (tiles_done - 1) & 1);
-        mbar_expect_tx(bar_v, (uint32_t)(2 * nb * 16384 + (n_mt > 1 ? 2 * 16384 : 0)));
-        for (int c = 0; c < 2; ++c) {
-          for (int b = 0; b < nb; ++b)
-            tma_load_2d(smem + SMEM_V + c * CHUNK_BYTES + b * 16384, &tmap_qkv, bar_v,
-                        2 * heads * HD + h * HD + c * 32, start + b * 128);
-          if (n_mt > 1)
+        for (uint32_t tt = tiles_done - prev_tiles; tt < tiles_done; ++tt)
+          mbar_wait(&bar_ofull[tt & 1], (tt >> 1) & 1);
+        const int n_vc = (Lk + 31) >> 5;  // 32-key chunks of V^T
+        mbar_expect_tx(bar_v, (uint32_t)(n_vc * VT_CHUNK + (n_mt > 1 ? 2 * 16384 : 0)));
+        for (int c = 0; c < n_vc; ++c)
+          tma_load_2d(smem + SMEM_V + c * VT_CHUNK, &tmap_vt, bar_v, a_start + c * 32, h * HD);
+        if (n_mt > 1)
+          for (int c = 0; c < 2; ++c)
             tma_load_2d(smem + SMEM_Q + QTILE_BYTES + c * 16384, &tmap_qkv, bar_v, h * HD + c * 32,
                         start + 128);
-        }
         tiles_done += n_mt;
-        first = false;
+        prev_tiles = n_mt;
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       uint32_t T = 0;       // global tile counter of this CTA
+      uint32_t G = 0;       // global P-chunk counter of this CTA
       uint32_t item_n = 0;  // items processed
       for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item_n) {
         const int seq = it / heads;
-        const int len = cu_seqlens[seq + 1] - cu_seqlens[seq];
+        const int start = cu_seqlens[seq];
+        const int len = cu_seqlens[seq + 1] - start;
         const int n_mt = (len + 127) >> 7;
-        const int NK = (len + 15) & ~15;  // keys, padded to the UMMA N granularity
+        const int NK = ((start & 3) + len + 15) & ~15;  // shifted key axis, padded to the UMMA N step
+        const int n_pc = (NK + 63) >> 6;  // 64-key chunks of P
         const uint32_t idesc_s = umma_idesc(2, 128, NK);
-        const uint32_t idesc_o = umma_idesc(2, 128, HD) | (1u << 16);  // B (= V) is MN-major
+        const uint32_t idesc_o = umma_idesc(2, 128, HD);
         for (int t = 0; t < n_mt; ++t, ++T) {
           if (t == 0) mbar_wait(bar_kq, item_n & 1);
-          else mbar_wait(bar_v, item_n & 1);  // Q tile 1 travels with V
+          else mbar_wait(bar_v, item_n & 1);  // Q tile 1 travels with V^T
           tc_fence_after();
           // ---- S = Q_t K^T ----
 #pragma unroll
@@ -164,18 +159,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, float* __restr
             for (int k = 0; k < 4; ++k)
               tc_mma_tf32(tmem_base + S_COL, da + 2 * k, db + 2 * k, idesc_s, (c | k) != 0);
           }
-          tc_commit(bar_sfull);
-          // ---- O = P V ----
-          mbar_wait(bar_pfull, T & 1);
+          tc_commit(&bar_sfull[T & 1]);
+          // ---- O = sum over 64-key chunks of P_chunk V_chunk ----
           if (t == 0) mbar_wait(bar_v, item_n & 1);
           mbar_wait(bar_ofree, (T & 1) ^ 1);
-          tc_fence_after();
-          const uint32_t v0 = smem_u32(smem + SMEM_V);
-          for (int j = 0; j < NK / 8; ++j)
-            mma_tf32_ts(tmem_base + O_COL, tmem_base + S_COL + 8 * j,
-                        desc_mnmajor(v0 + j * 1024, CHUNK_BYTES), idesc_o, j != 0);
-          tc_commit(bar_ofull);
-          mbar_wait(bar_ofull, T & 1);  // S region is rewritten by the next tile's first MMA
+          for (int pc = 0; pc < n_pc; ++pc, ++G) {
+            mbar_wait(bar_pready, G & 1);
+            tc_fence_after();
+            const int keys = min(64, NK - pc * 64);
+            for (int k8 = 0; k8 < keys / 8; ++k8) {
+              const int sub = k8 >> 2, k = k8 & 3;  // 32-key sub-chunk, 8-key step inside it
+              const uint64_t da = desc_kmajor(smem_u32(smem + SMEM_P + sub * 16384)) + 2 * k;
+              const uint64_t db = desc_kmajor(smem_u32(smem + SMEM_V + (2 * pc + sub) * VT_CHUNK)) + 2 * k;
+              tc_mma_tf32(tmem_base + O_COL, da, db, idesc_o, (pc | k8) != 0);
+            }
+            tc_commit(bar_pfree);
+          }
+          tc_commit(&bar_ofull[T & 1]);
+          mbar_wait(&bar_ofull[T & 1], (T >> 1) & 1);  // S is rewritten by the next tile
         }
       }
     }
@@ -185,16 +186,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, float* __restr
     const uint32_t t_lane = tmem_base + (uint32_t(q * 32) << 16);
     constexpr float SCALE_LOG2 = 0.125f * 1.4426950408889634f;
     const int ldc = heads * HD;
-    uint32_t T = 0;
+    uint32_t T = 0, G = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
       const int seq = it / heads, h = it % heads;
       const int start = cu_seqlens[seq];
       const int len = cu_seqlens[seq + 1] - start;
       const int n_mt = (len + 127) >> 7;
-      const int n_chunks = (len + 31) >> 5;
+      const int shift = start & 3;   // keys live at columns [shift, shift + len) of S
+      const int Lk = shift + len;
+      const int n_chunks = (Lk + 31) >> 5;
       for (int t = 0; t < n_mt; ++t, ++T) {
         const int row = t * 128 + q * 32 + lane;  // query row inside the sequence
-        mbar_wait(bar_sfull, T & 1);
+        mbar_wait(&bar_sfull[T & 1], (T >> 1) & 1);
         tc_fence_after();
         // pass 1: row maximum over the valid keys
         float mx = -INFINITY;
@@ -204,31 +207,46 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, float* __restr
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (c * 32 + j < len) mx = fmaxf(mx, __uint_as_float(r[j]));
+            if (c * 32 + j >= shift && c * 32 + j < Lk) mx = fmaxf(mx, __uint_as_float(r[j]));
         }
         const float mb = mx * SCALE_LOG2;
-        // pass 2: p = exp2((s - max) / 8 * log2 e), row sum, tf32-rounded P back in place
+        // pass 2, per 64-key chunk: p = exp2((s - max) / 8 * log2 e) -> row sum, tf32-rounded P into
+        // the swizzled smem chunk (A operand of the P V MMA)
         float sum = 0.f;
-        for (int c = 0; c < n_chunks; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(t_lane + S_COL + c * 32, r);
+        const int r_tile = q * 32 + lane;  // row inside the 128-row tile
+        const int NKs = (Lk + 15) & ~15;
+        const int n_pc = (NKs + 63) >> 6;
+        for (int pc = 0; pc < n_pc; ++pc, ++G) {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(t_lane + S_COL + pc * 64, r0);
+          tmem_ld_32x32(t_lane + S_COL + pc * 64 + 32, r1);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float p = 0.f;
-            if (c * 32 + j < len) p = exp2f(fmaf(__uint_as_float(r[j]), SCALE_LOG2, -mb));
-            sum += p;
-            r[j] = __float_as_uint(round_tf32(p));
+            float p0 = 0.f, p1 = 0.f;
+            const int k0 = pc * 64 + j, k1 = k0 + 32;
+            if (k0 >= shift && k0 < Lk) p0 = exp2f(fmaf(__uint_as_float(r0[j]), SCALE_LOG2, -mb));
+            if (k1 >= shift && k1 < Lk) p1 = exp2f(fmaf(__uint_as_float(r1[j]), SCALE_LOG2, -mb));
+            sum += p0 + p1;
+            r0[j] = __float_as_uint(round_tf32(p0));
+            r1[j] = __float_as_uint(round_tf32(p1));
           }
-          tmem_st_32x32(t_lane + S_COL + c * 32, r);
+          mbar_wait(bar_pfree, (G & 1) ^ 1);  // previous chunk's MMAs have read the buffer
+          float* p_lo = reinterpret_cast<float*>(smem + SMEM_P) + r_tile * 32;
+          float* p_hi = reinterpret_cast<float*>(smem + SMEM_P + 16384) + r_tile * 32;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int sj = (j ^ (r_tile & 7)) << 2;
+            *reinterpret_cast<uint4*>(p_lo + sj) = make_uint4(r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]);
+            *reinterpret_cast<uint4*>(p_hi + sj) = make_uint4(r1[4 * j], r1[4 * j + 1], r1[4 * j + 2], r1[4 * j + 3]);
+          }
+          fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_pready);
         }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_pfull);
         const float inv = 1.0f / sum;
         // epilogue: O / sum -> ctx
-        mbar_wait(bar_ofull, T & 1);
+        mbar_wait(&bar_ofull[T & 1], (T >> 1) & 1);
         tc_fence_after();
         uint32_t o0[32], o1[32];
         tmem_ld_32x32(t_lane + O_COL, o0);
@@ -272,15 +290,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, float* __restr
 
 }  // namespace
 
-int mer_attention_tc_launch(const float* qkv, float* ctx, const int* cu_seqlens, int n_seq,
-                            long long tokens, int heads, int flags, cudaStream_t stream) {
-  CUtensorMap tm;
-  const uint64_t dims[2] = {(uint64_t)(3 * heads * HD), (uint64_t)tokens};
-  const uint64_t strides[1] = {(uint64_t)(3 * heads * HD) * 4ull};
-  const uint32_t box[2] = {32, 128};
-  if (int rc = mer_make_tmap(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, qkv, dims, strides, box,
-                             CU_TENSOR_MAP_SWIZZLE_128B))
-    return rc;
+int mer_attention_tc_launch(const float* qkv, const float* vt, long long vt_ld, float* ctx,
+                            const int* cu_seqlens, int n_seq, long long tokens, int heads, int flags,
+                            cudaStream_t stream) {
+  MER_REQUIRE(vt && vt_ld >= tokens && vt_ld % 4 == 0, "mer_attention_tc: V^T buffer missing or mis-pitched");
+  CUtensorMap tm, tv;
+  {
+    const uint64_t dims[2] = {(uint64_t)(3 * heads * HD), (uint64_t)tokens};
+    const uint64_t strides[1] = {(uint64_t)(3 * heads * HD) * 4ull};
+    const uint32_t box[2] = {32, 128};
+    if (int rc = mer_make_tmap(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, qkv, dims, strides, box,
+                               CU_TENSOR_MAP_SWIZZLE_128B))
+      return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)tokens, (uint64_t)(heads * HD)};
+    const uint64_t strides[1] = {(uint64_t)vt_ld * 4ull};
+    const uint32_t box[2] = {32, HD};
+    if (int rc = mer_make_tmap(&tv, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, vt, dims, strides, box,
+                               CU_TENSOR_MAP_SWIZZLE_128B))
+      return rc;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     MER_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -291,7 +321,7 @@ int mer_attention_tc_launch(const float* qkv, float* ctx, const int* cu_seqlens,
   int grid = mer_num_sms();
   if (items < grid) grid = (int)items;
   const int out_mode = (flags & MER_EPI_SPLIT_BF16) ? 2 : ((flags & MER_EPI_ROUND_TF32) ? 1 : 0);
-  attention_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(tm, ctx, cu_seqlens, n_seq, heads, out_mode);
+  attention_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(tm, tv, ctx, cu_seqlens, n_seq, heads, out_mode);
   MER_CUDA_CHECK(cudaGetLastError());
   mer_count_launches(1);
   return 0;

@@ -19,7 +19,8 @@ constexpr int DFF = 3072;
 constexpr int HEADS = 12;
 
 int linear(int mode, const float* A, const float* W, const float* bias, const float* res, float* out,
-           long long M, int N, int K, int flags, cudaStream_t stream) {
+           long long M, int N, int K, int flags, cudaStream_t stream, float* vt = nullptr,
+           long long vt_ld = 0, int vt_col0 = 0) {
   MerGemmDesc g;
   memset(&g, 0, sizeof(g));
   g.A = A;
@@ -41,6 +42,9 @@ int linear(int mode, const float* A, const float* W, const float* bias, const fl
   g.ep.ld_res = N;
   g.ep.flags = flags;
   g.ep.split_off = N;
+  g.ep.vt = vt;
+  g.ep.vt_ld = vt_ld;
+  g.ep.vt_col0 = vt_col0;
   g.mode = mode;
   return mer_gemm_launch(&g, stream);
 }
@@ -62,13 +66,18 @@ int mer_run_stack(const MerStackArgs& a, cudaStream_t stream) {
     const int first_acc = a.n_layers - a.acc_last;  // hidden state index l+1 > first_acc is summed
     // operand format of the tensor-core inputs in this stack: tf32-rounded fp32, or split bf16
     const bool split = a.mode == MER_GEMM_BF16X3;
+    // tcgen05 attention (sequences <= 256): the QKV GEMM writes V transposed into a.vt instead of
+    // the V columns of qkv
+    float* vt = (a.vt && mer_attention_uses_tc(a.max_seqlen)) ? a.vt : nullptr;
     const int opnd = split ? MER_EPI_SPLIT_BF16 : MER_EPI_ROUND_TF32;
     if (a.pre_ln) {
       // x = x + Wo * Attn(LN1(x));  x = x + W2 * GELU(W1 * LN2(x))
       MER_TRY(mer_layernorm_launch(a.x, w.ln1_g, w.ln1_b, split ? nullptr : a.xn, split ? a.xn : nullptr,
                                    nullptr, M, D, a.eps, MER_LN_ROUND_TF32, stream));
-      MER_TRY(linear(a.mode, a.xn, w.w_qkv, w.b_qkv, nullptr, a.qkv, M, DQKV, D, MER_EPI_ROUND_TF32, stream));
-      MER_TRY(mer_attention_launch(a.qkv, a.xn, a.cu_seqlens, a.n_seq, M, a.max_seqlen, HEADS, opnd, stream));
+      MER_TRY(linear(a.mode, a.xn, w.w_qkv, w.b_qkv, nullptr, a.qkv, M, DQKV, D, MER_EPI_ROUND_TF32, stream,
+                     vt, a.vt_ld, 2 * D));
+      MER_TRY(mer_attention_launch(a.qkv, vt, a.vt_ld, a.xn, a.cu_seqlens, a.n_seq, M, a.max_seqlen, HEADS,
+                                   opnd, stream));
       MER_TRY(linear(a.mode, a.xn, w.w_o, w.b_o, a.x, a.x, M, D, D, 0, stream));
       MER_TRY(mer_layernorm_launch(a.x, w.ln2_g, w.ln2_b, split ? nullptr : a.xn, split ? a.xn : nullptr,
                                    nullptr, M, D, a.eps, MER_LN_ROUND_TF32, stream));
@@ -79,8 +88,10 @@ int mer_run_stack(const MerStackArgs& a, cudaStream_t stream) {
       // TF32: x itself is tf32-rounded and doubles as the GEMM operand.  BF16X3: x stays exact fp32
       // (residual) and xs carries its split copy (GEMM operand).
       const float* xop = split ? a.xs : a.x;
-      MER_TRY(linear(a.mode, xop, w.w_qkv, w.b_qkv, nullptr, a.qkv, M, DQKV, D, MER_EPI_ROUND_TF32, stream));
-      MER_TRY(mer_attention_launch(a.qkv, a.xn, a.cu_seqlens, a.n_seq, M, a.max_seqlen, HEADS, opnd, stream));
+      MER_TRY(linear(a.mode, xop, w.w_qkv, w.b_qkv, nullptr, a.qkv, M, DQKV, D, MER_EPI_ROUND_TF32, stream,
+                     vt, a.vt_ld, 2 * D));
+      MER_TRY(mer_attention_launch(a.qkv, vt, a.vt_ld, a.xn, a.cu_seqlens, a.n_seq, M, a.max_seqlen, HEADS,
+                                   opnd, stream));
       // the pre-LN sum goes to the (now dead) qkv buffer: ctx in xn is still being read
       MER_TRY(linear(a.mode, a.xn, w.w_o, w.b_o, a.x, a.qkv, M, D, D, 0, stream));
       MER_TRY(mer_layernorm_launch(a.qkv, w.ln1_g, w.ln1_b, a.x, split ? a.xs : nullptr, nullptr, M, D,
@@ -114,8 +125,8 @@ extern "C" {
 
 long long mer_vit_workspace_bytes(int n_frames) {
   const long long M = (long long)n_frames * 197;
-  // x, xn, qkv, h (+ patch operand aliasing h) + offsets
-  return (M * (D + D + DQKV + DFF)) * 4 + ((long long)n_frames + 1) * 4 + 1024;
+  // x, xn, qkv, h (+ patch operand aliasing h), V^T + offsets
+  return (M * (D + D + DQKV + DFF) + (long long)D * ((M + 3) & ~3ll)) * 4 + ((long long)n_frames + 1) * 4 + 1024;
 }
 
 int mer_vit_forward(const MerVitModel* m, const uint8_t* frames_bgr, int n_frames, void* workspace,
@@ -133,7 +144,9 @@ int mer_vit_forward(const MerVitModel* m, const uint8_t* frames_bgr, int n_frame
   float* xn = x + M * D;
   float* qkv = xn + M * D;
   float* h = qkv + M * DQKV;
-  int* offsets = reinterpret_cast<int*>(h + M * DFF);
+  float* vt = h + M * DFF;
+  const long long vt_ld = (M + 3) & ~3ll;
+  int* offsets = reinterpret_cast<int*>(vt + (long long)D * vt_ld);
   float* a_patch = h;  // [n_frames*196, 768] patch operand lives in the (not yet used) FFN buffer
 
   MER_TRY(mer_iota_offsets_launch(offsets, n_frames, 197, stream));
@@ -180,6 +193,8 @@ int mer_vit_forward(const MerVitModel* m, const uint8_t* frames_bgr, int n_frame
   a.xn = xn;
   a.qkv = qkv;
   a.h = h;
+  a.vt = vt;
+  a.vt_ld = vt_ld;
   a.opt_hidden = opt_hidden;
   MER_TRY(mer_run_stack(a, stream));
   MER_TRY(mer_segment_reduce_launch(x, offsets, offsets + 1, n_frames, D, MER_SEG_SUM, out_frame_feats, stream));
@@ -196,7 +211,7 @@ struct HubertPlan {
   int T[7];      // frames after conv i
   int Tpad[7];   // allocated rows per clip (even)
   long long off_wave, off_stats, off_ping, off_pong, off_x, off_xs, off_xn, off_qkv, off_h, off_acc,
-      off_cu, total;
+      off_vt, off_cu, total;
   long long M;
 };
 
@@ -222,6 +237,7 @@ static HubertPlan hubert_plan(int B, int L) {
   p.off_qkv = o;   o += al(p.M * DQKV * 4);
   p.off_h = o;     o += al(p.M * DFF * 4);
   p.off_acc = o;   o += al(p.M * D * 4);
+  p.off_vt = o;    o += al((long long)D * ((p.M + 3) & ~3ll) * 4);
   p.off_cu = o;    o += al(((long long)B + 1) * 4);
   p.total = o;
   return p;
@@ -326,6 +342,8 @@ int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L,
   a.h = h;
   a.acc = acc;
   a.acc_last = 4;
+  a.vt = reinterpret_cast<float*>(ws + p.off_vt);
+  a.vt_ld = (M + 3) & ~3ll;
   a.opt_hidden = opt_hidden;
   a.hidden0_done = 1;
   MER_TRY(mer_run_stack(a, stream));
@@ -341,7 +359,7 @@ int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L,
 // ------------------------------------------------------------------------------------------------
 long long mer_bert_workspace_bytes(int tokens, int n_seq) {
   const long long M = tokens;
-  return M * (D + D + D + DQKV + DFF + D) * 4 + 4096;
+  return (M * (D + D + D + DQKV + DFF + D) + (long long)D * ((M + 3) & ~3ll)) * 4 + 4096;
 }
 
 int mer_bert_forward(const MerBertModel* m, const int32_t* ids, const int32_t* pos_ids,
@@ -363,6 +381,7 @@ int mer_bert_forward(const MerBertModel* m, const int32_t* ids, const int32_t* p
   float* qkv = xn + M * D;
   float* h = qkv + M * DQKV;
   float* acc = h + M * DFF;
+  float* vt = acc + M * D;
   MER_TRY(mer_bert_embed_launch(ids, pos_ids, m->word_emb, m->pos_emb, m->type_emb0, m->emb_ln_g,
                                 m->emb_ln_b, m->ln_eps, tokens, x, xs, stream));
   if (opt_hidden)
@@ -385,6 +404,8 @@ int mer_bert_forward(const MerBertModel* m, const int32_t* ids, const int32_t* p
   a.h = h;
   a.acc = acc;
   a.acc_last = 4;
+  a.vt = vt;
+  a.vt_ld = (M + 3) & ~3ll;
   a.opt_hidden = opt_hidden;
   a.hidden0_done = 1;
   MER_TRY(mer_run_stack(a, stream));

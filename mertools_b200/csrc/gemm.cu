@@ -276,6 +276,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           __syncwarp();
         }
         tmem_ld_wait();
+        // columns of the transposed side output (V^T of the QKV GEMM): lanes = consecutive rows, so
+        // each scalar store instruction is one contiguous 128-byte run of vt
+        const bool to_vt = ep.vt != nullptr && n0 >= ep.vt_col0;
+        float* vt_col = to_vt ? ep.vt + (long long)(n0 - ep.vt_col0) * ep.vt_ld +
+                                    ((long long)b * ep.out_bstride + ep.out_row0 + m0 + lane)
+                              : nullptr;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 v;
@@ -292,6 +298,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (res_base) {
             v.x += rr[j].x; v.y += rr[j].y; v.z += rr[j].z; v.w += rr[j].w;
           }
+          if (to_vt) {
+            if (do_round) {
+              v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+            }
+            if (lane < rows_left) {
+              vt_col[(long long)(4 * j + 0) * ep.vt_ld] = v.x;
+              vt_col[(long long)(4 * j + 1) * ep.vt_ld] = v.y;
+              vt_col[(long long)(4 * j + 2) * ep.vt_ld] = v.z;
+              vt_col[(long long)(4 * j + 3) * ep.vt_ld] = v.w;
+            }
+            continue;
+          }
           if (do_split) {
             // the row's 128 bytes are [32 x bf16 hi | 32 x bf16 lo]: 8 bytes of each half per j
             const float hx = bf16_round(v.x), hy = bf16_round(v.y), hz = bf16_round(v.z), hw = bf16_round(v.w);
@@ -306,6 +324,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             *slot(lane, j) = v;
           }
         }
+        if (to_vt) continue;
         __syncwarp();
         // coalesced write-out: 4 rows x 128 contiguous bytes per warp instruction
 #pragma unroll

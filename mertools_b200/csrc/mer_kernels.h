@@ -13,11 +13,14 @@ int mer_layernorm_launch(const float* x, const float* gamma, const float* beta, 
                          cudaStream_t stream);
 
 // attention.cu
-int mer_attention_launch(const float* qkv, float* ctx, const int* cu_seqlens, int n_seq,
-                         long long tokens, int max_seqlen, int heads, int flags, cudaStream_t stream);
+int mer_attention_launch(const float* qkv, const float* vt, long long vt_ld, float* ctx,
+                         const int* cu_seqlens, int n_seq, long long tokens, int max_seqlen, int heads,
+                         int flags, cudaStream_t stream);
+bool mer_attention_uses_tc(int max_seqlen);  // the tcgen05 kernel needs V^T from the QKV GEMM
 // attention_tc.cu (tcgen05; max_seqlen <= 256)
-int mer_attention_tc_launch(const float* qkv, float* ctx, const int* cu_seqlens, int n_seq,
-                            long long tokens, int heads, int flags, cudaStream_t stream);
+int mer_attention_tc_launch(const float* qkv, const float* vt, long long vt_ld, float* ctx,
+                            const int* cu_seqlens, int n_seq, long long tokens, int heads, int flags,
+                            cudaStream_t stream);
 
 // helpers.cu
 int mer_vit_patchify_launch(const uint8_t* frames_bgr, int n_frames, float* a_patches,
@@ -54,6 +57,8 @@ struct MerStackArgs {
   float* x;                  // [tokens,768] residual stream (in/out)
   float* xn;                 // [tokens,768] scratch (LN out / attention ctx / pre-LN sum)
   float* xs;                 // BF16X3 only: [tokens,768] slots holding the split copy of x
+  float* vt;                 // [768, vt_ld] V^T for the tcgen05 attention (or null: flash kernel)
+  long long vt_ld;           // >= tokens, multiple of 4
   float* qkv;                // [tokens,2304]
   float* h;                  // [tokens,3072]
   float* acc;                // optional [tokens,768]: sum of the last `acc_last` hidden states

@@ -108,9 +108,10 @@ int mer_layernorm(const float* x, const float* gamma, const float* beta, float* 
                               static_cast<cudaStream_t>(stream));
 }
 
-int mer_attention(const float* qkv, float* ctx, const int32_t* cu_seqlens, int n_seq,
-                  long long tokens, int max_seqlen, int heads, int flags, void* stream) {
-  return mer_attention_launch(qkv, ctx, cu_seqlens, n_seq, tokens, max_seqlen, heads, flags,
+int mer_attention(const float* qkv, const float* vt, long long vt_ld, float* ctx,
+                  const int32_t* cu_seqlens, int n_seq, long long tokens, int max_seqlen, int heads,
+                  int flags, void* stream) {
+  return mer_attention_launch(qkv, vt, vt_ld, ctx, cu_seqlens, n_seq, tokens, max_seqlen, heads, flags,
                               static_cast<cudaStream_t>(stream));
 }
 

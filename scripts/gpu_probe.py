@@ -100,6 +100,21 @@ def sec_gemm():
     ok &= check_gemm("gemm_bias_res", 1000, 768, 3072, bias=True, res=True)
     ok &= check_gemm("gemm_big_256", 20000, 2304, 768, bias=True, force=256)
     ok &= check_gemm("gemm_big_128", 20000, 768, 768, bias=True, force=128)
+    # transposed side output (V^T of the QKV GEMM)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = tf32(torch.randn(1000, 768, device="cuda", generator=g))
+    W = tf32(torch.randn(2304, 768, device="cuda", generator=g) * 0.05)
+    bq = torch.randn(2304, device="cuda", generator=g)
+    out = torch.full((1000, 2304), float("nan"), device="cuda")
+    vt = torch.full((768, 1000), float("nan"), device="cuda")
+    L.gemm(A, W, out, bias=bq, round_out=True, vt=vt, vt_col0=1536)
+    torch.cuda.synchronize()
+    ref = tf32((A.double() @ W.double().t() + bq.double()).float())
+    e1 = (out[:, :1536] - ref[:, :1536]).abs().max().item()
+    e2 = (vt - ref[:, 1536:].t()).abs().max().item()
+    good = e1 < 2e-2 and e2 < 2e-2 and bool(torch.isnan(out[:, 1536:]).all())
+    emit(check="gemm_vt_side_output", ok=bool(good), err_qk=e1, err_vt=e2)
+    ok &= good
     # CTA pairs with multicast weight tiles (odd and even numbers of row tiles, residual in place)
     ok &= check_gemm("gemm_pair_int", 256, 256, 64, ints=True, force=256, cluster=2)
     ok &= check_gemm("gemm_pair_odd_tiles", 128 * 5 + 7, 768, 768, bias=True, res=True, force=256, cluster=2)
@@ -240,7 +255,10 @@ def sec_attn():
         tot = sum(lens)
         qkv = tf32(torch.randn(tot, 3 * heads * 64, device="cuda") * 1.5)
         ctx = torch.full((tot, heads * 64), float("nan"), device="cuda")
-        L.attention(qkv, ctx, cu, max(lens), heads)
+        ld = (tot + 3) // 4 * 4
+        vt = torch.zeros(heads * 64, ld, device="cuda")
+        vt[:, :tot] = qkv[:, 2 * heads * 64:].t()
+        L.attention(qkv, ctx, cu, max(lens), heads, vt=vt)
         torch.cuda.synchronize()
         err = 0.0
         s0 = 0
@@ -257,7 +275,8 @@ def sec_attn():
     cu = (torch.arange(n_seq + 1, device="cuda", dtype=torch.int32) * 197)
     qkv = torch.randn(n_seq * 197, 2304, device="cuda")
     ctx = torch.empty(n_seq * 197, 768, device="cuda")
-    ms = time_cuda(lambda: L.attention(qkv, ctx, cu, 197, heads, round_out=True), iters=5)
+    vt = qkv[:, 1536:].t().contiguous()
+    ms = time_cuda(lambda: L.attention(qkv, ctx, cu, 197, heads, round_out=True, vt=vt), iters=5)
     flops = n_seq * heads * 4.0 * 197 * 197 * 64
     emit(perf="attention_vit_2048x197", ms=ms, tflops=flops / ms / 1e9)
     return ok
