@@ -49,8 +49,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
                     const __grid_constant__ CUtensorMap tmap_vt, float* __restrict__ ctx,
                     const int* __restrict__ cu_seqlens, int n_seq, int heads, int out_mode) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment by OFFSET (not through an integer round trip) so the compiler keeps the
+  // shared address space of everything derived from it (st.shared / ld.shared, not generic ST / LD)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
   uint64_t* bar_kq = bars + 0;
   uint64_t* bar_v = bars + 1;

@@ -86,8 +86,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             int rows_per_batch, int batches, int N, int K, int K_inner, int P) {
   using Cfg = GemmCfg<BLOCK_N, MODE>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment by OFFSET (not through an integer round trip) so the compiler keeps the
+  // shared address space of everything derived from it (st.shared / ld.shared, not generic ST / LD)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
   uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
