@@ -37,8 +37,8 @@ constexpr int QTILE_BYTES = 2 * 128 * 128;        // one 128-row Q tile: 2 chunk
 constexpr int VT_CHUNK = HD * 128;                // V^T chunk: 64 d-rows x 32 keys (128 B)
 constexpr int SMEM_K = 0;
 constexpr int SMEM_V = 2 * CHUNK_BYTES;           // 8 V^T chunks = 64 KB
-constexpr int SMEM_Q = 4 * CHUNK_BYTES;           // Q tile t; after S_t it becomes the P-chunk / output
-                                                  // staging buffer of tile t (2 x [128 rows][128 B])
+constexpr int SMEM_Q = 4 * CHUNK_BYTES;           // Q tile t; after S_t it becomes the P-chunk buffer of
+                                                  // tile t (2 x [128 rows][128 B])
 constexpr int SMEM_BAR = SMEM_Q + 2 * QTILE_BYTES;
 constexpr int TC_SMEM = SMEM_BAR + 256 + 1024;
 constexpr uint32_t TILE_COLS = 256, TMEM_COLS = 512;  // tile t: S_t at [256t, 256t+NK), O_t aliases its first 64
@@ -62,8 +62,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   uint64_t* bar_pready = bars + 5;  // [2] softmax group t -> MMA: a P chunk of tile t sits in smem
   uint64_t* bar_pfree = bars + 7;   // [2] MMA -> softmax group t: that chunk has been consumed
   uint64_t* bar_ofull = bars + 9;   // [2] MMA -> softmax group t: O_t complete
-  uint64_t* bar_ofree = bars + 11;  // [2] softmax group t -> MMA / producer: O_t read, staging consumed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* bar_ofree = bars + 11;  // [2] softmax group t -> producer: output staging (V^T region) consumed
+  uint64_t* bar_otfree = bars + 13; // [2] softmax group t -> MMA: O_t has been read out of TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = n_seq * heads;
@@ -80,6 +81,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
       mbar_init(&bar_pfree[t], 1);
       mbar_init(&bar_ofull[t], 1);
       mbar_init(&bar_ofree[t], 4);
+      mbar_init(&bar_otfree[t], 4);
     }
     fence_mbar_init();
   }
@@ -115,14 +117,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
           for (int b = 0; b < nb; ++b)
             tma_load_2d(smem + SMEM_K + c * CHUNK_BYTES + b * 16384, &tmap_qkv, bar_k,
                         heads * HD + h * HD + c * 32, a_start + b * 128);
-        // Q tiles and V^T: the previous item's P V MMAs and epilogues are done (the Q_t regions double
-        // as P-chunk and output-staging buffers)
-        for (int t = 0; t < prev_nmt; ++t) mbar_wait(&bar_ofree[t], (uses[t] - 1) & 1);
+        // Q tiles: the previous item's P V MMAs are done (the Q_t regions double as P-chunk buffers)
+        for (int t = 0; t < prev_nmt; ++t) mbar_wait(&bar_ofull[t], (uses[t] - 1) & 1);
         mbar_expect_tx(bar_q, (uint32_t)(n_mt * QTILE_BYTES));
         for (int t = 0; t < n_mt; ++t)
           for (int c = 0; c < 2; ++c)
             tma_load_2d(smem + SMEM_Q + t * QTILE_BYTES + c * 16384, &tmap_qkv, bar_q, h * HD + c * 32,
                         start + t * 128);
+        // V^T: the previous item's epilogues are done (they stage their output in the V^T region)
+        for (int t = 0; t < prev_nmt; ++t) mbar_wait(&bar_ofree[t], (uses[t] - 1) & 1);
         const int n_vc = (Lk + 31) >> 5;
         mbar_expect_tx(bar_v, (uint32_t)(n_vc * VT_CHUNK));
         for (int c = 0; c < n_vc; ++c)
@@ -150,7 +153,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
         mbar_wait(bar_q, item_n & 1);
         // ---- S_t = Q_t K^T for both tiles ----
         for (int t = 0; t < n_mt; ++t) {
-          if (uses[t] > 0) mbar_wait(&bar_ofree[t], (uses[t] - 1) & 1);  // S_t / O_t columns free again
+          if (uses[t] > 0) mbar_wait(&bar_otfree[t], (uses[t] - 1) & 1);  // S_t / O_t columns free again
           tc_fence_after();
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -194,7 +197,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
     const int r_tile = q * 32 + lane;  // row inside the 128-row tile
     float* p_lo = reinterpret_cast<float*>(smem + SMEM_Q + grp * QTILE_BYTES) + r_tile * 32;
     float* p_hi = p_lo + 4096;         // second 32-key sub-chunk ([128][32] floats further)
-    float* stg = reinterpret_cast<float*>(smem + SMEM_Q + grp * QTILE_BYTES) + q * 32 * 32;  // this warp's rows
+    // output staging: 32 KB of the V^T region per tile (V^T is dead once O_t is complete)
+    float* o_lo = reinterpret_cast<float*>(smem + SMEM_V + grp * QTILE_BYTES) + r_tile * 32;
+    float* o_hi = o_lo + 4096;
+    float* stg = reinterpret_cast<float*>(smem + SMEM_V + grp * QTILE_BYTES) + q * 32 * 32;  // this warp's rows
     const int sub_r = lane >> 3, sub_c = lane & 7;
     uint32_t uses = 0, G = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
@@ -258,10 +264,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
       tmem_ld_32x32(t_lane, o0);
       tmem_ld_32x32(t_lane + 32, o1);
       tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_otfree[grp]);  // the MMA warp may start the next item's S_t
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const uint32_t* o = half ? o1 : o0;
-        float* dst_row = (half ? p_hi : p_lo);
+        float* dst_row = (half ? o_hi : o_lo);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 v = make_float4(__uint_as_float(o[4 * j]) * inv, __uint_as_float(o[4 * j + 1]) * inv,
@@ -297,7 +306,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
         }
       }
       (void)row;
-      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_ofree[grp]);
       ++uses;
