@@ -91,7 +91,8 @@ typedef struct MerGemmDesc {
   long long a_batch_stride;
   int force_block_n; /* 0 = auto, 128 or 256 */
   int mode;          /* MER_GEMM_TF32 | MER_GEMM_BF16X3; all A strides are in 4-byte slots either way */
-  int cluster;       /* 0 = auto, 1 = single CTAs, 2 = CTA pairs sharing a multicast weight tile */
+  int cluster;       /* 0 = auto, 1 = single CTAs, 2 = CTA pairs sharing a multicast weight tile,
+                        3 = CTA pairs issuing one 256-row tcgen05.mma.cta_group::2 per K step */
   MerGemmEpilogue ep;
 } MerGemmDesc;
 

@@ -26,6 +26,8 @@
 //                     kind::f16 MMAs per 16-wide K step (hi*hi + lo*hi + hi*lo), fp32 accumulate.
 //                     ~2e-5 relative error per GEMM: what the post-LN HuBERT/BERT stacks need to stay
 //                     inside 1e-3 after 12 layers (measured: single-pass TF32 reaches 1.0e-3 after 4).
+#include <stdlib.h>
+
 #include <vector>
 
 #include "mer_common.cuh"
@@ -49,16 +51,17 @@ constexpr int NUM_THREADS = 384;  // 4 control warps + 8 epilogue warps
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_WARPS = 8;      // two per TMEM lane quarter, each taking half of the tile's columns
 
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, bool TWOSM = false>
 struct GemmCfg {
   static constexpr bool kSplit = MODE == MER_GEMM_BF16X3;
   static constexpr int kRowBytes = 128;                 // bytes of K per smem row = swizzle span
   static constexpr int kSBO = 8 * kRowBytes;            // byte stride between 8-row core groups
   static constexpr int kLayout = 2;                     // UMMA LayoutType SWIZZLE_128B
   static constexpr int kFmt = kSplit ? 1 : 2;           // instr-desc operand format: bf16 / tf32
-  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  // TWOSM (cta_group::2): each CTA of the pair keeps only ITS half of the weight tile in smem
+  static constexpr int kStages = (BLOCK_N == 256 && !TWOSM) ? 4 : 6;
   static constexpr int kABytes = BLOCK_M * kRowBytes;
-  static constexpr int kBBytes = BLOCK_N * kRowBytes;
+  static constexpr int kBBytes = (TWOSM ? BLOCK_N / 2 : BLOCK_N) * kRowBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N;
   static constexpr int kBarBytes = 256;
@@ -79,12 +82,18 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, int sbo_bytes,
 // CLUSTER == 2: a pair of CTAs works on two vertically adjacent 128-row tiles of the same BLOCK_N
 // column block; each loads its own A tile and HALF of the shared B tile, multicast into both CTAs'
 // shared memory (L2 -> SM traffic per CTA drops from 128+BLOCK_N to 128+BLOCK_N/2 rows per stage).
-template <int BLOCK_N, int MODE, int CLUSTER>
+// TWOSM (requires CLUSTER == 2): the pair issues ONE tcgen05.mma.cta_group::2 of shape 256 x BLOCK_N
+// per K step from the even ("leader") CTA.  Each CTA loads its own 128 A rows and its own half of the
+// weight tile into its own smem (TMA .cta_group::2, completing on the leader's barrier), so per SM
+// and stage the TMA writes 32 KB instead of 48 KB and the tensor core reads 8 KB instead of 12 KB per
+// MMA: the single-CTA form is shared-memory-bandwidth bound at ~2/3 of the tensor peak (measured).
+template <int BLOCK_N, int MODE, int CLUSTER, bool TWOSM>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             const __grid_constant__ CUtensorMap tmap_b, const MerGemmEpilogue ep,
             int rows_per_batch, int batches, int N, int K, int K_inner, int P) {
-  using Cfg = GemmCfg<BLOCK_N, MODE>;
+  using Cfg = GemmCfg<BLOCK_N, MODE, TWOSM>;
+  static_assert(!TWOSM || CLUSTER == 2, "the 2-SM MMA needs CTA pairs");
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by OFFSET (not through an integer round trip) so the compiler keeps the
   // shared address space of everything derived from it (st.shared / ld.shared, not generic ST / LD)
@@ -118,18 +127,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], CLUSTER);  // one tcgen05.commit arrival per CTA of the cluster
+      mbar_init(&full_bar[i], TWOSM ? 2 : 1);       // 2-SM: one expect-tx arrival per CTA, on the leader
+      mbar_init(&empty_bar[i], TWOSM ? 1 : CLUSTER);  // commit arrivals (2-SM: one multicast commit)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], EPI_WARPS * (TWOSM ? 2 : 1));  // one arrive per epilogue warp (of the pair)
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (TWOSM) {
+      tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   if (CLUSTER > 1) cluster_sync_all(); else __syncthreads();
@@ -148,11 +162,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int mt = mb % m_tiles;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           const int kk = kb * BLOCK_K;
           const int tap = kk / K_inner;
           const int c0 = kk - tap * K_inner;
           constexpr int kEl = Cfg::kSplit ? 2 : 1;  // tensor-map elements per operand value
+          if (TWOSM) {
+            const uint32_t lbar = leader_addr(&full_bar[stage]);
+            mbar_expect_tx_cluster(lbar, Cfg::kStageBytes);
+            tma_load_4d_2sm(smem_a + stage * Cfg::kABytes, &tmap_a, lbar, c0 * kEl, tap % P,
+                            mt * BLOCK_M + tap / P, b);
+            tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &tmap_b, lbar, kk * kEl,
+                            n_blk * BLOCK_N + cta_rank * (BLOCK_N / 2));
+            if (++stage == Cfg::kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], c0 * kEl, tap % P,
                       mt * BLOCK_M + tap / P, b);
           if (CLUSTER == 1) {
@@ -172,8 +199,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(Cfg::kFmt, BLOCK_M, BLOCK_N);
+    if (lane == 0 && (!TWOSM || cta_rank == 0)) {
+      constexpr uint32_t idesc = umma_idesc(Cfg::kFmt, TWOSM ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -190,25 +217,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           // advance the start address by 32-byte K steps inside the 128B swizzle row (>>4 => +2)
           if (!Cfg::kSplit) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)  // 4 x 8 tf32
-              tc_mma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < 4; ++k) {  // 4 x 8 tf32
+              if (TWOSM) tc_mma_tf32_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+              else tc_mma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            }
           } else {
 #pragma unroll
             for (int k = 0; k < 2; ++k) {  // 2 x 16 bf16; hi at bytes [0,64), lo at [64,128) of the row
-              tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);  // hi * hi
-              tc_mma_bf16(d_tmem, da + 4 + 2 * k, db + 2 * k, idesc, 1);          // lo * hi
-              tc_mma_bf16(d_tmem, da + 2 * k, db + 4 + 2 * k, idesc, 1);          // hi * lo
+              if (TWOSM) {
+                tc_mma_bf16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                tc_mma_bf16_2sm(d_tmem, da + 4 + 2 * k, db + 2 * k, idesc, 1);
+                tc_mma_bf16_2sm(d_tmem, da + 2 * k, db + 4 + 2 * k, idesc, 1);
+              } else {
+                tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);  // hi * hi
+                tc_mma_bf16(d_tmem, da + 4 + 2 * k, db + 2 * k, idesc, 1);          // lo * hi
+                tc_mma_bf16(d_tmem, da + 2 * k, db + 4 + 2 * k, idesc, 1);          // hi * lo
+              }
             }
           }
-          // free the smem slot when these MMAs retire (in every CTA that multicasts into it)
-          if (CLUSTER == 1) tc_commit(&empty_bar[stage]);
+          // free the smem slot when these MMAs retire (in every CTA that writes into it / owns a copy)
+          if (TWOSM) tc_commit_2sm(&empty_bar[stage]);
+          else if (CLUSTER == 1) tc_commit(&empty_bar[stage]);
           else tc_commit_mc(&empty_bar[stage], (uint16_t)((1u << CLUSTER) - 1));
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        tc_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        if (TWOSM) tc_commit_2sm(&tfull_bar[as]);  // accumulator complete -> both CTAs' epilogues
+        else tc_commit(&tfull_bar[as]);           // accumulator complete -> epilogue
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
@@ -294,7 +331,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             v.x += bb[j].x; v.y += bb[j].y; v.z += bb[j].z; v.w += bb[j].w;
           }
           if (do_gelu) {
-            v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+            v.x = gelu_erf_fast(v.x); v.y = gelu_erf_fast(v.y); v.z = gelu_erf_fast(v.z); v.w = gelu_erf_fast(v.w);
           }
           if (res_base) {
             v.x += rr[j].x; v.y += rr[j].y; v.z += rr[j].z; v.w += rr[j].w;
@@ -340,7 +377,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       // all TMEM reads of this stage are complete (wait::ld above) -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (TWOSM) mbar_arrive_cluster(leader_addr(&tempty_bar[as]));  // the leader's MMA warp waits for both CTAs
+        else mbar_arrive(&tempty_bar[as]);
+      }
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
@@ -353,13 +393,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (CLUSTER > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (TWOSM) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int BLOCK_N, int MODE, int CLUSTER>
+template <int BLOCK_N, int MODE, int CLUSTER, bool TWOSM = false>
 int launch_gemm(const MerGemmDesc* g, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, MODE>;
+  using Cfg = GemmCfg<BLOCK_N, MODE, TWOSM>;
   CUtensorMap ta, tb;
   const CUtensorMapDataType dt =
       Cfg::kSplit ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
@@ -385,7 +426,7 @@ int launch_gemm(const MerGemmDesc* g, cudaStream_t stream) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    MER_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BLOCK_N, MODE, CLUSTER>,
+    MER_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BLOCK_N, MODE, CLUSTER, TWOSM>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes));
     attr_set = true;
@@ -422,7 +463,7 @@ int launch_gemm(const MerGemmDesc* g, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    MER_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<BLOCK_N, MODE, CLUSTER>, ta, tb, g->ep,
+    MER_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<BLOCK_N, MODE, CLUSTER, TWOSM>, ta, tb, g->ep,
                                       g->rows_per_batch, g->batches, g->N, g->K_inner * g->taps,
                                       g->K_inner, g->P));
   }
@@ -457,12 +498,18 @@ int mer_gemm_launch(const MerGemmDesc* g, cudaStream_t stream) {
   const bool wide = (tiles256 >= mer_num_sms() && g->force_block_n != 128) ||
                     (g->force_block_n == 256 && tiles256 > 0);
   // CTA pairs with a multicast B tile once there is more than a wave of 128x256 tiles
-  const bool pair = wide && g->cluster != 1 && (g->cluster == 2 || tiles256 >= 2 * mer_num_sms());
+  const bool pair = wide && g->cluster != 1 && (g->cluster >= 2 || tiles256 >= 2 * mer_num_sms());
+  // CTA pairs issue cta_group::2 MMAs by default (measured +3..9% over single-CTA MMAs with a multicast
+  // weight tile); MER_GEMM_NO_2SM=1 or cluster == 2 selects the multicast variant
+  static const bool no_twosm_env = getenv("MER_GEMM_NO_2SM") != nullptr;
+  const bool twosm = pair && (g->cluster == 3 || (g->cluster == 0 && !no_twosm_env));
   if (g->mode == MER_GEMM_BF16X3) {
+    if (twosm) return launch_gemm<256, MER_GEMM_BF16X3, 2, true>(g, stream);
     if (pair) return launch_gemm<256, MER_GEMM_BF16X3, 2>(g, stream);
     return wide ? launch_gemm<256, MER_GEMM_BF16X3, 1>(g, stream)
                 : launch_gemm<128, MER_GEMM_BF16X3, 1>(g, stream);
   }
+  if (twosm) return launch_gemm<256, MER_GEMM_TF32, 2, true>(g, stream);
   if (pair) return launch_gemm<256, MER_GEMM_TF32, 2>(g, stream);
   return wide ? launch_gemm<256, MER_GEMM_TF32, 1>(g, stream) : launch_gemm<128, MER_GEMM_TF32, 1>(g, stream);
 }

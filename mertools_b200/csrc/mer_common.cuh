@@ -151,6 +151,78 @@ __device__ __forceinline__ void tma_load_2d_mc(void* smem, const CUtensorMap* m,
       : "memory");
 }
 
+// ---- CTA-pair (cta_group::2) forms: the pair's barriers live in the even ("leader") CTA; clearing bit
+// 24 of a shared-window address turns a CTA-local barrier address into the leader's copy of it ----
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t leader_addr(const void* p) { return smem_u32(p) & kPeerBitMask; }
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem, const CUtensorMap* m, uint32_t bar_addr,
+                                                int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(void* smem, const CUtensorMap* m, uint32_t bar_addr,
+                                                int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+// commit of the pair's MMAs, arriving on the barrier at this offset in both CTAs
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+          "r"(smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+// D[tmem of both CTAs] (+)= A[2 x 128 rows, one half per CTA] * B[N rows, one half per CTA]
+__device__ __forceinline__ void tc_mma_tf32_2sm(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // ---- thread-block clusters ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -302,6 +374,22 @@ __device__ __forceinline__ void store_split1(void* row_base, int col, float v) {
 // exact (erf) GELU, as torch.nn.functional.gelu default
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+// erf-GELU for the GEMM epilogues, where the libdevice erff (~30 instructions, two branches) made the
+// FC1 epilogue as long as its mainloop: Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7 in exact
+// arithmetic); measured in fp32 over [-12, 12]: |gelu error| <= 4.7e-7 absolute, <= 2.9e-7 * |x| —
+// three orders of magnitude below the TF32 / split-bf16 operand rounding that follows.
+// One MUFU.RCP, one MUFU.EX2, 8 FMA-class ops.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = exp2f(-1.4426950408889634f * z * z);
+  const float erf_abs = fmaf(-p * t, e, 1.0f);  // erf(|x| / sqrt 2)
+  return 0.5f * x + 0.5f * fabsf(x) * erf_abs;   // x/2 * (1 + sign(x) erf(|x|/sqrt 2))
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

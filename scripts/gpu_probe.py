@@ -158,6 +158,31 @@ def sec_gemm_x3():
     return ok
 
 
+def sec_gemm_2sm():
+    """cta_group::2 variant: correctness, then speed against the single-CTA-MMA pair kernel."""
+    ok = True
+    ok &= check_gemm("2sm_int", 256, 256, 64, ints=True, force=256, cluster=3)
+    ok &= check_gemm("2sm_odd_tiles", 128 * 5 + 7, 768, 768, bias=True, res=True, force=256, cluster=3)
+    ok &= check_gemm("2sm_big", 40000, 2304, 768, bias=True, rnd=True, cluster=3)
+    ok &= check_gemm("2sm_fc2", 40000, 768, 3072, bias=True, res=True, cluster=3)
+    for (name, M, N, K, kw) in [("qkv", 100864, 2304, 768, dict(rnd=True)), ("outproj", 100864, 768, 768, dict(res=True)),
+                                ("fc1", 100864, 3072, 768, dict(gelu=True, rnd=True)), ("fc2", 100864, 768, 3072, dict(res=True)),
+                                ("fc1_full", 403456, 3072, 768, dict(gelu=True, rnd=True))]:
+        A = tf32(torch.randn(M, K, device="cuda"))
+        W = tf32(torch.randn(N, K, device="cuda") * 0.02)
+        b = torch.randn(N, device="cuda")
+        R = torch.randn(M, N, device="cuda") if kw.get("res") else None
+        out = torch.empty(M, N, device="cuda")
+        res = {}
+        for cl in (2, 3):
+            ms = time_cuda(lambda: L.gemm(A, W, out, bias=b, res=R, gelu=kw.get("gelu", False),
+                                          round_out=kw.get("rnd", False), cluster=cl), iters=10)
+            res[cl] = 2.0 * M * N * K / ms / 1e9
+        emit(perf=name, tflops_pair=res[2], tflops_2sm=res[3])
+        del A, W, out, R
+    return ok
+
+
 def sec_conv():
     """Conv1d(k=3,s=2) and (k=2,s=2) over time-major activations through the tap-aware A map."""
     ok = True
@@ -294,7 +319,7 @@ def sec_vit():
     return True
 
 
-SECTIONS = dict(vit=sec_vit, gemm_x3=sec_gemm_x3, gemm=sec_gemm, conv=sec_conv, gemm_perf=sec_gemm_perf, ln=sec_ln, attn=sec_attn)
+SECTIONS = dict(vit=sec_vit, gemm_x3=sec_gemm_x3, gemm_2sm=sec_gemm_2sm, gemm=sec_gemm, conv=sec_conv, gemm_perf=sec_gemm_perf, ln=sec_ln, attn=sec_attn)
 
 if __name__ == "__main__":
     os.makedirs("gpurun_out", exist_ok=True)
