@@ -44,7 +44,8 @@ MER_API int mer_profile_enable(int on);
 MER_API int mer_profile_collect(int mode, double* total_ms, double* total_flops, int* launches);
 
 /* ---- GEMM (nn.Linear / Conv1d-as-GEMM / patch-embed) ---------------------------------- */
-enum { MER_EPI_GELU = 1, MER_EPI_ROUND_TF32 = 2, MER_EPI_SPLIT_BF16 = 4 };
+enum { MER_EPI_GELU = 1, MER_EPI_ROUND_TF32 = 2, MER_EPI_SPLIT_BF16 = 4,
+       MER_EPI_GELU_LIBM = 8 /* with MER_EPI_GELU: libdevice erff instead of the 12-op polynomial */ };
 /* Arithmetic mode of a GEMM.  TF32: operands are fp32 arrays (pre-rounded to tf32).  BF16X3: every
  * operand value x is stored as a bf16 pair (hi, lo), x = hi + lo to 2^-17; a row of K values (K % 32
  * == 0) occupies the bytes K fp32 values would, as 128-byte groups [32 x hi | 32 x lo]; three bf16

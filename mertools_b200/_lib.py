@@ -111,7 +111,7 @@ def gemm(A, W, out, *, bias=None, res=None, gelu=False, round_out=False, split_o
          mode=MER_GEMM_TF32, rows_per_batch=None, batches=1, a_rows_dim=None, K_inner=None, taps=1, P=1,
          a_phase_stride=0, a_row_stride=None, a_batch_stride=0,
          out_bstride=0, out_row0=0, res_bstride=0, res_row0=0,
-         ld_out=None, ld_res=None, force_block_n=0, cluster=0, vt=None, vt_col0=0):
+         ld_out=None, ld_res=None, force_block_n=0, cluster=0, vt=None, vt_col0=0, gelu_libm=False):
     """out = epilogue(A @ W.T).  A, W: fp32 CUDA tensors of LOGICAL shape [rows, K] / [N, K] (holding
     tf32-rounded fp32, or split bf16 hi|lo bytes when mode is BF16X3); see MerGemmDesc in mer_b200.h."""
     N, K = W.shape
@@ -138,7 +138,7 @@ def gemm(A, W, out, *, bias=None, res=None, gelu=False, round_out=False, split_o
     d.ep.ld_out = ld_out if ld_out is not None else N
     d.ep.ld_res = ld_res if ld_res is not None else N
     d.ep.flags = ((MER_EPI_GELU if gelu else 0) | (MER_EPI_ROUND_TF32 if round_out else 0)
-                  | (MER_EPI_SPLIT_BF16 if split_out else 0))
+                  | (MER_EPI_SPLIT_BF16 if split_out else 0) | (8 if gelu_libm else 0))
     d.ep.split_off = N
     if vt is not None:
         d.ep.vt, d.ep.vt_ld, d.ep.vt_col0 = vt.data_ptr(), vt.shape[1], vt_col0

@@ -268,6 +268,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     int as = 0;
     uint32_t aphase = 0;
     const bool do_gelu = (ep.flags & MER_EPI_GELU) != 0;
+    const bool gelu_libm = (ep.flags & MER_EPI_GELU_LIBM) != 0;
     const bool do_round = (ep.flags & MER_EPI_ROUND_TF32) != 0;
     const bool do_split = (ep.flags & MER_EPI_SPLIT_BF16) != 0;
     for (int t = first_tile; t < num_tiles; t += tile_step) {
@@ -331,7 +332,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             v.x += bb[j].x; v.y += bb[j].y; v.z += bb[j].z; v.w += bb[j].w;
           }
           if (do_gelu) {
-            v.x = gelu_erf_fast(v.x); v.y = gelu_erf_fast(v.y); v.z = gelu_erf_fast(v.z); v.w = gelu_erf_fast(v.w);
+            if (gelu_libm) {
+              v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+            } else {
+              v.x = gelu_erf_fast(v.x); v.y = gelu_erf_fast(v.y); v.z = gelu_erf_fast(v.z); v.w = gelu_erf_fast(v.w);
+            }
           }
           if (res_base) {
             v.x += rr[j].x; v.y += rr[j].y; v.z += rr[j].z; v.w += rr[j].w;

@@ -382,14 +382,16 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // One MUFU.RCP, one MUFU.EX2, 8 FMA-class ops.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  const float e = exp2f(-1.4426950408889634f * z * z);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
   const float erf_abs = fmaf(-p * t, e, 1.0f);  // erf(|x| / sqrt 2)
-  return 0.5f * x + 0.5f * fabsf(x) * erf_abs;   // x/2 * (1 + sign(x) erf(|x|/sqrt 2))
+  const float hx = 0.5f * x;
+  return fmaf(fabsf(hx), erf_abs, hx);           // x/2 * (1 + sign(x) erf(|x|/sqrt 2))
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -183,6 +183,25 @@ def sec_gemm_2sm():
     return ok
 
 
+def sec_gelu_ab():
+    """A/B in one process: polynomial vs libdevice erf in the FC1 epilogue, interleaved repeats."""
+    M, N, K = 403456, 3072, 768
+    A = tf32(torch.randn(M, K, device="cuda"))
+    W = tf32(torch.randn(N, K, device="cuda") * 0.02)
+    b = torch.randn(N, device="cuda")
+    out = torch.empty(M, N, device="cuda")
+    for rep in range(3):
+        r = {}
+        for name, kw in (("poly", {}), ("libm", dict(gelu_libm=True)), ("nogelu", None)):
+            if kw is None:
+                fn = lambda: L.gemm(A, W, out, bias=b, round_out=True)  # noqa: E731
+            else:
+                fn = lambda kw=kw: L.gemm(A, W, out, bias=b, gelu=True, round_out=True, **kw)  # noqa: E731
+            r[name] = 2.0 * M * N * K / time_cuda(fn, iters=8) / 1e9
+        emit(perf="fc1_full_gelu_ab", rep=rep, **r)
+    return True
+
+
 def sec_conv():
     """Conv1d(k=3,s=2) and (k=2,s=2) over time-major activations through the tap-aware A map."""
     ok = True
@@ -319,7 +338,7 @@ def sec_vit():
     return True
 
 
-SECTIONS = dict(vit=sec_vit, gemm_x3=sec_gemm_x3, gemm_2sm=sec_gemm_2sm, gemm=sec_gemm, conv=sec_conv, gemm_perf=sec_gemm_perf, ln=sec_ln, attn=sec_attn)
+SECTIONS = dict(vit=sec_vit, gemm_x3=sec_gemm_x3, gemm_2sm=sec_gemm_2sm, gelu_ab=sec_gelu_ab, gemm=sec_gemm, conv=sec_conv, gemm_perf=sec_gemm_perf, ln=sec_ln, attn=sec_attn)
 
 if __name__ == "__main__":
     os.makedirs("gpurun_out", exist_ok=True)
