@@ -118,7 +118,7 @@ conv0_apply_kernel(const float* __restrict__ wave, long long ld_wave, const floa
     float y = 0.f;
 #pragma unroll
     for (int k = 0; k < K0; ++k) y = fmaf(w[k], xs[t * S0 + k], y);
-    const float v = gelu_erf((y - mean) * g + bt);
+    const float v = gelu_erf_fast((y - mean) * g + bt);
     if (split_out) store_split1(orow + (long long)t * C0, c, v);
     else orow[(long long)t * C0 + c] = round_tf32(v);
   }

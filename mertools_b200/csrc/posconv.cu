@@ -137,13 +137,13 @@ posconv_kernel(const float* __restrict__ x0, const float* __restrict__ wp,
     if (f_lo < len) {
       const long long off = (long long)(start + f_lo) * 768 + col;
       const float2 r = *reinterpret_cast<const float2*>(x0 + off);
-      float2 o = make_float2(r.x + gelu_erf(acc[nt][0] + b0), r.y + gelu_erf(acc[nt][1] + b1));
+      float2 o = make_float2(r.x + gelu_erf_fast(acc[nt][0] + b0), r.y + gelu_erf_fast(acc[nt][1] + b1));
       *reinterpret_cast<float2*>(x1 + off) = o;
     }
     if (f_hi < len) {
       const long long off = (long long)(start + f_hi) * 768 + col;
       const float2 r = *reinterpret_cast<const float2*>(x0 + off);
-      float2 o = make_float2(r.x + gelu_erf(acc[nt][2] + b0), r.y + gelu_erf(acc[nt][3] + b1));
+      float2 o = make_float2(r.x + gelu_erf_fast(acc[nt][2] + b0), r.y + gelu_erf_fast(acc[nt][3] + b1));
       *reinterpret_cast<float2*>(x1 + off) = o;
     }
   }
