@@ -59,14 +59,17 @@ struct GemmCfg {
   static constexpr int kLayout = 2;                     // UMMA LayoutType SWIZZLE_128B
   static constexpr int kFmt = kSplit ? 1 : 2;           // instr-desc operand format: bf16 / tf32
   // TWOSM (cta_group::2): each CTA of the pair keeps only ITS half of the weight tile in smem
-  static constexpr int kStages = (BLOCK_N == 256 && !TWOSM) ? 4 : 6;
+  // stage count: what fits beside the epilogue's 68 KB of staging (227 KB usable per CTA)
+  static constexpr int kStages = TWOSM ? 4 : (BLOCK_N == 256 ? 3 : 4);
   static constexpr int kABytes = BLOCK_M * kRowBytes;
   static constexpr int kBBytes = (TWOSM ? BLOCK_N / 2 : BLOCK_N) * kRowBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N;
   static constexpr int kBarBytes = 256;
-  static constexpr int kStagingBytes = 8 * 4096;  // one 32 x 128 B transpose buffer per epilogue warp
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;  // +align slack
+  // per epilogue warp: a 32 x 128 B output transpose tile and a 32 x 128 B residual prefetch tile
+  static constexpr int kStagingBytes = 8 * 8192;
+  static constexpr int kBiasBytes = 8 * 512;  // per epilogue warp: its half of the tile's bias values
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBiasBytes + kBarBytes + 1024;
 };
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, int sbo_bytes, int layout) {
@@ -101,7 +104,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
   uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
+  float* bias_smem = reinterpret_cast<float*>(staging + Cfg::kStagingBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes + Cfg::kBiasBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + Cfg::kStages;
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;
@@ -259,11 +263,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // load / store touches 4 rows x 128 contiguous bytes instead of 32 rows x 16 bytes.
     const int ew = (warp - EPI_WARP0) & 3;      // == warp % 4: the TMEM lane quarter this warp may read
     const int chalf = (warp - EPI_WARP0) >> 2;  // which half of the tile's columns this warp handles
-    float* stg = reinterpret_cast<float*>(staging) + (warp - EPI_WARP0) * 1024;
+    float* stg = reinterpret_cast<float*>(staging) + (warp - EPI_WARP0) * 2048;  // output transpose tile
+    float* stg_r = stg + 1024;                                                    // residual prefetch tile
+    float* bias_s = bias_smem + (warp - EPI_WARP0) * 128;  // private: warps drift across tile boundaries
     const int sub_r = lane >> 3;  // row within a group of 4 rows (coalesced phase)
     const int sub_c = lane & 7;   // 16-byte slot within the 128-byte row (coalesced phase)
     auto slot = [&](int row, int j) -> float4* {
       return reinterpret_cast<float4*>(stg + row * 32 + ((j ^ (row & 7)) << 2));
+    };
+    auto slot_r = [&](int row, int j) -> float4* {
+      return reinterpret_cast<float4*>(stg_r + row * 32 + ((j ^ (row & 7)) << 2));
     };
     int as = 0;
     uint32_t aphase = 0;
@@ -282,38 +291,45 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const float* res_base =
           ep.res ? ep.res + ((long long)b * ep.res_bstride + ep.res_row0 + m0) * (long long)ep.ld_res
                  : nullptr;
+      // asynchronous coalesced fetch of a 32 x 32 residual tile into the swizzled prefetch tile
+      auto prefetch_res = [&](int c) {
+        const int n0 = n_blk * BLOCK_N + c * 32;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = 4 * i + sub_r;
+          const int ok = row < rows_left ? 16 : 0;
+          const float* src = res_base + (long long)(ok ? row : 0) * ep.ld_res + n0 + sub_c * 4;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(slot_r(row, sub_c))),
+                       "l"(src), "r"(ok)
+                       : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      const int c_first = chalf * (BLOCK_N / 64), c_last = (chalf + 1) * (BLOCK_N / 64);
+      // while the accumulator is still being produced: this tile's bias slice and the first residual tile
+      if (ep.bias && lane < BLOCK_N / 8)
+        *reinterpret_cast<float4*>(bias_s + lane * 4) =
+            __ldg(reinterpret_cast<const float4*>(ep.bias + n_blk * BLOCK_N + chalf * (BLOCK_N / 2)) + lane);
+      if (res_base) prefetch_res(c_first);
+      __syncwarp();
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(ew * 32) << 16) + as * BLOCK_N;
 #pragma unroll 1
-      for (int c = chalf * (BLOCK_N / 64); c < (chalf + 1) * (BLOCK_N / 64); ++c) {
+      for (int c = c_first; c < c_last; ++c) {
         uint32_t r[32];
         tmem_ld_32x32(t_row + c * 32, r);
         const int n0 = n_blk * BLOCK_N + c * 32;
-        // residual tile: coalesced loads (row 4i + sub_r, slot sub_c), issued before anything else
         float4 rr[8];
-        if (res_base) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = 4 * i + sub_r;
-            rr[i] = (row < rows_left)
-                        ? *reinterpret_cast<const float4*>(res_base + (long long)row * ep.ld_res + n0 + sub_c * 4)
-                        : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-        float4 bb[8];
-        if (ep.bias) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) bb[j] = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + j);
-        }
-        if (res_base) {  // transpose the residual tile: coalesced layout -> one row per thread
-#pragma unroll
-          for (int i = 0; i < 8; ++i) *slot(4 * i + sub_r, sub_c) = rr[i];
+        if (res_base) {  // residual tile c has landed: one row per thread, then start fetching tile c+1
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
           __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) rr[j] = *slot(lane, j);
+          for (int j = 0; j < 8; ++j) rr[j] = *slot_r(lane, j);
           __syncwarp();
+          if (c + 1 < c_last) prefetch_res(c + 1);
         }
+        const float* bias_c = bias_s + (c - c_first) * 32;
         tmem_ld_wait();
         // columns of the transposed side output (V^T of the QKV GEMM): lanes = consecutive rows, so
         // each scalar store instruction is one contiguous 128-byte run of vt
@@ -329,7 +345,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           v.z = __uint_as_float(r[4 * j + 2]);
           v.w = __uint_as_float(r[4 * j + 3]);
           if (ep.bias) {
-            v.x += bb[j].x; v.y += bb[j].y; v.z += bb[j].z; v.w += bb[j].w;
+            const float4 q = *reinterpret_cast<const float4*>(bias_c + 4 * j);  // smem broadcast
+            v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
           }
           if (do_gelu) {
             if (gelu_libm) {
