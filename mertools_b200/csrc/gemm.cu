@@ -13,7 +13,7 @@
 //   warp 0      TMA producer: A/B tiles -> swizzled smem ring (mbarrier full/empty)
 //   warp 1      MMA issuer  : tcgen05.mma, UMMA 128 x BLOCK_N x (32 bytes of K), fp32 accum in TMEM
 //   warp 2      TMEM allocator
-//   warps 4..11 epilogue    : tcgen05.ld TMEM -> registers -> bias/GELU/residual -> swizzled smem
+//   warps 4..19 epilogue    : tcgen05.ld TMEM -> registers -> bias/GELU -> swizzled smem -> +residual
 //                             transpose -> 512-byte coalesced st.global (two warps per TMEM lane
 //                             quarter, half of the columns each)
 // TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
@@ -47,9 +47,9 @@ using namespace mer;
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;  // K elements per stage in BOTH modes (128 B of tf32 / 64 B of bf16 per part)
-constexpr int NUM_THREADS = 384;  // 4 control warps + 8 epilogue warps
 constexpr int EPI_WARP0 = 4;
-constexpr int EPI_WARPS = 8;      // two per TMEM lane quarter, each taking half of the tile's columns
+constexpr int EPI_WARPS = 16;     // four per TMEM lane quarter, each taking a quarter of the tile's columns
+constexpr int NUM_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);  // 4 control warps + 16 epilogue warps
 
 template <int BLOCK_N, int MODE, bool TWOSM = false>
 struct GemmCfg {
@@ -59,17 +59,17 @@ struct GemmCfg {
   static constexpr int kLayout = 2;                     // UMMA LayoutType SWIZZLE_128B
   static constexpr int kFmt = kSplit ? 1 : 2;           // instr-desc operand format: bf16 / tf32
   // TWOSM (cta_group::2): each CTA of the pair keeps only ITS half of the weight tile in smem
-  // stage count: what fits beside the epilogue's 68 KB of staging (227 KB usable per CTA)
-  static constexpr int kStages = TWOSM ? 4 : (BLOCK_N == 256 ? 3 : 4);
+  // stage count: what fits beside the epilogue's 32 KB of staging (227 KB usable per CTA)
+  static constexpr int kStages = TWOSM ? 6 : (BLOCK_N == 256 ? 4 : 6);
   static constexpr int kABytes = BLOCK_M * kRowBytes;
   static constexpr int kBBytes = (TWOSM ? BLOCK_N / 2 : BLOCK_N) * kRowBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N;
   static constexpr int kBarBytes = 256;
-  // per epilogue warp: a 32 x 128 B output transpose tile and a 32 x 128 B residual prefetch tile
-  static constexpr int kStagingBytes = 8 * 8192;
-  static constexpr int kBiasBytes = 8 * 512;  // per epilogue warp: its half of the tile's bias values
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBiasBytes + kBarBytes + 1024;
+  // per epilogue warp: a 32 x 64 B transpose tile
+  static constexpr int kStagingBytes = EPI_WARPS * 2048;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, int sbo_bytes, int layout) {
@@ -80,6 +80,139 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, int sbo_bytes,
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(layout) << 61;
   return d;
+}
+
+// tcgen05.wait::ld that also names the destination registers, so no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]),
+                 "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]),
+                 "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]),
+                 "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]),
+                 "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
+template <int GELU>
+__device__ __forceinline__ float epi_act(float v) {
+  if (GELU == 1) return gelu_erf_fast(v);
+  if (GELU == 2) return gelu_erf(v);
+  return v;
+}
+
+// What one epilogue warp needs to know about its share of the current output tile.
+struct EpiTile {
+  uint32_t t_addr;        // TMEM address: this warp's lane quarter, accumulator stage, first column
+  int n0;                 // first global output column of the warp's slice
+  int rows_left;          // rows r < rows_left of the warp's 32 are real
+  float* out_lane;        // &out[row0 + lane / 4][n0 + 4 * (lane % 4)]  (write-out phase)
+  const float* res_lane;  // same position in the residual, or nullptr
+  float* vt_lane;         // &vt[0][row0 + lane] for the transposed side output, or nullptr
+  long long ld_out8, ld_res8;  // 8 rows of out / res, in floats
+};
+
+// Epilogue of one warp for one tile: CH chunks of 32 accumulator columns, each handled as two
+// 16-column halves through a 32 x 64 B staging tile (XOR-swizzled 16-byte slots, conflict-free both
+// ways):
+//   phase 1 (thread = accumulator row): tcgen05.ld registers -> smem, raw
+//   phase 2 (lane = (row % 8, 16-byte slot); one warp instruction = 8 rows x 64 contiguous bytes):
+//           smem -> + bias -> GELU -> + residual -> TF32 round / bf16 split -> st.global.
+// All arithmetic sits in phase 2, where bias values are per-lane constants and the residual is read in
+// the shape it is written (its lines were prefetched into L2 at tile start, under the MMAs).
+// The TMEM stage is handed back to the MMA warp as soon as the LAST chunk has been read into
+// registers, i.e. before that chunk's math and stores.
+// GELU: 0 none, 1 polynomial erf, 2 libdevice erff.  OUT: 0 fp32, 1 TF32-rounded fp32, 2 bf16 (hi|lo).
+// RES: add the residual (GELU == 0, OUT != 2 only).  The transposed side output exists for GELU == 0.
+template <int CH, int GELU, int OUT, bool RES, typename ReleaseFn>
+__device__ __forceinline__ void epi_tile(const EpiTile& tl, const MerGemmEpilogue& ep, float* stg,
+                                         int lane, ReleaseFn release_tmem) {
+  constexpr bool kVt = GELU == 0 && !RES;
+  const int p_row = lane >> 2, p_slot = lane & 3;  // phase-2 coordinates
+  auto slot = [&](int row, int j) -> float4* {       // 16-byte slot j (0..3) of staging row `row`
+    return reinterpret_cast<float4*>(stg + row * 16 + ((j ^ ((row >> 1) & 3)) << 2));
+  };
+  uint32_t r[32];
+  tmem_ld_32x32(tl.t_addr, r);
+#pragma unroll
+  for (int ci = 0; ci < CH; ++ci) {
+    const int n0 = tl.n0 + ci * 32;
+    tmem_ld_wait_regs(r);
+    if (ci == CH - 1) release_tmem();
+    if (kVt && tl.vt_lane != nullptr && n0 >= ep.vt_col0) {
+      // transposed side output (V^T of the QKV GEMM): lanes = consecutive rows, so each scalar store
+      // instruction is one contiguous 128-byte run of vt
+      float* vt_col = tl.vt_lane + (long long)(n0 - ep.vt_col0) * ep.vt_ld;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ep.bias) q = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + j);  // warp-uniform address
+        float4 v = make_float4(__uint_as_float(r[4 * j + 0]) + q.x, __uint_as_float(r[4 * j + 1]) + q.y,
+                               __uint_as_float(r[4 * j + 2]) + q.z, __uint_as_float(r[4 * j + 3]) + q.w);
+        if (OUT == 1) {
+          v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+        }
+        if (lane < tl.rows_left) {
+          vt_col[(long long)(4 * j + 0) * ep.vt_ld] = v.x;
+          vt_col[(long long)(4 * j + 1) * ep.vt_ld] = v.y;
+          vt_col[(long long)(4 * j + 2) * ep.vt_ld] = v.z;
+          vt_col[(long long)(4 * j + 3) * ep.vt_ld] = v.w;
+        }
+      }
+      if (ci + 1 < CH) tmem_ld_32x32(tl.t_addr + (ci + 1) * 32, r);
+      continue;
+    }
+#pragma unroll
+    for (int sub = 0; sub < 2; ++sub) {
+      const int col = ci * 32 + sub * 16 + 4 * p_slot;  // this lane's 4 columns, relative to tl.n0
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ep.bias) q = __ldg(reinterpret_cast<const float4*>(ep.bias + tl.n0 + col));
+      float4 rr[4];
+      if (RES) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (8 * i + p_row < tl.rows_left)
+            rr[i] = __ldg(reinterpret_cast<const float4*>(tl.res_lane + i * tl.ld_res8 + col));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *slot(lane, j) = make_float4(__uint_as_float(r[16 * sub + 4 * j + 0]), __uint_as_float(r[16 * sub + 4 * j + 1]),
+                                     __uint_as_float(r[16 * sub + 4 * j + 2]), __uint_as_float(r[16 * sub + 4 * j + 3]));
+      if (sub == 1 && ci + 1 < CH) tmem_ld_32x32(tl.t_addr + (ci + 1) * 32, r);  // flies during the write-out
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = 8 * i + p_row;
+        float4 v = *slot(row, p_slot);
+        v.x = epi_act<GELU>(v.x + q.x);
+        v.y = epi_act<GELU>(v.y + q.y);
+        v.z = epi_act<GELU>(v.z + q.z);
+        v.w = epi_act<GELU>(v.w + q.w);
+        if (RES) {
+          v.x += rr[i].x; v.y += rr[i].y; v.z += rr[i].z; v.w += rr[i].w;
+        }
+        if (OUT == 2) {
+          // the 32-column group's 128 bytes are [32 x bf16 hi | 32 x bf16 lo]
+          const float hx = bf16_round(v.x), hy = bf16_round(v.y), hz = bf16_round(v.z), hw = bf16_round(v.w);
+          if (row < tl.rows_left) {
+            uint16_t* grp = reinterpret_cast<uint16_t*>(tl.out_lane + i * tl.ld_out8 + ci * 32);
+            const int c = sub * 16 + 4 * p_slot;
+            *reinterpret_cast<uint2*>(grp + c) = make_uint2(pack_bf16x2(hx, hy), pack_bf16x2(hz, hw));
+            *reinterpret_cast<uint2*>(grp + 32 + c) =
+                make_uint2(pack_bf16x2(v.x - hx, v.y - hy), pack_bf16x2(v.z - hz, v.w - hw));
+          }
+        } else {
+          if (OUT == 1) {
+            v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+          }
+          if (row < tl.rows_left) *reinterpret_cast<float4*>(tl.out_lane + i * tl.ld_out8 + col) = v;
+        }
+      }
+      __syncwarp();
+    }
+  }
 }
 
 // CLUSTER == 2: a pair of CTAs works on two vertically adjacent 128-row tiles of the same BLOCK_N
@@ -104,8 +237,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
   uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
-  float* bias_smem = reinterpret_cast<float*>(staging + Cfg::kStagingBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes + Cfg::kBiasBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + Cfg::kStages;
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;
@@ -258,150 +390,71 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp >= EPI_WARP0) {
     // ===================== epilogue =====================
-    // Thread = accumulator row (TMEM lane).  Global traffic is re-shaped through a per-warp 32 x 128 B
-    // staging tile (XOR-swizzled 16-byte slots, conflict-free both ways) so that every warp-level
-    // load / store touches 4 rows x 128 contiguous bytes instead of 32 rows x 16 bytes.
-    const int ew = (warp - EPI_WARP0) & 3;      // == warp % 4: the TMEM lane quarter this warp may read
-    const int chalf = (warp - EPI_WARP0) >> 2;  // which half of the tile's columns this warp handles
-    float* stg = reinterpret_cast<float*>(staging) + (warp - EPI_WARP0) * 2048;  // output transpose tile
-    float* stg_r = stg + 1024;                                                    // residual prefetch tile
-    float* bias_s = bias_smem + (warp - EPI_WARP0) * 128;  // private: warps drift across tile boundaries
-    const int sub_r = lane >> 3;  // row within a group of 4 rows (coalesced phase)
-    const int sub_c = lane & 7;   // 16-byte slot within the 128-byte row (coalesced phase)
-    auto slot = [&](int row, int j) -> float4* {
-      return reinterpret_cast<float4*>(stg + row * 32 + ((j ^ (row & 7)) << 2));
-    };
-    auto slot_r = [&](int row, int j) -> float4* {
-      return reinterpret_cast<float4*>(stg_r + row * 32 + ((j ^ (row & 7)) << 2));
-    };
+    // 16 warps: warp % 4 = the TMEM lane quarter it may read (32 accumulator rows), (warp - 4) / 4 = the
+    // quarter of the tile's columns it handles.  See epi_tile for the per-chunk data path.
+    const int ew = (warp - EPI_WARP0) & 3;
+    const int cq = (warp - EPI_WARP0) >> 2;
+    constexpr int CH = BLOCK_N / 128;           // 32-column chunks per warp and tile
+    float* stg = reinterpret_cast<float*>(staging) + (warp - EPI_WARP0) * 512;
+    const int p_row = lane >> 2;
     int as = 0;
     uint32_t aphase = 0;
-    const bool do_gelu = (ep.flags & MER_EPI_GELU) != 0;
-    const bool gelu_libm = (ep.flags & MER_EPI_GELU_LIBM) != 0;
-    const bool do_round = (ep.flags & MER_EPI_ROUND_TF32) != 0;
-    const bool do_split = (ep.flags & MER_EPI_SPLIT_BF16) != 0;
+    const int gelu_kind = (ep.flags & MER_EPI_GELU) ? ((ep.flags & MER_EPI_GELU_LIBM) ? 2 : 1) : 0;
+    const int out_kind = (ep.flags & MER_EPI_SPLIT_BF16) ? 2 : ((ep.flags & MER_EPI_ROUND_TF32) ? 1 : 0);
+    const int kind = gelu_kind * 3 + out_kind;
     for (int t = first_tile; t < num_tiles; t += tile_step) {
       const int n_blk = t % n_tiles;
       const int mb = (t / n_tiles) * CLUSTER + cta_rank;
       const int b = mb / m_tiles;
       const int mt = mb % m_tiles;
       const int m0 = mt * BLOCK_M + ew * 32;  // first row (inside the batch entry) of this warp's 32
-      const int rows_left = (mb < total_m) ? rows_per_batch - m0 : 0;  // rows r < rows_left are real
-      float* out_base = ep.out + ((long long)b * ep.out_bstride + ep.out_row0 + m0) * (long long)ep.ld_out;
-      const float* res_base =
-          ep.res ? ep.res + ((long long)b * ep.res_bstride + ep.res_row0 + m0) * (long long)ep.ld_res
-                 : nullptr;
-      // asynchronous coalesced fetch of a 32 x 32 residual tile into the swizzled prefetch tile
-      auto prefetch_res = [&](int c) {
-        const int n0 = n_blk * BLOCK_N + c * 32;
+      EpiTile tl;
+      tl.n0 = n_blk * BLOCK_N + cq * (BLOCK_N / 4);
+      tl.rows_left = (mb < total_m) ? rows_per_batch - m0 : 0;
+      const long long out_row = (long long)b * ep.out_bstride + ep.out_row0 + m0;
+      tl.out_lane = ep.out + (out_row + p_row) * (long long)ep.ld_out + tl.n0;
+      tl.res_lane = ep.res ? ep.res + ((long long)b * ep.res_bstride + ep.res_row0 + m0 + p_row) *
+                                          (long long)ep.ld_res + tl.n0
+                           : nullptr;
+      tl.vt_lane = ep.vt ? ep.vt + out_row + lane : nullptr;
+      tl.ld_out8 = 8ll * ep.ld_out;
+      tl.ld_res8 = 8ll * ep.ld_res;
+      if (ep.res && lane < tl.rows_left) {
+        // this warp's 32 x (BLOCK_N / 4) residual block: pull its lines into L2 while the MMAs run
+        const float* rrow = ep.res + ((long long)b * ep.res_bstride + ep.res_row0 + m0 + lane) *
+                                         (long long)ep.ld_res + tl.n0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = 4 * i + sub_r;
-          const int ok = row < rows_left ? 16 : 0;
-          const float* src = res_base + (long long)(ok ? row : 0) * ep.ld_res + n0 + sub_c * 4;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(slot_r(row, sub_c))),
-                       "l"(src), "r"(ok)
-                       : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-      };
-      const int c_first = chalf * (BLOCK_N / 64), c_last = (chalf + 1) * (BLOCK_N / 64);
-      // while the accumulator is still being produced: this tile's bias slice and the first residual tile
-      if (ep.bias && lane < BLOCK_N / 8)
-        *reinterpret_cast<float4*>(bias_s + lane * 4) =
-            __ldg(reinterpret_cast<const float4*>(ep.bias + n_blk * BLOCK_N + chalf * (BLOCK_N / 2)) + lane);
-      if (res_base) prefetch_res(c_first);
+        for (int i = 0; i < BLOCK_N / 128; ++i)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + 32 * i));
+      }
       __syncwarp();
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (uint32_t(ew * 32) << 16) + as * BLOCK_N;
-#pragma unroll 1
-      for (int c = c_first; c < c_last; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_row + c * 32, r);
-        const int n0 = n_blk * BLOCK_N + c * 32;
-        float4 rr[8];
-        if (res_base) {  // residual tile c has landed: one row per thread, then start fetching tile c+1
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) rr[j] = *slot_r(lane, j);
-          __syncwarp();
-          if (c + 1 < c_last) prefetch_res(c + 1);
-        }
-        const float* bias_c = bias_s + (c - c_first) * 32;
-        tmem_ld_wait();
-        // columns of the transposed side output (V^T of the QKV GEMM): lanes = consecutive rows, so
-        // each scalar store instruction is one contiguous 128-byte run of vt
-        const bool to_vt = ep.vt != nullptr && n0 >= ep.vt_col0;
-        float* vt_col = to_vt ? ep.vt + (long long)(n0 - ep.vt_col0) * ep.vt_ld +
-                                    ((long long)b * ep.out_bstride + ep.out_row0 + m0 + lane)
-                              : nullptr;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 v;
-          v.x = __uint_as_float(r[4 * j + 0]);
-          v.y = __uint_as_float(r[4 * j + 1]);
-          v.z = __uint_as_float(r[4 * j + 2]);
-          v.w = __uint_as_float(r[4 * j + 3]);
-          if (ep.bias) {
-            const float4 q = *reinterpret_cast<const float4*>(bias_c + 4 * j);  // smem broadcast
-            v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
-          }
-          if (do_gelu) {
-            if (gelu_libm) {
-              v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
-            } else {
-              v.x = gelu_erf_fast(v.x); v.y = gelu_erf_fast(v.y); v.z = gelu_erf_fast(v.z); v.w = gelu_erf_fast(v.w);
-            }
-          }
-          if (res_base) {
-            v.x += rr[j].x; v.y += rr[j].y; v.z += rr[j].z; v.w += rr[j].w;
-          }
-          if (to_vt) {
-            if (do_round) {
-              v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
-            }
-            if (lane < rows_left) {
-              vt_col[(long long)(4 * j + 0) * ep.vt_ld] = v.x;
-              vt_col[(long long)(4 * j + 1) * ep.vt_ld] = v.y;
-              vt_col[(long long)(4 * j + 2) * ep.vt_ld] = v.z;
-              vt_col[(long long)(4 * j + 3) * ep.vt_ld] = v.w;
-            }
-            continue;
-          }
-          if (do_split) {
-            // the row's 128 bytes are [32 x bf16 hi | 32 x bf16 lo]: 8 bytes of each half per j
-            const float hx = bf16_round(v.x), hy = bf16_round(v.y), hz = bf16_round(v.z), hw = bf16_round(v.w);
-            uint2* hi = reinterpret_cast<uint2*>(slot(lane, j >> 1)) + (j & 1);
-            uint2* lo = reinterpret_cast<uint2*>(slot(lane, 4 + (j >> 1))) + (j & 1);
-            *hi = make_uint2(pack_bf16x2(hx, hy), pack_bf16x2(hz, hw));
-            *lo = make_uint2(pack_bf16x2(v.x - hx, v.y - hy), pack_bf16x2(v.z - hz, v.w - hw));
-          } else {
-            if (do_round) {
-              v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
-            }
-            *slot(lane, j) = v;
-          }
-        }
-        if (to_vt) continue;
+      tl.t_addr = tmem_base + (uint32_t(ew * 32) << 16) + as * BLOCK_N + cq * (BLOCK_N / 4);
+      // all of this warp's TMEM reads of the stage are complete -> hand it back to the MMA warp
+      auto release = [&]() {
+        tc_fence_before();
         __syncwarp();
-        // coalesced write-out: 4 rows x 128 contiguous bytes per warp instruction
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = 4 * i + sub_r;
-          const float4 d = *slot(row, sub_c);
-          if (row < rows_left)
-            *reinterpret_cast<float4*>(out_base + (long long)row * ep.ld_out + n0 + sub_c * 4) = d;
+        if (lane == 0) {
+          if (TWOSM) mbar_arrive_cluster(leader_addr(&tempty_bar[as]));  // the leader's MMA warp waits for both CTAs
+          else mbar_arrive(&tempty_bar[as]);
         }
-        __syncwarp();
-      }
-      // all TMEM reads of this stage are complete (wait::ld above) -> hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (TWOSM) mbar_arrive_cluster(leader_addr(&tempty_bar[as]));  // the leader's MMA warp waits for both CTAs
-        else mbar_arrive(&tempty_bar[as]);
+      };
+      if (tl.res_lane != nullptr) {  // warp-uniform; each variant is straight-line code
+        if (out_kind == 1) epi_tile<CH, 0, 1, true>(tl, ep, stg, lane, release);
+        else epi_tile<CH, 0, 0, true>(tl, ep, stg, lane, release);
+      } else {
+        switch (kind) {
+          case 0: epi_tile<CH, 0, 0, false>(tl, ep, stg, lane, release); break;
+          case 1: epi_tile<CH, 0, 1, false>(tl, ep, stg, lane, release); break;
+          case 2: epi_tile<CH, 0, 2, false>(tl, ep, stg, lane, release); break;
+          case 3: epi_tile<CH, 1, 0, false>(tl, ep, stg, lane, release); break;
+          case 4: epi_tile<CH, 1, 1, false>(tl, ep, stg, lane, release); break;
+          case 5: epi_tile<CH, 1, 2, false>(tl, ep, stg, lane, release); break;
+          case 6: epi_tile<CH, 2, 0, false>(tl, ep, stg, lane, release); break;
+          case 7: epi_tile<CH, 2, 1, false>(tl, ep, stg, lane, release); break;
+          default: epi_tile<CH, 2, 2, false>(tl, ep, stg, lane, release); break;
+        }
       }
       if (++as == 2) {
         as = 0;
@@ -514,6 +567,11 @@ int mer_gemm_launch(const MerGemmDesc* g, cudaStream_t stream) {
               "mer_gemm: A strides must be multiples of 16 bytes");
   MER_REQUIRE(g->ep.ld_out % 4 == 0 && (g->ep.res == nullptr || g->ep.ld_res % 4 == 0),
               "mer_gemm: out/res leading dims must be multiples of 4 floats");
+  MER_REQUIRE(!((g->ep.flags & MER_EPI_SPLIT_BF16) && (g->ep.res || g->ep.vt)),
+              "mer_gemm: a bf16-split output cannot be combined with a residual or the transposed side output");
+  MER_REQUIRE(!(g->ep.res && (g->ep.vt || (g->ep.flags & MER_EPI_GELU))),
+              "mer_gemm: a residual cannot be combined with GELU or the transposed side output");
+  MER_REQUIRE(!(g->ep.vt && (g->ep.flags & MER_EPI_GELU)), "mer_gemm: GELU + transposed side output is not supported");
   const int m_tiles = (g->rows_per_batch + BLOCK_M - 1) / BLOCK_M;
   const long long tiles256 = (g->N % 256 == 0) ? (long long)g->batches * m_tiles * (g->N / 256) : 0;
   // 128 x 256 tiles whenever they fill the machine; 128 x 128 for small problems / N % 256 != 0
