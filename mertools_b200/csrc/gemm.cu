@@ -288,55 +288,65 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = first_tile; t < num_tiles; t += tile_step) {
-        const int n_blk = t % n_tiles;
-        const int mb = (t / n_tiles) * CLUSTER + cta_rank;  // >= total_m: padding tile (TMA zero-fills)
-        const int b = mb / m_tiles;
-        const int mt = mb % m_tiles;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          const int kk = kb * BLOCK_K;
-          const int tap = kk / K_inner;
-          const int c0 = kk - tap * K_inner;
-          constexpr int kEl = Cfg::kSplit ? 2 : 1;  // tensor-map elements per operand value
+    // The whole warp runs the loop (so addresses and coordinates stay in uniform registers); one
+    // elected lane issues the copies.  No division inside the K loop.
+    int stage = 0;
+    uint32_t phase = 0;
+    constexpr int kEl = Cfg::kSplit ? 2 : 1;  // tensor-map elements per operand value
+    for (int t = first_tile; t < num_tiles; t += tile_step) {
+      const int n_blk = t % n_tiles;
+      const int mb = (t / n_tiles) * CLUSTER + cta_rank;  // >= total_m: padding tile (TMA zero-fills)
+      const int b = mb / m_tiles;
+      const int mt = mb % m_tiles;
+      int c0 = 0, tap_phase = 0, tap_row = 0;  // K offset inside the tap; tap % P; tap / P
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           if (TWOSM) {
             const uint32_t lbar = leader_addr(&full_bar[stage]);
             mbar_expect_tx_cluster(lbar, Cfg::kStageBytes);
-            tma_load_4d_2sm(smem_a + stage * Cfg::kABytes, &tmap_a, lbar, c0 * kEl, tap % P,
-                            mt * BLOCK_M + tap / P, b);
-            tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &tmap_b, lbar, kk * kEl,
+            tma_load_4d_2sm(smem_a + stage * Cfg::kABytes, &tmap_a, lbar, c0 * kEl, tap_phase,
+                            mt * BLOCK_M + tap_row, b);
+            tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &tmap_b, lbar, kb * BLOCK_K * kEl,
                             n_blk * BLOCK_N + cta_rank * (BLOCK_N / 2));
-            if (++stage == Cfg::kStages) {
-              stage = 0;
-              phase ^= 1;
-            }
-            continue;
-          }
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], c0 * kEl, tap % P,
-                      mt * BLOCK_M + tap / P, b);
-          if (CLUSTER == 1) {
-            tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kk * kEl,
-                        n_blk * BLOCK_N);
           } else {
-            tma_load_2d_mc(smem_b + stage * Cfg::kBBytes + cta_rank * (Cfg::kBBytes / CLUSTER), &tmap_b,
-                           &full_bar[stage], kk * kEl, n_blk * BLOCK_N + cta_rank * (BLOCK_N / CLUSTER),
-                           (uint16_t)((1u << CLUSTER) - 1));
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], c0 * kEl, tap_phase,
+                        mt * BLOCK_M + tap_row, b);
+            if (CLUSTER == 1) {
+              tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * BLOCK_K * kEl,
+                          n_blk * BLOCK_N);
+            } else {
+              tma_load_2d_mc(smem_b + stage * Cfg::kBBytes + cta_rank * (Cfg::kBBytes / CLUSTER), &tmap_b,
+                             &full_bar[stage], kb * BLOCK_K * kEl,
+                             n_blk * BLOCK_N + cta_rank * (BLOCK_N / CLUSTER),
+                             (uint16_t)((1u << CLUSTER) - 1));
+            }
           }
-          if (++stage == Cfg::kStages) {
-            stage = 0;
-            phase ^= 1;
+        }
+        __syncwarp();
+        c0 += BLOCK_K;
+        if (c0 == K_inner) {
+          c0 = 0;
+          if (++tap_phase == P) {
+            tap_phase = 0;
+            ++tap_row;
           }
+        }
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && (!TWOSM || cta_rank == 0)) {
+    // Warp-uniform loop; one elected lane issues the MMAs and their commits (a commit tracks the
+    // MMAs of the thread that executes it).
+    if (!TWOSM || cta_rank == 0) {
       constexpr uint32_t idesc = umma_idesc(Cfg::kFmt, TWOSM ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
+      const uint64_t desc_a0 = umma_desc(smem_u32(smem_a), Cfg::kSBO, Cfg::kLayout);
+      const uint64_t desc_b0 = umma_desc(smem_u32(smem_b), Cfg::kSBO, Cfg::kLayout);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -348,40 +358,46 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t da = umma_desc(smem_u32(smem_a + stage * Cfg::kABytes), Cfg::kSBO, Cfg::kLayout);
-          const uint64_t db = umma_desc(smem_u32(smem_b + stage * Cfg::kBBytes), Cfg::kSBO, Cfg::kLayout);
-          // advance the start address by 32-byte K steps inside the 128B swizzle row (>>4 => +2)
-          if (!Cfg::kSplit) {
+          if (elect_one()) {
+            // descriptors: start address field counts 16-byte units; a stage is kABytes / kBBytes further
+            const uint64_t da = desc_a0 + (uint64_t)(stage * (Cfg::kABytes >> 4));
+            const uint64_t db = desc_b0 + (uint64_t)(stage * (Cfg::kBBytes >> 4));
+            // advance the start address by 32-byte K steps inside the 128B swizzle row (>>4 => +2)
+            if (!Cfg::kSplit) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {  // 4 x 8 tf32
-              if (TWOSM) tc_mma_tf32_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-              else tc_mma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-            }
-          } else {
+              for (int k = 0; k < 4; ++k) {  // 4 x 8 tf32
+                if (TWOSM) tc_mma_tf32_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                else tc_mma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+              }
+            } else {
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {  // 2 x 16 bf16; hi at bytes [0,64), lo at [64,128) of the row
-              if (TWOSM) {
-                tc_mma_bf16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                tc_mma_bf16_2sm(d_tmem, da + 4 + 2 * k, db + 2 * k, idesc, 1);
-                tc_mma_bf16_2sm(d_tmem, da + 2 * k, db + 4 + 2 * k, idesc, 1);
-              } else {
-                tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);  // hi * hi
-                tc_mma_bf16(d_tmem, da + 4 + 2 * k, db + 2 * k, idesc, 1);          // lo * hi
-                tc_mma_bf16(d_tmem, da + 2 * k, db + 4 + 2 * k, idesc, 1);          // hi * lo
+              for (int k = 0; k < 2; ++k) {  // 2 x 16 bf16; hi at bytes [0,64), lo at [64,128) of the row
+                if (TWOSM) {
+                  tc_mma_bf16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                  tc_mma_bf16_2sm(d_tmem, da + 4 + 2 * k, db + 2 * k, idesc, 1);
+                  tc_mma_bf16_2sm(d_tmem, da + 2 * k, db + 4 + 2 * k, idesc, 1);
+                } else {
+                  tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);  // hi * hi
+                  tc_mma_bf16(d_tmem, da + 4 + 2 * k, db + 2 * k, idesc, 1);          // lo * hi
+                  tc_mma_bf16(d_tmem, da + 2 * k, db + 4 + 2 * k, idesc, 1);          // hi * lo
+                }
               }
             }
+            // free the smem slot when these MMAs retire (in every CTA that writes into it / owns a copy)
+            if (TWOSM) tc_commit_2sm(&empty_bar[stage]);
+            else if (CLUSTER == 1) tc_commit(&empty_bar[stage]);
+            else tc_commit_mc(&empty_bar[stage], (uint16_t)((1u << CLUSTER) - 1));
+            if (kb == num_kb - 1) {
+              if (TWOSM) tc_commit_2sm(&tfull_bar[as]);  // accumulator complete -> both CTAs' epilogues
+              else tc_commit(&tfull_bar[as]);           // accumulator complete -> epilogue
+            }
           }
-          // free the smem slot when these MMAs retire (in every CTA that writes into it / owns a copy)
-          if (TWOSM) tc_commit_2sm(&empty_bar[stage]);
-          else if (CLUSTER == 1) tc_commit(&empty_bar[stage]);
-          else tc_commit_mc(&empty_bar[stage], (uint16_t)((1u << CLUSTER) - 1));
+          __syncwarp();
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        if (TWOSM) tc_commit_2sm(&tfull_bar[as]);  // accumulator complete -> both CTAs' epilogues
-        else tc_commit(&tfull_bar[as]);           // accumulator complete -> epilogue
         if (++as == 2) {
           as = 0;
           aphase ^= 1;

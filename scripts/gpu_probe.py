@@ -261,6 +261,24 @@ def sec_gemm_perf():
     return True
 
 
+def sec_one():
+    """One ViT GEMM shape, a few launches (for ncu): MER_PROBE_SHAPE = qkv | outproj | fc1 | fc2."""
+    M = 403456
+    shapes = dict(qkv=(2304, 768, dict(rnd=True)), outproj=(768, 768, dict(res=True)),
+                  fc1=(3072, 768, dict(gelu=True, rnd=True)), fc2=(768, 3072, dict(res=True)))
+    name = os.environ.get("MER_PROBE_SHAPE", "fc1")
+    N, K, kw = shapes[name]
+    A = tf32(torch.randn(M, K, device="cuda"))
+    W = tf32(torch.randn(N, K, device="cuda") * 0.02)
+    b = torch.randn(N, device="cuda")
+    R = torch.randn(M, N, device="cuda") if kw.get("res") else None
+    out = torch.empty(M, N, device="cuda")
+    for _ in range(3):
+        L.gemm_tf32(A, W, out, bias=b, res=R, gelu=kw.get("gelu", False), round_out=kw.get("rnd", False))
+    torch.cuda.synchronize()
+    return True
+
+
 def sec_ln():
     ok = True
     for dim, eps in [(768, 1e-12), (512, 1e-5), (768, 1e-5)]:
@@ -336,7 +354,7 @@ def sec_vit():
     return True
 
 
-SECTIONS = dict(vit=sec_vit, gemm_x3=sec_gemm_x3, gemm_2sm=sec_gemm_2sm, gelu_ab=sec_gelu_ab, gemm=sec_gemm, conv=sec_conv, gemm_perf=sec_gemm_perf, ln=sec_ln, attn=sec_attn)
+SECTIONS = dict(one=sec_one, vit=sec_vit, gemm_x3=sec_gemm_x3, gemm_2sm=sec_gemm_2sm, gelu_ab=sec_gelu_ab, gemm=sec_gemm, conv=sec_conv, gemm_perf=sec_gemm_perf, ln=sec_ln, attn=sec_attn)
 
 if __name__ == "__main__":
     os.makedirs("gpurun_out", exist_ok=True)
