@@ -204,7 +204,12 @@ def run_ours(args):
         pk = peaks()
         total_clips = clips * world * args.steps
         t_ms, t_fl, t_n = prof["tf32"]
-        tf32_peak = pk["bf16_sustained"] / 2.0
+        # denominator: the BURST bf16 figure / 2 (tf32 pipe rate = half the bf16 rate).  The kernel is timed
+        # inside a long step, where the recipe would allow the lower sustained figure, but it now exceeds
+        # sustained / 2 (the power-capped torch.matmul number), so the harder denominator is the honest one;
+        # frac_vs_sustained is given beside it
+        tf32_peak = pk["bf16"] / 2.0
+        tf32_sust = pk["bf16_sustained"] / 2.0
         ach = t_fl / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
         traffic = None
         tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
@@ -230,11 +235,14 @@ def run_ours(args):
             "roofline": {"kernel": "gemm_kernel<256, TF32, CTA pair, cta_group::2> (tcgen05 kind::tf32; ViT linear layers)",
                          "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
                          "frac": ach / tf32_peak if tf32_peak else None, "traffic": traffic,
+                         "frac_vs_sustained": ach / tf32_sust if tf32_sust else None,
                          "launches_timed": t_n, "share_of_step": t_ms / ms_dev if ms_dev else None,
-                         "peak_source": f"{pk['src']} MEASURED_PEAKS bf16_tflops_sustained / 2 (tf32 pipe rate = half the bf16 rate)"},
+                         "peak_source": f"{pk['src']} MEASURED_PEAKS bf16_tflops (burst) / 2 (tf32 pipe rate = half the bf16 rate); "
+                                        f"sustained / 2 = {tf32_sust:.1f}"},
             "roofline_other": [{"kernel": "gemm_kernel<*, BF16X3> (3 bf16 MMAs per product; HuBERT/BERT)",
                                 "bound": "tensor", "achieved": b_fl / (b_ms * 1e-3) / 1e12 if b_ms > 0 else 0.0,
-                                "peak": pk["bf16_sustained"] / 3.0, "unit": "TFLOP/s (useful)",
+                                "peak": pk["bf16"] / 3.0, "unit": "TFLOP/s (useful)",
+                                "frac": (b_fl / (b_ms * 1e-3) / 1e12) / (pk["bf16"] / 3.0) if b_ms > 0 else None,
                                 "launches_timed": b_n, "share_of_step": b_ms / ms_dev if ms_dev else None}],
         }
         line["cpu_baseline"] = cpu_baseline(sample_clips=args.cpu_clips)

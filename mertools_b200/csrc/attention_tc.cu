@@ -43,6 +43,12 @@ constexpr int SMEM_BAR = SMEM_Q + 2 * QTILE_BYTES;
 constexpr int TC_SMEM = SMEM_BAR + 256 + 1024;
 constexpr uint32_t TILE_COLS = 256, TMEM_COLS = 512;  // tile t: S_t at [256t, 256t+NK), O_t aliases its first 64
 
+__device__ __forceinline__ float fast_ex2(float x) {  // MUFU.EX2, flush-to-zero: 2 ulp, no range fix-up
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) {  // SW128, SBO 1024
   return static_cast<uint64_t>((addr & 0x3FFFF) >> 4) | (1ull << 16) | (uint64_t(1024 >> 4) << 32) |
          (1ull << 46) | (2ull << 61);
@@ -96,96 +102,111 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      uint32_t uses[2] = {0, 0};  // how often tile slot t has been used so far
-      int prev_nmt = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const int seq = it / heads, h = it % heads;
-        const int start = cu_seqlens[seq];
-        const int len = cu_seqlens[seq + 1] - start;
-        const int n_mt = (len + 127) >> 7;
-        // TMA needs 16-byte aligned inner-dimension starts: V^T (keys contiguous) is read from the
-        // token rounded down to a multiple of 4, and K rows likewise, so both MMAs see the same key
-        // axis k' = key + shift; the (up to 3) leading keys of the previous sequence are masked
-        const int a_start = start & ~3, shift = start - a_start;
-        const int Lk = shift + len;
-        const int nb = (Lk + 127) >> 7;
-        // K: the previous item's S MMAs are done
-        for (int t = 0; t < prev_nmt; ++t) mbar_wait(&bar_sfull[t], (uses[t] - 1) & 1);
+    // warp-uniform loop (coordinates stay in uniform registers); one elected lane issues the copies
+    uint32_t uses[2] = {0, 0};  // how often tile slot t has been used so far
+    int prev_nmt = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const int seq = it / heads, h = it % heads;
+      const int start = cu_seqlens[seq];
+      const int len = cu_seqlens[seq + 1] - start;
+      const int n_mt = (len + 127) >> 7;
+      // TMA needs 16-byte aligned inner-dimension starts: V^T (keys contiguous) is read from the
+      // token rounded down to a multiple of 4, and K rows likewise, so both MMAs see the same key
+      // axis k' = key + shift; the (up to 3) leading keys of the previous sequence are masked
+      const int a_start = start & ~3, shift = start - a_start;
+      const int Lk = shift + len;
+      const int nb = (Lk + 127) >> 7;
+      // K: the previous item's S MMAs are done
+      for (int t = 0; t < prev_nmt; ++t) mbar_wait(&bar_sfull[t], (uses[t] - 1) & 1);
+      if (elect_one()) {
         mbar_expect_tx(bar_k, (uint32_t)(2 * nb * 16384));
         for (int c = 0; c < 2; ++c)
           for (int b = 0; b < nb; ++b)
             tma_load_2d(smem + SMEM_K + c * CHUNK_BYTES + b * 16384, &tmap_qkv, bar_k,
                         heads * HD + h * HD + c * 32, a_start + b * 128);
-        // Q tiles: the previous item's P V MMAs are done (the Q_t regions double as P-chunk buffers)
-        for (int t = 0; t < prev_nmt; ++t) mbar_wait(&bar_ofull[t], (uses[t] - 1) & 1);
+      }
+      __syncwarp();
+      // Q tiles: the previous item's P V MMAs are done (the Q_t regions double as P-chunk buffers)
+      for (int t = 0; t < prev_nmt; ++t) mbar_wait(&bar_ofull[t], (uses[t] - 1) & 1);
+      if (elect_one()) {
         mbar_expect_tx(bar_q, (uint32_t)(n_mt * QTILE_BYTES));
         for (int t = 0; t < n_mt; ++t)
           for (int c = 0; c < 2; ++c)
             tma_load_2d(smem + SMEM_Q + t * QTILE_BYTES + c * 16384, &tmap_qkv, bar_q, h * HD + c * 32,
                         start + t * 128);
-        // V^T: the previous item's epilogues are done (they stage their output in the V^T region)
-        for (int t = 0; t < prev_nmt; ++t) mbar_wait(&bar_ofree[t], (uses[t] - 1) & 1);
-        const int n_vc = (Lk + 31) >> 5;
+      }
+      __syncwarp();
+      // V^T: the previous item's epilogues are done (they stage their output in the V^T region)
+      for (int t = 0; t < prev_nmt; ++t) mbar_wait(&bar_ofree[t], (uses[t] - 1) & 1);
+      const int n_vc = (Lk + 31) >> 5;
+      if (elect_one()) {
         mbar_expect_tx(bar_v, (uint32_t)(n_vc * VT_CHUNK));
         for (int c = 0; c < n_vc; ++c)
           tma_load_2d(smem + SMEM_V + c * VT_CHUNK, &tmap_vt, bar_v, a_start + c * 32, h * HD);
-        for (int t = 0; t < n_mt; ++t) ++uses[t];
-        prev_nmt = n_mt;
       }
+      __syncwarp();
+      for (int t = 0; t < n_mt; ++t) ++uses[t];
+      prev_nmt = n_mt;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      uint32_t uses[2] = {0, 0};
-      uint32_t g[2] = {0, 0};  // P chunks consumed per tile slot
-      uint32_t item_n = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item_n) {
-        const int seq = it / heads;
-        const int start = cu_seqlens[seq];
-        const int len = cu_seqlens[seq + 1] - start;
-        const int n_mt = (len + 127) >> 7;
-        const int NK = ((start & 3) + len + 15) & ~15;  // shifted key axis, padded to the UMMA N step
-        const int n_pc = (NK + 63) >> 6;
-        const uint32_t idesc_s = umma_idesc(2, 128, NK);
-        const uint32_t idesc_o = umma_idesc(2, 128, HD);
-        mbar_wait(bar_k, item_n & 1);
-        mbar_wait(bar_q, item_n & 1);
-        // ---- S_t = Q_t K^T for both tiles ----
-        for (int t = 0; t < n_mt; ++t) {
-          if (uses[t] > 0) mbar_wait(&bar_otfree[t], (uses[t] - 1) & 1);  // S_t / O_t columns free again
-          tc_fence_after();
+    // warp-uniform loop; one elected lane issues the MMAs and their commits
+    uint32_t uses[2] = {0, 0};
+    uint32_t g[2] = {0, 0};  // P chunks consumed per tile slot
+    uint32_t item_n = 0;
+    const uint64_t desc_q = desc_kmajor(smem_u32(smem + SMEM_Q));
+    const uint64_t desc_k = desc_kmajor(smem_u32(smem + SMEM_K));
+    const uint64_t desc_v = desc_kmajor(smem_u32(smem + SMEM_V));
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item_n) {
+      const int seq = it / heads;
+      const int start = cu_seqlens[seq];
+      const int len = cu_seqlens[seq + 1] - start;
+      const int n_mt = (len + 127) >> 7;
+      const int NK = ((start & 3) + len + 15) & ~15;  // shifted key axis, padded to the UMMA N step
+      const int n_pc = (NK + 63) >> 6;
+      const uint32_t idesc_s = umma_idesc(2, 128, NK);
+      const uint32_t idesc_o = umma_idesc(2, 128, HD);
+      mbar_wait(bar_k, item_n & 1);
+      mbar_wait(bar_q, item_n & 1);
+      // ---- S_t = Q_t K^T for both tiles ----
+      for (int t = 0; t < n_mt; ++t) {
+        if (uses[t] > 0) mbar_wait(&bar_otfree[t], (uses[t] - 1) & 1);  // S_t / O_t columns free again
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
-            const uint64_t da = desc_kmajor(smem_u32(smem + SMEM_Q + t * QTILE_BYTES + c * 16384));
-            const uint64_t db = desc_kmajor(smem_u32(smem + SMEM_K + c * CHUNK_BYTES));
+            const uint64_t da = desc_q + (uint64_t)((t * QTILE_BYTES + c * 16384) >> 4);
+            const uint64_t db = desc_k + (uint64_t)((c * CHUNK_BYTES) >> 4);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               tc_mma_tf32(tmem_base + t * TILE_COLS, da + 2 * k, db + 2 * k, idesc_s, (c | k) != 0);
           }
           tc_commit(&bar_sfull[t]);
         }
-        // ---- O_t += P_t chunk * V chunk, the two tiles interleaved ----
-        mbar_wait(bar_v, item_n & 1);
-        for (int pc = 0; pc < n_pc; ++pc) {
-          const int keys = min(64, NK - pc * 64);
-          for (int t = 0; t < n_mt; ++t) {
-            mbar_wait(&bar_pready[t], g[t] & 1);
-            tc_fence_after();
+        __syncwarp();
+      }
+      // ---- O_t += P_t chunk * V chunk, the two tiles interleaved ----
+      mbar_wait(bar_v, item_n & 1);
+      for (int pc = 0; pc < n_pc; ++pc) {
+        const int keys = min(64, NK - pc * 64);
+        for (int t = 0; t < n_mt; ++t) {
+          mbar_wait(&bar_pready[t], g[t] & 1);
+          tc_fence_after();
+          if (elect_one()) {
             for (int k8 = 0; k8 < keys / 8; ++k8) {
               const int sub = k8 >> 2, k = k8 & 3;  // 32-key sub-chunk, 8-key step inside it
-              const uint64_t da =
-                  desc_kmajor(smem_u32(smem + SMEM_Q + t * QTILE_BYTES + sub * 16384)) + 2 * k;
-              const uint64_t db = desc_kmajor(smem_u32(smem + SMEM_V + (2 * pc + sub) * VT_CHUNK)) + 2 * k;
+              const uint64_t da = desc_q + (uint64_t)((t * QTILE_BYTES + sub * 16384) >> 4) + 2 * k;
+              const uint64_t db = desc_v + (uint64_t)(((2 * pc + sub) * VT_CHUNK) >> 4) + 2 * k;
               tc_mma_tf32(tmem_base + t * TILE_COLS, da, db, idesc_o, (pc | k8) != 0);
             }
             tc_commit(&bar_pfree[t]);
-            ++g[t];
             if (pc == n_pc - 1) tc_commit(&bar_ofull[t]);
           }
+          __syncwarp();
+          ++g[t];
         }
-        for (int t = 0; t < n_mt; ++t) ++uses[t];
       }
+      for (int t = 0; t < n_mt; ++t) ++uses[t];
     }
   } else {
     // ===================== softmax + epilogue: group 0 = warps 2..5 (tile 0), group 1 = warps 6..9 =====
@@ -239,8 +260,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
         for (int j = 0; j < 32; ++j) {
           float p0 = 0.f, p1 = 0.f;
           const int k0 = pc * 64 + j, k1 = k0 + 32;
-          if (k0 >= shift && k0 < Lk) p0 = exp2f(fmaf(__uint_as_float(r0[j]), SCALE_LOG2, -mb));
-          if (k1 >= shift && k1 < Lk) p1 = exp2f(fmaf(__uint_as_float(r1[j]), SCALE_LOG2, -mb));
+          if (k0 >= shift && k0 < Lk) p0 = fast_ex2(fmaf(__uint_as_float(r0[j]), SCALE_LOG2, -mb));
+          if (k1 >= shift && k1 < Lk) p1 = fast_ex2(fmaf(__uint_as_float(r1[j]), SCALE_LOG2, -mb));
           sum += p0 + p1;
           r0[j] = __float_as_uint(round_tf32(p0));
           r1[j] = __float_as_uint(round_tf32(p1));

@@ -1,3 +1,3 @@
-timeout 300 python scripts/gpu_probe.py gemm gemm_x3 gemm_2sm conv gemm_perf 2>&1 | grep -v '"ok": true' | cut -c1-400 | tail -30
+timeout 300 python scripts/gpu_probe.py attn 2>&1 | cut -c1-300 | tail -8
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-timeout 600 python bench.py --steps 4 --warmup 3 > gpurun_out/bench_r1_d.json 2> gpurun_out/bench_r1_d.err; tail -c 1500 gpurun_out/bench_r1_d.json; tail -3 gpurun_out/bench_r1_d.err
+timeout 600 python bench.py --steps 4 --warmup 3 > gpurun_out/bench_r1_d.json 2> gpurun_out/bench_r1_d.err; tail -c 1700 gpurun_out/bench_r1_d.json; tail -3 gpurun_out/bench_r1_d.err
