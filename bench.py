@@ -164,7 +164,7 @@ def run_ours(args):
     ms = ev[0].elapsed_time(ev[1])
     launches = int(L.lib().mer_launch_count() - l0 + models[3].graph_launches - g0)
     prof = {}
-    for name, mode in (("tf32", 0), ("bf16x3", 1)):
+    for name, mode in (("tf32", 0), ("bf16x3", 1), ("f16", 2)):
         t, f, n = C.c_double(), C.c_double(), C.c_int()
         L.lib().mer_profile_collect(mode, C.byref(t), C.byref(f), C.byref(n))
         prof[name] = (t.value, f.value, n.value)
@@ -203,13 +203,15 @@ def run_ours(args):
     if rank == 0:
         pk = peaks()
         total_clips = clips * world * args.steps
-        t_ms, t_fl, t_n = prof["tf32"]
-        # denominator: the BURST bf16 figure / 2 (tf32 pipe rate = half the bf16 rate).  The kernel is timed
-        # inside a long step, where the recipe would allow the lower sustained figure, but it now exceeds
-        # sustained / 2 (the power-capped torch.matmul number), so the harder denominator is the honest one;
-        # frac_vs_sustained is given beside it
-        tf32_peak = pk["bf16"] / 2.0
-        tf32_sust = pk["bf16_sustained"] / 2.0
+        # dominant kernel: the ViT stack's linear layers, fp16 operands by default (MER_VIT_PRECISION=tf32
+        # selects the TF32 variant).  Denominator (B200_PROFILING.md rule): the kernel is timed inside a long
+        # step -> the SUSTAINED bf16 figure of MEASURED_PEAKS (fp16 and bf16 share the tensor-pipe rate; tf32
+        # runs at half of it); the fraction of the burst figure is given beside it.
+        use_f16 = prof["f16"][2] > 0
+        t_ms, t_fl, t_n = prof["f16"] if use_f16 else prof["tf32"]
+        div = 1.0 if use_f16 else 2.0
+        tf32_peak = pk["bf16_sustained"] / div
+        burst_peak = pk["bf16"] / div
         ach = t_fl / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
         traffic = None
         tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
@@ -220,7 +222,8 @@ def run_ours(args):
             "metric": METRIC, "value": total_clips / (ms_dev * 1e-3), "unit": "clips/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32 (ViT) / bf16x3 (HuBERT, BERT) tensor-core products, fp32 accumulate; fp32 elsewhere",
+            "vs_baseline": None, "dtype": ("f16 operands (ViT linears) / tf32 (attention, patch embed)" if use_f16 else "tf32 (ViT)") +
+                                          " / bf16x3 (HuBERT, BERT) tensor-core products, fp32 accumulate; fp32 elsewhere",
             "data": "synthetic inputs, seeded random-init weights (no network)",
             "config": {"workload": f"tri-modal extract (ViT-B/16 {FRAMES}x224x224 frames + HuBERT-base 5 s @16 kHz + "
                                    f"BERT-base {TOKENS} tokens) + Attention-fusion train step (hidden 128, dropout 0.3), "
@@ -232,17 +235,21 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"kernel": "gemm_kernel<256, TF32, CTA pair, cta_group::2> (tcgen05 kind::tf32; ViT linear layers)",
+            "roofline": {"kernel": ("gemm_kernel<256, F16, CTA pair, cta_group::2> (tcgen05 kind::f16; ViT linear layers)"
+                                    if use_f16 else
+                                    "gemm_kernel<256, TF32, CTA pair, cta_group::2> (tcgen05 kind::tf32; ViT linear layers)"),
                          "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
                          "frac": ach / tf32_peak if tf32_peak else None, "traffic": traffic,
-                         "frac_vs_sustained": ach / tf32_sust if tf32_sust else None,
+                         "frac_vs_burst": ach / burst_peak if burst_peak else None,
                          "launches_timed": t_n, "share_of_step": t_ms / ms_dev if ms_dev else None,
-                         "peak_source": f"{pk['src']} MEASURED_PEAKS bf16_tflops (burst) / 2 (tf32 pipe rate = half the bf16 rate); "
-                                        f"sustained / 2 = {tf32_sust:.1f}"},
+                         "peak_source": (f"{pk['src']} MEASURED_PEAKS bf16_tflops_sustained (kernel timed inside a long "
+                                         f"step; fp16 = bf16 pipe rate); burst = {burst_peak:.1f}") if use_f16 else
+                                        (f"{pk['src']} MEASURED_PEAKS bf16_tflops_sustained / 2 (tf32 pipe rate = half "
+                                         f"the bf16 rate); burst / 2 = {burst_peak:.1f}")},
             "roofline_other": [{"kernel": "gemm_kernel<*, BF16X3> (3 bf16 MMAs per product; HuBERT/BERT)",
                                 "bound": "tensor", "achieved": b_fl / (b_ms * 1e-3) / 1e12 if b_ms > 0 else 0.0,
-                                "peak": pk["bf16"] / 3.0, "unit": "TFLOP/s (useful)",
-                                "frac": (b_fl / (b_ms * 1e-3) / 1e12) / (pk["bf16"] / 3.0) if b_ms > 0 else None,
+                                "peak": pk["bf16_sustained"] / 3.0, "unit": "TFLOP/s (useful)",
+                                "frac": (b_fl / (b_ms * 1e-3) / 1e12) / (pk["bf16_sustained"] / 3.0) if b_ms > 0 else None,
                                 "launches_timed": b_n, "share_of_step": b_ms / ms_dev if ms_dev else None}],
         }
         line["cpu_baseline"] = cpu_baseline(sample_clips=args.cpu_clips)

@@ -45,12 +45,17 @@ MER_API int mer_profile_collect(int mode, double* total_ms, double* total_flops,
 
 /* ---- GEMM (nn.Linear / Conv1d-as-GEMM / patch-embed) ---------------------------------- */
 enum { MER_EPI_GELU = 1, MER_EPI_ROUND_TF32 = 2, MER_EPI_SPLIT_BF16 = 4,
-       MER_EPI_GELU_LIBM = 8 /* with MER_EPI_GELU: libdevice erff instead of the 12-op polynomial */ };
+       MER_EPI_GELU_LIBM = 8, /* with MER_EPI_GELU: libdevice erff instead of the 12-op polynomial */
+       MER_EPI_OUT_F16 = 16   /* out is an IEEE fp16 array (round-to-nearest, saturating); ld_out in elements */ };
 /* Arithmetic mode of a GEMM.  TF32: operands are fp32 arrays (pre-rounded to tf32).  BF16X3: every
  * operand value x is stored as a bf16 pair (hi, lo), x = hi + lo to 2^-17; a row of K values (K % 32
  * == 0) occupies the bytes K fp32 values would, as 128-byte groups [32 x hi | 32 x lo]; three bf16
- * MMAs per product (hi*hi + lo*hi + hi*lo) recover ~fp32 accuracy ("split rows" below). */
-enum { MER_GEMM_TF32 = 0, MER_GEMM_BF16X3 = 1 };
+ * MMAs per product (hi*hi + lo*hi + hi*lo) recover ~fp32 accuracy ("split rows" below).
+ * F16: operands are IEEE fp16 arrays (A and W), products exact, fp32 accumulate.  fp16 carries the
+ * same 10 mantissa bits as tf32, so a GEMM on fp16-rounded operands equals the TF32 GEMM on the same
+ * values (|x| in [6.1e-5, 65504]; smaller magnitudes lose at most 3e-8 absolute) at twice the
+ * tensor-pipe rate and half the operand bytes.  K_inner % 64 == 0; all A strides in fp16 elements. */
+enum { MER_GEMM_TF32 = 0, MER_GEMM_BF16X3 = 1, MER_GEMM_F16 = 2 };
 
 typedef struct MerGemmEpilogue {
   const float* bias; /* [N] or NULL */
@@ -91,7 +96,8 @@ typedef struct MerGemmDesc {
   long long a_row_stride;
   long long a_batch_stride;
   int force_block_n; /* 0 = auto, 128 or 256 */
-  int mode;          /* MER_GEMM_TF32 | MER_GEMM_BF16X3; all A strides are in 4-byte slots either way */
+  int mode;          /* MER_GEMM_TF32 | MER_GEMM_BF16X3 (A strides in 4-byte slots) | MER_GEMM_F16 (A strides in
+                        2-byte elements) */
   int cluster;       /* 0 = auto, 1 = single CTAs, 2 = CTA pairs sharing a multicast weight tile,
                         3 = CTA pairs issuing one 256-row tcgen05.mma.cta_group::2 per K step */
   MerGemmEpilogue ep;
@@ -104,7 +110,8 @@ MER_API int mer_gemm(const MerGemmDesc* desc, void* stream);
 MER_API int mer_split_bf16(const float* in, void* out, long long rows, int K, void* stream);
 
 /* ---- row-wise kernels ------------------------------------------------------------------ */
-enum { MER_LN_ROUND_TF32 = 1, MER_LN_ACC_INIT = 2, MER_LN_ACC_ADD = 4 };
+enum { MER_LN_ROUND_TF32 = 1, MER_LN_ACC_INIT = 2, MER_LN_ACC_ADD = 4,
+       MER_LN_OUT_F16 = 8 /* y is an fp16 array (the MER_GEMM_F16 operand) */ };
 /* y = LayerNorm(x) * gamma + beta over the last dim (768 or 512).  y (fp32, tf32-rounded when
  * MER_LN_ROUND_TF32) and y_split (bf16 hi|lo rows, the BF16X3 GEMM operand) are both optional;
  * at least one must be given.  Optional side buffer acc
@@ -126,7 +133,8 @@ MER_API int mer_round_tf32(float* x, long long n, void* stream);
  * through smem, both MMAs on K-major operands) and the V columns of qkv are not read; otherwise the
  * flash-style kernel.
  * ctx is [tokens, heads*64].  flags: MER_EPI_ROUND_TF32 rounds ctx for a TF32 out-proj GEMM,
- * MER_EPI_SPLIT_BF16 writes ctx as bf16 hi|lo rows for a BF16X3 out-proj GEMM.
+ * MER_EPI_SPLIT_BF16 writes ctx as bf16 hi|lo rows for a BF16X3 out-proj GEMM, MER_EPI_OUT_F16 writes
+ * ctx as fp16 for an F16 out-proj GEMM (tcgen05 kernel only).
  * Replaces HF eager/sdpa attention (modeling_vit.py:171-196, modeling_hubert.py:262-345). */
 MER_API int mer_attention(const float* qkv, const float* vt, long long vt_ld, float* ctx,
                           const int32_t* cu_seqlens, int n_seq, long long tokens, int max_seqlen,
@@ -163,6 +171,7 @@ typedef struct MerLayerWeights {
 typedef struct MerVitModel {
   int n_layers;        /* 12 */
   float ln_eps;        /* 1e-12 */
+  int gemm_mode;       /* MER_GEMM_F16 (layer weights w_* are fp16 [N,K]) or MER_GEMM_TF32 (tf32-rounded fp32) */
   const float* patch_w;   /* [768, 768]  conv weight flattened (c, ph, pw), tf32-rounded */
   const float* patch_b;   /* [768] */
   const float* cls_pos0;  /* [768]  cls_token + position_embeddings[0] */

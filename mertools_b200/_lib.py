@@ -17,6 +17,9 @@ MER_EPI_ROUND_TF32 = 2
 MER_EPI_SPLIT_BF16 = 4
 MER_GEMM_TF32 = 0
 MER_GEMM_BF16X3 = 1
+MER_GEMM_F16 = 2
+MER_EPI_OUT_F16 = 16
+MER_LN_OUT_F16 = 8
 MER_LN_ROUND_TF32 = 1
 MER_LN_ACC_INIT = 2
 MER_LN_ACC_ADD = 4
@@ -111,9 +114,11 @@ def gemm(A, W, out, *, bias=None, res=None, gelu=False, round_out=False, split_o
          mode=MER_GEMM_TF32, rows_per_batch=None, batches=1, a_rows_dim=None, K_inner=None, taps=1, P=1,
          a_phase_stride=0, a_row_stride=None, a_batch_stride=0,
          out_bstride=0, out_row0=0, res_bstride=0, res_row0=0,
-         ld_out=None, ld_res=None, force_block_n=0, cluster=0, vt=None, vt_col0=0, gelu_libm=False):
+         ld_out=None, ld_res=None, force_block_n=0, cluster=0, vt=None, vt_col0=0, gelu_libm=False,
+         f16_out=False):
     """out = epilogue(A @ W.T).  A, W: fp32 CUDA tensors of LOGICAL shape [rows, K] / [N, K] (holding
-    tf32-rounded fp32, or split bf16 hi|lo bytes when mode is BF16X3); see MerGemmDesc in mer_b200.h."""
+    tf32-rounded fp32, or split bf16 hi|lo bytes when mode is BF16X3; fp16 tensors when mode is F16);
+    see MerGemmDesc in mer_b200.h."""
     N, K = W.shape
     d = MerGemmDesc()
     d.A, d.W = A.data_ptr(), W.data_ptr()
@@ -138,7 +143,8 @@ def gemm(A, W, out, *, bias=None, res=None, gelu=False, round_out=False, split_o
     d.ep.ld_out = ld_out if ld_out is not None else N
     d.ep.ld_res = ld_res if ld_res is not None else N
     d.ep.flags = ((MER_EPI_GELU if gelu else 0) | (MER_EPI_ROUND_TF32 if round_out else 0)
-                  | (MER_EPI_SPLIT_BF16 if split_out else 0) | (8 if gelu_libm else 0))
+                  | (MER_EPI_SPLIT_BF16 if split_out else 0) | (8 if gelu_libm else 0)
+                  | (MER_EPI_OUT_F16 if f16_out else 0))
     d.ep.split_off = N
     if vt is not None:
         d.ep.vt, d.ep.vt_ld, d.ep.vt_col0 = vt.data_ptr(), vt.shape[1], vt_col0
@@ -179,9 +185,10 @@ def round_tf32_(x):
     return x
 
 
-def attention(qkv, ctx, cu_seqlens, max_seqlen, heads, round_out=False, vt=None):
-    """vt: optional V^T [heads*64, ld] (enables the tcgen05 kernel for max_seqlen <= 256)."""
+def attention(qkv, ctx, cu_seqlens, max_seqlen, heads, round_out=False, vt=None, f16_out=False):
+    """vt: optional V^T [heads*64, ld] (enables the tcgen05 kernel for max_seqlen <= 253)."""
     check(lib().mer_attention(ptr(qkv), ptr(vt), vt.shape[1] if vt is not None else 0, ptr(ctx),
                               ptr(cu_seqlens), cu_seqlens.numel() - 1, qkv.shape[0], max_seqlen, heads,
-                              MER_EPI_ROUND_TF32 if round_out else 0, stream_ptr()))
+                              MER_EPI_OUT_F16 if f16_out else (MER_EPI_ROUND_TF32 if round_out else 0),
+                              stream_ptr()))
     return ctx

@@ -247,6 +247,8 @@ int mer_attention_launch(const float* qkv, const float* vt, long long vt_ld, flo
   // which reads V^T (written by the QKV GEMM epilogue) instead of the V columns of qkv
   if (vt && mer_attention_uses_tc(max_seqlen) && tokens > 0)
     return mer_attention_tc_launch(qkv, vt, vt_ld, ctx, cu_seqlens, n_seq, tokens, heads, flags, stream);
+  MER_REQUIRE(!(flags & MER_EPI_OUT_F16),
+              "mer_attention: fp16 ctx needs the tcgen05 kernel (V^T given, sequences <= 253 tokens)");
   MER_REQUIRE(heads > 0 && heads <= 65535 && n_seq <= 65535, "mer_attention: bad grid (%d heads, %d seqs)",
               heads, n_seq);
   if (n_seq <= 0 || max_seqlen <= 0) return 0;

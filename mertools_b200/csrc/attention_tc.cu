@@ -321,9 +321,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
           const int rr = 4 * i + sub_r;
           const int rt = q * 32 + rr;  // row inside the tile (swizzle key)
           const float4 d = *reinterpret_cast<const float4*>(src + rr * 32 + ((sub_c ^ (rt & 7)) << 2));
-          if (row0 + rr < len)
-            *reinterpret_cast<float4*>(ctx + (long long)(start + row0 + rr) * ldc + h * HD + half * 32 +
-                                       sub_c * 4) = d;
+          if (row0 + rr < len) {
+            const long long e = (long long)(start + row0 + rr) * ldc + h * HD + half * 32 + sub_c * 4;
+            if (out_mode == 3)  // fp16 ctx (operand of an F16 out-proj GEMM)
+              *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(ctx) + e) =
+                  make_uint2(pack_f16x2(d.x, d.y), pack_f16x2(d.z, d.w));
+            else
+              *reinterpret_cast<float4*>(ctx + e) = d;
+          }
         }
       }
       (void)row;
@@ -373,7 +378,7 @@ int mer_attention_tc_launch(const float* qkv, const float* vt, long long vt_ld, 
   const long long items = (long long)n_seq * heads;
   int grid = mer_num_sms();
   if (items < grid) grid = (int)items;
-  const int out_mode = (flags & MER_EPI_SPLIT_BF16) ? 2 : ((flags & MER_EPI_ROUND_TF32) ? 1 : 0);
+  const int out_mode = (flags & MER_EPI_OUT_F16) ? 3 : (flags & MER_EPI_SPLIT_BF16) ? 2 : ((flags & MER_EPI_ROUND_TF32) ? 1 : 0);
   attention_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(tm, tv, ctx, cu_seqlens, n_seq, heads, out_mode);
   MER_CUDA_CHECK(cudaGetLastError());
   mer_count_launches(1);

@@ -58,6 +58,7 @@ int linear(int mode, const float* A, const float* W, const float* bias, const fl
 
 int mer_run_stack(const MerStackArgs& a, cudaStream_t stream) {
   MER_REQUIRE(a.tokens > 0 && a.tokens < (1ll << 31), "mer_run_stack: bad token count %lld", a.tokens);
+  MER_REQUIRE(a.mode != MER_GEMM_F16 || a.pre_ln, "mer_run_stack: the F16 mode is for the pre-LN stack");
   const long long M = a.tokens;
   const size_t hs_bytes = (size_t)M * D * sizeof(float);
   if (a.opt_hidden && !a.hidden0_done) MER_CUDA_CHECK(cudaMemcpyAsync(a.opt_hidden, a.x, hs_bytes, cudaMemcpyDeviceToDevice, stream));
@@ -70,7 +71,25 @@ int mer_run_stack(const MerStackArgs& a, cudaStream_t stream) {
     // the V columns of qkv
     float* vt = (a.vt && mer_attention_uses_tc(a.max_seqlen)) ? a.vt : nullptr;
     const int opnd = split ? MER_EPI_SPLIT_BF16 : MER_EPI_ROUND_TF32;
-    if (a.pre_ln) {
+    if (a.pre_ln && a.mode == MER_GEMM_F16) {
+      // same chain with fp16 GEMM operands: LN and attention write fp16 (into xn), FC1 writes fp16 (into
+      // h); the residual stream x, the QKV output and V^T stay fp32
+      float* xn16 = a.xn;  // fp16 [M, 768] inside the fp32-sized scratch
+      float* h16 = a.h;    // fp16 [M, 3072]
+      MER_REQUIRE(vt != nullptr, "mer_run_stack: the F16 stack needs the tcgen05 attention (sequences <= 253)");
+      MER_TRY(mer_layernorm_launch(a.x, w.ln1_g, w.ln1_b, xn16, nullptr, nullptr, M, D, a.eps, MER_LN_OUT_F16,
+                                   stream));
+      MER_TRY(linear(a.mode, xn16, w.w_qkv, w.b_qkv, nullptr, a.qkv, M, DQKV, D, MER_EPI_ROUND_TF32, stream,
+                     vt, a.vt_ld, 2 * D));
+      MER_TRY(mer_attention_launch(a.qkv, vt, a.vt_ld, xn16, a.cu_seqlens, a.n_seq, M, a.max_seqlen, HEADS,
+                                   MER_EPI_OUT_F16, stream));
+      MER_TRY(linear(a.mode, xn16, w.w_o, w.b_o, a.x, a.x, M, D, D, 0, stream));
+      MER_TRY(mer_layernorm_launch(a.x, w.ln2_g, w.ln2_b, xn16, nullptr, nullptr, M, D, a.eps, MER_LN_OUT_F16,
+                                   stream));
+      MER_TRY(linear(a.mode, xn16, w.w_fc1, w.b_fc1, nullptr, h16, M, DFF, D, MER_EPI_GELU | MER_EPI_OUT_F16,
+                     stream));
+      MER_TRY(linear(a.mode, h16, w.w_fc2, w.b_fc2, a.x, a.x, M, D, DFF, 0, stream));
+    } else if (a.pre_ln) {
       // x = x + Wo * Attn(LN1(x));  x = x + W2 * GELU(W1 * LN2(x))
       MER_TRY(mer_layernorm_launch(a.x, w.ln1_g, w.ln1_b, split ? nullptr : a.xn, split ? a.xn : nullptr,
                                    nullptr, M, D, a.eps, MER_LN_ROUND_TF32, stream));
@@ -183,7 +202,9 @@ int mer_vit_forward(const MerVitModel* m, const uint8_t* frames_bgr, int n_frame
   a.layers = m->layers;
   a.n_layers = m->n_layers;
   a.pre_ln = 1;
-  a.mode = MER_GEMM_TF32;
+  MER_REQUIRE(m->gemm_mode == MER_GEMM_TF32 || m->gemm_mode == MER_GEMM_F16,
+              "mer_vit_forward: gemm_mode %d (MER_GEMM_TF32 or MER_GEMM_F16)", m->gemm_mode);
+  a.mode = m->gemm_mode;
   a.eps = m->ln_eps;
   a.tokens = M;
   a.cu_seqlens = offsets;

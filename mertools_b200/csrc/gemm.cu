@@ -18,7 +18,9 @@
 //                             quarter, half of the columns each)
 // TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
-// Two arithmetic modes share the pipeline (both move 4 bytes per operand element):
+// Three arithmetic modes share the pipeline (128 bytes of K per smem row and stage in each):
+//   MER_GEMM_F16    : IEEE fp16 operands (64 K elements per stage), kind::f16.  Same 10-bit mantissa as
+//                     tf32, twice the MMA rate, half the operand bytes: the ViT stack's default.
 //   MER_GEMM_TF32   : fp32 operands (pre-rounded to tf32 by their producers), kind::tf32, 128B swizzle.
 //                     ~2.4e-4 relative error per GEMM: enough for the pre-LN ViT at 1e-3.
 //   MER_GEMM_BF16X3 : every operand stored as bf16 (hi, lo) pairs, x = hi + lo to 2^-17, in 128-byte
@@ -46,7 +48,7 @@ namespace {
 using namespace mer;
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 32;  // K elements per stage in BOTH modes (128 B of tf32 / 64 B of bf16 per part)
+constexpr int BLOCK_K = 32;  // K elements per stage in TF32 / BF16X3 mode (128 B of tf32 / 64 B of bf16 per part)
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_WARPS = 16;     // four per TMEM lane quarter, each taking a quarter of the tile's columns
 constexpr int NUM_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);  // 4 control warps + 16 epilogue warps
@@ -54,10 +56,12 @@ constexpr int NUM_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);  // 4 control warps + 
 template <int BLOCK_N, int MODE, bool TWOSM = false>
 struct GemmCfg {
   static constexpr bool kSplit = MODE == MER_GEMM_BF16X3;
+  static constexpr bool kF16 = MODE == MER_GEMM_F16;
+  static constexpr int kBlockK = kF16 ? 64 : BLOCK_K;  // K elements per stage
   static constexpr int kRowBytes = 128;                 // bytes of K per smem row = swizzle span
   static constexpr int kSBO = 8 * kRowBytes;            // byte stride between 8-row core groups
   static constexpr int kLayout = 2;                     // UMMA LayoutType SWIZZLE_128B
-  static constexpr int kFmt = kSplit ? 1 : 2;           // instr-desc operand format: bf16 / tf32
+  static constexpr int kFmt = kSplit ? 1 : (kF16 ? 0 : 2);  // instr-desc operand format: bf16 / f16 / tf32
   // TWOSM (cta_group::2): each CTA of the pair keeps only ITS half of the weight tile in smem
   // stage count: what fits beside the epilogue's 32 KB of staging (227 KB usable per CTA)
   static constexpr int kStages = TWOSM ? 6 : (BLOCK_N == 256 ? 4 : 6);
@@ -106,7 +110,7 @@ struct EpiTile {
   uint32_t t_addr;        // TMEM address: this warp's lane quarter, accumulator stage, first column
   int n0;                 // first global output column of the warp's slice
   int rows_left;          // rows r < rows_left of the warp's 32 are real
-  float* out_lane;        // &out[row0 + lane / 4][n0 + 4 * (lane % 4)]  (write-out phase)
+  long long out_off;      // element index of out[row0 + lane / 4][n0]  (write-out phase)
   const float* res_lane;  // same position in the residual, or nullptr
   float* vt_lane;         // &vt[0][row0 + lane] for the transposed side output, or nullptr
   long long ld_out8, ld_res8;  // 8 rows of out / res, in floats
@@ -122,7 +126,8 @@ struct EpiTile {
 // the shape it is written (its lines were prefetched into L2 at tile start, under the MMAs).
 // The TMEM stage is handed back to the MMA warp as soon as the LAST chunk has been read into
 // registers, i.e. before that chunk's math and stores.
-// GELU: 0 none, 1 polynomial erf, 2 libdevice erff.  OUT: 0 fp32, 1 TF32-rounded fp32, 2 bf16 (hi|lo).
+// GELU: 0 none, 1 polynomial erf, 2 libdevice erff.  OUT: 0 fp32, 1 TF32-rounded fp32, 2 bf16 (hi|lo),
+// 3 fp16.
 // RES: add the residual (GELU == 0, OUT != 2 only).  The transposed side output exists for GELU == 0.
 template <int CH, int GELU, int OUT, bool RES, typename ReleaseFn>
 __device__ __forceinline__ void epi_tile(const EpiTile& tl, const MerGemmEpilogue& ep, float* stg,
@@ -197,17 +202,21 @@ __device__ __forceinline__ void epi_tile(const EpiTile& tl, const MerGemmEpilogu
           // the 32-column group's 128 bytes are [32 x bf16 hi | 32 x bf16 lo]
           const float hx = bf16_round(v.x), hy = bf16_round(v.y), hz = bf16_round(v.z), hw = bf16_round(v.w);
           if (row < tl.rows_left) {
-            uint16_t* grp = reinterpret_cast<uint16_t*>(tl.out_lane + i * tl.ld_out8 + ci * 32);
+            uint16_t* grp = reinterpret_cast<uint16_t*>(ep.out + tl.out_off + i * tl.ld_out8 + ci * 32);
             const int c = sub * 16 + 4 * p_slot;
             *reinterpret_cast<uint2*>(grp + c) = make_uint2(pack_bf16x2(hx, hy), pack_bf16x2(hz, hw));
             *reinterpret_cast<uint2*>(grp + 32 + c) =
                 make_uint2(pack_bf16x2(v.x - hx, v.y - hy), pack_bf16x2(v.z - hz, v.w - hw));
           }
+        } else if (OUT == 3) {
+          if (row < tl.rows_left)
+            *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(ep.out) + tl.out_off + i * tl.ld_out8 + col) =
+                make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w));
         } else {
           if (OUT == 1) {
             v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
           }
-          if (row < tl.rows_left) *reinterpret_cast<float4*>(tl.out_lane + i * tl.ld_out8 + col) = v;
+          if (row < tl.rows_left) *reinterpret_cast<float4*>(ep.out + tl.out_off + i * tl.ld_out8 + col) = v;
         }
       }
       __syncwarp();
@@ -249,7 +258,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   const int m_tiles = (rows_per_batch + BLOCK_M - 1) / BLOCK_M;
   const int n_tiles = N / BLOCK_N;
-  const int num_kb = K / BLOCK_K;
+  const int num_kb = K / Cfg::kBlockK;
   // work items: (row-tile group, column block); a group is CLUSTER consecutive (batch, m-tile) tiles
   const int total_m = batches * m_tiles;
   const int num_tiles = ((total_m + CLUSTER - 1) / CLUSTER) * n_tiles;
@@ -307,25 +316,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             mbar_expect_tx_cluster(lbar, Cfg::kStageBytes);
             tma_load_4d_2sm(smem_a + stage * Cfg::kABytes, &tmap_a, lbar, c0 * kEl, tap_phase,
                             mt * BLOCK_M + tap_row, b);
-            tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &tmap_b, lbar, kb * BLOCK_K * kEl,
+            tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &tmap_b, lbar, kb * Cfg::kBlockK * kEl,
                             n_blk * BLOCK_N + cta_rank * (BLOCK_N / 2));
           } else {
             mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
             tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], c0 * kEl, tap_phase,
                         mt * BLOCK_M + tap_row, b);
             if (CLUSTER == 1) {
-              tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * BLOCK_K * kEl,
+              tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * Cfg::kBlockK * kEl,
                           n_blk * BLOCK_N);
             } else {
               tma_load_2d_mc(smem_b + stage * Cfg::kBBytes + cta_rank * (Cfg::kBBytes / CLUSTER), &tmap_b,
-                             &full_bar[stage], kb * BLOCK_K * kEl,
+                             &full_bar[stage], kb * Cfg::kBlockK * kEl,
                              n_blk * BLOCK_N + cta_rank * (BLOCK_N / CLUSTER),
                              (uint16_t)((1u << CLUSTER) - 1));
             }
           }
         }
         __syncwarp();
-        c0 += BLOCK_K;
+        c0 += Cfg::kBlockK;
         if (c0 == K_inner) {
           c0 = 0;
           if (++tap_phase == P) {
@@ -363,7 +372,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             const uint64_t da = desc_a0 + (uint64_t)(stage * (Cfg::kABytes >> 4));
             const uint64_t db = desc_b0 + (uint64_t)(stage * (Cfg::kBBytes >> 4));
             // advance the start address by 32-byte K steps inside the 128B swizzle row (>>4 => +2)
-            if (!Cfg::kSplit) {
+            if (Cfg::kF16) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {  // 4 x 16 fp16
+                if (TWOSM) tc_mma_bf16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                else tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+              }
+            } else if (!Cfg::kSplit) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {  // 4 x 8 tf32
                 if (TWOSM) tc_mma_tf32_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
@@ -416,8 +431,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     int as = 0;
     uint32_t aphase = 0;
     const int gelu_kind = (ep.flags & MER_EPI_GELU) ? ((ep.flags & MER_EPI_GELU_LIBM) ? 2 : 1) : 0;
-    const int out_kind = (ep.flags & MER_EPI_SPLIT_BF16) ? 2 : ((ep.flags & MER_EPI_ROUND_TF32) ? 1 : 0);
-    const int kind = gelu_kind * 3 + out_kind;
+    const int out_kind = (ep.flags & MER_EPI_OUT_F16) ? 3 : (ep.flags & MER_EPI_SPLIT_BF16) ? 2 :
+                         ((ep.flags & MER_EPI_ROUND_TF32) ? 1 : 0);
+    const int kind = gelu_kind * 4 + out_kind;
     for (int t = first_tile; t < num_tiles; t += tile_step) {
       const int n_blk = t % n_tiles;
       const int mb = (t / n_tiles) * CLUSTER + cta_rank;
@@ -428,7 +444,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       tl.n0 = n_blk * BLOCK_N + cq * (BLOCK_N / 4);
       tl.rows_left = (mb < total_m) ? rows_per_batch - m0 : 0;
       const long long out_row = (long long)b * ep.out_bstride + ep.out_row0 + m0;
-      tl.out_lane = ep.out + (out_row + p_row) * (long long)ep.ld_out + tl.n0;
+      tl.out_off = (out_row + p_row) * (long long)ep.ld_out + tl.n0;
       tl.res_lane = ep.res ? ep.res + ((long long)b * ep.res_bstride + ep.res_row0 + m0 + p_row) *
                                           (long long)ep.ld_res + tl.n0
                            : nullptr;
@@ -464,12 +480,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           case 0: epi_tile<CH, 0, 0, false>(tl, ep, stg, lane, release); break;
           case 1: epi_tile<CH, 0, 1, false>(tl, ep, stg, lane, release); break;
           case 2: epi_tile<CH, 0, 2, false>(tl, ep, stg, lane, release); break;
-          case 3: epi_tile<CH, 1, 0, false>(tl, ep, stg, lane, release); break;
-          case 4: epi_tile<CH, 1, 1, false>(tl, ep, stg, lane, release); break;
-          case 5: epi_tile<CH, 1, 2, false>(tl, ep, stg, lane, release); break;
-          case 6: epi_tile<CH, 2, 0, false>(tl, ep, stg, lane, release); break;
-          case 7: epi_tile<CH, 2, 1, false>(tl, ep, stg, lane, release); break;
-          default: epi_tile<CH, 2, 2, false>(tl, ep, stg, lane, release); break;
+          case 3: epi_tile<CH, 0, 3, false>(tl, ep, stg, lane, release); break;
+          case 4: epi_tile<CH, 1, 0, false>(tl, ep, stg, lane, release); break;
+          case 5: epi_tile<CH, 1, 1, false>(tl, ep, stg, lane, release); break;
+          case 6: epi_tile<CH, 1, 2, false>(tl, ep, stg, lane, release); break;
+          case 7: epi_tile<CH, 1, 3, false>(tl, ep, stg, lane, release); break;
+          case 8: epi_tile<CH, 2, 0, false>(tl, ep, stg, lane, release); break;
+          case 9: epi_tile<CH, 2, 1, false>(tl, ep, stg, lane, release); break;
+          case 10: epi_tile<CH, 2, 2, false>(tl, ep, stg, lane, release); break;
+          default: epi_tile<CH, 2, 3, false>(tl, ep, stg, lane, release); break;
         }
       }
       if (++as == 2) {
@@ -493,26 +512,28 @@ template <int BLOCK_N, int MODE, int CLUSTER, bool TWOSM = false>
 int launch_gemm(const MerGemmDesc* g, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, MODE, TWOSM>;
   CUtensorMap ta, tb;
-  const CUtensorMapDataType dt =
-      Cfg::kSplit ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapDataType dt = Cfg::kSplit ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                 : Cfg::kF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                             : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
   const uint64_t mult = Cfg::kSplit ? 2 : 1;  // bf16 elements per 4-byte operand slot
+  const uint64_t sbytes = Cfg::kF16 ? 2 : 4;  // bytes per stride unit (fp16 element / 4-byte slot)
   {
     // strides are given in 4-byte operand slots in both modes (a split row of K (hi|lo) pairs
     // occupies exactly the bytes of K fp32 values)
     const uint64_t dims[4] = {(uint64_t)g->K_inner * mult, (uint64_t)g->P, (uint64_t)g->a_rows_dim,
                               (uint64_t)g->batches};
-    const uint64_t strides[3] = {(uint64_t)g->a_phase_stride * 4ull,
-                                 (uint64_t)g->a_row_stride * 4ull,
-                                 (uint64_t)g->a_batch_stride * 4ull};
-    const uint32_t box[4] = {(uint32_t)(BLOCK_K * mult), 1, BLOCK_M, 1};
+    const uint64_t strides[3] = {(uint64_t)g->a_phase_stride * sbytes,
+                                 (uint64_t)g->a_row_stride * sbytes,
+                                 (uint64_t)g->a_batch_stride * sbytes};
+    const uint32_t box[4] = {(uint32_t)(Cfg::kBlockK * mult), 1, BLOCK_M, 1};
     if (int rc = mer_make_tmap(&ta, dt, 4, g->A, dims, strides, box, sw)) return rc;
   }
   {
     const int K = g->K_inner * g->taps;
     const uint64_t dims[2] = {(uint64_t)K * mult, (uint64_t)g->N};
-    const uint64_t strides[1] = {(uint64_t)K * 4ull};
-    const uint32_t box[2] = {(uint32_t)(BLOCK_K * mult), BLOCK_N / CLUSTER};  // each CTA loads its share
+    const uint64_t strides[1] = {(uint64_t)K * sbytes};
+    const uint32_t box[2] = {(uint32_t)(Cfg::kBlockK * mult), BLOCK_N / CLUSTER};  // each CTA loads its share
     if (int rc = mer_make_tmap(&tb, dt, 2, g->W, dims, strides, box, sw)) return rc;
   }
   static bool attr_set = false;
@@ -571,16 +592,23 @@ int launch_gemm(const MerGemmDesc* g, cudaStream_t stream) {
 
 int mer_gemm_launch(const MerGemmDesc* g, cudaStream_t stream) {
   MER_REQUIRE(g && g->A && g->W && g->ep.out, "mer_gemm: null operand");
-  MER_REQUIRE(g->mode == MER_GEMM_TF32 || g->mode == MER_GEMM_BF16X3, "mer_gemm: unknown mode %d", g->mode);
+  MER_REQUIRE(g->mode == MER_GEMM_TF32 || g->mode == MER_GEMM_BF16X3 || g->mode == MER_GEMM_F16,
+              "mer_gemm: unknown mode %d", g->mode);
+  const int kstep = g->mode == MER_GEMM_F16 ? 64 : BLOCK_K;
+  const int salign = g->mode == MER_GEMM_F16 ? 8 : 4;  // stride units per 16 bytes
 
-  MER_REQUIRE(g->K_inner > 0 && g->K_inner % BLOCK_K == 0 && g->taps > 0 && g->P > 0,
+  MER_REQUIRE(g->K_inner > 0 && g->K_inner % kstep == 0 && g->taps > 0 && g->P > 0,
               "mer_gemm: K_inner=%d must be a positive multiple of %d (taps=%d P=%d)",
-              g->K_inner, BLOCK_K, g->taps, g->P);
+              g->K_inner, kstep, g->taps, g->P);
   MER_REQUIRE(g->a_rows_dim >= g->rows_per_batch, "mer_gemm: a_rows_dim < rows_per_batch");
   MER_REQUIRE(g->N > 0 && g->N % 128 == 0, "mer_gemm: N=%d must be a multiple of 128", g->N);
   MER_REQUIRE(g->rows_per_batch > 0 && g->batches > 0, "mer_gemm: empty problem");
-  MER_REQUIRE(g->a_row_stride % 4 == 0 && g->a_batch_stride % 4 == 0 && g->a_phase_stride % 4 == 0,
+  MER_REQUIRE(g->a_row_stride % salign == 0 && g->a_batch_stride % salign == 0 &&
+                  g->a_phase_stride % salign == 0,
               "mer_gemm: A strides must be multiples of 16 bytes");
+  MER_REQUIRE(!((g->ep.flags & MER_EPI_OUT_F16) &&
+                ((g->ep.flags & (MER_EPI_SPLIT_BF16 | MER_EPI_ROUND_TF32)) || g->ep.res)),
+              "mer_gemm: an fp16 output excludes the other output formats and a residual");
   MER_REQUIRE(g->ep.ld_out % 4 == 0 && (g->ep.res == nullptr || g->ep.ld_res % 4 == 0),
               "mer_gemm: out/res leading dims must be multiples of 4 floats");
   MER_REQUIRE(!((g->ep.flags & MER_EPI_SPLIT_BF16) && (g->ep.res || g->ep.vt)),
@@ -599,6 +627,10 @@ int mer_gemm_launch(const MerGemmDesc* g, cudaStream_t stream) {
   // weight tile); MER_GEMM_NO_2SM=1 or cluster == 2 selects the multicast variant
   static const bool no_twosm_env = getenv("MER_GEMM_NO_2SM") != nullptr;
   const bool twosm = pair && (g->cluster == 3 || (g->cluster == 0 && !no_twosm_env));
+  if (g->mode == MER_GEMM_F16) {
+    if (pair) return launch_gemm<256, MER_GEMM_F16, 2, true>(g, stream);  // pairs always issue cta_group::2
+    return wide ? launch_gemm<256, MER_GEMM_F16, 1>(g, stream) : launch_gemm<128, MER_GEMM_F16, 1>(g, stream);
+  }
   if (g->mode == MER_GEMM_BF16X3) {
     if (twosm) return launch_gemm<256, MER_GEMM_BF16X3, 2, true>(g, stream);
     if (pair) return launch_gemm<256, MER_GEMM_BF16X3, 2>(g, stream);

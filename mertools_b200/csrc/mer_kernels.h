@@ -48,7 +48,7 @@ struct MerStackArgs {
   const MerLayerWeights* layers;
   int n_layers;
   int pre_ln;
-  int mode;                  // MER_GEMM_TF32 | MER_GEMM_BF16X3
+  int mode;                  // MER_GEMM_TF32 | MER_GEMM_BF16X3 | MER_GEMM_F16 (pre-LN only)
   float eps;
   long long tokens;          // total packed tokens (rows of x)
   const int* cu_seqlens;     // device [n_seq+1]

@@ -48,7 +48,9 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
       q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
     }
     const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / DIM) + eps);
-    float4* yr = y ? reinterpret_cast<float4*>(y + row * DIM) : nullptr;
+    const bool y16 = (flags & MER_LN_OUT_F16) != 0;  // y is an fp16 row (the F16 GEMM operand)
+    float4* yr = (y && !y16) ? reinterpret_cast<float4*>(y + row * DIM) : nullptr;
+    uint2* yh = (y && y16) ? reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(y) + row * DIM) : nullptr;
     float* ysr = ys ? reinterpret_cast<float*>(ys) + row * DIM : nullptr;  // split row: DIM 4-byte slots
     float4* ar = acc ? reinterpret_cast<float4*>(acc + row * DIM) : nullptr;
 #pragma unroll
@@ -68,6 +70,7 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
         }
       }
       if (ysr) store_split4(ysr, 4 * (lane + 32 * i), o);
+      if (yh) yh[lane + 32 * i] = make_uint2(pack_f16x2(o.x, o.y), pack_f16x2(o.z, o.w));
       if (yr) {
         if (flags & MER_LN_ROUND_TF32) {
           o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
@@ -105,7 +108,10 @@ int mer_layernorm_launch(const float* x, const float* gamma, const float* beta, 
                          cudaStream_t stream) {
   MER_REQUIRE(x && gamma && beta && (y || y_split), "mer_layernorm: null operand");
   // y == x and y_split == x are both fine: a warp holds its whole row in registers before it
-  // writes, and a split row occupies exactly the bytes of the fp32 row it replaces.
+  // writes, and a split row occupies exactly the bytes of the fp32 row it replaces.  (An fp16 y must
+  // not alias x: its rows are half as long.)
+  MER_REQUIRE(!((flags & MER_LN_OUT_F16) && (const void*)y == (const void*)x),
+              "mer_layernorm: an fp16 output cannot alias the input");
   MER_REQUIRE(dim == 768 || dim == 512, "mer_layernorm: dim %d not supported (768 or 512)", dim);
   if (rows <= 0) return 0;
   const int warps_per_block = 8;

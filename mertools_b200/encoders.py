@@ -17,7 +17,7 @@ from . import weights as W
 
 
 class MerVitModel(C.Structure):
-    _fields_ = [("n_layers", C.c_int), ("ln_eps", C.c_float), ("patch_w", C.c_void_p),
+    _fields_ = [("n_layers", C.c_int), ("ln_eps", C.c_float), ("gemm_mode", C.c_int), ("patch_w", C.c_void_p),
                 ("patch_b", C.c_void_p), ("cls_pos0", C.c_void_p), ("pos_rest", C.c_void_p),
                 ("layers", C.POINTER(W.MerLayerWeights))]
 
@@ -39,9 +39,14 @@ class _Workspace:
 class VitEncoder:
     """ViT-B/16 frame encoder (HF ``ViTModel``) + ``hidden_states[-1].sum(dim=1)`` readout.
 
-    Reference: MERBench/feature_extraction/visual/extract_vision_huggingface.py:135-145."""
+    Reference: MERBench/feature_extraction/visual/extract_vision_huggingface.py:135-145.
 
-    def __init__(self, state_dict, device="cuda", ln_eps=1e-12):
+    precision: "f16" (default) runs the 12 layers' linear layers on fp16 operands (LayerNorm / attention /
+    GELU outputs and the weights stored as fp16, fp32 accumulation, fp32 residual stream); "tf32" keeps
+    them as tf32-rounded fp32.  Both carry a 10-bit mantissa, i.e. the same products; fp16 halves the
+    operand traffic and doubles the tensor-pipe rate.  MER_VIT_PRECISION overrides the default."""
+
+    def __init__(self, state_dict, device="cuda", ln_eps=1e-12, precision=None):
         L.check(L.lib().mer_check_device())
         sd = W._np(state_dict)
         self.device = torch.device(device)
@@ -55,8 +60,13 @@ class VitEncoder:
         self.patch_b = self.pk.keep(sd["embeddings.patch_embeddings.projection.bias"])
         self.cls_pos0 = self.pk.keep(sd["embeddings.cls_token"].reshape(768) + pos[0])
         self.pos_rest = self.pk.keep(pos[1:])
-        self.layers = W.pack_layers(sd, W.VIT_NAMES, self.n_layers, self.pk)
-        self.model = MerVitModel(self.n_layers, ln_eps, self.patch_w.data_ptr(),
+        import os
+        self.precision = precision or os.environ.get("MER_VIT_PRECISION", "f16")
+        assert self.precision in ("f16", "tf32"), self.precision
+        f16 = self.precision == "f16"
+        self.layers = W.pack_layers(sd, W.VIT_NAMES, self.n_layers, self.pk, f16=f16)
+        self.model = MerVitModel(self.n_layers, ln_eps, L.MER_GEMM_F16 if f16 else L.MER_GEMM_TF32,
+                                 self.patch_w.data_ptr(),
                                  self.patch_b.data_ptr(), self.cls_pos0.data_ptr(),
                                  self.pos_rest.data_ptr(), self.layers)
         self.ws = _Workspace(self.device)

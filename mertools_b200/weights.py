@@ -33,24 +33,28 @@ class Packed:
         self.device = device
         self.tensors = []
 
-    def keep(self, x, tf32=False, split=False):
-        """tf32: round-to-nearest in place (TF32 GEMM operand); split: bf16 hi|lo rows (BF16X3)."""
+    def keep(self, x, tf32=False, split=False, f16=False):
+        """tf32: round-to-nearest in place (TF32 GEMM operand); split: bf16 hi|lo rows (BF16X3);
+        f16: IEEE fp16, round-to-nearest, saturating (F16 GEMM operand)."""
         t = _dev(x, self.device)
         if tf32:
             L.round_tf32_(t)
         if split:
             t = L.split_bf16(t)
+        if f16:
+            t = t.clamp(-65504.0, 65504.0).to(torch.float16)
         self.tensors.append(t)
         return t
 
     def nbytes(self):
-        return sum(t.numel() * 4 for t in self.tensors)
+        return sum(t.numel() * t.element_size() for t in self.tensors)
 
 
-def pack_layers(sd, names, n_layers, pk: Packed, split=False):
-    """names: dict role -> key template with ``{i}``.  split=False: tf32-rounded fp32 GEMM weights
-    (MER_GEMM_TF32 stack); split=True: bf16 hi|lo rows (MER_GEMM_BF16X3 stack)."""
-    kw = dict(split=True) if split else dict(tf32=True)
+def pack_layers(sd, names, n_layers, pk: Packed, split=False, f16=False):
+    """names: dict role -> key template with ``{i}``.  Default: tf32-rounded fp32 GEMM weights
+    (MER_GEMM_TF32 stack); split=True: bf16 hi|lo rows (MER_GEMM_BF16X3 stack); f16=True: fp16
+    (MER_GEMM_F16 stack)."""
+    kw = dict(f16=True) if f16 else (dict(split=True) if split else dict(tf32=True))
     arr = (MerLayerWeights * n_layers)()
     for i in range(n_layers):
         g = lambda role: sd[names[role].format(i=i)]  # noqa: E731

@@ -261,6 +261,59 @@ def sec_gemm_perf():
     return True
 
 
+def sec_gemm_f16():
+    """F16 mode: fp16 operands, fp32 accumulate; fp32 / tf32 / fp16 outputs, residual, V^T side output."""
+    ok = True
+    for (name, M, N, K, force, cl) in [("f16_1tile", 128, 128, 64, 0, 0), ("f16_tail", 300, 256, 768, 256, 0),
+                                       ("f16_fc1", 45000, 3072, 768, 0, 0), ("f16_fc2", 45000, 768, 3072, 0, 0),
+                                       ("f16_qkv_1cta", 5000, 2304, 768, 0, 1)]:
+        g = torch.Generator(device="cuda").manual_seed(11)
+        A = torch.randn(M, K, device="cuda", generator=g).half()
+        W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).half()
+        b = torch.randn(N, device="cuda", generator=g)
+        R = torch.randn(M, N, device="cuda", generator=g)
+        ref = A.double() @ W.double().t() + b.double()
+        out = torch.full((M, N), float("nan"), device="cuda")
+        L.gemm(A, W, out, bias=b, res=R, mode=L.MER_GEMM_F16, force_block_n=force, cluster=cl)
+        out16 = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float16)
+        L.gemm(A, W, out16, bias=b, gelu=True, f16_out=True, mode=L.MER_GEMM_F16, force_block_n=force, cluster=cl)
+        torch.cuda.synchronize()
+        e1 = (out.double() - (ref + R.double())).abs().max().item() / ref.abs().max().item()
+        refg = gelu(ref)
+        e2 = (out16.double() - refg).abs().max().item() / refg.abs().max().item()
+        good = e1 < 2e-5 and e2 < 6e-4 and not torch.isnan(out16).any().item()
+        info = dict(check=name, ok=bool(good), M=M, N=N, K=K, rel_err_f32_res=e1, rel_err_gelu_f16=e2)
+        if N == 2304:  # QKV shape: tf32-rounded output + transposed V
+            ld = (M + 3) // 4 * 4
+            vt = torch.zeros(768, ld, device="cuda")
+            q = torch.full((M, N), float("nan"), device="cuda")
+            L.gemm(A, W, q, bias=b, round_out=True, mode=L.MER_GEMM_F16, vt=vt, vt_col0=1536, cluster=cl)
+            torch.cuda.synchronize()
+            rq = tf32(ref.float()).double()
+            e3 = (q[:, :1536].double() - rq[:, :1536]).abs().max().item() / rq.abs().max().item()
+            e4 = (vt[:, :M].double() - rq[:, 1536:].t()).abs().max().item() / rq.abs().max().item()
+            info.update(rel_err_qk=e3, rel_err_vt=e4)
+            good = good and e3 < 1e-3 and e4 < 1e-3
+            info["ok"] = bool(good)
+        emit(**info)
+        ok &= good
+    M = 403456
+    for (name, N, K, kw) in [("qkv", 2304, 768, dict(round_out=True)), ("outproj", 768, 768, dict(res=True)),
+                             ("fc1", 3072, 768, dict(gelu=True, f16_out=True)), ("fc2", 768, 3072, dict(res=True))]:
+        A = torch.randn(M, K, device="cuda").half()
+        W = (torch.randn(N, K, device="cuda") * 0.02).half()
+        b = torch.randn(N, device="cuda")
+        R = torch.randn(M, N, device="cuda") if kw.pop("res", False) else None
+        out = torch.empty(M, N, device="cuda", dtype=torch.float16 if kw.get("f16_out") else torch.float32)
+        ms = time_cuda(lambda: L.gemm(A, W, out, bias=b, res=R, mode=L.MER_GEMM_F16, **kw), iters=10)
+        o2 = torch.empty(M, N, device="cuda", dtype=torch.float16)
+        ms_t = time_cuda(lambda: torch.matmul(A, W.t(), out=o2), iters=5)
+        emit(perf="f16_" + name, M=M, N=N, K=K, ms=ms, tflops=2.0 * M * N * K / ms / 1e9, torch_f16_ms=ms_t,
+             torch_tflops=2.0 * M * N * K / ms_t / 1e9)
+        del A, W, out, R, o2
+    return ok
+
+
 def sec_one():
     """One ViT GEMM shape, a few launches (for ncu): MER_PROBE_SHAPE = qkv | outproj | fc1 | fc2."""
     M = 403456
@@ -354,7 +407,7 @@ def sec_vit():
     return True
 
 
-SECTIONS = dict(one=sec_one, vit=sec_vit, gemm_x3=sec_gemm_x3, gemm_2sm=sec_gemm_2sm, gelu_ab=sec_gelu_ab, gemm=sec_gemm, conv=sec_conv, gemm_perf=sec_gemm_perf, ln=sec_ln, attn=sec_attn)
+SECTIONS = dict(one=sec_one, gemm_f16=sec_gemm_f16, vit=sec_vit, gemm_x3=sec_gemm_x3, gemm_2sm=sec_gemm_2sm, gelu_ab=sec_gelu_ab, gemm=sec_gemm, conv=sec_conv, gemm_perf=sec_gemm_perf, ln=sec_ln, attn=sec_attn)
 
 if __name__ == "__main__":
     os.makedirs("gpurun_out", exist_ok=True)

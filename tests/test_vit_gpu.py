@@ -1,8 +1,9 @@
 """GPU parity of the visual hot path against the oracle (bit-identical weights and inputs).
 
 Tolerance (north_star): 1e-3 relative fp32, measured as max|got - ref| / max|ref| over the tensor
-and as the relative L2 norm.  The CUDA path computes GEMM/attention products in TF32 with fp32
-accumulation (round-to-nearest operands), everything else in fp32.
+and as the relative L2 norm.  The CUDA path computes the linear layers' products on fp16 operands
+(default) or TF32 operands (both 10-bit mantissas, round-to-nearest), attention in TF32, all with fp32
+accumulation; everything else in fp32.  Both precisions must pass.
 """
 import numpy as np
 import pytest
@@ -21,12 +22,13 @@ def rel(got, ref):
     return float((got - ref).abs().max() / ref.abs().max()), float((got - ref).norm() / ref.norm())
 
 
+@pytest.mark.parametrize("precision", ["f16", "tf32"])
 @pytest.mark.parametrize("layers,scale", [(2, 1.0), (12, 1.0), (4, 3.0)])
-def test_vit_hidden_states_and_readout(cuda, layers, scale):
+def test_vit_hidden_states_and_readout(cuda, layers, scale, precision):
     from mertools_b200.encoders import VitEncoder
     sd = S.vit_state_dict(seed=0, layers=layers, scale=scale)
     frames = S.synth_frames(1, 3, seed=11)[0]
-    enc = VitEncoder(sd, device=cuda)
+    enc = VitEncoder(sd, device=cuda, precision=precision)
     feats, hidden = enc.frame_features(torch.from_numpy(frames).to(cuda), return_hidden=True)
     torch.cuda.synchronize()
     ref_hs = E.vit_hidden_states(sd, P.vit_preprocess(frames), layers=layers)
