@@ -46,7 +46,10 @@ MER_API int mer_profile_collect(int mode, double* total_ms, double* total_flops,
 /* ---- GEMM (nn.Linear / Conv1d-as-GEMM / patch-embed) ---------------------------------- */
 enum { MER_EPI_GELU = 1, MER_EPI_ROUND_TF32 = 2, MER_EPI_SPLIT_BF16 = 4,
        MER_EPI_GELU_LIBM = 8, /* with MER_EPI_GELU: libdevice erff instead of the 12-op polynomial */
-       MER_EPI_OUT_F16 = 16   /* out is an IEEE fp16 array (round-to-nearest, saturating); ld_out in elements */ };
+       MER_EPI_OUT_F16 = 16,  /* out (and vt, if given) are IEEE fp16 arrays (round-to-nearest, saturating);
+                                 ld_out / vt_ld in elements */
+       MER_ATT_QKV_F16 = 32   /* mer_attention only: qkv and vt are fp16 arrays (needs MER_EPI_OUT_F16, vt,
+                                 max_seqlen <= 249, vt_ld % 8 == 0) */ };
 /* Arithmetic mode of a GEMM.  TF32: operands are fp32 arrays (pre-rounded to tf32).  BF16X3: every
  * operand value x is stored as a bf16 pair (hi, lo), x = hi + lo to 2^-17; a row of K values (K % 32
  * == 0) occupies the bytes K fp32 values would, as 128-byte groups [32 x hi | 32 x lo]; three bf16
@@ -134,7 +137,8 @@ MER_API int mer_round_tf32(float* x, long long n, void* stream);
  * flash-style kernel.
  * ctx is [tokens, heads*64].  flags: MER_EPI_ROUND_TF32 rounds ctx for a TF32 out-proj GEMM,
  * MER_EPI_SPLIT_BF16 writes ctx as bf16 hi|lo rows for a BF16X3 out-proj GEMM, MER_EPI_OUT_F16 writes
- * ctx as fp16 for an F16 out-proj GEMM (tcgen05 kernel only).
+ * ctx as fp16 for an F16 out-proj GEMM (tcgen05 kernels only); with MER_ATT_QKV_F16 the inputs are
+ * fp16 as well (attention_f16.cu: kind::f16 MMAs, half the traffic).
  * Replaces HF eager/sdpa attention (modeling_vit.py:171-196, modeling_hubert.py:262-345). */
 MER_API int mer_attention(const float* qkv, const float* vt, long long vt_ld, float* ctx,
                           const int32_t* cu_seqlens, int n_seq, long long tokens, int max_seqlen,

@@ -20,6 +20,7 @@ MER_GEMM_BF16X3 = 1
 MER_GEMM_F16 = 2
 MER_EPI_OUT_F16 = 16
 MER_LN_OUT_F16 = 8
+MER_ATT_QKV_F16 = 32
 MER_LN_ROUND_TF32 = 1
 MER_LN_ACC_INIT = 2
 MER_LN_ACC_ADD = 4
@@ -186,7 +187,15 @@ def round_tf32_(x):
 
 
 def attention(qkv, ctx, cu_seqlens, max_seqlen, heads, round_out=False, vt=None, f16_out=False):
-    """vt: optional V^T [heads*64, ld] (enables the tcgen05 kernel for max_seqlen <= 253)."""
+    """vt: optional V^T [heads*64, ld] (enables the tcgen05 kernel for max_seqlen <= 253).  fp16 qkv / vt /
+    ctx tensors select the all-fp16 kernel (max_seqlen <= 249)."""
+    import torch
+    if qkv.dtype == torch.float16:
+        assert vt is not None and vt.dtype == torch.float16 and ctx.dtype == torch.float16
+        check(lib().mer_attention(ptr(qkv), ptr(vt), vt.shape[1], ptr(ctx), ptr(cu_seqlens),
+                                  cu_seqlens.numel() - 1, qkv.shape[0], max_seqlen, heads,
+                                  MER_EPI_OUT_F16 | MER_ATT_QKV_F16, stream_ptr()))
+        return ctx
     check(lib().mer_attention(ptr(qkv), ptr(vt), vt.shape[1] if vt is not None else 0, ptr(ctx),
                               ptr(cu_seqlens), cu_seqlens.numel() - 1, qkv.shape[0], max_seqlen, heads,
                               MER_EPI_OUT_F16 if f16_out else (MER_EPI_ROUND_TF32 if round_out else 0),

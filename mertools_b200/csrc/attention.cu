@@ -243,6 +243,13 @@ int mer_attention_launch(const float* qkv, const float* vt, long long vt_ld, flo
                          const int* cu_seqlens, int n_seq, long long tokens, int max_seqlen, int heads,
                          int flags, cudaStream_t stream) {
   MER_REQUIRE(qkv && ctx && cu_seqlens, "mer_attention: null operand");
+  if (flags & MER_ATT_QKV_F16) {
+    MER_REQUIRE((flags & MER_EPI_OUT_F16) && vt && mer_attention_f16_supported(max_seqlen),
+                "mer_attention: fp16 inputs need MER_EPI_OUT_F16, V^T and sequences <= 249 tokens (max_seqlen %d)",
+                max_seqlen);
+    if (tokens <= 0) return 0;
+    return mer_attention_f16_launch(qkv, vt, vt_ld, ctx, cu_seqlens, n_seq, tokens, heads, stream);
+  }
   // sequences of up to 256 tokens (ViT 197, HuBERT 5 s = 249, most sentences): tcgen05 kernel,
   // which reads V^T (written by the QKV GEMM epilogue) instead of the V columns of qkv
   if (vt && mer_attention_uses_tc(max_seqlen) && tokens > 0)

@@ -1,0 +1,350 @@
+// attention_f16.cu — tcgen05 attention on fp16 operands (sequences of up to 249 tokens, head_dim 64).
+//
+// softmax(Q K^T / 8) V per (sequence, head) for the ViT stack when it runs in MER_GEMM_F16 mode: the
+// QKV GEMM writes q | k (fp16 rows) and V^T (fp16, keys contiguous), this kernel writes ctx as fp16,
+// the operand of the out-proj GEMM.  fp16 carries the 10 mantissa bits the TF32 kernel
+// (attention_tc.cu) rounds to, so the products are the same; the tensor-pipe rate doubles and every
+// tile is half as large.  Replaces the same reference op (HF eager/sdpa attention,
+// modeling_vit.py:171-196).
+//
+// Persistent, one CTA per SM, work item = (sequence, head); roles and barrier scheme as in
+// attention_tc.cu:
+//   warp 0      TMA producer: K [keys][64 d] (one 128-byte swizzle row per key), V^T [64 d][keys] in
+//               64-key chunks, the 128-row Q tiles
+//   warp 1      tcgen05 issuer: S_t = Q_t K^T (UMMA 128 x NK x 16, kind::f16) into TMEM columns
+//               [256 t, 256 t + NK); per 64-key chunk of P: O_t += P_chunk V_chunk (UMMA 128 x 64 x 16)
+//               into the first 64 columns of S_t's range
+//   warps 2..9  two softmax + epilogue groups (one per query tile): S rows TMEM -> registers (thread =
+//               query row), max, exp2, sum, fp16 P chunks -> swizzled smem (the tile's dead Q buffer);
+//               O / sum -> fp16 -> swizzled smem (the dead V^T region) -> 512-byte coalesced stores
+// TMA boxes start on 16-byte boundaries: the key axis of an item begins at the sequence start rounded
+// down to a multiple of 8 tokens; the (up to 7) leading foreign keys are masked.
+// Algorithmic HBM traffic per token and layer: 4.5 KB of q|k|v^T in, 1.5 KB of ctx out.
+#include <stdlib.h>
+
+#include "mer_common.cuh"
+#include "mer_kernels.h"
+
+namespace {
+
+using namespace mer;
+
+constexpr int HD = 64;
+constexpr int F16_THREADS = 320;          // producer, MMA issuer, 2 x 4 softmax/epilogue warps
+constexpr int K_BYTES = 256 * 128;        // K: up to 256 keys x 128 B
+constexpr int VT_CHUNK = HD * 128;        // V^T chunk: 64 d-rows x 64 keys (128 B)
+constexpr int QTILE_BYTES = 128 * 128;    // one 128-row Q tile; later the P-chunk buffer of the tile
+constexpr int SMEM_K = 0;
+constexpr int SMEM_V = K_BYTES;           // 4 V^T chunks = 32 KB; later the output staging (2 x 16 KB)
+constexpr int SMEM_Q = SMEM_V + 4 * VT_CHUNK;
+constexpr int SMEM_BAR = SMEM_Q + 2 * QTILE_BYTES;
+constexpr int F16_SMEM = SMEM_BAR + 256 + 1024;
+constexpr uint32_t TILE_COLS = 256, TMEM_COLS = 512;
+
+__device__ __forceinline__ float fast_ex2(float x) {  // MUFU.EX2, flush-to-zero
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) {  // SW128, SBO 1024
+  return static_cast<uint64_t>((addr & 0x3FFFF) >> 4) | (1ull << 16) | (uint64_t(1024 >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(F16_THREADS, 1)
+attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
+                     const __grid_constant__ CUtensorMap tmap_vt, uint16_t* __restrict__ ctx,
+                     const int* __restrict__ cu_seqlens, int n_seq, int heads) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
+  uint64_t* bar_k = bars + 0;       // producer -> MMA: K tile of the item
+  uint64_t* bar_q = bars + 1;       // producer -> MMA: Q tiles
+  uint64_t* bar_v = bars + 2;       // producer -> MMA: V^T chunks
+  uint64_t* bar_sfull = bars + 3;   // [2] MMA -> softmax group t / producer: S_t complete
+  uint64_t* bar_pready = bars + 5;  // [2] softmax group t -> MMA: a P chunk of tile t sits in smem
+  uint64_t* bar_pfree = bars + 7;   // [2] MMA -> softmax group t: that chunk has been consumed
+  uint64_t* bar_ofull = bars + 9;   // [2] MMA -> softmax group t: O_t complete
+  uint64_t* bar_ofree = bars + 11;  // [2] softmax group t -> producer: output staging (V^T region) consumed
+  uint64_t* bar_otfree = bars + 13; // [2] softmax group t -> MMA: O_t has been read out of TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = n_seq * heads;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_vt);
+    mbar_init(bar_k, 1);
+    mbar_init(bar_q, 1);
+    mbar_init(bar_v, 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&bar_sfull[t], 1);
+      mbar_init(&bar_pready[t], 4);
+      mbar_init(&bar_pfree[t], 1);
+      mbar_init(&bar_ofull[t], 1);
+      mbar_init(&bar_ofree[t], 4);
+      mbar_init(&bar_otfree[t], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (warp-uniform; one elected lane issues) =====================
+    uint32_t uses[2] = {0, 0};  // how often tile slot t has been used so far
+    int prev_nmt = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const int seq = it / heads, h = it % heads;
+      const int start = cu_seqlens[seq];
+      const int len = cu_seqlens[seq + 1] - start;
+      const int n_mt = (len + 127) >> 7;
+      const int a_start = start & ~7, shift = start - a_start;  // 16-byte aligned V^T column start
+      const int Lk = shift + len;
+      const int nb = (Lk + 127) >> 7;
+      // K: the previous item's S MMAs are done
+      for (int t = 0; t < prev_nmt; ++t) mbar_wait(&bar_sfull[t], (uses[t] - 1) & 1);
+      if (elect_one()) {
+        mbar_expect_tx(bar_k, (uint32_t)(nb * 16384));
+        for (int b = 0; b < nb; ++b)
+          tma_load_2d(smem + SMEM_K + b * 16384, &tmap_qkv, bar_k, heads * HD + h * HD, a_start + b * 128);
+      }
+      __syncwarp();
+      // Q tiles: the previous item's P V MMAs are done (the Q_t regions double as P-chunk buffers)
+      for (int t = 0; t < prev_nmt; ++t) mbar_wait(&bar_ofull[t], (uses[t] - 1) & 1);
+      if (elect_one()) {
+        mbar_expect_tx(bar_q, (uint32_t)(n_mt * QTILE_BYTES));
+        for (int t = 0; t < n_mt; ++t)
+          tma_load_2d(smem + SMEM_Q + t * QTILE_BYTES, &tmap_qkv, bar_q, h * HD, start + t * 128);
+      }
+      __syncwarp();
+      // V^T: the previous item's epilogues are done (they stage their output in the V^T region)
+      for (int t = 0; t < prev_nmt; ++t) mbar_wait(&bar_ofree[t], (uses[t] - 1) & 1);
+      const int n_vc = (Lk + 63) >> 6;
+      if (elect_one()) {
+        mbar_expect_tx(bar_v, (uint32_t)(n_vc * VT_CHUNK));
+        for (int c = 0; c < n_vc; ++c)
+          tma_load_2d(smem + SMEM_V + c * VT_CHUNK, &tmap_vt, bar_v, a_start + c * 64, h * HD);
+      }
+      __syncwarp();
+      for (int t = 0; t < n_mt; ++t) ++uses[t];
+      prev_nmt = n_mt;
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform; one elected lane issues and commits) =========
+    uint32_t uses[2] = {0, 0};
+    uint32_t g[2] = {0, 0};  // P chunks consumed per tile slot
+    uint32_t item_n = 0;
+    const uint64_t desc_q = desc_kmajor(smem_u32(smem + SMEM_Q));
+    const uint64_t desc_k = desc_kmajor(smem_u32(smem + SMEM_K));
+    const uint64_t desc_v = desc_kmajor(smem_u32(smem + SMEM_V));
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item_n) {
+      const int seq = it / heads;
+      const int start = cu_seqlens[seq];
+      const int len = cu_seqlens[seq + 1] - start;
+      const int n_mt = (len + 127) >> 7;
+      const int NK = ((start & 7) + len + 15) & ~15;  // shifted key axis, padded to the UMMA N / K step
+      const int n_pc = (NK + 63) >> 6;
+      const uint32_t idesc_s = umma_idesc(0, 128, NK);
+      const uint32_t idesc_o = umma_idesc(0, 128, HD);
+      mbar_wait(bar_k, item_n & 1);
+      mbar_wait(bar_q, item_n & 1);
+      // ---- S_t = Q_t K^T for both tiles ----
+      for (int t = 0; t < n_mt; ++t) {
+        if (uses[t] > 0) mbar_wait(&bar_otfree[t], (uses[t] - 1) & 1);  // S_t / O_t columns free again
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t da = desc_q + (uint64_t)((t * QTILE_BYTES) >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // 4 x 16 of the 64 head dims
+            tc_mma_bf16(tmem_base + t * TILE_COLS, da + 2 * k, desc_k + 2 * k, idesc_s, k != 0);
+          tc_commit(&bar_sfull[t]);
+        }
+        __syncwarp();
+      }
+      // ---- O_t += P_t chunk * V chunk, the two tiles interleaved ----
+      mbar_wait(bar_v, item_n & 1);
+      for (int pc = 0; pc < n_pc; ++pc) {
+        const int keys = min(64, NK - pc * 64);
+        for (int t = 0; t < n_mt; ++t) {
+          mbar_wait(&bar_pready[t], g[t] & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t da = desc_q + (uint64_t)((t * QTILE_BYTES) >> 4);
+            const uint64_t db = desc_v + (uint64_t)((pc * VT_CHUNK) >> 4);
+            for (int k = 0; k < keys / 16; ++k)
+              tc_mma_bf16(tmem_base + t * TILE_COLS, da + 2 * k, db + 2 * k, idesc_o, (pc | k) != 0);
+            tc_commit(&bar_pfree[t]);
+            if (pc == n_pc - 1) tc_commit(&bar_ofull[t]);
+          }
+          __syncwarp();
+          ++g[t];
+        }
+      }
+      for (int t = 0; t < n_mt; ++t) ++uses[t];
+    }
+  } else {
+    // ===================== softmax + epilogue: group 0 = warps 2..5 (tile 0), group 1 = warps 6..9 =====
+    const int grp = (warp - 2) >> 2;
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const uint32_t t_lane = tmem_base + (uint32_t(q * 32) << 16) + grp * TILE_COLS;
+    constexpr float SCALE_LOG2 = 0.125f * 1.4426950408889634f;
+    const int ldc = heads * HD;
+    const int r_tile = q * 32 + lane;  // row inside the 128-row tile
+    // P chunk buffer of this tile: [128 rows][128 B]; this thread's row
+    uint8_t* p_row = smem + SMEM_Q + grp * QTILE_BYTES + r_tile * 128;
+    // output staging: 16 KB of the V^T region per tile (V^T is dead once O_t is complete)
+    uint8_t* o_row = smem + SMEM_V + grp * QTILE_BYTES + r_tile * 128;
+    const uint8_t* stg = smem + SMEM_V + grp * QTILE_BYTES + q * 32 * 128;  // this warp's 32 rows
+    const int sub_r = lane >> 3, sub_c = lane & 7;
+    uint32_t uses = 0, G = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const int seq = it / heads, h = it % heads;
+      const int start = cu_seqlens[seq];
+      const int len = cu_seqlens[seq + 1] - start;
+      const int n_mt = (len + 127) >> 7;
+      if (grp >= n_mt) continue;  // single-tile item: group 1 has nothing to do
+      const int shift = start & 7;  // keys live at columns [shift, shift + len) of S
+      const int Lk = shift + len;
+      const int n_chunks = (Lk + 31) >> 5;
+      const int n_pc = (((Lk + 15) & ~15) + 63) >> 6;
+      mbar_wait(&bar_sfull[grp], uses & 1);
+      tc_fence_after();
+      // pass 1: row maximum over the valid keys
+      float mx = -INFINITY;
+      for (int c = 0; c < n_chunks; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_lane + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c * 32 + j >= shift && c * 32 + j < Lk) mx = fmaxf(mx, __uint_as_float(r[j]));
+      }
+      const float mb = mx * SCALE_LOG2;
+      // pass 2, per 64-key chunk: p = exp2((s - max) / 8 * log2 e) -> row sum, fp16 P into the swizzled
+      // smem chunk (A operand of the P V MMA)
+      float sum = 0.f;
+      for (int pc = 0; pc < n_pc; ++pc, ++G) {
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(t_lane + pc * 64, r0);
+        tmem_ld_32x32(t_lane + pc * 64 + 32, r1);
+        tmem_ld_wait();
+        uint32_t pk[32];  // 64 fp16 values of this row
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+          const int k0 = pc * 64 + j, k1 = k0 + 32;
+          if (k0 >= shift && k0 < Lk) a0 = fast_ex2(fmaf(__uint_as_float(r0[j]), SCALE_LOG2, -mb));
+          if (k0 + 1 >= shift && k0 + 1 < Lk) a1 = fast_ex2(fmaf(__uint_as_float(r0[j + 1]), SCALE_LOG2, -mb));
+          if (k1 >= shift && k1 < Lk) b0 = fast_ex2(fmaf(__uint_as_float(r1[j]), SCALE_LOG2, -mb));
+          if (k1 + 1 >= shift && k1 + 1 < Lk) b1 = fast_ex2(fmaf(__uint_as_float(r1[j + 1]), SCALE_LOG2, -mb));
+          sum += (a0 + a1) + (b0 + b1);
+          pk[j >> 1] = pack_f16x2(a0, a1);
+          pk[16 + (j >> 1)] = pack_f16x2(b0, b1);
+        }
+        mbar_wait(&bar_pfree[grp], (G & 1) ^ 1);  // the previous chunk's MMAs have read the buffer
+#pragma unroll
+        for (int j = 0; j < 8; ++j)  // 16-byte slot j = keys 8j .. 8j+7
+          *reinterpret_cast<uint4*>(p_row + ((j ^ (r_tile & 7)) << 4)) =
+              make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_pready[grp]);
+      }
+      const float inv = 1.0f / sum;
+      // epilogue: O / sum -> fp16 -> (swizzled smem transpose) -> 512-byte coalesced stores into ctx
+      mbar_wait(&bar_ofull[grp], uses & 1);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      tmem_ld_32x32(t_lane, o0);
+      tmem_ld_32x32(t_lane + 32, o1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_otfree[grp]);  // the MMA warp may start the next item's S_t
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {  // 16-byte slot j = head dims 8j .. 8j+7
+        const uint32_t* o = (j < 4) ? (o0 + 8 * j) : (o1 + 8 * (j - 4));
+        *reinterpret_cast<uint4*>(o_row + ((j ^ (r_tile & 7)) << 4)) =
+            make_uint4(pack_f16x2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv),
+                       pack_f16x2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv),
+                       pack_f16x2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv),
+                       pack_f16x2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv));
+      }
+      __syncwarp();
+      const int row0 = grp * 128 + q * 32;  // first sequence row of this warp's 32
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + sub_r;
+        const int rt = q * 32 + rr;  // row inside the tile (swizzle key)
+        const uint4 d = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((sub_c ^ (rt & 7)) << 4));
+        if (row0 + rr < len)
+          *reinterpret_cast<uint4*>(ctx + (long long)(start + row0 + rr) * ldc + h * HD + sub_c * 8) = d;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_ofree[grp]);
+      ++uses;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace
+
+bool mer_attention_f16_supported(int max_seqlen) { return max_seqlen > 0 && max_seqlen <= 249; }
+
+// qkv16: fp16 [tokens, 3*heads*64] (V columns unused), vt16: fp16 [heads*64, vt_ld] with vt[d, token],
+// ctx16: fp16 [tokens, heads*64]
+int mer_attention_f16_launch(const void* qkv16, const void* vt16, long long vt_ld, void* ctx16,
+                             const int* cu_seqlens, int n_seq, long long tokens, int heads,
+                             cudaStream_t stream) {
+  MER_REQUIRE(qkv16 && vt16 && ctx16 && cu_seqlens, "mer_attention_f16: null operand");
+  MER_REQUIRE(vt_ld >= tokens && vt_ld % 8 == 0, "mer_attention_f16: V^T pitch %lld must be a multiple of 8 >= tokens",
+              vt_ld);
+  CUtensorMap tm, tv;
+  {
+    const uint64_t dims[2] = {(uint64_t)(3 * heads * HD), (uint64_t)tokens};
+    const uint64_t strides[1] = {(uint64_t)(3 * heads * HD) * 2ull};
+    const uint32_t box[2] = {64, 128};
+    if (int rc = mer_make_tmap(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, qkv16, dims, strides, box,
+                               CU_TENSOR_MAP_SWIZZLE_128B))
+      return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)tokens, (uint64_t)(heads * HD)};
+    const uint64_t strides[1] = {(uint64_t)vt_ld * 2ull};
+    const uint32_t box[2] = {64, HD};
+    if (int rc = mer_make_tmap(&tv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, vt16, dims, strides, box,
+                               CU_TENSOR_MAP_SWIZZLE_128B))
+      return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    MER_CUDA_CHECK(cudaFuncSetAttribute(attention_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        F16_SMEM));
+    attr_set = true;
+  }
+  const long long items = (long long)n_seq * heads;
+  if (items <= 0) return 0;
+  int grid = mer_num_sms();
+  if (items < grid) grid = (int)items;
+  attention_f16_kernel<<<grid, F16_THREADS, F16_SMEM, stream>>>(tm, tv, static_cast<uint16_t*>(ctx16),
+                                                                 cu_seqlens, n_seq, heads);
+  MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
+  return 0;
+}

@@ -72,17 +72,17 @@ int mer_run_stack(const MerStackArgs& a, cudaStream_t stream) {
     float* vt = (a.vt && mer_attention_uses_tc(a.max_seqlen)) ? a.vt : nullptr;
     const int opnd = split ? MER_EPI_SPLIT_BF16 : MER_EPI_ROUND_TF32;
     if (a.pre_ln && a.mode == MER_GEMM_F16) {
-      // same chain with fp16 GEMM operands: LN and attention write fp16 (into xn), FC1 writes fp16 (into
-      // h); the residual stream x, the QKV output and V^T stay fp32
-      float* xn16 = a.xn;  // fp16 [M, 768] inside the fp32-sized scratch
+      // same chain on fp16 operands: LN, the QKV GEMM (q | k rows and V^T), attention and FC1 write fp16
+      // into the (fp32-sized) scratch buffers; only the residual stream x stays fp32
+      float* xn16 = a.xn;  // fp16 [M, 768]
       float* h16 = a.h;    // fp16 [M, 3072]
       MER_REQUIRE(vt != nullptr, "mer_run_stack: the F16 stack needs the tcgen05 attention (sequences <= 253)");
       MER_TRY(mer_layernorm_launch(a.x, w.ln1_g, w.ln1_b, xn16, nullptr, nullptr, M, D, a.eps, MER_LN_OUT_F16,
                                    stream));
-      MER_TRY(linear(a.mode, xn16, w.w_qkv, w.b_qkv, nullptr, a.qkv, M, DQKV, D, MER_EPI_ROUND_TF32, stream,
+      MER_TRY(linear(a.mode, xn16, w.w_qkv, w.b_qkv, nullptr, a.qkv, M, DQKV, D, MER_EPI_OUT_F16, stream,
                      vt, a.vt_ld, 2 * D));
       MER_TRY(mer_attention_launch(a.qkv, vt, a.vt_ld, xn16, a.cu_seqlens, a.n_seq, M, a.max_seqlen, HEADS,
-                                   MER_EPI_OUT_F16, stream));
+                                   MER_EPI_OUT_F16 | MER_ATT_QKV_F16, stream));
       MER_TRY(linear(a.mode, xn16, w.w_o, w.b_o, a.x, a.x, M, D, D, 0, stream));
       MER_TRY(mer_layernorm_launch(a.x, w.ln2_g, w.ln2_b, xn16, nullptr, nullptr, M, D, a.eps, MER_LN_OUT_F16,
                                    stream));
@@ -145,7 +145,7 @@ extern "C" {
 long long mer_vit_workspace_bytes(int n_frames) {
   const long long M = (long long)n_frames * 197;
   // x, xn, qkv, h (+ patch operand aliasing h), V^T + offsets
-  return (M * (D + D + DQKV + DFF) + (long long)D * ((M + 3) & ~3ll)) * 4 + ((long long)n_frames + 1) * 4 + 1024;
+  return (M * (D + D + DQKV + DFF) + (long long)D * ((M + 7) & ~7ll)) * 4 + ((long long)n_frames + 1) * 4 + 1024;
 }
 
 int mer_vit_forward(const MerVitModel* m, const uint8_t* frames_bgr, int n_frames, void* workspace,
@@ -164,7 +164,7 @@ int mer_vit_forward(const MerVitModel* m, const uint8_t* frames_bgr, int n_frame
   float* qkv = xn + M * D;
   float* h = qkv + M * DQKV;
   float* vt = h + M * DFF;
-  const long long vt_ld = (M + 3) & ~3ll;
+  const long long vt_ld = (M + 7) & ~7ll;  // fp32 or fp16 V^T rows start on 16-byte boundaries
   int* offsets = reinterpret_cast<int*>(vt + (long long)D * vt_ld);
   float* a_patch = h;  // [n_frames*196, 768] patch operand lives in the (not yet used) FFN buffer
 

@@ -112,7 +112,7 @@ struct EpiTile {
   int rows_left;          // rows r < rows_left of the warp's 32 are real
   long long out_off;      // element index of out[row0 + lane / 4][n0]  (write-out phase)
   const float* res_lane;  // same position in the residual, or nullptr
-  float* vt_lane;         // &vt[0][row0 + lane] for the transposed side output, or nullptr
+  long long vt_idx;       // column (= output row) of this lane in the transposed side output
   long long ld_out8, ld_res8;  // 8 rows of out / res, in floats
 };
 
@@ -144,10 +144,10 @@ __device__ __forceinline__ void epi_tile(const EpiTile& tl, const MerGemmEpilogu
     const int n0 = tl.n0 + ci * 32;
     tmem_ld_wait_regs(r);
     if (ci == CH - 1) release_tmem();
-    if (kVt && tl.vt_lane != nullptr && n0 >= ep.vt_col0) {
+    if (kVt && ep.vt != nullptr && n0 >= ep.vt_col0) {
       // transposed side output (V^T of the QKV GEMM): lanes = consecutive rows, so each scalar store
       // instruction is one contiguous 128-byte run of vt
-      float* vt_col = tl.vt_lane + (long long)(n0 - ep.vt_col0) * ep.vt_ld;
+      const long long vt_off = (long long)(n0 - ep.vt_col0) * ep.vt_ld;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -158,10 +158,20 @@ __device__ __forceinline__ void epi_tile(const EpiTile& tl, const MerGemmEpilogu
           v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
         }
         if (lane < tl.rows_left) {
-          vt_col[(long long)(4 * j + 0) * ep.vt_ld] = v.x;
-          vt_col[(long long)(4 * j + 1) * ep.vt_ld] = v.y;
-          vt_col[(long long)(4 * j + 2) * ep.vt_ld] = v.z;
-          vt_col[(long long)(4 * j + 3) * ep.vt_ld] = v.w;
+          if (OUT == 3) {  // fp16 V^T: 64-byte runs per store instruction
+            uint16_t* vt16 = reinterpret_cast<uint16_t*>(ep.vt) + tl.vt_idx + vt_off;
+            const uint32_t xy = pack_f16x2(v.x, v.y), zw = pack_f16x2(v.z, v.w);
+            vt16[(long long)(4 * j + 0) * ep.vt_ld] = (uint16_t)(xy & 0xffffu);
+            vt16[(long long)(4 * j + 1) * ep.vt_ld] = (uint16_t)(xy >> 16);
+            vt16[(long long)(4 * j + 2) * ep.vt_ld] = (uint16_t)(zw & 0xffffu);
+            vt16[(long long)(4 * j + 3) * ep.vt_ld] = (uint16_t)(zw >> 16);
+          } else {
+            float* vt_col = ep.vt + tl.vt_idx + vt_off;
+            vt_col[(long long)(4 * j + 0) * ep.vt_ld] = v.x;
+            vt_col[(long long)(4 * j + 1) * ep.vt_ld] = v.y;
+            vt_col[(long long)(4 * j + 2) * ep.vt_ld] = v.z;
+            vt_col[(long long)(4 * j + 3) * ep.vt_ld] = v.w;
+          }
         }
       }
       if (ci + 1 < CH) tmem_ld_32x32(tl.t_addr + (ci + 1) * 32, r);
@@ -448,7 +458,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       tl.res_lane = ep.res ? ep.res + ((long long)b * ep.res_bstride + ep.res_row0 + m0 + p_row) *
                                           (long long)ep.ld_res + tl.n0
                            : nullptr;
-      tl.vt_lane = ep.vt ? ep.vt + out_row + lane : nullptr;
+      tl.vt_idx = out_row + lane;
       tl.ld_out8 = 8ll * ep.ld_out;
       tl.ld_res8 = 8ll * ep.ld_res;
       if (ep.res && lane < tl.rows_left) {

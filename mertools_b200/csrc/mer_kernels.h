@@ -22,6 +22,12 @@ int mer_attention_tc_launch(const float* qkv, const float* vt, long long vt_ld, 
                             const int* cu_seqlens, int n_seq, long long tokens, int heads, int flags,
                             cudaStream_t stream);
 
+// attention_f16.cu (tcgen05, fp16 q | k | v^T in, fp16 ctx out; max_seqlen <= 249)
+bool mer_attention_f16_supported(int max_seqlen);
+int mer_attention_f16_launch(const void* qkv16, const void* vt16, long long vt_ld, void* ctx16,
+                             const int* cu_seqlens, int n_seq, long long tokens, int heads,
+                             cudaStream_t stream);
+
 // helpers.cu
 int mer_vit_patchify_launch(const uint8_t* frames_bgr, int n_frames, float* a_patches,
                             cudaStream_t stream);

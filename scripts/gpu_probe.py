@@ -395,6 +395,42 @@ def sec_attn():
     return ok
 
 
+def sec_attn_f16():
+    """All-fp16 tcgen05 attention (fp16 q | k | v^T in, fp16 ctx out) against fp64 softmax attention."""
+    ok = True
+    heads = 12
+    for lens in [[197] * 5, [249] * 3, [7, 64, 65, 1, 130, 240], [7, 64, 65, 1, 130, 200, 128, 129, 3], [16] * 40]:
+        cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device="cuda")
+        tot = sum(lens)
+        qkv = (torch.randn(tot, 3 * heads * 64, device="cuda") * 1.5).half()
+        ctx = torch.full((tot, heads * 64), float("nan"), device="cuda", dtype=torch.float16)
+        ld = (tot + 7) // 8 * 8
+        vt = torch.zeros(heads * 64, ld, device="cuda", dtype=torch.float16)
+        vt[:, :tot] = qkv[:, 2 * heads * 64:].t()
+        L.attention(qkv, ctx, cu, max(lens), heads, vt=vt)
+        torch.cuda.synchronize()
+        err = 0.0
+        s0 = 0
+        for n in lens:
+            q, k, v = qkv[s0:s0 + n].double().view(n, 3, heads, 64).permute(1, 2, 0, 3)
+            p = torch.softmax(q @ k.transpose(-1, -2) / 8.0, -1)
+            ref = (p @ v).permute(1, 0, 2).reshape(n, heads * 64)
+            err = max(err, (ctx[s0:s0 + n].double() - ref).abs().max().item())
+            s0 += n
+        good = err < 3e-3 and not torch.isnan(ctx).any().item()
+        emit(check=f"attention_f16_{lens[0]}x{len(lens)}", ok=bool(good), max_err=err)
+        ok &= good
+    n_seq = 2048
+    cu = (torch.arange(n_seq + 1, device="cuda", dtype=torch.int32) * 197)
+    qkv = torch.randn(n_seq * 197, 2304, device="cuda").half()
+    ctx = torch.empty(n_seq * 197, 768, device="cuda", dtype=torch.float16)
+    vt = qkv[:, 1536:].t().contiguous()
+    ms = time_cuda(lambda: L.attention(qkv, ctx, cu, 197, heads, vt=vt), iters=5)
+    flops = n_seq * heads * 4.0 * 197 * 197 * 64
+    emit(perf="attention_f16_vit_2048x197", ms=ms, tflops=flops / ms / 1e9)
+    return ok
+
+
 def sec_vit():
     from mertools_b200 import synthetic as S
     from mertools_b200.encoders import VitEncoder
@@ -407,7 +443,7 @@ def sec_vit():
     return True
 
 
-SECTIONS = dict(one=sec_one, gemm_f16=sec_gemm_f16, vit=sec_vit, gemm_x3=sec_gemm_x3, gemm_2sm=sec_gemm_2sm, gelu_ab=sec_gelu_ab, gemm=sec_gemm, conv=sec_conv, gemm_perf=sec_gemm_perf, ln=sec_ln, attn=sec_attn)
+SECTIONS = dict(attn_f16=sec_attn_f16, one=sec_one, gemm_f16=sec_gemm_f16, vit=sec_vit, gemm_x3=sec_gemm_x3, gemm_2sm=sec_gemm_2sm, gelu_ab=sec_gelu_ab, gemm=sec_gemm, conv=sec_conv, gemm_perf=sec_gemm_perf, ln=sec_ln, attn=sec_attn)
 
 if __name__ == "__main__":
     os.makedirs("gpurun_out", exist_ok=True)
