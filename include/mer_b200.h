@@ -171,6 +171,15 @@ typedef struct MerLayerWeights {
   const float* b_fc2;
 } MerLayerWeights;
 
+/* ---- frame resize (visual preprocessing) ------------------------------------------------------- */
+/* PIL.Image.resize((OW, OH), BILINEAR) on uint8 [n, H, W, 3] frames, bit-exact: the resize step of HF
+ * ViTImageProcessor (extract_vision_huggingface.py:137-138) for faces that are not 224x224 already
+ * (OpenFace crops are 112x112).  Horizontal pass, then vertical pass, uint8 in between.  workspace:
+ * mer_resize_workspace_bytes(...) bytes (0 when only one axis changes). */
+MER_API long long mer_resize_workspace_bytes(int n, int H, int W, int OH, int OW);
+MER_API int mer_resize_bilinear_u8(const uint8_t* in, int n, int H, int W, uint8_t* out, int OH, int OW,
+                                   void* workspace, void* stream);
+
 /* ---- ViT-B/16 frame encoder (visual) ------------------------------------------------------------ */
 typedef struct MerVitModel {
   int n_layers;        /* 12 */

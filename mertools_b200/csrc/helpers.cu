@@ -1,5 +1,9 @@
 // helpers.cu — small HBM-bound kernels around the encoders: ViT frame preprocessing + patch
 // gather, CLS rows, and the segment reduce used by every readout.
+#include <math.h>
+
+#include <vector>
+
 #include "mer_common.cuh"
 #include "mer_kernels.h"
 
@@ -42,6 +46,38 @@ vit_patchify_kernel(const uint8_t* __restrict__ frames, float* __restrict__ a, l
 #pragma unroll
     for (int q = 0; q < 4; ++q) d4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   }
+}
+
+// One pass of Pillow's 8-bit bilinear resampling (src/libImaging/Resample.c, ImagingResampleHorizontal_8bpc
+// / Vertical_8bpc; reached through HF ViTImageProcessor.resize from extract_vision_huggingface.py:137-138)
+// over uint8 HWC frames: out = clip8((2^21 + sum_k in[lo + k] * kk[k]) >> 22) along one axis.
+// One thread = one output pixel (3 channels).  in: [n, H, W, 3]; AXIS 0: rows H -> OUT; AXIS 1: columns W -> OUT.
+template <int AXIS>
+__global__ void __launch_bounds__(256)
+resize_pass_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, long long total, int H, int W,
+                   int OUT, const int* __restrict__ lo, const int* __restrict__ cnt,
+                   const int* __restrict__ kk, int ksize) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int oh = AXIS == 0 ? OUT : H, ow = AXIS == 1 ? OUT : W;
+  const int x = (int)(idx % ow);
+  const int y = (int)((idx / ow) % oh);
+  const long long n = idx / ((long long)ow * oh);
+  const int o = AXIS == 0 ? y : x;
+  const int first = __ldg(lo + o), m = __ldg(cnt + o);
+  int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+  for (int k = 0; k < m; ++k) {
+    const int w = __ldg(kk + o * ksize + k);
+    const int sy = AXIS == 0 ? first + k : y, sx = AXIS == 1 ? first + k : x;
+    const uint8_t* p = in + ((n * H + sy) * W + sx) * 3;
+    a0 += (int)p[0] * w;
+    a1 += (int)p[1] * w;
+    a2 += (int)p[2] * w;
+  }
+  uint8_t* d = out + idx * 3;
+  d[0] = (uint8_t)min(max(a0 >> 22, 0), 255);
+  d[1] = (uint8_t)min(max(a1 >> 22, 0), 255);
+  d[2] = (uint8_t)min(max(a2 >> 22, 0), 255);
 }
 
 // x[n, 0, :] = cls_token + position_embeddings[0]  (HF ViTEmbeddings, modeling_vit.py:117-124)
@@ -195,4 +231,95 @@ extern "C" int mer_segment_reduce(const float* in, const int32_t* begins, const 
                                   int n_seg, int dim, int mode, float* out, void* stream) {
   return mer_segment_reduce_launch(in, begins, ends, n_seg, dim, mode, out,
                                    static_cast<cudaStream_t>(stream));
+}
+
+// ---- Pillow bilinear resize (uint8) ----------------------------------------------------------------
+namespace {
+struct ResizeTable { int in, out, ksize; int* d_lo; int* d_cnt; int* d_kk; };
+std::vector<ResizeTable> g_resize_tables;  // per process (= per device: one process per GPU)
+
+// Pillow precompute_coeffs + normalize_coeffs_8bpc for the bilinear filter, in double as Pillow does
+int resize_table(int in_size, int out_size, const ResizeTable** res, cudaStream_t stream) {
+  for (auto& t : g_resize_tables)
+    if (t.in == in_size && t.out == out_size) { *res = &t; return 0; }
+  const double scale = (double)in_size / out_size;
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = 1.0 * filterscale;
+  const int ksize = (int)ceil(support) * 2 + 1;
+  std::vector<int> lo(out_size), cnt(out_size), kk((size_t)out_size * ksize, 0);
+  std::vector<double> w(ksize);
+  const double ss = 1.0 / filterscale;
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = (xx + 0.5) * scale;
+    int a = (int)(center - support + 0.5);
+    if (a < 0) a = 0;
+    int b = (int)(center + support + 0.5);
+    if (b > in_size) b = in_size;
+    const int n = b - a;
+    double tot = 0.0;
+    for (int x = 0; x < n; ++x) {
+      double v = (x + a - center + 0.5) * ss;
+      if (v < 0.0) v = -v;
+      w[x] = v < 1.0 ? 1.0 - v : 0.0;
+      tot += w[x];
+    }
+    for (int x = 0; x < n; ++x) {
+      const double k = tot != 0.0 ? w[x] / tot : w[x];
+      kk[(size_t)xx * ksize + x] = (int)(k * (double)(1 << 22) + 0.5);  // weights are >= 0
+    }
+    lo[xx] = a;
+    cnt[xx] = n;
+  }
+  ResizeTable t{in_size, out_size, ksize, nullptr, nullptr, nullptr};
+  MER_CUDA_CHECK(cudaMalloc(&t.d_lo, out_size * sizeof(int)));
+  MER_CUDA_CHECK(cudaMalloc(&t.d_cnt, out_size * sizeof(int)));
+  MER_CUDA_CHECK(cudaMalloc(&t.d_kk, kk.size() * sizeof(int)));
+  // pageable-host copies are staged before the call returns, so the vectors may go out of scope
+  MER_CUDA_CHECK(cudaMemcpyAsync(t.d_lo, lo.data(), out_size * sizeof(int), cudaMemcpyHostToDevice, stream));
+  MER_CUDA_CHECK(cudaMemcpyAsync(t.d_cnt, cnt.data(), out_size * sizeof(int), cudaMemcpyHostToDevice, stream));
+  MER_CUDA_CHECK(cudaMemcpyAsync(t.d_kk, kk.data(), kk.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+  MER_CUDA_CHECK(cudaStreamSynchronize(stream));
+  g_resize_tables.push_back(t);
+  *res = &g_resize_tables.back();
+  return 0;
+}
+}  // namespace
+
+extern "C" long long mer_resize_workspace_bytes(int n, int H, int W, int OH, int OW) {
+  (void)OH;
+  return (H != 0 && W != OW) ? (long long)n * H * OW * 3 : 0;  // the horizontally resampled frames
+}
+
+extern "C" int mer_resize_bilinear_u8(const uint8_t* in, int n, int H, int W, uint8_t* out, int OH, int OW,
+                                      void* workspace, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MER_REQUIRE(in && out && n > 0 && H > 0 && W > 0 && OH > 0 && OW > 0, "mer_resize_bilinear_u8: bad arguments");
+  const bool horiz = W != OW, vert = H != OH;
+  if (!horiz && !vert) {
+    MER_CUDA_CHECK(cudaMemcpyAsync(out, in, (size_t)n * H * W * 3, cudaMemcpyDeviceToDevice, stream));
+    return 0;
+  }
+  MER_REQUIRE(!(horiz && vert) || workspace, "mer_resize_bilinear_u8: workspace needed for a two-pass resize");
+  const uint8_t* src = in;
+  if (horiz) {
+    const ResizeTable* t;
+    if (int rc = resize_table(W, OW, &t, stream)) return rc;
+    uint8_t* dst = vert ? static_cast<uint8_t*>(workspace) : out;
+    const long long total = (long long)n * H * OW;
+    resize_pass_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, dst, total, H, W, OW, t->d_lo,
+                                                                               t->d_cnt, t->d_kk, t->ksize);
+    MER_CUDA_CHECK(cudaGetLastError());
+    mer_count_launches(1);
+    src = dst;
+  }
+  if (vert) {
+    const ResizeTable* t;
+    if (int rc = resize_table(H, OH, &t, stream)) return rc;
+    const long long total = (long long)n * OH * OW;
+    resize_pass_kernel<0><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, out, total, H, OW, OH, t->d_lo,
+                                                                               t->d_cnt, t->d_kk, t->ksize);
+    MER_CUDA_CHECK(cudaGetLastError());
+    mer_count_launches(1);
+  }
+  return 0;
 }

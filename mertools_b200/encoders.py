@@ -75,13 +75,32 @@ class VitEncoder:
                                                   C.c_void_p, C.c_void_p])
         L.lib().mer_vit_workspace_bytes.restype = C.c_longlong
         L.lib().mer_vit_workspace_bytes.argtypes = [C.c_int]
+        self._resize = L.declare("mer_resize_bilinear_u8", [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                                            C.c_int, C.c_int, C.c_void_p, C.c_void_p])
+        L.lib().mer_resize_workspace_bytes.restype = C.c_longlong
+        L.lib().mer_resize_workspace_bytes.argtypes = [C.c_int] * 5
+        self.ws_resize = _Workspace(self.device)
+
+    def resize_frames(self, frames_u8: torch.Tensor, size=224):
+        """PIL-bilinear resize of uint8 CUDA frames [N,H,W,3] to [N,size,size,3] (the resize step of HF
+        ViTImageProcessor, extract_vision_huggingface.py:137-138), bit-exact, on the device."""
+        assert frames_u8.dtype == torch.uint8 and frames_u8.is_cuda and frames_u8.dim() == 4 \
+            and frames_u8.shape[-1] == 3, f"frames must be uint8 CUDA [N,H,W,3], got {tuple(frames_u8.shape)}"
+        n, h, w, _ = frames_u8.shape
+        if (h, w) == (size, size):
+            return frames_u8
+        frames_u8 = frames_u8.contiguous()
+        out = torch.empty(n, size, size, 3, dtype=torch.uint8, device=self.device)
+        need = L.lib().mer_resize_workspace_bytes(n, h, w, size, size)
+        ws = self.ws_resize.get(max(int(need), 1))
+        L.check(self._resize(L.ptr(frames_u8), n, h, w, L.ptr(out), size, size, L.ptr(ws), L.stream_ptr()))
+        return out
 
     def frame_features(self, frames_bgr_u8: torch.Tensor, return_hidden=False):
-        """frames: uint8 CUDA tensor [N,224,224,3] (BGR).  Returns [N,768] fp32 (CUDA)."""
+        """frames: uint8 CUDA tensor [N,H,W,3] (BGR); frames that are not 224x224 are resized first
+        (PIL bilinear, as the HF processor does).  Returns [N,768] fp32 (CUDA)."""
         assert frames_bgr_u8.dtype == torch.uint8 and frames_bgr_u8.is_cuda
-        assert tuple(frames_bgr_u8.shape[1:]) == (224, 224, 3), \
-            f"mer_vit_forward takes 224x224x3 frames, got {tuple(frames_bgr_u8.shape)}"
-        frames = frames_bgr_u8.contiguous()
+        frames = self.resize_frames(frames_bgr_u8, 224).contiguous()
         n = frames.shape[0]
         need = L.lib().mer_vit_workspace_bytes(n)
         ws = self.ws.get(need)

@@ -55,37 +55,53 @@ class VisualExtractor:
         self.max_frames = max_frames_per_launch
         self._pinned = None
 
-    def _stage(self, frame_list):
+    def _stage(self, frame_list, hw):
         n = sum(len(f) for f in frame_list)
-        if self._pinned is None or self._pinned.shape[0] < n:
-            self._pinned = torch.empty((n, 224, 224, 3), dtype=torch.uint8, pin_memory=True)
-        host = self._pinned[:n]
+        numel = n * hw[0] * hw[1] * 3
+        if self._pinned is None or self._pinned.numel() < numel:
+            self._pinned = torch.empty(numel, dtype=torch.uint8, pin_memory=True)
+        host = self._pinned[:numel].view(n, hw[0], hw[1], 3)
         o = 0
         for f in frame_list:
-            f = np.asarray(f)
-            assert f.dtype == np.uint8 and f.shape[1:] == (224, 224, 3), \
-                f"frames must be uint8 [n,224,224,3] BGR, got {f.dtype} {f.shape}"
             host[o:o + len(f)] = torch.from_numpy(np.ascontiguousarray(f))
             o += len(f)
         return host
 
-    def frame_features(self, frame_list):
-        """list of [n_i,224,224,3] uint8 -> list of [n_i,768] float32 numpy (one H2D, one D2H)."""
-        lens = [len(f) for f in frame_list]
-        host = self._stage(frame_list)
+    def _frame_features_same_size(self, frame_list, hw):
+        host = self._stage(frame_list, hw)
+        # frames smaller than 224x224 cost less to move: size the launches by their resized footprint
         outs = []
         for s in range(0, len(host), self.max_frames):
             dev = host[s:s + self.max_frames].to(self.device, non_blocking=True)
-            outs.append(self.enc.frame_features(dev))
-        feats = torch.cat(outs).cpu().numpy()
-        res, o = [], 0
-        for n in lens:
-            res.append(feats[o:o + n])
-            o += n
+            outs.append(self.enc.frame_features(dev))  # resizes to 224x224 on the device when needed
+        return torch.cat(outs).cpu().numpy()
+
+    def frame_features(self, frame_list):
+        """list of [n_i,H_i,W_i,3] uint8 (BGR) -> list of [n_i,768] float32 numpy.  Clips of the same frame
+        size share one H2D copy and one launch sequence; any size other than 224x224 is resized on the
+        device exactly as the HF processor does (PIL bilinear on uint8)."""
+        frame_list = [np.asarray(f) for f in frame_list]
+        for f in frame_list:
+            assert f.dtype == np.uint8 and f.ndim == 4 and f.shape[-1] == 3, \
+                f"frames must be uint8 [n,H,W,3] BGR, got {f.dtype} {f.shape}"
+        res = [None] * len(frame_list)
+        by_size = {}
+        for i, f in enumerate(frame_list):
+            if len(f) == 0:
+                res[i] = np.zeros((0, 768), np.float32)
+            else:
+                by_size.setdefault(f.shape[1:3], []).append(i)
+        for hw, idxs in by_size.items():
+            feats = self._frame_features_same_size([frame_list[i] for i in idxs], hw)
+            o = 0
+            for i in idxs:
+                n = len(frame_list[i])
+                res[i] = feats[o:o + n]
+                o += n
         return res
 
     def extract_clips(self, clips, feature_level="UTTERANCE", nframe=None, save_files=None):
-        """clips: list of uint8 [vlen,224,224,3] BGR arrays.  ``nframe`` resamples every clip
+        """clips: list of uint8 [vlen,H,W,3] BGR arrays (any H, W; the reference's OpenFace crops).  ``nframe`` resamples every clip
         first (64 in the reference's DINOv2 branch :136, None in the data2vec branch)."""
         if nframe is not None:
             clips = [resample_frames_uniform(np.asarray(c), nframe) for c in clips]

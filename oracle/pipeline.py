@@ -35,12 +35,74 @@ def split_into_batch(inputs, bsize=32):
     return [inputs[i * bsize:(i + 1) * bsize] for i in range(math.ceil(len(inputs) / bsize))]
 
 
+def pil_bilinear_coeffs(in_size, out_size):
+    """8-bit coefficient table of Pillow's ``Image.resize(..., BILINEAR)`` along one axis
+    (Pillow src/libImaging/Resample.c: precompute_coeffs + normalize_coeffs_8bpc; Pillow is an un-vendored
+    dependency of HF ``ViTImageProcessor.resize``, reached from extract_vision_huggingface.py:137-138;
+    the container's Pillow 12.2 and transformers 5.5 agree with this table for up-scaling, pinned in
+    tests/test_oracle.py).  Returns (xmin[out], count[out], kk[out, ksize] int32), PRECISION_BITS = 22."""
+    scale = in_size / out_size
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale            # bilinear filter support
+    ksize = int(np.ceil(support)) * 2 + 1
+    xmin = np.zeros(out_size, np.int32)
+    cnt = np.zeros(out_size, np.int32)
+    kk = np.zeros((out_size, ksize), np.int32)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        lo = int(center - support + 0.5)
+        lo = max(lo, 0)
+        hi = int(center + support + 0.5)
+        hi = min(hi, in_size)
+        n = hi - lo
+        w = np.zeros(n, np.float64)
+        for x in range(n):
+            a = abs((x + lo - center + 0.5) * ss)
+            w[x] = 1.0 - a if a < 1.0 else 0.0
+        tot = 0.0                      # Pillow accumulates the weights in index order
+        for x in range(n):
+            tot += w[x]
+        if tot != 0.0:
+            w = w / tot
+        xmin[xx], cnt[xx] = lo, n
+        kk[xx, :n] = np.trunc(w * (1 << 22) + 0.5).astype(np.int32)  # weights are >= 0
+    return xmin, cnt, kk
+
+
+def _pil_resample_axis(img, out_size, axis):
+    """One Pillow resampling pass over uint8 ``img`` [..., H, W, C] along ``axis`` (-3 rows, -2 columns):
+    out = clip8((2^21 + sum_k in[xmin + k] * kk[k]) >> 22)."""
+    in_size = img.shape[axis]
+    if in_size == out_size:
+        return img
+    xmin, cnt, kk = pil_bilinear_coeffs(in_size, out_size)
+    src = np.moveaxis(img, axis, 0).astype(np.int64)
+    out = np.empty((out_size,) + src.shape[1:], np.uint8)
+    for xx in range(out_size):
+        acc = np.full(src.shape[1:], 1 << 21, np.int64)
+        for k in range(cnt[xx]):
+            acc += src[xmin[xx] + k] * int(kk[xx, k])
+        out[xx] = np.clip(acc >> 22, 0, 255).astype(np.uint8)
+    return np.moveaxis(out, 0, axis)
+
+
+def pil_resize_bilinear_u8(frames, out_h=224, out_w=224):
+    """``PIL.Image.resize((out_w, out_h), BILINEAR)`` on uint8 [..., H, W, C]: horizontal pass, then
+    vertical pass, uint8 in between (ImagingResample)."""
+    f = np.asarray(frames)
+    assert f.dtype == np.uint8
+    return _pil_resample_axis(_pil_resample_axis(f, out_w, -2), out_h, -3)
+
+
 def vit_preprocess(frames_bgr):
     """``func_opencv_to_image`` (:29-31, BGR->RGB) + HF ``ViTImageProcessor`` as called at
-    :137-138 for frames that already are 224x224: rescale by 1/255 then (x - 0.5) / 0.5, fp32,
-    NCHW.  (Resize is the identity at 224x224; other sizes are outside round-1 scope.)"""
+    :137-138: resize to 224x224 (PIL bilinear on uint8; the identity for 224x224 frames), rescale by
+    1/255, then (x - 0.5) / 0.5, fp32, NCHW."""
     f = np.asarray(frames_bgr)
-    assert f.dtype == np.uint8 and f.shape[1:] == (224, 224, 3), f.shape
+    assert f.dtype == np.uint8 and f.ndim == 4 and f.shape[-1] == 3, f.shape
+    if f.shape[1:3] != (224, 224):
+        f = pil_resize_bilinear_u8(f, 224, 224)
     rgb = f[..., ::-1].astype(np.float32)
     x = rgb * np.float32(1.0 / 255.0)
     x = (x - np.float32(0.5)) / np.float32(0.5)

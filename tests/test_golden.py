@@ -38,6 +38,20 @@ def test_visual_oracle_matches_reference_script():
     assert _rel(fra, g["fra1"]) < 2e-5
 
 
+@pytest.mark.slow
+def test_visual_oracle_matches_reference_script_on_112px_faces():
+    """Resize step (a2): 112x112 crops through the unmodified script vs the oracle's PIL-resize restatement."""
+    g = np.load(os.path.join(G, "visual112_golden.npz"))
+    sd = _t(S.vit_state_dict(seed=0))
+    clips = S.synth_frames(int(g["n_clips"]), 8, size=int(g["size"]), seed=int(g["seed"]))
+    with torch.no_grad():
+        utt = P.visual_clip_features(sd, clips[0], nframe=int(g["nframe"]))
+        fra = P.visual_clip_features(sd, clips[1], nframe=None, feature_level="FRAME")
+    assert utt.shape == g["utt0"].shape == (768,)
+    assert _rel(utt, g["utt0"]) < 2e-5
+    assert _rel(fra, g["fra1"]) < 2e-5
+
+
 def test_audio_oracle_matches_reference_script():
     g = np.load(os.path.join(G, "audio_golden.npz"))
     sd = _t(S.hubert_state_dict(seed=1))

@@ -30,6 +30,20 @@ def test_visual_extractor_vs_reference_golden(cuda):
         assert fra[i].shape == g[f"fra{i}"].shape and _rel(fra[i], g[f"fra{i}"]) < TOL
 
 
+def test_visual_extractor_vs_reference_golden_112px(cuda):
+    """112x112 face crops: resized on the device (bit-exact PIL bilinear), then the same path."""
+    from mertools_b200.extract.visual import VisualExtractor
+    g = np.load(os.path.join(G, "visual112_golden.npz"))
+    clips = S.synth_frames(int(g["n_clips"]), 8, size=int(g["size"]), seed=int(g["seed"]))
+    ext = VisualExtractor(S.vit_state_dict(seed=0), device=cuda)
+    utt = ext.extract_clips(list(clips), "UTTERANCE", nframe=int(g["nframe"]))
+    fra = ext.extract_clips(list(clips), "FRAME", nframe=None)
+    for i in range(len(clips)):
+        assert utt[i].shape == (768,) and utt[i].dtype == g[f"utt{i}"].dtype
+        assert _rel(utt[i], g[f"utt{i}"]) < TOL
+        assert fra[i].shape == (8, 768) and _rel(fra[i], g[f"fra{i}"]) < TOL
+
+
 def test_audio_extractor_vs_reference_golden(cuda):
     from mertools_b200.extract.audio import AudioExtractor
     g = np.load(os.path.join(G, "audio_golden.npz"))

@@ -89,3 +89,26 @@ def test_vit_image_processor_matches_oracle_preprocess():
     ref = proc(images=pil, return_tensors="pt")["pixel_values"]
     got = P.vit_preprocess(frames)
     assert float((ref - got).abs().max()) <= 2.4e-7
+
+
+@pytest.mark.parametrize("hw", [(112, 112), (300, 260), (57, 91), (448, 448), (225, 223), (1, 1), (500, 30)])
+def test_pil_resize_restatement_is_bit_exact(hw):
+    """oracle/pipeline.py:pil_resize_bilinear_u8 against Pillow itself (the resize inside HF ViTImageProcessor)."""
+    from PIL import Image
+    from oracle import pipeline as P
+    rng = np.random.default_rng(hw[0] * 1000 + hw[1])
+    img = rng.integers(0, 256, (hw[0], hw[1], 3), dtype=np.uint8)
+    ref = np.asarray(Image.fromarray(img).resize((224, 224), resample=Image.BILINEAR))
+    assert np.array_equal(P.pil_resize_bilinear_u8(img), ref)
+
+
+def test_vit_preprocess_matches_hf_processor_on_upscaled_faces():
+    """112x112 -> 224x224: the oracle's preprocessing equals HF ViTImageProcessor (5.5.0 here) to fp32 rounding."""
+    from PIL import Image
+    from transformers import ViTImageProcessor
+    from oracle import pipeline as P
+    rng = np.random.default_rng(5)
+    bgr = rng.integers(0, 256, (2, 112, 112, 3), dtype=np.uint8)
+    ref = ViTImageProcessor()(images=[Image.fromarray(f[..., ::-1].copy()) for f in bgr], return_tensors="pt")["pixel_values"]
+    got = P.vit_preprocess(bgr)
+    assert float((got - ref).abs().max()) < 2e-7

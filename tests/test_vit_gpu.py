@@ -70,3 +70,29 @@ def test_vit_batch_invariance(cuda):
     # element, hence ~1e-5 on the output
     d = float((a - b).abs().max() / a.abs().max())
     assert d < 2e-4, f"batch dependence {d:.2e}"
+
+
+@pytest.mark.parametrize("hw", [(112, 112), (300, 260), (57, 91), (448, 224), (224, 100), (1, 1)])
+def test_resize_kernel_is_bit_exact(cuda, hw):
+    """mer_resize_bilinear_u8 == the oracle's Pillow restatement (itself pinned to Pillow), byte for byte."""
+    from mertools_b200.encoders import VitEncoder
+    rng = np.random.default_rng(hw[0] * 7 + hw[1])
+    frames = rng.integers(0, 256, (3, hw[0], hw[1], 3), dtype=np.uint8)
+    enc = VitEncoder(S.vit_state_dict(seed=0, layers=1), device=cuda)
+    got = enc.resize_frames(torch.from_numpy(frames).to(cuda), 224).cpu().numpy()
+    ref = P.pil_resize_bilinear_u8(frames, 224, 224)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+
+
+def test_mixed_frame_sizes_in_one_call(cuda):
+    """Clips of different crop sizes (and an empty clip) in one extractor call."""
+    from mertools_b200.extract import visual
+    sd = S.vit_state_dict(seed=0, layers=2)
+    a = S.synth_frames(1, 3, size=112, seed=21)[0]
+    b = S.synth_frames(1, 2, size=224, seed=22)[0]
+    ext = visual.VisualExtractor(sd, device=cuda)
+    got = ext.frame_features([a, np.zeros((0, 112, 112, 3), np.uint8), b])
+    assert got[1].shape == (0, 768)
+    for g, c in ((got[0], a), (got[2], b)):
+        ref = P.visual_clip_features(sd, c, nframe=None, layers=2, feature_level="FRAME")
+        assert np.abs(g - ref).max() / np.abs(ref).max() < TOL
