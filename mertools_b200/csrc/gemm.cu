@@ -177,8 +177,36 @@ __device__ __forceinline__ void epi_tile(const EpiTile& tl, const MerGemmEpilogu
       if (ci + 1 < CH) tmem_ld_32x32(tl.t_addr + (ci + 1) * 32, r);
       continue;
     }
+    if (OUT == 3) {
+      // fp16 output: the arithmetic runs here, on the accumulator-row thread (bias values come as
+      // warp-uniform L1 loads), so that the staging tile already holds fp16 -- one 32 x 64 B pass per
+      // chunk and 16-byte stores (8 rows x 64 B per instruction) instead of two passes of 8-byte stores
+      uint32_t pk[16];
 #pragma unroll
-    for (int sub = 0; sub < 2; ++sub) {
+      for (int j = 0; j < 8; ++j) {
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ep.bias) q = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + j);
+        pk[2 * j] = pack_f16x2(epi_act<GELU>(__uint_as_float(r[4 * j + 0]) + q.x),
+                               epi_act<GELU>(__uint_as_float(r[4 * j + 1]) + q.y));
+        pk[2 * j + 1] = pack_f16x2(epi_act<GELU>(__uint_as_float(r[4 * j + 2]) + q.z),
+                                   epi_act<GELU>(__uint_as_float(r[4 * j + 3]) + q.w));
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)  // 16-byte slot j = columns 8j .. 8j+7 of the chunk
+        *reinterpret_cast<uint4*>(slot(lane, j)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      if (ci + 1 < CH) tmem_ld_32x32(tl.t_addr + (ci + 1) * 32, r);  // flies during the write-out
+      __syncwarp();
+      uint16_t* o16 = reinterpret_cast<uint16_t*>(ep.out) + tl.out_off + ci * 32 + 8 * p_slot;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = 8 * i + p_row;
+        const uint4 d = *reinterpret_cast<const uint4*>(slot(row, p_slot));
+        if (row < tl.rows_left) *reinterpret_cast<uint4*>(o16 + i * tl.ld_out8) = d;
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int sub = 0; sub < (OUT == 3 ? 0 : 2); ++sub) {
       const int col = ci * 32 + sub * 16 + 4 * p_slot;  // this lane's 4 columns, relative to tl.n0
       float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
       if (ep.bias) q = __ldg(reinterpret_cast<const float4*>(ep.bias + tl.n0 + col));
@@ -218,10 +246,6 @@ __device__ __forceinline__ void epi_tile(const EpiTile& tl, const MerGemmEpilogu
             *reinterpret_cast<uint2*>(grp + 32 + c) =
                 make_uint2(pack_bf16x2(v.x - hx, v.y - hy), pack_bf16x2(v.z - hz, v.w - hw));
           }
-        } else if (OUT == 3) {
-          if (row < tl.rows_left)
-            *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(ep.out) + tl.out_off + i * tl.ld_out8 + col) =
-                make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w));
         } else {
           if (OUT == 1) {
             v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
