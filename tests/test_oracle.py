@@ -112,3 +112,22 @@ def test_vit_preprocess_matches_hf_processor_on_upscaled_faces():
     ref = ViTImageProcessor()(images=[Image.fromarray(f[..., ::-1].copy()) for f in bgr], return_tensors="pt")["pixel_values"]
     got = P.vit_preprocess(bgr)
     assert float((got - ref).abs().max()) < 2e-7
+
+
+def test_oracle_audio_restatement_also_is_wav2vec2_base():
+    """wav2vec2-base-960h / chinese-wav2vec2-base (extract_audio_huggingface.py:20,28; group-norm feature
+    extractor, post-LN encoder) have HuBERT-base's parameter names and arithmetic: the same restatement
+    -- hence the same CUDA path -- serves both model families."""
+    from transformers import HubertConfig, HubertModel, Wav2Vec2Config, Wav2Vec2Model
+    torch.manual_seed(3)
+    cfg = Wav2Vec2Config(num_hidden_layers=2)
+    assert cfg.feat_extract_norm == "group" and not cfg.do_stable_layer_norm and not cfg.conv_bias
+    m = Wav2Vec2Model(cfg).eval()
+    sd = dict(m.state_dict())
+    assert set(sd) == set(HubertModel(HubertConfig(num_hidden_layers=2)).state_dict())
+    x = torch.randn(2, 8000)
+    with torch.no_grad():
+        ref = m(x, output_hidden_states=True).hidden_states
+        got = E.hubert_hidden_states(sd, x, layers=2)
+    for a, b in zip(got, ref):
+        assert float((a - b).abs().max() / b.abs().max()) < 5e-5
