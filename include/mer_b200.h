@@ -37,9 +37,11 @@ MER_API int mer_check_device(void);
 /* cumulative number of CUDA kernels this library has launched in this process (bench.py's
  * gpu_launches); CUDA-graph replays are not seen here and are counted by their owner */
 MER_API long long mer_launch_count(void);
-/* per-launch CUDA-event timing of the GEMM kernel (roofline in bench.py): enable(1) starts a fresh
- * recording, enable(0) stops; collect sums duration / algorithmic FLOPs (2*M*N*K) / launches of one
- * MER_GEMM_* mode since the last enable(1). */
+/* per-launch CUDA-event timing (roofline in bench.py): enable(1) starts a fresh recording, enable(0)
+ * stops; collect sums duration / algorithmic work / launches of one kernel class since the last
+ * enable(1).  Classes: MER_GEMM_* (work = 2*M*N*K flop), 10 = fp16 tcgen05 attention, 11 = TF32 tcgen05
+ * attention (work = 4*S^2*64 flop per (sequence, head), S = tokens / n_seq), 12 = LayerNorm, 14 = HuBERT
+ * conv0 (work = algorithmic HBM bytes), 13 = HuBERT positional conv (flop). */
 MER_API int mer_profile_enable(int on);
 MER_API int mer_profile_collect(int mode, double* total_ms, double* total_flops, int* launches);
 

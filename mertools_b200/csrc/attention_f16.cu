@@ -342,8 +342,11 @@ int mer_attention_f16_launch(const void* qkv16, const void* vt16, long long vt_l
   if (items <= 0) return 0;
   int grid = mer_num_sms();
   if (items < grid) grid = (int)items;
+  const double s_avg = (double)tokens / n_seq;  // exact for equal-length batches (ViT frames)
+  const int prof = mer_prof_begin(MER_PROF_ATT_F16, 4.0 * s_avg * s_avg * HD * (double)items, stream);
   attention_f16_kernel<<<grid, F16_THREADS, F16_SMEM, stream>>>(tm, tv, static_cast<uint16_t*>(ctx16),
                                                                  cu_seqlens, n_seq, heads);
+  mer_prof_end(prof, stream);
   MER_CUDA_CHECK(cudaGetLastError());
   mer_count_launches(1);
   return 0;

@@ -379,7 +379,10 @@ int mer_attention_tc_launch(const float* qkv, const float* vt, long long vt_ld, 
   int grid = mer_num_sms();
   if (items < grid) grid = (int)items;
   const int out_mode = (flags & MER_EPI_OUT_F16) ? 3 : (flags & MER_EPI_SPLIT_BF16) ? 2 : ((flags & MER_EPI_ROUND_TF32) ? 1 : 0);
+  const double s_avg = (double)tokens / n_seq;  // exact for equal-length batches
+  const int prof = mer_prof_begin(MER_PROF_ATT_TC, 4.0 * s_avg * s_avg * HD * (double)items, stream);
   attention_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(tm, tv, ctx, cu_seqlens, n_seq, heads, out_mode);
+  mer_prof_end(prof, stream);
   MER_CUDA_CHECK(cudaGetLastError());
   mer_count_launches(1);
   return 0;

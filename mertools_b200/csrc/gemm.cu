@@ -30,18 +30,8 @@
 //                     inside 1e-3 after 12 layers (measured: single-pass TF32 reaches 1.0e-3 after 4).
 #include <stdlib.h>
 
-#include <vector>
-
 #include "mer_common.cuh"
 #include "mer_kernels.h"
-
-// ---- optional per-launch timing (bench.py roofline): CUDA events on the launching stream ----
-namespace {
-struct ProfSlot { cudaEvent_t a, b; double flops; int mode; };
-bool g_prof_on = false;
-std::vector<ProfSlot> g_prof;          // slots in use since the last enable
-std::vector<ProfSlot> g_prof_pool;     // recycled event pairs
-}  // namespace
 
 namespace {
 
@@ -582,19 +572,8 @@ int launch_gemm(const MerGemmDesc* g, cudaStream_t stream) {
   const long long tiles = groups * (g->N / BLOCK_N);
   int grid = (mer_num_sms() / CLUSTER) * CLUSTER;
   if (tiles * CLUSTER < grid) grid = (int)tiles * CLUSTER;
-  ProfSlot slot;
-  if (g_prof_on) {
-    if (!g_prof_pool.empty()) {
-      slot = g_prof_pool.back();
-      g_prof_pool.pop_back();
-    } else {
-      MER_CUDA_CHECK(cudaEventCreate(&slot.a));
-      MER_CUDA_CHECK(cudaEventCreate(&slot.b));
-    }
-    slot.flops = 2.0 * (double)g->rows_per_batch * g->batches * g->N * (double)(g->K_inner * g->taps);
-    slot.mode = MODE;
-    MER_CUDA_CHECK(cudaEventRecord(slot.a, stream));
-  }
+  const int prof = mer_prof_begin(MODE, 2.0 * (double)g->rows_per_batch * g->batches * g->N *
+                                            (double)(g->K_inner * g->taps), stream);
   {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -615,10 +594,7 @@ int launch_gemm(const MerGemmDesc* g, cudaStream_t stream) {
   }
   MER_CUDA_CHECK(cudaGetLastError());
   mer_count_launches(1);
-  if (g_prof_on) {
-    MER_CUDA_CHECK(cudaEventRecord(slot.b, stream));
-    g_prof.push_back(slot);
-  }
+  mer_prof_end(prof, stream);
   return 0;
 }
 
@@ -674,31 +650,4 @@ int mer_gemm_launch(const MerGemmDesc* g, cudaStream_t stream) {
   if (twosm) return launch_gemm<256, MER_GEMM_TF32, 2, true>(g, stream);
   if (pair) return launch_gemm<256, MER_GEMM_TF32, 2>(g, stream);
   return wide ? launch_gemm<256, MER_GEMM_TF32, 1>(g, stream) : launch_gemm<128, MER_GEMM_TF32, 1>(g, stream);
-}
-
-extern "C" int mer_profile_enable(int on) {
-  for (auto& sl : g_prof) g_prof_pool.push_back(sl);
-  g_prof.clear();
-  g_prof_on = on != 0;
-  return 0;
-}
-
-// Sum of the event-timed durations and algorithmic FLOPs (2*M*N*K) of the GEMM launches of `mode`
-// recorded since mer_profile_enable(1).  Synchronises on the recorded events.
-extern "C" int mer_profile_collect(int mode, double* total_ms, double* total_flops, int* launches) {
-  double ms = 0.0, fl = 0.0;
-  int n = 0;
-  for (auto& sl : g_prof) {
-    if (sl.mode != mode) continue;
-    MER_CUDA_CHECK(cudaEventSynchronize(sl.b));
-    float t = 0.f;
-    MER_CUDA_CHECK(cudaEventElapsedTime(&t, sl.a, sl.b));
-    ms += t;
-    fl += sl.flops;
-    ++n;
-  }
-  if (total_ms) *total_ms = ms;
-  if (total_flops) *total_flops = fl;
-  if (launches) *launches = n;
-  return 0;
 }

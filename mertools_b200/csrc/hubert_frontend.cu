@@ -142,10 +142,13 @@ int mer_hubert_conv0_launch(const float* wave, long long ld_wave, int B, int L, 
   MER_REQUIRE(T0 > 0, "mer_hubert_conv0: waveform too short (%d samples)", L);
   MER_CUDA_CHECK(cudaMemsetAsync(stats, 0, (size_t)B * C0 * 2 * sizeof(double), stream));
   dim3 grid((T0 + TCHUNK - 1) / TCHUNK, B);
+  // both passes: the waveform in twice, the [T0, 512] operand (4 B per element) out once
+  const int prof = mer_prof_begin(MER_PROF_CONV0, (double)B * (2.0 * L * 4.0 + (double)T0 * C0 * 4.0), stream);
   conv0_stats_kernel<<<grid, C0, 0, stream>>>(wave, ld_wave, w0, T0, stats);
   MER_CUDA_CHECK(cudaGetLastError());
   conv0_apply_kernel<<<grid, C0, 0, stream>>>(wave, ld_wave, w0, gamma, beta, stats, T0,
                                               out_bstride, split_out, out);
+  mer_prof_end(prof, stream);
   MER_CUDA_CHECK(cudaGetLastError());
   mer_count_launches(2);
   return 0;

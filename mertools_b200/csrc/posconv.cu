@@ -162,7 +162,11 @@ int mer_posconv_launch(const float* x0, const float* wp, const float* bias, cons
     attr_set = true;
   }
   dim3 grid((max_seqlen + BT - 1) / BT, NG, n_seq);
+  // 2 * frames * 768 outputs * (48 inputs * 128 taps); frames bounded by n_seq * max_seqlen (exact for
+  // equal-length batches)
+  const int prof = mer_prof_begin(MER_PROF_POSCONV, 2.0 * (double)n_seq * max_seqlen * 768.0 * 48.0 * 128.0, stream);
   posconv_kernel<<<grid, PC_THREADS, PC_SMEM, stream>>>(x0, wp, bias, cu_seqlens, x1);
+  mer_prof_end(prof, stream);
   MER_CUDA_CHECK(cudaGetLastError());
   mer_count_launches(1);
   return 0;

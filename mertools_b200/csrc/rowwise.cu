@@ -118,10 +118,15 @@ int mer_layernorm_launch(const float* x, const float* gamma, const float* beta, 
   long long blocks = (rows + warps_per_block - 1) / warps_per_block;
   const long long max_blocks = (long long)mer_num_sms() * 16;
   if (blocks > max_blocks) blocks = max_blocks;
+  // algorithmic bytes: the fp32 row in, each output row (fp16: 2 B/elem), the accumulator (write, or read+write)
+  const double out_b = (y ? ((flags & MER_LN_OUT_F16) ? 2.0 : 4.0) : 0.0) + (y_split ? 4.0 : 0.0) +
+                       (acc ? ((flags & MER_LN_ACC_ADD) ? 8.0 : 4.0) : 0.0);
+  const int prof = mer_prof_begin(MER_PROF_LAYERNORM, (double)rows * dim * (4.0 + out_b), stream);
   if (dim == 768)
     layernorm_kernel<6><<<(int)blocks, 256, 0, stream>>>(x, gamma, beta, y, y_split, acc, rows, eps, flags);
   else
     layernorm_kernel<4><<<(int)blocks, 256, 0, stream>>>(x, gamma, beta, y, y_split, acc, rows, eps, flags);
+  mer_prof_end(prof, stream);
   MER_CUDA_CHECK(cudaGetLastError());
   mer_count_launches(1);
   return 0;

@@ -4,6 +4,8 @@
 // entry points declared in include/mer_b200.h.
 #include <stdarg.h>
 
+#include <vector>
+
 #include "mer_common.cuh"
 #include "mer_kernels.h"
 
@@ -14,6 +16,61 @@ void mer_set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+// ---- optional per-launch timing (bench.py roofline): CUDA events on the launching stream ----
+namespace {
+struct ProfSlot { cudaEvent_t a, b; double work; int klass; };
+bool g_prof_on = false;
+std::vector<ProfSlot> g_prof;       // slots in use since the last enable
+std::vector<ProfSlot> g_prof_pool;  // recycled event pairs
+}  // namespace
+
+int mer_prof_begin(int klass, double work, cudaStream_t stream) {
+  if (!g_prof_on) return -1;
+  ProfSlot slot;
+  if (!g_prof_pool.empty()) {
+    slot = g_prof_pool.back();
+    g_prof_pool.pop_back();
+  } else {
+    if (cudaEventCreate(&slot.a) != cudaSuccess || cudaEventCreate(&slot.b) != cudaSuccess) return -1;
+  }
+  slot.work = work;
+  slot.klass = klass;
+  cudaEventRecord(slot.a, stream);
+  g_prof.push_back(slot);
+  return (int)g_prof.size() - 1;
+}
+
+void mer_prof_end(int slot, cudaStream_t stream) {
+  if (slot >= 0 && slot < (int)g_prof.size()) cudaEventRecord(g_prof[slot].b, stream);
+}
+
+extern "C" int mer_profile_enable(int on) {
+  for (auto& sl : g_prof) g_prof_pool.push_back(sl);
+  g_prof.clear();
+  g_prof_on = on != 0;
+  return 0;
+}
+
+// Sum of the event-timed durations and algorithmic work (FLOPs, or bytes for the HBM-bound classes) of the
+// launches of `klass` recorded since mer_profile_enable(1).  Synchronises on the recorded events.
+extern "C" int mer_profile_collect(int klass, double* total_ms, double* total_work, int* launches) {
+  double ms = 0.0, wk = 0.0;
+  int n = 0;
+  for (auto& sl : g_prof) {
+    if (sl.klass != klass) continue;
+    MER_CUDA_CHECK(cudaEventSynchronize(sl.b));
+    float t = 0.f;
+    MER_CUDA_CHECK(cudaEventElapsedTime(&t, sl.a, sl.b));
+    ms += t;
+    wk += sl.work;
+    ++n;
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_work) *total_work = wk;
+  if (launches) *launches = n;
+  return 0;
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
