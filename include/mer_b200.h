@@ -105,6 +105,16 @@ typedef struct MerGemmDesc {
                         2-byte elements) */
   int cluster;       /* 0 = auto, 1 = single CTAs, 2 = CTA pairs sharing a multicast weight tile,
                         3 = CTA pairs issuing one 256-row tcgen05.mma.cta_group::2 per K step */
+  /* grouped-convolution support (the HuBERT positional conv runs as a block-diagonal GEMM):
+   * a_row0     : added to every A row index (may be negative); rows outside [0, a_rows_dim) of a batch
+   *              entry read as zero -- the conv's zero padding.
+   * a_cols     : addressable A columns per row (0 = K_inner).
+   * a_col_group: when > 0, the K_inner-wide column window of output column block j starts at
+   *              floor(j * block_n / a_col_group) * a_col_group (block_n = force_block_n, required);
+   *              columns beyond a_cols read as zero.  W holds the matching windowed weights. */
+  int a_row0;
+  int a_cols;
+  int a_col_group;
   MerGemmEpilogue ep;
 } MerGemmDesc;
 
@@ -220,6 +230,9 @@ typedef struct MerHubertModel {
   const float* fp_w;       /* [768, 512] split bf16 (BF16X3) */
   const float* fp_b;
   const float* pos_w;      /* [16][128][48][48] = [group][tap][out][in], weight-norm folded, tf32 */
+  const void* pos_w_bd;    /* optional fp16 [768][128 * 320]: the same weights as a windowed block-diagonal
+                              matrix (window of output block j starts at channel floor(256 j / 48) * 48), which
+                              runs the positional conv through mer_gemm (MER_GEMM_F16); NULL = mma.sync kernel */
   const float* pos_b;      /* [768] */
   const float* enc_ln_g;   /* encoder.layer_norm */
   const float* enc_ln_b;

@@ -47,7 +47,8 @@ class MerGemmDesc(C.Structure):
         ("N", C.c_int), ("K_inner", C.c_int), ("taps", C.c_int), ("P", C.c_int),
         ("a_phase_stride", C.c_longlong), ("a_row_stride", C.c_longlong),
         ("a_batch_stride", C.c_longlong), ("force_block_n", C.c_int), ("mode", C.c_int),
-        ("cluster", C.c_int), ("ep", MerGemmEpilogue),
+        ("cluster", C.c_int), ("a_row0", C.c_int), ("a_cols", C.c_int), ("a_col_group", C.c_int),
+        ("ep", MerGemmEpilogue),
     ]
 
 
@@ -116,7 +117,7 @@ def gemm(A, W, out, *, bias=None, res=None, gelu=False, round_out=False, split_o
          a_phase_stride=0, a_row_stride=None, a_batch_stride=0,
          out_bstride=0, out_row0=0, res_bstride=0, res_row0=0,
          ld_out=None, ld_res=None, force_block_n=0, cluster=0, vt=None, vt_col0=0, gelu_libm=False,
-         f16_out=False):
+         f16_out=False, a_row0=0, a_cols=0, a_col_group=0):
     """out = epilogue(A @ W.T).  A, W: fp32 CUDA tensors of LOGICAL shape [rows, K] / [N, K] (holding
     tf32-rounded fp32, or split bf16 hi|lo bytes when mode is BF16X3; fp16 tensors when mode is F16);
     see MerGemmDesc in mer_b200.h."""
@@ -136,6 +137,7 @@ def gemm(A, W, out, *, bias=None, res=None, gelu=False, round_out=False, split_o
     d.force_block_n = force_block_n
     d.mode = mode
     d.cluster = cluster
+    d.a_row0, d.a_cols, d.a_col_group = a_row0, a_cols, a_col_group
     d.ep.bias = bias.data_ptr() if bias is not None else None
     d.ep.res = res.data_ptr() if res is not None else None
     d.ep.out = out.data_ptr()

@@ -34,10 +34,13 @@ constexpr int F16_THREADS = 320;          // producer, MMA issuer, 2 x 4 softmax
 constexpr int K_BYTES = 256 * 128;        // K: up to 256 keys x 128 B
 constexpr int VT_CHUNK = HD * 128;        // V^T chunk: 64 d-rows x 64 keys (128 B)
 constexpr int QTILE_BYTES = 128 * 128;    // one 128-row Q tile; later the P-chunk buffer of the tile
+// two operand sets (items alternate between them, so the next item's K / V^T / Q are in flight while the
+// current one computes); inside a set:
 constexpr int SMEM_K = 0;
 constexpr int SMEM_V = K_BYTES;           // 4 V^T chunks = 32 KB; later the output staging (2 x 16 KB)
 constexpr int SMEM_Q = SMEM_V + 4 * VT_CHUNK;
-constexpr int SMEM_BAR = SMEM_Q + 2 * QTILE_BYTES;
+constexpr int SET_BYTES = SMEM_Q + 2 * QTILE_BYTES;  // 96 KB
+constexpr int SMEM_BAR = 2 * SET_BYTES;
 constexpr int F16_SMEM = SMEM_BAR + 256 + 1024;
 constexpr uint32_t TILE_COLS = 256, TMEM_COLS = 512;
 
@@ -59,16 +62,16 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
-  uint64_t* bar_k = bars + 0;       // producer -> MMA: K tile of the item
-  uint64_t* bar_q = bars + 1;       // producer -> MMA: Q tiles
-  uint64_t* bar_v = bars + 2;       // producer -> MMA: V^T chunks
-  uint64_t* bar_sfull = bars + 3;   // [2] MMA -> softmax group t / producer: S_t complete
-  uint64_t* bar_pready = bars + 5;  // [2] softmax group t -> MMA: a P chunk of tile t sits in smem
-  uint64_t* bar_pfree = bars + 7;   // [2] MMA -> softmax group t: that chunk has been consumed
-  uint64_t* bar_ofull = bars + 9;   // [2] MMA -> softmax group t: O_t complete
-  uint64_t* bar_ofree = bars + 11;  // [2] softmax group t -> producer: output staging (V^T region) consumed
-  uint64_t* bar_otfree = bars + 13; // [2] softmax group t -> MMA: O_t has been read out of TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* bar_k = bars + 0;       // [2 sets] producer -> MMA: K tile of the item
+  uint64_t* bar_q = bars + 2;       // [2 sets] producer -> MMA: Q tiles
+  uint64_t* bar_v = bars + 4;       // [2 sets] producer -> MMA: V^T chunks
+  uint64_t* bar_sfull = bars + 6;   // [2 tiles] MMA -> softmax group t: S_t complete
+  uint64_t* bar_pready = bars + 8;  // [2] softmax group t -> MMA: a P chunk of tile t sits in smem
+  uint64_t* bar_pfree = bars + 10;  // [2] MMA -> softmax group t: that chunk has been consumed
+  uint64_t* bar_ofull = bars + 12;  // [2] MMA -> softmax group t: O_t complete
+  uint64_t* bar_ofree = bars + 14;  // [2] softmax group t -> producer: output staging (V^T region) consumed
+  uint64_t* bar_otfree = bars + 16; // [2] softmax group t -> MMA: O_t has been read out of TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = n_seq * heads;
@@ -76,10 +79,10 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
     tma_prefetch_desc(&tmap_vt);
-    mbar_init(bar_k, 1);
-    mbar_init(bar_q, 1);
-    mbar_init(bar_v, 1);
     for (int t = 0; t < 2; ++t) {
+      mbar_init(&bar_k[t], 1);
+      mbar_init(&bar_q[t], 1);
+      mbar_init(&bar_v[t], 1);
       mbar_init(&bar_sfull[t], 1);
       mbar_init(&bar_pready[t], 4);
       mbar_init(&bar_pfree[t], 1);
@@ -100,9 +103,15 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
 
   if (warp == 0) {
     // ===================== TMA producer (warp-uniform; one elected lane issues) =====================
-    uint32_t uses[2] = {0, 0};  // how often tile slot t has been used so far
-    int prev_nmt = 0;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    // Item n uses operand set n & 1: its K, Q tiles and V^T are requested as soon as item n - 2 has left
+    // that set (its epilogues, the last users, are done), i.e. while item n - 1 is still computing.
+    uint32_t uses[2] = {0, 0};      // how often tile slot t has been used so far
+    int h_nmt[2] = {0, 0};          // per set: tiles of the item that used it last ...
+    uint32_t h_use[2][2] = {{0, 0}, {0, 0}};  // ... and the use index of each tile slot at that item
+    uint32_t item_n = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item_n) {
+      const int set = item_n & 1;
+      uint8_t* sm = smem + set * SET_BYTES;
       const int seq = it / heads, h = it % heads;
       const int start = cu_seqlens[seq];
       const int len = cu_seqlens[seq + 1] - start;
@@ -110,43 +119,37 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
       const int a_start = start & ~7, shift = start - a_start;  // 16-byte aligned V^T column start
       const int Lk = shift + len;
       const int nb = (Lk + 127) >> 7;
-      // K: the previous item's S MMAs are done
-      for (int t = 0; t < prev_nmt; ++t) mbar_wait(&bar_sfull[t], (uses[t] - 1) & 1);
-      if (elect_one()) {
-        mbar_expect_tx(bar_k, (uint32_t)(nb * 16384));
-        for (int b = 0; b < nb; ++b)
-          tma_load_2d(smem + SMEM_K + b * 16384, &tmap_qkv, bar_k, heads * HD + h * HD, a_start + b * 128);
-      }
-      __syncwarp();
-      // Q tiles: the previous item's P V MMAs are done (the Q_t regions double as P-chunk buffers)
-      for (int t = 0; t < prev_nmt; ++t) mbar_wait(&bar_ofull[t], (uses[t] - 1) & 1);
-      if (elect_one()) {
-        mbar_expect_tx(bar_q, (uint32_t)(n_mt * QTILE_BYTES));
-        for (int t = 0; t < n_mt; ++t)
-          tma_load_2d(smem + SMEM_Q + t * QTILE_BYTES, &tmap_qkv, bar_q, h * HD, start + t * 128);
-      }
-      __syncwarp();
-      // V^T: the previous item's epilogues are done (they stage their output in the V^T region)
-      for (int t = 0; t < prev_nmt; ++t) mbar_wait(&bar_ofree[t], (uses[t] - 1) & 1);
       const int n_vc = (Lk + 63) >> 6;
+      if (item_n >= 2)
+        for (int t = 0; t < h_nmt[set]; ++t) mbar_wait(&bar_ofree[t], h_use[set][t] & 1);
       if (elect_one()) {
-        mbar_expect_tx(bar_v, (uint32_t)(n_vc * VT_CHUNK));
+        mbar_expect_tx(&bar_k[set], (uint32_t)(nb * 16384));
+        for (int b = 0; b < nb; ++b)
+          tma_load_2d(sm + SMEM_K + b * 16384, &tmap_qkv, &bar_k[set], heads * HD + h * HD, a_start + b * 128);
+        mbar_expect_tx(&bar_q[set], (uint32_t)(n_mt * QTILE_BYTES));
+        for (int t = 0; t < n_mt; ++t)
+          tma_load_2d(sm + SMEM_Q + t * QTILE_BYTES, &tmap_qkv, &bar_q[set], h * HD, start + t * 128);
+        mbar_expect_tx(&bar_v[set], (uint32_t)(n_vc * VT_CHUNK));
         for (int c = 0; c < n_vc; ++c)
-          tma_load_2d(smem + SMEM_V + c * VT_CHUNK, &tmap_vt, bar_v, a_start + c * 64, h * HD);
+          tma_load_2d(sm + SMEM_V + c * VT_CHUNK, &tmap_vt, &bar_v[set], a_start + c * 64, h * HD);
       }
       __syncwarp();
-      for (int t = 0; t < n_mt; ++t) ++uses[t];
-      prev_nmt = n_mt;
+      h_nmt[set] = n_mt;
+      for (int t = 0; t < n_mt; ++t) h_use[set][t] = uses[t]++;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (warp-uniform; one elected lane issues and commits) =========
     uint32_t uses[2] = {0, 0};
     uint32_t g[2] = {0, 0};  // P chunks consumed per tile slot
     uint32_t item_n = 0;
-    const uint64_t desc_q = desc_kmajor(smem_u32(smem + SMEM_Q));
-    const uint64_t desc_k = desc_kmajor(smem_u32(smem + SMEM_K));
-    const uint64_t desc_v = desc_kmajor(smem_u32(smem + SMEM_V));
+    const uint64_t desc_q0 = desc_kmajor(smem_u32(smem + SMEM_Q));
+    const uint64_t desc_k0 = desc_kmajor(smem_u32(smem + SMEM_K));
+    const uint64_t desc_v0 = desc_kmajor(smem_u32(smem + SMEM_V));
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item_n) {
+      const int set = item_n & 1;
+      const uint32_t set_par = (item_n >> 1) & 1;
+      const uint64_t set_off = (uint64_t)((set * SET_BYTES) >> 4);
+      const uint64_t desc_q = desc_q0 + set_off, desc_k = desc_k0 + set_off, desc_v = desc_v0 + set_off;
       const int seq = it / heads;
       const int start = cu_seqlens[seq];
       const int len = cu_seqlens[seq + 1] - start;
@@ -155,8 +158,8 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
       const int n_pc = (NK + 63) >> 6;
       const uint32_t idesc_s = umma_idesc(0, 128, NK);
       const uint32_t idesc_o = umma_idesc(0, 128, HD);
-      mbar_wait(bar_k, item_n & 1);
-      mbar_wait(bar_q, item_n & 1);
+      mbar_wait(&bar_k[set], set_par);
+      mbar_wait(&bar_q[set], set_par);
       // ---- S_t = Q_t K^T for both tiles ----
       for (int t = 0; t < n_mt; ++t) {
         if (uses[t] > 0) mbar_wait(&bar_otfree[t], (uses[t] - 1) & 1);  // S_t / O_t columns free again
@@ -171,7 +174,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
         __syncwarp();
       }
       // ---- O_t += P_t chunk * V chunk, the two tiles interleaved ----
-      mbar_wait(bar_v, item_n & 1);
+      mbar_wait(&bar_v[set], set_par);
       for (int pc = 0; pc < n_pc; ++pc) {
         const int keys = min(64, NK - pc * 64);
         for (int t = 0; t < n_mt; ++t) {
@@ -199,14 +202,15 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
     constexpr float SCALE_LOG2 = 0.125f * 1.4426950408889634f;
     const int ldc = heads * HD;
     const int r_tile = q * 32 + lane;  // row inside the 128-row tile
-    // P chunk buffer of this tile: [128 rows][128 B]; this thread's row
-    uint8_t* p_row = smem + SMEM_Q + grp * QTILE_BYTES + r_tile * 128;
-    // output staging: 16 KB of the V^T region per tile (V^T is dead once O_t is complete)
-    uint8_t* o_row = smem + SMEM_V + grp * QTILE_BYTES + r_tile * 128;
-    const uint8_t* stg = smem + SMEM_V + grp * QTILE_BYTES + q * 32 * 128;  // this warp's 32 rows
     const int sub_r = lane >> 3, sub_c = lane & 7;
-    uint32_t uses = 0, G = 0;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    uint32_t uses = 0, G = 0, item_n = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item_n) {
+      uint8_t* sm = smem + (item_n & 1) * SET_BYTES;  // this item's operand set
+      // P chunk buffer of this tile: [128 rows][128 B] (the tile's Q buffer, dead after S_t); this thread's row
+      uint8_t* p_row = sm + SMEM_Q + grp * QTILE_BYTES + r_tile * 128;
+      // output staging: 16 KB of the V^T region per tile (V^T is dead once O_t is complete)
+      uint8_t* o_row = sm + SMEM_V + grp * QTILE_BYTES + r_tile * 128;
+      const uint8_t* stg = sm + SMEM_V + grp * QTILE_BYTES + q * 32 * 128;  // this warp's 32 rows
       const int seq = it / heads, h = it % heads;
       const int start = cu_seqlens[seq];
       const int len = cu_seqlens[seq + 1] - start;

@@ -341,7 +341,51 @@ int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L,
   MER_TRY(linear(MER_GEMM_BF16X3, feat, m->fp_w, m->fp_b, nullptr, x0, M, D, 512, 0, stream));
   // positional conv + GELU + residual -> xn ; encoder.layer_norm -> x
   MER_TRY(mer_iota_offsets_launch(cu, B, T, stream));
-  MER_TRY(mer_posconv_launch(x0, m->pos_w, m->pos_b, cu, B, T, xn, stream));
+  if (m->pos_w_bd) {
+    // grouped conv (k = 128, 16 groups of 48 channels, zero padding 64, last frame dropped) as ONE fp16 GEMM
+    // over windowed block-diagonal weights: output block j (256 columns) reads the 320-channel window that
+    // starts at floor(256 j / 48) * 48; tap k reads frame t + k - 64 (rows outside the clip are zero).
+    // 6.67x the algorithmic FLOPs, still ~2x faster than the mma.sync kernel.  x1 = x0 + GELU(conv + bias).
+    void* x0h = h;  // fp16 copy of x0 in the (still unused) FFN buffer
+    const int prof = mer_prof_begin(MER_PROF_POSCONV, 2.0 * (double)M * 768.0 * 48.0 * 128.0, stream);
+    mer_prof_pause(1);
+    int rc = mer_cast_f16_launch(x0, x0h, M * D, stream);
+    if (rc == 0) {
+      MerGemmDesc g;
+      memset(&g, 0, sizeof(g));
+      g.A = static_cast<const float*>(x0h);
+      g.W = static_cast<const float*>(m->pos_w_bd);
+      g.rows_per_batch = T;
+      g.a_rows_dim = T;
+      g.batches = B;
+      g.N = D;
+      g.K_inner = 320;
+      g.taps = 128;
+      g.P = 1;
+      g.a_phase_stride = D;
+      g.a_row_stride = D;
+      g.a_batch_stride = (long long)T * D;
+      g.a_row0 = -64;
+      g.a_cols = D;
+      g.a_col_group = 48;
+      g.force_block_n = 256;
+      g.mode = MER_GEMM_F16;
+      g.ep.bias = m->pos_b;
+      g.ep.res = x0;
+      g.ep.res_bstride = T;
+      g.ep.out = xn;
+      g.ep.out_bstride = T;
+      g.ep.ld_out = D;
+      g.ep.ld_res = D;
+      g.ep.flags = MER_EPI_GELU;
+      rc = mer_gemm_launch(&g, stream);
+    }
+    mer_prof_pause(0);
+    mer_prof_end(prof, stream);
+    if (rc) return rc;
+  } else {
+    MER_TRY(mer_posconv_launch(x0, m->pos_w, m->pos_b, cu, B, T, xn, stream));
+  }
   MER_TRY(mer_layernorm_launch(xn, m->enc_ln_g, m->enc_ln_b, x, xs, nullptr, M, D, m->ln_eps, 0, stream));
   if (opt_hidden)
     MER_CUDA_CHECK(cudaMemcpyAsync(opt_hidden, x, (size_t)M * D * 4, cudaMemcpyDeviceToDevice, stream));

@@ -118,7 +118,8 @@ struct EpiTile {
 // registers, i.e. before that chunk's math and stores.
 // GELU: 0 none, 1 polynomial erf, 2 libdevice erff.  OUT: 0 fp32, 1 TF32-rounded fp32, 2 bf16 (hi|lo),
 // 3 fp16.
-// RES: add the residual (GELU == 0, OUT != 2 only).  The transposed side output exists for GELU == 0.
+// RES: add the residual after the activation (OUT 0 or 1).  The transposed side output exists for
+// GELU == 0 without residual.
 template <int CH, int GELU, int OUT, bool RES, typename ReleaseFn>
 __device__ __forceinline__ void epi_tile(const EpiTile& tl, const MerGemmEpilogue& ep, float* stg,
                                          int lane, ReleaseFn release_tmem) {
@@ -260,7 +261,7 @@ template <int BLOCK_N, int MODE, int CLUSTER, bool TWOSM>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
             const __grid_constant__ CUtensorMap tmap_b, const MerGemmEpilogue ep,
-            int rows_per_batch, int batches, int N, int K, int K_inner, int P) {
+            int rows_per_batch, int batches, int N, int K, int K_inner, int P, int a_row0, int a_col_group) {
   using Cfg = GemmCfg<BLOCK_N, MODE, TWOSM>;
   static_assert(!TWOSM || CLUSTER == 2, "the 2-SM MMA needs CTA pairs");
   extern __shared__ uint8_t smem_raw[];
@@ -332,20 +333,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int b = mb / m_tiles;
       const int mt = mb % m_tiles;
       int c0 = 0, tap_phase = 0, tap_row = 0;  // K offset inside the tap; tap % P; tap / P
+      // block-diagonal (grouped conv) mode: this column block's window of A columns
+      const int c_win = a_col_group > 0 ? ((n_blk * BLOCK_N) / a_col_group) * a_col_group : 0;
+      const int row_base = mt * BLOCK_M + a_row0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
           if (TWOSM) {
             const uint32_t lbar = leader_addr(&full_bar[stage]);
             mbar_expect_tx_cluster(lbar, Cfg::kStageBytes);
-            tma_load_4d_2sm(smem_a + stage * Cfg::kABytes, &tmap_a, lbar, c0 * kEl, tap_phase,
-                            mt * BLOCK_M + tap_row, b);
+            tma_load_4d_2sm(smem_a + stage * Cfg::kABytes, &tmap_a, lbar, (c_win + c0) * kEl, tap_phase,
+                            row_base + tap_row, b);
             tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &tmap_b, lbar, kb * Cfg::kBlockK * kEl,
                             n_blk * BLOCK_N + cta_rank * (BLOCK_N / 2));
           } else {
             mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], c0 * kEl, tap_phase,
-                        mt * BLOCK_M + tap_row, b);
+            tma_load_4d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], (c_win + c0) * kEl, tap_phase,
+                        row_base + tap_row, b);
             if (CLUSTER == 1) {
               tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * Cfg::kBlockK * kEl,
                           n_blk * BLOCK_N);
@@ -497,7 +501,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
       };
       if (tl.res_lane != nullptr) {  // warp-uniform; each variant is straight-line code
-        if (out_kind == 1) epi_tile<CH, 0, 1, true>(tl, ep, stg, lane, release);
+        if (gelu_kind != 0) epi_tile<CH, 1, 0, true>(tl, ep, stg, lane, release);  // res + GELU(acc + bias)
+        else if (out_kind == 1) epi_tile<CH, 0, 1, true>(tl, ep, stg, lane, release);
         else epi_tile<CH, 0, 0, true>(tl, ep, stg, lane, release);
       } else {
         switch (kind) {
@@ -545,8 +550,8 @@ int launch_gemm(const MerGemmDesc* g, cudaStream_t stream) {
   {
     // strides are given in 4-byte operand slots in both modes (a split row of K (hi|lo) pairs
     // occupies exactly the bytes of K fp32 values)
-    const uint64_t dims[4] = {(uint64_t)g->K_inner * mult, (uint64_t)g->P, (uint64_t)g->a_rows_dim,
-                              (uint64_t)g->batches};
+    const uint64_t dims[4] = {(uint64_t)(g->a_cols > 0 ? g->a_cols : g->K_inner) * mult, (uint64_t)g->P,
+                              (uint64_t)g->a_rows_dim, (uint64_t)g->batches};
     const uint64_t strides[3] = {(uint64_t)g->a_phase_stride * sbytes,
                                  (uint64_t)g->a_row_stride * sbytes,
                                  (uint64_t)g->a_batch_stride * sbytes};
@@ -590,7 +595,7 @@ int launch_gemm(const MerGemmDesc* g, cudaStream_t stream) {
     cfg.numAttrs = 1;
     MER_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<BLOCK_N, MODE, CLUSTER, TWOSM>, ta, tb, g->ep,
                                       g->rows_per_batch, g->batches, g->N, g->K_inner * g->taps,
-                                      g->K_inner, g->P));
+                                      g->K_inner, g->P, g->a_row0, g->a_col_group));
   }
   MER_CUDA_CHECK(cudaGetLastError());
   mer_count_launches(1);
@@ -623,8 +628,12 @@ int mer_gemm_launch(const MerGemmDesc* g, cudaStream_t stream) {
               "mer_gemm: out/res leading dims must be multiples of 4 floats");
   MER_REQUIRE(!((g->ep.flags & MER_EPI_SPLIT_BF16) && (g->ep.res || g->ep.vt)),
               "mer_gemm: a bf16-split output cannot be combined with a residual or the transposed side output");
-  MER_REQUIRE(!(g->ep.res && (g->ep.vt || (g->ep.flags & MER_EPI_GELU))),
-              "mer_gemm: a residual cannot be combined with GELU or the transposed side output");
+  MER_REQUIRE(!(g->ep.res && g->ep.vt), "mer_gemm: a residual cannot be combined with the transposed side output");
+  MER_REQUIRE(!(g->ep.res && (g->ep.flags & MER_EPI_GELU) &&
+                (g->ep.flags & (MER_EPI_ROUND_TF32 | MER_EPI_GELU_LIBM))),
+              "mer_gemm: residual + GELU is available with the polynomial GELU and a plain fp32 output");
+  MER_REQUIRE(g->a_col_group == 0 || g->force_block_n == 128 || g->force_block_n == 256,
+              "mer_gemm: a_col_group needs force_block_n (the weights are built for one block width)");
   MER_REQUIRE(!(g->ep.vt && (g->ep.flags & MER_EPI_GELU)), "mer_gemm: GELU + transposed side output is not supported");
   const int m_tiles = (g->rows_per_batch + BLOCK_M - 1) / BLOCK_M;
   const long long tiles256 = (g->N % 256 == 0) ? (long long)g->batches * m_tiles * (g->N / 256) : 0;

@@ -11,6 +11,8 @@ enum { MER_PROF_ATT_F16 = 10, MER_PROF_ATT_TC = 11, MER_PROF_LAYERNORM = 12, MER
        MER_PROF_CONV0 = 14 };
 int mer_prof_begin(int klass, double work, cudaStream_t stream);
 void mer_prof_end(int slot, cudaStream_t stream);
+void mer_prof_pause(int on);  // nest: launches of a composite op (timed as a whole) are not recorded themselves
+int mer_cast_f16_launch(const float* in, void* out, long long n, cudaStream_t stream);  // rowwise.cu
 
 // gemm.cu
 int mer_gemm_launch(const MerGemmDesc* g, cudaStream_t stream);

@@ -95,6 +95,16 @@ __global__ void split_bf16_kernel(const float* __restrict__ in, void* __restrict
   }
 }
 
+// fp32 -> fp16 (round-to-nearest, saturating), 4 elements per thread
+__global__ void cast_f16_kernel(const float4* __restrict__ in, uint2* __restrict__ out, long long n4) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    const float4 v = in[i];
+    out[i] = make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w));
+  }
+}
+
 __global__ void round_tf32_kernel(float* x, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -127,6 +137,18 @@ int mer_layernorm_launch(const float* x, const float* gamma, const float* beta, 
   else
     layernorm_kernel<4><<<(int)blocks, 256, 0, stream>>>(x, gamma, beta, y, y_split, acc, rows, eps, flags);
   mer_prof_end(prof, stream);
+  MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
+  return 0;
+}
+
+int mer_cast_f16_launch(const float* in, void* out, long long n, cudaStream_t stream) {
+  MER_REQUIRE(in && out && n % 4 == 0, "mer_cast_f16: bad operands");
+  if (n <= 0) return 0;
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  cast_f16_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(in),
+                                                   reinterpret_cast<uint2*>(out), n / 4);
   MER_CUDA_CHECK(cudaGetLastError());
   mer_count_launches(1);
   return 0;

@@ -22,12 +22,15 @@ void mer_set_error(const char* fmt, ...) {
 namespace {
 struct ProfSlot { cudaEvent_t a, b; double work; int klass; };
 bool g_prof_on = false;
+int g_prof_paused = 0;              // > 0: launches inside a composite op are not recorded on their own
 std::vector<ProfSlot> g_prof;       // slots in use since the last enable
 std::vector<ProfSlot> g_prof_pool;  // recycled event pairs
 }  // namespace
 
+void mer_prof_pause(int on) { g_prof_paused += on ? 1 : -1; }
+
 int mer_prof_begin(int klass, double work, cudaStream_t stream) {
-  if (!g_prof_on) return -1;
+  if (!g_prof_on || g_prof_paused > 0) return -1;
   ProfSlot slot;
   if (!g_prof_pool.empty()) {
     slot = g_prof_pool.back();

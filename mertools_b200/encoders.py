@@ -142,9 +142,26 @@ class MerHubertModel(C.Structure):
     _fields_ = [("n_layers", C.c_int), ("ln_eps", C.c_float), ("conv0_w", C.c_void_p),
                 ("gn_g", C.c_void_p), ("gn_b", C.c_void_p), ("conv_w", C.c_void_p * 6),
                 ("fp_ln_g", C.c_void_p), ("fp_ln_b", C.c_void_p), ("fp_w", C.c_void_p),
-                ("fp_b", C.c_void_p), ("pos_w", C.c_void_p), ("pos_b", C.c_void_p),
+                ("fp_b", C.c_void_p), ("pos_w", C.c_void_p), ("pos_w_bd", C.c_void_p), ("pos_b", C.c_void_p),
                 ("enc_ln_g", C.c_void_p), ("enc_ln_b", C.c_void_p),
                 ("layers", C.POINTER(W.MerLayerWeights))]
+
+
+def block_diagonal_pos_conv_weight(wpos, block_n=256, window=320, group=48):
+    """[768 out][48 in][128 taps] grouped-conv weight -> dense [768][128 * window]: row o holds, for every
+    tap k, its 48 input weights at columns k*window + (g*48 + i - win0(o)), zeros elsewhere, where
+    win0 = floor(block_n * (o // block_n) / group) * group is the first input channel the GEMM reads for
+    o's output column block (MerGemmDesc.a_col_group)."""
+    n_out, cin, taps = wpos.shape
+    out = np.zeros((n_out, taps, window), np.float32)
+    for o0 in range(0, n_out, group):            # one group of outputs at a time
+        g = o0 // group
+        for o in range(o0, o0 + group):
+            win0 = (block_n * (o // block_n) // group) * group
+            off = g * group - win0
+            assert 0 <= off and off + cin <= window, (o, off)
+            out[o, :, off:off + cin] = wpos[o].T  # [taps][in]
+    return out.reshape(n_out, taps * window)
 
 
 def fold_pos_conv_weight(sd):
@@ -198,6 +215,11 @@ class HubertEncoder:
         assert wpos.shape == (768, 48, 128), wpos.shape
         wp = wpos.reshape(16, 48, 48, 128).transpose(0, 3, 1, 2)  # [g][tap][out][in]
         m.pos_w = pk.keep(np.ascontiguousarray(wp), tf32=True).data_ptr()
+        # the same weights as a windowed block-diagonal fp16 matrix for the GEMM form of the conv
+        # (MerHubertModel.pos_w_bd in mer_b200.h); MER_POSCONV_LEGACY=1 keeps the mma.sync kernel
+        import os
+        m.pos_w_bd = None if os.environ.get("MER_POSCONV_LEGACY") else \
+            pk.keep(block_diagonal_pos_conv_weight(wpos), f16=True).data_ptr()
         m.pos_b = pk.keep(sd["encoder.pos_conv_embed.conv.bias"]).data_ptr()
         m.enc_ln_g = pk.keep(sd["encoder.layer_norm.weight"]).data_ptr()
         m.enc_ln_b = pk.keep(sd["encoder.layer_norm.bias"]).data_ptr()
