@@ -126,8 +126,9 @@ MER_API int mer_split_bf16(const float* in, void* out, long long rows, int K, vo
 
 /* ---- row-wise kernels ------------------------------------------------------------------ */
 enum { MER_LN_ROUND_TF32 = 1, MER_LN_ACC_INIT = 2, MER_LN_ACC_ADD = 4,
-       MER_LN_OUT_F16 = 8 /* y is an fp16 array (the MER_GEMM_F16 operand) */ };
-/* y = LayerNorm(x) * gamma + beta over the last dim (768 or 512).  y (fp32, tf32-rounded when
+       MER_LN_OUT_F16 = 8, /* y is an fp16 array (the MER_GEMM_F16 operand) */
+       MER_LN_GELU = 16    /* GELU(erf) after the affine (HubertLayerNormConvLayer) */ };
+/* y = LayerNorm(x) * gamma + beta over the last dim (512, 768 or 1024).  y (fp32, tf32-rounded when
  * MER_LN_ROUND_TF32) and y_split (bf16 hi|lo rows, the BF16X3 GEMM operand) are both optional;
  * at least one must be given.  Optional side buffer acc
  * (same shape): acc = y (ACC_INIT) or acc += y (ACC_ADD) — the "sum of the last four hidden
@@ -237,6 +238,20 @@ typedef struct MerHubertModel {
   const float* enc_ln_g;   /* encoder.layer_norm */
   const float* enc_ln_b;
   const MerLayerWeights* layers;
+  /* ---- model family (zero-initialised fields = HuBERT-base / wav2vec2-base) ----
+   * hubert-large / chinese-hubert-large / wav2vec2-large-lv60 (extract_audio_huggingface.py:21,27,29):
+   * hidden 1024, 16 heads, FFN 4096, feat_extract_norm="layer" (every conv followed by LayerNorm over its 512
+   * channels instead of GroupNorm on conv0; conv biases), do_stable_layer_norm (pre-LN layers,
+   * encoder.layer_norm applied after the last layer; hidden states taken before each layer). */
+  int hidden;              /* 0 = 768; 768 or 1024 */
+  int ffn;                 /* 0 = 3072 */
+  int heads;               /* 0 = 12; hidden / 64 */
+  int feat_norm_layer;     /* 1: LayerNorm after every conv (conv_ln_*), conv biases (conv_b) */
+  int stable_layer_norm;   /* 1: pre-LN encoder (HubertEncoderStableLayerNorm) */
+  const float* conv_b[7];      /* conv biases [512] (feat_norm_layer) */
+  const float* conv_ln_g[7];   /* per-conv LayerNorm affine [512] (feat_norm_layer) */
+  const float* conv_ln_b[7];
+  int pos_window;          /* K window of pos_w_bd (0 = 320; 256 for 64-channel groups) */
 } MerHubertModel;
 
 /* per-row zero-mean / unit-variance (eps 1e-7) of HF Wav2Vec2FeatureExtractor(do_normalize=True)
@@ -247,7 +262,8 @@ MER_API int mer_wave_normalize(const float* in, float* out, int batch, int n_sam
 
 /* frames produced for n_samples input samples (conv kernels 10,3,3,3,3,2,2 / strides 5,2,2,2,2,2,2) */
 MER_API int mer_hubert_num_frames(int n_samples);
-MER_API long long mer_hubert_workspace_bytes(int batch, int n_samples);
+MER_API long long mer_hubert_workspace_bytes(int batch, int n_samples);               /* base dims */
+MER_API long long mer_hubert_model_workspace_bytes(const MerHubertModel* model, int batch, int n_samples);
 
 /* wave: fp32 [batch, n_samples] raw samples (every row the same length; the reference feeds one
  * clip at a time, or 10 s rows from split_into_batch, extract_audio_huggingface.py:40-50,95).

@@ -11,12 +11,12 @@
 #include "mer_common.cuh"
 #include "mer_kernels.h"
 
-namespace {
-
-constexpr int D = 768;
-constexpr int DQKV = 2304;
+constexpr int D = 768;      // base-model dims (ViT-B, HuBERT-base, BERT-base); the large audio family
+constexpr int DQKV = 2304;  // passes its own through MerStackArgs / MerHubertModel
 constexpr int DFF = 3072;
 constexpr int HEADS = 12;
+
+namespace {
 
 int linear(int mode, const float* A, const float* W, const float* bias, const float* res, float* out,
            long long M, int N, int K, int flags, cudaStream_t stream, float* vt = nullptr,
@@ -60,6 +60,12 @@ int mer_run_stack(const MerStackArgs& a, cudaStream_t stream) {
   MER_REQUIRE(a.tokens > 0 && a.tokens < (1ll << 31), "mer_run_stack: bad token count %lld", a.tokens);
   MER_REQUIRE(a.mode != MER_GEMM_F16 || a.pre_ln, "mer_run_stack: the F16 mode is for the pre-LN stack");
   const long long M = a.tokens;
+  // model dims (the file-level constants are the base-model defaults)
+  const int D = a.dim > 0 ? a.dim : ::D;
+  const int DFF = a.ffn > 0 ? a.ffn : ::DFF;
+  const int HEADS = a.heads > 0 ? a.heads : ::HEADS;
+  const int DQKV = 3 * D;
+  MER_REQUIRE(HEADS * 64 == D, "mer_run_stack: heads %d x 64 != hidden %d", HEADS, D);
   const size_t hs_bytes = (size_t)M * D * sizeof(float);
   if (a.opt_hidden && !a.hidden0_done) MER_CUDA_CHECK(cudaMemcpyAsync(a.opt_hidden, a.x, hs_bytes, cudaMemcpyDeviceToDevice, stream));
   for (int l = 0; l < a.n_layers; ++l) {
@@ -236,7 +242,8 @@ struct HubertPlan {
   long long M;
 };
 
-static HubertPlan hubert_plan(int B, int L) {
+static HubertPlan hubert_plan(int B, int L, int D = ::D, int DFF = ::DFF) {
+  const int DQKV = 3 * D;
   HubertPlan p;
   int t = L;
   for (int i = 0; i < 7; ++i) {
@@ -258,10 +265,19 @@ static HubertPlan hubert_plan(int B, int L) {
   p.off_qkv = o;   o += al(p.M * DQKV * 4);
   p.off_h = o;     o += al(p.M * DFF * 4);
   p.off_acc = o;   o += al(p.M * D * 4);
-  p.off_vt = o;    o += al((long long)D * ((p.M + 3) & ~3ll) * 4);
+  p.off_vt = o;    o += al((long long)D * ((p.M + 7) & ~7ll) * 4);
   p.off_cu = o;    o += al(((long long)B + 1) * 4);
   p.total = o;
   return p;
+}
+
+static int hub_dim(const MerHubertModel* m) { return m->hidden > 0 ? m->hidden : ::D; }
+static int hub_ffn(const MerHubertModel* m) { return m->ffn > 0 ? m->ffn : ::DFF; }
+static int hub_heads(const MerHubertModel* m) { return m->heads > 0 ? m->heads : ::HEADS; }
+
+long long mer_hubert_model_workspace_bytes(const MerHubertModel* m, int batch, int n_samples) {
+  if (!m) return -1;
+  return hubert_plan(batch, n_samples, hub_dim(m), hub_ffn(m)).total;
 }
 
 int mer_hubert_num_frames(int n_samples) { return hubert_plan(1, n_samples).T[6]; }
@@ -277,7 +293,11 @@ int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L,
   MER_REQUIRE(m && wave && workspace, "mer_hubert_forward: null operand");
   MER_REQUIRE(B > 0 && L > 0, "mer_hubert_forward: batch=%d n_samples=%d", B, L);
   MER_REQUIRE(m->n_layers >= 4, "mer_hubert_forward: the last-four readout needs >= 4 layers");
-  const HubertPlan p = hubert_plan(B, L);
+  const int D = hub_dim(m), DFF = hub_ffn(m), HEADS = hub_heads(m);
+  MER_REQUIRE((D == 768 || D == 1024) && HEADS * 64 == D && DFF % 128 == 0,
+              "mer_hubert_forward: hidden %d / heads %d / ffn %d not supported", D, HEADS, DFF);
+  MER_REQUIRE(!m->stable_layer_norm || m->pos_w_bd, "mer_hubert_forward: the stable-layer-norm family needs pos_w_bd");
+  const HubertPlan p = hubert_plan(B, L, D, DFF);
   MER_REQUIRE(p.T[6] > 0, "mer_hubert_forward: %d samples give no output frame", L);
   MER_REQUIRE(workspace_bytes >= p.total, "mer_hubert_forward: workspace %lld B < required %lld B",
               workspace_bytes, p.total);
@@ -301,9 +321,14 @@ int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L,
     MER_TRY(mer_wave_normalize_launch(wave, wave_n, B, L, L, L, stream));
     wsrc = wave_n;
   }
-  // conv0 + GroupNorm + GELU -> ping [B, Tpad0, 512]
-  MER_TRY(mer_hubert_conv0_launch(wsrc, L, B, L, m->conv0_w, m->gn_g, m->gn_b, stats, ping,
-                                  (long long)p.Tpad[0] * 512, /*split_out=*/1, stream));
+  // conv0 + GroupNorm + GELU (or, layer-norm family: conv0 + bias + LayerNorm + GELU) -> ping [B, Tpad0, 512]
+  if (m->feat_norm_layer) {
+    MER_TRY(mer_hubert_conv0_ln_launch(wsrc, L, B, L, m->conv0_w, m->conv_b[0], m->conv_ln_g[0], m->conv_ln_b[0],
+                                       ping, (long long)p.Tpad[0] * 512, stream));
+  } else {
+    MER_TRY(mer_hubert_conv0_launch(wsrc, L, B, L, m->conv0_w, m->gn_g, m->gn_b, stats, ping,
+                                    (long long)p.Tpad[0] * 512, /*split_out=*/1, stream));
+  }
   // conv1..6 as implicit GEMMs over the time-major activations
   float* src = ping;
   float* dst = pong;
@@ -325,10 +350,20 @@ int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L,
     g.ep.out = dst;
     g.ep.out_bstride = (i == 6) ? p.T[6] : p.Tpad[i];  // conv6 output is packed [B*T, 512]
     g.ep.ld_out = 512;
-    g.ep.flags = MER_EPI_GELU | (i == 6 ? 0 : MER_EPI_SPLIT_BF16);  // conv6 feeds a LayerNorm: fp32
     g.ep.split_off = 512;
     g.mode = MER_GEMM_BF16X3;
-    MER_TRY(mer_gemm_launch(&g, stream));
+    if (m->feat_norm_layer) {
+      // conv + bias -> fp32; LayerNorm(512) + GELU in place -> split rows (conv6: fp32, it feeds another LayerNorm)
+      g.ep.bias = m->conv_b[i];
+      g.ep.flags = 0;
+      MER_TRY(mer_gemm_launch(&g, stream));
+      const long long rows = (i == 6) ? (long long)B * p.T[6] : (long long)B * p.Tpad[i];
+      MER_TRY(mer_layernorm_launch(dst, m->conv_ln_g[i], m->conv_ln_b[i], i == 6 ? dst : nullptr,
+                                   i == 6 ? nullptr : dst, nullptr, rows, 512, 1e-5f, MER_LN_GELU, stream));
+    } else {
+      g.ep.flags = MER_EPI_GELU | (i == 6 ? 0 : MER_EPI_SPLIT_BF16);  // conv6 feeds a LayerNorm: fp32
+      MER_TRY(mer_gemm_launch(&g, stream));
+    }
     float* tmp = src;
     src = dst;
     dst = tmp;
@@ -339,7 +374,7 @@ int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L,
                                m->ln_eps, 0, stream));
   float* x0 = qkv;
   MER_TRY(linear(MER_GEMM_BF16X3, feat, m->fp_w, m->fp_b, nullptr, x0, M, D, 512, 0, stream));
-  // positional conv + GELU + residual -> xn ; encoder.layer_norm -> x
+  // positional conv + GELU + residual -> xn
   MER_TRY(mer_iota_offsets_launch(cu, B, T, stream));
   if (m->pos_w_bd) {
     // grouped conv (k = 128, 16 groups of 48 channels, zero padding 64, last frame dropped) as ONE fp16 GEMM
@@ -347,7 +382,9 @@ int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L,
     // starts at floor(256 j / 48) * 48; tap k reads frame t + k - 64 (rows outside the clip are zero).
     // 6.67x the algorithmic FLOPs, still ~2x faster than the mma.sync kernel.  x1 = x0 + GELU(conv + bias).
     void* x0h = h;  // fp16 copy of x0 in the (still unused) FFN buffer
-    const int prof = mer_prof_begin(MER_PROF_POSCONV, 2.0 * (double)M * 768.0 * 48.0 * 128.0, stream);
+    const int gch = D / 16;                                   // channels per group: 48 or 64
+    const int window = m->pos_window > 0 ? m->pos_window : 320;
+    const int prof = mer_prof_begin(MER_PROF_POSCONV, 2.0 * (double)M * D * gch * 128.0, stream);
     mer_prof_pause(1);
     int rc = mer_cast_f16_launch(x0, x0h, M * D, stream);
     if (rc == 0) {
@@ -359,7 +396,7 @@ int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L,
       g.a_rows_dim = T;
       g.batches = B;
       g.N = D;
-      g.K_inner = 320;
+      g.K_inner = window;
       g.taps = 128;
       g.P = 1;
       g.a_phase_stride = D;
@@ -367,7 +404,7 @@ int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L,
       g.a_batch_stride = (long long)T * D;
       g.a_row0 = -64;
       g.a_cols = D;
-      g.a_col_group = 48;
+      g.a_col_group = gch;
       g.force_block_n = 256;
       g.mode = MER_GEMM_F16;
       g.ep.bias = m->pos_b;
@@ -386,16 +423,12 @@ int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L,
   } else {
     MER_TRY(mer_posconv_launch(x0, m->pos_w, m->pos_b, cu, B, T, xn, stream));
   }
-  MER_TRY(mer_layernorm_launch(xn, m->enc_ln_g, m->enc_ln_b, x, xs, nullptr, M, D, m->ln_eps, 0, stream));
-  if (opt_hidden)
-    MER_CUDA_CHECK(cudaMemcpyAsync(opt_hidden, x, (size_t)M * D * 4, cudaMemcpyDeviceToDevice, stream));
   MerStackArgs a;
   memset(&a, 0, sizeof(a));
-  a.layers = m->layers;
-  a.n_layers = m->n_layers;
-  a.pre_ln = 0;
-  a.mode = MER_GEMM_BF16X3;
   a.eps = m->ln_eps;
+  a.dim = D;
+  a.ffn = DFF;
+  a.heads = HEADS;
   a.tokens = M;
   a.cu_seqlens = cu;
   a.n_seq = B;
@@ -405,15 +438,55 @@ int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L,
   a.xn = xn;
   a.qkv = qkv;
   a.h = h;
-  a.acc = acc;
-  a.acc_last = 4;
   a.vt = reinterpret_cast<float*>(ws + p.off_vt);
-  a.vt_ld = (M + 3) & ~3ll;
-  a.opt_hidden = opt_hidden;
+  a.vt_ld = (M + 7) & ~7ll;
   a.hidden0_done = 1;
-  MER_TRY(mer_run_stack(a, stream));
+  const size_t hs_bytes = (size_t)M * D * 4;
+  if (!m->stable_layer_norm) {
+    // encoder.layer_norm -> x ; post-LN layers; readout = sum of the last four LayerNorm outputs
+    MER_TRY(mer_layernorm_launch(xn, m->enc_ln_g, m->enc_ln_b, x, xs, nullptr, M, D, m->ln_eps, 0, stream));
+    if (opt_hidden) MER_CUDA_CHECK(cudaMemcpyAsync(opt_hidden, x, hs_bytes, cudaMemcpyDeviceToDevice, stream));
+    a.layers = m->layers;
+    a.n_layers = m->n_layers;
+    a.pre_ln = 0;
+    a.mode = MER_GEMM_BF16X3;
+    a.acc = acc;
+    a.acc_last = 4;
+    a.opt_hidden = opt_hidden;
+    MER_TRY(mer_run_stack(a, stream));
+  } else {
+    // HubertEncoderStableLayerNorm: the positional-conv sum is hidden state 0; pre-LN layers (BF16X3 like
+    // the rest of the audio path, any sequence length); hidden states are the residual stream BEFORE each
+    // layer, and encoder.layer_norm of the
+    // last one closes the tuple: readout = x_{L-4} + x_{L-3} + x_{L-2} + LayerNorm(x_{L-1})
+    // (x_l = stream after layer l).
+    MER_CUDA_CHECK(cudaMemcpyAsync(x, xn, hs_bytes, cudaMemcpyDeviceToDevice, stream));
+    if (opt_hidden) MER_CUDA_CHECK(cudaMemcpyAsync(opt_hidden, x, hs_bytes, cudaMemcpyDeviceToDevice, stream));
+    a.pre_ln = 1;
+    a.mode = MER_GEMM_BF16X3;
+    const int L0 = m->n_layers - 4;  // layers before the readout window
+    int done = 0;
+    auto run = [&](int n) -> int {
+      a.layers = m->layers + done;
+      a.n_layers = n;
+      a.opt_hidden = opt_hidden ? opt_hidden + (size_t)done * M * D : nullptr;
+      const int rc = n > 0 ? mer_run_stack(a, stream) : 0;
+      done += n;
+      return rc;
+    };
+    MER_TRY(run(L0 + 1));                                        // x = x_{L-4}
+    MER_TRY(mer_accumulate_launch(x, acc, M * D, 1, stream));
+    for (int k = 0; k < 2; ++k) {
+      MER_TRY(run(1));                                           // x_{L-3}, x_{L-2}
+      MER_TRY(mer_accumulate_launch(x, acc, M * D, 0, stream));
+    }
+    MER_TRY(run(1));                                             // x_{L-1}
+    float* last = opt_hidden ? opt_hidden + (size_t)m->n_layers * M * D : xn;
+    MER_TRY(mer_layernorm_launch(x, m->enc_ln_g, m->enc_ln_b, last, nullptr, acc, M, D, m->ln_eps,
+                                 MER_LN_ACC_ADD, stream));
+  }
   if (out_frames)
-    MER_CUDA_CHECK(cudaMemcpyAsync(out_frames, acc, (size_t)M * D * 4, cudaMemcpyDeviceToDevice, stream));
+    MER_CUDA_CHECK(cudaMemcpyAsync(out_frames, acc, hs_bytes, cudaMemcpyDeviceToDevice, stream));
   if (out_utt)
     MER_TRY(mer_segment_reduce_launch(acc, cu, cu + 1, B, D, MER_SEG_MEAN, out_utt, stream));
   return 0;

@@ -124,6 +124,67 @@ conv0_apply_kernel(const float* __restrict__ wave, long long ld_wave, const floa
   }
 }
 
+// conv0 (k = 10, stride 5, + bias) -> LayerNorm over the 512 channels -> GELU, the first layer of the
+// feat_extract_norm="layer" feature encoder (HF HubertLayerNormConvLayer; hubert-large family).
+// One warp = LN_ROWS consecutive frames; lane owns channels lane + 32 j (j < 16), weights transposed in
+// smem ([tap][channel]: conflict-free), two-pass LayerNorm in registers via warp shuffles.
+constexpr int LN_ROWS = 4;
+__global__ void __launch_bounds__(256)
+conv0_ln_kernel(const float* __restrict__ wave, long long ld_wave, const float* __restrict__ w0,
+                const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
+                int T0, long long out_bstride, float* __restrict__ out) {
+  __shared__ float ws[K0][C0];  // 20 KB
+  __shared__ float xs[8][LN_ROWS * S0 + K0];
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < C0 * K0; i += blockDim.x) ws[i % K0][i / K0] = __ldg(w0 + i);
+  __syncthreads();
+  const int t0 = (blockIdx.x * 8 + warp) * LN_ROWS;
+  if (t0 >= T0) return;
+  const int nt = min(LN_ROWS, T0 - t0);
+  const float* x = wave + (long long)b * ld_wave + (long long)t0 * S0;
+  for (int i = lane; i < (nt - 1) * S0 + K0; i += 32) xs[warp][i] = x[i];
+  __syncwarp();
+  float acc[LN_ROWS][16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float bj = bias ? __ldg(bias + lane + 32 * j) : 0.f;
+#pragma unroll
+    for (int r = 0; r < LN_ROWS; ++r) acc[r][j] = bj;
+  }
+#pragma unroll
+  for (int k = 0; k < K0; ++k) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float w = ws[k][lane + 32 * j];
+#pragma unroll
+      for (int r = 0; r < LN_ROWS; ++r) acc[r][j] = fmaf(w, xs[warp][r * S0 + k], acc[r][j]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < LN_ROWS; ++r) {
+    if (r >= nt) break;
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s += acc[r][j];
+    const float mean = warp_sum(s) * (1.0f / C0);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      acc[r][j] -= mean;
+      q += acc[r][j] * acc[r][j];
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / C0) + 1e-5f);
+    float* orow = out + (long long)b * out_bstride + (long long)(t0 + r) * C0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = lane + 32 * j;
+      const float v = gelu_erf_fast(acc[r][j] * rstd * __ldg(gamma + c) + __ldg(beta + c));
+      store_split1(orow, c, v);
+    }
+  }
+}
+
 }  // namespace
 
 int mer_wave_normalize_launch(const float* in, float* out, int B, int L, long long ld_in,
@@ -151,6 +212,18 @@ int mer_hubert_conv0_launch(const float* wave, long long ld_wave, int B, int L, 
   mer_prof_end(prof, stream);
   MER_CUDA_CHECK(cudaGetLastError());
   mer_count_launches(2);
+  return 0;
+}
+
+int mer_hubert_conv0_ln_launch(const float* wave, long long ld_wave, int B, int L, const float* w0,
+                               const float* bias, const float* gamma, const float* beta, float* out,
+                               long long out_bstride, cudaStream_t stream) {
+  const int T0 = (L - K0) / S0 + 1;
+  MER_REQUIRE(T0 > 0, "mer_hubert_conv0_ln: waveform too short (%d samples)", L);
+  dim3 grid((T0 + 8 * LN_ROWS - 1) / (8 * LN_ROWS), B);
+  conv0_ln_kernel<<<grid, 256, 0, stream>>>(wave, ld_wave, w0, bias, gamma, beta, T0, out_bstride, out);
+  MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
   return 0;
 }
 

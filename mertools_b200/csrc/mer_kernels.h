@@ -13,6 +13,7 @@ int mer_prof_begin(int klass, double work, cudaStream_t stream);
 void mer_prof_end(int slot, cudaStream_t stream);
 void mer_prof_pause(int on);  // nest: launches of a composite op (timed as a whole) are not recorded themselves
 int mer_cast_f16_launch(const float* in, void* out, long long n, cudaStream_t stream);  // rowwise.cu
+int mer_accumulate_launch(const float* x, float* acc, long long n, int init, cudaStream_t stream);  // acc (+)= x
 
 // gemm.cu
 int mer_gemm_launch(const MerGemmDesc* g, cudaStream_t stream);
@@ -51,6 +52,10 @@ int mer_bert_embed_launch(const int* ids, const int* pos_ids, const float* word,
 // hubert_frontend.cu
 int mer_wave_normalize_launch(const float* in, float* out, int B, int L, long long ld_in,
                               long long ld_out, cudaStream_t stream);
+// conv0 (+ bias) + LayerNorm over the 512 channels + GELU (HubertLayerNormConvLayer), split-bf16 rows out
+int mer_hubert_conv0_ln_launch(const float* wave, long long ld_wave, int B, int L, const float* w0,
+                               const float* bias, const float* gamma, const float* beta, float* out,
+                               long long out_bstride, cudaStream_t stream);
 int mer_hubert_conv0_launch(const float* wave, long long ld_wave, int B, int L, const float* w0,
                             const float* gamma, const float* beta, double* stats, float* out,
                             long long out_bstride, int split_out, cudaStream_t stream);
@@ -65,6 +70,7 @@ struct MerStackArgs {
   int n_layers;
   int pre_ln;
   int mode;                  // MER_GEMM_TF32 | MER_GEMM_BF16X3 | MER_GEMM_F16 (pre-LN only)
+  int dim, ffn, heads;       // 0 = 768 / 3072 / 12
   float eps;
   long long tokens;          // total packed tokens (rows of x)
   const int* cu_seqlens;     // device [n_seq+1]

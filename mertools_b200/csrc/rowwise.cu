@@ -60,6 +60,9 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
       o.y = v[i].y * rstd * g[i].y + b[i].y;
       o.z = v[i].z * rstd * g[i].z + b[i].z;
       o.w = v[i].w * rstd * g[i].w + b[i].w;
+      if (flags & MER_LN_GELU) {
+        o.x = gelu_erf_fast(o.x); o.y = gelu_erf_fast(o.y); o.z = gelu_erf_fast(o.z); o.w = gelu_erf_fast(o.w);
+      }
       if (ar) {
         if (flags & MER_LN_ACC_INIT) {
           ar[lane + 32 * i] = o;
@@ -105,6 +108,20 @@ __global__ void cast_f16_kernel(const float4* __restrict__ in, uint2* __restrict
   }
 }
 
+// acc = x (init) or acc += x, float4-wise
+__global__ void accumulate_kernel(const float4* __restrict__ x, float4* __restrict__ acc, long long n4, int init) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    float4 v = x[i];
+    if (!init) {
+      const float4 a = acc[i];
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    acc[i] = v;
+  }
+}
+
 __global__ void round_tf32_kernel(float* x, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -122,7 +139,7 @@ int mer_layernorm_launch(const float* x, const float* gamma, const float* beta, 
   // not alias x: its rows are half as long.)
   MER_REQUIRE(!((flags & MER_LN_OUT_F16) && (const void*)y == (const void*)x),
               "mer_layernorm: an fp16 output cannot alias the input");
-  MER_REQUIRE(dim == 768 || dim == 512, "mer_layernorm: dim %d not supported (768 or 512)", dim);
+  MER_REQUIRE(dim == 768 || dim == 512 || dim == 1024, "mer_layernorm: dim %d not supported (512, 768, 1024)", dim);
   if (rows <= 0) return 0;
   const int warps_per_block = 8;
   long long blocks = (rows + warps_per_block - 1) / warps_per_block;
@@ -134,9 +151,23 @@ int mer_layernorm_launch(const float* x, const float* gamma, const float* beta, 
   const int prof = mer_prof_begin(MER_PROF_LAYERNORM, (double)rows * dim * (4.0 + out_b), stream);
   if (dim == 768)
     layernorm_kernel<6><<<(int)blocks, 256, 0, stream>>>(x, gamma, beta, y, y_split, acc, rows, eps, flags);
+  else if (dim == 1024)
+    layernorm_kernel<8><<<(int)blocks, 256, 0, stream>>>(x, gamma, beta, y, y_split, acc, rows, eps, flags);
   else
     layernorm_kernel<4><<<(int)blocks, 256, 0, stream>>>(x, gamma, beta, y, y_split, acc, rows, eps, flags);
   mer_prof_end(prof, stream);
+  MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
+  return 0;
+}
+
+int mer_accumulate_launch(const float* x, float* acc, long long n, int init, cudaStream_t stream) {
+  MER_REQUIRE(x && acc && n % 4 == 0, "mer_accumulate: bad operands");
+  if (n <= 0) return 0;
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  accumulate_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(x),
+                                                     reinterpret_cast<float4*>(acc), n / 4, init);
   MER_CUDA_CHECK(cudaGetLastError());
   mer_count_launches(1);
   return 0;

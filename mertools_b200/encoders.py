@@ -144,7 +144,10 @@ class MerHubertModel(C.Structure):
                 ("fp_ln_g", C.c_void_p), ("fp_ln_b", C.c_void_p), ("fp_w", C.c_void_p),
                 ("fp_b", C.c_void_p), ("pos_w", C.c_void_p), ("pos_w_bd", C.c_void_p), ("pos_b", C.c_void_p),
                 ("enc_ln_g", C.c_void_p), ("enc_ln_b", C.c_void_p),
-                ("layers", C.POINTER(W.MerLayerWeights))]
+                ("layers", C.POINTER(W.MerLayerWeights)),
+                ("hidden", C.c_int), ("ffn", C.c_int), ("heads", C.c_int), ("feat_norm_layer", C.c_int),
+                ("stable_layer_norm", C.c_int), ("conv_b", C.c_void_p * 7), ("conv_ln_g", C.c_void_p * 7),
+                ("conv_ln_b", C.c_void_p * 7), ("pos_window", C.c_int)]
 
 
 def block_diagonal_pos_conv_weight(wpos, block_n=256, window=320, group=48):
@@ -180,12 +183,17 @@ def fold_pos_conv_weight(sd):
 
 
 class HubertEncoder:
-    """HuBERT-base (HF ``HubertModel``, group-norm feature extractor, post-LN) + the reference
-    readout ``torch.stack(hidden_states)[[-4,-3,-2,-1]].sum(0)``.
+    """HF ``HubertModel`` / ``Wav2Vec2Model`` + the reference readout
+    ``torch.stack(hidden_states)[[-4,-3,-2,-1]].sum(0)``.  Two families, recognised from the checkpoint:
+    base (hidden 768, group-norm feature extractor, post-LN: hubert-base, wav2vec2-base) and large
+    (hidden 1024, 16 heads, LayerNorm after every conv, conv biases, stable / pre-LN encoder: hubert-large,
+    chinese-hubert-large, wav2vec2-large-lv60).  ``stable_layer_norm`` overrides the inference of
+    ``config.do_stable_layer_norm`` from the feature extractor type (they coincide in every released
+    checkpoint of the extractor's model list except wav2vec2-large-960h, which is not supported).
 
-    Reference: MERBench/feature_extraction/audio/extract_audio_huggingface.py:93-110."""
+    Reference: MERBench/feature_extraction/audio/extract_audio_huggingface.py:18-36,93-110."""
 
-    def __init__(self, state_dict, device="cuda", ln_eps=1e-5):
+    def __init__(self, state_dict, device="cuda", ln_eps=1e-5, stable_layer_norm=None):
         L.check(L.lib().mer_check_device())
         sd = W._np(state_dict)
         self.device = torch.device(device)
@@ -194,17 +202,29 @@ class HubertEncoder:
         m = MerHubertModel()
         m.n_layers, m.ln_eps = self.n_layers, ln_eps
         w0 = sd["feature_extractor.conv_layers.0.conv.weight"]
-        assert w0.shape == (512, 1, 10), f"HuBERT-base feature extractor only, conv0 {w0.shape}"
-        assert "feature_extractor.conv_layers.0.layer_norm.weight" in sd and \
-            "feature_extractor.conv_layers.1.layer_norm.weight" not in sd, \
-            "only feat_extract_norm='group' (HuBERT/wav2vec2 base) is implemented"
+        assert w0.shape == (512, 1, 10), f"wav2vec2-style feature extractor (512 x 10 conv0) only, got {w0.shape}"
+        assert "feature_extractor.conv_layers.0.layer_norm.weight" in sd
+        ln_convs = "feature_extractor.conv_layers.1.layer_norm.weight" in sd  # feat_extract_norm == "layer"
+        self.hidden = int(sd["encoder.layer_norm.weight"].shape[0])
+        ffn = int(sd["encoder.layers.0.feed_forward.intermediate_dense.weight"].shape[0])
+        assert self.hidden in (768, 1024) and ffn % 128 == 0, (self.hidden, ffn)
+        m.hidden, m.ffn, m.heads = self.hidden, ffn, self.hidden // 64
+        m.feat_norm_layer = 1 if ln_convs else 0
+        m.stable_layer_norm = int(ln_convs if stable_layer_norm is None else stable_layer_norm)
         m.conv0_w = pk.keep(w0.reshape(512, 10)).data_ptr()
         m.gn_g = pk.keep(sd["feature_extractor.conv_layers.0.layer_norm.weight"]).data_ptr()
         m.gn_b = pk.keep(sd["feature_extractor.conv_layers.0.layer_norm.bias"]).data_ptr()
+        for i in range(7):
+            pre = f"feature_extractor.conv_layers.{i}."
+            has_b = pre + "conv.bias" in sd
+            assert has_b == ln_convs, "conv biases are implemented with the layer-norm feature extractor only"
+            if ln_convs:
+                m.conv_b[i] = pk.keep(sd[pre + "conv.bias"]).data_ptr()
+                m.conv_ln_g[i] = pk.keep(sd[pre + "layer_norm.weight"]).data_ptr()
+                m.conv_ln_b[i] = pk.keep(sd[pre + "layer_norm.bias"]).data_ptr()
         for i, k in enumerate((3, 3, 3, 3, 2, 2)):
             w = sd[f"feature_extractor.conv_layers.{i + 1}.conv.weight"]
             assert w.shape == (512, 512, k), w.shape
-            assert f"feature_extractor.conv_layers.{i + 1}.conv.bias" not in sd, "conv_bias=True unsupported"
             m.conv_w[i] = pk.keep(np.ascontiguousarray(w.transpose(0, 2, 1)).reshape(512, k * 512),
                                   split=True).data_ptr()
         m.fp_ln_g = pk.keep(sd["feature_projection.layer_norm.weight"]).data_ptr()
@@ -212,14 +232,19 @@ class HubertEncoder:
         m.fp_w = pk.keep(sd["feature_projection.projection.weight"], split=True).data_ptr()
         m.fp_b = pk.keep(sd["feature_projection.projection.bias"]).data_ptr()
         wpos = fold_pos_conv_weight(sd)
-        assert wpos.shape == (768, 48, 128), wpos.shape
-        wp = wpos.reshape(16, 48, 48, 128).transpose(0, 3, 1, 2)  # [g][tap][out][in]
-        m.pos_w = pk.keep(np.ascontiguousarray(wp), tf32=True).data_ptr()
-        # the same weights as a windowed block-diagonal fp16 matrix for the GEMM form of the conv
-        # (MerHubertModel.pos_w_bd in mer_b200.h); MER_POSCONV_LEGACY=1 keeps the mma.sync kernel
+        gch = self.hidden // 16
+        assert wpos.shape == (self.hidden, gch, 128), wpos.shape
+        # the weights as a windowed block-diagonal fp16 matrix for the GEMM form of the conv
+        # (MerHubertModel.pos_w_bd in mer_b200.h): 48-channel groups need a 320-wide window per 256-column
+        # block, 64-channel groups exactly 256.  MER_POSCONV_LEGACY=1 keeps the mma.sync kernel (base only)
         import os
-        m.pos_w_bd = None if os.environ.get("MER_POSCONV_LEGACY") else \
-            pk.keep(block_diagonal_pos_conv_weight(wpos), f16=True).data_ptr()
+        m.pos_window = 320 if gch == 48 else 256
+        legacy = bool(os.environ.get("MER_POSCONV_LEGACY")) and gch == 48
+        if gch == 48:
+            wp = wpos.reshape(16, 48, 48, 128).transpose(0, 3, 1, 2)  # [g][tap][out][in]
+            m.pos_w = pk.keep(np.ascontiguousarray(wp), tf32=True).data_ptr()
+        m.pos_w_bd = None if legacy else \
+            pk.keep(block_diagonal_pos_conv_weight(wpos, window=m.pos_window, group=gch), f16=True).data_ptr()
         m.pos_b = pk.keep(sd["encoder.pos_conv_embed.conv.bias"]).data_ptr()
         m.enc_ln_g = pk.keep(sd["encoder.layer_norm.weight"]).data_ptr()
         m.enc_ln_b = pk.keep(sd["encoder.layer_norm.bias"]).data_ptr()
@@ -228,8 +253,8 @@ class HubertEncoder:
         self.model = m
         self.ws = _Workspace(self.device)
         lib = L.lib()
-        lib.mer_hubert_workspace_bytes.restype = C.c_longlong
-        lib.mer_hubert_workspace_bytes.argtypes = [C.c_int, C.c_int]
+        lib.mer_hubert_model_workspace_bytes.restype = C.c_longlong
+        lib.mer_hubert_model_workspace_bytes.argtypes = [C.POINTER(MerHubertModel), C.c_int, C.c_int]
         lib.mer_hubert_num_frames.argtypes = [C.c_int]
         self._fwd = L.declare("mer_hubert_forward", [C.POINTER(MerHubertModel), C.c_void_p, C.c_int,
                                                      C.c_int, C.c_int, C.c_void_p, C.c_longlong,
@@ -239,16 +264,17 @@ class HubertEncoder:
         return L.lib().mer_hubert_num_frames(int(n_samples))
 
     def forward(self, wave: torch.Tensor, normalize=True, want_frames=False, return_hidden=False):
-        """wave: fp32 CUDA [B, L] (equal-length rows).  Returns (utt [B,768], frames [B,T,768]|None
-        [, hidden [(layers+1), B, T, 768]])."""
+        """wave: fp32 CUDA [B, L] (equal-length rows).  Returns (utt [B,D], frames [B,T,D]|None
+        [, hidden [(layers+1), B, T, D]]), D = 768 or 1024."""
         assert wave.dtype == torch.float32 and wave.is_cuda and wave.dim() == 2
         wave = wave.contiguous()
         B, Ls = wave.shape
         T = self.num_frames(Ls)
-        ws = self.ws.get(L.lib().mer_hubert_workspace_bytes(B, Ls))
-        utt = torch.empty(B, 768, dtype=torch.float32, device=self.device)
-        frames = torch.empty(B, T, 768, dtype=torch.float32, device=self.device) if want_frames else None
-        hidden = (torch.empty(self.n_layers + 1, B, T, 768, dtype=torch.float32, device=self.device)
+        D = self.hidden
+        ws = self.ws.get(L.lib().mer_hubert_model_workspace_bytes(C.byref(self.model), B, Ls))
+        utt = torch.empty(B, D, dtype=torch.float32, device=self.device)
+        frames = torch.empty(B, T, D, dtype=torch.float32, device=self.device) if want_frames else None
+        hidden = (torch.empty(self.n_layers + 1, B, T, D, dtype=torch.float32, device=self.device)
                   if return_hidden else None)
         L.check(self._fwd(C.byref(self.model), L.ptr(wave), B, Ls, 1 if normalize else 0, L.ptr(ws),
                           ws.numel(), L.ptr(frames), L.ptr(utt), L.ptr(hidden), L.stream_ptr()))

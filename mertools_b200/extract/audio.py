@@ -49,7 +49,7 @@ class AudioExtractor:
                                                       C.c_longlong, C.c_longlong, C.c_void_p])
 
     def _run_rows(self, rows, normalize):
-        """rows: CUDA fp32 [R, L] -> frames [R, T, 768] (sum of the last four hidden states)."""
+        """rows: CUDA fp32 [R, L] -> frames [R, T, D] (sum of the last four hidden states; D = 768 or 1024)."""
         outs = []
         for s in range(0, rows.shape[0], self.max_rows):
             _, fr = self.enc.forward(rows[s:s + self.max_rows], normalize=normalize, want_frames=True)
@@ -84,7 +84,7 @@ class AudioExtractor:
             L.check(self._norm(L.ptr(x), L.ptr(xn), 1, x.shape[1], x.shape[1], x.shape[1],
                                L.stream_ptr()))
             rows = split_into_batch(xn)
-            fr = self._run_rows(rows.contiguous(), normalize=False).reshape(-1, 768)
+            fr = self._run_rows(rows.contiguous(), normalize=False).reshape(-1, self.enc.hidden)
             res[i] = (fr.mean(dim=0) if feature_level == "UTTERANCE" else fr).cpu().numpy()
         if save_files is not None:
             for f, r in zip(save_files, res):

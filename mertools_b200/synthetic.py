@@ -62,9 +62,15 @@ def vit_state_dict(seed=0, layers=12, scale=1.0):
     return g.sd
 
 
-def hubert_state_dict(seed=1, layers=12, scale=1.0):
-    """Keys of ``transformers.HubertModel(HubertConfig(num_hidden_layers=layers))``."""
-    c = HUBERT_CFG
+HUBERT_LARGE_CFG = dict(HUBERT_CFG, hidden=1024, heads=16, ffn=4096, layers=24)
+
+
+def hubert_state_dict(seed=1, layers=12, scale=1.0, large=False):
+    """Keys of ``transformers.HubertModel(HubertConfig(num_hidden_layers=layers))``; ``large=True``: the
+    hubert-large / chinese-hubert-large family (hidden 1024, 16 heads, FFN 4096, feat_extract_norm="layer",
+    conv_bias=True, do_stable_layer_norm=True) -- same parameter names plus conv biases and one LayerNorm
+    per conv layer."""
+    c = HUBERT_LARGE_CFG if large else HUBERT_CFG
     g = _Gen(seed)
     d, cd = c["hidden"], c["conv_dim"]
     g.sd["masked_spec_embed"] = g.rng.random(d, dtype=np.float32)
@@ -72,8 +78,10 @@ def hubert_state_dict(seed=1, layers=12, scale=1.0):
     for i, k in enumerate(c["conv_kernel"]):
         g.normal(f"feature_extractor.conv_layers.{i}.conv.weight", (cd, cin, k),
                  np.sqrt(2.0 / (cin * k)))
-        if i == 0:
-            g.ln("feature_extractor.conv_layers.0.layer_norm", cd)
+        if large:
+            g.normal(f"feature_extractor.conv_layers.{i}.conv.bias", (cd,), 0.05)
+        if i == 0 or large:
+            g.ln(f"feature_extractor.conv_layers.{i}.layer_norm", cd)
         cin = cd
     g.ln("feature_projection.layer_norm", cd)
     g.linear("feature_projection.projection", d, cd, 0.04)

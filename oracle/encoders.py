@@ -102,20 +102,31 @@ def hubert_pos_conv_weight(sd, dtype=torch.float32):
 
 
 def hubert_hidden_states(sd, input_values, layers=12, heads=12, eps=1e-5,
-                         conv_stride=(5, 2, 2, 2, 2, 2, 2), pos_groups=16, dtype=torch.float32):
+                         conv_stride=(5, 2, 2, 2, 2, 2, 2), pos_groups=16, dtype=torch.float32,
+                         stable_layer_norm=None):
     """``HubertModel(input_values, output_hidden_states=True).hidden_states`` in eval mode.
 
     input_values [B, L] (already zero-mean/unit-variance).  Feature encoder (:178-213): conv0 +
-    GroupNorm(512 groups) + GELU (:154-175), conv1..6 + GELU (:106-124), no biases.  Feature
+    GroupNorm(512 groups) + GELU (:154-175), conv1..6 + GELU (:106-124), no biases -- or, for the
+    ``feat_extract_norm="layer"`` family (hubert-large; recognised by a LayerNorm on conv layer 1),
+    every conv (+ bias) followed by LayerNorm over channels and GELU (HubertLayerNormConvLayer).  Feature
     projection (:216-231): LayerNorm(512) -> Linear.  Positional conv (:45-103): grouped conv
-    k=128 pad=64, drop last frame, GELU; add; encoder.layer_norm (:440-442).  POST-LN layers
-    (:372-405)."""
+    k=128 pad=64, drop last frame, GELU; add.  Then either encoder.layer_norm (:440-442) and POST-LN
+    layers (:372-405), or -- ``do_stable_layer_norm`` (hubert-large; default: same as the layer-norm
+    feature extractor) -- PRE-LN layers (HubertEncoderLayerStableLayerNorm) with hidden states taken
+    before each layer and encoder.layer_norm applied after the last one (HubertEncoderStableLayerNorm)."""
     x = input_values.to(dtype)[:, None, :]
     n_conv = len(conv_stride)
+    layer_norm_convs = "feature_extractor.conv_layers.1.layer_norm.weight" in sd
+    if stable_layer_norm is None:
+        stable_layer_norm = layer_norm_convs
     for i in range(n_conv):
         w = _t(sd, f"feature_extractor.conv_layers.{i}.conv.weight", dtype)
-        x = F.conv1d(x, w, stride=conv_stride[i])
-        if i == 0:
+        bname = f"feature_extractor.conv_layers.{i}.conv.bias"
+        x = F.conv1d(x, w, _t(sd, bname, dtype) if bname in sd else None, stride=conv_stride[i])
+        if layer_norm_convs:
+            x = _ln(x.transpose(1, 2), sd, f"feature_extractor.conv_layers.{i}.layer_norm", 1e-5, dtype).transpose(1, 2)
+        elif i == 0:
             x = F.group_norm(x, w.shape[0],
                              _t(sd, "feature_extractor.conv_layers.0.layer_norm.weight", dtype),
                              _t(sd, "feature_extractor.conv_layers.0.layer_norm.bias", dtype), 1e-5)
@@ -129,19 +140,34 @@ def hubert_hidden_states(sd, input_values, layers=12, heads=12, eps=1e-5,
     if wpos.shape[-1] % 2 == 0:
         pos = pos[:, :, :-1]
     x = x + F.gelu(pos).transpose(1, 2)
-    x = _ln(x, sd, "encoder.layer_norm", eps, dtype)
-    hs = [x]
+    hs = []
+    if not stable_layer_norm:
+        x = _ln(x, sd, "encoder.layer_norm", eps, dtype)
+        hs.append(x)
     for i in range(layers):
         p = f"encoder.layers.{i}."
-        q = _linear(x, sd, p + "attention.q_proj", dtype)
-        k = _linear(x, sd, p + "attention.k_proj", dtype)
-        v = _linear(x, sd, p + "attention.v_proj", dtype)
+        if stable_layer_norm:
+            hs.append(x)
+            y = _ln(x, sd, p + "layer_norm", eps, dtype)
+        else:
+            y = x
+        q = _linear(y, sd, p + "attention.q_proj", dtype)
+        k = _linear(y, sd, p + "attention.k_proj", dtype)
+        v = _linear(y, sd, p + "attention.v_proj", dtype)
         a = _linear(_mha(q, k, v, heads), sd, p + "attention.out_proj", dtype)
-        x = _ln(x + a, sd, p + "layer_norm", eps, dtype)
-        h = F.gelu(_linear(x, sd, p + "feed_forward.intermediate_dense", dtype))
-        h = _linear(h, sd, p + "feed_forward.output_dense", dtype)
-        x = _ln(x + h, sd, p + "final_layer_norm", eps, dtype)
-        hs.append(x)
+        if stable_layer_norm:
+            x = x + a
+            h = F.gelu(_linear(_ln(x, sd, p + "final_layer_norm", eps, dtype), sd,
+                               p + "feed_forward.intermediate_dense", dtype))
+            x = x + _linear(h, sd, p + "feed_forward.output_dense", dtype)
+        else:
+            x = _ln(x + a, sd, p + "layer_norm", eps, dtype)
+            h = F.gelu(_linear(x, sd, p + "feed_forward.intermediate_dense", dtype))
+            h = _linear(h, sd, p + "feed_forward.output_dense", dtype)
+            x = _ln(x + h, sd, p + "final_layer_norm", eps, dtype)
+            hs.append(x)
+    if stable_layer_norm:
+        hs.append(_ln(x, sd, "encoder.layer_norm", eps, dtype))
     return tuple(hs)
 
 

@@ -41,6 +41,32 @@ def test_hubert_hidden_states_and_readout(cuda, layers, n_samples, batch):
     assert m < TOL and l2 < TOL, f"utterance readout: max-rel {m:.2e} l2-rel {l2:.2e}"
 
 
+@pytest.mark.parametrize("layers,n_samples,batch", [(4, 16000, 2), (6, 80000, 2), (5, 100000, 1)])
+def test_hubert_large_family_hidden_states_and_readout(cuda, layers, n_samples, batch):
+    """hubert-large / chinese-hubert-large style checkpoint: hidden 1024, 16 heads, LayerNorm after every
+    conv, conv biases, stable (pre-LN) encoder; 100,000 samples = 312 frames exercises the long-sequence
+    attention path."""
+    from mertools_b200.encoders import HubertEncoder
+    sd = S.hubert_state_dict(seed=7, layers=layers, large=True)
+    wav = (S.synth_waves(batch, n_samples, seed=23).astype(np.float64) / 32768.0).astype(np.float32)
+    enc = HubertEncoder(sd, device=cuda)
+    assert enc.hidden == 1024
+    utt, frames, hidden = enc.forward(torch.from_numpy(wav).to(cuda), normalize=True,
+                                      want_frames=True, return_hidden=True)
+    torch.cuda.synchronize()
+    iv = torch.from_numpy(np.stack([P.wav2vec2_normalize(w) for w in wav]))
+    ref_hs = E.hubert_hidden_states(sd, iv, layers=layers, heads=16)
+    assert hidden.shape[2] == ref_hs[0].shape[1] == E.hubert_num_frames(n_samples)
+    for l in range(layers + 1):
+        m, l2 = rel(hidden[l].cpu(), ref_hs[l])
+        assert m < 4 * TOL, f"hidden state {l}: max-rel {m:.2e} l2-rel {l2:.2e}"
+    ref_sum = torch.stack(ref_hs)[[-4, -3, -2, -1]].sum(dim=0)
+    m, l2 = rel(frames.cpu(), ref_sum)
+    assert m < 2 * TOL and l2 < TOL, f"frame readout: max-rel {m:.2e} l2-rel {l2:.2e}"
+    m, l2 = rel(utt.cpu(), ref_sum.mean(dim=1))
+    assert m < TOL and l2 < TOL, f"utterance readout: max-rel {m:.2e} l2-rel {l2:.2e}"
+
+
 def test_audio_extractor_matches_oracle_pipeline(cuda):
     """Public API, including a >10 s clip that the reference splits into 10 s rows."""
     from mertools_b200.extract import audio

@@ -131,3 +131,22 @@ def test_oracle_audio_restatement_also_is_wav2vec2_base():
         got = E.hubert_hidden_states(sd, x, layers=2)
     for a, b in zip(got, ref):
         assert float((a - b).abs().max() / b.abs().max()) < 5e-5
+
+
+def test_oracle_hubert_large_family_matches_hf():
+    """feat_extract_norm="layer", conv_bias, do_stable_layer_norm (hubert-large / chinese-hubert-large,
+    extract_audio_huggingface.py:27): the restatement vs HF HubertModel, every hidden state."""
+    from transformers import HubertConfig, HubertModel
+    cfg = HubertConfig(hidden_size=1024, num_hidden_layers=3, num_attention_heads=16, intermediate_size=4096,
+                       feat_extract_norm="layer", do_stable_layer_norm=True, conv_bias=True)
+    m = HubertModel(cfg).eval()
+    sd = {k: torch.from_numpy(v) for k, v in S.hubert_state_dict(seed=5, layers=3, large=True).items()}
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all("masked_spec_embed" in k or "parametrizations" in k for k in missing), (missing, unexpected)
+    x = torch.randn(2, 4000, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        ref = m(x, output_hidden_states=True).hidden_states
+        got = E.hubert_hidden_states(sd, x, layers=3, heads=16)
+    assert len(got) == len(ref) == 4
+    for a, b in zip(got, ref):
+        assert float((a - b).abs().max() / b.abs().max()) < 5e-5
