@@ -165,12 +165,12 @@ def audio_split_into_batch(input_values, maxlen=16000 * 10):
     return out.view(-1, maxlen)
 
 
-def audio_clip_features(sd, samples, layers=12, feature_level="UTTERANCE", dtype=torch.float32):
+def audio_clip_features(sd, samples, layers=12, feature_level="UTTERANCE", dtype=torch.float32, heads=12):
     """One wav through ``extract`` (:72-110): normalise, chunk, HuBERT, sum of the last four
     hidden states (:98), flatten (B*T, D) (:100), UTTERANCE -> mean over axis 0 (:105-108)."""
     iv = torch.from_numpy(wav2vec2_normalize(samples))[None]
     iv = audio_split_into_batch(iv)
-    hs = E.hubert_hidden_states(sd, iv, layers=layers, dtype=dtype)
+    hs = E.hubert_hidden_states(sd, iv, layers=layers, heads=heads, dtype=dtype)
     feat = torch.stack(hs)[[-4, -3, -2, -1]].sum(dim=0)
     feat = feat.reshape(-1, feat.shape[-1]).float().squeeze().numpy()
     if feature_level == "UTTERANCE":

@@ -65,6 +65,20 @@ def test_audio_oracle_matches_reference_script():
         assert _rel(fra[::8], g[f"fra{i}"]) < 5e-5
 
 
+def test_audio_oracle_matches_reference_script_hubert_large_family():
+    g = np.load(os.path.join(G, "audio_large_golden.npz"))
+    layers = int(g["layers"])
+    sd = _t(S.hubert_state_dict(seed=int(g["seed"]), layers=layers, large=True))
+    for i, n in enumerate(g["lens"]):
+        w = S.synth_waves(1, int(n), seed=int(g["seed0"]) + i)[0].astype(np.float64) / 32768.0
+        with torch.no_grad():
+            utt = P.audio_clip_features(sd, w, layers=layers, heads=16)
+            fra = P.audio_clip_features(sd, w, layers=layers, heads=16, feature_level="FRAME")
+        assert utt.shape == (1024,) and utt.dtype == g[f"utt{i}"].dtype
+        assert _rel(utt, g[f"utt{i}"]) < 5e-5, f"clip {i} ({n} samples)"
+        assert _rel(fra[::16], g[f"fra{i}"]) < 5e-5
+
+
 def test_text_oracle_and_token_ids_match_reference_script():
     transformers = pytest.importorskip("transformers")
     g = np.load(os.path.join(G, "text_golden.npz"))

@@ -58,6 +58,20 @@ def test_audio_extractor_vs_reference_golden(cuda):
         assert _rel(fra[i][::8], g[f"fra{i}"]) < 2 * TOL, f"clip {i} frames"
 
 
+def test_audio_extractor_vs_reference_golden_hubert_large_family(cuda):
+    from mertools_b200.extract.audio import AudioExtractor
+    g = np.load(os.path.join(G, "audio_large_golden.npz"))
+    waves = [S.synth_waves(1, int(n), seed=int(g["seed0"]) + i)[0].astype(np.float64) / 32768.0
+             for i, n in enumerate(g["lens"])]
+    ext = AudioExtractor(S.hubert_state_dict(seed=int(g["seed"]), layers=int(g["layers"]), large=True), device=cuda)
+    utt = ext.extract_waves(waves, "UTTERANCE")
+    fra = ext.extract_waves(waves, "FRAME")
+    for i in range(len(waves)):
+        assert utt[i].shape == (1024,) and utt[i].dtype == g[f"utt{i}"].dtype
+        assert _rel(utt[i], g[f"utt{i}"]) < TOL, f"clip {i}"
+        assert _rel(fra[i][::16], g[f"fra{i}"]) < 2 * TOL, f"clip {i} frames"
+
+
 def test_text_extractor_vs_reference_golden(cuda):
     transformers = pytest.importorskip("transformers")
     from mertools_b200.extract.text import TextExtractor
