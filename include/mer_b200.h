@@ -338,6 +338,29 @@ MER_API int mer_fusion_fwd_bwd(const MerFusionDims* dims, const float* params, f
                                float* loss_out, float* features, float* emos_out, float* vals_out,
                                void* stream);
 
+/* ---- frame-level variant: feat_type = frm_align / frm_unalign (main-release.py:131-142) ----------------
+ * Attention with LSTMEncoder per modality (toolkit/models/modules/encoder.py:45-72: nn.LSTM(in, hidden, one
+ * layer, batch_first) over the zero-pre-padded sequence -> final hidden state -> dropout -> Linear(hidden,
+ * hidden)) in front of the same attention head.  audios / texts / videos are [batch, seq_x, dim_x]; parameters
+ * in the reference's state_dict order (rnn.weight_ih_l0, rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0,
+ * linear_1.weight, linear_1.bias per encoder, then attention_mlp, fc_att, fc_out_1, fc_out_2); hidden is a
+ * multiple of 32 up to 128.  Dropout masks 0..2 act on the [batch, hidden] final hidden states.  Everything
+ * else as in the utterance-level entry points above. */
+MER_API long long mer_fusion_frm_param_count(const MerFusionDims* dims);
+MER_API long long mer_fusion_frm_workspace_bytes(const MerFusionDims* dims, int max_batch, int seq_a, int seq_t,
+                                                 int seq_v);
+MER_API int mer_fusion_frm_forward(const MerFusionDims* dims, const float* params, const float* audios,
+                                   const float* texts, const float* videos, int seq_a, int seq_t, int seq_v,
+                                   int batch, void* workspace, long long workspace_bytes, float* features,
+                                   float* emos_out, float* vals_out, void* stream);
+MER_API int mer_fusion_frm_fwd_bwd(const MerFusionDims* dims, const float* params, float* grads,
+                                   const float* audios, const float* texts, const float* videos, int seq_a,
+                                   int seq_t, int seq_v, const int64_t* emos, const float* vals, int batch,
+                                   float loss_inv_batch, float dropout_p, unsigned long long seed,
+                                   const int* step_counter, const float* const* ext_masks, void* workspace,
+                                   long long workspace_bytes, float* loss_out, float* features, float* emos_out,
+                                   float* vals_out, void* stream);
+
 /* torch.optim.Adam(lr, betas, eps, weight_decay) with coupled L2, after multiplying the gradient by
  * grad_scale and (grad_clip > 0) clamping it to [-grad_clip, grad_clip] (clip_grad_value_,
  * main-release.py:64-65).  *step_counter (device int) is read as t-1 and incremented. */

@@ -383,6 +383,215 @@ int run_forward(const MerFusionDims& d, const Layout& L, const float* P, const S
   return 0;
 }
 
+
+// ================================================================================================
+// Frame-level fusion (feat_type = frm_align / frm_unalign): LSTMEncoder (modules/encoder.py:45-72) per
+// modality -- nn.LSTM(in, H, 1 layer, batch_first) over the zero-pre-padded sequence, final hidden state,
+// dropout, Linear(H, H) -- feeding the same attention head.  fp32 throughout, fixed summation order.
+// ================================================================================================
+constexpr int LSTM_MAXH = 128;  // one W_hh row (H floats) lives in the registers of each gate thread
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// One block per batch row, 4H threads: thread j = gate row j of torch's (i, f, g, o) stacking.
+// xw: [B, T, 4H] = x W_ih^T + b_ih (precomputed).  Writes the ACTIVATED gates, the cell state, the hidden
+// state after and before each step (the backward pass and the weight gradients read them).
+__global__ void __launch_bounds__(4 * LSTM_MAXH)
+lstm_fwd_kernel(const float* __restrict__ xw, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
+                int T, int H, float* __restrict__ gates, float* __restrict__ cs, float* __restrict__ hs,
+                float* __restrict__ hprev, float* __restrict__ h_last) {
+  __shared__ float h_s[LSTM_MAXH];
+  __shared__ float g_s[4 * LSTM_MAXH];
+  const int b = blockIdx.x, j = threadIdx.x;
+  float w[LSTM_MAXH];
+#pragma unroll
+  for (int k = 0; k < LSTM_MAXH; ++k) w[k] = k < H ? w_hh[(long long)j * H + k] : 0.f;
+  const float bj = b_hh[j];
+  const int type = j / H;
+  float c = 0.f;
+  if (j < H) h_s[j] = 0.f;
+  __syncthreads();
+  for (int t = 0; t < T; ++t) {
+    const long long row = (long long)b * T + t;
+    float pre = xw[row * 4 * H + j] + bj;
+#pragma unroll
+    for (int k = 0; k < LSTM_MAXH; ++k)
+      if (k < H) pre = fmaf(w[k], h_s[k], pre);
+    const float act = type == 2 ? tanhf(pre) : sigmoidf_(pre);
+    g_s[j] = act;
+    gates[row * 4 * H + j] = act;
+    __syncthreads();
+    if (j < H) {
+      hprev[row * H + j] = h_s[j];
+      c = g_s[H + j] * c + g_s[j] * g_s[2 * H + j];
+      const float h = g_s[3 * H + j] * tanhf(c);
+      cs[row * H + j] = c;
+      hs[row * H + j] = h;
+      h_s[j] = h;
+      if (t == T - 1) h_last[(long long)b * H + j] = h;
+    }
+    __syncthreads();
+  }
+}
+
+// Back-propagation through time for one batch row: d_hT in, pre-activation gate gradients out.
+// thread tid: unit k = tid % H; quarter q = tid / H holds W_hh[q*H + jj][k] (jj < H) for the
+// dh_{t-1}[k] = sum_j W_hh[j][k] dpre[j] product, reduced over the four quarters through smem.
+__global__ void __launch_bounds__(4 * LSTM_MAXH)
+lstm_bwd_kernel(const float* __restrict__ d_hT, const float* __restrict__ w_hh, const float* __restrict__ gates,
+                const float* __restrict__ cs, int T, int H, float* __restrict__ dgates) {
+  __shared__ float dp_s[4 * LSTM_MAXH];
+  __shared__ float part[4][LSTM_MAXH];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int k = tid % H, q = tid / H;
+  float w[LSTM_MAXH];
+#pragma unroll
+  for (int jj = 0; jj < LSTM_MAXH; ++jj) w[jj] = jj < H ? w_hh[(long long)(q * H + jj) * H + k] : 0.f;
+  float dh = tid < H ? d_hT[(long long)b * H + tid] : 0.f;
+  float dc = 0.f;
+  for (int t = T - 1; t >= 0; --t) {
+    const long long row = (long long)b * T + t;
+    if (tid < H) {
+      const float* g = gates + row * 4 * H;
+      const float gi = g[tid], gf = g[H + tid], gg = g[2 * H + tid], go = g[3 * H + tid];
+      const float c = cs[row * H + tid];
+      const float c_prev = t > 0 ? cs[(row - 1) * H + tid] : 0.f;
+      const float tc = tanhf(c);
+      const float d_o = dh * tc;
+      dc += dh * go * (1.f - tc * tc);
+      const float d_i = dc * gg, d_g = dc * gi, d_f = dc * c_prev;
+      dc *= gf;
+      const float pi = d_i * gi * (1.f - gi), pf = d_f * gf * (1.f - gf), pg = d_g * (1.f - gg * gg),
+                  po = d_o * go * (1.f - go);
+      dp_s[tid] = pi; dp_s[H + tid] = pf; dp_s[2 * H + tid] = pg; dp_s[3 * H + tid] = po;
+      float* dg = dgates + row * 4 * H;
+      dg[tid] = pi; dg[H + tid] = pf; dg[2 * H + tid] = pg; dg[3 * H + tid] = po;
+    }
+    __syncthreads();
+    float acc = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < LSTM_MAXH; ++jj)
+      if (jj < H) acc = fmaf(w[jj], dp_s[q * H + jj], acc);
+    part[q][k] = acc;
+    __syncthreads();
+    if (tid < H) dh = (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
+    __syncthreads();
+  }
+}
+
+struct FrmLayout {  // reference state_dict order of Attention with LSTMEncoders (attention.py:25-33)
+  long long w_ih[3], w_hh[3], b_ih[3], b_hh[3], lin_w[3], lin_b[3];
+  long long att_w1, att_b1, att_w2, att_b2, att_w3, att_b3;
+  long long fa_w, fa_b, o1_w, o1_b, o2_w, o2_b, total;
+};
+
+FrmLayout make_frm_layout(const MerFusionDims& d) {
+  FrmLayout L;
+  long long o = 0;
+  const int in[3] = {d.audio_dim, d.text_dim, d.video_dim};
+  const long long H = d.hidden;
+  for (int m = 0; m < 3; ++m) {
+    L.w_ih[m] = o; o += 4 * H * in[m];
+    L.w_hh[m] = o; o += 4 * H * H;
+    L.b_ih[m] = o; o += 4 * H;
+    L.b_hh[m] = o; o += 4 * H;
+    L.lin_w[m] = o; o += H * H;
+    L.lin_b[m] = o; o += H;
+  }
+  L.att_w1 = o; o += H * 3 * H;
+  L.att_b1 = o; o += H;
+  L.att_w2 = o; o += H * H;
+  L.att_b2 = o; o += H;
+  L.att_w3 = o; o += H * H;
+  L.att_b3 = o; o += H;
+  L.fa_w = o; o += 3 * H;
+  L.fa_b = o; o += 3;
+  L.o1_w = o; o += (long long)d.out1 * H;
+  L.o1_b = o; o += d.out1;
+  L.o2_w = o; o += (long long)d.out2 * H;
+  L.o2_b = o; o += d.out2;
+  L.total = o;
+  return L;
+}
+
+struct FrmScratch {
+  float *xw[3], *gates[3], *dgates[3], *cs[3], *hs[3], *hprev[3];
+  float *hT, *d_hT, *mask_h[3];      // [3][B,H]
+  float *h3cat, *a1, *a2, *a3, *d_cat, *d_a1, *d_a2, *d_a3, *d_emos, *d_vals, *d_att, *loss_terms, *mask_cat;
+};
+
+long long frm_scratch_floats(const MerFusionDims& d, int B, const int T[3]) {
+  const long long H = d.hidden;
+  long long n = 0;
+  for (int m = 0; m < 3; ++m) n += (long long)B * T[m] * (4 * H * 3 + H * 3);
+  n += (long long)B * H * (3 + 3 + 3);                       // hT, d_hT, mask_h
+  n += (long long)B * (3 * H + 3 * H + 3 * H + 3 * H + 3 * H)  // h3cat, a1..3, d_cat, d_a1..3, mask_cat
+       + (long long)B * (d.out1 + d.out2 + 3 + 2);
+  return n + 64;
+}
+
+FrmScratch frm_carve(const MerFusionDims& d, int B, const int T[3], float* base) {
+  FrmScratch s;
+  const long long H = d.hidden;
+  float* p = base;
+  auto take = [&](long long n) { float* r = p; p += n; return r; };
+  for (int m = 0; m < 3; ++m) {
+    const long long R = (long long)B * T[m];
+    s.xw[m] = take(R * 4 * H); s.gates[m] = take(R * 4 * H); s.dgates[m] = take(R * 4 * H);
+    s.cs[m] = take(R * H); s.hs[m] = take(R * H); s.hprev[m] = take(R * H);
+  }
+  s.hT = take(3 * B * H); s.d_hT = take(3 * B * H);
+  for (int m = 0; m < 3; ++m) s.mask_h[m] = take(B * H);
+  s.h3cat = take(3 * B * H); s.a1 = take(B * H); s.a2 = take(B * H); s.a3 = take(B * H);
+  s.d_cat = take(3 * B * H); s.d_a1 = take(B * H); s.d_a2 = take(B * H); s.d_a3 = take(B * H);
+  s.mask_cat = take(3 * B * H);
+  s.d_emos = take((long long)B * d.out1); s.d_vals = take((long long)B * d.out2);
+  s.d_att = take(3ll * B); s.loss_terms = take(2ll * B);
+  return s;
+}
+
+int frm_check(const MerFusionDims* d, int B, const int T[3]) {
+  if (int rc = check_dims(d, B)) return rc;
+  MER_REQUIRE(d->hidden <= LSTM_MAXH && d->hidden % 32 == 0,
+              "mer_fusion_frm: hidden %d (multiples of 32 up to %d)", d->hidden, LSTM_MAXH);
+  MER_REQUIRE(T[0] > 0 && T[1] > 0 && T[2] > 0, "mer_fusion_frm: empty sequences");
+  return 0;
+}
+
+// LSTM encoders + linear_1 + attention MLP (everything before the head)
+int frm_forward(const MerFusionDims& d, const FrmLayout& L, const float* P, const FrmScratch& s,
+                const float* const x[3], int B, const int T[3], float p_drop, const float* const masks[4],
+                bool use_dropout, cudaStream_t st) {
+  const int H = d.hidden;
+  const int in[3] = {d.audio_dim, d.text_dim, d.video_dim};
+  const float mscale = use_dropout ? 1.f / (1.f - p_drop) : 1.f;
+  LinBatch lb;
+  for (int m = 0; m < 3; ++m) {
+    const int R = B * T[m];
+    lb.p[0] = LinP{x[m], in[m], nullptr, 1.f, P + L.w_ih[m], P + L.b_ih[m], s.xw[m], 4 * H, in[m], 4 * H, 0};
+    dim3 g((4 * H + 7) / 8, (R + 31) / 32, 1);
+    fus_linear_fwd_kernel<<<g, 256, 0, st>>>(lb, R);
+    lstm_fwd_kernel<<<B, 4 * H, 0, st>>>(s.xw[m], P + L.w_hh[m], P + L.b_hh[m], T[m], H, s.gates[m], s.cs[m],
+                                         s.hs[m], s.hprev[m], s.hT + (long long)m * B * H);
+  }
+  for (int m = 0; m < 3; ++m)  // linear_1(dropout(h_T)), no activation, straight into the [B,3H] concat
+    lb.p[m] = LinP{s.hT + (long long)m * B * H, H, use_dropout ? masks[m] : nullptr, mscale, P + L.lin_w[m],
+                   P + L.lin_b[m], s.h3cat + m * H, 3 * H, H, H, 0};
+  dim3 g1((H + 7) / 8, (B + 31) / 32, 3);
+  fus_linear_fwd_kernel<<<g1, 256, 0, st>>>(lb, B);
+  dim3 g2((H + 7) / 8, (B + 31) / 32, 1);
+  lb.p[0] = LinP{s.h3cat, 3 * H, use_dropout ? masks[3] : nullptr, mscale, P + L.att_w1, P + L.att_b1, s.a1, H,
+                 3 * H, H, 1};
+  fus_linear_fwd_kernel<<<g2, 256, 0, st>>>(lb, B);
+  lb.p[0] = LinP{s.a1, H, nullptr, 1.f, P + L.att_w2, P + L.att_b2, s.a2, H, H, H, 1};
+  fus_linear_fwd_kernel<<<g2, 256, 0, st>>>(lb, B);
+  lb.p[0] = LinP{s.a2, H, nullptr, 1.f, P + L.att_w3, P + L.att_b3, s.a3, H, H, H, 1};
+  fus_linear_fwd_kernel<<<g2, 256, 0, st>>>(lb, B);
+  MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(10);
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -536,6 +745,145 @@ int mer_fusion_adam(float* params, const float* grads, float* exp_avg, float* ex
   fus_step_inc_kernel<<<1, 32, 0, st>>>(step_counter);
   MER_CUDA_CHECK(cudaGetLastError());
   mer_count_launches(2);
+  return 0;
+}
+
+// ---- frame-level variant (LSTM encoders) ----------------------------------------------------------
+long long mer_fusion_frm_param_count(const MerFusionDims* d) {
+  if (!d) return -1;
+  return make_frm_layout(*d).total;
+}
+
+long long mer_fusion_frm_workspace_bytes(const MerFusionDims* d, int max_batch, int seq_a, int seq_t, int seq_v) {
+  if (!d) return -1;
+  const int T[3] = {seq_a, seq_t, seq_v};
+  return frm_scratch_floats(*d, max_batch, T) * 4;
+}
+
+int mer_fusion_frm_forward(const MerFusionDims* d, const float* params, const float* audios, const float* texts,
+                           const float* videos, int seq_a, int seq_t, int seq_v, int B, void* workspace,
+                           long long workspace_bytes, float* features, float* emos_out, float* vals_out,
+                           void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const int T[3] = {seq_a, seq_t, seq_v};
+  if (int rc = frm_check(d, B, T)) return rc;
+  MER_REQUIRE(params && audios && texts && videos && workspace && features && emos_out && vals_out,
+              "mer_fusion_frm_forward: null operand");
+  MER_REQUIRE(workspace_bytes >= frm_scratch_floats(*d, B, T) * 4, "mer_fusion_frm_forward: workspace too small");
+  const FrmLayout L = make_frm_layout(*d);
+  const FrmScratch s = frm_carve(*d, B, T, static_cast<float*>(workspace));
+  const float* x[3] = {audios, texts, videos};
+  if (int rc = frm_forward(*d, L, params, s, x, B, T, 0.f, nullptr, false, st)) return rc;
+  HeadArgs h;
+  memset(&h, 0, sizeof(h));
+  h.h3cat = s.h3cat; h.a3 = s.a3;
+  h.w_att = params + L.fa_w; h.b_att = params + L.fa_b;
+  h.w_o1 = params + L.o1_w; h.b_o1 = params + L.o1_b;
+  h.w_o2 = params + L.o2_w; h.b_o2 = params + L.o2_b;
+  h.features = features; h.emos_out = emos_out; h.vals_out = vals_out;
+  h.H = d->hidden; h.O1 = d->out1; h.O2 = d->out2;
+  fus_head_kernel<<<B, 128, 0, st>>>(h);
+  MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
+  return 0;
+}
+
+int mer_fusion_frm_fwd_bwd(const MerFusionDims* d, const float* params, float* grads, const float* audios,
+                           const float* texts, const float* videos, int seq_a, int seq_t, int seq_v,
+                           const int64_t* emos, const float* vals, int B, float loss_inv_batch, float dropout_p,
+                           unsigned long long seed, const int* step_counter, const float* const* ext_masks,
+                           void* workspace, long long workspace_bytes, float* loss_out, float* features,
+                           float* emos_out, float* vals_out, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  const int T[3] = {seq_a, seq_t, seq_v};
+  if (int rc = frm_check(d, B, T)) return rc;
+  MER_REQUIRE(params && grads && audios && texts && videos && emos && vals && workspace && loss_out &&
+                  features && emos_out && vals_out && step_counter,
+              "mer_fusion_frm_fwd_bwd: null operand");
+  MER_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "mer_fusion_frm_fwd_bwd: dropout %f", dropout_p);
+  MER_REQUIRE(workspace_bytes >= frm_scratch_floats(*d, B, T) * 4, "mer_fusion_frm_fwd_bwd: workspace too small");
+  const FrmLayout L = make_frm_layout(*d);
+  const FrmScratch s = frm_carve(*d, B, T, static_cast<float*>(workspace));
+  const int H = d->hidden;
+  const int in[3] = {d->audio_dim, d->text_dim, d->video_dim};
+  const float* x[3] = {audios, texts, videos};
+  const bool drop = dropout_p > 0.f;
+  const float mscale = drop ? 1.f / (1.f - dropout_p) : 1.f;
+  const float* masks[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (drop) {
+    for (int m = 0; m < 4; ++m) {  // masks 0..2 act on the [B,H] final hidden states, 3 on the concat
+      if (ext_masks && ext_masks[m]) { masks[m] = ext_masks[m]; continue; }
+      float* dst = m < 3 ? s.mask_h[m] : s.mask_cat;
+      const long long n = (long long)B * (m < 3 ? H : 3 * H);
+      fus_dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+          dst, n, dropout_p, seed + 0x1000ull * (m + 1), step_counter);
+      mer_count_launches(1);
+      masks[m] = dst;
+    }
+  }
+  if (int rc = frm_forward(*d, L, params, s, x, B, T, dropout_p, masks, drop, st)) return rc;
+  HeadArgs h;
+  memset(&h, 0, sizeof(h));
+  h.h3cat = s.h3cat; h.a3 = s.a3;
+  h.w_att = params + L.fa_w; h.b_att = params + L.fa_b;
+  h.w_o1 = params + L.o1_w; h.b_o1 = params + L.o1_b;
+  h.w_o2 = params + L.o2_w; h.b_o2 = params + L.o2_b;
+  h.emo = reinterpret_cast<const long long*>(emos); h.val = vals;
+  h.features = features; h.emos_out = emos_out; h.vals_out = vals_out;
+  h.loss_terms = s.loss_terms; h.d_emos = s.d_emos; h.d_vals = s.d_vals; h.d_att = s.d_att;
+  h.d_cat = s.d_cat; h.d_a3 = s.d_a3;
+  h.H = H; h.O1 = d->out1; h.O2 = d->out2; h.inv_batch = loss_inv_batch;
+  fus_head_kernel<<<B, 128, 0, st>>>(h);
+  fus_loss_reduce_kernel<<<1, 32, 0, st>>>(s.loss_terms, B, loss_inv_batch, loss_out);
+  mer_count_launches(2);
+
+  float* G = grads;
+  BwdBatch bb;
+  auto launch_w = [&](int nprob, int K, int N, int rows) {
+    dim3 g((K + 255) / 256, N, nprob);
+    fus_linear_bwd_w_kernel<<<g, 256, 0, st>>>(bb, rows);
+    mer_count_launches(1);
+  };
+  auto launch_x = [&](int nprob, int K, int rows) {
+    dim3 g((K + 255) / 256, rows, nprob);
+    fus_linear_bwd_x_kernel<<<g, 256, 0, st>>>(bb, rows);
+    mer_count_launches(1);
+  };
+  bb.p[0] = BwdP{s.d_emos, d->out1, nullptr, 0, features, H, nullptr, 1.f, params + L.o1_w,
+                 G + L.o1_w, G + L.o1_b, nullptr, 0, 0, H, d->out1};
+  bb.p[1] = BwdP{s.d_vals, d->out2, nullptr, 0, features, H, nullptr, 1.f, params + L.o2_w,
+                 G + L.o2_w, G + L.o2_b, nullptr, 0, 0, H, d->out2};
+  bb.p[2] = BwdP{s.d_att, 3, nullptr, 0, s.a3, H, nullptr, 1.f, params + L.fa_w, G + L.fa_w,
+                 G + L.fa_b, nullptr, 0, 0, H, 3};
+  launch_w(3, H, 16, B);
+  bb.p[0] = BwdP{s.d_a3, H, s.a3, H, s.a2, H, nullptr, 1.f, params + L.att_w3, G + L.att_w3,
+                 G + L.att_b3, s.d_a2, H, 0, H, H};
+  launch_w(1, H, H, B); launch_x(1, H, B);
+  bb.p[0] = BwdP{s.d_a2, H, s.a2, H, s.a1, H, nullptr, 1.f, params + L.att_w2, G + L.att_w2,
+                 G + L.att_b2, s.d_a1, H, 0, H, H};
+  launch_w(1, H, H, B); launch_x(1, H, B);
+  bb.p[0] = BwdP{s.d_a1, H, s.a1, H, s.h3cat, 3 * H, masks[3], mscale, params + L.att_w1,
+                 G + L.att_w1, G + L.att_b1, s.d_cat, 3 * H, 1, 3 * H, H};
+  launch_w(1, 3 * H, H, B); launch_x(1, 3 * H, B);
+  // linear_1 of the three encoders (no activation): dW, db, and d(h_T) through the dropout mask
+  for (int m = 0; m < 3; ++m)
+    bb.p[m] = BwdP{s.d_cat + m * H, 3 * H, nullptr, 0, s.hT + (long long)m * B * H, H, masks[m], mscale,
+                   params + L.lin_w[m], G + L.lin_w[m], G + L.lin_b[m], s.d_hT + (long long)m * B * H, H, 0, H, H};
+  launch_w(3, H, H, B); launch_x(3, H, B);
+  // LSTMs: BPTT per batch row, then the weight gradients as [4H, rows]^T x [rows, K] products
+  for (int m = 0; m < 3; ++m) {
+    const int R = B * T[m];
+    lstm_bwd_kernel<<<B, 4 * H, 0, st>>>(s.d_hT + (long long)m * B * H, params + L.w_hh[m], s.gates[m], s.cs[m],
+                                         T[m], H, s.dgates[m]);
+    mer_count_launches(1);
+    bb.p[0] = BwdP{s.dgates[m], 4 * H, nullptr, 0, x[m], in[m], nullptr, 1.f, params + L.w_ih[m], G + L.w_ih[m],
+                   G + L.b_ih[m], nullptr, 0, 0, in[m], 4 * H};
+    launch_w(1, in[m], 4 * H, R);
+    bb.p[0] = BwdP{s.dgates[m], 4 * H, nullptr, 0, s.hprev[m], H, nullptr, 1.f, params + L.w_hh[m], G + L.w_hh[m],
+                   G + L.b_hh[m], nullptr, 0, 0, H, 4 * H};
+    launch_w(1, H, 4 * H, R);
+  }
+  MER_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 

@@ -24,9 +24,16 @@ class MerFusionDims(C.Structure):
                 ("hidden", C.c_int), ("out1", C.c_int), ("out2", C.c_int)]
 
 
-def param_names():
+LSTM_PARAMS = ("rnn.weight_ih_l0", "rnn.weight_hh_l0", "rnn.bias_ih_l0", "rnn.bias_hh_l0",
+               "linear_1.weight", "linear_1.bias")
+
+
+def param_names(feat_type="utt"):
     names = []
     for e in ENC:
+        if feat_type != "utt" and e != "attention_mlp":  # LSTMEncoder (encoder.py:45-72)
+            names += [f"{e}.{n}" for n in LSTM_PARAMS]
+            continue
         for l in ("linear_1", "linear_2", "linear_3"):
             names += [f"{e}.{l}.weight", f"{e}.{l}.bias"]
     for l in ("fc_att", "fc_out_1", "fc_out_2"):
@@ -34,11 +41,19 @@ def param_names():
     return names
 
 
-def param_shapes(audio_dim, text_dim, video_dim, hidden, out1, out2):
+def param_shapes(audio_dim, text_dim, video_dim, hidden, out1, out2, feat_type="utt"):
     ins = dict(audio_encoder=audio_dim, text_encoder=text_dim, video_encoder=video_dim,
                attention_mlp=3 * hidden)
     shapes = {}
     for e in ENC:
+        if feat_type != "utt" and e != "attention_mlp":
+            shapes[f"{e}.rnn.weight_ih_l0"] = (4 * hidden, ins[e])
+            shapes[f"{e}.rnn.weight_hh_l0"] = (4 * hidden, hidden)
+            shapes[f"{e}.rnn.bias_ih_l0"] = (4 * hidden,)
+            shapes[f"{e}.rnn.bias_hh_l0"] = (4 * hidden,)
+            shapes[f"{e}.linear_1.weight"] = (hidden, hidden)
+            shapes[f"{e}.linear_1.bias"] = (hidden,)
+            continue
         shapes[f"{e}.linear_1.weight"] = (hidden, ins[e])
         shapes[f"{e}.linear_1.bias"] = (hidden,)
         for l in ("linear_2", "linear_3"):
@@ -51,11 +66,16 @@ def param_shapes(audio_dim, text_dim, video_dim, hidden, out1, out2):
 
 
 class FusionNet:
-    """Device-resident Attention fusion model (feat_type='utt')."""
+    """Device-resident Attention fusion model.  feat_type 'utt': MLP encoders on [B, D] features;
+    'frm_align' / 'frm_unalign': LSTM encoders on [B, T, D] sequences (attention.py:25-33)."""
 
     def __init__(self, audio_dim=768, text_dim=768, video_dim=768, hidden_dim=128, output_dim1=6,
-                 output_dim2=1, dropout=0.0, grad_clip=-1.0, device="cuda", max_batch=4096, seed=0):
+                 output_dim2=1, dropout=0.0, grad_clip=-1.0, device="cuda", max_batch=4096, seed=0,
+                 feat_type="utt"):
         L.check(L.lib().mer_check_device())
+        assert feat_type in ("utt", "frm_align", "frm_unalign"), feat_type
+        self.feat_type = feat_type
+        self.frm = feat_type != "utt"
         self.device = torch.device(device)
         self.dims = MerFusionDims(audio_dim, text_dim, video_dim, hidden_dim, output_dim1, output_dim2)
         self.dropout, self.grad_clip, self.seed = float(dropout), float(grad_clip), int(seed)
@@ -72,16 +92,29 @@ class FusionNet:
                                                     vp, vp, vp, vp])
         self._adam = L.declare("mer_fusion_adam", [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32,
                                                    f32, vp, vp])
-        self.n_params = int(lib.mer_fusion_param_count(C.byref(self.dims)))
-        self.shapes = param_shapes(audio_dim, text_dim, video_dim, hidden_dim, output_dim1, output_dim2)
+        if self.frm:
+            lib.mer_fusion_frm_param_count.restype = C.c_longlong
+            lib.mer_fusion_frm_param_count.argtypes = [C.POINTER(MerFusionDims)]
+            lib.mer_fusion_frm_workspace_bytes.restype = C.c_longlong
+            lib.mer_fusion_frm_workspace_bytes.argtypes = [C.POINTER(MerFusionDims)] + [i32] * 4
+            self._fwd_frm = L.declare("mer_fusion_frm_forward", [C.POINTER(MerFusionDims), vp, vp, vp, vp, i32,
+                                                                 i32, i32, i32, vp, i64, vp, vp, vp, vp])
+            self._fb_frm = L.declare("mer_fusion_frm_fwd_bwd", [C.POINTER(MerFusionDims), vp, vp, vp, vp, vp,
+                                                                i32, i32, i32, vp, vp, i32, f32, f32,
+                                                                C.c_ulonglong, vp, vp, vp, i64, vp, vp, vp, vp,
+                                                                vp])
+        self.n_params = int((lib.mer_fusion_frm_param_count if self.frm else lib.mer_fusion_param_count)(
+            C.byref(self.dims)))
+        self.shapes = param_shapes(audio_dim, text_dim, video_dim, hidden_dim, output_dim1, output_dim2,
+                                   feat_type)
         assert sum(int(np.prod(s)) for s in self.shapes.values()) == self.n_params
         z = lambda: torch.zeros(self.n_params, dtype=torch.float32, device=self.device)  # noqa: E731
         self.params, self.grads, self.exp_avg, self.exp_avg_sq = z(), z(), z(), z()
         self.step_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.loss = torch.zeros(3, dtype=torch.float32, device=self.device)
         self.max_batch = max_batch
-        self.ws = torch.empty(int(lib.mer_fusion_workspace_bytes(C.byref(self.dims), max_batch)),
-                              dtype=torch.uint8, device=self.device)
+        self.ws = torch.empty(int(lib.mer_fusion_workspace_bytes(C.byref(self.dims), max_batch)) if not self.frm
+                              else 0, dtype=torch.uint8, device=self.device)
         self.training = True
         self.graph_launches = 0  # kernels launched through CUDA-graph replays (not seen by the library counter)
         lib.mer_launch_count.restype = C.c_longlong
@@ -105,7 +138,7 @@ class FusionNet:
     def named_views(self, flat=None):
         flat = self.params if flat is None else flat
         out, o = {}, 0
-        for n in param_names():
+        for n in param_names(self.feat_type):
             k = int(np.prod(self.shapes[n]))
             out[n] = flat[o:o + k].view(self.shapes[n])
             o += k
@@ -142,12 +175,28 @@ class FusionNet:
         B = a.shape[0]
         assert B <= self.max_batch
         feats, emos, vals = self._bufs(B)
+        if self.frm:
+            ws = self._frm_ws(B, a, t, v)
+            L.check(self._fwd_frm(C.byref(self.dims), L.ptr(self.params), L.ptr(a), L.ptr(t), L.ptr(v),
+                                  a.shape[1], t.shape[1], v.shape[1], B, L.ptr(ws), ws.numel(), L.ptr(feats),
+                                  L.ptr(emos), L.ptr(vals), L.stream_ptr()))
+            return feats, emos, vals, torch.zeros((), dtype=torch.int64, device=self.device)
         L.check(self._fwd(C.byref(self.dims), L.ptr(self.params), L.ptr(a), L.ptr(t), L.ptr(v), B,
                           L.ptr(self.ws), self.ws.numel(), L.ptr(feats), L.ptr(emos), L.ptr(vals),
                           L.stream_ptr()))
         return feats, emos, vals, torch.zeros((), dtype=torch.int64, device=self.device)
 
     __call__ = forward
+
+    def _frm_ws(self, B, a, t, v):
+        """Workspace of the frame-level variant: depends on the three padded sequence lengths."""
+        assert a.dim() == t.dim() == v.dim() == 3, "frame-level features are [B, T, D] (read_data.py:118-125)"
+        need = int(L.lib().mer_fusion_frm_workspace_bytes(C.byref(self.dims), B, a.shape[1], t.shape[1],
+                                                          v.shape[1]))
+        if self.ws.numel() < need:
+            self.ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._invalidate()
+        return self.ws
 
     def _launch_step(self, a, t, v, emo, val, feats, emos_out, vals_out, lr, betas, eps, wd,
                      world, ext_masks):
@@ -156,10 +205,18 @@ class FusionNet:
         if ext_masks is not None:
             arr = (C.c_void_p * 4)(*[m.data_ptr() if m is not None else None for m in ext_masks])
             masks = C.cast(arr, C.c_void_p)
-        L.check(self._fb(C.byref(self.dims), L.ptr(self.params), L.ptr(self.grads), L.ptr(a), L.ptr(t),
-                         L.ptr(v), L.ptr(emo), L.ptr(val), B, 1.0 / (B * world), self.dropout,
-                         self.seed, L.ptr(self.step_counter), masks, L.ptr(self.ws), self.ws.numel(),
-                         L.ptr(self.loss), L.ptr(feats), L.ptr(emos_out), L.ptr(vals_out), L.stream_ptr()))
+        if self.frm:
+            ws = self._frm_ws(B, a, t, v)
+            L.check(self._fb_frm(C.byref(self.dims), L.ptr(self.params), L.ptr(self.grads), L.ptr(a), L.ptr(t),
+                                 L.ptr(v), a.shape[1], t.shape[1], v.shape[1], L.ptr(emo), L.ptr(val), B,
+                                 1.0 / (B * world), self.dropout, self.seed, L.ptr(self.step_counter), masks,
+                                 L.ptr(ws), ws.numel(), L.ptr(self.loss), L.ptr(feats), L.ptr(emos_out),
+                                 L.ptr(vals_out), L.stream_ptr()))
+        else:
+            L.check(self._fb(C.byref(self.dims), L.ptr(self.params), L.ptr(self.grads), L.ptr(a), L.ptr(t),
+                             L.ptr(v), L.ptr(emo), L.ptr(val), B, 1.0 / (B * world), self.dropout,
+                             self.seed, L.ptr(self.step_counter), masks, L.ptr(self.ws), self.ws.numel(),
+                             L.ptr(self.loss), L.ptr(feats), L.ptr(emos_out), L.ptr(vals_out), L.stream_ptr()))
         if world > 1:
             import torch.distributed as dist
             dist.all_reduce(self.grads)  # SUM: loss already carries 1/global_batch
@@ -183,7 +240,10 @@ class FusionNet:
                               val.contiguous(), feats, emos_out, vals_out, lr, betas, eps,
                               weight_decay, world_size, ext_masks)
             return self.loss, emos_out, vals_out
-        key = (B, lr, betas, eps, weight_decay, world_size, self.dropout, self.grad_clip)
+        if self.frm:
+            self._frm_ws(B, a, t, v)  # sized (and graphs invalidated on growth) before any capture
+        key = (B, tuple(a.shape[1:]), tuple(t.shape[1:]), tuple(v.shape[1:]), lr, betas, eps, weight_decay,
+               world_size, self.dropout, self.grad_clip)
         if key not in self._graphs:
             st = dict(a=torch.empty_like(a), t=torch.empty_like(t), v=torch.empty_like(v),
                       emo=torch.empty_like(emo), val=torch.empty_like(val))
@@ -236,13 +296,13 @@ class _Wrapper:
 
 
 def get_models(args):
-    """args: .model ('attention'), .feat_type ('utt'), .audio_dim/.text_dim/.video_dim,
-    .output_dim1/.output_dim2, .dropout, .hidden_dim, .grad_clip  (models/__init__.py:18-46)."""
+    """args: .model ('attention'), .feat_type ('utt' | 'frm_align' | 'frm_unalign'),
+    .audio_dim/.text_dim/.video_dim, .output_dim1/.output_dim2, .dropout, .hidden_dim, .grad_clip
+    (models/__init__.py:18-46)."""
     assert args.model == "attention", "only the Attention fusion net is on the B200 path"
-    assert args.feat_type == "utt", "frame-level (LSTM) fusion is SURVEY.md §8f row N1 (next)"
     net = FusionNet(args.audio_dim, args.text_dim, args.video_dim, args.hidden_dim, args.output_dim1,
                     args.output_dim2, dropout=args.dropout, grad_clip=args.grad_clip,
-                    device=getattr(args, "device", "cuda"))
+                    device=getattr(args, "device", "cuda"), feat_type=args.feat_type)
     return _Wrapper(net)
 
 

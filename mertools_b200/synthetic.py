@@ -129,9 +129,10 @@ def bert_state_dict(vocab_size, seed=2, layers=12, scale=1.0, max_pos=None, type
 
 
 def fusion_state_dict(seed=3, audio_dim=768, text_dim=768, video_dim=768, hidden=128,
-                      out1=6, out2=1):
-    """Keys of toolkit/models/attention.py:Attention (feat_type='utt'), nn.Linear-style
-    uniform(-1/sqrt(fan_in), 1/sqrt(fan_in)) init, in construction order (attention.py:21-34)."""
+                      out1=6, out2=1, feat_type="utt"):
+    """Keys of toolkit/models/attention.py:Attention, nn.Linear / nn.LSTM-style
+    uniform(-1/sqrt(fan), 1/sqrt(fan)) init, in construction order (attention.py:21-34).  feat_type 'utt':
+    MLPEncoder per modality; 'frm_align' / 'frm_unalign': LSTMEncoder (encoder.py:45-72)."""
     rng = np.random.default_rng(seed)
     sd = {}
 
@@ -145,9 +146,18 @@ def fusion_state_dict(seed=3, audio_dim=768, text_dim=768, video_dim=768, hidden
         lin(prefix + ".linear_2", hidden, hidden)
         lin(prefix + ".linear_3", hidden, hidden)
 
-    mlp("audio_encoder", audio_dim)
-    mlp("text_encoder", text_dim)
-    mlp("video_encoder", video_dim)
+    def lstm(prefix, i):
+        b = 1.0 / np.sqrt(hidden)
+        sd[prefix + ".rnn.weight_ih_l0"] = rng.uniform(-b, b, (4 * hidden, i)).astype(np.float32)
+        sd[prefix + ".rnn.weight_hh_l0"] = rng.uniform(-b, b, (4 * hidden, hidden)).astype(np.float32)
+        sd[prefix + ".rnn.bias_ih_l0"] = rng.uniform(-b, b, (4 * hidden,)).astype(np.float32)
+        sd[prefix + ".rnn.bias_hh_l0"] = rng.uniform(-b, b, (4 * hidden,)).astype(np.float32)
+        lin(prefix + ".linear_1", hidden, hidden)
+
+    enc = mlp if feat_type == "utt" else lstm
+    enc("audio_encoder", audio_dim)
+    enc("text_encoder", text_dim)
+    enc("video_encoder", video_dim)
     mlp("attention_mlp", hidden * 3)
     lin("fc_att", 3, hidden)
     lin("fc_out_1", out1, hidden)
@@ -166,6 +176,22 @@ def synth_waves(n_clips, n_samples=80000, seed=0):
     """int16 waveforms round(3000 * N(0,1)) at 16 kHz, [n_clips, n_samples]."""
     rng = np.random.default_rng(2000 + seed)
     return np.round(3000.0 * rng.standard_normal((n_clips, n_samples))).astype(np.int16)
+
+
+def synth_fusion_sequences(n, lens=(9, 5, 12), dim=768, seed=0):
+    """Frame-level batch as pad_to_maxlen_pre_modality (read_data.py:118-125) hands it to the model:
+    [n, T_m, dim] per modality, shorter clips zero-padded IN FRONT."""
+    rng = np.random.default_rng(4000 + seed)
+    out = []
+    for T in lens:
+        x = rng.standard_normal((n, T, dim), dtype=np.float32)
+        for i in range(n):
+            pad = int(rng.integers(0, max(1, T // 2)))
+            x[i, :pad] = 0.0
+        out.append(x)
+    emo = rng.integers(0, 6, n).astype(np.int64)
+    val = rng.uniform(-3, 3, n).astype(np.float32)
+    return out[0], out[1], out[2], emo, val
 
 
 def synth_fusion_features(n, dim=768, seed=0):

@@ -27,13 +27,35 @@ def _mlp(sd, prefix, x, mask, p):
     return x
 
 
+def _lstm_encoder(sd, prefix, x, mask, p):
+    """LSTMEncoder.forward (encoder.py:62-72): one-layer nn.LSTM over [B, T, D] (zero state, gate order
+    i, f, g, o), final hidden state -> dropout -> linear_1 (no activation)."""
+    w_ih, w_hh = sd[f"{prefix}.rnn.weight_ih_l0"], sd[f"{prefix}.rnn.weight_hh_l0"]
+    b_ih, b_hh = sd[f"{prefix}.rnn.bias_ih_l0"], sd[f"{prefix}.rnn.bias_hh_l0"]
+    B, T, _ = x.shape
+    H = w_hh.shape[1]
+    h = torch.zeros(B, H, dtype=x.dtype)
+    c = torch.zeros(B, H, dtype=x.dtype)
+    for t in range(T):
+        g = F.linear(x[:, t], w_ih, b_ih) + F.linear(h, w_hh, b_hh)
+        i, f, gg, o = g.chunk(4, dim=1)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+        h = torch.sigmoid(o) * torch.tanh(c)
+    if mask is not None:
+        h = h * mask / (1.0 - p)
+    return F.linear(h, sd[f"{prefix}.linear_1.weight"], sd[f"{prefix}.linear_1.bias"])
+
+
 def attention_forward(sd, audios, texts, videos, masks=None, p=0.0):
     """Attention.forward (attention.py:36-57).  masks: None (eval) or 4 keep-masks
-    [audio, text, video, concat].  Returns (features, emos_out, vals_out)."""
+    [audio, text, video, concat].  Returns (features, emos_out, vals_out).  Frame-level checkpoints
+    (feat_type frm_align / frm_unalign, attention.py:29-33: LSTMEncoder per modality, inputs [B, T, D], masks
+    0..2 on the [B, H] final hidden states) are recognised by their rnn.* parameters."""
     m = masks or (None, None, None, None)
-    ha = _mlp(sd, "audio_encoder", audios, m[0], p)
-    ht = _mlp(sd, "text_encoder", texts, m[1], p)
-    hv = _mlp(sd, "video_encoder", videos, m[2], p)
+    enc = _lstm_encoder if "audio_encoder.rnn.weight_ih_l0" in sd else _mlp
+    ha = enc(sd, "audio_encoder", audios, m[0], p)
+    ht = enc(sd, "text_encoder", texts, m[1], p)
+    hv = enc(sd, "video_encoder", videos, m[2], p)
     cat = torch.cat([ha, ht, hv], dim=1)
     att = F.linear(_mlp(sd, "attention_mlp", cat, m[3], p), sd["fc_att.weight"], sd["fc_att.bias"])
     fused = torch.matmul(torch.stack([ha, ht, hv], dim=2), att.unsqueeze(2)).squeeze(2)

@@ -80,3 +80,57 @@ def test_fusion_eval_forward(cuda):
     rf, re, rv = OF.attention_forward(tsd, a, t, v)
     assert (f.cpu() - rf).abs().max() < 1e-4 and (e.cpu() - re).abs().max() < 1e-4
     assert (vv.cpu() - rv).abs().max() < 1e-4 and int(inter) == 0
+
+
+def _seq_data(n, lens, seed):
+    a, t, v, emo, val = S.synth_fusion_sequences(n, lens=lens, seed=seed)
+    tt = lambda x: torch.from_numpy(x)  # noqa: E731
+    return tt(a), tt(t), tt(v), tt(emo), tt(val).view(-1, 1)
+
+
+@pytest.mark.parametrize("B,lens,hidden,dropout,clip", [(32, (9, 5, 12), 128, 0.0, -1.0), (13, (1, 7, 3), 64, 0.3, -1.0),
+                                                          (20, (40, 16, 25), 128, 0.2, 0.01)])
+def test_frame_level_fusion_trajectory_matches_oracle(cuda, B, lens, hidden, dropout, clip):
+    """feat_type = frm_align: LSTM encoders (forward, BPTT, weight gradients) + the same head, 20 Adam steps."""
+    from mertools_b200.fusion import FusionNet, param_names
+    sd = S.fusion_state_dict(seed=5, hidden=hidden, feat_type="frm_align")
+    net = FusionNet(hidden_dim=hidden, dropout=dropout, grad_clip=clip, device=cuda, feat_type="frm_align")
+    net.load_state_dict(sd)
+    ref = OF.Trainer(sd, lr=1e-3, l2=1e-5, grad_clip=clip, dropout=dropout)
+    a, t, v, emo, val = _seq_data(B, lens, seed=17)
+    dev = [x.to(cuda) for x in (a, t, v, emo, val)]
+    rng = np.random.default_rng(19)
+    for step in range(20):
+        masks = dmasks = None
+        if dropout > 0:
+            masks = [torch.from_numpy((rng.random((B, d)) >= dropout).astype(np.float32))
+                     for d in (hidden, hidden, hidden, 3 * hidden)]
+            dmasks = [m.to(cuda) for m in masks]
+        ce, mse, tot, eo, vo, grads = ref.step(a, t, v, emo, val, masks)
+        loss3, emos_out, vals_out = net.train_step(*dev, lr=1e-3, weight_decay=1e-5,
+                                                   ext_masks=dmasks, use_graph=False)
+        got = loss3.cpu().numpy()
+        assert abs(got[2] - tot) <= 1e-3 * max(1.0, abs(tot)), f"step {step}: loss {got[2]} vs {tot}"
+        if step == 0:
+            gv = net.named_views(net.grads)
+            for n in param_names("frm_align"):
+                g, r = gv[n].cpu(), grads[n]
+                assert (g - r).abs().max() <= 2e-4 * max(r.abs().max().item(), 1e-3), f"grad {n}"
+            assert (emos_out.cpu() - eo).abs().max() < 1e-4
+
+
+def test_frame_level_fusion_graph_and_eval(cuda):
+    from mertools_b200.fusion import FusionNet
+    sd = S.fusion_state_dict(seed=5, feat_type="frm_unalign")
+    a, t, v, emo, val = (x.to(cuda) for x in _seq_data(16, (6, 4, 9), seed=21))
+    nets = [FusionNet(device=cuda, feat_type="frm_unalign").load_state_dict(sd) for _ in range(2)]
+    for step in range(4):
+        l0, _, _ = nets[0].train_step(a, t, v, emo, val, weight_decay=1e-5, use_graph=False)
+        l0 = l0.clone()
+        l1, _, _ = nets[1].train_step(a, t, v, emo, val, weight_decay=1e-5, use_graph=True)
+        assert torch.equal(l0, l1), f"step {step}"
+    assert torch.equal(nets[0].params, nets[1].params)
+    f, e, vv, inter = nets[0]({"audios": a, "texts": t, "videos": v})
+    tsd = {k: x.cpu() for k, x in nets[0].state_dict().items()}
+    rf, re, rv = OF.attention_forward(tsd, a.cpu(), t.cpu(), v.cpu())
+    assert (f.cpu() - rf).abs().max() < 1e-4 and (e.cpu() - re).abs().max() < 1e-4 and int(inter) == 0

@@ -117,3 +117,22 @@ def test_fusion_oracle_matches_reference_trainer():
             assert _rel(grads["audio_encoder.linear_1.bias"].numpy(), g["grad_audio_l1_b"]) < 1e-4
     assert _rel(tr.sd["fc_out_1.weight"].detach().numpy(), g["final_fc_out_1_w"]) < 1e-4
     assert _rel(tr.sd["audio_encoder.linear_1.weight"].detach().numpy()[0], g["final_audio_l1_w_row0"]) < 1e-4
+
+
+def test_frame_level_fusion_oracle_matches_reference_classes():
+    """feat_type = frm_align: oracle Trainer vs the reference's Attention(LSTMEncoder) + losses + Adam."""
+    from oracle import fusion as OF
+    g = np.load(os.path.join(G, "fusion_frm_golden.npz"))
+    sd = S.fusion_state_dict(seed=int(g["seed"]), feat_type="frm_align")
+    a, t, v, emo, val = S.synth_fusion_sequences(int(g["batch"]), lens=tuple(int(x) for x in g["lens"]),
+                                                 seed=int(g["data_seed"]))
+    tt = torch.from_numpy
+    tr = OF.Trainer(sd, lr=1e-3, l2=1e-5)
+    for step in range(len(g["losses"])):
+        ce, mse, tot, eo, vo, grads = tr.step(tt(a), tt(t), tt(v), tt(emo), tt(val).view(-1, 1))
+        assert abs(tot - g["losses"][step]) < 1e-5 * max(1.0, abs(g["losses"][step])), step
+        if step == 0:
+            assert _rel(eo.numpy(), g["emos0"]) < 1e-5 and _rel(vo.numpy(), g["vals0"]) < 1e-5
+            assert _rel(grads["audio_encoder.rnn.weight_hh_l0"][0].numpy(), g["grad_audio_whh_row0"]) < 1e-4
+            assert _rel(grads["text_encoder.rnn.bias_ih_l0"].numpy(), g["grad_text_bih"]) < 1e-4
+            assert _rel(grads["video_encoder.rnn.weight_ih_l0"][5].numpy(), g["grad_video_wih_row5"]) < 1e-4

@@ -109,3 +109,23 @@ def test_fusion_vs_reference_golden(cuda):
             gv = net.named_views(net.grads)
             assert _rel(gv["fc_att.weight"].cpu().numpy(), g["grad_fc_att_w"]) < 1e-3
     assert _rel(net.named_views()["fc_out_1.weight"].cpu().numpy(), g["final_fc_out_1_w"]) < 1e-2
+
+
+def test_frame_level_fusion_vs_reference_golden(cuda):
+    """LSTM-encoder fusion (feat_type = frm_align) against the reference's own classes, 20 steps."""
+    from mertools_b200.fusion import FusionNet
+    g = np.load(os.path.join(G, "fusion_frm_golden.npz"))
+    net = FusionNet(device=cuda, feat_type="frm_align").load_state_dict(
+        S.fusion_state_dict(seed=int(g["seed"]), feat_type="frm_align"))
+    a, t, v, emo, val = S.synth_fusion_sequences(int(g["batch"]), lens=tuple(int(x) for x in g["lens"]),
+                                                 seed=int(g["data_seed"]))
+    dev = [torch.from_numpy(x).to(cuda) for x in (a, t, v, emo, val.reshape(-1, 1))]
+    for step, ref in enumerate(g["losses"]):
+        loss3, eo, vo = net.train_step(*dev, lr=1e-3, weight_decay=1e-5, use_graph=False)
+        got = float(loss3[2])
+        assert abs(got - ref) <= 1e-3 * max(1.0, abs(ref)), f"step {step}: {got} vs {ref}"
+        if step == 0:
+            assert _rel(eo.cpu().numpy(), g["emos0"]) < 1e-4
+            gv = net.named_views(net.grads)
+            assert _rel(gv["audio_encoder.rnn.weight_hh_l0"][0].cpu().numpy(), g["grad_audio_whh_row0"]) < 1e-3
+            assert _rel(gv["text_encoder.rnn.bias_ih_l0"].cpu().numpy(), g["grad_text_bih"]) < 1e-3

@@ -150,3 +150,21 @@ def test_oracle_hubert_large_family_matches_hf():
     assert len(got) == len(ref) == 4
     for a, b in zip(got, ref):
         assert float((a - b).abs().max() / b.abs().max()) < 5e-5
+
+
+def test_oracle_lstm_encoder_matches_torch_lstm():
+    """oracle/fusion.py:_lstm_encoder vs the module the reference builds (modules/encoder.py:45-72:
+    nn.LSTM(batch_first) -> final hidden -> dropout -> linear_1), eval mode."""
+    from oracle import fusion as OF
+    torch.manual_seed(0)
+    D, H, B, T = 40, 32, 5, 7
+    rnn = torch.nn.LSTM(D, H, num_layers=1, batch_first=True)
+    lin = torch.nn.Linear(H, H)
+    sd = {"e.rnn." + k: v.detach() for k, v in rnn.state_dict().items()}
+    sd.update({"e.linear_1.weight": lin.weight.detach(), "e.linear_1.bias": lin.bias.detach()})
+    x = torch.randn(B, T, D)
+    with torch.no_grad():
+        _, (h, _) = rnn(x)
+        ref = lin(h.squeeze(0))
+        got = OF._lstm_encoder(sd, "e", x, None, 0.0)
+    assert float((got - ref).abs().max()) < 1e-6
