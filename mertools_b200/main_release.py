@@ -57,6 +57,21 @@ def read_utt_feature(feature_root, name):
     return np.mean(feat, axis=0)
 
 
+def read_frm_feature(feature_root, name):
+    """read_data.py:15-41 (func_read_one_feat): one clip -> [T, D] (a single vector becomes [1, D])."""
+    path = os.path.join(feature_root, name + ".npy")
+    d = os.path.join(feature_root, name)
+    if os.path.exists(path):
+        feat = np.load(path).squeeze()
+    elif os.path.isdir(d):
+        feat = np.array([np.load(os.path.join(d, f)) for f in sorted(os.listdir(d))]).squeeze()
+    else:
+        raise Exception("feature path or dir do not exist!")
+    if feat.ndim == 1:
+        feat = feat[np.newaxis, :]
+    return feat
+
+
 def random_split_indexes(whole_num, num_folder):
     """mer2023.py:108-134 (python ``random`` shuffle, last fold takes the remainder)."""
     indices = np.arange(whole_num)
@@ -71,19 +86,27 @@ def random_split_indexes(whole_num, num_folder):
 
 
 class DeviceSplit:
-    """One corpus split resident on the GPU: A/T/V [N,768] fp32, emo int64, val fp32."""
+    """One corpus split resident on the GPU: A/T/V fp32 -- [N, D] for feat_type 'utt', [N, T_m, D] for the
+    frame-level types (shaped exactly as Data_Feat does, feat_data.py:33-44) -- emo int64, val fp32."""
 
     def __init__(self, args, names, labels, config, device):
         root = config.PATH_TO_FEATURES[args.dataset]
         feats = []
-        for fname in (args.audio_feature, args.text_feature, args.video_feature):
-            fr = os.path.join(root, fname)
-            feats.append(np.stack([read_utt_feature(fr, n) for n in names]).astype(np.float32))
+        if args.feat_type == "utt":
+            for fname in (args.audio_feature, args.text_feature, args.video_feature):
+                fr = os.path.join(root, fname)
+                feats.append(np.stack([read_utt_feature(fr, n) for n in names]).astype(np.float32))
+        else:
+            from . import frame_features as FF
+            raw = [[read_frm_feature(os.path.join(root, fname), n) for n in names]
+                   for fname in (args.audio_feature, args.text_feature, args.video_feature)]
+            shaped = FF.shape_split(raw[0], raw[1], raw[2], args.feat_type, args.feat_scale)
+            feats = [np.array(x).astype(np.float32) for x in shaped]  # torch.FloatTensor(np.array(...)) in the collater
         self.names = names
         self.a, self.t, self.v = (torch.from_numpy(f).to(device) for f in feats)
         self.emo = torch.tensor([l["emo"] for l in labels], dtype=torch.int64, device=device)
         self.val = torch.tensor([l["val"] for l in labels], dtype=torch.float32, device=device).view(-1, 1)
-        self.dims = tuple(int(f.shape[1]) for f in feats)
+        self.dims = tuple(int(f.shape[-1]) for f in feats)
 
     def __len__(self):
         return len(self.names)
@@ -174,11 +197,18 @@ def build_parser():
 def main(args, config=None):
     if config is None:
         from . import config as config  # noqa: PLW0127
-    assert args.model == "attention" and args.feat_type == "utt" and args.dataset == "MER2023", \
-        "the B200 path covers --model attention --feat_type utt --dataset MER2023 (SURVEY.md §8)"
+    assert args.model == "attention" and args.dataset == "MER2023", \
+        "the B200 path covers --model attention --dataset MER2023 (SURVEY.md §8)"
     torch.cuda.set_device(args.gpu)
     device = torch.device("cuda", args.gpu)
-    args.feat_scale = 1
+    # pre-compression of the frame-level types (main-release.py:131-142)
+    if args.feat_type == "utt":
+        args.feat_scale = 1
+    else:
+        assert args.feat_type in ("frm_align", "frm_unalign"), args.feat_type
+        for f in (args.audio_feature, args.text_feature, args.video_feature):
+            assert f.endswith("FRA"), f"feat_type {args.feat_type} needs frame-level features, got {f}"
+        args.feat_scale = 6 if args.feat_type == "frm_align" else 12
     feats = [f for f in (args.audio_feature, args.text_feature, args.video_feature) if f is not None]
     args.save_root = f"{args.save_root}-" + {0: "others", 1: "unimodal", 2: "bimodal", 3: "trimodal"}[len(set(feats))]
     if args.hyper_path is None:
@@ -218,7 +248,7 @@ def main(args, config=None):
         start_time = name_time = time.time()
         net = FusionNet(args.audio_dim, args.text_dim, args.video_dim, args.hidden_dim, 6, 1,
                         dropout=args.dropout, grad_clip=args.grad_clip, device=device,
-                        seed=random.randint(0, 2 ** 31 - 1))
+                        seed=random.randint(0, 2 ** 31 - 1), feat_type=args.feat_type)
         net.load_state_dict(default_init(net))
         optimizer = Adam(lr=args.lr, weight_decay=args.l2)
         whole_store, whole_metrics = [], []
@@ -271,7 +301,10 @@ def default_init(net):
     weight and bias), drawn from torch's global CPU generator as ``get_models(args)`` would."""
     sd = {}
     for name, shape in net.shapes.items():
-        fan_in = shape[1] if len(shape) == 2 else net.shapes[name.replace(".bias", ".weight")][1]
+        if ".rnn." in name:  # nn.LSTM.reset_parameters: every tensor U(-1/sqrt(hidden), 1/sqrt(hidden))
+            fan_in = net.dims.hidden
+        else:
+            fan_in = shape[1] if len(shape) == 2 else net.shapes[name.replace(".bias", ".weight")][1]
         bound = 1.0 / np.sqrt(fan_in)
         sd[name] = (torch.rand(shape) * 2 - 1) * bound
     return sd

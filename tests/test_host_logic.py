@@ -152,3 +152,25 @@ def test_data_parallel_gradient_equals_full_batch_gradient_gloo():
     for r in (0, 1):
         assert np.abs(outs[r] - full).max() <= 1e-5 * np.abs(full).max()
     assert np.array_equal(outs[0], outs[1])
+
+
+def test_frame_level_shaping_is_bit_identical_to_the_reference_functions():
+    """feature_scale_compress / align_to_text / pad_to_maxlen_pre_modality (read_data.py:72-125) in
+    Data_Feat's order, against arrays produced by the reference's own functions."""
+    import os
+    import numpy as np
+    from mertools_b200 import frame_features as FF
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "frame_shaping_golden.npz"))
+    n, dim = int(g["n"]), int(g["dim"])
+
+    def ragged(seed):
+        rng = np.random.default_rng(seed)
+        lens = rng.integers(1, 60, (3, n))
+        return [[rng.standard_normal((int(t), dim)).astype(np.float32) for t in lens[m]] for m in range(3)]
+
+    for feat_type, scale in (("frm_align", 6), ("frm_unalign", 12), ("frm_unalign", 1)):
+        a, t, v = FF.shape_split(*ragged(int(g["seed"])), feat_type, scale)
+        for name, x in (("a", a), ("t", t), ("v", v)):
+            ref = g[f"{feat_type}_{scale}_{name}"]
+            got = np.array(x)
+            assert got.shape == ref.shape and got.dtype == ref.dtype and np.array_equal(got, ref), (feat_type, scale, name)

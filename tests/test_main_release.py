@@ -21,11 +21,13 @@ def _make_corpus(root, n_train=32, n_test=8, seed=0):
             for i in range(n)}
     np.savez(os.path.join(root, "label-6way.npz"), **corp)
     feats = os.path.join(root, "features")
-    for fname, frame_level in (("synA-UTT", False), ("synT-UTT", False), ("synV-FRA", True)):
+    for fname, frame_level in (("synA-UTT", False), ("synT-UTT", False), ("synV-FRA", True), ("synA-FRA", True),
+                               ("synT-FRA", True)):
         os.makedirs(os.path.join(feats, fname))
         for split in corp.values():
             for name in split:
-                x = rng.standard_normal((int(rng.integers(2, 6)), 768) if frame_level else (768,)).astype(np.float32)
+                hi = 40 if fname == "synA-FRA" else 6
+                x = rng.standard_normal((int(rng.integers(2, hi)), 768) if frame_level else (768,)).astype(np.float32)
                 np.save(os.path.join(feats, fname, name + ".npy"), x)
     cfg = types.SimpleNamespace(PATH_TO_LABEL={"MER2023": os.path.join(root, "label-6way.npz")},
                                 PATH_TO_FEATURES={"MER2023": feats})
@@ -71,3 +73,22 @@ def test_main_release_end_to_end(cuda, tmp_path):
     assert os.path.basename(saved[0]).startswith("cv_features:synA-UTT+synT-UTT+synV-FRA_dataset:MER2023_model:attention+utt+None_f1:")
     stored = np.load(saved[0], allow_pickle=True)["args"].item()
     assert stored.hidden_dim == 128 and stored.audio_dim == 768 and stored.duration > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("feat_type", ["frm_align", "frm_unalign"])
+def test_main_release_frame_level(cuda, tmp_path, feat_type):
+    """--feat_type frm_align / frm_unalign: FRA features, feat_scale pooling / pre-padding, LSTM encoders."""
+    cfg = _make_corpus(str(tmp_path))
+    hyper = tmp_path / "hyper.yaml"
+    hyper.write_text("attention:\n  hidden_dim: 64\n  dropout: 0.2\n  grad_clip: -1.0\n  lr: 0.001\n")
+    args = MR.build_parser().parse_args([
+        "--audio_feature=synA-FRA", "--text_feature=synT-FRA", "--video_feature=synV-FRA", f"--feat_type={feat_type}",
+        f"--hyper_path={hyper}", "--epochs=2", f"--save_root={tmp_path}/saved", "--gpu=0"])
+    torch.manual_seed(0)
+    random.seed(0)
+    saved = MR.main(args, config=cfg)
+    assert len(saved) == 4 and all(os.path.exists(p) for p in saved)
+    assert f"model:attention+{feat_type}+None_f1:" in os.path.basename(saved[0])
+    stored = np.load(saved[0], allow_pickle=True)["args"].item()
+    assert stored.feat_scale == (6 if feat_type == "frm_align" else 12) and stored.hidden_dim == 64
