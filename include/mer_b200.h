@@ -276,6 +276,15 @@ MER_API int mer_hubert_forward(const MerHubertModel* model, const float* wave, i
                                int normalize, void* workspace, long long workspace_bytes,
                                float* out_frames, float* out_utt, float* opt_hidden, void* stream);
 
+/* ---- log mel spectrogram (VGGish front-end) --------------------------------------------------------- */
+/* mel_features.log_mel_spectrogram as called by vggish_input.waveform_to_examples
+ * (MERBench/feature_extraction/audio/vggish/mel_features.py:166-223, vggish_input.py:66-75,
+ * vggish_params.py:22-34): 16 kHz input, 25 ms periodic-Hann frames every 10 ms, |rFFT-512|, 64 HTK mel
+ * bands over 125-7500 Hz, log(mel + 0.01).  wave: fp32 [batch, n_samples] (row pitch ld_wave floats);
+ * out: fp32 [batch, mer_logmel_num_frames(n_samples), 64]. */
+MER_API int mer_logmel_num_frames(int n_samples);
+MER_API int mer_logmel(const float* wave, int batch, int n_samples, long long ld_wave, float* out, void* stream);
+
 /* ---- BERT / RoBERTa-base text encoder ------------------------------------------------------------ */
 typedef struct MerBertModel {
   int n_layers;

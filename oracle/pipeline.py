@@ -226,3 +226,41 @@ def text_clip_features(sd, input_ids, start, end, layers=12, feature_level="UTTE
     if emb.ndim == 2:
         emb = np.mean(emb, axis=0)
     return emb
+
+
+# ------------------------------------------------------------------------------------------------
+# log-mel front-end  (audio/vggish/mel_features.py, vggish_input.py, vggish_params.py)
+# ------------------------------------------------------------------------------------------------
+def log_mel_spectrogram(data, sample_rate=16000, log_offset=0.01, window_secs=0.025, hop_secs=0.010,
+                        num_mel_bins=64, lower_edge_hertz=125.0, upper_edge_hertz=7500.0):
+    """mel_features.log_mel_spectrogram (:166-223) with the VGGish constants (vggish_params.py:22-34):
+    frames (no padding, :21-45) x periodic Hann (:48-69) -> |rfft| (:72-93) -> HTK mel matrix (:96-164)
+    -> log(mel + offset).  float64 numpy like the reference."""
+    data = np.asarray(data, dtype=np.float64)
+    wl = int(round(sample_rate * window_secs))
+    hl = int(round(sample_rate * hop_secs))
+    nfft = 2 ** int(np.ceil(np.log(wl) / np.log(2.0)))
+    nfrm = 1 + int(np.floor((data.shape[0] - wl) / hl))
+    frames = np.stack([data[i * hl:i * hl + wl] for i in range(nfrm)])
+    window = 0.5 - 0.5 * np.cos(2 * np.pi / wl * np.arange(wl))
+    spec = np.abs(np.fft.rfft(frames * window, nfft))
+    nbins = spec.shape[1]
+
+    def h2m(hz):
+        return 1127.0 * np.log(1.0 + hz / 700.0)
+    bins_mel = h2m(np.linspace(0.0, sample_rate / 2.0, nbins))
+    edges = np.linspace(h2m(lower_edge_hertz), h2m(upper_edge_hertz), num_mel_bins + 2)
+    mel = np.empty((nbins, num_mel_bins))
+    for i in range(num_mel_bins):
+        lo, ce, up = edges[i:i + 3]
+        mel[:, i] = np.maximum(0.0, np.minimum((bins_mel - lo) / (ce - lo), (up - bins_mel) / (up - ce)))
+    mel[0, :] = 0.0
+    return np.log(np.dot(spec, mel) + log_offset)
+
+
+def waveform_to_examples(data, hop_sec, num_frames=96):
+    """vggish_input.waveform_to_examples (:37-82) for 16 kHz mono input: [num_examples, 96, 64]."""
+    lm = log_mel_spectrogram(data)
+    hop = int(round(hop_sec * 100.0))
+    n = 1 + int(np.floor((lm.shape[0] - num_frames) / hop))
+    return np.stack([lm[i * hop:i * hop + num_frames] for i in range(n)]) if n > 0 else np.zeros((0, num_frames, lm.shape[1]))

@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+timeout 600 python -m pytest tests/test_golden_gpu.py -m gpu -x -q -k logmel 2>&1 | tail -8

@@ -136,3 +136,14 @@ def test_frame_level_fusion_oracle_matches_reference_classes():
             assert _rel(grads["audio_encoder.rnn.weight_hh_l0"][0].numpy(), g["grad_audio_whh_row0"]) < 1e-4
             assert _rel(grads["text_encoder.rnn.bias_ih_l0"].numpy(), g["grad_text_bih"]) < 1e-4
             assert _rel(grads["video_encoder.rnn.weight_ih_l0"][5].numpy(), g["grad_video_wih_row5"]) < 1e-4
+
+
+def test_logmel_oracle_matches_reference_vggish_input():
+    """oracle/pipeline.py:waveform_to_examples vs the reference's vggish_input.waveform_to_examples."""
+    g = np.load(os.path.join(G, "logmel_golden.npz"))
+    for i, n in enumerate(g["lens"]):
+        w = S.synth_waves(1, int(n), seed=int(g["seed0"]) + i)[0].astype(np.float64) / 32768.0
+        ex = P.waveform_to_examples(w, float(g["hop_sec"]))
+        assert tuple(ex.shape) == tuple(g[f"n{i}"])
+        sub = ex[:: max(1, len(ex) // 4)]
+        assert np.abs(sub - g[f"ex{i}"]).max() < 1e-5

@@ -129,3 +129,27 @@ def test_frame_level_fusion_vs_reference_golden(cuda):
             gv = net.named_views(net.grads)
             assert _rel(gv["audio_encoder.rnn.weight_hh_l0"][0].cpu().numpy(), g["grad_audio_whh_row0"]) < 1e-3
             assert _rel(gv["text_encoder.rnn.bias_ih_l0"].cpu().numpy(), g["grad_text_bih"]) < 1e-3
+
+
+def test_logmel_examples_vs_reference_golden(cuda):
+    """mer_logmel through the vggish_input mirror against the reference's numpy front-end."""
+    from mertools_b200.extract import vggish_input as VI
+    g = np.load(os.path.join(G, "logmel_golden.npz"))
+    for i, n in enumerate(g["lens"]):
+        w = S.synth_waves(1, int(n), seed=int(g["seed0"]) + i)[0].astype(np.float64) / 32768.0
+        ex = VI.waveform_to_examples(w, 16000, float(g["hop_sec"]), device=cuda)
+        assert tuple(ex.shape) == tuple(g[f"n{i}"]) and ex.dtype == np.float32
+        sub = ex[:: max(1, len(ex) // 4)]
+        ref = g[f"ex{i}"]
+        assert np.abs(sub - ref).max() <= TOL * np.abs(ref).max(), f"clip {i}: {np.abs(sub - ref).max():.2e}"
+
+
+def test_logmel_batch_matches_oracle(cuda):
+    from mertools_b200.extract import vggish_input as VI
+    from oracle import pipeline as P
+    w = (S.synth_waves(3, 24000, seed=77).astype(np.float64) / 32768.0)
+    got = VI.log_mel_spectrogram(torch.from_numpy(w.astype(np.float32)).to(cuda)).cpu().numpy()
+    for r in range(3):
+        ref = P.log_mel_spectrogram(w[r].astype(np.float32))
+        assert got[r].shape == ref.shape == (148, 64)
+        assert np.abs(got[r] - ref).max() <= TOL * np.abs(ref).max()
