@@ -48,6 +48,7 @@ MER_API int mer_profile_collect(int mode, double* total_ms, double* total_flops,
 /* ---- GEMM (nn.Linear / Conv1d-as-GEMM / patch-embed) ---------------------------------- */
 enum { MER_EPI_GELU = 1, MER_EPI_ROUND_TF32 = 2, MER_EPI_SPLIT_BF16 = 4,
        MER_EPI_GELU_LIBM = 8, /* with MER_EPI_GELU: libdevice erff instead of the 12-op polynomial */
+       MER_EPI_QUICK_GELU = 64, /* x * sigmoid(1.702 x) (CLIP's hidden_act) instead of GELU; excludes MER_EPI_GELU */
        MER_EPI_OUT_F16 = 16,  /* out (and vt, if given) are IEEE fp16 arrays (round-to-nearest, saturating);
                                  ld_out / vt_ld in elements */
        MER_ATT_QKV_F16 = 32   /* mer_attention only: qkv and vt are fp16 arrays (needs MER_EPI_OUT_F16, vt,
@@ -192,6 +193,9 @@ typedef struct MerLayerWeights {
 MER_API long long mer_resize_workspace_bytes(int n, int H, int W, int OH, int OW);
 MER_API int mer_resize_bilinear_u8(const uint8_t* in, int n, int H, int W, uint8_t* out, int OH, int OW,
                                    void* workspace, void* stream);
+/* same with a filter choice: 0 = BILINEAR, 1 = BICUBIC (Pillow's a = -0.5 cubic; HF CLIPImageProcessor) */
+MER_API int mer_resize_u8(const uint8_t* in, int n, int H, int W, uint8_t* out, int OH, int OW, int filter,
+                          void* workspace, void* stream);
 
 /* ---- ViT-B/16 frame encoder (visual) ------------------------------------------------------------ */
 typedef struct MerVitModel {
@@ -217,6 +221,38 @@ MER_API long long mer_vit_workspace_bytes(int n_frames);
 MER_API int mer_vit_forward(const MerVitModel* model, const uint8_t* frames_bgr, int n_frames,
                             void* workspace, long long workspace_bytes, float* out_frame_feats,
                             float* opt_hidden, void* stream);
+
+/* ---- CLIP vision tower (clip-vit-base-patch32 / clip-vit-large-patch14) ---------------------------- */
+/* model.get_image_features(pixel_values) of the reference's CLIP branch (extract_vision_huggingface.py:
+ * 114-122; HF modeling_clip.py): patch embedding (no bias) + class / position embeddings, pre_layrnorm,
+ * pre-LN layers with quick_gelu, post_layernorm of the class token, visual_projection. */
+typedef struct MerClipVisionModel {
+  int n_layers;
+  float ln_eps;        /* 1e-5 */
+  int hidden, ffn, heads, patch, image, proj_dim; /* 768/3072/12/32/224/512 or 1024/4096/16/14/224/768 */
+  int kpad;            /* columns of patch_w: 3*patch*patch rounded up to a multiple of 32 (zero-filled) */
+  int gemm_mode;       /* MER_GEMM_F16 (<= 249 tokens per frame) or MER_GEMM_TF32: format of the layer weights */
+  float mean[3], std[3];  /* CLIPImageProcessor image_mean / image_std (RGB) */
+  const float* patch_w;   /* [hidden, kpad] conv weight flattened (c, ph, pw), tf32-rounded */
+  const float* cls_pos0;  /* [hidden] class_embedding + position_embedding[0] */
+  const float* pos_rest;  /* [(image/patch)^2, hidden] position_embedding[1:] */
+  const float* pre_ln_g;  /* pre_layrnorm */
+  const float* pre_ln_b;
+  const float* post_ln_g; /* post_layernorm */
+  const float* post_ln_b;
+  const float* proj_w;    /* visual_projection.weight [proj_dim, hidden], tf32-rounded */
+  const MerLayerWeights* layers;
+} MerClipVisionModel;
+
+MER_API long long mer_clip_vision_workspace_bytes(const MerClipVisionModel* model, int n_frames);
+
+/* frames: uint8 [n_frames, H, W, 3] BGR already resized so that the shorter edge is `image` (mer_resize_u8,
+ * bicubic); the image x image window at (crop_y0, crop_x0) is the processor's center crop.  Does BGR->RGB,
+ * x/255, (x - mean) / std, the tower and the projection.  out_embeds: [n_frames, proj_dim].
+ * opt_hidden: NULL or [(n_layers+1), n_frames*tokens, hidden] (hidden state 0 = pre_layrnorm output). */
+MER_API int mer_clip_vision_forward(const MerClipVisionModel* model, const uint8_t* frames_bgr, int n_frames,
+                                    int H, int W, int crop_y0, int crop_x0, void* workspace,
+                                    long long workspace_bytes, float* out_embeds, float* opt_hidden, void* stream);
 
 /* ---- HuBERT-base audio encoder ------------------------------------------------------------------ */
 typedef struct MerHubertModel {

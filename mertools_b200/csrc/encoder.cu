@@ -66,6 +66,7 @@ int mer_run_stack(const MerStackArgs& a, cudaStream_t stream) {
   const int HEADS = a.heads > 0 ? a.heads : ::HEADS;
   const int DQKV = 3 * D;
   MER_REQUIRE(HEADS * 64 == D, "mer_run_stack: heads %d x 64 != hidden %d", HEADS, D);
+  const int ACT = a.quick_gelu ? MER_EPI_QUICK_GELU : MER_EPI_GELU;  // FC1 activation
   const size_t hs_bytes = (size_t)M * D * sizeof(float);
   if (a.opt_hidden && !a.hidden0_done) MER_CUDA_CHECK(cudaMemcpyAsync(a.opt_hidden, a.x, hs_bytes, cudaMemcpyDeviceToDevice, stream));
   for (int l = 0; l < a.n_layers; ++l) {
@@ -92,7 +93,7 @@ int mer_run_stack(const MerStackArgs& a, cudaStream_t stream) {
       MER_TRY(linear(a.mode, xn16, w.w_o, w.b_o, a.x, a.x, M, D, D, 0, stream));
       MER_TRY(mer_layernorm_launch(a.x, w.ln2_g, w.ln2_b, xn16, nullptr, nullptr, M, D, a.eps, MER_LN_OUT_F16,
                                    stream));
-      MER_TRY(linear(a.mode, xn16, w.w_fc1, w.b_fc1, nullptr, h16, M, DFF, D, MER_EPI_GELU | MER_EPI_OUT_F16,
+      MER_TRY(linear(a.mode, xn16, w.w_fc1, w.b_fc1, nullptr, h16, M, DFF, D, ACT | MER_EPI_OUT_F16,
                      stream));
       MER_TRY(linear(a.mode, h16, w.w_fc2, w.b_fc2, a.x, a.x, M, D, DFF, 0, stream));
     } else if (a.pre_ln) {
@@ -106,7 +107,7 @@ int mer_run_stack(const MerStackArgs& a, cudaStream_t stream) {
       MER_TRY(linear(a.mode, a.xn, w.w_o, w.b_o, a.x, a.x, M, D, D, 0, stream));
       MER_TRY(mer_layernorm_launch(a.x, w.ln2_g, w.ln2_b, split ? nullptr : a.xn, split ? a.xn : nullptr,
                                    nullptr, M, D, a.eps, MER_LN_ROUND_TF32, stream));
-      MER_TRY(linear(a.mode, a.xn, w.w_fc1, w.b_fc1, nullptr, a.h, M, DFF, D, MER_EPI_GELU | opnd, stream));
+      MER_TRY(linear(a.mode, a.xn, w.w_fc1, w.b_fc1, nullptr, a.h, M, DFF, D, ACT | opnd, stream));
       MER_TRY(linear(a.mode, a.h, w.w_fc2, w.b_fc2, a.x, a.x, M, D, DFF, 0, stream));
     } else {
       // x = LN1(x + Wo * Attn(x));  x = LN2(x + W2 * GELU(W1 * x)).
@@ -225,6 +226,123 @@ int mer_vit_forward(const MerVitModel* m, const uint8_t* frames_bgr, int n_frame
   a.opt_hidden = opt_hidden;
   MER_TRY(mer_run_stack(a, stream));
   MER_TRY(mer_segment_reduce_launch(x, offsets, offsets + 1, n_frames, D, MER_SEG_SUM, out_frame_feats, stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CLIP vision tower
+// ------------------------------------------------------------------------------------------------
+struct ClipPlan { long long M, vt_ld, off_x, off_xn, off_qkv, off_h, off_vt, off_cu, total; int tokens, P; };
+
+static ClipPlan clip_plan(const MerClipVisionModel* m, int n_frames) {
+  ClipPlan p;
+  const int g = m->image / m->patch;
+  p.P = g * g;
+  p.tokens = p.P + 1;
+  p.M = (long long)n_frames * p.tokens;
+  p.vt_ld = (p.M + 7) & ~7ll;
+  auto al = [](long long x) { return (x + 255) & ~255ll; };
+  const long long D = m->hidden;
+  long long o = 0;
+  p.off_x = o;   o += al(p.M * D * 4);
+  p.off_xn = o;  o += al(p.M * D * 4);
+  p.off_qkv = o; o += al(p.M * 3 * D * 4);
+  long long hb = p.M * (long long)m->ffn * 4, pb = (long long)n_frames * p.P * m->kpad * 4;
+  p.off_h = o;   o += al(hb > pb ? hb : pb);   // FFN buffer; the patch operand lives here first
+  p.off_vt = o;  o += al(D * p.vt_ld * 4);
+  p.off_cu = o;  o += al(((long long)n_frames + 1) * 4);
+  p.total = o;
+  return p;
+}
+
+long long mer_clip_vision_workspace_bytes(const MerClipVisionModel* m, int n_frames) {
+  if (!m || m->patch <= 0 || m->image % m->patch) return -1;
+  return clip_plan(m, n_frames).total;
+}
+
+int mer_clip_vision_forward(const MerClipVisionModel* m, const uint8_t* frames_bgr, int n_frames, int H, int W,
+                            int crop_y0, int crop_x0, void* workspace, long long workspace_bytes,
+                            float* out_embeds, float* opt_hidden, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MER_REQUIRE(m && frames_bgr && workspace && out_embeds && n_frames > 0, "mer_clip_vision_forward: bad operands");
+  const int D = m->hidden;
+  MER_REQUIRE((D == 768 || D == 1024) && m->heads * 64 == D && m->ffn % 128 == 0 && m->proj_dim % 128 == 0 &&
+                  m->image % m->patch == 0 && m->kpad % 32 == 0 && m->kpad >= 3 * m->patch * m->patch,
+              "mer_clip_vision_forward: unsupported dims (hidden %d, heads %d, ffn %d, proj %d, patch %d)", D,
+              m->heads, m->ffn, m->proj_dim, m->patch);
+  MER_REQUIRE(m->gemm_mode == MER_GEMM_TF32 || m->gemm_mode == MER_GEMM_F16, "mer_clip_vision_forward: gemm_mode");
+  const ClipPlan p = clip_plan(m, n_frames);
+  MER_REQUIRE(workspace_bytes >= p.total, "mer_clip_vision_forward: workspace %lld B < required %lld B",
+              workspace_bytes, p.total);
+  MER_REQUIRE(p.M < (1ll << 31) / 4, "mer_clip_vision_forward: too many frames");
+  char* ws = static_cast<char*>(workspace);
+  float* x = reinterpret_cast<float*>(ws + p.off_x);
+  float* xn = reinterpret_cast<float*>(ws + p.off_xn);
+  float* qkv = reinterpret_cast<float*>(ws + p.off_qkv);
+  float* h = reinterpret_cast<float*>(ws + p.off_h);
+  float* vt = reinterpret_cast<float*>(ws + p.off_vt);
+  int* offsets = reinterpret_cast<int*>(ws + p.off_cu);
+  float* a_patch = h;
+  MER_TRY(mer_iota_offsets_launch(offsets, n_frames, p.tokens, stream));
+  MER_TRY(mer_patchify_generic_launch(frames_bgr, n_frames, H, W, crop_y0, crop_x0, m->image, m->patch, m->kpad,
+                                      m->mean, m->std, a_patch, stream));
+  MER_TRY(mer_cls_rows_generic_launch(m->cls_pos0, x, n_frames, p.tokens, D, stream));
+  {
+    MerGemmDesc g;
+    memset(&g, 0, sizeof(g));
+    g.A = a_patch;
+    g.W = m->patch_w;
+    g.rows_per_batch = p.P;
+    g.a_rows_dim = p.P;
+    g.batches = n_frames;
+    g.N = D;
+    g.K_inner = m->kpad;
+    g.taps = 1;
+    g.P = 1;
+    g.a_phase_stride = m->kpad;
+    g.a_row_stride = m->kpad;
+    g.a_batch_stride = (long long)p.P * m->kpad;
+    g.ep.res = m->pos_rest;  // + position_embedding[1:], same for every frame (no conv bias in CLIP)
+    g.ep.res_bstride = 0;
+    g.ep.out = x;
+    g.ep.out_bstride = p.tokens;
+    g.ep.out_row0 = 1;
+    g.ep.ld_out = D;
+    g.ep.ld_res = D;
+    g.mode = MER_GEMM_TF32;
+    MER_TRY(mer_gemm_launch(&g, stream));
+  }
+  MER_TRY(mer_layernorm_launch(x, m->pre_ln_g, m->pre_ln_b, x, nullptr, nullptr, p.M, D, m->ln_eps, 0, stream));
+  MerStackArgs a;
+  memset(&a, 0, sizeof(a));
+  a.layers = m->layers;
+  a.n_layers = m->n_layers;
+  a.pre_ln = 1;
+  a.mode = m->gemm_mode;
+  a.dim = D;
+  a.ffn = m->ffn;
+  a.heads = m->heads;
+  a.quick_gelu = 1;
+  a.eps = m->ln_eps;
+  a.tokens = p.M;
+  a.cu_seqlens = offsets;
+  a.n_seq = n_frames;
+  a.max_seqlen = p.tokens;
+  a.x = x;
+  a.xn = xn;
+  a.qkv = qkv;
+  a.h = h;
+  a.vt = vt;
+  a.vt_ld = p.vt_ld;
+  a.opt_hidden = opt_hidden;
+  MER_TRY(mer_run_stack(a, stream));
+  // class-token rows -> post_layernorm (tf32-rounded: GEMM operand) -> visual_projection
+  float* cls = qkv;                        // [n_frames, D]   (the QKV buffer is dead now)
+  float* pooled = qkv + (long long)n_frames * D;
+  MER_TRY(mer_gather_rows_launch(x, 0, p.tokens, n_frames, D, cls, stream));
+  MER_TRY(mer_layernorm_launch(cls, m->post_ln_g, m->post_ln_b, pooled, nullptr, nullptr, n_frames, D, m->ln_eps,
+                               MER_LN_ROUND_TF32, stream));
+  MER_TRY(linear(MER_GEMM_TF32, pooled, m->proj_w, nullptr, nullptr, out_embeds, n_frames, m->proj_dim, D, 0, stream));
   return 0;
 }
 

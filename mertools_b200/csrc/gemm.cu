@@ -92,6 +92,7 @@ template <int GELU>
 __device__ __forceinline__ float epi_act(float v) {
   if (GELU == 1) return gelu_erf_fast(v);
   if (GELU == 2) return gelu_erf(v);
+  if (GELU == 3) return quick_gelu_fast(v);
   return v;
 }
 
@@ -458,7 +459,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int p_row = lane >> 2;
     int as = 0;
     uint32_t aphase = 0;
-    const int gelu_kind = (ep.flags & MER_EPI_GELU) ? ((ep.flags & MER_EPI_GELU_LIBM) ? 2 : 1) : 0;
+    const int gelu_kind = (ep.flags & MER_EPI_QUICK_GELU) ? 3
+                          : (ep.flags & MER_EPI_GELU) ? ((ep.flags & MER_EPI_GELU_LIBM) ? 2 : 1) : 0;
     const int out_kind = (ep.flags & MER_EPI_OUT_F16) ? 3 : (ep.flags & MER_EPI_SPLIT_BF16) ? 2 :
                          ((ep.flags & MER_EPI_ROUND_TF32) ? 1 : 0);
     const int kind = gelu_kind * 4 + out_kind;
@@ -501,7 +503,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
       };
       if (tl.res_lane != nullptr) {  // warp-uniform; each variant is straight-line code
-        if (gelu_kind != 0) epi_tile<CH, 1, 0, true>(tl, ep, stg, lane, release);  // res + GELU(acc + bias)
+        if (gelu_kind != 0) epi_tile<CH, 1, 0, true>(tl, ep, stg, lane, release);  // res + GELU(acc + bias), erf form
         else if (out_kind == 1) epi_tile<CH, 0, 1, true>(tl, ep, stg, lane, release);
         else epi_tile<CH, 0, 0, true>(tl, ep, stg, lane, release);
       } else {
@@ -517,7 +519,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           case 8: epi_tile<CH, 2, 0, false>(tl, ep, stg, lane, release); break;
           case 9: epi_tile<CH, 2, 1, false>(tl, ep, stg, lane, release); break;
           case 10: epi_tile<CH, 2, 2, false>(tl, ep, stg, lane, release); break;
-          default: epi_tile<CH, 2, 3, false>(tl, ep, stg, lane, release); break;
+          case 11: epi_tile<CH, 2, 3, false>(tl, ep, stg, lane, release); break;
+          case 13: epi_tile<CH, 3, 1, false>(tl, ep, stg, lane, release); break;   // quick-GELU: the operand
+          case 15: epi_tile<CH, 3, 3, false>(tl, ep, stg, lane, release); break;   // formats FC1 can feed
+          default: epi_tile<CH, 3, 0, false>(tl, ep, stg, lane, release); break;
         }
       }
       if (++as == 2) {
@@ -632,6 +637,9 @@ int mer_gemm_launch(const MerGemmDesc* g, cudaStream_t stream) {
   MER_REQUIRE(!(g->ep.res && (g->ep.flags & MER_EPI_GELU) &&
                 (g->ep.flags & (MER_EPI_ROUND_TF32 | MER_EPI_GELU_LIBM))),
               "mer_gemm: residual + GELU is available with the polynomial GELU and a plain fp32 output");
+  MER_REQUIRE(!((g->ep.flags & MER_EPI_QUICK_GELU) &&
+                ((g->ep.flags & (MER_EPI_GELU | MER_EPI_SPLIT_BF16)) || g->ep.res || g->ep.vt)),
+              "mer_gemm: quick-GELU comes alone (fp32, tf32 or fp16 output; no residual / split / V^T)");
   MER_REQUIRE(g->a_col_group == 0 || g->force_block_n == 128 || g->force_block_n == 256,
               "mer_gemm: a_col_group needs force_block_n (the weights are built for one block width)");
   MER_REQUIRE(!(g->ep.vt && (g->ep.flags & MER_EPI_GELU)), "mer_gemm: GELU + transposed side output is not supported");

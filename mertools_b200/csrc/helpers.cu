@@ -80,6 +80,46 @@ resize_pass_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, lo
   d[2] = (uint8_t)min(max(a2 >> 22, 0), 255);
 }
 
+// Generic patch gather for the CLIP vision towers: uint8 BGR HWC frames [n, H, W, 3] (a size x size window
+// at (y0, x0): the processor's center crop) -> A[(n, py, px), c*p*p + i*p + j] = (frame[..., 2-c] / 255 -
+// mean[c]) / std[c], tf32-rounded; columns 3*p*p .. kpad-1 are zero (the GEMM's K is a multiple of 32).
+// One thread per output element; consecutive threads write consecutive columns.
+__global__ void __launch_bounds__(256)
+patchify_generic_kernel(const uint8_t* __restrict__ frames, int H, int W, int y0, int x0, int size, int p,
+                        int kpad, float m0, float m1, float m2, float s0, float s1, float s2,
+                        float* __restrict__ a, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int k = (int)(idx % kpad);
+  const long long patch = idx / kpad;
+  const int g = size / p;
+  const int px = (int)(patch % g);
+  const int py = (int)((patch / g) % g);
+  const long long n = patch / ((long long)g * g);
+  float v = 0.f;
+  if (k < 3 * p * p) {
+    const int c = k / (p * p), r = k - c * p * p, i = r / p, j = r - i * p;
+    const float pix = (float)frames[((n * H + (y0 + py * p + i)) * W + (x0 + px * p + j)) * 3 + (2 - c)];
+    const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), std = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    v = round_tf32((pix * 0.00392156862745098f - mean) / std);
+  }
+  a[idx] = v;
+}
+
+// x[n * tokens, :] = row  (class-token row: class embedding + position embedding 0)
+__global__ void cls_rows_generic_kernel(const float* __restrict__ row, float* __restrict__ x, int tokens, int dim) {
+  float* dst = x + (long long)blockIdx.x * tokens * dim;
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) dst[i] = __ldg(row + i);
+}
+
+// out[i, :] = in[(first + i * step), :]
+__global__ void gather_rows_kernel(const float* __restrict__ in, long long first, long long step, int dim,
+                                   float* __restrict__ out) {
+  const float* src = in + (first + (long long)blockIdx.x * step) * dim;
+  float* dst = out + (long long)blockIdx.x * dim;
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) dst[i] = src[i];
+}
+
 // x[n, 0, :] = cls_token + position_embeddings[0]  (HF ViTEmbeddings, modeling_vit.py:117-124)
 __global__ void vit_cls_rows_kernel(const float* __restrict__ cls_pos0, float* __restrict__ x,
                                     int n_frames) {
@@ -197,6 +237,36 @@ int mer_vit_cls_rows_launch(const float* cls_pos0, float* x, int n_frames, cudaS
   return 0;
 }
 
+int mer_patchify_generic_launch(const uint8_t* frames, int n, int H, int W, int y0, int x0, int size, int patch,
+                                int kpad, const float mean[3], const float std[3], float* a, cudaStream_t stream) {
+  MER_REQUIRE(size % patch == 0 && kpad >= 3 * patch * patch && y0 >= 0 && x0 >= 0 && y0 + size <= H && x0 + size <= W,
+              "mer_patchify_generic: bad geometry");
+  const long long g = size / patch;
+  const long long total = (long long)n * g * g * kpad;
+  patchify_generic_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      frames, H, W, y0, x0, size, patch, kpad, mean[0], mean[1], mean[2], std[0], std[1], std[2], a, total);
+  MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
+  return 0;
+}
+
+int mer_cls_rows_generic_launch(const float* row, float* x, int n_frames, int tokens, int dim, cudaStream_t stream) {
+  if (n_frames <= 0) return 0;
+  cls_rows_generic_kernel<<<n_frames, 256, 0, stream>>>(row, x, tokens, dim);
+  MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
+  return 0;
+}
+
+int mer_gather_rows_launch(const float* in, long long first, long long step, int n, int dim, float* out,
+                           cudaStream_t stream) {
+  if (n <= 0) return 0;
+  gather_rows_kernel<<<n, 256, 0, stream>>>(in, first, step, dim, out);
+  MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
+  return 0;
+}
+
 int mer_segment_reduce_launch(const float* in, const int* begins, const int* ends, int n_seg,
                               int dim, int mode, float* out, cudaStream_t stream) {
   MER_REQUIRE(in && begins && ends && out, "mer_segment_reduce: null operand");
@@ -235,16 +305,25 @@ extern "C" int mer_segment_reduce(const float* in, const int32_t* begins, const 
 
 // ---- Pillow bilinear resize (uint8) ----------------------------------------------------------------
 namespace {
-struct ResizeTable { int in, out, ksize; int* d_lo; int* d_cnt; int* d_kk; };
+struct ResizeTable { int in, out, filter, ksize; int* d_lo; int* d_cnt; int* d_kk; };
 std::vector<ResizeTable> g_resize_tables;  // per process (= per device: one process per GPU)
 
-// Pillow precompute_coeffs + normalize_coeffs_8bpc for the bilinear filter, in double as Pillow does
-int resize_table(int in_size, int out_size, const ResizeTable** res, cudaStream_t stream) {
+// Pillow's filters (Resample.c): bilinear (support 1) and bicubic with a = -0.5 (support 2)
+double pil_filter(int filter, double x) {
+  if (filter == 0) return x < 1.0 ? 1.0 - x : 0.0;
+  const double a = -0.5;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+  if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+  return 0.0;
+}
+
+// Pillow precompute_coeffs + normalize_coeffs_8bpc, in double as Pillow does.  filter: 0 bilinear, 1 bicubic
+int resize_table(int in_size, int out_size, int filter, const ResizeTable** res, cudaStream_t stream) {
   for (auto& t : g_resize_tables)
-    if (t.in == in_size && t.out == out_size) { *res = &t; return 0; }
+    if (t.in == in_size && t.out == out_size && t.filter == filter) { *res = &t; return 0; }
   const double scale = (double)in_size / out_size;
   const double filterscale = scale < 1.0 ? 1.0 : scale;
-  const double support = 1.0 * filterscale;
+  const double support = (filter == 0 ? 1.0 : 2.0) * filterscale;
   const int ksize = (int)ceil(support) * 2 + 1;
   std::vector<int> lo(out_size), cnt(out_size), kk((size_t)out_size * ksize, 0);
   std::vector<double> w(ksize);
@@ -260,17 +339,17 @@ int resize_table(int in_size, int out_size, const ResizeTable** res, cudaStream_
     for (int x = 0; x < n; ++x) {
       double v = (x + a - center + 0.5) * ss;
       if (v < 0.0) v = -v;
-      w[x] = v < 1.0 ? 1.0 - v : 0.0;
+      w[x] = pil_filter(filter, v);
       tot += w[x];
     }
     for (int x = 0; x < n; ++x) {
       const double k = tot != 0.0 ? w[x] / tot : w[x];
-      kk[(size_t)xx * ksize + x] = (int)(k * (double)(1 << 22) + 0.5);  // weights are >= 0
+      kk[(size_t)xx * ksize + x] = (int)(k * (double)(1 << 22) + (k < 0 ? -0.5 : 0.5));
     }
     lo[xx] = a;
     cnt[xx] = n;
   }
-  ResizeTable t{in_size, out_size, ksize, nullptr, nullptr, nullptr};
+  ResizeTable t{in_size, out_size, filter, ksize, nullptr, nullptr, nullptr};
   MER_CUDA_CHECK(cudaMalloc(&t.d_lo, out_size * sizeof(int)));
   MER_CUDA_CHECK(cudaMalloc(&t.d_cnt, out_size * sizeof(int)));
   MER_CUDA_CHECK(cudaMalloc(&t.d_kk, kk.size() * sizeof(int)));
@@ -290,20 +369,29 @@ extern "C" long long mer_resize_workspace_bytes(int n, int H, int W, int OH, int
   return (H != 0 && W != OW) ? (long long)n * H * OW * 3 : 0;  // the horizontally resampled frames
 }
 
+extern "C" int mer_resize_u8(const uint8_t* in, int n, int H, int W, uint8_t* out, int OH, int OW, int filter,
+                             void* workspace, void* stream_);
+
 extern "C" int mer_resize_bilinear_u8(const uint8_t* in, int n, int H, int W, uint8_t* out, int OH, int OW,
                                       void* workspace, void* stream_) {
+  return mer_resize_u8(in, n, H, W, out, OH, OW, 0, workspace, stream_);
+}
+
+extern "C" int mer_resize_u8(const uint8_t* in, int n, int H, int W, uint8_t* out, int OH, int OW, int filter,
+                             void* workspace, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  MER_REQUIRE(in && out && n > 0 && H > 0 && W > 0 && OH > 0 && OW > 0, "mer_resize_bilinear_u8: bad arguments");
+  MER_REQUIRE(in && out && n > 0 && H > 0 && W > 0 && OH > 0 && OW > 0 && (filter == 0 || filter == 1),
+              "mer_resize_u8: bad arguments");
   const bool horiz = W != OW, vert = H != OH;
   if (!horiz && !vert) {
     MER_CUDA_CHECK(cudaMemcpyAsync(out, in, (size_t)n * H * W * 3, cudaMemcpyDeviceToDevice, stream));
     return 0;
   }
-  MER_REQUIRE(!(horiz && vert) || workspace, "mer_resize_bilinear_u8: workspace needed for a two-pass resize");
+  MER_REQUIRE(!(horiz && vert) || workspace, "mer_resize_u8: workspace needed for a two-pass resize");
   const uint8_t* src = in;
   if (horiz) {
     const ResizeTable* t;
-    if (int rc = resize_table(W, OW, &t, stream)) return rc;
+    if (int rc = resize_table(W, OW, filter, &t, stream)) return rc;
     uint8_t* dst = vert ? static_cast<uint8_t*>(workspace) : out;
     const long long total = (long long)n * H * OW;
     resize_pass_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, dst, total, H, W, OW, t->d_lo,
@@ -314,7 +402,7 @@ extern "C" int mer_resize_bilinear_u8(const uint8_t* in, int n, int H, int W, ui
   }
   if (vert) {
     const ResizeTable* t;
-    if (int rc = resize_table(H, OH, &t, stream)) return rc;
+    if (int rc = resize_table(H, OH, filter, &t, stream)) return rc;
     const long long total = (long long)n * OH * OW;
     resize_pass_kernel<0><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, out, total, H, OW, OH, t->d_lo,
                                                                                t->d_cnt, t->d_kk, t->ksize);

@@ -402,6 +402,14 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return fmaf(fabsf(hx), erf_abs, hx);           // x/2 * (1 + sign(x) erf(|x|/sqrt 2))
 }
 
+// CLIP's quick_gelu: x * sigmoid(1.702 x), with ex2.approx / rcp.approx (|rel err| ~2e-7)
+__device__ __forceinline__ float quick_gelu_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.702f * 1.4426950408889634f * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -43,6 +43,11 @@ int mer_attention_f16_launch(const void* qkv16, const void* vt16, long long vt_l
 int mer_vit_patchify_launch(const uint8_t* frames_bgr, int n_frames, float* a_patches,
                             cudaStream_t stream);
 int mer_vit_cls_rows_launch(const float* cls_pos0, float* x, int n_frames, cudaStream_t stream);
+int mer_patchify_generic_launch(const uint8_t* frames, int n, int H, int W, int y0, int x0, int size, int patch,
+                                int kpad, const float mean[3], const float std[3], float* a, cudaStream_t stream);
+int mer_cls_rows_generic_launch(const float* row, float* x, int n_frames, int tokens, int dim, cudaStream_t stream);
+int mer_gather_rows_launch(const float* in, long long first, long long step, int n, int dim, float* out,
+                           cudaStream_t stream);
 int mer_segment_reduce_launch(const float* in, const int* begins, const int* ends, int n_seg,
                               int dim, int mode, float* out, cudaStream_t stream);
 int mer_bert_embed_launch(const int* ids, const int* pos_ids, const float* word, const float* pos,
@@ -71,6 +76,7 @@ struct MerStackArgs {
   int pre_ln;
   int mode;                  // MER_GEMM_TF32 | MER_GEMM_BF16X3 | MER_GEMM_F16 (pre-LN only)
   int dim, ffn, heads;       // 0 = 768 / 3072 / 12
+  int quick_gelu;            // FC1 activation: x * sigmoid(1.702 x) (CLIP) instead of erf-GELU
   float eps;
   long long tokens;          // total packed tokens (rows of x)
   const int* cu_seqlens;     // device [n_seq+1]

@@ -138,6 +138,108 @@ class VitEncoder:
 VIT_PROBE = "encoder.layer.{i}.layernorm_before.weight"
 
 
+class MerClipVisionModel(C.Structure):
+    _fields_ = [("n_layers", C.c_int), ("ln_eps", C.c_float), ("hidden", C.c_int), ("ffn", C.c_int),
+                ("heads", C.c_int), ("patch", C.c_int), ("image", C.c_int), ("proj_dim", C.c_int),
+                ("kpad", C.c_int), ("gemm_mode", C.c_int), ("mean", C.c_float * 3), ("std", C.c_float * 3),
+                ("patch_w", C.c_void_p), ("cls_pos0", C.c_void_p), ("pos_rest", C.c_void_p),
+                ("pre_ln_g", C.c_void_p), ("pre_ln_b", C.c_void_p), ("post_ln_g", C.c_void_p),
+                ("post_ln_b", C.c_void_p), ("proj_w", C.c_void_p), ("layers", C.POINTER(W.MerLayerWeights))]
+
+
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+class ClipVisionEncoder:
+    """CLIP vision tower + projection (HF ``CLIPModel.get_image_features``) for clip-vit-base-patch32 and
+    clip-vit-large-patch14, including the CLIPImageProcessor steps (bicubic resize of the shorter edge to
+    224, center crop, rescale, normalise) on the device.
+
+    Reference: MERBench/feature_extraction/visual/extract_vision_huggingface.py:114-122."""
+
+    def __init__(self, state_dict, device="cuda", ln_eps=1e-5, image=224):
+        L.check(L.lib().mer_check_device())
+        sd = W._np(state_dict)
+        self.device = torch.device(device)
+        pk = self.pk = W.Packed(self.device)
+        v = "vision_model."
+        self.n_layers = W.count_layers(sd, v + "encoder.layers.{i}.layer_norm1.weight")
+        pw = sd[v + "embeddings.patch_embedding.weight"]
+        D, _, p, _ = pw.shape
+        pos = sd[v + "embeddings.position_embedding.weight"]
+        assert D in (768, 1024) and image % p == 0 and pos.shape == ((image // p) ** 2 + 1, D), (pw.shape, pos.shape)
+        self.hidden, self.patch, self.image = int(D), int(p), image
+        self.tokens = (image // p) ** 2 + 1
+        self.proj_dim = int(sd["visual_projection.weight"].shape[0])
+        ffn = int(sd[v + "encoder.layers.0.mlp.fc1.weight"].shape[0])
+        kpad = (3 * p * p + 31) // 32 * 32
+        wflat = np.zeros((D, kpad), np.float32)
+        wflat[:, :3 * p * p] = pw.reshape(D, 3 * p * p)
+        # fp16 operands need the fp16 attention kernel (<= 249 tokens per frame): B/32 yes, L/14 (257) runs TF32
+        self.precision = "f16" if self.tokens <= 249 else "tf32"
+        f16 = self.precision == "f16"
+        self.layers = W.pack_layers(sd, W.CLIP_NAMES, self.n_layers, pk, f16=f16)
+        m = MerClipVisionModel()
+        m.n_layers, m.ln_eps = self.n_layers, ln_eps
+        m.hidden, m.ffn, m.heads, m.patch, m.image, m.proj_dim, m.kpad = D, ffn, D // 64, p, image, self.proj_dim, kpad
+        m.gemm_mode = L.MER_GEMM_F16 if f16 else L.MER_GEMM_TF32
+        m.mean = (C.c_float * 3)(*CLIP_MEAN)
+        m.std = (C.c_float * 3)(*CLIP_STD)
+        m.patch_w = pk.keep(wflat, tf32=True).data_ptr()
+        m.cls_pos0 = pk.keep(sd[v + "embeddings.class_embedding"].reshape(D) + pos[0]).data_ptr()
+        m.pos_rest = pk.keep(pos[1:]).data_ptr()
+        m.pre_ln_g = pk.keep(sd[v + "pre_layrnorm.weight"]).data_ptr()
+        m.pre_ln_b = pk.keep(sd[v + "pre_layrnorm.bias"]).data_ptr()
+        m.post_ln_g = pk.keep(sd[v + "post_layernorm.weight"]).data_ptr()
+        m.post_ln_b = pk.keep(sd[v + "post_layernorm.bias"]).data_ptr()
+        m.proj_w = pk.keep(sd["visual_projection.weight"], tf32=True).data_ptr()
+        m.layers = self.layers
+        self.model = m
+        self.ws, self.ws_resize = _Workspace(self.device), _Workspace(self.device)
+        lib = L.lib()
+        lib.mer_clip_vision_workspace_bytes.restype = C.c_longlong
+        lib.mer_clip_vision_workspace_bytes.argtypes = [C.POINTER(MerClipVisionModel), C.c_int]
+        lib.mer_resize_workspace_bytes.restype = C.c_longlong
+        lib.mer_resize_workspace_bytes.argtypes = [C.c_int] * 5
+        self._fwd = L.declare("mer_clip_vision_forward", [C.POINTER(MerClipVisionModel), C.c_void_p, C.c_int, C.c_int,
+                                                          C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong,
+                                                          C.c_void_p, C.c_void_p, C.c_void_p])
+        self._resize = L.declare("mer_resize_u8", [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                                   C.c_int, C.c_int, C.c_void_p, C.c_void_p])
+
+    def preprocess_geometry(self, h, w):
+        """(new_h, new_w, crop_y0, crop_x0) of CLIPImageProcessor: shorter edge -> image, center crop."""
+        size = self.image
+        short, long = (w, h) if w <= h else (h, w)
+        new_long = int(size * long / short)
+        nh, nw = (new_long, size) if w <= h else (size, new_long)
+        return nh, nw, (nh - size) // 2, (nw - size) // 2
+
+    def frame_features(self, frames_bgr_u8: torch.Tensor, return_hidden=False):
+        """frames: uint8 CUDA [N, H, W, 3] (BGR).  Returns image embeddings [N, proj_dim] fp32 (CUDA)."""
+        assert frames_bgr_u8.dtype == torch.uint8 and frames_bgr_u8.is_cuda and frames_bgr_u8.dim() == 4
+        frames = frames_bgr_u8.contiguous()
+        n, h, w, _ = frames.shape
+        nh, nw, y0, x0 = self.preprocess_geometry(h, w)
+        if (nh, nw) != (h, w):
+            out = torch.empty(n, nh, nw, 3, dtype=torch.uint8, device=self.device)
+            need = L.lib().mer_resize_workspace_bytes(n, h, w, nh, nw)
+            ws = self.ws_resize.get(max(int(need), 1))
+            L.check(self._resize(L.ptr(frames), n, h, w, L.ptr(out), nh, nw, 1, L.ptr(ws), L.stream_ptr()))
+            frames = out
+        need = L.lib().mer_clip_vision_workspace_bytes(C.byref(self.model), n)
+        ws = self.ws.get(need)
+        emb = torch.empty(n, self.proj_dim, dtype=torch.float32, device=self.device)
+        hidden = (torch.empty(self.n_layers + 1, n * self.tokens, self.hidden, dtype=torch.float32, device=self.device)
+                  if return_hidden else None)
+        L.check(self._fwd(C.byref(self.model), L.ptr(frames), n, nh, nw, y0, x0, L.ptr(ws), ws.numel(), L.ptr(emb),
+                          L.ptr(hidden), L.stream_ptr()))
+        if return_hidden:
+            return emb, hidden.view(self.n_layers + 1, n, self.tokens, self.hidden)
+        return emb
+
+
 class MerHubertModel(C.Structure):
     _fields_ = [("n_layers", C.c_int), ("ln_eps", C.c_float), ("conv0_w", C.c_void_p),
                 ("gn_g", C.c_void_p), ("gn_b", C.c_void_p), ("conv_w", C.c_void_p * 6),

@@ -50,7 +50,14 @@ class VisualExtractor:
     """ViT frame encoder + readout over batches of clips."""
 
     def __init__(self, state_dict, device="cuda", max_frames_per_launch=2048):
-        self.enc = VitEncoder(state_dict, device=device)
+        # the CLIP checkpoints of the reference's model list carry a `vision_model.` tower + projection
+        if any(k.startswith("vision_model.") for k in state_dict):
+            from ..encoders import ClipVisionEncoder
+            self.enc = ClipVisionEncoder(state_dict, device=device)
+            self.feature_dim = self.enc.proj_dim
+        else:
+            self.enc = VitEncoder(state_dict, device=device)
+            self.feature_dim = 768
         self.device = self.enc.device
         self.max_frames = max_frames_per_launch
         self._pinned = None
@@ -88,7 +95,7 @@ class VisualExtractor:
         by_size = {}
         for i, f in enumerate(frame_list):
             if len(f) == 0:
-                res[i] = np.zeros((0, 768), np.float32)
+                res[i] = np.zeros((0, self.feature_dim), np.float32)
             else:
                 by_size.setdefault(f.shape[1:3], []).append(i)
         for hw, idxs in by_size.items():
@@ -109,7 +116,7 @@ class VisualExtractor:
         out = []
         for i, f in enumerate(feats):
             sf = save_files[i] if save_files is not None else None
-            out.append(common.save_feature(sf, f.squeeze(), feature_level, 768))
+            out.append(common.save_feature(sf, f.squeeze(), feature_level, self.feature_dim))
         return out
 
 

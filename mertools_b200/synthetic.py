@@ -62,6 +62,36 @@ def vit_state_dict(seed=0, layers=12, scale=1.0):
     return g.sd
 
 
+CLIP_CFGS = dict(b32=dict(hidden=768, heads=12, ffn=3072, layers=12, patch=32, proj=512),
+                 l14=dict(hidden=1024, heads=16, ffn=4096, layers=24, patch=14, proj=768))
+
+
+def clip_vision_state_dict(seed=4, variant="b32", layers=None, scale=1.0, image=224):
+    """Vision-tower keys of ``transformers.CLIPModel`` (clip-vit-base-patch32 / clip-vit-large-patch14):
+    ``vision_model.*`` and ``visual_projection.weight``."""
+    c = CLIP_CFGS[variant]
+    layers = c["layers"] if layers is None else layers
+    g = _Gen(seed)
+    d, p = c["hidden"], c["patch"]
+    v = "vision_model."
+    g.normal(v + "embeddings.class_embedding", (d,), 0.02)
+    g.normal(v + "embeddings.patch_embedding.weight", (d, 3, p, p), 0.02)
+    g.normal(v + "embeddings.position_embedding.weight", ((image // p) ** 2 + 1, d), 0.02)
+    g.ln(v + "pre_layrnorm", d)
+    std = 0.02 * scale
+    for i in range(layers):
+        q = f"{v}encoder.layers.{i}."
+        for n in ("k_proj", "v_proj", "q_proj", "out_proj"):
+            g.linear(q + f"self_attn.{n}", d, d, std)
+        g.ln(q + "layer_norm1", d)
+        g.linear(q + "mlp.fc1", c["ffn"], d, std)
+        g.linear(q + "mlp.fc2", d, c["ffn"], std)
+        g.ln(q + "layer_norm2", d)
+    g.ln(v + "post_layernorm", d)
+    g.normal("visual_projection.weight", (c["proj"], d), 0.03)
+    return g.sd
+
+
 HUBERT_LARGE_CFG = dict(HUBERT_CFG, hidden=1024, heads=16, ffn=4096, layers=24)
 
 

@@ -89,6 +89,17 @@ VIT_NAMES = dict(
     fc2_w="encoder.layer.{i}.output.dense.weight", fc2_b="encoder.layer.{i}.output.dense.bias",
 )
 
+CLIP_NAMES = dict(
+    ln1_g="vision_model.encoder.layers.{i}.layer_norm1.weight", ln1_b="vision_model.encoder.layers.{i}.layer_norm1.bias",
+    q_w="vision_model.encoder.layers.{i}.self_attn.q_proj.weight", q_b="vision_model.encoder.layers.{i}.self_attn.q_proj.bias",
+    k_w="vision_model.encoder.layers.{i}.self_attn.k_proj.weight", k_b="vision_model.encoder.layers.{i}.self_attn.k_proj.bias",
+    v_w="vision_model.encoder.layers.{i}.self_attn.v_proj.weight", v_b="vision_model.encoder.layers.{i}.self_attn.v_proj.bias",
+    o_w="vision_model.encoder.layers.{i}.self_attn.out_proj.weight", o_b="vision_model.encoder.layers.{i}.self_attn.out_proj.bias",
+    ln2_g="vision_model.encoder.layers.{i}.layer_norm2.weight", ln2_b="vision_model.encoder.layers.{i}.layer_norm2.bias",
+    fc1_w="vision_model.encoder.layers.{i}.mlp.fc1.weight", fc1_b="vision_model.encoder.layers.{i}.mlp.fc1.bias",
+    fc2_w="vision_model.encoder.layers.{i}.mlp.fc2.weight", fc2_b="vision_model.encoder.layers.{i}.mlp.fc2.bias",
+)
+
 HUBERT_NAMES = dict(
     q_w="encoder.layers.{i}.attention.q_proj.weight", q_b="encoder.layers.{i}.attention.q_proj.bias",
     k_w="encoder.layers.{i}.attention.k_proj.weight", k_b="encoder.layers.{i}.attention.k_proj.bias",

@@ -84,6 +84,33 @@ def vit_hidden_states(sd, pixel_values, layers=12, heads=12, eps=1e-12, dtype=to
 # ------------------------------------------------------------------------------------------------
 # HuBERT  (HF models/hubert/modeling_hubert.py)
 # ------------------------------------------------------------------------------------------------
+def clip_image_features(sd, pixel_values, layers=12, heads=12, eps=1e-5, dtype=torch.float32):
+    """``CLIPModel.get_image_features(pixel_values)`` (extract_vision_huggingface.py:114-122; HF
+    modeling_clip.py: CLIPVisionEmbeddings, pre_layrnorm, pre-LN CLIPEncoderLayer with quick_gelu,
+    post_layernorm on the class token, visual_projection).  sd: CLIPModel state_dict names
+    (``vision_model.*``, ``visual_projection.weight``).  Returns (image_embeds [N, proj], hidden states)."""
+    v = "vision_model."
+    w = _t(sd, v + "embeddings.patch_embedding.weight", dtype)
+    x = F.conv2d(pixel_values.to(dtype), w, None, stride=w.shape[-1]).flatten(2).transpose(1, 2)
+    cls = _t(sd, v + "embeddings.class_embedding", dtype).expand(x.shape[0], 1, -1)
+    x = torch.cat([cls, x], dim=1) + _t(sd, v + "embeddings.position_embedding.weight", dtype)[None]
+    x = _ln(x, sd, v + "pre_layrnorm", eps, dtype)
+    hs = [x]
+    for i in range(layers):
+        p = f"{v}encoder.layers.{i}."
+        y = _ln(x, sd, p + "layer_norm1", eps, dtype)
+        q = _linear(y, sd, p + "self_attn.q_proj", dtype)
+        k = _linear(y, sd, p + "self_attn.k_proj", dtype)
+        vv = _linear(y, sd, p + "self_attn.v_proj", dtype)
+        x = x + _linear(_mha(q, k, vv, heads), sd, p + "self_attn.out_proj", dtype)
+        h = _linear(_ln(x, sd, p + "layer_norm2", eps, dtype), sd, p + "mlp.fc1", dtype)
+        h = h * torch.sigmoid(1.702 * h)  # quick_gelu
+        x = x + _linear(h, sd, p + "mlp.fc2", dtype)
+        hs.append(x)
+    pooled = _ln(x[:, 0], sd, v + "post_layernorm", eps, dtype)
+    return F.linear(pooled, _t(sd, "visual_projection.weight", dtype)), tuple(hs)
+
+
 def hubert_pos_conv_weight(sd, dtype=torch.float32):
     """Effective weight of the weight-normed positional conv (:45-92): W = g * v / ||v||, the
     norm taken over dims (0,1) per kernel tap (weight_norm dim=2).  Older checkpoints name the

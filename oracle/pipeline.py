@@ -35,15 +35,31 @@ def split_into_batch(inputs, bsize=32):
     return [inputs[i * bsize:(i + 1) * bsize] for i in range(math.ceil(len(inputs) / bsize))]
 
 
-def pil_bilinear_coeffs(in_size, out_size):
-    """8-bit coefficient table of Pillow's ``Image.resize(..., BILINEAR)`` along one axis
+def _pil_filter(name):
+    """(filter function, support) of Pillow's resampling filters (Resample.c: bilinear_filter, bicubic_filter
+    with a = -0.5)."""
+    if name == "bilinear":
+        return (lambda x: 1.0 - x if x < 1.0 else 0.0), 1.0
+
+    def bicubic(x, a=-0.5):
+        if x < 1.0:
+            return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+        if x < 2.0:
+            return (((x - 5) * x + 8) * x - 4) * a
+        return 0.0
+    return bicubic, 2.0
+
+
+def pil_bilinear_coeffs(in_size, out_size, filter="bilinear"):
+    """8-bit coefficient table of Pillow's ``Image.resize(..., BILINEAR | BICUBIC)`` along one axis
     (Pillow src/libImaging/Resample.c: precompute_coeffs + normalize_coeffs_8bpc; Pillow is an un-vendored
     dependency of HF ``ViTImageProcessor.resize``, reached from extract_vision_huggingface.py:137-138;
     the container's Pillow 12.2 and transformers 5.5 agree with this table for up-scaling, pinned in
     tests/test_oracle.py).  Returns (xmin[out], count[out], kk[out, ksize] int32), PRECISION_BITS = 22."""
+    fn, fsupport = _pil_filter(filter)
     scale = in_size / out_size
     filterscale = max(scale, 1.0)
-    support = 1.0 * filterscale            # bilinear filter support
+    support = fsupport * filterscale
     ksize = int(np.ceil(support)) * 2 + 1
     xmin = np.zeros(out_size, np.int32)
     cnt = np.zeros(out_size, np.int32)
@@ -58,25 +74,25 @@ def pil_bilinear_coeffs(in_size, out_size):
         n = hi - lo
         w = np.zeros(n, np.float64)
         for x in range(n):
-            a = abs((x + lo - center + 0.5) * ss)
-            w[x] = 1.0 - a if a < 1.0 else 0.0
+            w[x] = fn(abs((x + lo - center + 0.5) * ss))
         tot = 0.0                      # Pillow accumulates the weights in index order
         for x in range(n):
             tot += w[x]
         if tot != 0.0:
             w = w / tot
         xmin[xx], cnt[xx] = lo, n
-        kk[xx, :n] = np.trunc(w * (1 << 22) + 0.5).astype(np.int32)  # weights are >= 0
+        # normalize_coeffs_8bpc: round half away from zero (bicubic weights can be negative)
+        kk[xx, :n] = np.trunc(w * (1 << 22) + np.where(w < 0, -0.5, 0.5)).astype(np.int32)
     return xmin, cnt, kk
 
 
-def _pil_resample_axis(img, out_size, axis):
+def _pil_resample_axis(img, out_size, axis, filter="bilinear"):
     """One Pillow resampling pass over uint8 ``img`` [..., H, W, C] along ``axis`` (-3 rows, -2 columns):
     out = clip8((2^21 + sum_k in[xmin + k] * kk[k]) >> 22)."""
     in_size = img.shape[axis]
     if in_size == out_size:
         return img
-    xmin, cnt, kk = pil_bilinear_coeffs(in_size, out_size)
+    xmin, cnt, kk = pil_bilinear_coeffs(in_size, out_size, filter)
     src = np.moveaxis(img, axis, 0).astype(np.int64)
     out = np.empty((out_size,) + src.shape[1:], np.uint8)
     for xx in range(out_size):
@@ -87,12 +103,12 @@ def _pil_resample_axis(img, out_size, axis):
     return np.moveaxis(out, 0, axis)
 
 
-def pil_resize_bilinear_u8(frames, out_h=224, out_w=224):
-    """``PIL.Image.resize((out_w, out_h), BILINEAR)`` on uint8 [..., H, W, C]: horizontal pass, then
-    vertical pass, uint8 in between (ImagingResample)."""
+def pil_resize_bilinear_u8(frames, out_h=224, out_w=224, filter="bilinear"):
+    """``PIL.Image.resize((out_w, out_h), BILINEAR | BICUBIC)`` on uint8 [..., H, W, C]: horizontal pass,
+    then vertical pass, uint8 in between (ImagingResample)."""
     f = np.asarray(frames)
     assert f.dtype == np.uint8
-    return _pil_resample_axis(_pil_resample_axis(f, out_w, -2), out_h, -3)
+    return _pil_resample_axis(_pil_resample_axis(f, out_w, -2, filter), out_h, -3, filter)
 
 
 def vit_preprocess(frames_bgr):
@@ -107,6 +123,42 @@ def vit_preprocess(frames_bgr):
     x = rgb * np.float32(1.0 / 255.0)
     x = (x - np.float32(0.5)) / np.float32(0.5)
     return torch.from_numpy(np.ascontiguousarray(x.transpose(0, 3, 1, 2)))
+
+
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def clip_preprocess(frames_bgr, size=224):
+    """``func_opencv_to_image`` (BGR->RGB) + HF ``CLIPImageProcessor`` as the CLIP branch calls it
+    (extract_vision_huggingface.py:115-116): resize the SHORTER edge to 224 (PIL bicubic on uint8, the
+    longer edge scaled by the same ratio and truncated), center crop 224x224, x/255, per-channel
+    (x - mean) / std, fp32 NCHW.  (transformers 5.5 resizes through torchvision and differs from Pillow by
+    at most one uint8 level on some pixels; the pinned 4.28 processor is Pillow -- this follows Pillow.)"""
+    f = np.asarray(frames_bgr)
+    assert f.dtype == np.uint8 and f.ndim == 4 and f.shape[-1] == 3, f.shape
+    h, w = f.shape[1:3]
+    short, long = (w, h) if w <= h else (h, w)
+    new_short, new_long = size, int(size * long / short)
+    nh, nw = (new_long, new_short) if w <= h else (new_short, new_long)
+    if (nh, nw) != (h, w):
+        f = pil_resize_bilinear_u8(f, nh, nw, filter="bicubic")
+    top, left = (nh - size) // 2, (nw - size) // 2
+    f = f[:, top:top + size, left:left + size]
+    rgb = f[..., ::-1].astype(np.float32) * np.float32(1.0 / 255.0)
+    x = (rgb - np.asarray(CLIP_MEAN, np.float32)) / np.asarray(CLIP_STD, np.float32)
+    return torch.from_numpy(np.ascontiguousarray(x.transpose(0, 3, 1, 2)))
+
+
+def clip_visual_features(sd, frames_bgr, layers=12, heads=12, feature_level="UTTERANCE", dtype=torch.float32):
+    """One clip through the CLIP branch (:114-122) and the save logic (:171-189): every frame (no
+    resampling), batches of 32, ``get_image_features``; UTTERANCE -> mean over frames."""
+    inputs = clip_preprocess(np.asarray(frames_bgr))
+    embs = [E.clip_image_features(sd, b, layers=layers, heads=heads, dtype=dtype)[0] for b in split_into_batch(inputs, 32)]
+    emb = np.array(torch.cat(embs, dim=0).float().squeeze().numpy()).squeeze()
+    if feature_level == "FRAME":
+        return emb[np.newaxis, :] if emb.ndim == 1 else emb
+    return np.mean(emb, axis=0) if emb.ndim == 2 else emb
 
 
 def visual_clip_features(sd, frames_bgr, nframe=None, layers=12, feature_level="UTTERANCE",

@@ -168,3 +168,46 @@ def test_oracle_lstm_encoder_matches_torch_lstm():
         ref = lin(h.squeeze(0))
         got = OF._lstm_encoder(sd, "e", x, None, 0.0)
     assert float((got - ref).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("variant", ["b32", "l14"])
+def test_oracle_clip_image_features_match_hf(variant):
+    """oracle/encoders.py:clip_image_features vs HF CLIPModel.get_image_features (the call of the reference's
+    CLIP branch, extract_vision_huggingface.py:121), 2 layers of each released shape."""
+    from transformers import CLIPConfig, CLIPModel
+    c = S.CLIP_CFGS[variant]
+    cfg = CLIPConfig(vision_config=dict(hidden_size=c["hidden"], intermediate_size=c["ffn"], num_hidden_layers=2,
+                                        num_attention_heads=c["heads"], patch_size=c["patch"], image_size=224,
+                                        projection_dim=c["proj"]),
+                     text_config=dict(num_hidden_layers=1, hidden_size=64, intermediate_size=64, num_attention_heads=2,
+                                      projection_dim=c["proj"]), projection_dim=c["proj"])
+    m = CLIPModel(cfg).eval()
+    sd = {k: torch.from_numpy(v) for k, v in S.clip_vision_state_dict(seed=4, variant=variant, layers=2).items()}
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all(not k.startswith(("vision_model", "visual_projection")) for k in missing)
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        ref = m.get_image_features(x)
+        ref = getattr(ref, "pooler_output", ref)
+        got, _ = E.clip_image_features(sd, x, layers=2, heads=c["heads"])
+    assert got.shape == ref.shape == (2, c["proj"])
+    assert float((got - ref).abs().max() / ref.abs().max()) < 5e-5
+
+
+def test_clip_preprocess_restatement():
+    """Bicubic resize restatement == Pillow bit for bit; the whole CLIP preprocessing vs the container's HF
+    processor to within the one-uint8-level resize difference documented in oracle/pipeline.py."""
+    from PIL import Image
+    from transformers import CLIPImageProcessor
+    rng = np.random.default_rng(9)
+    for hw in [(112, 112), (300, 260), (57, 91)]:
+        img = rng.integers(0, 256, (hw[0], hw[1], 3), dtype=np.uint8)
+        ref = np.asarray(Image.fromarray(img).resize((224, 224), resample=Image.BICUBIC))
+        assert np.array_equal(P.pil_resize_bilinear_u8(img, 224, 224, filter="bicubic"), ref)
+    bgr = rng.integers(0, 256, (2, 112, 112, 3), dtype=np.uint8)
+    hf = CLIPImageProcessor()(images=[Image.fromarray(f[..., ::-1].copy()) for f in bgr], return_tensors="pt")["pixel_values"]
+    got = P.clip_preprocess(bgr)
+    assert got.shape == hf.shape
+    assert float((got - hf).abs().max()) <= 1.01 / 255.0 / min(P.CLIP_STD)
+    non_square = rng.integers(0, 256, (1, 150, 100, 3), dtype=np.uint8)  # shorter edge -> 224, center crop
+    assert tuple(P.clip_preprocess(non_square).shape) == (1, 3, 224, 224)

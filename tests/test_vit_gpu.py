@@ -96,3 +96,61 @@ def test_mixed_frame_sizes_in_one_call(cuda):
     for g, c in ((got[0], a), (got[2], b)):
         ref = P.visual_clip_features(sd, c, nframe=None, layers=2, feature_level="FRAME")
         assert np.abs(g - ref).max() / np.abs(ref).max() < TOL
+
+
+@pytest.mark.parametrize("variant,layers,hw", [("b32", 3, (224, 224)), ("b32", 2, (112, 112)), ("l14", 2, (224, 224)),
+                                                ("l14", 2, (150, 100))])
+def test_clip_vision_tower_matches_oracle(cuda, variant, layers, hw):
+    """CLIP branch (extract_vision_huggingface.py:114-122): bicubic shorter-edge resize + center crop +
+    normalise on the device, patch 32 / 14 embedding, pre_layrnorm, quick-GELU layers (fp16 operands for the
+    50-token B/32, TF32 + the long-sequence attention for the 257-token L/14), post_layernorm, projection."""
+    from mertools_b200.encoders import ClipVisionEncoder
+    c = S.CLIP_CFGS[variant]
+    sd = S.clip_vision_state_dict(seed=4, variant=variant, layers=layers)
+    rng = np.random.default_rng(31)
+    frames = rng.integers(0, 256, (3, hw[0], hw[1], 3), dtype=np.uint8)
+    enc = ClipVisionEncoder(sd, device=cuda)
+    assert enc.precision == ("f16" if variant == "b32" else "tf32")
+    emb, hidden = enc.frame_features(torch.from_numpy(frames).to(cuda), return_hidden=True)
+    torch.cuda.synchronize()
+    tsd = {k: torch.from_numpy(v) for k, v in sd.items()}
+    ref_emb, ref_hs = E.clip_image_features(tsd, P.clip_preprocess(frames), layers=layers, heads=c["heads"])
+    for l in range(layers + 1):
+        m, l2 = rel(hidden[l].cpu(), ref_hs[l])
+        assert m < 4 * TOL, f"hidden state {l}: max-rel {m:.2e} l2-rel {l2:.2e}"
+    m, l2 = rel(emb.cpu(), ref_emb)
+    assert emb.shape == (3, c["proj"]) and m < TOL and l2 < TOL, f"image embeds: max-rel {m:.2e} l2-rel {l2:.2e}"
+
+
+def test_clip_through_the_visual_extractor(cuda):
+    """The extractor recognises a CLIP checkpoint, keeps every frame (no resampling) and writes [proj] / [T, proj]."""
+    from mertools_b200.extract import visual
+    sd = S.clip_vision_state_dict(seed=4, variant="b32", layers=2)
+    clips = [c for c in S.synth_frames(2, 5, size=112, seed=41)]
+    ext = visual.VisualExtractor(sd, device=cuda)
+    utt = ext.extract_clips(clips, "UTTERANCE", nframe=None)
+    fra = ext.extract_clips(clips, "FRAME", nframe=None)
+    tsd = {k: torch.from_numpy(v) for k, v in sd.items()}
+    for u, f, c in zip(utt, fra, clips):
+        ref = P.clip_visual_features(tsd, c, layers=2, heads=12, feature_level="FRAME")
+        assert u.shape == (512,) and f.shape == (5, 512)
+        assert np.abs(f - ref).max() / np.abs(ref).max() < TOL
+        assert np.abs(u - ref.mean(0)).max() / np.abs(ref.mean(0)).max() < TOL
+
+
+@pytest.mark.parametrize("hw", [(112, 112), (300, 260), (57, 91)])
+def test_bicubic_resize_kernel_is_bit_exact(cuda, hw):
+    import ctypes as C
+    from mertools_b200 import _lib as L
+    rng = np.random.default_rng(hw[0] + hw[1])
+    frames = rng.integers(0, 256, (2, hw[0], hw[1], 3), dtype=np.uint8)
+    dev = torch.from_numpy(frames).to(cuda)
+    out = torch.empty(2, 224, 224, 3, dtype=torch.uint8, device=cuda)
+    lib = L.lib()
+    lib.mer_resize_workspace_bytes.restype = C.c_longlong
+    lib.mer_resize_workspace_bytes.argtypes = [C.c_int] * 5
+    ws = torch.empty(max(1, lib.mer_resize_workspace_bytes(2, hw[0], hw[1], 224, 224)), dtype=torch.uint8, device=cuda)
+    fn = L.declare("mer_resize_u8", [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_void_p])
+    L.check(fn(L.ptr(dev), 2, hw[0], hw[1], L.ptr(out), 224, 224, 1, L.ptr(ws), L.stream_ptr()))
+    assert np.array_equal(out.cpu().numpy(), P.pil_resize_bilinear_u8(frames, 224, 224, filter="bicubic"))
