@@ -174,3 +174,35 @@ def test_frame_level_shaping_is_bit_identical_to_the_reference_functions():
             ref = g[f"{feat_type}_{scale}_{name}"]
             got = np.array(x)
             assert got.shape == ref.shape and got.dtype == ref.dtype and np.array_equal(got, ref), (feat_type, scale, name)
+
+
+def test_c_abi_host_side_contract():
+    """Pure host answers of the C ABI (no GPU work): sizes, counts, and argument validation that fails with a
+    message before anything is launched."""
+    import ctypes as C
+    from mertools_b200 import _lib
+    from mertools_b200.fusion import MerFusionDims
+    dll = _lib.lib()
+    dll.mer_last_error.restype = C.c_char_p
+    assert dll.mer_hubert_num_frames(80000) == 249 and dll.mer_hubert_num_frames(160000) == 499
+    assert dll.mer_logmel_num_frames(80000) == 498 and dll.mer_logmel_num_frames(399) == 0
+    dims = MerFusionDims(768, 768, 768, 128, 6, 1)
+    for fn in (dll.mer_fusion_param_count, dll.mer_fusion_frm_param_count):
+        fn.restype = C.c_longlong
+        fn.argtypes = [C.POINTER(MerFusionDims)]
+    assert dll.mer_fusion_param_count(C.byref(dims)) == 477962           # SURVEY.md §8 a10
+    lstm = 3 * (512 * 768 + 512 * 128 + 512 + 512 + 128 * 128 + 128)
+    head = 128 * 384 + 128 + 2 * (128 * 128 + 128) + 3 * 128 + 3 + 6 * 128 + 6 + 128 + 1
+    assert dll.mer_fusion_frm_param_count(C.byref(dims)) == lstm + head
+    dll.mer_vit_workspace_bytes.restype = C.c_longlong
+    assert dll.mer_vit_workspace_bytes(32) > 32 * 197 * (768 * 2 + 2304 + 3072) * 4
+    # validation errors: non-zero status + message, nothing launched
+    rc = dll.mer_layernorm(None, None, None, None, None, None, 4, 768, C.c_float(1e-5), 0, None)
+    assert rc != 0 and b"null operand" in dll.mer_last_error()
+    desc = _lib.MerGemmDesc()
+    rc = dll.mer_gemm(C.byref(desc), None)
+    assert rc != 0 and b"null operand" in dll.mer_last_error()
+    dll.mer_resize_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_void_p]
+    rc = dll.mer_resize_u8(None, 1, 10, 10, None, 224, 224, 0, None, None)
+    assert rc != 0 and b"bad arguments" in dll.mer_last_error()
