@@ -49,6 +49,8 @@ MER_API int mer_profile_collect(int mode, double* total_ms, double* total_flops,
 enum { MER_EPI_GELU = 1, MER_EPI_ROUND_TF32 = 2, MER_EPI_SPLIT_BF16 = 4,
        MER_EPI_GELU_LIBM = 8, /* with MER_EPI_GELU: libdevice erff instead of the 12-op polynomial */
        MER_EPI_QUICK_GELU = 64, /* x * sigmoid(1.702 x) (CLIP's hidden_act) instead of GELU; excludes MER_EPI_GELU */
+       MER_EPI_RELU = 128,    /* max(x, 0), applied AFTER the residual add when there is one (ResNet BasicBlock);
+                                 fp32 output only, excludes the GELU flags */
        MER_EPI_OUT_F16 = 16,  /* out (and vt, if given) are IEEE fp16 arrays (round-to-nearest, saturating);
                                  ld_out / vt_ld in elements */
        MER_ATT_QKV_F16 = 32   /* mer_attention only: qkv and vt are fp16 arrays (needs MER_EPI_OUT_F16, vt,
@@ -253,6 +255,30 @@ MER_API long long mer_clip_vision_workspace_bytes(const MerClipVisionModel* mode
 MER_API int mer_clip_vision_forward(const MerClipVisionModel* model, const uint8_t* frames_bgr, int n_frames,
                                     int H, int W, int crop_y0, int crop_x0, void* workspace,
                                     long long workspace_bytes, float* out_embeds, float* opt_hidden, void* stream);
+
+/* ---- ResNet-18 frame encoder (the reference's ImageNet CNN extractor) ------------------------------- */
+/* One convolution with its BatchNorm folded in (eval mode): w' = w * gamma / sqrt(var + eps),
+ * b' = beta - mean * gamma / sqrt(var + eps).  w: fp16 [cout_pad, kpad] in (ky, kx, c) order, rows >= cout and
+ * columns >= k*k*cin zero; b: fp32 [cout_pad].  cout_pad = max(cout, 128); kpad = k*k*cin (192 for conv1). */
+typedef struct MerResnetConv {
+  const void* w;
+  const float* b;
+  int cin, cout, cout_pad, k, stride, pad, kpad;
+} MerResnetConv;
+
+/* torchvision.models.resnet18 without fc, in module order: conv1; layer1.{0,1}.{conv1,conv2};
+ * layerX.0.{conv1,conv2,downsample}, layerX.1.{conv1,conv2} for X = 2..4  (20 convolutions). */
+typedef struct MerResnet18Model {
+  MerResnetConv convs[20];
+  float mean[3], std[3]; /* transforms.Normalize (RGB): 0.485 0.456 0.406 / 0.229 0.224 0.225 */
+} MerResnet18Model;
+
+MER_API long long mer_resnet18_workspace_bytes(int n_frames);
+/* frames: uint8 [n_frames, 224, 224, 3] BGR (resize other sizes first: transforms.Resize((224, 224)) is PIL
+ * bilinear = mer_resize_bilinear_u8).  Does BGR->RGB, ToTensor, Normalize, the network up to the global average
+ * pool (extract_imagenet_embedding.py:47-55, dataset.py:40-47).  out_feats: [n_frames, 512]. */
+MER_API int mer_resnet18_forward(const MerResnet18Model* model, const uint8_t* frames_bgr, int n_frames,
+                                 void* workspace, long long workspace_bytes, float* out_feats, void* stream);
 
 /* ---- HuBERT-base audio encoder ------------------------------------------------------------------ */
 typedef struct MerHubertModel {

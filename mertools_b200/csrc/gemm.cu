@@ -93,7 +93,7 @@ __device__ __forceinline__ float epi_act(float v) {
   if (GELU == 1) return gelu_erf_fast(v);
   if (GELU == 2) return gelu_erf(v);
   if (GELU == 3) return quick_gelu_fast(v);
-  return v;
+  return v;  // GELU == 4 (ReLU) is applied after the residual add, in the write-out phase
 }
 
 // What one epilogue warp needs to know about its share of the current output tile.
@@ -227,6 +227,9 @@ __device__ __forceinline__ void epi_tile(const EpiTile& tl, const MerGemmEpilogu
         v.w = epi_act<GELU>(v.w + q.w);
         if (RES) {
           v.x += rr[i].x; v.y += rr[i].y; v.z += rr[i].z; v.w += rr[i].w;
+        }
+        if (GELU == 4) {
+          v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
         }
         if (OUT == 2) {
           // the 32-column group's 128 bytes are [32 x bf16 hi | 32 x bf16 lo]
@@ -459,7 +462,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int p_row = lane >> 2;
     int as = 0;
     uint32_t aphase = 0;
-    const int gelu_kind = (ep.flags & MER_EPI_QUICK_GELU) ? 3
+    const int gelu_kind = (ep.flags & MER_EPI_RELU) ? 4 : (ep.flags & MER_EPI_QUICK_GELU) ? 3
                           : (ep.flags & MER_EPI_GELU) ? ((ep.flags & MER_EPI_GELU_LIBM) ? 2 : 1) : 0;
     const int out_kind = (ep.flags & MER_EPI_OUT_F16) ? 3 : (ep.flags & MER_EPI_SPLIT_BF16) ? 2 :
                          ((ep.flags & MER_EPI_ROUND_TF32) ? 1 : 0);
@@ -503,7 +506,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
       };
       if (tl.res_lane != nullptr) {  // warp-uniform; each variant is straight-line code
-        if (gelu_kind != 0) epi_tile<CH, 1, 0, true>(tl, ep, stg, lane, release);  // res + GELU(acc + bias), erf form
+        if (gelu_kind == 4) epi_tile<CH, 4, 0, true>(tl, ep, stg, lane, release);   // relu(acc + bias + res)
+        else if (gelu_kind != 0) epi_tile<CH, 1, 0, true>(tl, ep, stg, lane, release);  // res + GELU(acc + bias), erf form
         else if (out_kind == 1) epi_tile<CH, 0, 1, true>(tl, ep, stg, lane, release);
         else epi_tile<CH, 0, 0, true>(tl, ep, stg, lane, release);
       } else {
@@ -522,6 +526,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           case 11: epi_tile<CH, 2, 3, false>(tl, ep, stg, lane, release); break;
           case 13: epi_tile<CH, 3, 1, false>(tl, ep, stg, lane, release); break;   // quick-GELU: the operand
           case 15: epi_tile<CH, 3, 3, false>(tl, ep, stg, lane, release); break;   // formats FC1 can feed
+          case 16: epi_tile<CH, 4, 0, false>(tl, ep, stg, lane, release); break;   // relu(acc + bias)
           default: epi_tile<CH, 3, 0, false>(tl, ep, stg, lane, release); break;
         }
       }
@@ -640,6 +645,10 @@ int mer_gemm_launch(const MerGemmDesc* g, cudaStream_t stream) {
   MER_REQUIRE(!((g->ep.flags & MER_EPI_QUICK_GELU) &&
                 ((g->ep.flags & (MER_EPI_GELU | MER_EPI_SPLIT_BF16)) || g->ep.res || g->ep.vt)),
               "mer_gemm: quick-GELU comes alone (fp32, tf32 or fp16 output; no residual / split / V^T)");
+  MER_REQUIRE(!((g->ep.flags & MER_EPI_RELU) &&
+                ((g->ep.flags & (MER_EPI_GELU | MER_EPI_QUICK_GELU | MER_EPI_SPLIT_BF16 | MER_EPI_ROUND_TF32 |
+                                 MER_EPI_OUT_F16)) || g->ep.vt)),
+              "mer_gemm: ReLU goes with a plain fp32 output (optionally + residual)");
   MER_REQUIRE(g->a_col_group == 0 || g->force_block_n == 128 || g->force_block_n == 256,
               "mer_gemm: a_col_group needs force_block_n (the weights are built for one block width)");
   MER_REQUIRE(!(g->ep.vt && (g->ep.flags & MER_EPI_GELU)), "mer_gemm: GELU + transposed side output is not supported");

@@ -240,6 +240,91 @@ class ClipVisionEncoder:
         return emb
 
 
+class MerResnetConv(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("b", C.c_void_p), ("cin", C.c_int), ("cout", C.c_int), ("cout_pad", C.c_int),
+                ("k", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("kpad", C.c_int)]
+
+
+class MerResnet18Model(C.Structure):
+    _fields_ = [("convs", MerResnetConv * 20), ("mean", C.c_float * 3), ("std", C.c_float * 3)]
+
+
+class ResNet18Encoder:
+    """torchvision resnet18 without its fc layer (the reference's ImageNet CNN extractor): BatchNorm folded
+    into the convolutions at load, every convolution an fp16 im2col + tcgen05 GEMM with a ReLU epilogue.
+
+    Reference: MERBench/feature_extraction/visual/extract_imagenet_embedding.py:47-55."""
+
+    IMAGENET_MEAN = (0.485, 0.456, 0.406)
+    IMAGENET_STD = (0.229, 0.224, 0.225)
+
+    def __init__(self, state_dict, device="cuda", bn_eps=1e-5):
+        L.check(L.lib().mer_check_device())
+        sd = W._np(state_dict)
+        self.device = torch.device(device)
+        pk = self.pk = W.Packed(self.device)
+        m = MerResnet18Model()
+        specs = [("conv1", "bn1", 2, 3)]
+        for li in range(1, 5):
+            for b in range(2):
+                p = f"layer{li}.{b}."
+                stride = 2 if (li > 1 and b == 0) else 1
+                specs += [(p + "conv1", p + "bn1", stride, 1), (p + "conv2", p + "bn2", 1, 1)]
+                if p + "downsample.0.weight" in sd:
+                    specs.append((p + "downsample.0", p + "downsample.1", stride, 0))
+        assert len(specs) == 20, "not a torchvision resnet18 state_dict"
+        for i, (cn, bn, stride, pad) in enumerate(specs):
+            w = sd[cn + ".weight"].astype(np.float64)                       # [cout, cin, k, k]
+            scale = sd[bn + ".weight"].astype(np.float64) / np.sqrt(sd[bn + ".running_var"].astype(np.float64) + bn_eps)
+            wf = w * scale[:, None, None, None]
+            bf = sd[bn + ".bias"].astype(np.float64) - sd[bn + ".running_mean"].astype(np.float64) * scale
+            cout, cin, k, _ = w.shape
+            cout_pad = max(cout, 128)
+            kk = k * k * cin
+            kpad = 192 if i == 0 else kk
+            wp = np.zeros((cout_pad, kpad), np.float32)
+            wp[:cout, :kk] = wf.transpose(0, 2, 3, 1).reshape(cout, kk)       # (ky, kx, c) order
+            bp = np.zeros(cout_pad, np.float32)
+            bp[:cout] = bf
+            c = m.convs[i]
+            c.w, c.b = pk.keep(wp, f16=True).data_ptr(), pk.keep(bp).data_ptr()
+            c.cin, c.cout, c.cout_pad, c.k, c.stride, c.pad, c.kpad = cin, cout, cout_pad, k, stride, pad, kpad
+        m.mean = (C.c_float * 3)(*self.IMAGENET_MEAN)
+        m.std = (C.c_float * 3)(*self.IMAGENET_STD)
+        self.model = m
+        self.feature_dim = 512
+        self.ws, self.ws_resize = _Workspace(self.device), _Workspace(self.device)
+        lib = L.lib()
+        lib.mer_resnet18_workspace_bytes.restype = C.c_longlong
+        lib.mer_resnet18_workspace_bytes.argtypes = [C.c_int]
+        lib.mer_resize_workspace_bytes.restype = C.c_longlong
+        lib.mer_resize_workspace_bytes.argtypes = [C.c_int] * 5
+        self._fwd = L.declare("mer_resnet18_forward", [C.POINTER(MerResnet18Model), C.c_void_p, C.c_int, C.c_void_p,
+                                                       C.c_longlong, C.c_void_p, C.c_void_p])
+        self._resize = L.declare("mer_resize_u8", [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                                   C.c_int, C.c_int, C.c_void_p, C.c_void_p])
+
+    def frame_features(self, frames_bgr_u8: torch.Tensor, max_frames=64):
+        """frames: uint8 CUDA [N, H, W, 3] (BGR); transforms.Resize((224, 224)) on the device when needed.
+        Returns [N, 512] fp32 (CUDA)."""
+        assert frames_bgr_u8.dtype == torch.uint8 and frames_bgr_u8.is_cuda and frames_bgr_u8.dim() == 4
+        frames = frames_bgr_u8.contiguous()
+        n, h, w, _ = frames.shape
+        if (h, w) != (224, 224):
+            out = torch.empty(n, 224, 224, 3, dtype=torch.uint8, device=self.device)
+            need = L.lib().mer_resize_workspace_bytes(n, h, w, 224, 224)
+            ws = self.ws_resize.get(max(int(need), 1))
+            L.check(self._resize(L.ptr(frames), n, h, w, L.ptr(out), 224, 224, 0, L.ptr(ws), L.stream_ptr()))
+            frames = out
+        feats = torch.empty(n, 512, dtype=torch.float32, device=self.device)
+        for s in range(0, n, max_frames):  # the fp32 activations of conv1 cost 6.4 MB per frame
+            m = min(max_frames, n - s)
+            ws = self.ws.get(L.lib().mer_resnet18_workspace_bytes(m))
+            L.check(self._fwd(C.byref(self.model), L.ptr(frames[s:s + m]), m, L.ptr(ws), ws.numel(),
+                              L.ptr(feats[s:s + m]), L.stream_ptr()))
+        return feats
+
+
 class MerHubertModel(C.Structure):
     _fields_ = [("n_layers", C.c_int), ("ln_eps", C.c_float), ("conv0_w", C.c_void_p),
                 ("gn_g", C.c_void_p), ("gn_b", C.c_void_p), ("conv_w", C.c_void_p * 6),

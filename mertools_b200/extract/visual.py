@@ -51,7 +51,11 @@ class VisualExtractor:
 
     def __init__(self, state_dict, device="cuda", max_frames_per_launch=2048):
         # the CLIP checkpoints of the reference's model list carry a `vision_model.` tower + projection
-        if any(k.startswith("vision_model.") for k in state_dict):
+        if "layer1.0.conv1.weight" in state_dict:  # torchvision resnet18 (the ImageNet CNN extractor)
+            from ..encoders import ResNet18Encoder
+            self.enc = ResNet18Encoder(state_dict, device=device)
+            self.feature_dim = 512
+        elif any(k.startswith("vision_model.") for k in state_dict):
             from ..encoders import ClipVisionEncoder
             self.enc = ClipVisionEncoder(state_dict, device=device)
             self.feature_dim = self.enc.proj_dim

@@ -92,6 +92,38 @@ def clip_vision_state_dict(seed=4, variant="b32", layers=None, scale=1.0, image=
     return g.sd
 
 
+def resnet18_state_dict(seed=6):
+    """Keys of ``torchvision.models.resnet18()`` without fc (conv*/bn* with running statistics), He-style conv
+    init and non-trivial BatchNorm statistics / affines so that the folding is exercised."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+
+    def conv(name, cout, cin, k):
+        sd[name + ".weight"] = (rng.standard_normal((cout, cin, k, k)) * np.sqrt(2.0 / (cin * k * k))).astype(np.float32)
+
+    def bn(name, c):
+        sd[name + ".weight"] = rng.uniform(0.5, 1.5, c).astype(np.float32)
+        sd[name + ".bias"] = (0.2 * rng.standard_normal(c)).astype(np.float32)
+        sd[name + ".running_mean"] = (0.2 * rng.standard_normal(c)).astype(np.float32)
+        sd[name + ".running_var"] = rng.uniform(0.5, 1.5, c).astype(np.float32)
+
+    conv("conv1", 64, 3, 7)
+    bn("bn1", 64)
+    cin = 64
+    for li, cout in enumerate((64, 128, 256, 512), start=1):
+        for b in range(2):
+            pre = f"layer{li}.{b}."
+            conv(pre + "conv1", cout, cin if b == 0 else cout, 3)
+            bn(pre + "bn1", cout)
+            conv(pre + "conv2", cout, cout, 3)
+            bn(pre + "bn2", cout)
+            if b == 0 and li > 1:
+                conv(pre + "downsample.0", cout, cin, 1)
+                bn(pre + "downsample.1", cout)
+        cin = cout
+    return sd
+
+
 HUBERT_LARGE_CFG = dict(HUBERT_CFG, hidden=1024, heads=16, ffn=4096, layers=24)
 
 

@@ -111,6 +111,30 @@ def clip_image_features(sd, pixel_values, layers=12, heads=12, eps=1e-5, dtype=t
     return F.linear(pooled, _t(sd, "visual_projection.weight", dtype)), tuple(hs)
 
 
+def resnet18_features(sd, x, dtype=torch.float32, eps=1e-5):
+    """``nn.Sequential(*list(torchvision.models.resnet18().children())[:-1])(x).squeeze()`` in eval mode
+    (extract_imagenet_embedding.py:24,47-49; torchvision resnet.py BasicBlock): conv1 7x7/2 + bn + relu,
+    maxpool 3x3/2, four stages of two BasicBlocks (1x1/2 downsample in the first block of stages 2-4),
+    global average pool.  x: [N, 3, 224, 224] normalised.  Returns [N, 512]."""
+    def cb(x, conv, bn, stride, pad):
+        y = F.conv2d(x, _t(sd, conv + ".weight", dtype), None, stride=stride, padding=pad)
+        return F.batch_norm(y, _t(sd, bn + ".running_mean", dtype), _t(sd, bn + ".running_var", dtype),
+                            _t(sd, bn + ".weight", dtype), _t(sd, bn + ".bias", dtype), False, 0.0, eps)
+    y = F.relu(cb(x.to(dtype), "conv1", "bn1", 2, 3))
+    y = F.max_pool2d(y, 3, 2, 1)
+    for li in range(1, 5):
+        for b in range(2):
+            p = f"layer{li}.{b}."
+            stride = 2 if (li > 1 and b == 0) else 1
+            idt = y
+            o = F.relu(cb(y, p + "conv1", p + "bn1", stride, 1))
+            o = cb(o, p + "conv2", p + "bn2", 1, 1)
+            if p + "downsample.0.weight" in sd:
+                idt = cb(y, p + "downsample.0", p + "downsample.1", stride, 0)
+            y = F.relu(o + idt)
+    return y.mean(dim=(2, 3))
+
+
 def hubert_pos_conv_weight(sd, dtype=torch.float32):
     """Effective weight of the weight-normed positional conv (:45-92): W = g * v / ||v||, the
     norm taken over dims (0,1) per kernel tap (weight_norm dim=2).  Older checkpoints name the

@@ -125,6 +125,36 @@ def vit_preprocess(frames_bgr):
     return torch.from_numpy(np.ascontiguousarray(x.transpose(0, 3, 1, 2)))
 
 
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def imagenet_preprocess(frames_bgr):
+    """FaceDataset.__getitem__ (dataset.py:40-47: BGR->RGB PIL image) + the transform of
+    extract_imagenet_embedding.py:52-54: Resize((224, 224)) (PIL bilinear), ToTensor, Normalize."""
+    f = np.asarray(frames_bgr)
+    assert f.dtype == np.uint8 and f.ndim == 4 and f.shape[-1] == 3, f.shape
+    if f.shape[1:3] != (224, 224):
+        f = pil_resize_bilinear_u8(f, 224, 224)
+    rgb = f[..., ::-1].astype(np.float32) / np.float32(255.0)
+    x = (rgb - np.asarray(IMAGENET_MEAN, np.float32)) / np.asarray(IMAGENET_STD, np.float32)
+    return torch.from_numpy(np.ascontiguousarray(x.transpose(0, 3, 1, 2)))
+
+
+def imagenet_clip_features(sd, frames_bgr, feature_level="UTTERANCE"):
+    """One video through extract_imagenet_embedding.py:57-94: batches of 32 frames, [N, 512] embeddings,
+    FRAME -> [T, 512] (zeros((1, 512)) when empty), UTTERANCE -> mean over frames."""
+    frames = np.asarray(frames_bgr)
+    if len(frames) == 0:
+        return np.zeros((1, 512)) if feature_level == "FRAME" else np.zeros((512,))
+    x = imagenet_preprocess(frames)
+    emb = torch.cat([E.resnet18_features(sd, b) for b in split_into_batch(x, 32)], dim=0).float().numpy()
+    emb = np.array(emb).squeeze()
+    if feature_level == "FRAME":
+        return emb[np.newaxis, :] if emb.ndim == 1 else emb
+    return np.mean(emb, axis=0) if emb.ndim == 2 else emb
+
+
 CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
 CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
 

@@ -211,3 +211,27 @@ def test_clip_preprocess_restatement():
     assert float((got - hf).abs().max()) <= 1.01 / 255.0 / min(P.CLIP_STD)
     non_square = rng.integers(0, 256, (1, 150, 100, 3), dtype=np.uint8)  # shorter edge -> 224, center crop
     assert tuple(P.clip_preprocess(non_square).shape) == (1, 3, 224, 224)
+
+
+def test_oracle_resnet18_matches_torchvision():
+    """oracle/encoders.py:resnet18_features vs torchvision.models.resnet18 minus fc (the module the reference
+    builds at extract_imagenet_embedding.py:47-49); ToTensor/Normalize restatement vs torchvision transforms."""
+    torchvision = pytest.importorskip("torchvision")
+    from PIL import Image
+    m = torchvision.models.resnet18(weights=None).eval()
+    sd = {k: torch.from_numpy(v) for k, v in S.resnet18_state_dict(seed=6).items()}
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith("fc.") or k.endswith("num_batches_tracked") for k in missing), missing
+    feat = torch.nn.Sequential(*list(m.children())[:-1])
+    x = torch.randn(3, 3, 224, 224, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        ref = feat(x).squeeze()
+        got = E.resnet18_features(sd, x)
+    assert got.shape == ref.shape == (3, 512)
+    assert float((got - ref).abs().max() / ref.abs().max()) < 2e-5
+    tf = torchvision.transforms.Compose([torchvision.transforms.Resize((224, 224)), torchvision.transforms.ToTensor(),
+                                         torchvision.transforms.Normalize(mean=[0.485, 0.456, 0.406],
+                                                                          std=[0.229, 0.224, 0.225])])
+    bgr = np.random.default_rng(3).integers(0, 256, (2, 112, 112, 3), dtype=np.uint8)
+    ref_in = torch.stack([tf(Image.fromarray(f[..., ::-1].copy())) for f in bgr])
+    assert float((P.imagenet_preprocess(bgr) - ref_in).abs().max()) < 1e-6

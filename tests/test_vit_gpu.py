@@ -5,6 +5,8 @@ and as the relative L2 norm.  The CUDA path computes the linear layers' products
 (default) or TF32 operands (both 10-bit mantissas, round-to-nearest), attention in TF32, all with fp32
 accumulation; everything else in fp32.  Both precisions must pass.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -154,3 +156,39 @@ def test_bicubic_resize_kernel_is_bit_exact(cuda, hw):
                                      C.c_void_p, C.c_void_p])
     L.check(fn(L.ptr(dev), 2, hw[0], hw[1], L.ptr(out), 224, 224, 1, L.ptr(ws), L.stream_ptr()))
     assert np.array_equal(out.cpu().numpy(), P.pil_resize_bilinear_u8(frames, 224, 224, filter="bicubic"))
+
+
+@pytest.mark.parametrize("hw,n", [((224, 224), 3), ((112, 112), 2)])
+def test_resnet18_frame_features_match_oracle(cuda, hw, n):
+    """ImageNet CNN extractor (extract_imagenet_embedding.py): Resize + ToTensor + Normalize, 20 BN-folded
+    convolutions as fp16 im2col GEMMs with ReLU / residual epilogues, max-pool, global average pool."""
+    from mertools_b200.encoders import ResNet18Encoder
+    sd = S.resnet18_state_dict(seed=6)
+    frames = np.random.default_rng(51).integers(0, 256, (n, hw[0], hw[1], 3), dtype=np.uint8)
+    enc = ResNet18Encoder(sd, device=cuda)
+    got = enc.frame_features(torch.from_numpy(frames).to(cuda)).cpu()
+    tsd = {k: torch.from_numpy(v) for k, v in sd.items()}
+    ref = E.resnet18_features(tsd, P.imagenet_preprocess(frames))
+    m, l2 = rel(got, ref)
+    assert got.shape == (n, 512) and m < TOL and l2 < TOL, f"resnet18 features: max-rel {m:.2e} l2-rel {l2:.2e}"
+
+
+def test_imagenet_extractor_save_rules(cuda, tmp_path):
+    """imagenet_UTT / imagenet_FRA outputs through the mirrored script, incl. a one-frame video."""
+    import types
+    from mertools_b200.extract import imagenet
+    sd = S.resnet18_state_dict(seed=6)
+    face = tmp_path / "face"
+    clips = {"vidA": S.synth_frames(1, 3, seed=61)[0], "vidB": S.synth_frames(1, 1, size=112, seed=62)[0]}
+    for vid, c in clips.items():
+        os.makedirs(face / vid)
+        np.save(face / vid / f"{vid}.npy", c)
+    cfg = types.SimpleNamespace(PATH_TO_RAW_FACE={"D": str(face)}, PATH_TO_FEATURES={"D": str(tmp_path / "feat")})
+    tsd = {k: torch.from_numpy(v) for k, v in sd.items()}
+    for level in ("UTTERANCE", "FRAME"):
+        imagenet.main(imagenet.build_parser().parse_args(["--dataset=D", f"--feature_level={level}", "--gpu=0"]),
+                      config=cfg, state_dict=sd)
+        for vid, c in clips.items():
+            got = np.load(tmp_path / "feat" / f"imagenet_{level[:3]}" / f"{vid}.npy")
+            ref = P.imagenet_clip_features(tsd, c, feature_level=level)
+            assert got.shape == ref.shape and np.abs(got - ref).max() / np.abs(ref).max() < TOL
