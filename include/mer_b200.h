@@ -432,6 +432,25 @@ MER_API int mer_fusion_frm_fwd_bwd(const MerFusionDims* dims, const float* param
                                    long long workspace_bytes, float* loss_out, float* features, float* emos_out,
                                    float* vals_out, void* stream);
 
+/* ---- Attention_TOPN: N <= 18 utterance-level features (MER2026_Track1/toolkit/models/attention_topn.py) ----
+ * One MLPEncoder per feature (encoder0 .. encoder{N-1}), attention_mlp over the N*hidden concat, fc_att
+ * [N, hidden], fc_out_1, fc_out_2; parameters in that (state_dict) order.  feats: HOST array of n_feats device
+ * pointers.  emos == NULL -> eval-mode forward only.  ext_masks: NULL or HOST array of n_feats + 1 device
+ * pointers (per-feature input keep-masks, then the concat mask). */
+typedef struct MerFusionTopnDims {
+  int n_feats;
+  int feat_dims[18];
+  int hidden, out1, out2;
+} MerFusionTopnDims;
+MER_API long long mer_fusion_topn_param_count(const MerFusionTopnDims* dims);
+MER_API long long mer_fusion_topn_workspace_bytes(const MerFusionTopnDims* dims, int max_batch);
+MER_API int mer_fusion_topn_step(const MerFusionTopnDims* dims, const float* params, float* grads,
+                                 const float* const* feats, const int64_t* emos, const float* vals, int batch,
+                                 float loss_inv_batch, float dropout_p, unsigned long long seed,
+                                 const int* step_counter, const float* const* ext_masks, void* workspace,
+                                 long long workspace_bytes, float* loss_out, float* features, float* emos_out,
+                                 float* vals_out, void* stream);
+
 /* torch.optim.Adam(lr, betas, eps, weight_decay) with coupled L2, after multiplying the gradient by
  * grad_scale and (grad_clip > 0) clamping it to [-grad_clip, grad_clip] (clip_grad_value_,
  * main-release.py:64-65).  *step_counter (device int) is read as t-1 and incremented. */

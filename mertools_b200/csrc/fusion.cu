@@ -592,6 +592,222 @@ int frm_forward(const MerFusionDims& d, const FrmLayout& L, const float* P, cons
   return 0;
 }
 
+
+// ================================================================================================
+// Attention_TOPN (MER2026/MER2026_Track1/toolkit/models/attention_topn.py:8-90): the utterance-level net
+// generalised to N <= 18 input features, each with its own MLPEncoder; attention over the N hidden vectors.
+// Same kernels as the three-modality net (three encoders per launch), a head kernel with N as a parameter.
+// ================================================================================================
+constexpr int TOPN_MAX = 18;
+
+struct TopnHeadArgs {
+  const float* hcat;   // [B, N*H]
+  const float* a3;     // [B, H]
+  const float* w_att; const float* b_att;  // [N,H],[N]
+  const float* w_o1; const float* b_o1;
+  const float* w_o2; const float* b_o2;
+  const long long* emo; const float* val;
+  float* features; float* emos_out; float* vals_out;
+  float* loss_terms; float* d_emos; float* d_vals; float* d_att; float* d_cat; float* d_a3;
+  int N, H, O1, O2;
+  float inv_batch;
+};
+
+__global__ void __launch_bounds__(128)
+fus_head_topn_kernel(const TopnHeadArgs a) {
+  __shared__ float sh[4];
+  __shared__ float fused[256], dfused[256];
+  __shared__ float att[TOPN_MAX], datt[TOPN_MAX], logits[16], dlog[16], dval[4];
+  const int b = blockIdx.x, H = a.H, N = a.N, tid = threadIdx.x;
+  const float* hc = a.hcat + (long long)b * N * H;
+  const float* a3 = a.a3 + (long long)b * H;
+  for (int m = 0; m < N; ++m) {
+    float s = 0.f;
+    for (int j = tid; j < H; j += 128) s = fmaf(a.w_att[m * H + j], a3[j], s);
+    s = block_sum128(s, sh);
+    if (tid == 0) att[m] = s + a.b_att[m];
+  }
+  __syncthreads();
+  for (int j = tid; j < H; j += 128) {
+    float f = 0.f;
+    for (int m = 0; m < N; ++m) f = fmaf(hc[m * H + j], att[m], f);
+    fused[j] = f;
+    a.features[(long long)b * H + j] = f;
+  }
+  __syncthreads();
+  for (int c = 0; c < a.O1; ++c) {
+    float s = 0.f;
+    for (int j = tid; j < H; j += 128) s = fmaf(a.w_o1[c * H + j], fused[j], s);
+    s = block_sum128(s, sh);
+    if (tid == 0) { logits[c] = s + a.b_o1[c]; a.emos_out[(long long)b * a.O1 + c] = logits[c]; }
+  }
+  for (int c = 0; c < a.O2; ++c) {
+    float s = 0.f;
+    for (int j = tid; j < H; j += 128) s = fmaf(a.w_o2[c * H + j], fused[j], s);
+    s = block_sum128(s, sh);
+    if (tid == 0) { dval[c] = s + a.b_o2[c]; a.vals_out[(long long)b * a.O2 + c] = dval[c]; }
+  }
+  __syncthreads();
+  if (!a.emo) return;
+  if (tid == 0) {
+    float mx = logits[0];
+    for (int c = 1; c < a.O1; ++c) mx = fmaxf(mx, logits[c]);
+    float se = 0.f;
+    for (int c = 0; c < a.O1; ++c) se += expf(logits[c] - mx);
+    const float lse = mx + logf(se);
+    const int tgt = (int)a.emo[b];
+    a.loss_terms[2 * b + 0] = lse - logits[tgt];
+    for (int c = 0; c < a.O1; ++c) {
+      const float sm = expf(logits[c] - lse);
+      dlog[c] = (sm - (c == tgt ? 1.f : 0.f)) * a.inv_batch;
+      a.d_emos[(long long)b * a.O1 + c] = dlog[c];
+    }
+    float mse = 0.f;
+    for (int c = 0; c < a.O2; ++c) {
+      const float d = dval[c] - a.val[(long long)b * a.O2 + c];
+      mse += d * d;
+      dval[c] = 2.f * d * a.inv_batch;
+      a.d_vals[(long long)b * a.O2 + c] = dval[c];
+    }
+    a.loss_terms[2 * b + 1] = mse;
+  }
+  __syncthreads();
+  for (int j = tid; j < H; j += 128) {
+    float s = 0.f;
+    for (int c = 0; c < a.O1; ++c) s = fmaf(a.w_o1[c * H + j], dlog[c], s);
+    for (int c = 0; c < a.O2; ++c) s = fmaf(a.w_o2[c * H + j], dval[c], s);
+    dfused[j] = s;
+  }
+  __syncthreads();
+  for (int m = 0; m < N; ++m) {
+    float s = 0.f;
+    for (int j = tid; j < H; j += 128) s = fmaf(hc[m * H + j], dfused[j], s);
+    s = block_sum128(s, sh);
+    if (tid == 0) { datt[m] = s; a.d_att[(long long)N * b + m] = s; }
+  }
+  __syncthreads();
+  for (int j = tid; j < H; j += 128) {
+    float da = 0.f;
+    for (int m = 0; m < N; ++m) {
+      a.d_cat[(long long)b * N * H + m * H + j] = att[m] * dfused[j];
+      da = fmaf(a.w_att[m * H + j], datt[m], da);
+    }
+    a.d_a3[(long long)b * H + j] = da;
+  }
+}
+
+struct TopnLayout {
+  long long enc_w1[TOPN_MAX], enc_b1[TOPN_MAX], enc_w2[TOPN_MAX], enc_b2[TOPN_MAX], enc_w3[TOPN_MAX], enc_b3[TOPN_MAX];
+  long long att_w1, att_b1, att_w2, att_b2, att_w3, att_b3, fa_w, fa_b, o1_w, o1_b, o2_w, o2_b, total;
+};
+
+TopnLayout make_topn_layout(const MerFusionTopnDims& d) {
+  TopnLayout L;
+  long long o = 0;
+  const long long H = d.hidden, N = d.n_feats;
+  for (int m = 0; m < d.n_feats; ++m) {
+    L.enc_w1[m] = o; o += H * d.feat_dims[m];
+    L.enc_b1[m] = o; o += H;
+    L.enc_w2[m] = o; o += H * H;
+    L.enc_b2[m] = o; o += H;
+    L.enc_w3[m] = o; o += H * H;
+    L.enc_b3[m] = o; o += H;
+  }
+  L.att_w1 = o; o += H * N * H;
+  L.att_b1 = o; o += H;
+  L.att_w2 = o; o += H * H;
+  L.att_b2 = o; o += H;
+  L.att_w3 = o; o += H * H;
+  L.att_b3 = o; o += H;
+  L.fa_w = o; o += N * H;
+  L.fa_b = o; o += N;
+  L.o1_w = o; o += (long long)d.out1 * H;
+  L.o1_b = o; o += d.out1;
+  L.o2_w = o; o += (long long)d.out2 * H;
+  L.o2_b = o; o += d.out2;
+  L.total = o;
+  return L;
+}
+
+struct TopnScratch {
+  float *h1, *h2, *hcat, *a1, *a2, *a3, *d_h1, *d_h2, *d_cat, *d_a1, *d_a2, *d_a3, *d_emos, *d_vals, *d_att,
+      *loss_terms, *mask_cat;
+  float* mask_in[TOPN_MAX];
+};
+
+long long topn_scratch_floats(const MerFusionTopnDims& d, int B) {
+  const long long H = d.hidden, N = d.n_feats;
+  long long in_sum = 0;
+  for (int m = 0; m < d.n_feats; ++m) in_sum += d.feat_dims[m];
+  return (long long)B * (N * H * 7 + H * 6 + d.out1 + d.out2 + N + 2 + in_sum) + 64;
+}
+
+TopnScratch topn_carve(const MerFusionTopnDims& d, int B, float* base) {
+  TopnScratch s;
+  const long long H = d.hidden, N = d.n_feats;
+  float* p = base;
+  auto take = [&](long long n) { float* r = p; p += n; return r; };
+  s.h1 = take(N * B * H); s.h2 = take(N * B * H); s.hcat = take(N * B * H);
+  s.d_h1 = take(N * B * H); s.d_h2 = take(N * B * H); s.d_cat = take(N * B * H); s.mask_cat = take(N * B * H);
+  s.a1 = take(B * H); s.a2 = take(B * H); s.a3 = take(B * H);
+  s.d_a1 = take(B * H); s.d_a2 = take(B * H); s.d_a3 = take(B * H);
+  s.d_emos = take((long long)B * d.out1); s.d_vals = take((long long)B * d.out2);
+  s.d_att = take(N * B); s.loss_terms = take(2ll * B);
+  for (int m = 0; m < d.n_feats; ++m) s.mask_in[m] = take((long long)B * d.feat_dims[m]);
+  return s;
+}
+
+int topn_check(const MerFusionTopnDims* d, int B) {
+  MER_REQUIRE(d && d->n_feats >= 1 && d->n_feats <= TOPN_MAX && d->hidden > 0 && d->hidden <= 256 && d->out1 > 0 &&
+                  d->out1 <= 16 && d->out2 > 0 && d->out2 <= 4,
+              "mer_fusion_topn: unsupported dims (1..18 features, hidden <= 256, out1 <= 16, out2 <= 4)");
+  for (int m = 0; m < d->n_feats; ++m) MER_REQUIRE(d->feat_dims[m] > 0, "mer_fusion_topn: feature %d has no width", m);
+  MER_REQUIRE(B > 0 && B <= 65535, "mer_fusion_topn: batch %d out of range", B);
+  return 0;
+}
+
+int topn_forward(const MerFusionTopnDims& d, const TopnLayout& L, const float* P, const TopnScratch& s,
+                 const float* const* x, int B, float p_drop, const float* const* masks, bool use_dropout,
+                 cudaStream_t st) {
+  const int H = d.hidden, N = d.n_feats;
+  const float mscale = use_dropout ? 1.f / (1.f - p_drop) : 1.f;
+  LinBatch lb;
+  for (int m0 = 0; m0 < N; m0 += 3) {  // three encoders per launch
+    const int np = min(3, N - m0);
+    dim3 g1((H + 7) / 8, (B + 31) / 32, np);
+    for (int i = 0; i < np; ++i) {
+      const int m = m0 + i;
+      lb.p[i] = LinP{x[m], d.feat_dims[m], use_dropout ? masks[m] : nullptr, mscale, P + L.enc_w1[m], P + L.enc_b1[m],
+                     s.h1 + (long long)m * B * H, H, d.feat_dims[m], H, 1};
+    }
+    fus_linear_fwd_kernel<<<g1, 256, 0, st>>>(lb, B);
+    for (int i = 0; i < np; ++i) {
+      const int m = m0 + i;
+      lb.p[i] = LinP{s.h1 + (long long)m * B * H, H, nullptr, 1.f, P + L.enc_w2[m], P + L.enc_b2[m],
+                     s.h2 + (long long)m * B * H, H, H, H, 1};
+    }
+    fus_linear_fwd_kernel<<<g1, 256, 0, st>>>(lb, B);
+    for (int i = 0; i < np; ++i) {
+      const int m = m0 + i;
+      lb.p[i] = LinP{s.h2 + (long long)m * B * H, H, nullptr, 1.f, P + L.enc_w3[m], P + L.enc_b3[m],
+                     s.hcat + m * H, N * H, H, H, 1};
+    }
+    fus_linear_fwd_kernel<<<g1, 256, 0, st>>>(lb, B);
+    mer_count_launches(3);
+  }
+  dim3 g2((H + 7) / 8, (B + 31) / 32, 1);
+  lb.p[0] = LinP{s.hcat, N * H, use_dropout ? masks[N] : nullptr, mscale, P + L.att_w1, P + L.att_b1, s.a1, H, N * H,
+                 H, 1};
+  fus_linear_fwd_kernel<<<g2, 256, 0, st>>>(lb, B);
+  lb.p[0] = LinP{s.a1, H, nullptr, 1.f, P + L.att_w2, P + L.att_b2, s.a2, H, H, H, 1};
+  fus_linear_fwd_kernel<<<g2, 256, 0, st>>>(lb, B);
+  lb.p[0] = LinP{s.a2, H, nullptr, 1.f, P + L.att_w3, P + L.att_b3, s.a3, H, H, H, 1};
+  fus_linear_fwd_kernel<<<g2, 256, 0, st>>>(lb, B);
+  MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(3);
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -882,6 +1098,131 @@ int mer_fusion_frm_fwd_bwd(const MerFusionDims* d, const float* params, float* g
     bb.p[0] = BwdP{s.dgates[m], 4 * H, nullptr, 0, s.hprev[m], H, nullptr, 1.f, params + L.w_hh[m], G + L.w_hh[m],
                    G + L.b_hh[m], nullptr, 0, 0, H, 4 * H};
     launch_w(1, H, 4 * H, R);
+  }
+  MER_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// ---- Attention_TOPN (N <= 18 utterance-level features) ----------------------------------------------
+long long mer_fusion_topn_param_count(const MerFusionTopnDims* d) {
+  if (!d || d->n_feats < 1 || d->n_feats > TOPN_MAX) return -1;
+  return make_topn_layout(*d).total;
+}
+
+long long mer_fusion_topn_workspace_bytes(const MerFusionTopnDims* d, int max_batch) {
+  if (!d || d->n_feats < 1 || d->n_feats > TOPN_MAX) return -1;
+  return topn_scratch_floats(*d, max_batch) * 4;
+}
+
+// feats: HOST array of n_feats device pointers, feature i is [batch, feat_dims[i]].  emos == NULL: eval-mode
+// forward only (grads / loss_out / masks unused).  ext_masks: NULL or HOST array of n_feats + 1 device pointers
+// (one keep-mask per input feature, then the [batch, n_feats * hidden] concat mask).
+int mer_fusion_topn_step(const MerFusionTopnDims* d, const float* params, float* grads, const float* const* feats,
+                         const int64_t* emos, const float* vals, int B, float loss_inv_batch, float dropout_p,
+                         unsigned long long seed, const int* step_counter, const float* const* ext_masks,
+                         void* workspace, long long workspace_bytes, float* loss_out, float* features,
+                         float* emos_out, float* vals_out, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  if (int rc = topn_check(d, B)) return rc;
+  const bool train = emos != nullptr;
+  MER_REQUIRE(params && feats && workspace && features && emos_out && vals_out, "mer_fusion_topn_step: null operand");
+  MER_REQUIRE(!train || (grads && vals && loss_out && step_counter), "mer_fusion_topn_step: training needs grads, "
+                                                                     "vals, loss_out and step_counter");
+  MER_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "mer_fusion_topn_step: dropout %f", dropout_p);
+  MER_REQUIRE(workspace_bytes >= topn_scratch_floats(*d, B) * 4, "mer_fusion_topn_step: workspace too small");
+  const int N = d->n_feats, H = d->hidden;
+  for (int m = 0; m < N; ++m) MER_REQUIRE(feats[m], "mer_fusion_topn_step: feature %d is null", m);
+  const TopnLayout L = make_topn_layout(*d);
+  const TopnScratch s = topn_carve(*d, B, static_cast<float*>(workspace));
+  const bool drop = train && dropout_p > 0.f;
+  const float mscale = drop ? 1.f / (1.f - dropout_p) : 1.f;
+  const float* masks[TOPN_MAX + 1];
+  for (int m = 0; m <= N; ++m) masks[m] = nullptr;
+  if (drop) {
+    for (int m = 0; m <= N; ++m) {
+      if (ext_masks && ext_masks[m]) { masks[m] = ext_masks[m]; continue; }
+      float* dst = m < N ? s.mask_in[m] : s.mask_cat;
+      const long long n = (long long)B * (m < N ? d->feat_dims[m] : N * H);
+      fus_dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dst, n, dropout_p,
+                                                                            seed + 0x1000ull * (m + 1), step_counter);
+      mer_count_launches(1);
+      masks[m] = dst;
+    }
+  }
+  if (int rc = topn_forward(*d, L, params, s, feats, B, dropout_p, masks, drop, st)) return rc;
+  TopnHeadArgs h;
+  memset(&h, 0, sizeof(h));
+  h.hcat = s.hcat; h.a3 = s.a3;
+  h.w_att = params + L.fa_w; h.b_att = params + L.fa_b;
+  h.w_o1 = params + L.o1_w; h.b_o1 = params + L.o1_b;
+  h.w_o2 = params + L.o2_w; h.b_o2 = params + L.o2_b;
+  h.features = features; h.emos_out = emos_out; h.vals_out = vals_out;
+  h.N = N; h.H = H; h.O1 = d->out1; h.O2 = d->out2; h.inv_batch = loss_inv_batch;
+  if (train) {
+    h.emo = reinterpret_cast<const long long*>(emos); h.val = vals;
+    h.loss_terms = s.loss_terms; h.d_emos = s.d_emos; h.d_vals = s.d_vals; h.d_att = s.d_att;
+    h.d_cat = s.d_cat; h.d_a3 = s.d_a3;
+  }
+  fus_head_topn_kernel<<<B, 128, 0, st>>>(h);
+  mer_count_launches(1);
+  if (!train) {
+    MER_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
+  fus_loss_reduce_kernel<<<1, 32, 0, st>>>(s.loss_terms, B, loss_inv_batch, loss_out);
+  mer_count_launches(1);
+
+  float* G = grads;
+  BwdBatch bb;
+  auto launch_w = [&](int nprob, int K, int Nn) {
+    dim3 g((K + 255) / 256, Nn, nprob);
+    fus_linear_bwd_w_kernel<<<g, 256, 0, st>>>(bb, B);
+    mer_count_launches(1);
+  };
+  auto launch_x = [&](int nprob, int K) {
+    dim3 g((K + 255) / 256, B, nprob);
+    fus_linear_bwd_x_kernel<<<g, 256, 0, st>>>(bb, B);
+    mer_count_launches(1);
+  };
+  bb.p[0] = BwdP{s.d_emos, d->out1, nullptr, 0, features, H, nullptr, 1.f, params + L.o1_w, G + L.o1_w, G + L.o1_b,
+                 nullptr, 0, 0, H, d->out1};
+  bb.p[1] = BwdP{s.d_vals, d->out2, nullptr, 0, features, H, nullptr, 1.f, params + L.o2_w, G + L.o2_w, G + L.o2_b,
+                 nullptr, 0, 0, H, d->out2};
+  bb.p[2] = BwdP{s.d_att, N, nullptr, 0, s.a3, H, nullptr, 1.f, params + L.fa_w, G + L.fa_w, G + L.fa_b, nullptr, 0, 0,
+                 H, N};
+  launch_w(3, H, TOPN_MAX);
+  bb.p[0] = BwdP{s.d_a3, H, s.a3, H, s.a2, H, nullptr, 1.f, params + L.att_w3, G + L.att_w3, G + L.att_b3, s.d_a2, H, 0,
+                 H, H};
+  launch_w(1, H, H); launch_x(1, H);
+  bb.p[0] = BwdP{s.d_a2, H, s.a2, H, s.a1, H, nullptr, 1.f, params + L.att_w2, G + L.att_w2, G + L.att_b2, s.d_a1, H, 0,
+                 H, H};
+  launch_w(1, H, H); launch_x(1, H);
+  bb.p[0] = BwdP{s.d_a1, H, s.a1, H, s.hcat, N * H, masks[N], mscale, params + L.att_w1, G + L.att_w1, G + L.att_b1,
+                 s.d_cat, N * H, 1, N * H, H};
+  launch_w(1, N * H, H); launch_x(1, N * H);
+  for (int m0 = 0; m0 < N; m0 += 3) {
+    const int np = min(3, N - m0);
+    for (int i = 0; i < np; ++i) {
+      const int m = m0 + i;
+      bb.p[i] = BwdP{s.d_cat + m * H, N * H, s.hcat + m * H, N * H, s.h2 + (long long)m * B * H, H, nullptr, 1.f,
+                     params + L.enc_w3[m], G + L.enc_w3[m], G + L.enc_b3[m], s.d_h2 + (long long)m * B * H, H, 0, H, H};
+    }
+    launch_w(np, H, H); launch_x(np, H);
+    for (int i = 0; i < np; ++i) {
+      const int m = m0 + i;
+      bb.p[i] = BwdP{s.d_h2 + (long long)m * B * H, H, s.h2 + (long long)m * B * H, H, s.h1 + (long long)m * B * H, H,
+                     nullptr, 1.f, params + L.enc_w2[m], G + L.enc_w2[m], G + L.enc_b2[m],
+                     s.d_h1 + (long long)m * B * H, H, 0, H, H};
+    }
+    launch_w(np, H, H); launch_x(np, H);
+    int kmax = 0;
+    for (int i = 0; i < np; ++i) {
+      const int m = m0 + i;
+      bb.p[i] = BwdP{s.d_h1 + (long long)m * B * H, H, s.h1 + (long long)m * B * H, H, feats[m], d->feat_dims[m], masks[m],
+                     mscale, params + L.enc_w1[m], G + L.enc_w1[m], G + L.enc_b1[m], nullptr, 0, 0, d->feat_dims[m], H};
+      kmax = d->feat_dims[m] > kmax ? d->feat_dims[m] : kmax;
+    }
+    launch_w(np, kmax, H);
   }
   MER_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -274,6 +274,120 @@ class FusionNet:
         return self.loss, st["emos"], st["vals"]
 
 
+class MerFusionTopnDims(C.Structure):
+    _fields_ = [("n_feats", C.c_int), ("feat_dims", C.c_int * 18), ("hidden", C.c_int), ("out1", C.c_int),
+                ("out2", C.c_int)]
+
+
+class TopnFusionNet:
+    """Attention_TOPN (MER2026_Track1/toolkit/models/attention_topn.py): the utterance-level fusion net over
+    N <= 18 features ``batch['feat0'] .. batch['feat{N-1}']`` ([B, feat_dims[i]] each)."""
+
+    def __init__(self, feat_dims, hidden_dim=128, output_dim1=6, output_dim2=1, dropout=0.0, grad_clip=-1.0,
+                 device="cuda", seed=0):
+        L.check(L.lib().mer_check_device())
+        assert 1 <= len(feat_dims) <= 18
+        self.device = torch.device(device)
+        self.feat_dims = [int(d) for d in feat_dims]
+        self.dims = MerFusionTopnDims(len(feat_dims), (C.c_int * 18)(*self.feat_dims), hidden_dim, output_dim1,
+                                      output_dim2)
+        self.dropout, self.grad_clip, self.seed = float(dropout), float(grad_clip), int(seed)
+        lib = L.lib()
+        lib.mer_fusion_topn_param_count.restype = C.c_longlong
+        lib.mer_fusion_topn_param_count.argtypes = [C.POINTER(MerFusionTopnDims)]
+        lib.mer_fusion_topn_workspace_bytes.restype = C.c_longlong
+        lib.mer_fusion_topn_workspace_bytes.argtypes = [C.POINTER(MerFusionTopnDims), C.c_int]
+        vp, i32, f32, i64 = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+        self._step = L.declare("mer_fusion_topn_step", [C.POINTER(MerFusionTopnDims), vp, vp, vp, vp, vp, i32, f32, f32,
+                                                        C.c_ulonglong, vp, vp, vp, i64, vp, vp, vp, vp, vp])
+        self._adam = L.declare("mer_fusion_adam", [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, f32, vp, vp])
+        self.n_params = int(lib.mer_fusion_topn_param_count(C.byref(self.dims)))
+        self.names, self.shapes = [], {}
+        H = hidden_dim
+        for i, d in enumerate(self.feat_dims + [H * len(self.feat_dims)]):
+            e = f"encoder{i}" if i < len(self.feat_dims) else "attention_mlp"
+            for l, k in (("linear_1", d), ("linear_2", H), ("linear_3", H)):
+                self.names += [f"{e}.{l}.weight", f"{e}.{l}.bias"]
+                self.shapes[f"{e}.{l}.weight"], self.shapes[f"{e}.{l}.bias"] = (H, k), (H,)
+        for l, o in (("fc_att", len(self.feat_dims)), ("fc_out_1", output_dim1), ("fc_out_2", output_dim2)):
+            self.names += [f"{l}.weight", f"{l}.bias"]
+            self.shapes[f"{l}.weight"], self.shapes[f"{l}.bias"] = (o, H), (o,)
+        assert sum(int(np.prod(s)) for s in self.shapes.values()) == self.n_params
+        z = lambda: torch.zeros(self.n_params, dtype=torch.float32, device=self.device)  # noqa: E731
+        self.params, self.grads, self.exp_avg, self.exp_avg_sq = z(), z(), z(), z()
+        self.step_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.loss = torch.zeros(3, dtype=torch.float32, device=self.device)
+        self.ws = torch.empty(0, dtype=torch.uint8, device=self.device)
+        self.training = True
+
+    def train(self, mode=True):
+        self.training = mode
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def named_views(self, flat=None):
+        flat = self.params if flat is None else flat
+        out, o = {}, 0
+        for n in self.names:
+            k = int(np.prod(self.shapes[n]))
+            out[n] = flat[o:o + k].view(self.shapes[n])
+            o += k
+        return out
+
+    def state_dict(self):
+        return {k: v.clone() for k, v in self.named_views().items()}
+
+    def load_state_dict(self, sd):
+        for n, dst in self.named_views().items():
+            src = sd[n] if n in sd else sd["model." + n]
+            if isinstance(src, np.ndarray):
+                src = torch.from_numpy(src)
+            dst.copy_(src.to(self.device, torch.float32))
+        return self
+
+    def _run(self, feats, emo, val, ext_masks, world):
+        B = feats[0].shape[0]
+        need = int(L.lib().mer_fusion_topn_workspace_bytes(C.byref(self.dims), B))
+        if self.ws.numel() < need:
+            self.ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        feats = [f.contiguous() for f in feats]
+        fp = (C.c_void_p * len(feats))(*[f.data_ptr() for f in feats])
+        mp = None
+        if ext_masks is not None:
+            mp = (C.c_void_p * len(ext_masks))(*[m.data_ptr() if m is not None else None for m in ext_masks])
+        d = self.dims
+        out = [torch.empty(B, n, dtype=torch.float32, device=self.device) for n in (d.hidden, d.out1, d.out2)]
+        L.check(self._step(C.byref(d), L.ptr(self.params), L.ptr(self.grads), C.cast(fp, C.c_void_p), L.ptr(emo),
+                           L.ptr(val), B, 1.0 / (B * world), self.dropout if emo is not None else 0.0, self.seed,
+                           L.ptr(self.step_counter), C.cast(mp, C.c_void_p) if mp is not None else None,
+                           L.ptr(self.ws), self.ws.numel(), L.ptr(self.loss), L.ptr(out[0]), L.ptr(out[1]),
+                           L.ptr(out[2]), L.stream_ptr()))
+        return out
+
+    def forward(self, batch):
+        """batch: {'feat0': [B, d0], ...}; eval-mode forward -> (features, emos_out, vals_out, interloss)."""
+        feats = [batch[f"feat{i}"] for i in range(len(self.feat_dims))]
+        f, e, v = self._run(feats, None, None, None, 1)
+        return f, e, v, torch.zeros((), dtype=torch.int64, device=self.device)
+
+    __call__ = forward
+
+    def train_step(self, feats, emo, val, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, world_size=1,
+                   ext_masks=None):
+        """One optimisation step (forward, CE + MSE, backward, optional all-reduce, Adam)."""
+        assert emo.dtype == torch.int64 and val.dtype == torch.float32
+        _, eo, vo = self._run(feats, emo.contiguous(), val.contiguous(), ext_masks, world_size)
+        if world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.grads)
+        L.check(self._adam(L.ptr(self.params), L.ptr(self.grads), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq),
+                           self.n_params, lr, betas[0], betas[1], eps, weight_decay, 1.0,
+                           self.grad_clip if self.grad_clip != -1 else 0.0, L.ptr(self.step_counter), L.stream_ptr()))
+        return self.loss, eo, vo
+
+
 class _Wrapper:
     """``get_models`` wraps the chosen net as ``.model`` (toolkit/models/__init__.py:18-46)."""
 
@@ -299,7 +413,11 @@ def get_models(args):
     """args: .model ('attention'), .feat_type ('utt' | 'frm_align' | 'frm_unalign'),
     .audio_dim/.text_dim/.video_dim, .output_dim1/.output_dim2, .dropout, .hidden_dim, .grad_clip
     (models/__init__.py:18-46)."""
-    assert args.model == "attention", "only the Attention fusion net is on the B200 path"
+    if args.model == "attention_topn":  # MER2026 toolkit: args.audio_dim holds the list of feature widths
+        return _Wrapper(TopnFusionNet(args.audio_dim, args.hidden_dim, args.output_dim1, args.output_dim2,
+                                      dropout=args.dropout, grad_clip=args.grad_clip,
+                                      device=getattr(args, "device", "cuda")))
+    assert args.model == "attention", "only the Attention / Attention_TOPN fusion nets are on the B200 path"
     net = FusionNet(args.audio_dim, args.text_dim, args.video_dim, args.hidden_dim, args.output_dim1,
                     args.output_dim2, dropout=args.dropout, grad_clip=args.grad_clip,
                     device=getattr(args, "device", "cuda"), feat_type=args.feat_type)

@@ -240,6 +240,30 @@ def synth_waves(n_clips, n_samples=80000, seed=0):
     return np.round(3000.0 * rng.standard_normal((n_clips, n_samples))).astype(np.int16)
 
 
+def fusion_topn_state_dict(feat_dims, seed=8, hidden=128, out1=6, out2=1):
+    """Keys of MER2026 toolkit/models/attention_topn.py:Attention_TOPN in construction order."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+
+    def lin(prefix, o, i):
+        b = 1.0 / np.sqrt(i)
+        sd[prefix + ".weight"] = rng.uniform(-b, b, (o, i)).astype(np.float32)
+        sd[prefix + ".bias"] = rng.uniform(-b, b, (o,)).astype(np.float32)
+
+    def mlp(prefix, i):
+        lin(prefix + ".linear_1", hidden, i)
+        lin(prefix + ".linear_2", hidden, hidden)
+        lin(prefix + ".linear_3", hidden, hidden)
+
+    for i, d in enumerate(feat_dims):
+        mlp(f"encoder{i}", d)
+    mlp("attention_mlp", hidden * len(feat_dims))
+    lin("fc_att", len(feat_dims), hidden)
+    lin("fc_out_1", out1, hidden)
+    lin("fc_out_2", out2, hidden)
+    return sd
+
+
 def synth_fusion_sequences(n, lens=(9, 5, 12), dim=768, seed=0):
     """Frame-level batch as pad_to_maxlen_pre_modality (read_data.py:118-125) hands it to the model:
     [n, T_m, dim] per modality, shorter clips zero-padded IN FRONT."""

@@ -64,6 +64,19 @@ def attention_forward(sd, audios, texts, videos, masks=None, p=0.0):
     return fused, emos, vals
 
 
+def attention_topn_forward(sd, feats, masks=None, p=0.0):
+    """Attention_TOPN.forward (MER2026_Track1/toolkit/models/attention_topn.py:55-90): one MLPEncoder per
+    feature (encoder0..), attention_mlp on the concat, fc_att -> one weight per feature (no softmax), weighted
+    sum.  masks: None or len(feats) + 1 keep-masks (inputs, then the concat)."""
+    n = len(feats)
+    m = masks or [None] * (n + 1)
+    hs = [_mlp(sd, f"encoder{i}", feats[i], m[i], p) for i in range(n)]
+    att = F.linear(_mlp(sd, "attention_mlp", torch.cat(hs, dim=1), m[n], p), sd["fc_att.weight"], sd["fc_att.bias"])
+    fused = torch.matmul(torch.stack(hs, dim=2), att.unsqueeze(2)).squeeze(2)
+    return fused, F.linear(fused, sd["fc_out_1.weight"], sd["fc_out_1.bias"]), \
+        F.linear(fused, sd["fc_out_2.weight"], sd["fc_out_2.bias"])
+
+
 def losses(emos_out, vals_out, emos, vals):
     """CELoss + MSELoss (loss.py:11-28)."""
     ce = F.nll_loss(F.log_softmax(emos_out, 1), emos.long(), reduction="sum") / len(emos_out)
@@ -83,7 +96,10 @@ class Trainer:
     def step(self, a, t, v, emos, vals, masks=None):
         """main-release.py:31-66 for one batch.  Returns (ce, mse, total, emos_out, vals_out, grads)."""
         self.opt.zero_grad()
-        _, eo, vo = attention_forward(self.sd, a, t, v, masks, self.p)
+        if "encoder0.linear_1.weight" in self.sd:  # Attention_TOPN: `a` is the list of features
+            _, eo, vo = attention_topn_forward(self.sd, a, masks, self.p)
+        else:
+            _, eo, vo = attention_forward(self.sd, a, t, v, masks, self.p)
         ce, mse = losses(eo, vo, emos, vals)
         loss = ce + mse
         loss.backward()

@@ -147,3 +147,26 @@ def test_logmel_oracle_matches_reference_vggish_input():
         assert tuple(ex.shape) == tuple(g[f"n{i}"])
         sub = ex[:: max(1, len(ex) // 4)]
         assert np.abs(sub - g[f"ex{i}"]).max() < 1e-5
+
+
+def _topn_data(g):
+    rng = np.random.default_rng(5000 + int(g["data_seed"]))
+    dims, B = [int(d) for d in g["dims"]], int(g["batch"])
+    feats = [rng.standard_normal((B, d), dtype=np.float32) for d in dims]
+    return dims, feats, rng.integers(0, 6, B).astype(np.int64), rng.uniform(-3, 3, B).astype(np.float32)
+
+
+def test_attention_topn_oracle_matches_reference_class():
+    """oracle Trainer vs the reference's Attention_TOPN + losses + Adam (MER2026 toolkit), 15 steps."""
+    from oracle import fusion as OF
+    g = np.load(os.path.join(G, "fusion_topn_golden.npz"))
+    dims, feats, emo, val = _topn_data(g)
+    tr = OF.Trainer(S.fusion_topn_state_dict(dims, seed=int(g["seed"])), lr=1e-3, l2=1e-5)
+    tt = torch.from_numpy
+    for step in range(len(g["losses"])):
+        ce, mse, tot, eo, vo, grads = tr.step([tt(f) for f in feats], None, None, tt(emo), tt(val).view(-1, 1))
+        assert abs(tot - g["losses"][step]) < 1e-5 * max(1.0, abs(g["losses"][step])), step
+        if step == 0:
+            assert _rel(eo.numpy(), g["emos0"]) < 1e-5
+            assert _rel(grads["fc_att.weight"].numpy(), g["grad_fc_att_w"]) < 1e-4
+            assert _rel(grads["encoder3.linear_1.bias"].numpy(), g["grad_enc3_l1_b"]) < 1e-4

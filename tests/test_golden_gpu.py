@@ -153,3 +153,29 @@ def test_logmel_batch_matches_oracle(cuda):
         ref = P.log_mel_spectrogram(w[r].astype(np.float32))
         assert got[r].shape == ref.shape == (148, 64)
         assert np.abs(got[r] - ref).max() <= TOL * np.abs(ref).max()
+
+
+def test_attention_topn_vs_reference_golden(cuda):
+    """Attention_TOPN (five features of different widths) against the reference's own class, 15 Adam steps."""
+    from mertools_b200.fusion import TopnFusionNet
+    g = np.load(os.path.join(G, "fusion_topn_golden.npz"))
+    rng = np.random.default_rng(5000 + int(g["data_seed"]))
+    dims, B = [int(d) for d in g["dims"]], int(g["batch"])
+    feats = [rng.standard_normal((B, d), dtype=np.float32) for d in dims]
+    emo, val = rng.integers(0, 6, B).astype(np.int64), rng.uniform(-3, 3, B).astype(np.float32)
+    net = TopnFusionNet(dims, device=cuda).load_state_dict(S.fusion_topn_state_dict(dims, seed=int(g["seed"])))
+    dev = [torch.from_numpy(f).to(cuda) for f in feats]
+    demo, dval = torch.from_numpy(emo).to(cuda), torch.from_numpy(val.reshape(-1, 1)).to(cuda)
+    for step, ref in enumerate(g["losses"]):
+        loss3, eo, vo = net.train_step(dev, demo, dval, lr=1e-3, weight_decay=1e-5)
+        got = float(loss3[2])
+        assert abs(got - ref) <= 1e-3 * max(1.0, abs(ref)), f"step {step}: {got} vs {ref}"
+        if step == 0:
+            assert _rel(eo.cpu().numpy(), g["emos0"]) < 1e-4
+            gv = net.named_views(net.grads)
+            assert _rel(gv["fc_att.weight"].cpu().numpy(), g["grad_fc_att_w"]) < 1e-3
+            assert _rel(gv["encoder3.linear_1.bias"].cpu().numpy(), g["grad_enc3_l1_b"]) < 1e-3
+            # row 0 of attention_mlp.linear_1 is a dead ReLU unit in the reference run: its gradient is exactly 0
+            assert np.abs(gv["attention_mlp.linear_1.weight"][0].cpu().numpy() - g["grad_attmlp_l1_w_row0"]).max() <= 1e-7
+    f, e, v, inter = net.eval()({f"feat{i}": d for i, d in enumerate(dev)})
+    assert f.shape == (B, 128) and e.shape == (B, 6) and int(inter) == 0
