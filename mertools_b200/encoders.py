@@ -151,6 +151,23 @@ CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
 CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
 
 
+def clip_preprocess_geometry(h, w, size=224):
+    """(new_h, new_w, crop_y0, crop_x0) of HF CLIPImageProcessor: the shorter edge becomes ``size`` (the longer
+    one int(size * long / short)), then a centered size x size crop."""
+    short, long = (w, h) if w <= h else (h, w)
+    new_long = int(size * long / short)
+    nh, nw = (new_long, size) if w <= h else (size, new_long)
+    return nh, nw, (nh - size) // 2, (nw - size) // 2
+
+
+def fold_conv_bn(w, gamma, beta, mean, var, eps=1e-5):
+    """Eval-mode BatchNorm folded into the preceding bias-free convolution (float64 math):
+    w' = w * gamma / sqrt(var + eps), b' = beta - mean * gamma / sqrt(var + eps)."""
+    scale = np.asarray(gamma, np.float64) / np.sqrt(np.asarray(var, np.float64) + eps)
+    return np.asarray(w, np.float64) * scale[:, None, None, None], \
+        np.asarray(beta, np.float64) - np.asarray(mean, np.float64) * scale
+
+
 class ClipVisionEncoder:
     """CLIP vision tower + projection (HF ``CLIPModel.get_image_features``) for clip-vit-base-patch32 and
     clip-vit-large-patch14, including the CLIPImageProcessor steps (bicubic resize of the shorter edge to
@@ -210,11 +227,7 @@ class ClipVisionEncoder:
 
     def preprocess_geometry(self, h, w):
         """(new_h, new_w, crop_y0, crop_x0) of CLIPImageProcessor: shorter edge -> image, center crop."""
-        size = self.image
-        short, long = (w, h) if w <= h else (h, w)
-        new_long = int(size * long / short)
-        nh, nw = (new_long, size) if w <= h else (size, new_long)
-        return nh, nw, (nh - size) // 2, (nw - size) // 2
+        return clip_preprocess_geometry(h, w, self.image)
 
     def frame_features(self, frames_bgr_u8: torch.Tensor, return_hidden=False):
         """frames: uint8 CUDA [N, H, W, 3] (BGR).  Returns image embeddings [N, proj_dim] fp32 (CUDA)."""
@@ -274,10 +287,9 @@ class ResNet18Encoder:
                     specs.append((p + "downsample.0", p + "downsample.1", stride, 0))
         assert len(specs) == 20, "not a torchvision resnet18 state_dict"
         for i, (cn, bn, stride, pad) in enumerate(specs):
-            w = sd[cn + ".weight"].astype(np.float64)                       # [cout, cin, k, k]
-            scale = sd[bn + ".weight"].astype(np.float64) / np.sqrt(sd[bn + ".running_var"].astype(np.float64) + bn_eps)
-            wf = w * scale[:, None, None, None]
-            bf = sd[bn + ".bias"].astype(np.float64) - sd[bn + ".running_mean"].astype(np.float64) * scale
+            w = sd[cn + ".weight"]                                          # [cout, cin, k, k]
+            wf, bf = fold_conv_bn(w, sd[bn + ".weight"], sd[bn + ".bias"], sd[bn + ".running_mean"],
+                                  sd[bn + ".running_var"], bn_eps)
             cout, cin, k, _ = w.shape
             cout_pad = max(cout, 128)
             kk = k * k * cin

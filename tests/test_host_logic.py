@@ -206,3 +206,45 @@ def test_c_abi_host_side_contract():
                                   C.c_void_p, C.c_void_p]
     rc = dll.mer_resize_u8(None, 1, 10, 10, None, 224, 224, 0, None, None)
     assert rc != 0 and b"bad arguments" in dll.mer_last_error()
+
+
+@pytest.mark.parametrize("hidden", [768, 1024])
+def test_block_diagonal_pos_conv_weights_reproduce_the_grouped_conv(hidden):
+    """The windowed block-diagonal matrix that lets the positional conv run as one GEMM
+    (encoders.block_diagonal_pos_conv_weight + MerGemmDesc.a_row0 / a_col_group semantics, emulated here in
+    torch) against F.conv1d(groups=16, k=128, padding=64) minus its last frame."""
+    import torch.nn.functional as F
+    from mertools_b200.encoders import block_diagonal_pos_conv_weight
+    g = torch.Generator().manual_seed(hidden)
+    gch, T, taps = hidden // 16, 37, 128
+    window = 320 if gch == 48 else 256
+    w = torch.randn(hidden, gch, taps, generator=g, dtype=torch.float64) * 0.05
+    x = torch.randn(T, hidden, generator=g, dtype=torch.float64)
+    ref = F.conv1d(x.t()[None], w, None, padding=64, groups=16)[0, :, :-1].t()              # [T, hidden]
+    wbd = torch.from_numpy(block_diagonal_pos_conv_weight(w.numpy().astype(np.float32), window=window, group=gch)).double()
+    xp = torch.zeros(T + taps, hidden + window, dtype=torch.float64)                          # zero rows / columns = TMA fill
+    xp[64:64 + T, :hidden] = x
+    out = torch.empty(T, hidden, dtype=torch.float64)
+    for j in range(hidden // 256):                                                            # one 256-column output block
+        win0 = (256 * j // gch) * gch
+        a = torch.stack([xp[t:t + taps, win0:win0 + window].reshape(-1) for t in range(T)])  # row t: taps x window
+        out[:, 256 * j:256 * (j + 1)] = a @ wbd[256 * j:256 * (j + 1)].t()
+    assert float((out - ref).abs().max() / ref.abs().max()) < 1e-6
+
+
+def test_clip_geometry_and_bn_folding_helpers():
+    from mertools_b200.encoders import clip_preprocess_geometry, fold_conv_bn
+    assert clip_preprocess_geometry(112, 112) == (224, 224, 0, 0)
+    assert clip_preprocess_geometry(150, 100) == (336, 224, 56, 0)
+    assert clip_preprocess_geometry(100, 151) == (224, 338, 0, 57)
+    rng = np.random.default_rng(1)
+    w = rng.standard_normal((8, 4, 3, 3)).astype(np.float32)
+    gamma, beta = rng.uniform(0.5, 1.5, 8), rng.standard_normal(8)
+    mean, var = rng.standard_normal(8), rng.uniform(0.5, 1.5, 8)
+    x = torch.from_numpy(rng.standard_normal((2, 4, 9, 9)))
+    ref = torch.nn.functional.batch_norm(torch.nn.functional.conv2d(x, torch.from_numpy(w).double(), None, padding=1),
+                                         torch.from_numpy(mean), torch.from_numpy(var), torch.from_numpy(gamma),
+                                         torch.from_numpy(beta), False, 0.0, 1e-5)
+    wf, bf = fold_conv_bn(w, gamma, beta, mean, var)
+    got = torch.nn.functional.conv2d(x, torch.from_numpy(wf), torch.from_numpy(bf), padding=1)
+    assert float((got - ref).abs().max()) < 1e-10
