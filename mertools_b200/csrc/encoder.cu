@@ -1,13 +1,15 @@
 // encoder.cu — host-side launch sequences of the encoder forwards (no kernels here).
 //
-// mer_run_stack   : the 12-layer transformer stack shared by the three modalities
-//                   pre-LN  (HF ViTLayer,            modeling_vit.py:328-346)
-//                   post-LN (HF HubertEncoderLayer,  modeling_hubert.py:372-405; BertLayer)
+// mer_run_stack   : the transformer stack shared by the modalities (dims at run time)
+//                   pre-LN  (HF ViTLayer, modeling_vit.py:328-346; CLIPEncoderLayer; the stable-layer-norm
+//                            HuBERT encoder) in fp16 / TF32 / BF16X3 operand formats
+//                   post-LN (HF HubertEncoderLayer, modeling_hubert.py:372-405; BertLayer) in BF16X3
 // mer_vit_forward : frames (uint8 BGR) -> patchify -> patch-embed GEMM (+bias +pos) -> stack ->
 //                   token-sum readout  (reference: extract_vision_huggingface.py:137-144)
+// mer_clip_vision_forward, mer_hubert_forward (base and large families), mer_bert_forward: see each.
 //
-// Per layer and token the chain moves (fp32 activations): LN 6 KB x2, QKV 3+9 KB, attention
-// 9+3 KB, out-proj 3+3+3 KB, FC1 3+12 KB, FC2 12+3+3 KB  = 72 KB  (see DESIGN.md).
+// Per layer and token the fp16 ViT chain moves: LN 3+1.5 KB x2, QKV 1.5+4.5 KB, attention 4.5+1.5 KB,
+// out-proj 1.5+3+3 KB, FC1 1.5+6 KB, FC2 6+3+3 KB = 48 KB (TF32 chain: 72 KB).
 #include "mer_common.cuh"
 #include "mer_kernels.h"
 

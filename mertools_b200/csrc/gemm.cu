@@ -1,21 +1,25 @@
 // gemm.cu — the one GEMM every encoder layer goes through.
 //
 //   out[b*out_bstride + out_row0 + m, n] =
-//       round?( act( sum_k A[b, m, k] * W[n, k] + bias[n] ) + res[b*res_bstride + res_row0 + m, n] )
+//       fmt( act( sum_k A[b, m, k] * W[n, k] + bias[n] ) + res[b*res_bstride + res_row0 + m, n] )
+//   act: none | erf-GELU | quick-GELU | ReLU (ReLU after the residual);  fmt: fp32 | tf32-rounded | bf16 hi|lo | fp16
 //
 // A is a (K, rows, batches) tensor described by a TMA map with ARBITRARY row / batch strides,
-// which is how the strided HuBERT convolutions (time-major activations, overlapping windows)
-// and the ViT patch embedding run through the same kernel as the Linear layers
-// (reference ops: HF ViT/HuBERT/BERT nn.Linear + nn.Conv1d, see DESIGN.md kernel table).
+// which is how the strided HuBERT convolutions (time-major activations, overlapping windows),
+// the HuBERT positional conv (block-diagonal windows, negative row offset = zero padding), the
+// ViT / CLIP patch embeddings and the ResNet im2col operands run through the same kernel as the
+// Linear layers (reference ops: HF ViT/CLIP/HuBERT/BERT nn.Linear + nn.Conv1d, torchvision Conv2d;
+// see DESIGN.md kernel table).
 // W is the nn.Linear weight as stored: [N, K] row-major == K-major B operand.
 //
 // Structure (persistent, warp-specialised, one CTA per SM):
 //   warp 0      TMA producer: A/B tiles -> swizzled smem ring (mbarrier full/empty)
 //   warp 1      MMA issuer  : tcgen05.mma, UMMA 128 x BLOCK_N x (32 bytes of K), fp32 accum in TMEM
 //   warp 2      TMEM allocator
-//   warps 4..19 epilogue    : tcgen05.ld TMEM -> registers -> bias/GELU -> swizzled smem -> +residual
-//                             transpose -> 512-byte coalesced st.global (two warps per TMEM lane
-//                             quarter, half of the columns each)
+//   warps 4..19 epilogue    : tcgen05.ld TMEM -> registers -> swizzled smem transpose -> bias / activation /
+//                             residual / output format on the coalesced side -> 8 rows x 64 B per
+//                             st.global (four warps per TMEM lane quarter, a quarter of the columns
+//                             each; compile-time specialised variants, see epi_tile)
 // TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // Three arithmetic modes share the pipeline (128 bytes of K per smem row and stage in each):
