@@ -314,6 +314,9 @@ typedef struct MerHubertModel {
   const float* conv_ln_g[7];   /* per-conv LayerNorm affine [512] (feat_norm_layer) */
   const float* conv_ln_b[7];
   int pos_window;          /* K window of pos_w_bd (0 = 320; 256 for 64-channel groups) */
+  const MerLayerWeights* layers_f16; /* optional (stable_layer_norm only): the same layers with fp16 GEMM weights;
+                              when given, clips of <= 249 frames run the pre-LN stack on fp16 operands
+                              (MER_GEMM_F16 + the fp16 attention), longer ones stay BF16X3 */
 } MerHubertModel;
 
 /* per-row zero-mean / unit-variance (eps 1e-7) of HF Wav2Vec2FeatureExtractor(do_normalize=True)

@@ -583,11 +583,13 @@ int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L,
     MER_CUDA_CHECK(cudaMemcpyAsync(x, xn, hs_bytes, cudaMemcpyDeviceToDevice, stream));
     if (opt_hidden) MER_CUDA_CHECK(cudaMemcpyAsync(opt_hidden, x, hs_bytes, cudaMemcpyDeviceToDevice, stream));
     a.pre_ln = 1;
-    a.mode = MER_GEMM_BF16X3;
+    const bool f16 = m->layers_f16 != nullptr && mer_attention_f16_supported(T);
+    a.mode = f16 ? MER_GEMM_F16 : MER_GEMM_BF16X3;
+    const MerLayerWeights* layers = f16 ? m->layers_f16 : m->layers;
     const int L0 = m->n_layers - 4;  // layers before the readout window
     int done = 0;
     auto run = [&](int n) -> int {
-      a.layers = m->layers + done;
+      a.layers = layers + done;
       a.n_layers = n;
       a.opt_hidden = opt_hidden ? opt_hidden + (size_t)done * M * D : nullptr;
       const int rc = n > 0 ? mer_run_stack(a, stream) : 0;

@@ -346,7 +346,7 @@ class MerHubertModel(C.Structure):
                 ("layers", C.POINTER(W.MerLayerWeights)),
                 ("hidden", C.c_int), ("ffn", C.c_int), ("heads", C.c_int), ("feat_norm_layer", C.c_int),
                 ("stable_layer_norm", C.c_int), ("conv_b", C.c_void_p * 7), ("conv_ln_g", C.c_void_p * 7),
-                ("conv_ln_b", C.c_void_p * 7), ("pos_window", C.c_int)]
+                ("conv_ln_b", C.c_void_p * 7), ("pos_window", C.c_int), ("layers_f16", C.POINTER(W.MerLayerWeights))]
 
 
 def block_diagonal_pos_conv_weight(wpos, block_n=256, window=320, group=48):
@@ -392,7 +392,7 @@ class HubertEncoder:
 
     Reference: MERBench/feature_extraction/audio/extract_audio_huggingface.py:18-36,93-110."""
 
-    def __init__(self, state_dict, device="cuda", ln_eps=1e-5, stable_layer_norm=None):
+    def __init__(self, state_dict, device="cuda", ln_eps=1e-5, stable_layer_norm=None, stack_precision=None):
         L.check(L.lib().mer_check_device())
         sd = W._np(state_dict)
         self.device = torch.device(device)
@@ -449,6 +449,14 @@ class HubertEncoder:
         m.enc_ln_b = pk.keep(sd["encoder.layer_norm.bias"]).data_ptr()
         self.layers = W.pack_layers(sd, W.HUBERT_NAMES, self.n_layers, pk, split=True)
         m.layers = self.layers
+        # opt-in for the large (pre-LN) family: a second, fp16 copy of the layer weights; clips of <= 249 frames
+        # (5 s) then run the stack on fp16 operands like the ViT, longer ones keep BF16X3
+        import os as _os
+        self.stack_precision = stack_precision or _os.environ.get("MER_HUBERT_LARGE_PRECISION", "bf16x3")
+        assert self.stack_precision in ("bf16x3", "f16"), self.stack_precision
+        if self.stack_precision == "f16" and m.stable_layer_norm:
+            self.layers_f16 = W.pack_layers(sd, W.HUBERT_NAMES, self.n_layers, pk, f16=True)
+            m.layers_f16 = self.layers_f16
         self.model = m
         self.ws = _Workspace(self.device)
         lib = L.lib()

@@ -41,15 +41,16 @@ def test_hubert_hidden_states_and_readout(cuda, layers, n_samples, batch):
     assert m < TOL and l2 < TOL, f"utterance readout: max-rel {m:.2e} l2-rel {l2:.2e}"
 
 
+@pytest.mark.parametrize("precision", ["bf16x3", "f16"])
 @pytest.mark.parametrize("layers,n_samples,batch", [(4, 16000, 2), (6, 80000, 2), (5, 100000, 1)])
-def test_hubert_large_family_hidden_states_and_readout(cuda, layers, n_samples, batch):
+def test_hubert_large_family_hidden_states_and_readout(cuda, layers, n_samples, batch, precision):
     """hubert-large / chinese-hubert-large style checkpoint: hidden 1024, 16 heads, LayerNorm after every
     conv, conv biases, stable (pre-LN) encoder; 100,000 samples = 312 frames exercises the long-sequence
     attention path."""
     from mertools_b200.encoders import HubertEncoder
     sd = S.hubert_state_dict(seed=7, layers=layers, large=True)
     wav = (S.synth_waves(batch, n_samples, seed=23).astype(np.float64) / 32768.0).astype(np.float32)
-    enc = HubertEncoder(sd, device=cuda)
+    enc = HubertEncoder(sd, device=cuda, stack_precision=precision)  # f16: opt-in fp16 stack for <= 249 frames
     assert enc.hidden == 1024
     utt, frames, hidden = enc.forward(torch.from_numpy(wav).to(cuda), normalize=True,
                                       want_frames=True, return_hidden=True)
