@@ -11,6 +11,7 @@ import torch
 
 from mertools_b200 import synthetic as S
 from oracle import fusion as OF
+from oracle import encoders as E
 from oracle import pipeline as P
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -170,3 +171,38 @@ def test_attention_topn_oracle_matches_reference_class():
             assert _rel(eo.numpy(), g["emos0"]) < 1e-5
             assert _rel(grads["fc_att.weight"].numpy(), g["grad_fc_att_w"]) < 1e-4
             assert _rel(grads["encoder3.linear_1.bias"].numpy(), g["grad_enc3_l1_b"]) < 1e-4
+
+
+class _OracleBert:
+    """Checker-side stand-in for BertEncoder.forward(want_tokens=True): last-four sums from the oracle."""
+
+    def __init__(self, sd, layers):
+        self.sd, self.layers = sd, layers
+
+    def forward(self, id_lists, start=0, end=None, want_tokens=True):
+        toks = []
+        for ids in id_lists:
+            with torch.no_grad():
+                hs = E.bert_hidden_states(self.sd, torch.tensor([ids]), layers=self.layers)
+            toks.append(torch.stack(hs)[[-4, -3, -2, -1]].sum(dim=0)[0])
+        return None, torch.cat(toks)
+
+
+def test_english_word_alignment_host_logic_matches_reference_function():
+    """Sentence splitting + sub-word -> word merging + save rules of extract_bert_embedding_english
+    (MER2023 extract_text_embedding_LZ.py:168-311) against outputs of the unmodified reference function; the
+    encoder behind the host logic is the oracle here (the CUDA encoder has its own parity tests)."""
+    transformers = pytest.importorskip("transformers")
+    from mertools_b200.extract import text_english as TE
+    g = np.load(os.path.join(G, "text_words_golden.npz"))
+    tok = transformers.BertTokenizer(os.path.join(G, "text_words_vocab.txt"), do_lower_case=True)
+    layers = int(g["layers"])
+    sd = _t(S.bert_state_dict(len(tok), seed=int(g["seed"]), layers=layers))
+    enc = _OracleBert(sd, layers)
+    for name, sent in zip(g["names"], g["sentences"]):
+        emb = TE.transcript_word_features(enc, tok, str(sent), lower=True)
+        fra = TE.save_word_features(None, emb, "FRAME", 768)
+        utt = TE.save_word_features(None, emb, "UTTERANCE", 768)
+        assert fra.shape == g[f"fra_{name}"].shape and _rel(fra, g[f"fra_{name}"]) < 5e-5, name
+        assert utt.shape == (768,) and _rel(utt, g[f"utt_{name}"]) < 5e-5, name
+    assert TE.split_words_and_sentences("Wow!!! ok.", True) == [["wow"], ["ok"]]
