@@ -179,20 +179,3 @@ def test_attention_topn_vs_reference_golden(cuda):
             assert np.abs(gv["attention_mlp.linear_1.weight"][0].cpu().numpy() - g["grad_attmlp_l1_w_row0"]).max() <= 1e-7
     f, e, v, inter = net.eval()({f"feat{i}": d for i, d in enumerate(dev)})
     assert f.shape == (B, 128) and e.shape == (B, 6) and int(inter) == 0
-
-
-def test_english_word_aligned_text_features_vs_reference_golden(cuda):
-    """extract_bert_embedding_english (MER2023 extract_text_embedding_LZ.py:168-311): host word / sentence logic
-    around the CUDA BERT encoder, against outputs of the unmodified reference function."""
-    transformers = pytest.importorskip("transformers")
-    from mertools_b200.encoders import BertEncoder
-    from mertools_b200.extract import text_english as TE
-    g = np.load(os.path.join(G, "text_words_golden.npz"))
-    tok = transformers.BertTokenizer(os.path.join(G, "text_words_vocab.txt"), do_lower_case=True)
-    enc = BertEncoder(S.bert_state_dict(len(tok), seed=int(g["seed"]), layers=int(g["layers"])), device=cuda)
-    for name, sent in zip(g["names"], g["sentences"]):
-        emb = TE.transcript_word_features(enc, tok, str(sent), lower=True)
-        fra = TE.save_word_features(None, emb, "FRAME", 768)
-        utt = TE.save_word_features(None, emb, "UTTERANCE", 768)
-        assert fra.shape == g[f"fra_{name}"].shape and _rel(fra, g[f"fra_{name}"]) < 2 * TOL, name
-        assert _rel(utt, g[f"utt_{name}"]) < TOL, name
