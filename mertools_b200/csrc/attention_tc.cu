@@ -54,6 +54,34 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) {  // SW128, SBO 
          (1ull << 46) | (2ull << 61);
 }
 
+// helpers of the VER 2 softmax (same scheme as attention_f16.cu): FMNMX3 and the packed fp32 pair pipe
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// VER 1 masks every score against the valid key range; VER 2 works in 16-key granules, unmasked (FMNMX3 /
+// FFMA2 / FADD2) wherever a granule lies inside [shift, Lk), and skips granules beyond the UMMA key count.
+template <int VER>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
                     const __grid_constant__ CUtensorMap tmap_vt, float* __restrict__ ctx,
@@ -237,6 +265,81 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
       const int row = grp * 128 + r_tile;  // query row inside the sequence
       mbar_wait(&bar_sfull[grp], uses & 1);
       tc_fence_after();
+      float mb, sum = 0.f;
+      if constexpr (VER == 2) {
+        const int NK = (Lk + 15) & ~15;  // the UMMA key count of this item (MMA warp: same expression)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+        for (int c = 0; c < n_chunks; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_lane + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int gi = 0; gi < 2; ++gi) {
+            const int c0 = c * 32 + gi * 16;
+            if (c0 >= shift && c0 + 16 <= Lk) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                mx0 = max3(mx0, __uint_as_float(r[gi * 16 + j]), __uint_as_float(r[gi * 16 + j + 1]));
+                mx1 = max3(mx1, __uint_as_float(r[gi * 16 + j + 2]), __uint_as_float(r[gi * 16 + j + 3]));
+              }
+            } else if (c0 < Lk) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j >= shift && c0 + j < Lk) mx0 = fmaxf(mx0, __uint_as_float(r[gi * 16 + j]));
+            }
+          }
+        }
+        mb = fmaxf(mx0, mx1) * SCALE_LOG2;
+        const uint64_t scale2 = pack2(SCALE_LOG2, SCALE_LOG2), nmb2 = pack2(-mb, -mb);
+        uint64_t acc2 = pack2(0.f, 0.f);
+        for (int pc = 0; pc < n_pc; ++pc, ++G) {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(t_lane + pc * 64, r0);
+          tmem_ld_32x32(t_lane + pc * 64 + 32, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int gi = 0; gi < 4; ++gi) {  // in place: scores -> tf32-rounded probabilities
+            uint32_t* rr = gi < 2 ? r0 + gi * 16 : r1 + (gi - 2) * 16;
+            const int c0 = pc * 64 + gi * 16;
+            if (c0 >= shift && c0 + 16 <= Lk) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                float a, b;
+                unpack2(fma2(pack2(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1])), scale2, nmb2), a, b);
+                a = fast_ex2(a);
+                b = fast_ex2(b);
+                acc2 = add2(acc2, pack2(a, b));
+                rr[j] = __float_as_uint(round_tf32(a));
+                rr[j + 1] = __float_as_uint(round_tf32(b));
+              }
+            } else if (c0 < NK) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float a = 0.f;
+                if (c0 + j >= shift && c0 + j < Lk) a = fast_ex2(fmaf(__uint_as_float(rr[j]), SCALE_LOG2, -mb));
+                sum += a;
+                rr[j] = __float_as_uint(round_tf32(a));
+              }
+            }
+          }
+          const int keys = min(64, NK - pc * 64);  // keys of this chunk the P V MMAs read (multiple of 16)
+          mbar_wait(&bar_pfree[grp], (G & 1) ^ 1);  // the previous chunk's MMAs have read the buffer
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {  // 16-byte slot j = keys 4j .. 4j+3 of either 32-key sub-chunk
+            const int sj = (j ^ (r_tile & 7)) << 2;
+            if (4 * j < keys)
+              *reinterpret_cast<uint4*>(p_lo + sj) = make_uint4(r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]);
+            if (32 + 4 * j < keys)
+              *reinterpret_cast<uint4*>(p_hi + sj) = make_uint4(r1[4 * j], r1[4 * j + 1], r1[4 * j + 2], r1[4 * j + 3]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_pready[grp]);
+        }
+        float s_lo, s_hi;
+        unpack2(acc2, s_lo, s_hi);
+        sum += s_lo + s_hi;
+      } else {
       // pass 1: row maximum over the valid keys
       float mx = -INFINITY;
       for (int c = 0; c < n_chunks; ++c) {
@@ -247,10 +350,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
         for (int j = 0; j < 32; ++j)
           if (c * 32 + j >= shift && c * 32 + j < Lk) mx = fmaxf(mx, __uint_as_float(r[j]));
       }
-      const float mb = mx * SCALE_LOG2;
+      mb = mx * SCALE_LOG2;
       // pass 2, per 64-key chunk: p = exp2((s - max) / 8 * log2 e) -> row sum, tf32-rounded P into the
       // swizzled smem chunk (A operand of the P V MMA)
-      float sum = 0.f;
       for (int pc = 0; pc < n_pc; ++pc, ++G) {
         uint32_t r0[32], r1[32];
         tmem_ld_32x32(t_lane + pc * 64, r0);
@@ -276,6 +378,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
         fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_pready[grp]);
+      }
       }
       const float inv = 1.0f / sum;
       // epilogue: O / sum -> (swizzled smem transpose) -> 512-byte coalesced stores into ctx
@@ -369,10 +472,15 @@ int mer_attention_tc_launch(const float* qkv, const float* vt, long long vt_ld, 
                                CU_TENSOR_MAP_SWIZZLE_128B))
       return rc;
   }
+  // MER_ATT_TC_VER=2 selects the granule softmax (see the kernel's header comment); read at every launch so that
+  // a test can run both versions in one process.
+  const char* ver_env = getenv("MER_ATT_TC_VER");
+  const bool ver2 = ver_env && atoi(ver_env) == 2;
+  auto kern = ver2 ? attention_tc_kernel<2> : attention_tc_kernel<1>;
   static bool attr_set = false;
   if (!attr_set) {
-    MER_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        TC_SMEM));
+    MER_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    MER_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     attr_set = true;
   }
   const long long items = (long long)n_seq * heads;
@@ -381,7 +489,7 @@ int mer_attention_tc_launch(const float* qkv, const float* vt, long long vt_ld, 
   const int out_mode = (flags & MER_EPI_OUT_F16) ? 3 : (flags & MER_EPI_SPLIT_BF16) ? 2 : ((flags & MER_EPI_ROUND_TF32) ? 1 : 0);
   const double s_avg = (double)tokens / n_seq;  // exact for equal-length batches
   const int prof = mer_prof_begin(MER_PROF_ATT_TC, 4.0 * s_avg * s_avg * HD * (double)items, stream);
-  attention_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(tm, tv, ctx, cu_seqlens, n_seq, heads, out_mode);
+  kern<<<grid, TC_THREADS, TC_SMEM, stream>>>(tm, tv, ctx, cu_seqlens, n_seq, heads, out_mode);
   mer_prof_end(prof, stream);
   MER_CUDA_CHECK(cudaGetLastError());
   mer_count_launches(1);

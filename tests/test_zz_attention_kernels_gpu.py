@@ -1,0 +1,92 @@
+"""The two tcgen05 attention kernels on their own (fp16 operands: ViT; TF32 operands: HuBERT / BERT), ragged
+batches, both softmax versions (MER_ATT_F16_VER / MER_ATT_TC_VER = 1 default, 2 = 16-key granules), against a
+float64 softmax(Q K^T / 8) V of the same operand values (HF eager attention, modeling_vit.py:171-196)."""
+import os
+
+import pytest
+import torch
+
+from mertools_b200 import _lib as L
+
+# Written after the round's GPU budget was spent: neither this harness nor the VER 2 kernels have run on a GPU
+# yet, so the file is opt-in (MER_RUN_UNVERIFIED=1) until it has been seen green once.
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("MER_RUN_UNVERIFIED") != "1",
+                                 reason="not yet validated on a GPU; set MER_RUN_UNVERIFIED=1")]
+HEADS, HD = 3, 64
+LENS_F16 = [197, 197, 5, 1, 64, 128, 129, 249, 16, 17, 200, 33]
+LENS_TC = LENS_F16 + [253, 250]
+
+
+def _reference(q, k, v, cu):
+    out = torch.zeros(q.shape, dtype=torch.float64)
+    for s in range(len(cu) - 1):
+        a, b = cu[s], cu[s + 1]
+        for h in range(HEADS):
+            c = slice(h * HD, (h + 1) * HD)
+            p = torch.softmax(q[a:b, c] @ k[a:b, c].T / 8.0, dim=-1)
+            out[a:b, c] = p @ v[a:b, c]
+    return out
+
+
+def _operands(lens, dtype, cuda, align):
+    g = torch.Generator().manual_seed(7)
+    tokens = sum(lens)
+    qkv = (torch.randn(tokens, 3 * HEADS * HD, generator=g) * 1.5).to(dtype).to(cuda)
+    if dtype == torch.float32:
+        L.round_tf32_(qkv)
+    ld = (tokens + align - 1) // align * align
+    vt = torch.zeros(HEADS * HD, ld, dtype=dtype, device=cuda)
+    vt[:, :tokens] = qkv[:, 2 * HEADS * HD:].T
+    cu = [0]
+    for n in lens:
+        cu.append(cu[-1] + n)
+    host = qkv.double().cpu()
+    ref = _reference(host[:, :HEADS * HD], host[:, HEADS * HD:2 * HEADS * HD], host[:, 2 * HEADS * HD:], cu)
+    return qkv, vt, torch.tensor(cu, dtype=torch.int32, device=cuda), ref
+
+
+def _run(env, ver, qkv, vt, cu, lens):
+    old = os.environ.get(env)
+    os.environ[env] = str(ver)
+    try:
+        ctx = torch.full((qkv.shape[0], HEADS * HD), float("nan"), dtype=qkv.dtype, device=qkv.device)
+        L.attention(qkv, ctx, cu, max(lens), HEADS, vt=vt)
+        torch.cuda.synchronize()
+        return ctx.double().cpu()
+    finally:
+        if old is None:
+            os.environ.pop(env, None)
+        else:
+            os.environ[env] = old
+
+
+@pytest.mark.parametrize("ver", [1, 2])
+def test_attention_f16_kernel_vs_float64(cuda, ver):
+    qkv, vt, cu, ref = _operands(LENS_F16, torch.float16, cuda, 8)
+    out = _run("MER_ATT_F16_VER", ver, qkv, vt, cu, LENS_F16)
+    assert torch.isfinite(out).all()
+    # fp16 P (2^-11 relative per probability) and the fp16 output rounding
+    assert float((out - ref).abs().max() / ref.abs().max()) < 2e-3
+
+
+@pytest.mark.parametrize("ver", [1, 2])
+def test_attention_tf32_kernel_vs_float64(cuda, ver):
+    qkv, vt, cu, ref = _operands(LENS_TC, torch.float32, cuda, 4)
+    out = _run("MER_ATT_TC_VER", ver, qkv, vt, cu, LENS_TC)
+    assert torch.isfinite(out).all()
+    # TF32-rounded P (2^-11 relative per probability), fp32 output
+    assert float((out - ref).abs().max() / ref.abs().max()) < 1e-3
+
+
+def test_attention_softmax_versions_agree(cuda):
+    """Both versions compute the same probabilities (same fma / ex2 per element); only the order of the row sum
+    differs, i.e. the outputs agree to an fp16 ulp / a few fp32 ulps."""
+    qkv, vt, cu, ref = _operands(LENS_F16, torch.float16, cuda, 8)
+    a = _run("MER_ATT_F16_VER", 1, qkv, vt, cu, LENS_F16)
+    b = _run("MER_ATT_F16_VER", 2, qkv, vt, cu, LENS_F16)
+    assert float((a - b).abs().max() / ref.abs().max()) < 1.5e-3
+    qkv, vt, cu, ref = _operands(LENS_TC, torch.float32, cuda, 4)
+    a = _run("MER_ATT_TC_VER", 1, qkv, vt, cu, LENS_TC)
+    b = _run("MER_ATT_TC_VER", 2, qkv, vt, cu, LENS_TC)
+    assert float((a - b).abs().max() / ref.abs().max()) < 1e-5
