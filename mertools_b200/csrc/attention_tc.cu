@@ -54,31 +54,6 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) {  // SW128, SBO 
          (1ull << 46) | (2ull << 61);
 }
 
-// helpers of the VER 2 softmax (same scheme as attention_f16.cu): FMNMX3 and the packed fp32 pair pipe
-__device__ __forceinline__ float max3(float a, float b, float c) {
-  float d;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-
 // VER 1 masks every score against the valid key range; VER 2 works in 16-key granules, unmasked (FMNMX3 /
 // FFMA2 / FADD2) wherever a granule lies inside [shift, Lk), and skips granules beyond the UMMA key count.
 template <int VER>

@@ -92,12 +92,26 @@ __device__ __forceinline__ void tmem_ld_wait_regs(uint32_t* r) {
                : "memory");
 }
 
+// internal epilogue flag (set by mer_gemm_launch when MER_GELU_PACKED=1): erf-GELU on value pairs through the
+// packed fp32 pipe (GELU kind 5; fp16 and split-bf16 outputs, no residual).  Off by default until measured.
+constexpr int EPI_GELU_PACKED = 1 << 16;
+
 template <int GELU>
 __device__ __forceinline__ float epi_act(float v) {
   if (GELU == 1) return gelu_erf_fast(v);
   if (GELU == 2) return gelu_erf(v);
   if (GELU == 3) return quick_gelu_fast(v);
   return v;  // GELU == 4 (ReLU) is applied after the residual add, in the write-out phase
+}
+// two adjacent values at once (GELU == 5: the packed polynomial; otherwise the scalar form twice)
+template <int GELU>
+__device__ __forceinline__ void epi_act2(float a, float b, float& ga, float& gb) {
+  if (GELU == 5) {
+    gelu_erf_fast2(a, b, ga, gb);
+  } else {
+    ga = epi_act<GELU>(a);
+    gb = epi_act<GELU>(b);
+  }
 }
 
 // What one epilogue warp needs to know about its share of the current output tile.
@@ -182,10 +196,11 @@ __device__ __forceinline__ void epi_tile(const EpiTile& tl, const MerGemmEpilogu
       for (int j = 0; j < 8; ++j) {
         float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ep.bias) q = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + j);
-        pk[2 * j] = pack_f16x2(epi_act<GELU>(__uint_as_float(r[4 * j + 0]) + q.x),
-                               epi_act<GELU>(__uint_as_float(r[4 * j + 1]) + q.y));
-        pk[2 * j + 1] = pack_f16x2(epi_act<GELU>(__uint_as_float(r[4 * j + 2]) + q.z),
-                                   epi_act<GELU>(__uint_as_float(r[4 * j + 3]) + q.w));
+        float g0, g1, g2, g3;
+        epi_act2<GELU>(__uint_as_float(r[4 * j + 0]) + q.x, __uint_as_float(r[4 * j + 1]) + q.y, g0, g1);
+        epi_act2<GELU>(__uint_as_float(r[4 * j + 2]) + q.z, __uint_as_float(r[4 * j + 3]) + q.w, g2, g3);
+        pk[2 * j] = pack_f16x2(g0, g1);
+        pk[2 * j + 1] = pack_f16x2(g2, g3);
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j)  // 16-byte slot j = columns 8j .. 8j+7 of the chunk
@@ -225,10 +240,8 @@ __device__ __forceinline__ void epi_tile(const EpiTile& tl, const MerGemmEpilogu
       for (int i = 0; i < 4; ++i) {
         const int row = 8 * i + p_row;
         float4 v = *slot(row, p_slot);
-        v.x = epi_act<GELU>(v.x + q.x);
-        v.y = epi_act<GELU>(v.y + q.y);
-        v.z = epi_act<GELU>(v.z + q.z);
-        v.w = epi_act<GELU>(v.w + q.w);
+        epi_act2<GELU>(v.x + q.x, v.y + q.y, v.x, v.y);
+        epi_act2<GELU>(v.z + q.z, v.w + q.w, v.z, v.w);
         if (RES) {
           v.x += rr[i].x; v.y += rr[i].y; v.z += rr[i].z; v.w += rr[i].w;
         }
@@ -467,7 +480,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
     int as = 0;
     uint32_t aphase = 0;
     const int gelu_kind = (ep.flags & MER_EPI_RELU) ? 4 : (ep.flags & MER_EPI_QUICK_GELU) ? 3
-                          : (ep.flags & MER_EPI_GELU) ? ((ep.flags & MER_EPI_GELU_LIBM) ? 2 : 1) : 0;
+                          : (ep.flags & MER_EPI_GELU)
+                              ? ((ep.flags & MER_EPI_GELU_LIBM) ? 2 : ((ep.flags & EPI_GELU_PACKED) ? 5 : 1)) : 0;
     const int out_kind = (ep.flags & MER_EPI_OUT_F16) ? 3 : (ep.flags & MER_EPI_SPLIT_BF16) ? 2 :
                          ((ep.flags & MER_EPI_ROUND_TF32) ? 1 : 0);
     const int kind = gelu_kind * 4 + out_kind;
@@ -531,6 +545,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
           case 13: epi_tile<CH, 3, 1, false>(tl, ep, stg, lane, release); break;   // quick-GELU: the operand
           case 15: epi_tile<CH, 3, 3, false>(tl, ep, stg, lane, release); break;   // formats FC1 can feed
           case 16: epi_tile<CH, 4, 0, false>(tl, ep, stg, lane, release); break;   // relu(acc + bias)
+          case 22: epi_tile<CH, 5, 2, false>(tl, ep, stg, lane, release); break;   // packed erf-GELU (opt-in)
+          case 23: epi_tile<CH, 5, 3, false>(tl, ep, stg, lane, release); break;
           default: epi_tile<CH, 3, 0, false>(tl, ep, stg, lane, release); break;
         }
       }
@@ -607,7 +623,14 @@ int launch_gemm(const MerGemmDesc* g, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    MER_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<BLOCK_N, MODE, CLUSTER, TWOSM>, ta, tb, g->ep,
+    MerGemmEpilogue ep = g->ep;
+    {
+      const char* e = getenv("MER_GELU_PACKED");  // read at every launch: tests run both forms in one process
+      const bool plain_gelu = (ep.flags & MER_EPI_GELU) && !(ep.flags & MER_EPI_GELU_LIBM) && !ep.res;
+      if (e && atoi(e) == 1 && plain_gelu && (ep.flags & (MER_EPI_OUT_F16 | MER_EPI_SPLIT_BF16)))
+        ep.flags |= EPI_GELU_PACKED;
+    }
+    MER_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<BLOCK_N, MODE, CLUSTER, TWOSM>, ta, tb, ep,
                                       g->rows_per_batch, g->batches, g->N, g->K_inner * g->taps,
                                       g->K_inner, g->P, g->a_row0, g->a_col_group));
   }

@@ -410,6 +410,59 @@ __device__ __forceinline__ float quick_gelu_fast(float x) {
   return x * r;
 }
 
+// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: one issue slot for two lanes' worth of fp32 math;
+//      operands are 64-bit register pairs, broadcast scalars and |x| modifiers fold into the instruction) and
+//      the three-input max (FMNMX3) ----
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// gelu_erf_fast on two values at once: 7 FFMA2 + 5 FMUL2 + 4 MUFU for the pair (the scalar form spends
+// 7 FFMA + 5 FMUL + 2 MUFU per value).  Same polynomial; the constants of the first two steps are folded
+// (0.3275911 / sqrt 2 and -log2(e) / 2), which moves individual results by at most an ulp of the intermediate.
+__device__ __forceinline__ void gelu_erf_fast2(float x0, float x1, float& g0, float& g1) {
+  const uint64_t x = pack2(x0, x1), ax = pack2(fabsf(x0), fabsf(x1));
+  const auto bc = [](float v) { return pack2(v, v); };
+  float d0, d1, t0, t1, a0, a1, e0, e1;
+  unpack2(fma2(bc(0.3275911f * 0.70710678118654752440f), ax, bc(1.0f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  const uint64_t t = pack2(t0, t1);
+  uint64_t p = fma2(bc(-1.061405429f), t, bc(1.453152027f));  // -(a5 t + a4): the sign of erfc's series folded in
+  p = fma2(p, t, bc(-1.421413741f));
+  p = fma2(p, t, bc(0.284496736f));
+  p = fma2(p, t, bc(-0.254829592f));
+  unpack2(mul2(mul2(x, x), bc(-0.5f * 1.4426950408889634f)), a0, a1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  const uint64_t erf_abs = fma2(mul2(p, t), pack2(e0, e1), bc(1.0f));  // erf(|x| / sqrt 2)
+  unpack2(fma2(mul2(ax, bc(0.5f)), erf_abs, mul2(x, bc(0.5f))), g0, g1);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

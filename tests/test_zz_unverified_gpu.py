@@ -1,4 +1,7 @@
-"""The two tcgen05 attention kernels on their own (fp16 operands: ViT; TF32 operands: HuBERT / BERT), ragged
+"""Kernel-level tests of the opt-in variants prepared after the round-1 GPU budget ran out, plus the default
+kernels through the same harness.
+
+The two tcgen05 attention kernels on their own (fp16 operands: ViT; TF32 operands: HuBERT / BERT), ragged
 batches, both softmax versions (MER_ATT_F16_VER / MER_ATT_TC_VER = 1 default, 2 = 16-key granules), against a
 float64 softmax(Q K^T / 8) V of the same operand values (HF eager attention, modeling_vit.py:171-196)."""
 import os
@@ -90,3 +93,53 @@ def test_attention_softmax_versions_agree(cuda):
     a = _run("MER_ATT_TC_VER", 1, qkv, vt, cu, LENS_TC)
     b = _run("MER_ATT_TC_VER", 2, qkv, vt, cu, LENS_TC)
     assert float((a - b).abs().max() / ref.abs().max()) < 1e-5
+
+
+def _with_env(env, val, fn):
+    old = os.environ.get(env)
+    os.environ[env] = val
+    try:
+        out = fn()
+        torch.cuda.synchronize()
+        return out
+    finally:
+        if old is None:
+            os.environ.pop(env, None)
+        else:
+            os.environ[env] = old
+
+
+def test_gemm_packed_gelu_epilogue(cuda):
+    """MER_GELU_PACKED=1 (erf-GELU on value pairs, FFMA2 / FMUL2) against the scalar epilogue and float64, for
+    the two operand formats FC1 writes: fp16 (ViT) and split bf16 (HuBERT / BERT)."""
+    g = torch.Generator().manual_seed(3)
+    M, K, N = 777, 768, 1024
+    a = torch.randn(M, K, generator=g) * 0.5
+    w = torch.randn(N, K, generator=g) * 0.05
+    bias = (torch.randn(N, generator=g) * 0.1).to(cuda)
+
+    def gelu64(x):
+        return 0.5 * x * (1.0 + torch.erf(x / 2.0 ** 0.5))
+
+    # fp16 operands and output
+    a16, w16 = a.half().to(cuda), w.half().to(cuda)
+    ref = gelu64(a16.double().cpu() @ w16.double().cpu().T + bias.double().cpu())
+    outs = []
+    for flag in ("0", "1"):
+        out = torch.empty(M, N, dtype=torch.float16, device=cuda)
+        _with_env("MER_GELU_PACKED", flag, lambda: L.gemm(a16, w16, out, bias=bias, gelu=True, mode=L.MER_GEMM_F16,
+                                                          f16_out=True))
+        outs.append(out.double().cpu())
+        assert float((outs[-1] - ref).abs().max() / ref.abs().max()) < 1e-3
+    assert float((outs[0] - outs[1]).abs().max() / ref.abs().max()) < 6e-4  # at most an fp16 ulp apart
+    # split bf16 operands and output
+    a_s, w_s = L.split_bf16(a.to(cuda)), L.split_bf16(w.to(cuda))
+    ref = gelu64(a.double() @ w.double().T + bias.double().cpu())
+    outs = []
+    for flag in ("0", "1"):
+        out = torch.empty(M, N, dtype=torch.float32, device=cuda)
+        _with_env("MER_GELU_PACKED", flag, lambda: L.gemm(a_s, w_s, out, bias=bias, gelu=True,
+                                                          mode=L.MER_GEMM_BF16X3, split_out=True))
+        outs.append(L.unsplit_bf16(out).double().cpu())
+        assert float((outs[-1] - ref).abs().max() / ref.abs().max()) < 3e-5
+    assert float((outs[0] - outs[1]).abs().max() / ref.abs().max()) < 1e-5
