@@ -230,79 +230,92 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
       tc_fence_after();
       float mb, sum = 0.f;
       if constexpr (VER == 2) {
-        const int NK = (Lk + 15) & ~15;  // the UMMA key count of this item (MMA warp: same expression)
-        // pass 1: row maximum over the valid keys
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-        for (int c = 0; c < n_chunks; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(t_lane + c * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int gi = 0; gi < 2; ++gi) {
-            const int c0 = c * 32 + gi * 16;
-            if (c0 >= shift && c0 + 16 <= Lk) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                mx0 = max3(mx0, __uint_as_float(r[gi * 16 + j]), __uint_as_float(r[gi * 16 + j + 1]));
-                mx1 = max3(mx1, __uint_as_float(r[gi * 16 + j + 2]), __uint_as_float(r[gi * 16 + j + 3]));
-              }
-            } else if (c0 < Lk) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (c0 + j >= shift && c0 + j < Lk) mx0 = fmaxf(mx0, __uint_as_float(r[gi * 16 + j]));
-            }
+        if (grp * 128 + q * 32 >= len) {
+          // all 32 query rows of this warp lie beyond the sequence (rows 224..255 at 197 tokens): nothing to
+          // compute -- the P rows it would write feed output rows that are never stored -- but the chunk
+          // hand-shake with the MMA warp still counts four arrivals per tile
+          mb = 0.f;
+          sum = 1.f;
+          for (int pc = 0; pc < n_pc; ++pc, ++G) {
+            mbar_wait(&bar_pfree[grp], (G & 1) ^ 1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_pready[grp]);
           }
-        }
-        mb = fmaxf(mx0, mx1) * SCALE_LOG2;
-        // pass 2, per 64-key chunk (see VER 1 below), in 16-key granules
-        const uint64_t scale2 = pack2(SCALE_LOG2, SCALE_LOG2), nmb2 = pack2(-mb, -mb);
-        uint64_t acc2 = pack2(0.f, 0.f);
-        for (int pc = 0; pc < n_pc; ++pc, ++G) {
-          uint32_t r0[32], r1[32];
-          tmem_ld_32x32(t_lane + pc * 64, r0);
-          tmem_ld_32x32(t_lane + pc * 64 + 32, r1);
-          tmem_ld_wait();
-          uint32_t pk[32];  // 64 fp16 values of this row; words of granules >= NK stay unwritten and unstored
+        } else {
+          const int NK = (Lk + 15) & ~15;  // the UMMA key count of this item (MMA warp: same expression)
+          // pass 1: row maximum over the valid keys
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+          for (int c = 0; c < n_chunks; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(t_lane + c * 32, r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int gi = 0; gi < 4; ++gi) {
-            const uint32_t* rr = gi < 2 ? r0 + gi * 16 : r1 + (gi - 2) * 16;
-            const int c0 = pc * 64 + gi * 16;
-            if (c0 >= shift && c0 + 16 <= Lk) {
+            for (int gi = 0; gi < 2; ++gi) {
+              const int c0 = c * 32 + gi * 16;
+              if (c0 >= shift && c0 + 16 <= Lk) {
 #pragma unroll
-              for (int j = 0; j < 16; j += 2) {
-                float a, b;
-                unpack2(fma2(pack2(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1])), scale2, nmb2), a, b);
-                a = fast_ex2(a);
-                b = fast_ex2(b);
-                acc2 = add2(acc2, pack2(a, b));
-                pk[gi * 8 + (j >> 1)] = pack_f16x2(a, b);
-              }
-            } else if (c0 < NK) {
+                for (int j = 0; j < 16; j += 4) {
+                  mx0 = max3(mx0, __uint_as_float(r[gi * 16 + j]), __uint_as_float(r[gi * 16 + j + 1]));
+                  mx1 = max3(mx1, __uint_as_float(r[gi * 16 + j + 2]), __uint_as_float(r[gi * 16 + j + 3]));
+                }
+              } else if (c0 < Lk) {
 #pragma unroll
-              for (int j = 0; j < 16; j += 2) {
-                float a = 0.f, b = 0.f;
-                if (c0 + j >= shift && c0 + j < Lk) a = fast_ex2(fmaf(__uint_as_float(rr[j]), SCALE_LOG2, -mb));
-                if (c0 + j + 1 >= shift && c0 + j + 1 < Lk)
-                  b = fast_ex2(fmaf(__uint_as_float(rr[j + 1]), SCALE_LOG2, -mb));
-                sum += a + b;
-                pk[gi * 8 + (j >> 1)] = pack_f16x2(a, b);
+                for (int j = 0; j < 16; ++j)
+                  if (c0 + j >= shift && c0 + j < Lk) mx0 = fmaxf(mx0, __uint_as_float(r[gi * 16 + j]));
               }
             }
           }
-          const int n_slots = min(64, NK - pc * 64) >> 3;  // 16-byte slots the P V MMAs of this chunk read
-          mbar_wait(&bar_pfree[grp], (G & 1) ^ 1);  // the previous chunk's MMAs have read the buffer
+          mb = fmaxf(mx0, mx1) * SCALE_LOG2;
+          // pass 2, per 64-key chunk (see VER 1 below), in 16-key granules
+          const uint64_t scale2 = pack2(SCALE_LOG2, SCALE_LOG2), nmb2 = pack2(-mb, -mb);
+          uint64_t acc2 = pack2(0.f, 0.f);
+          for (int pc = 0; pc < n_pc; ++pc, ++G) {
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32(t_lane + pc * 64, r0);
+            tmem_ld_32x32(t_lane + pc * 64 + 32, r1);
+            tmem_ld_wait();
+            uint32_t pk[32];  // 64 fp16 values of this row; words of granules >= NK stay unwritten and unstored
 #pragma unroll
-          for (int j = 0; j < 8; ++j)  // 16-byte slot j = keys 8j .. 8j+7
-            if (j < n_slots)
-              *reinterpret_cast<uint4*>(p_row + ((j ^ (r_tile & 7)) << 4)) =
-                  make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar_pready[grp]);
+            for (int gi = 0; gi < 4; ++gi) {
+              const uint32_t* rr = gi < 2 ? r0 + gi * 16 : r1 + (gi - 2) * 16;
+              const int c0 = pc * 64 + gi * 16;
+              if (c0 >= shift && c0 + 16 <= Lk) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                  float a, b;
+                  unpack2(fma2(pack2(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1])), scale2, nmb2), a, b);
+                  a = fast_ex2(a);
+                  b = fast_ex2(b);
+                  acc2 = add2(acc2, pack2(a, b));
+                  pk[gi * 8 + (j >> 1)] = pack_f16x2(a, b);
+                }
+              } else if (c0 < NK) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                  float a = 0.f, b = 0.f;
+                  if (c0 + j >= shift && c0 + j < Lk) a = fast_ex2(fmaf(__uint_as_float(rr[j]), SCALE_LOG2, -mb));
+                  if (c0 + j + 1 >= shift && c0 + j + 1 < Lk)
+                    b = fast_ex2(fmaf(__uint_as_float(rr[j + 1]), SCALE_LOG2, -mb));
+                  sum += a + b;
+                  pk[gi * 8 + (j >> 1)] = pack_f16x2(a, b);
+                }
+              }
+            }
+            const int n_slots = min(64, NK - pc * 64) >> 3;  // 16-byte slots the P V MMAs of this chunk read
+            mbar_wait(&bar_pfree[grp], (G & 1) ^ 1);  // the previous chunk's MMAs have read the buffer
+#pragma unroll
+            for (int j = 0; j < 8; ++j)  // 16-byte slot j = keys 8j .. 8j+7
+              if (j < n_slots)
+                *reinterpret_cast<uint4*>(p_row + ((j ^ (r_tile & 7)) << 4)) =
+                    make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_pready[grp]);
+          }
+          float s_lo, s_hi;
+          unpack2(acc2, s_lo, s_hi);
+          sum += s_lo + s_hi;
         }
-        float s_lo, s_hi;
-        unpack2(acc2, s_lo, s_hi);
-        sum += s_lo + s_hi;
       } else {
       // pass 1: row maximum over the valid keys
       float mx = -INFINITY;

@@ -242,78 +242,91 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
       tc_fence_after();
       float mb, sum = 0.f;
       if constexpr (VER == 2) {
-        const int NK = (Lk + 15) & ~15;  // the UMMA key count of this item (MMA warp: same expression)
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-        for (int c = 0; c < n_chunks; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(t_lane + c * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int gi = 0; gi < 2; ++gi) {
-            const int c0 = c * 32 + gi * 16;
-            if (c0 >= shift && c0 + 16 <= Lk) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                mx0 = max3(mx0, __uint_as_float(r[gi * 16 + j]), __uint_as_float(r[gi * 16 + j + 1]));
-                mx1 = max3(mx1, __uint_as_float(r[gi * 16 + j + 2]), __uint_as_float(r[gi * 16 + j + 3]));
-              }
-            } else if (c0 < Lk) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (c0 + j >= shift && c0 + j < Lk) mx0 = fmaxf(mx0, __uint_as_float(r[gi * 16 + j]));
-            }
+        if (grp * 128 + q * 32 >= len) {
+          // all 32 query rows of this warp lie beyond the sequence (rows 224..255 at 197 tokens): nothing to
+          // compute -- the P rows it would write feed output rows that are never stored -- but the chunk
+          // hand-shake with the MMA warp still counts four arrivals per tile
+          mb = 0.f;
+          sum = 1.f;
+          for (int pc = 0; pc < n_pc; ++pc, ++G) {
+            mbar_wait(&bar_pfree[grp], (G & 1) ^ 1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_pready[grp]);
           }
-        }
-        mb = fmaxf(mx0, mx1) * SCALE_LOG2;
-        const uint64_t scale2 = pack2(SCALE_LOG2, SCALE_LOG2), nmb2 = pack2(-mb, -mb);
-        uint64_t acc2 = pack2(0.f, 0.f);
-        for (int pc = 0; pc < n_pc; ++pc, ++G) {
-          uint32_t r0[32], r1[32];
-          tmem_ld_32x32(t_lane + pc * 64, r0);
-          tmem_ld_32x32(t_lane + pc * 64 + 32, r1);
-          tmem_ld_wait();
+        } else {
+          const int NK = (Lk + 15) & ~15;  // the UMMA key count of this item (MMA warp: same expression)
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+          for (int c = 0; c < n_chunks; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(t_lane + c * 32, r);
+            tmem_ld_wait();
 #pragma unroll
-          for (int gi = 0; gi < 4; ++gi) {  // in place: scores -> tf32-rounded probabilities
-            uint32_t* rr = gi < 2 ? r0 + gi * 16 : r1 + (gi - 2) * 16;
-            const int c0 = pc * 64 + gi * 16;
-            if (c0 >= shift && c0 + 16 <= Lk) {
+            for (int gi = 0; gi < 2; ++gi) {
+              const int c0 = c * 32 + gi * 16;
+              if (c0 >= shift && c0 + 16 <= Lk) {
 #pragma unroll
-              for (int j = 0; j < 16; j += 2) {
-                float a, b;
-                unpack2(fma2(pack2(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1])), scale2, nmb2), a, b);
-                a = fast_ex2(a);
-                b = fast_ex2(b);
-                acc2 = add2(acc2, pack2(a, b));
-                rr[j] = __float_as_uint(round_tf32(a));
-                rr[j + 1] = __float_as_uint(round_tf32(b));
-              }
-            } else if (c0 < NK) {
+                for (int j = 0; j < 16; j += 4) {
+                  mx0 = max3(mx0, __uint_as_float(r[gi * 16 + j]), __uint_as_float(r[gi * 16 + j + 1]));
+                  mx1 = max3(mx1, __uint_as_float(r[gi * 16 + j + 2]), __uint_as_float(r[gi * 16 + j + 3]));
+                }
+              } else if (c0 < Lk) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                float a = 0.f;
-                if (c0 + j >= shift && c0 + j < Lk) a = fast_ex2(fmaf(__uint_as_float(rr[j]), SCALE_LOG2, -mb));
-                sum += a;
-                rr[j] = __float_as_uint(round_tf32(a));
+                for (int j = 0; j < 16; ++j)
+                  if (c0 + j >= shift && c0 + j < Lk) mx0 = fmaxf(mx0, __uint_as_float(r[gi * 16 + j]));
               }
             }
           }
-          const int keys = min(64, NK - pc * 64);  // keys of this chunk the P V MMAs read (multiple of 16)
-          mbar_wait(&bar_pfree[grp], (G & 1) ^ 1);  // the previous chunk's MMAs have read the buffer
+          mb = fmaxf(mx0, mx1) * SCALE_LOG2;
+          const uint64_t scale2 = pack2(SCALE_LOG2, SCALE_LOG2), nmb2 = pack2(-mb, -mb);
+          uint64_t acc2 = pack2(0.f, 0.f);
+          for (int pc = 0; pc < n_pc; ++pc, ++G) {
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32(t_lane + pc * 64, r0);
+            tmem_ld_32x32(t_lane + pc * 64 + 32, r1);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {  // 16-byte slot j = keys 4j .. 4j+3 of either 32-key sub-chunk
-            const int sj = (j ^ (r_tile & 7)) << 2;
-            if (4 * j < keys)
-              *reinterpret_cast<uint4*>(p_lo + sj) = make_uint4(r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]);
-            if (32 + 4 * j < keys)
-              *reinterpret_cast<uint4*>(p_hi + sj) = make_uint4(r1[4 * j], r1[4 * j + 1], r1[4 * j + 2], r1[4 * j + 3]);
+            for (int gi = 0; gi < 4; ++gi) {  // in place: scores -> tf32-rounded probabilities
+              uint32_t* rr = gi < 2 ? r0 + gi * 16 : r1 + (gi - 2) * 16;
+              const int c0 = pc * 64 + gi * 16;
+              if (c0 >= shift && c0 + 16 <= Lk) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                  float a, b;
+                  unpack2(fma2(pack2(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1])), scale2, nmb2), a, b);
+                  a = fast_ex2(a);
+                  b = fast_ex2(b);
+                  acc2 = add2(acc2, pack2(a, b));
+                  rr[j] = __float_as_uint(round_tf32(a));
+                  rr[j + 1] = __float_as_uint(round_tf32(b));
+                }
+              } else if (c0 < NK) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  float a = 0.f;
+                  if (c0 + j >= shift && c0 + j < Lk) a = fast_ex2(fmaf(__uint_as_float(rr[j]), SCALE_LOG2, -mb));
+                  sum += a;
+                  rr[j] = __float_as_uint(round_tf32(a));
+                }
+              }
+            }
+            const int keys = min(64, NK - pc * 64);  // keys of this chunk the P V MMAs read (multiple of 16)
+            mbar_wait(&bar_pfree[grp], (G & 1) ^ 1);  // the previous chunk's MMAs have read the buffer
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {  // 16-byte slot j = keys 4j .. 4j+3 of either 32-key sub-chunk
+              const int sj = (j ^ (r_tile & 7)) << 2;
+              if (4 * j < keys)
+                *reinterpret_cast<uint4*>(p_lo + sj) = make_uint4(r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]);
+              if (32 + 4 * j < keys)
+                *reinterpret_cast<uint4*>(p_hi + sj) = make_uint4(r1[4 * j], r1[4 * j + 1], r1[4 * j + 2], r1[4 * j + 3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_pready[grp]);
           }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar_pready[grp]);
+          float s_lo, s_hi;
+          unpack2(acc2, s_lo, s_hi);
+          sum += s_lo + s_hi;
         }
-        float s_lo, s_hi;
-        unpack2(acc2, s_lo, s_hi);
-        sum += s_lo + s_hi;
       } else {
       // pass 1: row maximum over the valid keys
       float mx = -INFINITY;
