@@ -280,6 +280,26 @@ MER_API long long mer_resnet18_workspace_bytes(int n_frames);
 MER_API int mer_resnet18_forward(const MerResnet18Model* model, const uint8_t* frames_bgr, int n_frames,
                                  void* workspace, long long workspace_bytes, float* out_feats, void* stream);
 
+/* ---- VGGish audio embedding network (MERBench/feature_extraction/audio/vggish/vggish_slim.py:37-100, called by
+ * extract_vggish_embedding.py:30-49 through the TF graph tensors vggish/input_features -> vggish/embedding).
+ * convs: conv1, conv2, conv3_1, conv3_2, conv4_1, conv4_2 (3x3, 'SAME', ReLU) in MerResnetConv structs whose w is
+ * a SPLIT-BF16 (MER_GEMM_BF16X3) [cout_pad, kpad] matrix, rows in (ky, kx, cin) order = the TF HWIO variable
+ * transposed to [O, H, W, I]; conv1: cin 1, kpad 32, cout_pad 128.  fc_w: split-bf16 [N, K] (= the TF [K, N]
+ * variable transposed) for fc1_1 (K 12288 = the NHWC flatten of [6, 4, 512]), fc1_2 (4096 x 4096) and fc2
+ * (128 x 4096); fc_b fp32 [N]. */
+typedef struct MerVggishModel {
+  MerResnetConv convs[6];
+  const void* fc_w[3];
+  const float* fc_b[3];
+} MerVggishModel;
+
+MER_API long long mer_vggish_workspace_bytes(int n_examples);
+/* examples: fp32 [n_examples, 96, 64] log-mel patches (mer_logmel + the framing of vggish_input.py:37-82);
+ * out_embeddings: fp32 [n_examples, 128] = the 'vggish/embedding' tensor (ReLU output of fc2, no PCA
+ * post-processing: the reference script saves it as is). */
+MER_API int mer_vggish_forward(const MerVggishModel* model, const float* examples, int n_examples, void* workspace,
+                               long long workspace_bytes, float* out_embeddings, void* stream);
+
 /* ---- HuBERT-base audio encoder ------------------------------------------------------------------ */
 typedef struct MerHubertModel {
   int n_layers;  /* 12 (>= 4: the readout sums the last four hidden states) */

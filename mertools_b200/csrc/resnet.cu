@@ -1,4 +1,4 @@
-// resnet.cu — ResNet-18 frame encoder of the reference's ImageNet CNN extractor
+// resnet.cu — the convolutional extractors: ResNet-18 frame encoder of the reference's ImageNet CNN extractor
 // (MERBench/feature_extraction/visual/extract_imagenet_embedding.py:47-55: torchvision resnet18 without its
 // fc layer on Resize(224) / ToTensor / Normalize(ImageNet) frames -> one 512-vector per frame).
 //
@@ -40,8 +40,11 @@ im2col_stem_kernel(const uint8_t* __restrict__ frames, int H, int W, int OH, int
   out[idx] = (uint16_t)(pack_f16x2(v, 0.f) & 0xffffu);
 }
 
-// generic gather: NHWC fp32 activations [n, H, W, cs] (first C channels real) -> fp16 rows (n, oy, ox) of
-// K = k*k*C in (ky, kx, c) order; one thread = 8 consecutive channels (16 bytes out).
+// generic gather: NHWC fp32 activations [n, H, W, cs] (first C channels real) -> operand rows (n, oy, ox) of
+// K = k*k*C values in (ky, kx, c) order; one thread = 8 consecutive channels.  SPLIT = false: fp16 (16 bytes
+// out, MER_GEMM_F16); SPLIT = true: bf16 hi | lo in the 128-byte groups of MER_GEMM_BF16X3 (two 16-byte stores:
+// 8 consecutive K indices never straddle a 32-value group).
+template <bool SPLIT>
 __global__ void __launch_bounds__(256)
 im2col_kernel(const float* __restrict__ x, int H, int W, int cs, int C, int ksz, int stride, int pad, int OH, int OW,
               uint4* __restrict__ out, long long total8) {
@@ -55,13 +58,23 @@ im2col_kernel(const float* __restrict__ x, int H, int W, int cs, int C, int ksz,
   const int ox = (int)(row % OW), oy = (int)((row / OW) % OH);
   const long long n = row / ((long long)OW * OH);
   const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
-  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
   if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
     const float4* src = reinterpret_cast<const float4*>(x + ((n * H + iy) * W + ix) * (long long)cs + cg * 8);
-    const float4 a = __ldg(src), b = __ldg(src + 1);
-    o = make_uint4(pack_f16x2(a.x, a.y), pack_f16x2(a.z, a.w), pack_f16x2(b.x, b.y), pack_f16x2(b.z, b.w));
+    a = __ldg(src);
+    b = __ldg(src + 1);
   }
-  out[idx] = o;
+  if (SPLIT) {
+    const int k = q * 8;  // K index of the first of the 8 values
+    uint4* grp = out + (row * kc + (k >> 5) * 4) * 2 + ((k & 31) >> 3);  // 16-byte slot of the hi half
+    const float h0 = bf16_round(a.x), h1 = bf16_round(a.y), h2 = bf16_round(a.z), h3 = bf16_round(a.w);
+    const float h4 = bf16_round(b.x), h5 = bf16_round(b.y), h6 = bf16_round(b.z), h7 = bf16_round(b.w);
+    grp[0] = make_uint4(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3), pack_bf16x2(h4, h5), pack_bf16x2(h6, h7));
+    grp[4] = make_uint4(pack_bf16x2(a.x - h0, a.y - h1), pack_bf16x2(a.z - h2, a.w - h3),
+                        pack_bf16x2(b.x - h4, b.y - h5), pack_bf16x2(b.z - h6, b.w - h7));
+  } else {
+    out[idx] = make_uint4(pack_f16x2(a.x, a.y), pack_f16x2(a.z, a.w), pack_f16x2(b.x, b.y), pack_f16x2(b.z, b.w));
+  }
 }
 
 // MaxPool2d(3, stride 2, padding 1) on NHWC fp32, 4 channels per thread
@@ -88,18 +101,67 @@ maxpool3x3s2_kernel(const float4* __restrict__ x, int H, int W, int c4, int OH, 
   y[idx] = m;
 }
 
+// VGGish conv1 gather: fp32 log-mel examples [n, H, W] (one channel) -> split-bf16 rows (n, y, x) of K = 9 taps
+// (ky, kx) zero-padded to one 32-value group = 128 bytes [32 hi | 32 lo]; one thread = one 16-byte slot
+// (slots 0..3: hi of taps 8 s .. 8 s + 7, slots 4..7: the lo halves).
+__global__ void __launch_bounds__(256)
+im2col_1ch_kernel(const float* __restrict__ x, int H, int W, uint4* __restrict__ out, long long total_slots) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total_slots) return;
+  const int slot = (int)(idx & 7), ks = (slot & 3) * 8;
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (ks < 9) {
+    const long long row = idx >> 3;
+    const int px = (int)(row % W), py = (int)((row / W) % H);
+    const float* img = x + (row / ((long long)W * H)) * H * W;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = ks + j, iy = py - 1 + k / 3, ix = px - 1 + k % 3;
+      const float val = (k < 9 && iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(img + iy * W + ix) : 0.f;
+      const float hi = bf16_round(val);
+      v[j] = slot < 4 ? hi : val - hi;
+    }
+    o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+  out[idx] = o;
+}
+
+// max_pool2d 2x2 / stride 2 on NHWC fp32 (even H and W: TF 'SAME' == 'VALID'), 4 channels per thread
+__global__ void __launch_bounds__(256)
+maxpool2x2_kernel(const float4* __restrict__ x, int H, int W, int c4, float4* __restrict__ y, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int OW = W / 2, OH = H / 2;
+  const int c = (int)(idx % c4);
+  const long long pos = idx / c4;
+  const int ox = (int)(pos % OW), oy = (int)((pos / OW) % OH);
+  const long long n = pos / ((long long)OW * OH);
+  const float4* p = x + ((n * H + 2 * oy) * W + 2 * ox) * (long long)c4 + c;
+  const float4 a = __ldg(p), b = __ldg(p + c4), d = __ldg(p + (long long)W * c4), e = __ldg(p + (long long)(W + 1) * c4);
+  y[idx] = make_float4(fmaxf(fmaxf(a.x, b.x), fmaxf(d.x, e.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(d.y, e.y)),
+                       fmaxf(fmaxf(a.z, b.z), fmaxf(d.z, e.z)), fmaxf(fmaxf(a.w, b.w), fmaxf(d.w, e.w)));
+}
+
 struct Shape { int H, W, C, Cs; };  // C real channels, Cs stored channels (>= 128)
 
+// mode: MER_GEMM_F16 (fp16 operand, weights fp16) or MER_GEMM_BF16X3 (split-bf16 operand and weights)
 int conv(const MerResnetConv& cv, const float* x, Shape in, int n, uint16_t* col, const float* res, bool relu,
-         float* y, Shape* out, cudaStream_t st) {
+         float* y, Shape* out, cudaStream_t st, int mode = MER_GEMM_F16) {
   const int OH = (in.H + 2 * cv.pad - cv.k) / cv.stride + 1, OW = (in.W + 2 * cv.pad - cv.k) / cv.stride + 1;
   const long long rows = (long long)n * OH * OW;
   const int K = cv.k * cv.k * in.C;
-  MER_REQUIRE(cv.cin == in.C && cv.kpad == K && K % 64 == 0 && in.C % 8 == 0, "resnet conv: geometry (cin %d K %d)",
-              cv.cin, K);
+  const bool split = mode == MER_GEMM_BF16X3;
+  MER_REQUIRE(cv.cin == in.C && cv.kpad == K && K % (split ? 32 : 64) == 0 && in.C % 8 == 0,
+              "conv: geometry (cin %d K %d)", cv.cin, K);
   const long long total8 = rows * (K / 8);
-  im2col_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(x, in.H, in.W, in.Cs, in.C, cv.k, cv.stride, cv.pad,
-                                                                  OH, OW, reinterpret_cast<uint4*>(col), total8);
+  const unsigned blocks = (unsigned)((total8 + 255) / 256);
+  if (split)
+    im2col_kernel<true><<<blocks, 256, 0, st>>>(x, in.H, in.W, in.Cs, in.C, cv.k, cv.stride, cv.pad, OH, OW,
+                                                reinterpret_cast<uint4*>(col), total8);
+  else
+    im2col_kernel<false><<<blocks, 256, 0, st>>>(x, in.H, in.W, in.Cs, in.C, cv.k, cv.stride, cv.pad, OH, OW,
+                                                 reinterpret_cast<uint4*>(col), total8);
   MER_CUDA_CHECK(cudaGetLastError());
   mer_count_launches(1);
   MerGemmDesc g;
@@ -116,7 +178,7 @@ int conv(const MerResnetConv& cv, const float* x, Shape in, int n, uint16_t* col
   g.a_phase_stride = K;
   g.a_row_stride = K;
   g.a_batch_stride = rows * K;
-  g.mode = MER_GEMM_F16;
+  g.mode = mode;
   g.ep.bias = cv.b;
   g.ep.res = res;
   g.ep.out = y;
@@ -233,6 +295,135 @@ int mer_resnet18_forward(const MerResnet18Model* m, const uint8_t* frames_bgr, i
   MER_REQUIRE(s.H == 7 && s.W == 7 && s.C == 512 && s.Cs == 512, "mer_resnet18_forward: unexpected final shape");
   if (int rc = mer_iota_offsets_launch(offsets, n_frames, 49, st)) return rc;
   return mer_segment_reduce_launch(x, offsets, offsets + 1, n_frames, 512, MER_SEG_MEAN, out_feats, st);
+}
+
+}  // extern "C"
+
+// ---- VGGish (MERBench/feature_extraction/audio/vggish/vggish_slim.py:37-100): six 3x3 'SAME' convolutions with
+// ReLU, four 2x2 max-pools, three fully connected layers with ReLU, on [96, 64] log-mel examples.
+// All nine GEMMs run MER_GEMM_BF16X3: nothing normalises between the layers, and an fp32 emulation of fp16
+// operands put the embedding 1.1e-3 off the fp32 result (every layer adds 2-5e-4), over the 1e-3 bar; at
+// 1.7 GFLOP per 0.96 s example the 3x MMA count is immaterial next to the HuBERT path (14 GFLOP per second). ----
+namespace {
+struct VggishPlan { long long off_a, off_p, off_col, off_h16, off_f, total; };
+VggishPlan vggish_plan(int n_examples) {
+  const long long n = n_examples;
+  auto al = [](long long x) { return (x + 255) & ~255ll; };
+  VggishPlan p;
+  long long o = 0;
+  p.off_a = o;   o += al(n * 96 * 64 * 128 * 4);      // conv outputs (conv1: 64 real channels stored as 128)
+  p.off_p = o;   o += al(n * 48 * 32 * 128 * 4);      // pooled maps / the second buffer of a conv pair
+  p.off_col = o; o += al(n * 48 * 32 * 576 * 4);      // split-bf16 im2col operand (largest: conv2; conv1 is 96*64*32)
+  p.off_h16 = o; o += al(n * 12288 * 4);              // split-bf16 operand of a fully connected layer
+  p.off_f = o;   o += al(n * 4096 * 4);               // fp32 output of fc1_1 / fc1_2
+  p.total = o;
+  return p;
+}
+
+// relu(x W^T + b): x fp32 [rows, K] -> split-bf16 scratch -> MER_GEMM_BF16X3 against split-bf16 weights [N, K]
+int fc(const void* w_split, const float* b, const float* x, void* x_split, int rows, int K, int N, float* out,
+       cudaStream_t st) {
+  if (int rc = mer_split_bf16(x, x_split, rows, K, st)) return rc;
+  MerGemmDesc g;
+  memset(&g, 0, sizeof(g));
+  g.A = static_cast<const float*>(x_split);
+  g.W = static_cast<const float*>(w_split);
+  g.rows_per_batch = rows;
+  g.a_rows_dim = rows;
+  g.batches = 1;
+  g.N = N;
+  g.K_inner = K;
+  g.taps = 1;
+  g.P = 1;
+  g.a_phase_stride = K;
+  g.a_row_stride = K;
+  g.a_batch_stride = (long long)rows * K;
+  g.mode = MER_GEMM_BF16X3;
+  g.ep.bias = b;
+  g.ep.out = out;
+  g.ep.ld_out = N;
+  g.ep.flags = MER_EPI_RELU;
+  return mer_gemm_launch(&g, st);
+}
+
+int pool2(const float* x, Shape* s, int n, float* y, cudaStream_t st) {
+  const long long total = (long long)n * (s->H / 2) * (s->W / 2) * (s->Cs / 4);
+  maxpool2x2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(x), s->H, s->W,
+                                                                     s->Cs / 4, reinterpret_cast<float4*>(y), total);
+  MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
+  s->H /= 2;
+  s->W /= 2;
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+long long mer_vggish_workspace_bytes(int n_examples) { return vggish_plan(n_examples).total; }
+
+int mer_vggish_forward(const MerVggishModel* m, const float* examples, int n_examples, void* workspace,
+                       long long workspace_bytes, float* out_embeddings, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  MER_REQUIRE(m && examples && workspace && out_embeddings && n_examples > 0, "mer_vggish_forward: bad operands");
+  const VggishPlan p = vggish_plan(n_examples);
+  MER_REQUIRE(workspace_bytes >= p.total, "mer_vggish_forward: workspace %lld B < required %lld B", workspace_bytes,
+              p.total);
+  MER_REQUIRE((long long)n_examples * 96 * 64 < (1ll << 31), "mer_vggish_forward: too many examples per call");
+  char* ws = static_cast<char*>(workspace);
+  float* A = reinterpret_cast<float*>(ws + p.off_a);
+  float* P = reinterpret_cast<float*>(ws + p.off_p);
+  uint16_t* col = reinterpret_cast<uint16_t*>(ws + p.off_col);
+  uint16_t* h16 = reinterpret_cast<uint16_t*>(ws + p.off_h16);
+  float* F = reinterpret_cast<float*>(ws + p.off_f);
+  const int n = n_examples;
+
+  // conv1 (1 -> 64): 9 taps gathered into one 32-value split group
+  {
+    const MerResnetConv& cv = m->convs[0];
+    MER_REQUIRE(cv.k == 3 && cv.cin == 1 && cv.kpad == 32 && cv.cout == 64 && cv.cout_pad == 128,
+                "mer_vggish_forward: conv1 packing");
+    const long long rows = (long long)n * 96 * 64, slots = rows * 8;
+    im2col_1ch_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(examples, 96, 64, reinterpret_cast<uint4*>(col),
+                                                                       slots);
+    MER_CUDA_CHECK(cudaGetLastError());
+    mer_count_launches(1);
+    MerGemmDesc g;
+    memset(&g, 0, sizeof(g));
+    g.A = reinterpret_cast<const float*>(col);
+    g.W = static_cast<const float*>(cv.w);
+    g.rows_per_batch = (int)rows;
+    g.a_rows_dim = (int)rows;
+    g.batches = 1;
+    g.N = 128;
+    g.K_inner = 32;
+    g.taps = 1;
+    g.P = 1;
+    g.a_phase_stride = 32;
+    g.a_row_stride = 32;
+    g.a_batch_stride = rows * 32;
+    g.mode = MER_GEMM_BF16X3;
+    g.ep.bias = cv.b;
+    g.ep.out = A;
+    g.ep.ld_out = 128;
+    g.ep.flags = MER_EPI_RELU;
+    if (int rc = mer_gemm_launch(&g, st)) return rc;
+  }
+  Shape s{96, 64, 64, 128};
+  if (int rc = pool2(A, &s, n, P, st)) return rc;  // [48, 32, 64]
+  if (int rc = conv(m->convs[1], P, s, n, col, nullptr, true, A, &s, st, MER_GEMM_BF16X3)) return rc;  // conv2 -> 128
+  if (int rc = pool2(A, &s, n, P, st)) return rc;  // [24, 16, 128]
+  if (int rc = conv(m->convs[2], P, s, n, col, nullptr, true, A, &s, st, MER_GEMM_BF16X3)) return rc;  // conv3_1 -> 256
+  if (int rc = conv(m->convs[3], A, s, n, col, nullptr, true, P, &s, st, MER_GEMM_BF16X3)) return rc;  // conv3_2
+  if (int rc = pool2(P, &s, n, A, st)) return rc;  // [12, 8, 256]
+  if (int rc = conv(m->convs[4], A, s, n, col, nullptr, true, P, &s, st, MER_GEMM_BF16X3)) return rc;  // conv4_1 -> 512
+  if (int rc = conv(m->convs[5], P, s, n, col, nullptr, true, A, &s, st, MER_GEMM_BF16X3)) return rc;  // conv4_2
+  if (int rc = pool2(A, &s, n, P, st)) return rc;  // [6, 4, 512]
+  MER_REQUIRE(s.H == 6 && s.W == 4 && s.C == 512 && s.Cs == 512, "mer_vggish_forward: unexpected final shape");
+  // slim.flatten of the NHWC map = the buffer as it lies; fc1_1, fc1_2, fc2 (all with ReLU)
+  if (int rc = fc(m->fc_w[0], m->fc_b[0], P, h16, n, 12288, 4096, F, st)) return rc;
+  if (int rc = fc(m->fc_w[1], m->fc_b[1], F, h16, n, 4096, 4096, A, st)) return rc;  // A is free again
+  return fc(m->fc_w[2], m->fc_b[2], A, h16, n, 4096, 128, out_embeddings, st);
 }
 
 }  // extern "C"

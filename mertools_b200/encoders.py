@@ -337,6 +337,89 @@ class ResNet18Encoder:
         return feats
 
 
+class MerVggishModel(C.Structure):
+    _fields_ = [("convs", MerResnetConv * 6), ("fc_w", C.c_void_p * 3), ("fc_b", C.c_void_p * 3)]
+
+
+VGGISH_CONVS = ("conv1", "conv2", "conv3/conv3_1", "conv3/conv3_2", "conv4/conv4_1", "conv4/conv4_2")
+VGGISH_FCS = ("fc1/fc1_1", "fc1/fc1_2", "fc2")
+# torchvggish port (harritaylor/torchvggish, vggish-10086976.pth): same tensors under nn.Sequential names
+_TORCHVGGISH = {"conv1": "features.0", "conv2": "features.3", "conv3/conv3_1": "features.6",
+                "conv3/conv3_2": "features.8", "conv4/conv4_1": "features.11", "conv4/conv4_2": "features.13",
+                "fc1/fc1_1": "embeddings.0", "fc1/fc1_2": "embeddings.2", "fc2": "embeddings.4"}
+
+
+def vggish_tf_names(state_dict):
+    """Accepts the TF checkpoint variables (``vggish/<scope>/weights|biases``, e.g. exported to .npz) or the
+    state_dict of the torchvggish port (OIHW convs, [out, in] linears) and returns the TF-named / TF-laid-out
+    dict the encoder packs from."""
+    sd = W._np(state_dict)
+    if "vggish/conv1/weights" in sd:
+        return sd
+    assert "features.0.weight" in sd, "neither TF VGGish variable names nor a torchvggish state_dict"
+    out = {}
+    for tf_name, pt in _TORCHVGGISH.items():
+        w = sd[pt + ".weight"]
+        out[f"vggish/{tf_name}/weights"] = w.transpose(2, 3, 1, 0) if w.ndim == 4 else w.T   # -> HWIO / [in, out]
+        out[f"vggish/{tf_name}/biases"] = sd[pt + ".bias"]
+    return out
+
+
+class VggishEncoder:
+    """VGGish embedding network of the reference's audio extractor: six 3x3 convolutions as im2col + tcgen05
+    GEMMs with ReLU epilogues, 2x2 max-pools, three fully connected layers; all GEMMs on split-bf16 operands
+    (MER_GEMM_BF16X3, ~fp32 accuracy: there is no normalisation between the nine layers).
+
+    Reference: MERBench/feature_extraction/audio/vggish/vggish_slim.py:37-100 (graph),
+    extract_vggish_embedding.py:30-49 (fetch of vggish/embedding for batches of log-mel examples)."""
+
+    def __init__(self, state_dict, device="cuda"):
+        L.check(L.lib().mer_check_device())
+        sd = vggish_tf_names(state_dict)
+        self.device = torch.device(device)
+        pk = self.pk = W.Packed(self.device)
+        m = MerVggishModel()
+        for i, name in enumerate(VGGISH_CONVS):
+            w = sd[f"vggish/{name}/weights"]                                   # HWIO [3, 3, cin, cout]
+            k, _, cin, cout = w.shape
+            assert k == 3, name
+            cout_pad, kk = max(cout, 128), 9 * cin
+            kpad = 32 if i == 0 else kk
+            wp = np.zeros((cout_pad, kpad), np.float32)
+            wp[:cout, :kk] = w.transpose(3, 0, 1, 2).reshape(cout, kk)         # (ky, kx, c) order
+            bp = np.zeros(cout_pad, np.float32)
+            bp[:cout] = sd[f"vggish/{name}/biases"]
+            c = m.convs[i]
+            c.w, c.b = pk.keep(wp, split=True).data_ptr(), pk.keep(bp).data_ptr()
+            c.cin, c.cout, c.cout_pad, c.k, c.stride, c.pad, c.kpad = cin, cout, cout_pad, 3, 1, 1, kpad
+        for i, name in enumerate(VGGISH_FCS):
+            w = sd[f"vggish/{name}/weights"]                                   # [in, out]
+            m.fc_w[i] = pk.keep(np.ascontiguousarray(w.T), split=True).data_ptr()
+            m.fc_b[i] = pk.keep(sd[f"vggish/{name}/biases"]).data_ptr()
+        self.model = m
+        self.feature_dim = 128
+        self.ws = _Workspace(self.device)
+        lib = L.lib()
+        lib.mer_vggish_workspace_bytes.restype = C.c_longlong
+        lib.mer_vggish_workspace_bytes.argtypes = [C.c_int]
+        self._fwd = L.declare("mer_vggish_forward", [C.POINTER(MerVggishModel), C.c_void_p, C.c_int, C.c_void_p,
+                                                     C.c_longlong, C.c_void_p, C.c_void_p])
+
+    def embeddings(self, examples: torch.Tensor, max_examples=256):
+        """examples: fp32 CUDA [n, 96, 64] log-mel patches -> [n, 128] fp32 (CUDA).  Chunks of ``max_examples``
+        bound the workspace (7.8 MB per example; the reference feeds 2048 at a time)."""
+        assert examples.is_cuda and examples.dtype == torch.float32 and examples.shape[1:] == (96, 64)
+        examples = examples.contiguous()
+        n = examples.shape[0]
+        out = torch.empty(n, 128, dtype=torch.float32, device=self.device)
+        for s in range(0, n, max_examples):
+            k = min(max_examples, n - s)
+            ws = self.ws.get(L.lib().mer_vggish_workspace_bytes(k))
+            L.check(self._fwd(C.byref(self.model), L.ptr(examples[s:s + k]), k, L.ptr(ws), ws.numel(),
+                              L.ptr(out[s:s + k]), L.stream_ptr()))
+        return out
+
+
 class MerHubertModel(C.Structure):
     _fields_ = [("n_layers", C.c_int), ("ln_eps", C.c_float), ("conv0_w", C.c_void_p),
                 ("gn_g", C.c_void_p), ("gn_b", C.c_void_p), ("conv_w", C.c_void_p * 6),

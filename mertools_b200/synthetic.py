@@ -124,6 +124,24 @@ def resnet18_state_dict(seed=6):
     return sd
 
 
+def vggish_state_dict(seed=8):
+    """Variables of the reference's VGGish graph under their TF checkpoint names (vggish_slim.py:63-99): conv
+    kernels HWIO, fully connected [in, out].  He-style scales and non-zero biases (the checkpoint-less default,
+    N(0, 0.01) with zero biases, would drive every activation to ~0 after nine ReLU layers)."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+    cin = 1
+    for name, cout in (("conv1", 64), ("conv2", 128), ("conv3/conv3_1", 256), ("conv3/conv3_2", 256),
+                       ("conv4/conv4_1", 512), ("conv4/conv4_2", 512)):
+        sd[f"vggish/{name}/weights"] = (rng.standard_normal((3, 3, cin, cout)) * np.sqrt(2.0 / (9 * cin))).astype(np.float32)
+        sd[f"vggish/{name}/biases"] = (0.1 * rng.standard_normal(cout)).astype(np.float32)
+        cin = cout
+    for name, k, n in (("fc1/fc1_1", 12288, 4096), ("fc1/fc1_2", 4096, 4096), ("fc2", 4096, 128)):
+        sd[f"vggish/{name}/weights"] = (rng.standard_normal((k, n)) * np.sqrt(2.0 / k)).astype(np.float32)
+        sd[f"vggish/{name}/biases"] = (0.1 * rng.standard_normal(n)).astype(np.float32)
+    return sd
+
+
 HUBERT_LARGE_CFG = dict(HUBERT_CFG, hidden=1024, heads=16, ffn=4096, layers=24)
 
 

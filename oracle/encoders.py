@@ -135,6 +135,32 @@ def resnet18_features(sd, x, dtype=torch.float32, eps=1e-5):
     return y.mean(dim=(2, 3))
 
 
+VGGISH_CONVS = ("conv1", "conv2", "conv3/conv3_1", "conv3/conv3_2", "conv4/conv4_1", "conv4/conv4_2")
+VGGISH_FCS = ("fc1/fc1_1", "fc1/fc1_2", "fc2")
+VGGISH_POOL_AFTER = ("conv1", "conv2", "conv3/conv3_2", "conv4/conv4_2")
+
+
+def vggish_embeddings(sd, examples, dtype=torch.float32):
+    """``define_vggish_slim`` (vggish_slim.py:37-100) restated: sd holds the TF variables under their checkpoint
+    names (``vggish/<scope>/weights`` HWIO or [in, out], ``vggish/<scope>/biases``); every conv is 3x3 / stride 1
+    / 'SAME' + ReLU, every pool 2x2 / stride 2 (even sizes: 'SAME' == 'VALID'), ``slim.flatten`` runs over the
+    NHWC map, all three fully connected layers end in ReLU (the arg_scope default, :58-62), the result is the
+    ``vggish/embedding`` tensor the reference fetches (extract_vggish_embedding.py:35-49).
+    examples: [n, 96, 64] log-mel patches.  Returns [n, 128].
+    PARITY UNPINNED for this function: TensorFlow / tf_slim are not installed here, so the reference graph
+    cannot be executed; the restatement follows the definition file only."""
+    x = examples.to(dtype)[:, None]
+    for name in VGGISH_CONVS:
+        w = _t(sd, f"vggish/{name}/weights", dtype).permute(3, 2, 0, 1)  # HWIO -> OIHW
+        x = F.relu(F.conv2d(x, w, _t(sd, f"vggish/{name}/biases", dtype), padding=1))
+        if name in VGGISH_POOL_AFTER:
+            x = F.max_pool2d(x, 2)
+    x = x.permute(0, 2, 3, 1).reshape(x.shape[0], -1)
+    for name in VGGISH_FCS:
+        x = F.relu(x @ _t(sd, f"vggish/{name}/weights", dtype) + _t(sd, f"vggish/{name}/biases", dtype))
+    return x
+
+
 def hubert_pos_conv_weight(sd, dtype=torch.float32):
     """Effective weight of the weight-normed positional conv (:45-92): W = g * v / ||v||, the
     norm taken over dims (0,1) per kernel tap (weight_norm dim=2).  Older checkpoints name the

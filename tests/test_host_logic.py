@@ -266,3 +266,14 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "clips/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
+
+
+def test_vggish_save_rules_match_reference_script():
+    """extract_vggish_embedding.py:52-59: UTTERANCE squeezes and averages over segments, FRAME saves [segments, 128]."""
+    from mertools_b200.extract import vggish
+    one, many = np.arange(128.0)[None], np.stack([np.arange(128.0), np.ones(128)])
+    assert vggish.save_embeddings(None, one, "UTTERANCE").shape == (128,)
+    assert np.array_equal(vggish.save_embeddings(None, many, "UTTERANCE"), many.mean(0))
+    assert vggish.save_embeddings(None, one, "FRAME").shape == (1, 128)
+    args = vggish.build_parser().parse_args([])
+    assert (args.gpu, args.feature_level, args.dataset) == (0, "FRAME", "MER2023")

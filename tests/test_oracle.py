@@ -235,3 +235,32 @@ def test_oracle_resnet18_matches_torchvision():
     bgr = np.random.default_rng(3).integers(0, 256, (2, 112, 112, 3), dtype=np.uint8)
     ref_in = torch.stack([tf(Image.fromarray(f[..., ::-1].copy())) for f in bgr])
     assert float((P.imagenet_preprocess(bgr) - ref_in).abs().max()) < 1e-6
+
+
+def test_oracle_vggish_matches_the_torch_port_graph():
+    """The VGGish restatement (TF variable names, HWIO kernels, NHWC flatten) against the graph of the public
+    PyTorch port (torchvggish: nn.Sequential features + embeddings, NCHW convs, two transposes before the
+    flatten), weights converted by ``encoders.vggish_tf_names``.  TensorFlow is absent, so this pins the layout
+    conventions to a second, independently written form of the same network, not to the reference graph."""
+    from torch import nn
+
+    from mertools_b200.encoders import vggish_tf_names
+    torch.manual_seed(5)
+    feats = nn.Sequential(
+        nn.Conv2d(1, 64, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2), nn.Conv2d(64, 128, 3, padding=1), nn.ReLU(),
+        nn.MaxPool2d(2), nn.Conv2d(128, 256, 3, padding=1), nn.ReLU(), nn.Conv2d(256, 256, 3, padding=1), nn.ReLU(),
+        nn.MaxPool2d(2), nn.Conv2d(256, 512, 3, padding=1), nn.ReLU(), nn.Conv2d(512, 512, 3, padding=1), nn.ReLU(),
+        nn.MaxPool2d(2))
+    emb = nn.Sequential(nn.Linear(512 * 4 * 6, 4096), nn.ReLU(), nn.Linear(4096, 4096), nn.ReLU(),
+                        nn.Linear(4096, 128), nn.ReLU())
+    sd = {f"features.{k}": v for k, v in feats.state_dict().items()}
+    sd.update({f"embeddings.{k}": v for k, v in emb.state_dict().items()})
+    x = torch.randn(2, 96, 64) * 2.0 - 1.0
+    with torch.no_grad():
+        y = feats(x[:, None])
+        y = torch.transpose(torch.transpose(y, 1, 3), 1, 2).contiguous().view(2, -1)
+        ref = emb(y)
+        tf_sd = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in vggish_tf_names(sd).items()}
+        got = E.vggish_embeddings(tf_sd, x)
+    assert tf_sd["vggish/conv2/weights"].shape == (3, 3, 64, 128) and tf_sd["vggish/fc1/fc1_1/weights"].shape == (12288, 4096)
+    assert got.shape == (2, 128) and float((got - ref).abs().max()) < 1e-5 * float(ref.abs().max())

@@ -143,3 +143,51 @@ def test_gemm_packed_gelu_epilogue(cuda):
         outs.append(L.unsplit_bf16(out).double().cpu())
         assert float((outs[-1] - ref).abs().max() / ref.abs().max()) < 3e-5
     assert float((outs[0] - outs[1]).abs().max() / ref.abs().max()) < 1e-5
+
+
+def test_vggish_embeddings_match_oracle(cuda):
+    """VGGish network (vggish_slim.py:37-100) on split-bf16 tcgen05 GEMMs against the fp32 restatement."""
+    import numpy as np
+
+    from mertools_b200 import synthetic as S
+    from mertools_b200.encoders import VggishEncoder
+    from oracle import encoders as E
+    sd = S.vggish_state_dict(seed=8)
+    x = np.random.default_rng(9).normal(-2.0, 2.0, (5, 96, 64)).astype(np.float32)
+    got = VggishEncoder(sd, device=cuda).embeddings(torch.from_numpy(x).to(cuda), max_examples=3).cpu()
+    ref = E.vggish_embeddings({k: torch.from_numpy(v) for k, v in sd.items()}, torch.from_numpy(x))
+    assert got.shape == (5, 128)
+    assert float((got - ref).abs().max() / ref.abs().max()) < 1e-3
+
+
+def test_vggish_extractor_files(cuda, tmp_path):
+    """extract_vggish_embedding.extract mirror: wav -> log-mel examples (0.5 s / 0.05 s hops) -> embeddings ->
+    vggish_UTT / vggish_FRA save rules, against the oracle pipeline on the same waveform."""
+    import sys
+    import types
+
+    import numpy as np
+    from scipy.io import wavfile
+
+    from mertools_b200 import synthetic as S
+    from mertools_b200.extract import vggish
+    from oracle import encoders as E
+    from oracle import pipeline as P
+    sd = S.vggish_state_dict(seed=8)
+    rng = np.random.default_rng(4)
+    wave = np.clip(np.round(3000 * rng.standard_normal(16000 * 3)), -32768, 32767).astype(np.int16)
+    wav = tmp_path / "clipA.wav"
+    wavfile.write(wav, 16000, wave)
+    stub = types.ModuleType("soundfile")
+    stub.read = lambda path, dtype=None: (wavfile.read(path)[1], wavfile.read(path)[0])
+    sys.modules.setdefault("soundfile", stub)
+    tsd = {k: torch.from_numpy(v) for k, v in sd.items()}
+    for level, hop in (("UTTERANCE", 0.5), ("FRAME", 0.05)):
+        out = tmp_path / level
+        out.mkdir()
+        vggish.extract([str(wav)], str(out), level, state_dict=sd, device="cuda:0")
+        got = np.load(out / "clipA.npy")
+        ex = P.waveform_to_examples(wave / 32768.0, hop)
+        ref = E.vggish_embeddings(tsd, torch.from_numpy(ex.astype(np.float32))).numpy()
+        ref = ref.mean(0) if level == "UTTERANCE" else ref
+        assert got.shape == ref.shape and np.abs(got - ref).max() / np.abs(ref).max() < 1e-3
