@@ -259,11 +259,11 @@ int mer_attention_launch(const float* qkv, const float* vt, long long vt_ld, flo
   MER_REQUIRE(heads > 0 && heads <= 65535 && n_seq <= 65535, "mer_attention: bad grid (%d heads, %d seqs)",
               heads, n_seq);
   if (n_seq <= 0 || max_seqlen <= 0) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static MerPerDevice attr_set;
+  if (attr_set.needs_setup()) {
     MER_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         ATT_SMEM));
-    attr_set = true;
+    attr_set.mark();
   }
   dim3 grid((max_seqlen + BQ - 1) / BQ, heads, n_seq);
   attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(qkv, ctx, cu_seqlens, heads,

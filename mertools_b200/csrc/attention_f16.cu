@@ -436,11 +436,11 @@ int mer_attention_f16_launch(const void* qkv16, const void* vt16, long long vt_l
   const char* ver_env = getenv("MER_ATT_F16_VER");
   const bool ver2 = ver_env && atoi(ver_env) == 2;
   auto kern = ver2 ? attention_f16_kernel<2> : attention_f16_kernel<1>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static MerPerDevice attr_set;
+  if (attr_set.needs_setup()) {
     MER_CUDA_CHECK(cudaFuncSetAttribute(attention_f16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM));
     MER_CUDA_CHECK(cudaFuncSetAttribute(attention_f16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM));
-    attr_set = true;
+    attr_set.mark();
   }
   const long long items = (long long)n_seq * heads;
   if (items <= 0) return 0;

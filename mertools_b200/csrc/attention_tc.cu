@@ -465,11 +465,11 @@ int mer_attention_tc_launch(const float* qkv, const float* vt, long long vt_ld, 
   const char* ver_env = getenv("MER_ATT_TC_VER");
   const bool ver2 = ver_env && atoi(ver_env) == 2;
   auto kern = ver2 ? attention_tc_kernel<2> : attention_tc_kernel<1>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static MerPerDevice attr_set;
+  if (attr_set.needs_setup()) {
     MER_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     MER_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    attr_set = true;
+    attr_set.mark();
   }
   const long long items = (long long)n_seq * heads;
   int grid = mer_num_sms();

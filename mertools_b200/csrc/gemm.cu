@@ -595,12 +595,12 @@ int launch_gemm(const MerGemmDesc* g, cudaStream_t stream) {
     const uint32_t box[2] = {(uint32_t)(Cfg::kBlockK * mult), BLOCK_N / CLUSTER};  // each CTA loads its share
     if (int rc = mer_make_tmap(&tb, dt, 2, g->W, dims, strides, box, sw)) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static MerPerDevice attr_set;
+  if (attr_set.needs_setup()) {
     MER_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BLOCK_N, MODE, CLUSTER, TWOSM>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes));
-    attr_set = true;
+    attr_set.mark();
   }
   const int m_tiles = (g->rows_per_batch + BLOCK_M - 1) / BLOCK_M;
   const long long groups = ((long long)g->batches * m_tiles + CLUSTER - 1) / CLUSTER;

@@ -155,11 +155,11 @@ int mer_posconv_launch(const float* x0, const float* wp, const float* bias, cons
                        int n_seq, int max_seqlen, float* x1, cudaStream_t stream) {
   MER_REQUIRE(x0 && wp && bias && cu_seqlens && x1 && x0 != x1, "mer_posconv: bad operands");
   if (n_seq <= 0 || max_seqlen <= 0) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static MerPerDevice attr_set;
+  if (attr_set.needs_setup()) {
     MER_CUDA_CHECK(cudaFuncSetAttribute(posconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         PC_SMEM));
-    attr_set = true;
+    attr_set.mark();
   }
   dim3 grid((max_seqlen + BT - 1) / BT, NG, n_seq);
   // 2 * frames * 768 outputs * (48 inputs * 128 taps); frames bounded by n_seq * max_seqlen (exact for

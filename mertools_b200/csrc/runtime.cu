@@ -128,12 +128,11 @@ int mer_make_tmap(CUtensorMap* out, CUtensorMapDataType dtype, int rank, const v
 }
 
 int mer_num_sms() {
-  static int n = 0;
+  static int cache[64] = {};
+  const int dev = MerPerDevice::current();
+  int& n = cache[dev];
   if (!n) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   }
   return n;
 }
