@@ -12,6 +12,8 @@
 // The fp32 conv0 output (32.8 MB per 5 s clip) is never materialised un-normalised: the waveform
 // (320 KB per clip) is read three times instead.  Algorithmic traffic per clip:
 // 3 x 320 KB in + 15,999 x 512 x 4 B = 32.8 MB out.
+#include <stdlib.h>
+
 #include "mer_common.cuh"
 #include "mer_kernels.h"
 
@@ -124,6 +126,90 @@ conv0_apply_kernel(const float* __restrict__ wave, long long ld_wave, const floa
   }
 }
 
+// ---- opt-in variants (MER_CONV0_PACKED=1): two adjacent channels per thread on the packed fp32 pipe (FFMA2 with
+// the sample as a broadcast operand), half the shared-memory loads per output, the packed GELU, 4 + 4 byte split
+// stores.  Per channel the conv / statistics arithmetic is the same sequence of fma.rn as the scalar kernels. ----
+__global__ void __launch_bounds__(C0 / 2)
+conv0_stats2_kernel(const float* __restrict__ wave, long long ld_wave, const float* __restrict__ w0,
+                    int T0, double* __restrict__ stats /*[B,512,2]*/) {
+  __shared__ float xs[TCHUNK * S0 + K0];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * TCHUNK;
+  const int nt = min(TCHUNK, T0 - t0);
+  const float* x = wave + (long long)b * ld_wave + (long long)t0 * S0;
+  const int nx = (nt - 1) * S0 + K0;
+  for (int i = threadIdx.x; i < nx; i += blockDim.x) xs[i] = x[i];
+  __syncthreads();
+  const int c = 2 * threadIdx.x;
+  uint64_t w[K0];
+#pragma unroll
+  for (int k = 0; k < K0; ++k) w[k] = pack2(__ldg(w0 + c * K0 + k), __ldg(w0 + (c + 1) * K0 + k));
+  uint64_t s = pack2(0.f, 0.f), q = s;
+  for (int t = 0; t < nt; ++t) {
+    uint64_t y = pack2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < K0; ++k) {
+      const float xv = xs[t * S0 + k];
+      y = fma2(w[k], pack2(xv, xv), y);
+    }
+    s = add2(s, y);
+    q = fma2(y, y, q);
+  }
+  float s0, s1, q0, q1;
+  unpack2(s, s0, s1);
+  unpack2(q, q0, q1);
+  double* st = stats + ((long long)b * C0 + c) * 2;
+  atomicAdd(st + 0, (double)s0);
+  atomicAdd(st + 1, (double)q0);
+  atomicAdd(st + 2, (double)s1);
+  atomicAdd(st + 3, (double)q1);
+}
+
+__global__ void __launch_bounds__(C0 / 2)
+conv0_apply2_kernel(const float* __restrict__ wave, long long ld_wave, const float* __restrict__ w0,
+                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                    const double* __restrict__ stats, int T0, long long out_bstride /*floats*/,
+                    float* __restrict__ out /*split bf16 rows*/) {
+  __shared__ float xs[TCHUNK * S0 + K0];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * TCHUNK;
+  const int nt = min(TCHUNK, T0 - t0);
+  const float* x = wave + (long long)b * ld_wave + (long long)t0 * S0;
+  const int nx = (nt - 1) * S0 + K0;
+  for (int i = threadIdx.x; i < nx; i += blockDim.x) xs[i] = x[i];
+  __syncthreads();
+  const int c = 2 * threadIdx.x;
+  uint64_t w[K0];
+#pragma unroll
+  for (int k = 0; k < K0; ++k) w[k] = pack2(__ldg(w0 + c * K0 + k), __ldg(w0 + (c + 1) * K0 + k));
+  float nmean[2], g[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {  // GroupNorm with num_groups == channels: biased variance over time, eps 1e-5
+    const double sum = stats[((long long)b * C0 + c + j) * 2 + 0];
+    const double sq = stats[((long long)b * C0 + c + j) * 2 + 1];
+    const double mean_d = sum / (double)T0;
+    double var_d = sq / (double)T0 - mean_d * mean_d;
+    if (var_d < 0.0) var_d = 0.0;
+    nmean[j] = -(float)mean_d;
+    g[j] = __ldg(gamma + c + j) * (float)(1.0 / sqrt(var_d + 1e-5));
+  }
+  const uint64_t nmean2 = pack2(nmean[0], nmean[1]), g2 = pack2(g[0], g[1]);
+  const uint64_t bt2 = pack2(__ldg(beta + c), __ldg(beta + c + 1));
+  float* orow = out + (long long)b * out_bstride + (long long)t0 * C0;
+  for (int t = 0; t < nt; ++t) {
+    uint64_t y = pack2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < K0; ++k) {
+      const float xv = xs[t * S0 + k];
+      y = fma2(w[k], pack2(xv, xv), y);
+    }
+    float a0, a1, v0, v1;
+    unpack2(fma2(add2(y, nmean2), g2, bt2), a0, a1);
+    gelu_erf_fast2(a0, a1, v0, v1);
+    store_split2(orow + (long long)t * C0, c, v0, v1);
+  }
+}
+
 // conv0 (k = 10, stride 5, + bias) -> LayerNorm over the 512 channels -> GELU, the first layer of the
 // feat_extract_norm="layer" feature encoder (HF HubertLayerNormConvLayer; hubert-large family).
 // One warp = LN_ROWS consecutive frames; lane owns channels lane + 32 j (j < 16), weights transposed in
@@ -205,10 +291,17 @@ int mer_hubert_conv0_launch(const float* wave, long long ld_wave, int B, int L, 
   dim3 grid((T0 + TCHUNK - 1) / TCHUNK, B);
   // both passes: the waveform in twice, the [T0, 512] operand (4 B per element) out once
   const int prof = mer_prof_begin(MER_PROF_CONV0, (double)B * (2.0 * L * 4.0 + (double)T0 * C0 * 4.0), stream);
-  conv0_stats_kernel<<<grid, C0, 0, stream>>>(wave, ld_wave, w0, T0, stats);
-  MER_CUDA_CHECK(cudaGetLastError());
-  conv0_apply_kernel<<<grid, C0, 0, stream>>>(wave, ld_wave, w0, gamma, beta, stats, T0,
-                                              out_bstride, split_out, out);
+  const char* pk = getenv("MER_CONV0_PACKED");  // read at every launch: tests run both forms in one process
+  if (pk && atoi(pk) == 1 && split_out) {
+    conv0_stats2_kernel<<<grid, C0 / 2, 0, stream>>>(wave, ld_wave, w0, T0, stats);
+    MER_CUDA_CHECK(cudaGetLastError());
+    conv0_apply2_kernel<<<grid, C0 / 2, 0, stream>>>(wave, ld_wave, w0, gamma, beta, stats, T0, out_bstride, out);
+  } else {
+    conv0_stats_kernel<<<grid, C0, 0, stream>>>(wave, ld_wave, w0, T0, stats);
+    MER_CUDA_CHECK(cudaGetLastError());
+    conv0_apply_kernel<<<grid, C0, 0, stream>>>(wave, ld_wave, w0, gamma, beta, stats, T0,
+                                                out_bstride, split_out, out);
+  }
   mer_prof_end(prof, stream);
   MER_CUDA_CHECK(cudaGetLastError());
   mer_count_launches(2);

@@ -191,3 +191,34 @@ def test_vggish_extractor_files(cuda, tmp_path):
         ref = E.vggish_embeddings(tsd, torch.from_numpy(ex.astype(np.float32))).numpy()
         ref = ref.mean(0) if level == "UTTERANCE" else ref
         assert got.shape == ref.shape and np.abs(got - ref).max() / np.abs(ref).max() < 1e-3
+
+
+def test_hubert_packed_conv0_and_switches_keep_parity(cuda):
+    """HuBERT-base with MER_CONV0_PACKED=1 (two channels per thread on the packed fp32 pipe), MER_GELU_PACKED=1 and
+    MER_ATT_TC_VER=2 against the default kernels (tight) and the oracle (1e-3)."""
+    import numpy as np
+
+    from mertools_b200 import synthetic as S
+    from mertools_b200.encoders import HubertEncoder
+    from oracle import encoders as E
+    from oracle import pipeline as P
+    sd = S.hubert_state_dict(seed=1, layers=4)
+    wav = (S.synth_waves(2, 40000, seed=23).astype(np.float64) / 32768.0).astype(np.float32)
+    enc = HubertEncoder(sd, device=cuda)
+    dev = torch.from_numpy(wav).to(cuda)
+
+    def run():
+        utt, frames = enc.forward(dev, normalize=True, want_frames=True)[:2]
+        return frames.double().cpu()
+
+    base = run()
+    torch.cuda.synchronize()
+    ref_hs = E.hubert_hidden_states(sd, torch.from_numpy(np.stack([P.wav2vec2_normalize(w) for w in wav])), layers=4)
+    ref = torch.stack(ref_hs)[[-4, -3, -2, -1]].sum(dim=0).double()
+    scale = float(ref.abs().max())
+    assert float((base.reshape(ref.shape) - ref).abs().max()) / scale < 2e-3
+    for env in ("MER_CONV0_PACKED", "MER_GELU_PACKED"):
+        got = _with_env(env, "1", run)
+        assert float((got - base).abs().max()) / scale < 5e-5, env
+    got = _with_env("MER_ATT_TC_VER", "2", run)
+    assert float((got - base).abs().max()) / scale < 5e-5
