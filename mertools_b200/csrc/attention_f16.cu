@@ -57,6 +57,8 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) {  // SW128, SBO 
 
 // VER 1: every score is compared against the valid key range [shift, Lk) (3 integer instructions per element
 //        in both passes: 35 % of the kernel's issued instructions in the round-1 ncu capture).
+// VER 3: VER 2 with 3 of every 8 exponential pairs of the unmasked granules computed by ex2_poly2 on the FMA / ALU
+//        pipes (the MUFU floor of this kernel is 2.75x its MMA time at head_dim 64).
 // VER 2: the key axis is handled in 16-column granules; granules that lie inside [shift, Lk) — all but the
 //        first (leading foreign keys) and the last — run unmasked with FMNMX3 / FFMA2 / FADD2, and granules
 //        beyond the UMMA key count NK are skipped (the P V MMA never reads them).
@@ -229,7 +231,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
       mbar_wait(&bar_sfull[grp], uses & 1);
       tc_fence_after();
       float mb, sum = 0.f;
-      if constexpr (VER == 2) {
+      if constexpr (VER >= 2) {
         if (grp * 128 + q * 32 >= len) {
           // all 32 query rows of this warp lie beyond the sequence (rows 224..255 at 197 tokens): nothing to
           // compute -- the P rows it would write feed output rows that are never stored -- but the chunk
@@ -283,9 +285,14 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
 #pragma unroll
                 for (int j = 0; j < 16; j += 2) {
                   float a, b;
-                  unpack2(fma2(pack2(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1])), scale2, nmb2), a, b);
-                  a = fast_ex2(a);
-                  b = fast_ex2(b);
+                  const uint64_t x2 = fma2(pack2(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1])), scale2, nmb2);
+                  if (VER == 3 && (j == 2 || j == 8 || j == 12)) {  // 3 of the 8 pairs: polynomial, off the XU pipe
+                    ex2_poly2(x2, a, b);
+                  } else {
+                    unpack2(x2, a, b);
+                    a = fast_ex2(a);
+                    b = fast_ex2(b);
+                  }
                   acc2 = add2(acc2, pack2(a, b));
                   pk[gi * 8 + (j >> 1)] = pack_f16x2(a, b);
                 }
@@ -434,12 +441,13 @@ int mer_attention_f16_launch(const void* qkv16, const void* vt16, long long vt_l
   // MER_ATT_F16_VER=2 selects the granule softmax (see the kernel's header comment); read at every launch so that
   // a test can run both versions in one process.
   const char* ver_env = getenv("MER_ATT_F16_VER");
-  const bool ver2 = ver_env && atoi(ver_env) == 2;
-  auto kern = ver2 ? attention_f16_kernel<2> : attention_f16_kernel<1>;
+  const int ver = ver_env ? atoi(ver_env) : 1;
+  auto kern = ver == 3 ? attention_f16_kernel<3> : (ver == 2 ? attention_f16_kernel<2> : attention_f16_kernel<1>);
   static MerPerDevice attr_set;
   if (attr_set.needs_setup()) {
     MER_CUDA_CHECK(cudaFuncSetAttribute(attention_f16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM));
     MER_CUDA_CHECK(cudaFuncSetAttribute(attention_f16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM));
+    MER_CUDA_CHECK(cudaFuncSetAttribute(attention_f16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM));
     attr_set.mark();
   }
   const long long items = (long long)n_seq * heads;

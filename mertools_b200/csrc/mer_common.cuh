@@ -441,6 +441,27 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+// 2^x for two values on the FMA / ALU pipes instead of MUFU.EX2 (softmax kernels, where the 16 lanes of the XU
+// pipe are the floor): x = n + f with n = round(x) taken from the mantissa of x + 1.5 * 2^23, f in [-0.5, 0.5],
+// 2^f by a degree-4 polynomial (max relative error 2.7e-6 in fp32, below the fp16 / TF32 rounding of P that
+// follows), 2^n added into the exponent field.  x is clamped to >= -126 (the result then rounds to 0 in P).
+__device__ __forceinline__ void ex2_poly2(uint64_t x2, float& a, float& b) {
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  const uint64_t x = pack2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const auto bc = [](float v) { return pack2(v, v); };
+  const uint64_t r = add2(x, bc(12582912.f));
+  const uint64_t f = fma2(add2(r, bc(-12582912.f)), bc(-1.f), x);
+  uint64_t p = fma2(bc(0.00957401655614376f), f, bc(0.055918190628290176f));
+  p = fma2(p, f, bc(0.2402464896440506f));
+  p = fma2(p, f, bc(0.6931217312812805f));
+  p = fma2(p, f, bc(0.9999992847442627f));
+  float p0, p1, r0, r1;
+  unpack2(p, p0, p1);
+  unpack2(r, r0, r1);
+  a = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(r0) << 23));
+  b = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(r1) << 23));
+}
 // gelu_erf_fast on two values at once: 7 FFMA2 + 5 FMUL2 + 4 MUFU for the pair (the scalar form spends
 // 7 FFMA + 5 FMUL + 2 MUFU per value).  Same polynomial; the constants of the first two steps are folded
 // (0.3275911 / sqrt 2 and -log2(e) / 2), which moves individual results by at most an ulp of the intermediate.
