@@ -280,6 +280,39 @@ MER_API long long mer_resnet18_workspace_bytes(int n_frames);
 MER_API int mer_resnet18_forward(const MerResnet18Model* model, const uint8_t* frames_bgr, int n_frames,
                                  void* workspace, long long workspace_bytes, float* out_feats, void* stream);
 
+/* ---- table-driven CNN executor: frame-level CNN extractors as chains of conv (+ folded BatchNorm, + residual,
+ * + ReLU), MaxPool2d(3, 2) and a final global average pool over four NHWC fp32 activation buffers.
+ * First user: resnet50_ferplus_dag up to conv5_3_3x3_relu + AvgPool2d(7)
+ * (MERBench/feature_extraction/visual/extract_ferplus_embedding.py:81-115, default --layer_name;
+ * pytorch-benchmarks/model/resnet50_ferplus_dag.py:178-355). */
+enum { MER_CNN_STEM = 0,    /* dst = act(conv(frames)): 7x7 / 2 / pad 3 on the uint8 input, preprocessing fused */
+       MER_CNN_CONV = 1,    /* dst = act(conv(src) [+ res]); dst may equal res (in-place residual update) */
+       MER_CNN_MAXPOOL = 2, /* dst = MaxPool2d(3, 2, pad, ceil_mode)(src), windows clipped to the image */
+       MER_CNN_GAP = 3 };   /* out_feats = mean over H x W of src; must be the last op */
+typedef struct MerCnnOp {
+  int kind;  /* MER_CNN_* */
+  int conv;  /* STEM / CONV: index into convs */
+  int src, dst, res; /* buffer indices 0..3; res = -1 for none */
+  int relu;  /* STEM / CONV: ReLU (after the residual add) */
+  int k, stride, pad, ceil_mode; /* MAXPOOL (k = 3, stride = 2) */
+} MerCnnOp;
+typedef struct MerCnnModel {
+  const MerResnetConv* convs; /* BatchNorm folded; w in the layout of gemm_mode: fp16 [cout_pad, kpad] (stem kpad
+                                 192) or split bf16 (stem kpad 160), rows in (ky, kx, cin) order */
+  int n_convs;
+  const MerCnnOp* ops;
+  int n_ops;
+  int gemm_mode;       /* MER_GEMM_F16 or MER_GEMM_BF16X3 */
+  int in_h, in_w;      /* frames are uint8 [n, in_h, in_w, 3] BGR (resize / crop beforehand) */
+  float scale;         /* x = (pix * scale - mean[c]) / std[c] in RGB order: 1/255 (ToTensor) or 1 (ToTensor * 255) */
+  float mean[3], std[3];
+  int feat_dim;        /* channels of the pooled map */
+} MerCnnModel;
+
+MER_API long long mer_cnn_workspace_bytes(const MerCnnModel* model, int n_frames); /* -1: bad model (mer_last_error) */
+MER_API int mer_cnn_forward(const MerCnnModel* model, const uint8_t* frames_bgr, int n_frames, void* workspace,
+                            long long workspace_bytes, float* out_feats, void* stream);
+
 /* ---- VGGish audio embedding network (MERBench/feature_extraction/audio/vggish/vggish_slim.py:37-100, called by
  * extract_vggish_embedding.py:30-49 through the TF graph tensors vggish/input_features -> vggish/embedding).
  * convs: conv1, conv2, conv3_1, conv3_2, conv4_1, conv4_2 (3x3, 'SAME', ReLU) in MerResnetConv structs whose w is

@@ -16,11 +16,13 @@ namespace {
 
 using namespace mer;
 
-// conv1 gather: uint8 BGR frames [n, 224, 224, 3] -> rows (n, oy, ox) of K = 7*7*3 (ky, kx, c) fp16 values
-// ((pix/255 - mean[c]) / std[c], RGB order: ToTensor + Normalize), zero outside the image and for k >= 147.
+// conv1 gather: uint8 BGR frames [n, 224, 224, 3] -> rows (n, oy, ox) of K = 7*7*3 (ky, kx, c) operand values
+// ((pix * scale - mean[c]) / std[c], RGB order: ToTensor [* 255] + Normalize), zero outside the image and for
+// k >= 147.  SPLIT = false: fp16, kpad 192; SPLIT = true: bf16 hi | lo groups (MER_GEMM_BF16X3), kpad 160.
+template <bool SPLIT>
 __global__ void __launch_bounds__(256)
-im2col_stem_kernel(const uint8_t* __restrict__ frames, int H, int W, int OH, int OW, int kpad, float m0, float m1,
-                   float m2, float s0, float s1, float s2, uint16_t* __restrict__ out, long long total) {
+im2col_stem_kernel(const uint8_t* __restrict__ frames, int H, int W, int OH, int OW, int kpad, float scale, float m0,
+                   float m1, float m2, float s0, float s1, float s2, uint16_t* __restrict__ out, long long total) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int k = (int)(idx % kpad);
@@ -34,10 +36,17 @@ im2col_stem_kernel(const uint8_t* __restrict__ frames, int H, int W, int OH, int
     if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
       const float pix = (float)frames[((n * H + iy) * W + ix) * 3 + (2 - c)];
       const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
-      v = (pix * 0.00392156862745098f - mean) / sd;
+      v = (pix * scale - mean) / sd;
     }
   }
-  out[idx] = (uint16_t)(pack_f16x2(v, 0.f) & 0xffffu);
+  if (SPLIT) {
+    uint16_t* grp = out + row * (long long)kpad * 2 + (k >> 5) * 64 + (k & 31);
+    const float hi = bf16_round(v);
+    grp[0] = (uint16_t)(__float_as_uint(hi) >> 16);
+    grp[32] = (uint16_t)(pack_bf16x2(v - hi, 0.f) & 0xffffu);
+  } else {
+    out[idx] = (uint16_t)(pack_f16x2(v, 0.f) & 0xffffu);
+  }
 }
 
 // generic gather: NHWC fp32 activations [n, H, W, cs] (first C channels real) -> operand rows (n, oy, ox) of
@@ -77,9 +86,10 @@ im2col_kernel(const float* __restrict__ x, int H, int W, int cs, int C, int ksz,
   }
 }
 
-// MaxPool2d(3, stride 2, padding 1) on NHWC fp32, 4 channels per thread
+// MaxPool2d(3, stride 2, padding pad) on NHWC fp32, 4 channels per thread; windows are clipped to the image
+// (padding 1: torchvision ResNet; padding 0 with ceil_mode: the caffe-style FER+ models)
 __global__ void __launch_bounds__(256)
-maxpool3x3s2_kernel(const float4* __restrict__ x, int H, int W, int c4, int OH, int OW, float4* __restrict__ y,
+maxpool3x3s2_kernel(const float4* __restrict__ x, int H, int W, int c4, int OH, int OW, int pad, float4* __restrict__ y,
                     long long total) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -89,10 +99,10 @@ maxpool3x3s2_kernel(const float4* __restrict__ x, int H, int W, int c4, int OH, 
   const long long n = pos / ((long long)OW * OH);
   float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
   for (int ky = 0; ky < 3; ++ky) {
-    const int iy = oy * 2 - 1 + ky;
+    const int iy = oy * 2 - pad + ky;
     if (iy < 0 || iy >= H) continue;
     for (int kx = 0; kx < 3; ++kx) {
-      const int ix = ox * 2 - 1 + kx;
+      const int ix = ox * 2 - pad + kx;
       if (ix < 0 || ix >= W) continue;
       const float4 v = __ldg(x + ((n * H + iy) * W + ix) * (long long)c4 + c);
       m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
@@ -237,9 +247,9 @@ int mer_resnet18_forward(const MerResnet18Model* m, const uint8_t* frames_bgr, i
     const MerResnetConv& cv = m->convs[0];
     MER_REQUIRE(cv.k == 7 && cv.kpad == 192 && cv.cout_pad == 128, "mer_resnet18_forward: conv1 packing");
     const long long rows = n * 112 * 112, total = rows * 192;
-    im2col_stem_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(frames_bgr, 224, 224, 112, 112, 192,
-                                                                        m->mean[0], m->mean[1], m->mean[2], m->std[0],
-                                                                        m->std[1], m->std[2], col, total);
+    im2col_stem_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        frames_bgr, 224, 224, 112, 112, 192, 0.00392156862745098f, m->mean[0], m->mean[1], m->mean[2], m->std[0],
+        m->std[1], m->std[2], col, total);
     MER_CUDA_CHECK(cudaGetLastError());
     mer_count_launches(1);
     MerGemmDesc g;
@@ -267,7 +277,7 @@ int mer_resnet18_forward(const MerResnet18Model* m, const uint8_t* frames_bgr, i
   {
     const long long total = n * 56 * 56 * 32;
     maxpool3x3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(a0), 112, 112, 32,
-                                                                         56, 56, reinterpret_cast<float4*>(x), total);
+                                                                         56, 56, 1, reinterpret_cast<float4*>(x), total);
     MER_CUDA_CHECK(cudaGetLastError());
     mer_count_launches(1);
   }
@@ -424,6 +434,164 @@ int mer_vggish_forward(const MerVggishModel* m, const float* examples, int n_exa
   if (int rc = fc(m->fc_w[0], m->fc_b[0], P, h16, n, 12288, 4096, F, st)) return rc;
   if (int rc = fc(m->fc_w[1], m->fc_b[1], F, h16, n, 4096, 4096, A, st)) return rc;  // A is free again
   return fc(m->fc_w[2], m->fc_b[2], A, h16, n, 4096, 128, out_embeddings, st);
+}
+
+}  // extern "C"
+
+// ---- table-driven CNN executor (mer_cnn_forward): the frame-level CNN extractors whose graphs are chains of
+// conv (+ folded BN, + residual, + ReLU), 3x3/2 max-pool and a global average pool over four activation buffers.
+// First user: the FER+ ResNet-50 (extract_ferplus_embedding.py; pytorch-benchmarks/model/resnet50_ferplus_dag.py). ----
+namespace {
+struct CnnPlan { long long off_buf[4], off_col, off_cu, total; };
+
+int pool_out(int in, int pad, int ceil_mode) {  // torch MaxPool2d(3, 2, pad, ceil_mode) output size
+  const int num = in + 2 * pad - 3;
+  int o = (ceil_mode ? (num + 1) / 2 : num / 2) + 1;
+  if (ceil_mode && (o - 1) * 2 >= in + pad) --o;  // the last window must start inside the (left-padded) input
+  return o;
+}
+
+// walks the op table once: shapes per buffer, the largest extent of every buffer and of the im2col operand
+int cnn_plan(const MerCnnModel* m, int n_frames, CnnPlan* plan, Shape* final_shape) {
+  MER_REQUIRE(m && m->convs && m->ops && m->n_ops > 0 && m->n_convs > 0, "mer_cnn: empty model");
+  MER_REQUIRE(m->gemm_mode == MER_GEMM_F16 || m->gemm_mode == MER_GEMM_BF16X3, "mer_cnn: gemm_mode %d", m->gemm_mode);
+  const long long n = n_frames;
+  const long long vbytes = m->gemm_mode == MER_GEMM_F16 ? 2 : 4;  // bytes per operand value
+  Shape sh[4] = {};
+  long long need[4] = {0, 0, 0, 0}, col = 0;
+  Shape last{0, 0, 0, 0};
+  for (int i = 0; i < m->n_ops; ++i) {
+    const MerCnnOp& op = m->ops[i];
+    MER_REQUIRE(op.dst >= 0 && op.dst < 4 && op.src >= 0 && op.src < 4, "mer_cnn: op %d buffer index", i);
+    if (op.kind == MER_CNN_STEM || op.kind == MER_CNN_CONV) {
+      MER_REQUIRE(op.conv >= 0 && op.conv < m->n_convs, "mer_cnn: op %d conv index %d", i, op.conv);
+      const MerResnetConv& cv = m->convs[op.conv];
+      Shape in = op.kind == MER_CNN_STEM ? Shape{m->in_h, m->in_w, 3, 3} : sh[op.src];
+      MER_REQUIRE(in.H > 0, "mer_cnn: op %d reads an empty buffer", i);
+      const int OH = (in.H + 2 * cv.pad - cv.k) / cv.stride + 1, OW = (in.W + 2 * cv.pad - cv.k) / cv.stride + 1;
+      const long long rows = n * OH * OW;
+      MER_REQUIRE(rows < (1ll << 31), "mer_cnn: too many frames per call");
+      col = col > rows * cv.kpad * vbytes ? col : rows * cv.kpad * vbytes;
+      if (op.res >= 0) {
+        MER_REQUIRE(op.res < 4 && sh[op.res].H == OH && sh[op.res].W == OW && sh[op.res].Cs == cv.cout_pad,
+                    "mer_cnn: op %d residual shape", i);
+      }
+      sh[op.dst] = Shape{OH, OW, cv.cout, cv.cout_pad};
+    } else if (op.kind == MER_CNN_MAXPOOL) {
+      const Shape in = sh[op.src];
+      MER_REQUIRE(in.H > 0 && op.k == 3 && op.stride == 2 && op.src != op.dst, "mer_cnn: op %d max-pool", i);
+      sh[op.dst] = Shape{pool_out(in.H, op.pad, op.ceil_mode), pool_out(in.W, op.pad, op.ceil_mode), in.C, in.Cs};
+    } else {
+      MER_REQUIRE(op.kind == MER_CNN_GAP && i == m->n_ops - 1, "mer_cnn: op %d kind %d", i, op.kind);
+      MER_REQUIRE(sh[op.src].C == sh[op.src].Cs && sh[op.src].C == m->feat_dim, "mer_cnn: pooled width != feat_dim");
+      last = sh[op.src];
+      continue;
+    }
+    const long long fl = n * sh[op.dst].H * sh[op.dst].W * sh[op.dst].Cs;
+    need[op.dst] = need[op.dst] > fl ? need[op.dst] : fl;
+    last = sh[op.dst];
+  }
+  auto al = [](long long x) { return (x + 255) & ~255ll; };
+  long long o = 0;
+  for (int b = 0; b < 4; ++b) {
+    plan->off_buf[b] = o;
+    o += al(need[b] * 4);
+  }
+  plan->off_col = o;  o += al(col);
+  plan->off_cu = o;   o += al((n + 1) * 4);
+  plan->total = o;
+  if (final_shape) *final_shape = last;
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+long long mer_cnn_workspace_bytes(const MerCnnModel* m, int n_frames) {
+  CnnPlan p;
+  if (n_frames <= 0 || cnn_plan(m, n_frames, &p, nullptr)) return -1;
+  return p.total;
+}
+
+int mer_cnn_forward(const MerCnnModel* m, const uint8_t* frames_bgr, int n_frames, void* workspace,
+                    long long workspace_bytes, float* out_feats, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  MER_REQUIRE(m && frames_bgr && workspace && out_feats && n_frames > 0, "mer_cnn_forward: bad operands");
+  CnnPlan p;
+  Shape fin;
+  if (int rc = cnn_plan(m, n_frames, &p, &fin)) return rc;
+  MER_REQUIRE(workspace_bytes >= p.total, "mer_cnn_forward: workspace %lld B < required %lld B", workspace_bytes, p.total);
+  MER_REQUIRE(m->ops[m->n_ops - 1].kind == MER_CNN_GAP, "mer_cnn_forward: the op table must end with the average pool");
+  char* ws = static_cast<char*>(workspace);
+  float* buf[4];
+  for (int b = 0; b < 4; ++b) buf[b] = reinterpret_cast<float*>(ws + p.off_buf[b]);
+  uint16_t* col = reinterpret_cast<uint16_t*>(ws + p.off_col);
+  int* offsets = reinterpret_cast<int*>(ws + p.off_cu);
+  const bool split = m->gemm_mode == MER_GEMM_BF16X3;
+  Shape sh[4] = {};
+  for (int i = 0; i < m->n_ops; ++i) {
+    const MerCnnOp& op = m->ops[i];
+    if (op.kind == MER_CNN_STEM) {
+      const MerResnetConv& cv = m->convs[op.conv];
+      MER_REQUIRE(cv.k == 7 && cv.stride == 2 && cv.pad == 3 && cv.cin == 3 && cv.kpad == (split ? 160 : 192),
+                  "mer_cnn_forward: the stem is a 7x7 / 2 convolution packed to %d columns", split ? 160 : 192);
+      const int OH = (m->in_h + 6 - 7) / 2 + 1, OW = (m->in_w + 6 - 7) / 2 + 1;
+      const long long rows = (long long)n_frames * OH * OW, total = rows * cv.kpad;
+      const unsigned blocks = (unsigned)((total + 255) / 256);
+      if (split)
+        im2col_stem_kernel<true><<<blocks, 256, 0, st>>>(frames_bgr, m->in_h, m->in_w, OH, OW, cv.kpad, m->scale,
+                                                         m->mean[0], m->mean[1], m->mean[2], m->std[0], m->std[1],
+                                                         m->std[2], col, total);
+      else
+        im2col_stem_kernel<false><<<blocks, 256, 0, st>>>(frames_bgr, m->in_h, m->in_w, OH, OW, cv.kpad, m->scale,
+                                                          m->mean[0], m->mean[1], m->mean[2], m->std[0], m->std[1],
+                                                          m->std[2], col, total);
+      MER_CUDA_CHECK(cudaGetLastError());
+      mer_count_launches(1);
+      MerGemmDesc g;
+      memset(&g, 0, sizeof(g));
+      g.A = reinterpret_cast<const float*>(col);
+      g.W = static_cast<const float*>(cv.w);
+      g.rows_per_batch = (int)rows;
+      g.a_rows_dim = (int)rows;
+      g.batches = 1;
+      g.N = cv.cout_pad;
+      g.K_inner = cv.kpad;
+      g.taps = 1;
+      g.P = 1;
+      g.a_phase_stride = cv.kpad;
+      g.a_row_stride = cv.kpad;
+      g.a_batch_stride = rows * cv.kpad;
+      g.mode = m->gemm_mode;
+      g.ep.bias = cv.b;
+      g.ep.out = buf[op.dst];
+      g.ep.ld_out = cv.cout_pad;
+      g.ep.flags = op.relu ? MER_EPI_RELU : 0;
+      if (int rc = mer_gemm_launch(&g, st)) return rc;
+      sh[op.dst] = Shape{OH, OW, cv.cout, cv.cout_pad};
+    } else if (op.kind == MER_CNN_CONV) {
+      Shape out;
+      if (int rc = conv(m->convs[op.conv], buf[op.src], sh[op.src], n_frames, col, op.res >= 0 ? buf[op.res] : nullptr,
+                        op.relu != 0, buf[op.dst], &out, st, m->gemm_mode))
+        return rc;
+      sh[op.dst] = out;
+    } else if (op.kind == MER_CNN_MAXPOOL) {
+      const Shape in = sh[op.src];
+      const int OH = pool_out(in.H, op.pad, op.ceil_mode), OW = pool_out(in.W, op.pad, op.ceil_mode);
+      const long long total = (long long)n_frames * OH * OW * (in.Cs / 4);
+      maxpool3x3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+          reinterpret_cast<const float4*>(buf[op.src]), in.H, in.W, in.Cs / 4, OH, OW, op.pad,
+          reinterpret_cast<float4*>(buf[op.dst]), total);
+      MER_CUDA_CHECK(cudaGetLastError());
+      mer_count_launches(1);
+      sh[op.dst] = Shape{OH, OW, in.C, in.Cs};
+    } else {  // MER_CNN_GAP (last op, checked by cnn_plan)
+      const Shape in = sh[op.src];
+      if (int rc = mer_iota_offsets_launch(offsets, n_frames, in.H * in.W, st)) return rc;
+      return mer_segment_reduce_launch(buf[op.src], offsets, offsets + 1, n_frames, in.C, MER_SEG_MEAN, out_feats, st);
+    }
+  }
+  return 0;
 }
 
 }  // extern "C"

@@ -337,6 +337,138 @@ class ResNet18Encoder:
         return feats
 
 
+class MerCnnOp(C.Structure):
+    _fields_ = [("kind", C.c_int), ("conv", C.c_int), ("src", C.c_int), ("dst", C.c_int), ("res", C.c_int),
+                ("relu", C.c_int), ("k", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("ceil_mode", C.c_int)]
+
+
+class MerCnnModel(C.Structure):
+    _fields_ = [("convs", C.POINTER(MerResnetConv)), ("n_convs", C.c_int), ("ops", C.POINTER(MerCnnOp)),
+                ("n_ops", C.c_int), ("gemm_mode", C.c_int), ("in_h", C.c_int), ("in_w", C.c_int),
+                ("scale", C.c_float), ("mean", C.c_float * 3), ("std", C.c_float * 3), ("feat_dim", C.c_int)]
+
+
+CNN_STEM, CNN_CONV, CNN_MAXPOOL, CNN_GAP = 0, 1, 2, 3
+FERPLUS_BLOCKS = (3, 4, 6, 3)
+
+
+def ferplus_resnet50_tables(state_dict, pack, bn_eps=1e-5):
+    """Conv and op tables of ``resnet50_ferplus_dag`` up to conv5_3_3x3_relu + the 7x7 average pool, for
+    mer_cnn_forward.  ``pack(w [cout_pad, kpad] fp32, b [cout_pad] fp32) -> (w_ptr, b_ptr)`` places the folded
+    weights (split bf16) and biases on the device.  Returns (MerCnnModel, keep-alive list).
+    Buffers: 0 = the residual stream (block input / output), 1 and 2 = block-internal, 3 = projection shortcut."""
+    sd = W._np(state_dict)
+    convs, ops = [], []
+
+    def add_conv(name, stride, pad):
+        w = sd[name + ".weight"]
+        wf, bf = fold_conv_bn(w, sd[name + "_bn.weight"], sd[name + "_bn.bias"], sd[name + "_bn.running_mean"],
+                              sd[name + "_bn.running_var"], bn_eps)
+        cout, cin, k, _ = w.shape
+        cout_pad, kk = max(cout, 128), k * k * cin
+        kpad = 160 if cin == 3 else kk
+        wp = np.zeros((cout_pad, kpad), np.float32)
+        wp[:cout, :kk] = wf.transpose(0, 2, 3, 1).reshape(cout, kk)       # (ky, kx, c) order
+        bp = np.zeros(cout_pad, np.float32)
+        bp[:cout] = bf
+        c = MerResnetConv()
+        c.w, c.b = pack(wp, bp)
+        c.cin, c.cout, c.cout_pad, c.k, c.stride, c.pad, c.kpad = cin, cout, cout_pad, k, stride, pad, kpad
+        convs.append(c)
+        return len(convs) - 1
+
+    def op(kind, conv=-1, src=0, dst=0, res=-1, relu=0, k=0, stride=0, pad=0, ceil_mode=0):
+        ops.append(MerCnnOp(kind, conv, src, dst, res, relu, k, stride, pad, ceil_mode))
+
+    op(CNN_STEM, add_conv("conv1_7x7_s2", 2, 3), dst=1, relu=1)
+    op(CNN_MAXPOOL, src=1, dst=0, k=3, stride=2, pad=0, ceil_mode=1)
+    for si, nblk in enumerate(FERPLUS_BLOCKS):
+        for b in range(1, nblk + 1):
+            p = f"conv{si + 2}_{b}_"
+            stride = 2 if (si > 0 and b == 1) else 1
+            op(CNN_CONV, add_conv(p + "1x1_reduce", stride, 0), src=0, dst=1, relu=1)
+            op(CNN_CONV, add_conv(p + "3x3", 1, 1), src=1, dst=2, relu=1)
+            if si == 3 and b == nblk:
+                op(CNN_GAP, src=2)
+                break
+            if b == 1:
+                op(CNN_CONV, add_conv(p + "1x1_proj", stride, 0), src=0, dst=3, relu=0)
+                op(CNN_CONV, add_conv(p + "1x1_increase", 1, 0), src=2, dst=0, res=3, relu=1)
+            else:
+                op(CNN_CONV, add_conv(p + "1x1_increase", 1, 0), src=2, dst=0, res=0, relu=1)
+    assert len(convs) == 52 and ops[-1].kind == CNN_GAP
+    conv_arr = (MerResnetConv * len(convs))(*convs)
+    op_arr = (MerCnnOp * len(ops))(*ops)
+    m = MerCnnModel()
+    m.convs, m.n_convs = conv_arr, len(convs)
+    m.ops, m.n_ops = op_arr, len(ops)
+    m.gemm_mode = L.MER_GEMM_BF16X3
+    m.in_h = m.in_w = 224
+    m.scale = 1.0
+    m.mean = (C.c_float * 3)(131.0912, 103.8827, 91.4953)   # model.meta (resnet50_ferplus_dag.py:11-13); std 1
+    m.std = (C.c_float * 3)(1.0, 1.0, 1.0)
+    m.feat_dim = 512
+    return m, [conv_arr, op_arr]
+
+
+class FerplusResnet50Encoder:
+    """``resnet50_ferplus_dag`` up to ``conv5_3_3x3_relu`` + AvgPool2d(7) (what the reference's FER+ extractor keeps
+    with its default ``--layer_name``): 52 BatchNorm-folded convolutions through the table-driven CNN executor
+    (im2col + tcgen05 GEMMs on split-bf16 operands: fp16 operands measured 6e-4 in an fp32 emulation, too close
+    to the 1e-3 bar), caffe-style strides, ceil-mode max-pool.
+
+    Reference: MERBench/feature_extraction/visual/extract_ferplus_embedding.py:62-115,
+    pytorch-benchmarks/model/resnet50_ferplus_dag.py:10-355."""
+
+    def __init__(self, state_dict, device="cuda", bn_eps=1e-5):
+        L.check(L.lib().mer_check_device())
+        self.device = torch.device(device)
+        pk = self.pk = W.Packed(self.device)
+        self.model, self._keep = ferplus_resnet50_tables(
+            state_dict, lambda wp, bp: (pk.keep(wp, split=True).data_ptr(), pk.keep(bp).data_ptr()), bn_eps)
+        self.feature_dim = 512
+        self.ws, self.ws_resize = _Workspace(self.device), _Workspace(self.device)
+        lib = L.lib()
+        lib.mer_cnn_workspace_bytes.restype = C.c_longlong
+        lib.mer_cnn_workspace_bytes.argtypes = [C.POINTER(MerCnnModel), C.c_int]
+        lib.mer_resize_workspace_bytes.restype = C.c_longlong
+        lib.mer_resize_workspace_bytes.argtypes = [C.c_int] * 5
+        self._fwd = L.declare("mer_cnn_forward", [C.POINTER(MerCnnModel), C.c_void_p, C.c_int, C.c_void_p,
+                                                  C.c_longlong, C.c_void_p, C.c_void_p])
+        self._resize = L.declare("mer_resize_u8", [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                                   C.c_int, C.c_int, C.c_void_p, C.c_void_p])
+
+    def preprocess_geometry(self, h, w):
+        """transforms.Resize(256) + CenterCrop(224) (extract_ferplus_embedding.py:68-70): resized (h, w) and the
+        crop's (top, left)."""
+        nh, nw = (256, int(256 * w / h)) if h <= w else (int(256 * h / w), 256)
+        return nh, nw, int(round((nh - 224) / 2.0)), int(round((nw - 224) / 2.0))
+
+    def frame_features(self, frames_bgr_u8: torch.Tensor, max_frames=64):
+        """frames: uint8 CUDA [N, H, W, 3] (BGR).  Resize(256) (PIL bilinear, on the device) + CenterCrop(224), then
+        the network.  Returns [N, 512] fp32 (CUDA)."""
+        assert frames_bgr_u8.dtype == torch.uint8 and frames_bgr_u8.is_cuda and frames_bgr_u8.dim() == 4
+        frames = frames_bgr_u8.contiguous()
+        n, h, w, _ = frames.shape
+        nh, nw, top, left = self.preprocess_geometry(h, w)
+        if (nh, nw) != (h, w):
+            out = torch.empty(n, nh, nw, 3, dtype=torch.uint8, device=self.device)
+            need = L.lib().mer_resize_workspace_bytes(n, h, w, nh, nw)
+            ws = self.ws_resize.get(max(int(need), 1))
+            L.check(self._resize(L.ptr(frames), n, h, w, L.ptr(out), nh, nw, 0, L.ptr(ws), L.stream_ptr()))
+            frames = out
+        frames = frames[:, top:top + 224, left:left + 224].contiguous()
+        feats = torch.empty(n, 512, dtype=torch.float32, device=self.device)
+        for s in range(0, n, max_frames):
+            m = min(max_frames, n - s)
+            nbytes = L.lib().mer_cnn_workspace_bytes(C.byref(self.model), m)
+            L.check(0 if nbytes > 0 else 1)
+            ws = self.ws.get(nbytes)
+            L.check(self._fwd(C.byref(self.model), L.ptr(frames[s:s + m]), m, L.ptr(ws), ws.numel(),
+                              L.ptr(feats[s:s + m]), L.stream_ptr()))
+        return feats
+
+
 class MerVggishModel(C.Structure):
     _fields_ = [("convs", MerResnetConv * 6), ("fc_w", C.c_void_p * 3), ("fc_b", C.c_void_p * 3)]
 

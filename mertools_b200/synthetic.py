@@ -142,6 +142,41 @@ def vggish_state_dict(seed=8):
     return sd
 
 
+FERPLUS_BLOCKS = (3, 4, 6, 3)   # bottlenecks in conv2_x .. conv5_x
+
+
+def ferplus_resnet50_state_dict(seed=9):
+    """Parameters of the reference's ``resnet50_ferplus_dag`` (pytorch-benchmarks/model/resnet50_ferplus_dag.py:10-176):
+    caffe-style ResNet-50 (stride on the 1x1 reduce / proj of conv3_1, conv4_1, conv5_1), one BatchNorm per conv,
+    a 1x1 classifier conv with bias.  He-style conv scales, non-trivial BatchNorm statistics."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+
+    def conv_bn(name, cout, cin, k, gain=1.0):
+        sd[name + ".weight"] = (rng.standard_normal((cout, cin, k, k)) * np.sqrt(2.0 / (cin * k * k))).astype(np.float32)
+        sd[name + "_bn.weight"] = (gain * rng.uniform(0.5, 1.5, cout)).astype(np.float32)
+        sd[name + "_bn.bias"] = (0.2 * rng.standard_normal(cout)).astype(np.float32)
+        sd[name + "_bn.running_mean"] = (0.2 * rng.standard_normal(cout)).astype(np.float32)
+        sd[name + "_bn.running_var"] = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+        sd[name + "_bn.num_batches_tracked"] = np.zeros((), np.int64)
+
+    conv_bn("conv1_7x7_s2", 64, 3, 7, gain=0.02)   # inputs are raw pixels minus the mean (|x| up to ~160)
+    cin = 64
+    for si, nblk in enumerate(FERPLUS_BLOCKS):
+        mid, cout = 64 << si, 256 << si
+        for b in range(1, nblk + 1):
+            p = f"conv{si + 2}_{b}_"
+            conv_bn(p + "1x1_reduce", mid, cin, 1)
+            conv_bn(p + "3x3", mid, mid, 3)
+            conv_bn(p + "1x1_increase", cout, mid, 1, gain=0.5)
+            if b == 1:
+                conv_bn(p + "1x1_proj", cout, cin, 1)
+            cin = cout
+    sd["classifier.weight"] = (0.02 * rng.standard_normal((8, 2048, 1, 1))).astype(np.float32)
+    sd["classifier.bias"] = np.zeros(8, np.float32)
+    return sd
+
+
 HUBERT_LARGE_CFG = dict(HUBERT_CFG, hidden=1024, heads=16, ffn=4096, layers=24)
 
 

@@ -161,6 +161,37 @@ def vggish_embeddings(sd, examples, dtype=torch.float32):
     return x
 
 
+FERPLUS_BLOCKS = (3, 4, 6, 3)
+FERPLUS_MEAN = (131.0912, 103.8827, 91.4953)   # resnet50_ferplus_dag.py:11-13 (RGB, on the 0..255 scale; std 1)
+
+
+def ferplus_resnet50_features(sd, x, dtype=torch.float32, eps=1e-5):
+    """What extract_ferplus_embedding.py keeps of ``resnet50_ferplus_dag`` for its default
+    ``--layer_name conv5_3_3x3_relu`` (:81-115): the forward (resnet50_ferplus_dag.py:178-355) up to the ReLU
+    after conv5_3_3x3 + BN, then AvgPool2d(7) and a (no-op) ReLU -> [N, 512].  Caffe-style bottlenecks: 1x1 reduce
+    (stride 2 in conv3_1 / conv4_1 / conv5_1) - 3x3 - 1x1 increase, a projection shortcut in the first block of each
+    stage, one BatchNorm after every conv, MaxPool2d(3, 2, padding 0, ceil_mode=True) after the stem.
+    x: [N, 3, 224, 224] = RGB pixels on the 0..255 scale minus FERPLUS_MEAN."""
+    def cb(x, name, stride=1, pad=0):
+        y = F.conv2d(x, _t(sd, name + ".weight", dtype), None, stride=stride, padding=pad)
+        return F.batch_norm(y, _t(sd, name + "_bn.running_mean", dtype), _t(sd, name + "_bn.running_var", dtype),
+                            _t(sd, name + "_bn.weight", dtype), _t(sd, name + "_bn.bias", dtype), False, 0.0, eps)
+    y = F.relu(cb(x.to(dtype), "conv1_7x7_s2", 2, 3))
+    y = F.max_pool2d(y, 3, 2, 0, ceil_mode=True)
+    for si, nblk in enumerate(FERPLUS_BLOCKS):
+        for b in range(1, nblk + 1):
+            p = f"conv{si + 2}_{b}_"
+            stride = 2 if (si > 0 and b == 1) else 1
+            o = F.relu(cb(y, p + "1x1_reduce", stride))
+            o = F.relu(cb(o, p + "3x3", 1, 1))
+            if si == 3 and b == nblk:
+                return F.relu(o.mean(dim=(2, 3)))
+            o = cb(o, p + "1x1_increase")
+            idt = cb(y, p + "1x1_proj", stride) if b == 1 else y
+            y = F.relu(idt + o)
+    raise AssertionError("unreachable")
+
+
 def hubert_pos_conv_weight(sd, dtype=torch.float32):
     """Effective weight of the weight-normed positional conv (:45-92): W = g * v / ||v||, the
     norm taken over dims (0,1) per kernel tap (weight_norm dim=2).  Older checkpoints name the

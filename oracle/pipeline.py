@@ -155,6 +155,38 @@ def imagenet_clip_features(sd, frames_bgr, feature_level="UTTERANCE"):
     return np.mean(emb, axis=0) if emb.ndim == 2 else emb
 
 
+def ferplus_preprocess(frames_bgr):
+    """FaceDataset.__getitem__ (dataset.py:40-47) + compose_transforms (extract_ferplus_embedding.py:62-74) for the
+    FER+ models (meta std == [1, 1, 1]): Resize(256) (shorter side -> 256, PIL bilinear), CenterCrop(224), ToTensor,
+    x * 255, Normalize(mean, 1).  frames: uint8 [N, H, W, 3] BGR.  Returns [N, 3, 224, 224]."""
+    f = np.asarray(frames_bgr)
+    assert f.dtype == np.uint8 and f.ndim == 4 and f.shape[-1] == 3, f.shape
+    h, w = f.shape[1:3]
+    if min(h, w) != 256:  # torchvision Resize(int): the long side is int(256 * long / short)
+        nh, nw = (256, int(256 * w / h)) if h <= w else (int(256 * h / w), 256)
+        f = pil_resize_bilinear_u8(f, nh, nw)
+    h, w = f.shape[1:3]
+    top, left = int(round((h - 224) / 2.0)), int(round((w - 224) / 2.0))
+    f = f[:, top:top + 224, left:left + 224]
+    rgb = (f[..., ::-1].astype(np.float32) / np.float32(255.0)) * np.float32(255.0)
+    x = rgb - np.asarray(E.FERPLUS_MEAN, np.float32)
+    return torch.from_numpy(np.ascontiguousarray(x.transpose(0, 3, 1, 2)))
+
+
+def ferplus_clip_features(sd, frames_bgr, feature_level="UTTERANCE"):
+    """One video through extract_ferplus_embedding.py:150-194 (resnet50_ferplus_dag, layer conv5_3_3x3_relu): batches
+    of 32 frames -> [N, 512]; FRAME -> [T, 512] (zeros((1, D)) when empty), UTTERANCE -> mean over frames."""
+    frames = np.asarray(frames_bgr)
+    if len(frames) == 0:
+        return np.zeros((1, 512)) if feature_level == "FRAME" else np.zeros((512,))
+    x = ferplus_preprocess(frames)
+    emb = torch.cat([E.ferplus_resnet50_features(sd, b) for b in split_into_batch(x, 32)], dim=0).float().numpy()
+    emb = np.array(emb).squeeze()
+    if feature_level == "FRAME":
+        return emb[np.newaxis, :] if emb.ndim == 1 else emb
+    return np.mean(emb, axis=0) if emb.ndim == 2 else emb
+
+
 CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
 CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
 

@@ -206,3 +206,25 @@ def test_english_word_alignment_host_logic_matches_reference_function():
         assert fra.shape == g[f"fra_{name}"].shape and _rel(fra, g[f"fra_{name}"]) < 5e-5, name
         assert utt.shape == (768,) and _rel(utt, g[f"utt_{name}"]) < 5e-5, name
     assert TE.split_words_and_sentences("Wow!!! ok.", True) == [["wow"], ["ok"]]
+
+
+def _ferplus_clips():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_ferplus", os.path.join(G, "make_golden_ferplus.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.golden_clips()
+
+
+def test_ferplus_oracle_matches_reference_extractor_golden():
+    """resnet50_ferplus_dag restatement + compose_transforms restatement against outputs of the unmodified
+    reference functions (extract_ferplus_embedding.py: load_model, compose_transforms, FaceDataset, get_feature)."""
+    from oracle import pipeline as P
+    g = np.load(os.path.join(G, "ferplus_golden.npz"))
+    sd = _t(S.ferplus_resnet50_state_dict(int(g["seed"])))
+    for vid, frames in _ferplus_clips().items():
+        x = P.ferplus_preprocess(frames)
+        assert np.array_equal(x.numpy()[:, :, ::16, ::16], g[f"x_{vid}"]), vid   # Resize / crop / scale: bit-exact
+        for level, key in (("FRAME", "fra"), ("UTTERANCE", "utt")):
+            got, ref = P.ferplus_clip_features(sd, frames, level), g[f"{key}_{vid}"]
+            assert got.shape == ref.shape and _rel(got, ref) < 1e-5, (vid, level)

@@ -277,3 +277,27 @@ def test_vggish_save_rules_match_reference_script():
     assert vggish.save_embeddings(None, one, "FRAME").shape == (1, 128)
     args = vggish.build_parser().parse_args([])
     assert (args.gpu, args.feature_level, args.dataset) == (0, "FRAME", "MER2023")
+
+
+def test_cnn_executor_plans_the_ferplus_tables_without_a_gpu():
+    """mer_cnn_workspace_bytes walks the op table on the host (shape inference, buffer extents, table checks):
+    52 convolutions, ceil-mode max-pool 112 -> 56, caffe-style strides down to 7 x 7 x 512."""
+    from mertools_b200 import encoders as En
+    from mertools_b200 import synthetic as S
+    m, _keep = En.ferplus_resnet50_tables(S.ferplus_resnet50_state_dict(9), lambda wp, bp: (1, 1))
+    assert m.n_convs == 52 and m.ops[m.n_ops - 1].kind == En.CNN_GAP
+    import ctypes as C
+
+    from mertools_b200 import _lib
+    dll = _lib.lib()
+    dll.mer_cnn_workspace_bytes.restype = C.c_longlong
+    dll.mer_cnn_workspace_bytes.argtypes = [C.POINTER(En.MerCnnModel), C.c_int]
+    one, two = dll.mer_cnn_workspace_bytes(C.byref(m), 1), dll.mer_cnn_workspace_bytes(C.byref(m), 2)
+    # stem output 112*112*128 fp32 + stream / shortcut 56*56*256 fp32 each + 56*56*128 + the stem's split operand
+    expect = 4 * (112 * 112 * 128 + 2 * 56 * 56 * 256 + 56 * 56 * 128) + 112 * 112 * 160 * 4
+    assert expect <= one <= expect + 8 * 256 and 2 * expect <= two <= 2 * expect + 8 * 256
+    m.ops[3].res = 2   # 56 x 56 x 128 residual for a 256-channel output
+    assert dll.mer_cnn_workspace_bytes(C.byref(m), 1) == -1 and b"residual shape" in dll.mer_last_error()
+    m.ops[3].res = -1
+    m.ops[1].ceil_mode = 0   # floor mode: 55 x 55 maps, 4 x 4 at the end -> still a valid chain
+    assert dll.mer_cnn_workspace_bytes(C.byref(m), 1) > 0

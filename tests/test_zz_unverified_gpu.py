@@ -224,3 +224,42 @@ def test_hubert_packed_conv0_and_switches_keep_parity(cuda):
         assert float((got - base).abs().max()) / scale < 5e-5, env
     got = _with_env("MER_ATT_TC_VER", "2", run)
     assert float((got - base).abs().max()) / scale < 5e-5
+
+
+def test_ferplus_resnet50_vs_reference_golden(cuda, tmp_path):
+    """FER+ ResNet-50 through the table-driven CNN executor (Resize(256) / CenterCrop(224) on the device, 52
+    BN-folded convolutions on BF16X3 GEMMs) against outputs of the unmodified reference functions, plus the
+    mirrored script's files."""
+    import importlib.util
+    import types
+
+    import numpy as np
+
+    from mertools_b200 import synthetic as S
+    from mertools_b200.encoders import FerplusResnet50Encoder
+    from mertools_b200.extract import ferplus
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden_ferplus", os.path.join(gdir, "make_golden_ferplus.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(gdir, "ferplus_golden.npz"))
+    sd = S.ferplus_resnet50_state_dict(int(g["seed"]))
+    enc = FerplusResnet50Encoder(sd, device=cuda)
+    clips = mod.golden_clips()
+    for vid, frames in clips.items():
+        got = enc.frame_features(torch.from_numpy(frames).to(cuda), max_frames=2).cpu().numpy()
+        ref = g[f"fra_{vid}"]
+        assert got.shape == ref.shape and np.abs(got - ref).max() / np.abs(ref).max() < 1e-3, vid
+    face = tmp_path / "face"
+    for vid, frames in clips.items():
+        os.makedirs(face / vid)
+        np.save(face / vid / f"{vid}.npy", frames)
+    cfg = types.SimpleNamespace(PATH_TO_RAW_FACE={"D": str(face)}, PATH_TO_FEATURES={"D": str(tmp_path / "feat")})
+    for level, key in (("UTTERANCE", "utt"), ("FRAME", "fra")):
+        args = ferplus.build_parser().parse_args(["--dataset=D", f"--feature_level={level}",
+                                                  "--model_name=resnet50_ferplus_dag", "--gpu=0"])
+        ferplus.main(args, config=cfg, state_dict=sd)
+        for vid in clips:
+            got = np.load(tmp_path / "feat" / f"resnet50face_{level[:3]}" / f"{vid}.npy")
+            ref = g[f"{key}_{vid}"]
+            assert got.shape == ref.shape and np.abs(got - ref).max() / np.abs(ref).max() < 1e-3, (vid, level)
