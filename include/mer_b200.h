@@ -288,13 +288,17 @@ MER_API int mer_resnet18_forward(const MerResnet18Model* model, const uint8_t* f
 enum { MER_CNN_STEM = 0,    /* dst = act(conv(frames)): 7x7 / 2 / pad 3 on the uint8 input, preprocessing fused */
        MER_CNN_CONV = 1,    /* dst = act(conv(src) [+ res]); dst may equal res (in-place residual update) */
        MER_CNN_MAXPOOL = 2, /* dst = MaxPool2d(3, 2, pad, ceil_mode)(src), windows clipped to the image */
-       MER_CNN_GAP = 3 };   /* out_feats = mean over H x W of src; must be the last op */
+       MER_CNN_GAP = 3,     /* out_feats = mean over H x W of src; must be the last op */
+       MER_CNN_SE = 4 };    /* squeeze-and-excitation block end (senet50_ferplus_dag): dst = relu(g * src + res),
+                               g[n, c] = sigmoid(up(relu(down(mean over H x W of src)))); conv = index of the
+                               "down" layer, k = index of the "up" layer: convs entries with k = 1 whose w is a
+                               PLAIN fp32 [cout, cin] matrix (not a GEMM operand) and b an fp32 [cout] bias */
 typedef struct MerCnnOp {
   int kind;  /* MER_CNN_* */
   int conv;  /* STEM / CONV: index into convs */
   int src, dst, res; /* buffer indices 0..3; res = -1 for none */
   int relu;  /* STEM / CONV: ReLU (after the residual add) */
-  int k, stride, pad, ceil_mode; /* MAXPOOL (k = 3, stride = 2) */
+  int k, stride, pad, ceil_mode; /* MAXPOOL (k = 3, stride = 2); SE: k = index of the "up" layer */
 } MerCnnOp;
 typedef struct MerCnnModel {
   const MerResnetConv* convs; /* BatchNorm folded; w in the layout of gemm_mode: fp16 [cout_pad, kpad] (stem kpad

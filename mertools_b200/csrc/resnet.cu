@@ -153,6 +153,44 @@ maxpool2x2_kernel(const float4* __restrict__ x, int H, int W, int c4, float4* __
                        fmaxf(fmaxf(a.z, b.z), fmaxf(d.z, e.z)), fmaxf(fmaxf(a.w, b.w), fmaxf(d.w, e.w)));
 }
 
+// squeeze-and-excitation gate of senet50_ferplus_dag: scale[n, c] = sigmoid(up(relu(down(z[n, :])))) with z the
+// per-frame channel means; one block per frame, fp32 (2 * C * C/16 MACs per frame)
+__global__ void __launch_bounds__(256)
+se_mlp_kernel(const float* __restrict__ z, const float* __restrict__ wd, const float* __restrict__ bd,
+              const float* __restrict__ wu, const float* __restrict__ bu, int C, int R, float* __restrict__ scale) {
+  extern __shared__ float se_sm[];
+  float* zs = se_sm;
+  float* ds = se_sm + C;
+  const long long n = blockIdx.x;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) zs[i] = z[n * C + i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = warp; j < R; j += 8) {
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a = fmaf(__ldg(wd + (long long)j * C + c), zs[c], a);
+    a = warp_sum(a);
+    if (lane == 0) ds[j] = fmaxf(a + __ldg(bd + j), 0.f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = __ldg(bu + c);
+    for (int j = 0; j < R; ++j) a = fmaf(__ldg(wu + (long long)c * R + j), ds[j], a);
+    scale[n * C + c] = 1.0f / (1.0f + expf(-a));
+  }
+}
+
+// out = relu(scale[n, c] * y + res) on NHWC fp32 maps (C == stored channels), 4 channels per thread
+__global__ void __launch_bounds__(256)
+se_apply_kernel(const float4* __restrict__ y, const float4* __restrict__ res, const float4* __restrict__ scale,
+                long long hw_c4, int c4, float4* __restrict__ out, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const float4 sc = __ldg(scale + (idx / hw_c4) * c4 + idx % c4);
+  const float4 a = __ldg(y + idx), r = __ldg(res + idx);
+  out[idx] = make_float4(fmaxf(fmaf(sc.x, a.x, r.x), 0.f), fmaxf(fmaf(sc.y, a.y, r.y), 0.f),
+                         fmaxf(fmaf(sc.z, a.z, r.z), 0.f), fmaxf(fmaf(sc.w, a.w, r.w), 0.f));
+}
+
 struct Shape { int H, W, C, Cs; };  // C real channels, Cs stored channels (>= 128)
 
 // mode: MER_GEMM_F16 (fp16 operand, weights fp16) or MER_GEMM_BF16X3 (split-bf16 operand and weights)
@@ -442,7 +480,7 @@ int mer_vggish_forward(const MerVggishModel* m, const float* examples, int n_exa
 // conv (+ folded BN, + residual, + ReLU), 3x3/2 max-pool and a global average pool over four activation buffers.
 // First user: the FER+ ResNet-50 (extract_ferplus_embedding.py; pytorch-benchmarks/model/resnet50_ferplus_dag.py). ----
 namespace {
-struct CnnPlan { long long off_buf[4], off_col, off_cu, total; };
+struct CnnPlan { long long off_buf[4], off_col, off_cu, off_z, off_scale, total; };
 
 int pool_out(int in, int pad, int ceil_mode) {  // torch MaxPool2d(3, 2, pad, ceil_mode) output size
   const int num = in + 2 * pad - 3;
@@ -459,6 +497,7 @@ int cnn_plan(const MerCnnModel* m, int n_frames, CnnPlan* plan, Shape* final_sha
   const long long vbytes = m->gemm_mode == MER_GEMM_F16 ? 2 : 4;  // bytes per operand value
   Shape sh[4] = {};
   long long need[4] = {0, 0, 0, 0}, col = 0;
+  int se_c = 0;  // widest squeeze-and-excitation gate
   Shape last{0, 0, 0, 0};
   for (int i = 0; i < m->n_ops; ++i) {
     const MerCnnOp& op = m->ops[i];
@@ -481,6 +520,17 @@ int cnn_plan(const MerCnnModel* m, int n_frames, CnnPlan* plan, Shape* final_sha
       const Shape in = sh[op.src];
       MER_REQUIRE(in.H > 0 && op.k == 3 && op.stride == 2 && op.src != op.dst, "mer_cnn: op %d max-pool", i);
       sh[op.dst] = Shape{pool_out(in.H, op.pad, op.ceil_mode), pool_out(in.W, op.pad, op.ceil_mode), in.C, in.Cs};
+    } else if (op.kind == MER_CNN_SE) {
+      const Shape in = sh[op.src];
+      MER_REQUIRE(op.conv >= 0 && op.conv < m->n_convs && op.k >= 0 && op.k < m->n_convs, "mer_cnn: op %d SE layers", i);
+      const MerResnetConv &dn = m->convs[op.conv], &up = m->convs[op.k];
+      MER_REQUIRE(in.H > 0 && in.C == in.Cs && in.C % 4 == 0 && dn.cin == in.C && up.cout == in.C && dn.cout == up.cin &&
+                      dn.cout > 0 && dn.cout <= 1024,
+                  "mer_cnn: op %d SE geometry (C %d, %d -> %d -> %d)", i, in.C, dn.cin, dn.cout, up.cout);
+      MER_REQUIRE(op.res >= 0 && op.res < 4 && sh[op.res].H == in.H && sh[op.res].W == in.W && sh[op.res].Cs == in.Cs,
+                  "mer_cnn: op %d SE shortcut shape", i);
+      se_c = se_c > in.C ? se_c : in.C;
+      sh[op.dst] = in;
     } else {
       MER_REQUIRE(op.kind == MER_CNN_GAP && i == m->n_ops - 1, "mer_cnn: op %d kind %d", i, op.kind);
       MER_REQUIRE(sh[op.src].C == sh[op.src].Cs && sh[op.src].C == m->feat_dim, "mer_cnn: pooled width != feat_dim");
@@ -499,6 +549,8 @@ int cnn_plan(const MerCnnModel* m, int n_frames, CnnPlan* plan, Shape* final_sha
   }
   plan->off_col = o;  o += al(col);
   plan->off_cu = o;   o += al((n + 1) * 4);
+  plan->off_z = o;    o += al(n * se_c * 4);
+  plan->off_scale = o; o += al(n * se_c * 4);
   plan->total = o;
   if (final_shape) *final_shape = last;
   return 0;
@@ -585,6 +637,25 @@ int mer_cnn_forward(const MerCnnModel* m, const uint8_t* frames_bgr, int n_frame
       MER_CUDA_CHECK(cudaGetLastError());
       mer_count_launches(1);
       sh[op.dst] = Shape{OH, OW, in.C, in.Cs};
+    } else if (op.kind == MER_CNN_SE) {
+      // y = buf[src] (increase conv + BN, no ReLU); dst = relu(sigmoid(up(relu(down(mean_hw(y))))) * y + res)
+      const Shape in = sh[op.src];
+      const MerResnetConv &dn = m->convs[op.conv], &up = m->convs[op.k];
+      float* z = reinterpret_cast<float*>(ws + p.off_z);
+      float* scale = reinterpret_cast<float*>(ws + p.off_scale);
+      if (int rc = mer_iota_offsets_launch(offsets, n_frames, in.H * in.W, st)) return rc;
+      if (int rc = mer_segment_reduce_launch(buf[op.src], offsets, offsets + 1, n_frames, in.C, MER_SEG_MEAN, z, st))
+        return rc;
+      se_mlp_kernel<<<n_frames, 256, (size_t)(in.C + dn.cout) * sizeof(float), st>>>(
+          z, static_cast<const float*>(dn.w), dn.b, static_cast<const float*>(up.w), up.b, in.C, dn.cout, scale);
+      MER_CUDA_CHECK(cudaGetLastError());
+      const long long hw_c4 = (long long)in.H * in.W * (in.C / 4), total = hw_c4 * n_frames;
+      se_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+          reinterpret_cast<const float4*>(buf[op.src]), reinterpret_cast<const float4*>(buf[op.res]),
+          reinterpret_cast<const float4*>(scale), hw_c4, in.C / 4, reinterpret_cast<float4*>(buf[op.dst]), total);
+      MER_CUDA_CHECK(cudaGetLastError());
+      mer_count_launches(2);
+      sh[op.dst] = in;
     } else {  // MER_CNN_GAP (last op, checked by cnn_plan)
       const Shape in = sh[op.src];
       if (int rc = mer_iota_offsets_launch(offsets, n_frames, in.H * in.W, st)) return rc;

@@ -348,17 +348,29 @@ class MerCnnModel(C.Structure):
                 ("scale", C.c_float), ("mean", C.c_float * 3), ("std", C.c_float * 3), ("feat_dim", C.c_int)]
 
 
-CNN_STEM, CNN_CONV, CNN_MAXPOOL, CNN_GAP = 0, 1, 2, 3
+CNN_STEM, CNN_CONV, CNN_MAXPOOL, CNN_GAP, CNN_SE = 0, 1, 2, 3, 4
 FERPLUS_BLOCKS = (3, 4, 6, 3)
 
 
-def ferplus_resnet50_tables(state_dict, pack, bn_eps=1e-5):
-    """Conv and op tables of ``resnet50_ferplus_dag`` up to conv5_3_3x3_relu + the 7x7 average pool, for
-    mer_cnn_forward.  ``pack(w [cout_pad, kpad] fp32, b [cout_pad] fp32) -> (w_ptr, b_ptr)`` places the folded
-    weights (split bf16) and biases on the device.  Returns (MerCnnModel, keep-alive list).
+def ferplus_resnet50_tables(state_dict, pack, bn_eps=1e-5, pack_dense=None):
+    """Conv and op tables of ``resnet50_ferplus_dag`` / ``senet50_ferplus_dag`` up to conv5_3_3x3_relu + the 7x7
+    average pool, for mer_cnn_forward.  ``pack(w [cout_pad, kpad] fp32, b [cout_pad] fp32) -> (w_ptr, b_ptr)``
+    places the folded weights (split bf16) and biases on the device; ``pack_dense`` (default: ``pack``) does the
+    same for the plain fp32 squeeze-and-excitation matrices of the SENet (detected by its ``*_1x1_down`` keys).
+    Returns (MerCnnModel, keep-alive list).
     Buffers: 0 = the residual stream (block input / output), 1 and 2 = block-internal, 3 = projection shortcut."""
     sd = W._np(state_dict)
     convs, ops = [], []
+    se = "conv2_1_1x1_down.weight" in sd
+    pack_dense = pack_dense or pack
+
+    def add_dense(name):
+        w = np.ascontiguousarray(sd[name + ".weight"][:, :, 0, 0], np.float32)   # [cout, cin]
+        c = MerResnetConv()
+        c.w, c.b = pack_dense(w, np.asarray(sd[name + ".bias"], np.float32))
+        c.cin, c.cout, c.cout_pad, c.k, c.stride, c.pad, c.kpad = w.shape[1], w.shape[0], w.shape[0], 1, 1, 0, w.shape[1]
+        convs.append(c)
+        return len(convs) - 1
 
     def add_conv(name, stride, pad):
         w = sd[name + ".weight"]
@@ -393,10 +405,13 @@ def ferplus_resnet50_tables(state_dict, pack, bn_eps=1e-5):
                 break
             if b == 1:
                 op(CNN_CONV, add_conv(p + "1x1_proj", stride, 0), src=0, dst=3, relu=0)
-                op(CNN_CONV, add_conv(p + "1x1_increase", 1, 0), src=2, dst=0, res=3, relu=1)
+            shortcut = 3 if b == 1 else 0
+            if se:   # y -> buffer 1 (no ReLU), then the gate, the shortcut add and the ReLU in one op
+                op(CNN_CONV, add_conv(p + "1x1_increase", 1, 0), src=2, dst=1, relu=0)
+                op(CNN_SE, add_dense(p + "1x1_down"), src=1, dst=0, res=shortcut, relu=1, k=add_dense(p + "1x1_up"))
             else:
-                op(CNN_CONV, add_conv(p + "1x1_increase", 1, 0), src=2, dst=0, res=0, relu=1)
-    assert len(convs) == 52 and ops[-1].kind == CNN_GAP
+                op(CNN_CONV, add_conv(p + "1x1_increase", 1, 0), src=2, dst=0, res=shortcut, relu=1)
+    assert len(convs) == (52 + 30 if se else 52) and ops[-1].kind == CNN_GAP
     conv_arr = (MerResnetConv * len(convs))(*convs)
     op_arr = (MerCnnOp * len(ops))(*ops)
     m = MerCnnModel()
@@ -412,7 +427,8 @@ def ferplus_resnet50_tables(state_dict, pack, bn_eps=1e-5):
 
 
 class FerplusResnet50Encoder:
-    """``resnet50_ferplus_dag`` up to ``conv5_3_3x3_relu`` + AvgPool2d(7) (what the reference's FER+ extractor keeps
+    """``resnet50_ferplus_dag`` (or ``senet50_ferplus_dag``: same skeleton + a squeeze-and-excitation gate per block,
+    picked up from the state_dict) up to ``conv5_3_3x3_relu`` + AvgPool2d(7) (what the reference's FER+ extractor keeps
     with its default ``--layer_name``): 52 BatchNorm-folded convolutions through the table-driven CNN executor
     (im2col + tcgen05 GEMMs on split-bf16 operands: fp16 operands measured 6e-4 in an fp32 emulation, too close
     to the 1e-3 bar), caffe-style strides, ceil-mode max-pool.
@@ -425,7 +441,8 @@ class FerplusResnet50Encoder:
         self.device = torch.device(device)
         pk = self.pk = W.Packed(self.device)
         self.model, self._keep = ferplus_resnet50_tables(
-            state_dict, lambda wp, bp: (pk.keep(wp, split=True).data_ptr(), pk.keep(bp).data_ptr()), bn_eps)
+            state_dict, lambda wp, bp: (pk.keep(wp, split=True).data_ptr(), pk.keep(bp).data_ptr()), bn_eps,
+            pack_dense=lambda w, b: (pk.keep(w).data_ptr(), pk.keep(b).data_ptr()))
         self.feature_dim = 512
         self.ws, self.ws_resize = _Workspace(self.device), _Workspace(self.device)
         lib = L.lib()

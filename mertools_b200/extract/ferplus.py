@@ -2,10 +2,10 @@
 
 Same flags (``--dataset --feature_level --model_name --layer_name --gpu``, :130-136), input layout
 (``<face_dir>/<vid>/<vid>.npy`` through FaceDataset, dataset.py:12-47), output directory
-``<model prefix>face_<UTT|FRA>`` (:143-145) and save rules (:175-194).  Supported here: ``resnet50_ferplus_dag`` with
-the default ``--layer_name conv5_3_3x3_relu`` (the 512-d feature the benchmark uses); the preprocessing of
+``<model prefix>face_<UTT|FRA>`` (:143-145) and save rules (:175-194).  Supported here: both models of the script
+(``resnet50_ferplus_dag``, ``senet50_ferplus_dag``) with the default ``--layer_name conv5_3_3x3_relu`` (512-d); the preprocessing of
 ``compose_transforms`` (Resize(256), CenterCrop(224), ToTensor, x 255, Normalize) and the network run in
-libmer_b200.so.  The checkpoint is the reference's ``<PRETRAINED>/ferplus/resnet50_ferplus_dag.pth``.
+libmer_b200.so.  The checkpoint is the reference's ``<PRETRAINED>/ferplus/<model_name>.pth``.
 """
 from __future__ import annotations
 
@@ -19,7 +19,7 @@ from ..encoders import FerplusResnet50Encoder
 from . import common
 from .visual import func_read_frames
 
-SUPPORTED = {"resnet50_ferplus_dag": "conv5_3_3x3_relu"}
+SUPPORTED = {"resnet50_ferplus_dag": "conv5_3_3x3_relu", "senet50_ferplus_dag": "conv5_3_3x3_relu"}
 
 
 def extract_video(enc, frames_bgr, feature_level, save_file=None, frames_per_launch=64):
@@ -39,7 +39,7 @@ def main(params, config=None, state_dict=None):
     if config is None:
         from .. import config as config  # noqa: PLW0127
     assert params.model_name in SUPPORTED and params.layer_name == SUPPORTED[params.model_name], \
-        f"the B200 path covers {SUPPORTED} (senet50_ferplus_dag and other layers: use the reference script)"
+        f"the B200 path covers {SUPPORTED} (other hook layers: use the reference script)"
     print("==> Extracting ferplus embedding...")
     face_dir = config.PATH_TO_RAW_FACE[params.dataset]
     save_name = f"{params.model_name.split('_')[0]}face_{params.feature_level[:3]}"

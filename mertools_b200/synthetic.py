@@ -145,10 +145,12 @@ def vggish_state_dict(seed=8):
 FERPLUS_BLOCKS = (3, 4, 6, 3)   # bottlenecks in conv2_x .. conv5_x
 
 
-def ferplus_resnet50_state_dict(seed=9):
+def ferplus_resnet50_state_dict(seed=9, se=False):
     """Parameters of the reference's ``resnet50_ferplus_dag`` (pytorch-benchmarks/model/resnet50_ferplus_dag.py:10-176):
     caffe-style ResNet-50 (stride on the 1x1 reduce / proj of conv3_1, conv4_1, conv5_1), one BatchNorm per conv,
-    a 1x1 classifier conv with bias.  He-style conv scales, non-trivial BatchNorm statistics."""
+    a 1x1 classifier conv with bias.  He-style conv scales, non-trivial BatchNorm statistics.
+    ``se=True``: ``senet50_ferplus_dag`` (senet50_ferplus_dag.py:8-253) = the same skeleton plus a squeeze-and-
+    excitation pair ``<block>_1x1_down`` (C -> C/16) / ``<block>_1x1_up`` (C/16 -> C), both with bias, per block."""
     rng = np.random.default_rng(seed)
     sd = {}
 
@@ -169,6 +171,11 @@ def ferplus_resnet50_state_dict(seed=9):
             conv_bn(p + "1x1_reduce", mid, cin, 1)
             conv_bn(p + "3x3", mid, mid, 3)
             conv_bn(p + "1x1_increase", cout, mid, 1, gain=0.5)
+            if se:
+                sd[p + "1x1_down.weight"] = (rng.standard_normal((cout // 16, cout, 1, 1)) * np.sqrt(1.0 / cout)).astype(np.float32)
+                sd[p + "1x1_down.bias"] = (0.2 * rng.standard_normal(cout // 16)).astype(np.float32)
+                sd[p + "1x1_up.weight"] = (rng.standard_normal((cout, cout // 16, 1, 1)) * np.sqrt(16.0 / cout)).astype(np.float32)
+                sd[p + "1x1_up.bias"] = (0.5 * rng.standard_normal(cout)).astype(np.float32)
             if b == 1:
                 conv_bn(p + "1x1_proj", cout, cin, 1)
             cin = cout

@@ -171,6 +171,9 @@ def ferplus_resnet50_features(sd, x, dtype=torch.float32, eps=1e-5):
     after conv5_3_3x3 + BN, then AvgPool2d(7) and a (no-op) ReLU -> [N, 512].  Caffe-style bottlenecks: 1x1 reduce
     (stride 2 in conv3_1 / conv4_1 / conv5_1) - 3x3 - 1x1 increase, a projection shortcut in the first block of each
     stage, one BatchNorm after every conv, MaxPool2d(3, 2, padding 0, ceil_mode=True) after the stem.
+    A state_dict with ``<block>_1x1_down`` / ``_1x1_up`` entries is ``senet50_ferplus_dag`` (senet50_ferplus_dag.py:
+    255-470): every block's increase output y is rescaled per channel by sigmoid(up(relu(down(mean_hw(y))))) before
+    the shortcut is added.
     x: [N, 3, 224, 224] = RGB pixels on the 0..255 scale minus FERPLUS_MEAN."""
     def cb(x, name, stride=1, pad=0):
         y = F.conv2d(x, _t(sd, name + ".weight", dtype), None, stride=stride, padding=pad)
@@ -187,6 +190,10 @@ def ferplus_resnet50_features(sd, x, dtype=torch.float32, eps=1e-5):
             if si == 3 and b == nblk:
                 return F.relu(o.mean(dim=(2, 3)))
             o = cb(o, p + "1x1_increase")
+            if p + "1x1_down.weight" in sd:
+                z = o.mean(dim=(2, 3), keepdim=True)
+                z = F.relu(F.conv2d(z, _t(sd, p + "1x1_down.weight", dtype), _t(sd, p + "1x1_down.bias", dtype)))
+                o = torch.sigmoid(F.conv2d(z, _t(sd, p + "1x1_up.weight", dtype), _t(sd, p + "1x1_up.bias", dtype))) * o
             idt = cb(y, p + "1x1_proj", stride) if b == 1 else y
             y = F.relu(idt + o)
     raise AssertionError("unreachable")

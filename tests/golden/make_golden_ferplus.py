@@ -41,29 +41,31 @@ def main():
     ref = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(ref)
 
-    sd = S.ferplus_resnet50_state_dict(SEED)
     clips = golden_clips()
     out = {"seed": SEED, "names": np.array(list(clips))}
-    with tempfile.TemporaryDirectory() as tmp:
-        torch.save({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, os.path.join(tmp, "resnet50_ferplus_dag.pth"))
-        model = ref.load_model("resnet50_ferplus_dag", os.path.join(VIS, "pytorch-benchmarks/model"), tmp).eval()
-        transform = ref.compose_transforms(model.meta)
-        for vid, frames in clips.items():
-            os.makedirs(os.path.join(tmp, vid))
-            np.save(os.path.join(tmp, vid, f"{vid}.npy"), frames)
-            ds = ref.FaceDataset(vid, tmp, transform=transform)
-            loader = torch.utils.data.DataLoader(ds, batch_size=32)
-            feats, names = [], []
-            with torch.no_grad():
-                for imgs, ids in loader:
-                    feats.extend(ref.get_feature(model, "conv5_3_3x3_relu", imgs))
-                    names.extend(ids)
-            emb = np.array(feats)[np.argsort(np.array(names))]
-            fra = np.array(emb).squeeze()                      # __main__ :178-184
-            out[f"fra_{vid}"] = fra[np.newaxis, :] if len(fra.shape) == 1 else fra
-            utt = np.array(emb).squeeze()                      # :185-191
-            out[f"utt_{vid}"] = np.mean(utt, axis=0) if len(utt.shape) == 2 else utt
-            out[f"x_{vid}"] = torch.stack([ds[i][0] for i in range(len(ds))]).numpy()[:, :, ::16, ::16]  # preprocess probe
+    for model_name, prefix, se in (("resnet50_ferplus_dag", "", False), ("senet50_ferplus_dag", "se_", True)):
+        sd = S.ferplus_resnet50_state_dict(SEED, se=se)
+        with tempfile.TemporaryDirectory() as tmp:
+            torch.save({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, os.path.join(tmp, model_name + ".pth"))
+            model = ref.load_model(model_name, os.path.join(VIS, "pytorch-benchmarks/model"), tmp).eval()
+            transform = ref.compose_transforms(model.meta)
+            for vid, frames in clips.items():
+                os.makedirs(os.path.join(tmp, vid))
+                np.save(os.path.join(tmp, vid, f"{vid}.npy"), frames)
+                ds = ref.FaceDataset(vid, tmp, transform=transform)
+                loader = torch.utils.data.DataLoader(ds, batch_size=32)
+                feats, names = [], []
+                with torch.no_grad():
+                    for imgs, ids in loader:
+                        feats.extend(ref.get_feature(model, "conv5_3_3x3_relu", imgs))
+                        names.extend(ids)
+                emb = np.array(feats)[np.argsort(np.array(names))]
+                fra = np.array(emb).squeeze()                      # __main__ :178-184
+                out[f"{prefix}fra_{vid}"] = fra[np.newaxis, :] if len(fra.shape) == 1 else fra
+                utt = np.array(emb).squeeze()                      # :185-191
+                out[f"{prefix}utt_{vid}"] = np.mean(utt, axis=0) if len(utt.shape) == 2 else utt
+                if not se:  # preprocess probe (the two models share meta / transforms)
+                    out[f"x_{vid}"] = torch.stack([ds[i][0] for i in range(len(ds))]).numpy()[:, :, ::16, ::16]
     np.savez_compressed(os.path.join(HERE, "ferplus_golden.npz"), **out)
     for k, v in out.items():
         print(k, getattr(v, "shape", v))

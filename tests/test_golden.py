@@ -221,10 +221,11 @@ def test_ferplus_oracle_matches_reference_extractor_golden():
     reference functions (extract_ferplus_embedding.py: load_model, compose_transforms, FaceDataset, get_feature)."""
     from oracle import pipeline as P
     g = np.load(os.path.join(G, "ferplus_golden.npz"))
-    sd = _t(S.ferplus_resnet50_state_dict(int(g["seed"])))
-    for vid, frames in _ferplus_clips().items():
-        x = P.ferplus_preprocess(frames)
-        assert np.array_equal(x.numpy()[:, :, ::16, ::16], g[f"x_{vid}"]), vid   # Resize / crop / scale: bit-exact
-        for level, key in (("FRAME", "fra"), ("UTTERANCE", "utt")):
-            got, ref = P.ferplus_clip_features(sd, frames, level), g[f"{key}_{vid}"]
-            assert got.shape == ref.shape and _rel(got, ref) < 1e-5, (vid, level)
+    for se, prefix in ((False, ""), (True, "se_")):   # resnet50_ferplus_dag, senet50_ferplus_dag
+        sd = _t(S.ferplus_resnet50_state_dict(int(g["seed"]), se=se))
+        for vid, frames in _ferplus_clips().items():
+            x = P.ferplus_preprocess(frames)
+            assert np.array_equal(x.numpy()[:, :, ::16, ::16], g[f"x_{vid}"]), vid   # Resize / crop / scale: bit-exact
+            for level, key in (("FRAME", "fra"), ("UTTERANCE", "utt")):
+                got, ref = P.ferplus_clip_features(sd, frames, level), g[f"{prefix}{key}_{vid}"]
+                assert got.shape == ref.shape and _rel(got, ref) < 1e-5, (se, vid, level)

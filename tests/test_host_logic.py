@@ -301,3 +301,10 @@ def test_cnn_executor_plans_the_ferplus_tables_without_a_gpu():
     m.ops[3].res = -1
     m.ops[1].ceil_mode = 0   # floor mode: 55 x 55 maps, 4 x 4 at the end -> still a valid chain
     assert dll.mer_cnn_workspace_bytes(C.byref(m), 1) > 0
+    # senet50_ferplus_dag: 15 squeeze-and-excitation ops with their 30 dense layers
+    m, _keep = En.ferplus_resnet50_tables(S.ferplus_resnet50_state_dict(9, se=True), lambda wp, bp: (1, 1))
+    assert m.n_convs == 82 and sum(m.ops[i].kind == En.CNN_SE for i in range(m.n_ops)) == 15
+    assert dll.mer_cnn_workspace_bytes(C.byref(m), 1) >= one + 2 * 2048 * 4
+    se_op = next(i for i in range(m.n_ops) if m.ops[i].kind == En.CNN_SE)
+    m.ops[se_op].res = 2   # 64-channel map as the shortcut of a 256-channel block
+    assert dll.mer_cnn_workspace_bytes(C.byref(m), 1) == -1 and b"SE shortcut shape" in dll.mer_last_error()

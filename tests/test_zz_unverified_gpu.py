@@ -226,8 +226,9 @@ def test_hubert_packed_conv0_and_switches_keep_parity(cuda):
     assert float((got - base).abs().max()) / scale < 5e-5
 
 
-def test_ferplus_resnet50_vs_reference_golden(cuda, tmp_path):
-    """FER+ ResNet-50 through the table-driven CNN executor (Resize(256) / CenterCrop(224) on the device, 52
+@pytest.mark.parametrize("model_name,prefix,se", [("resnet50_ferplus_dag", "", False), ("senet50_ferplus_dag", "se_", True)])
+def test_ferplus_models_vs_reference_golden(cuda, tmp_path, model_name, prefix, se):
+    """FER+ ResNet-50 / SENet-50 through the table-driven CNN executor (Resize(256) / CenterCrop(224) on the device, 52
     BN-folded convolutions on BF16X3 GEMMs) against outputs of the unmodified reference functions, plus the
     mirrored script's files."""
     import importlib.util
@@ -243,12 +244,12 @@ def test_ferplus_resnet50_vs_reference_golden(cuda, tmp_path):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     g = np.load(os.path.join(gdir, "ferplus_golden.npz"))
-    sd = S.ferplus_resnet50_state_dict(int(g["seed"]))
+    sd = S.ferplus_resnet50_state_dict(int(g["seed"]), se=se)
     enc = FerplusResnet50Encoder(sd, device=cuda)
     clips = mod.golden_clips()
     for vid, frames in clips.items():
         got = enc.frame_features(torch.from_numpy(frames).to(cuda), max_frames=2).cpu().numpy()
-        ref = g[f"fra_{vid}"]
+        ref = g[f"{prefix}fra_{vid}"]
         assert got.shape == ref.shape and np.abs(got - ref).max() / np.abs(ref).max() < 1e-3, vid
     face = tmp_path / "face"
     for vid, frames in clips.items():
@@ -257,9 +258,9 @@ def test_ferplus_resnet50_vs_reference_golden(cuda, tmp_path):
     cfg = types.SimpleNamespace(PATH_TO_RAW_FACE={"D": str(face)}, PATH_TO_FEATURES={"D": str(tmp_path / "feat")})
     for level, key in (("UTTERANCE", "utt"), ("FRAME", "fra")):
         args = ferplus.build_parser().parse_args(["--dataset=D", f"--feature_level={level}",
-                                                  "--model_name=resnet50_ferplus_dag", "--gpu=0"])
+                                                  f"--model_name={model_name}", "--gpu=0"])
         ferplus.main(args, config=cfg, state_dict=sd)
         for vid in clips:
-            got = np.load(tmp_path / "feat" / f"resnet50face_{level[:3]}" / f"{vid}.npy")
-            ref = g[f"{key}_{vid}"]
+            got = np.load(tmp_path / "feat" / f"{model_name.split('_')[0]}face_{level[:3]}" / f"{vid}.npy")
+            ref = g[f"{prefix}{key}_{vid}"]
             assert got.shape == ref.shape and np.abs(got - ref).max() / np.abs(ref).max() < 1e-3, (vid, level)
