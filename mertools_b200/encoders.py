@@ -514,6 +514,30 @@ def vggish_tf_names(state_dict):
     return out
 
 
+def vggish_tables(state_dict, pack):
+    """MerVggishModel from the TF-named (or torchvggish) weights.  ``pack(w [rows, K] fp32, b fp32) -> (w_ptr, b_ptr)``
+    places one GEMM weight matrix (split bf16 on the device) and its bias."""
+    sd = vggish_tf_names(state_dict)
+    m = MerVggishModel()
+    for i, name in enumerate(VGGISH_CONVS):
+        w = sd[f"vggish/{name}/weights"]                                   # HWIO [3, 3, cin, cout]
+        k, _, cin, cout = w.shape
+        assert k == 3, name
+        cout_pad, kk = max(cout, 128), 9 * cin
+        kpad = 32 if i == 0 else kk
+        wp = np.zeros((cout_pad, kpad), np.float32)
+        wp[:cout, :kk] = w.transpose(3, 0, 1, 2).reshape(cout, kk)         # (ky, kx, c) order
+        bp = np.zeros(cout_pad, np.float32)
+        bp[:cout] = sd[f"vggish/{name}/biases"]
+        c = m.convs[i]
+        c.w, c.b = pack(wp, bp)
+        c.cin, c.cout, c.cout_pad, c.k, c.stride, c.pad, c.kpad = cin, cout, cout_pad, 3, 1, 1, kpad
+    for i, name in enumerate(VGGISH_FCS):
+        w = sd[f"vggish/{name}/weights"]                                   # [in, out]
+        m.fc_w[i], m.fc_b[i] = pack(np.ascontiguousarray(w.T, np.float32), np.asarray(sd[f"vggish/{name}/biases"], np.float32))
+    return m
+
+
 class VggishEncoder:
     """VGGish embedding network of the reference's audio extractor: six 3x3 convolutions as im2col + tcgen05
     GEMMs with ReLU epilogues, 2x2 max-pools, three fully connected layers; all GEMMs on split-bf16 operands
@@ -524,28 +548,9 @@ class VggishEncoder:
 
     def __init__(self, state_dict, device="cuda"):
         L.check(L.lib().mer_check_device())
-        sd = vggish_tf_names(state_dict)
         self.device = torch.device(device)
         pk = self.pk = W.Packed(self.device)
-        m = MerVggishModel()
-        for i, name in enumerate(VGGISH_CONVS):
-            w = sd[f"vggish/{name}/weights"]                                   # HWIO [3, 3, cin, cout]
-            k, _, cin, cout = w.shape
-            assert k == 3, name
-            cout_pad, kk = max(cout, 128), 9 * cin
-            kpad = 32 if i == 0 else kk
-            wp = np.zeros((cout_pad, kpad), np.float32)
-            wp[:cout, :kk] = w.transpose(3, 0, 1, 2).reshape(cout, kk)         # (ky, kx, c) order
-            bp = np.zeros(cout_pad, np.float32)
-            bp[:cout] = sd[f"vggish/{name}/biases"]
-            c = m.convs[i]
-            c.w, c.b = pk.keep(wp, split=True).data_ptr(), pk.keep(bp).data_ptr()
-            c.cin, c.cout, c.cout_pad, c.k, c.stride, c.pad, c.kpad = cin, cout, cout_pad, 3, 1, 1, kpad
-        for i, name in enumerate(VGGISH_FCS):
-            w = sd[f"vggish/{name}/weights"]                                   # [in, out]
-            m.fc_w[i] = pk.keep(np.ascontiguousarray(w.T), split=True).data_ptr()
-            m.fc_b[i] = pk.keep(sd[f"vggish/{name}/biases"]).data_ptr()
-        self.model = m
+        self.model = vggish_tables(state_dict, lambda w, b: (pk.keep(w, split=True).data_ptr(), pk.keep(b).data_ptr()))
         self.feature_dim = 128
         self.ws = _Workspace(self.device)
         lib = L.lib()

@@ -308,3 +308,112 @@ def test_cnn_executor_plans_the_ferplus_tables_without_a_gpu():
     se_op = next(i for i in range(m.n_ops) if m.ops[i].kind == En.CNN_SE)
     m.ops[se_op].res = 2   # 64-channel map as the shortcut of a 256-channel block
     assert dll.mer_cnn_workspace_bytes(C.byref(m), 1) == -1 and b"SE shortcut shape" in dll.mer_last_error()
+
+
+def _interpret_cnn_tables(m, store, frames_bgr):
+    """Test-side interpreter of a mer_cnn_forward op table (include/mer_b200.h: MerCnnOp): the same buffer / shape
+    semantics as resnet.cu's executor, in torch fp32 on NHWC maps with padded channel counts, so that the tables a
+    Python builder emits can be checked against a golden without a GPU."""
+    import torch.nn.functional as F
+    from mertools_b200 import encoders as En
+    n = len(frames_bgr)
+    mean = torch.tensor([m.mean[i] for i in range(3)])
+    std = torch.tensor([m.std[i] for i in range(3)])
+    x0 = (torch.from_numpy(np.ascontiguousarray(frames_bgr[..., ::-1])).float() * m.scale - mean) / std  # NHWC, RGB
+    buf, real = [None] * 4, [0] * 4
+
+    def conv(x, cin_real, c):
+        w, b = store[c.w], store[c.b]                       # [cout_pad, kpad], [cout_pad]
+        kk = c.k * c.k * c.cin
+        assert c.cin == cin_real and (c.kpad == kk or (c.cin == 3 and c.kpad in (160, 192)))
+        wt = torch.from_numpy(w[:, :kk]).reshape(c.cout_pad, c.k, c.k, c.cin).permute(0, 3, 1, 2)
+        y = F.conv2d(x[..., :c.cin].permute(0, 3, 1, 2), wt, torch.from_numpy(b), stride=c.stride, padding=c.pad)
+        return y.permute(0, 2, 3, 1)
+    for i in range(m.n_ops):
+        op = m.ops[i]
+        if op.kind in (En.CNN_STEM, En.CNN_CONV):
+            c = m.convs[op.conv]
+            y = conv(x0, 3, c) if op.kind == En.CNN_STEM else conv(buf[op.src], real[op.src], c)
+            if op.res >= 0:
+                assert buf[op.res].shape == y.shape
+                y = y + buf[op.res]
+            buf[op.dst], real[op.dst] = (torch.relu(y) if op.relu else y), c.cout
+        elif op.kind == En.CNN_MAXPOOL:
+            assert op.k == 3 and op.stride == 2 and op.src != op.dst
+            y = F.max_pool2d(buf[op.src].permute(0, 3, 1, 2), 3, 2, op.pad, ceil_mode=bool(op.ceil_mode))
+            buf[op.dst], real[op.dst] = y.permute(0, 2, 3, 1), real[op.src]
+        elif op.kind == En.CNN_SE:
+            dn, up = m.convs[op.conv], m.convs[op.k]
+            y = buf[op.src]
+            z = y.mean(dim=(1, 2))
+            d = torch.relu(z @ torch.from_numpy(store[dn.w]).T + torch.from_numpy(store[dn.b]))
+            g = torch.sigmoid(d @ torch.from_numpy(store[up.w]).T + torch.from_numpy(store[up.b]))
+            buf[op.dst], real[op.dst] = torch.relu(g[:, None, None, :] * y + buf[op.res]), real[op.src]
+        else:
+            assert op.kind == En.CNN_GAP and i == m.n_ops - 1
+            return buf[op.src].mean(dim=(1, 2))[:, :m.feat_dim].numpy()
+    raise AssertionError("table without a final average pool")
+
+
+@pytest.mark.parametrize("se,prefix", [(False, ""), (True, "se_")])
+def test_ferplus_op_tables_reproduce_the_reference_golden_on_a_cpu_interpreter(se, prefix):
+    """The conv / op tables FerplusResnet50Encoder hands to mer_cnn_forward (BN folding, (ky, kx, c) weight layout,
+    channel padding, caffe-style strides, shortcut wiring, SE layer indices), run by a torch interpreter of the op
+    semantics, against outputs of the unmodified reference extractor.  Checks the host side of the CUDA path; the
+    kernels themselves are covered by the GPU tests."""
+    import importlib.util
+    from mertools_b200 import encoders as En
+    from oracle import pipeline as P
+    gdir = os.path.join(ROOT, "tests", "golden")
+    spec = importlib.util.spec_from_file_location("make_golden_ferplus", os.path.join(gdir, "make_golden_ferplus.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(gdir, "ferplus_golden.npz"))
+    store = {}
+
+    def pack(w, b):
+        store[len(store) + 1] = np.asarray(w, np.float32)
+        store[len(store) + 1] = np.asarray(b, np.float32)
+        return len(store) - 1, len(store)
+    m, _keep = En.ferplus_resnet50_tables(S.ferplus_resnet50_state_dict(int(g["seed"]), se=se), pack)
+    frames = mod.golden_clips()["vidA"][:2]                       # 256 x 256: Resize(256) is the identity
+    crop = frames[:, 16:240, 16:240]                              # CenterCrop(224), as frame_features slices it
+    got = _interpret_cnn_tables(m, store, crop)
+    ref = g[f"{prefix}fra_vidA"][:2]
+    assert got.shape == ref.shape and np.abs(got - ref).max() / np.abs(ref).max() < 1e-4
+    enc_geom = En.FerplusResnet50Encoder.preprocess_geometry(None, 200, 300)
+    assert enc_geom == (256, 384, 16, 80) and P.ferplus_preprocess(mod.golden_clips()["vidC"]).shape == (1, 3, 224, 224)
+
+
+def test_vggish_tables_reproduce_the_oracle_on_a_cpu_interpreter():
+    """The packed VGGish weights (HWIO -> [cout_pad, (ky, kx, c)], conv1 padded to 32 columns, FC matrices transposed
+    to [N, K]) run through the op sequence of mer_vggish_forward (resnet.cu) in torch, against the oracle."""
+    import torch.nn.functional as F
+    from mertools_b200 import encoders as En
+    from oracle import encoders as E
+    sd = S.vggish_state_dict(seed=8)
+    store = {}
+
+    def pack(w, b):
+        store[len(store) + 1] = np.asarray(w, np.float32)
+        store[len(store) + 1] = np.asarray(b, np.float32)
+        return len(store) - 1, len(store)
+    m = En.vggish_tables(sd, pack)
+    x = torch.from_numpy(np.random.default_rng(2).normal(-2.0, 2.0, (2, 96, 64, 1)).astype(np.float32))  # NHWC
+    pool_after = (0, 1, 3, 5)
+    for i in range(6):
+        c = m.convs[i]
+        kk = 9 * c.cin
+        assert (c.k, c.stride, c.pad) == (3, 1, 1) and c.kpad == (32 if i == 0 else kk)
+        wt = torch.from_numpy(store[c.w][:, :kk]).reshape(c.cout_pad, 3, 3, c.cin).permute(0, 3, 1, 2)
+        y = F.conv2d(x[..., :c.cin].permute(0, 3, 1, 2), wt, torch.from_numpy(store[c.b]), padding=1)
+        x = torch.relu(y).permute(0, 2, 3, 1)
+        if i in pool_after:
+            x = F.max_pool2d(x.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    assert x.shape == (2, 6, 4, 512)
+    h = x.reshape(2, -1)                                            # the NHWC buffer as it lies
+    for i in range(3):
+        h = torch.relu(h @ torch.from_numpy(store[m.fc_w[i]]).T + torch.from_numpy(store[m.fc_b[i]]))
+    ref = E.vggish_embeddings({k: torch.from_numpy(v) for k, v in sd.items()},
+                              torch.from_numpy(np.random.default_rng(2).normal(-2.0, 2.0, (2, 96, 64, 1)).astype(np.float32))[..., 0])
+    assert h.shape == (2, 128) and float((h - ref).abs().max() / ref.abs().max()) < 1e-5
