@@ -398,6 +398,17 @@ MER_API int mer_hubert_forward(const MerHubertModel* model, const float* wave, i
                                int normalize, void* workspace, long long workspace_bytes,
                                float* out_frames, float* out_utt, float* opt_hidden, void* stream);
 
+/* Ragged batch: row b of wave [batch, n_samples] holds lengths_host[b] <= n_samples samples (HOST array; the rest
+ * of the row is ignored when normalize != 0 and must be finite otherwise).  Every clip is computed as if it were
+ * forwarded alone, which is what the reference does (one file per model call, extract_audio_huggingface.py:72-100):
+ * per-clip waveform normalisation and conv0 GroupNorm statistics, zero padding of the positional conv at the clip's
+ * own last frame, attention over the clip's own frames.  T_b = frames of clip b (the conv chain applied to
+ * lengths_host[b]).  out_frames: packed [sum_b T_b, hidden] (or NULL); out_utt: [batch, hidden] = mean over the
+ * clip's frames.  Needs model->pos_w_bd; workspace as for (batch, n_samples). */
+MER_API int mer_hubert_forward_ragged(const MerHubertModel* model, const float* wave, const int* lengths_host,
+                                      int batch, int n_samples, int normalize, void* workspace,
+                                      long long workspace_bytes, float* out_frames, float* out_utt, void* stream);
+
 /* ---- log mel spectrogram (VGGish front-end) --------------------------------------------------------- */
 /* mel_features.log_mel_spectrogram as called by vggish_input.waveform_to_examples
  * (MERBench/feature_extraction/audio/vggish/mel_features.py:166-223, vggish_input.py:66-75,

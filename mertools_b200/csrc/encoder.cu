@@ -10,6 +10,8 @@
 //
 // Per layer and token the fp16 ViT chain moves: LN 3+1.5 KB x2, QKV 1.5+4.5 KB, attention 4.5+1.5 KB,
 // out-proj 1.5+3+3 KB, FC1 1.5+6 KB, FC2 6+3+3 KB = 48 KB (TF32 chain: 72 KB).
+#include <vector>
+
 #include "mer_common.cuh"
 #include "mer_kernels.h"
 
@@ -358,7 +360,7 @@ struct HubertPlan {
   int T[7];      // frames after conv i
   int Tpad[7];   // allocated rows per clip (even)
   long long off_wave, off_stats, off_ping, off_pong, off_x, off_xs, off_xn, off_qkv, off_h, off_acc,
-      off_vt, off_cu, total;
+      off_vt, off_cu, off_meta, total;
   long long M;
 };
 
@@ -387,6 +389,7 @@ static HubertPlan hubert_plan(int B, int L, int D = ::D, int DFF = ::DFF) {
   p.off_acc = o;   o += al(p.M * D * 4);
   p.off_vt = o;    o += al((long long)D * ((p.M + 7) & ~7ll) * 4);
   p.off_cu = o;    o += al(((long long)B + 1) * 4);
+  p.off_meta = o;  o += al((4ll * B + 4) * 4);  // ragged batches: samples, conv0 frames, frames, cu_seqlens per clip
   p.total = o;
   return p;
 }
@@ -406,9 +409,15 @@ long long mer_hubert_workspace_bytes(int batch, int n_samples) {
   return hubert_plan(batch, n_samples).total;
 }
 
-int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L, int normalize,
-                       void* workspace, long long workspace_bytes, float* out_frames, float* out_utt,
-                       float* opt_hidden, void* stream_) {
+// lengths_host == nullptr: B equal-length rows of L samples.  Otherwise a RAGGED batch: row b holds
+// lengths_host[b] <= L samples (the rest of the row is ignored), every clip is computed as if it ran alone
+// (the reference feeds one file at a time, extract_audio_huggingface.py:72-100): waveform normalisation and the
+// GroupNorm statistics of conv0 use the clip's own extent, conv1..6 / projection run on the padded [B, Tmax]
+// layout (a frame only ever depends on earlier-or-equal frames of its own clip that exist for every clip length),
+// the positional conv sees zeros past the clip's last frame, and the transformer runs on the packed valid frames.
+static int hubert_forward_impl(const MerHubertModel* m, const float* wave, int B, int L, int normalize,
+                               const int* lengths_host, void* workspace, long long workspace_bytes,
+                               float* out_frames, float* out_utt, float* opt_hidden, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MER_REQUIRE(m && wave && workspace, "mer_hubert_forward: null operand");
   MER_REQUIRE(B > 0 && L > 0, "mer_hubert_forward: batch=%d n_samples=%d", B, L);
@@ -434,11 +443,44 @@ int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L,
   float* acc = reinterpret_cast<float*>(ws + p.off_acc);
   int* cu = reinterpret_cast<int*>(ws + p.off_cu);
   const int T = p.T[6];
-  const long long M = p.M;
+  long long M = p.M;  // rows of the padded layout; becomes the packed frame count once a ragged batch is packed
+
+  // ragged batch: per-clip extents, computed on the host and staged into the workspace
+  const bool ragged = lengths_host != nullptr;
+  int *d_len = nullptr, *d_t0 = nullptr, *d_tb = nullptr, *d_cu = nullptr;
+  long long M_packed = 0;
+  if (ragged) {
+    MER_REQUIRE(m->pos_w_bd && !opt_hidden, "mer_hubert_forward_ragged: needs pos_w_bd; hidden states are not returned");
+    std::vector<int> meta(4 * (size_t)B + 1);
+    int* h_len = meta.data();
+    int* h_t0 = h_len + B;
+    int* h_tb = h_t0 + B;
+    int* h_cu = h_tb + B;
+    h_cu[0] = 0;
+    for (int b = 0; b < B; ++b) {
+      int t = lengths_host[b];
+      MER_REQUIRE(t > 0 && t <= L, "mer_hubert_forward_ragged: clip %d has %d samples (row length %d)", b, t, L);
+      h_len[b] = t;
+      for (int i = 0; i < 7; ++i) {
+        t = (t - kHubK[i]) / kHubS[i] + 1;
+        if (i == 0) h_t0[b] = t;
+      }
+      MER_REQUIRE(t > 0, "mer_hubert_forward_ragged: clip %d (%d samples) gives no output frame", b, lengths_host[b]);
+      h_tb[b] = t;
+      h_cu[b + 1] = h_cu[b] + t;
+    }
+    M_packed = h_cu[B];
+    d_len = reinterpret_cast<int*>(ws + p.off_meta);
+    d_t0 = d_len + B;
+    d_tb = d_t0 + B;
+    d_cu = d_tb + B;
+    // pageable source: the call returns once the data is staged, so `meta` may go out of scope afterwards
+    MER_CUDA_CHECK(cudaMemcpyAsync(d_len, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+  }
 
   const float* wsrc = wave;
   if (normalize) {
-    MER_TRY(mer_wave_normalize_launch(wave, wave_n, B, L, L, L, stream));
+    MER_TRY(mer_wave_normalize_launch(wave, wave_n, B, L, L, L, stream, d_len));
     wsrc = wave_n;
   }
   // conv0 + GroupNorm + GELU (or, layer-norm family: conv0 + bias + LayerNorm + GELU) -> ping [B, Tpad0, 512]
@@ -447,7 +489,7 @@ int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L,
                                        ping, (long long)p.Tpad[0] * 512, stream));
   } else {
     MER_TRY(mer_hubert_conv0_launch(wsrc, L, B, L, m->conv0_w, m->gn_g, m->gn_b, stats, ping,
-                                    (long long)p.Tpad[0] * 512, /*split_out=*/1, stream));
+                                    (long long)p.Tpad[0] * 512, /*split_out=*/1, stream, d_t0));
   }
   // conv1..6 as implicit GEMMs over the time-major activations
   float* src = ping;
@@ -507,6 +549,7 @@ int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L,
     const int prof = mer_prof_begin(MER_PROF_POSCONV, 2.0 * (double)M * D * gch * 128.0, stream);
     mer_prof_pause(1);
     int rc = mer_cast_f16_launch(x0, x0h, M * D, stream);
+    if (rc == 0 && ragged) rc = mer_zero_tail_rows_f16_launch(x0h, d_tb, B, T, D, stream);  // conv padding = zeros
     if (rc == 0) {
       MerGemmDesc g;
       memset(&g, 0, sizeof(g));
@@ -542,6 +585,13 @@ int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L,
     if (rc) return rc;
   } else {
     MER_TRY(mer_posconv_launch(x0, m->pos_w, m->pos_b, cu, B, T, xn, stream));
+  }
+  if (ragged) {
+    // padded [B, Tmax, D] -> packed [sum T_b, D]; from here on the batch is a varlen batch like BERT's
+    MER_TRY(mer_pack_rows_launch(xn, d_cu, B, T, D, x, stream));
+    M = M_packed;
+    MER_CUDA_CHECK(cudaMemcpyAsync(xn, x, (size_t)M * D * 4, cudaMemcpyDeviceToDevice, stream));
+    cu = d_cu;
   }
   MerStackArgs a;
   memset(&a, 0, sizeof(a));
@@ -612,6 +662,21 @@ int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L,
   if (out_utt)
     MER_TRY(mer_segment_reduce_launch(acc, cu, cu + 1, B, D, MER_SEG_MEAN, out_utt, stream));
   return 0;
+}
+
+int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L, int normalize,
+                       void* workspace, long long workspace_bytes, float* out_frames, float* out_utt,
+                       float* opt_hidden, void* stream) {
+  return hubert_forward_impl(m, wave, B, L, normalize, nullptr, workspace, workspace_bytes, out_frames, out_utt,
+                             opt_hidden, stream);
+}
+
+int mer_hubert_forward_ragged(const MerHubertModel* m, const float* wave, const int* lengths_host, int B, int L,
+                              int normalize, void* workspace, long long workspace_bytes, float* out_frames,
+                              float* out_utt, void* stream) {
+  MER_REQUIRE(lengths_host, "mer_hubert_forward_ragged: null lengths");
+  return hubert_forward_impl(m, wave, B, L, normalize, lengths_host, workspace, workspace_bytes, out_frames, out_utt,
+                             nullptr, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -58,15 +58,41 @@ wave_normalize_kernel(const float* __restrict__ in, float* __restrict__ out, int
   for (int i = threadIdx.x; i < L; i += blockDim.x) y[i] = (x[i] - meanf) / denom;
 }
 
+// ragged batch: row b holds lengths[b] samples (statistics over those), the rest of the row is written as zeros
+__global__ void __launch_bounds__(1024)
+wave_normalize_ragged_kernel(const float* __restrict__ in, float* __restrict__ out, const int* __restrict__ lengths,
+                             int L, long long ld_in, long long ld_out) {
+  __shared__ double sh[32];
+  const float* x = in + (long long)blockIdx.x * ld_in;
+  float* y = out + (long long)blockIdx.x * ld_out;
+  const int n = lengths[blockIdx.x];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)x[i];
+  const double mean = block_sum_double(s, sh) / (double)n;
+  double q = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double d = (double)x[i] - mean;
+    q += d * d;
+  }
+  const double var = block_sum_double(q, sh) / (double)n;
+  const float meanf = (float)mean;
+  const float denom = sqrtf((float)var + 1e-7f);
+  for (int i = threadIdx.x; i < L; i += blockDim.x) y[i] = i < n ? (x[i] - meanf) / denom : 0.f;
+}
+
 // grid (chunks, B); 512 threads = one channel each; each block covers TCHUNK output frames.
 constexpr int TCHUNK = 128;
 
+// RAGGED: clip b has t0s[b] <= T0 frames; GroupNorm statistics and (in apply) their divisor use that count.
+template <bool RAGGED>
 __global__ void __launch_bounds__(C0)
 conv0_stats_kernel(const float* __restrict__ wave, long long ld_wave, const float* __restrict__ w0,
-                   int T0, double* __restrict__ stats /*[B,512,2]*/) {
+                   int T0, double* __restrict__ stats /*[B,512,2]*/, const int* __restrict__ t0s) {
   __shared__ float xs[TCHUNK * S0 + K0];
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * TCHUNK;
+  if (RAGGED) T0 = t0s[b];
+  if (RAGGED && t0 >= T0) return;  // block-uniform: this chunk lies past the clip
   const int nt = min(TCHUNK, T0 - t0);
   const float* x = wave + (long long)b * ld_wave + (long long)t0 * S0;
   const int nx = (nt - 1) * S0 + K0;
@@ -88,15 +114,17 @@ conv0_stats_kernel(const float* __restrict__ wave, long long ld_wave, const floa
   atomicAdd(&stats[((long long)b * C0 + c) * 2 + 1], (double)q);
 }
 
+template <bool RAGGED>
 __global__ void __launch_bounds__(C0)
 conv0_apply_kernel(const float* __restrict__ wave, long long ld_wave, const float* __restrict__ w0,
                    const float* __restrict__ gamma, const float* __restrict__ beta,
                    const double* __restrict__ stats, int T0, long long out_bstride /*floats*/,
-                   int split_out, float* __restrict__ out) {
+                   int split_out, float* __restrict__ out, const int* __restrict__ t0s) {
   __shared__ float xs[TCHUNK * S0 + K0];
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * TCHUNK;
-  const int nt = min(TCHUNK, T0 - t0);
+  const int nt = min(TCHUNK, T0 - t0);  // RAGGED: frames past the clip's own count are still written (finite, unused)
+  if (RAGGED) T0 = t0s[b];              // ... but the statistics were taken over the clip's own frames
   const float* x = wave + (long long)b * ld_wave + (long long)t0 * S0;
   const int nx = (nt - 1) * S0 + K0;
   for (int i = threadIdx.x; i < nx; i += blockDim.x) xs[i] = x[i];
@@ -274,9 +302,12 @@ conv0_ln_kernel(const float* __restrict__ wave, long long ld_wave, const float* 
 }  // namespace
 
 int mer_wave_normalize_launch(const float* in, float* out, int B, int L, long long ld_in,
-                              long long ld_out, cudaStream_t stream) {
+                              long long ld_out, cudaStream_t stream, const int* lengths) {
   MER_REQUIRE(in && out && B > 0 && L > 0, "mer_wave_normalize: bad arguments");
-  wave_normalize_kernel<<<B, 1024, 0, stream>>>(in, out, L, ld_in, ld_out);
+  if (lengths)
+    wave_normalize_ragged_kernel<<<B, 1024, 0, stream>>>(in, out, lengths, L, ld_in, ld_out);
+  else
+    wave_normalize_kernel<<<B, 1024, 0, stream>>>(in, out, L, ld_in, ld_out);
   MER_CUDA_CHECK(cudaGetLastError());
   mer_count_launches(1);
   return 0;
@@ -284,7 +315,7 @@ int mer_wave_normalize_launch(const float* in, float* out, int B, int L, long lo
 
 int mer_hubert_conv0_launch(const float* wave, long long ld_wave, int B, int L, const float* w0,
                             const float* gamma, const float* beta, double* stats, float* out,
-                            long long out_bstride, int split_out, cudaStream_t stream) {
+                            long long out_bstride, int split_out, cudaStream_t stream, const int* t0s) {
   const int T0 = (L - K0) / S0 + 1;
   MER_REQUIRE(T0 > 0, "mer_hubert_conv0: waveform too short (%d samples)", L);
   MER_CUDA_CHECK(cudaMemsetAsync(stats, 0, (size_t)B * C0 * 2 * sizeof(double), stream));
@@ -292,19 +323,63 @@ int mer_hubert_conv0_launch(const float* wave, long long ld_wave, int B, int L, 
   // both passes: the waveform in twice, the [T0, 512] operand (4 B per element) out once
   const int prof = mer_prof_begin(MER_PROF_CONV0, (double)B * (2.0 * L * 4.0 + (double)T0 * C0 * 4.0), stream);
   const char* pk = getenv("MER_CONV0_PACKED");  // read at every launch: tests run both forms in one process
-  if (pk && atoi(pk) == 1 && split_out) {
+  if (t0s) {  // ragged batch: per-clip frame counts for the GroupNorm statistics
+    conv0_stats_kernel<true><<<grid, C0, 0, stream>>>(wave, ld_wave, w0, T0, stats, t0s);
+    MER_CUDA_CHECK(cudaGetLastError());
+    conv0_apply_kernel<true><<<grid, C0, 0, stream>>>(wave, ld_wave, w0, gamma, beta, stats, T0, out_bstride, split_out,
+                                                      out, t0s);
+  } else if (pk && atoi(pk) == 1 && split_out) {
     conv0_stats2_kernel<<<grid, C0 / 2, 0, stream>>>(wave, ld_wave, w0, T0, stats);
     MER_CUDA_CHECK(cudaGetLastError());
     conv0_apply2_kernel<<<grid, C0 / 2, 0, stream>>>(wave, ld_wave, w0, gamma, beta, stats, T0, out_bstride, out);
   } else {
-    conv0_stats_kernel<<<grid, C0, 0, stream>>>(wave, ld_wave, w0, T0, stats);
+    conv0_stats_kernel<false><<<grid, C0, 0, stream>>>(wave, ld_wave, w0, T0, stats, nullptr);
     MER_CUDA_CHECK(cudaGetLastError());
-    conv0_apply_kernel<<<grid, C0, 0, stream>>>(wave, ld_wave, w0, gamma, beta, stats, T0,
-                                                out_bstride, split_out, out);
+    conv0_apply_kernel<false><<<grid, C0, 0, stream>>>(wave, ld_wave, w0, gamma, beta, stats, T0,
+                                                       out_bstride, split_out, out, nullptr);
   }
   mer_prof_end(prof, stream);
   MER_CUDA_CHECK(cudaGetLastError());
   mer_count_launches(2);
+  return 0;
+}
+
+// ragged batch helpers: clip b occupies rows [b * Tmax, b * Tmax + tb[b]) of a padded [B, Tmax, dim] activation
+__global__ void __launch_bounds__(256)
+zero_tail_rows_f16_kernel(uint4* __restrict__ x, const int* __restrict__ tb, int Tmax, int dim8) {
+  const int b = blockIdx.y;
+  const long long n = (long long)(Tmax - tb[b]) * dim8;  // 16-byte slots of the clip's tail rows
+  uint4* tail = x + ((long long)b * Tmax + tb[b]) * dim8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    tail[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const float4* __restrict__ padded, const int* __restrict__ cu, int Tmax, int dim4,
+                 float4* __restrict__ packed) {
+  const int b = blockIdx.y;
+  const long long n = (long long)(cu[b + 1] - cu[b]) * dim4;
+  const float4* src = padded + (long long)b * Tmax * dim4;
+  float4* dst = packed + (long long)cu[b] * dim4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+
+int mer_zero_tail_rows_f16_launch(void* x16, const int* tb, int B, int Tmax, int dim, cudaStream_t stream) {
+  MER_REQUIRE(x16 && tb && B > 0 && Tmax > 0 && dim % 8 == 0, "mer_zero_tail_rows_f16: bad operands");
+  zero_tail_rows_f16_kernel<<<dim3(32, B), 256, 0, stream>>>(static_cast<uint4*>(x16), tb, Tmax, dim / 8);
+  MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
+  return 0;
+}
+
+int mer_pack_rows_launch(const float* padded, const int* cu, int B, int Tmax, int dim, float* packed,
+                         cudaStream_t stream) {
+  MER_REQUIRE(padded && cu && packed && padded != packed && B > 0 && dim % 4 == 0, "mer_pack_rows: bad operands");
+  pack_rows_kernel<<<dim3(32, B), 256, 0, stream>>>(reinterpret_cast<const float4*>(padded), cu, Tmax, dim / 4,
+                                                    reinterpret_cast<float4*>(packed));
+  MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
   return 0;
 }
 

@@ -68,15 +68,21 @@ int mer_bert_embed_launch(const int* ids, const int* pos_ids, const float* word,
                           int tokens, float* out, void* out_split, cudaStream_t stream);
 
 // hubert_frontend.cu
+// lengths (device, optional): ragged batch, row b holds lengths[b] <= L samples; the tail is written as zeros
 int mer_wave_normalize_launch(const float* in, float* out, int B, int L, long long ld_in,
-                              long long ld_out, cudaStream_t stream);
+                              long long ld_out, cudaStream_t stream, const int* lengths = nullptr);
 // conv0 (+ bias) + LayerNorm over the 512 channels + GELU (HubertLayerNormConvLayer), split-bf16 rows out
 int mer_hubert_conv0_ln_launch(const float* wave, long long ld_wave, int B, int L, const float* w0,
                                const float* bias, const float* gamma, const float* beta, float* out,
                                long long out_bstride, cudaStream_t stream);
 int mer_hubert_conv0_launch(const float* wave, long long ld_wave, int B, int L, const float* w0,
                             const float* gamma, const float* beta, double* stats, float* out,
-                            long long out_bstride, int split_out, cudaStream_t stream);
+                            long long out_bstride, int split_out, cudaStream_t stream,
+                            const int* t0s = nullptr);  // t0s (device, optional): per-clip frame counts (ragged batch)
+// ragged batch: clip b owns rows [b * Tmax, b * Tmax + tb[b]) of a padded [B, Tmax, dim] activation
+int mer_zero_tail_rows_f16_launch(void* x16, const int* tb, int B, int Tmax, int dim, cudaStream_t stream);
+int mer_pack_rows_launch(const float* padded, const int* cu, int B, int Tmax, int dim, float* packed,
+                         cudaStream_t stream);
 // posconv.cu
 int mer_posconv_launch(const float* x0, const float* wp, const float* bias, const int* cu_seqlens,
                        int n_seq, int max_seqlen, float* x1, cudaStream_t stream);

@@ -41,10 +41,15 @@ def split_into_batch(input_values, maxlen=MAXLEN):
 
 
 class AudioExtractor:
-    def __init__(self, state_dict, device="cuda", max_rows_per_launch=128):
+    def __init__(self, state_dict, device="cuda", max_rows_per_launch=128, ragged=None, max_samples_per_launch=128 * MAXLEN // 2):
+        """ragged (default: env MER_AUDIO_RAGGED=1): clips of different lengths share one device pass
+        (``HubertEncoder.forward_ragged``: every clip computed as if alone) instead of one pass per distinct
+        length; sorted by length and cut into launches of at most ``max_samples_per_launch`` padded samples."""
         self.enc = HubertEncoder(state_dict, device=device)
         self.device = self.enc.device
         self.max_rows = max_rows_per_launch
+        self.ragged = (os.environ.get("MER_AUDIO_RAGGED") == "1") if ragged is None else bool(ragged)
+        self.max_samples = max_samples_per_launch
         self._norm = L.declare("mer_wave_normalize", [C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                                       C.c_longlong, C.c_longlong, C.c_void_p])
 
@@ -66,6 +71,25 @@ class AudioExtractor:
             assert w.ndim == 1, "mono audio only"
             if len(w) <= MAXLEN:
                 short.setdefault(len(w), []).append(i)
+        if self.ragged and len(short) > 1:
+            order = sorted((i for idxs in short.values() for i in idxs), key=lambda i: len(waves[i]))
+            s0 = 0
+            while s0 < len(order):   # launches of consecutive (sorted) clips: rows * longest <= max_samples
+                e = s0 + 1
+                while (e < len(order) and e - s0 < self.max_rows
+                       and (e - s0 + 1) * len(waves[order[e]]) <= self.max_samples):
+                    e += 1
+                idxs = order[s0:e]
+                lens = [len(waves[i]) for i in idxs]
+                host = torch.zeros((len(idxs), max(lens)), dtype=torch.float32, pin_memory=True)
+                for r, i in enumerate(idxs):
+                    host[r, :lens[r]] = torch.from_numpy(np.asarray(waves[i]).astype(np.float32))
+                utt, frames = self.enc.forward_ragged(host.to(self.device, non_blocking=True), lens, normalize=True,
+                                                      want_frames=feature_level != "UTTERANCE")
+                for r, i in enumerate(idxs):
+                    res[i] = (utt[r] if feature_level == "UTTERANCE" else frames[r]).cpu().numpy()
+                s0 = e
+            short = {}
         # clips <= 10 s: batch by identical length; normalisation fused on the device
         for n, idxs in short.items():
             host = torch.empty((len(idxs), n), dtype=torch.float32, pin_memory=True)

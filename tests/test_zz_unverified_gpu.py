@@ -264,3 +264,45 @@ def test_ferplus_models_vs_reference_golden(cuda, tmp_path, model_name, prefix, 
             got = np.load(tmp_path / "feat" / f"{model_name.split('_')[0]}face_{level[:3]}" / f"{vid}.npy")
             ref = g[f"{prefix}{key}_{vid}"]
             assert got.shape == ref.shape and np.abs(got - ref).max() / np.abs(ref).max() < 1e-3, (vid, level)
+
+
+@pytest.mark.parametrize("large", [False, True])
+def test_hubert_ragged_batch_equals_per_clip_forwards(cuda, large):
+    """mer_hubert_forward_ragged: clips of different lengths in one pass (per-clip normalisation / GroupNorm
+    statistics, zero-padded positional conv at each clip's end, varlen attention) against one forward per clip."""
+    import numpy as np
+
+    from mertools_b200 import synthetic as S
+    from mertools_b200.encoders import HubertEncoder
+    sd = S.hubert_state_dict(seed=1, layers=4, large=large)
+    enc = HubertEncoder(sd, device=cuda)
+    lens = [16000, 4321, 40000, 16000, 777, 25013]
+    waves = [(S.synth_waves(1, n, seed=30 + i)[0].astype(np.float64) / 32768.0).astype(np.float32)
+             for i, n in enumerate(lens)]
+    rows = torch.zeros(len(lens), max(lens))
+    for r, w in enumerate(waves):
+        rows[r, :len(w)] = torch.from_numpy(w)
+    rows[1, lens[1]:] = 1e3   # the tail of a row must not matter when the kernel normalises
+    utt, frames = enc.forward_ragged(rows.to(cuda), lens, normalize=True, want_frames=True)
+    torch.cuda.synchronize()
+    for r, w in enumerate(waves):
+        u1, f1 = enc.forward(torch.from_numpy(w)[None].to(cuda), normalize=True, want_frames=True)
+        scale = float(f1.abs().max())
+        assert frames[r].shape == f1[0].shape, (r, frames[r].shape, f1.shape)
+        assert float((frames[r] - f1[0]).abs().max()) / scale < 2e-4, r
+        assert float((utt[r] - u1[0]).abs().max()) / float(u1.abs().max()) < 2e-4, r
+
+
+def test_audio_extractor_ragged_mode_matches_default(cuda):
+    import numpy as np
+
+    from mertools_b200 import synthetic as S
+    from mertools_b200.extract.audio import AudioExtractor
+    sd = S.hubert_state_dict(seed=1, layers=4)
+    waves = [S.synth_waves(1, n, seed=40 + i)[0].astype(np.float64) / 32768.0 for i, n in enumerate([8000, 12345, 8000, 30000])]
+    a = AudioExtractor(sd, device="cuda:0", ragged=False)
+    b = AudioExtractor(sd, device="cuda:0", ragged=True)
+    for level in ("UTTERANCE", "FRAME"):
+        ra, rb = a.extract_waves(waves, level), b.extract_waves(waves, level)
+        for x, y in zip(ra, rb):
+            assert x.shape == y.shape and np.abs(x - y).max() / np.abs(x).max() < 2e-4
