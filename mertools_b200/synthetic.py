@@ -184,6 +184,68 @@ def ferplus_resnet50_state_dict(seed=9, se=False):
     return sd
 
 
+def manet_state_dict(seed=10):
+    """Parameters of the reference's MA-Net (``manet(num_classes=7)``, feature_extraction/visual/manet/model/manet.py:
+    156-220): a ResNet-18 trunk up to layer2, a local branch of four 14 x 14 patches through AttentionBlocks (CBAM)
+    ``layer3_1_p1..4`` / ``layer4_1_p1..4``, a multi-scale branch of MulScaleBlocks ``layer3_2`` / ``layer4_2``, two
+    classifier heads.  He-style conv scales, non-trivial BatchNorm statistics."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+
+    def conv(name, cout, cin, k):
+        sd[name + ".weight"] = (rng.standard_normal((cout, cin, k, k)) * np.sqrt(2.0 / (cin * k * k))).astype(np.float32)
+
+    def bn(name, c, gain=1.0):
+        sd[name + ".weight"] = (gain * rng.uniform(0.5, 1.5, c)).astype(np.float32)
+        sd[name + ".bias"] = (0.2 * rng.standard_normal(c)).astype(np.float32)
+        sd[name + ".running_mean"] = (0.2 * rng.standard_normal(c)).astype(np.float32)
+        sd[name + ".running_var"] = rng.uniform(0.5, 1.5, c).astype(np.float32)
+        sd[name + ".num_batches_tracked"] = np.zeros((), np.int64)
+
+    def downsample(p, cin, cout):
+        conv(p + "downsample.0", cout, cin, 1)
+        bn(p + "downsample.1", cout)
+
+    def basic(p, cin, cout, ds):
+        conv(p + "conv1", cout, cin, 3); bn(p + "bn1", cout)
+        conv(p + "conv2", cout, cout, 3); bn(p + "bn2", cout, 0.5)
+        if ds:
+            downsample(p, cin, cout)
+
+    def attention(p, cin, cout, ds):
+        basic(p, cin, cout, ds)
+        r = cout // 16
+        sd[p + "cbam.ChannelGate.mlp.1.weight"] = (rng.standard_normal((r, cout)) * np.sqrt(1.0 / cout)).astype(np.float32)
+        sd[p + "cbam.ChannelGate.mlp.1.bias"] = (0.2 * rng.standard_normal(r)).astype(np.float32)
+        sd[p + "cbam.ChannelGate.mlp.3.weight"] = (rng.standard_normal((cout, r)) * np.sqrt(1.0 / r)).astype(np.float32)
+        sd[p + "cbam.ChannelGate.mlp.3.bias"] = (0.3 * rng.standard_normal(cout)).astype(np.float32)
+        sd[p + "cbam.SpatialGate.spatial.conv.weight"] = (rng.standard_normal((1, 2, 7, 7)) * 0.2).astype(np.float32)
+        bn(p + "cbam.SpatialGate.spatial.bn", 1)
+
+    def mulscale(p, cin, cout, ds):
+        conv(p + "conv1", cout, cin, 3); bn(p + "bn1", cout)
+        sw = cout // 4
+        for chain in (1, 2):
+            for i in range(1, 5):
+                conv(p + f"conv{chain}_2_{i}", sw, sw, 3)
+                bn(p + f"bn{chain}_2_{i}", sw, 0.5)
+        if ds:
+            downsample(p, cin, cout)
+
+    conv("conv1", 64, 3, 7); bn("bn1", 64)
+    basic("layer1.0.", 64, 64, False); basic("layer1.1.", 64, 64, False)
+    basic("layer2.0.", 64, 128, True); basic("layer2.1.", 128, 128, False)
+    for pi in range(1, 5):
+        attention(f"layer3_1_p{pi}.0.", 128, 256, True); attention(f"layer3_1_p{pi}.1.", 256, 256, False)
+        attention(f"layer4_1_p{pi}.0.", 256, 512, True); attention(f"layer4_1_p{pi}.1.", 512, 512, False)
+    mulscale("layer3_2.0.", 128, 256, True); mulscale("layer3_2.1.", 256, 256, False)
+    mulscale("layer4_2.0.", 256, 512, True); mulscale("layer4_2.1.", 512, 512, False)
+    for h in ("fc_1", "fc_2"):
+        sd[h + ".weight"] = (0.02 * rng.standard_normal((7, 512))).astype(np.float32)
+        sd[h + ".bias"] = np.zeros(7, np.float32)
+    return sd
+
+
 HUBERT_LARGE_CFG = dict(HUBERT_CFG, hidden=1024, heads=16, ffn=4096, layers=24)
 
 

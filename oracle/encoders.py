@@ -199,6 +199,76 @@ def ferplus_resnet50_features(sd, x, dtype=torch.float32, eps=1e-5):
     raise AssertionError("unreachable")
 
 
+def manet_embedding(sd, x, dtype=torch.float32, eps=1e-5):
+    """``manet(...)(x, return_embedding=True)`` of the reference's MA-Net (feature_extraction/visual/manet/model/
+    manet.py:222-270, blocks :16-153; CBAM: manet/model/attention.py:27-84) in eval mode -> [N, 1024] =
+    cat(local-branch embedding, multi-scale-branch embedding).  x: [N, 3, 224, 224] in [0, 1] (ToTensor only,
+    extract_manet_embedding.py:60-61)."""
+    def cb(x, conv, bn, stride=1, pad=0):
+        y = F.conv2d(x, _t(sd, conv + ".weight", dtype), None, stride=stride, padding=pad)
+        return F.batch_norm(y, _t(sd, bn + ".running_mean", dtype), _t(sd, bn + ".running_var", dtype),
+                            _t(sd, bn + ".weight", dtype), _t(sd, bn + ".bias", dtype), False, 0.0, eps)
+
+    def shortcut(p, x, stride):
+        return cb(x, p + "downsample.0", p + "downsample.1", stride) if p + "downsample.0.weight" in sd else x
+
+    def basic(p, x, stride):                                  # BasicBlock :16-43
+        o = F.relu(cb(x, p + "conv1", p + "bn1", stride, 1))
+        o = cb(o, p + "conv2", p + "bn2", 1, 1)
+        return F.relu(o + shortcut(p, x, stride))
+
+    def cbam(p, y):                                           # attention.py:27-84
+        def mlp(v):
+            h = F.relu(F.linear(v, _t(sd, p + "ChannelGate.mlp.1.weight", dtype), _t(sd, p + "ChannelGate.mlp.1.bias", dtype)))
+            return F.linear(h, _t(sd, p + "ChannelGate.mlp.3.weight", dtype), _t(sd, p + "ChannelGate.mlp.3.bias", dtype))
+        att = mlp(y.mean(dim=(2, 3))) + mlp(y.amax(dim=(2, 3)))
+        y = y * torch.sigmoid(att)[:, :, None, None]
+        comp = torch.cat((y.amax(dim=1, keepdim=True), y.mean(dim=1, keepdim=True)), dim=1)
+        s = cb(comp, p + "SpatialGate.spatial.conv", p + "SpatialGate.spatial.bn", 1, 3)
+        return y * torch.sigmoid(s)
+
+    def attention(p, x, stride):                              # AttentionBlock :121-153
+        o = F.relu(cb(x, p + "conv1", p + "bn1", stride, 1))
+        o = cbam(p + "cbam.", cb(o, p + "conv2", p + "bn2", 1, 1))
+        return F.relu(o + shortcut(p, x, stride))
+
+    def mulscale(p, x, stride):                               # MulScaleBlock :46-118
+        t = F.relu(cb(x, p + "conv1", p + "bn1", stride, 1))
+        sw = t.shape[1] // 4
+        sp = torch.split(t, sw, 1)
+        total = 0
+        for chain in (1, 2):
+            outs, prev = [], None
+            for i in range(4):
+                inp = sp[i] if prev is None else F.relu(prev) + sp[i]
+                prev = cb(inp, p + f"conv{chain}_2_{i + 1}", p + f"bn{chain}_2_{i + 1}", 1, 1)
+                outs.append(prev)
+            total = total + torch.cat(outs, dim=1)
+        return F.relu(total + shortcut(p, x, stride))
+
+    y = F.relu(cb(x.to(dtype), "conv1", "bn1", 2, 3))
+    y = F.max_pool2d(y, 3, 2, 1)
+    for b in range(2):
+        y = basic(f"layer1.{b}.", y, 1)
+    for b in range(2):
+        y = basic(f"layer2.{b}.", y, 2 if b == 0 else 1)
+    local = []
+    for pi, (y0, x0) in enumerate(((0, 0), (0, 14), (14, 0), (14, 14)), start=1):
+        o = y[:, :, y0:y0 + 14, x0:x0 + 14]
+        for b in range(2):
+            o = attention(f"layer3_1_p{pi}.{b}.", o, 2 if b == 0 else 1)
+        for b in range(2):
+            o = attention(f"layer4_1_p{pi}.{b}.", o, 1)
+        local.append(o)
+    b1 = torch.cat([torch.cat(local[:2], dim=3), torch.cat(local[2:], dim=3)], dim=2).mean(dim=(2, 3))
+    o = y
+    for b in range(2):
+        o = mulscale(f"layer3_2.{b}.", o, 2 if b == 0 else 1)
+    for b in range(2):
+        o = mulscale(f"layer4_2.{b}.", o, 2 if b == 0 else 1)
+    return torch.cat([b1, o.mean(dim=(2, 3))], dim=1)
+
+
 def hubert_pos_conv_weight(sd, dtype=torch.float32):
     """Effective weight of the weight-normed positional conv (:45-92): W = g * v / ||v||, the
     norm taken over dims (0,1) per kernel tap (weight_norm dim=2).  Older checkpoints name the

@@ -155,6 +155,31 @@ def imagenet_clip_features(sd, frames_bgr, feature_level="UTTERANCE"):
     return np.mean(emb, axis=0) if emb.ndim == 2 else emb
 
 
+def manet_preprocess(frames_bgr):
+    """FaceDataset.__getitem__ (dataset.py:40-47) + the transform of extract_manet_embedding.py:60-61:
+    Resize((224, 224)) (PIL bilinear) and ToTensor only (no normalisation).  Returns [N, 3, 224, 224] in [0, 1]."""
+    f = np.asarray(frames_bgr)
+    assert f.dtype == np.uint8 and f.ndim == 4 and f.shape[-1] == 3, f.shape
+    if f.shape[1:3] != (224, 224):
+        f = pil_resize_bilinear_u8(f, 224, 224)
+    rgb = f[..., ::-1].astype(np.float32) / np.float32(255.0)
+    return torch.from_numpy(np.ascontiguousarray(rgb.transpose(0, 3, 1, 2)))
+
+
+def manet_clip_features(sd, frames_bgr, feature_level="UTTERANCE"):
+    """One video through extract_manet_embedding.py:69-103: batches of 32 frames -> [N, 1024]; FRAME -> [T, 1024]
+    (zeros((1, D)) when empty), UTTERANCE -> mean over frames."""
+    frames = np.asarray(frames_bgr)
+    if len(frames) == 0:
+        return np.zeros((1, 1024)) if feature_level == "FRAME" else np.zeros((1024,))
+    x = manet_preprocess(frames)
+    emb = torch.cat([E.manet_embedding(sd, b) for b in split_into_batch(x, 32)], dim=0).float().numpy()
+    emb = np.array(emb).squeeze()
+    if feature_level == "FRAME":
+        return emb[np.newaxis, :] if emb.ndim == 1 else emb
+    return np.mean(emb, axis=0) if emb.ndim == 2 else emb
+
+
 def ferplus_preprocess(frames_bgr):
     """FaceDataset.__getitem__ (dataset.py:40-47) + compose_transforms (extract_ferplus_embedding.py:62-74) for the
     FER+ models (meta std == [1, 1, 1]): Resize(256) (shorter side -> 256, PIL bilinear), CenterCrop(224), ToTensor,

@@ -229,3 +229,19 @@ def test_ferplus_oracle_matches_reference_extractor_golden():
             for level, key in (("FRAME", "fra"), ("UTTERANCE", "utt")):
                 got, ref = P.ferplus_clip_features(sd, frames, level), g[f"{prefix}{key}_{vid}"]
                 assert got.shape == ref.shape and _rel(got, ref) < 1e-5, (se, vid, level)
+
+
+def test_manet_oracle_matches_reference_extractor_golden():
+    """MA-Net restatement (ResNet trunk, four CBAM patch branches, multi-scale branch) + the script's transform
+    against outputs of the unmodified reference model definition and dataset / save rules."""
+    import importlib.util
+    from oracle import pipeline as P
+    spec = importlib.util.spec_from_file_location("make_golden_manet", os.path.join(G, "make_golden_manet.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(G, "manet_golden.npz"))
+    sd = _t(S.manet_state_dict(int(g["seed"])))
+    for vid, frames in mod.golden_clips().items():
+        for level, key in (("FRAME", "fra"), ("UTTERANCE", "utt")):
+            got, ref = P.manet_clip_features(sd, frames, level), g[f"{key}_{vid}"]
+            assert got.shape == ref.shape and _rel(got, ref) < 1e-5, (vid, level)
