@@ -281,24 +281,33 @@ MER_API int mer_resnet18_forward(const MerResnet18Model* model, const uint8_t* f
                                  void* workspace, long long workspace_bytes, float* out_feats, void* stream);
 
 /* ---- table-driven CNN executor: frame-level CNN extractors as chains of conv (+ folded BatchNorm, + residual,
- * + ReLU), MaxPool2d(3, 2) and a final global average pool over four NHWC fp32 activation buffers.
- * First user: resnet50_ferplus_dag up to conv5_3_3x3_relu + AvgPool2d(7)
+ * + ReLU), MaxPool2d(3, 2), crops / channel slices, gates and average pools over eight NHWC fp32 activation buffers.
+ * Users: resnet50_ferplus_dag / senet50_ferplus_dag up to conv5_3_3x3_relu + AvgPool2d(7)
  * (MERBench/feature_extraction/visual/extract_ferplus_embedding.py:81-115, default --layer_name;
- * pytorch-benchmarks/model/resnet50_ferplus_dag.py:178-355). */
+ * pytorch-benchmarks/model/resnet50_ferplus_dag.py:178-355) and MA-Net's 1024-d embedding
+ * (extract_manet_embedding.py:31-41; manet/model/manet.py:222-270). */
 enum { MER_CNN_STEM = 0,    /* dst = act(conv(frames)): 7x7 / 2 / pad 3 on the uint8 input, preprocessing fused */
-       MER_CNN_CONV = 1,    /* dst = act(conv(src) [+ res]); dst may equal res (in-place residual update) */
+       MER_CNN_CONV = 1,    /* dst = act(conv(src[..., p0 : p0 + cin]) [+ res]); dst may equal res (in-place update) */
        MER_CNN_MAXPOOL = 2, /* dst = MaxPool2d(3, 2, pad, ceil_mode)(src), windows clipped to the image */
-       MER_CNN_GAP = 3,     /* out_feats = mean over H x W of src; must be the last op */
-       MER_CNN_SE = 4 };    /* squeeze-and-excitation block end (senet50_ferplus_dag): dst = relu(g * src + res),
+       MER_CNN_GAP = 3,     /* out_feats[:, p0 : p0 + C] (+)= mean over H x W of src / max(p2, 1); p1 != 0 accumulates */
+       MER_CNN_SE = 4,      /* squeeze-and-excitation block end (senet50_ferplus_dag): dst = relu(g * src + res),
                                g[n, c] = sigmoid(up(relu(down(mean over H x W of src)))); conv = index of the
                                "down" layer, k = index of the "up" layer: convs entries with k = 1 whose w is a
                                PLAIN fp32 [cout, cin] matrix (not a GEMM operand) and b an fp32 [cout] bias */
+       MER_CNN_CROP = 5,    /* dst = src[:, p0 : p0 + p2, p1 : p1 + p3, :] */
+       MER_CNN_SHAPE = 6,   /* declares dst as an [H, W] map like src with p0 channels (filled by SLICE ops) */
+       MER_CNN_SLICE = 7,   /* dst[..., p1 : p1 + p2] = f(src[..., p0 : p0 + p2]) [+ res[..., p3 : p3 + p2]];
+                               relu = 1: f = ReLU; relu = 2: ReLU of the sum */
+       MER_CNN_CBAM = 8 };  /* MA-Net AttentionBlock end: dst = relu(CBAM(src) + res) on maps of <= 64 positions;
+                               conv = ChannelGate.mlp.1, p0 = ChannelGate.mlp.3 (plain fp32 dense layers as for SE),
+                               p1 = the SpatialGate 7x7 conv: w plain fp32 [2 * 49] with its BatchNorm folded, b [1] */
 typedef struct MerCnnOp {
   int kind;  /* MER_CNN_* */
-  int conv;  /* STEM / CONV: index into convs */
-  int src, dst, res; /* buffer indices 0..3; res = -1 for none */
-  int relu;  /* STEM / CONV: ReLU (after the residual add) */
+  int conv;  /* STEM / CONV / SE / CBAM: index into convs */
+  int src, dst, res; /* buffer indices 0..7; res = -1 for none */
+  int relu;  /* STEM / CONV: ReLU (after the residual add); SLICE: see above */
   int k, stride, pad, ceil_mode; /* MAXPOOL (k = 3, stride = 2); SE: k = index of the "up" layer */
+  int p[4];  /* op-specific parameters (see the enum) */
 } MerCnnOp;
 typedef struct MerCnnModel {
   const MerResnetConv* convs; /* BatchNorm folded; w in the layout of gemm_mode: fp16 [cout_pad, kpad] (stem kpad
@@ -310,7 +319,7 @@ typedef struct MerCnnModel {
   int in_h, in_w;      /* frames are uint8 [n, in_h, in_w, 3] BGR (resize / crop beforehand) */
   float scale;         /* x = (pix * scale - mean[c]) / std[c] in RGB order: 1/255 (ToTensor) or 1 (ToTensor * 255) */
   float mean[3], std[3];
-  int feat_dim;        /* channels of the pooled map */
+  int feat_dim;        /* width of out_feats (the GAP ops fill column ranges of it) */
 } MerCnnModel;
 
 MER_API long long mer_cnn_workspace_bytes(const MerCnnModel* model, int n_frames); /* -1: bad model (mer_last_error) */

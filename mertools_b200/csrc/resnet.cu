@@ -477,10 +477,144 @@ int mer_vggish_forward(const MerVggishModel* m, const float* examples, int n_exa
 }  // extern "C"
 
 // ---- table-driven CNN executor (mer_cnn_forward): the frame-level CNN extractors whose graphs are chains of
-// conv (+ folded BN, + residual, + ReLU), 3x3/2 max-pool and a global average pool over four activation buffers.
-// First user: the FER+ ResNet-50 (extract_ferplus_embedding.py; pytorch-benchmarks/model/resnet50_ferplus_dag.py). ----
+// conv (+ folded BN, + residual, + ReLU), max-pool, crops / channel slices, gates (SE, CBAM) and average pools over
+// up to eight NHWC fp32 activation buffers.  Users: the FER+ ResNet-50 / SENet-50 (extract_ferplus_embedding.py) and
+// MA-Net (extract_manet_embedding.py). ----
 namespace {
-struct CnnPlan { long long off_buf[4], off_col, off_cu, off_z, off_scale, total; };
+
+constexpr int CNN_BUFS = 8;
+
+// dst = src[:, y0:y0+h, x0:x0+w, :]  (NHWC fp32, 4 channels per thread)
+__global__ void __launch_bounds__(256)
+crop_kernel(const float4* __restrict__ x, int H, int W, int c4, int y0, int x0, int h, int w, float4* __restrict__ y,
+            long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % c4);
+  const long long pos = idx / c4;
+  const int px = (int)(pos % w), py = (int)((pos / w) % h);
+  const long long n = pos / ((long long)w * h);
+  y[idx] = __ldg(x + ((n * H + y0 + py) * W + x0 + px) * (long long)c4 + c);
+}
+
+// dst[r, d0 + j] = f(src[r, s0 + j]) (+ res[r, r0 + j]) for j < width; pre_relu: f = relu; post_relu: relu of the sum.
+// Row strides (stored channels) differ per operand; 4 channels per thread.
+__global__ void __launch_bounds__(256)
+slice_kernel(const float* __restrict__ src, int s_ld, int s0, const float* __restrict__ res, int r_ld, int r0,
+             float* __restrict__ dst, int d_ld, int d0, int w4, int pre_relu, int post_relu, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int j = (int)(idx % w4) * 4;
+  const long long r = idx / w4;
+  float4 v = __ldg(reinterpret_cast<const float4*>(src + r * s_ld + s0 + j));
+  if (pre_relu) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+  if (res) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(res + r * r_ld + r0 + j));
+    v = make_float4(v.x + q.x, v.y + q.y, v.z + q.z, v.w + q.w);
+  }
+  if (post_relu) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+  *reinterpret_cast<float4*>(dst + r * d_ld + d0 + j) = v;
+}
+
+// CBAM (manet/model/attention.py:27-84) + shortcut + ReLU on one frame's small map (hw <= 64 positions), one block
+// per frame:  cg = sigmoid(mlp(mean_hw y) + mlp(max_hw y));  y1 = y * cg;  comp = [max_c y1, mean_c y1];
+// sg = sigmoid(conv7x7(comp) with the BatchNorm folded);  out = relu(y1 * sg + res).
+// w1 [R, C], b1 [R], w2 [C, R], b2 [C]: the shared MLP; ws [2 * 49] (+ bs [1]): the folded spatial conv.
+__global__ void __launch_bounds__(256)
+cbam_kernel(const float* __restrict__ y, const float* __restrict__ res, const float* __restrict__ w1,
+            const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+            const float* __restrict__ wsp, const float* __restrict__ bsp, int H, int W, int C, int R,
+            float* __restrict__ out) {
+  extern __shared__ float cb_sm[];
+  const int hw = H * W;
+  float* avg = cb_sm;            // [C]
+  float* mx = avg + C;           // [C]
+  float* cg = mx + C;            // [C]
+  float* hid = cg + C;           // [2 R]
+  float* comp = hid + 2 * R;     // [2 hw]: max over channels, mean over channels
+  float* sg = comp + 2 * hw;     // [hw]
+  const long long base = (long long)blockIdx.x * hw * C;
+  const float* yf = y + base;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f, m = -INFINITY;
+    for (int p = 0; p < hw; ++p) {
+      const float v = yf[(long long)p * C + c];
+      s += v;
+      m = fmaxf(m, v);
+    }
+    avg[c] = s / (float)hw;
+    mx[c] = m;
+  }
+  __syncthreads();
+  for (int j = warp; j < 2 * R; j += nwarp) {   // rows 0..R-1: the avg input; R..2R-1: the max input
+    const float* in = j < R ? avg : mx;
+    const float* wr = w1 + (long long)(j % R) * C;
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a = fmaf(__ldg(wr + c), in[c], a);
+    a = warp_sum(a);
+    if (lane == 0) hid[j] = fmaxf(a + __ldg(b1 + j % R), 0.f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 2.f * __ldg(b2 + c);   // the second Linear's bias enters once per pooled input
+    for (int j = 0; j < R; ++j) a = fmaf(__ldg(w2 + (long long)c * R + j), hid[j] + hid[R + j], a);
+    cg[c] = 1.0f / (1.0f + expf(-a));
+  }
+  __syncthreads();
+  for (int p = warp; p < hw; p += nwarp) {
+    float m = -INFINITY, s = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float v = yf[(long long)p * C + c] * cg[c];
+      m = fmaxf(m, v);
+      s += v;
+    }
+    m = warp_max(m);
+    s = warp_sum(s);
+    if (lane == 0) {
+      comp[p] = m;
+      comp[hw + p] = s / (float)C;
+    }
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < hw; p += blockDim.x) {
+    const int py = p / W, px = p % W;
+    float a = __ldg(bsp);
+    for (int ch = 0; ch < 2; ++ch)
+      for (int ky = 0; ky < 7; ++ky) {
+        const int iy = py + ky - 3;
+        if (iy < 0 || iy >= H) continue;
+        for (int kx = 0; kx < 7; ++kx) {
+          const int ix = px + kx - 3;
+          if (ix >= 0 && ix < W) a = fmaf(__ldg(wsp + (ch * 7 + ky) * 7 + kx), comp[ch * hw + iy * W + ix], a);
+        }
+      }
+    sg[p] = 1.0f / (1.0f + expf(-a));
+  }
+  __syncthreads();
+  const float* rf = res + base;
+  float* of = out + base;
+  for (long long i = threadIdx.x; i < (long long)hw * C; i += blockDim.x) {
+    const int c = (int)(i % C), p = (int)(i / C);
+    of[i] = fmaxf(fmaf(yf[i] * cg[c], sg[p], rf[i]), 0.f);
+  }
+}
+
+// out[n, c0 + c] (+)= mean_hw(x[n, :, c]) / div   (one block per frame)
+__global__ void __launch_bounds__(256)
+gap_kernel(const float* __restrict__ x, int hw, int C, int Cs, float* __restrict__ out, int ld_out, int c0, int accumulate,
+           float inv) {
+  const long long n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < hw; ++p) s += x[(n * hw + p) * Cs + c];
+    float* o = out + n * ld_out + c0 + c;
+    const float v = s * inv;
+    *o = accumulate ? *o + v : v;
+  }
+}
+
+struct CnnPlan { long long off_buf[CNN_BUFS], off_col, off_cu, off_z, off_scale, total; };
 
 int pool_out(int in, int pad, int ceil_mode) {  // torch MaxPool2d(3, 2, pad, ceil_mode) output size
   const int num = in + 2 * pad - 3;
@@ -489,70 +623,235 @@ int pool_out(int in, int pad, int ceil_mode) {  // torch MaxPool2d(3, 2, pad, ce
   return o;
 }
 
-// walks the op table once: shapes per buffer, the largest extent of every buffer and of the im2col operand
-int cnn_plan(const MerCnnModel* m, int n_frames, CnnPlan* plan, Shape* final_shape) {
+// One pass over the op table.  exec == false: shape inference + buffer extents (cnn_plan); exec == true: launches.
+int cnn_walk(const MerCnnModel* m, int n_frames, bool exec, CnnPlan* plan, char* ws, const uint8_t* frames_bgr,
+             float* out_feats, cudaStream_t st) {
   MER_REQUIRE(m && m->convs && m->ops && m->n_ops > 0 && m->n_convs > 0, "mer_cnn: empty model");
   MER_REQUIRE(m->gemm_mode == MER_GEMM_F16 || m->gemm_mode == MER_GEMM_BF16X3, "mer_cnn: gemm_mode %d", m->gemm_mode);
   const long long n = n_frames;
-  const long long vbytes = m->gemm_mode == MER_GEMM_F16 ? 2 : 4;  // bytes per operand value
-  Shape sh[4] = {};
-  long long need[4] = {0, 0, 0, 0}, col = 0;
-  int se_c = 0;  // widest squeeze-and-excitation gate
-  Shape last{0, 0, 0, 0};
+  const bool split = m->gemm_mode == MER_GEMM_BF16X3;
+  const long long vbytes = split ? 4 : 2;  // bytes per operand value
+  Shape sh[CNN_BUFS] = {};
+  long long need[CNN_BUFS] = {}, col_need = 0;
+  int se_c = 0, gaps = 0;
+  float* buf[CNN_BUFS] = {};
+  uint16_t* col = nullptr;
+  int* offsets = nullptr;
+  if (exec) {
+    for (int b = 0; b < CNN_BUFS; ++b) buf[b] = reinterpret_cast<float*>(ws + plan->off_buf[b]);
+    col = reinterpret_cast<uint16_t*>(ws + plan->off_col);
+    offsets = reinterpret_cast<int*>(ws + plan->off_cu);
+  }
+  auto ok_buf = [](int b) { return b >= 0 && b < CNN_BUFS; };
+  auto define = [&](int b, Shape s) {
+    sh[b] = s;
+    const long long fl = n * s.H * s.W * s.Cs;
+    if (fl > need[b]) need[b] = fl;
+  };
   for (int i = 0; i < m->n_ops; ++i) {
     const MerCnnOp& op = m->ops[i];
-    MER_REQUIRE(op.dst >= 0 && op.dst < 4 && op.src >= 0 && op.src < 4, "mer_cnn: op %d buffer index", i);
-    if (op.kind == MER_CNN_STEM || op.kind == MER_CNN_CONV) {
-      MER_REQUIRE(op.conv >= 0 && op.conv < m->n_convs, "mer_cnn: op %d conv index %d", i, op.conv);
-      const MerResnetConv& cv = m->convs[op.conv];
-      Shape in = op.kind == MER_CNN_STEM ? Shape{m->in_h, m->in_w, 3, 3} : sh[op.src];
-      MER_REQUIRE(in.H > 0, "mer_cnn: op %d reads an empty buffer", i);
-      const int OH = (in.H + 2 * cv.pad - cv.k) / cv.stride + 1, OW = (in.W + 2 * cv.pad - cv.k) / cv.stride + 1;
-      const long long rows = n * OH * OW;
-      MER_REQUIRE(rows < (1ll << 31), "mer_cnn: too many frames per call");
-      col = col > rows * cv.kpad * vbytes ? col : rows * cv.kpad * vbytes;
-      if (op.res >= 0) {
-        MER_REQUIRE(op.res < 4 && sh[op.res].H == OH && sh[op.res].W == OW && sh[op.res].Cs == cv.cout_pad,
-                    "mer_cnn: op %d residual shape", i);
+    MER_REQUIRE(ok_buf(op.dst) && ok_buf(op.src) && (op.res < 0 || ok_buf(op.res)), "mer_cnn: op %d buffer index", i);
+    switch (op.kind) {
+      case MER_CNN_STEM: {
+        MER_REQUIRE(op.conv >= 0 && op.conv < m->n_convs, "mer_cnn: op %d conv index %d", i, op.conv);
+        const MerResnetConv& cv = m->convs[op.conv];
+        MER_REQUIRE(cv.k == 7 && cv.stride == 2 && cv.pad == 3 && cv.cin == 3 && cv.kpad == (split ? 160 : 192),
+                    "mer_cnn: the stem is a 7x7 / 2 convolution packed to %d columns", split ? 160 : 192);
+        const int OH = (m->in_h + 6 - 7) / 2 + 1, OW = (m->in_w + 6 - 7) / 2 + 1;
+        const long long rows = n * OH * OW, total = rows * cv.kpad;
+        MER_REQUIRE(rows < (1ll << 31), "mer_cnn: too many frames per call");
+        if (rows * cv.kpad * vbytes > col_need) col_need = rows * cv.kpad * vbytes;
+        define(op.dst, Shape{OH, OW, cv.cout, cv.cout_pad});
+        if (!exec) break;
+        const unsigned blocks = (unsigned)((total + 255) / 256);
+        if (split)
+          im2col_stem_kernel<true><<<blocks, 256, 0, st>>>(frames_bgr, m->in_h, m->in_w, OH, OW, cv.kpad, m->scale,
+                                                           m->mean[0], m->mean[1], m->mean[2], m->std[0], m->std[1],
+                                                           m->std[2], col, total);
+        else
+          im2col_stem_kernel<false><<<blocks, 256, 0, st>>>(frames_bgr, m->in_h, m->in_w, OH, OW, cv.kpad, m->scale,
+                                                            m->mean[0], m->mean[1], m->mean[2], m->std[0], m->std[1],
+                                                            m->std[2], col, total);
+        MER_CUDA_CHECK(cudaGetLastError());
+        mer_count_launches(1);
+        MerGemmDesc g;
+        memset(&g, 0, sizeof(g));
+        g.A = reinterpret_cast<const float*>(col);
+        g.W = static_cast<const float*>(cv.w);
+        g.rows_per_batch = (int)rows;
+        g.a_rows_dim = (int)rows;
+        g.batches = 1;
+        g.N = cv.cout_pad;
+        g.K_inner = cv.kpad;
+        g.taps = 1;
+        g.P = 1;
+        g.a_phase_stride = cv.kpad;
+        g.a_row_stride = cv.kpad;
+        g.a_batch_stride = rows * cv.kpad;
+        g.mode = m->gemm_mode;
+        g.ep.bias = cv.b;
+        g.ep.out = buf[op.dst];
+        g.ep.ld_out = cv.cout_pad;
+        g.ep.flags = op.relu ? MER_EPI_RELU : 0;
+        if (int rc = mer_gemm_launch(&g, st)) return rc;
+        break;
       }
-      sh[op.dst] = Shape{OH, OW, cv.cout, cv.cout_pad};
-    } else if (op.kind == MER_CNN_MAXPOOL) {
-      const Shape in = sh[op.src];
-      MER_REQUIRE(in.H > 0 && op.k == 3 && op.stride == 2 && op.src != op.dst, "mer_cnn: op %d max-pool", i);
-      sh[op.dst] = Shape{pool_out(in.H, op.pad, op.ceil_mode), pool_out(in.W, op.pad, op.ceil_mode), in.C, in.Cs};
-    } else if (op.kind == MER_CNN_SE) {
-      const Shape in = sh[op.src];
-      MER_REQUIRE(op.conv >= 0 && op.conv < m->n_convs && op.k >= 0 && op.k < m->n_convs, "mer_cnn: op %d SE layers", i);
-      const MerResnetConv &dn = m->convs[op.conv], &up = m->convs[op.k];
-      MER_REQUIRE(in.H > 0 && in.C == in.Cs && in.C % 4 == 0 && dn.cin == in.C && up.cout == in.C && dn.cout == up.cin &&
-                      dn.cout > 0 && dn.cout <= 1024,
-                  "mer_cnn: op %d SE geometry (C %d, %d -> %d -> %d)", i, in.C, dn.cin, dn.cout, up.cout);
-      MER_REQUIRE(op.res >= 0 && op.res < 4 && sh[op.res].H == in.H && sh[op.res].W == in.W && sh[op.res].Cs == in.Cs,
-                  "mer_cnn: op %d SE shortcut shape", i);
-      se_c = se_c > in.C ? se_c : in.C;
-      sh[op.dst] = in;
-    } else {
-      MER_REQUIRE(op.kind == MER_CNN_GAP && i == m->n_ops - 1, "mer_cnn: op %d kind %d", i, op.kind);
-      MER_REQUIRE(sh[op.src].C == sh[op.src].Cs && sh[op.src].C == m->feat_dim, "mer_cnn: pooled width != feat_dim");
-      last = sh[op.src];
-      continue;
+      case MER_CNN_CONV: {
+        MER_REQUIRE(op.conv >= 0 && op.conv < m->n_convs, "mer_cnn: op %d conv index %d", i, op.conv);
+        const MerResnetConv& cv = m->convs[op.conv];
+        const Shape full = sh[op.src];
+        const int c0 = op.p[0];  // the conv reads channels [c0, c0 + cin) of src
+        MER_REQUIRE(full.H > 0 && c0 >= 0 && c0 % 4 == 0 && c0 + cv.cin <= full.C && op.src != op.dst,
+                    "mer_cnn: op %d reads channels [%d, %d) of a %d-channel buffer", i, c0, c0 + cv.cin, full.C);
+        const Shape in{full.H, full.W, cv.cin, full.Cs};
+        const int OH = (in.H + 2 * cv.pad - cv.k) / cv.stride + 1, OW = (in.W + 2 * cv.pad - cv.k) / cv.stride + 1;
+        const long long rows = n * OH * OW;
+        MER_REQUIRE(rows < (1ll << 31), "mer_cnn: too many frames per call");
+        if (rows * cv.kpad * vbytes > col_need) col_need = rows * cv.kpad * vbytes;
+        if (op.res >= 0)
+          MER_REQUIRE(sh[op.res].H == OH && sh[op.res].W == OW && sh[op.res].Cs == cv.cout_pad,
+                      "mer_cnn: op %d residual shape", i);
+        if (exec) {
+          Shape out;
+          if (int rc = conv(cv, buf[op.src] + c0, in, n_frames, col, op.res >= 0 ? buf[op.res] : nullptr, op.relu != 0,
+                            buf[op.dst], &out, st, m->gemm_mode))
+            return rc;
+        }
+        define(op.dst, Shape{OH, OW, cv.cout, cv.cout_pad});
+        break;
+      }
+      case MER_CNN_MAXPOOL: {
+        const Shape in = sh[op.src];
+        MER_REQUIRE(in.H > 0 && op.k == 3 && op.stride == 2 && op.src != op.dst, "mer_cnn: op %d max-pool", i);
+        const int OH = pool_out(in.H, op.pad, op.ceil_mode), OW = pool_out(in.W, op.pad, op.ceil_mode);
+        define(op.dst, Shape{OH, OW, in.C, in.Cs});
+        if (!exec) break;
+        const long long total = n * OH * OW * (in.Cs / 4);
+        maxpool3x3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(buf[op.src]), in.H, in.W, in.Cs / 4, OH, OW, op.pad,
+            reinterpret_cast<float4*>(buf[op.dst]), total);
+        MER_CUDA_CHECK(cudaGetLastError());
+        mer_count_launches(1);
+        break;
+      }
+      case MER_CNN_SE: {
+        const Shape in = sh[op.src];
+        MER_REQUIRE(op.conv >= 0 && op.conv < m->n_convs && op.k >= 0 && op.k < m->n_convs, "mer_cnn: op %d SE layers", i);
+        const MerResnetConv &dn = m->convs[op.conv], &up = m->convs[op.k];
+        MER_REQUIRE(in.H > 0 && in.C == in.Cs && in.C % 4 == 0 && dn.cin == in.C && up.cout == in.C &&
+                        dn.cout == up.cin && dn.cout > 0 && dn.cout <= 1024,
+                    "mer_cnn: op %d SE geometry (C %d, %d -> %d -> %d)", i, in.C, dn.cin, dn.cout, up.cout);
+        MER_REQUIRE(op.res >= 0 && sh[op.res].H == in.H && sh[op.res].W == in.W && sh[op.res].Cs == in.Cs,
+                    "mer_cnn: op %d SE shortcut shape", i);
+        if (in.C > se_c) se_c = in.C;
+        define(op.dst, in);
+        if (!exec) break;
+        float* z = reinterpret_cast<float*>(ws + plan->off_z);
+        float* scale = reinterpret_cast<float*>(ws + plan->off_scale);
+        if (int rc = mer_iota_offsets_launch(offsets, n_frames, in.H * in.W, st)) return rc;
+        if (int rc = mer_segment_reduce_launch(buf[op.src], offsets, offsets + 1, n_frames, in.C, MER_SEG_MEAN, z, st))
+          return rc;
+        se_mlp_kernel<<<n_frames, 256, (size_t)(in.C + dn.cout) * sizeof(float), st>>>(
+            z, static_cast<const float*>(dn.w), dn.b, static_cast<const float*>(up.w), up.b, in.C, dn.cout, scale);
+        MER_CUDA_CHECK(cudaGetLastError());
+        const long long hw_c4 = (long long)in.H * in.W * (in.C / 4), total = hw_c4 * n_frames;
+        se_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(buf[op.src]), reinterpret_cast<const float4*>(buf[op.res]),
+            reinterpret_cast<const float4*>(scale), hw_c4, in.C / 4, reinterpret_cast<float4*>(buf[op.dst]), total);
+        MER_CUDA_CHECK(cudaGetLastError());
+        mer_count_launches(2);
+        break;
+      }
+      case MER_CNN_CROP: {
+        const Shape in = sh[op.src];
+        const int y0 = op.p[0], x0 = op.p[1], h = op.p[2], w = op.p[3];
+        MER_REQUIRE(in.H > 0 && op.src != op.dst && y0 >= 0 && x0 >= 0 && h > 0 && w > 0 && y0 + h <= in.H && x0 + w <= in.W,
+                    "mer_cnn: op %d crop [%d:%d, %d:%d] of a %d x %d map", i, y0, y0 + h, x0, x0 + w, in.H, in.W);
+        define(op.dst, Shape{h, w, in.C, in.Cs});
+        if (!exec) break;
+        const long long total = n * h * w * (in.Cs / 4);
+        crop_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(buf[op.src]), in.H,
+                                                                     in.W, in.Cs / 4, y0, x0, h, w,
+                                                                     reinterpret_cast<float4*>(buf[op.dst]), total);
+        MER_CUDA_CHECK(cudaGetLastError());
+        mer_count_launches(1);
+        break;
+      }
+      case MER_CNN_SHAPE: {  // dst becomes an [H, W] map like src with p[0] channels (contents undefined)
+        const Shape in = sh[op.src];
+        MER_REQUIRE(in.H > 0 && op.p[0] > 0 && op.p[0] % 4 == 0, "mer_cnn: op %d shape", i);
+        define(op.dst, Shape{in.H, in.W, op.p[0], op.p[0]});
+        break;
+      }
+      case MER_CNN_SLICE: {
+        const Shape a = sh[op.src], d = sh[op.dst];
+        const int s0 = op.p[0], d0 = op.p[1], w = op.p[2], r0 = op.p[3];
+        MER_REQUIRE(a.H > 0 && d.H == a.H && d.W == a.W && w > 0 && w % 4 == 0 && s0 % 4 == 0 && d0 % 4 == 0 &&
+                        s0 >= 0 && d0 >= 0 && s0 + w <= a.Cs && d0 + w <= d.Cs,
+                    "mer_cnn: op %d slice [%d, %d) -> [%d, %d)", i, s0, s0 + w, d0, d0 + w);
+        if (op.res >= 0)
+          MER_REQUIRE(sh[op.res].H == a.H && sh[op.res].W == a.W && r0 >= 0 && r0 % 4 == 0 && r0 + w <= sh[op.res].Cs,
+                      "mer_cnn: op %d slice addend", i);
+        if (!exec) break;
+        const long long total = n * a.H * a.W * (w / 4);
+        slice_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+            buf[op.src], a.Cs, s0, op.res >= 0 ? buf[op.res] : nullptr, op.res >= 0 ? sh[op.res].Cs : 0, r0, buf[op.dst],
+            d.Cs, d0, w / 4, op.relu == 1, op.relu == 2, total);
+        MER_CUDA_CHECK(cudaGetLastError());
+        mer_count_launches(1);
+        break;
+      }
+      case MER_CNN_CBAM: {
+        const Shape in = sh[op.src];
+        MER_REQUIRE(op.conv >= 0 && op.conv < m->n_convs && op.p[0] >= 0 && op.p[0] < m->n_convs && op.p[1] >= 0 &&
+                        op.p[1] < m->n_convs, "mer_cnn: op %d CBAM layers", i);
+        const MerResnetConv &l1 = m->convs[op.conv], &l2 = m->convs[op.p[0]], &sp = m->convs[op.p[1]];
+        MER_REQUIRE(in.H > 0 && in.C == in.Cs && in.H * in.W <= 64 && l1.cin == in.C && l2.cout == in.C &&
+                        l1.cout == l2.cin && l1.cout <= 64 && sp.k == 7 && sp.cin == 2 && sp.cout == 1,
+                    "mer_cnn: op %d CBAM geometry (%d x %d x %d)", i, in.H, in.W, in.C);
+        MER_REQUIRE(op.res >= 0 && sh[op.res].H == in.H && sh[op.res].W == in.W && sh[op.res].Cs == in.Cs,
+                    "mer_cnn: op %d CBAM shortcut shape", i);
+        define(op.dst, in);
+        if (!exec) break;
+        const size_t smem = (size_t)(3 * in.C + 2 * l1.cout + 3 * in.H * in.W) * sizeof(float);
+        cbam_kernel<<<n_frames, 256, smem, st>>>(buf[op.src], buf[op.res], static_cast<const float*>(l1.w), l1.b,
+                                                 static_cast<const float*>(l2.w), l2.b, static_cast<const float*>(sp.w),
+                                                 sp.b, in.H, in.W, in.C, l1.cout, buf[op.dst]);
+        MER_CUDA_CHECK(cudaGetLastError());
+        mer_count_launches(1);
+        break;
+      }
+      case MER_CNN_GAP: {
+        const Shape in = sh[op.src];
+        const int c0 = op.p[0], div = op.p[2] > 0 ? op.p[2] : 1;
+        MER_REQUIRE(in.H > 0 && c0 >= 0 && c0 + in.C <= m->feat_dim, "mer_cnn: op %d pools %d channels into [%d, %d)", i,
+                    in.C, c0, m->feat_dim);
+        ++gaps;
+        if (!exec) break;
+        gap_kernel<<<n_frames, 256, 0, st>>>(buf[op.src], in.H * in.W, in.C, in.Cs, out_feats, m->feat_dim, c0,
+                                             op.p[1] != 0, 1.0f / (float)(in.H * in.W * div));
+        MER_CUDA_CHECK(cudaGetLastError());
+        mer_count_launches(1);
+        break;
+      }
+      default:
+        MER_REQUIRE(false, "mer_cnn: op %d kind %d", i, op.kind);
     }
-    const long long fl = n * sh[op.dst].H * sh[op.dst].W * sh[op.dst].Cs;
-    need[op.dst] = need[op.dst] > fl ? need[op.dst] : fl;
-    last = sh[op.dst];
   }
-  auto al = [](long long x) { return (x + 255) & ~255ll; };
-  long long o = 0;
-  for (int b = 0; b < 4; ++b) {
-    plan->off_buf[b] = o;
-    o += al(need[b] * 4);
+  MER_REQUIRE(gaps > 0, "mer_cnn: the op table has no average pool (nothing is written to out_feats)");
+  if (!exec) {
+    auto al = [](long long x) { return (x + 255) & ~255ll; };
+    long long o = 0;
+    for (int b = 0; b < CNN_BUFS; ++b) {
+      plan->off_buf[b] = o;
+      o += al(need[b] * 4);
+    }
+    plan->off_col = o;   o += al(col_need);
+    plan->off_cu = o;    o += al((n + 1) * 4);
+    plan->off_z = o;     o += al(n * se_c * 4);
+    plan->off_scale = o; o += al(n * se_c * 4);
+    plan->total = o;
   }
-  plan->off_col = o;  o += al(col);
-  plan->off_cu = o;   o += al((n + 1) * 4);
-  plan->off_z = o;    o += al(n * se_c * 4);
-  plan->off_scale = o; o += al(n * se_c * 4);
-  plan->total = o;
-  if (final_shape) *final_shape = last;
   return 0;
 }
 }  // namespace
@@ -561,7 +860,7 @@ extern "C" {
 
 long long mer_cnn_workspace_bytes(const MerCnnModel* m, int n_frames) {
   CnnPlan p;
-  if (n_frames <= 0 || cnn_plan(m, n_frames, &p, nullptr)) return -1;
+  if (n_frames <= 0 || cnn_walk(m, n_frames, false, &p, nullptr, nullptr, nullptr, nullptr)) return -1;
   return p.total;
 }
 
@@ -570,99 +869,9 @@ int mer_cnn_forward(const MerCnnModel* m, const uint8_t* frames_bgr, int n_frame
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   MER_REQUIRE(m && frames_bgr && workspace && out_feats && n_frames > 0, "mer_cnn_forward: bad operands");
   CnnPlan p;
-  Shape fin;
-  if (int rc = cnn_plan(m, n_frames, &p, &fin)) return rc;
+  if (int rc = cnn_walk(m, n_frames, false, &p, nullptr, nullptr, nullptr, nullptr)) return rc;
   MER_REQUIRE(workspace_bytes >= p.total, "mer_cnn_forward: workspace %lld B < required %lld B", workspace_bytes, p.total);
-  MER_REQUIRE(m->ops[m->n_ops - 1].kind == MER_CNN_GAP, "mer_cnn_forward: the op table must end with the average pool");
-  char* ws = static_cast<char*>(workspace);
-  float* buf[4];
-  for (int b = 0; b < 4; ++b) buf[b] = reinterpret_cast<float*>(ws + p.off_buf[b]);
-  uint16_t* col = reinterpret_cast<uint16_t*>(ws + p.off_col);
-  int* offsets = reinterpret_cast<int*>(ws + p.off_cu);
-  const bool split = m->gemm_mode == MER_GEMM_BF16X3;
-  Shape sh[4] = {};
-  for (int i = 0; i < m->n_ops; ++i) {
-    const MerCnnOp& op = m->ops[i];
-    if (op.kind == MER_CNN_STEM) {
-      const MerResnetConv& cv = m->convs[op.conv];
-      MER_REQUIRE(cv.k == 7 && cv.stride == 2 && cv.pad == 3 && cv.cin == 3 && cv.kpad == (split ? 160 : 192),
-                  "mer_cnn_forward: the stem is a 7x7 / 2 convolution packed to %d columns", split ? 160 : 192);
-      const int OH = (m->in_h + 6 - 7) / 2 + 1, OW = (m->in_w + 6 - 7) / 2 + 1;
-      const long long rows = (long long)n_frames * OH * OW, total = rows * cv.kpad;
-      const unsigned blocks = (unsigned)((total + 255) / 256);
-      if (split)
-        im2col_stem_kernel<true><<<blocks, 256, 0, st>>>(frames_bgr, m->in_h, m->in_w, OH, OW, cv.kpad, m->scale,
-                                                         m->mean[0], m->mean[1], m->mean[2], m->std[0], m->std[1],
-                                                         m->std[2], col, total);
-      else
-        im2col_stem_kernel<false><<<blocks, 256, 0, st>>>(frames_bgr, m->in_h, m->in_w, OH, OW, cv.kpad, m->scale,
-                                                          m->mean[0], m->mean[1], m->mean[2], m->std[0], m->std[1],
-                                                          m->std[2], col, total);
-      MER_CUDA_CHECK(cudaGetLastError());
-      mer_count_launches(1);
-      MerGemmDesc g;
-      memset(&g, 0, sizeof(g));
-      g.A = reinterpret_cast<const float*>(col);
-      g.W = static_cast<const float*>(cv.w);
-      g.rows_per_batch = (int)rows;
-      g.a_rows_dim = (int)rows;
-      g.batches = 1;
-      g.N = cv.cout_pad;
-      g.K_inner = cv.kpad;
-      g.taps = 1;
-      g.P = 1;
-      g.a_phase_stride = cv.kpad;
-      g.a_row_stride = cv.kpad;
-      g.a_batch_stride = rows * cv.kpad;
-      g.mode = m->gemm_mode;
-      g.ep.bias = cv.b;
-      g.ep.out = buf[op.dst];
-      g.ep.ld_out = cv.cout_pad;
-      g.ep.flags = op.relu ? MER_EPI_RELU : 0;
-      if (int rc = mer_gemm_launch(&g, st)) return rc;
-      sh[op.dst] = Shape{OH, OW, cv.cout, cv.cout_pad};
-    } else if (op.kind == MER_CNN_CONV) {
-      Shape out;
-      if (int rc = conv(m->convs[op.conv], buf[op.src], sh[op.src], n_frames, col, op.res >= 0 ? buf[op.res] : nullptr,
-                        op.relu != 0, buf[op.dst], &out, st, m->gemm_mode))
-        return rc;
-      sh[op.dst] = out;
-    } else if (op.kind == MER_CNN_MAXPOOL) {
-      const Shape in = sh[op.src];
-      const int OH = pool_out(in.H, op.pad, op.ceil_mode), OW = pool_out(in.W, op.pad, op.ceil_mode);
-      const long long total = (long long)n_frames * OH * OW * (in.Cs / 4);
-      maxpool3x3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-          reinterpret_cast<const float4*>(buf[op.src]), in.H, in.W, in.Cs / 4, OH, OW, op.pad,
-          reinterpret_cast<float4*>(buf[op.dst]), total);
-      MER_CUDA_CHECK(cudaGetLastError());
-      mer_count_launches(1);
-      sh[op.dst] = Shape{OH, OW, in.C, in.Cs};
-    } else if (op.kind == MER_CNN_SE) {
-      // y = buf[src] (increase conv + BN, no ReLU); dst = relu(sigmoid(up(relu(down(mean_hw(y))))) * y + res)
-      const Shape in = sh[op.src];
-      const MerResnetConv &dn = m->convs[op.conv], &up = m->convs[op.k];
-      float* z = reinterpret_cast<float*>(ws + p.off_z);
-      float* scale = reinterpret_cast<float*>(ws + p.off_scale);
-      if (int rc = mer_iota_offsets_launch(offsets, n_frames, in.H * in.W, st)) return rc;
-      if (int rc = mer_segment_reduce_launch(buf[op.src], offsets, offsets + 1, n_frames, in.C, MER_SEG_MEAN, z, st))
-        return rc;
-      se_mlp_kernel<<<n_frames, 256, (size_t)(in.C + dn.cout) * sizeof(float), st>>>(
-          z, static_cast<const float*>(dn.w), dn.b, static_cast<const float*>(up.w), up.b, in.C, dn.cout, scale);
-      MER_CUDA_CHECK(cudaGetLastError());
-      const long long hw_c4 = (long long)in.H * in.W * (in.C / 4), total = hw_c4 * n_frames;
-      se_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-          reinterpret_cast<const float4*>(buf[op.src]), reinterpret_cast<const float4*>(buf[op.res]),
-          reinterpret_cast<const float4*>(scale), hw_c4, in.C / 4, reinterpret_cast<float4*>(buf[op.dst]), total);
-      MER_CUDA_CHECK(cudaGetLastError());
-      mer_count_launches(2);
-      sh[op.dst] = in;
-    } else {  // MER_CNN_GAP (last op, checked by cnn_plan)
-      const Shape in = sh[op.src];
-      if (int rc = mer_iota_offsets_launch(offsets, n_frames, in.H * in.W, st)) return rc;
-      return mer_segment_reduce_launch(buf[op.src], offsets, offsets + 1, n_frames, in.C, MER_SEG_MEAN, out_feats, st);
-    }
-  }
-  return 0;
+  return cnn_walk(m, n_frames, true, &p, static_cast<char*>(workspace), frames_bgr, out_feats, st);
 }
 
 }  // extern "C"

@@ -339,7 +339,8 @@ class ResNet18Encoder:
 
 class MerCnnOp(C.Structure):
     _fields_ = [("kind", C.c_int), ("conv", C.c_int), ("src", C.c_int), ("dst", C.c_int), ("res", C.c_int),
-                ("relu", C.c_int), ("k", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("ceil_mode", C.c_int)]
+                ("relu", C.c_int), ("k", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("ceil_mode", C.c_int),
+                ("p", C.c_int * 4)]
 
 
 class MerCnnModel(C.Structure):
@@ -348,7 +349,7 @@ class MerCnnModel(C.Structure):
                 ("scale", C.c_float), ("mean", C.c_float * 3), ("std", C.c_float * 3), ("feat_dim", C.c_int)]
 
 
-CNN_STEM, CNN_CONV, CNN_MAXPOOL, CNN_GAP, CNN_SE = 0, 1, 2, 3, 4
+CNN_STEM, CNN_CONV, CNN_MAXPOOL, CNN_GAP, CNN_SE, CNN_CROP, CNN_SHAPE, CNN_SLICE, CNN_CBAM = range(9)
 FERPLUS_BLOCKS = (3, 4, 6, 3)
 
 
