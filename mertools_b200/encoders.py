@@ -427,24 +427,132 @@ def ferplus_resnet50_tables(state_dict, pack, bn_eps=1e-5, pack_dense=None):
     return m, [conv_arr, op_arr]
 
 
-class FerplusResnet50Encoder:
-    """``resnet50_ferplus_dag`` (or ``senet50_ferplus_dag``: same skeleton + a squeeze-and-excitation gate per block,
-    picked up from the state_dict) up to ``conv5_3_3x3_relu`` + AvgPool2d(7) (what the reference's FER+ extractor keeps
-    with its default ``--layer_name``): 52 BatchNorm-folded convolutions through the table-driven CNN executor
-    (im2col + tcgen05 GEMMs on split-bf16 operands: fp16 operands measured 6e-4 in an fp32 emulation, too close
-    to the 1e-3 bar), caffe-style strides, ceil-mode max-pool.
+def manet_tables(state_dict, pack, pack_dense=None, bn_eps=1e-5):
+    """Conv and op tables of the reference's MA-Net (manet/model/manet.py:156-270) for mer_cnn_forward:
+    ``model(x, return_embedding=True)`` = cat(local branch [512], multi-scale branch [512]).
+    ``pack`` places a GEMM weight matrix ([cout_pad, kpad] fp32 -> split bf16) and its bias, ``pack_dense`` the plain
+    fp32 matrices of the CBAM gates.  Buffers: 0 = trunk output (28 x 28 x 128, read by all five branches),
+    1..5 = branch scratch, 7 = multi-scale stream."""
+    sd = W._np(state_dict)
+    pack_dense = pack_dense or pack
+    convs, ops = [], []
 
-    Reference: MERBench/feature_extraction/visual/extract_ferplus_embedding.py:62-115,
-    pytorch-benchmarks/model/resnet50_ferplus_dag.py:10-355."""
+    def fold(conv, bn):
+        return fold_conv_bn(sd[conv + ".weight"], sd[bn + ".weight"], sd[bn + ".bias"], sd[bn + ".running_mean"],
+                            sd[bn + ".running_var"], bn_eps)
 
-    def __init__(self, state_dict, device="cuda", bn_eps=1e-5):
+    def add_conv(conv, bn, stride, pad):
+        wf, bf = fold(conv, bn)
+        cout, cin, k, _ = wf.shape
+        cout_pad, kk = max(cout, 128), k * k * cin
+        kpad = 160 if cin == 3 else kk
+        wp = np.zeros((cout_pad, kpad), np.float32)
+        wp[:cout, :kk] = wf.transpose(0, 2, 3, 1).reshape(cout, kk)       # (ky, kx, c) order
+        bp = np.zeros(cout_pad, np.float32)
+        bp[:cout] = bf
+        c = MerResnetConv()
+        c.w, c.b = pack(wp, bp)
+        c.cin, c.cout, c.cout_pad, c.k, c.stride, c.pad, c.kpad = cin, cout, cout_pad, k, stride, pad, kpad
+        convs.append(c)
+        return len(convs) - 1
+
+    def add_dense(w, b, cin, cout, k=1):
+        c = MerResnetConv()
+        c.w, c.b = pack_dense(np.ascontiguousarray(w, np.float32), np.ascontiguousarray(b, np.float32))
+        c.cin, c.cout, c.cout_pad, c.k, c.stride, c.pad, c.kpad = cin, cout, cout, k, 1, k // 2, w.size // max(cout, 1)
+        convs.append(c)
+        return len(convs) - 1
+
+    def op(kind, conv=-1, src=0, dst=0, res=-1, relu=0, k=0, stride=0, pad=0, ceil_mode=0, p=(0, 0, 0, 0)):
+        ops.append(MerCnnOp(kind, conv, src, dst, res, relu, k, stride, pad, ceil_mode, (C.c_int * 4)(*p)))
+
+    def shortcut(pfx, src, dst, stride):
+        if pfx + "downsample.0.weight" not in sd:
+            return src
+        op(CNN_CONV, add_conv(pfx + "downsample.0", pfx + "downsample.1", stride, 0), src=src, dst=dst)
+        return dst
+
+    def basic(pfx, stride):                   # stream in buffer 0, in place
+        op(CNN_CONV, add_conv(pfx + "conv1", pfx + "bn1", stride, 1), src=0, dst=1, relu=1)
+        idt = shortcut(pfx, 0, 2, stride)
+        op(CNN_CONV, add_conv(pfx + "conv2", pfx + "bn2", 1, 1), src=1, dst=0, res=idt, relu=1)
+
+    def attention(pfx, src, stride):          # AttentionBlock: src (1 or 5) -> buffer 5
+        op(CNN_CONV, add_conv(pfx + "conv1", pfx + "bn1", stride, 1), src=src, dst=2, relu=1)
+        op(CNN_CONV, add_conv(pfx + "conv2", pfx + "bn2", 1, 1), src=2, dst=3)
+        idt = shortcut(pfx, src, 4, stride)
+        g = pfx + "cbam."
+        w1, w2 = sd[g + "ChannelGate.mlp.1.weight"], sd[g + "ChannelGate.mlp.3.weight"]
+        l1 = add_dense(w1, sd[g + "ChannelGate.mlp.1.bias"], w1.shape[1], w1.shape[0])
+        l2 = add_dense(w2, sd[g + "ChannelGate.mlp.3.bias"], w2.shape[1], w2.shape[0])
+        ws, bs = fold(g + "SpatialGate.spatial.conv", g + "SpatialGate.spatial.bn")     # [1, 2, 7, 7], [1]
+        sp = add_dense(ws.reshape(1, 98), bs.reshape(1), 2, 1, k=7)
+        op(CNN_CBAM, l1, src=3, dst=5, res=idt, p=(l2, sp, 0, 0))
+
+    def mulscale(pfx, src, stride):           # MulScaleBlock: src (0 or 7) -> buffer 7
+        c1 = add_conv(pfx + "conv1", pfx + "bn1", stride, 1)
+        planes = convs[c1].cout
+        sw = planes // 4
+        op(CNN_CONV, c1, src=src, dst=1, relu=1)                                  # t, split into 4 x sw channels
+        idt = shortcut(pfx, src, 5, stride)
+        op(CNN_SHAPE, src=1, dst=4, p=(planes, 0, 0, 0))                          # O = O_1 + O_2
+        op(CNN_SHAPE, src=1, dst=3, p=(sw, 0, 0, 0))                              # relu(o_{i-1}) + sp_i
+        for chain in (1, 2):
+            for i in range(4):
+                ci = add_conv(pfx + f"conv{chain}_2_{i + 1}", pfx + f"bn{chain}_2_{i + 1}", 1, 1)
+                if i == 0:
+                    op(CNN_CONV, ci, src=1, dst=2, p=(0, 0, 0, 0))                # conv(sp_0)
+                else:
+                    op(CNN_SLICE, src=2, dst=3, res=1, relu=1, p=(0, 0, sw, i * sw))
+                    op(CNN_CONV, ci, src=3, dst=2)
+                op(CNN_SLICE, src=2, dst=4, res=4 if chain == 2 else -1, p=(0, i * sw, sw, i * sw))
+        if idt != 7:
+            op(CNN_SHAPE, src=4, dst=7, p=(planes, 0, 0, 0))
+        op(CNN_SLICE, src=4, dst=7, res=idt, relu=2, p=(0, 0, planes, 0))
+
+    op(CNN_STEM, add_conv("conv1", "bn1", 2, 3), dst=1, relu=1)
+    op(CNN_MAXPOOL, src=1, dst=0, k=3, stride=2, pad=1, ceil_mode=0)
+    for b in range(2):
+        basic(f"layer1.{b}.", 1)
+    for b in range(2):
+        basic(f"layer2.{b}.", 2 if b == 0 else 1)
+    for pi, (y0, x0) in enumerate(((0, 0), (0, 14), (14, 0), (14, 14)), start=1):
+        op(CNN_CROP, src=0, dst=1, p=(y0, x0, 14, 14))
+        attention(f"layer3_1_p{pi}.0.", 1, 2)
+        attention(f"layer3_1_p{pi}.1.", 5, 1)
+        attention(f"layer4_1_p{pi}.0.", 5, 1)
+        attention(f"layer4_1_p{pi}.1.", 5, 1)
+        op(CNN_GAP, src=5, p=(0, 1 if pi > 1 else 0, 4, 0))       # mean of the 14 x 14 mosaic = mean of the 4 patch means
+    mulscale("layer3_2.0.", 0, 2)
+    mulscale("layer3_2.1.", 7, 1)
+    mulscale("layer4_2.0.", 7, 2)
+    mulscale("layer4_2.1.", 7, 1)
+    op(CNN_GAP, src=7, p=(512, 0, 1, 0))
+    conv_arr = (MerResnetConv * len(convs))(*convs)
+    op_arr = (MerCnnOp * len(ops))(*ops)
+    m = MerCnnModel()
+    m.convs, m.n_convs = conv_arr, len(convs)
+    m.ops, m.n_ops = op_arr, len(ops)
+    m.gemm_mode = L.MER_GEMM_BF16X3
+    m.in_h = m.in_w = 224
+    m.scale = 1.0 / 255.0                                          # ToTensor only (extract_manet_embedding.py:60-61)
+    m.mean = (C.c_float * 3)(0.0, 0.0, 0.0)
+    m.std = (C.c_float * 3)(1.0, 1.0, 1.0)
+    m.feat_dim = 1024
+    return m, [conv_arr, op_arr]
+
+
+class _CnnEncoder:
+    """Shared driver of the table-driven CNN extractors: device-side PIL-bilinear resize (+ optional centre crop) to
+    224 x 224, then mer_cnn_forward in chunks of frames."""
+
+    def _setup(self, device, tables, feature_dim):
         L.check(L.lib().mer_check_device())
         self.device = torch.device(device)
         pk = self.pk = W.Packed(self.device)
-        self.model, self._keep = ferplus_resnet50_tables(
-            state_dict, lambda wp, bp: (pk.keep(wp, split=True).data_ptr(), pk.keep(bp).data_ptr()), bn_eps,
-            pack_dense=lambda w, b: (pk.keep(w).data_ptr(), pk.keep(b).data_ptr()))
-        self.feature_dim = 512
+        self.model, self._keep = tables(lambda wp, bp: (pk.keep(wp, split=True).data_ptr(), pk.keep(bp).data_ptr()),
+                                        lambda w, b: (pk.keep(w).data_ptr(), pk.keep(b).data_ptr()))
+        self.feature_dim = feature_dim
         self.ws, self.ws_resize = _Workspace(self.device), _Workspace(self.device)
         lib = L.lib()
         lib.mer_cnn_workspace_bytes.restype = C.c_longlong
@@ -457,14 +565,11 @@ class FerplusResnet50Encoder:
                                                    C.c_int, C.c_int, C.c_void_p, C.c_void_p])
 
     def preprocess_geometry(self, h, w):
-        """transforms.Resize(256) + CenterCrop(224) (extract_ferplus_embedding.py:68-70): resized (h, w) and the
-        crop's (top, left)."""
-        nh, nw = (256, int(256 * w / h)) if h <= w else (int(256 * h / w), 256)
-        return nh, nw, int(round((nh - 224) / 2.0)), int(round((nw - 224) / 2.0))
+        """(resized h, resized w, crop top, crop left) of the reference transform; default: Resize((224, 224))."""
+        return 224, 224, 0, 0
 
     def frame_features(self, frames_bgr_u8: torch.Tensor, max_frames=64):
-        """frames: uint8 CUDA [N, H, W, 3] (BGR).  Resize(256) (PIL bilinear, on the device) + CenterCrop(224), then
-        the network.  Returns [N, 512] fp32 (CUDA)."""
+        """frames: uint8 CUDA [N, H, W, 3] (BGR) -> [N, feature_dim] fp32 (CUDA)."""
         assert frames_bgr_u8.dtype == torch.uint8 and frames_bgr_u8.is_cuda and frames_bgr_u8.dim() == 4
         frames = frames_bgr_u8.contiguous()
         n, h, w, _ = frames.shape
@@ -475,8 +580,9 @@ class FerplusResnet50Encoder:
             ws = self.ws_resize.get(max(int(need), 1))
             L.check(self._resize(L.ptr(frames), n, h, w, L.ptr(out), nh, nw, 0, L.ptr(ws), L.stream_ptr()))
             frames = out
-        frames = frames[:, top:top + 224, left:left + 224].contiguous()
-        feats = torch.empty(n, 512, dtype=torch.float32, device=self.device)
+        if (nh, nw) != (224, 224):
+            frames = frames[:, top:top + 224, left:left + 224].contiguous()
+        feats = torch.empty(n, self.feature_dim, dtype=torch.float32, device=self.device)
         for s in range(0, n, max_frames):
             m = min(max_frames, n - s)
             nbytes = L.lib().mer_cnn_workspace_bytes(C.byref(self.model), m)
@@ -485,6 +591,38 @@ class FerplusResnet50Encoder:
             L.check(self._fwd(C.byref(self.model), L.ptr(frames[s:s + m]), m, L.ptr(ws), ws.numel(),
                               L.ptr(feats[s:s + m]), L.stream_ptr()))
         return feats
+
+
+class FerplusResnet50Encoder(_CnnEncoder):
+    """``resnet50_ferplus_dag`` (or ``senet50_ferplus_dag``: same skeleton + a squeeze-and-excitation gate per block,
+    picked up from the state_dict) up to ``conv5_3_3x3_relu`` + AvgPool2d(7) (what the reference's FER+ extractor keeps
+    with its default ``--layer_name``): 52 BatchNorm-folded convolutions through the table-driven CNN executor
+    (im2col + tcgen05 GEMMs on split-bf16 operands: fp16 operands measured 6e-4 in an fp32 emulation, too close
+    to the 1e-3 bar), caffe-style strides, ceil-mode max-pool.
+
+    Reference: MERBench/feature_extraction/visual/extract_ferplus_embedding.py:62-115,
+    pytorch-benchmarks/model/resnet50_ferplus_dag.py:10-355."""
+
+    def __init__(self, state_dict, device="cuda", bn_eps=1e-5):
+        self._setup(device, lambda pack, dense: ferplus_resnet50_tables(state_dict, pack, bn_eps, pack_dense=dense), 512)
+
+    def preprocess_geometry(self, h, w):
+        """transforms.Resize(256) + CenterCrop(224) (extract_ferplus_embedding.py:68-70): resized (h, w) and the
+        crop's (top, left)."""
+        nh, nw = (256, int(256 * w / h)) if h <= w else (int(256 * h / w), 256)
+        return nh, nw, int(round((nh - 224) / 2.0)), int(round((nw - 224) / 2.0))
+
+
+class ManetEncoder(_CnnEncoder):
+    """MA-Net (the RAF-DB checkpoint the reference extracts ``manet_<UTT|FRA>`` features with): ResNet-18 trunk, four
+    14 x 14 patch branches of CBAM AttentionBlocks, a multi-scale branch of MulScaleBlocks; 1024-d embedding.
+    120 BatchNorm-folded convolutions on split-bf16 tcgen05 GEMMs + 16 fused CBAM gates.
+
+    Reference: MERBench/feature_extraction/visual/extract_manet_embedding.py:31-61,
+    manet/model/manet.py:16-270, manet/model/attention.py:27-84."""
+
+    def __init__(self, state_dict, device="cuda", bn_eps=1e-5):
+        self._setup(device, lambda pack, dense: manet_tables(state_dict, pack, dense, bn_eps), 1024)
 
 
 class MerVggishModel(C.Structure):

@@ -320,20 +320,27 @@ def _interpret_cnn_tables(m, store, frames_bgr):
     mean = torch.tensor([m.mean[i] for i in range(3)])
     std = torch.tensor([m.std[i] for i in range(3)])
     x0 = (torch.from_numpy(np.ascontiguousarray(frames_bgr[..., ::-1])).float() * m.scale - mean) / std  # NHWC, RGB
-    buf, real = [None] * 4, [0] * 4
+    buf, real = [None] * 8, [0] * 8
+    out = torch.full((n, m.feat_dim), float("nan"))
+    T = torch.from_numpy
 
-    def conv(x, cin_real, c):
+    def conv(x, c):
         w, b = store[c.w], store[c.b]                       # [cout_pad, kpad], [cout_pad]
         kk = c.k * c.k * c.cin
-        assert c.cin == cin_real and (c.kpad == kk or (c.cin == 3 and c.kpad in (160, 192)))
-        wt = torch.from_numpy(w[:, :kk]).reshape(c.cout_pad, c.k, c.k, c.cin).permute(0, 3, 1, 2)
-        y = F.conv2d(x[..., :c.cin].permute(0, 3, 1, 2), wt, torch.from_numpy(b), stride=c.stride, padding=c.pad)
+        assert c.kpad == kk or (c.cin == 3 and c.kpad in (160, 192))
+        wt = T(w[:, :kk]).reshape(c.cout_pad, c.k, c.k, c.cin).permute(0, 3, 1, 2)
+        y = F.conv2d(x.permute(0, 3, 1, 2), wt, T(b), stride=c.stride, padding=c.pad)
         return y.permute(0, 2, 3, 1)
     for i in range(m.n_ops):
         op = m.ops[i]
+        p = [op.p[j] for j in range(4)]
         if op.kind in (En.CNN_STEM, En.CNN_CONV):
             c = m.convs[op.conv]
-            y = conv(x0, 3, c) if op.kind == En.CNN_STEM else conv(buf[op.src], real[op.src], c)
+            if op.kind == En.CNN_STEM:
+                y = conv(x0, c)
+            else:
+                assert op.src != op.dst and p[0] + c.cin <= real[op.src]
+                y = conv(buf[op.src][..., p[0]:p[0] + c.cin], c)
             if op.res >= 0:
                 assert buf[op.res].shape == y.shape
                 y = y + buf[op.res]
@@ -345,14 +352,38 @@ def _interpret_cnn_tables(m, store, frames_bgr):
         elif op.kind == En.CNN_SE:
             dn, up = m.convs[op.conv], m.convs[op.k]
             y = buf[op.src]
-            z = y.mean(dim=(1, 2))
-            d = torch.relu(z @ torch.from_numpy(store[dn.w]).T + torch.from_numpy(store[dn.b]))
-            g = torch.sigmoid(d @ torch.from_numpy(store[up.w]).T + torch.from_numpy(store[up.b]))
+            d = torch.relu(y.mean(dim=(1, 2)) @ T(store[dn.w]).T + T(store[dn.b]))
+            g = torch.sigmoid(d @ T(store[up.w]).T + T(store[up.b]))
             buf[op.dst], real[op.dst] = torch.relu(g[:, None, None, :] * y + buf[op.res]), real[op.src]
+        elif op.kind == En.CNN_CROP:
+            buf[op.dst], real[op.dst] = buf[op.src][:, p[0]:p[0] + p[2], p[1]:p[1] + p[3]].clone(), real[op.src]
+        elif op.kind == En.CNN_SHAPE:
+            hh, ww = buf[op.src].shape[1:3]
+            buf[op.dst], real[op.dst] = torch.full((n, hh, ww, p[0]), float("nan")), p[0]
+        elif op.kind == En.CNN_SLICE:
+            v = buf[op.src][..., p[0]:p[0] + p[2]]
+            v = torch.relu(v) if op.relu == 1 else v
+            if op.res >= 0:
+                v = v + buf[op.res][..., p[3]:p[3] + p[2]]
+            buf[op.dst][..., p[1]:p[1] + p[2]] = torch.relu(v) if op.relu == 2 else v
+        elif op.kind == En.CNN_CBAM:
+            l1, l2, sp = m.convs[op.conv], m.convs[p[0]], m.convs[p[1]]
+            y = buf[op.src]
+            assert y.shape[-1] == real[op.src] == l1.cin
+
+            def mlp(v):
+                return torch.relu(v @ T(store[l1.w]).T + T(store[l1.b])) @ T(store[l2.w]).T + T(store[l2.b])
+            y1 = y * torch.sigmoid(mlp(y.mean(dim=(1, 2))) + mlp(y.amax(dim=(1, 2))))[:, None, None, :]
+            comp = torch.stack((y1.amax(dim=3), y1.mean(dim=3)), dim=1)              # [n, 2, H, W]: max, mean
+            sg = torch.sigmoid(F.conv2d(comp, T(store[sp.w]).reshape(1, 2, 7, 7), T(store[sp.b]), padding=3))
+            buf[op.dst], real[op.dst] = torch.relu(y1 * sg[:, 0, :, :, None] + buf[op.res]), real[op.src]
         else:
-            assert op.kind == En.CNN_GAP and i == m.n_ops - 1
-            return buf[op.src].mean(dim=(1, 2))[:, :m.feat_dim].numpy()
-    raise AssertionError("table without a final average pool")
+            assert op.kind == En.CNN_GAP
+            v = buf[op.src][..., :real[op.src]].mean(dim=(1, 2)) / max(p[2], 1)
+            cols = slice(p[0], p[0] + real[op.src])
+            out[:, cols] = out[:, cols] + v if p[1] else v
+    assert not torch.isnan(out).any(), "some output columns were never written"
+    return out.numpy()
 
 
 @pytest.mark.parametrize("se,prefix", [(False, ""), (True, "se_")])
@@ -382,6 +413,7 @@ def test_ferplus_op_tables_reproduce_the_reference_golden_on_a_cpu_interpreter(s
     ref = g[f"{prefix}fra_vidA"][:2]
     assert got.shape == ref.shape and np.abs(got - ref).max() / np.abs(ref).max() < 1e-4
     enc_geom = En.FerplusResnet50Encoder.preprocess_geometry(None, 200, 300)
+    assert En.ManetEncoder.preprocess_geometry(None, 200, 300) == (224, 224, 0, 0)
     assert enc_geom == (256, 384, 16, 80) and P.ferplus_preprocess(mod.golden_clips()["vidC"]).shape == (1, 3, 224, 224)
 
 
@@ -417,3 +449,33 @@ def test_vggish_tables_reproduce_the_oracle_on_a_cpu_interpreter():
     ref = E.vggish_embeddings({k: torch.from_numpy(v) for k, v in sd.items()},
                               torch.from_numpy(np.random.default_rng(2).normal(-2.0, 2.0, (2, 96, 64, 1)).astype(np.float32))[..., 0])
     assert h.shape == (2, 128) and float((h - ref).abs().max() / ref.abs().max()) < 1e-5
+
+
+def test_manet_op_tables_reproduce_the_reference_golden_on_a_cpu_interpreter():
+    """The 136 layers / 184 ops MA-Net hands to mer_cnn_forward (trunk, four cropped CBAM branches accumulated into
+    columns 0..511, the multi-scale branch assembled from channel slices into columns 512..1023), run by the torch
+    interpreter of the op semantics, against outputs of the unmodified reference model."""
+    import ctypes as C
+    import importlib.util
+
+    from mertools_b200 import _lib
+    from mertools_b200 import encoders as En
+    gdir = os.path.join(ROOT, "tests", "golden")
+    spec = importlib.util.spec_from_file_location("make_golden_manet", os.path.join(gdir, "make_golden_manet.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(gdir, "manet_golden.npz"))
+    store = {}
+
+    def pack(w, b):
+        store[len(store) + 1] = np.asarray(w, np.float32)
+        store[len(store) + 1] = np.asarray(b, np.float32)
+        return len(store) - 1, len(store)
+    m, _keep = En.manet_tables(S.manet_state_dict(int(g["seed"])), pack)
+    got = _interpret_cnn_tables(m, store, mod.golden_clips()["vidA"][:2])
+    ref = g["fra_vidA"][:2]
+    assert got.shape == ref.shape and np.abs(got - ref).max() / np.abs(ref).max() < 1e-4
+    dll = _lib.lib()
+    dll.mer_cnn_workspace_bytes.restype = C.c_longlong
+    dll.mer_cnn_workspace_bytes.argtypes = [C.POINTER(En.MerCnnModel), C.c_int]
+    assert m.n_convs == 136 and dll.mer_cnn_workspace_bytes(C.byref(m), 2) > 0   # the C++ planner accepts the table

@@ -306,3 +306,40 @@ def test_audio_extractor_ragged_mode_matches_default(cuda):
         ra, rb = a.extract_waves(waves, level), b.extract_waves(waves, level)
         for x, y in zip(ra, rb):
             assert x.shape == y.shape and np.abs(x - y).max() / np.abs(x).max() < 2e-4
+
+
+def test_manet_vs_reference_golden(cuda, tmp_path):
+    """MA-Net through the CNN executor (crop / slice / CBAM / ranged average-pool ops) against outputs of the
+    unmodified reference model, plus the mirrored script's files."""
+    import importlib.util
+    import types
+
+    import numpy as np
+
+    from mertools_b200 import synthetic as S
+    from mertools_b200.encoders import ManetEncoder
+    from mertools_b200.extract import manet
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden_manet", os.path.join(gdir, "make_golden_manet.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(gdir, "manet_golden.npz"))
+    sd = S.manet_state_dict(int(g["seed"]))
+    enc = ManetEncoder(sd, device=cuda)
+    clips = mod.golden_clips()
+    for vid, frames in clips.items():
+        got = enc.frame_features(torch.from_numpy(frames).to(cuda), max_frames=2).cpu().numpy()
+        ref = g[f"fra_{vid}"]
+        assert got.shape == ref.shape and np.abs(got - ref).max() / np.abs(ref).max() < 1e-3, vid
+    face = tmp_path / "face"
+    for vid, frames in clips.items():
+        os.makedirs(face / vid)
+        np.save(face / vid / f"{vid}.npy", frames)
+    cfg = types.SimpleNamespace(PATH_TO_RAW_FACE={"D": str(face)}, PATH_TO_FEATURES={"D": str(tmp_path / "feat")})
+    for level, key in (("UTTERANCE", "utt"), ("FRAME", "fra")):
+        manet.main(manet.build_parser().parse_args(["--dataset=D", f"--feature_level={level}", "--gpu=0"]),
+                   config=cfg, state_dict=sd)
+        for vid in clips:
+            got = np.load(tmp_path / "feat" / f"manet_{level[:3]}" / f"{vid}.npy")
+            ref = g[f"{key}_{vid}"]
+            assert got.shape == ref.shape and np.abs(got - ref).max() / np.abs(ref).max() < 1e-3, (vid, level)
