@@ -29,12 +29,14 @@ def load_resnet18_state_dict():
     return {k: v.float().numpy() for k, v in sd.items() if not k.startswith("fc.")}
 
 
-def main(params, config=None, state_dict=None, clips_per_launch=32):
+def main(params, config=None, state_dict=None, clips_per_launch=32, name="imagenet"):
+    """``name``: "imagenet" (this script) or "msceleb" (extract/msceleb.py: the same network and transform with the
+    MS-Celeb checkpoint, written to ``msceleb_<UTT|FRA>``)."""
     if config is None:
         from .. import config as config  # noqa: PLW0127
-    print("==> Extracting imagenet embedding...")
+    print(f"==> Extracting {name} embedding...")
     face_dir = config.PATH_TO_RAW_FACE[params.dataset]
-    save_dir = os.path.join(config.PATH_TO_FEATURES[params.dataset], f"imagenet_{params.feature_level[:3]}")
+    save_dir = os.path.join(config.PATH_TO_FEATURES[params.dataset], f"{name}_{params.feature_level[:3]}")
     os.makedirs(save_dir, exist_ok=True)
     gpu = int(params.gpu)
     assert gpu != -1, "mertools_b200 has no CPU path"

@@ -245,3 +245,20 @@ def test_manet_oracle_matches_reference_extractor_golden():
         for level, key in (("FRAME", "fra"), ("UTTERANCE", "utt")):
             got, ref = P.manet_clip_features(sd, frames, level), g[f"{key}_{vid}"]
             assert got.shape == ref.shape and _rel(got, ref) < 1e-5, (vid, level)
+
+
+def test_resnet18_oracle_matches_the_msceleb_reference_classes_golden():
+    """extract_msceleb_embedding.py defines its own ResNet-18 (same parameter names as torchvision's): outputs of
+    those reference classes + transform + save rules (make_golden_msceleb.py) against the oracle pipeline that also
+    serves the ImageNet extractor — bit for bit."""
+    import importlib.util
+    from oracle import pipeline as P
+    spec = importlib.util.spec_from_file_location("make_golden_msceleb", os.path.join(G, "make_golden_msceleb.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(G, "msceleb_golden.npz"))
+    sd = _t(S.resnet18_state_dict(int(g["seed"])))
+    for vid, frames in mod.golden_clips().items():
+        for level, key in (("FRAME", "fra"), ("UTTERANCE", "utt")):
+            got, ref = P.imagenet_clip_features(sd, frames, level), g[f"{key}_{vid}"]
+            assert got.shape == ref.shape and _rel(got, ref) < 1e-6, (vid, level)

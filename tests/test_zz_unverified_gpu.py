@@ -343,3 +343,33 @@ def test_manet_vs_reference_golden(cuda, tmp_path):
             got = np.load(tmp_path / "feat" / f"manet_{level[:3]}" / f"{vid}.npy")
             ref = g[f"{key}_{vid}"]
             assert got.shape == ref.shape and np.abs(got - ref).max() / np.abs(ref).max() < 1e-3, (vid, level)
+
+
+def test_msceleb_extractor_vs_reference_classes_golden(cuda, tmp_path):
+    """extract_msceleb_embedding mirror (the GPU-verified ResNet-18 path with another checkpoint / directory name)
+    against outputs of the reference script's own classes."""
+    import importlib.util
+    import types
+
+    import numpy as np
+
+    from mertools_b200 import synthetic as S
+    from mertools_b200.extract import msceleb
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden_msceleb", os.path.join(gdir, "make_golden_msceleb.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(gdir, "msceleb_golden.npz"))
+    sd = S.resnet18_state_dict(int(g["seed"]))
+    face = tmp_path / "face"
+    for vid, frames in mod.golden_clips().items():
+        os.makedirs(face / vid)
+        np.save(face / vid / f"{vid}.npy", frames)
+    cfg = types.SimpleNamespace(PATH_TO_RAW_FACE={"D": str(face)}, PATH_TO_FEATURES={"D": str(tmp_path / "feat")})
+    for level, key in (("UTTERANCE", "utt"), ("FRAME", "fra")):
+        msceleb.main(msceleb.build_parser().parse_args(["--dataset=D", f"--feature_level={level}", "--gpu=0"]),
+                     config=cfg, state_dict=sd)
+        for vid in mod.golden_clips():
+            got = np.load(tmp_path / "feat" / f"msceleb_{level[:3]}" / f"{vid}.npy")
+            ref = g[f"{key}_{vid}"]
+            assert got.shape == ref.shape and np.abs(got - ref).max() / np.abs(ref).max() < 1e-3, (vid, level)
