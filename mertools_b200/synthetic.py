@@ -246,6 +246,60 @@ def manet_state_dict(seed=10):
     return sd
 
 
+def emonet_state_dict(seed=11):
+    """Parameters of the reference's ``EmoNet()`` (feature_extraction/visual/emonet/models/emonet.py:20-170;
+    ``nn.InstanceNorm2d = nn.BatchNorm2d`` there, so every norm is a BatchNorm with running statistics): stem conv with
+    bias, pre-activation ConvBlocks, two depth-4 hourglasses with their heads, the emotion tower."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+
+    def bn(name, c):
+        sd[name + ".weight"] = rng.uniform(0.5, 1.5, c).astype(np.float32)
+        sd[name + ".bias"] = (0.2 * rng.standard_normal(c)).astype(np.float32)
+        sd[name + ".running_mean"] = (0.2 * rng.standard_normal(c)).astype(np.float32)
+        sd[name + ".running_var"] = rng.uniform(0.5, 1.5, c).astype(np.float32)
+        sd[name + ".num_batches_tracked"] = np.zeros((), np.int64)
+
+    def conv(name, cout, cin, k, bias=False, gain=1.0):
+        sd[name + ".weight"] = (gain * rng.standard_normal((cout, cin, k, k)) * np.sqrt(2.0 / (cin * k * k))).astype(np.float32)
+        if bias:
+            sd[name + ".bias"] = (0.1 * rng.standard_normal(cout)).astype(np.float32)
+
+    def block(p, cin, cout):
+        bn(p + "bn1", cin); conv(p + "conv1", cout // 2, cin, 3, gain=0.3)
+        bn(p + "bn2", cout // 2); conv(p + "conv2", cout // 4, cout // 2, 3, gain=0.5)
+        bn(p + "bn3", cout // 4); conv(p + "conv3", cout // 4, cout // 4, 3, gain=0.5)
+        if cin != cout:
+            bn(p + "downsample.0", cin); conv(p + "downsample.2", cout, cin, 1)
+
+    def hourglass(p, level):
+        block(p + f"b1_{level}.", 256, 256); block(p + f"b2_{level}.", 256, 256)
+        if level > 1:
+            hourglass(p, level - 1)
+        else:
+            block(p + f"b2_plus_{level}.", 256, 256)
+        block(p + f"b3_{level}.", 256, 256)
+
+    conv("conv1", 64, 3, 7, bias=True); bn("bn1", 64)
+    block("conv2.", 64, 128); block("conv3.", 128, 128); block("conv4.", 128, 256)
+    for i in range(2):
+        hourglass(f"m{i}.", 4)
+        block(f"top_m_{i}.", 256, 256)
+        conv(f"conv_last{i}", 256, 256, 1, bias=True); bn(f"bn_end{i}", 256)
+        conv(f"l{i}", 68, 256, 1, bias=True, gain=0.3)
+        if i < 1:
+            conv(f"bl{i}", 256, 256, 1, bias=True); conv(f"al{i}", 256, 68, 1, bias=True)
+    conv("conv1x1_input_emo_2", 256, 768, 1, bias=True)
+    for i in range(4):
+        block(f"emo_net_2.{2 * i}.", 256, 256)
+    sd["emo_fc_2.0.weight"] = (rng.standard_normal((128, 256)) * np.sqrt(2.0 / 256)).astype(np.float32)
+    sd["emo_fc_2.0.bias"] = np.zeros(128, np.float32)
+    bn("emo_fc_2.1", 128)
+    sd["emo_fc_2.3.weight"] = (rng.standard_normal((10, 128)) * np.sqrt(1.0 / 128)).astype(np.float32)
+    sd["emo_fc_2.3.bias"] = np.zeros(10, np.float32)
+    return sd
+
+
 HUBERT_LARGE_CFG = dict(HUBERT_CFG, hidden=1024, heads=16, ffn=4096, layers=24)
 
 

@@ -269,6 +269,52 @@ def manet_embedding(sd, x, dtype=torch.float32, eps=1e-5):
     return torch.cat([b1, o.mean(dim=(2, 3))], dim=1)
 
 
+def emonet_embedding(sd, x, dtype=torch.float32, eps=1e-5):
+    """``EmoNet()(x, return_embedding=True)`` of the reference (feature_extraction/visual/emonet/models/emonet.py:
+    173-222, blocks :20-112; attention=True, temporal_smoothing=False) in eval mode: the 256-d vector after the
+    emotion tower's 4 x 4 average pool.  Every norm is a BatchNorm2d (the file rebinds nn.InstanceNorm2d).
+    x: [N, 3, 256, 256] in [0, 1]."""
+    def bn(x, name):
+        return F.batch_norm(x, _t(sd, name + ".running_mean", dtype), _t(sd, name + ".running_var", dtype),
+                            _t(sd, name + ".weight", dtype), _t(sd, name + ".bias", dtype), False, 0.0, eps)
+
+    def conv(x, name, stride=1, pad=0):
+        b = _t(sd, name + ".bias", dtype) if name + ".bias" in sd else None
+        return F.conv2d(x, _t(sd, name + ".weight", dtype), b, stride=stride, padding=pad)
+
+    def block(p, x):                                          # ConvBlock :20-64 (pre-activation, concatenated outputs)
+        o1 = conv(F.relu(bn(x, p + "bn1")), p + "conv1", 1, 1)
+        o2 = conv(F.relu(bn(o1, p + "bn2")), p + "conv2", 1, 1)
+        o3 = conv(F.relu(bn(o2, p + "bn3")), p + "conv3", 1, 1)
+        res = conv(F.relu(bn(x, p + "downsample.0")), p + "downsample.2") if p + "downsample.2.weight" in sd else x
+        return torch.cat((o1, o2, o3), 1) + res
+
+    def hourglass(p, level, inp):                             # HourGlass._forward :87-109
+        up1 = block(p + f"b1_{level}.", inp)
+        low = block(p + f"b2_{level}.", F.max_pool2d(inp, 2, stride=2))
+        low = hourglass(p, level - 1, low) if level > 1 else block(p + f"b2_plus_{level}.", low)
+        low = block(p + f"b3_{level}.", low)
+        return up1 + F.interpolate(low, scale_factor=2, mode="nearest")
+
+    x = F.relu(bn(conv(x.to(dtype), "conv1", 2, 3), "bn1"))
+    x = F.max_pool2d(block("conv2.", x), 2, stride=2)
+    x = block("conv4.", block("conv3.", x))
+    previous, feats, heat = x, [], None
+    for i in range(2):
+        ll = block(f"top_m_{i}.", hourglass(f"m{i}.", 4, previous))
+        ll = F.relu(bn(conv(ll, f"conv_last{i}"), f"bn_end{i}"))
+        heat = conv(ll, f"l{i}")
+        if i < 1:
+            ll = conv(ll, f"bl{i}")
+            previous = previous + ll + conv(heat, f"al{i}")
+        feats.append(ll)
+    hg = torch.cat(feats, dim=1) * heat.sum(dim=1, keepdim=True)
+    y = conv(torch.cat((x, hg), dim=1), "conv1x1_input_emo_2")
+    for i in range(4):
+        y = F.max_pool2d(block(f"emo_net_2.{2 * i}.", y), 2, 2)
+    return F.avg_pool2d(y, 4).flatten(1)
+
+
 def hubert_pos_conv_weight(sd, dtype=torch.float32):
     """Effective weight of the weight-normed positional conv (:45-92): W = g * v / ||v||, the
     norm taken over dims (0,1) per kernel tap (weight_norm dim=2).  Older checkpoints name the

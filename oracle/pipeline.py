@@ -155,6 +155,65 @@ def imagenet_clip_features(sd, frames_bgr, feature_level="UTTERANCE"):
     return np.mean(emb, axis=0) if emb.ndim == 2 else emb
 
 
+def cv2_resize_linear_u8(img, oh, ow):
+    """``cv2.resize(img, (ow, oh))`` (INTER_LINEAR, the default) for uint8 [H, W, C] images, restated from OpenCV's
+    fixed-point resize (imgproc/src/resize.cpp: 11-bit coefficients, HResizeLinear then the 8-bit VResizeLinear
+    ``((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2 >> 2``; the x fraction is reset at the borders, the y
+    rows are only clamped; an exact 2x downscale takes the 2 x 2 area average).  Bit-exact against cv2 4.13 on the
+    sizes tests/test_oracle.py tries.  Used by the EmoNet extractor's DataAugmentor (emonet/data_augmentation.py:77)."""
+    img = np.asarray(img)
+    ih, iw = img.shape[:2]
+    a = img.astype(np.int32)
+    if ih == 2 * oh and iw == 2 * ow:
+        return ((a[0::2, 0::2] + a[0::2, 1::2] + a[1::2, 0::2] + a[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+
+    def frac(isz, osz):
+        f = ((np.arange(osz) + 0.5) * (isz / osz) - 0.5).astype(np.float32)
+        s = np.floor(f).astype(np.int32)
+        return s, (f - s).astype(np.float32)
+
+    def q(f):
+        return (np.rint((np.float32(1.0) - f) * np.float32(2048)).astype(np.int32),
+                np.rint(f * np.float32(2048)).astype(np.int32))
+    sx, fx = frac(iw, ow)
+    fx[sx < 0] = 0
+    sx[sx < 0] = 0
+    hi = sx >= iw - 1
+    fx[hi] = 0
+    sx[hi] = iw - 1
+    ax0, ax1 = q(fx)
+    sy, fy = frac(ih, oh)
+    ay0, ay1 = q(fy)
+    h = a[:, sx] * ax0[None, :, None] + a[:, np.minimum(sx + 1, iw - 1)] * ax1[None, :, None]
+    r0, r1 = h[np.clip(sy, 0, ih - 1)], h[np.clip(sy + 1, 0, ih - 1)]
+    out = (((ay0[:, None, None] * (r0 >> 4)) >> 16) + ((ay1[:, None, None] * (r1 >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def emonet_preprocess(frames_bgr):
+    """FaceDatasetForEmoNet.__getitem__ (dataset.py:72-86: BGR -> RGB) + DataAugmentor(256, 256) without a bounding
+    box (emonet/data_augmentation.py:68-87: cv2.resize to 256 x 256; the two warpAffine calls are identities at
+    rotation 0 / scale 1 / translation 0) + ToTensor.  Returns [N, 3, 256, 256] in [0, 1]."""
+    f = np.asarray(frames_bgr)
+    assert f.dtype == np.uint8 and f.ndim == 4 and f.shape[-1] == 3, f.shape
+    rgb = np.stack([cv2_resize_linear_u8(x[..., ::-1], 256, 256) for x in f])
+    return torch.from_numpy(np.ascontiguousarray((rgb.astype(np.float32) / np.float32(255.0)).transpose(0, 3, 1, 2)))
+
+
+def emonet_clip_features(sd, frames_bgr, feature_level="UTTERANCE"):
+    """One video through extract_emonet_embedding.py:62-94: batches of 32 frames -> [N, 256]; FRAME -> [T, 256]
+    (zeros((1, D)) when empty), UTTERANCE -> mean over frames."""
+    frames = np.asarray(frames_bgr)
+    if len(frames) == 0:
+        return np.zeros((1, 256)) if feature_level == "FRAME" else np.zeros((256,))
+    x = emonet_preprocess(frames)
+    emb = torch.cat([E.emonet_embedding(sd, b) for b in split_into_batch(x, 32)], dim=0).float().numpy()
+    emb = np.array(emb).squeeze()
+    if feature_level == "FRAME":
+        return emb[np.newaxis, :] if emb.ndim == 1 else emb
+    return np.mean(emb, axis=0) if emb.ndim == 2 else emb
+
+
 def manet_preprocess(frames_bgr):
     """FaceDataset.__getitem__ (dataset.py:40-47) + the transform of extract_manet_embedding.py:60-61:
     Resize((224, 224)) (PIL bilinear) and ToTensor only (no normalisation).  Returns [N, 3, 224, 224] in [0, 1]."""

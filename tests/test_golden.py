@@ -262,3 +262,21 @@ def test_resnet18_oracle_matches_the_msceleb_reference_classes_golden():
         for level, key in (("FRAME", "fra"), ("UTTERANCE", "utt")):
             got, ref = P.imagenet_clip_features(sd, frames, level), g[f"{key}_{vid}"]
             assert got.shape == ref.shape and _rel(got, ref) < 1e-6, (vid, level)
+
+
+def test_emonet_oracle_matches_reference_extractor_golden():
+    """EmoNet restatement (pre-activation ConvBlocks, two hourglasses, heat-map mask, emotion tower) + the
+    DataAugmentor / ToTensor restatement against outputs of the unmodified reference model, dataset and augmentor."""
+    import importlib.util
+    from oracle import pipeline as P
+    spec = importlib.util.spec_from_file_location("make_golden_emonet", os.path.join(G, "make_golden_emonet.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(G, "emonet_golden.npz"))
+    sd = _t(S.emonet_state_dict(int(g["seed"])))
+    for vid, frames in mod.golden_clips().items():
+        x = (P.emonet_preprocess(frames[:1]).numpy()[0] * 255.0).round().astype(np.uint8)
+        assert np.array_equal(x[:, ::8, ::8], g[f"x_{vid}"]), vid          # cv2.resize restatement: bit-exact
+        for level, key in (("FRAME", "fra"), ("UTTERANCE", "utt")):
+            got, ref = P.emonet_clip_features(sd, frames, level), g[f"{key}_{vid}"]
+            assert got.shape == ref.shape and _rel(got, ref) < 2e-5, (vid, level)

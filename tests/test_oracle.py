@@ -264,3 +264,11 @@ def test_oracle_vggish_matches_the_torch_port_graph():
         got = E.vggish_embeddings(tf_sd, x)
     assert tf_sd["vggish/conv2/weights"].shape == (3, 3, 64, 128) and tf_sd["vggish/fc1/fc1_1/weights"].shape == (12288, 4096)
     assert got.shape == (2, 128) and float((got - ref).abs().max()) < 1e-5 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("hw", [(112, 112), (300, 300), (224, 224), (256, 256), (100, 180), (512, 512), (31, 47), (513, 257)])
+def test_cv2_resize_restatement_is_bit_exact(hw):
+    """oracle.pipeline.cv2_resize_linear_u8 against cv2.resize itself (OpenCV is part of this image)."""
+    cv2 = pytest.importorskip("cv2")
+    img = np.random.default_rng(hw[0]).integers(0, 256, (hw[0], hw[1], 3), dtype=np.uint8)
+    assert np.array_equal(P.cv2_resize_linear_u8(img, 256, 256), cv2.resize(img, (256, 256)))
