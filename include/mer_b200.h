@@ -198,6 +198,11 @@ MER_API int mer_resize_bilinear_u8(const uint8_t* in, int n, int H, int W, uint8
 /* same with a filter choice: 0 = BILINEAR, 1 = BICUBIC (Pillow's a = -0.5 cubic; HF CLIPImageProcessor) */
 MER_API int mer_resize_u8(const uint8_t* in, int n, int H, int W, uint8_t* out, int OH, int OW, int filter,
                           void* workspace, void* stream);
+/* cv2.resize(frame, (out_w, out_h)) with the default INTER_LINEAR, bit-exact against OpenCV 4.13 (fixed-point
+ * coefficients, border rules and the 2x-downscale area path of imgproc/src/resize.cpp): what the EmoNet extractor's
+ * DataAugmentor does to every face (emonet/data_augmentation.py:77).  frames uint8 [n, h, w, 3] -> [n, out_h, out_w, 3]. */
+MER_API int mer_resize_cv2_linear_u8(const uint8_t* frames, int n, int h, int w, uint8_t* out, int out_h, int out_w,
+                                     void* stream);
 
 /* ---- ViT-B/16 frame encoder (visual) ------------------------------------------------------------ */
 typedef struct MerVitModel {
@@ -281,11 +286,13 @@ MER_API int mer_resnet18_forward(const MerResnet18Model* model, const uint8_t* f
                                  void* workspace, long long workspace_bytes, float* out_feats, void* stream);
 
 /* ---- table-driven CNN executor: frame-level CNN extractors as chains of conv (+ folded BatchNorm, + residual,
- * + ReLU), MaxPool2d(3, 2), crops / channel slices, gates and average pools over eight NHWC fp32 activation buffers.
+ * + ReLU), max-pools, crops / channel slices, gates, per-channel affines, upsample-adds and average pools over up to
+ * 24 NHWC fp32 activation buffers.
  * Users: resnet50_ferplus_dag / senet50_ferplus_dag up to conv5_3_3x3_relu + AvgPool2d(7)
  * (MERBench/feature_extraction/visual/extract_ferplus_embedding.py:81-115, default --layer_name;
- * pytorch-benchmarks/model/resnet50_ferplus_dag.py:178-355) and MA-Net's 1024-d embedding
- * (extract_manet_embedding.py:31-41; manet/model/manet.py:222-270). */
+ * pytorch-benchmarks/model/resnet50_ferplus_dag.py:178-355), MA-Net's 1024-d embedding
+ * (extract_manet_embedding.py:31-41; manet/model/manet.py:222-270) and EmoNet's 256-d embedding
+ * (extract_emonet_embedding.py:22-33; emonet/models/emonet.py:173-222). */
 enum { MER_CNN_STEM = 0,    /* dst = act(conv(frames)): 7x7 / 2 / pad 3 on the uint8 input, preprocessing fused */
        MER_CNN_CONV = 1,    /* dst = act(conv(src[..., p0 : p0 + cin]) [+ res]); dst may equal res (in-place update) */
        MER_CNN_MAXPOOL = 2, /* dst = MaxPool2d(3, 2, pad, ceil_mode)(src), windows clipped to the image */
@@ -298,15 +305,19 @@ enum { MER_CNN_STEM = 0,    /* dst = act(conv(frames)): 7x7 / 2 / pad 3 on the u
        MER_CNN_SHAPE = 6,   /* declares dst as an [H, W] map like src with p0 channels (filled by SLICE ops) */
        MER_CNN_SLICE = 7,   /* dst[..., p1 : p1 + p2] = f(src[..., p0 : p0 + p2]) [+ res[..., p3 : p3 + p2]];
                                relu = 1: f = ReLU; relu = 2: ReLU of the sum */
+       MER_CNN_AFFINE = 9,  /* dst = act(src[..., p0 : p0 + C] * a + b) per channel (a pre-activation BatchNorm): conv = an
+                               entry whose w is a plain fp32 [C] scale and b the [C] shift, C = its cout; relu = ReLU */
+       MER_CNN_UPADD = 10,  /* dst = res + nearest x2 upsample of src (res is [2H, 2W]); dst may equal res */
+       MER_CNN_MASKMUL = 11,/* dst[..., p1 : p1 + p2] = src[..., p0 : p0 + p2] * sum over the first p3 channels of res */
        MER_CNN_CBAM = 8 };  /* MA-Net AttentionBlock end: dst = relu(CBAM(src) + res) on maps of <= 64 positions;
                                conv = ChannelGate.mlp.1, p0 = ChannelGate.mlp.3 (plain fp32 dense layers as for SE),
                                p1 = the SpatialGate 7x7 conv: w plain fp32 [2 * 49] with its BatchNorm folded, b [1] */
 typedef struct MerCnnOp {
   int kind;  /* MER_CNN_* */
   int conv;  /* STEM / CONV / SE / CBAM: index into convs */
-  int src, dst, res; /* buffer indices 0..7; res = -1 for none */
+  int src, dst, res; /* buffer indices 0..23; res = -1 for none */
   int relu;  /* STEM / CONV: ReLU (after the residual add); SLICE: see above */
-  int k, stride, pad, ceil_mode; /* MAXPOOL (k = 3, stride = 2); SE: k = index of the "up" layer */
+  int k, stride, pad, ceil_mode; /* MAXPOOL (3 / 2 / pad / ceil, or k = 2: plain 2x2 / 2); SE: k = the "up" layer */
   int p[4];  /* op-specific parameters (see the enum) */
 } MerCnnOp;
 typedef struct MerCnnModel {

@@ -411,3 +411,59 @@ extern "C" int mer_resize_u8(const uint8_t* in, int n, int H, int W, uint8_t* ou
   }
   return 0;
 }
+
+// ---- cv2.resize(..., INTER_LINEAR) on uint8 HWC frames, bit-exact (OpenCV imgproc/src/resize.cpp: 11-bit fixed-point
+// coefficients; the x fraction is reset at the borders, the y rows are only clamped; vertical pass
+// ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2 >> 2; an exact 2x downscale is the 2 x 2 area average).
+// The EmoNet extractor's DataAugmentor resizes faces this way (emonet/data_augmentation.py:77). ----
+namespace {
+__device__ __forceinline__ void cv_coeff(int d, double scale, int& s, int& a0, int& a1) {
+  float f = (float)__dsub_rn(__dmul_rn((double)d + 0.5, scale), 0.5);  // two roundings, as the host code (no FMA)
+  s = (int)floorf(f);
+  f -= (float)s;
+  a1 = __float2int_rn(f * 2048.f);
+  a0 = __float2int_rn((1.f - f) * 2048.f);
+}
+
+__global__ void __launch_bounds__(256)
+resize_cv2_linear_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, long long total, int H, int W, int OH,
+                         int OW, double sy_scale, double sx_scale) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int ox = (int)(idx % OW), oy = (int)((idx / OW) % OH);
+  const long long n = idx / ((long long)OW * OH);
+  const uint8_t* img = in + n * H * W * 3;
+  uint8_t* o = out + idx * 3;
+  if (H == 2 * OH && W == 2 * OW) {
+    const uint8_t* p = img + ((long long)(2 * oy) * W + 2 * ox) * 3;
+    for (int c = 0; c < 3; ++c) o[c] = (uint8_t)((p[c] + p[3 + c] + p[W * 3 + c] + p[W * 3 + 3 + c] + 2) >> 2);
+    return;
+  }
+  int sx, ax0, ax1, sy, ay0, ay1;
+  cv_coeff(ox, sx_scale, sx, ax0, ax1);
+  if (sx < 0) { sx = 0; ax0 = 2048; ax1 = 0; }
+  if (sx >= W - 1) { sx = W - 1; ax0 = 2048; ax1 = 0; }
+  cv_coeff(oy, sy_scale, sy, ay0, ay1);
+  const int y0 = min(max(sy, 0), H - 1), y1 = min(max(sy + 1, 0), H - 1), x1 = min(sx + 1, W - 1);
+  const uint8_t* r0 = img + (long long)y0 * W * 3;
+  const uint8_t* r1 = img + (long long)y1 * W * 3;
+  for (int c = 0; c < 3; ++c) {
+    const int h0 = r0[sx * 3 + c] * ax0 + r0[x1 * 3 + c] * ax1;
+    const int h1 = r1[sx * 3 + c] * ax0 + r1[x1 * 3 + c] * ax1;
+    const int v = (((ay0 * (h0 >> 4)) >> 16) + ((ay1 * (h1 >> 4)) >> 16) + 2) >> 2;
+    o[c] = (uint8_t)min(max(v, 0), 255);
+  }
+}
+}  // namespace
+
+extern "C" int mer_resize_cv2_linear_u8(const uint8_t* in, int n, int H, int W, uint8_t* out, int OH, int OW,
+                                        void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MER_REQUIRE(in && out && in != out && n > 0 && H > 0 && W > 0 && OH > 0 && OW > 0, "mer_resize_cv2_linear_u8: bad arguments");
+  const long long total = (long long)n * OH * OW;
+  resize_cv2_linear_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, out, total, H, W, OH, OW,
+                                                                                (double)H / OH, (double)W / OW);
+  MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
+  return 0;
+}

@@ -482,7 +482,7 @@ int mer_vggish_forward(const MerVggishModel* m, const float* examples, int n_exa
 // MA-Net (extract_manet_embedding.py). ----
 namespace {
 
-constexpr int CNN_BUFS = 8;
+constexpr int CNN_BUFS = 24;
 
 // dst = src[:, y0:y0+h, x0:x0+w, :]  (NHWC fp32, 4 channels per thread)
 __global__ void __launch_bounds__(256)
@@ -614,6 +614,49 @@ gap_kernel(const float* __restrict__ x, int hw, int C, int Cs, float* __restrict
   }
 }
 
+// dst[r, j] = act(src[r, s0 + j] * a[j] + b[j]) for j < C (pre-activation BatchNorm of EmoNet's ConvBlocks); 4 channels
+// per thread, dst rows are C wide
+__global__ void __launch_bounds__(256)
+affine_kernel(const float* __restrict__ src, int s_ld, int s0, const float4* __restrict__ a, const float4* __restrict__ b,
+              float4* __restrict__ dst, int c4, int relu, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int j = (int)(idx % c4);
+  const long long r = idx / c4;
+  const float4 v = __ldg(reinterpret_cast<const float4*>(src + r * s_ld + s0) + j), sa = __ldg(a + j), sb = __ldg(b + j);
+  float4 o = make_float4(fmaf(v.x, sa.x, sb.x), fmaf(v.y, sa.y, sb.y), fmaf(v.z, sa.z, sb.z), fmaf(v.w, sa.w, sb.w));
+  if (relu) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+  dst[idx] = o;
+}
+
+// dst = big + nearest-neighbour x2 upsample of small (F.interpolate(scale_factor=2)); big / dst are [n, 2h, 2w, c]
+__global__ void __launch_bounds__(256)
+upadd_kernel(const float4* __restrict__ big, const float4* __restrict__ small, int h2, int w2, int c4,
+             float4* __restrict__ dst, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % c4);
+  const long long pos = idx / c4;
+  const int x = (int)(pos % w2), y = (int)((pos / w2) % h2);
+  const long long n = pos / ((long long)w2 * h2);
+  const float4 a = __ldg(big + idx), s = __ldg(small + ((n * (h2 / 2) + y / 2) * (w2 / 2) + x / 2) * (long long)c4 + c);
+  dst[idx] = make_float4(a.x + s.x, a.y + s.y, a.z + s.z, a.w + s.w);
+}
+
+// dst[r, d0 + j] = src[r, s0 + j] * sum_{c < mc} mask[r, c]   (EmoNet: features times the summed heat-maps);
+// one warp per row
+__global__ void __launch_bounds__(256)
+maskmul_kernel(const float* __restrict__ src, int s_ld, int s0, const float* __restrict__ mask, int m_ld, int mc,
+               float* __restrict__ dst, int d_ld, int d0, int width, long long rows) {
+  const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float m = 0.f;
+  for (int c = lane; c < mc; c += 32) m += mask[r * m_ld + c];
+  m = warp_sum(m);
+  for (int j = lane; j < width; j += 32) dst[r * d_ld + d0 + j] = src[r * s_ld + s0 + j] * m;
+}
+
 struct CnnPlan { long long off_buf[CNN_BUFS], off_col, off_cu, off_z, off_scale, total; };
 
 int pool_out(int in, int pad, int ceil_mode) {  // torch MaxPool2d(3, 2, pad, ceil_mode) output size
@@ -722,7 +765,21 @@ int cnn_walk(const MerCnnModel* m, int n_frames, bool exec, CnnPlan* plan, char*
       }
       case MER_CNN_MAXPOOL: {
         const Shape in = sh[op.src];
-        MER_REQUIRE(in.H > 0 && op.k == 3 && op.stride == 2 && op.src != op.dst, "mer_cnn: op %d max-pool", i);
+        MER_REQUIRE(in.H > 0 && (op.k == 3 || op.k == 2) && op.stride == 2 && op.src != op.dst,
+                    "mer_cnn: op %d max-pool", i);
+        if (op.k == 2) {  // max_pool2d(x, 2, 2) on even maps
+          MER_REQUIRE(in.H % 2 == 0 && in.W % 2 == 0 && op.pad == 0, "mer_cnn: op %d 2x2 max-pool of a %d x %d map", i,
+                      in.H, in.W);
+          define(op.dst, Shape{in.H / 2, in.W / 2, in.C, in.Cs});
+          if (!exec) break;
+          const long long total2 = n * (in.H / 2) * (in.W / 2) * (in.Cs / 4);
+          maxpool2x2_kernel<<<(unsigned)((total2 + 255) / 256), 256, 0, st>>>(
+              reinterpret_cast<const float4*>(buf[op.src]), in.H, in.W, in.Cs / 4, reinterpret_cast<float4*>(buf[op.dst]),
+              total2);
+          MER_CUDA_CHECK(cudaGetLastError());
+          mer_count_launches(1);
+          break;
+        }
         const int OH = pool_out(in.H, op.pad, op.ceil_mode), OW = pool_out(in.W, op.pad, op.ceil_mode);
         define(op.dst, Shape{OH, OW, in.C, in.Cs});
         if (!exec) break;
@@ -817,6 +874,53 @@ int cnn_walk(const MerCnnModel* m, int n_frames, bool exec, CnnPlan* plan, char*
         cbam_kernel<<<n_frames, 256, smem, st>>>(buf[op.src], buf[op.res], static_cast<const float*>(l1.w), l1.b,
                                                  static_cast<const float*>(l2.w), l2.b, static_cast<const float*>(sp.w),
                                                  sp.b, in.H, in.W, in.C, l1.cout, buf[op.dst]);
+        MER_CUDA_CHECK(cudaGetLastError());
+        mer_count_launches(1);
+        break;
+      }
+      case MER_CNN_AFFINE: {
+        const Shape in = sh[op.src];
+        MER_REQUIRE(op.conv >= 0 && op.conv < m->n_convs, "mer_cnn: op %d affine layer", i);
+        const MerResnetConv& af = m->convs[op.conv];
+        const int s0 = op.p[0], Cc = af.cout;
+        MER_REQUIRE(in.H > 0 && op.src != op.dst && Cc > 0 && Cc % 4 == 0 && s0 >= 0 && s0 % 4 == 0 && s0 + Cc <= in.Cs,
+                    "mer_cnn: op %d affine over channels [%d, %d) of %d", i, s0, s0 + Cc, in.Cs);
+        define(op.dst, Shape{in.H, in.W, Cc, Cc});
+        if (!exec) break;
+        const long long total = n * in.H * in.W * (Cc / 4);
+        affine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+            buf[op.src], in.Cs, s0, static_cast<const float4*>(af.w), reinterpret_cast<const float4*>(af.b),
+            reinterpret_cast<float4*>(buf[op.dst]), Cc / 4, op.relu != 0, total);
+        MER_CUDA_CHECK(cudaGetLastError());
+        mer_count_launches(1);
+        break;
+      }
+      case MER_CNN_UPADD: {
+        const Shape lo = sh[op.src];
+        MER_REQUIRE(op.res >= 0 && lo.H > 0 && sh[op.res].H == 2 * lo.H && sh[op.res].W == 2 * lo.W &&
+                        sh[op.res].Cs == lo.Cs && op.src != op.dst,
+                    "mer_cnn: op %d upsample-add shapes", i);
+        define(op.dst, sh[op.res]);
+        if (!exec) break;
+        const long long total = n * 4 * lo.H * lo.W * (lo.Cs / 4);
+        upadd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(buf[op.res]), reinterpret_cast<const float4*>(buf[op.src]), 2 * lo.H, 2 * lo.W,
+            lo.Cs / 4, reinterpret_cast<float4*>(buf[op.dst]), total);
+        MER_CUDA_CHECK(cudaGetLastError());
+        mer_count_launches(1);
+        break;
+      }
+      case MER_CNN_MASKMUL: {
+        const Shape a = sh[op.src], d = sh[op.dst];
+        const int s0 = op.p[0], d0 = op.p[1], w = op.p[2], mc = op.p[3];
+        MER_REQUIRE(op.res >= 0 && a.H > 0 && d.H == a.H && d.W == a.W && sh[op.res].H == a.H && sh[op.res].W == a.W &&
+                        w > 0 && s0 >= 0 && d0 >= 0 && s0 + w <= a.Cs && d0 + w <= d.Cs && mc > 0 && mc <= sh[op.res].Cs,
+                    "mer_cnn: op %d mask-multiply", i);
+        if (!exec) break;
+        const long long rows = n * a.H * a.W;
+        maskmul_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(buf[op.src], a.Cs, s0, buf[op.res],
+                                                                            sh[op.res].Cs, mc, buf[op.dst], d.Cs, d0, w,
+                                                                            rows);
         MER_CUDA_CHECK(cudaGetLastError());
         mer_count_launches(1);
         break;

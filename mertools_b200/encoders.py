@@ -349,7 +349,8 @@ class MerCnnModel(C.Structure):
                 ("scale", C.c_float), ("mean", C.c_float * 3), ("std", C.c_float * 3), ("feat_dim", C.c_int)]
 
 
-CNN_STEM, CNN_CONV, CNN_MAXPOOL, CNN_GAP, CNN_SE, CNN_CROP, CNN_SHAPE, CNN_SLICE, CNN_CBAM = range(9)
+CNN_STEM, CNN_CONV, CNN_MAXPOOL, CNN_GAP, CNN_SE, CNN_CROP, CNN_SHAPE, CNN_SLICE, CNN_CBAM, CNN_AFFINE, CNN_UPADD, \
+    CNN_MASKMUL = range(12)
 FERPLUS_BLOCKS = (3, 4, 6, 3)
 
 
@@ -542,6 +543,143 @@ def manet_tables(state_dict, pack, pack_dense=None, bn_eps=1e-5):
     return m, [conv_arr, op_arr]
 
 
+def emonet_tables(state_dict, pack, pack_dense=None, bn_eps=1e-5):
+    """Conv and op tables of the reference's EmoNet (emonet/models/emonet.py:173-222) for mer_cnn_forward: the 256-d
+    embedding after the emotion tower's average pool.  Pre-activation ConvBlocks become AFFINE (BatchNorm + ReLU) ->
+    CONV triples whose outputs land in channel slices next to the shortcut; the hourglass recursion keeps one
+    skip buffer and one low-resolution buffer per level.
+    Buffers: 0 = x (trunk, 64 x 64 x 256), 1 = the hourglass input ("previous"), 2 / 3 = the two modules' features,
+    4 = heat-maps, 5 = concatenation, 6..10 = ConvBlock scratch, 11..14 = skip buffers, 15..18 = low buffers of
+    hourglass levels 1..4, 19 / 20 = stem / tower ping-pong."""
+    sd = W._np(state_dict)
+    pack_dense = pack_dense or pack
+    convs, ops = [], []
+    A_, U1, U2, U3, R_ = 6, 7, 8, 9, 10
+
+    def bn_affine(name):
+        scale = np.asarray(sd[name + ".weight"], np.float64) / np.sqrt(np.asarray(sd[name + ".running_var"], np.float64) + bn_eps)
+        return scale, np.asarray(sd[name + ".bias"], np.float64) - np.asarray(sd[name + ".running_mean"], np.float64) * scale
+
+    def add_conv(name, stride=1, pad=0, post_bn=None, cin_pad=None, cout_real=None):
+        w = np.asarray(sd[name + ".weight"], np.float64)
+        b = np.asarray(sd[name + ".bias"], np.float64) if name + ".bias" in sd else np.zeros(w.shape[0])
+        if post_bn is not None:                                # conv (+ bias) followed by a BatchNorm: fold
+            sc, sh = bn_affine(post_bn)
+            w, b = w * sc[:, None, None, None], b * sc + sh
+        cout, cin, k, _ = w.shape
+        cin_p = cin_pad or cin
+        cout_r = cout_real or cout                             # channels declared real (zero rows beyond cout)
+        cout_pad, kk = max(cout_r, 128), k * k * cin_p
+        kpad = 160 if cin == 3 else kk
+        wp = np.zeros((cout_pad, k, k, cin_p), np.float32)
+        wp[:cout, :, :, :cin] = w.transpose(0, 2, 3, 1)
+        wp = wp.reshape(cout_pad, k * k * cin_p)
+        if kpad != kk:
+            wp = np.concatenate([wp, np.zeros((cout_pad, kpad - kk), np.float32)], axis=1)
+        bp = np.zeros(cout_pad, np.float32)
+        bp[:cout] = b
+        c = MerResnetConv()
+        c.w, c.b = pack(np.ascontiguousarray(wp), bp)
+        c.cin, c.cout, c.cout_pad, c.k, c.stride, c.pad, c.kpad = cin_p, cout_r, cout_pad, k, stride, pad, kpad
+        convs.append(c)
+        return len(convs) - 1
+
+    def add_affine(bn_name):
+        sc, sh = bn_affine(bn_name)
+        c = MerResnetConv()
+        c.w, c.b = pack_dense(sc.astype(np.float32), sh.astype(np.float32))
+        c.cin = c.cout = c.cout_pad = c.kpad = len(sc)
+        c.k, c.stride, c.pad = 1, 1, 0
+        convs.append(c)
+        return len(convs) - 1
+
+    def op(kind, conv=-1, src=0, dst=0, res=-1, relu=0, k=0, stride=0, pad=0, ceil_mode=0, p=(0, 0, 0, 0)):
+        ops.append(MerCnnOp(kind, conv, src, dst, res, relu, k, stride, pad, ceil_mode, (C.c_int * 4)(*p)))
+
+    def block(pfx, src, dst):
+        """ConvBlock (:20-64): dst = cat(o1, o2, o3) + shortcut; dst may be src when there is no downsample."""
+        c1 = add_conv(pfx + "conv1", 1, 1)
+        c2 = add_conv(pfx + "conv2", 1, 1)
+        c3 = add_conv(pfx + "conv3", 1, 1)
+        h, q = convs[c1].cout, convs[c2].cout                  # out / 2, out / 4
+        op(CNN_AFFINE, add_affine(pfx + "bn1"), src=src, dst=A_, relu=1)
+        op(CNN_CONV, c1, src=A_, dst=U1)
+        op(CNN_AFFINE, add_affine(pfx + "bn2"), src=U1, dst=A_, relu=1)
+        op(CNN_CONV, c2, src=A_, dst=U2)
+        op(CNN_AFFINE, add_affine(pfx + "bn3"), src=U2, dst=A_, relu=1)
+        op(CNN_CONV, c3, src=A_, dst=U3)
+        if pfx + "downsample.2.weight" in sd:
+            assert dst != src
+            op(CNN_AFFINE, add_affine(pfx + "downsample.0"), src=src, dst=A_, relu=1)
+            op(CNN_CONV, add_conv(pfx + "downsample.2"), src=A_, dst=R_)
+            shortcut = R_
+        else:
+            shortcut = src
+        if dst != src:
+            op(CNN_SHAPE, src=U1, dst=dst, p=(h + 2 * q, 0, 0, 0))
+        op(CNN_SLICE, src=U1, dst=dst, res=shortcut, p=(0, 0, h, 0))
+        op(CNN_SLICE, src=U2, dst=dst, res=shortcut, p=(0, h, q, h))
+        op(CNN_SLICE, src=U3, dst=dst, res=shortcut, p=(0, h + q, q, h + q))
+
+    def hourglass(pfx, level, inp):
+        """HourGlass._forward (:87-109); the result lands in the level's skip buffer."""
+        up, low = 10 + level, 14 + level
+        block(pfx + f"b1_{level}.", inp, up)
+        op(CNN_MAXPOOL, src=inp, dst=low, k=2, stride=2)
+        block(pfx + f"b2_{level}.", low, low)
+        if level > 1:
+            low2 = hourglass(pfx, level - 1, low)
+        else:
+            block(pfx + f"b2_plus_{level}.", low, low)
+            low2 = low
+        block(pfx + f"b3_{level}.", low2, low2)
+        op(CNN_UPADD, src=low2, dst=up, res=up)
+        return up
+
+    op(CNN_STEM, add_conv("conv1", 2, 3, post_bn="bn1"), dst=19, relu=1)              # [128, 128, 64]
+    block("conv2.", 19, 20)                                                           # -> 128 channels
+    op(CNN_MAXPOOL, src=20, dst=19, k=2, stride=2)                                    # [64, 64, 128]
+    block("conv3.", 19, 19)
+    block("conv4.", 19, 0)                                                            # x
+    op(CNN_SHAPE, src=0, dst=1, p=(256, 0, 0, 0))
+    op(CNN_SLICE, src=0, dst=1, p=(0, 0, 256, 0))                                     # previous = x
+    for i in range(2):
+        hg = hourglass(f"m{i}.", 4, 1)
+        block(f"top_m_{i}.", hg, hg)
+        feat = 2 + i
+        op(CNN_CONV, add_conv(f"conv_last{i}", post_bn=f"bn_end{i}"), src=hg, dst=feat if i == 1 else 20, relu=1)
+        ll = feat if i == 1 else 20
+        op(CNN_CONV, add_conv(f"l{i}", cout_real=128), src=ll, dst=4)                  # 68 heat-maps (+ 60 zero channels)
+        if i < 1:
+            op(CNN_CONV, add_conv(f"bl{i}"), src=ll, dst=feat)                          # the feature kept for module 0
+            op(CNN_CONV, add_conv(f"al{i}", cin_pad=128), src=4, dst=A_)
+            op(CNN_SLICE, src=feat, dst=1, res=1, p=(0, 0, 256, 0))                     # previous += ll
+            op(CNN_SLICE, src=A_, dst=1, res=1, p=(0, 0, 256, 0))                       # previous += al(heat)
+    op(CNN_SHAPE, src=0, dst=5, p=(768, 0, 0, 0))
+    op(CNN_SLICE, src=0, dst=5, p=(0, 0, 256, 0))
+    op(CNN_MASKMUL, src=2, dst=5, res=4, p=(0, 256, 256, 68))
+    op(CNN_MASKMUL, src=3, dst=5, res=4, p=(0, 512, 256, 68))
+    op(CNN_CONV, add_conv("conv1x1_input_emo_2"), src=5, dst=19)
+    cur, other = 19, 20
+    for i in range(4):
+        block(f"emo_net_2.{2 * i}.", cur, cur)
+        op(CNN_MAXPOOL, src=cur, dst=other, k=2, stride=2)
+        cur, other = other, cur
+    op(CNN_GAP, src=cur, p=(0, 0, 1, 0))
+    conv_arr = (MerResnetConv * len(convs))(*convs)
+    op_arr = (MerCnnOp * len(ops))(*ops)
+    m = MerCnnModel()
+    m.convs, m.n_convs = conv_arr, len(convs)
+    m.ops, m.n_ops = op_arr, len(ops)
+    m.gemm_mode = L.MER_GEMM_BF16X3
+    m.in_h = m.in_w = 256
+    m.scale = 1.0 / 255.0
+    m.mean = (C.c_float * 3)(0.0, 0.0, 0.0)
+    m.std = (C.c_float * 3)(1.0, 1.0, 1.0)
+    m.feat_dim = 256
+    return m, [conv_arr, op_arr]
+
+
 class _CnnEncoder:
     """Shared driver of the table-driven CNN extractors: device-side PIL-bilinear resize (+ optional centre crop) to
     224 x 224, then mer_cnn_forward in chunks of frames."""
@@ -623,6 +761,39 @@ class ManetEncoder(_CnnEncoder):
 
     def __init__(self, state_dict, device="cuda", bn_eps=1e-5):
         self._setup(device, lambda pack, dense: manet_tables(state_dict, pack, dense, bn_eps), 1024)
+
+
+class EmonetEncoder(_CnnEncoder):
+    """EmoNet (the 8-class AffectNet checkpoint the reference extracts ``emonet_<UTT|FRA>`` features with): stem,
+    pre-activation ConvBlocks, two depth-4 hourglasses, heat-map mask, emotion tower; 256-d embedding.
+    Faces are resized to 256 x 256 with the bit-exact cv2 INTER_LINEAR kernel (the reference's DataAugmentor).
+
+    Reference: MERBench/feature_extraction/visual/extract_emonet_embedding.py:22-61,
+    emonet/models/emonet.py:20-222, emonet/data_augmentation.py:68-87."""
+
+    def __init__(self, state_dict, device="cuda", bn_eps=1e-5):
+        self._setup(device, lambda pack, dense: emonet_tables(state_dict, pack, dense, bn_eps), 256)
+        self._cv2 = L.declare("mer_resize_cv2_linear_u8", [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                                           C.c_int, C.c_void_p])
+
+    def frame_features(self, frames_bgr_u8: torch.Tensor, max_frames=8):
+        """frames: uint8 CUDA [N, H, W, 3] (BGR) -> [N, 256] fp32 (CUDA).  125 MB of workspace per frame."""
+        assert frames_bgr_u8.dtype == torch.uint8 and frames_bgr_u8.is_cuda and frames_bgr_u8.dim() == 4
+        frames = frames_bgr_u8.contiguous()
+        n, h, w, _ = frames.shape
+        if (h, w) != (256, 256):
+            out = torch.empty(n, 256, 256, 3, dtype=torch.uint8, device=self.device)
+            L.check(self._cv2(L.ptr(frames), n, h, w, L.ptr(out), 256, 256, L.stream_ptr()))
+            frames = out
+        feats = torch.empty(n, self.feature_dim, dtype=torch.float32, device=self.device)
+        for s in range(0, n, max_frames):
+            m = min(max_frames, n - s)
+            nbytes = L.lib().mer_cnn_workspace_bytes(C.byref(self.model), m)
+            L.check(0 if nbytes > 0 else 1)
+            ws = self.ws.get(nbytes)
+            L.check(self._fwd(C.byref(self.model), L.ptr(frames[s:s + m]), m, L.ptr(ws), ws.numel(),
+                              L.ptr(feats[s:s + m]), L.stream_ptr()))
+        return feats
 
 
 class MerVggishModel(C.Structure):

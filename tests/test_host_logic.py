@@ -320,7 +320,7 @@ def _interpret_cnn_tables(m, store, frames_bgr):
     mean = torch.tensor([m.mean[i] for i in range(3)])
     std = torch.tensor([m.std[i] for i in range(3)])
     x0 = (torch.from_numpy(np.ascontiguousarray(frames_bgr[..., ::-1])).float() * m.scale - mean) / std  # NHWC, RGB
-    buf, real = [None] * 8, [0] * 8
+    buf, real = [None] * 24, [0] * 24
     out = torch.full((n, m.feat_dim), float("nan"))
     T = torch.from_numpy
 
@@ -346,9 +346,21 @@ def _interpret_cnn_tables(m, store, frames_bgr):
                 y = y + buf[op.res]
             buf[op.dst], real[op.dst] = (torch.relu(y) if op.relu else y), c.cout
         elif op.kind == En.CNN_MAXPOOL:
-            assert op.k == 3 and op.stride == 2 and op.src != op.dst
-            y = F.max_pool2d(buf[op.src].permute(0, 3, 1, 2), 3, 2, op.pad, ceil_mode=bool(op.ceil_mode))
+            assert op.k in (2, 3) and op.stride == 2 and op.src != op.dst
+            xin = buf[op.src].permute(0, 3, 1, 2)
+            y = F.max_pool2d(xin, 2, 2) if op.k == 2 else F.max_pool2d(xin, 3, 2, op.pad, ceil_mode=bool(op.ceil_mode))
             buf[op.dst], real[op.dst] = y.permute(0, 2, 3, 1), real[op.src]
+        elif op.kind == En.CNN_AFFINE:
+            af = m.convs[op.conv]
+            v = buf[op.src][..., p[0]:p[0] + af.cout] * T(store[af.w]) + T(store[af.b])
+            assert op.src != op.dst
+            buf[op.dst], real[op.dst] = (torch.relu(v) if op.relu else v), af.cout
+        elif op.kind == En.CNN_UPADD:
+            up = buf[op.src].repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+            buf[op.dst], real[op.dst] = buf[op.res] + up, real[op.res]
+        elif op.kind == En.CNN_MASKMUL:
+            mask = buf[op.res][..., :p[3]].sum(dim=3, keepdim=True)
+            buf[op.dst][..., p[1]:p[1] + p[2]] = buf[op.src][..., p[0]:p[0] + p[2]] * mask
         elif op.kind == En.CNN_SE:
             dn, up = m.convs[op.conv], m.convs[op.k]
             y = buf[op.src]
@@ -479,3 +491,33 @@ def test_manet_op_tables_reproduce_the_reference_golden_on_a_cpu_interpreter():
     dll.mer_cnn_workspace_bytes.restype = C.c_longlong
     dll.mer_cnn_workspace_bytes.argtypes = [C.POINTER(En.MerCnnModel), C.c_int]
     assert m.n_convs == 136 and dll.mer_cnn_workspace_bytes(C.byref(m), 2) > 0   # the C++ planner accepts the table
+
+
+def test_emonet_op_tables_reproduce_the_reference_golden_on_a_cpu_interpreter():
+    """The 222 layers / 367 ops EmoNet hands to mer_cnn_forward (folded stem, AFFINE -> CONV pre-activation triples
+    written into channel slices, the two depth-4 hourglasses with their skip / low buffers, heat-map mask,
+    emotion tower), run by the torch interpreter, against outputs of the unmodified reference model."""
+    import ctypes as C
+    import importlib.util
+
+    from mertools_b200 import _lib
+    from mertools_b200 import encoders as En
+    gdir = os.path.join(ROOT, "tests", "golden")
+    spec = importlib.util.spec_from_file_location("make_golden_emonet", os.path.join(gdir, "make_golden_emonet.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(gdir, "emonet_golden.npz"))
+    store = {}
+
+    def pack(w, b):
+        store[len(store) + 1] = np.asarray(w, np.float32)
+        store[len(store) + 1] = np.asarray(b, np.float32)
+        return len(store) - 1, len(store)
+    m, _keep = En.emonet_tables(S.emonet_state_dict(int(g["seed"])), pack)
+    got = _interpret_cnn_tables(m, store, mod.golden_clips()["vidA"][:1])           # 256 x 256: no resize needed
+    ref = g["fra_vidA"][:1]
+    assert got.shape == ref.shape and np.abs(got - ref).max() / np.abs(ref).max() < 1e-4
+    dll = _lib.lib()
+    dll.mer_cnn_workspace_bytes.restype = C.c_longlong
+    dll.mer_cnn_workspace_bytes.argtypes = [C.POINTER(En.MerCnnModel), C.c_int]
+    assert dll.mer_cnn_workspace_bytes(C.byref(m), 2) > 0

@@ -373,3 +373,56 @@ def test_msceleb_extractor_vs_reference_classes_golden(cuda, tmp_path):
             got = np.load(tmp_path / "feat" / f"msceleb_{level[:3]}" / f"{vid}.npy")
             ref = g[f"{key}_{vid}"]
             assert got.shape == ref.shape and np.abs(got - ref).max() / np.abs(ref).max() < 1e-3, (vid, level)
+
+
+def test_cv2_resize_kernel_is_bit_exact(cuda):
+    cv2 = pytest.importorskip("cv2")
+    import ctypes as C
+
+    import numpy as np
+    fn = L.declare("mer_resize_cv2_linear_u8", [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                                C.c_void_p])
+    for hw in [(112, 112), (300, 300), (224, 224), (100, 180), (512, 512), (31, 47)]:
+        frames = np.random.default_rng(hw[0]).integers(0, 256, (2, hw[0], hw[1], 3), dtype=np.uint8)
+        dev = torch.from_numpy(frames).to(cuda)
+        out = torch.empty(2, 256, 256, 3, dtype=torch.uint8, device=cuda)
+        L.check(fn(L.ptr(dev), 2, hw[0], hw[1], L.ptr(out), 256, 256, L.stream_ptr()))
+        ref = np.stack([cv2.resize(f, (256, 256)) for f in frames])
+        assert np.array_equal(out.cpu().numpy(), ref), hw
+
+
+def test_emonet_vs_reference_golden(cuda, tmp_path):
+    """EmoNet through the CNN executor (affine / slice / upsample-add / mask-multiply ops, cv2-exact resize) against
+    outputs of the unmodified reference model + augmentor, plus the mirrored script's files."""
+    import importlib.util
+    import types
+
+    import numpy as np
+
+    from mertools_b200 import synthetic as S
+    from mertools_b200.encoders import EmonetEncoder
+    from mertools_b200.extract import emonet
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden_emonet", os.path.join(gdir, "make_golden_emonet.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(gdir, "emonet_golden.npz"))
+    sd = S.emonet_state_dict(int(g["seed"]))
+    enc = EmonetEncoder(sd, device=cuda)
+    clips = mod.golden_clips()
+    for vid, frames in clips.items():
+        got = enc.frame_features(torch.from_numpy(frames).to(cuda), max_frames=2).cpu().numpy()
+        ref = g[f"fra_{vid}"]
+        assert got.shape == ref.shape and np.abs(got - ref).max() / np.abs(ref).max() < 1e-3, vid
+    face = tmp_path / "face"
+    for vid, frames in clips.items():
+        os.makedirs(face / vid)
+        np.save(face / vid / f"{vid}.npy", frames)
+    cfg = types.SimpleNamespace(PATH_TO_RAW_FACE={"D": str(face)}, PATH_TO_FEATURES={"D": str(tmp_path / "feat")})
+    for level, key in (("UTTERANCE", "utt"), ("FRAME", "fra")):
+        emonet.main(emonet.build_parser().parse_args(["--dataset=D", f"--feature_level={level}", "--gpu=0"]),
+                    config=cfg, state_dict=sd)
+        for vid in clips:
+            got = np.load(tmp_path / "feat" / f"emonet_{level[:3]}" / f"{vid}.npy")
+            ref = g[f"{key}_{vid}"]
+            assert got.shape == ref.shape and np.abs(got - ref).max() / np.abs(ref).max() < 1e-3, (vid, level)
