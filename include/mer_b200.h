@@ -394,6 +394,16 @@ typedef struct MerHubertModel {
   const MerLayerWeights* layers_f16; /* optional (stable_layer_norm only): the same layers with fp16 GEMM weights;
                               when given, clips of <= 249 frames run the pre-LN stack on fp16 operands
                               (MER_GEMM_F16 + the fp16 attention), longer ones stay BF16X3 */
+  /* ---- data2vec-audio (Data2VecAudioModel, extract_audio_huggingface.py:19-20): instead of the single k = 128
+   * positional conv, a chain of n_pos_layers grouped convs (pos_taps = 19 taps, padding 9, 16 groups, bias), each
+   * followed by an affine-free LayerNorm (eps 1e-5) and GELU; the chain's output is added to its input once.
+   * Used with feat_norm_layer = 1 (bias-free convs: conv_b NULL), stable_layer_norm = 0.  0 = classic conv. */
+  int n_pos_layers;            /* 0, or up to 8 */
+  int pos_taps;                /* odd kernel size of the chain's convs (19) */
+  const void* pos_layers_w[8]; /* fp16 windowed block-diagonal matrices [hidden][pos_taps * pos_window] (as pos_w_bd) */
+  const float* pos_layers_b[8];/* [hidden] */
+  const float* ln_ones;        /* [hidden] ones / zeros: the affine of the affine-free LayerNorms */
+  const float* ln_zeros;
 } MerHubertModel;
 
 /* per-row zero-mean / unit-variance (eps 1e-7) of HF Wav2Vec2FeatureExtractor(do_normalize=True)

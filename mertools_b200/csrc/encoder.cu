@@ -425,7 +425,8 @@ static int hubert_forward_impl(const MerHubertModel* m, const float* wave, int B
   const int D = hub_dim(m), DFF = hub_ffn(m), HEADS = hub_heads(m);
   MER_REQUIRE((D == 768 || D == 1024) && HEADS * 64 == D && DFF % 128 == 0,
               "mer_hubert_forward: hidden %d / heads %d / ffn %d not supported", D, HEADS, DFF);
-  MER_REQUIRE(!m->stable_layer_norm || m->pos_w_bd, "mer_hubert_forward: the stable-layer-norm family needs pos_w_bd");
+  MER_REQUIRE(!m->stable_layer_norm || m->pos_w_bd || m->n_pos_layers > 0,
+              "mer_hubert_forward: the stable-layer-norm family needs pos_w_bd");
   const HubertPlan p = hubert_plan(B, L, D, DFF);
   MER_REQUIRE(p.T[6] > 0, "mer_hubert_forward: %d samples give no output frame", L);
   MER_REQUIRE(workspace_bytes >= p.total, "mer_hubert_forward: workspace %lld B < required %lld B",
@@ -450,7 +451,8 @@ static int hubert_forward_impl(const MerHubertModel* m, const float* wave, int B
   int *d_len = nullptr, *d_t0 = nullptr, *d_tb = nullptr, *d_cu = nullptr;
   long long M_packed = 0;
   if (ragged) {
-    MER_REQUIRE(m->pos_w_bd && !opt_hidden, "mer_hubert_forward_ragged: needs pos_w_bd; hidden states are not returned");
+    MER_REQUIRE((m->pos_w_bd || m->n_pos_layers > 0) && !opt_hidden,
+                "mer_hubert_forward_ragged: needs the GEMM positional conv; hidden states are not returned");
     std::vector<int> meta(4 * (size_t)B + 1);
     int* h_len = meta.data();
     int* h_t0 = h_len + B;
@@ -538,7 +540,48 @@ static int hubert_forward_impl(const MerHubertModel* m, const float* wave, int B
   MER_TRY(linear(MER_GEMM_BF16X3, feat, m->fp_w, m->fp_b, nullptr, x0, M, D, 512, 0, stream));
   // positional conv + GELU + residual -> xn
   MER_TRY(mer_iota_offsets_launch(cu, B, T, stream));
-  if (m->pos_w_bd) {
+  if (m->n_pos_layers > 0) {
+    // data2vec-audio: p_0 = x0;  p_{l+1} = GELU(LayerNorm_noaffine(conv_l(p_l) + b_l));  x1 = x0 + p_L.  Every conv is
+    // the windowed block-diagonal fp16 GEMM of the classic positional conv with pos_taps taps and padding taps / 2.
+    MER_REQUIRE(m->n_pos_layers <= 8 && (m->pos_taps & 1) && m->ln_ones && m->ln_zeros,
+                "mer_hubert_forward: data2vec positional conv chain (%d layers, %d taps)", m->n_pos_layers, m->pos_taps);
+    void* ph = h;  // fp16 copy of the current chain input (the FFN buffer is still unused)
+    const int gch = D / 16;
+    const int window = m->pos_window > 0 ? m->pos_window : 320;
+    const float* cur = x0;
+    for (int l = 0; l < m->n_pos_layers; ++l) {
+      MER_REQUIRE(m->pos_layers_w[l] && m->pos_layers_b[l], "mer_hubert_forward: positional conv layer %d missing", l);
+      MER_TRY(mer_cast_f16_launch(cur, ph, M * D, stream));
+      if (ragged) MER_TRY(mer_zero_tail_rows_f16_launch(ph, d_tb, B, T, D, stream));
+      MerGemmDesc g;
+      memset(&g, 0, sizeof(g));
+      g.A = static_cast<const float*>(ph);
+      g.W = static_cast<const float*>(m->pos_layers_w[l]);
+      g.rows_per_batch = T;
+      g.a_rows_dim = T;
+      g.batches = B;
+      g.N = D;
+      g.K_inner = window;
+      g.taps = m->pos_taps;
+      g.P = 1;
+      g.a_phase_stride = D;
+      g.a_row_stride = D;
+      g.a_batch_stride = (long long)T * D;
+      g.a_row0 = -(m->pos_taps / 2);
+      g.a_cols = D;
+      g.a_col_group = gch;
+      g.force_block_n = 256;
+      g.mode = MER_GEMM_F16;
+      g.ep.bias = m->pos_layers_b[l];
+      g.ep.out = xn;
+      g.ep.out_bstride = T;
+      g.ep.ld_out = D;
+      MER_TRY(mer_gemm_launch(&g, stream));
+      MER_TRY(mer_layernorm_launch(xn, m->ln_ones, m->ln_zeros, xn, nullptr, nullptr, M, D, 1e-5f, MER_LN_GELU, stream));
+      cur = xn;
+    }
+    MER_TRY(mer_accumulate_launch(x0, xn, M * D, 0, stream));  // x1 = p_L + x0
+  } else if (m->pos_w_bd) {
     // grouped conv (k = 128, 16 groups of 48 channels, zero padding 64, last frame dropped) as ONE fp16 GEMM
     // over windowed block-diagonal weights: output block j (256 columns) reads the 320-channel window that
     // starts at floor(256 j / 48) * 48; tap k reads frame t + k - 64 (rows outside the clip are zero).

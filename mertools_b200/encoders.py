@@ -893,7 +893,9 @@ class MerHubertModel(C.Structure):
                 ("layers", C.POINTER(W.MerLayerWeights)),
                 ("hidden", C.c_int), ("ffn", C.c_int), ("heads", C.c_int), ("feat_norm_layer", C.c_int),
                 ("stable_layer_norm", C.c_int), ("conv_b", C.c_void_p * 7), ("conv_ln_g", C.c_void_p * 7),
-                ("conv_ln_b", C.c_void_p * 7), ("pos_window", C.c_int), ("layers_f16", C.POINTER(W.MerLayerWeights))]
+                ("conv_ln_b", C.c_void_p * 7), ("pos_window", C.c_int), ("layers_f16", C.POINTER(W.MerLayerWeights)),
+                ("n_pos_layers", C.c_int), ("pos_taps", C.c_int), ("pos_layers_w", C.c_void_p * 8),
+                ("pos_layers_b", C.c_void_p * 8), ("ln_ones", C.c_void_p), ("ln_zeros", C.c_void_p)]
 
 
 def block_diagonal_pos_conv_weight(wpos, block_n=256, window=320, group=48):
@@ -955,17 +957,19 @@ class HubertEncoder:
         ffn = int(sd["encoder.layers.0.feed_forward.intermediate_dense.weight"].shape[0])
         assert self.hidden in (768, 1024) and ffn % 128 == 0, (self.hidden, ffn)
         m.hidden, m.ffn, m.heads = self.hidden, ffn, self.hidden // 64
+        data2vec = "encoder.pos_conv_embed.layers.0.conv.weight" in sd   # Data2VecAudioModel (data2vec-audio-base-960h)
         m.feat_norm_layer = 1 if ln_convs else 0
-        m.stable_layer_norm = int(ln_convs if stable_layer_norm is None else stable_layer_norm)
+        m.stable_layer_norm = int((ln_convs and not data2vec) if stable_layer_norm is None else stable_layer_norm)
         m.conv0_w = pk.keep(w0.reshape(512, 10)).data_ptr()
         m.gn_g = pk.keep(sd["feature_extractor.conv_layers.0.layer_norm.weight"]).data_ptr()
         m.gn_b = pk.keep(sd["feature_extractor.conv_layers.0.layer_norm.bias"]).data_ptr()
         for i in range(7):
             pre = f"feature_extractor.conv_layers.{i}."
             has_b = pre + "conv.bias" in sd
-            assert has_b == ln_convs, "conv biases are implemented with the layer-norm feature extractor only"
+            assert ln_convs or not has_b, "conv biases are implemented with the layer-norm feature extractor only"
             if ln_convs:
-                m.conv_b[i] = pk.keep(sd[pre + "conv.bias"]).data_ptr()
+                if has_b:
+                    m.conv_b[i] = pk.keep(sd[pre + "conv.bias"]).data_ptr()
                 m.conv_ln_g[i] = pk.keep(sd[pre + "layer_norm.weight"]).data_ptr()
                 m.conv_ln_b[i] = pk.keep(sd[pre + "layer_norm.bias"]).data_ptr()
         for i, k in enumerate((3, 3, 3, 3, 2, 2)):
@@ -977,21 +981,37 @@ class HubertEncoder:
         m.fp_ln_b = pk.keep(sd["feature_projection.layer_norm.bias"]).data_ptr()
         m.fp_w = pk.keep(sd["feature_projection.projection.weight"], split=True).data_ptr()
         m.fp_b = pk.keep(sd["feature_projection.projection.bias"]).data_ptr()
-        wpos = fold_pos_conv_weight(sd)
         gch = self.hidden // 16
-        assert wpos.shape == (self.hidden, gch, 128), wpos.shape
+        if data2vec:
+            # a chain of k = 19 grouped convs, each as a windowed block-diagonal fp16 GEMM operand
+            m.pos_window = 320 if gch == 48 else 256
+            n_pos = W.count_layers(sd, "encoder.pos_conv_embed.layers.{i}.conv.weight")
+            assert 0 < n_pos <= 8
+            m.n_pos_layers = n_pos
+            for l in range(n_pos):
+                w = np.asarray(sd[f"encoder.pos_conv_embed.layers.{l}.conv.weight"], np.float32)
+                assert w.shape[:2] == (self.hidden, gch) and w.shape[2] % 2 == 1, w.shape
+                m.pos_taps = int(w.shape[2])
+                m.pos_layers_w[l] = pk.keep(block_diagonal_pos_conv_weight(w, window=m.pos_window, group=gch),
+                                            f16=True).data_ptr()
+                m.pos_layers_b[l] = pk.keep(sd[f"encoder.pos_conv_embed.layers.{l}.conv.bias"]).data_ptr()
+            m.ln_ones = pk.keep(np.ones(self.hidden, np.float32)).data_ptr()
+            m.ln_zeros = pk.keep(np.zeros(self.hidden, np.float32)).data_ptr()
+        wpos = None if data2vec else fold_pos_conv_weight(sd)
+        assert data2vec or wpos.shape == (self.hidden, gch, 128), wpos.shape
         # the weights as a windowed block-diagonal fp16 matrix for the GEMM form of the conv
         # (MerHubertModel.pos_w_bd in mer_b200.h): 48-channel groups need a 320-wide window per 256-column
         # block, 64-channel groups exactly 256.  MER_POSCONV_LEGACY=1 keeps the mma.sync kernel (base only)
         import os
         m.pos_window = 320 if gch == 48 else 256
-        legacy = bool(os.environ.get("MER_POSCONV_LEGACY")) and gch == 48
-        if gch == 48:
-            wp = wpos.reshape(16, 48, 48, 128).transpose(0, 3, 1, 2)  # [g][tap][out][in]
-            m.pos_w = pk.keep(np.ascontiguousarray(wp), tf32=True).data_ptr()
-        m.pos_w_bd = None if legacy else \
-            pk.keep(block_diagonal_pos_conv_weight(wpos, window=m.pos_window, group=gch), f16=True).data_ptr()
-        m.pos_b = pk.keep(sd["encoder.pos_conv_embed.conv.bias"]).data_ptr()
+        if not data2vec:
+            legacy = bool(os.environ.get("MER_POSCONV_LEGACY")) and gch == 48
+            if gch == 48:
+                wp = wpos.reshape(16, 48, 48, 128).transpose(0, 3, 1, 2)  # [g][tap][out][in]
+                m.pos_w = pk.keep(np.ascontiguousarray(wp), tf32=True).data_ptr()
+            m.pos_w_bd = None if legacy else \
+                pk.keep(block_diagonal_pos_conv_weight(wpos, window=m.pos_window, group=gch), f16=True).data_ptr()
+            m.pos_b = pk.keep(sd["encoder.pos_conv_embed.conv.bias"]).data_ptr()
         m.enc_ln_g = pk.keep(sd["encoder.layer_norm.weight"]).data_ptr()
         m.enc_ln_b = pk.keep(sd["encoder.layer_norm.bias"]).data_ptr()
         self.layers = W.pack_layers(sd, W.HUBERT_NAMES, self.n_layers, pk, split=True)

@@ -25,6 +25,7 @@ from . import common
 
 HUBERT_BASE_CHINESE = "chinese-hubert-base"
 WAV2VEC2_BASE_CHINESE = "chinese-wav2vec2-base"
+DATA2VEC_AUDIO_BASE = "data2vec-audio-base-960h"   # Data2VecAudioModel: recognised from its positional conv chain
 MAXLEN = 16000 * 10
 
 

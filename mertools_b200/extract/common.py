@@ -21,8 +21,8 @@ def load_hf_state_dict(model_dir):
         sd = {k: v.float().numpy() for k, v in torch.load(pt, map_location="cpu").items()}
     out = {}
     for k, v in sd.items():
-        # AutoModel strips the task-model prefix ("vit.", "hubert.", "bert.", "roberta.")
-        for pre in ("vit.", "hubert.", "bert.", "roberta.", "wav2vec2."):
+        # AutoModel strips the task-model prefix ("vit.", "hubert.", "bert.", "roberta.", ...)
+        for pre in ("vit.", "hubert.", "bert.", "roberta.", "wav2vec2.", "data2vec_audio."):
             if k.startswith(pre):
                 k = k[len(pre):]
                 break

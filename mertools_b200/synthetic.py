@@ -303,11 +303,14 @@ def emonet_state_dict(seed=11):
 HUBERT_LARGE_CFG = dict(HUBERT_CFG, hidden=1024, heads=16, ffn=4096, layers=24)
 
 
-def hubert_state_dict(seed=1, layers=12, scale=1.0, large=False):
+def hubert_state_dict(seed=1, layers=12, scale=1.0, large=False, data2vec=False):
     """Keys of ``transformers.HubertModel(HubertConfig(num_hidden_layers=layers))``; ``large=True``: the
     hubert-large / chinese-hubert-large family (hidden 1024, 16 heads, FFN 4096, feat_extract_norm="layer",
     conv_bias=True, do_stable_layer_norm=True) -- same parameter names plus conv biases and one LayerNorm
-    per conv layer."""
+    per conv layer.  ``data2vec=True``: ``Data2VecAudioModel(Data2VecAudioConfig())`` (data2vec-audio-base-960h):
+    a LayerNorm after every bias-free conv, five positional conv layers (k = 19, 16 groups, bias; each followed by
+    an affine-free LayerNorm and GELU), post-LN layers."""
+    assert not (large and data2vec)
     c = HUBERT_LARGE_CFG if large else HUBERT_CFG
     g = _Gen(seed)
     d, cd = c["hidden"], c["conv_dim"]
@@ -318,18 +321,24 @@ def hubert_state_dict(seed=1, layers=12, scale=1.0, large=False):
                  np.sqrt(2.0 / (cin * k)))
         if large:
             g.normal(f"feature_extractor.conv_layers.{i}.conv.bias", (cd,), 0.05)
-        if i == 0 or large:
+        if i == 0 or large or data2vec:
             g.ln(f"feature_extractor.conv_layers.{i}.layer_norm", cd)
         cin = cd
     g.ln("feature_projection.layer_norm", cd)
     g.linear("feature_projection.projection", d, cd, 0.04)
     pk, pg = c["pos_kernel"], c["pos_groups"]
-    g.normal("encoder.pos_conv_embed.conv.bias", (d,), 0.02)
-    v = g.normal("encoder.pos_conv_embed.conv.parametrizations.weight.original1", (d, d // pg, pk),
+    if data2vec:
+        for l in range(5):
+            g.normal(f"encoder.pos_conv_embed.layers.{l}.conv.weight", (d, d // pg, 19), np.sqrt(2.0 / (19 * d // pg)))
+            g.normal(f"encoder.pos_conv_embed.layers.{l}.conv.bias", (d,), 0.05)
+    else:
+        g.normal("encoder.pos_conv_embed.conv.bias", (d,), 0.02)
+    v = None if data2vec else g.normal("encoder.pos_conv_embed.conv.parametrizations.weight.original1", (d, d // pg, pk),
                  2.0 * np.sqrt(1.0 / (pk * d)))
-    norm = np.sqrt((v.astype(np.float64) ** 2).sum(axis=(0, 1), keepdims=True))
-    g.sd["encoder.pos_conv_embed.conv.parametrizations.weight.original0"] = (
-        norm * (1.0 + 0.1 * g.rng.standard_normal(norm.shape))).astype(np.float32)
+    if not data2vec:
+        norm = np.sqrt((v.astype(np.float64) ** 2).sum(axis=(0, 1), keepdims=True))
+        g.sd["encoder.pos_conv_embed.conv.parametrizations.weight.original0"] = (
+            norm * (1.0 + 0.1 * g.rng.standard_normal(norm.shape))).astype(np.float32)
     g.ln("encoder.layer_norm", d)
     std = 0.02 * scale
     for i in range(layers):

@@ -349,8 +349,9 @@ def hubert_hidden_states(sd, input_values, layers=12, heads=12, eps=1e-5,
     x = input_values.to(dtype)[:, None, :]
     n_conv = len(conv_stride)
     layer_norm_convs = "feature_extractor.conv_layers.1.layer_norm.weight" in sd
+    data2vec = "encoder.pos_conv_embed.layers.0.conv.weight" in sd   # Data2VecAudioModel: see below
     if stable_layer_norm is None:
-        stable_layer_norm = layer_norm_convs
+        stable_layer_norm = layer_norm_convs and not data2vec
     for i in range(n_conv):
         w = _t(sd, f"feature_extractor.conv_layers.{i}.conv.weight", dtype)
         bname = f"feature_extractor.conv_layers.{i}.conv.bias"
@@ -365,12 +366,27 @@ def hubert_hidden_states(sd, input_values, layers=12, heads=12, eps=1e-5,
     x = x.transpose(1, 2)  # [B,T,512]
     x = _ln(x, sd, "feature_projection.layer_norm", eps, dtype)
     x = _linear(x, sd, "feature_projection.projection", dtype)
-    wpos = hubert_pos_conv_weight(sd, dtype)
-    pos = F.conv1d(x.transpose(1, 2), wpos, _t(sd, "encoder.pos_conv_embed.conv.bias", dtype),
-                   padding=wpos.shape[-1] // 2, groups=pos_groups)
-    if wpos.shape[-1] % 2 == 0:
-        pos = pos[:, :, :-1]
-    x = x + F.gelu(pos).transpose(1, 2)
+    if data2vec:
+        # Data2VecAudioPositionalConvEmbedding (HF models/data2vec/modeling_data2vec_audio.py): a chain of grouped
+        # convs (k = 19, pad 9) each followed by LayerNorm(elementwise_affine=False) and GELU; the chain's output
+        # is added to its input once
+        pos, l = x.transpose(1, 2), 0
+        while f"encoder.pos_conv_embed.layers.{l}.conv.weight" in sd:
+            w = _t(sd, f"encoder.pos_conv_embed.layers.{l}.conv.weight", dtype)
+            pos = F.conv1d(pos, w, _t(sd, f"encoder.pos_conv_embed.layers.{l}.conv.bias", dtype),
+                           padding=w.shape[-1] // 2, groups=pos_groups)
+            if w.shape[-1] % 2 == 0:
+                pos = pos[:, :, :-1]
+            pos = F.gelu(F.layer_norm(pos.transpose(1, 2), (pos.shape[1],), None, None, 1e-5)).transpose(1, 2)
+            l += 1
+        x = x + pos.transpose(1, 2)
+    else:
+        wpos = hubert_pos_conv_weight(sd, dtype)
+        pos = F.conv1d(x.transpose(1, 2), wpos, _t(sd, "encoder.pos_conv_embed.conv.bias", dtype),
+                       padding=wpos.shape[-1] // 2, groups=pos_groups)
+        if wpos.shape[-1] % 2 == 0:
+            pos = pos[:, :, :-1]
+        x = x + F.gelu(pos).transpose(1, 2)
     hs = []
     if not stable_layer_norm:
         x = _ln(x, sd, "encoder.layer_norm", eps, dtype)

@@ -280,3 +280,18 @@ def test_emonet_oracle_matches_reference_extractor_golden():
         for level, key in (("FRAME", "fra"), ("UTTERANCE", "utt")):
             got, ref = P.emonet_clip_features(sd, frames, level), g[f"{key}_{vid}"]
             assert got.shape == ref.shape and _rel(got, ref) < 2e-5, (vid, level)
+
+
+def test_audio_oracle_matches_reference_script_data2vec_audio():
+    """Data2VecAudioModel branch of the oracle (LayerNorm convs, chain of five k = 19 positional convs, post-LN)
+    against the unmodified reference extract() on a data2vec-audio-base-960h-style checkpoint."""
+    g = np.load(os.path.join(G, "audio_data2vec_golden.npz"))
+    layers = int(g["layers"])
+    sd = _t(S.hubert_state_dict(seed=int(g["seed"]), layers=layers, data2vec=True))
+    for i, n in enumerate(g["lens"]):
+        w = S.synth_waves(1, int(n), seed=int(g["seed0"]) + i)[0].astype(np.float64) / 32768.0
+        with torch.no_grad():
+            utt = P.audio_clip_features(sd, w, layers=layers)
+            fra = P.audio_clip_features(sd, w, layers=layers, feature_level="FRAME")
+        assert utt.shape == (768,) and _rel(utt, g[f"utt{i}"]) < 5e-5, f"clip {i} ({n} samples)"
+        assert _rel(fra[::16], g[f"fra{i}"]) < 5e-5

@@ -426,3 +426,32 @@ def test_emonet_vs_reference_golden(cuda, tmp_path):
             got = np.load(tmp_path / "feat" / f"emonet_{level[:3]}" / f"{vid}.npy")
             ref = g[f"{key}_{vid}"]
             assert got.shape == ref.shape and np.abs(got - ref).max() / np.abs(ref).max() < 1e-3, (vid, level)
+
+
+def test_data2vec_audio_vs_reference_golden_and_oracle(cuda):
+    """data2vec-audio-base (chain of five k = 19 positional convs as block-diagonal GEMMs + affine-free LayerNorm +
+    GELU, LayerNorm feature encoder without biases, post-LN stack): hidden states against the oracle, the extractor
+    against outputs of the unmodified reference extract()."""
+    import numpy as np
+
+    from mertools_b200 import synthetic as S
+    from mertools_b200.encoders import HubertEncoder
+    from mertools_b200.extract.audio import AudioExtractor
+    from oracle import encoders as E
+    from oracle import pipeline as P
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(gdir, "audio_data2vec_golden.npz"))
+    layers = int(g["layers"])
+    sd = S.hubert_state_dict(seed=int(g["seed"]), layers=layers, data2vec=True)
+    wav = (S.synth_waves(2, 16000, seed=25).astype(np.float64) / 32768.0).astype(np.float32)
+    utt, frames, hidden = HubertEncoder(sd, device=cuda).forward(torch.from_numpy(wav).to(cuda), normalize=True,
+                                                                 want_frames=True, return_hidden=True)
+    ref_hs = E.hubert_hidden_states(sd, torch.from_numpy(np.stack([P.wav2vec2_normalize(w) for w in wav])), layers=layers)
+    for l in range(layers + 1):
+        assert float((hidden[l].cpu() - ref_hs[l]).abs().max() / ref_hs[l].abs().max()) < 4e-3, l
+    waves = [S.synth_waves(1, int(n), seed=int(g["seed0"]) + i)[0].astype(np.float64) / 32768.0 for i, n in enumerate(g["lens"])]
+    ext = AudioExtractor(sd, device="cuda:0")
+    u, f = ext.extract_waves(waves, "UTTERANCE"), ext.extract_waves(waves, "FRAME")
+    for i in range(len(waves)):
+        assert np.abs(u[i] - g[f"utt{i}"]).max() / np.abs(g[f"utt{i}"]).max() < 1e-3, i
+        assert np.abs(f[i][::16] - g[f"fra{i}"]).max() / np.abs(g[f"fra{i}"]).max() < 2e-3, i
