@@ -87,14 +87,24 @@ int mer_run_stack(const MerStackArgs& a, cudaStream_t stream) {
       // into the (fp32-sized) scratch buffers; only the residual stream x stays fp32
       float* xn16 = a.xn;  // fp16 [M, 768]
       float* h16 = a.h;    // fp16 [M, 3072]
-      MER_REQUIRE(vt != nullptr, "mer_run_stack: the F16 stack needs the tcgen05 attention (sequences <= 253)");
+      const bool f16_att = vt != nullptr && mer_attention_f16_supported(a.max_seqlen);
       MER_TRY(mer_layernorm_launch(a.x, w.ln1_g, w.ln1_b, xn16, nullptr, nullptr, M, D, a.eps, MER_LN_OUT_F16,
                                    stream));
-      MER_TRY(linear(a.mode, xn16, w.w_qkv, w.b_qkv, nullptr, a.qkv, M, DQKV, D, MER_EPI_OUT_F16, stream,
-                     vt, a.vt_ld, 2 * D));
-      MER_TRY(mer_attention_launch(a.qkv, vt, a.vt_ld, xn16, a.cu_seqlens, a.n_seq, M, a.max_seqlen, HEADS,
-                                   MER_EPI_OUT_F16 | MER_ATT_QKV_F16, stream));
-      MER_TRY(linear(a.mode, xn16, w.w_o, w.b_o, a.x, a.x, M, D, D, 0, stream));
+      if (f16_att) {
+        MER_TRY(linear(a.mode, xn16, w.w_qkv, w.b_qkv, nullptr, a.qkv, M, DQKV, D, MER_EPI_OUT_F16, stream,
+                       vt, a.vt_ld, 2 * D));
+        MER_TRY(mer_attention_launch(a.qkv, vt, a.vt_ld, xn16, a.cu_seqlens, a.n_seq, M, a.max_seqlen, HEADS,
+                                     MER_EPI_OUT_F16 | MER_ATT_QKV_F16, stream));
+        MER_TRY(linear(a.mode, xn16, w.w_o, w.b_o, a.x, a.x, M, D, D, 0, stream));
+      } else {
+        // sequences beyond the fp16 attention kernel (CLIP L/14: 257 tokens): the linear layers stay on fp16
+        // operands, attention runs the fp32-operand flash kernel on a TF32-rounded fp32 q | k | v (same 10-bit
+        // mantissa) and its fp32 context is cast to the fp16 out-proj operand through the idle FFN buffer
+        MER_TRY(linear(a.mode, xn16, w.w_qkv, w.b_qkv, nullptr, a.qkv, M, DQKV, D, MER_EPI_ROUND_TF32, stream));
+        MER_TRY(mer_attention_launch(a.qkv, nullptr, 0, a.xn, a.cu_seqlens, a.n_seq, M, a.max_seqlen, HEADS, 0, stream));
+        MER_TRY(mer_cast_f16_launch(a.xn, h16, M * D, stream));
+        MER_TRY(linear(a.mode, h16, w.w_o, w.b_o, a.x, a.x, M, D, D, 0, stream));
+      }
       MER_TRY(mer_layernorm_launch(a.x, w.ln2_g, w.ln2_b, xn16, nullptr, nullptr, M, D, a.eps, MER_LN_OUT_F16,
                                    stream));
       MER_TRY(linear(a.mode, xn16, w.w_fc1, w.b_fc1, nullptr, h16, M, DFF, D, ACT | MER_EPI_OUT_F16,

@@ -175,7 +175,10 @@ class ClipVisionEncoder:
 
     Reference: MERBench/feature_extraction/visual/extract_vision_huggingface.py:114-122."""
 
-    def __init__(self, state_dict, device="cuda", ln_eps=1e-5, image=224):
+    def __init__(self, state_dict, device="cuda", ln_eps=1e-5, image=224, precision=None):
+        """precision: None = "f16" when the fp16 attention kernel covers the token count (B/32), else "tf32";
+        "f16" forces fp16 linear layers for longer sequences too (L/14: attention then runs the fp32-operand flash
+        kernel between them; env MER_CLIP_PRECISION=f16; not yet measured)."""
         L.check(L.lib().mer_check_device())
         sd = W._np(state_dict)
         self.device = torch.device(device)
@@ -194,7 +197,10 @@ class ClipVisionEncoder:
         wflat = np.zeros((D, kpad), np.float32)
         wflat[:, :3 * p * p] = pw.reshape(D, 3 * p * p)
         # fp16 operands need the fp16 attention kernel (<= 249 tokens per frame): B/32 yes, L/14 (257) runs TF32
-        self.precision = "f16" if self.tokens <= 249 else "tf32"
+        import os
+        precision = precision or os.environ.get("MER_CLIP_PRECISION")
+        assert precision in (None, "f16", "tf32"), precision
+        self.precision = precision or ("f16" if self.tokens <= 249 else "tf32")
         f16 = self.precision == "f16"
         self.layers = W.pack_layers(sd, W.CLIP_NAMES, self.n_layers, pk, f16=f16)
         m = MerClipVisionModel()

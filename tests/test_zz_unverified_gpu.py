@@ -455,3 +455,23 @@ def test_data2vec_audio_vs_reference_golden_and_oracle(cuda):
     for i in range(len(waves)):
         assert np.abs(u[i] - g[f"utt{i}"]).max() / np.abs(g[f"utt{i}"]).max() < 1e-3, i
         assert np.abs(f[i][::16] - g[f"fra{i}"]).max() / np.abs(g[f"fra{i}"]).max() < 2e-3, i
+
+
+def test_clip_l14_with_fp16_linear_layers(cuda):
+    """CLIP L/14 (257 tokens) with precision="f16": fp16 linear layers around the fp32-operand flash attention
+    (the hybrid branch of mer_run_stack) against the oracle, like the TF32 default."""
+    import numpy as np
+
+    from mertools_b200 import synthetic as S
+    from mertools_b200.encoders import ClipVisionEncoder
+    from oracle import encoders as E
+    from oracle import pipeline as P
+    c = S.CLIP_CFGS["l14"]
+    sd = S.clip_vision_state_dict(seed=4, variant="l14", layers=2)
+    frames = np.random.default_rng(31).integers(0, 256, (3, 224, 224, 3), dtype=np.uint8)
+    enc = ClipVisionEncoder(sd, device=cuda, precision="f16")
+    assert enc.tokens == 257 and enc.precision == "f16"
+    emb = enc.frame_features(torch.from_numpy(frames).to(cuda))
+    ref_emb, _ = E.clip_image_features({k: torch.from_numpy(v) for k, v in sd.items()}, P.clip_preprocess(frames),
+                                       layers=2, heads=c["heads"])
+    assert float((emb.cpu() - ref_emb).abs().max() / ref_emb.abs().max()) < 1e-3
