@@ -521,3 +521,43 @@ def test_emonet_op_tables_reproduce_the_reference_golden_on_a_cpu_interpreter():
     dll.mer_cnn_workspace_bytes.restype = C.c_longlong
     dll.mer_cnn_workspace_bytes.argtypes = [C.POINTER(En.MerCnnModel), C.c_int]
     assert dll.mer_cnn_workspace_bytes(C.byref(m), 2) > 0
+
+
+def test_ctypes_struct_layouts_match_the_header(tmp_path):
+    """Every struct the Python side passes by pointer is mirrored by hand in ctypes: compile a C probe against
+    include/mer_b200.h and compare sizes and the offsets of the trailing fields."""
+    import ctypes as C
+    import shutil
+    import subprocess
+
+    from mertools_b200 import _lib
+    from mertools_b200 import encoders as En
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    probes = [("MerHubertModel", En.MerHubertModel, ["pos_window", "layers_f16", "n_pos_layers", "pos_layers_w", "ln_zeros"]),
+              ("MerCnnOp", En.MerCnnOp, ["relu", "ceil_mode", "p"]),
+              ("MerCnnModel", En.MerCnnModel, ["ops", "scale", "mean", "feat_dim"]),
+              ("MerVggishModel", En.MerVggishModel, ["fc_w", "fc_b"]),
+              ("MerResnetConv", En.MerResnetConv, ["b", "kpad"]),
+              ("MerResnet18Model", En.MerResnet18Model, ["mean", "std"]),
+              ("MerClipVisionModel", En.MerClipVisionModel, []),
+              ("MerVitModel", En.MerVitModel, []),
+              ("MerBertModel", En.MerBertModel, ["layers"]),
+              ("MerGemmDesc", _lib.MerGemmDesc, ["a_row0", "a_col_group", "ep"])]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "mer_b200.h")}"',
+             "int main(void) {"]
+    for name, _cls, fields in probes:
+        lines.append(f'  printf("{name} %zu", sizeof({name}));')
+        for f in fields:
+            lines.append(f'  printf(" %zu", offsetof({name}, {f}));')
+        lines.append('  printf("\\n");')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    for (name, cls, fields), line in zip(probes, out):
+        want = [int(v) for v in line.split()[1:]]
+        got = [C.sizeof(cls)] + [getattr(cls, f).offset for f in fields]
+        assert got == want, f"{name}: ctypes {got} != C {want}"
