@@ -530,7 +530,7 @@ def test_ctypes_struct_layouts_match_the_header(tmp_path):
     import shutil
     import subprocess
 
-    from mertools_b200 import _lib
+    from mertools_b200 import _lib, fusion, weights
     from mertools_b200 import encoders as En
     if shutil.which("gcc") is None:
         pytest.skip("no C compiler")
@@ -543,7 +543,11 @@ def test_ctypes_struct_layouts_match_the_header(tmp_path):
               ("MerClipVisionModel", En.MerClipVisionModel, []),
               ("MerVitModel", En.MerVitModel, []),
               ("MerBertModel", En.MerBertModel, ["layers"]),
-              ("MerGemmDesc", _lib.MerGemmDesc, ["a_row0", "a_col_group", "ep"])]
+              ("MerGemmDesc", _lib.MerGemmDesc, ["a_row0", "a_col_group", "ep"]),
+              ("MerGemmEpilogue", _lib.MerGemmEpilogue, []),
+              ("MerLayerWeights", weights.MerLayerWeights, []),
+              ("MerFusionDims", fusion.MerFusionDims, []),
+              ("MerFusionTopnDims", fusion.MerFusionTopnDims, [])]
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "mer_b200.h")}"',
              "int main(void) {"]
     for name, _cls, fields in probes:
