@@ -565,3 +565,32 @@ def test_ctypes_struct_layouts_match_the_header(tmp_path):
         want = [int(v) for v in line.split()[1:]]
         got = [C.sizeof(cls)] + [getattr(cls, f).offset for f in fields]
         assert got == want, f"{name}: ctypes {got} != C {want}"
+
+
+def test_ctypes_declarations_have_the_arity_of_the_header_prototypes():
+    """Every ``_lib.declare("mer_...", [argtypes])`` in the package against the parameter count of the MER_API
+    prototype in include/mer_b200.h (a wrong count would only show up as garbage arguments on a GPU)."""
+    import glob
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "mer_b200.h")).read(), flags=re.S)
+    protos = {}
+    for m in re.finditer(r"MER_API\s+[\w\s\*]+?\b(mer_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    assert len(protos) >= 40
+    checked = 0
+    for f in glob.glob(os.path.join(ROOT, "mertools_b200", "**", "*.py"), recursive=True) + [os.path.join(ROOT, "bench.py")]:
+        src = open(f).read()
+        for m in re.finditer(r'declare\(\s*"(mer_\w+)"\s*,\s*\[', src):
+            i = j = m.end()
+            depth = 1
+            while depth:
+                depth += (src[j] == "[") - (src[j] == "]")
+                j += 1
+            body, d, n = src[i:j - 1].strip().rstrip(","), 0, 1
+            for ch in body:
+                d += (ch in "([") - (ch in ")]")
+                n += ch == "," and d == 0
+            assert m.group(1) in protos, (f, m.group(1))
+            assert protos[m.group(1)] == n, (os.path.basename(f), m.group(1), n, protos[m.group(1)])
+            checked += 1
+    assert checked >= 25
