@@ -593,4 +593,4 @@ def test_ctypes_declarations_have_the_arity_of_the_header_prototypes():
             assert m.group(1) in protos, (f, m.group(1))
             assert protos[m.group(1)] == n, (os.path.basename(f), m.group(1), n, protos[m.group(1)])
             checked += 1
-    assert checked >= 25
+    assert checked >= 20
