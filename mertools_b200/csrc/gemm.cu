@@ -625,10 +625,12 @@ int launch_gemm(const MerGemmDesc* g, cudaStream_t stream) {
     cfg.numAttrs = 1;
     MerGemmEpilogue ep = g->ep;
     {
-      const char* e = getenv("MER_GELU_PACKED");  // read at every launch: tests run both forms in one process
       const bool plain_gelu = (ep.flags & MER_EPI_GELU) && !(ep.flags & MER_EPI_GELU_LIBM) && !ep.res;
-      if (e && atoi(e) == 1 && plain_gelu && (ep.flags & (MER_EPI_OUT_F16 | MER_EPI_SPLIT_BF16)))
-        ep.flags |= EPI_GELU_PACKED;
+      if (plain_gelu && (ep.flags & (MER_EPI_OUT_F16 | MER_EPI_SPLIT_BF16))) {
+        // FC1 launches only; read at every such launch so that tests can run both forms in one process
+        const char* e = getenv("MER_GELU_PACKED");
+        if (e && atoi(e) == 1) ep.flags |= EPI_GELU_PACKED;
+      }
     }
     MER_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<BLOCK_N, MODE, CLUSTER, TWOSM>, ta, tb, ep,
                                       g->rows_per_batch, g->batches, g->N, g->K_inner * g->taps,
