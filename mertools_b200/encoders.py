@@ -942,8 +942,10 @@ class HubertEncoder:
     base (hidden 768, group-norm feature extractor, post-LN: hubert-base, wav2vec2-base) and large
     (hidden 1024, 16 heads, LayerNorm after every conv, conv biases, stable / pre-LN encoder: hubert-large,
     chinese-hubert-large, wav2vec2-large-lv60).  ``stable_layer_norm`` overrides the inference of
-    ``config.do_stable_layer_norm`` from the feature extractor type (they coincide in every released
-    checkpoint of the extractor's model list except wav2vec2-large-960h, which is not supported).
+    ``config.do_stable_layer_norm`` from the feature extractor type (they coincide in every released checkpoint of
+    the extractor's model list).  Two more combinations are wired but have not run on a GPU yet: hidden 1024 on the
+    group-norm extractor with post-LN layers (wav2vec2-large-960h) and ``Data2VecAudioModel``
+    (data2vec-audio-base-960h: LayerNorm convs without biases, a chain of positional convs, post-LN).
 
     Reference: MERBench/feature_extraction/audio/extract_audio_huggingface.py:18-36,93-110."""
 

@@ -303,15 +303,18 @@ def emonet_state_dict(seed=11):
 HUBERT_LARGE_CFG = dict(HUBERT_CFG, hidden=1024, heads=16, ffn=4096, layers=24)
 
 
-def hubert_state_dict(seed=1, layers=12, scale=1.0, large=False, data2vec=False):
+def hubert_state_dict(seed=1, layers=12, scale=1.0, large=False, data2vec=False, group_norm=False):
     """Keys of ``transformers.HubertModel(HubertConfig(num_hidden_layers=layers))``; ``large=True``: the
     hubert-large / chinese-hubert-large family (hidden 1024, 16 heads, FFN 4096, feat_extract_norm="layer",
     conv_bias=True, do_stable_layer_norm=True) -- same parameter names plus conv biases and one LayerNorm
     per conv layer.  ``data2vec=True``: ``Data2VecAudioModel(Data2VecAudioConfig())`` (data2vec-audio-base-960h):
     a LayerNorm after every bias-free conv, five positional conv layers (k = 19, 16 groups, bias; each followed by
     an affine-free LayerNorm and GELU), post-LN layers."""
+    """``large=True, group_norm=True``: wav2vec2-large-960h (hidden 1024 with the base feature extractor: GroupNorm on
+    conv0, no conv biases, post-LN layers)."""
     assert not (large and data2vec)
     c = HUBERT_LARGE_CFG if large else HUBERT_CFG
+    ln_convs = (large and not group_norm) or data2vec
     g = _Gen(seed)
     d, cd = c["hidden"], c["conv_dim"]
     g.sd["masked_spec_embed"] = g.rng.random(d, dtype=np.float32)
@@ -319,9 +322,9 @@ def hubert_state_dict(seed=1, layers=12, scale=1.0, large=False, data2vec=False)
     for i, k in enumerate(c["conv_kernel"]):
         g.normal(f"feature_extractor.conv_layers.{i}.conv.weight", (cd, cin, k),
                  np.sqrt(2.0 / (cin * k)))
-        if large:
+        if large and not group_norm:
             g.normal(f"feature_extractor.conv_layers.{i}.conv.bias", (cd,), 0.05)
-        if i == 0 or large or data2vec:
+        if i == 0 or ln_convs:
             g.ln(f"feature_extractor.conv_layers.{i}.layer_norm", cd)
         cin = cd
     g.ln("feature_projection.layer_norm", cd)

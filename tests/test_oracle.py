@@ -272,3 +272,26 @@ def test_cv2_resize_restatement_is_bit_exact(hw):
     cv2 = pytest.importorskip("cv2")
     img = np.random.default_rng(hw[0]).integers(0, 256, (hw[0], hw[1], 3), dtype=np.uint8)
     assert np.array_equal(P.cv2_resize_linear_u8(img, 256, 256), cv2.resize(img, (256, 256)))
+
+
+def test_oracle_audio_restatement_covers_wav2vec2_large_960h_and_data2vec():
+    """Two more configurations of the reference's audio model list (extract_audio_huggingface.py:18-29) pinned to HF:
+    wav2vec2-large-960h (hidden 1024 on the GroupNorm feature extractor, post-LN) and data2vec-audio-base
+    (LayerNorm convs without biases, a chain of five k = 19 positional convs)."""
+    from transformers import Data2VecAudioConfig, Data2VecAudioModel, Wav2Vec2Config, Wav2Vec2Model
+    x = torch.randn(2, 12000, generator=torch.Generator().manual_seed(3))
+    cases = [(S.hubert_state_dict(seed=5, layers=2, large=True, group_norm=True), 16,
+              Wav2Vec2Model(Wav2Vec2Config(hidden_size=1024, num_hidden_layers=2, num_attention_heads=16,
+                                           intermediate_size=4096, feat_extract_norm="group",
+                                           do_stable_layer_norm=False, conv_bias=False))),
+             (S.hubert_state_dict(seed=3, layers=2, data2vec=True), 12,
+              Data2VecAudioModel(Data2VecAudioConfig(num_hidden_layers=2)))]
+    for sd, heads, model in cases:
+        model.eval()
+        res = model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+        with torch.no_grad():
+            ref = model(x, output_hidden_states=True).hidden_states
+        got = E.hubert_hidden_states({k: torch.from_numpy(v) for k, v in sd.items()}, x, layers=2, heads=heads)
+        for a, b in zip(got, ref):
+            assert float((a - b).abs().max() / b.abs().max()) < 2e-5

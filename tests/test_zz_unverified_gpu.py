@@ -475,3 +475,25 @@ def test_clip_l14_with_fp16_linear_layers(cuda):
     ref_emb, _ = E.clip_image_features({k: torch.from_numpy(v) for k, v in sd.items()}, P.clip_preprocess(frames),
                                        layers=2, heads=c["heads"])
     assert float((emb.cpu() - ref_emb).abs().max() / ref_emb.abs().max()) < 1e-3
+
+
+def test_wav2vec2_large_960h_family(cuda):
+    """hidden 1024 / 16 heads on the GroupNorm feature extractor with post-LN layers (wav2vec2-large-960h): a
+    combination of paths that exist (conv0 GroupNorm kernels, 64-channel-group positional conv GEMM, post-LN BF16X3
+    stack at runtime dims) but had never been run together."""
+    import numpy as np
+
+    from mertools_b200 import synthetic as S
+    from mertools_b200.encoders import HubertEncoder
+    from oracle import encoders as E
+    from oracle import pipeline as P
+    sd = S.hubert_state_dict(seed=5, layers=4, large=True, group_norm=True)
+    wav = (S.synth_waves(2, 16000, seed=27).astype(np.float64) / 32768.0).astype(np.float32)
+    enc = HubertEncoder(sd, device=cuda)
+    assert enc.hidden == 1024 and not enc.model.stable_layer_norm and not enc.model.feat_norm_layer
+    utt, frames, hidden = enc.forward(torch.from_numpy(wav).to(cuda), normalize=True, want_frames=True, return_hidden=True)
+    ref_hs = E.hubert_hidden_states(sd, torch.from_numpy(np.stack([P.wav2vec2_normalize(w) for w in wav])), layers=4, heads=16)
+    for l in range(5):
+        assert float((hidden[l].cpu() - ref_hs[l]).abs().max() / ref_hs[l].abs().max()) < 4e-3, l
+    ref = torch.stack(ref_hs)[[-4, -3, -2, -1]].sum(dim=0)
+    assert float((frames.cpu() - ref).abs().max() / ref.abs().max()) < 2e-3
