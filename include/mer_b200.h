@@ -458,9 +458,15 @@ typedef struct MerBertModel {
   const float* emb_ln_g;
   const float* emb_ln_b;
   const MerLayerWeights* layers;
+  /* zero-initialised = the base models; bert-large-uncased / roberta-large / chinese-roberta-wwm-ext-large /
+   * chinese-macbert-large ... (extract_text_huggingface.py:21,26,41,49): 1024 / 4096 / 16 */
+  int hidden;               /* 0 = 768; 768 or 1024 (embedding tables are then [*, hidden]) */
+  int ffn;                  /* 0 = 3072 */
+  int heads;                /* 0 = 12; hidden / 64 */
 } MerBertModel;
 
-MER_API long long mer_bert_workspace_bytes(int tokens, int n_seq);
+MER_API long long mer_bert_workspace_bytes(int tokens, int n_seq); /* base models */
+MER_API long long mer_bert_model_workspace_bytes(const MerBertModel* model, int tokens, int n_seq);
 
 /* Packed variable-length batch of tokenised sentences (ids from the HF tokenizer on the host, as in
  * extract_text_huggingface.py:222).  ids/pos_ids: device int32 [tokens]; cu_seqlens: device int32

@@ -735,9 +735,21 @@ int mer_hubert_forward_ragged(const MerHubertModel* m, const float* wave, const 
 // ------------------------------------------------------------------------------------------------
 // BERT / RoBERTa
 // ------------------------------------------------------------------------------------------------
+static long long bert_ws(long long M, int D, int DFF) {
+  return (M * (D + D + D + 3ll * D + DFF + D) + (long long)D * ((M + 3) & ~3ll)) * 4 + 4096;
+}
+static int bert_dim(const MerBertModel* m) { return m->hidden > 0 ? m->hidden : ::D; }
+static int bert_ffn(const MerBertModel* m) { return m->ffn > 0 ? m->ffn : ::DFF; }
+
 long long mer_bert_workspace_bytes(int tokens, int n_seq) {
-  const long long M = tokens;
-  return (M * (D + D + D + DQKV + DFF + D) + (long long)D * ((M + 3) & ~3ll)) * 4 + 4096;
+  (void)n_seq;
+  return bert_ws(tokens, ::D, ::DFF);
+}
+
+long long mer_bert_model_workspace_bytes(const MerBertModel* m, int tokens, int n_seq) {
+  (void)n_seq;
+  if (!m) return -1;
+  return bert_ws(tokens, bert_dim(m), bert_ffn(m));
 }
 
 int mer_bert_forward(const MerBertModel* m, const int32_t* ids, const int32_t* pos_ids,
@@ -749,9 +761,12 @@ int mer_bert_forward(const MerBertModel* m, const int32_t* ids, const int32_t* p
   MER_REQUIRE(m && ids && pos_ids && cu_seqlens && workspace, "mer_bert_forward: null operand");
   MER_REQUIRE(n_seq > 0 && tokens > 0 && max_seqlen > 0, "mer_bert_forward: empty batch");
   MER_REQUIRE(m->n_layers >= 4, "mer_bert_forward: the last-four readout needs >= 4 layers");
-  MER_REQUIRE(workspace_bytes >= mer_bert_workspace_bytes(tokens, n_seq),
-              "mer_bert_forward: workspace %lld B < required %lld B", workspace_bytes,
-              mer_bert_workspace_bytes(tokens, n_seq));
+  // model dims: zero-initialised fields = the base models (768 / 12 heads / 3072); -large: 1024 / 16 / 4096
+  const int D = bert_dim(m), DFF = bert_ffn(m), HEADS = m->heads > 0 ? m->heads : ::HEADS, DQKV = 3 * D;
+  MER_REQUIRE((D == 768 || D == 1024) && HEADS * 64 == D && DFF % 128 == 0,
+              "mer_bert_forward: hidden %d / heads %d / ffn %d not supported", D, HEADS, DFF);
+  MER_REQUIRE(workspace_bytes >= bert_ws(tokens, D, DFF), "mer_bert_forward: workspace %lld B < required %lld B",
+              workspace_bytes, bert_ws(tokens, D, DFF));
   const long long M = tokens;
   float* x = static_cast<float*>(workspace);
   float* xs = x + M * D;
@@ -761,7 +776,7 @@ int mer_bert_forward(const MerBertModel* m, const int32_t* ids, const int32_t* p
   float* acc = h + M * DFF;
   float* vt = acc + M * D;
   MER_TRY(mer_bert_embed_launch(ids, pos_ids, m->word_emb, m->pos_emb, m->type_emb0, m->emb_ln_g,
-                                m->emb_ln_b, m->ln_eps, tokens, x, xs, stream));
+                                m->emb_ln_b, m->ln_eps, tokens, x, xs, stream, D));
   if (opt_hidden)
     MER_CUDA_CHECK(cudaMemcpyAsync(opt_hidden, x, (size_t)M * D * 4, cudaMemcpyDeviceToDevice, stream));
   MerStackArgs a;
@@ -769,6 +784,9 @@ int mer_bert_forward(const MerBertModel* m, const int32_t* ids, const int32_t* p
   a.layers = m->layers;
   a.n_layers = m->n_layers;
   a.pre_ln = 0;
+  a.dim = D;
+  a.ffn = DFF;
+  a.heads = HEADS;
   a.mode = MER_GEMM_BF16X3;
   a.eps = m->ln_eps;
   a.tokens = M;

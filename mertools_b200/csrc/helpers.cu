@@ -167,40 +167,42 @@ segment_reduce_kernel(const float* __restrict__ in, const int* __restrict__ begi
 
 // BERT/RoBERTa embeddings (HF modeling_bert.py BertEmbeddings / modeling_roberta.py:56-122):
 // (word[id] + token_type[0]) + position[pos] -> LayerNorm -> x (fp32) and its split-bf16 copy.
-// One warp per token.
+// One warp per token; hidden size 128 * VEC (VEC 6: the base models, VEC 8: the -large ones).
+template <int VEC>
 __global__ void __launch_bounds__(256)
 bert_embed_ln_kernel(const int* __restrict__ ids, const int* __restrict__ pos_ids,
                      const float* __restrict__ word, const float* __restrict__ pos,
                      const float* __restrict__ type0, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float eps, int tokens, float* __restrict__ out,
                      void* __restrict__ out_split) {
+  constexpr int DIM = 128 * VEC;
   const int lane = threadIdx.x & 31;
   const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (tok >= tokens) return;
-  const float4* w = reinterpret_cast<const float4*>(word + (long long)ids[tok] * 768);
-  const float4* p = reinterpret_cast<const float4*>(pos + (long long)pos_ids[tok] * 768);
+  const float4* w = reinterpret_cast<const float4*>(word + (long long)ids[tok] * DIM);
+  const float4* p = reinterpret_cast<const float4*>(pos + (long long)pos_ids[tok] * DIM);
   const float4* ty = reinterpret_cast<const float4*>(type0);
-  float4 v[6];
+  float4 v[VEC];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 6; ++i) {
+  for (int i = 0; i < VEC; ++i) {
     const float4 a = __ldg(w + lane + 32 * i), b = __ldg(ty + lane + 32 * i), c = __ldg(p + lane + 32 * i);
     v[i].x = (a.x + b.x) + c.x; v[i].y = (a.y + b.y) + c.y;
     v[i].z = (a.z + b.z) + c.z; v[i].w = (a.w + b.w) + c.w;
     s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
-  const float mean = warp_sum(s) * (1.0f / 768);
+  const float mean = warp_sum(s) * (1.0f / DIM);
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < 6; ++i) {
+  for (int i = 0; i < VEC; ++i) {
     v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
     q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
   }
-  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / 768) + eps);
-  float4* o = reinterpret_cast<float4*>(out + (long long)tok * 768);
-  float* os = out_split ? reinterpret_cast<float*>(out_split) + (long long)tok * 768 : nullptr;
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / DIM) + eps);
+  float4* o = reinterpret_cast<float4*>(out + (long long)tok * DIM);
+  float* os = out_split ? reinterpret_cast<float*>(out_split) + (long long)tok * DIM : nullptr;
 #pragma unroll
-  for (int i = 0; i < 6; ++i) {
+  for (int i = 0; i < VEC; ++i) {
     const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
     const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
     float4 r;
@@ -281,10 +283,15 @@ int mer_segment_reduce_launch(const float* in, const int* begins, const int* end
 
 int mer_bert_embed_launch(const int* ids, const int* pos_ids, const float* word, const float* pos,
                           const float* type0, const float* gamma, const float* beta, float eps,
-                          int tokens, float* out, void* out_split, cudaStream_t stream) {
+                          int tokens, float* out, void* out_split, cudaStream_t stream, int dim) {
   if (tokens <= 0) return 0;
-  bert_embed_ln_kernel<<<(tokens + 7) / 8, 256, 0, stream>>>(ids, pos_ids, word, pos, type0, gamma,
-                                                            beta, eps, tokens, out, out_split);
+  MER_REQUIRE(dim == 768 || dim == 1024, "mer_bert_embed: hidden size %d (768 or 1024)", dim);
+  if (dim == 1024)
+    bert_embed_ln_kernel<8><<<(tokens + 7) / 8, 256, 0, stream>>>(ids, pos_ids, word, pos, type0, gamma, beta, eps,
+                                                                  tokens, out, out_split);
+  else
+    bert_embed_ln_kernel<6><<<(tokens + 7) / 8, 256, 0, stream>>>(ids, pos_ids, word, pos, type0, gamma, beta, eps,
+                                                                  tokens, out, out_split);
   MER_CUDA_CHECK(cudaGetLastError());
   mer_count_launches(1);
   return 0;

@@ -65,7 +65,7 @@ int mer_segment_reduce_launch(const float* in, const int* begins, const int* end
                               int dim, int mode, float* out, cudaStream_t stream);
 int mer_bert_embed_launch(const int* ids, const int* pos_ids, const float* word, const float* pos,
                           const float* type0, const float* gamma, const float* beta, float eps,
-                          int tokens, float* out, void* out_split, cudaStream_t stream);
+                          int tokens, float* out, void* out_split, cudaStream_t stream, int dim = 768);
 
 // hubert_frontend.cu
 // lengths (device, optional): ragged batch, row b holds lengths[b] <= L samples; the tail is written as zeros

@@ -1093,7 +1093,40 @@ HubertEncoder.forward_ragged = _hubert_forward_ragged
 class MerBertModel(C.Structure):
     _fields_ = [("n_layers", C.c_int), ("ln_eps", C.c_float), ("word_emb", C.c_void_p),
                 ("pos_emb", C.c_void_p), ("type_emb0", C.c_void_p), ("emb_ln_g", C.c_void_p),
-                ("emb_ln_b", C.c_void_p), ("layers", C.POINTER(W.MerLayerWeights))]
+                ("emb_ln_b", C.c_void_p), ("layers", C.POINTER(W.MerLayerWeights)),
+                ("hidden", C.c_int), ("ffn", C.c_int), ("heads", C.c_int)]
+
+
+def _hubert_forward_ragged(self, rows: torch.Tensor, lengths, normalize=True, want_frames=False):
+    """rows: fp32 CUDA [B, Lmax]; row b holds ``lengths[b]`` samples (the rest is ignored when ``normalize``, and must
+    be finite otherwise).  Every clip is computed as if it were forwarded alone (mer_hubert_forward_ragged).
+    Returns (utt [B, D], frames): frames = list of [T_b, D] tensors (views of one packed tensor) or None."""
+    assert rows.dtype == torch.float32 and rows.is_cuda and rows.dim() == 2
+    rows = rows.contiguous()
+    B, Lmax = rows.shape
+    lengths = [int(n) for n in lengths]
+    assert len(lengths) == B and all(0 < n <= Lmax for n in lengths)
+    tb = [self.num_frames(n) for n in lengths]
+    D = self.hidden
+    ws = self.ws.get(L.lib().mer_hubert_model_workspace_bytes(C.byref(self.model), B, Lmax))
+    utt = torch.empty(B, D, dtype=torch.float32, device=self.device)
+    packed = torch.empty(sum(tb), D, dtype=torch.float32, device=self.device) if want_frames else None
+    fwd = L.declare("mer_hubert_forward_ragged", [C.POINTER(MerHubertModel), C.c_void_p, C.POINTER(C.c_int), C.c_int,
+                                                  C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
+                                                  C.c_void_p])
+    L.check(fwd(C.byref(self.model), L.ptr(rows), (C.c_int * B)(*lengths), B, Lmax, 1 if normalize else 0, L.ptr(ws),
+                ws.numel(), L.ptr(packed), L.ptr(utt), L.stream_ptr()))
+    return utt, (list(torch.split(packed, tb)) if want_frames else None)
+
+
+HubertEncoder.forward_ragged = _hubert_forward_ragged
+
+
+class MerBertModel(C.Structure):
+    _fields_ = [("n_layers", C.c_int), ("ln_eps", C.c_float), ("word_emb", C.c_void_p),
+                ("pos_emb", C.c_void_p), ("type_emb0", C.c_void_p), ("emb_ln_g", C.c_void_p),
+                ("emb_ln_b", C.c_void_p), ("layers", C.POINTER(W.MerLayerWeights)),
+                ("hidden", C.c_int), ("ffn", C.c_int), ("heads", C.c_int)]
 
 
 class BertEncoder:

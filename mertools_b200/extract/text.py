@@ -81,7 +81,7 @@ class TextExtractor:
                 o += n
             b = e
         return [common.save_feature(save_files[i] if save_files is not None else None, r,
-                                    feature_level, 768) for i, r in enumerate(res)]
+                                    feature_level, self.enc.hidden) for i, r in enumerate(res)]
 
 
 def extract_embedding(model_name, trans_dir, save_dir, feature_level, gpu=-1, punc_case=None,

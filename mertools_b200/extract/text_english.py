@@ -145,5 +145,5 @@ def extract_bert_embedding_english(model_name, trans_dir, save_dir, feature_leve
         name = row["name"]
         print(f"Processing {name} ({idx}/{len(df)})...")
         emb = transcript_word_features(enc, tokenizer, row["sentence"], lower, combine_type)
-        save_word_features(os.path.join(save_dir, f"{name}.npy"), emb, feature_level, 768)
+        save_word_features(os.path.join(save_dir, f"{name}.npy"), emb, feature_level, enc.hidden)
     print(f"Total {len(df)} files done! Time used ({model_name}): {time.time() - start_time:.1f}s.")

@@ -355,9 +355,9 @@ def hubert_state_dict(seed=1, layers=12, scale=1.0, large=False, data2vec=False,
     return g.sd
 
 
-def bert_state_dict(vocab_size, seed=2, layers=12, scale=1.0, max_pos=None, type_vocab=None):
+def bert_state_dict(vocab_size, seed=2, layers=12, scale=1.0, max_pos=None, type_vocab=None, large=False):
     """Keys of ``transformers.BertModel`` / ``RobertaModel`` (identical names)."""
-    c = BERT_CFG
+    c = dict(BERT_CFG, hidden=1024, heads=16, ffn=4096) if large else BERT_CFG   # large: bert-large / roberta-large
     g = _Gen(seed)
     d = c["hidden"]
     g.normal("embeddings.word_embeddings.weight", (vocab_size, d), 0.05)

@@ -295,3 +295,19 @@ def test_oracle_audio_restatement_covers_wav2vec2_large_960h_and_data2vec():
         got = E.hubert_hidden_states({k: torch.from_numpy(v) for k, v in sd.items()}, x, layers=2, heads=heads)
         for a, b in zip(got, ref):
             assert float((a - b).abs().max() / b.abs().max()) < 2e-5
+
+
+def test_bert_oracle_matches_hf_large_configuration():
+    """bert-large / roberta-large shape (1024 / 16 heads / 4096): the same restatement at other dims, pinned to HF."""
+    from transformers import BertConfig, BertModel
+    sd = S.bert_state_dict(300, seed=4, layers=2, large=True)
+    m = BertModel(BertConfig(vocab_size=300, hidden_size=1024, num_hidden_layers=2, num_attention_heads=16,
+                             intermediate_size=4096), add_pooling_layer=False).eval()
+    res = m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    assert not res.missing_keys
+    ids = torch.tensor([[2, 17, 250, 99, 42, 7, 3]])
+    with torch.no_grad():
+        ref = m(ids, output_hidden_states=True).hidden_states
+    got = E.bert_hidden_states({k: torch.from_numpy(v) for k, v in sd.items()}, ids, layers=2, heads=16)
+    for a, b in zip(got, ref):
+        assert float((a - b).abs().max() / b.abs().max()) < 2e-5

@@ -497,3 +497,28 @@ def test_wav2vec2_large_960h_family(cuda):
         assert float((hidden[l].cpu() - ref_hs[l]).abs().max() / ref_hs[l].abs().max()) < 4e-3, l
     ref = torch.stack(ref_hs)[[-4, -3, -2, -1]].sum(dim=0)
     assert float((frames.cpu() - ref).abs().max() / ref.abs().max()) < 2e-3
+
+
+@pytest.mark.parametrize("roberta", [False, True])
+def test_bert_large_hidden_states_and_readout(cuda, roberta):
+    """bert-large / roberta-large shape (1024 / 16 heads / 4096) through mer_bert_forward: templated embedding
+    kernel, post-LN BF16X3 stack at runtime dims, last-four readout."""
+    from mertools_b200 import synthetic as S
+    from mertools_b200.encoders import BertEncoder
+    from oracle import encoders as E
+    layers, off = 4, (2 if roberta else 0)
+    sd = S.bert_state_dict(400, seed=6, layers=layers, large=True, max_pos=64)
+    enc = BertEncoder(sd, device=cuda, ln_eps=1e-5 if roberta else 1e-12, position_offset=off)
+    assert enc.hidden == 1024
+    sents = [[2, 17, 250, 99, 42, 7, 3], [2, 5, 3], [2] + list(range(10, 40)) + [3]]
+    utt, toks, hidden, cu = enc.forward(sents, start=1, end=-1, want_tokens=True, return_hidden=True)
+    tsd = {k: torch.from_numpy(v) for k, v in sd.items()}
+    for i, ids in enumerate(sents):
+        ref_hs = E.bert_hidden_states(tsd, torch.tensor([ids]), layers=layers, heads=16, eps=1e-5 if roberta else 1e-12,
+                                      position_offset=off)
+        a, b = int(cu[i]), int(cu[i + 1])
+        for l in range(layers + 1):
+            assert float((hidden[l, a:b].cpu() - ref_hs[l][0]).abs().max() / ref_hs[l].abs().max()) < 4e-3, (i, l)
+        ref = torch.stack(ref_hs)[[-4, -3, -2, -1]].sum(dim=0)[0]
+        assert float((toks[a:b].cpu() - ref).abs().max() / ref.abs().max()) < 2e-3, i
+        assert float((utt[i].cpu() - ref[1:-1].mean(dim=0)).abs().max() / ref.abs().max()) < 1e-3, i
