@@ -1097,38 +1097,6 @@ class MerBertModel(C.Structure):
                 ("hidden", C.c_int), ("ffn", C.c_int), ("heads", C.c_int)]
 
 
-def _hubert_forward_ragged(self, rows: torch.Tensor, lengths, normalize=True, want_frames=False):
-    """rows: fp32 CUDA [B, Lmax]; row b holds ``lengths[b]`` samples (the rest is ignored when ``normalize``, and must
-    be finite otherwise).  Every clip is computed as if it were forwarded alone (mer_hubert_forward_ragged).
-    Returns (utt [B, D], frames): frames = list of [T_b, D] tensors (views of one packed tensor) or None."""
-    assert rows.dtype == torch.float32 and rows.is_cuda and rows.dim() == 2
-    rows = rows.contiguous()
-    B, Lmax = rows.shape
-    lengths = [int(n) for n in lengths]
-    assert len(lengths) == B and all(0 < n <= Lmax for n in lengths)
-    tb = [self.num_frames(n) for n in lengths]
-    D = self.hidden
-    ws = self.ws.get(L.lib().mer_hubert_model_workspace_bytes(C.byref(self.model), B, Lmax))
-    utt = torch.empty(B, D, dtype=torch.float32, device=self.device)
-    packed = torch.empty(sum(tb), D, dtype=torch.float32, device=self.device) if want_frames else None
-    fwd = L.declare("mer_hubert_forward_ragged", [C.POINTER(MerHubertModel), C.c_void_p, C.POINTER(C.c_int), C.c_int,
-                                                  C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
-                                                  C.c_void_p])
-    L.check(fwd(C.byref(self.model), L.ptr(rows), (C.c_int * B)(*lengths), B, Lmax, 1 if normalize else 0, L.ptr(ws),
-                ws.numel(), L.ptr(packed), L.ptr(utt), L.stream_ptr()))
-    return utt, (list(torch.split(packed, tb)) if want_frames else None)
-
-
-HubertEncoder.forward_ragged = _hubert_forward_ragged
-
-
-class MerBertModel(C.Structure):
-    _fields_ = [("n_layers", C.c_int), ("ln_eps", C.c_float), ("word_emb", C.c_void_p),
-                ("pos_emb", C.c_void_p), ("type_emb0", C.c_void_p), ("emb_ln_g", C.c_void_p),
-                ("emb_ln_b", C.c_void_p), ("layers", C.POINTER(W.MerLayerWeights)),
-                ("hidden", C.c_int), ("ffn", C.c_int), ("heads", C.c_int)]
-
-
 class BertEncoder:
     """BERT / RoBERTa-base (HF ``BertModel`` / ``RobertaModel``) over a packed variable-length batch
     + the reference readout (sum of the last four hidden states, strip specials, mean).
@@ -1147,6 +1115,11 @@ class BertEncoder:
         self.word = pk.keep(sd["embeddings.word_embeddings.weight"])
         self.pos = pk.keep(sd["embeddings.position_embeddings.weight"])
         self.vocab_size, self.max_pos = self.word.shape[0], self.pos.shape[0]
+        # base (768 / 12 heads / 3072) or -large (1024 / 16 / 4096) BERT-architecture checkpoints
+        self.hidden = int(self.word.shape[1])
+        ffn = int(sd["encoder.layer.0.intermediate.dense.weight"].shape[0])
+        assert self.hidden in (768, 1024) and ffn % 128 == 0, (self.hidden, ffn)
+        m.hidden, m.ffn, m.heads = self.hidden, ffn, self.hidden // 64
         m.word_emb, m.pos_emb = self.word.data_ptr(), self.pos.data_ptr()
         m.type_emb0 = pk.keep(sd["embeddings.token_type_embeddings.weight"][0]).data_ptr()
         m.emb_ln_g = pk.keep(sd["embeddings.LayerNorm.weight"]).data_ptr()
@@ -1156,8 +1129,8 @@ class BertEncoder:
         self.model = m
         self.ws = _Workspace(self.device)
         lib = L.lib()
-        lib.mer_bert_workspace_bytes.restype = C.c_longlong
-        lib.mer_bert_workspace_bytes.argtypes = [C.c_int, C.c_int]
+        lib.mer_bert_model_workspace_bytes.restype = C.c_longlong
+        lib.mer_bert_model_workspace_bytes.argtypes = [C.POINTER(MerBertModel), C.c_int, C.c_int]
         vp, i32 = C.c_void_p, C.c_int
         self._fwd = L.declare("mer_bert_forward", [C.POINTER(MerBertModel), vp, vp, vp, i32, i32, i32,
                                                    vp, vp, vp, C.c_longlong, vp, vp, vp, vp])
@@ -1177,8 +1150,8 @@ class BertEncoder:
             self._packed_key = key
         cu, pos, seg_b, seg_e = self._packed
         n_tok = n * seqlen
-        ws = self.ws.get(L.lib().mer_bert_workspace_bytes(n_tok, n))
-        utt = torch.empty(n, 768, dtype=torch.float32, device=self.device)
+        ws = self.ws.get(L.lib().mer_bert_model_workspace_bytes(C.byref(self.model), n_tok, n))
+        utt = torch.empty(n, self.hidden, dtype=torch.float32, device=self.device)
         L.check(self._fwd(C.byref(self.model), L.ptr(ids.contiguous()), L.ptr(pos), L.ptr(cu), n, n_tok,
                           seqlen, L.ptr(seg_b), L.ptr(seg_e), L.ptr(ws), ws.numel(), None, L.ptr(utt),
                           None, L.stream_ptr()))
@@ -1205,10 +1178,10 @@ class BertEncoder:
         d_cu = dev[2 * n_tok:2 * n_tok + n_seq + 1]
         d_b = dev[2 * n_tok + n_seq + 1:2 * n_tok + 2 * n_seq + 1]
         d_e = dev[2 * n_tok + 2 * n_seq + 1:]
-        ws = self.ws.get(L.lib().mer_bert_workspace_bytes(n_tok, n_seq))
-        utt = torch.empty(n_seq, 768, dtype=torch.float32, device=self.device)
-        toks = torch.empty(n_tok, 768, dtype=torch.float32, device=self.device) if want_tokens else None
-        hidden = (torch.empty(self.n_layers + 1, n_tok, 768, dtype=torch.float32, device=self.device)
+        ws = self.ws.get(L.lib().mer_bert_model_workspace_bytes(C.byref(self.model), n_tok, n_seq))
+        utt = torch.empty(n_seq, self.hidden, dtype=torch.float32, device=self.device)
+        toks = torch.empty(n_tok, self.hidden, dtype=torch.float32, device=self.device) if want_tokens else None
+        hidden = (torch.empty(self.n_layers + 1, n_tok, self.hidden, dtype=torch.float32, device=self.device)
                   if return_hidden else None)
         L.check(self._fwd(C.byref(self.model), L.ptr(d_ids), L.ptr(d_pos), L.ptr(d_cu), n_seq, n_tok,
                           max(lens), L.ptr(d_b), L.ptr(d_e), L.ptr(ws), ws.numel(), L.ptr(toks),
