@@ -300,6 +300,49 @@ def emonet_state_dict(seed=11):
     return sd
 
 
+WHISPER_BASE_CFG = dict(d_model=512, heads=8, ffn=2048, enc_layers=6, dec_layers=6, mels=80, src_pos=1500, tgt_pos=448,
+                        vocab=51865, start_token=50258)
+
+
+def whisper_state_dict(seed=13, enc_layers=6, dec_layers=6, vocab=64, cfg=WHISPER_BASE_CFG):
+    """Keys of ``transformers.WhisperModel`` (whisper-base shape; a small vocabulary keeps the fixture light — the
+    reference only ever embeds ``decoder_start_token_id``): encoder convs / sinusoid-initialised (here random)
+    position table / pre-LN layers (k_proj without bias), decoder with self- and cross-attention."""
+    g = _Gen(seed)
+    d, f = cfg["d_model"], cfg["ffn"]
+    g.normal("encoder.conv1.weight", (d, cfg["mels"], 3), np.sqrt(2.0 / (3 * cfg["mels"])))
+    g.normal("encoder.conv1.bias", (d,), 0.05)
+    g.normal("encoder.conv2.weight", (d, d, 3), np.sqrt(2.0 / (3 * d)))
+    g.normal("encoder.conv2.bias", (d,), 0.05)
+    g.normal("encoder.embed_positions.weight", (cfg["src_pos"], d), 0.1)
+    g.normal("decoder.embed_tokens.weight", (vocab, d), 0.3)
+    g.normal("decoder.embed_positions.weight", (cfg["tgt_pos"], d), 0.1)
+
+    def attn(p):
+        for n in ("q_proj", "v_proj", "out_proj"):
+            g.linear(p + n, d, d, 0.03)
+        g.normal(p + "k_proj.weight", (d, d), 0.03)
+    for i in range(enc_layers):
+        p = f"encoder.layers.{i}."
+        attn(p + "self_attn.")
+        g.ln(p + "self_attn_layer_norm", d)
+        g.linear(p + "fc1", f, d, 0.03)
+        g.linear(p + "fc2", d, f, 0.03)
+        g.ln(p + "final_layer_norm", d)
+    g.ln("encoder.layer_norm", d)
+    for i in range(dec_layers):
+        p = f"decoder.layers.{i}."
+        attn(p + "self_attn.")
+        g.ln(p + "self_attn_layer_norm", d)
+        attn(p + "encoder_attn.")
+        g.ln(p + "encoder_attn_layer_norm", d)
+        g.linear(p + "fc1", f, d, 0.03)
+        g.linear(p + "fc2", d, f, 0.03)
+        g.ln(p + "final_layer_norm", d)
+    g.ln("decoder.layer_norm", d)
+    return g.sd
+
+
 HUBERT_LARGE_CFG = dict(HUBERT_CFG, hidden=1024, heads=16, ffn=4096, layers=24)
 
 

@@ -315,6 +315,51 @@ def emonet_embedding(sd, x, dtype=torch.float32, eps=1e-5):
     return F.avg_pool2d(y, 4).flatten(1)
 
 
+def whisper_last_hidden_state(sd, input_features, decoder_input_ids, heads=8, dtype=torch.float32, eps=1e-5):
+    """``WhisperModel(input_features, decoder_input_ids=ids).last_hidden_state`` (the reference's Whisper branch,
+    extract_audio_huggingface.py:83-91) in eval mode -> [B, len(ids), d_model].  Encoder (HF modeling_whisper.py
+    WhisperEncoder): GELU(conv1 k3 p1), GELU(conv2 k3 s2 p1), + embed_positions, pre-LN layers (k_proj has no bias),
+    layer_norm.  Decoder: embed_tokens + embed_positions, pre-LN layers of causal self-attention, cross-attention over
+    the encoder output and an FFN, layer_norm.  input_features: [B, 80, 3000]."""
+    def mha(xq, xkv, p, causal):
+        B, Tq, D = xq.shape
+        hd = D // heads
+        q = _linear(xq, sd, p + "q_proj", dtype).view(B, Tq, heads, hd).transpose(1, 2)
+        k = F.linear(xkv, _t(sd, p + "k_proj.weight", dtype)).view(B, -1, heads, hd).transpose(1, 2)
+        v = _linear(xkv, sd, p + "v_proj", dtype).view(B, -1, heads, hd).transpose(1, 2)
+        s = q @ k.transpose(-1, -2) / hd ** 0.5
+        if causal:
+            s = s + torch.full((Tq, k.shape[2]), float("-inf")).triu(1)
+        o = (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(B, Tq, D)
+        return _linear(o, sd, p + "out_proj", dtype)
+
+    def ffn(x, p):
+        return _linear(F.gelu(_linear(x, sd, p + "fc1", dtype)), sd, p + "fc2", dtype)
+    x = input_features.to(dtype)
+    x = F.gelu(F.conv1d(x, _t(sd, "encoder.conv1.weight", dtype), _t(sd, "encoder.conv1.bias", dtype), padding=1))
+    x = F.gelu(F.conv1d(x, _t(sd, "encoder.conv2.weight", dtype), _t(sd, "encoder.conv2.bias", dtype), stride=2, padding=1))
+    x = x.transpose(1, 2) + _t(sd, "encoder.embed_positions.weight", dtype)
+    i = 0
+    while f"encoder.layers.{i}.fc1.weight" in sd:
+        p = f"encoder.layers.{i}."
+        y = _ln(x, sd, p + "self_attn_layer_norm", eps, dtype)
+        x = x + mha(y, y, p + "self_attn.", False)
+        x = x + ffn(_ln(x, sd, p + "final_layer_norm", eps, dtype), p)
+        i += 1
+    enc = _ln(x, sd, "encoder.layer_norm", eps, dtype)
+    ids = torch.as_tensor(decoder_input_ids, dtype=torch.long)
+    y = _t(sd, "decoder.embed_tokens.weight", dtype)[ids] + _t(sd, "decoder.embed_positions.weight", dtype)[:ids.shape[1]]
+    i = 0
+    while f"decoder.layers.{i}.fc1.weight" in sd:
+        p = f"decoder.layers.{i}."
+        z = _ln(y, sd, p + "self_attn_layer_norm", eps, dtype)
+        y = y + mha(z, z, p + "self_attn.", True)
+        y = y + mha(_ln(y, sd, p + "encoder_attn_layer_norm", eps, dtype), enc, p + "encoder_attn.", False)
+        y = y + ffn(_ln(y, sd, p + "final_layer_norm", eps, dtype), p)
+        i += 1
+    return _ln(y, sd, "decoder.layer_norm", eps, dtype)
+
+
 def hubert_pos_conv_weight(sd, dtype=torch.float32):
     """Effective weight of the weight-normed positional conv (:45-92): W = g * v / ||v||, the
     norm taken over dims (0,1) per kernel tap (weight_norm dim=2).  Older checkpoints name the

@@ -155,6 +155,61 @@ def imagenet_clip_features(sd, frames_bgr, feature_level="UTTERANCE"):
     return np.mean(emb, axis=0) if emb.ndim == 2 else emb
 
 
+def whisper_mel_filters(n_freq=201, n_mel=80, fmin=0.0, fmax=8000.0, sr=16000):
+    """The [201, 80] filter bank WhisperFeatureExtractor builds (HF audio_utils.mel_filter_bank with
+    norm="slaney", mel_scale="slaney"): triangles on the Slaney mel scale (linear below 1 kHz, logarithmic above),
+    each scaled by 2 / (its band width in Hz).  Equal to ``WhisperFeatureExtractor().mel_filters`` (tests)."""
+    def hz_to_mel(f):
+        f = np.asarray(f, dtype=np.float64)
+        m = 3.0 * f / 200.0
+        lg = f >= 1000.0
+        m[lg] = 15.0 + np.log(f[lg] / 1000.0) * (27.0 / np.log(6.4))
+        return m
+
+    def mel_to_hz(m):
+        m = np.asarray(m, dtype=np.float64)
+        f = 200.0 * m / 3.0
+        lg = m >= 15.0
+        f[lg] = 1000.0 * np.exp((np.log(6.4) / 27.0) * (m[lg] - 15.0))
+        return f
+    fft_freqs = np.linspace(0, sr // 2, n_freq)
+    f_pts = mel_to_hz(np.linspace(hz_to_mel(np.array([fmin]))[0], hz_to_mel(np.array([fmax]))[0], n_mel + 2))
+    fdiff = np.diff(f_pts)
+    slopes = f_pts[None, :] - fft_freqs[:, None]
+    fb = np.maximum(0, np.minimum(-slopes[:, :-2] / fdiff[:-1], slopes[:, 2:] / fdiff[1:]))
+    return fb * (2.0 / (f_pts[2:n_mel + 2] - f_pts[:n_mel]))[None, :]
+
+
+def whisper_log_mel(wave):
+    """``WhisperFeatureExtractor()(wave, sampling_rate=16000).input_features[0]`` (the reference's Whisper branch,
+    extract_audio_huggingface.py:85): zero-pad / cut to 30 s, reflect-padded STFT (periodic Hann 400, hop 160),
+    power spectrum, mel filter bank, log10 (floor 1e-10), drop the last frame, clamp to max - 8, (x + 4) / 4.
+    Returns float32 [80, 3000]."""
+    x = np.zeros(480000, np.float64)
+    n = min(len(wave), 480000)
+    x[:n] = np.asarray(wave, np.float64)[:n]
+    p = np.pad(x, (200, 200), mode="reflect")
+    nfr = 1 + (len(p) - 400) // 160
+    idx = np.arange(400)[None, :] + 160 * np.arange(nfr)[:, None]
+    win = 0.5 - 0.5 * np.cos(2 * np.pi * np.arange(400) / 400)
+    spec = np.abs(np.fft.rfft(p[idx] * win, n=400, axis=1)) ** 2
+    lm = np.log10(np.maximum(1e-10, spec @ whisper_mel_filters())).T[:, :-1]
+    lm = np.maximum(lm, lm.max() - 8.0)
+    return ((lm + 4.0) / 4.0).astype(np.float32)
+
+
+def whisper_clip_features(sd, wave, start_token, feature_level="UTTERANCE", heads=8):
+    """One file through the Whisper branch of extract_audio_huggingface.py:83-110: log-mel features, the model with
+    ``decoder_input_ids = [[start, start]]``, ``last_hidden_state[0]`` = [2, D]; UTTERANCE -> mean over the two rows."""
+    f = torch.from_numpy(whisper_log_mel(wave))[None]
+    with torch.no_grad():
+        feat = E.whisper_last_hidden_state(sd, f, torch.tensor([[start_token, start_token]]), heads=heads)[0].numpy()
+    feat = np.array(feat).squeeze()
+    if feature_level == "UTTERANCE" and len(feat.shape) != 1:
+        feat = np.mean(feat, axis=0)
+    return feat
+
+
 def cv2_resize_linear_u8(img, oh, ow):
     """``cv2.resize(img, (ow, oh))`` (INTER_LINEAR, the default) for uint8 [H, W, C] images, restated from OpenCV's
     fixed-point resize (imgproc/src/resize.cpp: 11-bit coefficients, HResizeLinear then the 8-bit VResizeLinear

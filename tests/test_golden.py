@@ -295,3 +295,16 @@ def test_audio_oracle_matches_reference_script_data2vec_audio():
             fra = P.audio_clip_features(sd, w, layers=layers, feature_level="FRAME")
         assert utt.shape == (768,) and _rel(utt, g[f"utt{i}"]) < 5e-5, f"clip {i} ({n} samples)"
         assert _rel(fra[::16], g[f"fra{i}"]) < 5e-5
+
+
+def test_audio_oracle_matches_reference_script_whisper_branch():
+    """Whisper branch (extract_audio_huggingface.py:83-110): log-mel restatement + encoder / decoder restatement against
+    the unmodified reference extract() on a whisper-base-shaped checkpoint."""
+    g = np.load(os.path.join(G, "audio_whisper_golden.npz"))
+    layers = int(g["layers"])
+    sd = _t(S.whisper_state_dict(seed=int(g["seed"]), enc_layers=layers, dec_layers=layers))
+    for i, n in enumerate(g["lens"]):
+        w = S.synth_waves(1, int(n), seed=int(g["seed0"]) + i)[0].astype(np.float64) / 32768.0
+        for level, key in (("UTTERANCE", "utt"), ("FRAME", "fra")):
+            got, ref = P.whisper_clip_features(sd, w, int(g["start"]), level), g[f"{key}{i}"]
+            assert got.shape == ref.shape and _rel(got, ref) < 5e-5, (i, level)

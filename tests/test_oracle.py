@@ -311,3 +311,26 @@ def test_bert_oracle_matches_hf_large_configuration():
     got = E.bert_hidden_states({k: torch.from_numpy(v) for k, v in sd.items()}, ids, layers=2, heads=16)
     for a, b in zip(got, ref):
         assert float((a - b).abs().max() / b.abs().max()) < 2e-5
+
+
+def test_whisper_restatements_match_hf():
+    """Log-mel front-end and mel filter bank against WhisperFeatureExtractor, encoder + decoder against WhisperModel."""
+    from transformers import WhisperConfig, WhisperFeatureExtractor, WhisperModel
+    fe = WhisperFeatureExtractor()
+    assert np.array_equal(P.whisper_mel_filters(), fe.mel_filters)
+    rng = np.random.default_rng(0)
+    for n in (30000, 16000 * 7 + 123):
+        x = rng.standard_normal(n) * 0.1
+        ref = fe(x, sampling_rate=16000, return_tensors="np").input_features[0]
+        assert np.abs(P.whisper_log_mel(x) - ref).max() < 1e-5
+    sd = S.whisper_state_dict(seed=13, enc_layers=2, dec_layers=2)
+    m = WhisperModel(WhisperConfig(vocab_size=64, d_model=512, encoder_layers=2, decoder_layers=2, encoder_attention_heads=8,
+                                   decoder_attention_heads=8, encoder_ffn_dim=2048, decoder_ffn_dim=2048,
+                                   decoder_start_token_id=5, pad_token_id=0, bos_token_id=1, eos_token_id=2)).eval()
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    f = torch.randn(2, 80, 3000, generator=torch.Generator().manual_seed(1)) * 0.5
+    ids = torch.tensor([[5, 5], [5, 5]])
+    with torch.no_grad():
+        ref = m(f, decoder_input_ids=ids).last_hidden_state
+    got = E.whisper_last_hidden_state({k: torch.from_numpy(v) for k, v in sd.items()}, f, ids)
+    assert float((got - ref).abs().max() / ref.abs().max()) < 2e-5
