@@ -448,6 +448,21 @@ MER_API int mer_hubert_forward_ragged(const MerHubertModel* model, const float* 
 MER_API int mer_logmel_num_frames(int n_samples);
 MER_API int mer_logmel(const float* wave, int batch, int n_samples, long long ld_wave, float* out, void* stream);
 
+/* ---- Whisper branch of the audio extractor (extract_audio_huggingface.py:83-91): the two kernels the shared GEMM /
+ * LayerNorm / attention entry points do not cover; the encoder / decoder are orchestrated from the host over those
+ * (mertools_b200/extract/whisper.py). ---- */
+/* WhisperFeatureExtractor: waves fp32 [batch, ld_wave >= 480000] (30 s at 16 kHz, zero-padded by the caller) ->
+ * out fp32 [batch, 3000, ld_out] TIME-MAJOR log-mel features (columns >= 80 zeroed; ld_out = 96 makes it the K-padded
+ * operand of the first convolution), TF32-rounded when round_tf32_out.  mel_filters: fp32 [201, 80] (the Slaney bank
+ * of the feature extractor).  scratch: int [batch]. */
+MER_API int mer_whisper_logmel(const float* waves, int batch, long long ld_wave, const float* mel_filters, float* out,
+                               int ld_out, int round_tf32_out, int* scratch, void* stream);
+/* softmax(q k^T / 8) v per (clip, head) for nq <= 8 query rows and nk <= 1536 keys (the decoder's causal self-attention
+ * over its start tokens, its cross-attention over the encoder frames).  q [batch * nq, ld_q], k / v [batch * nk, ld_*],
+ * out [batch * nq, ld_out]; head h uses columns [64 h, 64 h + 64) of each; k rows 16-byte aligned. */
+MER_API int mer_small_attention(const float* q, int ld_q, const float* k, int ld_k, const float* v, int ld_v, int batch,
+                                int heads, int nq, int nk, int causal, float* out, int ld_out, void* stream);
+
 /* ---- BERT / RoBERTa-base text encoder ------------------------------------------------------------ */
 typedef struct MerBertModel {
   int n_layers;

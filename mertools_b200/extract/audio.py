@@ -26,6 +26,7 @@ from . import common
 HUBERT_BASE_CHINESE = "chinese-hubert-base"
 WAV2VEC2_BASE_CHINESE = "chinese-wav2vec2-base"
 DATA2VEC_AUDIO_BASE = "data2vec-audio-base-960h"   # Data2VecAudioModel: recognised from its positional conv chain
+WHISPER_BASE = "whisper-base"                      # encoder-decoder branch (:83-91): extract/whisper.py
 MAXLEN = 16000 * 10
 
 
@@ -125,7 +126,16 @@ def extract(model_name, audio_files, save_dir, feature_level, gpu, config=None, 
     start_time = time.time()
     assert gpu != -1, "mertools_b200 has no CPU path (reference: gpu=-1 means CPU)"
     model_file = os.path.join(config.PATH_TO_PRETRAINED_MODELS, f"transformers/{model_name}")
-    ext = AudioExtractor(common.load_hf_state_dict(model_file), device=f"cuda:{gpu}")
+    if model_name == WHISPER_BASE:
+        import json
+
+        from .whisper import WhisperExtractor
+        with open(os.path.join(model_file, "config.json")) as f:
+            cfg = json.load(f)
+        sd = {k[len("model."):] if k.startswith("model.") else k: v for k, v in common.load_hf_state_dict(model_file).items()}
+        ext = WhisperExtractor(sd, cfg["decoder_start_token_id"], device=f"cuda:{gpu}", heads=cfg["encoder_attention_heads"])
+    else:
+        ext = AudioExtractor(common.load_hf_state_dict(model_file), device=f"cuda:{gpu}")
     for s in range(0, len(audio_files), clips_per_launch):
         chunk = audio_files[s:s + clips_per_launch]
         waves = []

@@ -594,3 +594,80 @@ def test_ctypes_declarations_have_the_arity_of_the_header_prototypes():
             assert protos[m.group(1)] == n, (os.path.basename(f), m.group(1), n, protos[m.group(1)])
             checked += 1
     assert checked >= 20
+
+
+class _TorchWhisperOps:
+    """CPU stand-in for mertools_b200.extract.whisper.CudaOps with the same op semantics (test infrastructure): lets the
+    backend-agnostic orchestration run against the reference golden without a GPU."""
+
+    def tensor(self, a):
+        return torch.from_numpy(np.ascontiguousarray(a, np.float32))
+
+    weight = tensor
+
+    def logmel(self, waves):
+        out = torch.zeros(len(waves), 3000, 96)
+        for i, w in enumerate(waves):
+            out[i, :, :80] = torch.from_numpy(P.whisper_log_mel(w)).T          # time-major, K padded to 96
+        return out
+
+    def conv1(self, mel, w, b):
+        B, T, K = mel.shape
+        d = w.shape[0]
+        xp = torch.zeros(B, T + 2, K)
+        xp[:, 1:T + 1] = mel                                                    # a_row0 = -1: one zero row before / after
+        y = sum(xp[:, k:k + T] @ w[:, k * K:(k + 1) * K].T for k in range(3)) + b
+        out = torch.zeros(B, T + 2, d)
+        out[:, 1:T + 1] = torch.nn.functional.gelu(y)
+        return out
+
+    def conv2(self, xpad, w, b, pos):
+        B, rows, d = xpad.shape
+        T = 1500
+        y = sum(xpad[:, k:k + 2 * T:2] @ w[:, k * d:(k + 1) * d].T for k in range(3)) + b
+        return pos + torch.nn.functional.gelu(y).reshape(B * T, d)
+
+    def layernorm(self, x, g, b, operand):
+        return torch.nn.functional.layer_norm(x, (x.shape[-1],), g, b, 1e-5)
+
+    def linear(self, x, w, b, gelu=False, res=None, operand=False):
+        y = x @ w.T + b
+        y = torch.nn.functional.gelu(y) if gelu else y
+        return y if res is None else res + y
+
+    def _att(self, q, k, v, heads, causal):
+        B, nq, d = q.shape
+        hd = d // heads
+        q, k, v = (t.reshape(B, -1, heads, hd).transpose(1, 2) for t in (q, k, v))
+        s = q @ k.transpose(-1, -2) / 8.0
+        if causal:
+            s = s + torch.full(s.shape[-2:], float("-inf")).triu(1)
+        return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * nq, d)
+
+    def self_attention(self, qkv, B, T, heads):
+        d = qkv.shape[1] // 3
+        q, k, v = (qkv[:, i * d:(i + 1) * d].reshape(B, T, d) for i in range(3))
+        return self._att(q, k, v, heads, False)
+
+    def small_attention(self, q, q0, k, k0, v, v0, B, heads, nq, nk, causal):
+        d = heads * 64
+        return self._att(q[:, q0:q0 + d].reshape(B, nq, d), k[:, k0:k0 + d].reshape(B, nk, d),
+                         v[:, v0:v0 + d].reshape(B, nk, d), heads, causal)
+
+
+def test_whisper_orchestration_reproduces_the_reference_golden_with_a_cpu_backend():
+    """mertools_b200.extract.whisper.WhisperNet (weight packing: tap-major conv matrices with the mel axis padded to 96,
+    fused q|k|v with a zero k bias, fused cross k|v; op order, residuals, position tables, decoder start tokens) run
+    with a torch backend of the same op semantics, against outputs of the unmodified reference extract()."""
+    from mertools_b200.extract.whisper import WhisperNet, whisper_mel_filters
+    g = np.load(os.path.join(ROOT, "tests", "golden", "audio_whisper_golden.npz"))
+    layers = int(g["layers"])
+    net = WhisperNet(S.whisper_state_dict(seed=int(g["seed"]), enc_layers=layers, dec_layers=layers), _TorchWhisperOps())
+    waves = [S.synth_waves(1, int(n), seed=int(g["seed0"]) + i)[0].astype(np.float64) / 32768.0 for i, n in enumerate(g["lens"])]
+    with torch.no_grad():
+        out = net.last_hidden_state(waves, int(g["start"])).numpy()
+    for i in range(len(waves)):
+        ref = g[f"fra{i}"]
+        assert out[i].shape == ref.shape and np.abs(out[i] - ref).max() / np.abs(ref).max() < 1e-4, i
+        assert np.abs(out[i].mean(0) - g[f"utt{i}"]).max() / np.abs(g[f"utt{i}"]).max() < 1e-4
+    assert np.array_equal(whisper_mel_filters(), P.whisper_mel_filters().astype(np.float32))

@@ -522,3 +522,28 @@ def test_bert_large_hidden_states_and_readout(cuda, roberta):
         ref = torch.stack(ref_hs)[[-4, -3, -2, -1]].sum(dim=0)[0]
         assert float((toks[a:b].cpu() - ref).abs().max() / ref.abs().max()) < 2e-3, i
         assert float((utt[i].cpu() - ref[1:-1].mean(dim=0)).abs().max() / ref.abs().max()) < 1e-3, i
+
+
+def test_whisper_branch_vs_reference_golden(cuda):
+    """Whisper branch: mer_whisper_logmel against the oracle front-end, then the whole WhisperNet on CudaOps (3-tap
+    GEMM convolutions, TF32 linears, flash attention over 1500 frames, mer_small_attention in the decoder) against
+    outputs of the unmodified reference extract()."""
+    import numpy as np
+
+    from mertools_b200 import synthetic as S
+    from mertools_b200.extract.whisper import CudaOps, WhisperExtractor
+    from oracle import pipeline as P
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(gdir, "audio_whisper_golden.npz"))
+    layers = int(g["layers"])
+    waves = [S.synth_waves(1, int(n), seed=int(g["seed0"]) + i)[0].astype(np.float64) / 32768.0 for i, n in enumerate(g["lens"])]
+    mel = CudaOps("cuda:0").logmel(waves).cpu().numpy()
+    for i, w in enumerate(waves):
+        ref = P.whisper_log_mel(w).T
+        assert np.abs(mel[i, :, :80] - ref).max() < 2e-3 and not mel[i, :, 80:].any()   # TF32-rounded values in [-1.5, 1.5]
+    ext = WhisperExtractor(S.whisper_state_dict(seed=int(g["seed"]), enc_layers=layers, dec_layers=layers), int(g["start"]),
+                           device="cuda:0")
+    utt, fra = ext.extract_waves(waves, "UTTERANCE"), ext.extract_waves(waves, "FRAME")
+    for i in range(len(waves)):
+        assert fra[i].shape == (2, 512) and np.abs(fra[i] - g[f"fra{i}"]).max() / np.abs(g[f"fra{i}"]).max() < 2e-3, i
+        assert np.abs(utt[i] - g[f"utt{i}"]).max() / np.abs(g[f"utt{i}"]).max() < 2e-3, i
