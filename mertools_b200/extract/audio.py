@@ -27,6 +27,7 @@ HUBERT_BASE_CHINESE = "chinese-hubert-base"
 WAV2VEC2_BASE_CHINESE = "chinese-wav2vec2-base"
 DATA2VEC_AUDIO_BASE = "data2vec-audio-base-960h"   # Data2VecAudioModel: recognised from its positional conv chain
 WHISPER_BASE = "whisper-base"                      # encoder-decoder branch (:83-91): extract/whisper.py
+WHISPER_LARGE = "whisper-large-v2"
 MAXLEN = 16000 * 10
 
 
@@ -126,7 +127,7 @@ def extract(model_name, audio_files, save_dir, feature_level, gpu, config=None, 
     start_time = time.time()
     assert gpu != -1, "mertools_b200 has no CPU path (reference: gpu=-1 means CPU)"
     model_file = os.path.join(config.PATH_TO_PRETRAINED_MODELS, f"transformers/{model_name}")
-    if model_name == WHISPER_BASE:
+    if model_name in (WHISPER_BASE, WHISPER_LARGE):
         import json
 
         from .whisper import WhisperExtractor

@@ -1,5 +1,5 @@
 """Whisper branch of the audio extractor: mirror of MERBench/feature_extraction/audio/extract_audio_huggingface.py:83-110
-for ``whisper-base`` (d_model 512; 1280 of large-v2 is outside the LayerNorm kernel's sizes).
+for ``whisper-base`` (d_model 512, 8 heads) and ``whisper-large-v2`` (1280, 20 heads).
 
 ``WhisperFeatureExtractor`` -> ``WhisperModel(input_features, decoder_input_ids=[[start, start]]).last_hidden_state[0]``
 = the decoder's two output rows.  The network is orchestrated here over kernel-level entry points of libmer_b200.so —
