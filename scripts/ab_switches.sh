@@ -8,8 +8,9 @@ steps=${1:-6}
 warmup=${2:-3}
 out=gpurun_out
 mkdir -p "$out"
-MER_RUN_UNVERIFIED=1 python -m pytest tests/test_zz_unverified_gpu.py -q -x > "$out/ab_tests.log" 2>&1
+MER_RUN_UNVERIFIED=1 timeout 1500 python -m pytest tests/test_zz_unverified_gpu.py -q -rA -p no:cacheprovider > "$out/ab_tests.log" 2>&1
 echo "unverified tests exit $?" | tee "$out/ab_tests.status"
+grep -E "^(PASSED|FAILED|ERROR)" "$out/ab_tests.log" | tee -a "$out/ab_tests.status"
 run() {  # name, then VAR=value pairs
   local name=$1
   shift
