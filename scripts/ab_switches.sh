@@ -12,7 +12,7 @@ mkdir -p "$out"
 # not hide the others (a timeout shows up as exit 124)
 : > "$out/ab_tests.status"
 for t in $(MER_RUN_UNVERIFIED=1 python -m pytest tests/test_zz_unverified_gpu.py --collect-only -q -p no:cacheprovider 2>/dev/null | grep "::"); do
-  MER_RUN_UNVERIFIED=1 timeout 300 python -m pytest "$t" -q -x -p no:cacheprovider > "$out/ab_test_last.log" 2>&1
+  MER_RUN_UNVERIFIED=1 timeout -k 10 300 python -m pytest "$t" -q -x -p no:cacheprovider > "$out/ab_test_last.log" 2>&1
   rc=$?
   echo "$rc $t" | tee -a "$out/ab_tests.status"
   if [ $rc -ne 0 ]; then { echo "==== $t (exit $rc)"; tail -40 "$out/ab_test_last.log"; } >> "$out/ab_tests.log"; fi
