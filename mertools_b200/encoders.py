@@ -1098,8 +1098,9 @@ class MerBertModel(C.Structure):
 
 
 class BertEncoder:
-    """BERT / RoBERTa-base (HF ``BertModel`` / ``RobertaModel``) over a packed variable-length batch
-    + the reference readout (sum of the last four hidden states, strip specials, mean).
+    """BERT-architecture encoders (HF ``BertModel`` / ``RobertaModel`` / ``ElectraModel`` with embedding_size ==
+    hidden_size; hidden 768 or 1024: BERT, RoBERTa, MacBERT, PERT, LERT, ELECTRA base and large) over a packed
+    variable-length batch + the reference readout (sum of the last four hidden states, strip specials, mean).
 
     Reference: MERBench/feature_extraction/text/extract_text_huggingface.py:222-249."""
 
@@ -1110,6 +1111,8 @@ class BertEncoder:
         pk = self.pk = W.Packed(self.device)
         self.position_offset = position_offset  # 0 = BERT, 2 = RoBERTa (pad_token_id + 1)
         self.n_layers = W.count_layers(sd, "encoder.layer.{i}.output.LayerNorm.weight")
+        assert "embeddings_project.weight" not in sd, \
+            "ELECTRA-small style checkpoints (embedding_size != hidden_size) are not on the B200 path"
         m = MerBertModel()
         m.n_layers, m.ln_eps = self.n_layers, ln_eps
         self.word = pk.keep(sd["embeddings.word_embeddings.weight"])

@@ -334,3 +334,18 @@ def test_whisper_restatements_match_hf():
         ref = m(f, decoder_input_ids=ids).last_hidden_state
     got = E.whisper_last_hidden_state({k: torch.from_numpy(v) for k, v in sd.items()}, f, ids)
     assert float((got - ref).abs().max() / ref.abs().max()) < 2e-5
+
+
+def test_electra_base_is_the_bert_graph_under_the_same_names():
+    """electra-base / -large discriminators (extract_text_huggingface.py:27-28,44-46): embedding_size == hidden_size, so
+    ElectraModel is BertModel's graph with identical parameter names — the BERT restatement applies as is."""
+    from transformers import ElectraConfig, ElectraModel
+    m = ElectraModel(ElectraConfig(vocab_size=300, num_hidden_layers=2, embedding_size=768, hidden_size=768,
+                                   num_attention_heads=12, intermediate_size=3072)).eval()
+    sd = m.state_dict()
+    assert not any("embeddings_project" in k for k in sd)
+    ids = torch.tensor([[2, 17, 250, 99, 42, 7, 3]])
+    with torch.no_grad():
+        ref = m(ids, output_hidden_states=True).hidden_states
+    for a, b in zip(E.bert_hidden_states(sd, ids, layers=2), ref):
+        assert float((a - b).abs().max() / b.abs().max()) < 2e-5
