@@ -671,3 +671,45 @@ def test_whisper_orchestration_reproduces_the_reference_golden_with_a_cpu_backen
         assert out[i].shape == ref.shape and np.abs(out[i] - ref).max() / np.abs(ref).max() < 1e-4, i
         assert np.abs(out[i].mean(0) - g[f"utt{i}"]).max() / np.abs(g[f"utt{i}"]).max() < 1e-4
     assert np.array_equal(whisper_mel_filters(), P.whisper_mel_filters().astype(np.float32))
+
+
+def test_encoder_constructors_run_with_the_device_layer_stubbed(monkeypatch):
+    """Every encoder's __init__ (checkpoint inspection, weight re-layout, ctypes model structs) executed on CPU with
+    only the device-touching calls stubbed: tensors stay on the host, rounding / splitting kernels become identities.
+    Catches host-side mistakes in constructor paths that the GPU tests of this round have not exercised yet."""
+    from mertools_b200 import _lib
+    from mertools_b200 import encoders as En
+    from mertools_b200 import weights as Wt
+    monkeypatch.setattr(_lib, "check", lambda rc: None)
+    monkeypatch.setattr(_lib, "round_tf32_", lambda t: t)
+    monkeypatch.setattr(_lib, "split_bf16", lambda t: t.clone())
+    monkeypatch.setattr(Wt, "_dev", lambda x, device: (torch.from_numpy(np.ascontiguousarray(x)) if isinstance(x, np.ndarray)
+                                                        else x).detach().to(dtype=torch.float32).contiguous())
+    made = {
+        "vit": En.VitEncoder(S.vit_state_dict(seed=0, layers=2)),
+        "clip_b32": En.ClipVisionEncoder(S.clip_vision_state_dict(variant="b32", layers=2)),
+        "clip_l14_f16": En.ClipVisionEncoder(S.clip_vision_state_dict(variant="l14", layers=1), precision="f16"),
+        "resnet18": En.ResNet18Encoder(S.resnet18_state_dict()),
+        "ferplus": En.FerplusResnet50Encoder(S.ferplus_resnet50_state_dict()),
+        "senet": En.FerplusResnet50Encoder(S.ferplus_resnet50_state_dict(se=True)),
+        "manet": En.ManetEncoder(S.manet_state_dict()),
+        "emonet": En.EmonetEncoder(S.emonet_state_dict()),
+        "vggish": En.VggishEncoder(S.vggish_state_dict()),
+        "hubert": En.HubertEncoder(S.hubert_state_dict(layers=4)),
+        "hubert_large": En.HubertEncoder(S.hubert_state_dict(layers=4, large=True)),
+        "wav2vec2_large_960h": En.HubertEncoder(S.hubert_state_dict(layers=4, large=True, group_norm=True)),
+        "data2vec": En.HubertEncoder(S.hubert_state_dict(layers=4, data2vec=True)),
+        "bert": En.BertEncoder(S.bert_state_dict(100, layers=4)),
+        "bert_large": En.BertEncoder(S.bert_state_dict(100, layers=4, large=True)),
+    }
+    assert made["clip_l14_f16"].precision == "f16" and made["clip_l14_f16"].tokens == 257
+    assert (made["ferplus"].model.n_convs, made["senet"].model.n_convs, made["manet"].model.n_convs,
+            made["emonet"].model.n_convs) == (52, 82, 136, 222)
+    h = made["data2vec"].model
+    assert (h.n_pos_layers, h.pos_taps, h.feat_norm_layer, h.stable_layer_norm, bool(h.conv_b[1])) == (5, 19, 1, 0, False)
+    h = made["wav2vec2_large_960h"].model
+    assert (h.hidden, h.heads, h.feat_norm_layer, h.stable_layer_norm, h.pos_window) == (1024, 16, 0, 0, 256)
+    h = made["hubert_large"].model
+    assert (h.hidden, h.feat_norm_layer, h.stable_layer_norm, bool(h.conv_b[1])) == (1024, 1, 1, True)
+    b = made["bert_large"].model
+    assert (made["bert_large"].hidden, b.hidden, b.ffn, b.heads) == (1024, 1024, 4096, 16) and made["bert"].model.hidden == 768
