@@ -42,6 +42,57 @@ def resample_frames_uniform(frames, nframe=16):
     return frames[indices[:nframe]]
 
 
+def select_frame_indices(vlen, n_frms=8, readtype="uniform", rng=np.random):
+    """The frame indices ``load_video_from_npy`` reads (MERBench/toolkit/utils/functions.py:81-104), bit for bit:
+    ``all``, ``uniform`` (the rule of resample_frames_uniform), ``continuous`` and ``continuous_polish`` (one
+    ``rng.randint`` call each, so a seeded ``np.random`` gives the reference's draw), then padding with the last index /
+    truncation to ``n_frms`` (skipped when n_frms == 0)."""
+    start, end = 0, vlen
+    if readtype == "all":
+        indices = np.arange(start, end, 1).astype(int).tolist()
+    elif readtype == "uniform":
+        m = min(n_frms, vlen)
+        indices = np.arange(start, end, vlen / m).astype(int).tolist()
+    elif readtype == "continuous":
+        ii = rng.randint(start, max(start + 1, end - n_frms))
+        indices = np.arange(ii, min(end, ii + n_frms)).astype(int).tolist()
+    elif readtype == "continuous_polish":
+        start += 25
+        end -= 25
+        ii = rng.randint(start, max(start + 1, end - n_frms * 4))
+        indices = np.linspace(ii, min(end, ii + n_frms * 4), n_frms).astype(int).tolist()
+    else:
+        raise ValueError(f"readtype {readtype!r}")
+    if n_frms != 0:
+        while len(indices) < n_frms:
+            indices.append(indices[-1])
+        indices = indices[:n_frms]
+    return indices
+
+
+def load_video_from_npy(frames, n_frms=8, height=224, width=224, readtype="uniform", return_raw=False, device="cuda",
+                        rng=np.random):
+    """Mirror of ``load_video_from_npy`` (functions.py:79-118) for a clip already in memory (uint8 [vlen, H, W, 3] BGR,
+    what ``func_video_to_face`` returns): index selection on the host, then on the device the selected frames through
+    the bit-exact ``cv2.resize`` kernel (mer_resize_cv2_linear_u8) and BGR -> RGB.  Returns float [3, T, H, W] (CUDA)
+    or, with ``return_raw``, uint8 [T, H, W, 3] RGB."""
+    import ctypes as C
+
+    from .. import _lib as L
+    frames = np.asarray(frames)
+    idx = select_frame_indices(len(frames), n_frms, readtype, rng)
+    sel = torch.from_numpy(np.ascontiguousarray(frames[idx])).to(device)
+    n, h, w, _ = sel.shape
+    if (h, w) != (height, width):
+        out = torch.empty(n, height, width, 3, dtype=torch.uint8, device=sel.device)
+        fn = L.declare("mer_resize_cv2_linear_u8", [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                                    C.c_void_p])
+        L.check(fn(L.ptr(sel), n, h, w, L.ptr(out), height, width, L.stream_ptr()))
+        sel = out
+    rgb = sel.flip(-1)                       # func_opencv_to_decord
+    return rgb if return_raw else rgb.permute(3, 0, 1, 2).float()
+
+
 def split_into_batch(inputs, bsize=32):
     return [inputs[i * bsize:(i + 1) * bsize] for i in range(math.ceil(len(inputs) / bsize))]
 

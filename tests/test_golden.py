@@ -308,3 +308,24 @@ def test_audio_oracle_matches_reference_script_whisper_branch():
         for level, key in (("UTTERANCE", "utt"), ("FRAME", "fra")):
             got, ref = P.whisper_clip_features(sd, w, int(g["start"]), level), g[f"{key}{i}"]
             assert got.shape == ref.shape and _rel(got, ref) < 5e-5, (i, level)
+
+
+def test_frame_index_selection_and_cv2_path_match_load_video_from_npy_golden():
+    """``select_frame_indices`` (all four readtypes, seeded draws) + the cv2.resize restatement + BGR->RGB against outputs
+    of the reference's own ``load_video_from_npy`` source (make_golden_video_npy.py)."""
+    import importlib.util
+    from mertools_b200.extract.visual import select_frame_indices
+    from oracle import pipeline as P
+    spec = importlib.util.spec_from_file_location("make_golden_video_npy", os.path.join(G, "make_golden_video_npy.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(G, "video_npy_golden.npz"))
+    for ci, (readtype, n_frms, vlen, size) in enumerate(mod.CASES):
+        frames = mod.golden_clip(vlen, size, 200 + ci)
+        np.random.seed(1000 + ci)
+        idx = select_frame_indices(vlen, n_frms, readtype)
+        rgb = np.stack([P.cv2_resize_linear_u8(frames[i], 224, 224)[..., ::-1] for i in idx])      # [T, 224, 224, 3]
+        x = rgb.transpose(3, 0, 1, 2).astype(np.float32)
+        assert list(x.shape) == list(g[f"shape{ci}"]), (readtype, x.shape)
+        assert np.array_equal(x[:, :, ::16, ::16].astype(np.uint8), g[f"probe{ci}"]), readtype
+        assert float(x.sum(dtype=np.float64)) == float(g[f"sum{ci}"][0]), readtype

@@ -547,3 +547,23 @@ def test_whisper_branch_vs_reference_golden(cuda):
     for i in range(len(waves)):
         assert fra[i].shape == (2, 512) and np.abs(fra[i] - g[f"fra{i}"]).max() / np.abs(g[f"fra{i}"]).max() < 2e-3, i
         assert np.abs(utt[i] - g[f"utt{i}"]).max() / np.abs(g[f"utt{i}"]).max() < 2e-3, i
+
+
+def test_load_video_from_npy_device_path(cuda):
+    """load_video_from_npy mirror on the device (gather, cv2-exact resize kernel, BGR->RGB) against the golden of the
+    reference's own function source, all four readtypes."""
+    import importlib.util
+
+    import numpy as np
+
+    from mertools_b200.extract.visual import load_video_from_npy
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden_video_npy", os.path.join(gdir, "make_golden_video_npy.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(gdir, "video_npy_golden.npz"))
+    for ci, (readtype, n_frms, vlen, size) in enumerate(mod.CASES):
+        np.random.seed(1000 + ci)
+        x = load_video_from_npy(mod.golden_clip(vlen, size, 200 + ci), n_frms=n_frms, readtype=readtype, device=cuda).cpu().numpy()
+        assert list(x.shape) == list(g[f"shape{ci}"])
+        assert np.array_equal(x[:, :, ::16, ::16].astype(np.uint8), g[f"probe{ci}"]) and float(x.sum(dtype=np.float64)) == float(g[f"sum{ci}"][0])
