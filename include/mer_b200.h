@@ -448,6 +448,14 @@ MER_API int mer_hubert_forward_ragged(const MerHubertModel* model, const float* 
 MER_API int mer_logmel_num_frames(int n_samples);
 MER_API int mer_logmel(const float* wave, int batch, int n_samples, long long ld_wave, float* out, void* stream);
 
+/* VideoMAE tubelet patches (extract_vision_huggingface.py:147-159; HF VideoMAEPatchEmbeddings): frames uint8 BGR
+ * [n_clips * 16, 224, 224, 3] (resized / cropped beforehand) -> out fp32, TF32-rounded [n_clips * 1568, 1536]: the A
+ * operand of the patch-embedding GEMM against the flattened Conv3d kernel [hidden, 3 * 2 * 16 * 16]; mean / std are
+ * HOST arrays of 3 floats (RGB, the image processor's).  The encoder runs from the host over mer_gemm / mer_layernorm /
+ * mer_attention (mertools_b200/extract/videomae.py). */
+MER_API int mer_videomae_patchify(const uint8_t* frames_bgr, int n_clips, const float* mean, const float* std,
+                                  float* out, void* stream);
+
 /* ---- Whisper branch of the audio extractor (extract_audio_huggingface.py:83-91): the two kernels the shared GEMM /
  * LayerNorm / attention entry points do not cover; the encoder / decoder are orchestrated from the host over those
  * (mertools_b200/extract/whisper.py). ---- */

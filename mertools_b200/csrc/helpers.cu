@@ -474,3 +474,38 @@ extern "C" int mer_resize_cv2_linear_u8(const uint8_t* in, int n, int H, int W, 
   mer_count_launches(1);
   return 0;
 }
+
+// ---- VideoMAE tubelet patches (HF VideoMAEPatchEmbeddings: Conv3d(3, hidden, (2, 16, 16), stride = kernel) on
+// [B, C, 16, 224, 224]): uint8 BGR frames [B * 16, 224, 224, 3] -> TF32-rounded fp32 rows [B * 1568, 1536], row =
+// (tubelet, patch row, patch column), K = (channel, frame in tubelet, dy, dx) = the flattened conv kernel, values
+// (pix / 255 - mean[c]) / std[c] in RGB order (VideoMAEImageProcessor's rescale + normalise). ----
+namespace {
+__global__ void __launch_bounds__(256)
+videomae_patchify_kernel(const uint8_t* __restrict__ frames, float* __restrict__ out, long long total, float m0, float m1,
+                         float m2, float s0, float s1, float s2) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int k = (int)(idx % 1536);
+  const long long row = idx / 1536;
+  const int token = (int)(row % 1568);
+  const long long b = row / 1568;
+  const int c = k >> 9, dt = (k >> 8) & 1, dy = (k >> 4) & 15, dx = k & 15;
+  const int tt = token / 196, py = (token % 196) / 14, px = token % 14;
+  const long long frame = b * 16 + tt * 2 + dt;
+  const float pix = (float)frames[((frame * 224 + py * 16 + dy) * 224 + px * 16 + dx) * 3 + (2 - c)];
+  const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+  out[idx] = round_tf32((pix * 0.00392156862745098f - mean) / sd);
+}
+}  // namespace
+
+extern "C" int mer_videomae_patchify(const uint8_t* frames_bgr, int n_clips, const float* mean, const float* std,
+                                     float* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MER_REQUIRE(frames_bgr && mean && std && out && n_clips > 0, "mer_videomae_patchify: bad arguments");
+  const long long total = (long long)n_clips * 1568 * 1536;
+  videomae_patchify_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(frames_bgr, out, total, mean[0], mean[1],
+                                                                                mean[2], std[0], std[1], std[2]);
+  MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
+  return 0;
+}

@@ -22,6 +22,8 @@ from . import common
 DINO2_LARGE = "dinov2-large"
 DINO2_GIANT = "dinov2-giant"
 DATA2VEC_VISUAL = "data2vec-vision-base-ft1k"
+VIDEOMAE_BASE = "videomae-base"
+VIDEOMAE_LARGE = "videomae-large"
 
 
 def func_read_frames(face_dir, vid):
@@ -188,7 +190,11 @@ def main(params, config=None, clips_per_launch=32):
     model_dir = os.path.join(config.PATH_TO_PRETRAINED_MODELS, f"transformers/{params.model_name}")
     assert params.gpu != -1, "mertools_b200 has no CPU path (reference: --gpu=-1 means CPU)"
     torch.cuda.set_device(params.gpu)
-    ext = VisualExtractor(common.load_hf_state_dict(model_dir), device=f"cuda:{params.gpu}")
+    if params.model_name in (VIDEOMAE_BASE, VIDEOMAE_LARGE):                    # :147-159: 16 frames -> 8 tubelet rows
+        from .videomae import VideoMaeExtractor
+        ext = VideoMaeExtractor.from_pretrained(model_dir, device=f"cuda:{params.gpu}")
+    else:
+        ext = VisualExtractor(common.load_hf_state_dict(model_dir), device=f"cuda:{params.gpu}")
     nframe = 64 if params.model_name in (DINO2_LARGE, DINO2_GIANT) else None
     vids = os.listdir(face_dir)
     print(f'Find total "{len(vids)}" videos.')

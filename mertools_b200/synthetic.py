@@ -343,6 +343,27 @@ def whisper_state_dict(seed=13, enc_layers=6, dec_layers=6, vocab=64, cfg=WHISPE
     return g.sd
 
 
+def videomae_state_dict(seed=15, layers=12, hidden=768, ffn=3072):
+    """Keys of ``transformers.VideoMAEModel`` (videomae-base shape): tubelet patch embedding Conv3d(3, 768, (2, 16, 16)),
+    pre-LN layers whose attention carries separate ``q_bias`` / ``v_bias`` (no key bias); the position table is a fixed
+    sinusoid, not a parameter."""
+    g = _Gen(seed)
+    g.normal("embeddings.patch_embeddings.projection.weight", (hidden, 3, 2, 16, 16), 0.02)
+    g.normal("embeddings.patch_embeddings.projection.bias", (hidden,), 0.02)
+    for i in range(layers):
+        p = f"encoder.layer.{i}."
+        for n in ("query", "key", "value"):
+            g.normal(p + f"attention.attention.{n}.weight", (hidden, hidden), 0.02)
+        g.normal(p + "attention.attention.q_bias", (hidden,), 0.02)
+        g.normal(p + "attention.attention.v_bias", (hidden,), 0.02)
+        g.linear(p + "attention.output.dense", hidden, hidden, 0.02)
+        g.ln(p + "layernorm_before", hidden)
+        g.ln(p + "layernorm_after", hidden)
+        g.linear(p + "intermediate.dense", ffn, hidden, 0.02)
+        g.linear(p + "output.dense", hidden, ffn, 0.02)
+    return g.sd
+
+
 HUBERT_LARGE_CFG = dict(HUBERT_CFG, hidden=1024, heads=16, ffn=4096, layers=24)
 
 

@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import math
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -358,6 +359,40 @@ def whisper_last_hidden_state(sd, input_features, decoder_input_ids, heads=8, dt
         y = y + ffn(_ln(y, sd, p + "final_layer_norm", eps, dtype), p)
         i += 1
     return _ln(y, sd, "decoder.layer_norm", eps, dtype)
+
+
+def videomae_sinusoid_table(n_position, d):
+    """``get_sinusoid_encoding_table`` of HF modeling_videomae.py: angle[p, j] = p / 10000^(2 (j // 2) / d), sine on
+    the even columns, cosine on the odd ones (float64 math, float32 result)."""
+    pos = np.arange(n_position, dtype=np.float64)[:, None]
+    j = np.arange(d)
+    tab = pos / np.power(10000.0, 2 * (j // 2) / d)[None, :]
+    tab[:, 0::2] = np.sin(tab[:, 0::2])
+    tab[:, 1::2] = np.cos(tab[:, 1::2])
+    return torch.from_numpy(tab.astype(np.float32))
+
+
+def videomae_last_hidden_state(sd, pixel_values, heads=12, eps=1e-12, dtype=torch.float32):
+    """``VideoMAEModel(pixel_values).last_hidden_state`` with ``use_mean_pooling=True`` (no final LayerNorm: the
+    released videomae-base / -large encoders; extract_vision_huggingface.py:147-159) in eval mode.
+    pixel_values: [B, 16, 3, 224, 224] -> [B, 1568, hidden]; token = (tubelet, patch row, patch column)."""
+    x = pixel_values.to(dtype).permute(0, 2, 1, 3, 4)                       # [B, C, T, H, W]
+    w = _t(sd, "embeddings.patch_embeddings.projection.weight", dtype)
+    x = F.conv3d(x, w, _t(sd, "embeddings.patch_embeddings.projection.bias", dtype), stride=w.shape[2:])
+    x = x.flatten(2).transpose(1, 2)
+    x = x + videomae_sinusoid_table(x.shape[1], x.shape[2]).to(dtype)
+    i = 0
+    while f"encoder.layer.{i}.output.dense.weight" in sd:
+        p = f"encoder.layer.{i}."
+        y = _ln(x, sd, p + "layernorm_before", eps, dtype)
+        q = F.linear(y, _t(sd, p + "attention.attention.query.weight", dtype), _t(sd, p + "attention.attention.q_bias", dtype))
+        k = F.linear(y, _t(sd, p + "attention.attention.key.weight", dtype))
+        v = F.linear(y, _t(sd, p + "attention.attention.value.weight", dtype), _t(sd, p + "attention.attention.v_bias", dtype))
+        x = x + _linear(_mha(q, k, v, heads), sd, p + "attention.output.dense", dtype)
+        h = F.gelu(_linear(_ln(x, sd, p + "layernorm_after", eps, dtype), sd, p + "intermediate.dense", dtype))
+        x = x + _linear(h, sd, p + "output.dense", dtype)
+        i += 1
+    return x
 
 
 def hubert_pos_conv_weight(sd, dtype=torch.float32):

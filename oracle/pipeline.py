@@ -269,6 +269,31 @@ def emonet_clip_features(sd, frames_bgr, feature_level="UTTERANCE"):
     return np.mean(emb, axis=0) if emb.ndim == 2 else emb
 
 
+def videomae_preprocess(frames_bgr, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    """extract_vision_huggingface.py:148-152: ``resample_frames_uniform(frames)`` (16 frames), BGR -> RGB
+    (func_opencv_to_numpy), VideoMAEImageProcessor: shortest edge -> 224 (bilinear, Pillow arithmetic as for the other
+    processors), centre crop 224, / 255, normalise.  Returns [1, 16, 3, 224, 224]."""
+    f = np.asarray(frames_bgr)
+    f = f[resample_frames_uniform_indices(len(f), 16)]
+    h, w = f.shape[1:3]
+    nh, nw = (224, int(224 * w / h)) if h <= w else (int(224 * h / w), 224)
+    if (nh, nw) != (h, w):
+        f = pil_resize_bilinear_u8(f, nh, nw)
+    top, left = (nh - 224) // 2, (nw - 224) // 2
+    f = f[:, top:top + 224, left:left + 224]
+    x = (f[..., ::-1].astype(np.float32) / np.float32(255.0) - np.asarray(mean, np.float32)) / np.asarray(std, np.float32)
+    return torch.from_numpy(np.ascontiguousarray(x.transpose(0, 3, 1, 2)))[None]
+
+
+def videomae_clip_features(sd, frames_bgr, feature_level="UTTERANCE", heads=12, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    """One video through the VideoMAE branch (:147-159, :175-189): last_hidden_state [1568, D] -> view(8, 196, D)
+    .mean(1) -> FRAME [8, D]; UTTERANCE -> mean over the 8 tubelets."""
+    with torch.no_grad():
+        hs = E.videomae_last_hidden_state(sd, videomae_preprocess(frames_bgr, mean, std), heads=heads)
+    emb = hs.view(8, 196, -1).mean(dim=1).numpy().squeeze()
+    return np.mean(emb, axis=0) if feature_level == "UTTERANCE" and emb.ndim == 2 else emb
+
+
 def manet_preprocess(frames_bgr):
     """FaceDataset.__getitem__ (dataset.py:40-47) + the transform of extract_manet_embedding.py:60-61:
     Resize((224, 224)) (PIL bilinear) and ToTensor only (no normalisation).  Returns [N, 3, 224, 224] in [0, 1]."""

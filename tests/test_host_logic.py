@@ -9,6 +9,7 @@ import torch
 
 from mertools_b200 import shard
 from mertools_b200 import synthetic as S
+from oracle import encoders as E
 from oracle import pipeline as P
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -713,3 +714,69 @@ def test_encoder_constructors_run_with_the_device_layer_stubbed(monkeypatch):
     assert (h.hidden, h.feat_norm_layer, h.stable_layer_norm, bool(h.conv_b[1])) == (1024, 1, 1, True)
     b = made["bert_large"].model
     assert (made["bert_large"].hidden, b.hidden, b.ffn, b.heads) == (1024, 1024, 4096, 16) and made["bert"].model.hidden == 768
+
+
+def _videomae_frames(n=21, h=120, w=160, seed=31):
+    return np.random.default_rng(seed).integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+
+
+def test_videomae_oracle_is_pinned_to_the_hf_model_and_processor():
+    """extract_vision_huggingface.py:147-159 restated in oracle/: VideoMAEImageProcessor (shortest edge 224 bilinear,
+    centre crop, rescale, normalise) and VideoMAEModel (use_mean_pooling=True: no final LayerNorm) on a synthetic
+    checkpoint that strict-loads into the HF class."""
+    transformers = pytest.importorskip("transformers")
+    sd = S.videomae_state_dict(seed=15, layers=2)
+    cfg = transformers.VideoMAEConfig(num_hidden_layers=2)
+    model = transformers.VideoMAEModel(cfg).eval()
+    missing = model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    assert not missing.unexpected_keys and all("position" in k for k in missing.missing_keys), missing
+    # the Pillow-backed processor = the transformers-4.x one the reference ran (5.x's default is torchvision-backed and
+    # differs from Pillow by one grey level on ~1 % of the upscaled pixels)
+    proc = transformers.VideoMAEImageProcessorPil()
+    frames = _videomae_frames()
+    sel = [frames[i] for i in P.resample_frames_uniform_indices(len(frames), 16)]
+    inputs = proc([f[:, :, ::-1].copy() for f in sel], return_tensors="pt")["pixel_values"]
+    mine = P.videomae_preprocess(frames, proc.image_mean, proc.image_std)
+    assert tuple(inputs.shape) == tuple(mine.shape) == (1, 16, 3, 224, 224)
+    assert float((inputs - mine).abs().max()) < 2e-6
+    with torch.no_grad():
+        ref = model(inputs).last_hidden_state
+    got = E.videomae_last_hidden_state(sd, mine)
+    assert float((got - ref).abs().max() / ref.abs().max()) < 1e-5
+    utt = P.videomae_clip_features(sd, frames, "UTTERANCE", mean=proc.image_mean, std=proc.image_std)
+    fra = P.videomae_clip_features(sd, frames, "FRAME", mean=proc.image_mean, std=proc.image_std)
+    assert utt.shape == (768,) and fra.shape == (8, 768)
+    np.testing.assert_allclose(fra, ref.view(8, 196, -1).mean(1).numpy(), rtol=0, atol=1e-5 * float(ref.abs().max()))
+
+
+class _TorchVideoMaeOps(_TorchWhisperOps):
+    """CPU stand-in for the VideoMAE product backend: the patch gather in the layout mer_videomae_patchify writes
+    (rows = (clip, tubelet, patch row, patch column); K = (channel RGB, frame-in-tubelet, dy, dx))."""
+
+    def patchify(self, frames, mean, std):
+        n = frames.shape[0] // 16
+        x = torch.from_numpy(np.ascontiguousarray(np.asarray(frames)[..., ::-1])).float() / 255.0
+        x = (x - torch.tensor(mean)) / torch.tensor(std)                              # [n*16, 224, 224, 3] RGB
+        x = x.reshape(n, 8, 2, 14, 16, 14, 16, 3).permute(0, 1, 3, 5, 7, 2, 4, 6)    # n, tt, py, px, c, dt, dy, dx
+        return x.reshape(n * 1568, 1536)
+
+    def layernorm(self, x, g, b, operand, eps=1e-5):
+        return torch.nn.functional.layer_norm(x, (x.shape[-1],), g, b, eps)
+
+
+def test_videomae_orchestration_matches_the_oracle_with_a_cpu_backend():
+    """mertools_b200.extract.videomae.VideoMaeNet (Conv3d weight flattened to the patch-gather K order, fused q|k|v with
+    the zero key bias, fixed sinusoid positions, pre-LN layers, no final LayerNorm) run over a torch backend."""
+    from mertools_b200.extract.videomae import VideoMaeNet, sinusoid_table
+    sd = S.videomae_state_dict(seed=16, layers=2)
+    np.testing.assert_allclose(sinusoid_table(1568, 768), E.videomae_sinusoid_table(1568, 768).numpy(), atol=1e-6)
+    frames = _videomae_frames(n=16, h=224, w=224, seed=32)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    net = VideoMaeNet(sd, _TorchVideoMaeOps())
+    assert net.heads == 12 and len(net.layers) == 2
+    got = net.last_hidden_state(frames, mean, std)
+    ref = E.videomae_last_hidden_state(sd, P.videomae_preprocess(frames, mean, std))
+    assert tuple(got.shape) == tuple(ref.shape) == (1, 1568, 768)
+    assert float((got - ref).abs().max() / ref.abs().max()) < 1e-5
+    two = net.last_hidden_state(np.concatenate([frames, frames[::-1]]), mean, std)     # clip-major rows for B > 1
+    assert float((two[0] - ref[0]).abs().max() / ref.abs().max()) < 1e-5

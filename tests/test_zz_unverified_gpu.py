@@ -567,3 +567,18 @@ def test_load_video_from_npy_device_path(cuda):
         x = load_video_from_npy(mod.golden_clip(vlen, size, 200 + ci), n_frms=n_frms, readtype=readtype, device=cuda).cpu().numpy()
         assert list(x.shape) == list(g[f"shape{ci}"])
         assert np.array_equal(x[:, :, ::16, ::16].astype(np.uint8), g[f"probe{ci}"]) and float(x.sum(dtype=np.float64)) == float(g[f"sum{ci}"][0])
+
+
+def test_videomae_extractor_vs_oracle(cuda):
+    """VideoMAE branch (extract_vision_huggingface.py:147-159): tubelet patch gather + host-orchestrated encoder."""
+    from mertools_b200.extract.videomae import VideoMaeExtractor
+    sd = S.videomae_state_dict(seed=15, layers=3)
+    frames = np.random.default_rng(31).integers(0, 256, (21, 120, 160, 3), dtype=np.uint8)
+    ext = VideoMaeExtractor(sd, device=cuda)
+    pre = ext.preprocess(frames).cpu().numpy()
+    sel = frames[P.resample_frames_uniform_indices(len(frames), 16)]
+    ref_px = P.pil_resize_bilinear_u8(sel, 224, 298)[:, :, 37:261]
+    np.testing.assert_array_equal(pre, ref_px)                                          # geometry bit-exact
+    for level in ("UTTERANCE", "FRAME"):
+        got, ref = ext.extract_clip(frames, level), P.videomae_clip_features(sd, frames, level)
+        assert got.shape == ref.shape and _rel(got, ref) < TOL
