@@ -249,7 +249,15 @@ typedef struct MerClipVisionModel {
   const float* post_ln_b;
   const float* proj_w;    /* visual_projection.weight [proj_dim, hidden], tf32-rounded */
   const MerLayerWeights* layers;
+  /* 0 (zero-initialised): CLIP as described above.  MER_VISION_DINOV2 (1): HF Dinov2Model (dinov2-large,
+   * extract_vision_huggingface.py:135-145) on the same tower: no pre_layrnorm (pre_ln_g NULL), erf GELU, LayerScale
+   * folded into the out-proj / FC2 weights and the patch-conv bias into pos_rest by the loader, position table already
+   * interpolated to the image grid; out_embeds [n_frames, hidden] = sum over the tokens of the LAST LAYER's output
+   * (hidden_states[-1], before Dinov2Model.layernorm); post_ln_* / proj_w unused, proj_dim = hidden. */
+  int variant;
 } MerClipVisionModel;
+#define MER_VISION_CLIP 0
+#define MER_VISION_DINOV2 1
 
 MER_API long long mer_clip_vision_workspace_bytes(const MerClipVisionModel* model, int n_frames);
 

@@ -326,7 +326,11 @@ int mer_clip_vision_forward(const MerClipVisionModel* m, const uint8_t* frames_b
     g.mode = MER_GEMM_TF32;
     MER_TRY(mer_gemm_launch(&g, stream));
   }
-  MER_TRY(mer_layernorm_launch(x, m->pre_ln_g, m->pre_ln_b, x, nullptr, nullptr, p.M, D, m->ln_eps, 0, stream));
+  const bool dinov2 = m->variant == MER_VISION_DINOV2;
+  MER_REQUIRE(dinov2 ? (m->pre_ln_g == nullptr && m->proj_dim == D) : (m->pre_ln_g && m->post_ln_g && m->proj_w),
+              "mer_clip_vision_forward: variant %d operands", m->variant);
+  if (!dinov2)
+    MER_TRY(mer_layernorm_launch(x, m->pre_ln_g, m->pre_ln_b, x, nullptr, nullptr, p.M, D, m->ln_eps, 0, stream));
   MerStackArgs a;
   memset(&a, 0, sizeof(a));
   a.layers = m->layers;
@@ -336,7 +340,7 @@ int mer_clip_vision_forward(const MerClipVisionModel* m, const uint8_t* frames_b
   a.dim = D;
   a.ffn = m->ffn;
   a.heads = m->heads;
-  a.quick_gelu = 1;
+  a.quick_gelu = dinov2 ? 0 : 1;
   a.eps = m->ln_eps;
   a.tokens = p.M;
   a.cu_seqlens = offsets;
@@ -350,6 +354,8 @@ int mer_clip_vision_forward(const MerClipVisionModel* m, const uint8_t* frames_b
   a.vt_ld = p.vt_ld;
   a.opt_hidden = opt_hidden;
   MER_TRY(mer_run_stack(a, stream));
+  if (dinov2)  // hidden_states[-1].sum(dim=1): every token of the last layer's output, per frame
+    return mer_segment_reduce_launch(x, offsets, offsets + 1, n_frames, D, MER_SEG_SUM, out_embeds, stream);
   // class-token rows -> post_layernorm (tf32-rounded: GEMM operand) -> visual_projection
   float* cls = qkv;                        // [n_frames, D]   (the QKV buffer is dead now)
   float* pooled = qkv + (long long)n_frames * D;

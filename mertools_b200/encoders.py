@@ -144,7 +144,7 @@ class MerClipVisionModel(C.Structure):
                 ("kpad", C.c_int), ("gemm_mode", C.c_int), ("mean", C.c_float * 3), ("std", C.c_float * 3),
                 ("patch_w", C.c_void_p), ("cls_pos0", C.c_void_p), ("pos_rest", C.c_void_p),
                 ("pre_ln_g", C.c_void_p), ("pre_ln_b", C.c_void_p), ("post_ln_g", C.c_void_p),
-                ("post_ln_b", C.c_void_p), ("proj_w", C.c_void_p), ("layers", C.POINTER(W.MerLayerWeights))]
+                ("post_ln_b", C.c_void_p), ("proj_w", C.c_void_p), ("layers", C.POINTER(W.MerLayerWeights)), ("variant", C.c_int)]
 
 
 CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
@@ -175,8 +175,10 @@ class ClipVisionEncoder:
 
     Reference: MERBench/feature_extraction/visual/extract_vision_huggingface.py:114-122."""
 
-    def __init__(self, state_dict, device="cuda", ln_eps=1e-5, image=224, precision=None):
-        """precision: None = "f16" when the fp16 attention kernel covers the token count (B/32), else "tf32";
+    def __init__(self, state_dict, device="cuda", ln_eps=1e-5, image=224, precision=None, variant=0, mean=CLIP_MEAN,
+                 std=CLIP_STD, resize=None):
+        """variant / mean / std / resize: set by Dinov2Encoder (same tower, MER_VISION_DINOV2 readout).
+        precision: None = "f16" when the fp16 attention kernel covers the token count (B/32), else "tf32";
         "f16" forces fp16 linear layers for longer sequences too (L/14: attention then runs the fp32-operand flash
         kernel between them; env MER_CLIP_PRECISION=f16; not yet measured)."""
         L.check(L.lib().mer_check_device())
@@ -191,7 +193,8 @@ class ClipVisionEncoder:
         assert D in (768, 1024) and image % p == 0 and pos.shape == ((image // p) ** 2 + 1, D), (pw.shape, pos.shape)
         self.hidden, self.patch, self.image = int(D), int(p), image
         self.tokens = (image // p) ** 2 + 1
-        self.proj_dim = int(sd["visual_projection.weight"].shape[0])
+        self.variant, self.resize = int(variant), int(resize or image)
+        self.proj_dim = int(sd["visual_projection.weight"].shape[0]) if variant == 0 else int(D)
         ffn = int(sd[v + "encoder.layers.0.mlp.fc1.weight"].shape[0])
         kpad = (3 * p * p + 31) // 32 * 32
         wflat = np.zeros((D, kpad), np.float32)
@@ -207,16 +210,18 @@ class ClipVisionEncoder:
         m.n_layers, m.ln_eps = self.n_layers, ln_eps
         m.hidden, m.ffn, m.heads, m.patch, m.image, m.proj_dim, m.kpad = D, ffn, D // 64, p, image, self.proj_dim, kpad
         m.gemm_mode = L.MER_GEMM_F16 if f16 else L.MER_GEMM_TF32
-        m.mean = (C.c_float * 3)(*CLIP_MEAN)
-        m.std = (C.c_float * 3)(*CLIP_STD)
+        m.mean = (C.c_float * 3)(*mean)
+        m.std = (C.c_float * 3)(*std)
         m.patch_w = pk.keep(wflat, tf32=True).data_ptr()
         m.cls_pos0 = pk.keep(sd[v + "embeddings.class_embedding"].reshape(D) + pos[0]).data_ptr()
         m.pos_rest = pk.keep(pos[1:]).data_ptr()
-        m.pre_ln_g = pk.keep(sd[v + "pre_layrnorm.weight"]).data_ptr()
-        m.pre_ln_b = pk.keep(sd[v + "pre_layrnorm.bias"]).data_ptr()
-        m.post_ln_g = pk.keep(sd[v + "post_layernorm.weight"]).data_ptr()
-        m.post_ln_b = pk.keep(sd[v + "post_layernorm.bias"]).data_ptr()
-        m.proj_w = pk.keep(sd["visual_projection.weight"], tf32=True).data_ptr()
+        m.variant = self.variant
+        if self.variant == 0:
+            m.pre_ln_g = pk.keep(sd[v + "pre_layrnorm.weight"]).data_ptr()
+            m.pre_ln_b = pk.keep(sd[v + "pre_layrnorm.bias"]).data_ptr()
+            m.post_ln_g = pk.keep(sd[v + "post_layernorm.weight"]).data_ptr()
+            m.post_ln_b = pk.keep(sd[v + "post_layernorm.bias"]).data_ptr()
+            m.proj_w = pk.keep(sd["visual_projection.weight"], tf32=True).data_ptr()
         m.layers = self.layers
         self.model = m
         self.ws, self.ws_resize = _Workspace(self.device), _Workspace(self.device)
@@ -232,8 +237,10 @@ class ClipVisionEncoder:
                                                    C.c_int, C.c_int, C.c_void_p, C.c_void_p])
 
     def preprocess_geometry(self, h, w):
-        """(new_h, new_w, crop_y0, crop_x0) of CLIPImageProcessor: shorter edge -> image, center crop."""
-        return clip_preprocess_geometry(h, w, self.image)
+        """(new_h, new_w, crop_y0, crop_x0) of CLIPImageProcessor: shorter edge -> image, center crop
+        (Dinov2Encoder: shorter edge -> 256, then the 224 crop)."""
+        nh, nw, _, _ = clip_preprocess_geometry(h, w, self.resize)
+        return nh, nw, (nh - self.image) // 2, (nw - self.image) // 2
 
     def frame_features(self, frames_bgr_u8: torch.Tensor, return_hidden=False):
         """frames: uint8 CUDA [N, H, W, 3] (BGR).  Returns image embeddings [N, proj_dim] fp32 (CUDA)."""
@@ -257,6 +264,62 @@ class ClipVisionEncoder:
         if return_hidden:
             return emb, hidden.view(self.n_layers + 1, n, self.tokens, self.hidden)
         return emb
+
+
+def dinov2_to_clip_layout(state_dict, image=224):
+    """HF ``Dinov2Model`` tensors re-expressed in the layout of the CLIP tower (what mer_clip_vision_forward walks), so
+    that DINOv2 needs no kernel of its own:  the position table is interpolated to the image grid (bicubic,
+    align_corners=False: Dinov2Embeddings.interpolate_pos_encoding of transformers 5.x), the patch-conv bias is folded
+    into the patch rows of the position table (both are added to every patch token), LayerScale is folded into the
+    branch's last linear layer (lambda * (W x + b) = (lambda W) x + lambda b).  Pure numpy / torch-CPU weight
+    preparation, checked on CPU against HF in tests/test_host_logic.py."""
+    sd = W._np(state_dict)
+    pw = np.asarray(sd["embeddings.patch_embeddings.projection.weight"], np.float32)
+    D, _, p, _ = pw.shape
+    g = image // p
+    pos = torch.from_numpy(np.asarray(sd["embeddings.position_embeddings"], np.float32))
+    side = int(round((pos.shape[1] - 1) ** 0.5))
+    assert side * side + 1 == pos.shape[1], pos.shape
+    if side != g:
+        grid = pos[:, 1:].reshape(1, side, side, D).permute(0, 3, 1, 2)
+        grid = torch.nn.functional.interpolate(grid, size=(g, g), mode="bicubic", align_corners=False)
+        pos = torch.cat([pos[:, :1], grid.permute(0, 2, 3, 1).reshape(1, g * g, D)], dim=1)
+    pos = pos[0].numpy().copy()
+    pos[1:] += np.asarray(sd["embeddings.patch_embeddings.projection.bias"], np.float32)
+    v = "vision_model."
+    out = {v + "embeddings.patch_embedding.weight": pw,
+           v + "embeddings.class_embedding": np.asarray(sd["embeddings.cls_token"], np.float32).reshape(D),
+           v + "embeddings.position_embedding.weight": pos}
+    i = 0
+    while f"encoder.layer.{i}.mlp.fc2.weight" in sd:
+        assert f"encoder.layer.{i}.mlp.fc1.weight" in sd, "SwiGLU MLP (dinov2-giant) is not supported"
+        s_, d_ = f"encoder.layer.{i}.", f"{v}encoder.layers.{i}."
+        l1 = np.asarray(sd[s_ + "layer_scale1.lambda1"], np.float32)
+        l2 = np.asarray(sd[s_ + "layer_scale2.lambda1"], np.float32)
+        for a, b in (("norm1", "layer_norm1"), ("norm2", "layer_norm2"), ("attention.attention.query", "self_attn.q_proj"),
+                     ("attention.attention.key", "self_attn.k_proj"), ("attention.attention.value", "self_attn.v_proj"),
+                     ("mlp.fc1", "mlp.fc1")):
+            out[d_ + b + ".weight"], out[d_ + b + ".bias"] = sd[s_ + a + ".weight"], sd[s_ + a + ".bias"]
+        out[d_ + "self_attn.out_proj.weight"] = np.asarray(sd[s_ + "attention.output.dense.weight"], np.float32) * l1[:, None]
+        out[d_ + "self_attn.out_proj.bias"] = np.asarray(sd[s_ + "attention.output.dense.bias"], np.float32) * l1
+        out[d_ + "mlp.fc2.weight"] = np.asarray(sd[s_ + "mlp.fc2.weight"], np.float32) * l2[:, None]
+        out[d_ + "mlp.fc2.bias"] = np.asarray(sd[s_ + "mlp.fc2.bias"], np.float32) * l2
+        i += 1
+    return out
+
+
+class Dinov2Encoder(ClipVisionEncoder):
+    """HF ``Dinov2Model`` (dinov2-large: 24 layers, hidden 1024, patch 14, 257 tokens at the 224 crop) with the reference's
+    readout ``hidden_states[-1].sum(dim=1)`` per frame, on the CLIP L/14 tower kernels (MER_VISION_DINOV2): BitImageProcessor
+    steps on the device (shorter edge -> 256 bicubic, centre crop 224, rescale, ImageNet normalise).  ``frame_features``
+    returns [N, hidden].  dinov2-giant (SwiGLU MLP, hidden 1536) is not supported.
+
+    Reference: MERBench/feature_extraction/visual/extract_vision_huggingface.py:135-145.  Not yet run on a GPU."""
+
+    def __init__(self, state_dict, device="cuda", ln_eps=1e-6, image=224, resize=256, precision=None,
+                 mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+        super().__init__(dinov2_to_clip_layout(state_dict, image), device=device, ln_eps=ln_eps, image=image,
+                         precision=precision, variant=1, mean=mean, std=std, resize=resize)
 
 
 class MerResnetConv(C.Structure):

@@ -112,6 +112,10 @@ class VisualExtractor:
             from ..encoders import ClipVisionEncoder
             self.enc = ClipVisionEncoder(state_dict, device=device)
             self.feature_dim = self.enc.proj_dim
+        elif "encoder.layer.0.layer_scale1.lambda1" in state_dict:  # HF Dinov2Model (dinov2-large; :135-145)
+            from ..encoders import Dinov2Encoder
+            self.enc = Dinov2Encoder(state_dict, device=device)
+            self.feature_dim = self.enc.hidden
         else:
             self.enc = VitEncoder(state_dict, device=device)
             self.feature_dim = 768

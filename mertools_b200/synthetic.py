@@ -343,6 +343,30 @@ def whisper_state_dict(seed=13, enc_layers=6, dec_layers=6, vocab=64, cfg=WHISPE
     return g.sd
 
 
+def dinov2_state_dict(seed=17, layers=24, hidden=1024, ffn=4096, patch=14, n_pos_side=37):
+    """Keys of ``transformers.Dinov2Model`` (dinov2-large shape: 24 layers, hidden 1024, 16 heads, patch 14, position
+    table for 518 / 14 = 37 x 37 patches + the class token, LayerScale after the attention and MLP branches)."""
+    g = _Gen(seed)
+    g.normal("embeddings.cls_token", (1, 1, hidden), 0.02)
+    g.normal("embeddings.mask_token", (1, hidden), 0.02)
+    g.normal("embeddings.position_embeddings", (1, n_pos_side * n_pos_side + 1, hidden), 0.05)
+    g.normal("embeddings.patch_embeddings.projection.weight", (hidden, 3, patch, patch), 0.02)
+    g.normal("embeddings.patch_embeddings.projection.bias", (hidden,), 0.02)
+    for i in range(layers):
+        p = f"encoder.layer.{i}."
+        g.ln(p + "norm1", hidden)
+        for n in ("query", "key", "value"):
+            g.linear(p + f"attention.attention.{n}", hidden, hidden, 0.02)
+        g.linear(p + "attention.output.dense", hidden, hidden, 0.02)
+        g.sd[p + "layer_scale1.lambda1"] = (0.5 + 0.5 * g.rng.random(hidden)).astype(np.float32)
+        g.ln(p + "norm2", hidden)
+        g.linear(p + "mlp.fc1", ffn, hidden, 0.02)
+        g.linear(p + "mlp.fc2", hidden, ffn, 0.02)
+        g.sd[p + "layer_scale2.lambda1"] = (0.5 + 0.5 * g.rng.random(hidden)).astype(np.float32)
+    g.ln("layernorm", hidden)
+    return g.sd
+
+
 def videomae_state_dict(seed=15, layers=12, hidden=768, ffn=3072):
     """Keys of ``transformers.VideoMAEModel`` (videomae-base shape): tubelet patch embedding Conv3d(3, 768, (2, 16, 16)),
     pre-LN layers whose attention carries separate ``q_bias`` / ``v_bias`` (no key bias); the position table is a fixed

@@ -82,6 +82,49 @@ def vit_hidden_states(sd, pixel_values, layers=12, heads=12, eps=1e-12, dtype=to
     return tuple(hs)
 
 
+def dinov2_position_embeddings(sd, grid_h, grid_w, dtype=torch.float32):
+    """HF Dinov2Embeddings.interpolate_pos_encoding (modeling_dinov2.py:57-95, transformers 5.x: bicubic resize of the
+    [side, side] table to ``size=(grid_h, grid_w)``, align_corners=False; 4.x releases passed a scale factor computed
+    from grid + 0.1 instead, which samples at slightly different coordinates)."""
+    pos = _t(sd, "embeddings.position_embeddings", torch.float32)
+    n = pos.shape[1] - 1
+    side = int(n ** 0.5)
+    if n == grid_h * grid_w and grid_h == grid_w:
+        return pos.to(dtype)
+    grid = pos[:, 1:].reshape(1, side, side, -1).permute(0, 3, 1, 2)
+    grid = F.interpolate(grid, size=(grid_h, grid_w), mode="bicubic", align_corners=False)
+    return torch.cat([pos[:, :1], grid.permute(0, 2, 3, 1).reshape(1, grid_h * grid_w, -1)], dim=1).to(dtype)
+
+
+def dinov2_hidden_states(sd, pixel_values, heads=16, eps=1e-6, dtype=torch.float32):
+    """``Dinov2Model(pixel_values, output_hidden_states=True).hidden_states`` (extract_vision_huggingface.py:135-145
+    reads ``[-1]``: the last layer's output BEFORE ``Dinov2Model.layernorm``).  Patch conv k = s = 14 with bias,
+    class token, interpolated positions; PRE-LN layers with LayerScale on both branches (modeling_dinov2.py
+    Dinov2Layer): x += lambda1 * attn(norm1(x)); x += lambda2 * mlp(norm2(x)), erf GELU."""
+    x = pixel_values.to(dtype)
+    w = _t(sd, "embeddings.patch_embeddings.projection.weight", dtype)
+    gh, gw = x.shape[2] // w.shape[-1], x.shape[3] // w.shape[-1]
+    x = F.conv2d(x, w, _t(sd, "embeddings.patch_embeddings.projection.bias", dtype), stride=w.shape[-1])
+    x = x.flatten(2).transpose(1, 2)
+    x = torch.cat([_t(sd, "embeddings.cls_token", dtype).expand(x.shape[0], -1, -1), x], dim=1)
+    x = x + dinov2_position_embeddings(sd, gh, gw, dtype)
+    hs = [x]
+    i = 0
+    while f"encoder.layer.{i}.mlp.fc2.weight" in sd:
+        p = f"encoder.layer.{i}."
+        h = _ln(x, sd, p + "norm1", eps, dtype)
+        q = _linear(h, sd, p + "attention.attention.query", dtype)
+        k = _linear(h, sd, p + "attention.attention.key", dtype)
+        v = _linear(h, sd, p + "attention.attention.value", dtype)
+        a = _linear(_mha(q, k, v, heads), sd, p + "attention.output.dense", dtype)
+        x = x + a * _t(sd, p + "layer_scale1.lambda1", dtype)
+        h = F.gelu(_linear(_ln(x, sd, p + "norm2", eps, dtype), sd, p + "mlp.fc1", dtype))
+        x = x + _linear(h, sd, p + "mlp.fc2", dtype) * _t(sd, p + "layer_scale2.lambda1", dtype)
+        hs.append(x)
+        i += 1
+    return tuple(hs)
+
+
 # ------------------------------------------------------------------------------------------------
 # HuBERT  (HF models/hubert/modeling_hubert.py)
 # ------------------------------------------------------------------------------------------------

@@ -269,6 +269,33 @@ def emonet_clip_features(sd, frames_bgr, feature_level="UTTERANCE"):
     return np.mean(emb, axis=0) if emb.ndim == 2 else emb
 
 
+def dinov2_preprocess(frames_bgr, mean=IMAGENET_MEAN, std=IMAGENET_STD, resize=256, crop=224):
+    """``AutoImageProcessor`` of dinov2-large / -giant = BitImageProcessor (preprocessor_config.json: shortest edge 256,
+    BICUBIC, centre crop 224, rescale 1 / 255, ImageNet mean / std) on ``func_opencv_to_image`` frames (BGR -> RGB PIL,
+    extract_vision_huggingface.py:37-41,137-138).  Returns [n, 3, 224, 224]."""
+    f = np.asarray(frames_bgr)
+    h, w = f.shape[1:3]
+    nh, nw = (resize, int(resize * w / h)) if h <= w else (int(resize * h / w), resize)
+    if (nh, nw) != (h, w):
+        f = pil_resize_bilinear_u8(f, nh, nw, filter="bicubic")
+    top, left = (nh - crop) // 2, (nw - crop) // 2
+    f = f[:, top:top + crop, left:left + crop]
+    x = (f[..., ::-1].astype(np.float32) / np.float32(255.0) - np.asarray(mean, np.float32)) / np.asarray(std, np.float32)
+    return torch.from_numpy(np.ascontiguousarray(x.transpose(0, 3, 1, 2)))
+
+
+def dinov2_clip_features(sd, frames_bgr, feature_level="UTTERANCE", heads=16, nframe=64, bsize=32):
+    """One video through the DINOv2 branch (:135-145, :175-189): ``resample_frames_uniform(frames, 64)``, batches of 32,
+    ``hidden_states[-1].sum(dim=1)`` per frame -> FRAME [64, D]; UTTERANCE -> mean over the frames."""
+    f = np.asarray(frames_bgr)
+    f = f[resample_frames_uniform_indices(len(f), nframe)]
+    x = dinov2_preprocess(f)
+    with torch.no_grad():
+        emb = torch.cat([E.dinov2_hidden_states(sd, x[s:s + bsize], heads=heads)[-1].sum(dim=1)
+                         for s in range(0, len(x), bsize)]).numpy().squeeze()
+    return np.mean(emb, axis=0) if feature_level == "UTTERANCE" and emb.ndim == 2 else emb
+
+
 def videomae_preprocess(frames_bgr, mean=IMAGENET_MEAN, std=IMAGENET_STD):
     """extract_vision_huggingface.py:148-152: ``resample_frames_uniform(frames)`` (16 frames), BGR -> RGB
     (func_opencv_to_numpy), VideoMAEImageProcessor: shortest edge -> 224 (bilinear, Pillow arithmetic as for the other

@@ -690,6 +690,7 @@ def test_encoder_constructors_run_with_the_device_layer_stubbed(monkeypatch):
         "vit": En.VitEncoder(S.vit_state_dict(seed=0, layers=2)),
         "clip_b32": En.ClipVisionEncoder(S.clip_vision_state_dict(variant="b32", layers=2)),
         "clip_l14_f16": En.ClipVisionEncoder(S.clip_vision_state_dict(variant="l14", layers=1), precision="f16"),
+        "dinov2": En.Dinov2Encoder(S.dinov2_state_dict(layers=1)),
         "resnet18": En.ResNet18Encoder(S.resnet18_state_dict()),
         "ferplus": En.FerplusResnet50Encoder(S.ferplus_resnet50_state_dict()),
         "senet": En.FerplusResnet50Encoder(S.ferplus_resnet50_state_dict(se=True)),
@@ -704,6 +705,9 @@ def test_encoder_constructors_run_with_the_device_layer_stubbed(monkeypatch):
         "bert_large": En.BertEncoder(S.bert_state_dict(100, layers=4, large=True)),
     }
     assert made["clip_l14_f16"].precision == "f16" and made["clip_l14_f16"].tokens == 257
+    d = made["dinov2"]
+    assert (d.precision, d.tokens, d.proj_dim, d.model.variant, bool(d.model.pre_ln_g), d.model.kpad) == ("tf32", 257, 1024, 1, False, 608)
+    assert d.preprocess_geometry(120, 160) == (256, 341, 16, 58) and made["clip_b32"].preprocess_geometry(120, 160) == (224, 298, 0, 37)
     assert (made["ferplus"].model.n_convs, made["senet"].model.n_convs, made["manet"].model.n_convs,
             made["emonet"].model.n_convs) == (52, 82, 136, 222)
     h = made["data2vec"].model
@@ -780,3 +784,51 @@ def test_videomae_orchestration_matches_the_oracle_with_a_cpu_backend():
     assert float((got - ref).abs().max() / ref.abs().max()) < 1e-5
     two = net.last_hidden_state(np.concatenate([frames, frames[::-1]]), mean, std)     # clip-major rows for B > 1
     assert float((two[0] - ref[0]).abs().max() / ref.abs().max()) < 1e-5
+
+
+def test_dinov2_oracle_is_pinned_to_hf_and_the_clip_layout_conversion_reproduces_it():
+    """extract_vision_huggingface.py:135-145 (DINOv2 branch).  (1) oracle restatement vs HF Dinov2Model and the
+    Pillow-backed BitImageProcessor on a synthetic dinov2-large-shaped checkpoint that strict-loads; (2) the product's
+    weight re-layout (dinov2_to_clip_layout: interpolated positions, folded patch bias and LayerScale) run through a
+    torch emulation of what mer_clip_vision_forward computes for MER_VISION_DINOV2 (no pre_layrnorm, erf GELU, token
+    sum of the last layer's output)."""
+    transformers = pytest.importorskip("transformers")
+    from PIL import Image
+
+    from mertools_b200.encoders import dinov2_to_clip_layout
+    sd = S.dinov2_state_dict(seed=17, layers=2)
+    cfg = transformers.Dinov2Config(hidden_size=1024, num_hidden_layers=2, num_attention_heads=16, image_size=518, patch_size=14)
+    model = transformers.Dinov2Model(cfg).eval()
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    proc = transformers.BitImageProcessorPil(do_resize=True, size={"shortest_edge": 256}, resample=3, do_center_crop=True,
+                                             crop_size={"height": 224, "width": 224}, do_rescale=True, do_normalize=True,
+                                             image_mean=[0.485, 0.456, 0.406], image_std=[0.229, 0.224, 0.225], do_convert_rgb=True)
+    frames = np.random.default_rng(3).integers(0, 256, (3, 120, 160, 3), dtype=np.uint8)
+    inputs = proc(images=[Image.fromarray(f[:, :, ::-1].copy()) for f in frames], return_tensors="pt")["pixel_values"]
+    mine = P.dinov2_preprocess(frames)
+    assert float((inputs - mine).abs().max()) < 2e-6
+    with torch.no_grad():
+        ref = model(inputs, output_hidden_states=True).hidden_states[-1]
+    got = E.dinov2_hidden_states(sd, mine)[-1]
+    assert float((got - ref).abs().max() / ref.abs().max()) < 1e-5
+    fra = P.dinov2_clip_features(sd, frames, "FRAME", nframe=4)
+    assert fra.shape == (4, 1024)                                       # 3 frames resampled to 4 (last one repeated)
+    np.testing.assert_allclose(fra[:3], ref.sum(dim=1).numpy(), rtol=0, atol=2e-5 * float(ref.sum(dim=1).abs().max()))
+    # (2) the CLIP-layout tensors through the tower as the kernels walk it
+    c = {k: torch.from_numpy(np.asarray(v, np.float32)) for k, v in dinov2_to_clip_layout(sd).items()}
+    v = "vision_model."
+    pw = c[v + "embeddings.patch_embedding.weight"]
+    x = torch.nn.functional.conv2d(mine, pw, None, stride=14).flatten(2).transpose(1, 2)
+    pos = c[v + "embeddings.position_embedding.weight"]
+    assert tuple(pos.shape) == (257, 1024)
+    x = torch.cat([(c[v + "embeddings.class_embedding"] + pos[0]).expand(len(x), 1, -1), x + pos[1:]], dim=1)
+    lin = lambda t, n: torch.nn.functional.linear(t, c[n + ".weight"], c[n + ".bias"])  # noqa: E731
+    ln = lambda t, n: torch.nn.functional.layer_norm(t, (1024,), c[n + ".weight"], c[n + ".bias"], 1e-6)  # noqa: E731
+    for i in range(2):
+        p = f"{v}encoder.layers.{i}."
+        y = ln(x, p + "layer_norm1")
+        q, k, vv = (lin(y, p + f"self_attn.{n}_proj").reshape(len(x), 257, 16, 64).transpose(1, 2) for n in "qkv")
+        ctx = (torch.softmax(q @ k.transpose(-1, -2) / 8.0, -1) @ vv).transpose(1, 2).reshape(len(x), 257, 1024)
+        x = x + lin(ctx, p + "self_attn.out_proj")
+        x = x + lin(torch.nn.functional.gelu(lin(ln(x, p + "layer_norm2"), p + "mlp.fc1")), p + "mlp.fc2")
+    assert float((x.sum(dim=1) - ref.sum(dim=1)).abs().max() / ref.sum(dim=1).abs().max()) < 1e-5

@@ -571,6 +571,12 @@ def test_load_video_from_npy_device_path(cuda):
 
 def test_videomae_extractor_vs_oracle(cuda):
     """VideoMAE branch (extract_vision_huggingface.py:147-159): tubelet patch gather + host-orchestrated encoder."""
+    import numpy as np
+
+    from mertools_b200 import synthetic as S
+    from oracle import pipeline as P
+    TOL = 1e-3
+    _rel = lambda a, b: float(np.abs(np.asarray(a, np.float64) - b).max() / np.abs(b).max())  # noqa: E731
     from mertools_b200.extract.videomae import VideoMaeExtractor
     sd = S.videomae_state_dict(seed=15, layers=3)
     frames = np.random.default_rng(31).integers(0, 256, (21, 120, 160, 3), dtype=np.uint8)
@@ -581,4 +587,23 @@ def test_videomae_extractor_vs_oracle(cuda):
     np.testing.assert_array_equal(pre, ref_px)                                          # geometry bit-exact
     for level in ("UTTERANCE", "FRAME"):
         got, ref = ext.extract_clip(frames, level), P.videomae_clip_features(sd, frames, level)
+        assert got.shape == ref.shape and _rel(got, ref) < TOL
+
+
+def test_dinov2_extractor_vs_oracle(cuda):
+    """DINOv2 branch (extract_vision_huggingface.py:135-145) on the CLIP L/14 tower kernels (MER_VISION_DINOV2)."""
+    import numpy as np
+
+    from mertools_b200 import synthetic as S
+    from oracle import pipeline as P
+    TOL = 1e-3
+    _rel = lambda a, b: float(np.abs(np.asarray(a, np.float64) - b).max() / np.abs(b).max())  # noqa: E731
+    from mertools_b200.extract.visual import VisualExtractor
+    sd = S.dinov2_state_dict(seed=17, layers=3)
+    frames = np.random.default_rng(3).integers(0, 256, (5, 120, 160, 3), dtype=np.uint8)
+    ext = VisualExtractor(sd, device=cuda)
+    assert ext.feature_dim == 1024
+    for level in ("UTTERANCE", "FRAME"):
+        got = ext.extract_clips([frames], level, nframe=8)[0]
+        ref = P.dinov2_clip_features(sd, frames, level, nframe=8)
         assert got.shape == ref.shape and _rel(got, ref) < TOL
