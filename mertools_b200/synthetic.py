@@ -400,7 +400,6 @@ def hubert_state_dict(seed=1, layers=12, scale=1.0, large=False, data2vec=False,
     an affine-free LayerNorm and GELU), post-LN layers."""
     """``large=True, group_norm=True``: wav2vec2-large-960h (hidden 1024 with the base feature extractor: GroupNorm on
     conv0, no conv biases, post-LN layers)."""
-    assert not (large and data2vec)
     c = HUBERT_LARGE_CFG if large else HUBERT_CFG
     ln_convs = (large and not group_norm) or data2vec
     g = _Gen(seed)
@@ -410,7 +409,7 @@ def hubert_state_dict(seed=1, layers=12, scale=1.0, large=False, data2vec=False,
     for i, k in enumerate(c["conv_kernel"]):
         g.normal(f"feature_extractor.conv_layers.{i}.conv.weight", (cd, cin, k),
                  np.sqrt(2.0 / (cin * k)))
-        if large and not group_norm:
+        if large and not group_norm and not data2vec:   # data2vec-audio-large: LayerNorm convs without biases
             g.normal(f"feature_extractor.conv_layers.{i}.conv.bias", (cd,), 0.05)
         if i == 0 or ln_convs:
             g.ln(f"feature_extractor.conv_layers.{i}.layer_norm", cd)

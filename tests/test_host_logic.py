@@ -701,6 +701,7 @@ def test_encoder_constructors_run_with_the_device_layer_stubbed(monkeypatch):
         "hubert_large": En.HubertEncoder(S.hubert_state_dict(layers=4, large=True)),
         "wav2vec2_large_960h": En.HubertEncoder(S.hubert_state_dict(layers=4, large=True, group_norm=True)),
         "data2vec": En.HubertEncoder(S.hubert_state_dict(layers=4, data2vec=True)),
+        "data2vec_large": En.HubertEncoder(S.hubert_state_dict(layers=4, data2vec=True, large=True)),
         "bert": En.BertEncoder(S.bert_state_dict(100, layers=4)),
         "bert_large": En.BertEncoder(S.bert_state_dict(100, layers=4, large=True)),
     }
@@ -712,6 +713,8 @@ def test_encoder_constructors_run_with_the_device_layer_stubbed(monkeypatch):
             made["emonet"].model.n_convs) == (52, 82, 136, 222)
     h = made["data2vec"].model
     assert (h.n_pos_layers, h.pos_taps, h.feat_norm_layer, h.stable_layer_norm, bool(h.conv_b[1])) == (5, 19, 1, 0, False)
+    h = made["data2vec_large"].model
+    assert (h.hidden, h.heads, h.n_pos_layers, h.pos_window, h.stable_layer_norm, bool(h.conv_b[1])) == (1024, 16, 5, 256, 0, False)
     h = made["wav2vec2_large_960h"].model
     assert (h.hidden, h.heads, h.feat_norm_layer, h.stable_layer_norm, h.pos_window) == (1024, 16, 0, 0, 256)
     h = made["hubert_large"].model

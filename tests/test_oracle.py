@@ -285,7 +285,11 @@ def test_oracle_audio_restatement_covers_wav2vec2_large_960h_and_data2vec():
                                            intermediate_size=4096, feat_extract_norm="group",
                                            do_stable_layer_norm=False, conv_bias=False))),
              (S.hubert_state_dict(seed=3, layers=2, data2vec=True), 12,
-              Data2VecAudioModel(Data2VecAudioConfig(num_hidden_layers=2)))]
+              Data2VecAudioModel(Data2VecAudioConfig(num_hidden_layers=2))),
+             # data2vec-audio-large: the same graph at hidden 1024 / 16 heads / 4096
+             (S.hubert_state_dict(seed=4, layers=2, data2vec=True, large=True), 16,
+              Data2VecAudioModel(Data2VecAudioConfig(num_hidden_layers=2, hidden_size=1024, num_attention_heads=16,
+                                                     intermediate_size=4096)))]
     for sd, heads, model in cases:
         model.eval()
         res = model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)

@@ -457,6 +457,27 @@ def test_data2vec_audio_vs_reference_golden_and_oracle(cuda):
         assert np.abs(f[i][::16] - g[f"fra{i}"]).max() / np.abs(g[f"fra{i}"]).max() < 2e-3, i
 
 
+def test_data2vec_audio_large_vs_oracle(cuda):
+    """data2vec-audio-large: the data2vec graph at hidden 1024 / 16 heads (64-channel positional conv groups)."""
+    import numpy as np
+
+    from mertools_b200 import synthetic as S
+    from mertools_b200.encoders import HubertEncoder
+    from oracle import encoders as E
+    from oracle import pipeline as P
+    layers = 4
+    sd = S.hubert_state_dict(seed=4, layers=layers, data2vec=True, large=True)
+    wav = (S.synth_waves(2, 16000, seed=26).astype(np.float64) / 32768.0).astype(np.float32)
+    utt, frames, hidden = HubertEncoder(sd, device=cuda).forward(torch.from_numpy(wav).to(cuda), normalize=True,
+                                                                 want_frames=True, return_hidden=True)
+    ref_hs = E.hubert_hidden_states(sd, torch.from_numpy(np.stack([P.wav2vec2_normalize(w) for w in wav])), layers=layers,
+                                    heads=16)
+    for l in range(layers + 1):
+        assert float((hidden[l].cpu() - ref_hs[l]).abs().max() / ref_hs[l].abs().max()) < 4e-3, l
+    ref = torch.stack(ref_hs)[-4:].sum(dim=0)
+    assert float((frames.cpu().view_as(ref) - ref).abs().max() / ref.abs().max()) < 1e-3
+
+
 def test_clip_l14_with_fp16_linear_layers(cuda):
     """CLIP L/14 (257 tokens) with precision="f16": fp16 linear layers around the fp32-operand flash attention
     (the hybrid branch of mer_run_stack) against the oracle, like the TF32 default."""
