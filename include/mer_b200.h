@@ -447,6 +447,25 @@ MER_API int mer_hubert_forward_ragged(const MerHubertModel* model, const float* 
                                       int batch, int n_samples, int normalize, void* workspace,
                                       long long workspace_bytes, float* out_frames, float* out_utt, void* stream);
 
+/* The part of mer_hubert_forward before the transformer layers: waveform normalisation, the 7-layer conv feature
+ * encoder, feature projection, positional convolution (+ encoder.layer_norm for the post-LN family).
+ * out_hidden0: [batch * frames, hidden] = hidden_states[0] of the HF model.  Used by the WavLM branch, whose layers
+ * (gated relative position bias, HF modeling_wavlm.py WavLMAttention) are orchestrated over the kernel-level entry
+ * points below.  Workspace as for mer_hubert_forward. */
+MER_API int mer_hubert_frontend(const MerHubertModel* model, const float* wave, int batch, int n_samples, int normalize,
+                                void* workspace, long long workspace_bytes, float* out_hidden0, void* stream);
+
+/* ---- WavLM attention pieces (extract_audio_huggingface.py:36-37 wavlm-base / wavlm-large) ------------------- */
+/* gate[token, head] = ga * (gb * c[head] - 1) + 2 with (ga, gb) = sigmoid of the two 4-sums of
+ * w [8, 64] . x[token, head * 64 : head * 64 + 64] + b [8]   (WavLMAttention.forward steps 1-3). */
+MER_API int mer_wavlm_gate(const float* x, long long tokens, int heads, const float* w, const float* b, const float* c,
+                           float* gate, void* stream);
+/* ctx[b * T + i, h * 64 ...] = softmax_j(q_i . k_j / 8 + rowscale[b * T + i, h] * bias[h, i, j]) v_j over the T tokens
+ * of clip b.  qkv: fp32 [batch * T, 3 * heads * 64] (q | k | v); bias: fp32 [heads, T, T]; rowscale: [batch * T, heads]
+ * or NULL (= 1).  T <= 1024.  fp32 CUDA-core kernel (not tuned). */
+MER_API int mer_biased_attention(const float* qkv, const float* bias, const float* rowscale, int batch, int T, int heads,
+                                 float* ctx, int round_tf32_out, void* stream);
+
 /* ---- log mel spectrogram (VGGish front-end) --------------------------------------------------------- */
 /* mel_features.log_mel_spectrogram as called by vggish_input.waveform_to_examples
  * (MERBench/feature_extraction/audio/vggish/mel_features.py:166-223, vggish_input.py:66-75,

@@ -431,9 +431,12 @@ long long mer_hubert_workspace_bytes(int batch, int n_samples) {
 // GroupNorm statistics of conv0 use the clip's own extent, conv1..6 / projection run on the padded [B, Tmax]
 // layout (a frame only ever depends on earlier-or-equal frames of its own clip that exist for every clip length),
 // the positional conv sees zeros past the clip's last frame, and the transformer runs on the packed valid frames.
+// front_out != nullptr: stop after the positional convolution and write hidden_states[0] (the input of transformer
+// layer 0: after encoder.layer_norm for the post-LN family, the positional-conv sum for the stable-layer-norm one).
 static int hubert_forward_impl(const MerHubertModel* m, const float* wave, int B, int L, int normalize,
                                const int* lengths_host, void* workspace, long long workspace_bytes,
-                               float* out_frames, float* out_utt, float* opt_hidden, void* stream_) {
+                               float* out_frames, float* out_utt, float* opt_hidden, void* stream_,
+                               float* front_out = nullptr) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MER_REQUIRE(m && wave && workspace, "mer_hubert_forward: null operand");
   MER_REQUIRE(B > 0 && L > 0, "mer_hubert_forward: batch=%d n_samples=%d", B, L);
@@ -652,6 +655,15 @@ static int hubert_forward_impl(const MerHubertModel* m, const float* wave, int B
     MER_CUDA_CHECK(cudaMemcpyAsync(xn, x, (size_t)M * D * 4, cudaMemcpyDeviceToDevice, stream));
     cu = d_cu;
   }
+  if (front_out) {
+    const float* h0 = xn;
+    if (!m->stable_layer_norm) {
+      MER_TRY(mer_layernorm_launch(xn, m->enc_ln_g, m->enc_ln_b, x, nullptr, nullptr, M, D, m->ln_eps, 0, stream));
+      h0 = x;
+    }
+    MER_CUDA_CHECK(cudaMemcpyAsync(front_out, h0, (size_t)M * D * 4, cudaMemcpyDeviceToDevice, stream));
+    return 0;
+  }
   MerStackArgs a;
   memset(&a, 0, sizeof(a));
   a.eps = m->ln_eps;
@@ -728,6 +740,13 @@ int mer_hubert_forward(const MerHubertModel* m, const float* wave, int B, int L,
                        float* opt_hidden, void* stream) {
   return hubert_forward_impl(m, wave, B, L, normalize, nullptr, workspace, workspace_bytes, out_frames, out_utt,
                              opt_hidden, stream);
+}
+
+int mer_hubert_frontend(const MerHubertModel* m, const float* wave, int B, int L, int normalize, void* workspace,
+                        long long workspace_bytes, float* out_hidden0, void* stream) {
+  MER_REQUIRE(out_hidden0, "mer_hubert_frontend: null output");
+  return hubert_forward_impl(m, wave, B, L, normalize, nullptr, workspace, workspace_bytes, nullptr, nullptr, nullptr,
+                             stream, out_hidden0);
 }
 
 int mer_hubert_forward_ragged(const MerHubertModel* m, const float* wave, const int* lengths_host, int B, int L,

@@ -26,6 +26,8 @@ from . import common
 HUBERT_BASE_CHINESE = "chinese-hubert-base"
 WAV2VEC2_BASE_CHINESE = "chinese-wav2vec2-base"
 DATA2VEC_AUDIO_BASE = "data2vec-audio-base-960h"   # Data2VecAudioModel: recognised from its positional conv chain
+WAVLM_BASE = "wavlm-base"                          # WavLMModel: extract/wavlm.py (gated relative position bias)
+WAVLM_LARGE = "wavlm-large"
 WHISPER_BASE = "whisper-base"                      # encoder-decoder branch (:83-91): extract/whisper.py
 WHISPER_LARGE = "whisper-large-v2"
 MAXLEN = 16000 * 10
@@ -48,7 +50,13 @@ class AudioExtractor:
         """ragged (default: env MER_AUDIO_RAGGED=1): clips of different lengths share one device pass
         (``HubertEncoder.forward_ragged``: every clip computed as if alone) instead of one pass per distinct
         length; sorted by length and cut into launches of at most ``max_samples_per_launch`` padded samples."""
-        self.enc = HubertEncoder(state_dict, device=device)
+        if "encoder.layers.0.attention.gru_rel_pos_linear.weight" in state_dict:   # WavLMModel (wavlm-base / -large)
+            from .wavlm import WavLmEncoder
+            self.enc = WavLmEncoder(state_dict, device=device)
+            assert not ragged, "ragged batches are implemented for the HuBERT / wav2vec2 families only"
+            ragged = False
+        else:
+            self.enc = HubertEncoder(state_dict, device=device)
         self.device = self.enc.device
         self.max_rows = max_rows_per_launch
         self.ragged = (os.environ.get("MER_AUDIO_RAGGED") == "1") if ragged is None else bool(ragged)

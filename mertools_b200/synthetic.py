@@ -391,7 +391,7 @@ def videomae_state_dict(seed=15, layers=12, hidden=768, ffn=3072):
 HUBERT_LARGE_CFG = dict(HUBERT_CFG, hidden=1024, heads=16, ffn=4096, layers=24)
 
 
-def hubert_state_dict(seed=1, layers=12, scale=1.0, large=False, data2vec=False, group_norm=False):
+def hubert_state_dict(seed=1, layers=12, scale=1.0, large=False, data2vec=False, group_norm=False, wavlm=False):
     """Keys of ``transformers.HubertModel(HubertConfig(num_hidden_layers=layers))``; ``large=True``: the
     hubert-large / chinese-hubert-large family (hidden 1024, 16 heads, FFN 4096, feat_extract_norm="layer",
     conv_bias=True, do_stable_layer_norm=True) -- same parameter names plus conv biases and one LayerNorm
@@ -409,7 +409,7 @@ def hubert_state_dict(seed=1, layers=12, scale=1.0, large=False, data2vec=False,
     for i, k in enumerate(c["conv_kernel"]):
         g.normal(f"feature_extractor.conv_layers.{i}.conv.weight", (cd, cin, k),
                  np.sqrt(2.0 / (cin * k)))
-        if large and not group_norm and not data2vec:   # data2vec-audio-large: LayerNorm convs without biases
+        if large and not group_norm and not data2vec and not wavlm:   # data2vec-audio-large / wavlm-large: no conv biases
             g.normal(f"feature_extractor.conv_layers.{i}.conv.bias", (cd,), 0.05)
         if i == 0 or ln_convs:
             g.ln(f"feature_extractor.conv_layers.{i}.layer_norm", cd)
@@ -435,6 +435,11 @@ def hubert_state_dict(seed=1, layers=12, scale=1.0, large=False, data2vec=False,
         p = f"encoder.layers.{i}."
         for n in ("k_proj", "v_proj", "q_proj", "out_proj"):
             g.linear(p + f"attention.{n}", d, d, std)
+        if wavlm:   # WavLMAttention: gate parameters on every layer, the bucket embedding (320 x heads) on layer 0 only
+            g.linear(p + "attention.gru_rel_pos_linear", 8, 64, 0.3)
+            g.sd[p + "attention.gru_rel_pos_const"] = (1.0 + 0.3 * g.rng.standard_normal((1, c["heads"], 1, 1))).astype(np.float32)
+            if i == 0:
+                g.normal(p + "attention.rel_attn_embed.weight", (320, c["heads"]), 0.5)
         g.ln(p + "layer_norm", d)
         g.linear(p + "feed_forward.intermediate_dense", c["ffn"], d, std)
         g.linear(p + "feed_forward.output_dense", d, c["ffn"], std)

@@ -38,16 +38,42 @@ def _ln(x, sd, prefix, eps, dtype):
                         _t(sd, prefix + ".bias", dtype), eps)
 
 
-def _mha(q, k, v, heads):
-    """softmax(q k^T / sqrt(d)) v, no mask (HF eager_attention_forward, modeling_vit.py:171-196;
-    HubertAttention modeling_hubert.py:262-345; BertSelfAttention)."""
+def _mha(q, k, v, heads, bias=None):
+    """softmax(q k^T / sqrt(d) (+ bias [B, heads, T, T])) v, no mask (HF eager_attention_forward,
+    modeling_vit.py:171-196; HubertAttention modeling_hubert.py:262-345; BertSelfAttention)."""
     B, T, D = q.shape
     hd = D // heads
     q = q.view(B, T, heads, hd).transpose(1, 2)
     k = k.view(B, T, heads, hd).transpose(1, 2)
     v = v.view(B, T, heads, hd).transpose(1, 2)
-    p = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), dim=-1)
+    s = q @ k.transpose(-1, -2) / math.sqrt(hd)
+    p = torch.softmax(s if bias is None else s + bias, dim=-1)
     return (p @ v).transpose(1, 2).reshape(B, T, D)
+
+
+def wavlm_relative_buckets(T, num_buckets=320, max_distance=800):
+    """HF WavLMAttention._relative_positions_bucket on ``j - i`` for i, j < T (modeling_wavlm.py:243-271; the float32
+    log arithmetic of the original is kept: bucket boundaries depend on it).  int64 [T, T]."""
+    rel = torch.arange(T)[None, :] - torch.arange(T)[:, None]
+    nb = num_buckets // 2
+    buckets = (rel > 0).to(torch.long) * nb
+    rel = rel.abs()
+    max_exact = nb // 2
+    large = torch.log(rel.float() / max_exact) / math.log(max_distance / max_exact) * (nb - max_exact)
+    large = torch.min((max_exact + large).to(torch.long), torch.full_like(rel, nb - 1))
+    return buckets + torch.where(rel < max_exact, rel, large)
+
+
+def wavlm_gated_position_bias(sd, prefix, y, pos_bias, heads, dtype=torch.float32):
+    """WavLMAttention.forward steps 1-4 (modeling_wavlm.py:165-180): per (clip, head, query) gate from the head's 64
+    input features through ``gru_rel_pos_linear`` (64 -> 8 = 2 x 4, summed over the 4), sigmoid,
+    ``gate_a * (gate_b * const - 1) + 2``, times the shared position bias [heads, T, T]."""
+    B, T, D = y.shape
+    g = y.view(B, T, heads, D // heads).permute(0, 2, 1, 3)
+    proj = _linear(g, sd, prefix + "gru_rel_pos_linear", dtype).view(B, heads, T, 2, 4).sum(-1)
+    ga, gb = torch.sigmoid(proj).chunk(2, dim=-1)
+    gate = ga * (gb * _t(sd, prefix + "gru_rel_pos_const", dtype) - 1.0) + 2.0          # [B, heads, T, 1]
+    return gate * pos_bias[None]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -514,6 +540,7 @@ def hubert_hidden_states(sd, input_values, layers=12, heads=12, eps=1e-5,
     if not stable_layer_norm:
         x = _ln(x, sd, "encoder.layer_norm", eps, dtype)
         hs.append(x)
+    wavlm, pos_bias = "encoder.layers.0.attention.gru_rel_pos_linear.weight" in sd, None
     for i in range(layers):
         p = f"encoder.layers.{i}."
         if stable_layer_norm:
@@ -524,7 +551,13 @@ def hubert_hidden_states(sd, input_values, layers=12, heads=12, eps=1e-5,
         q = _linear(y, sd, p + "attention.q_proj", dtype)
         k = _linear(y, sd, p + "attention.k_proj", dtype)
         v = _linear(y, sd, p + "attention.v_proj", dtype)
-        a = _linear(_mha(q, k, v, heads), sd, p + "attention.out_proj", dtype)
+        bias = None
+        if wavlm:   # WavLMModel: layer 0's bucket embedding gives the position bias of every layer, gated per layer
+            if pos_bias is None:
+                emb = _t(sd, "encoder.layers.0.attention.rel_attn_embed.weight", dtype)           # [buckets, heads]
+                pos_bias = emb[wavlm_relative_buckets(y.shape[1], emb.shape[0])].permute(2, 0, 1)  # [heads, T, T]
+            bias = wavlm_gated_position_bias(sd, p + "attention.", y, pos_bias, heads, dtype)
+        a = _linear(_mha(q, k, v, heads, bias), sd, p + "attention.out_proj", dtype)
         if stable_layer_norm:
             x = x + a
             h = F.gelu(_linear(_ln(x, sd, p + "final_layer_norm", eps, dtype), sd,

@@ -702,6 +702,9 @@ def test_encoder_constructors_run_with_the_device_layer_stubbed(monkeypatch):
         "wav2vec2_large_960h": En.HubertEncoder(S.hubert_state_dict(layers=4, large=True, group_norm=True)),
         "data2vec": En.HubertEncoder(S.hubert_state_dict(layers=4, data2vec=True)),
         "data2vec_large": En.HubertEncoder(S.hubert_state_dict(layers=4, data2vec=True, large=True)),
+        # WavLM checkpoints: the front-end of the WavLM branch is this struct (mer_hubert_frontend)
+        "wavlm": En.HubertEncoder(S.hubert_state_dict(layers=4, wavlm=True)),
+        "wavlm_large": En.HubertEncoder(S.hubert_state_dict(layers=4, wavlm=True, large=True)),
         "bert": En.BertEncoder(S.bert_state_dict(100, layers=4)),
         "bert_large": En.BertEncoder(S.bert_state_dict(100, layers=4, large=True)),
     }
@@ -713,6 +716,8 @@ def test_encoder_constructors_run_with_the_device_layer_stubbed(monkeypatch):
             made["emonet"].model.n_convs) == (52, 82, 136, 222)
     h = made["data2vec"].model
     assert (h.n_pos_layers, h.pos_taps, h.feat_norm_layer, h.stable_layer_norm, bool(h.conv_b[1])) == (5, 19, 1, 0, False)
+    h = made["wavlm_large"].model
+    assert (h.hidden, h.feat_norm_layer, h.stable_layer_norm, bool(h.conv_b[1]), made["wavlm"].model.stable_layer_norm) == (1024, 1, 1, False, 0)
     h = made["data2vec_large"].model
     assert (h.hidden, h.heads, h.n_pos_layers, h.pos_window, h.stable_layer_norm, bool(h.conv_b[1])) == (1024, 16, 5, 256, 0, False)
     h = made["wav2vec2_large_960h"].model
@@ -835,3 +840,44 @@ def test_dinov2_oracle_is_pinned_to_hf_and_the_clip_layout_conversion_reproduces
         x = x + lin(ctx, p + "self_attn.out_proj")
         x = x + lin(torch.nn.functional.gelu(lin(ln(x, p + "layer_norm2"), p + "mlp.fc1")), p + "mlp.fc2")
     assert float((x.sum(dim=1) - ref.sum(dim=1)).abs().max() / ref.sum(dim=1).abs().max()) < 1e-5
+
+
+class _TorchWavLmOps(_TorchWhisperOps):
+    """CPU stand-in for the WavLM product backend, with the semantics of mer_wavlm_gate / mer_biased_attention."""
+
+    def operand(self, x):
+        return x
+
+    def layernorm(self, x, g, b, operand, eps=1e-5):
+        return torch.nn.functional.layer_norm(x, (x.shape[-1],), g, b, eps)
+
+    def gate(self, x, heads, w, b, c):
+        proj = (x.reshape(x.shape[0], heads, 64) @ w.T + b).reshape(x.shape[0], heads, 2, 4).sum(-1)
+        ga, gb = torch.sigmoid(proj[..., 0]), torch.sigmoid(proj[..., 1])
+        return ga * (gb * c - 1.0) + 2.0                                            # [tokens, heads]
+
+    def biased_attention(self, qkv, bias, gate, B, T, heads):
+        d = qkv.shape[1] // 3
+        q, k, v = (qkv[:, i * d:(i + 1) * d].reshape(B, T, heads, 64).transpose(1, 2) for i in range(3))
+        s = (q * 0.125) @ k.transpose(-1, -2) + gate.reshape(B, T, heads).permute(0, 2, 1)[..., None] * bias[None]
+        return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * T, d)
+
+
+@pytest.mark.parametrize("large", [False, True])
+def test_wavlm_orchestration_matches_the_oracle_with_a_cpu_backend(large):
+    """mertools_b200.extract.wavlm.WavLmNet (fused q|k|v, bucketed relative position bias built on the host, per-layer
+    gate, post-LN base / pre-LN large layer order, hidden-state tuple) over a torch backend, against the oracle's
+    WavLM restatement (itself pinned to HF WavLMModel in tests/test_oracle.py)."""
+    from mertools_b200.extract.wavlm import WavLmNet, relative_buckets
+    assert np.array_equal(relative_buckets(300), E.wavlm_relative_buckets(300).numpy())
+    layers, heads = 4, 16 if large else 12
+    sd = S.hubert_state_dict(seed=6, layers=layers, wavlm=True, large=large)
+    x = torch.randn(2, 8000, generator=torch.Generator().manual_seed(5))
+    ref = E.hubert_hidden_states({k: torch.from_numpy(v) for k, v in sd.items()}, x, layers=layers, heads=heads)
+    B, T, D = ref[0].shape
+    net = WavLmNet(sd, _TorchWavLmOps())
+    assert (net.heads, net.stable, len(net.layers)) == (heads, large, layers)
+    got = net.hidden_states(ref[0].reshape(B * T, D), B, T)
+    assert len(got) == len(ref) == layers + 1
+    for a, b in zip(got, ref):
+        assert float((a.reshape(B, T, D) - b).abs().max() / b.abs().max()) < 2e-5

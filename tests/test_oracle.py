@@ -353,3 +353,23 @@ def test_electra_base_is_the_bert_graph_under_the_same_names():
         ref = m(ids, output_hidden_states=True).hidden_states
     for a, b in zip(E.bert_hidden_states(sd, ids, layers=2), ref):
         assert float((a - b).abs().max() / b.abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("large", [False, True])
+def test_oracle_audio_restatement_covers_wavlm(large):
+    """wavlm-base / wavlm-large (extract_audio_huggingface.py:36-37) pinned to HF WavLMModel: bucketed relative position
+    bias from layer 0's embedding, gated per layer / head / query; post-LN base, stable-layer-norm large."""
+    from transformers import WavLMConfig, WavLMModel
+    x = torch.randn(2, 12000, generator=torch.Generator().manual_seed(3))
+    sd = S.hubert_state_dict(seed=6, layers=3, wavlm=True, large=large)
+    kw = dict(hidden_size=1024, num_attention_heads=16, intermediate_size=4096, feat_extract_norm="layer",
+              do_stable_layer_norm=True, conv_bias=False) if large else {}
+    model = WavLMModel(WavLMConfig(num_hidden_layers=3, **kw)).eval()
+    res = model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    with torch.no_grad():
+        ref = model(x, output_hidden_states=True).hidden_states
+    got = E.hubert_hidden_states({k: torch.from_numpy(v) for k, v in sd.items()}, x, layers=3, heads=16 if large else 12)
+    assert len(got) == len(ref) == 4
+    for a, b in zip(got, ref):
+        assert float((a - b).abs().max() / b.abs().max()) < 2e-5

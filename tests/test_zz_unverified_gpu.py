@@ -628,3 +628,33 @@ def test_dinov2_extractor_vs_oracle(cuda):
         got = ext.extract_clips([frames], level, nframe=8)[0]
         ref = P.dinov2_clip_features(sd, frames, level, nframe=8)
         assert got.shape == ref.shape and _rel(got, ref) < TOL
+
+
+@pytest.mark.parametrize("large", [False, True])
+def test_wavlm_encoder_vs_oracle(cuda, large):
+    """WavLM branch: mer_hubert_frontend + mer_wavlm_gate + mer_biased_attention under the host orchestration."""
+    import numpy as np
+
+    from mertools_b200 import synthetic as S
+    from mertools_b200.extract.audio import AudioExtractor
+    from mertools_b200.extract.wavlm import WavLmEncoder
+    from oracle import encoders as E
+    from oracle import pipeline as P
+    layers, heads = 4, 16 if large else 12
+    sd = S.hubert_state_dict(seed=6, layers=layers, wavlm=True, large=large)
+    wav = (S.synth_waves(2, 16000, seed=27).astype(np.float64) / 32768.0).astype(np.float32)
+    utt, frames, hidden = WavLmEncoder(sd, device=cuda).forward(torch.from_numpy(wav).to(cuda), normalize=True,
+                                                               want_frames=True, return_hidden=True)
+    ref = E.hubert_hidden_states({k: torch.from_numpy(v) for k, v in sd.items()},
+                                 torch.from_numpy(np.stack([P.wav2vec2_normalize(w) for w in wav])), layers=layers, heads=heads)
+    for l in range(layers + 1):
+        assert float((hidden[l].cpu() - ref[l]).abs().max() / ref[l].abs().max()) < 4e-3, l
+    want = torch.stack(ref)[-4:].sum(dim=0)
+    assert float((frames.cpu() - want).abs().max() / want.abs().max()) < 2e-3
+    waves = [S.synth_waves(1, n, seed=40 + i)[0].astype(np.float64) / 32768.0 for i, n in enumerate((9000, 16000, 9000))]
+    got = AudioExtractor(sd, device="cuda:0").extract_waves(waves, "UTTERANCE")
+    for w, g in zip(waves, got):
+        r = E.hubert_hidden_states({k: torch.from_numpy(v) for k, v in sd.items()},
+                                   torch.from_numpy(P.wav2vec2_normalize(w))[None], layers=layers, heads=heads)
+        r = torch.stack(r)[-4:].sum(dim=0)[0].mean(dim=0).numpy()
+        assert g.shape == r.shape and np.abs(g - r).max() / np.abs(r).max() < 2e-3
