@@ -254,10 +254,14 @@ typedef struct MerClipVisionModel {
    * folded into the out-proj / FC2 weights and the patch-conv bias into pos_rest by the loader, position table already
    * interpolated to the image grid; out_embeds [n_frames, hidden] = sum over the tokens of the LAST LAYER's output
    * (hidden_states[-1], before Dinov2Model.layernorm); post_ln_* / proj_w unused, proj_dim = hidden. */
+  /* MER_VISION_EMBED_ONLY (2): stop after the embeddings; out_embeds [n_frames * tokens, hidden] = class row
+   * (cls_pos0) + patch rows (patch conv + pos_rest) = hidden_states[0] of a model whose layers the host orchestrates
+   * (data2vec-vision: relative position bias in attention, extract/data2vec_vision.py); layers / n_layers unused. */
   int variant;
 } MerClipVisionModel;
 #define MER_VISION_CLIP 0
 #define MER_VISION_DINOV2 1
+#define MER_VISION_EMBED_ONLY 2
 
 MER_API long long mer_clip_vision_workspace_bytes(const MerClipVisionModel* model, int n_frames);
 

@@ -327,8 +327,15 @@ int mer_clip_vision_forward(const MerClipVisionModel* m, const uint8_t* frames_b
     MER_TRY(mer_gemm_launch(&g, stream));
   }
   const bool dinov2 = m->variant == MER_VISION_DINOV2;
-  MER_REQUIRE(dinov2 ? (m->pre_ln_g == nullptr && m->proj_dim == D) : (m->pre_ln_g && m->post_ln_g && m->proj_w),
+  MER_REQUIRE(m->variant >= MER_VISION_CLIP && m->variant <= MER_VISION_EMBED_ONLY, "mer_clip_vision_forward: variant %d",
+              m->variant);
+  MER_REQUIRE(m->variant != MER_VISION_CLIP ? (m->pre_ln_g == nullptr && m->proj_dim == D)
+                                            : (m->pre_ln_g && m->post_ln_g && m->proj_w),
               "mer_clip_vision_forward: variant %d operands", m->variant);
+  if (m->variant == MER_VISION_EMBED_ONLY) {  // the embedding output (hidden_states[0]) for a host-orchestrated stack
+    MER_CUDA_CHECK(cudaMemcpyAsync(out_embeds, x, (size_t)p.M * D * 4, cudaMemcpyDeviceToDevice, stream));
+    return 0;
+  }
   if (!dinov2)
     MER_TRY(mer_layernorm_launch(x, m->pre_ln_g, m->pre_ln_b, x, nullptr, nullptr, p.M, D, m->ln_eps, 0, stream));
   MerStackArgs a;

@@ -22,7 +22,7 @@ def load_hf_state_dict(model_dir):
     out = {}
     for k, v in sd.items():
         # AutoModel strips the task-model prefix ("vit.", "hubert.", "bert.", "roberta.", ...)
-        for pre in ("vit.", "hubert.", "bert.", "roberta.", "wav2vec2.", "data2vec_audio.", "electra.", "videomae.", "wavlm."):
+        for pre in ("vit.", "hubert.", "bert.", "roberta.", "wav2vec2.", "data2vec_audio.", "electra.", "videomae.", "wavlm.", "data2vec_vision.", "dinov2."):
             if k.startswith(pre):
                 k = k[len(pre):]
                 break

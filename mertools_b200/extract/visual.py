@@ -112,6 +112,10 @@ class VisualExtractor:
             from ..encoders import ClipVisionEncoder
             self.enc = ClipVisionEncoder(state_dict, device=device)
             self.feature_dim = self.enc.proj_dim
+        elif "encoder.layer.0.lambda_1" in state_dict:  # HF Data2VecVisionModel (data2vec-vision-base-ft1k; :124-133)
+            from .data2vec_vision import Data2VecVisionEncoder
+            self.enc = Data2VecVisionEncoder(state_dict, device=device)
+            self.feature_dim = self.enc.hidden
         elif "encoder.layer.0.layer_scale1.lambda1" in state_dict:  # HF Dinov2Model (dinov2-large; :135-145)
             from ..encoders import Dinov2Encoder
             self.enc = Dinov2Encoder(state_dict, device=device)
@@ -199,6 +203,9 @@ def main(params, config=None, clips_per_launch=32):
         ext = VideoMaeExtractor.from_pretrained(model_dir, device=f"cuda:{params.gpu}")
     else:
         ext = VisualExtractor(common.load_hf_state_dict(model_dir), device=f"cuda:{params.gpu}")
+        if params.model_name == DATA2VEC_VISUAL:   # processor settings from the checkpoint's preprocessor_config.json
+            from .data2vec_vision import Data2VecVisionEncoder
+            ext.enc = Data2VecVisionEncoder.from_pretrained(model_dir, device=f"cuda:{params.gpu}")
     nframe = 64 if params.model_name in (DINO2_LARGE, DINO2_GIANT) else None
     vids = os.listdir(face_dir)
     print(f'Find total "{len(vids)}" videos.')

@@ -367,6 +367,30 @@ def dinov2_state_dict(seed=17, layers=24, hidden=1024, ffn=4096, patch=14, n_pos
     return g.sd
 
 
+def data2vec_vision_state_dict(seed=19, layers=12, hidden=768, ffn=3072, heads=12, patch=16, window=14):
+    """Keys of ``transformers.Data2VecVisionModel`` (data2vec-vision-base-ft1k: BEiT graph; no absolute positions, a
+    relative position bias table per layer, key projection without bias, LayerScale ``lambda_1`` / ``lambda_2``)."""
+    g = _Gen(seed)
+    g.normal("embeddings.cls_token", (1, 1, hidden), 0.02)
+    g.normal("embeddings.patch_embeddings.projection.weight", (hidden, 3, patch, patch), 0.02)
+    g.normal("embeddings.patch_embeddings.projection.bias", (hidden,), 0.02)
+    for i in range(layers):
+        p = f"encoder.layer.{i}."
+        g.sd[p + "lambda_1"] = (0.5 + 0.5 * g.rng.random(hidden)).astype(np.float32)
+        g.sd[p + "lambda_2"] = (0.5 + 0.5 * g.rng.random(hidden)).astype(np.float32)
+        g.linear(p + "attention.attention.query", hidden, hidden, 0.02)
+        g.normal(p + "attention.attention.key.weight", (hidden, hidden), 0.02)
+        g.linear(p + "attention.attention.value", hidden, hidden, 0.02)
+        g.normal(p + "attention.attention.relative_position_bias.relative_position_bias_table",
+                 ((2 * window - 1) ** 2 + 3, heads), 0.5)
+        g.linear(p + "attention.output.dense", hidden, hidden, 0.02)
+        g.linear(p + "intermediate.dense", ffn, hidden, 0.02)
+        g.linear(p + "output.dense", hidden, ffn, 0.02)
+        g.ln(p + "layernorm_before", hidden)
+        g.ln(p + "layernorm_after", hidden)
+    return g.sd
+
+
 def videomae_state_dict(seed=15, layers=12, hidden=768, ffn=3072):
     """Keys of ``transformers.VideoMAEModel`` (videomae-base shape): tubelet patch embedding Conv3d(3, 768, (2, 16, 16)),
     pre-LN layers whose attention carries separate ``q_bias`` / ``v_bias`` (no key bias); the position table is a fixed

@@ -108,6 +108,55 @@ def vit_hidden_states(sd, pixel_values, layers=12, heads=12, eps=1e-12, dtype=to
     return tuple(hs)
 
 
+def beit_relative_position_index(window=14):
+    """HF Data2VecVisionRelativePositionBias.generate_relative_position_index (modeling_data2vec_vision.py:534-556):
+    index into the (2w-1)^2 + 3 table for every (query, key) pair of the 1 + w*w tokens; the three extra rows are
+    cls->token, token->cls and cls->cls.  int64 [1 + w*w, 1 + w*w]."""
+    n = (2 * window - 1) ** 2 + 3
+    c = torch.stack(torch.meshgrid(torch.arange(window), torch.arange(window), indexing="ij")).flatten(1)
+    rel = (c[:, :, None] - c[:, None, :]).permute(1, 2, 0).contiguous()
+    rel[:, :, 0] += window - 1
+    rel[:, :, 1] += window - 1
+    rel[:, :, 0] *= 2 * window - 1
+    idx = torch.zeros((window * window + 1,) * 2, dtype=rel.dtype)
+    idx[1:, 1:] = rel.sum(-1)
+    idx[0, 0:] = n - 3
+    idx[0:, 0] = n - 2
+    idx[0, 0] = n - 1
+    return idx
+
+
+def data2vec_vision_hidden_states(sd, pixel_values, heads=12, eps=1e-12, dtype=torch.float32):
+    """``Data2VecVisionModel(pixel_values, output_hidden_states=True).hidden_states`` (extract_vision_huggingface.py:
+    124-133 reads ``[-1].sum(dim=1)``): patch conv with bias + class token, NO absolute positions; pre-LN BEiT layers
+    whose attention adds a per-layer relative position bias to the scaled scores (key projection has no bias) and
+    whose two branches are scaled by ``lambda_1`` / ``lambda_2``."""
+    x = pixel_values.to(dtype)
+    w = _t(sd, "embeddings.patch_embeddings.projection.weight", dtype)
+    window = x.shape[2] // w.shape[-1]
+    x = F.conv2d(x, w, _t(sd, "embeddings.patch_embeddings.projection.bias", dtype), stride=w.shape[-1])
+    x = x.flatten(2).transpose(1, 2)
+    x = torch.cat([_t(sd, "embeddings.cls_token", dtype).expand(x.shape[0], -1, -1), x], dim=1)
+    idx = beit_relative_position_index(window)
+    hs = [x]
+    i = 0
+    while f"encoder.layer.{i}.output.dense.weight" in sd:
+        p = f"encoder.layer.{i}."
+        a = p + "attention.attention."
+        y = _ln(x, sd, p + "layernorm_before", eps, dtype)
+        q = _linear(y, sd, a + "query", dtype)
+        k = F.linear(y, _t(sd, a + "key.weight", dtype))
+        v = _linear(y, sd, a + "value", dtype)
+        bias = _t(sd, a + "relative_position_bias.relative_position_bias_table", dtype)[idx].permute(2, 0, 1)[None]
+        att = _linear(_mha(q, k, v, heads, bias), sd, p + "attention.output.dense", dtype)
+        x = x + att * _t(sd, p + "lambda_1", dtype)
+        h = F.gelu(_linear(_ln(x, sd, p + "layernorm_after", eps, dtype), sd, p + "intermediate.dense", dtype))
+        x = x + _linear(h, sd, p + "output.dense", dtype) * _t(sd, p + "lambda_2", dtype)
+        hs.append(x)
+        i += 1
+    return tuple(hs)
+
+
 def dinov2_position_embeddings(sd, grid_h, grid_w, dtype=torch.float32):
     """HF Dinov2Embeddings.interpolate_pos_encoding (modeling_dinov2.py:57-95, transformers 5.x: bicubic resize of the
     [side, side] table to ``size=(grid_h, grid_w)``, align_corners=False; 4.x releases passed a scale factor computed

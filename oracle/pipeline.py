@@ -426,7 +426,10 @@ def visual_clip_features(sd, frames_bgr, nframe=None, layers=12, feature_level="
     inputs = vit_preprocess(frames)
     embs = []
     for batch in split_into_batch(inputs, 32):
-        hs = E.vit_hidden_states(sd, batch, layers=layers, dtype=dtype)
+        if "encoder.layer.0.lambda_1" in sd:   # Data2VecVisionModel (data2vec-vision-base-ft1k): the BEiT graph
+            hs = E.data2vec_vision_hidden_states(sd, batch, dtype=dtype)
+        else:
+            hs = E.vit_hidden_states(sd, batch, layers=layers, dtype=dtype)
         embs.append(torch.stack(hs)[-1].sum(dim=1))  # :143-144
     emb = torch.cat(embs, dim=0).float().squeeze().numpy()  # :171
     emb = np.array(emb).squeeze()

@@ -859,7 +859,8 @@ class _TorchWavLmOps(_TorchWhisperOps):
     def biased_attention(self, qkv, bias, gate, B, T, heads):
         d = qkv.shape[1] // 3
         q, k, v = (qkv[:, i * d:(i + 1) * d].reshape(B, T, heads, 64).transpose(1, 2) for i in range(3))
-        s = (q * 0.125) @ k.transpose(-1, -2) + gate.reshape(B, T, heads).permute(0, 2, 1)[..., None] * bias[None]
+        g = 1.0 if gate is None else gate.reshape(B, T, heads).permute(0, 2, 1)[..., None]
+        s = (q * 0.125) @ k.transpose(-1, -2) + g * bias[None]
         return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * T, d)
 
 
@@ -881,3 +882,30 @@ def test_wavlm_orchestration_matches_the_oracle_with_a_cpu_backend(large):
     assert len(got) == len(ref) == layers + 1
     for a, b in zip(got, ref):
         assert float((a.reshape(B, T, D) - b).abs().max() / b.abs().max()) < 2e-5
+
+
+def test_data2vec_vision_oracle_is_pinned_to_hf_and_the_orchestration_reproduces_it():
+    """extract_vision_huggingface.py:124-133 (data2vec-vision-base-ft1k = the BEiT graph).  (1) oracle restatement vs HF
+    Data2VecVisionModel on a synthetic checkpoint that strict-loads (relative position bias on); (2) BeitNet (fused
+    q|k|v with the zero key bias, per-layer bias tables gathered on the host, folded LayerScale) over a torch backend."""
+    transformers = pytest.importorskip("transformers")
+    from mertools_b200.extract.data2vec_vision import BeitNet, relative_position_index
+    assert np.array_equal(relative_position_index(14), E.beit_relative_position_index(14).numpy())
+    sd = S.data2vec_vision_state_dict(seed=19, layers=2)
+    model = transformers.Data2VecVisionModel(
+        transformers.Data2VecVisionConfig(num_hidden_layers=2, use_relative_position_bias=True), add_pooling_layer=False).eval()
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    frames = np.random.default_rng(8).integers(0, 256, (2, 112, 112, 3), dtype=np.uint8)
+    x = P.vit_preprocess(frames)
+    with torch.no_grad():
+        ref = model(x, output_hidden_states=True).hidden_states
+    got = E.data2vec_vision_hidden_states(sd, x)
+    assert len(got) == len(ref) == 3
+    for a, b in zip(got, ref):
+        assert float((a - b).abs().max() / b.abs().max()) < 1e-5
+    fra = P.visual_clip_features(sd, frames, feature_level="FRAME")
+    np.testing.assert_allclose(fra, ref[-1].sum(dim=1).numpy(), rtol=0, atol=2e-5 * float(ref[-1].sum(dim=1).abs().max()))
+    net = BeitNet(sd, _TorchWavLmOps())
+    assert (net.heads, net.tokens, len(net.layers)) == (12, 197, 2)
+    out = net.last_hidden(ref[0].reshape(2 * 197, 768), 2).reshape(2, 197, 768)
+    assert float((out - ref[-1]).abs().max() / ref[-1].abs().max()) < 1e-5

@@ -658,3 +658,20 @@ def test_wavlm_encoder_vs_oracle(cuda, large):
                                    torch.from_numpy(P.wav2vec2_normalize(w))[None], layers=layers, heads=heads)
         r = torch.stack(r)[-4:].sum(dim=0)[0].mean(dim=0).numpy()
         assert g.shape == r.shape and np.abs(g - r).max() / np.abs(r).max() < 2e-3
+
+
+def test_data2vec_vision_extractor_vs_oracle(cuda):
+    """data2vec-vision branch: MER_VISION_EMBED_ONLY embeddings + host-orchestrated BEiT layers (mer_biased_attention)."""
+    import numpy as np
+
+    from mertools_b200 import synthetic as S
+    from mertools_b200.extract.visual import VisualExtractor
+    from oracle import pipeline as P
+    sd = S.data2vec_vision_state_dict(seed=19, layers=3)
+    frames = np.random.default_rng(8).integers(0, 256, (5, 112, 112, 3), dtype=np.uint8)
+    ext = VisualExtractor(sd, device=cuda)
+    assert ext.feature_dim == 768
+    for level in ("UTTERANCE", "FRAME"):
+        got = ext.extract_clips([frames], level)[0]
+        ref = P.visual_clip_features(sd, frames, feature_level=level)
+        assert got.shape == ref.shape and np.abs(got - ref).max() / np.abs(ref).max() < 1e-3
