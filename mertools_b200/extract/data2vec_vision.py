@@ -72,6 +72,85 @@ class BeitNet:
         return x
 
 
+class PatchEmbedder:
+    """``hidden_states[0]`` of a ViT-style model on the device: mer_clip_vision_forward with MER_VISION_EMBED_ONLY
+    (BGR -> RGB, rescale, normalise, patch gather, TF32 patch GEMM, class row).  ``cls_row`` [D] = class token (+ its
+    position), ``patch_rows`` [tokens - 1, D] = what is added to every frame's patch tokens (positions + conv bias).
+    Shared by the host-orchestrated visual branches (data2vec-vision, dinov2-giant)."""
+
+    def __init__(self, patch_weight, cls_row, patch_rows, device, image=224, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5)):
+        import ctypes as C
+
+        from .. import _lib as L
+        from .. import weights as W
+        from ..encoders import MerClipVisionModel, _Workspace
+        L.check(L.lib().mer_check_device())
+        self.device = torch.device(device)
+        pw = np.asarray(patch_weight, np.float32)
+        D, _, p, _ = pw.shape
+        assert D % 256 == 0 and image % p == 0, (pw.shape, image)
+        self.hidden, self.image, self.tokens = int(D), int(image), (image // p) ** 2 + 1
+        assert np.shape(cls_row) == (D,) and np.shape(patch_rows) == (self.tokens - 1, D)
+        pk = self.pk = W.Packed(self.device)
+        kpad = (3 * p * p + 31) // 32 * 32
+        wflat = np.zeros((D, kpad), np.float32)
+        wflat[:, :3 * p * p] = pw.reshape(D, 3 * p * p)
+        m = MerClipVisionModel()
+        m.n_layers, m.ln_eps = 0, 1e-6
+        m.hidden, m.ffn, m.heads, m.patch, m.image, m.proj_dim, m.kpad = D, 4 * D, D // 64, p, image, D, kpad
+        m.gemm_mode, m.variant = L.MER_GEMM_TF32, 2                                      # MER_VISION_EMBED_ONLY
+        m.mean, m.std = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+        m.patch_w = pk.keep(wflat, tf32=True).data_ptr()
+        m.cls_pos0 = pk.keep(np.asarray(cls_row, np.float32)).data_ptr()
+        m.pos_rest = pk.keep(np.asarray(patch_rows, np.float32)).data_ptr()
+        self.model = m
+        self.ws = _Workspace(self.device)
+        lib = L.lib()
+        lib.mer_clip_vision_workspace_bytes.restype = C.c_longlong
+        lib.mer_clip_vision_workspace_bytes.argtypes = [C.POINTER(MerClipVisionModel), C.c_int]
+        self._fwd = L.declare("mer_clip_vision_forward", [C.POINTER(MerClipVisionModel), C.c_void_p, C.c_int, C.c_int,
+                                                          C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong,
+                                                          C.c_void_p, C.c_void_p, C.c_void_p])
+        self._L, self._C = L, C
+
+    def __call__(self, frames_u8, crop_y0=0, crop_x0=0):
+        """frames: uint8 CUDA [n, H, W, 3] BGR, already resized; the image x image window at (crop_y0, crop_x0) is
+        embedded.  Returns fp32 [n * tokens, D]."""
+        L, C = self._L, self._C
+        n, h, w, _ = frames_u8.shape
+        assert crop_y0 + self.image <= h and crop_x0 + self.image <= w
+        ws = self.ws.get(L.lib().mer_clip_vision_workspace_bytes(C.byref(self.model), n))
+        x = torch.empty(n * self.tokens, self.hidden, dtype=torch.float32, device=self.device)
+        L.check(self._fwd(C.byref(self.model), L.ptr(frames_u8), n, h, w, crop_y0, crop_x0, L.ptr(ws), ws.numel(),
+                          L.ptr(x), None, L.stream_ptr()))
+        return x
+
+
+class DeviceResizer:
+    """Pillow-exact uint8 resize on the device (mer_resize_u8; filter 0 = bilinear, 1 = bicubic)."""
+
+    def __init__(self, device):
+        import ctypes as C
+
+        from .. import _lib as L
+        from ..encoders import _Workspace
+        self.device, self.ws, self._L = torch.device(device), _Workspace(torch.device(device)), L
+        L.lib().mer_resize_workspace_bytes.restype = C.c_longlong
+        L.lib().mer_resize_workspace_bytes.argtypes = [C.c_int] * 5
+        self._resize = L.declare("mer_resize_u8", [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                                   C.c_int, C.c_int, C.c_void_p, C.c_void_p])
+
+    def __call__(self, frames_u8, out_h, out_w, filter=0):
+        L = self._L
+        n, h, w, _ = frames_u8.shape
+        if (h, w) == (out_h, out_w):
+            return frames_u8
+        out = torch.empty(n, out_h, out_w, 3, dtype=torch.uint8, device=self.device)
+        ws = self.ws.get(max(int(L.lib().mer_resize_workspace_bytes(n, h, w, out_h, out_w)), 1))
+        L.check(self._resize(L.ptr(frames_u8), n, h, w, L.ptr(out), out_h, out_w, filter, L.ptr(ws), L.stream_ptr()))
+        return out
+
+
 class Data2VecVisionEncoder:
     """``frame_features(uint8 CUDA [N, H, W, 3] BGR) -> [N, hidden]`` (the contract VisualExtractor drives).  Processor:
     BeitImageProcessor as configured by the checkpoint's preprocessor_config.json — resize to size x size
@@ -80,49 +159,22 @@ class Data2VecVisionEncoder:
 
     def __init__(self, state_dict, device="cuda", eps=1e-12, image=224, size=224, resample=2, center_crop=False,
                  mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5)):
-        import ctypes as C
-
-        from .. import _lib as L
         from .. import weights as W
-        from ..encoders import MerClipVisionModel, _Workspace
         from .wavlm import _cuda_ops
-        L.check(L.lib().mer_check_device())
-        self.device = torch.device(device)
         sd = W._np(state_dict)
         pw = np.asarray(sd["embeddings.patch_embeddings.projection.weight"], np.float32)
-        D, _, p, _ = pw.shape
-        assert D in (768, 1024) and image % p == 0 and size >= image, (pw.shape, image, size)
+        D, p = pw.shape[0], pw.shape[-1]
+        assert D in (768, 1024) and size >= image, (pw.shape, image, size)
         self.hidden, self.image, self.size = int(D), int(image), int(size)
         self.filter, self.center_crop = {2: 0, 3: 1}[int(resample)], bool(center_crop)
         self.tokens = (image // p) ** 2 + 1
         self.net = BeitNet(sd, _cuda_ops(device), eps=eps, window=image // p)
-        pk = self.pk = W.Packed(self.device)
-        kpad = (3 * p * p + 31) // 32 * 32
-        wflat = np.zeros((D, kpad), np.float32)
-        wflat[:, :3 * p * p] = pw.reshape(D, 3 * p * p)
-        m = MerClipVisionModel()
-        m.n_layers, m.ln_eps = 0, eps
-        m.hidden, m.ffn, m.heads, m.patch, m.image, m.proj_dim, m.kpad = D, 4 * D, D // 64, p, image, D, kpad
-        m.gemm_mode, m.variant = L.MER_GEMM_TF32, 2                                      # MER_VISION_EMBED_ONLY
-        m.mean, m.std = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
-        m.patch_w = pk.keep(wflat, tf32=True).data_ptr()
-        m.cls_pos0 = pk.keep(np.asarray(sd["embeddings.cls_token"], np.float32).reshape(D)).data_ptr()
         # no absolute positions: the residual operand of the patch GEMM carries the conv bias alone
         bias = np.asarray(sd["embeddings.patch_embeddings.projection.bias"], np.float32)
-        m.pos_rest = pk.keep(np.tile(bias, (self.tokens - 1, 1))).data_ptr()
-        self.model = m
-        self.ws, self.ws_resize = _Workspace(self.device), _Workspace(self.device)
-        lib = L.lib()
-        lib.mer_clip_vision_workspace_bytes.restype = C.c_longlong
-        lib.mer_clip_vision_workspace_bytes.argtypes = [C.POINTER(MerClipVisionModel), C.c_int]
-        lib.mer_resize_workspace_bytes.restype = C.c_longlong
-        lib.mer_resize_workspace_bytes.argtypes = [C.c_int] * 5
-        self._fwd = L.declare("mer_clip_vision_forward", [C.POINTER(MerClipVisionModel), C.c_void_p, C.c_int, C.c_int,
-                                                          C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong,
-                                                          C.c_void_p, C.c_void_p, C.c_void_p])
-        self._resize = L.declare("mer_resize_u8", [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
-                                                   C.c_int, C.c_int, C.c_void_p, C.c_void_p])
-        self._L, self._C = L, C
+        self.embed = PatchEmbedder(pw, np.asarray(sd["embeddings.cls_token"], np.float32).reshape(D),
+                                   np.tile(bias, (self.tokens - 1, 1)), device, image=image, mean=mean, std=std)
+        self.device = self.embed.device
+        self.resize = DeviceResizer(device)
 
     @classmethod
     def from_pretrained(cls, model_dir, device="cuda"):
@@ -144,19 +196,9 @@ class Data2VecVisionEncoder:
         return cls(common.load_hf_state_dict(model_dir), device=device, **kw)
 
     def frame_features(self, frames_bgr_u8):
-        L, C = self._L, self._C
         assert frames_bgr_u8.dtype == torch.uint8 and frames_bgr_u8.is_cuda and frames_bgr_u8.dim() == 4
-        frames = frames_bgr_u8.contiguous()
-        n, h, w, _ = frames.shape
-        if (h, w) != (self.size, self.size):
-            out = torch.empty(n, self.size, self.size, 3, dtype=torch.uint8, device=self.device)
-            ws = self.ws_resize.get(max(int(L.lib().mer_resize_workspace_bytes(n, h, w, self.size, self.size)), 1))
-            L.check(self._resize(L.ptr(frames), n, h, w, L.ptr(out), self.size, self.size, self.filter, L.ptr(ws),
-                                 L.stream_ptr()))
-            frames = out
+        frames = self.resize(frames_bgr_u8.contiguous(), self.size, self.size, self.filter)
         off = (self.size - self.image) // 2
-        ws = self.ws.get(L.lib().mer_clip_vision_workspace_bytes(C.byref(self.model), n))
-        x = torch.empty(n * self.tokens, self.hidden, dtype=torch.float32, device=self.device)
-        L.check(self._fwd(C.byref(self.model), L.ptr(frames), n, self.size, self.size, off, off, L.ptr(ws), ws.numel(),
-                          L.ptr(x), None, L.stream_ptr()))
+        n = frames.shape[0]
+        x = self.embed(frames, off, off)
         return self.net.last_hidden(x, n).view(n, self.tokens, self.hidden).sum(dim=1)

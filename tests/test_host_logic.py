@@ -909,3 +909,35 @@ def test_data2vec_vision_oracle_is_pinned_to_hf_and_the_orchestration_reproduces
     assert (net.heads, net.tokens, len(net.layers)) == (12, 197, 2)
     out = net.last_hidden(ref[0].reshape(2 * 197, 768), 2).reshape(2, 197, 768)
     assert float((out - ref[-1]).abs().max() / ref[-1].abs().max()) < 1e-5
+
+
+def test_host_orchestrated_encoder_constructors_run_with_the_device_layer_stubbed(monkeypatch):
+    """The WavLM / data2vec-vision / VideoMAE encoder classes (checkpoint inspection, weight folding, the embed-only
+    model struct) constructed on CPU: device ops replaced by the torch backends of the orchestration tests."""
+    from mertools_b200 import _lib
+    from mertools_b200 import weights as Wt
+    from mertools_b200.extract import data2vec_vision as DV
+    from mertools_b200.extract import videomae as VM
+    from mertools_b200.extract import wavlm as WL
+    monkeypatch.setattr(_lib, "check", lambda rc: None)
+    monkeypatch.setattr(_lib, "round_tf32_", lambda t: t)
+    monkeypatch.setattr(_lib, "split_bf16", lambda t: t.clone())
+    monkeypatch.setattr(Wt, "_dev", lambda x, device: (torch.from_numpy(np.ascontiguousarray(x)) if isinstance(x, np.ndarray)
+                                                        else x).detach().to(dtype=torch.float32).contiguous())
+
+    def torch_ops(cls):
+        def make(device):
+            ops = cls()
+            ops.device = torch.device("cpu")
+            return ops
+        return make
+    monkeypatch.setattr(WL, "_cuda_ops", torch_ops(_TorchWavLmOps))
+    monkeypatch.setattr(VM, "_cuda_ops", torch_ops(_TorchVideoMaeOps))
+    w = WL.WavLmEncoder(S.hubert_state_dict(layers=4, wavlm=True, large=True))
+    assert (w.hidden, w.n_layers, w.net.stable, w.net.heads, w.front.model.stable_layer_norm) == (1024, 4, True, 16, 1)
+    d = DV.Data2VecVisionEncoder(S.data2vec_vision_state_dict(layers=2))
+    m = d.embed.model
+    assert (d.hidden, d.tokens, m.variant, m.kpad, m.patch, m.image, m.n_layers, bool(m.pre_ln_g)) == (768, 197, 2, 768, 16, 224, 0, False)
+    assert len(d.net.layers) == 2 and tuple(d.net.layers[0]["bias"].shape) == (12, 197, 197)
+    v = VM.VideoMaeExtractor(S.videomae_state_dict(layers=1))
+    assert (v.net.d, v.net.heads, len(v.net.layers)) == (768, 12, 1)
