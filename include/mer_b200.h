@@ -487,6 +487,10 @@ MER_API int mer_logmel(const float* wave, int batch, int n_samples, long long ld
 MER_API int mer_videomae_patchify(const uint8_t* frames_bgr, int n_clips, const float* mean, const float* std,
                                   float* out, void* stream);
 
+/* SwiGLU gate of HF Dinov2SwiGLUFFN (dinov2-giant, extract_vision_huggingface.py:135-145): in fp32 [rows, 2 * hidden]
+ * = weights_in(x); out [rows, hidden] = silu(in[:, :hidden]) * in[:, hidden:], TF32-rounded when round_tf32_out. */
+MER_API int mer_swiglu(const float* in, float* out, long long rows, int hidden, int round_tf32_out, void* stream);
+
 /* ---- Whisper branch of the audio extractor (extract_audio_huggingface.py:83-91): the two kernels the shared GEMM /
  * LayerNorm / attention entry points do not cover; the encoder / decoder are orchestrated from the host over those
  * (mertools_b200/extract/whisper.py). ---- */

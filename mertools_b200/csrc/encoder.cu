@@ -280,7 +280,8 @@ int mer_clip_vision_forward(const MerClipVisionModel* m, const uint8_t* frames_b
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MER_REQUIRE(m && frames_bgr && workspace && out_embeds && n_frames > 0, "mer_clip_vision_forward: bad operands");
   const int D = m->hidden;
-  MER_REQUIRE((D == 768 || D == 1024) && m->heads * 64 == D && m->ffn % 128 == 0 && m->proj_dim % 128 == 0 &&
+  MER_REQUIRE((D == 768 || D == 1024 || (D == 1536 && m->variant == MER_VISION_EMBED_ONLY)) && m->heads * 64 == D &&
+                  m->ffn % 128 == 0 && m->proj_dim % 128 == 0 &&
                   m->image % m->patch == 0 && m->kpad % 32 == 0 && m->kpad >= 3 * m->patch * m->patch,
               "mer_clip_vision_forward: unsupported dims (hidden %d, heads %d, ffn %d, proj %d, patch %d)", D,
               m->heads, m->ffn, m->proj_dim, m->patch);

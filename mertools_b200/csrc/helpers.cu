@@ -509,3 +509,35 @@ extern "C" int mer_videomae_patchify(const uint8_t* frames_bgr, int n_clips, con
   mer_count_launches(1);
   return 0;
 }
+
+// ---- SwiGLU gate of HF Dinov2SwiGLUFFN (dinov2-giant): out[r, j] = silu(in[r, j]) * in[r, H + j] for j < H,
+// in [rows, 2 H] = weights_in(x); 4 columns per thread, optionally TF32-rounded (operand of weights_out). ----
+namespace {
+__global__ void __launch_bounds__(256)
+swiglu_kernel(const float4* __restrict__ in, float4* __restrict__ out, long long total4, int h4, int round_out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total4) return;
+  const long long r = idx / h4;
+  const int j = (int)(idx % h4);
+  const float4 a = __ldg(in + r * 2 * h4 + j), b = __ldg(in + r * 2 * h4 + h4 + j);
+  float4 o;
+  o.x = a.x / (1.0f + expf(-a.x)) * b.x;
+  o.y = a.y / (1.0f + expf(-a.y)) * b.y;
+  o.z = a.z / (1.0f + expf(-a.z)) * b.z;
+  o.w = a.w / (1.0f + expf(-a.w)) * b.w;
+  if (round_out) o = make_float4(mer::round_tf32(o.x), mer::round_tf32(o.y), mer::round_tf32(o.z), mer::round_tf32(o.w));
+  out[idx] = o;
+}
+}  // namespace
+
+extern "C" int mer_swiglu(const float* in, float* out, long long rows, int hidden, int round_tf32_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MER_REQUIRE(in && out && in != out && rows > 0 && hidden > 0 && hidden % 4 == 0, "mer_swiglu: bad arguments");
+  const long long total4 = rows * (hidden / 4);
+  swiglu_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(in),
+                                                                      reinterpret_cast<float4*>(out), total4, hidden / 4,
+                                                                      round_tf32_out);
+  MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
+  return 0;
+}

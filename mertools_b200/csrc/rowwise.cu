@@ -139,8 +139,8 @@ int mer_layernorm_launch(const float* x, const float* gamma, const float* beta, 
   // not alias x: its rows are half as long.)
   MER_REQUIRE(!((flags & MER_LN_OUT_F16) && (const void*)y == (const void*)x),
               "mer_layernorm: an fp16 output cannot alias the input");
-  MER_REQUIRE(dim == 768 || dim == 512 || dim == 1024 || dim == 1280,
-              "mer_layernorm: dim %d not supported (512, 768, 1024, 1280)", dim);
+  MER_REQUIRE(dim == 768 || dim == 512 || dim == 1024 || dim == 1280 || dim == 1536,
+              "mer_layernorm: dim %d not supported (512, 768, 1024, 1280, 1536)", dim);
   if (rows <= 0) return 0;
   const int warps_per_block = 8;
   long long blocks = (rows + warps_per_block - 1) / warps_per_block;
@@ -156,6 +156,8 @@ int mer_layernorm_launch(const float* x, const float* gamma, const float* beta, 
     layernorm_kernel<8><<<(int)blocks, 256, 0, stream>>>(x, gamma, beta, y, y_split, acc, rows, eps, flags);
   else if (dim == 1280)  // whisper-large-v2
     layernorm_kernel<10><<<(int)blocks, 256, 0, stream>>>(x, gamma, beta, y, y_split, acc, rows, eps, flags);
+  else if (dim == 1536)  // dinov2-giant
+    layernorm_kernel<12><<<(int)blocks, 256, 0, stream>>>(x, gamma, beta, y, y_split, acc, rows, eps, flags);
   else
     layernorm_kernel<4><<<(int)blocks, 256, 0, stream>>>(x, gamma, beta, y, y_split, acc, rows, eps, flags);
   mer_prof_end(prof, stream);

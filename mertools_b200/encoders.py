@@ -266,14 +266,10 @@ class ClipVisionEncoder:
         return emb
 
 
-def dinov2_to_clip_layout(state_dict, image=224):
-    """HF ``Dinov2Model`` tensors re-expressed in the layout of the CLIP tower (what mer_clip_vision_forward walks), so
-    that DINOv2 needs no kernel of its own:  the position table is interpolated to the image grid (bicubic,
-    align_corners=False: Dinov2Embeddings.interpolate_pos_encoding of transformers 5.x), the patch-conv bias is folded
-    into the patch rows of the position table (both are added to every patch token), LayerScale is folded into the
-    branch's last linear layer (lambda * (W x + b) = (lambda W) x + lambda b).  Pure numpy / torch-CPU weight
-    preparation, checked on CPU against HF in tests/test_host_logic.py."""
-    sd = W._np(state_dict)
+def dinov2_embedding_rows(sd, image=224):
+    """(patch conv weight [D, 3, p, p], class token [D], position rows [1 + g*g, D]) of HF ``Dinov2Embeddings`` at an
+    ``image`` x ``image`` input: the position table interpolated to the g x g patch grid (bicubic, align_corners=False:
+    interpolate_pos_encoding of transformers 5.x) with the patch-conv bias folded into its patch rows."""
     pw = np.asarray(sd["embeddings.patch_embeddings.projection.weight"], np.float32)
     D, _, p, _ = pw.shape
     g = image // p
@@ -286,9 +282,20 @@ def dinov2_to_clip_layout(state_dict, image=224):
         pos = torch.cat([pos[:, :1], grid.permute(0, 2, 3, 1).reshape(1, g * g, D)], dim=1)
     pos = pos[0].numpy().copy()
     pos[1:] += np.asarray(sd["embeddings.patch_embeddings.projection.bias"], np.float32)
+    return pw, np.asarray(sd["embeddings.cls_token"], np.float32).reshape(D), pos
+
+
+def dinov2_to_clip_layout(state_dict, image=224):
+    """HF ``Dinov2Model`` tensors re-expressed in the layout of the CLIP tower (what mer_clip_vision_forward walks), so
+    that DINOv2 needs no kernel of its own:  the position table is interpolated to the image grid (bicubic,
+    align_corners=False: Dinov2Embeddings.interpolate_pos_encoding of transformers 5.x), the patch-conv bias is folded
+    into the patch rows of the position table (both are added to every patch token), LayerScale is folded into the
+    branch's last linear layer (lambda * (W x + b) = (lambda W) x + lambda b).  Pure numpy / torch-CPU weight
+    preparation, checked on CPU against HF in tests/test_host_logic.py."""
+    sd = W._np(state_dict)
+    pw, cls, pos = dinov2_embedding_rows(sd, image)
     v = "vision_model."
-    out = {v + "embeddings.patch_embedding.weight": pw,
-           v + "embeddings.class_embedding": np.asarray(sd["embeddings.cls_token"], np.float32).reshape(D),
+    out = {v + "embeddings.patch_embedding.weight": pw, v + "embeddings.class_embedding": cls,
            v + "embeddings.position_embedding.weight": pos}
     i = 0
     while f"encoder.layer.{i}.mlp.fc2.weight" in sd:

@@ -116,6 +116,10 @@ class VisualExtractor:
             from .data2vec_vision import Data2VecVisionEncoder
             self.enc = Data2VecVisionEncoder(state_dict, device=device)
             self.feature_dim = self.enc.hidden
+        elif "encoder.layer.0.mlp.weights_in.weight" in state_dict:  # Dinov2Model with the SwiGLU MLP (dinov2-giant)
+            from .dinov2_giant import Dinov2GiantEncoder
+            self.enc = Dinov2GiantEncoder(state_dict, device=device)
+            self.feature_dim = self.enc.hidden
         elif "encoder.layer.0.layer_scale1.lambda1" in state_dict:  # HF Dinov2Model (dinov2-large; :135-145)
             from ..encoders import Dinov2Encoder
             self.enc = Dinov2Encoder(state_dict, device=device)

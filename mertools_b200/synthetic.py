@@ -343,7 +343,7 @@ def whisper_state_dict(seed=13, enc_layers=6, dec_layers=6, vocab=64, cfg=WHISPE
     return g.sd
 
 
-def dinov2_state_dict(seed=17, layers=24, hidden=1024, ffn=4096, patch=14, n_pos_side=37):
+def dinov2_state_dict(seed=17, layers=24, hidden=1024, ffn=4096, patch=14, n_pos_side=37, swiglu=False):
     """Keys of ``transformers.Dinov2Model`` (dinov2-large shape: 24 layers, hidden 1024, 16 heads, patch 14, position
     table for 518 / 14 = 37 x 37 patches + the class token, LayerScale after the attention and MLP branches)."""
     g = _Gen(seed)
@@ -360,8 +360,13 @@ def dinov2_state_dict(seed=17, layers=24, hidden=1024, ffn=4096, patch=14, n_pos
         g.linear(p + "attention.output.dense", hidden, hidden, 0.02)
         g.sd[p + "layer_scale1.lambda1"] = (0.5 + 0.5 * g.rng.random(hidden)).astype(np.float32)
         g.ln(p + "norm2", hidden)
-        g.linear(p + "mlp.fc1", ffn, hidden, 0.02)
-        g.linear(p + "mlp.fc2", hidden, ffn, 0.02)
+        if swiglu:   # dinov2-giant: Dinov2SwiGLUFFN, hidden_features = (int(4 * hidden * 2 / 3) + 7) // 8 * 8
+            hf = (int(4 * hidden * 2 / 3) + 7) // 8 * 8
+            g.linear(p + "mlp.weights_in", 2 * hf, hidden, 0.02)
+            g.linear(p + "mlp.weights_out", hidden, hf, 0.02)
+        else:
+            g.linear(p + "mlp.fc1", ffn, hidden, 0.02)
+            g.linear(p + "mlp.fc2", hidden, ffn, 0.02)
         g.sd[p + "layer_scale2.lambda1"] = (0.5 + 0.5 * g.rng.random(hidden)).astype(np.float32)
     g.ln("layernorm", hidden)
     return g.sd

@@ -185,7 +185,7 @@ def dinov2_hidden_states(sd, pixel_values, heads=16, eps=1e-6, dtype=torch.float
     x = x + dinov2_position_embeddings(sd, gh, gw, dtype)
     hs = [x]
     i = 0
-    while f"encoder.layer.{i}.mlp.fc2.weight" in sd:
+    while f"encoder.layer.{i}.norm2.weight" in sd:
         p = f"encoder.layer.{i}."
         h = _ln(x, sd, p + "norm1", eps, dtype)
         q = _linear(h, sd, p + "attention.attention.query", dtype)
@@ -193,8 +193,13 @@ def dinov2_hidden_states(sd, pixel_values, heads=16, eps=1e-6, dtype=torch.float
         v = _linear(h, sd, p + "attention.attention.value", dtype)
         a = _linear(_mha(q, k, v, heads), sd, p + "attention.output.dense", dtype)
         x = x + a * _t(sd, p + "layer_scale1.lambda1", dtype)
-        h = F.gelu(_linear(_ln(x, sd, p + "norm2", eps, dtype), sd, p + "mlp.fc1", dtype))
-        x = x + _linear(h, sd, p + "mlp.fc2", dtype) * _t(sd, p + "layer_scale2.lambda1", dtype)
+        h = _ln(x, sd, p + "norm2", eps, dtype)
+        if p + "mlp.weights_in.weight" in sd:   # Dinov2SwiGLUFFN (dinov2-giant): silu(x1) * x2 of one fused projection
+            x1, x2 = _linear(h, sd, p + "mlp.weights_in", dtype).chunk(2, dim=-1)
+            h = _linear(F.silu(x1) * x2, sd, p + "mlp.weights_out", dtype)
+        else:
+            h = _linear(F.gelu(_linear(h, sd, p + "mlp.fc1", dtype)), sd, p + "mlp.fc2", dtype)
+        x = x + h * _t(sd, p + "layer_scale2.lambda1", dtype)
         hs.append(x)
         i += 1
     return tuple(hs)

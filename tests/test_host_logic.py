@@ -856,6 +856,10 @@ class _TorchWavLmOps(_TorchWhisperOps):
         ga, gb = torch.sigmoid(proj[..., 0]), torch.sigmoid(proj[..., 1])
         return ga * (gb * c - 1.0) + 2.0                                            # [tokens, heads]
 
+    def swiglu(self, x):
+        a, b = x.chunk(2, dim=-1)
+        return torch.nn.functional.silu(a) * b
+
     def biased_attention(self, qkv, bias, gate, B, T, heads):
         d = qkv.shape[1] // 3
         q, k, v = (qkv[:, i * d:(i + 1) * d].reshape(B, T, heads, 64).transpose(1, 2) for i in range(3))
@@ -931,6 +935,8 @@ def test_host_orchestrated_encoder_constructors_run_with_the_device_layer_stubbe
             ops.device = torch.device("cpu")
             return ops
         return make
+    from mertools_b200.extract import dinov2_giant as DG
+    monkeypatch.setattr(DG, "_cuda_ops", torch_ops(_TorchWavLmOps))
     monkeypatch.setattr(WL, "_cuda_ops", torch_ops(_TorchWavLmOps))
     monkeypatch.setattr(VM, "_cuda_ops", torch_ops(_TorchVideoMaeOps))
     w = WL.WavLmEncoder(S.hubert_state_dict(layers=4, wavlm=True, large=True))
@@ -939,5 +945,37 @@ def test_host_orchestrated_encoder_constructors_run_with_the_device_layer_stubbe
     m = d.embed.model
     assert (d.hidden, d.tokens, m.variant, m.kpad, m.patch, m.image, m.n_layers, bool(m.pre_ln_g)) == (768, 197, 2, 768, 16, 224, 0, False)
     assert len(d.net.layers) == 2 and tuple(d.net.layers[0]["bias"].shape) == (12, 197, 197)
+    gi = DG.Dinov2GiantEncoder(S.dinov2_state_dict(layers=1, hidden=1536, swiglu=True))
+    m = gi.embed.model
+    assert (gi.hidden, gi.tokens, gi.net.heads, m.variant, m.kpad, m.patch, m.heads) == (1536, 257, 24, 2, 608, 14, 24)
+    assert tuple(gi.net.layers[0]["w_in"].shape) == (8192, 1536) and tuple(gi.net.layers[0]["w_out"].shape) == (1536, 4096)
     v = VM.VideoMaeExtractor(S.videomae_state_dict(layers=1))
     assert (v.net.d, v.net.heads, len(v.net.layers)) == (768, 12, 1)
+
+
+def test_dinov2_swiglu_oracle_is_pinned_to_hf_and_the_orchestration_reproduces_it():
+    """dinov2-giant's graph (Dinov2Model with use_swiglu_ffn) at a small width: oracle vs HF; Dinov2SwigluNet (fused
+    q|k|v, folded LayerScale, silu(x1) * x2 of the fused input projection) over a torch backend vs HF."""
+    transformers = pytest.importorskip("transformers")
+    from mertools_b200.encoders import dinov2_embedding_rows
+    from mertools_b200.extract.dinov2_giant import Dinov2SwigluNet
+    sd = S.dinov2_state_dict(seed=21, layers=2, hidden=384, swiglu=True)
+    cfg = transformers.Dinov2Config(hidden_size=384, num_hidden_layers=2, num_attention_heads=6, image_size=518, patch_size=14,
+                                    use_swiglu_ffn=True)
+    model = transformers.Dinov2Model(cfg).eval()
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        ref = model(x, output_hidden_states=True).hidden_states
+    got = E.dinov2_hidden_states(sd, x, heads=6)
+    for a, b in zip(got, ref):
+        assert float((a - b).abs().max() / b.abs().max()) < 1e-5
+    # the embedding rows the device patch embedder is given reproduce hidden_states[0]
+    pw, cls, pos = dinov2_embedding_rows(sd, 224)
+    patches = torch.nn.functional.conv2d(x, torch.from_numpy(pw), None, stride=14).flatten(2).transpose(1, 2)
+    h0 = torch.cat([torch.from_numpy(cls + pos[0]).expand(2, 1, -1), patches + torch.from_numpy(pos[1:])], dim=1)
+    assert float((h0 - ref[0]).abs().max() / ref[0].abs().max()) < 1e-5
+    net = Dinov2SwigluNet(sd, _TorchWavLmOps())
+    assert (net.heads, len(net.layers)) == (6, 2)
+    out = net.last_hidden(h0.reshape(2 * 257, 384), 2, 257).reshape(2, 257, 384)
+    assert float((out - ref[-1]).abs().max() / ref[-1].abs().max()) < 1e-5

@@ -675,3 +675,19 @@ def test_data2vec_vision_extractor_vs_oracle(cuda):
         got = ext.extract_clips([frames], level)[0]
         ref = P.visual_clip_features(sd, frames, feature_level=level)
         assert got.shape == ref.shape and np.abs(got - ref).max() / np.abs(ref).max() < 1e-3
+
+
+def test_dinov2_giant_extractor_vs_oracle(cuda):
+    """dinov2-giant branch: embed-only patch embedding at 1536 columns + host-orchestrated SwiGLU layers."""
+    import numpy as np
+
+    from mertools_b200 import synthetic as S
+    from mertools_b200.extract.visual import VisualExtractor
+    from oracle import pipeline as P
+    sd = S.dinov2_state_dict(seed=21, layers=2, hidden=1536, swiglu=True)
+    frames = np.random.default_rng(3).integers(0, 256, (3, 120, 160, 3), dtype=np.uint8)
+    ext = VisualExtractor(sd, device=cuda)
+    assert ext.feature_dim == 1536
+    got = ext.extract_clips([frames], "FRAME", nframe=4)[0]
+    ref = P.dinov2_clip_features(sd, frames, "FRAME", heads=24, nframe=4)
+    assert got.shape == ref.shape and np.abs(got - ref).max() / np.abs(ref).max() < 1e-3
