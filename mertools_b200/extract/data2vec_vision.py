@@ -46,7 +46,11 @@ class BeitNet:
             p = f"encoder.layer.{i}."
             a = p + "attention.attention."
             l1, l2 = sd[p + "lambda_1"], sd[p + "lambda_2"]
-            table = sd[a + "relative_position_bias.relative_position_bias_table"]
+            # per-layer table (data2vec-vision, BEiT fine-tuned), else the encoder's shared one, else no bias
+            table = sd.get(a + "relative_position_bias.relative_position_bias_table",
+                           sd.get("encoder.relative_position_bias.relative_position_bias_table"))
+            if table is None:
+                table = np.zeros(((2 * window - 1) ** 2 + 3, self.heads), np.float32)
             assert table.shape == ((2 * window - 1) ** 2 + 3, self.heads), table.shape
             self.layers.append(dict(
                 ln1=(ops.tensor(sd[p + "layernorm_before.weight"]), ops.tensor(sd[p + "layernorm_before.bias"])),

@@ -27,7 +27,7 @@ def sinusoid_table(n_position, d):
 
 
 class VideoMaeNet:
-    """Backend-agnostic orchestration of VideoMAEModel (use_mean_pooling=True checkpoints: no final LayerNorm).
+    """Backend-agnostic orchestration of VideoMAEModel (final LayerNorm when the checkpoint has one).
     ``ops``: tensor, weight, patchify, layernorm, linear, self_attention."""
 
     def __init__(self, state_dict, ops, eps=1e-12):
@@ -40,6 +40,9 @@ class VideoMaeNet:
         self.patch_w, self.patch_b = ops.weight(w.reshape(d, -1)), ops.tensor(sd["embeddings.patch_embeddings.projection.bias"])
         self.pos = sinusoid_table(TOKENS, d)
         zeros = np.zeros(d, np.float32)
+        # self-supervised checkpoints (use_mean_pooling=False: videomae-base / -large) close with VideoMAEModel.layernorm
+        self.final_ln = ((ops.tensor(sd["layernorm.weight"]), ops.tensor(sd["layernorm.bias"]))
+                         if "layernorm.weight" in sd else None)
         self.layers = []
         i = 0
         while f"encoder.layer.{i}.output.dense.weight" in sd:
@@ -67,6 +70,8 @@ class VideoMaeNet:
             x = ops.linear(ctx, L["o_w"], L["o_b"], res=x)
             y = ops.layernorm(x, *L["ln2"], operand=True, eps=self.eps)
             x = ops.linear(ops.linear(y, L["w1"], L["b1"], gelu=True, operand=True), L["w2"], L["b2"], res=x)
+        if self.final_ln is not None:
+            x = ops.layernorm(x, *self.final_ln, operand=False, eps=self.eps)
         return x.reshape(B, TOKENS, self.d)
 
 

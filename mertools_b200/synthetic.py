@@ -396,7 +396,7 @@ def data2vec_vision_state_dict(seed=19, layers=12, hidden=768, ffn=3072, heads=1
     return g.sd
 
 
-def videomae_state_dict(seed=15, layers=12, hidden=768, ffn=3072):
+def videomae_state_dict(seed=15, layers=12, hidden=768, ffn=3072, final_norm=False):
     """Keys of ``transformers.VideoMAEModel`` (videomae-base shape): tubelet patch embedding Conv3d(3, 768, (2, 16, 16)),
     pre-LN layers whose attention carries separate ``q_bias`` / ``v_bias`` (no key bias); the position table is a fixed
     sinusoid, not a parameter."""
@@ -414,6 +414,8 @@ def videomae_state_dict(seed=15, layers=12, hidden=768, ffn=3072):
         g.ln(p + "layernorm_after", hidden)
         g.linear(p + "intermediate.dense", ffn, hidden, 0.02)
         g.linear(p + "output.dense", hidden, ffn, 0.02)
+    if final_norm:   # use_mean_pooling=False (self-supervised checkpoints): VideoMAEModel.layernorm closes the encoder
+        g.ln("layernorm", hidden)
     return g.sd
 
 

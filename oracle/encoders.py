@@ -147,7 +147,10 @@ def data2vec_vision_hidden_states(sd, pixel_values, heads=12, eps=1e-12, dtype=t
         q = _linear(y, sd, a + "query", dtype)
         k = F.linear(y, _t(sd, a + "key.weight", dtype))
         v = _linear(y, sd, a + "value", dtype)
-        bias = _t(sd, a + "relative_position_bias.relative_position_bias_table", dtype)[idx].permute(2, 0, 1)[None]
+        tname = a + "relative_position_bias.relative_position_bias_table"
+        if tname not in sd:   # use_shared_relative_position_bias, or none at all
+            tname = "encoder.relative_position_bias.relative_position_bias_table"
+        bias = _t(sd, tname, dtype)[idx].permute(2, 0, 1)[None] if tname in sd else None
         att = _linear(_mha(q, k, v, heads, bias), sd, p + "attention.output.dense", dtype)
         x = x + att * _t(sd, p + "lambda_1", dtype)
         h = F.gelu(_linear(_ln(x, sd, p + "layernorm_after", eps, dtype), sd, p + "intermediate.dense", dtype))
@@ -515,7 +518,9 @@ def videomae_last_hidden_state(sd, pixel_values, heads=12, eps=1e-12, dtype=torc
         h = F.gelu(_linear(_ln(x, sd, p + "layernorm_after", eps, dtype), sd, p + "intermediate.dense", dtype))
         x = x + _linear(h, sd, p + "output.dense", dtype)
         i += 1
-    return x
+    # use_mean_pooling=False checkpoints (the self-supervised videomae-base / -large the reference lists) end with
+    # VideoMAEModel.layernorm; the fine-tuned ones (use_mean_pooling=True) have no such parameter
+    return _ln(x, sd, "layernorm", eps, dtype) if "layernorm.weight" in sd else x
 
 
 def hubert_pos_conv_weight(sd, dtype=torch.float32):

@@ -732,13 +732,15 @@ def _videomae_frames(n=21, h=120, w=160, seed=31):
     return np.random.default_rng(seed).integers(0, 256, (n, h, w, 3), dtype=np.uint8)
 
 
-def test_videomae_oracle_is_pinned_to_the_hf_model_and_processor():
+@pytest.mark.parametrize("final_norm", [False, True])
+def test_videomae_oracle_is_pinned_to_the_hf_model_and_processor(final_norm):
     """extract_vision_huggingface.py:147-159 restated in oracle/: VideoMAEImageProcessor (shortest edge 224 bilinear,
     centre crop, rescale, normalise) and VideoMAEModel (use_mean_pooling=True: no final LayerNorm) on a synthetic
     checkpoint that strict-loads into the HF class."""
     transformers = pytest.importorskip("transformers")
-    sd = S.videomae_state_dict(seed=15, layers=2)
-    cfg = transformers.VideoMAEConfig(num_hidden_layers=2)
+    # final_norm: the self-supervised checkpoints (use_mean_pooling=False, what `videomae-base` is) end with a LayerNorm
+    sd = S.videomae_state_dict(seed=15, layers=2, final_norm=final_norm)
+    cfg = transformers.VideoMAEConfig(num_hidden_layers=2, use_mean_pooling=not final_norm)
     model = transformers.VideoMAEModel(cfg).eval()
     missing = model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
     assert not missing.unexpected_keys and all("position" in k for k in missing.missing_keys), missing
@@ -776,11 +778,12 @@ class _TorchVideoMaeOps(_TorchWhisperOps):
         return torch.nn.functional.layer_norm(x, (x.shape[-1],), g, b, eps)
 
 
-def test_videomae_orchestration_matches_the_oracle_with_a_cpu_backend():
+@pytest.mark.parametrize("final_norm", [False, True])
+def test_videomae_orchestration_matches_the_oracle_with_a_cpu_backend(final_norm):
     """mertools_b200.extract.videomae.VideoMaeNet (Conv3d weight flattened to the patch-gather K order, fused q|k|v with
     the zero key bias, fixed sinusoid positions, pre-LN layers, no final LayerNorm) run over a torch backend."""
     from mertools_b200.extract.videomae import VideoMaeNet, sinusoid_table
-    sd = S.videomae_state_dict(seed=16, layers=2)
+    sd = S.videomae_state_dict(seed=16, layers=2, final_norm=final_norm)
     np.testing.assert_allclose(sinusoid_table(1568, 768), E.videomae_sinusoid_table(1568, 768).numpy(), atol=1e-6)
     frames = _videomae_frames(n=16, h=224, w=224, seed=32)
     mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
@@ -913,6 +916,21 @@ def test_data2vec_vision_oracle_is_pinned_to_hf_and_the_orchestration_reproduces
     assert (net.heads, net.tokens, len(net.layers)) == (12, 197, 2)
     out = net.last_hidden(ref[0].reshape(2 * 197, 768), 2).reshape(2, 197, 768)
     assert float((out - ref[-1]).abs().max() / ref[-1].abs().max()) < 1e-5
+    # the other two configurations of the HF class: one table shared by all layers, and no relative bias at all
+    shared = {k: v for k, v in sd.items() if "relative_position_bias" not in k}
+    shared["encoder.relative_position_bias.relative_position_bias_table"] = \
+        sd["encoder.layer.0.attention.attention.relative_position_bias.relative_position_bias_table"]
+    plain = {k: v for k, v in shared.items() if "relative_position" not in k}
+    for d, kw in ((shared, dict(use_shared_relative_position_bias=True)), (plain, {})):
+        model = transformers.Data2VecVisionModel(transformers.Data2VecVisionConfig(num_hidden_layers=2, **kw),
+                                                 add_pooling_layer=False).eval()
+        model.load_state_dict({k: torch.from_numpy(v) for k, v in d.items()}, strict=True)
+        with torch.no_grad():
+            r = model(x[:1], output_hidden_states=True).hidden_states
+        o = E.data2vec_vision_hidden_states(d, x[:1])[-1]
+        assert float((o - r[-1]).abs().max() / r[-1].abs().max()) < 1e-5
+        o = BeitNet(d, _TorchWavLmOps()).last_hidden(r[0].reshape(197, 768), 1).reshape(1, 197, 768)
+        assert float((o - r[-1]).abs().max() / r[-1].abs().max()) < 1e-5
 
 
 def test_host_orchestrated_encoder_constructors_run_with_the_device_layer_stubbed(monkeypatch):

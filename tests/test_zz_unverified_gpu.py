@@ -599,7 +599,7 @@ def test_videomae_extractor_vs_oracle(cuda):
     TOL = 1e-3
     _rel = lambda a, b: float(np.abs(np.asarray(a, np.float64) - b).max() / np.abs(b).max())  # noqa: E731
     from mertools_b200.extract.videomae import VideoMaeExtractor
-    sd = S.videomae_state_dict(seed=15, layers=3)
+    sd = S.videomae_state_dict(seed=15, layers=3, final_norm=True)
     frames = np.random.default_rng(31).integers(0, 256, (21, 120, 160, 3), dtype=np.uint8)
     ext = VideoMaeExtractor(sd, device=cuda)
     pre = ext.preprocess(frames).cpu().numpy()
