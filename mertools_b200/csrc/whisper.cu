@@ -155,7 +155,7 @@ int mer_whisper_logmel(const float* waves, int batch, long long ld_wave, const f
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MER_REQUIRE(waves && mel_filters && out && scratch && batch > 0 && ld_wave >= WH_SAMPLES && ld_out >= WH_MELS,
               "mer_whisper_logmel: bad arguments (rows of 480000 samples, ld_out >= 80)");
-  MER_CUDA_CHECK(cudaMemsetAsync(scratch, 0x80, (size_t)batch * sizeof(int), stream));  // 0x80808080: below any image
+  MER_CUDA_CHECK(cudaMemsetAsync(scratch, 0x80, (size_t)batch * sizeof(int), stream));  // 0x80808080: below the image of every value here (log10 >= -10)
   whisper_logmel_kernel<<<dim3(WH_FRAMES, batch), 256, 0, stream>>>(waves, ld_wave, mel_filters, out, ld_out, scratch);
   MER_CUDA_CHECK(cudaGetLastError());
   const long long total = (long long)batch * WH_FRAMES * ld_out;
