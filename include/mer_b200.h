@@ -131,7 +131,7 @@ MER_API int mer_split_bf16(const float* in, void* out, long long rows, int K, vo
 enum { MER_LN_ROUND_TF32 = 1, MER_LN_ACC_INIT = 2, MER_LN_ACC_ADD = 4,
        MER_LN_OUT_F16 = 8, /* y is an fp16 array (the MER_GEMM_F16 operand) */
        MER_LN_GELU = 16    /* GELU(erf) after the affine (HubertLayerNormConvLayer) */ };
-/* y = LayerNorm(x) * gamma + beta over the last dim (512, 768, 1024 or 1280).  y (fp32, tf32-rounded when
+/* y = LayerNorm(x) * gamma + beta over the last dim (512, 768, 1024, 1280 or 1536).  y (fp32, tf32-rounded when
  * MER_LN_ROUND_TF32) and y_split (bf16 hi|lo rows, the BF16X3 GEMM operand) are both optional;
  * at least one must be given.  Optional side buffer acc
  * (same shape): acc = y (ACC_INIT) or acc += y (ACC_ADD) — the "sum of the last four hidden
