@@ -1,11 +1,15 @@
-"""Frame-level feature shaping of the reference's data path (feat_type = frm_align / frm_unalign), host side.
+"""Frame-level feature shaping for feat_type = frm_align / frm_unalign (host side, numpy).
 
-Mirrors MERBench/toolkit/utils/read_data.py:72-125 and the order in which Data_Feat applies them
-(toolkit/data/feat_data.py:33-44): pre-compress every clip by ``feat_scale`` (mean-pool groups of adjacent
-frames, zero-padded IN FRONT), optionally align audio / video to the text length, then pad every modality to
-its maximum length over the whole split -- again in front, because LSTMEncoder reads the final state.
-Pure numpy, same arithmetic and dtypes (float64 as soon as a zero block is concatenated), so the arrays are
-bit-identical to the reference's (tests/test_host_logic.py against tests/golden/frame_shaping_golden.npz).
+Contract (names and results) of MERBench/toolkit/utils/read_data.py:72-125 as Data_Feat applies it
+(toolkit/data/feat_data.py:33-44): every clip is first compressed by ``feat_scale``, then either averaged to one row
+('utt'), or -- optionally after audio / video are brought to the text length ('frm_align') -- padded to the longest
+clip of its modality over the whole split.  Padding always goes IN FRONT because LSTMEncoder reads the final state.
+
+Everything is one primitive, :func:`front_pool`: place the T rows at the END of a zeroed float64 buffer of
+``dst_len * ceil(T / dst_len)`` rows and average each run of ``ceil(T / dst_len)`` consecutive rows.  The three
+list-level rules only differ in how the target length of a clip is chosen, so they are instances of
+:func:`_retarget` with a length policy.  Results are bit-identical to the reference's arrays, dtype included
+(tests/test_host_logic.py against tests/golden/frame_shaping_golden.npz, generated from the unmodified module).
 """
 from __future__ import annotations
 
@@ -13,74 +17,65 @@ import math
 
 import numpy as np
 
+_FEAT_TYPES = ("utt", "frm_align", "frm_unalign")
 
-def func_mapping_feature(feature, dst_len):
-    """(seqlen, featdim) -> (dst_len, featdim): identity, zero pre-padding, or mean-pooling of
-    ceil(seqlen / dst_len) adjacent frames after zero pre-padding to a multiple (read_data.py:74-90)."""
-    featlen, featdim = feature.shape
-    if featlen == dst_len:
-        return feature
-    if featlen < dst_len:
-        pad_feature = np.zeros((dst_len - featlen, featdim))
-        return np.concatenate((pad_feature, feature), axis=0)
-    if featlen // dst_len == featlen / dst_len:
-        pad_len = 0
-        pool_size = featlen // dst_len
-    else:
-        pad_len = dst_len - featlen % dst_len
-        pool_size = featlen // dst_len + 1
-    pad_feature = np.zeros((pad_len, featdim))
-    feature = np.concatenate([pad_feature, feature]).reshape(dst_len, pool_size, featdim)
-    return np.mean(feature, axis=1)
+
+def front_pool(rows: np.ndarray, dst_len: int) -> np.ndarray:
+    """[T, D] -> [dst_len, D].  T == dst_len: the input itself (dtype kept); otherwise float64: zero rows in front,
+    then the mean over runs of ceil(T / dst_len) rows (run length 1 when T < dst_len, i.e. plain front padding)."""
+    n_rows, dim = rows.shape
+    if n_rows == dst_len:
+        return rows
+    run = max(1, -(-n_rows // dst_len))
+    buf = np.zeros((dst_len * run, dim))
+    buf[dst_len * run - n_rows:] = rows
+    return buf if run == 1 else buf.reshape(dst_len, run, dim).mean(axis=1)
+
+
+# the reference's name for the primitive (read_data.py:74)
+func_mapping_feature = front_pool
+
+
+def _retarget(modalities, target_len):
+    """Apply front_pool clip by clip, in place; ``target_len(m, i)`` = destination length of clip i of modality m."""
+    for m, clips in enumerate(modalities):
+        for i, clip in enumerate(clips):
+            clips[i] = front_pool(clip, target_len(m, i))
+    return modalities
 
 
 def align_to_utt(audios, texts, videos):
-    """read_data.py:93-98."""
-    for ii in range(len(audios)):
-        audios[ii] = np.mean(audios[ii], axis=0)
-        texts[ii] = np.mean(texts[ii], axis=0)
-        videos[ii] = np.mean(videos[ii], axis=0)
+    """One row per clip: the mean over its frames (read_data.py:93-98)."""
+    for clips in (audios, texts, videos):
+        clips[:] = [clip.mean(axis=0) for clip in clips]
     return audios, texts, videos
 
 
 def feature_scale_compress(audios, texts, videos, scale_factor=1):
-    """read_data.py:101-106."""
-    for ii in range(len(audios)):
-        audios[ii] = func_mapping_feature(audios[ii], math.ceil(len(audios[ii]) / scale_factor))
-        texts[ii] = func_mapping_feature(texts[ii], math.ceil(len(texts[ii]) / scale_factor))
-        videos[ii] = func_mapping_feature(videos[ii], math.ceil(len(videos[ii]) / scale_factor))
-    return audios, texts, videos
+    """Every clip to ceil(T / scale_factor) rows (read_data.py:101-106)."""
+    mods = (audios, texts, videos)
+    return _retarget(mods, lambda m, i: math.ceil(len(mods[m][i]) / scale_factor))
 
 
 def align_to_text(audios, texts, videos):
-    """read_data.py:109-115."""
-    for ii in range(len(audios)):
-        dst_len = len(texts[ii])
-        audios[ii] = func_mapping_feature(audios[ii], dst_len)
-        texts[ii] = func_mapping_feature(texts[ii], dst_len)
-        videos[ii] = func_mapping_feature(videos[ii], dst_len)
-    return audios, texts, videos
+    """Audio and video of clip i to the number of text rows of clip i (read_data.py:109-115)."""
+    text_len = [len(clip) for clip in texts]
+    return _retarget((audios, texts, videos), lambda m, i: text_len[i])
 
 
 def pad_to_maxlen_pre_modality(audios, texts, videos):
-    """read_data.py:118-126."""
-    audio_maxlen = max(len(feature) for feature in audios)
-    text_maxlen = max(len(feature) for feature in texts)
-    video_maxlen = max(len(feature) for feature in videos)
-    for ii in range(len(audios)):
-        audios[ii] = func_mapping_feature(audios[ii], audio_maxlen)
-        texts[ii] = func_mapping_feature(texts[ii], text_maxlen)
-        videos[ii] = func_mapping_feature(videos[ii], video_maxlen)
-    return audios, texts, videos
+    """Every clip to the longest clip of its own modality (read_data.py:118-126)."""
+    longest = [max(map(len, clips)) for clips in (audios, texts, videos)]
+    return _retarget((audios, texts, videos), lambda m, i: longest[m])
 
 
 def shape_split(audios, texts, videos, feat_type, feat_scale):
     """Data_Feat.__init__ (feat_data.py:33-44) for one split: lists of (T_i, D) arrays -> lists ready for
     ``np.array(...)`` in the collater ([D] rows for 'utt', equal-length [T, D] otherwise)."""
-    assert feat_scale >= 1 and feat_type in ("utt", "frm_align", "frm_unalign")
-    audios, texts, videos = feature_scale_compress(list(audios), list(texts), list(videos), feat_scale)
+    assert feat_scale >= 1 and feat_type in _FEAT_TYPES
+    mods = feature_scale_compress(list(audios), list(texts), list(videos), feat_scale)
     if feat_type == "utt":
-        return align_to_utt(audios, texts, videos)
+        return align_to_utt(*mods)
     if feat_type == "frm_align":
-        audios, texts, videos = align_to_text(audios, texts, videos)
-    return pad_to_maxlen_pre_modality(audios, texts, videos)
+        mods = align_to_text(*mods)
+    return pad_to_maxlen_pre_modality(*mods)
