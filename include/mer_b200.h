@@ -544,7 +544,7 @@ MER_API int mer_bert_forward(const MerBertModel* model, const int32_t* ids, cons
  * reference's state_dict order (audio_encoder.linear_1.weight, .bias, ... fc_out_2.bias). */
 typedef struct MerFusionDims {
   int audio_dim, text_dim, video_dim; /* 768 each for the base encoders */
-  int hidden;                         /* <= 256 */
+  int hidden;                         /* a multiple of 4, <= 256 */
   int out1;                           /* emotion classes (6) */
   int out2;                           /* valence outputs (1) */
 } MerFusionDims;
@@ -573,6 +573,41 @@ MER_API int mer_fusion_fwd_bwd(const MerFusionDims* dims, const float* params, f
                                const float* const* ext_masks, void* workspace, long long workspace_bytes,
                                float* loss_out, float* features, float* emos_out, float* vals_out,
                                void* stream);
+
+/* One whole optimisation step of main-release.py:31-66 (zero_grad, forward, CE + MSE, backward, optional
+ * clip_grad_value_, Adam.step) in two launches: a row-parallel cluster kernel (forward, losses, data gradients)
+ * and a parameter-parallel kernel in which every weight-gradient element is consumed by its Adam update
+ * (torch.optim.Adam(lr, betas, eps, weight_decay) with coupled L2; grad_clip <= 0: no clipping).  Operands as
+ * mer_fusion_fwd_bwd; grads still receives the gradient; *step_counter (device int) is read as t-1 and
+ * incremented by the kernel.  Data-parallel steps use mer_fusion_fwd_bwd + all-reduce + mer_fusion_adam instead. */
+typedef struct MerAdamHyper {
+  float lr, beta1, beta2, eps, weight_decay, grad_clip;
+} MerAdamHyper;
+MER_API int mer_fusion_step(const MerFusionDims* dims, float* params, float* grads, float* exp_avg,
+                            float* exp_avg_sq, const float* audios, const float* texts, const float* videos,
+                            const int64_t* emos, const float* vals, int batch, float loss_inv_batch,
+                            float dropout_p, unsigned long long seed, int* step_counter,
+                            const float* const* ext_masks, const MerAdamHyper* adam, void* workspace,
+                            long long workspace_bytes, float* loss_out, float* features, float* emos_out,
+                            float* vals_out, void* stream);
+
+/* The two halves behind an autograd node (the reference loop calls model(batch), builds the loss itself, then
+ * loss.backward(), main-release.py:44-63): train-mode forward (dropout on, masks from (seed, *step_counter) or
+ * ext_masks), and the backward pass from the upstream gradients d_features [B,hidden], d_emos [B,out1],
+ * d_vals [B,out2] (each may be NULL = zero).  The backward recomputes the forward from the same inputs, seed and
+ * step counter (cheaper than keeping activations: 0.48 MMAC per row) and writes d(loss)/d(params) to grads;
+ * features / emos_out / vals_out are rewritten as scratch. */
+MER_API int mer_fusion_forward_train(const MerFusionDims* dims, const float* params, const float* audios,
+                                     const float* texts, const float* videos, int batch, float dropout_p,
+                                     unsigned long long seed, const int* step_counter,
+                                     const float* const* ext_masks, void* workspace, long long workspace_bytes,
+                                     float* features, float* emos_out, float* vals_out, void* stream);
+MER_API int mer_fusion_backward(const MerFusionDims* dims, const float* params, float* grads,
+                                const float* audios, const float* texts, const float* videos, int batch,
+                                const float* d_features, const float* d_emos, const float* d_vals,
+                                float dropout_p, unsigned long long seed, const int* step_counter,
+                                const float* const* ext_masks, void* workspace, long long workspace_bytes,
+                                float* features, float* emos_out, float* vals_out, void* stream);
 
 /* ---- frame-level variant: feat_type = frm_align / frm_unalign (main-release.py:131-142) ----------------
  * Attention with LSTMEncoder per modality (toolkit/models/modules/encoder.py:45-72: nn.LSTM(in, hidden, one

@@ -441,7 +441,7 @@ int mer_attention_f16_launch(const void* qkv16, const void* vt16, long long vt_l
   // MER_ATT_F16_VER=2 selects the granule softmax (see the kernel's header comment); read at every launch so that
   // a test can run both versions in one process.
   const char* ver_env = getenv("MER_ATT_F16_VER");
-  const int ver = ver_env ? atoi(ver_env) : 1;
+  const int ver = ver_env ? atoi(ver_env) : 3;  // round-2 A/B on B200 (gpurun_out -> profiles/r2_ab_switches.json): 3 > 2 > 1
   auto kern = ver == 3 ? attention_f16_kernel<3> : (ver == 2 ? attention_f16_kernel<2> : attention_f16_kernel<1>);
   static MerPerDevice attr_set;
   if (attr_set.needs_setup()) {

@@ -463,7 +463,7 @@ int mer_attention_tc_launch(const float* qkv, const float* vt, long long vt_ld, 
   // MER_ATT_TC_VER=2 selects the granule softmax (see the kernel's header comment); read at every launch so that
   // a test can run both versions in one process.
   const char* ver_env = getenv("MER_ATT_TC_VER");
-  const bool ver2 = ver_env && atoi(ver_env) == 2;
+  const bool ver2 = !(ver_env && atoi(ver_env) == 1);  // granule softmax is the default since round 2 (measured)
   auto kern = ver2 ? attention_tc_kernel<2> : attention_tc_kernel<1>;
   static MerPerDevice attr_set;
   if (attr_set.needs_setup()) {

@@ -271,73 +271,6 @@ fus_dropout_mask_kernel(float* mask, long long n, float p, unsigned long long se
   mask[i] = u >= p ? 1.f : 0.f;
 }
 
-struct Layout {  // offsets (floats) into the flat parameter buffer, reference state_dict order
-  long long enc_w1[3], enc_b1[3], enc_w2[3], enc_b2[3], enc_w3[3], enc_b3[3];
-  long long att_w1, att_b1, att_w2, att_b2, att_w3, att_b3;
-  long long fa_w, fa_b, o1_w, o1_b, o2_w, o2_b, total;
-};
-
-Layout make_layout(const MerFusionDims& d) {
-  Layout L;
-  long long o = 0;
-  const int in[3] = {d.audio_dim, d.text_dim, d.video_dim};
-  const int H = d.hidden;
-  for (int m = 0; m < 3; ++m) {
-    L.enc_w1[m] = o; o += (long long)H * in[m];
-    L.enc_b1[m] = o; o += H;
-    L.enc_w2[m] = o; o += (long long)H * H;
-    L.enc_b2[m] = o; o += H;
-    L.enc_w3[m] = o; o += (long long)H * H;
-    L.enc_b3[m] = o; o += H;
-  }
-  L.att_w1 = o; o += (long long)H * 3 * H;
-  L.att_b1 = o; o += H;
-  L.att_w2 = o; o += (long long)H * H;
-  L.att_b2 = o; o += H;
-  L.att_w3 = o; o += (long long)H * H;
-  L.att_b3 = o; o += H;
-  L.fa_w = o; o += 3ll * H;
-  L.fa_b = o; o += 3;
-  L.o1_w = o; o += (long long)d.out1 * H;
-  L.o1_b = o; o += d.out1;
-  L.o2_w = o; o += (long long)d.out2 * H;
-  L.o2_b = o; o += d.out2;
-  L.total = o;
-  return L;
-}
-
-struct Scratch {  // activations + activation grads, floats
-  float *h1, *h2, *h3cat, *a1, *a2, *a3, *features_unused;
-  float *d_h1, *d_h2, *d_cat, *d_a1, *d_a2, *d_a3, *d_emos, *d_vals, *d_att, *loss_terms;
-  float *mask_in[3], *mask_cat;
-};
-
-long long scratch_floats(const MerFusionDims& d, int B) {
-  const long long H = d.hidden;
-  const long long in_sum = (long long)d.audio_dim + d.text_dim + d.video_dim;
-  return (long long)B * (3 * H * 2 /*h1,h2*/ + 3 * H /*h3cat*/ + 3 * H /*a1..a3*/ +
-                         3 * H * 2 /*d_h1,d_h2*/ + 3 * H /*d_cat*/ + 3 * H /*d_a*/ + d.out1 + d.out2 +
-                         3 + 2 + in_sum + 3 * H) + 64;
-}
-
-Scratch carve(const MerFusionDims& d, int B, float* base) {
-  Scratch s;
-  const long long H = d.hidden;
-  float* p = base;
-  auto take = [&](long long n) { float* r = p; p += n; return r; };
-  s.h1 = take(3 * B * H); s.h2 = take(3 * B * H); s.h3cat = take(3 * B * H);
-  s.a1 = take(B * H); s.a2 = take(B * H); s.a3 = take(B * H);
-  s.d_h1 = take(3 * B * H); s.d_h2 = take(3 * B * H); s.d_cat = take(3 * B * H);
-  s.d_a1 = take(B * H); s.d_a2 = take(B * H); s.d_a3 = take(B * H);
-  s.d_emos = take((long long)B * d.out1); s.d_vals = take((long long)B * d.out2);
-  s.d_att = take(3ll * B); s.loss_terms = take(2ll * B);
-  s.mask_in[0] = take((long long)B * d.audio_dim);
-  s.mask_in[1] = take((long long)B * d.text_dim);
-  s.mask_in[2] = take((long long)B * d.video_dim);
-  s.mask_cat = take(3 * B * H);
-  return s;
-}
-
 int check_dims(const MerFusionDims* d, int B) {
   MER_REQUIRE(d && d->hidden > 0 && d->hidden <= 256 && d->out1 > 0 && d->out1 <= 16 &&
                   d->out2 > 0 && d->out2 <= 4 && d->audio_dim > 0 && d->text_dim > 0 &&
@@ -346,43 +279,6 @@ int check_dims(const MerFusionDims* d, int B) {
   MER_REQUIRE(B > 0 && B <= 65535, "mer_fusion: batch %d out of range", B);
   return 0;
 }
-
-// forward through the head; train != 0 also generates/uses dropout masks
-int run_forward(const MerFusionDims& d, const Layout& L, const float* P, const Scratch& s,
-                const float* const x[3], int B, float p_drop, const float* const ext_masks[4],
-                bool use_dropout, cudaStream_t st) {
-  const int H = d.hidden;
-  const int in[3] = {d.audio_dim, d.text_dim, d.video_dim};
-  const float mscale = use_dropout ? 1.f / (1.f - p_drop) : 1.f;
-  LinBatch lb;
-  for (int m = 0; m < 3; ++m) {
-    const float* mk = use_dropout ? (ext_masks && ext_masks[m] ? ext_masks[m] : s.mask_in[m]) : nullptr;
-    lb.p[m] = LinP{x[m], in[m], mk, mscale, P + L.enc_w1[m], P + L.enc_b1[m],
-                   s.h1 + (long long)m * B * H, H, in[m], H, 1};
-  }
-  dim3 g1((H + 7) / 8, (B + 31) / 32, 3);
-  fus_linear_fwd_kernel<<<g1, 256, 0, st>>>(lb, B);
-  for (int m = 0; m < 3; ++m)
-    lb.p[m] = LinP{s.h1 + (long long)m * B * H, H, nullptr, 1.f, P + L.enc_w2[m], P + L.enc_b2[m],
-                   s.h2 + (long long)m * B * H, H, H, H, 1};
-  fus_linear_fwd_kernel<<<g1, 256, 0, st>>>(lb, B);
-  for (int m = 0; m < 3; ++m)  // h3 written straight into the concatenated [B,3H] layout
-    lb.p[m] = LinP{s.h2 + (long long)m * B * H, H, nullptr, 1.f, P + L.enc_w3[m], P + L.enc_b3[m],
-                   s.h3cat + m * H, 3 * H, H, H, 1};
-  fus_linear_fwd_kernel<<<g1, 256, 0, st>>>(lb, B);
-  dim3 g2((H + 7) / 8, (B + 31) / 32, 1);
-  const float* mkc = use_dropout ? (ext_masks && ext_masks[3] ? ext_masks[3] : s.mask_cat) : nullptr;
-  lb.p[0] = LinP{s.h3cat, 3 * H, mkc, mscale, P + L.att_w1, P + L.att_b1, s.a1, H, 3 * H, H, 1};
-  fus_linear_fwd_kernel<<<g2, 256, 0, st>>>(lb, B);
-  lb.p[0] = LinP{s.a1, H, nullptr, 1.f, P + L.att_w2, P + L.att_b2, s.a2, H, H, H, 1};
-  fus_linear_fwd_kernel<<<g2, 256, 0, st>>>(lb, B);
-  lb.p[0] = LinP{s.a2, H, nullptr, 1.f, P + L.att_w3, P + L.att_b3, s.a3, H, H, H, 1};
-  fus_linear_fwd_kernel<<<g2, 256, 0, st>>>(lb, B);
-  MER_CUDA_CHECK(cudaGetLastError());
-  mer_count_launches(6);
-  return 0;
-}
-
 
 // ================================================================================================
 // Frame-level fusion (feat_type = frm_align / frm_unalign): LSTMEncoder (modules/encoder.py:45-72) per
@@ -811,144 +707,6 @@ int topn_forward(const MerFusionTopnDims& d, const TopnLayout& L, const float* P
 }  // namespace
 
 extern "C" {
-
-long long mer_fusion_param_count(const MerFusionDims* d) {
-  if (!d) return -1;
-  return make_layout(*d).total;
-}
-
-long long mer_fusion_workspace_bytes(const MerFusionDims* d, int max_batch) {
-  if (!d) return -1;
-  return scratch_floats(*d, max_batch) * 4;
-}
-
-int mer_fusion_forward(const MerFusionDims* d, const float* params, const float* audios,
-                       const float* texts, const float* videos, int B, void* workspace,
-                       long long workspace_bytes, float* features, float* emos_out, float* vals_out,
-                       void* stream_) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  if (int rc = check_dims(d, B)) return rc;
-  MER_REQUIRE(params && audios && texts && videos && workspace && features && emos_out && vals_out,
-              "mer_fusion_forward: null operand");
-  MER_REQUIRE(workspace_bytes >= mer_fusion_workspace_bytes(d, B), "mer_fusion_forward: workspace too small");
-  const Layout L = make_layout(*d);
-  const Scratch s = carve(*d, B, static_cast<float*>(workspace));
-  const float* x[3] = {audios, texts, videos};
-  if (int rc = run_forward(*d, L, params, s, x, B, 0.f, nullptr, false, st)) return rc;
-  HeadArgs h;
-  memset(&h, 0, sizeof(h));
-  h.h3cat = s.h3cat; h.a3 = s.a3;
-  h.w_att = params + L.fa_w; h.b_att = params + L.fa_b;
-  h.w_o1 = params + L.o1_w; h.b_o1 = params + L.o1_b;
-  h.w_o2 = params + L.o2_w; h.b_o2 = params + L.o2_b;
-  h.features = features; h.emos_out = emos_out; h.vals_out = vals_out;
-  h.H = d->hidden; h.O1 = d->out1; h.O2 = d->out2;
-  fus_head_kernel<<<B, 128, 0, st>>>(h);
-  MER_CUDA_CHECK(cudaGetLastError());
-  mer_count_launches(1);
-  return 0;
-}
-
-int mer_fusion_fwd_bwd(const MerFusionDims* d, const float* params, float* grads, const float* audios,
-                       const float* texts, const float* videos, const int64_t* emos, const float* vals,
-                       int B, float loss_inv_batch, float dropout_p, unsigned long long seed,
-                       const int* step_counter, const float* const* ext_masks, void* workspace,
-                       long long workspace_bytes, float* loss_out, float* features, float* emos_out,
-                       float* vals_out, void* stream_) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  if (int rc = check_dims(d, B)) return rc;
-  MER_REQUIRE(params && grads && audios && texts && videos && emos && vals && workspace && loss_out &&
-                  features && emos_out && vals_out && step_counter,
-              "mer_fusion_fwd_bwd: null operand");
-  MER_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "mer_fusion_fwd_bwd: dropout %f", dropout_p);
-  MER_REQUIRE(workspace_bytes >= mer_fusion_workspace_bytes(d, B), "mer_fusion_fwd_bwd: workspace too small");
-  const Layout L = make_layout(*d);
-  const Scratch s = carve(*d, B, static_cast<float*>(workspace));
-  const int H = d->hidden;
-  const int in[3] = {d->audio_dim, d->text_dim, d->video_dim};
-  const float* x[3] = {audios, texts, videos};
-  const bool drop = dropout_p > 0.f;
-  const float mscale = drop ? 1.f / (1.f - dropout_p) : 1.f;
-  const float* masks[4] = {nullptr, nullptr, nullptr, nullptr};
-  if (drop) {
-    for (int m = 0; m < 4; ++m) {
-      if (ext_masks && ext_masks[m]) { masks[m] = ext_masks[m]; continue; }
-      float* dst = m < 3 ? s.mask_in[m] : s.mask_cat;
-      const long long n = (long long)B * (m < 3 ? in[m] : 3 * H);
-      fus_dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-          dst, n, dropout_p, seed + 0x1000ull * (m + 1), step_counter);
-      mer_count_launches(1);
-      masks[m] = dst;
-    }
-  }
-  if (int rc = run_forward(*d, L, params, s, x, B, dropout_p, masks, drop, st)) return rc;
-  HeadArgs h;
-  memset(&h, 0, sizeof(h));
-  h.h3cat = s.h3cat; h.a3 = s.a3;
-  h.w_att = params + L.fa_w; h.b_att = params + L.fa_b;
-  h.w_o1 = params + L.o1_w; h.b_o1 = params + L.o1_b;
-  h.w_o2 = params + L.o2_w; h.b_o2 = params + L.o2_b;
-  h.emo = reinterpret_cast<const long long*>(emos); h.val = vals;
-  h.features = features; h.emos_out = emos_out; h.vals_out = vals_out;
-  h.loss_terms = s.loss_terms; h.d_emos = s.d_emos; h.d_vals = s.d_vals; h.d_att = s.d_att;
-  h.d_cat = s.d_cat; h.d_a3 = s.d_a3;
-  h.H = H; h.O1 = d->out1; h.O2 = d->out2; h.inv_batch = loss_inv_batch;
-  fus_head_kernel<<<B, 128, 0, st>>>(h);
-  fus_loss_reduce_kernel<<<1, 32, 0, st>>>(s.loss_terms, B, loss_inv_batch, loss_out);
-  mer_count_launches(2);
-
-  float* G = grads;
-  BwdBatch bb;
-  auto launch_w = [&](int nprob, int K, int N) {
-    dim3 g((K + 255) / 256, N, nprob);
-    fus_linear_bwd_w_kernel<<<g, 256, 0, st>>>(bb, B);
-    mer_count_launches(1);
-  };
-  auto launch_x = [&](int nprob, int K) {
-    dim3 g((K + 255) / 256, B, nprob);
-    fus_linear_bwd_x_kernel<<<g, 256, 0, st>>>(bb, B);
-    mer_count_launches(1);
-  };
-  // heads: fc_out_1, fc_out_2 (x = fused features), fc_att (x = a3); no relu, no dx needed here
-  bb.p[0] = BwdP{s.d_emos, d->out1, nullptr, 0, features, H, nullptr, 1.f, params + L.o1_w,
-                 G + L.o1_w, G + L.o1_b, nullptr, 0, 0, H, d->out1};
-  bb.p[1] = BwdP{s.d_vals, d->out2, nullptr, 0, features, H, nullptr, 1.f, params + L.o2_w,
-                 G + L.o2_w, G + L.o2_b, nullptr, 0, 0, H, d->out2};
-  bb.p[2] = BwdP{s.d_att, 3, nullptr, 0, s.a3, H, nullptr, 1.f, params + L.fa_w, G + L.fa_w,
-                 G + L.fa_b, nullptr, 0, 0, H, 3};
-  launch_w(3, H, 16);
-  // attention_mlp: linear_3, linear_2, linear_1 (its dx is accumulated into d_cat through the mask)
-  bb.p[0] = BwdP{s.d_a3, H, s.a3, H, s.a2, H, nullptr, 1.f, params + L.att_w3, G + L.att_w3,
-                 G + L.att_b3, s.d_a2, H, 0, H, H};
-  launch_w(1, H, H); launch_x(1, H);
-  bb.p[0] = BwdP{s.d_a2, H, s.a2, H, s.a1, H, nullptr, 1.f, params + L.att_w2, G + L.att_w2,
-                 G + L.att_b2, s.d_a1, H, 0, H, H};
-  launch_w(1, H, H); launch_x(1, H);
-  bb.p[0] = BwdP{s.d_a1, H, s.a1, H, s.h3cat, 3 * H, masks[3], mscale, params + L.att_w1,
-                 G + L.att_w1, G + L.att_b1, s.d_cat, 3 * H, 1, 3 * H, H};
-  launch_w(1, 3 * H, H); launch_x(1, 3 * H);
-  // modality encoders, three at a time
-  for (int m = 0; m < 3; ++m)
-    bb.p[m] = BwdP{s.d_cat + m * H, 3 * H, s.h3cat + m * H, 3 * H, s.h2 + (long long)m * B * H, H,
-                   nullptr, 1.f, params + L.enc_w3[m], G + L.enc_w3[m], G + L.enc_b3[m],
-                   s.d_h2 + (long long)m * B * H, H, 0, H, H};
-  launch_w(3, H, H); launch_x(3, H);
-  for (int m = 0; m < 3; ++m)
-    bb.p[m] = BwdP{s.d_h2 + (long long)m * B * H, H, s.h2 + (long long)m * B * H, H,
-                   s.h1 + (long long)m * B * H, H, nullptr, 1.f, params + L.enc_w2[m],
-                   G + L.enc_w2[m], G + L.enc_b2[m], s.d_h1 + (long long)m * B * H, H, 0, H, H};
-  launch_w(3, H, H); launch_x(3, H);
-  int kmax = 0;
-  for (int m = 0; m < 3; ++m) {
-    bb.p[m] = BwdP{s.d_h1 + (long long)m * B * H, H, s.h1 + (long long)m * B * H, H, x[m], in[m],
-                   masks[m], mscale, params + L.enc_w1[m], G + L.enc_w1[m], G + L.enc_b1[m],
-                   nullptr, 0, 0, in[m], H};
-    kmax = in[m] > kmax ? in[m] : kmax;
-  }
-  launch_w(3, kmax, H);
-  MER_CUDA_CHECK(cudaGetLastError());
-  return 0;
-}
 
 int mer_fusion_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
                     float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,

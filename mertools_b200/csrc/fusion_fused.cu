@@ -1,0 +1,852 @@
+// fusion_fused.cu — the utterance-level Attention-fusion step (MERBench/toolkit/models/attention.py:8-57 with
+// MLPEncoder, modules/encoder.py:9-41; CELoss / MSELoss, toolkit/utils/loss.py:5-28; the optimiser step of
+// main-release.py:50-66,205) as TWO kernels instead of one launch per layer:
+//
+//   fus_rows_kernel   row-parallel: a cluster of 8 CTAs owns RB batch rows and walks them through the whole
+//                     network -- six dense layers forward, the attention head, both losses, and the data-gradient
+//                     chain backward.  Activations of the RB rows live in shared memory, replicated in all 8
+//                     CTAs; each CTA computes 1/8 of every layer's output columns (forward) or input columns
+//                     (backward) and broadcasts its slice into its peers' shared memory (DSMEM), so a layer
+//                     boundary costs one hardware cluster barrier, not a kernel launch or a trip through L2.
+//                     Weights stream from L2 (1.9 MB at hidden 128), 1/8 of them per CTA.
+//   fus_wgrad_kernel  parameter-parallel: dW[n,k] = sum_b g[b,n] x[b,k] over the whole batch for all 28 tensors in
+//                     one grid, each gradient element consumed on the spot by Adam (torch.optim.Adam, coupled L2)
+//                     when the step is not data-parallel; block 0 folds the per-row loss terms, the last block to
+//                     finish advances the device-side step counter.
+//
+// fp32 SIMT throughout with a fixed summation order (no atomics on data): results are bit-reproducible, eager ==
+// CUDA-graph replay.  2.86 MFLOP per clip: this is the latency regime, so the design removes launches and L2 round
+// trips rather than chasing tensor cores.
+#include <cooperative_groups.h>
+
+#include "mer_common.cuh"
+#include "mer_kernels.h"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+using namespace mer;
+
+constexpr int CL = 8;      // CTAs per cluster (portable maximum)
+constexpr int NT = 256;    // threads per CTA
+constexpr int NW = NT / 32;
+constexpr int XCH = 1024;  // staging chunk of an input row (floats)
+constexpr int MAXC = 4;    // output columns per warp and layer: ceil(ceil(256 / CL) / NW)
+
+struct ULayout {  // offsets (floats) into the flat parameter buffer, reference state_dict order
+  long long enc_w1[3], enc_b1[3], enc_w2[3], enc_b2[3], enc_w3[3], enc_b3[3];
+  long long att_w1, att_b1, att_w2, att_b2, att_w3, att_b3;
+  long long fa_w, fa_b, o1_w, o1_b, o2_w, o2_b, total;
+};
+
+ULayout make_layout(const MerFusionDims& d) {
+  ULayout L;
+  long long o = 0;
+  const int in[3] = {d.audio_dim, d.text_dim, d.video_dim};
+  const long long H = d.hidden;
+  for (int m = 0; m < 3; ++m) {
+    L.enc_w1[m] = o; o += H * in[m];
+    L.enc_b1[m] = o; o += H;
+    L.enc_w2[m] = o; o += H * H;
+    L.enc_b2[m] = o; o += H;
+    L.enc_w3[m] = o; o += H * H;
+    L.enc_b3[m] = o; o += H;
+  }
+  L.att_w1 = o; o += H * 3 * H;
+  L.att_b1 = o; o += H;
+  L.att_w2 = o; o += H * H;
+  L.att_b2 = o; o += H;
+  L.att_w3 = o; o += H * H;
+  L.att_b3 = o; o += H;
+  L.fa_w = o; o += 3 * H;
+  L.fa_b = o; o += 3;
+  L.o1_w = o; o += (long long)d.out1 * H;
+  L.o1_b = o; o += d.out1;
+  L.o2_w = o; o += (long long)d.out2 * H;
+  L.o2_b = o; o += d.out2;
+  L.total = o;
+  return L;
+}
+
+// global workspace: what the row kernel hands to the weight-gradient kernel ([B, .] row-major)
+struct GWs {
+  float* xd[3];               // inputs after dropout (only written / read when dropout is on)
+  float *h1, *h2;             // [3][B][H] encoder activations
+  float* hcd;                 // [B][3H]  concatenated encoder outputs after dropout = attention_mlp input
+  float *a1, *a2, *a3;        // [B][H]
+  float *g1, *g2;             // [3][B][H] gradients w.r.t. the PRE-activations of encoder layers 1, 2
+  float* g3;                  // [B][3H]   same for layer 3 (concatenated layout)
+  float *ga1, *ga2, *ga3;     // [B][H]    attention_mlp layers
+  float *d_att, *d_emos, *d_vals, *loss_terms;  // [B][3], [B][O1], [B][O2], [B][2]
+  int* done;                  // block-completion ticket of fus_wgrad_kernel
+};
+
+long long ws_floats(const MerFusionDims& d, int B) {
+  const long long H = d.hidden, in_sum = (long long)d.audio_dim + d.text_dim + d.video_dim;
+  return (long long)B * (in_sum + 6 * H + 3 * H + 3 * H + 6 * H + 3 * H + 3 * H + 3 + d.out1 + d.out2 + 2) + 64;
+}
+
+GWs carve(const MerFusionDims& d, int B, float* base) {
+  GWs s;
+  const long long H = d.hidden;
+  float* p = base;
+  auto take = [&](long long n) { float* r = p; p += (n + 3) / 4 * 4; return r; };  // keep 16-byte alignment
+  s.done = reinterpret_cast<int*>(take(4));
+  s.xd[0] = take((long long)B * d.audio_dim);
+  s.xd[1] = take((long long)B * d.text_dim);
+  s.xd[2] = take((long long)B * d.video_dim);
+  s.h1 = take(3 * B * H); s.h2 = take(3 * B * H); s.hcd = take(3 * B * H);
+  s.a1 = take(B * H); s.a2 = take(B * H); s.a3 = take(B * H);
+  s.g1 = take(3 * B * H); s.g2 = take(3 * B * H); s.g3 = take(3 * B * H);
+  s.ga1 = take(B * H); s.ga2 = take(B * H); s.ga3 = take(B * H);
+  s.d_att = take(3ll * B); s.d_emos = take((long long)B * d.out1); s.d_vals = take((long long)B * d.out2);
+  s.loss_terms = take(2ll * B);
+  return s;
+}
+
+enum { MODE_FWD = 0, MODE_LOSS = 1, MODE_UPSTREAM = 2, MODE_FWD_TRAIN = 3 };  // eval forward | fused loss step | backward from upstream gradients | train-mode forward only
+
+struct RowArgs {
+  MerFusionDims d;
+  ULayout L;
+  const float* P;
+  const float* x[3];
+  const float* ext_mask[4];            // device keep-masks (0/1) or null -> counter hash
+  const long long* emo; const float* val;                     // MODE_LOSS
+  const float *up_feat, *up_emos, *up_vals;                   // MODE_UPSTREAM (each may be null)
+  int B, mode;
+  float inv_batch, p_drop, mscale;
+  unsigned long long seed;
+  const int* step;
+  float *features, *emos_out, *vals_out;
+  GWs ws;
+};
+
+// the keep-mask of fusion.cu:fus_dropout_mask_kernel, element i of mask tensor m
+__device__ __forceinline__ float keep_hash(unsigned long long seed, int m, int step, long long i, float p) {
+  unsigned long long z = seed + 0x1000ull * (unsigned long long)(m + 1) +
+                         0x9E3779B97F4A7C15ull * (unsigned long long)(step + 1) +
+                         0xD1B54A32D192ED03ull * (unsigned long long)(i + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const float u = (float)(z >> 40) * (1.0f / 16777216.0f);
+  return u >= p ? 1.f : 0.f;
+}
+
+__device__ __forceinline__ float warp_allsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
+  acc = fmaf(a.x, b.x, acc);
+  acc = fmaf(a.y, b.y, acc);
+  acc = fmaf(a.z, b.z, acc);
+  return fmaf(a.w, b.w, acc);
+}
+
+// acc[c][r] += sum_k in[r][k] * W[n_c][k] over k in [0, K) for this warp's columns n_c = n0 + warp + NW c < n1;
+// `in` is shared memory [RB][ldin]; lanes stride over k (float4 when rows are 16-byte aligned).
+template <int RB>
+__device__ __forceinline__ void accumulate_cols(float (&acc)[MAXC][RB], const float* __restrict__ in, int ldin, int K,
+                                                const float* __restrict__ W, long long ldw, int n0, int n1) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool vec = (K % 4 == 0) && (ldw % 4 == 0) && (ldin % 4 == 0) && ((reinterpret_cast<size_t>(W) & 15) == 0);
+  if (vec) {
+    for (int k4 = lane; k4 < K / 4; k4 += 32) {
+      float4 w[MAXC];
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        const int n = n0 + warp + NW * c;
+        if (n < n1) w[c] = __ldg(reinterpret_cast<const float4*>(W + (long long)n * ldw) + k4);
+      }
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const float4 xv = *reinterpret_cast<const float4*>(in + r * ldin + 4 * k4);
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c)
+          if (n0 + warp + NW * c < n1) acc[c][r] = dot4(xv, w[c], acc[c][r]);
+      }
+    }
+  } else {
+    for (int k = lane; k < K; k += 32) {
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        const int n = n0 + warp + NW * c;
+        if (n >= n1) continue;
+        const float w = __ldg(W + (long long)n * ldw + k);
+#pragma unroll
+        for (int r = 0; r < RB; ++r) acc[c][r] = fmaf(in[r * ldin + k], w, acc[c][r]);
+      }
+    }
+  }
+}
+
+// Finish this warp's columns: cross-lane sum, then emit(c, n, r, value) on every lane (all lanes hold the sums).
+template <int RB, class Emit>
+__device__ __forceinline__ void finish_cols(float (&acc)[MAXC][RB], int n0, int n1, Emit emit) {
+  const int warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int n = n0 + warp + NW * c;
+    if (n >= n1) continue;
+#pragma unroll
+    for (int r = 0; r < RB; ++r) emit(n, r, warp_allsum(acc[c][r]));
+  }
+}
+
+// dx[r][k] = sum_n dy[r][n] W[n][k] for this CTA's input columns k in [k0, k1): thread = (k, n-lane), partial sums
+// over n-lanes meet in `red`, then fin(r, k, sum).  dy: shared [RB][lddy].
+template <int RB, class Fin>
+__device__ __forceinline__ void backward_cols(const float* __restrict__ dy, int lddy, int N, const float* __restrict__ W,
+                                              long long ldw, int k0, int k1, float* red, Fin fin) {
+  const int KS = k1 - k0;
+  if (KS > 0) {
+    const int NL = NT / KS;  // KS <= 96: at least two n-lanes
+    const int tid = threadIdx.x;
+    if (tid < KS * NL) {
+      const int kk = tid % KS, nl = tid / KS;
+      float acc[RB];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) acc[r] = 0.f;
+      for (int n = nl; n < N; n += NL) {
+        const float w = __ldg(W + (long long)n * ldw + k0 + kk);
+#pragma unroll
+        for (int r = 0; r < RB; ++r) acc[r] = fmaf(dy[r * lddy + n], w, acc[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < RB; ++r) red[(nl * RB + r) * KS + kk] = acc[r];
+    }
+    __syncthreads();
+    for (int i = tid; i < RB * KS; i += NT) {
+      const int r = i / KS, kk = i % KS;
+      float s = 0.f;
+      for (int nl = 0; nl < NL; ++nl) s += red[(nl * RB + r) * KS + kk];
+      fin(r, k0 + kk, s);
+    }
+  } else {
+    __syncthreads();
+  }
+  __syncthreads();
+}
+
+template <int RB>
+__global__ void __launch_bounds__(NT, 1) fus_rows_kernel(const __grid_constant__ RowArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = a.d.hidden, H3 = 3 * H, B = a.B;
+  const int O1 = a.d.out1, O2 = a.d.out2;
+  const int in[3] = {a.d.audio_dim, a.d.text_dim, a.d.video_dim};
+  const int row0 = (int)(blockIdx.x / CL) * RB;
+  const bool drop = a.p_drop > 0.f && a.mode != MODE_FWD;
+  const bool train = a.mode == MODE_LOSS || a.mode == MODE_UPSTREAM;  // backward follows: keep what it needs
+  const int step = drop ? *a.step : 0;
+  const float* P = a.P;
+
+  // ---- shared-memory carve (identical in every CTA of the cluster: peers are addressed by the same offsets) ----
+  float* sp = smem;
+  auto take = [&](int n) { float* r = sp; sp += n; return r; };
+  float* xs = take(RB * XCH);
+  float* h1 = take(3 * RB * H);   // [m][r][H]
+  float* h2 = take(3 * RB * H);
+  float* hc = take(RB * H3);      // [r][3H] encoder outputs (before dropout)
+  float* hcd = take(RB * H3);     // after dropout
+  float* mf = take(RB * H3);      // dropout factor (mask * scale) of the concat
+  float* a1 = take(RB * H);
+  float* a2 = take(RB * H);
+  float* a3 = take(RB * H);
+  float* feat = take(RB * H);
+  float* dfu = take(RB * H);      // d loss / d fused features
+  float* g3h = take(RB * H3);     // head's contribution to d(concat)
+  float* g3p = take(RB * H3);     // gradient w.r.t. the pre-activation of encoder layer 3
+  float* ga1 = take(RB * H);
+  float* ga2 = take(RB * H);
+  float* ga3 = take(RB * H);
+  float* g2 = take(3 * RB * H);
+  float* red = take(NT * RB);
+
+  const int HC = (H + CL - 1) / CL;
+  const int n0 = min(H, rank * HC), n1 = min(H, n0 + HC);          // this CTA's slice of an H-wide layer
+  const int C3 = (H3 + CL - 1) / CL;
+  const int c0 = min(H3, rank * C3), c1 = min(H3, c0 + C3);        // ... of the 3H-wide concat
+
+  if (blockIdx.x == 0 && tid == 0 && train) *a.ws.done = 0;
+  cluster.sync();  // every CTA of the cluster is running: DSMEM stores may begin
+
+  // all 8 peers' views of a local shared buffer (lanes 0..7 each keep one)
+  auto peer = [&](float* local) { return cluster.map_shared_rank(local, lane & (CL - 1)); };
+
+  // ================= forward =================
+  // encoder layer 1: inputs come from global memory in chunks (dropout applied while staging)
+  for (int m = 0; m < 3; ++m) {
+    const int K = in[m];
+    const float* W = P + a.L.enc_w1[m];
+    float acc[MAXC][RB];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+#pragma unroll
+      for (int r = 0; r < RB; ++r) acc[c][r] = 0.f;
+    for (int k0 = 0, chunk = 0; k0 < K; k0 += XCH, ++chunk) {
+      const int kc = min(XCH, K - k0);
+      const bool writer = drop && train && rank == (m + chunk) % CL;
+      for (int r = 0; r < RB; ++r) {
+        const int row = row0 + r;
+        for (int k = tid; k < kc; k += NT) {
+          float v = 0.f;
+          if (row < B) {
+            const long long i = (long long)row * K + k0 + k;
+            v = a.x[m][i];
+            if (drop) {
+              const float keep = a.ext_mask[m] ? a.ext_mask[m][i] : keep_hash(a.seed, m, step, i, a.p_drop);
+              v *= keep * a.mscale;
+              if (writer) a.ws.xd[m][i] = v;
+            }
+          }
+          xs[r * XCH + k] = v;
+        }
+      }
+      __syncthreads();
+      accumulate_cols<RB>(acc, xs, XCH, kc, W + k0, K, n0, n1);
+      __syncthreads();
+    }
+    float* dst = peer(h1);
+    finish_cols<RB>(acc, n0, n1, [&](int n, int r, float v) {
+      v = fmaxf(v + P[a.L.enc_b1[m] + n], 0.f);
+      if (lane < CL) dst[(m * RB + r) * H + n] = v;
+      if (lane == CL + r && train && row0 + r < B) a.ws.h1[((long long)m * B + row0 + r) * H + n] = v;
+    });
+  }
+  cluster.sync();
+  // encoder layer 2
+  for (int m = 0; m < 3; ++m) {
+    float acc[MAXC][RB] = {};
+    accumulate_cols<RB>(acc, h1 + m * RB * H, H, H, P + a.L.enc_w2[m], H, n0, n1);
+    float* dst = peer(h2);
+    finish_cols<RB>(acc, n0, n1, [&](int n, int r, float v) {
+      v = fmaxf(v + P[a.L.enc_b2[m] + n], 0.f);
+      if (lane < CL) dst[(m * RB + r) * H + n] = v;
+      if (lane == CL + r && train && row0 + r < B) a.ws.h2[((long long)m * B + row0 + r) * H + n] = v;
+    });
+  }
+  cluster.sync();
+  // encoder layer 3 -> concat (+ dropout of the concat)
+  for (int m = 0; m < 3; ++m) {
+    float acc[MAXC][RB] = {};
+    accumulate_cols<RB>(acc, h2 + m * RB * H, H, H, P + a.L.enc_w3[m], H, n0, n1);
+    float* dhc = peer(hc);
+    float* dhcd = peer(hcd);
+    float* dmf = peer(mf);
+    finish_cols<RB>(acc, n0, n1, [&](int n, int r, float v) {
+      v = fmaxf(v + P[a.L.enc_b3[m] + n], 0.f);
+      const int row = row0 + r, col = m * H + n;
+      float f = 1.f;
+      if (drop && row < B) {
+        const long long i = (long long)row * H3 + col;
+        f = (a.ext_mask[3] ? a.ext_mask[3][i] : keep_hash(a.seed, 3, step, i, a.p_drop)) * a.mscale;
+      }
+      if (lane < CL) {
+        dhc[r * H3 + col] = v;
+        dhcd[r * H3 + col] = v * f;
+        dmf[r * H3 + col] = f;
+      }
+      if (lane == CL + r && train && row < B) a.ws.hcd[(long long)row * H3 + col] = v * f;
+    });
+  }
+  cluster.sync();
+  // attention_mlp
+  {
+    float acc[MAXC][RB] = {};
+    accumulate_cols<RB>(acc, hcd, H3, H3, P + a.L.att_w1, H3, n0, n1);
+    float* dst = peer(a1);
+    finish_cols<RB>(acc, n0, n1, [&](int n, int r, float v) {
+      v = fmaxf(v + P[a.L.att_b1 + n], 0.f);
+      if (lane < CL) dst[r * H + n] = v;
+      if (lane == CL + r && train && row0 + r < B) a.ws.a1[(long long)(row0 + r) * H + n] = v;
+    });
+  }
+  cluster.sync();
+  {
+    float acc[MAXC][RB] = {};
+    accumulate_cols<RB>(acc, a1, H, H, P + a.L.att_w2, H, n0, n1);
+    float* dst = peer(a2);
+    finish_cols<RB>(acc, n0, n1, [&](int n, int r, float v) {
+      v = fmaxf(v + P[a.L.att_b2 + n], 0.f);
+      if (lane < CL) dst[r * H + n] = v;
+      if (lane == CL + r && train && row0 + r < B) a.ws.a2[(long long)(row0 + r) * H + n] = v;
+    });
+  }
+  cluster.sync();
+  {
+    float acc[MAXC][RB] = {};
+    accumulate_cols<RB>(acc, a2, H, H, P + a.L.att_w3, H, n0, n1);
+    float* dst = peer(a3);
+    finish_cols<RB>(acc, n0, n1, [&](int n, int r, float v) {
+      v = fmaxf(v + P[a.L.att_b3 + n], 0.f);
+      if (lane < CL) dst[r * H + n] = v;
+      if (lane == CL + r && train && row0 + r < B) a.ws.a3[(long long)(row0 + r) * H + n] = v;
+    });
+  }
+  cluster.sync();
+
+  // ================= head: replicated in every CTA (warp r <-> row r), so no exchange is needed =================
+  for (int r = warp; r < RB; r += NW) {
+    const int row = row0 + r;
+    const bool live = row < B;
+    const float* a3r = a3 + r * H;
+    const float* hcr = hc + r * H3;
+    float att[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      float s = 0.f;
+      for (int j = lane; j < H; j += 32) s = fmaf(P[a.L.fa_w + m * H + j], a3r[j], s);
+      att[m] = warp_allsum(s) + P[a.L.fa_b + m];
+    }
+    for (int j = lane; j < H; j += 32) {
+      const float f = (hcr[j] * att[0] + hcr[H + j] * att[1]) + hcr[2 * H + j] * att[2];
+      feat[r * H + j] = f;
+      if (rank == 0 && live) a.features[(long long)row * H + j] = f;
+    }
+    __syncwarp();
+    float logit[16], vout[4];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      if (c >= O1) break;
+      float s = 0.f;
+      for (int j = lane; j < H; j += 32) s = fmaf(P[a.L.o1_w + c * H + j], feat[r * H + j], s);
+      logit[c] = warp_allsum(s) + P[a.L.o1_b + c];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c >= O2) break;
+      float s = 0.f;
+      for (int j = lane; j < H; j += 32) s = fmaf(P[a.L.o2_w + c * H + j], feat[r * H + j], s);
+      vout[c] = warp_allsum(s) + P[a.L.o2_b + c];
+    }
+    if (rank == 0 && live && lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (c < O1) a.emos_out[(long long)row * O1 + c] = logit[c];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < O2) a.vals_out[(long long)row * O2 + c] = vout[c];
+    }
+    if (!train) continue;
+    // upstream gradients of the two heads (every lane computes the same scalars)
+    float dlog[16], dval[4];
+    if (a.mode == MODE_LOSS) {
+      // CELoss: NLL(log_softmax) summed / N; MSELoss: squared error summed / N  (loss.py:11-28)
+      float mx = logit[0];
+#pragma unroll
+      for (int c = 1; c < 16; ++c)
+        if (c < O1) mx = fmaxf(mx, logit[c]);
+      float se = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (c < O1) se += expf(logit[c] - mx);
+      const float lse = mx + logf(se);
+      const int tgt = live ? (int)a.emo[row] : 0;
+      float ce = 0.f, mse = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        if (c >= O1) break;
+        if (c == tgt) ce = lse - logit[c];
+        dlog[c] = live ? (expf(logit[c] - lse) - (c == tgt ? 1.f : 0.f)) * a.inv_batch : 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c >= O2) break;
+        const float dd = live ? vout[c] - a.val[(long long)row * O2 + c] : 0.f;
+        mse += dd * dd;
+        dval[c] = 2.f * dd * a.inv_batch;
+      }
+      if (rank == 0 && live && lane == 0) {
+        a.ws.loss_terms[2 * row] = ce;
+        a.ws.loss_terms[2 * row + 1] = mse;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (c < O1) dlog[c] = (live && a.up_emos) ? a.up_emos[(long long)row * O1 + c] : 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < O2) dval[c] = (live && a.up_vals) ? a.up_vals[(long long)row * O2 + c] : 0.f;
+    }
+    if (rank == 0 && live && lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (c < O1) a.ws.d_emos[(long long)row * O1 + c] = dlog[c];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < O2) a.ws.d_vals[(long long)row * O2 + c] = dval[c];
+    }
+    float datt[3] = {0.f, 0.f, 0.f};
+    for (int j = lane; j < H; j += 32) {
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (c < O1) s = fmaf(P[a.L.o1_w + c * H + j], dlog[c], s);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < O2) s = fmaf(P[a.L.o2_w + c * H + j], dval[c], s);
+      if (a.mode == MODE_UPSTREAM && a.up_feat && live) s += a.up_feat[(long long)row * H + j];
+      dfu[r * H + j] = s;
+#pragma unroll
+      for (int m = 0; m < 3; ++m) datt[m] = fmaf(hcr[m * H + j], s, datt[m]);
+    }
+#pragma unroll
+    for (int m = 0; m < 3; ++m) datt[m] = warp_allsum(datt[m]);
+    if (rank == 0 && live && lane < 3) a.ws.d_att[3 * row + lane] = lane == 0 ? datt[0] : (lane == 1 ? datt[1] : datt[2]);
+    for (int j = lane; j < H; j += 32) {
+      const float s = dfu[r * H + j];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) g3h[r * H3 + m * H + j] = att[m] * s;
+      const float da3 = (P[a.L.fa_w + j] * datt[0] + P[a.L.fa_w + H + j] * datt[1]) + P[a.L.fa_w + 2 * H + j] * datt[2];
+      const float g = a3r[j] > 0.f ? da3 : 0.f;
+      ga3[r * H + j] = g;
+      if (rank == 0 && live) a.ws.ga3[(long long)row * H + j] = g;
+    }
+  }
+  if (!train) {
+    cluster.sync();  // no CTA may exit while a peer could still be storing into its shared memory
+    return;
+  }
+  __syncthreads();
+
+  // ================= backward: data gradients =================
+  // attention_mlp.linear_3 -> d a2 (every finisher broadcasts its value into the 8 copies of the buffer)
+  backward_cols<RB>(ga3, H, H, P + a.L.att_w3, H, n0, n1, red, [&](int r, int k, float s) {
+    const float g = a2[r * H + k] > 0.f ? s : 0.f;
+    for (int p = 0; p < CL; ++p) cluster.map_shared_rank(ga2, p)[r * H + k] = g;
+    if (row0 + r < B) a.ws.ga2[(long long)(row0 + r) * H + k] = g;
+  });
+  cluster.sync();
+  backward_cols<RB>(ga2, H, H, P + a.L.att_w2, H, n0, n1, red, [&](int r, int k, float s) {
+    const float g = a1[r * H + k] > 0.f ? s : 0.f;
+    for (int p = 0; p < CL; ++p) cluster.map_shared_rank(ga1, p)[r * H + k] = g;
+    if (row0 + r < B) a.ws.ga1[(long long)(row0 + r) * H + k] = g;
+  });
+  cluster.sync();
+  // attention_mlp.linear_1 -> d concat (through the concat dropout), plus the head's share, through layer 3's ReLU
+  backward_cols<RB>(ga1, H, H, P + a.L.att_w1, H3, c0, c1, red, [&](int r, int k, float s) {
+    const float tot = g3h[r * H3 + k] + s * mf[r * H3 + k];
+    const float g = hc[r * H3 + k] > 0.f ? tot : 0.f;
+    for (int p = 0; p < CL; ++p) cluster.map_shared_rank(g3p, p)[r * H3 + k] = g;
+    if (row0 + r < B) a.ws.g3[(long long)(row0 + r) * H3 + k] = g;
+  });
+  cluster.sync();
+  for (int m = 0; m < 3; ++m) {  // encoder layer 3 -> d h2
+    backward_cols<RB>(g3p + m * H, H3, H, P + a.L.enc_w3[m], H, n0, n1, red, [&](int r, int k, float s) {
+      const float g = h2[(m * RB + r) * H + k] > 0.f ? s : 0.f;
+      for (int p = 0; p < CL; ++p) cluster.map_shared_rank(g2, p)[(m * RB + r) * H + k] = g;
+      if (row0 + r < B) a.ws.g2[((long long)m * B + row0 + r) * H + k] = g;
+    });
+  }
+  cluster.sync();
+  for (int m = 0; m < 3; ++m) {  // encoder layer 2 -> d h1 (the input gradient of layer 1 is not needed)
+    backward_cols<RB>(g2 + m * RB * H, H, H, P + a.L.enc_w2[m], H, n0, n1, red, [&](int r, int k, float s) {
+      const float g = h1[(m * RB + r) * H + k] > 0.f ? s : 0.f;
+      if (row0 + r < B) a.ws.g1[((long long)m * B + row0 + r) * H + k] = g;
+    });
+  }
+  // the last DSMEM stores (g2) were fenced by the barrier above: CTAs may retire independently
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct WProb {
+  const float* dy; int lddy;
+  const float* x; int ldx;
+  int N, K;
+  long long w_off, b_off;
+  int blk0;
+};
+struct WArgs {
+  WProb p[15];
+  int nblocks, B;
+  float* G;
+  float *P, *M, *V;     // Adam operands (do_adam)
+  float lr, beta1, beta2, eps, wd, clip;
+  int do_adam;
+  int* step;
+  int* done;
+  const float* loss_terms; float inv_batch; float* loss_out;
+};
+
+__device__ __forceinline__ void adam_update(const WArgs& a, long long i, float grad, float t) {
+  // torch.optim.Adam (coupled L2), same operation order as fusion.cu:fus_adam_kernel
+  const float bc1 = 1.f - powf(a.beta1, t);
+  const float bc2_sqrt = sqrtf(1.f - powf(a.beta2, t));
+  if (a.clip > 0.f) grad = fminf(fmaxf(grad, -a.clip), a.clip);
+  const float pi = a.P[i];
+  grad = fmaf(a.wd, pi, grad);
+  const float mi = a.M[i] + (grad - a.M[i]) * (1.f - a.beta1);
+  const float vi = a.V[i] * a.beta2 + (1.f - a.beta2) * grad * grad;
+  a.M[i] = mi;
+  a.V[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + a.eps;
+  a.P[i] = pi - (a.lr / bc1) * (mi / denom);
+}
+
+__global__ void __launch_bounds__(NT) fus_wgrad_kernel(const __grid_constant__ WArgs a) {
+  const int tid = threadIdx.x;
+  const float t = a.do_adam ? (float)(*a.step + 1) : 0.f;
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < 15; ++i)
+    if ((int)blockIdx.x >= a.p[i].blk0) pi = i;
+  const WProb& p = a.p[pi];
+  const long long e = (long long)(blockIdx.x - p.blk0) * NT + tid;
+  if (e < (long long)p.N * p.K) {
+    const int n = (int)(e / p.K), k = (int)(e % p.K);
+    float acc = 0.f, accb = 0.f;
+    const float* dy = p.dy + n;
+    const float* x = p.x + k;
+#pragma unroll 8
+    for (int b = 0; b < a.B; ++b) {
+      const float g = dy[(long long)b * p.lddy];
+      accb += g;
+      acc = fmaf(g, x[(long long)b * p.ldx], acc);
+    }
+    a.G[p.w_off + e] = acc;
+    if (a.do_adam) adam_update(a, p.w_off + e, acc, t);
+    if (k == 0) {
+      a.G[p.b_off + n] = accb;
+      if (a.do_adam) adam_update(a, p.b_off + n, accb, t);
+    }
+  }
+  if (blockIdx.x == 0 && tid == 0 && a.loss_out) {
+    float ce = 0.f, mse = 0.f;
+    for (int b = 0; b < a.B; ++b) { ce += a.loss_terms[2 * b]; mse += a.loss_terms[2 * b + 1]; }
+    a.loss_out[0] = ce * a.inv_batch;
+    a.loss_out[1] = mse * a.inv_batch;
+    a.loss_out[2] = ce * a.inv_batch + mse * a.inv_batch;
+  }
+  if (a.do_adam) {  // the last block to get here advances the step counter (every block has read it by then)
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      if (atomicAdd(a.done, 1) == (int)gridDim.x - 1) {
+        *a.step = *a.step + 1;
+        *a.done = 0;
+      }
+    }
+  }
+}
+
+int check_dims(const MerFusionDims* d, int B) {
+  MER_REQUIRE(d && d->hidden >= 4 && d->hidden <= 256 && d->hidden % 4 == 0 && d->out1 > 0 && d->out1 <= 16 &&
+                  d->out2 > 0 && d->out2 <= 4 && d->audio_dim > 0 && d->text_dim > 0 && d->video_dim > 0,
+              "mer_fusion: unsupported dims (hidden a multiple of 4 up to 256, out1 <= 16, out2 <= 4)");
+  MER_REQUIRE(B > 0 && B <= 65535, "mer_fusion: batch %d out of range", B);
+  return 0;
+}
+
+size_t rows_smem_bytes(int H, int RB) { return sizeof(float) * (size_t)RB * (XCH + 32 * (size_t)H + NT); }
+
+template <int RB>
+int launch_rows_t(const RowArgs& a, cudaStream_t st) {
+  static MerPerDevice once;
+  const size_t smem = rows_smem_bytes(a.d.hidden, RB);
+  if (once.needs_setup()) {
+    MER_CUDA_CHECK(cudaFuncSetAttribute(fus_rows_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    once.mark();
+  }
+  MER_REQUIRE(smem <= 200 * 1024, "mer_fusion: shared-memory plan of %zu bytes", smem);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(CL * ((a.B + RB - 1) / RB)));
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MER_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fus_rows_kernel<RB>, a));
+  mer_count_launches(1);
+  return 0;
+}
+
+int launch_rows(const RowArgs& a, cudaStream_t st) {
+  // 8 rows per cluster once there are enough rows to fill the GPU with clusters and the plan fits shared memory
+  if (a.B >= 128 && a.d.hidden <= 128) return launch_rows_t<8>(a, st);
+  return launch_rows_t<4>(a, st);
+}
+
+int launch_wgrad(const MerFusionDims& d, const ULayout& L, const GWs& ws, const float* const x[3], bool drop, int B,
+                 float* grads, const float* features, float* params, float* exp_avg, float* exp_avg_sq,
+                 const MerAdamHyper* adam, int* step, float inv_batch, float* loss_out, cudaStream_t st) {
+  WArgs w;
+  memset(&w, 0, sizeof(w));
+  const int H = d.hidden;
+  const int in[3] = {d.audio_dim, d.text_dim, d.video_dim};
+  int np = 0, blk = 0;
+  auto add = [&](const float* dy, int lddy, const float* xin, int ldx, int N, int K, long long w_off, long long b_off) {
+    w.p[np] = WProb{dy, lddy, xin, ldx, N, K, w_off, b_off, blk};
+    blk += (int)(((long long)N * K + NT - 1) / NT);
+    ++np;
+  };
+  for (int m = 0; m < 3; ++m) {
+    add(ws.g1 + (long long)m * B * H, H, drop ? ws.xd[m] : x[m], in[m], H, in[m], L.enc_w1[m], L.enc_b1[m]);
+    add(ws.g2 + (long long)m * B * H, H, ws.h1 + (long long)m * B * H, H, H, H, L.enc_w2[m], L.enc_b2[m]);
+    add(ws.g3 + m * H, 3 * H, ws.h2 + (long long)m * B * H, H, H, H, L.enc_w3[m], L.enc_b3[m]);
+  }
+  add(ws.ga1, H, ws.hcd, 3 * H, H, 3 * H, L.att_w1, L.att_b1);
+  add(ws.ga2, H, ws.a1, H, H, H, L.att_w2, L.att_b2);
+  add(ws.ga3, H, ws.a2, H, H, H, L.att_w3, L.att_b3);
+  add(ws.d_att, 3, ws.a3, H, 3, H, L.fa_w, L.fa_b);
+  add(ws.d_emos, d.out1, features, H, d.out1, H, L.o1_w, L.o1_b);
+  add(ws.d_vals, d.out2, features, H, d.out2, H, L.o2_w, L.o2_b);
+  w.nblocks = blk;
+  w.B = B;
+  w.G = grads;
+  if (adam) {
+    w.do_adam = 1;
+    w.P = params; w.M = exp_avg; w.V = exp_avg_sq;
+    w.lr = adam->lr; w.beta1 = adam->beta1; w.beta2 = adam->beta2; w.eps = adam->eps;
+    w.wd = adam->weight_decay; w.clip = adam->grad_clip;
+  }
+  w.step = step;
+  w.done = ws.done;
+  w.loss_terms = ws.loss_terms;
+  w.inv_batch = inv_batch;
+  w.loss_out = loss_out;
+  fus_wgrad_kernel<<<blk, NT, 0, st>>>(w);
+  MER_CUDA_CHECK(cudaGetLastError());
+  mer_count_launches(1);
+  return 0;
+}
+
+int fill_rows(RowArgs& a, const MerFusionDims* d, const float* params, const float* audios, const float* texts,
+              const float* videos, int B, float dropout_p, unsigned long long seed, const int* step,
+              const float* const* ext_masks, void* workspace, long long workspace_bytes, float* features,
+              float* emos_out, float* vals_out) {
+  if (int rc = check_dims(d, B)) return rc;
+  MER_REQUIRE(params && audios && texts && videos && workspace && features && emos_out && vals_out,
+              "mer_fusion: null operand");
+  MER_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "mer_fusion: dropout %f", dropout_p);
+  MER_REQUIRE(dropout_p == 0.f || step, "mer_fusion: dropout needs the step counter");
+  MER_REQUIRE(workspace_bytes >= ws_floats(*d, B) * 4, "mer_fusion: workspace too small");
+  memset(&a, 0, sizeof(a));
+  a.d = *d;
+  a.L = make_layout(*d);
+  a.P = params;
+  a.x[0] = audios; a.x[1] = texts; a.x[2] = videos;
+  if (ext_masks)
+    for (int m = 0; m < 4; ++m) a.ext_mask[m] = ext_masks[m];
+  a.B = B;
+  a.p_drop = dropout_p;
+  a.mscale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+  a.seed = seed;
+  a.step = step;
+  a.features = features; a.emos_out = emos_out; a.vals_out = vals_out;
+  a.ws = carve(*d, B, static_cast<float*>(workspace));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+long long mer_fusion_param_count(const MerFusionDims* d) {
+  if (!d) return -1;
+  return make_layout(*d).total;
+}
+
+long long mer_fusion_workspace_bytes(const MerFusionDims* d, int max_batch) {
+  if (!d) return -1;
+  return ws_floats(*d, max_batch) * 4;
+}
+
+int mer_fusion_forward(const MerFusionDims* d, const float* params, const float* audios, const float* texts,
+                       const float* videos, int B, void* workspace, long long workspace_bytes, float* features,
+                       float* emos_out, float* vals_out, void* stream_) {
+  RowArgs a;
+  if (int rc = fill_rows(a, d, params, audios, texts, videos, B, 0.f, 0, nullptr, nullptr, workspace, workspace_bytes,
+                         features, emos_out, vals_out))
+    return rc;
+  a.mode = MODE_FWD;
+  return launch_rows(a, static_cast<cudaStream_t>(stream_));
+}
+
+int mer_fusion_fwd_bwd(const MerFusionDims* d, const float* params, float* grads, const float* audios,
+                       const float* texts, const float* videos, const int64_t* emos, const float* vals, int B,
+                       float loss_inv_batch, float dropout_p, unsigned long long seed, const int* step_counter,
+                       const float* const* ext_masks, void* workspace, long long workspace_bytes, float* loss_out,
+                       float* features, float* emos_out, float* vals_out, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  RowArgs a;
+  if (int rc = fill_rows(a, d, params, audios, texts, videos, B, dropout_p, seed, step_counter, ext_masks, workspace,
+                         workspace_bytes, features, emos_out, vals_out))
+    return rc;
+  MER_REQUIRE(grads && emos && vals && loss_out && step_counter, "mer_fusion_fwd_bwd: null operand");
+  a.mode = MODE_LOSS;
+  a.emo = reinterpret_cast<const long long*>(emos);
+  a.val = vals;
+  a.inv_batch = loss_inv_batch;
+  if (int rc = launch_rows(a, st)) return rc;
+  return launch_wgrad(*d, a.L, a.ws, a.x, dropout_p > 0.f, B, grads, features, nullptr, nullptr, nullptr, nullptr,
+                      nullptr, loss_inv_batch, loss_out, st);
+}
+
+int mer_fusion_step(const MerFusionDims* d, float* params, float* grads, float* exp_avg, float* exp_avg_sq,
+                    const float* audios, const float* texts, const float* videos, const int64_t* emos,
+                    const float* vals, int B, float loss_inv_batch, float dropout_p, unsigned long long seed,
+                    int* step_counter, const float* const* ext_masks, const MerAdamHyper* adam, void* workspace,
+                    long long workspace_bytes, float* loss_out, float* features, float* emos_out, float* vals_out,
+                    void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  RowArgs a;
+  if (int rc = fill_rows(a, d, params, audios, texts, videos, B, dropout_p, seed, step_counter, ext_masks, workspace,
+                         workspace_bytes, features, emos_out, vals_out))
+    return rc;
+  MER_REQUIRE(grads && exp_avg && exp_avg_sq && emos && vals && loss_out && step_counter && adam,
+              "mer_fusion_step: null operand");
+  a.mode = MODE_LOSS;
+  a.emo = reinterpret_cast<const long long*>(emos);
+  a.val = vals;
+  a.inv_batch = loss_inv_batch;
+  if (int rc = launch_rows(a, st)) return rc;
+  return launch_wgrad(*d, a.L, a.ws, a.x, dropout_p > 0.f, B, grads, features, params, exp_avg, exp_avg_sq, adam,
+                      step_counter, loss_inv_batch, loss_out, st);
+}
+
+int mer_fusion_forward_train(const MerFusionDims* d, const float* params, const float* audios, const float* texts,
+                             const float* videos, int B, float dropout_p, unsigned long long seed,
+                             const int* step_counter, const float* const* ext_masks, void* workspace,
+                             long long workspace_bytes, float* features, float* emos_out, float* vals_out,
+                             void* stream_) {
+  RowArgs a;
+  if (int rc = fill_rows(a, d, params, audios, texts, videos, B, dropout_p, seed, step_counter, ext_masks, workspace,
+                         workspace_bytes, features, emos_out, vals_out))
+    return rc;
+  a.mode = MODE_FWD_TRAIN;
+  return launch_rows(a, static_cast<cudaStream_t>(stream_));
+}
+
+int mer_fusion_backward(const MerFusionDims* d, const float* params, float* grads, const float* audios,
+                        const float* texts, const float* videos, int B, const float* d_features,
+                        const float* d_emos, const float* d_vals, float dropout_p, unsigned long long seed,
+                        const int* step_counter, const float* const* ext_masks, void* workspace,
+                        long long workspace_bytes, float* features, float* emos_out, float* vals_out, void* stream_) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  RowArgs a;
+  if (int rc = fill_rows(a, d, params, audios, texts, videos, B, dropout_p, seed, step_counter, ext_masks, workspace,
+                         workspace_bytes, features, emos_out, vals_out))
+    return rc;
+  MER_REQUIRE(grads, "mer_fusion_backward: null operand");
+  a.mode = MODE_UPSTREAM;
+  a.up_feat = d_features; a.up_emos = d_emos; a.up_vals = d_vals;
+  if (int rc = launch_rows(a, st)) return rc;
+  return launch_wgrad(*d, a.L, a.ws, a.x, dropout_p > 0.f, B, grads, features, nullptr, nullptr, nullptr, nullptr,
+                      nullptr, 0.f, nullptr, st);
+}
+
+}  // extern "C"

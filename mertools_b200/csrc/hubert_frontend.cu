@@ -328,7 +328,7 @@ int mer_hubert_conv0_launch(const float* wave, long long ld_wave, int B, int L, 
     MER_CUDA_CHECK(cudaGetLastError());
     conv0_apply_kernel<true><<<grid, C0, 0, stream>>>(wave, ld_wave, w0, gamma, beta, stats, T0, out_bstride, split_out,
                                                       out, t0s);
-  } else if (pk && atoi(pk) == 1 && split_out) {
+  } else if (!(pk && atoi(pk) == 0) && split_out) {  // default since round 2 (0.21 -> 0.29 of HBM peak measured); MER_CONV0_PACKED=0: one channel per thread
     conv0_stats2_kernel<<<grid, C0 / 2, 0, stream>>>(wave, ld_wave, w0, T0, stats);
     MER_CUDA_CHECK(cudaGetLastError());
     conv0_apply2_kernel<<<grid, C0 / 2, 0, stream>>>(wave, ld_wave, w0, gamma, beta, stats, T0, out_bstride, out);

@@ -47,19 +47,21 @@ def split_into_batch(input_values, maxlen=MAXLEN):
 
 class AudioExtractor:
     def __init__(self, state_dict, device="cuda", max_rows_per_launch=128, ragged=None, max_samples_per_launch=128 * MAXLEN // 2):
-        """ragged (default: env MER_AUDIO_RAGGED=1): clips of different lengths share one device pass
+        """ragged (default on; env MER_AUDIO_RAGGED=0 switches it off): clips of different lengths share one device pass
         (``HubertEncoder.forward_ragged``: every clip computed as if alone) instead of one pass per distinct
         length; sorted by length and cut into launches of at most ``max_samples_per_launch`` padded samples."""
         if "encoder.layers.0.attention.gru_rel_pos_linear.weight" in state_dict:   # WavLMModel (wavlm-base / -large)
             from .wavlm import WavLmEncoder
             self.enc = WavLmEncoder(state_dict, device=device)
-            assert not ragged, "ragged batches are implemented for the HuBERT / wav2vec2 families only"
+            assert not ragged, "ragged batches are implemented for the HuBERT / wav2vec2 families only"  # None: default
             ragged = False
         else:
             self.enc = HubertEncoder(state_dict, device=device)
         self.device = self.enc.device
         self.max_rows = max_rows_per_launch
-        self.ragged = (os.environ.get("MER_AUDIO_RAGGED") == "1") if ragged is None else bool(ragged)
+        # measured on B200 (round 2): 979 clips/s ragged against 101 with one pass per distinct length, on 128 clips
+        # of U(2 s, 10 s); results agree to 9e-6
+        self.ragged = (os.environ.get("MER_AUDIO_RAGGED", "1") != "0") if ragged is None else bool(ragged)
         self.max_samples = max_samples_per_launch
         self._norm = L.declare("mer_wave_normalize", [C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                                       C.c_longlong, C.c_longlong, C.c_void_p])

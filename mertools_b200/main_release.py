@@ -5,9 +5,16 @@ a9-a12).  Same flags (:93-124), same hyper-parameter handling (model-tune.yaml `
 toolkit/utils/read_data.py:15-41,92-97), same 5-fold protocol (mer2023.py:108-134), metrics
 (toolkit/utils/metric.py) and result files ``cv_*.npz`` / ``test{j}_*.npz`` (:256-272).
 
-What changes is where the work happens: all features live on the GPU once, batches are index-selected
-on the device, and every training step is one fused FusionNet.train_step (forward + CE/MSE + backward
-+ Adam); evaluation passes run whole splits in one eval forward.
+What changes is where the work happens: all features live on the GPU once, torch's own ``DataLoader`` /
+``SubsetRandomSampler`` only shuffle and batch sample INDICES (so the order of samples and the consumption of
+torch's generator are the reference's by construction), batches are index-selected on the device, and every
+training step is one fused FusionNet.train_step (forward + CE/MSE + backward + Adam in two kernels).  The golden of
+the unmodified script (tests/golden/make_golden_main_release.py) is reproduced fold for fold, epoch for epoch.
+
+Under ``python -m torch.distributed.run --nproc-per-node W -m mertools_b200.main_release ...`` the trainer is
+data-parallel: rank 0's seed and initial weights are broadcast once, every rank draws the same
+permutation, takes the rank-strided slice ``batch[rank::W]`` of each reference batch, and the flat gradient (with
+the loss scalars) is all-reduced once per step; every rank evaluates the full splits, rank 0 writes the result files.
 """
 from __future__ import annotations
 
@@ -19,7 +26,8 @@ import time
 import numpy as np
 import torch
 
-from .fusion import Adam, FusionNet
+from . import shard
+from .fusion import Adam, get_models, mer2023_calculate_results
 
 EMOS_MER = ["neutral", "angry", "happy", "sad", "worried", "surprise"]      # toolkit/globals.py:2
 EMO2IDX = {e: i for i, e in enumerate(EMOS_MER)}
@@ -112,16 +120,35 @@ class DeviceSplit:
         return len(self.names)
 
 
-def calculate_results(emo_probs, emo_labels, val_preds, val_labels):
-    """mer2023.py:137-155."""
-    from sklearn.metrics import accuracy_score, f1_score, mean_squared_error
-    emo_preds = np.argmax(emo_probs, 1)
-    acc = accuracy_score(emo_labels, emo_preds)
-    f1 = f1_score(emo_labels, emo_preds, average="weighted")
-    mse = mean_squared_error(val_labels, val_preds)
-    res = dict(emoprobs=emo_probs, emolabels=emo_labels, emoacc=acc, emofscore=f1, valpreds=val_preds,
-               vallabels=val_labels, valmse=mse)
-    return res, f"f1:{f1:.4f}_acc:{acc:.4f}_val:{mse:.4f}"
+class _Indices(torch.utils.data.Dataset):
+    """What the DataLoaders iterate: sample numbers.  The features never leave the GPU."""
+
+    def __init__(self, n):
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        return int(i)
+
+
+def get_loaders(n_train, folds, n_tests, batch_size, num_workers=0):
+    """The loader objects of MER2023.get_loaders (mer2023.py:31-79), over sample indices: SubsetRandomSampler for the
+    train AND the eval part of each fold (the reference shuffles both), sequential order for the test sets."""
+    from torch.utils.data import DataLoader
+    from torch.utils.data.sampler import SubsetRandomSampler
+    train_set = _Indices(n_train)
+    mk = lambda idxs: DataLoader(train_set, batch_size=batch_size, sampler=SubsetRandomSampler(idxs),  # noqa: E731
+                                 num_workers=num_workers)
+    train_loaders = [mk(tr) for tr, _ in folds]
+    eval_loaders = [mk(ev) for _, ev in folds]
+    test_loaders = [DataLoader(_Indices(n), batch_size=batch_size, num_workers=num_workers, shuffle=False)
+                    for n in n_tests]
+    return train_loaders, eval_loaders, test_loaders
+
+
+calculate_results = mer2023_calculate_results  # mer2023.py:137-155
 
 
 def gain_metric_from_results(res, metric_name="emoval"):
@@ -135,27 +162,41 @@ def gain_metric_from_results(res, metric_name="emoval"):
     return -res["loss"]
 
 
+def _gather_strided(local, n_global, rank, world):
+    """Rows ``rank::world`` of a data-parallel batch from every rank -> the [n_global, C] batch in its own order."""
+    import torch.distributed as dist
+    per = -(-n_global // world)
+    pad = torch.zeros(per, local.shape[1], dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    out = torch.empty(n_global, local.shape[1], dtype=local.dtype, device=local.device)
+    for r in range(world):
+        out[r::world] = parts[r][:len(range(r, n_global, world))]
+    return out
+
+
 # ---- one pass over a split (main-release.py:17-87) ------------------------------------------------
-def run_split(args, net, split, idxs, optimizer=None, train=False, world_size=1):
-    """idxs: sample indices of this pass.  Training draws them in the order a SubsetRandomSampler would
-    (torch.randperm on the global generator), batch by batch, one fused step each."""
+def run_split(args, net, split, loader, optimizer=None, train=False, rank=0, world_size=1):
+    """``loader`` yields batches of sample indices in the reference's order.  Training: one fused step per batch
+    (under data parallelism on rows ``rank::world_size`` of it); evaluation: eval forward + the two losses."""
     dev = split.a.device
-    idxs = torch.as_tensor(idxs, dtype=torch.int64)
-    if train:
-        idxs = idxs[torch.randperm(len(idxs))]
-    names = [split.names[i] for i in idxs.tolist()]
-    idxs = idxs.to(dev)
-    emo_probs, val_preds, losses = [], [], []
+    names, emo_probs, val_preds, losses, order = [], [], [], [], []
     net.train(train)
-    for s in range(0, len(idxs), args.batch_size):
-        b = idxs[s:s + args.batch_size]
-        a, t, v = split.a.index_select(0, b), split.t.index_select(0, b), split.v.index_select(0, b)
-        emo, val = split.emo.index_select(0, b), split.val.index_select(0, b)
+    for b in loader:
+        names += [split.names[i] for i in b.tolist()]
+        b = b.to(dev)
+        order.append(b)
+        mine = b[rank::world_size] if (train and world_size > 1) else b
+        a, t, v = split.a.index_select(0, mine), split.t.index_select(0, mine), split.v.index_select(0, mine)
+        emo, val = split.emo.index_select(0, mine), split.val.index_select(0, mine)
         if train:
             loss3, eo, vo = net.train_step(a, t, v, emo, val, lr=optimizer.lr, betas=optimizer.betas,
                                            eps=optimizer.eps, weight_decay=optimizer.weight_decay,
-                                           world_size=world_size)
+                                           world_size=world_size, global_batch=len(b))
             losses.append(loss3[2:3].clone())
+            if world_size > 1:
+                eo, vo = (_gather_strided(x, len(b), rank, world_size) for x in (eo, vo))
         else:
             _, eo, vo, _ = net({"audios": a, "texts": t, "videos": v})
             ce = torch.nn.functional.cross_entropy(eo, emo, reduction="sum") / len(eo)
@@ -163,12 +204,13 @@ def run_split(args, net, split, idxs, optimizer=None, train=False, world_size=1)
             losses.append((ce + mse).view(1))
         emo_probs.append(eo.clone())
         val_preds.append(vo.clone())
+    order = torch.cat(order)
     emo_probs = torch.cat(emo_probs).cpu().numpy()
     val_preds = torch.cat(val_preds).cpu().numpy()
-    emo_labels = split.emo.index_select(0, idxs).cpu().numpy()
-    val_labels = split.val.index_select(0, idxs).cpu().numpy()
+    emo_labels = split.emo.index_select(0, order).cpu().numpy()
+    val_labels = split.val.index_select(0, order).cpu().numpy()
     res, _ = calculate_results(emo_probs, emo_labels, val_preds, val_labels)
-    return dict(names=names, loss=float(torch.cat(losses).mean().cpu()), **res)
+    return dict(names=names, loss=np.mean(torch.cat(losses).cpu().numpy()), **res)
 
 
 def build_parser():
@@ -194,13 +236,34 @@ def build_parser():
     return p
 
 
-def main(args, config=None):
+def _init_distributed(args):
+    """torchrun environment -> (rank, world).  One process per GPU; LOCAL_RANK overrides --gpu."""
+    rank, world = shard.env_rank_world()
+    if world > 1:
+        import torch.distributed as dist
+        args.gpu = int(os.environ.get("LOCAL_RANK", rank))
+        torch.cuda.set_device(args.gpu)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", args.gpu))
+        # the reference seeds nothing: make every rank continue rank 0's random streams
+        seed = torch.tensor([random.randrange(2 ** 31) if rank == 0 else 0], dtype=torch.int64, device="cuda")
+        dist.broadcast(seed, 0)
+        random.seed(int(seed))
+        torch.manual_seed(int(seed))
+    return rank, world
+
+
+def main(args, config=None, log=None):
+    """``log`` (optional dict) receives per-fold, per-epoch train / eval / test losses and the fold membership --
+    what tests/golden/main_release_golden.npz holds for the unmodified script."""
     if config is None:
         from . import config as config  # noqa: PLW0127
     assert args.model == "attention" and args.dataset == "MER2023", \
         "the B200 path covers --model attention --dataset MER2023 (SURVEY.md §8)"
+    rank, world = _init_distributed(args)
     torch.cuda.set_device(args.gpu)
     device = torch.device("cuda", args.gpu)
+    say = print if rank == 0 else (lambda *a, **k: None)
     # pre-compression of the frame-level types (main-release.py:131-142)
     if args.feat_type == "utt":
         args.feat_scale = 1
@@ -220,59 +283,74 @@ def main(args, config=None):
         if getattr(args, k, None) is None:
             setattr(args, k, v)
     args.output_dim1, args.output_dim2, args.metric_name = 6, 1, "emoval"
-    print("args: ", args)
+    say("args: ", args)
     save_resroot = os.path.join(args.save_root, "result")
-    os.makedirs(save_resroot, exist_ok=True)
-    os.makedirs(os.path.join(args.save_root, "model"), exist_ok=True)
+    if rank == 0:
+        os.makedirs(save_resroot, exist_ok=True)
+        os.makedirs(os.path.join(args.save_root, "model"), exist_ok=True)
     feature_name = "+".join(sorted(set(feats)))
     prefix_name = f"features:{feature_name}_dataset:{args.dataset}_model:{args.model}+{args.feat_type}+{args.e2e_name}"
 
-    print("====== Reading Data =======")
+    say("====== Reading Data =======")
     label_path = config.PATH_TO_LABEL[args.dataset]
     names, labels = read_names_labels(label_path, "train", args.debug)
-    print(f"train: sample number {len(names)}")
+    say(f"train: sample number {len(names)}")
     train_split = DeviceSplit(args, names, labels, config, device)
     folds = random_split_indexes(len(names), 5)
     tests = []
     for dt in ("test1", "test2", "test3"):
         n, l = read_names_labels(label_path, dt, args.debug)
-        print(f"{dt}: sample number {len(n)}")
+        say(f"{dt}: sample number {len(n)}")
         tests.append(DeviceSplit(args, n, l, config, device))
+    train_loaders, eval_loaders, test_loaders = get_loaders(len(names), folds, [len(ts) for ts in tests],
+                                                            args.batch_size, args.num_workers)
     args.audio_dim, args.text_dim, args.video_dim = train_split.dims
 
-    print("====== Training and Evaluation =======")
+    say("====== Training and Evaluation =======")
     folder_save, folder_duration = [], []
     name_time = time.time()
-    for ii, (train_idxs, eval_idxs) in enumerate(folds):
-        print(f">>>>> Cross-validation: training on the {ii + 1} folder >>>>>")
+    for ii in range(len(train_loaders)):
+        say(f">>>>> Cross-validation: training on the {ii + 1} folder >>>>>")
         start_time = name_time = time.time()
-        net = FusionNet(args.audio_dim, args.text_dim, args.video_dim, args.hidden_dim, 6, 1,
-                        dropout=args.dropout, grad_clip=args.grad_clip, device=device,
-                        seed=random.randint(0, 2 ** 31 - 1), feat_type=args.feat_type)
-        net.load_state_dict(default_init(net))
+        args.seed = random.randint(0, 2 ** 31 - 1)        # dropout-mask stream of this fold's model
+        model = get_models(args).cuda()                   # default init from torch's generator, as the reference
+        net = model.net
+        if world > 1:
+            net.broadcast_from(0)
         optimizer = Adam(lr=args.lr, weight_decay=args.l2)
         whole_store, whole_metrics = [], []
         for epoch in range(args.epochs):
             epoch_store = {}
-            train_res = run_split(args, net, train_split, train_idxs, optimizer, train=True)
-            eval_res = run_split(args, net, train_split, eval_idxs)
+            train_res = run_split(args, net, train_split, train_loaders[ii], optimizer, True, rank, world)
+            eval_res = run_split(args, net, train_split, eval_loaders[ii])
             for k, v in eval_res.items():
                 epoch_store[f"eval_{k}"] = v
             tm, em = (gain_metric_from_results(r, args.metric_name) for r in (train_res, eval_res))
             whole_metrics.append(em)
-            print("epoch:%d; metric:%s; train results:%.4f; eval results:%.4f" % (epoch + 1, args.metric_name, tm, em))
+            say("epoch:%d; metric:%s; train results:%.4f; eval results:%.4f" % (epoch + 1, args.metric_name, tm, em))
             for jj, ts in enumerate(tests):
-                res = run_split(args, net, ts, range(len(ts)))
+                res = run_split(args, net, ts, test_loaders[jj])
                 for k, v in res.items():
                     epoch_store[f"test{jj + 1}_{k}"] = v
             whole_store.append(epoch_store)
+            if log is not None:
+                log.setdefault("train_loss", []).append(float(train_res["loss"]))
+                log.setdefault("eval_loss", []).append(float(eval_res["loss"]))
+                log.setdefault("test_loss", []).append([float(epoch_store[f"test{j}_loss"]) for j in (1, 2, 3)])
+                log.setdefault("train_names", []).append(train_res["names"])
+                log.setdefault("eval_names", []).append(eval_res["names"])
         best_index = int(np.argmax(np.array(whole_metrics)))
         folder_save.append(whole_store[best_index])
         folder_duration.append(time.time() - start_time)
-        print(f">>>>> Finish: training on the {ii + 1}-th folder, best_index: {best_index}, "
-              f"duration: {folder_duration[-1]} >>>>>")
+        say(f">>>>> Finish: training on the {ii + 1}-th folder, best_index: {best_index}, "
+            f"duration: {folder_duration[-1]} >>>>>")
+        if log is not None:
+            log.setdefault("best_index", []).append(best_index)
+        del model, net
 
-    print("====== Prediction and Saving =======")
+    say("====== Prediction and Saving =======")
+    if log is not None:
+        log["folder_save"] = folder_save
     args.duration = float(np.sum(folder_duration))
     f1 = np.mean([e["eval_emofscore"] for e in folder_save])
     acc = np.mean([e["eval_emoacc"] for e in folder_save])
@@ -280,7 +358,6 @@ def main(args, config=None):
     cv_result = f"f1:{f1:.4f}_acc:{acc:.4f}_val:{mse:.4f}"
     saved = []
     path = f"{save_resroot}/cv_{prefix_name}_{cv_result}_{name_time}.npz"
-    np.savez_compressed(path, args=np.array(args, dtype=object))
     saved.append(path)
     for jj in range(len(tests)):
         emo_labels = folder_save[0][f"test{jj + 1}_emolabels"]
@@ -288,26 +365,12 @@ def main(args, config=None):
         val_labels = folder_save[0][f"test{jj + 1}_vallabels"]
         val_preds = np.mean(np.array([f[f"test{jj + 1}_valpreds"] for f in folder_save]), axis=0)
         _, test_result = calculate_results(emo_probs, emo_labels, val_preds, val_labels)
-        path = f"{save_resroot}/test{jj + 1}_{prefix_name}_{test_result}_{name_time}.npz"
-        np.savez_compressed(path, args=np.array(args, dtype=object))
-        saved.append(path)
-    for p in saved:
-        print(f"save results in {p}")
+        saved.append(f"{save_resroot}/test{jj + 1}_{prefix_name}_{test_result}_{name_time}.npz")
+    if rank == 0:
+        for p in saved:
+            np.savez_compressed(p, args=np.array(args, dtype=object))
+            print(f"save results in {p}")
     return saved
-
-
-def default_init(net):
-    """nn.Linear default init (kaiming-uniform a=sqrt(5) == U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for both
-    weight and bias), drawn from torch's global CPU generator as ``get_models(args)`` would."""
-    sd = {}
-    for name, shape in net.shapes.items():
-        if ".rnn." in name:  # nn.LSTM.reset_parameters: every tensor U(-1/sqrt(hidden), 1/sqrt(hidden))
-            fan_in = net.dims.hidden
-        else:
-            fan_in = shape[1] if len(shape) == 2 else net.shapes[name.replace(".bias", ".weight")][1]
-        bound = 1.0 / np.sqrt(fan_in)
-        sd[name] = (torch.rand(shape) * 2 - 1) * bound
-    return sd
 
 
 if __name__ == "__main__":

@@ -597,3 +597,34 @@ def synth_fusion_features(n, dim=768, seed=0):
     emo = rng.integers(0, 6, n).astype(np.int64)
     val = rng.uniform(-3, 3, n).astype(np.float32)
     return a, t, v, emo, val
+
+
+EMOS_MER = ("neutral", "angry", "happy", "sad", "worried", "surprise")  # toolkit/globals.py:2
+
+
+def write_mer2023_corpus(root, n_train=32, n_test=8, dim=768, seed=0, frame_level=False):
+    """A MER2023-format corpus under ``root``: ``label-6way.npz`` with the
+    ``{split}_corpus`` dict-of-dicts of toolkit/dataloader/mer2023.py:82-104 (every 7th valence left '' = missing)
+    and N(0,1) float32 ``.npy`` features under ``features/{synA,synT,synV}-UTT/`` (and ``-FRA`` with 2..39 / 2..5
+    rows per clip when ``frame_level``).  Returns (label_path, feature_root)."""
+    import os
+    rng = np.random.default_rng(seed)
+    corp = {}
+    for split, n in (("train", n_train), ("test1", n_test), ("test2", n_test), ("test3", n_test)):
+        corp[f"{split}_corpus"] = {
+            f"{split}_{i:04d}": {"emo": EMOS_MER[int(rng.integers(0, 6))],
+                                 "val": float(rng.uniform(-3, 3)) if i % 7 else ""}
+            for i in range(n)}
+    label_path = os.path.join(root, "label-6way.npz")
+    np.savez(label_path, **corp)
+    feats = os.path.join(root, "features")
+    sets = [("synA-UTT", 0), ("synT-UTT", 0), ("synV-UTT", 0)]
+    if frame_level:
+        sets += [("synA-FRA", 40), ("synT-FRA", 6), ("synV-FRA", 6)]
+    for fname, hi in sets:
+        os.makedirs(os.path.join(feats, fname), exist_ok=True)
+        for split in corp.values():
+            for name in split:
+                shape = (int(rng.integers(2, hi)), dim) if hi else (dim,)
+                np.save(os.path.join(feats, fname, name + ".npy"), rng.standard_normal(shape).astype(np.float32))
+    return label_path, feats

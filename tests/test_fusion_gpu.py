@@ -134,3 +134,99 @@ def test_frame_level_fusion_graph_and_eval(cuda):
     tsd = {k: x.cpu() for k, x in nets[0].state_dict().items()}
     rf, re, rv = OF.attention_forward(tsd, a.cpu(), t.cpu(), v.cpu())
     assert (f.cpu() - rf).abs().max() < 1e-4 and (e.cpu() - re).abs().max() < 1e-4 and int(inter) == 0
+
+
+def _args(**kw):
+    import types
+    base = dict(model="attention", feat_type="utt", audio_dim=768, text_dim=768, video_dim=768, output_dim1=6,
+                output_dim2=1, dropout=0.0, hidden_dim=128, grad_clip=-1.0)
+    base.update(kw)
+    return types.SimpleNamespace(**base)
+
+
+def test_get_models_runs_the_reference_training_loop(cuda):
+    """``get_models(args)`` must be what main-release.py:44-66,205 needs -- an nn.Module whose
+    parameters() feed torch.optim.Adam and whose forward is differentiable.  The loop below is the reference's
+    (zero_grad, forward, interloss + CELoss + MSELoss, backward, clip_grad_value_, Adam.step); the trajectory is
+    compared with the golden recorded from the reference's own Attention class + losses + torch.optim.Adam."""
+    import os
+    from mertools_b200.fusion import CELoss, MSELoss, get_models
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fusion_golden.npz"))
+    model = get_models(_args()).cuda()
+    assert isinstance(model, torch.nn.Module) and model.model.grad_clip == -1.0
+    names = [n for n, _ in model.named_parameters()]
+    assert names[0] == "model.audio_encoder.linear_1.weight" and names[-1] == "model.fc_out_2.bias" and len(names) == 28
+    model.model.net.load_state_dict(S.fusion_state_dict(seed=3))
+    assert torch.equal(dict(model.named_parameters())["model.fc_att.bias"].data,
+                       torch.from_numpy(S.fusion_state_dict(seed=3)["fc_att.bias"]).to(cuda))  # views, not copies
+    cls_loss, reg_loss = CELoss().cuda(), MSELoss().cuda()
+    optimizer = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5)
+    a, t, v, emo, val = S.synth_fusion_features(32, seed=7)
+    batch = {"audios": torch.from_numpy(a), "texts": torch.from_numpy(t), "videos": torch.from_numpy(v)}
+    emos, vals = torch.from_numpy(emo), torch.from_numpy(val)
+    model.train()
+    worst = 0.0
+    for step, ref in enumerate(g["losses"]):
+        optimizer.zero_grad()
+        b = {k: x.cuda() for k, x in batch.items()}
+        features, emos_out, vals_out, interloss = model(b)
+        loss = interloss + cls_loss(emos_out, emos.cuda()) + reg_loss(vals_out, vals.cuda())
+        loss.backward()
+        if model.model.grad_clip != -1:
+            torch.nn.utils.clip_grad_value_([p for p in model.parameters() if p.requires_grad], model.model.grad_clip)
+        if step == 0:
+            gw = dict(model.named_parameters())["model.fc_att.weight"].grad.cpu().numpy()
+            assert np.abs(gw - g["grad_fc_att_w"]).max() <= 1e-3 * np.abs(g["grad_fc_att_w"]).max()
+        optimizer.step()
+        worst = max(worst, abs(float(loss) - float(ref)))
+        assert abs(float(loss) - float(ref)) <= 1e-3, f"step {step}: {float(loss)} vs {ref}"
+    w = model.state_dict()["model.fc_out_1.weight"].cpu().numpy()
+    assert np.abs(w - g["final_fc_out_1_w"]).max() <= 1e-2 * np.abs(g["final_fc_out_1_w"]).max()
+    print(f"reference loop on get_models: worst |loss diff| over {len(g['losses'])} steps {worst:.2e}")
+    # eval mode / no_grad: same 4-tuple, no graph
+    model.eval()
+    with torch.no_grad():
+        f, e, vv, inter = model({k: x.cuda() for k, x in batch.items()})
+    assert f.shape == (32, 128) and e.shape == (32, 6) and vv.shape == (32, 1) and int(inter) == 0 and not e.requires_grad
+
+
+def test_autograd_node_with_dropout_and_upstream_feature_gradient(cuda):
+    """The backward half recomputes the forward under the same masks: gradients of an arbitrary scalar of all three
+    outputs (features included) against torch autograd on the oracle net with the masks the kernel used."""
+    from mertools_b200.fusion import get_models
+    model = get_models(_args(dropout=0.3, hidden_dim=64)).cuda()
+    net = model.model.net
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    B = 19
+    a, t, v, emo, val = _data(B, seed=5)
+    rng = np.random.default_rng(2)
+    masks = [torch.from_numpy((rng.random((B, d)) >= 0.3).astype(np.float32)) for d in (768, 768, 768, 192)]
+    wf, we, wv = torch.randn(B, 64), torch.randn(B, 6), torch.randn(B, 1)
+    rf, re, rv = OF.attention_forward(sd, a, t, v, masks=masks, p=0.3)
+    ((rf * wf).sum() + (re * we).sum() + (rv * wv).sum()).backward()
+    ad, td, vd = a.to(cuda), t.to(cuda), v.to(cuda)
+    dm = [m.to(cuda) for m in masks]
+    f, e, vv = net.forward_train(ad, td, vd, ext_masks=dm)
+    assert (f.cpu() - rf.detach()).abs().max() < 1e-4 and (e.cpu() - re.detach()).abs().max() < 1e-4
+    flat = net.backward(ad, td, vd, wf.to(cuda), we.to(cuda), wv.to(cuda), ext_masks=dm)
+    for n, gv in net.named_views(flat).items():
+        r = sd[n].grad
+        assert (gv.cpu() - r).abs().max() <= 2e-4 * max(r.abs().max().item(), 1e-3), f"grad {n}"
+
+
+@pytest.mark.parametrize("B,hidden,dropout", [(32, 128, 0.0), (256, 128, 0.3), (45, 256, 0.2), (7, 64, 0.5)])
+def test_fused_step_equals_backward_then_adam(cuda, B, hidden, dropout):
+    """mer_fusion_step (Adam inside the weight-gradient kernel) against the data-parallel form of the same step
+    (mer_fusion_fwd_bwd, then mer_fusion_adam): bit-identical parameters and losses over 6 steps, for both row-tile
+    sizes of the cluster kernel (B >= 128 at hidden <= 128 takes 8 rows per cluster) and with the hash dropout."""
+    from mertools_b200.fusion import FusionNet
+    sd = S.fusion_state_dict(seed=3, hidden=hidden)
+    a, t, v, emo, val = (x.to(cuda) for x in _data(B, seed=8))
+    nets = [FusionNet(hidden_dim=hidden, dropout=dropout, device=cuda, seed=5).load_state_dict(sd) for _ in range(2)]
+    for step in range(6):
+        l0, e0, _ = nets[0].train_step(a, t, v, emo, val, weight_decay=1e-5, use_graph=False)
+        l0, e0 = l0.clone(), e0.clone()
+        l1, e1, _ = nets[1].train_step(a, t, v, emo, val, weight_decay=1e-5, use_graph=False, fused_adam=False)
+        assert torch.equal(l0, l1) and torch.equal(e0, e1), f"step {step}"
+        assert torch.equal(nets[0].grads, nets[1].grads)
+    assert torch.equal(nets[0].params, nets[1].params) and int(nets[0].step_counter) == int(nets[1].step_counter) == 6

@@ -11,27 +11,10 @@ import torch
 from mertools_b200 import main_release as MR
 
 
-def _make_corpus(root, n_train=32, n_test=8, seed=0):
-    rng = np.random.default_rng(seed)
-    corp = {}
-    for split, n in (("train", n_train), ("test1", n_test), ("test2", n_test), ("test3", n_test)):
-        corp[f"{split}_corpus"] = {
-            f"{split}_{i:04d}": {"emo": MR.EMOS_MER[int(rng.integers(0, 6))],
-                                 "val": float(rng.uniform(-3, 3)) if i % 7 else ""}
-            for i in range(n)}
-    np.savez(os.path.join(root, "label-6way.npz"), **corp)
-    feats = os.path.join(root, "features")
-    for fname, frame_level in (("synA-UTT", False), ("synT-UTT", False), ("synV-FRA", True), ("synA-FRA", True),
-                               ("synT-FRA", True)):
-        os.makedirs(os.path.join(feats, fname))
-        for split in corp.values():
-            for name in split:
-                hi = 40 if fname == "synA-FRA" else 6
-                x = rng.standard_normal((int(rng.integers(2, hi)), 768) if frame_level else (768,)).astype(np.float32)
-                np.save(os.path.join(feats, fname, name + ".npy"), x)
-    cfg = types.SimpleNamespace(PATH_TO_LABEL={"MER2023": os.path.join(root, "label-6way.npz")},
-                                PATH_TO_FEATURES={"MER2023": feats})
-    return cfg
+def _make_corpus(root, seed=0):
+    from mertools_b200 import synthetic as S
+    label_path, feats = S.write_mer2023_corpus(root, seed=seed, frame_level=True)
+    return types.SimpleNamespace(PATH_TO_LABEL={"MER2023": label_path}, PATH_TO_FEATURES={"MER2023": feats})
 
 
 def test_label_and_feature_readers(tmp_path):
@@ -73,6 +56,63 @@ def test_main_release_end_to_end(cuda, tmp_path):
     assert os.path.basename(saved[0]).startswith("cv_features:synA-UTT+synT-UTT+synV-FRA_dataset:MER2023_model:attention+utt+None_f1:")
     stored = np.load(saved[0], allow_pickle=True)["args"].item()
     assert stored.hidden_dim == 128 and stored.audio_dim == 768 and stored.duration > 0
+
+
+def _metrics_of(name):
+    """'..._f1:0.1533_acc:0.3167_val:18.1225' -> (prefix, [f1, acc, val])"""
+    head, f1, acc, val = name.rsplit("_", 3)
+    return head, [float(x.split(":")[1]) for x in (f1, acc, val)]
+
+
+@pytest.mark.gpu
+def test_main_release_reproduces_the_unmodified_reference_run(cuda, tmp_path):
+    """tests/golden/main_release_golden.npz was recorded from ``runpy`` of the
+    UNMODIFIED /root/reference/MERBench/main-release.py (tests/golden/make_golden_main_release.py: config C1, 32 + 3x8
+    clips, 5 folds x 3 epochs, dropout 0, torch / random seeded with 0).  The mirror, seeded the same way, must make
+    the same fold split, visit the samples in the same order (same sampler classes on the same generator), start
+    from the same initial weights (torch's own nn.Linear constructors in the reference's order) and land on the same
+    losses, best epochs, predictions and result-file names.  Floating point: 1e-3 relative (north_star)."""
+    from mertools_b200 import synthetic as S
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "main_release_golden.npz"))
+    label_path, feats = S.write_mer2023_corpus(str(tmp_path), seed=int(g["seed"]))
+    cfg = types.SimpleNamespace(PATH_TO_LABEL={"MER2023": label_path}, PATH_TO_FEATURES={"MER2023": feats})
+    hyper = tmp_path / "hyper.yaml"
+    hyper.write_text(str(g["hyper"]))
+    args = MR.build_parser().parse_args([
+        "--audio_feature=synA-UTT", "--text_feature=synT-UTT", "--video_feature=synV-UTT",
+        f"--hyper_path={hyper}", f"--epochs={int(g['epochs'])}", f"--save_root={tmp_path}/saved", "--gpu=0"])
+    torch.manual_seed(int(g["seed"]))
+    random.seed(int(g["seed"]))
+    np.random.seed(int(g["seed"]))
+    log = {}
+    saved = MR.main(args, config=cfg, log=log)
+    E = int(g["epochs"])
+    # bit-exact parts: who is in which fold, and in which order the loaders visited them
+    for f in range(5):
+        assert log["eval_names"][f * E] == list(g[f"fold{f}_eval_names_epoch0"]), f"fold {f}: eval split / order"
+        assert log["train_names"][f * E] == list(g[f"fold{f}_train_names_epoch0"]), f"fold {f}: train order"
+    assert log["best_index"] == list(g["best_index"])
+    # losses of every epoch of every fold
+    rel = lambda a, b: np.abs(np.asarray(a, np.float64) - b).max() / np.abs(b).max()  # noqa: E731
+    tr, ev = np.array(log["train_loss"]).reshape(5, E), np.array(log["eval_loss"]).reshape(5, E)
+    ts = np.array(log["test_loss"]).reshape(5, E, 3).transpose(2, 0, 1)
+    print(f"main-release golden: train loss rel {rel(tr, g['train_loss']):.2e}, eval {rel(ev, g['eval_loss']):.2e}, "
+          f"test {rel(ts, g['test_loss']):.2e}")
+    assert rel(tr, g["train_loss"]) < 1e-3 and rel(ev, g["eval_loss"]) < 1e-3 and rel(ts, g["test_loss"]) < 1e-3
+    # best-epoch predictions per fold
+    for f, best in enumerate(log["folder_save"]):
+        assert best["eval_names"] == list(g[f"fold{f}_eval_names"])
+        for k in ("eval_emoprobs", "eval_valpreds", "test1_emoprobs", "test1_valpreds", "test3_emoprobs"):
+            assert rel(best[k], g[f"fold{f}_{k}"]) < 1e-3, (f, k)
+        assert abs(best["eval_emofscore"] - float(g[f"fold{f}_eval_emofscore"])) < 1e-12
+        assert abs(best["eval_emoacc"] - float(g[f"fold{f}_eval_emoacc"])) < 1e-12
+        assert abs(best["eval_valmse"] - float(g[f"fold{f}_eval_valmse"])) < 1e-3 * float(g[f"fold{f}_eval_valmse"])
+    # result files: same names up to the wall-clock suffix (the val figure may differ in its last printed digit)
+    assert len(saved) == 4
+    for path, ref in zip(saved, g["saved"]):
+        name = os.path.basename(path).rsplit("_", 1)[0]
+        (h1, m1), (h2, m2) = _metrics_of(name), _metrics_of(str(ref))
+        assert h1 == h2 and m1[:2] == m2[:2] and abs(m1[2] - m2[2]) <= 2e-4 * max(1.0, m2[2]), (name, str(ref))
 
 
 @pytest.mark.gpu

@@ -1,9 +1,14 @@
-"""Kernel-level tests of the opt-in variants prepared after the round-1 GPU budget ran out, plus the default
-kernels through the same harness.
+"""GPU parity of the kernel variants and of the wider extractor families.
 
-The two tcgen05 attention kernels on their own (fp16 operands: ViT; TF32 operands: HuBERT / BERT), ragged
-batches, both softmax versions (MER_ATT_F16_VER / MER_ATT_TC_VER = 1 default, 2 = 16-key granules), against a
-float64 softmax(Q K^T / 8) V of the same operand values (HF eager attention, modeling_vit.py:171-196)."""
+First run on a B200 at the start of round 2 (all 33 green, `profiles/r2_ab_switches.json`), since then part of the
+always-on `-m gpu` suite.  Kernel level: the two tcgen05 attention kernels on their own (fp16 operands: ViT; TF32
+operands: HuBERT / BERT) on ragged batches in every softmax version (MER_ATT_F16_VER 1 | 2 | 3 = default,
+MER_ATT_TC_VER 1 | 2 = default) against a float64 softmax(Q K^T / 8) V of the same operand values (HF eager
+attention, modeling_vit.py:171-196); packed GELU / conv0 forms against the scalar ones.  Extractor level: ragged
+HuBERT batches, FER+ ResNet-50 / SENet-50, MA-Net, EmoNet, MS-Celeb, VGGish, Whisper, WavLM, data2vec-audio /
+-vision, wav2vec2-large-960h, BERT-large, CLIP L/14 with fp16 linears, DINOv2 (-giant), VideoMAE, the device path of
+load_video_from_npy -- each against its oracle and, where the reference code runs, a golden of the unmodified
+reference."""
 import os
 
 import pytest
@@ -11,11 +16,7 @@ import torch
 
 from mertools_b200 import _lib as L
 
-# Written after the round's GPU budget was spent: neither this harness nor the VER 2 kernels have run on a GPU
-# yet, so the file is opt-in (MER_RUN_UNVERIFIED=1) until it has been seen green once.
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MER_RUN_UNVERIFIED") != "1",
-                                 reason="not yet validated on a GPU; set MER_RUN_UNVERIFIED=1")]
+pytestmark = pytest.mark.gpu
 HEADS, HD = 3, 64
 LENS_F16 = [197, 197, 5, 1, 64, 128, 129, 249, 16, 17, 200, 33]
 LENS_TC = LENS_F16 + [253, 250]
@@ -196,8 +197,8 @@ def test_vggish_extractor_files(cuda, tmp_path):
 
 
 def test_hubert_packed_conv0_and_switches_keep_parity(cuda):
-    """HuBERT-base with MER_CONV0_PACKED=1 (two channels per thread on the packed fp32 pipe), MER_GELU_PACKED=1 and
-    MER_ATT_TC_VER=2 against the default kernels (tight) and the oracle (1e-3)."""
+    """HuBERT-base with the legacy forms (MER_CONV0_PACKED=0: one channel per thread; MER_ATT_TC_VER=1: per-score
+    masks) and with MER_GELU_PACKED=1 against the default kernels (tight), and the defaults against the oracle."""
     import numpy as np
 
     from mertools_b200 import synthetic as S
@@ -219,11 +220,9 @@ def test_hubert_packed_conv0_and_switches_keep_parity(cuda):
     ref = torch.stack(ref_hs)[[-4, -3, -2, -1]].sum(dim=0).double()
     scale = float(ref.abs().max())
     assert float((base.reshape(ref.shape) - ref).abs().max()) / scale < 2e-3
-    for env in ("MER_CONV0_PACKED", "MER_GELU_PACKED"):
-        got = _with_env(env, "1", run)
+    for env, val in (("MER_CONV0_PACKED", "0"), ("MER_GELU_PACKED", "1"), ("MER_ATT_TC_VER", "1")):
+        got = _with_env(env, val, run)
         assert float((got - base).abs().max()) / scale < 5e-5, env
-    got = _with_env("MER_ATT_TC_VER", "2", run)
-    assert float((got - base).abs().max()) / scale < 5e-5
 
 
 @pytest.mark.parametrize("model_name,prefix,se", [("resnet50_ferplus_dag", "", False), ("senet50_ferplus_dag", "se_", True)])
