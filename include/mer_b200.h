@@ -37,6 +37,9 @@ MER_API int mer_check_device(void);
 /* cumulative number of CUDA kernels this library has launched in this process (bench.py's
  * gpu_launches); CUDA-graph replays are not seen here and are counted by their owner */
 MER_API long long mer_launch_count(void);
+/* launches so far of the instantiation gemm_kernel<block_n (128 | 256), mode (MER_GEMM_*), cluster (1 | 2), twosm
+ * (0 | 1: tcgen05.mma.cta_group::2)>; -1 for a combination that does not exist. */
+MER_API long long mer_gemm_variant_launches(int block_n, int mode, int cluster, int twosm);
 /* per-launch CUDA-event timing (roofline in bench.py): enable(1) starts a fresh recording, enable(0)
  * stops; collect sums duration / algorithmic work / launches of one kernel class since the last
  * enable(1).  Classes: MER_GEMM_* (work = 2*M*N*K flop), 10 = fp16 tcgen05 attention, 11 = TF32 tcgen05

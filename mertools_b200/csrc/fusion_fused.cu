@@ -156,6 +156,7 @@ __device__ __forceinline__ void accumulate_cols(float (&acc)[MAXC][RB], const fl
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool vec = (K % 4 == 0) && (ldw % 4 == 0) && (ldin % 4 == 0) && ((reinterpret_cast<size_t>(W) & 15) == 0);
   if (vec) {
+#pragma unroll 3
     for (int k4 = lane; k4 < K / 4; k4 += 32) {
       float4 w[MAXC];
 #pragma unroll
@@ -212,6 +213,7 @@ __device__ __forceinline__ void backward_cols(const float* __restrict__ dy, int 
       float acc[RB];
 #pragma unroll
       for (int r = 0; r < RB; ++r) acc[r] = 0.f;
+#pragma unroll 8
       for (int n = nl; n < N; n += NL) {
         const float w = __ldg(W + (long long)n * ldw + k0 + kk);
 #pragma unroll

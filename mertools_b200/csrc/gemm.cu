@@ -567,9 +567,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 }
 
+// launches per kernel instantiation (tests assert that the variant a configuration is benchmarked on is the one a
+// parity test exercised): index = mode | (BLOCK_N == 256) << 2 | (CLUSTER == 2) << 3 | TWOSM << 4
+long long g_variant_launches[32] = {};
+
 template <int BLOCK_N, int MODE, int CLUSTER, bool TWOSM = false>
 int launch_gemm(const MerGemmDesc* g, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, MODE, TWOSM>;
+  ++g_variant_launches[(MODE & 3) | (BLOCK_N == 256 ? 4 : 0) | (CLUSTER == 2 ? 8 : 0) | (TWOSM ? 16 : 0)];
   CUtensorMap ta, tb;
   const CUtensorMapDataType dt = Cfg::kSplit ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                  : Cfg::kF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
@@ -643,6 +648,11 @@ int launch_gemm(const MerGemmDesc* g, cudaStream_t stream) {
 }
 
 }  // namespace
+
+extern "C" long long mer_gemm_variant_launches(int block_n, int mode, int cluster, int twosm) {
+  if ((block_n != 128 && block_n != 256) || mode < 0 || mode > 2 || cluster < 1 || cluster > 2) return -1;
+  return g_variant_launches[(mode & 3) | (block_n == 256 ? 4 : 0) | (cluster == 2 ? 8 : 0) | (twosm ? 16 : 0)];
+}
 
 int mer_gemm_launch(const MerGemmDesc* g, cudaStream_t stream) {
   MER_REQUIRE(g && g->A && g->W && g->ep.out, "mer_gemm: null operand");

@@ -155,7 +155,7 @@ def test_get_models_runs_the_reference_training_loop(cuda):
     model = get_models(_args()).cuda()
     assert isinstance(model, torch.nn.Module) and model.model.grad_clip == -1.0
     names = [n for n, _ in model.named_parameters()]
-    assert names[0] == "model.audio_encoder.linear_1.weight" and names[-1] == "model.fc_out_2.bias" and len(names) == 28
+    assert names[0] == "model.audio_encoder.linear_1.weight" and names[-1] == "model.fc_out_2.bias" and len(names) == 30
     model.model.net.load_state_dict(S.fusion_state_dict(seed=3))
     assert torch.equal(dict(model.named_parameters())["model.fc_att.bias"].data,
                        torch.from_numpy(S.fusion_state_dict(seed=3)["fc_att.bias"]).to(cuda))  # views, not copies
