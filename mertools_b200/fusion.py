@@ -615,6 +615,8 @@ class get_models(torch.nn.Module):  # noqa: N801 -- the reference's name (toolki
             model = self.__dict__.get("model") or self.__dict__.get("_modules", {}).get("model")
             if model is None:
                 raise
+            if hasattr(model, k):
+                return getattr(model, k)
             return getattr(getattr(model, "net", model), k)
 
 
