@@ -30,7 +30,8 @@ namespace {
 using namespace mer;
 
 constexpr int HD = 64;
-constexpr int F16_THREADS = 320;          // producer, MMA issuer, 2 x 4 softmax/epilogue warps
+constexpr int F16_THREADS = 320;          // producer, MMA issuer, 2 x 4 softmax/epilogue warps (VER 1..3)
+constexpr int F16_THREADS_V4 = 576;       // VER 4: 2 x 8 softmax/epilogue warps
 constexpr int K_BYTES = 256 * 128;        // K: up to 256 keys x 128 B
 constexpr int VT_CHUNK = HD * 128;        // V^T chunk: 64 d-rows x 64 keys (128 B)
 constexpr int QTILE_BYTES = 128 * 128;    // one 128-row Q tile; later the P-chunk buffer of the tile
@@ -41,7 +42,8 @@ constexpr int SMEM_V = K_BYTES;           // 4 V^T chunks = 32 KB; later the out
 constexpr int SMEM_Q = SMEM_V + 4 * VT_CHUNK;
 constexpr int SET_BYTES = SMEM_Q + 2 * QTILE_BYTES;  // 96 KB
 constexpr int SMEM_BAR = 2 * SET_BYTES;
-constexpr int F16_SMEM = SMEM_BAR + 256 + 1024;
+constexpr int SMEM_XCHG = SMEM_BAR + 256;   // VER 4: partial row max / row sum of the two warps sharing a row: [2 tiles][128][2] x 2
+constexpr int F16_SMEM = SMEM_XCHG + 4096 + 1024;
 constexpr uint32_t TILE_COLS = 256, TMEM_COLS = 512;
 
 __device__ __forceinline__ float fast_ex2(float x) {  // MUFU.EX2, flush-to-zero
@@ -62,11 +64,24 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) {  // SW128, SBO 
 // VER 2: the key axis is handled in 16-column granules; granules that lie inside [shift, Lk) — all but the
 //        first (leading foreign keys) and the last — run unmasked with FMNMX3 / FFMA2 / FADD2, and granules
 //        beyond the UMMA key count NK are skipped (the P V MMA never reads them).
+// VER 4: 16 softmax warps.  Measured on B200 (scripts/micro/tmem_mufu_bench.cu): one warp gets a 32-column
+//        tcgen05.ld every ~100 cycles whatever it has in flight (41 B/clk), the SM 317 B/clk from 8 warps and 435
+//        from 16; MUFU.EX2 runs at exactly 16 per clock and SM.  With one thread per query row a tile costs 17
+//        serialised loads and 208 exponentials per thread, and the kernel sat at ~10k cycles per (sequence, head)
+//        against a MUFU floor of 3.3k.  Here TWO warps share each 32-row quarter of a tile: warp `half` takes
+//        columns [32 half, 32 half + 32) of every 64-key chunk in both passes (9 loads, ~104 exponentials per
+//        thread), the partial row maxima / sums meet through shared memory under a 64-thread named barrier, both
+//        halves store their 64 bytes of each P row and of each output row.  Softmax body as VER 3.
 template <int VER>
-__global__ void __launch_bounds__(F16_THREADS, 1)
+__global__ void __launch_bounds__(VER == 4 ? F16_THREADS_V4 : F16_THREADS, 1)
 attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
                      const __grid_constant__ CUtensorMap tmap_vt, uint16_t* __restrict__ ctx,
-                     const int* __restrict__ cu_seqlens, int n_seq, int heads) {
+                     const int* __restrict__ cu_seqlens, int n_seq, int heads, long long* __restrict__ trace) {
+  // trace (debug, normally null): clock64() stamps of block 0's first 16 items, 32 slots per item (scripts/att_trace.py)
+#define ATT_TR(slot)                                                                           \
+  do {                                                                                         \
+    if (trace != nullptr && blockIdx.x == 0 && item_n < 16 && lane == 0) trace[item_n * 32 + (slot)] = clock64(); \
+  } while (0)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
@@ -92,11 +107,11 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
       mbar_init(&bar_q[t], 1);
       mbar_init(&bar_v[t], 1);
       mbar_init(&bar_sfull[t], 1);
-      mbar_init(&bar_pready[t], 4);
+      mbar_init(&bar_pready[t], VER == 4 ? 8 : 4);
       mbar_init(&bar_pfree[t], 1);
       mbar_init(&bar_ofull[t], 1);
-      mbar_init(&bar_ofree[t], 4);
-      mbar_init(&bar_otfree[t], 4);
+      mbar_init(&bar_ofree[t], VER == 4 ? 8 : 4);
+      mbar_init(&bar_otfree[t], VER == 4 ? 8 : 4);
     }
     fence_mbar_init();
   }
@@ -142,6 +157,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
           tma_load_2d(sm + SMEM_V + c * VT_CHUNK, &tmap_vt, &bar_v[set], a_start + c * 64, h * HD);
       }
       __syncwarp();
+      ATT_TR(0);
       h_nmt[set] = n_mt;
       for (int t = 0; t < n_mt; ++t) h_use[set][t] = uses[t]++;
     }
@@ -168,6 +184,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
       const uint32_t idesc_o = umma_idesc(0, 128, HD);
       mbar_wait(&bar_k[set], set_par);
       mbar_wait(&bar_q[set], set_par);
+      ATT_TR(1);
       // ---- S_t = Q_t K^T for both tiles ----
       for (int t = 0; t < n_mt; ++t) {
         if (uses[t] > 0) mbar_wait(&bar_otfree[t], (uses[t] - 1) & 1);  // S_t / O_t columns free again
@@ -180,9 +197,11 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
           tc_commit(&bar_sfull[t]);
         }
         __syncwarp();
+        ATT_TR(2 + t);
       }
       // ---- O_t += P_t chunk * V chunk, the two tiles interleaved ----
       mbar_wait(&bar_v[set], set_par);
+      ATT_TR(4);
       for (int pc = 0; pc < n_pc; ++pc) {
         const int keys = min(64, NK - pc * 64);
         for (int t = 0; t < n_mt; ++t) {
@@ -197,10 +216,180 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
             if (pc == n_pc - 1) tc_commit(&bar_ofull[t]);
           }
           __syncwarp();
+          ATT_TR(5 + 2 * pc + t);
           ++g[t];
         }
       }
       for (int t = 0; t < n_mt; ++t) ++uses[t];
+    }
+  } else if constexpr (VER == 4) {
+    // ===================== softmax + epilogue, 16 warps: tile = (warp - 2) / 8, column half = ((warp - 2) / 4) & 1 ====
+    const int sw = warp - 2;
+    const int grp = sw >> 3, half = (sw >> 2) & 1;
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const uint32_t t_lane = tmem_base + (uint32_t(q * 32) << 16) + grp * TILE_COLS;
+    constexpr float SCALE_LOG2 = 0.125f * 1.4426950408889634f;
+    const int ldc = heads * HD;
+    const int r_tile = q * 32 + lane;  // row inside the 128-row tile
+    float* xmax = reinterpret_cast<float*>(smem + SMEM_XCHG) + (grp * 128 + r_tile) * 2;
+    float* xsum = xmax + 512;
+    const uint32_t pair_bar = 1 + grp * 4 + q;  // named barrier of the two warps that share these 32 rows
+    uint32_t uses = 0, G = 0, item_n = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item_n) {
+      uint8_t* sm = smem + (item_n & 1) * SET_BYTES;
+      uint8_t* p_row = sm + SMEM_Q + grp * QTILE_BYTES + r_tile * 128;
+      uint8_t* o_row = sm + SMEM_V + grp * QTILE_BYTES + r_tile * 128;
+      const uint8_t* stg = sm + SMEM_V + grp * QTILE_BYTES + q * 32 * 128;
+      const int seq = it / heads, h = it % heads;
+      const int start = cu_seqlens[seq];
+      const int len = cu_seqlens[seq + 1] - start;
+      const int n_mt = (len + 127) >> 7;
+      if (grp >= n_mt) continue;
+      const int shift = start & 7;
+      const int Lk = shift + len;
+      const int NK = (Lk + 15) & ~15;
+      const int n_pc = (NK + 63) >> 6;
+      mbar_wait(&bar_sfull[grp], uses & 1);
+      tc_fence_after();
+      const bool tr = (q == 0 && half == 0);  // one warp per tile stamps: slots 13.. (tile 0), 22.. (tile 1)
+      if (tr) ATT_TR(13 + 9 * grp);
+      float mb = 0.f, sum = 1.f;
+      if (grp * 128 + q * 32 >= len) {
+        // all 32 rows beyond the sequence (both warps of the pair take this branch): only the chunk hand-shake
+        for (int pc = 0; pc < n_pc; ++pc, ++G) {
+          mbar_wait(&bar_pfree[grp], (G & 1) ^ 1);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_pready[grp]);
+        }
+      } else {
+        // pass 1: maximum of this half's columns, then the row maximum through shared memory
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+        for (int pc = 0; pc < n_pc; ++pc) {
+          const int cb = pc * 64 + half * 32;
+          if (cb >= Lk) break;
+          uint32_t r[32];
+          tmem_ld_32x32(t_lane + cb, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int gi = 0; gi < 2; ++gi) {
+            const int c0 = cb + gi * 16;
+            if (c0 >= shift && c0 + 16 <= Lk) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                mx0 = max3(mx0, __uint_as_float(r[gi * 16 + j]), __uint_as_float(r[gi * 16 + j + 1]));
+                mx1 = max3(mx1, __uint_as_float(r[gi * 16 + j + 2]), __uint_as_float(r[gi * 16 + j + 3]));
+              }
+            } else if (c0 < Lk) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j >= shift && c0 + j < Lk) mx0 = fmaxf(mx0, __uint_as_float(r[gi * 16 + j]));
+            }
+          }
+        }
+        xmax[half] = fmaxf(mx0, mx1);
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        mb = fmaxf(xmax[0], xmax[1]) * SCALE_LOG2;
+        if (tr) ATT_TR(14 + 9 * grp);
+        // pass 2: this half's 32 columns of every 64-key chunk
+        const uint64_t scale2 = pack2(SCALE_LOG2, SCALE_LOG2), nmb2 = pack2(-mb, -mb);
+        uint64_t acc2 = pack2(0.f, 0.f);
+        sum = 0.f;
+        for (int pc = 0; pc < n_pc; ++pc, ++G) {
+          const int cb = pc * 64 + half * 32;
+          uint32_t pk[16];  // 32 fp16 values of this row; granules >= NK stay unwritten and unstored
+          if (cb < NK) {
+            uint32_t r[32];
+            tmem_ld_32x32(t_lane + cb, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int gi = 0; gi < 2; ++gi) {
+              const uint32_t* rr = r + gi * 16;
+              const int c0 = cb + gi * 16;
+              if (c0 >= shift && c0 + 16 <= Lk) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                  float a, b;
+                  const uint64_t x2 = fma2(pack2(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1])), scale2, nmb2);
+                  if (j == 2 || j == 8 || j == 12) {  // 3 of the 8 pairs: polynomial, off the XU pipe
+                    ex2_poly2(x2, a, b);
+                  } else {
+                    unpack2(x2, a, b);
+                    a = fast_ex2(a);
+                    b = fast_ex2(b);
+                  }
+                  acc2 = add2(acc2, pack2(a, b));
+                  pk[gi * 8 + (j >> 1)] = pack_f16x2(a, b);
+                }
+              } else if (c0 < NK) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                  float a = 0.f, b = 0.f;
+                  if (c0 + j >= shift && c0 + j < Lk) a = fast_ex2(fmaf(__uint_as_float(rr[j]), SCALE_LOG2, -mb));
+                  if (c0 + j + 1 >= shift && c0 + j + 1 < Lk)
+                    b = fast_ex2(fmaf(__uint_as_float(rr[j + 1]), SCALE_LOG2, -mb));
+                  sum += a + b;
+                  pk[gi * 8 + (j >> 1)] = pack_f16x2(a, b);
+                }
+              }
+            }
+          }
+          const int n_slots = min(64, NK - pc * 64) >> 3;  // 16-byte slots the P V MMAs of this chunk read
+          mbar_wait(&bar_pfree[grp], (G & 1) ^ 1);  // the previous chunk's MMAs have read the buffer
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {  // this half's slots 4 half .. 4 half + 3 (keys 8 slot .. 8 slot + 7)
+            const int j = 4 * half + jj;
+            if (j < n_slots)
+              *reinterpret_cast<uint4*>(p_row + ((j ^ (r_tile & 7)) << 4)) =
+                  make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_pready[grp]);
+          if (tr && pc < 4) ATT_TR(15 + 9 * grp + pc);
+        }
+        float s_lo, s_hi;
+        unpack2(acc2, s_lo, s_hi);
+        xsum[half] = sum + (s_lo + s_hi);
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        sum = xsum[0] + xsum[1];
+      }
+      const float inv = 1.0f / sum;
+      // epilogue: this half's 32 head dims of O / sum -> fp16 -> swizzled staging -> 64-byte row segments of ctx
+      mbar_wait(&bar_ofull[grp], uses & 1);
+      tc_fence_after();
+      if (tr) ATT_TR(19 + 9 * grp);
+      uint32_t o[32];
+      tmem_ld_32x32(t_lane + half * 32, o);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_otfree[grp]);
+      if (tr) ATT_TR(20 + 9 * grp);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = 4 * half + jj;  // 16-byte slot = head dims 8j .. 8j+7
+        const uint32_t* ov = o + 8 * jj;
+        *reinterpret_cast<uint4*>(o_row + ((j ^ (r_tile & 7)) << 4)) =
+            make_uint4(pack_f16x2(__uint_as_float(ov[0]) * inv, __uint_as_float(ov[1]) * inv),
+                       pack_f16x2(__uint_as_float(ov[2]) * inv, __uint_as_float(ov[3]) * inv),
+                       pack_f16x2(__uint_as_float(ov[4]) * inv, __uint_as_float(ov[5]) * inv),
+                       pack_f16x2(__uint_as_float(ov[6]) * inv, __uint_as_float(ov[7]) * inv));
+      }
+      __syncwarp();
+      const int row0 = grp * 128 + q * 32;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {  // 8 rows x 64 bytes per instruction
+        const int rr = 8 * i + (lane >> 2);
+        const int rt = q * 32 + rr;
+        const int j = 4 * half + (lane & 3);
+        const uint4 d = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((j ^ (rt & 7)) << 4));
+        if (row0 + rr < len)
+          *reinterpret_cast<uint4*>(ctx + (long long)(start + row0 + rr) * ldc + h * HD + j * 8) = d;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_ofree[grp]);
+      if (tr) ATT_TR(21 + 9 * grp);
+      ++uses;
     }
   } else {
     // ===================== softmax + epilogue: group 0 = warps 2..5 (tile 0), group 1 = warps 6..9 =====
@@ -411,6 +600,11 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
 
 }  // namespace
 
+static long long* g_att_trace = nullptr;  // debug hook: device buffer of 16 x 32 stamps (scripts/att_trace.py)
+extern "C" __attribute__((visibility("default"))) void mer_debug_attention_trace(long long* device_buffer) {
+  g_att_trace = device_buffer;
+}
+
 bool mer_attention_f16_supported(int max_seqlen) { return max_seqlen > 0 && max_seqlen <= 249; }
 
 // qkv16: fp16 [tokens, 3*heads*64] (V columns unused), vt16: fp16 [heads*64, vt_ld] with vt[d, token],
@@ -441,13 +635,15 @@ int mer_attention_f16_launch(const void* qkv16, const void* vt16, long long vt_l
   // MER_ATT_F16_VER=2 selects the granule softmax (see the kernel's header comment); read at every launch so that
   // a test can run both versions in one process.
   const char* ver_env = getenv("MER_ATT_F16_VER");
-  const int ver = ver_env ? atoi(ver_env) : 3;  // round-2 A/B on B200 (gpurun_out -> profiles/r2_ab_switches.json): 3 > 2 > 1
-  auto kern = ver == 3 ? attention_f16_kernel<3> : (ver == 2 ? attention_f16_kernel<2> : attention_f16_kernel<1>);
+  const int ver = ver_env ? atoi(ver_env) : 4;  // round-2 A/B on B200 (profiles/r2_ab_switches.json): 3 > 2 > 1; 4: 16 warps
+  auto kern = ver == 4 ? attention_f16_kernel<4>
+                       : (ver == 3 ? attention_f16_kernel<3> : (ver == 2 ? attention_f16_kernel<2> : attention_f16_kernel<1>));
   static MerPerDevice attr_set;
   if (attr_set.needs_setup()) {
     MER_CUDA_CHECK(cudaFuncSetAttribute(attention_f16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM));
     MER_CUDA_CHECK(cudaFuncSetAttribute(attention_f16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM));
     MER_CUDA_CHECK(cudaFuncSetAttribute(attention_f16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM));
+    MER_CUDA_CHECK(cudaFuncSetAttribute(attention_f16_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM));
     attr_set.mark();
   }
   const long long items = (long long)n_seq * heads;
@@ -456,7 +652,8 @@ int mer_attention_f16_launch(const void* qkv16, const void* vt16, long long vt_l
   if (items < grid) grid = (int)items;
   const double s_avg = (double)tokens / n_seq;  // exact for equal-length batches (ViT frames)
   const int prof = mer_prof_begin(MER_PROF_ATT_F16, 4.0 * s_avg * s_avg * HD * (double)items, stream);
-  kern<<<grid, F16_THREADS, F16_SMEM, stream>>>(tm, tv, static_cast<uint16_t*>(ctx16), cu_seqlens, n_seq, heads);
+  kern<<<grid, ver == 4 ? F16_THREADS_V4 : F16_THREADS, F16_SMEM, stream>>>(tm, tv, static_cast<uint16_t*>(ctx16), cu_seqlens, n_seq, heads,
+                                                                               g_att_trace);
   mer_prof_end(prof, stream);
   MER_CUDA_CHECK(cudaGetLastError());
   mer_count_launches(1);

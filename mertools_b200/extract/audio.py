@@ -46,7 +46,8 @@ def split_into_batch(input_values, maxlen=MAXLEN):
 
 
 class AudioExtractor:
-    def __init__(self, state_dict, device="cuda", max_rows_per_launch=128, ragged=None, max_samples_per_launch=128 * MAXLEN // 2):
+    def __init__(self, state_dict, device="cuda", max_rows_per_launch=128, ragged=None, max_samples_per_launch=128 * MAXLEN // 2,
+                 do_normalize=True):
         """ragged (default on; env MER_AUDIO_RAGGED=0 switches it off): clips of different lengths share one device pass
         (``HubertEncoder.forward_ragged``: every clip computed as if alone) instead of one pass per distinct
         length; sorted by length and cut into launches of at most ``max_samples_per_launch`` padded samples."""
@@ -63,6 +64,8 @@ class AudioExtractor:
         # of U(2 s, 10 s); results agree to 9e-6
         self.ragged = (os.environ.get("MER_AUDIO_RAGGED", "1") != "0") if ragged is None else bool(ragged)
         self.max_samples = max_samples_per_launch
+        # Wav2Vec2FeatureExtractor.do_normalize of the checkpoint (common.read_do_normalize): zero-mean / unit-variance or not
+        self.do_normalize = bool(do_normalize)
         self._norm = L.declare("mer_wave_normalize", [C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                                       C.c_longlong, C.c_longlong, C.c_void_p])
 
@@ -97,7 +100,8 @@ class AudioExtractor:
                 host = torch.zeros((len(idxs), max(lens)), dtype=torch.float32, pin_memory=True)
                 for r, i in enumerate(idxs):
                     host[r, :lens[r]] = torch.from_numpy(np.asarray(waves[i]).astype(np.float32))
-                utt, frames = self.enc.forward_ragged(host.to(self.device, non_blocking=True), lens, normalize=True,
+                utt, frames = self.enc.forward_ragged(host.to(self.device, non_blocking=True), lens,
+                                                      normalize=self.do_normalize,
                                                       want_frames=feature_level != "UTTERANCE")
                 for r, i in enumerate(idxs):
                     res[i] = (utt[r] if feature_level == "UTTERANCE" else frames[r]).cpu().numpy()
@@ -108,7 +112,7 @@ class AudioExtractor:
             host = torch.empty((len(idxs), n), dtype=torch.float32, pin_memory=True)
             for r, i in enumerate(idxs):
                 host[r] = torch.from_numpy(np.asarray(waves[i]).astype(np.float32))
-            fr = self._run_rows(host.to(self.device, non_blocking=True), normalize=True)
+            fr = self._run_rows(host.to(self.device, non_blocking=True), normalize=self.do_normalize)
             feats = fr.mean(dim=1).cpu().numpy() if feature_level == "UTTERANCE" else fr.cpu().numpy()
             for r, i in enumerate(idxs):
                 res[i] = feats[r]
@@ -117,9 +121,11 @@ class AudioExtractor:
             if res[i] is not None:
                 continue
             x = torch.from_numpy(np.asarray(w).astype(np.float32))[None].to(self.device)
-            xn = torch.empty_like(x)
-            L.check(self._norm(L.ptr(x), L.ptr(xn), 1, x.shape[1], x.shape[1], x.shape[1],
-                               L.stream_ptr()))
+            xn = x
+            if self.do_normalize:
+                xn = torch.empty_like(x)
+                L.check(self._norm(L.ptr(x), L.ptr(xn), 1, x.shape[1], x.shape[1], x.shape[1],
+                                   L.stream_ptr()))
             rows = split_into_batch(xn)
             fr = self._run_rows(rows.contiguous(), normalize=False).reshape(-1, self.enc.hidden)
             res[i] = (fr.mean(dim=0) if feature_level == "UTTERANCE" else fr).cpu().numpy()
@@ -134,8 +140,15 @@ def extract(model_name, audio_files, save_dir, feature_level, gpu, config=None, 
     import soundfile as sf
     if config is None:
         from .. import config as config  # noqa: PLW0127
+    from .. import shard
     start_time = time.time()
     assert gpu != -1, "mertools_b200 has no CPU path (reference: gpu=-1 means CPU)"
+    gpu = shard.device_index(gpu)
+    torch.cuda.set_device(gpu)
+    # one process per GPU under torchrun: this rank's share of the files that do not have their .npy yet
+    audio_files, rank, world = shard.my_work(audio_files, lambda f: os.path.join(save_dir, os.path.basename(f)[:-4] + ".npy"))
+    if world > 1:
+        print(f"rank {rank}/{world}: {len(audio_files)} audio files on cuda:{gpu}")
     model_file = os.path.join(config.PATH_TO_PRETRAINED_MODELS, f"transformers/{model_name}")
     if model_name in (WHISPER_BASE, WHISPER_LARGE):
         import json
@@ -146,7 +159,8 @@ def extract(model_name, audio_files, save_dir, feature_level, gpu, config=None, 
         sd = {k[len("model."):] if k.startswith("model.") else k: v for k, v in common.load_hf_state_dict(model_file).items()}
         ext = WhisperExtractor(sd, cfg["decoder_start_token_id"], device=f"cuda:{gpu}", heads=cfg["encoder_attention_heads"])
     else:
-        ext = AudioExtractor(common.load_hf_state_dict(model_file), device=f"cuda:{gpu}")
+        ext = AudioExtractor(common.load_hf_state_dict(model_file), device=f"cuda:{gpu}",
+                             do_normalize=common.read_do_normalize(model_file))
     for s in range(0, len(audio_files), clips_per_launch):
         chunk = audio_files[s:s + clips_per_launch]
         waves = []
@@ -162,7 +176,7 @@ def extract(model_name, audio_files, save_dir, feature_level, gpu, config=None, 
 def build_parser():
     parser = argparse.ArgumentParser(description="Run.")
     parser.add_argument("--gpu", type=int, default=0, help="index of gpu")
-    parser.add_argument("--model_name", type=str, default="chinese-hubert-base", help="feature extractor")
+    parser.add_argument("--model_name", type=str, default="chinese-hubert-large", help="feature extractor")  # :120
     parser.add_argument("--feature_level", type=str, default="FRAME", help="FRAME or UTTERANCE")
     parser.add_argument("--dataset", type=str, default="MER2023", help="input dataset")
     parser.add_argument("--noise_case", type=str, default=None)

@@ -106,6 +106,8 @@ def extract_embedding(model_name, trans_dir, save_dir, feature_level, gpu=-1, pu
     if model_dir is None:
         model_dir = os.path.join(config.PATH_TO_PRETRAINED_MODELS, f"transformers/{model_name}")
     assert gpu != -1, "mertools_b200 has no CPU path (reference: gpu=-1 means CPU)"
+    from .. import shard
+    gpu = shard.device_index(gpu)
     cfg = AutoConfig.from_pretrained(model_dir)
     assert cfg.model_type in ("bert", "roberta", "xlm-roberta"), \
         f"only BERT/RoBERTa-base encoders are on the B200 path, got {cfg.model_type}"
@@ -116,7 +118,12 @@ def extract_embedding(model_name, trans_dir, save_dir, feature_level, gpu=-1, pu
                         position_offset=(cfg.pad_token_id + 1) if roberta else 0)
     df = pd.read_csv(trans_dir)
     col = "chinese" if language == "chinese" else "english"
-    names, sents = list(df["name"]), list(df[col])
+    by_name = dict(zip(df["name"], df[col]))
+    # one process per GPU under torchrun: this rank's share of the rows that do not have their .npy yet
+    names, rank, world = shard.my_work(list(by_name), lambda n: os.path.join(save_dir, f"{n}.npy"))
+    sents = [by_name[n] for n in names]
+    if world > 1:
+        print(f"rank {rank}/{world}: {len(names)} sentences on cuda:{gpu}")
     for s in range(0, len(names), sentences_per_launch):
         files = [os.path.join(save_dir, f"{n}.npy") for n in names[s:s + sentences_per_launch]]
         ext.extract_sentences(sents[s:s + sentences_per_launch], feature_level, save_files=files)

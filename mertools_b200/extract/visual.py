@@ -201,6 +201,8 @@ def main(params, config=None, clips_per_launch=32):
     os.makedirs(save_dir, exist_ok=True)
     model_dir = os.path.join(config.PATH_TO_PRETRAINED_MODELS, f"transformers/{params.model_name}")
     assert params.gpu != -1, "mertools_b200 has no CPU path (reference: --gpu=-1 means CPU)"
+    from .. import shard
+    params.gpu = shard.device_index(params.gpu)
     torch.cuda.set_device(params.gpu)
     if params.model_name in (VIDEOMAE_BASE, VIDEOMAE_LARGE):                    # :147-159: 16 frames -> 8 tubelet rows
         from .videomae import VideoMaeExtractor
@@ -213,6 +215,10 @@ def main(params, config=None, clips_per_launch=32):
     nframe = 64 if params.model_name in (DINO2_LARGE, DINO2_GIANT) else None
     vids = os.listdir(face_dir)
     print(f'Find total "{len(vids)}" videos.')
+    # one process per GPU under torchrun: this rank's share of the videos that do not have their .npy yet
+    vids, rank, world = shard.my_work(vids, lambda vid: os.path.join(save_dir, f"{vid}.npy"))
+    if world > 1:
+        print(f"rank {rank}/{world}: {len(vids)} videos on cuda:{params.gpu}")
     for s in range(0, len(vids), clips_per_launch):
         chunk = vids[s:s + clips_per_launch]
         clips = [func_read_frames(face_dir, vid) for vid in chunk]

@@ -28,6 +28,27 @@ def shard_list(items, rank, world):
     return [items[i] for i in shard_indices(len(items), rank, world)]
 
 
+def device_index(gpu):
+    """The GPU a process drives: under torchrun (one process per GPU) LOCAL_RANK, otherwise the script's --gpu."""
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return int(os.environ.get("LOCAL_RANK", os.environ.get("RANK", "0")))
+    return gpu
+
+
+def my_work(items, out_path, resume=None):
+    """The extractor CLIs' work-list rule: sort for a rank-independent order, drop the items
+    whose output file already exists (resume after a restart, as MER2024 extract_sun_videomae.py:344 does; env
+    MER_RESUME=0 or resume=False recomputes everything), then this rank's round-robin share ``[rank::world]``.
+    ``out_path(item)`` -> the .npy the item produces.  Each rank writes only its own files: no collective."""
+    rank, world = env_rank_world()
+    if resume is None:
+        resume = os.environ.get("MER_RESUME", "1") != "0"
+    todo = sorted(items)
+    if resume:
+        todo = [it for it in todo if not os.path.exists(out_path(it))]
+    return shard_list(todo, rank, world), rank, world
+
+
 def batch_slice(global_batch, rank, world):
     """Contiguous slice [lo, hi) of a global batch owned by `rank` (sizes differ by at most 1);
     the reference's sampler permutation is kept, each rank takes its contiguous part."""

@@ -65,7 +65,7 @@ def _run(env, ver, qkv, vt, cu, lens):
             os.environ[env] = old
 
 
-@pytest.mark.parametrize("ver", [1, 2, 3])
+@pytest.mark.parametrize("ver", [1, 2, 3, 4])
 def test_attention_f16_kernel_vs_float64(cuda, ver):
     qkv, vt, cu, ref = _operands(LENS_F16, torch.float16, cuda, 8)
     out = _run("MER_ATT_F16_VER", ver, qkv, vt, cu, LENS_F16)
@@ -92,6 +92,8 @@ def test_attention_softmax_versions_agree(cuda):
     assert float((a - b).abs().max() / ref.abs().max()) < 1.5e-3
     c = _run("MER_ATT_F16_VER", 3, qkv, vt, cu, LENS_F16)  # 3 of 8 exponentials by the 2.7e-6 polynomial
     assert float((a - c).abs().max() / ref.abs().max()) < 1.5e-3
+    d = _run("MER_ATT_F16_VER", 4, qkv, vt, cu, LENS_F16)  # 16 softmax warps: VER 3's arithmetic, other sum order
+    assert float((c - d).abs().max() / ref.abs().max()) < 1.5e-3
     qkv, vt, cu, ref = _operands(LENS_TC, torch.float32, cuda, 4)
     a = _run("MER_ATT_TC_VER", 1, qkv, vt, cu, LENS_TC)
     b = _run("MER_ATT_TC_VER", 2, qkv, vt, cu, LENS_TC)
