@@ -133,7 +133,9 @@ MER_API int mer_split_bf16(const float* in, void* out, long long rows, int K, vo
 /* ---- row-wise kernels ------------------------------------------------------------------ */
 enum { MER_LN_ROUND_TF32 = 1, MER_LN_ACC_INIT = 2, MER_LN_ACC_ADD = 4,
        MER_LN_OUT_F16 = 8, /* y is an fp16 array (the MER_GEMM_F16 operand) */
-       MER_LN_GELU = 16    /* GELU(erf) after the affine (HubertLayerNormConvLayer) */ };
+       MER_LN_GELU = 16,   /* GELU(erf) after the affine (HubertLayerNormConvLayer) */
+       MER_LN_SPLIT_F16 = 32 /* y_split is an fp16 array (the MER_GEMM_F16 operand) written NEXT TO the fp32 y:
+                                the post-LN stacks keep y as their residual stream */ };
 /* y = LayerNorm(x) * gamma + beta over the last dim (512, 768, 1024, 1280 or 1536).  y (fp32, tf32-rounded when
  * MER_LN_ROUND_TF32) and y_split (bf16 hi|lo rows, the BF16X3 GEMM operand) are both optional;
  * at least one must be given.  Optional side buffer acc
@@ -524,6 +526,9 @@ typedef struct MerBertModel {
   int hidden;               /* 0 = 768; 768 or 1024 (embedding tables are then [*, hidden]) */
   int ffn;                  /* 0 = 3072 */
   int heads;                /* 0 = 12; hidden / 64 */
+  /* optional: the same layers with fp16 GEMM weights -> the 12 layers run on fp16 operands (one MMA per product
+   * instead of three; readout error 2.9e-4 instead of 3.5e-5, profiles/r2_precision_table.json).  NULL: BF16X3. */
+  const MerLayerWeights* layers_f16;
 } MerBertModel;
 
 MER_API long long mer_bert_workspace_bytes(int tokens, int n_seq); /* base models */

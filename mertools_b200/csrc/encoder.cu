@@ -62,7 +62,6 @@ int linear(int mode, const float* A, const float* W, const float* bias, const fl
 
 int mer_run_stack(const MerStackArgs& a, cudaStream_t stream) {
   MER_REQUIRE(a.tokens > 0 && a.tokens < (1ll << 31), "mer_run_stack: bad token count %lld", a.tokens);
-  MER_REQUIRE(a.mode != MER_GEMM_F16 || a.pre_ln, "mer_run_stack: the F16 mode is for the pre-LN stack");
   const long long M = a.tokens;
   // model dims (the file-level constants are the base-model defaults)
   const int D = a.dim > 0 ? a.dim : ::D;
@@ -123,6 +122,40 @@ int mer_run_stack(const MerStackArgs& a, cudaStream_t stream) {
                                    nullptr, M, D, a.eps, MER_LN_ROUND_TF32, stream));
       MER_TRY(linear(a.mode, a.xn, w.w_fc1, w.b_fc1, nullptr, a.h, M, DFF, D, ACT | opnd, stream));
       MER_TRY(linear(a.mode, a.h, w.w_fc2, w.b_fc2, a.x, a.x, M, D, DFF, 0, stream));
+    } else if (a.mode == MER_GEMM_F16) {
+      // post-LN on fp16 operands (round 2; profiles/r2_precision_table.json): x stays the exact fp32 LayerNorm output
+      // (residual stream, hidden state), xs carries its fp16 copy (GEMM operand, written by the same LayerNorm
+      // pass); ctx and the FC1 output are fp16; the pre-LN sums are fp32.
+      float* x16 = a.xs;
+      float* c16 = a.xn;   // fp16 ctx; later the fp32 pre-LN sum of the FFN half
+      float* h16 = a.h;
+      const bool f16_att = vt != nullptr && mer_attention_f16_supported(a.max_seqlen);
+      if (f16_att) {
+        MER_TRY(linear(a.mode, x16, w.w_qkv, w.b_qkv, nullptr, a.qkv, M, DQKV, D, MER_EPI_OUT_F16, stream, vt,
+                       a.vt_ld, 2 * D));
+        MER_TRY(mer_attention_launch(a.qkv, vt, a.vt_ld, c16, a.cu_seqlens, a.n_seq, M, a.max_seqlen, HEADS,
+                                     MER_EPI_OUT_F16 | MER_ATT_QKV_F16, stream));
+        MER_TRY(linear(a.mode, c16, w.w_o, w.b_o, a.x, a.qkv, M, D, D, 0, stream));  // qkv is dead: holds the sum
+      } else {
+        // rows beyond the fp16 attention kernel (> 249 frames): TF32-rounded fp32 q | k | v (same 10-bit mantissa)
+        // through the fp32-operand attention kernels, fp32 context cast to the fp16 out-proj operand
+        MER_TRY(linear(a.mode, x16, w.w_qkv, w.b_qkv, nullptr, a.qkv, M, DQKV, D, MER_EPI_ROUND_TF32, stream, vt,
+                       a.vt_ld, 2 * D));
+        MER_TRY(mer_attention_launch(a.qkv, vt, a.vt_ld, a.xn, a.cu_seqlens, a.n_seq, M, a.max_seqlen, HEADS, 0,
+                                     stream));
+        MER_TRY(mer_cast_f16_launch(a.xn, h16, M * D, stream));
+        MER_TRY(linear(a.mode, h16, w.w_o, w.b_o, a.x, a.qkv, M, D, D, 0, stream));
+      }
+      MER_TRY(mer_layernorm_launch(a.qkv, w.ln1_g, w.ln1_b, a.x, x16, nullptr, M, D, a.eps, MER_LN_SPLIT_F16, stream));
+      MER_TRY(linear(a.mode, x16, w.w_fc1, w.b_fc1, nullptr, h16, M, DFF, D, MER_EPI_GELU | MER_EPI_OUT_F16, stream));
+      MER_TRY(linear(a.mode, h16, w.w_fc2, w.b_fc2, a.x, a.xn, M, D, DFF, 0, stream));
+      int fl = MER_LN_SPLIT_F16;
+      float* acc = nullptr;
+      if (a.acc && a.acc_last > 0 && l + 1 > first_acc) {
+        acc = a.acc;
+        fl |= (l + 1 == first_acc + 1) ? MER_LN_ACC_INIT : MER_LN_ACC_ADD;
+      }
+      MER_TRY(mer_layernorm_launch(a.xn, w.ln2_g, w.ln2_b, a.x, x16, acc, M, D, a.eps, fl, stream));
     } else {
       // x = LN1(x + Wo * Attn(x));  x = LN2(x + W2 * GELU(W1 * x)).
       // TF32: x itself is tf32-rounded and doubles as the GEMM operand.  BF16X3: x stays exact fp32
@@ -693,12 +726,16 @@ static int hubert_forward_impl(const MerHubertModel* m, const float* wave, int B
   const size_t hs_bytes = (size_t)M * D * 4;
   if (!m->stable_layer_norm) {
     // encoder.layer_norm -> x ; post-LN layers; readout = sum of the last four LayerNorm outputs
-    MER_TRY(mer_layernorm_launch(xn, m->enc_ln_g, m->enc_ln_b, x, xs, nullptr, M, D, m->ln_eps, 0, stream));
+    // layers_f16 given: the 12 layers run on fp16 operands (the conv feature encoder above stays BF16X3: it has no
+    // normalisation between its layers and is where the operand precision matters, profiles/r2_precision_table.json)
+    const bool f16 = m->layers_f16 != nullptr;
+    MER_TRY(mer_layernorm_launch(xn, m->enc_ln_g, m->enc_ln_b, x, xs, nullptr, M, D, m->ln_eps,
+                                 f16 ? MER_LN_SPLIT_F16 : 0, stream));
     if (opt_hidden) MER_CUDA_CHECK(cudaMemcpyAsync(opt_hidden, x, hs_bytes, cudaMemcpyDeviceToDevice, stream));
-    a.layers = m->layers;
+    a.layers = f16 ? m->layers_f16 : m->layers;
     a.n_layers = m->n_layers;
     a.pre_ln = 0;
-    a.mode = MER_GEMM_BF16X3;
+    a.mode = f16 ? MER_GEMM_F16 : MER_GEMM_BF16X3;
     a.acc = acc;
     a.acc_last = 4;
     a.opt_hidden = opt_hidden;
@@ -769,7 +806,7 @@ int mer_hubert_forward_ragged(const MerHubertModel* m, const float* wave, const 
 // BERT / RoBERTa
 // ------------------------------------------------------------------------------------------------
 static long long bert_ws(long long M, int D, int DFF) {
-  return (M * (D + D + D + 3ll * D + DFF + D) + (long long)D * ((M + 3) & ~3ll)) * 4 + 4096;
+  return (M * (D + D + D + 3ll * D + DFF + D) + (long long)D * ((M + 7) & ~7ll)) * 4 + 4096;
 }
 static int bert_dim(const MerBertModel* m) { return m->hidden > 0 ? m->hidden : ::D; }
 static int bert_ffn(const MerBertModel* m) { return m->ffn > 0 ? m->ffn : ::DFF; }
@@ -814,13 +851,15 @@ int mer_bert_forward(const MerBertModel* m, const int32_t* ids, const int32_t* p
     MER_CUDA_CHECK(cudaMemcpyAsync(opt_hidden, x, (size_t)M * D * 4, cudaMemcpyDeviceToDevice, stream));
   MerStackArgs a;
   memset(&a, 0, sizeof(a));
-  a.layers = m->layers;
+  const bool f16 = m->layers_f16 != nullptr;
+  if (f16) MER_TRY(mer_cast_f16_launch(x, xs, M * D, stream));  // the embedding LayerNorm's fp16 copy (operand)
+  a.layers = f16 ? m->layers_f16 : m->layers;
   a.n_layers = m->n_layers;
   a.pre_ln = 0;
   a.dim = D;
   a.ffn = DFF;
   a.heads = HEADS;
-  a.mode = MER_GEMM_BF16X3;
+  a.mode = f16 ? MER_GEMM_F16 : MER_GEMM_BF16X3;
   a.eps = m->ln_eps;
   a.tokens = M;
   a.cu_seqlens = cu_seqlens;
@@ -834,7 +873,7 @@ int mer_bert_forward(const MerBertModel* m, const int32_t* ids, const int32_t* p
   a.acc = acc;
   a.acc_last = 4;
   a.vt = vt;
-  a.vt_ld = (M + 3) & ~3ll;
+  a.vt_ld = (M + 7) & ~7ll;  // fp32 or fp16 V^T rows start on 16-byte boundaries
   a.opt_hidden = opt_hidden;
   a.hidden0_done = 1;
   MER_TRY(mer_run_stack(a, stream));

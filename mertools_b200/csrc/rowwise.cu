@@ -51,7 +51,9 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
     const bool y16 = (flags & MER_LN_OUT_F16) != 0;  // y is an fp16 row (the F16 GEMM operand)
     float4* yr = (y && !y16) ? reinterpret_cast<float4*>(y + row * DIM) : nullptr;
     uint2* yh = (y && y16) ? reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(y) + row * DIM) : nullptr;
-    float* ysr = ys ? reinterpret_cast<float*>(ys) + row * DIM : nullptr;  // split row: DIM 4-byte slots
+    const bool ys16 = (flags & MER_LN_SPLIT_F16) != 0;  // the second output is an fp16 row instead of a bf16 split row
+    float* ysr = (ys && !ys16) ? reinterpret_cast<float*>(ys) + row * DIM : nullptr;  // split row: DIM 4-byte slots
+    uint2* ysh = (ys && ys16) ? reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(ys) + row * DIM) : nullptr;
     float4* ar = acc ? reinterpret_cast<float4*>(acc + row * DIM) : nullptr;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
@@ -73,6 +75,7 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
         }
       }
       if (ysr) store_split4(ysr, 4 * (lane + 32 * i), o);
+      if (ysh) ysh[lane + 32 * i] = make_uint2(pack_f16x2(o.x, o.y), pack_f16x2(o.z, o.w));
       if (yh) yh[lane + 32 * i] = make_uint2(pack_f16x2(o.x, o.y), pack_f16x2(o.z, o.w));
       if (yr) {
         if (flags & MER_LN_ROUND_TF32) {

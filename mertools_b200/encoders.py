@@ -1094,12 +1094,20 @@ class HubertEncoder:
         m.enc_ln_b = pk.keep(sd["encoder.layer_norm.bias"]).data_ptr()
         self.layers = W.pack_layers(sd, W.HUBERT_NAMES, self.n_layers, pk, split=True)
         m.layers = self.layers
-        # opt-in for the large (pre-LN) family: a second, fp16 copy of the layer weights; clips of <= 249 frames
-        # (5 s) then run the stack on fp16 operands like the ViT, longer ones keep BF16X3
+        # Operand format of the transformer layers (the conv feature encoder always runs BF16X3):
+        #  * post-LN base family (HuBERT-base, wav2vec2-base, data2vec-audio): "f16" by default since round 2 -- one
+        #    MMA per product instead of three; emulated readout error at 12 layers 3.3e-4 against 4e-5
+        #    (profiles/r2_precision_table.json), measured in tests/test_bench_config_gpu.py; MER_AUDIO_PRECISION=bf16x3
+        #    (or stack_precision="bf16x3") keeps the split operands.
+        #  * large (pre-LN) family: BF16X3 by default, "f16" opt-in (MER_HUBERT_LARGE_PRECISION=f16; clips of <= 249
+        #    frames then run the stack on fp16 operands like the ViT, longer ones keep BF16X3).
         import os as _os
-        self.stack_precision = stack_precision or _os.environ.get("MER_HUBERT_LARGE_PRECISION", "bf16x3")
+        if m.stable_layer_norm:
+            self.stack_precision = stack_precision or _os.environ.get("MER_HUBERT_LARGE_PRECISION", "bf16x3")
+        else:
+            self.stack_precision = stack_precision or _os.environ.get("MER_AUDIO_PRECISION", "f16")
         assert self.stack_precision in ("bf16x3", "f16"), self.stack_precision
-        if self.stack_precision == "f16" and m.stable_layer_norm:
+        if self.stack_precision == "f16":
             self.layers_f16 = W.pack_layers(sd, W.HUBERT_NAMES, self.n_layers, pk, f16=True)
             m.layers_f16 = self.layers_f16
         self.model = m
@@ -1164,7 +1172,8 @@ class MerBertModel(C.Structure):
     _fields_ = [("n_layers", C.c_int), ("ln_eps", C.c_float), ("word_emb", C.c_void_p),
                 ("pos_emb", C.c_void_p), ("type_emb0", C.c_void_p), ("emb_ln_g", C.c_void_p),
                 ("emb_ln_b", C.c_void_p), ("layers", C.POINTER(W.MerLayerWeights)),
-                ("hidden", C.c_int), ("ffn", C.c_int), ("heads", C.c_int)]
+                ("hidden", C.c_int), ("ffn", C.c_int), ("heads", C.c_int),
+                ("layers_f16", C.POINTER(W.MerLayerWeights))]
 
 
 class BertEncoder:
@@ -1174,7 +1183,11 @@ class BertEncoder:
 
     Reference: MERBench/feature_extraction/text/extract_text_huggingface.py:222-249."""
 
-    def __init__(self, state_dict, device="cuda", ln_eps=1e-12, position_offset=0):
+    def __init__(self, state_dict, device="cuda", ln_eps=1e-12, position_offset=0, precision=None):
+        """precision: operand format of the layers' linear products.  "f16" (default for the 12-layer base models since
+        round 2; env MER_TEXT_PRECISION): one fp16 MMA per product, readout error 2.9e-4 at 12 layers; "bf16x3"
+        (default for the 24-layer -large models): three bf16 MMAs on (hi, lo) pairs, 3.5e-5
+        (profiles/r2_precision_table.json)."""
         L.check(L.lib().mer_check_device())
         sd = W._np(state_dict)
         self.device = torch.device(device)
@@ -1199,6 +1212,12 @@ class BertEncoder:
         m.emb_ln_b = pk.keep(sd["embeddings.LayerNorm.bias"]).data_ptr()
         self.layers = W.pack_layers(sd, W.BERT_NAMES, self.n_layers, pk, split=True)
         m.layers = self.layers
+        import os as _os
+        self.precision = precision or _os.environ.get("MER_TEXT_PRECISION", "f16" if self.hidden == 768 else "bf16x3")
+        assert self.precision in ("bf16x3", "f16"), self.precision
+        if self.precision == "f16":
+            self.layers_f16 = W.pack_layers(sd, W.BERT_NAMES, self.n_layers, pk, f16=True)
+            m.layers_f16 = self.layers_f16
         self.model = m
         self.ws = _Workspace(self.device)
         lib = L.lib()

@@ -19,12 +19,16 @@ def rel(got, ref):
     return float((got - ref).abs().max() / ref.abs().max()), float((got - ref).norm() / ref.norm())
 
 
-@pytest.mark.parametrize("layers,n_samples,batch", [(4, 16000, 3), (12, 80000, 2), (4, 5000, 1)])
-def test_hubert_hidden_states_and_readout(cuda, layers, n_samples, batch):
+@pytest.mark.parametrize("precision", ["f16", "bf16x3"])
+@pytest.mark.parametrize("layers,n_samples,batch", [(4, 16000, 3), (12, 80000, 2), (4, 5000, 1), (4, 96000, 2)])
+def test_hubert_hidden_states_and_readout(cuda, layers, n_samples, batch, precision):
+    """Both operand formats of the 12 layers: fp16 (default; 96,000 samples = 299 frames takes the fp32-operand
+    attention between fp16 GEMMs) and the bf16 (hi, lo) split."""
     from mertools_b200.encoders import HubertEncoder
     sd = S.hubert_state_dict(seed=1, layers=layers)
     wav = (S.synth_waves(batch, n_samples, seed=21).astype(np.float64) / 32768.0).astype(np.float32)
-    enc = HubertEncoder(sd, device=cuda)
+    enc = HubertEncoder(sd, device=cuda, stack_precision=precision)
+    assert enc.stack_precision == precision and HubertEncoder(sd, device=cuda).stack_precision == "f16"
     utt, frames, hidden = enc.forward(torch.from_numpy(wav).to(cuda), normalize=True,
                                       want_frames=True, return_hidden=True)
     torch.cuda.synchronize()
@@ -38,6 +42,7 @@ def test_hubert_hidden_states_and_readout(cuda, layers, n_samples, batch):
     m, l2 = rel(frames.cpu(), ref_sum)
     assert m < 2 * TOL and l2 < TOL, f"frame readout: max-rel {m:.2e} l2-rel {l2:.2e}"
     m, l2 = rel(utt.cpu(), ref_sum.mean(dim=1))
+    print(f"HuBERT-base {precision} {layers} layers: utterance readout max-rel {m:.2e}")
     assert m < TOL and l2 < TOL, f"utterance readout: max-rel {m:.2e} l2-rel {l2:.2e}"
 
 
@@ -88,10 +93,11 @@ def test_audio_extractor_matches_oracle_pipeline(cuda):
         assert np.abs(g - ref).max() / np.abs(ref).max() < 2 * TOL
 
 
+@pytest.mark.parametrize("precision", ["f16", "bf16x3"])
 @pytest.mark.parametrize("roberta", [False, True])
-def test_bert_hidden_states_and_readout(cuda, roberta):
+def test_bert_hidden_states_and_readout(cuda, roberta, precision):
     from mertools_b200.encoders import BertEncoder
-    layers, vocab = 4, 400
+    layers, vocab = (12 if precision == "f16" else 4), 400
     if roberta:
         sd = S.bert_state_dict(vocab, seed=2, layers=layers, max_pos=514, type_vocab=1)
         kw = dict(ln_eps=1e-5, position_offset=2)
@@ -100,7 +106,7 @@ def test_bert_hidden_states_and_readout(cuda, roberta):
         kw = dict(ln_eps=1e-12, position_offset=0)
     rng = np.random.default_rng(5)
     sents = [rng.integers(0, vocab, n).tolist() for n in (3, 9, 64, 65, 17, 130, 5)]
-    enc = BertEncoder(sd, device=cuda, **kw)
+    enc = BertEncoder(sd, device=cuda, precision=precision, **kw)
     utt, toks, hidden, cu = enc.forward(sents, start=1, end=-1, want_tokens=True, return_hidden=True)
     torch.cuda.synchronize()
     for i, s in enumerate(sents):
