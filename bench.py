@@ -96,6 +96,7 @@ def build_models(device):
     from mertools_b200.fusion import FusionNet
     vit = VitEncoder(S.vit_state_dict(seed=0), device=device)
     hub = HubertEncoder(S.hubert_state_dict(seed=1), device=device)
+    hub._bench_sd = S.hubert_state_dict(seed=1)
     bert = BertEncoder(S.bert_state_dict(VOCAB, seed=2), device=device)
     fus = FusionNet(dropout=0.3, device=device, seed=7).load_state_dict(S.fusion_state_dict(seed=3))
     return vit, hub, bert, fus
@@ -116,6 +117,40 @@ def device_step(models, dev_in, clips, world):
 def _log(msg):
     if os.environ.get("MER_BENCH_VERBOSE"):
         print(f"[bench rank {os.environ.get('RANK', '0')} {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
+def fusion_latency(device):
+    """the fusion step is latency-bound -> microseconds per step on CUDA-graph replay, B = 32 / 256."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from bench_fusion_step import fusion_step_us
+    out = {}
+    for B in (32, 256):
+        r = fusion_step_us(B, iters=200, device=str(device))
+        out[f"B{B}"] = {"graph_replay_us": r["graph_replay_us"], "clips_per_s": r["clips_per_s"],
+                        "kernels_per_step": r["kernels_per_step"]}
+    out["what"] = ("one Attention-fusion training step (forward + CE/MSE + backward + Adam; hidden 128, dropout 0.3) as a "
+                   "CUDA-graph replay of fus_rows_kernel + fus_wgrad_kernel, CUDA events over 200 replays")
+    return out
+
+
+def mixed_length_audio(hub_sd, device, clips=256, seed=5):
+    """The workload users see (reference loop extract_audio_huggingface.py:72-110: a different length per file):
+    `clips` waveforms of U(2 s, 10 s) from host memory through AudioExtractor (ragged batches, H2D inside)."""
+    from mertools_b200.extract.audio import AudioExtractor
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(2 * 16000, 10 * 16000 + 1, clips)
+    waves = [(rng.standard_normal(int(n)) * (3000.0 / 32768.0)) for n in lens]
+    ext = AudioExtractor(hub_sd, device=device)
+    ext.extract_waves(waves[:32])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ext.extract_waves(waves)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"workload": f"{clips} waveforms of U(2 s, 10 s) (mean {lens.mean() / 16000:.2f} s), host numpy in, UTTERANCE features "
+                        "out, ragged batches (AudioExtractor default); HuBERT-base only",
+            "clips_per_s": clips / dt, "audio_seconds_per_s": float(lens.sum()) / 16000 / dt,
+            "frames_over_249": int((lens > 80079).sum())}
 
 
 def run_ours(args):
@@ -200,6 +235,40 @@ def run_ours(args):
     e2e_ms = float(tmax.item())
     h2d = sum(x.numel() * x.element_size() for x in host_in) + 3 * clips * 768 * 4
     d2h = 3 * clips * 768 * 4 + 4
+    if world > 1:  # data-parallel replicas must agree: the all-reduced loss and the parameters are identical on every rank
+        sig = torch.stack([loss[2].double(), fus.params.double().sum()])
+        lo, hi = sig.clone(), sig.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert torch.equal(lo, hi), f"ranks disagree on the fusion loss / parameters: {lo.tolist()} vs {hi.tolist()}"
+    extras = {}
+    if rank == 0 and not args.no_extras:
+        try:
+            extras["fusion_step_us"] = fusion_latency(device)
+            extras["mixed_length_audio"] = mixed_length_audio(hub._bench_sd, device)
+            # the same step with the ViT linears on TF32 operands (MER_VIT_PRECISION=tf32), same inputs
+            from mertools_b200 import synthetic as S2
+            from mertools_b200.encoders import VitEncoder
+            vit32 = VitEncoder(S2.vit_state_dict(seed=0), device=device, precision="tf32")
+            m32 = (vit32, hub, bert, fus)
+            for _ in range(2):
+                device_step(m32, dev_in, clips, 1)
+            torch.cuda.synchronize()
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            e[0].record()
+            for _ in range(max(2, args.steps // 2)):
+                device_step(m32, dev_in, clips, 1)
+            e[1].record()
+            torch.cuda.synchronize()
+            ms32 = e[0].elapsed_time(e[1]) / max(2, args.steps // 2)
+            extras["tf32_vit"] = {"value": clips / (ms32 * 1e-3), "unit": "clips/s (this GPU alone)", "ms_per_step": ms32,
+                                  "what": "the device-resident step with VitEncoder(precision='tf32'): ViT linears on TF32 "
+                                          "operands at half the fp16 tensor rate; audio / text / fusion unchanged"}
+            del vit32
+        except Exception as ex:  # noqa: BLE001 -- the headline line must not depend on the side measurements
+            extras["error"] = repr(ex)
+    if world > 1:
+        dist.barrier()
 
     if rank == 0:
         pk = peaks()
@@ -228,7 +297,7 @@ def run_ours(args):
                     "launches_timed": k_n, "share_of_step": k_ms / ms_dev if ms_dev else None}
         sus = pk["bf16_sustained"]
         other = [e for e in (
-            entry("bf16x3", "gemm_kernel<*, BF16X3> (3 bf16 MMAs per product; HuBERT/BERT linears + conv1-6)", "tensor",
+            entry("bf16x3", "gemm_kernel<*, BF16X3> (3 bf16 MMAs per product; HuBERT conv1-6 + feature projection)", "tensor",
                   sus / 3.0, "TFLOP/s (useful)", 1e12),
             entry("att_f16", "attention_f16_kernel (tcgen05 kind::f16; ViT, 197 tokens)", "tensor", sus, "TFLOP/s", 1e12),
             entry("att_tc", "attention_tc_kernel (tcgen05 kind::tf32; HuBERT 249 tokens, BERT)", "tensor", sus / 2.0,
@@ -245,8 +314,9 @@ def run_ours(args):
             "metric": METRIC, "value": total_clips / (ms_dev * 1e-3), "unit": "clips/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": ("f16 operands (ViT linears) / tf32 (attention, patch embed)" if use_f16 else "tf32 (ViT)") +
-                                          " / bf16x3 (HuBERT, BERT) tensor-core products, fp32 accumulate; fp32 elsewhere",
+            "vs_baseline": None, "dtype": ("f16 operands (ViT / HuBERT / BERT layers, ViT attention) / tf32 (audio + text "
+                                          "attention, patch embed)" if use_f16 else "tf32 (ViT)") +
+                                          " / bf16x3 (HuBERT conv stack) tensor-core products, fp32 accumulate; fp32 elsewhere",
             "data": "synthetic inputs, seeded random-init weights (no network)",
             "config": {"workload": f"tri-modal extract (ViT-B/16 {FRAMES}x224x224 frames + HuBERT-base 5 s @16 kHz + "
                                    f"BERT-base {TOKENS} tokens) + Attention-fusion train step (hidden 128, dropout 0.3), "
@@ -258,7 +328,8 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"kernel": ("gemm_kernel<256, F16, CTA pair, cta_group::2> (tcgen05 kind::f16; ViT linear layers)"
+            "roofline": {"kernel": ("gemm_kernel<256, F16, CTA pair, cta_group::2> (tcgen05 kind::f16; linear layers of the "
+                                    "ViT, HuBERT and BERT stacks + HuBERT positional conv)"
                                     if use_f16 else
                                     "gemm_kernel<256, TF32, CTA pair, cta_group::2> (tcgen05 kind::tf32; ViT linear layers)"),
                          "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
@@ -271,7 +342,10 @@ def run_ours(args):
                                          f"the bf16 rate); burst / 2 = {burst_peak:.1f}")},
             "roofline_other": other,
         }
+        line.update(extras)
         line["cpu_baseline"] = cpu_baseline(sample_clips=args.cpu_clips)
+        if not args.no_extras:
+            line["cpu_baseline"]["whole_host"] = cpu_whole_host(line["cpu_baseline"]["cores"])
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -355,31 +429,73 @@ def cpu_baseline(sample_clips=48):
                       f"calibration over 8..{os.cpu_count()} on this {os.cpu_count()}-core host), {sec:.1f} s"}
 
 
+def cpu_whole_host(threads_per_proc, clips_per_proc=2):
+    """The whole host, not one process: P = cores // threads independent processes of the reference port, each on
+    `threads_per_proc` torch threads, started together; value = total clips / wall time of the slowest."""
+    ncpu = os.cpu_count() or 1
+    procs = max(1, min(16, ncpu // max(1, threads_per_proc)))
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-worker", str(clips_per_proc), "--cpu-threads", str(threads_per_proc)]
+    try:
+        t0 = time.perf_counter()
+        ps = [subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for _ in range(procs)]
+        secs = [float(p.communicate(timeout=600)[0].strip().splitlines()[-1]) for p in ps]
+        wall = time.perf_counter() - t0
+        return {"value": procs * clips_per_proc / max(secs), "unit": "clips/s", "processes": procs,
+                "threads_per_process": threads_per_proc, "cores_used": procs * threads_per_proc, "host_cores": ncpu,
+                "sample": f"{procs} processes x {clips_per_proc} clips, slowest {max(secs):.1f} s (wall incl. start-up {wall:.0f} s)"}
+    except Exception as ex:  # noqa: BLE001
+        return {"value": None, "error": repr(ex)}
+
+
+def cpu_worker(n_clips, threads, steps=1):
+    _CPU_STATE["threads"] = threads
+    torch.set_num_threads(threads)
+    from mertools_b200 import synthetic as S
+    to_t = lambda sd: {k: torch.from_numpy(v) for k, v in sd.items()}  # noqa: E731
+    _CPU_STATE.update(vit=to_t(S.vit_state_dict(seed=0)), hub=to_t(S.hubert_state_dict(seed=1)),
+                      bert=to_t(S.bert_state_dict(VOCAB, seed=2)), fus=S.fusion_state_dict(seed=3))
+    cpu_step(1)
+    for k in range(steps):
+        print(cpu_step(n_clips, seed=k), flush=True)
+
+
 def run_reference(args):
+    """The reference's CPU implementation of the path on ALL the host cores: P = cores // T processes of the oracle
+    port (T = the calibrated torch thread count at which one process is fastest), every process running the same
+    bounded K-step sample; a step's time is the slowest process's, value = P * n * K / sum of step times."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     _cpu_setup()
+    threads = _CPU_STATE["threads"]
     cpu_step(1)
     sec1 = cpu_step(1)
-    for _ in range(max(0, args.warmup - 2)):
-        cpu_step(1)
-    # bounded sample: keep the whole K-step run within a few minutes
-    n = int(max(1, min(args.cpu_clips, 120.0 / max(args.steps, 1) / max(sec1, 1e-3))))
-    secs = [cpu_step(n, seed=i) for i in range(args.steps)]
+    ncpu = os.cpu_count() or 1
+    procs = max(1, min(16, ncpu // max(1, threads)))
+    # bounded sample: keep the whole K-step run within a few minutes (contended processes run ~1.5x slower)
+    n = int(max(1, min(args.cpu_clips, 90.0 / max(args.steps, 1) / max(sec1, 1e-3))))
+    warm = max(1, args.warmup - 2)
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-worker", str(n), "--cpu-threads", str(threads),
+           "--cpu-steps", str(warm + args.steps)]
+    ps = [subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for _ in range(procs)]
+    per_proc = []
+    for p_ in ps:
+        lines = p_.communicate(timeout=3000)[0].strip().splitlines()
+        per_proc.append([float(x) for x in lines[-(warm + args.steps):]][warm:])
+    secs = [max(t[k] for t in per_proc) for k in range(args.steps)]
     total = sum(secs)
-    value = n * args.steps / total
+    value = procs * n * args.steps / total
+    sample = (f"{procs} processes x {threads} torch threads = {procs * threads} of {ncpu} host cores; {n} clips per process "
+              f"and step x {args.steps} steps; oracle port of the reference path (pure-Python reference; /root/reference is "
+              f"absent on the GPU box); one process alone: {1.0 / sec1:.2f} clips/s")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32 (torch CPU)",
         "data": "synthetic inputs, seeded random-init weights (no network)",
         "config": {"workload": f"tri-modal extract (ViT-B/16 {FRAMES}x224x224 + HuBERT-base 5 s + BERT-base {TOKENS} tok) "
-                               f"+ Attention-fusion train step; bounded sample of {n} clips per step on the host CPU"},
-        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{n} clips per step x {args.steps} steps, oracle port of the reference path "
-                                   f"(pure-Python reference; /root/reference absent on the GPU box), "
-                                   f"{torch.get_num_threads()} torch threads"},
+                               f"+ Attention-fusion train step; bounded sample of {procs} x {n} clips per step on the host CPU"},
+        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": procs * threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -394,8 +510,15 @@ if __name__ == "__main__":
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips", type=int, default=CLIPS, help="clips per GPU per step")
     ap.add_argument("--cpu-clips", type=int, default=48, help="upper bound of clips in the bounded CPU sample")
+    ap.add_argument("--no-extras", action="store_true", help="skip the side measurements (fusion latency, mixed-length "
+                    "audio, TF32 ViT, whole-host CPU figure)")
+    ap.add_argument("--cpu-worker", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-threads", type=int, default=16, help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-steps", type=int, default=1, help=argparse.SUPPRESS)
     a = ap.parse_args()
-    if a.impl == "reference":
+    if a.cpu_worker:
+        cpu_worker(a.cpu_worker, a.cpu_threads, a.cpu_steps)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)
