@@ -18,6 +18,7 @@
 // CUDA-graph replay.  2.86 MFLOP per clip: this is the latency regime, so the design removes launches and L2 round
 // trips rather than chasing tensor cores.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "mer_common.cuh"
 #include "mer_kernels.h"
@@ -235,6 +236,135 @@ __device__ __forceinline__ void backward_cols(const float* __restrict__ dy, int 
   __syncthreads();
 }
 
+// The attention head of Attention.forward (attention.py:44-53) for the RB rows of a cluster, replicated in every CTA
+// (warp r <-> row r: no exchange needed): att = fc_att(a3), fused = [h_a h_t h_v] att, the two output heads, and --
+// when a backward pass follows -- the loss terms / upstream gradients, d fused, the head's share of d(concat) (g3h)
+// and the gradient w.r.t. the pre-activation of attention_mlp.linear_3 (ga3).  All buffers are shared memory.
+template <int RB>
+__device__ __forceinline__ void head_rows(const RowArgs& a, int rank, int row0, bool train, const float* hc,
+                                          const float* a3, float* feat, float* dfu, float* g3h, float* ga3) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = a.d.hidden, H3 = 3 * H, B = a.B, O1 = a.d.out1, O2 = a.d.out2;
+  const float* P = a.P;
+  for (int r = warp; r < RB; r += NW) {
+    const int row = row0 + r;
+    const bool live = row < B;
+    const float* a3r = a3 + r * H;
+    const float* hcr = hc + r * H3;
+    float att[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      float s = 0.f;
+      for (int j = lane; j < H; j += 32) s = fmaf(P[a.L.fa_w + m * H + j], a3r[j], s);
+      att[m] = warp_allsum(s) + P[a.L.fa_b + m];
+    }
+    for (int j = lane; j < H; j += 32) {
+      const float f = (hcr[j] * att[0] + hcr[H + j] * att[1]) + hcr[2 * H + j] * att[2];
+      feat[r * H + j] = f;
+      if (rank == 0 && live) a.features[(long long)row * H + j] = f;
+    }
+    __syncwarp();
+    float logit[16], vout[4];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      if (c >= O1) break;
+      float s = 0.f;
+      for (int j = lane; j < H; j += 32) s = fmaf(P[a.L.o1_w + c * H + j], feat[r * H + j], s);
+      logit[c] = warp_allsum(s) + P[a.L.o1_b + c];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c >= O2) break;
+      float s = 0.f;
+      for (int j = lane; j < H; j += 32) s = fmaf(P[a.L.o2_w + c * H + j], feat[r * H + j], s);
+      vout[c] = warp_allsum(s) + P[a.L.o2_b + c];
+    }
+    if (rank == 0 && live && lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (c < O1) a.emos_out[(long long)row * O1 + c] = logit[c];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < O2) a.vals_out[(long long)row * O2 + c] = vout[c];
+    }
+    if (!train) continue;
+    // upstream gradients of the two heads (every lane computes the same scalars)
+    float dlog[16], dval[4];
+    if (a.mode == MODE_LOSS) {
+      // CELoss: NLL(log_softmax) summed / N; MSELoss: squared error summed / N  (loss.py:11-28)
+      float mx = logit[0];
+#pragma unroll
+      for (int c = 1; c < 16; ++c)
+        if (c < O1) mx = fmaxf(mx, logit[c]);
+      float se = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (c < O1) se += expf(logit[c] - mx);
+      const float lse = mx + logf(se);
+      const int tgt = live ? (int)a.emo[row] : 0;
+      float ce = 0.f, mse = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        if (c >= O1) break;
+        if (c == tgt) ce = lse - logit[c];
+        dlog[c] = live ? (expf(logit[c] - lse) - (c == tgt ? 1.f : 0.f)) * a.inv_batch : 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c >= O2) break;
+        const float dd = live ? vout[c] - a.val[(long long)row * O2 + c] : 0.f;
+        mse += dd * dd;
+        dval[c] = 2.f * dd * a.inv_batch;
+      }
+      if (rank == 0 && live && lane == 0) {
+        a.ws.loss_terms[2 * row] = ce;
+        a.ws.loss_terms[2 * row + 1] = mse;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (c < O1) dlog[c] = (live && a.up_emos) ? a.up_emos[(long long)row * O1 + c] : 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < O2) dval[c] = (live && a.up_vals) ? a.up_vals[(long long)row * O2 + c] : 0.f;
+    }
+    if (rank == 0 && live && lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (c < O1) a.ws.d_emos[(long long)row * O1 + c] = dlog[c];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < O2) a.ws.d_vals[(long long)row * O2 + c] = dval[c];
+    }
+    float datt[3] = {0.f, 0.f, 0.f};
+    for (int j = lane; j < H; j += 32) {
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (c < O1) s = fmaf(P[a.L.o1_w + c * H + j], dlog[c], s);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < O2) s = fmaf(P[a.L.o2_w + c * H + j], dval[c], s);
+      if (a.mode == MODE_UPSTREAM && a.up_feat && live) s += a.up_feat[(long long)row * H + j];
+      dfu[r * H + j] = s;
+#pragma unroll
+      for (int m = 0; m < 3; ++m) datt[m] = fmaf(hcr[m * H + j], s, datt[m]);
+    }
+#pragma unroll
+    for (int m = 0; m < 3; ++m) datt[m] = warp_allsum(datt[m]);
+    if (rank == 0 && live && lane < 3) a.ws.d_att[3 * row + lane] = lane == 0 ? datt[0] : (lane == 1 ? datt[1] : datt[2]);
+    for (int j = lane; j < H; j += 32) {
+      const float s = dfu[r * H + j];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) g3h[r * H3 + m * H + j] = att[m] * s;
+      const float da3 = (P[a.L.fa_w + j] * datt[0] + P[a.L.fa_w + H + j] * datt[1]) + P[a.L.fa_w + 2 * H + j] * datt[2];
+      const float g = a3r[j] > 0.f ? da3 : 0.f;
+      ga3[r * H + j] = g;
+      if (rank == 0 && live) a.ws.ga3[(long long)row * H + j] = g;
+    }
+  }
+}
+
 template <int RB>
 __global__ void __launch_bounds__(NT, 1) fus_rows_kernel(const __grid_constant__ RowArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -395,124 +525,8 @@ __global__ void __launch_bounds__(NT, 1) fus_rows_kernel(const __grid_constant__
   }
   cluster.sync();
 
-  // ================= head: replicated in every CTA (warp r <-> row r), so no exchange is needed =================
-  for (int r = warp; r < RB; r += NW) {
-    const int row = row0 + r;
-    const bool live = row < B;
-    const float* a3r = a3 + r * H;
-    const float* hcr = hc + r * H3;
-    float att[3];
-#pragma unroll
-    for (int m = 0; m < 3; ++m) {
-      float s = 0.f;
-      for (int j = lane; j < H; j += 32) s = fmaf(P[a.L.fa_w + m * H + j], a3r[j], s);
-      att[m] = warp_allsum(s) + P[a.L.fa_b + m];
-    }
-    for (int j = lane; j < H; j += 32) {
-      const float f = (hcr[j] * att[0] + hcr[H + j] * att[1]) + hcr[2 * H + j] * att[2];
-      feat[r * H + j] = f;
-      if (rank == 0 && live) a.features[(long long)row * H + j] = f;
-    }
-    __syncwarp();
-    float logit[16], vout[4];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      if (c >= O1) break;
-      float s = 0.f;
-      for (int j = lane; j < H; j += 32) s = fmaf(P[a.L.o1_w + c * H + j], feat[r * H + j], s);
-      logit[c] = warp_allsum(s) + P[a.L.o1_b + c];
-    }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      if (c >= O2) break;
-      float s = 0.f;
-      for (int j = lane; j < H; j += 32) s = fmaf(P[a.L.o2_w + c * H + j], feat[r * H + j], s);
-      vout[c] = warp_allsum(s) + P[a.L.o2_b + c];
-    }
-    if (rank == 0 && live && lane == 0) {
-#pragma unroll
-      for (int c = 0; c < 16; ++c)
-        if (c < O1) a.emos_out[(long long)row * O1 + c] = logit[c];
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c < O2) a.vals_out[(long long)row * O2 + c] = vout[c];
-    }
-    if (!train) continue;
-    // upstream gradients of the two heads (every lane computes the same scalars)
-    float dlog[16], dval[4];
-    if (a.mode == MODE_LOSS) {
-      // CELoss: NLL(log_softmax) summed / N; MSELoss: squared error summed / N  (loss.py:11-28)
-      float mx = logit[0];
-#pragma unroll
-      for (int c = 1; c < 16; ++c)
-        if (c < O1) mx = fmaxf(mx, logit[c]);
-      float se = 0.f;
-#pragma unroll
-      for (int c = 0; c < 16; ++c)
-        if (c < O1) se += expf(logit[c] - mx);
-      const float lse = mx + logf(se);
-      const int tgt = live ? (int)a.emo[row] : 0;
-      float ce = 0.f, mse = 0.f;
-#pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        if (c >= O1) break;
-        if (c == tgt) ce = lse - logit[c];
-        dlog[c] = live ? (expf(logit[c] - lse) - (c == tgt ? 1.f : 0.f)) * a.inv_batch : 0.f;
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c >= O2) break;
-        const float dd = live ? vout[c] - a.val[(long long)row * O2 + c] : 0.f;
-        mse += dd * dd;
-        dval[c] = 2.f * dd * a.inv_batch;
-      }
-      if (rank == 0 && live && lane == 0) {
-        a.ws.loss_terms[2 * row] = ce;
-        a.ws.loss_terms[2 * row + 1] = mse;
-      }
-    } else {
-#pragma unroll
-      for (int c = 0; c < 16; ++c)
-        if (c < O1) dlog[c] = (live && a.up_emos) ? a.up_emos[(long long)row * O1 + c] : 0.f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c < O2) dval[c] = (live && a.up_vals) ? a.up_vals[(long long)row * O2 + c] : 0.f;
-    }
-    if (rank == 0 && live && lane == 0) {
-#pragma unroll
-      for (int c = 0; c < 16; ++c)
-        if (c < O1) a.ws.d_emos[(long long)row * O1 + c] = dlog[c];
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c < O2) a.ws.d_vals[(long long)row * O2 + c] = dval[c];
-    }
-    float datt[3] = {0.f, 0.f, 0.f};
-    for (int j = lane; j < H; j += 32) {
-      float s = 0.f;
-#pragma unroll
-      for (int c = 0; c < 16; ++c)
-        if (c < O1) s = fmaf(P[a.L.o1_w + c * H + j], dlog[c], s);
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c < O2) s = fmaf(P[a.L.o2_w + c * H + j], dval[c], s);
-      if (a.mode == MODE_UPSTREAM && a.up_feat && live) s += a.up_feat[(long long)row * H + j];
-      dfu[r * H + j] = s;
-#pragma unroll
-      for (int m = 0; m < 3; ++m) datt[m] = fmaf(hcr[m * H + j], s, datt[m]);
-    }
-#pragma unroll
-    for (int m = 0; m < 3; ++m) datt[m] = warp_allsum(datt[m]);
-    if (rank == 0 && live && lane < 3) a.ws.d_att[3 * row + lane] = lane == 0 ? datt[0] : (lane == 1 ? datt[1] : datt[2]);
-    for (int j = lane; j < H; j += 32) {
-      const float s = dfu[r * H + j];
-#pragma unroll
-      for (int m = 0; m < 3; ++m) g3h[r * H3 + m * H + j] = att[m] * s;
-      const float da3 = (P[a.L.fa_w + j] * datt[0] + P[a.L.fa_w + H + j] * datt[1]) + P[a.L.fa_w + 2 * H + j] * datt[2];
-      const float g = a3r[j] > 0.f ? da3 : 0.f;
-      ga3[r * H + j] = g;
-      if (rank == 0 && live) a.ws.ga3[(long long)row * H + j] = g;
-    }
-  }
+  // ================= head (replicated in every CTA) =================
+  head_rows<RB>(a, rank, row0, train, hc, a3, feat, dfu, g3h, ga3);
   if (!train) {
     cluster.sync();  // no CTA may exit while a peer could still be storing into its shared memory
     return;
@@ -556,6 +570,361 @@ __global__ void __launch_bounds__(NT, 1) fus_rows_kernel(const __grid_constant__
     });
   }
   // the last DSMEM stores (g2) were fenced by the barrier above: CTAs may retire independently
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fus_rows_fast_kernel — the same row-parallel pass for the common shapes (hidden <= 128, feature widths that are
+// multiples of 4 and fit the plan below), rebuilt around what the first version measured on B200: 96 us per step at
+// B = 32, almost all of it exposed L2 latency (every layer began with a dependent weight load) -- not arithmetic.
+//   * Weights come in through the bulk-copy engine (cp.async.bulk + mbarrier), never through a load a warp waits on:
+//     this CTA's row slices W[n0:n1, :] of the five hidden-layer matrices (88 KB at hidden 128) are requested at kernel
+//     entry and stay in shared memory for BOTH directions; layer 1's slices (the bulk of the bytes) stream through two
+//     chunk buffers while the previous chunk is being consumed.
+//   * The backward pass splits the SAME row slices: CTA c holds rows n0:n1 of W and the gradient of exactly those
+//     pre-activations (it produced them), so it computes the partial d x[r, :] over its 16 n's for every input column
+//     and scatters the column slices to their owners through DSMEM (a reduce-scatter; 8 partials summed in rank
+//     order -> deterministic).  No weight is read twice, no gradient is broadcast.
+//   * 12 cluster barriers per step (6 forward layers, 5 backward exchanges, 1 at entry), each ~0.3 us of hardware.
+constexpr int FRB = 4;        // rows per cluster
+constexpr int HCP = 16;       // slice width bound: ceil(128 / 8)
+constexpr int FMAXC = 2;      // columns per warp: ceil(16 / 8)
+
+struct FastPlan {             // shared-memory offsets (floats) + sizes, computed on the host, identical in every CTA
+  int xs[3];                  // [FRB][in_m] staged inputs (after dropout)
+  int h1, h2, hc, hcd, a1, a2, a3, feat, dfu, g3h, ga3;   // activations / head gradients (full copies)
+  int own_a, own_3, own_2;    // this CTA's slices of pre-activation gradients: [FRB][HCP], [3][FRB][HCP] x 2
+  int rx;                     // [2][CL][3][FRB][HCP] reduce-scatter landing zones (ping-pong)
+  int wb;                     // [2][HCP][kc1] layer-1 weight chunks
+  int t2, t3, ta1, ta2, ta3;  // resident row slices
+  int bars;                   // 4 mbarriers (2 chunk buffers, resident set, spare)
+  int kc1;                    // layer-1 chunk length (floats per row)
+  int total;                  // floats
+};
+
+FastPlan make_fast_plan(const MerFusionDims& d, int kc1) {
+  FastPlan p;
+  const int H = d.hidden;
+  const int in[3] = {d.audio_dim, d.text_dim, d.video_dim};
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
+  for (int m = 0; m < 3; ++m) p.xs[m] = take(FRB * in[m]);
+  p.h1 = take(3 * FRB * H); p.h2 = take(3 * FRB * H);
+  p.hc = take(FRB * 3 * H); p.hcd = take(FRB * 3 * H);
+  p.a1 = take(FRB * H); p.a2 = take(FRB * H); p.a3 = take(FRB * H);
+  p.feat = take(FRB * H); p.dfu = take(FRB * H);
+  p.g3h = take(FRB * 3 * H); p.ga3 = take(FRB * H);
+  p.own_a = take(FRB * HCP); p.own_3 = take(3 * FRB * HCP); p.own_2 = take(3 * FRB * HCP);
+  p.rx = take(2 * CL * 3 * FRB * HCP);
+  p.wb = take(2 * HCP * kc1);
+  p.t2 = take(3 * HCP * H); p.t3 = take(3 * HCP * H);
+  p.ta1 = take(HCP * 3 * H); p.ta2 = take(HCP * H); p.ta3 = take(HCP * H);
+  p.bars = take(8);
+  p.kc1 = kc1;
+  p.total = o;
+  return p;
+}
+
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                   "r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// acc[c][r] += sum_k in[r][k] * tile[c_local][k]: `tile` is a shared-memory row slice [nloc][ldt]
+__device__ __forceinline__ void fast_accumulate(float (&acc)[FMAXC][FRB], const float* __restrict__ in, int ldin, int K,
+                                                const float* __restrict__ tile, int ldt, int nloc) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k4 = lane; k4 < K / 4; k4 += 32) {
+    float4 w[FMAXC];
+#pragma unroll
+    for (int c = 0; c < FMAXC; ++c)
+      if (warp + NW * c < nloc) w[c] = *reinterpret_cast<const float4*>(tile + (warp + NW * c) * ldt + 4 * k4);
+#pragma unroll
+    for (int r = 0; r < FRB; ++r) {
+      const float4 xv = *reinterpret_cast<const float4*>(in + r * ldin + 4 * k4);
+#pragma unroll
+      for (int c = 0; c < FMAXC; ++c)
+        if (warp + NW * c < nloc) acc[c][r] = dot4(xv, w[c], acc[c][r]);
+    }
+  }
+}
+
+template <class Emit>
+__device__ __forceinline__ void fast_finish(float (&acc)[FMAXC][FRB], int n0, int nloc, Emit emit) {
+  const int warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < FMAXC; ++c) {
+    if (warp + NW * c >= nloc) continue;
+#pragma unroll
+    for (int r = 0; r < FRB; ++r) emit(n0 + warp + NW * c, r, warp_allsum(acc[c][r]));
+  }
+}
+
+__global__ void __launch_bounds__(NT, 1) fus_rows_fast_kernel(const __grid_constant__ RowArgs a,
+                                                              const __grid_constant__ FastPlan pl) {
+  extern __shared__ __align__(16) float smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = a.d.hidden, H3 = 3 * H, B = a.B;
+  const int in[3] = {a.d.audio_dim, a.d.text_dim, a.d.video_dim};
+  const int row0 = (int)(blockIdx.x / CL) * FRB;
+  const bool drop = a.p_drop > 0.f && a.mode != MODE_FWD;
+  const bool train = a.mode == MODE_LOSS || a.mode == MODE_UPSTREAM;
+  const int step = drop ? *a.step : 0;
+  const float* P = a.P;
+  const int HC = (H + CL - 1) / CL;
+  const int n0 = min(H, rank * HC), n1 = min(H, n0 + HC), nloc = n1 - n0;
+
+  float* xs[3] = {smem + pl.xs[0], smem + pl.xs[1], smem + pl.xs[2]};
+  float* h1 = smem + pl.h1; float* h2 = smem + pl.h2; float* hc = smem + pl.hc; float* hcd = smem + pl.hcd;
+  float* a1 = smem + pl.a1; float* a2 = smem + pl.a2; float* a3 = smem + pl.a3;
+  float* feat = smem + pl.feat; float* dfu = smem + pl.dfu; float* g3h = smem + pl.g3h; float* ga3 = smem + pl.ga3;
+  float* own_a = smem + pl.own_a; float* own_3 = smem + pl.own_3; float* own_2 = smem + pl.own_2;
+  float* rx = smem + pl.rx; float* wb = smem + pl.wb;
+  float* t2 = smem + pl.t2; float* t3 = smem + pl.t3; float* ta1 = smem + pl.ta1; float* ta2 = smem + pl.ta2;
+  float* ta3 = smem + pl.ta3;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.bars);  // [0], [1]: chunk buffers; [2]: resident tiles
+  const int kc1 = pl.kc1;
+
+  // layer-1 chunk list: (modality, first column), in order
+  int nch[3], nc_total = 0;
+  for (int m = 0; m < 3; ++m) { nch[m] = (in[m] + kc1 - 1) / kc1; nc_total += nch[m]; }
+  auto chunk_of = [&](int c, int& m, int& k0, int& kc) {
+    m = 0;
+    while (c >= nch[m]) { c -= nch[m]; ++m; }
+    k0 = c * kc1;
+    kc = min(kc1, in[m] - k0);
+  };
+  auto issue_chunk = [&](int c) {  // one thread: this CTA's rows of chunk c -> buffer c & 1
+    int m, k0, kc;
+    chunk_of(c, m, k0, kc);
+    uint64_t* bar = &bars[c & 1];
+    mbar_expect_tx(bar, (uint32_t)(nloc * kc * 4));
+    const float* src = P + a.L.enc_w1[m] + (long long)n0 * in[m] + k0;
+    float* dst = wb + (c & 1) * HCP * kc1;
+    for (int nl = 0; nl < nloc; ++nl) bulk_g2s(dst + nl * kc1, src + (long long)nl * in[m], (uint32_t)(kc * 4), bar);
+  };
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    fence_mbar_init();
+    if (blockIdx.x == 0 && train) *a.ws.done = 0;
+    // resident row slices of the five hidden-layer matrices (contiguous in the parameter buffer)
+    mbar_expect_tx(&bars[2], (uint32_t)(nloc * (6 * H + 3 * H + 2 * H) * 4));
+    for (int m = 0; m < 3; ++m) {
+      bulk_g2s(t2 + m * HCP * H, P + a.L.enc_w2[m] + (long long)n0 * H, (uint32_t)(nloc * H * 4), &bars[2]);
+      bulk_g2s(t3 + m * HCP * H, P + a.L.enc_w3[m] + (long long)n0 * H, (uint32_t)(nloc * H * 4), &bars[2]);
+    }
+    bulk_g2s(ta1, P + a.L.att_w1 + (long long)n0 * H3, (uint32_t)(nloc * H3 * 4), &bars[2]);
+    bulk_g2s(ta2, P + a.L.att_w2 + (long long)n0 * H, (uint32_t)(nloc * H * 4), &bars[2]);
+    bulk_g2s(ta3, P + a.L.att_w3 + (long long)n0 * H, (uint32_t)(nloc * H * 4), &bars[2]);
+    issue_chunk(0);
+    if (nc_total > 1) issue_chunk(1);
+  }
+  // stage the three inputs of the FRB rows (dropout applied here; rank m also keeps the dropped copy for fus_wgrad)
+  for (int m = 0; m < 3; ++m) {
+    const int K = in[m];
+    for (int i = tid; i < FRB * K; i += NT) {
+      const int r = i / K, k = i - r * K, row = row0 + r;
+      float v = 0.f;
+      if (row < B) {
+        const long long gi = (long long)row * K + k;
+        v = a.x[m][gi];
+        if (drop) {
+          v *= (a.ext_mask[m] ? a.ext_mask[m][gi] : keep_hash(a.seed, m, step, gi, a.p_drop)) * a.mscale;
+          if (train && rank == m) a.ws.xd[m][gi] = v;
+        }
+      }
+      xs[m][i] = v;
+    }
+  }
+  __syncthreads();
+  cluster.sync();  // every CTA of the cluster is running: DSMEM stores may begin
+  auto peer = [&](float* local) { return cluster.map_shared_rank(local, lane & (CL - 1)); };
+
+  // ================= forward =================
+  {
+    float acc[FMAXC][FRB] = {};
+    int m_cur = 0, left = nch[0];
+    for (int c = 0; c < nc_total; ++c) {
+      int m, k0, kc;
+      chunk_of(c, m, k0, kc);
+      mbar_wait(&bars[c & 1], (c >> 1) & 1);
+      fast_accumulate(acc, xs[m] + k0, in[m], kc, wb + (c & 1) * HCP * kc1, kc1, nloc);
+      __syncthreads();  // every warp is done with this buffer
+      if (tid == 0 && c + 2 < nc_total) issue_chunk(c + 2);
+      if (--left == 0) {  // last chunk of modality m: its layer-1 output
+        float* dst = peer(h1);
+        fast_finish(acc, n0, nloc, [&](int n, int r, float v) {
+          v = fmaxf(v + P[a.L.enc_b1[m] + n], 0.f);
+          if (lane < CL) dst[(m * FRB + r) * H + n] = v;
+          if (lane == CL + r && train && row0 + r < B) a.ws.h1[((long long)m * B + row0 + r) * H + n] = v;
+        });
+#pragma unroll
+        for (int ci = 0; ci < FMAXC; ++ci)
+#pragma unroll
+          for (int r = 0; r < FRB; ++r) acc[ci][r] = 0.f;
+        m_cur = m + 1;
+        if (m_cur < 3) left = nch[m_cur];
+      }
+    }
+  }
+  cluster.sync();
+  mbar_wait(&bars[2], 0);  // resident tiles (requested at entry: long since there)
+  for (int m = 0; m < 3; ++m) {  // encoder layer 2
+    float acc[FMAXC][FRB] = {};
+    fast_accumulate(acc, h1 + m * FRB * H, H, H, t2 + m * HCP * H, H, nloc);
+    float* dst = peer(h2);
+    fast_finish(acc, n0, nloc, [&](int n, int r, float v) {
+      v = fmaxf(v + P[a.L.enc_b2[m] + n], 0.f);
+      if (lane < CL) dst[(m * FRB + r) * H + n] = v;
+      if (lane == CL + r && train && row0 + r < B) a.ws.h2[((long long)m * B + row0 + r) * H + n] = v;
+    });
+  }
+  cluster.sync();
+  auto cat_factor = [&](int row, int col) {  // dropout factor of concat element (row, col)
+    if (!drop || row >= B) return 1.f;
+    const long long gi = (long long)row * H3 + col;
+    return (a.ext_mask[3] ? a.ext_mask[3][gi] : keep_hash(a.seed, 3, step, gi, a.p_drop)) * a.mscale;
+  };
+  for (int m = 0; m < 3; ++m) {  // encoder layer 3 -> concat (+ its dropout)
+    float acc[FMAXC][FRB] = {};
+    fast_accumulate(acc, h2 + m * FRB * H, H, H, t3 + m * HCP * H, H, nloc);
+    float* dhc = peer(hc);
+    float* dhcd = peer(hcd);
+    fast_finish(acc, n0, nloc, [&](int n, int r, float v) {
+      v = fmaxf(v + P[a.L.enc_b3[m] + n], 0.f);
+      const int row = row0 + r, col = m * H + n;
+      const float f = cat_factor(row, col);
+      if (lane < CL) {
+        dhc[r * H3 + col] = v;
+        dhcd[r * H3 + col] = v * f;
+      }
+      if (lane == CL + r && train && row < B) a.ws.hcd[(long long)row * H3 + col] = v * f;
+    });
+  }
+  cluster.sync();
+  {  // attention_mlp
+    float acc[FMAXC][FRB] = {};
+    fast_accumulate(acc, hcd, H3, H3, ta1, H3, nloc);
+    float* dst = peer(a1);
+    fast_finish(acc, n0, nloc, [&](int n, int r, float v) {
+      v = fmaxf(v + P[a.L.att_b1 + n], 0.f);
+      if (lane < CL) dst[r * H + n] = v;
+      if (lane == CL + r && train && row0 + r < B) a.ws.a1[(long long)(row0 + r) * H + n] = v;
+    });
+  }
+  cluster.sync();
+  {
+    float acc[FMAXC][FRB] = {};
+    fast_accumulate(acc, a1, H, H, ta2, H, nloc);
+    float* dst = peer(a2);
+    fast_finish(acc, n0, nloc, [&](int n, int r, float v) {
+      v = fmaxf(v + P[a.L.att_b2 + n], 0.f);
+      if (lane < CL) dst[r * H + n] = v;
+      if (lane == CL + r && train && row0 + r < B) a.ws.a2[(long long)(row0 + r) * H + n] = v;
+    });
+  }
+  cluster.sync();
+  {
+    float acc[FMAXC][FRB] = {};
+    fast_accumulate(acc, a2, H, H, ta3, H, nloc);
+    float* dst = peer(a3);
+    fast_finish(acc, n0, nloc, [&](int n, int r, float v) {
+      v = fmaxf(v + P[a.L.att_b3 + n], 0.f);
+      if (lane < CL) dst[r * H + n] = v;
+      if (lane == CL + r && train && row0 + r < B) a.ws.a3[(long long)(row0 + r) * H + n] = v;
+    });
+  }
+  cluster.sync();
+
+  head_rows<FRB>(a, rank, row0, train, hc, a3, feat, dfu, g3h, ga3);
+  if (!train) {
+    cluster.sync();
+    return;
+  }
+  __syncthreads();
+
+  // ================= backward: reduce-scatter of partial data gradients =================
+  // partial[r][k] over this CTA's rows n0:n1 of one matrix (tile [nloc][K]) and its own pre-activation gradients
+  // down[r][nl]; column k of slot `slot_of(k)` goes to CTA (k % H) / HC, into landing zone `zone`
+  auto scatter = [&](const float* down, const float* tile, int K, int zone, int slot_base) {
+    for (int k = tid; k < K; k += NT) {
+      float acc[FRB] = {0.f, 0.f, 0.f, 0.f};
+      for (int nl = 0; nl < nloc; ++nl) {
+        const float w = tile[nl * K + k];
+#pragma unroll
+        for (int r = 0; r < FRB; ++r) acc[r] = fmaf(down[r * HCP + nl], w, acc[r]);
+      }
+      const int slot = slot_base + k / H, j = k % H;
+      const int dest = j / HC, kk = j - dest * HC;
+      float* z = cluster.map_shared_rank(rx + zone * (CL * 3 * FRB * HCP), dest);
+#pragma unroll
+      for (int r = 0; r < FRB; ++r) z[((rank * 3 + slot) * FRB + r) * HCP + kk] = acc[r];
+    }
+  };
+  // sum of the 8 partials for this CTA's columns, in rank order; fin(slot, r, kk, sum)
+  auto gather = [&](int zone, int nslot, auto fin) {
+    const float* z = rx + zone * (CL * 3 * FRB * HCP);
+    for (int i = tid; i < nslot * FRB * nloc; i += NT) {
+      const int kk = i % nloc, r = (i / nloc) % FRB, slot = i / (nloc * FRB);
+      float s = 0.f;
+#pragma unroll
+      for (int src = 0; src < CL; ++src) s += z[((src * 3 + slot) * FRB + r) * HCP + kk];
+      fin(slot, r, kk, s);
+    }
+  };
+  // own slice of the head's gradient w.r.t. attention_mlp.linear_3's pre-activation
+  for (int i = tid; i < FRB * nloc; i += NT) own_a[(i / nloc) * HCP + i % nloc] = ga3[(i / nloc) * H + n0 + i % nloc];
+  __syncthreads();
+  scatter(own_a, ta3, H, 0, 0);                                   // attention_mlp.linear_3 -> d a2
+  cluster.sync();
+  gather(0, 1, [&](int, int r, int kk, float s) {
+    const int k = n0 + kk;
+    const float g = a2[r * H + k] > 0.f ? s : 0.f;
+    own_a[r * HCP + kk] = g;
+    if (row0 + r < B) a.ws.ga2[(long long)(row0 + r) * H + k] = g;
+  });
+  __syncthreads();
+  scatter(own_a, ta2, H, 1, 0);                                   // linear_2 -> d a1
+  cluster.sync();
+  gather(1, 1, [&](int, int r, int kk, float s) {
+    const int k = n0 + kk;
+    const float g = a1[r * H + k] > 0.f ? s : 0.f;
+    own_a[r * HCP + kk] = g;
+    if (row0 + r < B) a.ws.ga1[(long long)(row0 + r) * H + k] = g;
+  });
+  __syncthreads();
+  scatter(own_a, ta1, H3, 0, 0);                                  // linear_1 -> d concat (slot = modality)
+  cluster.sync();
+  gather(0, 3, [&](int m, int r, int kk, float s) {
+    const int k = n0 + kk, col = m * H + k;
+    const float tot = g3h[r * H3 + col] + s * cat_factor(row0 + r, col);
+    const float g = hc[r * H3 + col] > 0.f ? tot : 0.f;
+    own_3[(m * FRB + r) * HCP + kk] = g;
+    if (row0 + r < B) a.ws.g3[(long long)(row0 + r) * H3 + col] = g;
+  });
+  __syncthreads();
+  for (int m = 0; m < 3; ++m) scatter(own_3 + m * FRB * HCP, t3 + m * HCP * H, H, 1, m);   // encoder layer 3 -> d h2
+  cluster.sync();
+  gather(1, 3, [&](int m, int r, int kk, float s) {
+    const int k = n0 + kk;
+    const float g = h2[(m * FRB + r) * H + k] > 0.f ? s : 0.f;
+    own_2[(m * FRB + r) * HCP + kk] = g;
+    if (row0 + r < B) a.ws.g2[((long long)m * B + row0 + r) * H + k] = g;
+  });
+  __syncthreads();
+  for (int m = 0; m < 3; ++m) scatter(own_2 + m * FRB * HCP, t2 + m * HCP * H, H, 0, m);   // encoder layer 2 -> d h1
+  cluster.sync();
+  gather(0, 3, [&](int m, int r, int kk, float s) {
+    const int k = n0 + kk;
+    const float g = h1[(m * FRB + r) * H + k] > 0.f ? s : 0.f;
+    if (row0 + r < B) a.ws.g1[((long long)m * B + row0 + r) * H + k] = g;
+  });
+  // zone 0 was last written before the barrier above and zone 1 two barriers ago: CTAs may retire independently
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -676,7 +1045,50 @@ int launch_rows_t(const RowArgs& a, cudaStream_t st) {
   return 0;
 }
 
+// fast path: hidden <= 128 (a multiple of 4), feature widths multiples of 4, everything within 227 KB of shared memory
+bool fast_plan_for(const MerFusionDims& d, FastPlan* out) {
+  const int in[3] = {d.audio_dim, d.text_dim, d.video_dim};
+  if (d.hidden > 128 || d.hidden % 4 != 0) return false;
+  for (int m = 0; m < 3; ++m)
+    if (in[m] % 4 != 0) return false;
+  for (int kc1 = 384; kc1 >= 64; kc1 -= 64) {
+    const FastPlan p = make_fast_plan(d, kc1);
+    if ((size_t)p.total * 4 <= 227 * 1024) {
+      *out = p;
+      return true;
+    }
+  }
+  return false;
+}
+
+int launch_rows_fast(const RowArgs& a, const FastPlan& pl, cudaStream_t st) {
+  static MerPerDevice once;
+  if (once.needs_setup()) {
+    MER_CUDA_CHECK(cudaFuncSetAttribute(fus_rows_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    once.mark();
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(CL * ((a.B + FRB - 1) / FRB)));
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = (size_t)pl.total * 4;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MER_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fus_rows_fast_kernel, a, pl));
+  mer_count_launches(1);
+  return 0;
+}
+
 int launch_rows(const RowArgs& a, cudaStream_t st) {
+  static const bool no_fast = getenv("MER_FUSION_GENERIC") != nullptr;  // A/B and fallback testing
+  FastPlan pl;
+  if (!no_fast && fast_plan_for(a.d, &pl)) return launch_rows_fast(a, pl, st);
   // 8 rows per cluster once there are enough rows to fill the GPU with clusters and the plan fits shared memory
   if (a.B >= 128 && a.d.hidden <= 128) return launch_rows_t<8>(a, st);
   return launch_rows_t<4>(a, st);
