@@ -128,3 +128,35 @@ def extract_embedding(model_name, trans_dir, save_dir, feature_level, gpu=-1, pu
         files = [os.path.join(save_dir, f"{n}.npy") for n in names[s:s + sentences_per_launch]]
         ext.extract_sentences(sents[s:s + sentences_per_launch], feature_level, save_files=files)
     print(f"Total {len(df)} files done! Time used ({model_name}): {time.time() - start_time:.1f}s.")
+
+
+def build_parser():
+    """Flags of extract_text_huggingface.py:270-281."""
+    import argparse
+    parser = argparse.ArgumentParser(description="Run.")
+    parser.add_argument("--dataset", type=str, help="input dataset")
+    parser.add_argument("--gpu", type=int, default=1, help="gpu id")
+    parser.add_argument("--model_name", type=str, help="name of pretrained model")
+    parser.add_argument("--feature_level", type=str, default="UTTERANCE", choices=["UTTERANCE", "FRAME"], help="output types")
+    parser.add_argument("--punc_case", type=str, default=None, help="test punc impact to the performance")
+    parser.add_argument("--language", type=str, default="chinese", help="used language")
+    parser.add_argument("--model_dir", type=str, default=None, help="used user-defined model_dir")
+    return parser
+
+
+def main(args, config=None):
+    """Script body (:283-299): transcription CSV and save directory from config.py, then extract_embedding."""
+    if config is None:
+        from .. import config as config  # noqa: PLW0127
+    trans_dir = config.PATH_TO_TRANSCRIPTIONS[args.dataset]
+    save_dir = config.PATH_TO_FEATURES[args.dataset]
+    if args.punc_case is not None:
+        assert args.punc_case in ["case1", "case2", "case3"]
+        trans_dir = trans_dir[:-4] + f"-{args.punc_case}.csv"
+        assert os.path.exists(trans_dir)
+    extract_embedding(model_name=args.model_name, trans_dir=trans_dir, save_dir=save_dir, feature_level=args.feature_level,
+                      gpu=args.gpu, punc_case=args.punc_case, language=args.language, model_dir=args.model_dir, config=config)
+
+
+if __name__ == "__main__":
+    main(build_parser().parse_args())
