@@ -45,6 +45,7 @@ constexpr int SMEM_BAR = 2 * SET_BYTES;
 constexpr int SMEM_XCHG = SMEM_BAR + 256;   // VER 4: partial row max / row sum of the two warps sharing a row: [2 tiles][128][2] x 2
 constexpr int F16_SMEM = SMEM_XCHG + 4096 + 1024;
 constexpr uint32_t TILE_COLS = 256, TMEM_COLS = 512;
+constexpr uint32_t V6_O_COL = 192;  // VER 6: O_t lives in columns [192, 256) of its slot (see the softmax block)
 
 __device__ __forceinline__ float fast_ex2(float x) {  // MUFU.EX2, flush-to-zero
   float y;
@@ -73,7 +74,7 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) {  // SW128, SBO 
 //        thread), the partial row maxima / sums meet through shared memory under a 64-thread named barrier, both
 //        halves store their 64 bytes of each P row and of each output row.  Softmax body as VER 3.
 template <int VER>
-__global__ void __launch_bounds__(VER == 4 ? F16_THREADS_V4 : F16_THREADS, 1)
+__global__ void __launch_bounds__(VER >= 4 ? F16_THREADS_V4 : F16_THREADS, 1)
 attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
                      const __grid_constant__ CUtensorMap tmap_vt, uint16_t* __restrict__ ctx,
                      const int* __restrict__ cu_seqlens, int n_seq, int heads, long long* __restrict__ trace) {
@@ -107,11 +108,11 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
       mbar_init(&bar_q[t], 1);
       mbar_init(&bar_v[t], 1);
       mbar_init(&bar_sfull[t], 1);
-      mbar_init(&bar_pready[t], VER == 4 ? 8 : 4);
+      mbar_init(&bar_pready[t], VER >= 4 ? 8 : 4);
       mbar_init(&bar_pfree[t], 1);
       mbar_init(&bar_ofull[t], 1);
-      mbar_init(&bar_ofree[t], VER == 4 ? 8 : 4);
-      mbar_init(&bar_otfree[t], VER == 4 ? 8 : 4);
+      mbar_init(&bar_ofree[t], VER >= 4 ? 8 : 4);
+      mbar_init(&bar_otfree[t], VER >= 4 ? 8 : 4);
     }
     fence_mbar_init();
   }
@@ -160,6 +161,127 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
       ATT_TR(0);
       h_nmt[set] = n_mt;
       for (int t = 0; t < n_mt; ++t) h_use[set][t] = uses[t]++;
+    }
+  } else if (warp == 1 && VER >= 5) {
+    // ===================== MMA issuer, VER 5: one state machine per tile slot =====================
+    // The phase trace of VER 4 (profiles/r2_attention_f16_v4_trace.txt) showed the two tiles of an item marching in
+    // lock-step: this warp served them in program order, so tile 0's next chunk waited for tile 1's previous one,
+    // and the next item's S_t waited for the other tile's last P V product and for a dependent global load of the
+    // sequence bounds (~1.3k cycles per item).  Here each tile slot walks through the items on its own: whenever
+    // slot t's next step is ready (operands landed, O_t drained, P chunk stored) it is issued, whatever the other
+    // slot is doing -- slot 0 may already be in item n + 1 (operand set B) while slot 1 finishes item n (set A).
+    // Sequence bounds of the item after next are loaded one item ahead.
+    const uint64_t desc_q0 = desc_kmajor(smem_u32(smem + SMEM_Q));
+    const uint64_t desc_k0 = desc_kmajor(smem_u32(smem + SMEM_K));
+    const uint64_t desc_v0 = desc_kmajor(smem_u32(smem + SMEM_V));
+    int it[2], stage[2], c_start[2], c_len[2], n_start[2], n_len[2];
+    uint32_t item_no[2], uses[2], g[2];
+    bool kq_ok[2], v_ok[2];
+    auto bounds = [&](int item, int& st, int& ln) {
+      if (item < n_items) {
+        const int seq = item / heads;
+        st = cu_seqlens[seq];
+        ln = cu_seqlens[seq + 1] - st;
+      } else {
+        st = 0;
+        ln = 0;
+      }
+    };
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      it[t] = blockIdx.x; stage[t] = 0; item_no[t] = 0; uses[t] = 0; g[t] = 0; kq_ok[t] = false; v_ok[t] = false;
+      bounds(it[t], c_start[t], c_len[t]);
+      bounds(it[t] + (int)gridDim.x, n_start[t], n_len[t]);
+    }
+    while (it[0] < n_items || it[1] < n_items) {
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (it[t] >= n_items) continue;
+        const int start = c_start[t], len = c_len[t];
+        const int n_mt = (len + 127) >> 7;
+        const int NK = ((start & 7) + len + 15) & ~15;
+        const int n_pc = (NK + 63) >> 6;
+        const int set = item_no[t] & 1;
+        const uint32_t set_par = (item_no[t] >> 1) & 1;
+        bool advance = false;
+        if (t >= n_mt) {
+          advance = true;  // this item has no second tile
+        } else if (stage[t] == 0) {
+          if (!kq_ok[t]) kq_ok[t] = mbar_try_wait(&bar_k[set], set_par) && mbar_try_wait(&bar_q[set], set_par);
+          if (kq_ok[t] && (uses[t] == 0 || mbar_try_wait(&bar_otfree[t], (uses[t] - 1) & 1))) {
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t set_off = (uint64_t)((set * SET_BYTES) >> 4);
+              const uint64_t da = desc_q0 + set_off + (uint64_t)((t * QTILE_BYTES) >> 4);
+              const uint64_t db = desc_k0 + set_off;
+              const uint32_t idesc_s = umma_idesc(0, 128, NK);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem_base + t * TILE_COLS, da + 2 * k, db + 2 * k, idesc_s, k != 0);
+              tc_commit(&bar_sfull[t]);
+            }
+            __syncwarp();
+            stage[t] = 1;
+          }
+        } else {
+          const int pc = stage[t] - 1;
+          if (!v_ok[t]) v_ok[t] = mbar_try_wait(&bar_v[set], set_par);
+          if (VER == 6) {
+            // P sits in tensor memory (written by the softmax warps): ONE hand-shake per tile, then every K step of
+            // O_t = P V in a row; A operand = the P columns of this step (see the VER 6 softmax block for the map)
+            if (v_ok[t] && mbar_try_wait(&bar_pready[t], g[t] & 1)) {
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t set_off = (uint64_t)((set * SET_BYTES) >> 4);
+                const uint64_t dbv = desc_v0 + set_off;
+                const uint32_t idesc_o = umma_idesc(0, 128, HD);
+                const int nks = NK >> 4, ks0 = (nks + 1) >> 1;
+                const uint32_t slot = tmem_base + t * TILE_COLS;
+                for (int ks = 0; ks < nks; ++ks) {
+                  const uint32_t a_col = ks < ks0 ? 8 * ks : 16 * ks0 + 8 * (ks - ks0);
+                  tc_mma_f16_ts(slot + V6_O_COL, slot + a_col, dbv + (uint64_t)(((ks >> 2) * VT_CHUNK) >> 4) + 2 * (ks & 3),
+                                idesc_o, ks != 0);
+                }
+                tc_commit(&bar_ofull[t]);
+              }
+              __syncwarp();
+              ++g[t];
+              ++uses[t];
+              advance = true;
+            }
+          } else if (v_ok[t] && mbar_try_wait(&bar_pready[t], g[t] & 1)) {
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t set_off = (uint64_t)((set * SET_BYTES) >> 4);
+              const uint64_t da = desc_q0 + set_off + (uint64_t)((t * QTILE_BYTES) >> 4);
+              const uint64_t db = desc_v0 + set_off + (uint64_t)((pc * VT_CHUNK) >> 4);
+              const uint32_t idesc_o = umma_idesc(0, 128, HD);
+              const int keys = min(64, NK - pc * 64);
+              for (int k = 0; k < keys / 16; ++k)
+                tc_mma_bf16(tmem_base + t * TILE_COLS, da + 2 * k, db + 2 * k, idesc_o, (pc | k) != 0);
+              tc_commit(&bar_pfree[t]);
+              if (pc == n_pc - 1) tc_commit(&bar_ofull[t]);
+            }
+            __syncwarp();
+            ++g[t];
+            if (pc == n_pc - 1) {
+              ++uses[t];
+              advance = true;
+            } else {
+              ++stage[t];
+            }
+          }
+        }
+        if (advance) {
+          it[t] += (int)gridDim.x;
+          ++item_no[t];
+          stage[t] = 0;
+          kq_ok[t] = false;
+          v_ok[t] = false;
+          c_start[t] = n_start[t];
+          c_len[t] = n_len[t];
+          bounds(it[t] + (int)gridDim.x, n_start[t], n_len[t]);
+        }
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (warp-uniform; one elected lane issues and commits) =========
@@ -360,6 +482,379 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
       if (tr) ATT_TR(19 + 9 * grp);
       uint32_t o[32];
       tmem_ld_32x32(t_lane + half * 32, o);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_otfree[grp]);
+      if (tr) ATT_TR(20 + 9 * grp);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = 4 * half + jj;  // 16-byte slot = head dims 8j .. 8j+7
+        const uint32_t* ov = o + 8 * jj;
+        *reinterpret_cast<uint4*>(o_row + ((j ^ (r_tile & 7)) << 4)) =
+            make_uint4(pack_f16x2(__uint_as_float(ov[0]) * inv, __uint_as_float(ov[1]) * inv),
+                       pack_f16x2(__uint_as_float(ov[2]) * inv, __uint_as_float(ov[3]) * inv),
+                       pack_f16x2(__uint_as_float(ov[4]) * inv, __uint_as_float(ov[5]) * inv),
+                       pack_f16x2(__uint_as_float(ov[6]) * inv, __uint_as_float(ov[7]) * inv));
+      }
+      __syncwarp();
+      const int row0 = grp * 128 + q * 32;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {  // 8 rows x 64 bytes per instruction
+        const int rr = 8 * i + (lane >> 2);
+        const int rt = q * 32 + rr;
+        const int j = 4 * half + (lane & 3);
+        const uint4 d = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((j ^ (rt & 7)) << 4));
+        if (row0 + rr < len)
+          *reinterpret_cast<uint4*>(ctx + (long long)(start + row0 + rr) * ldc + h * HD + j * 8) = d;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_ofree[grp]);
+      if (tr) ATT_TR(21 + 9 * grp);
+      ++uses;
+    }
+  } else if constexpr (VER == 5) {
+    // ===================== softmax + epilogue, VER 5 = VER 4 with the TMEM loads of the next chunk in flight while the
+    // current one is being turned into probabilities, P stored as it is produced, sequence bounds one item ahead ====
+    const int sw = warp - 2;
+    const int grp = sw >> 3, half = (sw >> 2) & 1;
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const uint32_t t_lane = tmem_base + (uint32_t(q * 32) << 16) + grp * TILE_COLS;
+    constexpr float SCALE_LOG2 = 0.125f * 1.4426950408889634f;
+    const int ldc = heads * HD;
+    const int r_tile = q * 32 + lane;  // row inside the 128-row tile
+    float* xmax = reinterpret_cast<float*>(smem + SMEM_XCHG) + (grp * 128 + r_tile) * 2;
+    float* xsum = xmax + 512;
+    const uint32_t pair_bar = 1 + grp * 4 + q;  // named barrier of the two warps that share these 32 rows
+    uint32_t uses = 0, G = 0, item_n = 0;
+    int nx_start = 0, nx_len = 0;
+    if ((int)blockIdx.x < n_items) {
+      nx_start = cu_seqlens[blockIdx.x / heads];
+      nx_len = cu_seqlens[blockIdx.x / heads + 1] - nx_start;
+    }
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item_n) {
+      uint8_t* sm = smem + (item_n & 1) * SET_BYTES;
+      uint8_t* p_row = sm + SMEM_Q + grp * QTILE_BYTES + r_tile * 128;
+      // output staging: the tile's own P buffer (dead once O_t is complete).  Not the V^T region VER 1..4 use: the
+      // other tile slot runs on its own clock here and may still need every V^T chunk of this item
+      uint8_t* o_row = sm + SMEM_Q + grp * QTILE_BYTES + r_tile * 128;
+      const uint8_t* stg = sm + SMEM_Q + grp * QTILE_BYTES + q * 32 * 128;
+      const int h = it % heads;
+      const int start = nx_start, len = nx_len;
+      if (it + (int)gridDim.x < n_items) {  // the next item's bounds: in flight while this item is processed
+        const int nseq = (it + (int)gridDim.x) / heads;
+        nx_start = cu_seqlens[nseq];
+        nx_len = cu_seqlens[nseq + 1] - nx_start;
+      }
+      const int n_mt = (len + 127) >> 7;
+      if (grp >= n_mt) continue;
+      const int shift = start & 7;
+      const int Lk = shift + len;
+      const int NK = (Lk + 15) & ~15;
+      const int n_pc = (NK + 63) >> 6;
+      mbar_wait(&bar_sfull[grp], uses & 1);
+      tc_fence_after();
+      const bool tr = (q == 0 && half == 0);  // one warp per tile stamps: slots 13.. (tile 0), 22.. (tile 1)
+      if (tr) ATT_TR(13 + 9 * grp);
+      float mb = 0.f, sum = 1.f;
+      if (grp * 128 + q * 32 >= len) {
+        // all 32 rows beyond the sequence (both warps of the pair take this branch): only the chunk hand-shake
+        for (int pc = 0; pc < n_pc; ++pc, ++G) {
+          mbar_wait(&bar_pfree[grp], (G & 1) ^ 1);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_pready[grp]);
+        }
+      } else {
+        // pass 1: maximum of this half's columns, in 16-column granules q = 0, 1, ...: granule q + 1 is loading
+        // while granule q is scanned (r[b] with b known after unrolling: both buffers stay in registers)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+        uint32_t r[2][16];
+        const int cb0 = half * 32;
+        const int nq = 2 * n_pc;
+        auto col = [&](int q) { return (q >> 1) * 64 + cb0 + (q & 1) * 16; };
+        if (cb0 < Lk) tmem_ld_32x16(t_lane + cb0, r[0]);
+        for (int q0 = 0; q0 < nq; q0 += 2) {
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const int q = q0 + b, c0 = col(q);
+            if (c0 < Lk) {
+              tmem_ld_wait();
+              if (q + 1 < nq && col(q + 1) < Lk) tmem_ld_32x16(t_lane + col(q + 1), r[b ^ 1]);
+              if (c0 >= shift && c0 + 16 <= Lk) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                  mx0 = max3(mx0, __uint_as_float(r[b][j]), __uint_as_float(r[b][j + 1]));
+                  mx1 = max3(mx1, __uint_as_float(r[b][j + 2]), __uint_as_float(r[b][j + 3]));
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (c0 + j >= shift && c0 + j < Lk) mx0 = fmaxf(mx0, __uint_as_float(r[b][j]));
+              }
+            }
+          }
+        }
+        if (cb0 < NK) tmem_ld_32x16(t_lane + cb0, r[0]);  // pass 2's first granule: under way during the exchange below
+        xmax[half] = fmaxf(mx0, mx1);
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        mb = fmaxf(xmax[0], xmax[1]) * SCALE_LOG2;
+        if (tr) ATT_TR(14 + 9 * grp);
+        // pass 2: the same granules; P is stored granule by granule (the chunk hand-shake wraps each pair)
+        const uint64_t scale2 = pack2(SCALE_LOG2, SCALE_LOG2), nmb2 = pack2(-mb, -mb);
+        uint64_t acc2 = pack2(0.f, 0.f);
+        sum = 0.f;
+        for (int q0 = 0; q0 < nq; q0 += 2) {
+          const int pc = q0 >> 1;
+          const int n_slots = min(64, NK - pc * 64) >> 3;  // 16-byte slots the P V MMAs of this chunk read
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const int q = q0 + b, c0 = col(q);
+            if (c0 < NK) {
+              tmem_ld_wait();
+              if (q + 1 < nq && col(q + 1) < NK) tmem_ld_32x16(t_lane + col(q + 1), r[b ^ 1]);
+            }
+            if (b == 0) mbar_wait(&bar_pfree[grp], (G & 1) ^ 1);  // the previous chunk's MMAs have read the buffer
+            if (c0 < NK) {
+              uint32_t pk[8];
+              if (c0 >= shift && c0 + 16 <= Lk) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                  float x0, x1;
+                  const uint64_t x2 = fma2(pack2(__uint_as_float(r[b][j]), __uint_as_float(r[b][j + 1])), scale2, nmb2);
+                  if (j == 2 || j == 8 || j == 12) {  // 3 of the 8 pairs: polynomial, off the XU pipe
+                    ex2_poly2(x2, x0, x1);
+                  } else {
+                    unpack2(x2, x0, x1);
+                    x0 = fast_ex2(x0);
+                    x1 = fast_ex2(x1);
+                  }
+                  acc2 = add2(acc2, pack2(x0, x1));
+                  pk[j >> 1] = pack_f16x2(x0, x1);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                  float x0 = 0.f, x1 = 0.f;
+                  if (c0 + j >= shift && c0 + j < Lk) x0 = fast_ex2(fmaf(__uint_as_float(r[b][j]), SCALE_LOG2, -mb));
+                  if (c0 + j + 1 >= shift && c0 + j + 1 < Lk)
+                    x1 = fast_ex2(fmaf(__uint_as_float(r[b][j + 1]), SCALE_LOG2, -mb));
+                  sum += x0 + x1;
+                  pk[j >> 1] = pack_f16x2(x0, x1);
+                }
+              }
+#pragma unroll
+              for (int jj = 0; jj < 2; ++jj) {  // the granule's two 16-byte slots (keys 8 slot .. 8 slot + 7)
+                const int sl = 4 * half + 2 * b + jj;
+                if (sl < n_slots)
+                  *reinterpret_cast<uint4*>(p_row + ((sl ^ (r_tile & 7)) << 4)) =
+                      make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+              }
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_pready[grp]);
+          if (tr && pc < 4) ATT_TR(15 + 9 * grp + pc);
+          ++G;
+        }
+        float s_lo, s_hi;
+        unpack2(acc2, s_lo, s_hi);
+        xsum[half] = sum + (s_lo + s_hi);
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        sum = xsum[0] + xsum[1];
+      }
+      const float inv = 1.0f / sum;
+      // epilogue: this half's 32 head dims of O / sum -> fp16 -> swizzled staging -> 64-byte row segments of ctx
+      mbar_wait(&bar_ofull[grp], uses & 1);
+      tc_fence_after();
+      if (tr) ATT_TR(19 + 9 * grp);
+      uint32_t o[32];
+      tmem_ld_32x32(t_lane + half * 32, o);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_otfree[grp]);
+      if (tr) ATT_TR(20 + 9 * grp);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = 4 * half + jj;  // 16-byte slot = head dims 8j .. 8j+7
+        const uint32_t* ov = o + 8 * jj;
+        *reinterpret_cast<uint4*>(o_row + ((j ^ (r_tile & 7)) << 4)) =
+            make_uint4(pack_f16x2(__uint_as_float(ov[0]) * inv, __uint_as_float(ov[1]) * inv),
+                       pack_f16x2(__uint_as_float(ov[2]) * inv, __uint_as_float(ov[3]) * inv),
+                       pack_f16x2(__uint_as_float(ov[4]) * inv, __uint_as_float(ov[5]) * inv),
+                       pack_f16x2(__uint_as_float(ov[6]) * inv, __uint_as_float(ov[7]) * inv));
+      }
+      __syncwarp();
+      const int row0 = grp * 128 + q * 32;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {  // 8 rows x 64 bytes per instruction
+        const int rr = 8 * i + (lane >> 2);
+        const int rt = q * 32 + rr;
+        const int j = 4 * half + (lane & 3);
+        const uint4 d = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((j ^ (rt & 7)) << 4));
+        if (row0 + rr < len)
+          *reinterpret_cast<uint4*>(ctx + (long long)(start + row0 + rr) * ldc + h * HD + j * 8) = d;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_ofree[grp]);
+      if (tr) ATT_TR(21 + 9 * grp);
+      ++uses;
+    }
+  } else if constexpr (VER == 6) {
+    // ===================== softmax + epilogue, VER 6: P never leaves tensor memory =====================
+    // VER 4 / 5 pass P through shared memory in 64-key chunks: four store -> fence.proxy.async -> mbarrier -> MMA ->
+    // commit round trips per tile (the trace: ~1.3k cycles each).  Here the two warps of a row split the KEY AXIS in
+    // two contiguous ranges ([0, 16 ks0) and [16 ks0, NK), ks0 = ceil(NK / 32)); each turns its scores into fp16
+    // probabilities 16 keys at a time and writes them back with tcgen05.st over the START of its own range -- step j
+    // of a range that begins at column c lands in columns [c + 8 j, c + 8 j + 8), which that same thread has already
+    // read (8 j + 8 <= 16 j + 16), so no ordering between threads is needed.  When all eight warps of the tile have
+    // arrived ONCE, the MMA warp issues every K step of O_t = P V with the A operand in tensor memory; O_t accumulates
+    // in columns [192, 256) (S is dead by then).  Granule-pipelined loads and the per-tile pipelines as VER 5.
+    const int sw = warp - 2;
+    const int grp = sw >> 3, half = (sw >> 2) & 1;
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const uint32_t t_lane = tmem_base + (uint32_t(q * 32) << 16) + grp * TILE_COLS;
+    constexpr float SCALE_LOG2 = 0.125f * 1.4426950408889634f;
+    const int ldc = heads * HD;
+    const int r_tile = q * 32 + lane;  // row inside the 128-row tile
+    float* xmax = reinterpret_cast<float*>(smem + SMEM_XCHG) + (grp * 128 + r_tile) * 2;
+    float* xsum = xmax + 512;
+    const uint32_t pair_bar = 1 + grp * 4 + q;  // named barrier of the two warps that share these 32 rows
+    uint32_t uses = 0, G = 0, item_n = 0;
+    int nx_start = 0, nx_len = 0;
+    if ((int)blockIdx.x < n_items) {
+      nx_start = cu_seqlens[blockIdx.x / heads];
+      nx_len = cu_seqlens[blockIdx.x / heads + 1] - nx_start;
+    }
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item_n) {
+      uint8_t* sm = smem + (item_n & 1) * SET_BYTES;
+      uint8_t* p_row = sm + SMEM_Q + grp * QTILE_BYTES + r_tile * 128;
+      // output staging: the tile's own P buffer (dead once O_t is complete).  Not the V^T region VER 1..4 use: the
+      // other tile slot runs on its own clock here and may still need every V^T chunk of this item
+      uint8_t* o_row = sm + SMEM_Q + grp * QTILE_BYTES + r_tile * 128;
+      const uint8_t* stg = sm + SMEM_Q + grp * QTILE_BYTES + q * 32 * 128;
+      const int h = it % heads;
+      const int start = nx_start, len = nx_len;
+      if (it + (int)gridDim.x < n_items) {  // the next item's bounds: in flight while this item is processed
+        const int nseq = (it + (int)gridDim.x) / heads;
+        nx_start = cu_seqlens[nseq];
+        nx_len = cu_seqlens[nseq + 1] - nx_start;
+      }
+      const int n_mt = (len + 127) >> 7;
+      if (grp >= n_mt) continue;
+      const int shift = start & 7;
+      const int Lk = shift + len;
+      const int NK = (Lk + 15) & ~15;
+      const int n_pc = (NK + 63) >> 6;
+      mbar_wait(&bar_sfull[grp], uses & 1);
+      tc_fence_after();
+      const bool tr = (q == 0 && half == 0);  // one warp per tile stamps: slots 13.. (tile 0), 22.. (tile 1)
+      if (tr) ATT_TR(13 + 9 * grp);
+      float mb = 0.f, sum = 1.f;
+      if (grp * 128 + q * 32 >= len) {
+        // all 32 rows beyond the sequence (both warps of the pair take this branch): only the tile's hand-shake (their
+        // P columns keep whatever bits S left there: rows of a product are independent and these are never stored)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_pready[grp]);
+        ++G;
+      } else {
+        // pass 1: maximum of this half's columns, in 16-column granules q = 0, 1, ...: granule q + 1 is loading
+        // while granule q is scanned (r[b] with b known after unrolling: both buffers stay in registers)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+        uint32_t r[2][16];
+        const int nks = NK >> 4, ks0 = (nks + 1) >> 1;
+        const int k_first = half ? ks0 : 0, nq = half ? nks - ks0 : ks0;  // this warp's 16-key steps
+        const int cb0 = 16 * k_first;
+        auto col = [&](int q) { return cb0 + 16 * q; };
+        if (nq > 0 && cb0 < Lk) tmem_ld_32x16(t_lane + cb0, r[0]);
+        for (int q0 = 0; q0 < nq; q0 += 2) {
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const int q = q0 + b, c0 = col(q);
+            if (q < nq && c0 < Lk) {
+              tmem_ld_wait();
+              if (q + 1 < nq && col(q + 1) < Lk) tmem_ld_32x16(t_lane + col(q + 1), r[b ^ 1]);
+              if (c0 >= shift && c0 + 16 <= Lk) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                  mx0 = max3(mx0, __uint_as_float(r[b][j]), __uint_as_float(r[b][j + 1]));
+                  mx1 = max3(mx1, __uint_as_float(r[b][j + 2]), __uint_as_float(r[b][j + 3]));
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (c0 + j >= shift && c0 + j < Lk) mx0 = fmaxf(mx0, __uint_as_float(r[b][j]));
+              }
+            }
+          }
+        }
+        if (nq > 0) tmem_ld_32x16(t_lane + cb0, r[0]);  // pass 2's first granule: under way during the exchange below
+        xmax[half] = fmaxf(mx0, mx1);
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        mb = fmaxf(xmax[0], xmax[1]) * SCALE_LOG2;
+        if (tr) ATT_TR(14 + 9 * grp);
+        // pass 2: the same granules; each becomes 8 columns of fp16 P written over this warp's own consumed range
+        const uint64_t scale2 = pack2(SCALE_LOG2, SCALE_LOG2), nmb2 = pack2(-mb, -mb);
+        uint64_t acc2 = pack2(0.f, 0.f);
+        sum = 0.f;
+        for (int q0 = 0; q0 < nq; q0 += 2) {
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const int q = q0 + b, c0 = col(q);
+            if (q < nq) {
+              tmem_ld_wait();
+              if (q + 1 < nq) tmem_ld_32x16(t_lane + col(q + 1), r[b ^ 1]);
+              uint32_t pk[8];
+              if (c0 >= shift && c0 + 16 <= Lk) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                  float x0, x1;
+                  const uint64_t x2 = fma2(pack2(__uint_as_float(r[b][j]), __uint_as_float(r[b][j + 1])), scale2, nmb2);
+                  if (j == 2 || j == 8 || j == 12) {  // 3 of the 8 pairs: polynomial, off the XU pipe
+                    ex2_poly2(x2, x0, x1);
+                  } else {
+                    unpack2(x2, x0, x1);
+                    x0 = fast_ex2(x0);
+                    x1 = fast_ex2(x1);
+                  }
+                  acc2 = add2(acc2, pack2(x0, x1));
+                  pk[j >> 1] = pack_f16x2(x0, x1);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                  float x0 = 0.f, x1 = 0.f;
+                  if (c0 + j >= shift && c0 + j < Lk) x0 = fast_ex2(fmaf(__uint_as_float(r[b][j]), SCALE_LOG2, -mb));
+                  if (c0 + j + 1 >= shift && c0 + j + 1 < Lk)
+                    x1 = fast_ex2(fmaf(__uint_as_float(r[b][j + 1]), SCALE_LOG2, -mb));
+                  sum += x0 + x1;
+                  pk[j >> 1] = pack_f16x2(x0, x1);
+                }
+              }
+              tmem_st_32x8(t_lane + cb0 + 8 * q, pk);
+            }
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_pready[grp]);
+        if (tr) ATT_TR(15 + 9 * grp);
+        ++G;
+        float s_lo, s_hi;
+        unpack2(acc2, s_lo, s_hi);
+        xsum[half] = sum + (s_lo + s_hi);
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        sum = xsum[0] + xsum[1];
+      }
+      const float inv = 1.0f / sum;
+      // epilogue: this half's 32 head dims of O / sum -> fp16 -> swizzled staging -> 64-byte row segments of ctx
+      mbar_wait(&bar_ofull[grp], uses & 1);
+      tc_fence_after();
+      if (tr) ATT_TR(19 + 9 * grp);
+      uint32_t o[32];
+      tmem_ld_32x32(t_lane + V6_O_COL + half * 32, o);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -635,8 +1130,8 @@ int mer_attention_f16_launch(const void* qkv16, const void* vt16, long long vt_l
   // MER_ATT_F16_VER=2 selects the granule softmax (see the kernel's header comment); read at every launch so that
   // a test can run both versions in one process.
   const char* ver_env = getenv("MER_ATT_F16_VER");
-  const int ver = ver_env ? atoi(ver_env) : 4;  // round-2 A/B on B200 (profiles/r2_ab_switches.json): 3 > 2 > 1; 4: 16 warps
-  auto kern = ver == 4 ? attention_f16_kernel<4>
+  const int ver = ver_env ? atoi(ver_env) : 6;  // round-2 A/B on B200 (profiles/r2_ab_switches.json): 3 > 2 > 1; 4: 16 warps
+  auto kern = ver == 6 ? attention_f16_kernel<6> : ver == 5 ? attention_f16_kernel<5> : ver == 4 ? attention_f16_kernel<4>
                        : (ver == 3 ? attention_f16_kernel<3> : (ver == 2 ? attention_f16_kernel<2> : attention_f16_kernel<1>));
   static MerPerDevice attr_set;
   if (attr_set.needs_setup()) {
@@ -644,6 +1139,8 @@ int mer_attention_f16_launch(const void* qkv16, const void* vt16, long long vt_l
     MER_CUDA_CHECK(cudaFuncSetAttribute(attention_f16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM));
     MER_CUDA_CHECK(cudaFuncSetAttribute(attention_f16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM));
     MER_CUDA_CHECK(cudaFuncSetAttribute(attention_f16_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM));
+    MER_CUDA_CHECK(cudaFuncSetAttribute(attention_f16_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM));
+    MER_CUDA_CHECK(cudaFuncSetAttribute(attention_f16_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM));
     attr_set.mark();
   }
   const long long items = (long long)n_seq * heads;
@@ -652,7 +1149,7 @@ int mer_attention_f16_launch(const void* qkv16, const void* vt16, long long vt_l
   if (items < grid) grid = (int)items;
   const double s_avg = (double)tokens / n_seq;  // exact for equal-length batches (ViT frames)
   const int prof = mer_prof_begin(MER_PROF_ATT_F16, 4.0 * s_avg * s_avg * HD * (double)items, stream);
-  kern<<<grid, ver == 4 ? F16_THREADS_V4 : F16_THREADS, F16_SMEM, stream>>>(tm, tv, static_cast<uint16_t*>(ctx16), cu_seqlens, n_seq, heads,
+  kern<<<grid, ver >= 4 ? F16_THREADS_V4 : F16_THREADS, F16_SMEM, stream>>>(tm, tv, static_cast<uint16_t*>(ctx16), cu_seqlens, n_seq, heads,
                                                                                g_att_trace);
   mer_prof_end(prof, stream);
   MER_CUDA_CHECK(cudaGetLastError());

@@ -1,4 +1,4 @@
-"""Phase timeline of attention_f16_kernel<4> (block 0, first items): clock64 stamps written by the kernel when the
+"""Phase timeline of attention_f16_kernel<4 | 5> (MER_ATT_F16_VER) (block 0, first items): clock64 stamps written by the kernel when the
 debug hook mer_debug_attention_trace() holds a buffer.  Prints, per item, cycles relative to the item's first stamp."""
 import ctypes as C
 import os
@@ -23,7 +23,7 @@ vt = torch.zeros(heads * 64, (tokens + 7) // 8 * 8, dtype=torch.float16, device=
 vt[:, :tokens] = qkv[:, 2 * heads * 64:].T
 cu = torch.arange(n_seq + 1, dtype=torch.int32, device=dev) * S
 ctx = torch.empty(tokens, heads * 64, dtype=torch.float16, device=dev)
-os.environ["MER_ATT_F16_VER"] = "4"
+os.environ["MER_ATT_F16_VER"] = os.environ.get("MER_ATT_F16_VER", "6")
 for _ in range(2):
     L.attention(qkv, ctx, cu, S, heads, vt=vt)
 buf = torch.zeros(16 * 32, dtype=torch.int64, device=dev)
