@@ -585,6 +585,7 @@ __global__ void __launch_bounds__(NT, 1) fus_rows_kernel(const __grid_constant__
 //     and scatters the column slices to their owners through DSMEM (a reduce-scatter; 8 partials summed in rank
 //     order -> deterministic).  No weight is read twice, no gradient is broadcast.
 //   * 12 cluster barriers per step (6 forward layers, 5 backward exchanges, 1 at entry), each ~0.3 us of hardware.
+long long* g_fus_trace = nullptr;  // debug: clock64 stamps of block 0 / thread 0 (scripts/micro/fusion_trace.py)
 constexpr int FRB = 4;        // rows per cluster
 constexpr int HCP = 16;       // slice width bound: ceil(128 / 8)
 constexpr int FMAXC = 2;      // columns per warp: ceil(16 / 8)
@@ -661,7 +662,13 @@ __device__ __forceinline__ void fast_finish(float (&acc)[FMAXC][FRB], int n0, in
 }
 
 __global__ void __launch_bounds__(NT, 1) fus_rows_fast_kernel(const __grid_constant__ RowArgs a,
-                                                              const __grid_constant__ FastPlan pl) {
+                                                              const __grid_constant__ FastPlan pl,
+                                                              long long* __restrict__ trace) {
+#define FUS_TR(slot)                                                                  \
+  do {                                                                                \
+    if (trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) trace[slot] = clock64(); \
+  } while (0)
+  FUS_TR(0);
   extern __shared__ __align__(16) float smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -742,7 +749,9 @@ __global__ void __launch_bounds__(NT, 1) fus_rows_fast_kernel(const __grid_const
     }
   }
   __syncthreads();
+  FUS_TR(1);
   cluster.sync();  // every CTA of the cluster is running: DSMEM stores may begin
+  FUS_TR(2);
   auto peer = [&](float* local) { return cluster.map_shared_rank(local, lane & (CL - 1)); };
 
   // ================= forward =================
@@ -772,8 +781,11 @@ __global__ void __launch_bounds__(NT, 1) fus_rows_fast_kernel(const __grid_const
       }
     }
   }
+  FUS_TR(3);
   cluster.sync();
+  FUS_TR(4);
   mbar_wait(&bars[2], 0);  // resident tiles (requested at entry: long since there)
+  FUS_TR(5);
   for (int m = 0; m < 3; ++m) {  // encoder layer 2
     float acc[FMAXC][FRB] = {};
     fast_accumulate(acc, h1 + m * FRB * H, H, H, t2 + m * HCP * H, H, nloc);
@@ -784,7 +796,9 @@ __global__ void __launch_bounds__(NT, 1) fus_rows_fast_kernel(const __grid_const
       if (lane == CL + r && train && row0 + r < B) a.ws.h2[((long long)m * B + row0 + r) * H + n] = v;
     });
   }
+  FUS_TR(6);
   cluster.sync();
+  FUS_TR(7);
   auto cat_factor = [&](int row, int col) {  // dropout factor of concat element (row, col)
     if (!drop || row >= B) return 1.f;
     const long long gi = (long long)row * H3 + col;
@@ -839,11 +853,15 @@ __global__ void __launch_bounds__(NT, 1) fus_rows_fast_kernel(const __grid_const
       if (lane == CL + r && train && row0 + r < B) a.ws.a3[(long long)(row0 + r) * H + n] = v;
     });
   }
+  FUS_TR(8);
   cluster.sync();
+  FUS_TR(9);
 
   head_rows<FRB>(a, rank, row0, train, hc, a3, feat, dfu, g3h, ga3);
+  FUS_TR(10);
   if (!train) {
     cluster.sync();
+    FUS_TR(11);
     return;
   }
   __syncthreads();
@@ -881,7 +899,9 @@ __global__ void __launch_bounds__(NT, 1) fus_rows_fast_kernel(const __grid_const
   for (int i = tid; i < FRB * nloc; i += NT) own_a[(i / nloc) * HCP + i % nloc] = ga3[(i / nloc) * H + n0 + i % nloc];
   __syncthreads();
   scatter(own_a, ta3, H, 0, 0);                                   // attention_mlp.linear_3 -> d a2
+  FUS_TR(11);
   cluster.sync();
+  FUS_TR(12);
   gather(0, 1, [&](int, int r, int kk, float s) {
     const int k = n0 + kk;
     const float g = a2[r * H + k] > 0.f ? s : 0.f;
@@ -924,6 +944,7 @@ __global__ void __launch_bounds__(NT, 1) fus_rows_fast_kernel(const __grid_const
     const float g = h1[(m * FRB + r) * H + k] > 0.f ? s : 0.f;
     if (row0 + r < B) a.ws.g1[((long long)m * B + row0 + r) * H + k] = g;
   });
+  FUS_TR(13);
   // zone 0 was last written before the barrier above and zone 1 two barriers ago: CTAs may retire independently
 }
 
@@ -1080,7 +1101,7 @@ int launch_rows_fast(const RowArgs& a, const FastPlan& pl, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MER_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fus_rows_fast_kernel, a, pl));
+  MER_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fus_rows_fast_kernel, a, pl, g_fus_trace));
   mer_count_launches(1);
   return 0;
 }
@@ -1168,6 +1189,8 @@ int fill_rows(RowArgs& a, const MerFusionDims* d, const float* params, const flo
 }  // namespace
 
 extern "C" {
+
+__attribute__((visibility("default"))) void mer_debug_fusion_trace(long long* device_buffer) { g_fus_trace = device_buffer; }
 
 long long mer_fusion_param_count(const MerFusionDims* d) {
   if (!d) return -1;

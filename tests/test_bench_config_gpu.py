@@ -127,12 +127,15 @@ def test_vit_stress_checkpoint_at_full_depth(cuda, precision, scale):
     assert bool(torch.isfinite(feats).all()) and m < bar
 
 
+@pytest.mark.parametrize("precision,bits", [("f16", 11), ("bf16x3", 17)])
 @pytest.mark.parametrize("scale", [3.0, 5.0, 10.0])
-def test_hubert_stress_checkpoint_at_full_depth(cuda, scale):
+def test_hubert_stress_checkpoint_at_full_depth(cuda, scale, precision, bits):
+    """Both operand formats of the 12 layers (the conv feature encoder is BF16X3 in both): fp16 (default since round
+    2, 11 significant bits) and the bf16 (hi, lo) split (17)."""
     from mertools_b200.encoders import HubertEncoder
     sd = S.hubert_state_dict(seed=1, layers=12, scale=scale)
     wav = (S.synth_waves(2, 48000, seed=29).astype(np.float64) / 32768.0).astype(np.float32)
-    enc = HubertEncoder(sd, device=cuda)
+    enc = HubertEncoder(sd, device=cuda, stack_precision=precision)
     utt, _ = enc.forward(torch.from_numpy(wav).to(cuda), normalize=True)
     worst, noise = 0.0, 0.0
     with torch.no_grad():
@@ -141,7 +144,7 @@ def test_hubert_stress_checkpoint_at_full_depth(cuda, scale):
             worst = max(worst, _rel(utt[i].cpu().numpy(), ref))
             if i == 0:
                 noise = _rel(ref, P.audio_clip_features(sd, wav[i].astype(np.float64), layers=12, dtype=torch.float64))
-    bar = _bar(noise, 17)
-    print(f"HuBERT x{scale:g} bf16x3: readout max-rel {worst:.2e}; bar {bar:.2e} (fp32-vs-fp64 {noise:.1e}); margin "
+    bar = _bar(noise, bits)
+    print(f"HuBERT x{scale:g} {precision}: readout max-rel {worst:.2e}; bar {bar:.2e} (fp32-vs-fp64 {noise:.1e}); margin "
           f"{bar / max(worst, 1e-12):.1f}x")
     assert bool(torch.isfinite(utt).all()) and worst < bar
