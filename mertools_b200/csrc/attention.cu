@@ -248,7 +248,7 @@ int mer_attention_launch(const float* qkv, const float* vt, long long vt_ld, flo
                 "mer_attention: fp16 inputs need MER_EPI_OUT_F16, V^T and sequences <= 249 tokens (max_seqlen %d)",
                 max_seqlen);
     if (tokens <= 0) return 0;
-    return mer_attention_f16_launch(qkv, vt, vt_ld, ctx, cu_seqlens, n_seq, tokens, heads, stream);
+    return mer_attention_f16_launch(qkv, vt, vt_ld, ctx, cu_seqlens, n_seq, tokens, heads, stream, max_seqlen);
   }
   // sequences of up to 256 tokens (ViT 197, HuBERT 5 s = 249, most sentences): tcgen05 kernel,
   // which reads V^T (written by the QKV GEMM epilogue) instead of the V columns of qkv

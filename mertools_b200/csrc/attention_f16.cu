@@ -32,6 +32,7 @@ using namespace mer;
 constexpr int HD = 64;
 constexpr int F16_THREADS = 320;          // producer, MMA issuer, 2 x 4 softmax/epilogue warps (VER 1..3)
 constexpr int F16_THREADS_V4 = 576;       // VER 4: 2 x 8 softmax/epilogue warps
+constexpr int F16_THREADS_V6 = 608;       // VER 6 / 7: + a second MMA issuer warp
 constexpr int K_BYTES = 256 * 128;        // K: up to 256 keys x 128 B
 constexpr int VT_CHUNK = HD * 128;        // V^T chunk: 64 d-rows x 64 keys (128 B)
 constexpr int QTILE_BYTES = 128 * 128;    // one 128-row Q tile; later the P-chunk buffer of the tile
@@ -58,6 +59,15 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) {  // SW128, SBO 
          (1ull << 46) | (2ull << 61);
 }
 
+// VER 7's shared-memory plan (bytes), sized on the host from the longest sequence of the launch: K and the second Q
+// tile are loaded with boxes of exactly the rows they need (197 tokens: 208 + 80 rows instead of 256 + 128)
+struct AttLay {
+  int off_k, off_v, off_q0, off_q1, set_bytes;  // inside an operand set
+  int off_stage;                                // 2 x 16 KB output staging, outside the sets
+  int off_bar, off_xchg;
+  int k_rows, q1_rows;
+};
+
 // VER 1: every score is compared against the valid key range [shift, Lk) (3 integer instructions per element
 //        in both passes: 35 % of the kernel's issued instructions in the round-1 ncu capture).
 // VER 3: VER 2 with 3 of every 8 exponential pairs of the unmasked granules computed by ex2_poly2 on the FMA / ALU
@@ -73,11 +83,22 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) {  // SW128, SBO 
 //        columns [32 half, 32 half + 32) of every 64-key chunk in both passes (9 loads, ~104 exponentials per
 //        thread), the partial row maxima / sums meet through shared memory under a 64-thread named barrier, both
 //        halves store their 64 bytes of each P row and of each output row.  Softmax body as VER 3.
-template <int VER>
-__global__ void __launch_bounds__(VER >= 4 ? F16_THREADS_V4 : F16_THREADS, 1)
+// VER 7: VER 6 with the operand loads taken off the critical path.  The trace of VER 6 showed every tile waiting ~2.7k
+//        cycles for K / Q of the next item: an operand set was reloaded only when BOTH tiles had finished their
+//        epilogues, and 96 KB of 128-byte rows take ~8k cycles to arrive (scripts/micro/tma_bench.cu: ~400 cycles per
+//        box plus ~2 per row from L2, 23 B/clk/SM from HBM with all SMs streaming).  Here the producer refills K and the
+//        Q tiles of a set as soon as the S = Q K^T products that read them are complete (a whole item earlier), V^T as
+//        soon as the P V products are; the output is staged in its own 2 x 16 KB buffers instead of a dead operand
+//        tile, and K / the second Q tile come in boxes of exactly the rows the launch needs.
+// POLY: pairs (of the 8 per 16-key granule) whose exponentials run on the FMA pipe (VER >= 6): the kernel is issue-
+//        bound with POLY = 3 and XU-bound with POLY = 0.
+template <int VER, int POLY = 3>
+__global__ void __launch_bounds__(VER >= 6 ? F16_THREADS_V6 : VER >= 4 ? F16_THREADS_V4 : F16_THREADS, 1)
 attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
-                     const __grid_constant__ CUtensorMap tmap_vt, uint16_t* __restrict__ ctx,
-                     const int* __restrict__ cu_seqlens, int n_seq, int heads, long long* __restrict__ trace) {
+                     const __grid_constant__ CUtensorMap tmap_vt, const __grid_constant__ CUtensorMap tmap_k,
+                     const __grid_constant__ CUtensorMap tmap_q1, const __grid_constant__ AttLay lay,
+                     uint16_t* __restrict__ ctx, const int* __restrict__ cu_seqlens, int n_seq, int heads,
+                     long long* __restrict__ trace) {
   // trace (debug, normally null): clock64() stamps of block 0's first 16 items, 32 slots per item (scripts/att_trace.py)
 #define ATT_TR(slot)                                                                           \
   do {                                                                                         \
@@ -85,7 +106,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   } while (0)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (VER == 7 ? lay.off_bar : SMEM_BAR));
   uint64_t* bar_k = bars + 0;       // [2 sets] producer -> MMA: K tile of the item
   uint64_t* bar_q = bars + 2;       // [2 sets] producer -> MMA: Q tiles
   uint64_t* bar_v = bars + 4;       // [2 sets] producer -> MMA: V^T chunks
@@ -96,6 +117,8 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   uint64_t* bar_ofree = bars + 14;  // [2] softmax group t -> producer: output staging (V^T region) consumed
   uint64_t* bar_otfree = bars + 16; // [2] softmax group t -> MMA: O_t has been read out of TMEM
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* bar_kfree = bars + 22;  // [2 sets] VER 7, MMA -> producer: both tile slots are done with the set's K / Q tiles
+  uint64_t* bar_vfree = bars + 24;  // [2 sets] VER 7, MMA -> producer: ... and with its V^T (a slot that skips the item arrives too)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = n_seq * heads;
@@ -113,6 +136,8 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
       mbar_init(&bar_ofull[t], 1);
       mbar_init(&bar_ofree[t], VER >= 4 ? 8 : 4);
       mbar_init(&bar_otfree[t], VER >= 4 ? 8 : 4);
+      mbar_init(&bar_kfree[t], 2);
+      mbar_init(&bar_vfree[t], 2);
     }
     fence_mbar_init();
   }
@@ -125,7 +150,47 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == 0 && VER == 7) {
+    // ===================== TMA producer, VER 7: refill as soon as the readers are done =====================
+    uint32_t uses[2] = {0, 0};
+    int h_nmt[2] = {0, 0};
+    uint32_t h_use[2][2] = {{0, 0}, {0, 0}};
+    uint32_t item_n = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item_n) {
+      const int set = item_n & 1;
+      uint8_t* sm = smem + set * lay.set_bytes;
+      const int seq = it / heads, h = it % heads;
+      const int start = cu_seqlens[seq];
+      const int len = cu_seqlens[seq + 1] - start;
+      const int n_mt = (len + 127) >> 7;
+      const int a_start = start & ~7;
+      const int Lk = (start - a_start) + len;
+      const int n_vc = (Lk + 63) >> 6;
+      // K and the Q tiles of this set were last read by the S products of item n - 2.  Own barriers (not sfull /
+      // ofull, whose phases the free-running tile pipelines may advance twice before this warp looks): kfree / vfree
+      // complete exactly once per item of the set, and the next completion needs the loads issued below
+      if (item_n >= 2) mbar_wait(&bar_kfree[set], ((item_n >> 1) - 1) & 1);
+      if (elect_one()) {
+        mbar_expect_tx(&bar_k[set], (uint32_t)(lay.k_rows * 128));
+        tma_load_2d(sm + lay.off_k, &tmap_k, &bar_k[set], heads * HD + h * HD, a_start);
+        mbar_expect_tx(&bar_q[set], (uint32_t)(QTILE_BYTES + (n_mt > 1 ? lay.q1_rows * 128 : 0)));
+        tma_load_2d(sm + lay.off_q0, &tmap_qkv, &bar_q[set], h * HD, start);
+        if (n_mt > 1) tma_load_2d(sm + lay.off_q1, &tmap_q1, &bar_q[set], h * HD, start + 128);
+      }
+      __syncwarp();
+      // V^T of this set was last read by the P V products of item n - 2
+      if (item_n >= 2) mbar_wait(&bar_vfree[set], ((item_n >> 1) - 1) & 1);
+      if (elect_one()) {
+        mbar_expect_tx(&bar_v[set], (uint32_t)(n_vc * VT_CHUNK));
+        for (int c = 0; c < n_vc; ++c)
+          tma_load_2d(sm + lay.off_v + c * VT_CHUNK, &tmap_vt, &bar_v[set], a_start + c * 64, h * HD);
+      }
+      __syncwarp();
+      ATT_TR(0);
+      h_nmt[set] = n_mt;
+      for (int t = 0; t < n_mt; ++t) h_use[set][t] = uses[t]++;
+    }
+  } else if (warp == 0) {
     // ===================== TMA producer (warp-uniform; one elected lane issues) =====================
     // Item n uses operand set n & 1: its K, Q tiles and V^T are requested as soon as item n - 2 has left
     // that set (its epilogues, the last users, are done), i.e. while item n - 1 is still computing.
@@ -162,126 +227,94 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
       h_nmt[set] = n_mt;
       for (int t = 0; t < n_mt; ++t) h_use[set][t] = uses[t]++;
     }
-  } else if (warp == 1 && VER >= 5) {
-    // ===================== MMA issuer, VER 5: one state machine per tile slot =====================
+  } else if (VER >= 6 && (warp == 1 || warp == 18)) {
+    // ===================== MMA issuers, VER 6 / 7: one warp per tile slot (warp 1: slot 0, warp 18: slot 1) ============
     // The phase trace of VER 4 (profiles/r2_attention_f16_v4_trace.txt) showed the two tiles of an item marching in
-    // lock-step: this warp served them in program order, so tile 0's next chunk waited for tile 1's previous one,
-    // and the next item's S_t waited for the other tile's last P V product and for a dependent global load of the
-    // sequence bounds (~1.3k cycles per item).  Here each tile slot walks through the items on its own: whenever
-    // slot t's next step is ready (operands landed, O_t drained, P chunk stored) it is issued, whatever the other
-    // slot is doing -- slot 0 may already be in item n + 1 (operand set B) while slot 1 finishes item n (set A).
-    // Sequence bounds of the item after next are loaded one item ahead.
-    const uint64_t desc_q0 = desc_kmajor(smem_u32(smem + SMEM_Q));
-    const uint64_t desc_k0 = desc_kmajor(smem_u32(smem + SMEM_K));
-    const uint64_t desc_v0 = desc_kmajor(smem_u32(smem + SMEM_V));
-    int it[2], stage[2], c_start[2], c_len[2], n_start[2], n_len[2];
-    uint32_t item_no[2], uses[2], g[2];
-    bool kq_ok[2], v_ok[2];
-    auto bounds = [&](int item, int& st, int& ln) {
-      if (item < n_items) {
-        const int seq = item / heads;
-        st = cu_seqlens[seq];
-        ln = cu_seqlens[seq + 1] - st;
-      } else {
-        st = 0;
-        ln = 0;
+    // lock-step behind one issuing warp that served them in program order; a single warp polling both slots (VER 5,
+    // dropped) reacted ~1.3k cycles late because the elected lane's issue loop competes for issue slots with four
+    // busy softmax warps of its scheduler.  Two warps on two schedulers, each walking through the items for its own
+    // slot with plain blocking waits: slot 0 may be in item n + 1 (operand set B) while slot 1 finishes item n (set A).
+    // The sequence bounds of the next item are loaded one item ahead (two independent loads, first touched later).
+    const int t = warp == 1 ? 0 : 1;
+    // these two warps have nothing else to do: spin on non-blocking probes (a try_wait that has gone to sleep reacted
+    // ~1k cycles late in the traces)
+    auto spin = [&](uint64_t* bar, uint32_t parity) {
+      while (!mbar_test_wait(bar, parity)) {
       }
     };
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      it[t] = blockIdx.x; stage[t] = 0; item_no[t] = 0; uses[t] = 0; g[t] = 0; kq_ok[t] = false; v_ok[t] = false;
-      bounds(it[t], c_start[t], c_len[t]);
-      bounds(it[t] + (int)gridDim.x, n_start[t], n_len[t]);
+    const int set_bytes = VER == 7 ? lay.set_bytes : SET_BYTES;
+    const uint64_t desc_q = desc_kmajor(smem_u32(smem + (VER == 7 ? (t ? lay.off_q1 : lay.off_q0) : SMEM_Q + t * QTILE_BYTES)));
+    const uint64_t desc_k = desc_kmajor(smem_u32(smem + (VER == 7 ? lay.off_k : SMEM_K)));
+    const uint64_t desc_v = desc_kmajor(smem_u32(smem + (VER == 7 ? lay.off_v : SMEM_V)));
+    const uint32_t slot = tmem_base + t * TILE_COLS;
+    const uint32_t idesc_o = umma_idesc(0, 128, HD);
+    uint32_t uses = 0, item_n = 0;
+    int nx_start = 0, nx_end = 0;
+    if ((int)blockIdx.x < n_items) {
+      nx_start = cu_seqlens[blockIdx.x / heads];
+      nx_end = cu_seqlens[blockIdx.x / heads + 1];
     }
-    while (it[0] < n_items || it[1] < n_items) {
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        if (it[t] >= n_items) continue;
-        const int start = c_start[t], len = c_len[t];
-        const int n_mt = (len + 127) >> 7;
-        const int NK = ((start & 7) + len + 15) & ~15;
-        const int n_pc = (NK + 63) >> 6;
-        const int set = item_no[t] & 1;
-        const uint32_t set_par = (item_no[t] >> 1) & 1;
-        bool advance = false;
-        if (t >= n_mt) {
-          advance = true;  // this item has no second tile
-        } else if (stage[t] == 0) {
-          if (!kq_ok[t]) kq_ok[t] = mbar_try_wait(&bar_k[set], set_par) && mbar_try_wait(&bar_q[set], set_par);
-          if (kq_ok[t] && (uses[t] == 0 || mbar_try_wait(&bar_otfree[t], (uses[t] - 1) & 1))) {
-            tc_fence_after();
-            if (elect_one()) {
-              const uint64_t set_off = (uint64_t)((set * SET_BYTES) >> 4);
-              const uint64_t da = desc_q0 + set_off + (uint64_t)((t * QTILE_BYTES) >> 4);
-              const uint64_t db = desc_k0 + set_off;
-              const uint32_t idesc_s = umma_idesc(0, 128, NK);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem_base + t * TILE_COLS, da + 2 * k, db + 2 * k, idesc_s, k != 0);
-              tc_commit(&bar_sfull[t]);
-            }
-            __syncwarp();
-            stage[t] = 1;
-          }
-        } else {
-          const int pc = stage[t] - 1;
-          if (!v_ok[t]) v_ok[t] = mbar_try_wait(&bar_v[set], set_par);
-          if (VER == 6) {
-            // P sits in tensor memory (written by the softmax warps): ONE hand-shake per tile, then every K step of
-            // O_t = P V in a row; A operand = the P columns of this step (see the VER 6 softmax block for the map)
-            if (v_ok[t] && mbar_try_wait(&bar_pready[t], g[t] & 1)) {
-              tc_fence_after();
-              if (elect_one()) {
-                const uint64_t set_off = (uint64_t)((set * SET_BYTES) >> 4);
-                const uint64_t dbv = desc_v0 + set_off;
-                const uint32_t idesc_o = umma_idesc(0, 128, HD);
-                const int nks = NK >> 4, ks0 = (nks + 1) >> 1;
-                const uint32_t slot = tmem_base + t * TILE_COLS;
-                for (int ks = 0; ks < nks; ++ks) {
-                  const uint32_t a_col = ks < ks0 ? 8 * ks : 16 * ks0 + 8 * (ks - ks0);
-                  tc_mma_f16_ts(slot + V6_O_COL, slot + a_col, dbv + (uint64_t)(((ks >> 2) * VT_CHUNK) >> 4) + 2 * (ks & 3),
-                                idesc_o, ks != 0);
-                }
-                tc_commit(&bar_ofull[t]);
-              }
-              __syncwarp();
-              ++g[t];
-              ++uses[t];
-              advance = true;
-            }
-          } else if (v_ok[t] && mbar_try_wait(&bar_pready[t], g[t] & 1)) {
-            tc_fence_after();
-            if (elect_one()) {
-              const uint64_t set_off = (uint64_t)((set * SET_BYTES) >> 4);
-              const uint64_t da = desc_q0 + set_off + (uint64_t)((t * QTILE_BYTES) >> 4);
-              const uint64_t db = desc_v0 + set_off + (uint64_t)((pc * VT_CHUNK) >> 4);
-              const uint32_t idesc_o = umma_idesc(0, 128, HD);
-              const int keys = min(64, NK - pc * 64);
-              for (int k = 0; k < keys / 16; ++k)
-                tc_mma_bf16(tmem_base + t * TILE_COLS, da + 2 * k, db + 2 * k, idesc_o, (pc | k) != 0);
-              tc_commit(&bar_pfree[t]);
-              if (pc == n_pc - 1) tc_commit(&bar_ofull[t]);
-            }
-            __syncwarp();
-            ++g[t];
-            if (pc == n_pc - 1) {
-              ++uses[t];
-              advance = true;
-            } else {
-              ++stage[t];
-            }
-          }
-        }
-        if (advance) {
-          it[t] += (int)gridDim.x;
-          ++item_no[t];
-          stage[t] = 0;
-          kq_ok[t] = false;
-          v_ok[t] = false;
-          c_start[t] = n_start[t];
-          c_len[t] = n_len[t];
-          bounds(it[t] + (int)gridDim.x, n_start[t], n_len[t]);
-        }
+    // The two slots run chains of equal length: started together they stay in phase -- both softmax groups fight for
+    // the XU / issue slots at the same time and the tensor pipe idles meanwhile (trace of the first two-warp build).
+    // Slot 1 therefore starts half a chain late; the hand-shakes keep the offset.
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item_n) {
+      const int start = nx_start, len = nx_end - nx_start;
+      if (it + (int)gridDim.x < n_items) {
+        const int nseq = (it + (int)gridDim.x) / heads;
+        nx_start = cu_seqlens[nseq];
+        nx_end = cu_seqlens[nseq + 1];
       }
+      const int set = item_n & 1;
+      const uint32_t set_par = (item_n >> 1) & 1;
+      const int n_mt = (len + 127) >> 7;
+      if (t >= n_mt) {  // this item has no second tile: the slot still releases the operand set (VER 7)
+        if (VER == 7 && elect_one()) {
+          mbar_arrive(&bar_kfree[set]);
+          mbar_arrive(&bar_vfree[set]);
+        }
+        __syncwarp();
+        continue;
+      }
+      const int NK = ((start & 7) + len + 15) & ~15;
+      const int nks = NK >> 4, ks0 = (nks + 1) >> 1;
+      const uint64_t set_off = (uint64_t)((set * set_bytes) >> 4);
+      const uint64_t da = desc_q + set_off, db = desc_k + set_off, dv = desc_v + set_off;
+      const uint32_t idesc_s = umma_idesc(0, 128, NK);
+      spin(&bar_k[set], set_par);
+      spin(&bar_q[set], set_par);
+      if (uses > 0) spin(&bar_otfree[t], (uses - 1) & 1);  // O_t of the previous item has been read out
+      if (uses == 0 && t == 1) __nanosleep(2400);  // (after the first operands have landed: their latency would swallow it)
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc_mma_bf16(slot, da + 2 * k, db + 2 * k, idesc_s, k != 0);
+        tc_commit(&bar_sfull[t]);
+        if (VER == 7) tc_commit(&bar_kfree[set]);
+      }
+      __syncwarp();
+      if (t == 0) ATT_TR(2);
+      if (t == 1) ATT_TR(3);
+      spin(&bar_v[set], set_par);
+      spin(&bar_pready[t], uses & 1);  // all eight softmax warps of the tile have written their P columns
+      tc_fence_after();
+      if (elect_one()) {
+        // K step ks: A = the 8 P columns of keys 16 ks .. 16 ks + 15 (the two key ranges of the softmax warps start at
+        // columns 0 and 16 ks0), B = 16 rows of V^T chunk ks / 4
+        uint32_t a_col = slot;
+        uint64_t b = dv;
+        for (int ks = 0; ks < nks; ++ks) {
+          if (ks == ks0) a_col = slot + 16 * ks0;
+          tc_mma_f16_ts(slot + V6_O_COL, a_col, b, idesc_o, ks != 0);
+          a_col += 8;
+          b += ((ks & 3) == 3) ? (uint64_t)((VT_CHUNK >> 4) - 6) : 2;
+        }
+        tc_commit(&bar_ofull[t]);
+        if (VER == 7) tc_commit(&bar_vfree[set]);
+      }
+      __syncwarp();
+      if (t == 0) ATT_TR(5);
+      if (t == 1) ATT_TR(6);
+      ++uses;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (warp-uniform; one elected lane issues and commits) =========
@@ -353,7 +386,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
     constexpr float SCALE_LOG2 = 0.125f * 1.4426950408889634f;
     const int ldc = heads * HD;
     const int r_tile = q * 32 + lane;  // row inside the 128-row tile
-    float* xmax = reinterpret_cast<float*>(smem + SMEM_XCHG) + (grp * 128 + r_tile) * 2;
+    float* xmax = reinterpret_cast<float*>(smem + (VER == 7 ? lay.off_xchg : SMEM_XCHG)) + (grp * 128 + r_tile) * 2;
     float* xsum = xmax + 512;
     const uint32_t pair_bar = 1 + grp * 4 + q;  // named barrier of the two warps that share these 32 rows
     uint32_t uses = 0, G = 0, item_n = 0;
@@ -513,196 +546,9 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
       if (tr) ATT_TR(21 + 9 * grp);
       ++uses;
     }
-  } else if constexpr (VER == 5) {
-    // ===================== softmax + epilogue, VER 5 = VER 4 with the TMEM loads of the next chunk in flight while the
-    // current one is being turned into probabilities, P stored as it is produced, sequence bounds one item ahead ====
-    const int sw = warp - 2;
-    const int grp = sw >> 3, half = (sw >> 2) & 1;
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const uint32_t t_lane = tmem_base + (uint32_t(q * 32) << 16) + grp * TILE_COLS;
-    constexpr float SCALE_LOG2 = 0.125f * 1.4426950408889634f;
-    const int ldc = heads * HD;
-    const int r_tile = q * 32 + lane;  // row inside the 128-row tile
-    float* xmax = reinterpret_cast<float*>(smem + SMEM_XCHG) + (grp * 128 + r_tile) * 2;
-    float* xsum = xmax + 512;
-    const uint32_t pair_bar = 1 + grp * 4 + q;  // named barrier of the two warps that share these 32 rows
-    uint32_t uses = 0, G = 0, item_n = 0;
-    int nx_start = 0, nx_len = 0;
-    if ((int)blockIdx.x < n_items) {
-      nx_start = cu_seqlens[blockIdx.x / heads];
-      nx_len = cu_seqlens[blockIdx.x / heads + 1] - nx_start;
-    }
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item_n) {
-      uint8_t* sm = smem + (item_n & 1) * SET_BYTES;
-      uint8_t* p_row = sm + SMEM_Q + grp * QTILE_BYTES + r_tile * 128;
-      // output staging: the tile's own P buffer (dead once O_t is complete).  Not the V^T region VER 1..4 use: the
-      // other tile slot runs on its own clock here and may still need every V^T chunk of this item
-      uint8_t* o_row = sm + SMEM_Q + grp * QTILE_BYTES + r_tile * 128;
-      const uint8_t* stg = sm + SMEM_Q + grp * QTILE_BYTES + q * 32 * 128;
-      const int h = it % heads;
-      const int start = nx_start, len = nx_len;
-      if (it + (int)gridDim.x < n_items) {  // the next item's bounds: in flight while this item is processed
-        const int nseq = (it + (int)gridDim.x) / heads;
-        nx_start = cu_seqlens[nseq];
-        nx_len = cu_seqlens[nseq + 1] - nx_start;
-      }
-      const int n_mt = (len + 127) >> 7;
-      if (grp >= n_mt) continue;
-      const int shift = start & 7;
-      const int Lk = shift + len;
-      const int NK = (Lk + 15) & ~15;
-      const int n_pc = (NK + 63) >> 6;
-      mbar_wait(&bar_sfull[grp], uses & 1);
-      tc_fence_after();
-      const bool tr = (q == 0 && half == 0);  // one warp per tile stamps: slots 13.. (tile 0), 22.. (tile 1)
-      if (tr) ATT_TR(13 + 9 * grp);
-      float mb = 0.f, sum = 1.f;
-      if (grp * 128 + q * 32 >= len) {
-        // all 32 rows beyond the sequence (both warps of the pair take this branch): only the chunk hand-shake
-        for (int pc = 0; pc < n_pc; ++pc, ++G) {
-          mbar_wait(&bar_pfree[grp], (G & 1) ^ 1);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar_pready[grp]);
-        }
-      } else {
-        // pass 1: maximum of this half's columns, in 16-column granules q = 0, 1, ...: granule q + 1 is loading
-        // while granule q is scanned (r[b] with b known after unrolling: both buffers stay in registers)
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-        uint32_t r[2][16];
-        const int cb0 = half * 32;
-        const int nq = 2 * n_pc;
-        auto col = [&](int q) { return (q >> 1) * 64 + cb0 + (q & 1) * 16; };
-        if (cb0 < Lk) tmem_ld_32x16(t_lane + cb0, r[0]);
-        for (int q0 = 0; q0 < nq; q0 += 2) {
-#pragma unroll
-          for (int b = 0; b < 2; ++b) {
-            const int q = q0 + b, c0 = col(q);
-            if (c0 < Lk) {
-              tmem_ld_wait();
-              if (q + 1 < nq && col(q + 1) < Lk) tmem_ld_32x16(t_lane + col(q + 1), r[b ^ 1]);
-              if (c0 >= shift && c0 + 16 <= Lk) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                  mx0 = max3(mx0, __uint_as_float(r[b][j]), __uint_as_float(r[b][j + 1]));
-                  mx1 = max3(mx1, __uint_as_float(r[b][j + 2]), __uint_as_float(r[b][j + 3]));
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (c0 + j >= shift && c0 + j < Lk) mx0 = fmaxf(mx0, __uint_as_float(r[b][j]));
-              }
-            }
-          }
-        }
-        if (cb0 < NK) tmem_ld_32x16(t_lane + cb0, r[0]);  // pass 2's first granule: under way during the exchange below
-        xmax[half] = fmaxf(mx0, mx1);
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-        mb = fmaxf(xmax[0], xmax[1]) * SCALE_LOG2;
-        if (tr) ATT_TR(14 + 9 * grp);
-        // pass 2: the same granules; P is stored granule by granule (the chunk hand-shake wraps each pair)
-        const uint64_t scale2 = pack2(SCALE_LOG2, SCALE_LOG2), nmb2 = pack2(-mb, -mb);
-        uint64_t acc2 = pack2(0.f, 0.f);
-        sum = 0.f;
-        for (int q0 = 0; q0 < nq; q0 += 2) {
-          const int pc = q0 >> 1;
-          const int n_slots = min(64, NK - pc * 64) >> 3;  // 16-byte slots the P V MMAs of this chunk read
-#pragma unroll
-          for (int b = 0; b < 2; ++b) {
-            const int q = q0 + b, c0 = col(q);
-            if (c0 < NK) {
-              tmem_ld_wait();
-              if (q + 1 < nq && col(q + 1) < NK) tmem_ld_32x16(t_lane + col(q + 1), r[b ^ 1]);
-            }
-            if (b == 0) mbar_wait(&bar_pfree[grp], (G & 1) ^ 1);  // the previous chunk's MMAs have read the buffer
-            if (c0 < NK) {
-              uint32_t pk[8];
-              if (c0 >= shift && c0 + 16 <= Lk) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                  float x0, x1;
-                  const uint64_t x2 = fma2(pack2(__uint_as_float(r[b][j]), __uint_as_float(r[b][j + 1])), scale2, nmb2);
-                  if (j == 2 || j == 8 || j == 12) {  // 3 of the 8 pairs: polynomial, off the XU pipe
-                    ex2_poly2(x2, x0, x1);
-                  } else {
-                    unpack2(x2, x0, x1);
-                    x0 = fast_ex2(x0);
-                    x1 = fast_ex2(x1);
-                  }
-                  acc2 = add2(acc2, pack2(x0, x1));
-                  pk[j >> 1] = pack_f16x2(x0, x1);
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                  float x0 = 0.f, x1 = 0.f;
-                  if (c0 + j >= shift && c0 + j < Lk) x0 = fast_ex2(fmaf(__uint_as_float(r[b][j]), SCALE_LOG2, -mb));
-                  if (c0 + j + 1 >= shift && c0 + j + 1 < Lk)
-                    x1 = fast_ex2(fmaf(__uint_as_float(r[b][j + 1]), SCALE_LOG2, -mb));
-                  sum += x0 + x1;
-                  pk[j >> 1] = pack_f16x2(x0, x1);
-                }
-              }
-#pragma unroll
-              for (int jj = 0; jj < 2; ++jj) {  // the granule's two 16-byte slots (keys 8 slot .. 8 slot + 7)
-                const int sl = 4 * half + 2 * b + jj;
-                if (sl < n_slots)
-                  *reinterpret_cast<uint4*>(p_row + ((sl ^ (r_tile & 7)) << 4)) =
-                      make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
-              }
-            }
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar_pready[grp]);
-          if (tr && pc < 4) ATT_TR(15 + 9 * grp + pc);
-          ++G;
-        }
-        float s_lo, s_hi;
-        unpack2(acc2, s_lo, s_hi);
-        xsum[half] = sum + (s_lo + s_hi);
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-        sum = xsum[0] + xsum[1];
-      }
-      const float inv = 1.0f / sum;
-      // epilogue: this half's 32 head dims of O / sum -> fp16 -> swizzled staging -> 64-byte row segments of ctx
-      mbar_wait(&bar_ofull[grp], uses & 1);
-      tc_fence_after();
-      if (tr) ATT_TR(19 + 9 * grp);
-      uint32_t o[32];
-      tmem_ld_32x32(t_lane + half * 32, o);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_otfree[grp]);
-      if (tr) ATT_TR(20 + 9 * grp);
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int j = 4 * half + jj;  // 16-byte slot = head dims 8j .. 8j+7
-        const uint32_t* ov = o + 8 * jj;
-        *reinterpret_cast<uint4*>(o_row + ((j ^ (r_tile & 7)) << 4)) =
-            make_uint4(pack_f16x2(__uint_as_float(ov[0]) * inv, __uint_as_float(ov[1]) * inv),
-                       pack_f16x2(__uint_as_float(ov[2]) * inv, __uint_as_float(ov[3]) * inv),
-                       pack_f16x2(__uint_as_float(ov[4]) * inv, __uint_as_float(ov[5]) * inv),
-                       pack_f16x2(__uint_as_float(ov[6]) * inv, __uint_as_float(ov[7]) * inv));
-      }
-      __syncwarp();
-      const int row0 = grp * 128 + q * 32;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {  // 8 rows x 64 bytes per instruction
-        const int rr = 8 * i + (lane >> 2);
-        const int rt = q * 32 + rr;
-        const int j = 4 * half + (lane & 3);
-        const uint4 d = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((j ^ (rt & 7)) << 4));
-        if (row0 + rr < len)
-          *reinterpret_cast<uint4*>(ctx + (long long)(start + row0 + rr) * ldc + h * HD + j * 8) = d;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_ofree[grp]);
-      if (tr) ATT_TR(21 + 9 * grp);
-      ++uses;
-    }
-  } else if constexpr (VER == 6) {
-    // ===================== softmax + epilogue, VER 6: P never leaves tensor memory =====================
+  } else if constexpr (VER >= 6) {
+    // (warp 18, the second MMA issuer, took the branch above)
+    // ===================== softmax + epilogue, VER 6 / 7: P never leaves tensor memory =====================
     // VER 4 / 5 pass P through shared memory in 64-key chunks: four store -> fence.proxy.async -> mbarrier -> MMA ->
     // commit round trips per tile (the trace: ~1.3k cycles each).  Here the two warps of a row split the KEY AXIS in
     // two contiguous ranges ([0, 16 ks0) and [16 ks0, NK), ks0 = ceil(NK / 32)); each turns its scores into fp16
@@ -718,28 +564,29 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
     constexpr float SCALE_LOG2 = 0.125f * 1.4426950408889634f;
     const int ldc = heads * HD;
     const int r_tile = q * 32 + lane;  // row inside the 128-row tile
-    float* xmax = reinterpret_cast<float*>(smem + SMEM_XCHG) + (grp * 128 + r_tile) * 2;
+    float* xmax = reinterpret_cast<float*>(smem + (VER == 7 ? lay.off_xchg : SMEM_XCHG)) + (grp * 128 + r_tile) * 2;
     float* xsum = xmax + 512;
     const uint32_t pair_bar = 1 + grp * 4 + q;  // named barrier of the two warps that share these 32 rows
     uint32_t uses = 0, G = 0, item_n = 0;
-    int nx_start = 0, nx_len = 0;
+    int nx_start = 0, nx_end = 0;  // raw loads of the next item's bounds: first touched when that item begins
     if ((int)blockIdx.x < n_items) {
       nx_start = cu_seqlens[blockIdx.x / heads];
-      nx_len = cu_seqlens[blockIdx.x / heads + 1] - nx_start;
+      nx_end = cu_seqlens[blockIdx.x / heads + 1];
     }
     for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++item_n) {
-      uint8_t* sm = smem + (item_n & 1) * SET_BYTES;
-      uint8_t* p_row = sm + SMEM_Q + grp * QTILE_BYTES + r_tile * 128;
-      // output staging: the tile's own P buffer (dead once O_t is complete).  Not the V^T region VER 1..4 use: the
-      // other tile slot runs on its own clock here and may still need every V^T chunk of this item
-      uint8_t* o_row = sm + SMEM_Q + grp * QTILE_BYTES + r_tile * 128;
-      const uint8_t* stg = sm + SMEM_Q + grp * QTILE_BYTES + q * 32 * 128;
+      // output staging: VER 6: the tile's own Q buffer of this item's set (dead once S_t is complete; not the V^T
+      // region VER 1..4 use: the other tile slot runs on its own clock and may still need every V^T chunk);
+      // VER 7: a buffer of its own -- the Q tiles are being refilled for the item after next by then
+      uint8_t* stage_t = VER == 7 ? smem + lay.off_stage + grp * QTILE_BYTES
+                                  : smem + (item_n & 1) * SET_BYTES + SMEM_Q + grp * QTILE_BYTES;
+      uint8_t* o_row = stage_t + r_tile * 128;
+      const uint8_t* stg = stage_t + q * 32 * 128;
       const int h = it % heads;
-      const int start = nx_start, len = nx_len;
+      const int start = nx_start, len = nx_end - nx_start;
       if (it + (int)gridDim.x < n_items) {  // the next item's bounds: in flight while this item is processed
         const int nseq = (it + (int)gridDim.x) / heads;
         nx_start = cu_seqlens[nseq];
-        nx_len = cu_seqlens[nseq + 1] - nx_start;
+        nx_end = cu_seqlens[nseq + 1];
       }
       const int n_mt = (len + 127) >> 7;
       if (grp >= n_mt) continue;
@@ -759,36 +606,38 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
         if (lane == 0) mbar_arrive(&bar_pready[grp]);
         ++G;
       } else {
-        // pass 1: maximum of this half's columns, in 16-column granules q = 0, 1, ...: granule q + 1 is loading
-        // while granule q is scanned (r[b] with b known after unrolling: both buffers stay in registers)
+        // pass 1: maximum of this warp's key range, 32 columns per load (few, large loads: this pass is all latency)
         float mx0 = -INFINITY, mx1 = -INFINITY;
-        uint32_t r[2][16];
         const int nks = NK >> 4, ks0 = (nks + 1) >> 1;
         const int k_first = half ? ks0 : 0, nq = half ? nks - ks0 : ks0;  // this warp's 16-key steps
         const int cb0 = 16 * k_first;
-        auto col = [&](int q) { return cb0 + 16 * q; };
-        if (nq > 0 && cb0 < Lk) tmem_ld_32x16(t_lane + cb0, r[0]);
-        for (int q0 = 0; q0 < nq; q0 += 2) {
+        auto col = [&](int g) { return cb0 + 16 * g; };
+        {
+          uint32_t w[32];
+          const int n32 = (nq + 1) >> 1;  // loads of 32 columns (the last one may reach 16 columns past the range)
+          for (int g = 0; g < n32; ++g) {
+            tmem_ld_32x32(t_lane + cb0 + 32 * g, w);
+            tmem_ld_wait();
 #pragma unroll
-          for (int b = 0; b < 2; ++b) {
-            const int q = q0 + b, c0 = col(q);
-            if (q < nq && c0 < Lk) {
-              tmem_ld_wait();
-              if (q + 1 < nq && col(q + 1) < Lk) tmem_ld_32x16(t_lane + col(q + 1), r[b ^ 1]);
-              if (c0 >= shift && c0 + 16 <= Lk) {
+            for (int hh = 0; hh < 2; ++hh) {  // the two 16-key steps of this load (the second may lie past the range)
+              const int c0 = cb0 + 32 * g + 16 * hh;
+              if (2 * g + hh < nq) {
+                if (c0 >= shift && c0 + 16 <= Lk) {
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                  mx0 = max3(mx0, __uint_as_float(r[b][j]), __uint_as_float(r[b][j + 1]));
-                  mx1 = max3(mx1, __uint_as_float(r[b][j + 2]), __uint_as_float(r[b][j + 3]));
+                  for (int j = 0; j < 16; j += 4) {
+                    mx0 = max3(mx0, __uint_as_float(w[16 * hh + j]), __uint_as_float(w[16 * hh + j + 1]));
+                    mx1 = max3(mx1, __uint_as_float(w[16 * hh + j + 2]), __uint_as_float(w[16 * hh + j + 3]));
+                  }
+                } else if (c0 < Lk) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    if (c0 + j >= shift && c0 + j < Lk) mx0 = fmaxf(mx0, __uint_as_float(w[16 * hh + j]));
                 }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (c0 + j >= shift && c0 + j < Lk) mx0 = fmaxf(mx0, __uint_as_float(r[b][j]));
               }
             }
           }
         }
+        uint32_t r[2][16];
         if (nq > 0) tmem_ld_32x16(t_lane + cb0, r[0]);  // pass 2's first granule: under way during the exchange below
         xmax[half] = fmaxf(mx0, mx1);
         asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
@@ -811,7 +660,7 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
                 for (int j = 0; j < 16; j += 2) {
                   float x0, x1;
                   const uint64_t x2 = fma2(pack2(__uint_as_float(r[b][j]), __uint_as_float(r[b][j + 1])), scale2, nmb2);
-                  if (j == 2 || j == 8 || j == 12) {  // 3 of the 8 pairs: polynomial, off the XU pipe
+                  if ((POLY >= 1 && j == 8) || (POLY >= 2 && j == 2) || (POLY >= 3 && j == 12)) {  // FMA-pipe exponentials
                     ex2_poly2(x2, x0, x1);
                   } else {
                     unpack2(x2, x0, x1);
@@ -1106,16 +955,53 @@ bool mer_attention_f16_supported(int max_seqlen) { return max_seqlen > 0 && max_
 // ctx16: fp16 [tokens, heads*64]
 int mer_attention_f16_launch(const void* qkv16, const void* vt16, long long vt_ld, void* ctx16,
                              const int* cu_seqlens, int n_seq, long long tokens, int heads,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, int max_seqlen) {
   MER_REQUIRE(qkv16 && vt16 && ctx16 && cu_seqlens, "mer_attention_f16: null operand");
   MER_REQUIRE(vt_ld >= tokens && vt_ld % 8 == 0, "mer_attention_f16: V^T pitch %lld must be a multiple of 8 >= tokens",
               vt_ld);
-  CUtensorMap tm, tv;
+  if (max_seqlen <= 0 || max_seqlen > 249) max_seqlen = 249;
+  // MER_ATT_F16_VER selects the kernel generation (see the header comments); read at every launch so that a test can
+  // run all of them in one process.  VER 7 needs its shared-memory plan to fit (sequences up to ~230 tokens), else 6.
+  const char* ver_env = getenv("MER_ATT_F16_VER");
+  int ver = ver_env ? atoi(ver_env) : 6;  // measured (profiles/r2_attention_f16_versions.json): 6 ~ 7 > 4 ~ 3 > 2 > 1
+  if (ver == 5) ver = 6;  // VER 5 (one polling MMA warp, P through shared memory) was measured slower than VER 3 and dropped
+  const char* poly_env = getenv("MER_ATT_F16_POLY");
+  const int poly = poly_env ? atoi(poly_env) : 1;
+  // VER 7 plan: exact-size boxes for K (all keys of the longest sequence, shifted by up to 7) and the second Q tile
+  AttLay lay;
+  memset(&lay, 0, sizeof(lay));
+  lay.k_rows = (max_seqlen + 7 + 15) & ~15;
+  if (lay.k_rows > 256) lay.k_rows = 256;
+  lay.q1_rows = max_seqlen > 128 ? ((max_seqlen - 128 + 7) & ~7) : 0;
+  auto up = [](int x) { return (x + 1023) & ~1023; };
+  lay.off_k = 0;
+  lay.off_v = up(lay.k_rows * 128);
+  lay.off_q0 = lay.off_v + ((lay.k_rows + 63) / 64) * VT_CHUNK;
+  lay.off_q1 = lay.off_q0 + QTILE_BYTES;
+  lay.set_bytes = lay.off_q1 + up(lay.q1_rows * 128);
+  lay.off_stage = 2 * lay.set_bytes;
+  lay.off_bar = lay.off_stage + 2 * QTILE_BYTES;
+  lay.off_xchg = lay.off_bar + 256;
+  const int smem7 = lay.off_xchg + 4096 + 1024;
+  if (ver == 7 && smem7 > 227 * 1024) ver = 6;
+  CUtensorMap tm, tv, tk, tq1;
+  const uint64_t qdims[2] = {(uint64_t)(3 * heads * HD), (uint64_t)tokens};
+  const uint64_t qstrides[1] = {(uint64_t)(3 * heads * HD) * 2ull};
   {
-    const uint64_t dims[2] = {(uint64_t)(3 * heads * HD), (uint64_t)tokens};
-    const uint64_t strides[1] = {(uint64_t)(3 * heads * HD) * 2ull};
     const uint32_t box[2] = {64, 128};
-    if (int rc = mer_make_tmap(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, qkv16, dims, strides, box,
+    if (int rc = mer_make_tmap(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, qkv16, qdims, qstrides, box,
+                               CU_TENSOR_MAP_SWIZZLE_128B))
+      return rc;
+  }
+  {
+    const uint32_t box[2] = {64, (uint32_t)lay.k_rows};
+    if (int rc = mer_make_tmap(&tk, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, qkv16, qdims, qstrides, box,
+                               CU_TENSOR_MAP_SWIZZLE_128B))
+      return rc;
+  }
+  {
+    const uint32_t box[2] = {64, (uint32_t)(lay.q1_rows > 0 ? lay.q1_rows : 8)};
+    if (int rc = mer_make_tmap(&tq1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, qkv16, qdims, qstrides, box,
                                CU_TENSOR_MAP_SWIZZLE_128B))
       return rc;
   }
@@ -1127,20 +1013,20 @@ int mer_attention_f16_launch(const void* qkv16, const void* vt16, long long vt_l
                                CU_TENSOR_MAP_SWIZZLE_128B))
       return rc;
   }
-  // MER_ATT_F16_VER=2 selects the granule softmax (see the kernel's header comment); read at every launch so that
-  // a test can run both versions in one process.
-  const char* ver_env = getenv("MER_ATT_F16_VER");
-  const int ver = ver_env ? atoi(ver_env) : 6;  // round-2 A/B on B200 (profiles/r2_ab_switches.json): 3 > 2 > 1; 4: 16 warps
-  auto kern = ver == 6 ? attention_f16_kernel<6> : ver == 5 ? attention_f16_kernel<5> : ver == 4 ? attention_f16_kernel<4>
-                       : (ver == 3 ? attention_f16_kernel<3> : (ver == 2 ? attention_f16_kernel<2> : attention_f16_kernel<1>));
+  using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttLay, uint16_t*,
+                        const int*, int, int, long long*);
+  Kern kern = ver == 7 ? (poly == 0 ? attention_f16_kernel<7, 0> : poly == 1 ? attention_f16_kernel<7, 1>
+                                   : poly == 2 ? attention_f16_kernel<7, 2> : attention_f16_kernel<7, 3>)
+            : ver == 6 ? (poly == 1 ? attention_f16_kernel<6, 1> : attention_f16_kernel<6, 3>)
+            : ver == 4 ? attention_f16_kernel<4>
+            : ver == 3 ? attention_f16_kernel<3> : ver == 2 ? attention_f16_kernel<2> : attention_f16_kernel<1>;
   static MerPerDevice attr_set;
   if (attr_set.needs_setup()) {
-    MER_CUDA_CHECK(cudaFuncSetAttribute(attention_f16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM));
-    MER_CUDA_CHECK(cudaFuncSetAttribute(attention_f16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM));
-    MER_CUDA_CHECK(cudaFuncSetAttribute(attention_f16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM));
-    MER_CUDA_CHECK(cudaFuncSetAttribute(attention_f16_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM));
-    MER_CUDA_CHECK(cudaFuncSetAttribute(attention_f16_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM));
-    MER_CUDA_CHECK(cudaFuncSetAttribute(attention_f16_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, F16_SMEM));
+    const Kern all[] = {attention_f16_kernel<1>, attention_f16_kernel<2>, attention_f16_kernel<3>, attention_f16_kernel<4>,
+                        attention_f16_kernel<6, 1>, attention_f16_kernel<6, 3>,
+                        attention_f16_kernel<7, 0>, attention_f16_kernel<7, 1>, attention_f16_kernel<7, 2>,
+                        attention_f16_kernel<7, 3>};
+    for (Kern k : all) MER_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set.mark();
   }
   const long long items = (long long)n_seq * heads;
@@ -1149,8 +1035,8 @@ int mer_attention_f16_launch(const void* qkv16, const void* vt16, long long vt_l
   if (items < grid) grid = (int)items;
   const double s_avg = (double)tokens / n_seq;  // exact for equal-length batches (ViT frames)
   const int prof = mer_prof_begin(MER_PROF_ATT_F16, 4.0 * s_avg * s_avg * HD * (double)items, stream);
-  kern<<<grid, ver >= 4 ? F16_THREADS_V4 : F16_THREADS, F16_SMEM, stream>>>(tm, tv, static_cast<uint16_t*>(ctx16), cu_seqlens, n_seq, heads,
-                                                                               g_att_trace);
+  kern<<<grid, ver >= 6 ? F16_THREADS_V6 : ver >= 4 ? F16_THREADS_V4 : F16_THREADS, ver == 7 ? smem7 : F16_SMEM, stream>>>(
+      tm, tv, tk, tq1, lay, static_cast<uint16_t*>(ctx16), cu_seqlens, n_seq, heads, g_att_trace);
   mer_prof_end(prof, stream);
   MER_CUDA_CHECK(cudaGetLastError());
   mer_count_launches(1);

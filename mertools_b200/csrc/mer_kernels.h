@@ -50,7 +50,7 @@ int mer_attention_tc_launch(const float* qkv, const float* vt, long long vt_ld, 
 bool mer_attention_f16_supported(int max_seqlen);
 int mer_attention_f16_launch(const void* qkv16, const void* vt16, long long vt_ld, void* ctx16,
                              const int* cu_seqlens, int n_seq, long long tokens, int heads,
-                             cudaStream_t stream);
+                             cudaStream_t stream, int max_seqlen = 0);
 
 // helpers.cu
 int mer_vit_patchify_launch(const uint8_t* frames_bgr, int n_frames, float* a_patches,

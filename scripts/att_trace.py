@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mertools_b200 import _lib as L  # noqa: E402
 
 NAMES = {0: "prod:issued", 1: "mma:kq_ready", 2: "mma:S0_issued", 3: "mma:S1_issued", 4: "mma:v_ready",
-         5: "mma:pv c0 t0", 6: "mma:pv c0 t1", 7: "mma:pv c1 t0", 8: "mma:pv c1 t1", 9: "mma:pv c2 t0", 10: "mma:pv c2 t1",
+         5: "mma:pv t0 (v6+) / c0 t0", 6: "mma:pv t1 (v6+) / c0 t1", 7: "mma:pv c1 t0", 8: "mma:pv c1 t1", 9: "mma:pv c2 t0", 10: "mma:pv c2 t1",
          11: "mma:pv c3 t0", 12: "mma:pv c3 t1", 13: "sm0:sfull", 14: "sm0:pass1", 15: "sm0:p0", 16: "sm0:p1", 17: "sm0:p2",
          18: "sm0:p3", 19: "sm0:ofull", 20: "sm0:otfree", 21: "sm0:ofree", 22: "sm1:sfull", 23: "sm1:pass1", 24: "sm1:p0",
          25: "sm1:p1", 26: "sm1:p2", 27: "sm1:p3", 28: "sm1:ofull", 29: "sm1:otfree", 30: "sm1:ofree"}
@@ -23,7 +23,7 @@ vt = torch.zeros(heads * 64, (tokens + 7) // 8 * 8, dtype=torch.float16, device=
 vt[:, :tokens] = qkv[:, 2 * heads * 64:].T
 cu = torch.arange(n_seq + 1, dtype=torch.int32, device=dev) * S
 ctx = torch.empty(tokens, heads * 64, dtype=torch.float16, device=dev)
-os.environ["MER_ATT_F16_VER"] = os.environ.get("MER_ATT_F16_VER", "6")
+os.environ["MER_ATT_F16_VER"] = os.environ.get("MER_ATT_F16_VER", "7")
 for _ in range(2):
     L.attention(qkv, ctx, cu, S, heads, vt=vt)
 buf = torch.zeros(16 * 32, dtype=torch.int64, device=dev)

@@ -46,10 +46,16 @@ if __name__ == "__main__":
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--f16-vers", type=int, nargs="*", default=[3, 4])
     ap.add_argument("--tc-vers", type=int, nargs="*", default=[2])
+    ap.add_argument("--poly", type=int, nargs="*", default=[None], help="MER_ATT_F16_POLY values to sweep")
     ap.add_argument("--n-seq", type=int, nargs="*", default=[2048], help="ViT sequences (37 = 3 items per SM, L2-resident)")
     a = ap.parse_args()
     for n in a.n_seq:
         for v in a.f16_vers:
-            print(json.dumps(run(torch.float16, n, 197, 12, "MER_ATT_F16_VER", v, a.iters)), flush=True)
+            for pl in a.poly:
+                if pl is not None:
+                    os.environ["MER_ATT_F16_POLY"] = str(pl)
+                r = run(torch.float16, n, 197, 12, "MER_ATT_F16_VER", v, a.iters)
+                r["poly"] = pl
+                print(json.dumps(r), flush=True)
     for v in a.tc_vers:
         print(json.dumps(run(torch.float32, 256, 249, 12, "MER_ATT_TC_VER", v, a.iters)), flush=True)

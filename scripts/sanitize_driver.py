@@ -32,7 +32,7 @@ def gemms():
 
 def attention():
     heads = 2
-    for dtype, env, vers, lens in ((torch.float16, "MER_ATT_F16_VER", (1, 3, 4, 5, 6), [197, 5, 64, 129, 249, 17]),
+    for dtype, env, vers, lens in ((torch.float16, "MER_ATT_F16_VER", (1, 3, 4, 6, 7), [197, 5, 64, 129, 249, 17]),
                                    (torch.float32, "MER_ATT_TC_VER", (1, 2), [197, 5, 64, 129, 253, 17])):
         tokens = sum(lens)
         qkv = (torch.randn(tokens, 3 * heads * 64, device=dev)).to(dtype)
