@@ -240,81 +240,123 @@ __device__ __forceinline__ void backward_cols(const float* __restrict__ dy, int 
 // (warp r <-> row r: no exchange needed): att = fc_att(a3), fused = [h_a h_t h_v] att, the two output heads, and --
 // when a backward pass follows -- the loss terms / upstream gradients, d fused, the head's share of d(concat) (g3h)
 // and the gradient w.r.t. the pre-activation of attention_mlp.linear_3 (ga3).  All buffers are shared memory.
-template <int RB>
+// JM: elements of a hidden vector per lane (hidden <= 32 JM); MO1: emotion classes the unrolled code covers.  The fast
+// kernel instantiates <4, 4, 8>: this code runs ONCE per launch, straight from a cold instruction cache, so its size is
+// its cost (the <4, 8, 16> form is 2.5x as long).
+template <int RB, int JM = 8, int MO1 = 16>
 __device__ __forceinline__ void head_rows(const RowArgs& a, int rank, int row0, bool train, const float* hc,
-                                          const float* a3, float* feat, float* dfu, float* g3h, float* ga3) {
+                                          const float* a3, float* feat, float* dfu, float* g3h, float* ga3,
+                                          const float* head_w = nullptr, long long* tr = nullptr) {
+#define HEAD_TR(i)                                                                        \
+  do {                                                                                    \
+    if (tr != nullptr && blockIdx.x == 0 && threadIdx.x == 0) tr[i] = clock64();          \
+  } while (0)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = a.d.hidden, H3 = 3 * H, B = a.B, O1 = a.d.out1, O2 = a.d.out2;
-  const float* P = a.P;
+  // the head's parameters (fc_att, fc_out_1, fc_out_2: contiguous from L.fa_w to L.total) read from global memory, or
+  // from a copy the caller has put in shared memory (head_w[i] = P[L.fa_w + i])
+  // Parameter tensors of the head, as pointers into global memory or into the caller's shared-memory copy
+  const float* Wb = head_w ? head_w : a.P + a.L.fa_w;   // Wb[i] = P[L.fa_w + i]
+  const float* w_att = Wb;
+  const float* b_att = Wb + (a.L.fa_b - a.L.fa_w);
+  const float* w_o1 = Wb + (a.L.o1_w - a.L.fa_w);
+  const float* b_o1 = Wb + (a.L.o1_b - a.L.fa_w);
+  const float* w_o2 = Wb + (a.L.o2_w - a.L.fa_w);
+  const float* b_o2 = Wb + (a.L.o2_b - a.L.fa_w);
+  // One warp per row, and every stage written so that its independent pieces are in flight together (the first build
+  // ran ten dot products one after the other on a scheduler with no other warp to hide their latencies: ~1k cycles each)
   for (int r = warp; r < RB; r += NW) {
     const int row = row0 + r;
     const bool live = row < B;
     const float* a3r = a3 + r * H;
     const float* hcr = hc + r * H3;
-    float att[3];
+    float att[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int m = 0; m < 3; ++m) {
-      float s = 0.f;
-      for (int j = lane; j < H; j += 32) s = fmaf(P[a.L.fa_w + m * H + j], a3r[j], s);
-      att[m] = warp_allsum(s) + P[a.L.fa_b + m];
-    }
-    for (int j = lane; j < H; j += 32) {
-      const float f = (hcr[j] * att[0] + hcr[H + j] * att[1]) + hcr[2 * H + j] * att[2];
-      feat[r * H + j] = f;
-      if (rank == 0 && live) a.features[(long long)row * H + j] = f;
-    }
-    __syncwarp();
-    float logit[16], vout[4];
+    for (int i = 0; i < JM; ++i) {
+      const int j = lane + 32 * i;
+      if (j < H) {
+        const float x = a3r[j];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      if (c >= O1) break;
-      float s = 0.f;
-      for (int j = lane; j < H; j += 32) s = fmaf(P[a.L.o1_w + c * H + j], feat[r * H + j], s);
-      logit[c] = warp_allsum(s) + P[a.L.o1_b + c];
+        for (int m = 0; m < 3; ++m) att[m] = fmaf(w_att[m * H + j], x, att[m]);
+      }
     }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      if (c >= O2) break;
-      float s = 0.f;
-      for (int j = lane; j < H; j += 32) s = fmaf(P[a.L.o2_w + c * H + j], feat[r * H + j], s);
-      vout[c] = warp_allsum(s) + P[a.L.o2_b + c];
+    for (int m = 0; m < 3; ++m) att[m] = warp_allsum(att[m]) + b_att[m];
+    HEAD_TR(0);
+    float f[JM];
+    float logit[MO1], vout[4];
+#pragma unroll
+    for (int c = 0; c < MO1; ++c) logit[c] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) vout[c] = 0.f;
+#pragma unroll
+    for (int i = 0; i < JM; ++i) {
+      const int j = lane + 32 * i;
+      f[i] = 0.f;
+      if (j < H) {
+        f[i] = (hcr[j] * att[0] + hcr[H + j] * att[1]) + hcr[2 * H + j] * att[2];
+        feat[r * H + j] = f[i];
+        if (rank == 0 && live) a.features[(long long)row * H + j] = f[i];
+#pragma unroll
+        for (int c = 0; c < MO1; ++c)
+          if (c < O1) logit[c] = fmaf(w_o1[c * H + j], f[i], logit[c]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < O2) vout[c] = fmaf(w_o2[c * H + j], f[i], vout[c]);
+      }
     }
+#pragma unroll
+    for (int c = 0; c < MO1; ++c)
+      if (c < O1) logit[c] = warp_allsum(logit[c]) + b_o1[c];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c < O2) vout[c] = warp_allsum(vout[c]) + b_o2[c];
     if (rank == 0 && live && lane == 0) {
 #pragma unroll
-      for (int c = 0; c < 16; ++c)
+      for (int c = 0; c < MO1; ++c)
         if (c < O1) a.emos_out[(long long)row * O1 + c] = logit[c];
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         if (c < O2) a.vals_out[(long long)row * O2 + c] = vout[c];
     }
+    HEAD_TR(1);
     if (!train) continue;
     // upstream gradients of the two heads (every lane computes the same scalars)
-    float dlog[16], dval[4];
+    float dlog[MO1], dval[4];
+#pragma unroll
+    for (int c = 0; c < MO1; ++c) dlog[c] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dval[c] = 0.f;
     if (a.mode == MODE_LOSS) {
       // CELoss: NLL(log_softmax) summed / N; MSELoss: squared error summed / N  (loss.py:11-28)
+      const int tgt = live ? (int)a.emo[row] : 0;   // (issued first: the loads fly while the softmax is evaluated)
+      float tval[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tval[c] = (live && c < O2) ? a.val[(long long)row * O2 + c] : 0.f;
       float mx = logit[0];
 #pragma unroll
-      for (int c = 1; c < 16; ++c)
+      for (int c = 1; c < MO1; ++c)
         if (c < O1) mx = fmaxf(mx, logit[c]);
       float se = 0.f;
 #pragma unroll
-      for (int c = 0; c < 16; ++c)
+      for (int c = 0; c < MO1; ++c)
         if (c < O1) se += expf(logit[c] - mx);
       const float lse = mx + logf(se);
-      const int tgt = live ? (int)a.emo[row] : 0;
       float ce = 0.f, mse = 0.f;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        if (c >= O1) break;
-        if (c == tgt) ce = lse - logit[c];
-        dlog[c] = live ? (expf(logit[c] - lse) - (c == tgt ? 1.f : 0.f)) * a.inv_batch : 0.f;
+      for (int c = 0; c < MO1; ++c) {
+        if (c < O1) {
+          if (c == tgt) ce = lse - logit[c];
+          dlog[c] = live ? (expf(logit[c] - lse) - (c == tgt ? 1.f : 0.f)) * a.inv_batch : 0.f;
+        }
       }
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        if (c >= O2) break;
-        const float dd = live ? vout[c] - a.val[(long long)row * O2 + c] : 0.f;
-        mse += dd * dd;
-        dval[c] = 2.f * dd * a.inv_batch;
+        if (c < O2) {
+          const float dd = live ? vout[c] - tval[c] : 0.f;
+          mse += dd * dd;
+          dval[c] = 2.f * dd * a.inv_batch;
+        }
       }
       if (rank == 0 && live && lane == 0) {
         a.ws.loss_terms[2 * row] = ce;
@@ -322,7 +364,7 @@ __device__ __forceinline__ void head_rows(const RowArgs& a, int rank, int row0, 
       }
     } else {
 #pragma unroll
-      for (int c = 0; c < 16; ++c)
+      for (int c = 0; c < MO1; ++c)
         if (c < O1) dlog[c] = (live && a.up_emos) ? a.up_emos[(long long)row * O1 + c] : 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -330,37 +372,50 @@ __device__ __forceinline__ void head_rows(const RowArgs& a, int rank, int row0, 
     }
     if (rank == 0 && live && lane == 0) {
 #pragma unroll
-      for (int c = 0; c < 16; ++c)
+      for (int c = 0; c < MO1; ++c)
         if (c < O1) a.ws.d_emos[(long long)row * O1 + c] = dlog[c];
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         if (c < O2) a.ws.d_vals[(long long)row * O2 + c] = dval[c];
     }
+    HEAD_TR(2);
     float datt[3] = {0.f, 0.f, 0.f};
-    for (int j = lane; j < H; j += 32) {
-      float s = 0.f;
+    float df[JM];
 #pragma unroll
-      for (int c = 0; c < 16; ++c)
-        if (c < O1) s = fmaf(P[a.L.o1_w + c * H + j], dlog[c], s);
+    for (int i = 0; i < JM; ++i) {
+      const int j = lane + 32 * i;
+      df[i] = 0.f;
+      if (j < H) {
+        float s = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c < O2) s = fmaf(P[a.L.o2_w + c * H + j], dval[c], s);
-      if (a.mode == MODE_UPSTREAM && a.up_feat && live) s += a.up_feat[(long long)row * H + j];
-      dfu[r * H + j] = s;
+        for (int c = 0; c < MO1; ++c)
+          if (c < O1) s = fmaf(w_o1[c * H + j], dlog[c], s);
 #pragma unroll
-      for (int m = 0; m < 3; ++m) datt[m] = fmaf(hcr[m * H + j], s, datt[m]);
+        for (int c = 0; c < 4; ++c)
+          if (c < O2) s = fmaf(w_o2[c * H + j], dval[c], s);
+        if (a.mode == MODE_UPSTREAM && a.up_feat && live) s += a.up_feat[(long long)row * H + j];
+        df[i] = s;
+        dfu[r * H + j] = s;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) datt[m] = fmaf(hcr[m * H + j], s, datt[m]);
+      }
     }
 #pragma unroll
     for (int m = 0; m < 3; ++m) datt[m] = warp_allsum(datt[m]);
+    HEAD_TR(3);
     if (rank == 0 && live && lane < 3) a.ws.d_att[3 * row + lane] = lane == 0 ? datt[0] : (lane == 1 ? datt[1] : datt[2]);
-    for (int j = lane; j < H; j += 32) {
-      const float s = dfu[r * H + j];
 #pragma unroll
-      for (int m = 0; m < 3; ++m) g3h[r * H3 + m * H + j] = att[m] * s;
-      const float da3 = (P[a.L.fa_w + j] * datt[0] + P[a.L.fa_w + H + j] * datt[1]) + P[a.L.fa_w + 2 * H + j] * datt[2];
-      const float g = a3r[j] > 0.f ? da3 : 0.f;
-      ga3[r * H + j] = g;
-      if (rank == 0 && live) a.ws.ga3[(long long)row * H + j] = g;
+    for (int i = 0; i < JM; ++i) {
+      const int j = lane + 32 * i;
+      if (j < H) {
+        const float s = df[i];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) g3h[r * H3 + m * H + j] = att[m] * s;
+        const float da3 = (w_att[j] * datt[0] + w_att[H + j] * datt[1]) + w_att[2 * H + j] * datt[2];
+        const float g = a3r[j] > 0.f ? da3 : 0.f;
+        ga3[r * H + j] = g;
+        if (rank == 0 && live) a.ws.ga3[(long long)row * H + j] = g;
+      }
     }
   }
 }
@@ -595,32 +650,46 @@ struct FastPlan {             // shared-memory offsets (floats) + sizes, compute
   int h1, h2, hc, hcd, a1, a2, a3, feat, dfu, g3h, ga3;   // activations / head gradients (full copies)
   int own_a, own_3, own_2;    // this CTA's slices of pre-activation gradients: [FRB][HCP], [3][FRB][HCP] x 2
   int rx;                     // [2][CL][3][FRB][HCP] reduce-scatter landing zones (ping-pong)
-  int wb;                     // [2][HCP][kc1] layer-1 weight chunks
+  int wb;                     // [3][rch][max_in] layer-1 weight chunks: rch whole rows of W1[m] = ONE bulk copy each
   int t2, t3, ta1, ta2, ta3;  // resident row slices
+  int hw;                     // head parameters fc_att | fc_out_1 | fc_out_2 (weights and biases)
+  int sl;                     // [2][3][FRB][HCP] this CTA's freshly computed output slices, before they are broadcast
   int bars;                   // 4 mbarriers (2 chunk buffers, resident set, spare)
-  int kc1;                    // layer-1 chunk length (floats per row)
+  int rch, max_in;            // layer-1 chunk: rows per chunk, row pitch of the buffers
   int total;                  // floats
 };
 
-FastPlan make_fast_plan(const MerFusionDims& d, int kc1) {
+FastPlan make_fast_plan(const MerFusionDims& d, int rch) {
   FastPlan p;
   const int H = d.hidden;
   const int in[3] = {d.audio_dim, d.text_dim, d.video_dim};
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
   for (int m = 0; m < 3; ++m) p.xs[m] = take(FRB * in[m]);
-  p.h1 = take(3 * FRB * H); p.h2 = take(3 * FRB * H);
+  p.h1 = take(3 * FRB * H);
+  // everything written after layer 1 (by this CTA or by its peers, who have passed the same cluster barrier) may live
+  // where the staged inputs were: they are dead by then
+  const int xs_end = o;
+  const bool alias = 17 * FRB * H <= xs_end - p.xs[0] - 3 * FRB * H - 16;
+  if (alias) o = p.xs[0];
+  p.h2 = take(3 * FRB * H);
   p.hc = take(FRB * 3 * H); p.hcd = take(FRB * 3 * H);
   p.a1 = take(FRB * H); p.a2 = take(FRB * H); p.a3 = take(FRB * H);
   p.feat = take(FRB * H); p.dfu = take(FRB * H);
-  p.g3h = take(FRB * 3 * H); p.ga3 = take(FRB * H);
+  p.g3h = take(FRB * 3 * H);
+  if (alias) o = xs_end;
+  p.ga3 = take(FRB * H);
   p.own_a = take(FRB * HCP); p.own_3 = take(3 * FRB * HCP); p.own_2 = take(3 * FRB * HCP);
-  p.rx = take(2 * CL * 3 * FRB * HCP);
-  p.wb = take(2 * HCP * kc1);
+  p.max_in = in[0] > in[1] ? (in[0] > in[2] ? in[0] : in[2]) : (in[1] > in[2] ? in[1] : in[2]);
+  p.rch = rch;
+  p.wb = take(3 * rch * p.max_in);      // three chunk buffers: two copies in flight behind the one being consumed
+  p.rx = p.wb;                          // the landing zones of the backward exchanges reuse them (layer 1 is long done)
+  if (3 * rch * p.max_in < 2 * CL * 3 * FRB * HCP) take(2 * CL * 3 * FRB * HCP - 3 * rch * p.max_in);
   p.t2 = take(3 * HCP * H); p.t3 = take(3 * HCP * H);
   p.ta1 = take(HCP * 3 * H); p.ta2 = take(HCP * H); p.ta3 = take(HCP * H);
+  p.hw = take(3 * H + 3 + (d.out1 + d.out2) * (H + 1));
+  p.sl = take(2 * 3 * FRB * HCP);
   p.bars = take(8);
-  p.kc1 = kc1;
   p.total = o;
   return p;
 }
@@ -691,173 +760,234 @@ __global__ void __launch_bounds__(NT, 1) fus_rows_fast_kernel(const __grid_const
   float* rx = smem + pl.rx; float* wb = smem + pl.wb;
   float* t2 = smem + pl.t2; float* t3 = smem + pl.t3; float* ta1 = smem + pl.ta1; float* ta2 = smem + pl.ta2;
   float* ta3 = smem + pl.ta3;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.bars);  // [0], [1]: chunk buffers; [2]: resident tiles
-  const int kc1 = pl.kc1;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.bars);  // [0..2]: chunk buffers; [3]: resident tiles
 
-  // layer-1 chunk list: (modality, first column), in order
-  int nch[3], nc_total = 0;
-  for (int m = 0; m < 3; ++m) { nch[m] = (in[m] + kc1 - 1) / kc1; nc_total += nch[m]; }
-  auto chunk_of = [&](int c, int& m, int& k0, int& kc) {
-    m = 0;
-    while (c >= nch[m]) { c -= nch[m]; ++m; }
-    k0 = c * kc1;
-    kc = min(kc1, in[m] - k0);
-  };
-  auto issue_chunk = [&](int c) {  // one thread: this CTA's rows of chunk c -> buffer c & 1
-    int m, k0, kc;
-    chunk_of(c, m, k0, kc);
-    uint64_t* bar = &bars[c & 1];
-    mbar_expect_tx(bar, (uint32_t)(nloc * kc * 4));
-    const float* src = P + a.L.enc_w1[m] + (long long)n0 * in[m] + k0;
-    float* dst = wb + (c & 1) * HCP * kc1;
-    for (int nl = 0; nl < nloc; ++nl) bulk_g2s(dst + nl * kc1, src + (long long)nl * in[m], (uint32_t)(kc * 4), bar);
+  float* hw = smem + pl.hw;
+  float* sl = smem + pl.sl;
+  const int rch = pl.rch, wb_ld = pl.max_in;
+  // layer-1 chunk list: modality m, rows [n0 + rch c, + rch) of W1[m] (whole rows: contiguous in the parameter buffer,
+  // ONE bulk copy per chunk -- the first build issued one copy per row and spent 29k cycles here, ~200 per copy)
+  const int cpm = (nloc + rch - 1) / rch;  // chunks per modality
+  const int nc_total = 3 * cpm;
+  auto issue_chunk = [&](int c) {  // one thread
+    const int m = c / cpm, r0 = (c % cpm) * rch, rows = min(rch, nloc - r0);
+    uint64_t* bar = &bars[c % 3];
+    const uint32_t bytes = (uint32_t)(rows * in[m] * 4);
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(wb + (c % 3) * rch * wb_ld, P + a.L.enc_w1[m] + (long long)(n0 + r0) * in[m], bytes, bar);
   };
 
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     mbar_init(&bars[2], 1);
+    mbar_init(&bars[3], 1);   // resident tiles
     fence_mbar_init();
     if (blockIdx.x == 0 && train) *a.ws.done = 0;
-    // resident row slices of the five hidden-layer matrices (contiguous in the parameter buffer)
-    mbar_expect_tx(&bars[2], (uint32_t)(nloc * (6 * H + 3 * H + 2 * H) * 4));
-    for (int m = 0; m < 3; ++m) {
-      bulk_g2s(t2 + m * HCP * H, P + a.L.enc_w2[m] + (long long)n0 * H, (uint32_t)(nloc * H * 4), &bars[2]);
-      bulk_g2s(t3 + m * HCP * H, P + a.L.enc_w3[m] + (long long)n0 * H, (uint32_t)(nloc * H * 4), &bars[2]);
-    }
-    bulk_g2s(ta1, P + a.L.att_w1 + (long long)n0 * H3, (uint32_t)(nloc * H3 * 4), &bars[2]);
-    bulk_g2s(ta2, P + a.L.att_w2 + (long long)n0 * H, (uint32_t)(nloc * H * 4), &bars[2]);
-    bulk_g2s(ta3, P + a.L.att_w3 + (long long)n0 * H, (uint32_t)(nloc * H * 4), &bars[2]);
-    issue_chunk(0);
-    if (nc_total > 1) issue_chunk(1);
+    mbar_expect_tx(&bars[3], (uint32_t)(nloc * (6 * H + 3 * H + 2 * H) * 4));
   }
-  // stage the three inputs of the FRB rows (dropout applied here; rank m also keeps the dropped copy for fus_wgrad)
-  for (int m = 0; m < 3; ++m) {
-    const int K = in[m];
-    for (int i = tid; i < FRB * K; i += NT) {
-      const int r = i / K, k = i - r * K, row = row0 + r;
-      float v = 0.f;
-      if (row < B) {
-        const long long gi = (long long)row * K + k;
-        v = a.x[m][gi];
-        if (drop) {
-          v *= (a.ext_mask[m] ? a.ext_mask[m][gi] : keep_hash(a.seed, m, step, gi, a.p_drop)) * a.mscale;
-          if (train && rank == m) a.ws.xd[m][gi] = v;
+  __syncthreads();
+  // the copies are issued by eight different warps (one thread issuing all twelve held its warp -- and with it the
+  // whole CTA at the next barrier -- for ~10k cycles)
+  if (lane == 0 && nloc > 0) {
+    if (warp < 3 && warp < nc_total) issue_chunk(warp);
+    if (warp >= 3 && warp < 6) {
+      const int m = warp - 3;
+      bulk_g2s(t2 + m * HCP * H, P + a.L.enc_w2[m] + (long long)n0 * H, (uint32_t)(nloc * H * 4), &bars[3]);
+      bulk_g2s(t3 + m * HCP * H, P + a.L.enc_w3[m] + (long long)n0 * H, (uint32_t)(nloc * H * 4), &bars[3]);
+    }
+    if (warp == 6) bulk_g2s(ta1, P + a.L.att_w1 + (long long)n0 * H3, (uint32_t)(nloc * H3 * 4), &bars[3]);
+    if (warp == 7) {
+      bulk_g2s(ta2, P + a.L.att_w2 + (long long)n0 * H, (uint32_t)(nloc * H * 4), &bars[3]);
+      bulk_g2s(ta3, P + a.L.att_w3 + (long long)n0 * H, (uint32_t)(nloc * H * 4), &bars[3]);
+    }
+  }
+  // the head's parameters and the three inputs of the FRB rows: plain copies first (independent 16-byte loads, many in
+  // flight per thread -- the first build hashed element by element behind each dependent load: 26k cycles), dropout
+  // applied in place afterwards by the thread that copied the element
+  {
+    const int n_hw = (int)(a.L.total - a.L.fa_w);
+    for (int i = tid; i < n_hw; i += NT) hw[i] = P[a.L.fa_w + i];
+    for (int m = 0; m < 3; ++m) {
+      const int K4 = in[m] >> 2;
+      const float4* src = reinterpret_cast<const float4*>(a.x[m]) + (long long)row0 * K4;
+      float4* dst = reinterpret_cast<float4*>(xs[m]);
+      const int live4 = max(0, min(FRB, B - row0)) * K4;
+#pragma unroll 4
+      for (int i = tid; i < FRB * K4; i += NT) dst[i] = i < live4 ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (drop) {
+      for (int m = 0; m < 3; ++m) {
+        const int K = in[m];
+        const int live = max(0, min(FRB, B - row0)) * K;
+        for (int i4 = tid; i4 < (FRB * K) >> 2; i4 += NT) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = 4 * i4 + e;
+            if (i < live) {
+              const long long gi = (long long)row0 * K + i;
+              const float v = xs[m][i] * (a.ext_mask[m] ? a.ext_mask[m][gi] : keep_hash(a.seed, m, step, gi, a.p_drop)) * a.mscale;
+              xs[m][i] = v;
+              if (train && rank == m) a.ws.xd[m][gi] = v;
+            }
+          }
         }
       }
-      xs[m][i] = v;
     }
   }
   __syncthreads();
   FUS_TR(1);
   cluster.sync();  // every CTA of the cluster is running: DSMEM stores may begin
   FUS_TR(2);
-  auto peer = [&](float* local) { return cluster.map_shared_rank(local, lane & (CL - 1)); };
+
+  // Totals of a warp's 2 x 4 partial sums with 9 shuffles instead of 40: halves are exchanged, not duplicated; lane l
+  // ends up with the total of (column slot c = bit 4 of l, row r = bits 3..2 of l); lanes with l % 4 == 0 use it.
+  auto reduce_2x4 = [&](float (&acc)[FMAXC][FRB]) {
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) v[c * 4 + r] = acc[c][r];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float keep = (lane & 16) ? v[i + 4] : v[i], send = (lane & 16) ? v[i] : v[i + 4];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float keep = (lane & 8) ? v[i + 2] : v[i], send = (lane & 8) ? v[i] : v[i + 2];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    {
+      const float keep = (lane & 4) ? v[1] : v[0], send = (lane & 4) ? v[0] : v[1];
+      v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    return v[0];
+  };
+  // this warp's finished outputs -> the CTA's slice buffer sl[which][m][r][nl] (value = relu(total + bias))
+  auto to_slice = [&](float (&acc)[FMAXC][FRB], int which, int m, const float* bias, auto post) {
+    const float tot = reduce_2x4(acc);
+    if ((lane & 3) == 0) {
+      const int c = lane >> 4, r = (lane >> 2) & 3, nl = warp + NW * c;
+      if (nl < nloc) post(which, m, r, nl, fmaxf(tot + bias[n0 + nl], 0.f));
+    }
+  };
+  // slice buffer -> the eight copies of the activation buffer (16-byte DSMEM stores, one or two per thread) and, when a
+  // backward pass follows, global memory for the weight-gradient kernel
+  auto broadcast = [&](int which, int nmod, float* act, int act_ld_row, int act_mod_stride, float* gdst, long long g_mod_stride,
+                       int g_ld) {
+    __syncthreads();
+    const int f4n = nloc >> 2;
+    for (int i = tid; i < nmod * FRB * f4n * CL; i += NT) {
+      const int peer_rank = i % CL, q = i / CL;
+      const int f4 = q % f4n, r = (q / f4n) % FRB, m = q / (f4n * FRB);
+      const float4 v4 = *reinterpret_cast<const float4*>(sl + ((which * 3 + m) * FRB + r) * HCP + 4 * f4);
+      float* dst = cluster.map_shared_rank(act, peer_rank);
+      *reinterpret_cast<float4*>(dst + m * act_mod_stride + r * act_ld_row + n0 + 4 * f4) = v4;
+    }
+    if (train && gdst != nullptr) {
+      for (int q = tid; q < nmod * FRB * f4n; q += NT) {
+        const int f4 = q % f4n, r = (q / f4n) % FRB, m = q / (f4n * FRB);
+        if (row0 + r < B)
+          *reinterpret_cast<float4*>(gdst + m * g_mod_stride + (long long)(row0 + r) * g_ld + n0 + 4 * f4) =
+              *reinterpret_cast<const float4*>(sl + ((which * 3 + m) * FRB + r) * HCP + 4 * f4);
+      }
+    }
+  };
+  auto plain = [&](int which, int m, int r, int nl, float v) { sl[((which * 3 + m) * FRB + r) * HCP + nl] = v; };
 
   // ================= forward =================
   {
     float acc[FMAXC][FRB] = {};
-    int m_cur = 0, left = nch[0];
     for (int c = 0; c < nc_total; ++c) {
-      int m, k0, kc;
-      chunk_of(c, m, k0, kc);
-      mbar_wait(&bars[c & 1], (c >> 1) & 1);
-      fast_accumulate(acc, xs[m] + k0, in[m], kc, wb + (c & 1) * HCP * kc1, kc1, nloc);
+      const int m = c / cpm, r0 = (c % cpm) * rch, rows = min(rch, nloc - r0);
+      mbar_wait(&bars[c % 3], (c / 3) & 1);
+      // this chunk's `rows` columns: warp w takes local columns r0 + w, r0 + w + 8 (accumulator slot = chunk parity when
+      // a chunk holds up to 8 rows, so that the 2 x 4 totals of a modality are reduced together)
+      {
+        const float* tile = wb + (c % 3) * rch * wb_ld;
+        const int K4 = in[m] >> 2;
+        for (int k4 = lane; k4 < K4; k4 += 32) {
+#pragma unroll
+          for (int cc = 0; cc < FMAXC; ++cc) {
+            const int rl = warp + NW * cc;       // row inside the chunk
+            const int slot = (r0 + rl) / NW;     // accumulator slot of local column r0 + rl (= warp + NW * slot)
+            if (rl < rows && slot < FMAXC) {
+              const float4 w4 = *reinterpret_cast<const float4*>(tile + rl * in[m] + 4 * k4);
+#pragma unroll
+              for (int r = 0; r < FRB; ++r) {
+                const float4 xv = *reinterpret_cast<const float4*>(xs[m] + r * in[m] + 4 * k4);
+                if (slot == 0) acc[0][r] = dot4(xv, w4, acc[0][r]);
+                else acc[1][r] = dot4(xv, w4, acc[1][r]);
+              }
+            }
+          }
+        }
+      }
       __syncthreads();  // every warp is done with this buffer
-      if (tid == 0 && c + 2 < nc_total) issue_chunk(c + 2);
-      if (--left == 0) {  // last chunk of modality m: its layer-1 output
-        float* dst = peer(h1);
-        fast_finish(acc, n0, nloc, [&](int n, int r, float v) {
-          v = fmaxf(v + P[a.L.enc_b1[m] + n], 0.f);
-          if (lane < CL) dst[(m * FRB + r) * H + n] = v;
-          if (lane == CL + r && train && row0 + r < B) a.ws.h1[((long long)m * B + row0 + r) * H + n] = v;
-        });
+      if (tid == 0 && c + 3 < nc_total) issue_chunk(c + 3);
+      if ((c + 1) % cpm == 0) {  // last chunk of modality m: its layer-1 output
+        to_slice(acc, 0, m, P + a.L.enc_b1[m], plain);
 #pragma unroll
         for (int ci = 0; ci < FMAXC; ++ci)
 #pragma unroll
           for (int r = 0; r < FRB; ++r) acc[ci][r] = 0.f;
-        m_cur = m + 1;
-        if (m_cur < 3) left = nch[m_cur];
       }
     }
   }
   FUS_TR(3);
+  broadcast(0, 3, h1, H, FRB * H, a.ws.h1, (long long)B * H, H);
   cluster.sync();
   FUS_TR(4);
-  mbar_wait(&bars[2], 0);  // resident tiles (requested at entry: long since there)
+  mbar_wait(&bars[3], 0);  // resident tiles (requested at entry: long since there)
   FUS_TR(5);
-  for (int m = 0; m < 3; ++m) {  // encoder layer 2
-    float acc[FMAXC][FRB] = {};
-    fast_accumulate(acc, h1 + m * FRB * H, H, H, t2 + m * HCP * H, H, nloc);
-    float* dst = peer(h2);
-    fast_finish(acc, n0, nloc, [&](int n, int r, float v) {
-      v = fmaxf(v + P[a.L.enc_b2[m] + n], 0.f);
-      if (lane < CL) dst[(m * FRB + r) * H + n] = v;
-      if (lane == CL + r && train && row0 + r < B) a.ws.h2[((long long)m * B + row0 + r) * H + n] = v;
-    });
-  }
-  FUS_TR(6);
-  cluster.sync();
-  FUS_TR(7);
   auto cat_factor = [&](int row, int col) {  // dropout factor of concat element (row, col)
     if (!drop || row >= B) return 1.f;
     const long long gi = (long long)row * H3 + col;
     return (a.ext_mask[3] ? a.ext_mask[3][gi] : keep_hash(a.seed, 3, step, gi, a.p_drop)) * a.mscale;
   };
-  for (int m = 0; m < 3; ++m) {  // encoder layer 3 -> concat (+ its dropout)
-    float acc[FMAXC][FRB] = {};
-    fast_accumulate(acc, h2 + m * FRB * H, H, H, t3 + m * HCP * H, H, nloc);
-    float* dhc = peer(hc);
-    float* dhcd = peer(hcd);
-    fast_finish(acc, n0, nloc, [&](int n, int r, float v) {
-      v = fmaxf(v + P[a.L.enc_b3[m] + n], 0.f);
-      const int row = row0 + r, col = m * H + n;
-      const float f = cat_factor(row, col);
-      if (lane < CL) {
-        dhc[r * H3 + col] = v;
-        dhcd[r * H3 + col] = v * f;
-      }
-      if (lane == CL + r && train && row < B) a.ws.hcd[(long long)row * H3 + col] = v * f;
-    });
+  // The five hidden layers behind layer 1, ONE copy of the code in a loop over a small table: this kernel executes every
+  // instruction once per launch out of a cold instruction cache, so code size IS time (the unrolled first build spent
+  // ~8 cycles per SASS instruction; halving the head's code halved its time).
+#pragma unroll 1
+  for (int L = 0; L < 5; ++L) {
+    const float *inb, *tileb;
+    float* act;
+    float* gdst;
+    long long bias0 = 0, g_ms = 0;
+    int nmod = 1, ldin = H, K = H, in_ms = 0, tile_ms = 0, act_ms = 0, act_ld = H, g_ld = H;
+    if (L == 0) {         // encoder layer 2
+      inb = h1; tileb = t2; act = h2; gdst = a.ws.h2;
+      nmod = 3; in_ms = FRB * H; tile_ms = HCP * H; act_ms = FRB * H; g_ms = (long long)B * H;
+    } else if (L == 1) {  // encoder layer 3 -> concat (slice 0: as computed, slice 1: after the concat's dropout)
+      inb = h2; tileb = t3; act = hc; gdst = nullptr;
+      nmod = 3; in_ms = FRB * H; tile_ms = HCP * H; act_ms = H; act_ld = H3;
+    } else if (L == 2) {  // attention_mlp
+      inb = hcd; tileb = ta1; act = a1; gdst = a.ws.a1; bias0 = a.L.att_b1; ldin = H3; K = H3;
+    } else if (L == 3) {
+      inb = a1; tileb = ta2; act = a2; gdst = a.ws.a2; bias0 = a.L.att_b2;
+    } else {
+      inb = a2; tileb = ta3; act = a3; gdst = a.ws.a3; bias0 = a.L.att_b3;
+    }
+#pragma unroll 1
+    for (int m = 0; m < nmod; ++m) {
+      float acc[FMAXC][FRB] = {};
+      fast_accumulate(acc, inb + m * in_ms, ldin, K, tileb + m * tile_ms, K, nloc);
+      const long long boff = L == 0 ? a.L.enc_b2[m] : (L == 1 ? a.L.enc_b3[m] : bias0);
+      to_slice(acc, 0, m, P + boff, [&](int, int mm, int r, int nl, float v) {
+        sl[((0 * 3 + mm) * FRB + r) * HCP + nl] = v;
+        if (L == 1) sl[((1 * 3 + mm) * FRB + r) * HCP + nl] = v * cat_factor(row0 + r, mm * H + n0 + nl);
+      });
+    }
+    broadcast(0, nmod, act, act_ld, act_ms, gdst, g_ms, g_ld);
+    if (L == 1) broadcast(1, 3, hcd, H3, H, a.ws.hcd, H, H3);
+    cluster.sync();
   }
-  cluster.sync();
-  {  // attention_mlp
-    float acc[FMAXC][FRB] = {};
-    fast_accumulate(acc, hcd, H3, H3, ta1, H3, nloc);
-    float* dst = peer(a1);
-    fast_finish(acc, n0, nloc, [&](int n, int r, float v) {
-      v = fmaxf(v + P[a.L.att_b1 + n], 0.f);
-      if (lane < CL) dst[r * H + n] = v;
-      if (lane == CL + r && train && row0 + r < B) a.ws.a1[(long long)(row0 + r) * H + n] = v;
-    });
-  }
-  cluster.sync();
-  {
-    float acc[FMAXC][FRB] = {};
-    fast_accumulate(acc, a1, H, H, ta2, H, nloc);
-    float* dst = peer(a2);
-    fast_finish(acc, n0, nloc, [&](int n, int r, float v) {
-      v = fmaxf(v + P[a.L.att_b2 + n], 0.f);
-      if (lane < CL) dst[r * H + n] = v;
-      if (lane == CL + r && train && row0 + r < B) a.ws.a2[(long long)(row0 + r) * H + n] = v;
-    });
-  }
-  cluster.sync();
-  {
-    float acc[FMAXC][FRB] = {};
-    fast_accumulate(acc, a2, H, H, ta3, H, nloc);
-    float* dst = peer(a3);
-    fast_finish(acc, n0, nloc, [&](int n, int r, float v) {
-      v = fmaxf(v + P[a.L.att_b3 + n], 0.f);
-      if (lane < CL) dst[r * H + n] = v;
-      if (lane == CL + r && train && row0 + r < B) a.ws.a3[(long long)(row0 + r) * H + n] = v;
-    });
-  }
-  FUS_TR(8);
-  cluster.sync();
   FUS_TR(9);
 
-  head_rows<FRB>(a, rank, row0, train, hc, a3, feat, dfu, g3h, ga3);
+  head_rows<FRB, 4, 8>(a, rank, row0, train, hc, a3, feat, dfu, g3h, ga3, hw, trace ? trace + 16 : nullptr);
   FUS_TR(10);
   if (!train) {
     cluster.sync();
@@ -866,84 +996,69 @@ __global__ void __launch_bounds__(NT, 1) fus_rows_fast_kernel(const __grid_const
   }
   __syncthreads();
 
-  // ================= backward: reduce-scatter of partial data gradients =================
-  // partial[r][k] over this CTA's rows n0:n1 of one matrix (tile [nloc][K]) and its own pre-activation gradients
-  // down[r][nl]; column k of slot `slot_of(k)` goes to CTA (k % H) / HC, into landing zone `zone`
-  auto scatter = [&](const float* down, const float* tile, int K, int zone, int slot_base) {
-    for (int k = tid; k < K; k += NT) {
-      float acc[FRB] = {0.f, 0.f, 0.f, 0.f};
-      for (int nl = 0; nl < nloc; ++nl) {
-        const float w = tile[nl * K + k];
-#pragma unroll
-        for (int r = 0; r < FRB; ++r) acc[r] = fmaf(down[r * HCP + nl], w, acc[r]);
-      }
-      const int slot = slot_base + k / H, j = k % H;
-      const int dest = j / HC, kk = j - dest * HC;
-      float* z = cluster.map_shared_rank(rx + zone * (CL * 3 * FRB * HCP), dest);
-#pragma unroll
-      for (int r = 0; r < FRB; ++r) z[((rank * 3 + slot) * FRB + r) * HCP + kk] = acc[r];
-    }
-  };
-  // sum of the 8 partials for this CTA's columns, in rank order; fin(slot, r, kk, sum)
-  auto gather = [&](int zone, int nslot, auto fin) {
-    const float* z = rx + zone * (CL * 3 * FRB * HCP);
-    for (int i = tid; i < nslot * FRB * nloc; i += NT) {
-      const int kk = i % nloc, r = (i / nloc) % FRB, slot = i / (nloc * FRB);
-      float s = 0.f;
-#pragma unroll
-      for (int src = 0; src < CL; ++src) s += z[((src * 3 + slot) * FRB + r) * HCP + kk];
-      fin(slot, r, kk, s);
-    }
-  };
+  // ================= backward: reduce-scatter of partial data gradients (five exchanges, one copy of the code) ========
   // own slice of the head's gradient w.r.t. attention_mlp.linear_3's pre-activation
   for (int i = tid; i < FRB * nloc; i += NT) own_a[(i / nloc) * HCP + i % nloc] = ga3[(i / nloc) * H + n0 + i % nloc];
-  __syncthreads();
-  scatter(own_a, ta3, H, 0, 0);                                   // attention_mlp.linear_3 -> d a2
-  FUS_TR(11);
-  cluster.sync();
-  FUS_TR(12);
-  gather(0, 1, [&](int, int r, int kk, float s) {
-    const int k = n0 + kk;
-    const float g = a2[r * H + k] > 0.f ? s : 0.f;
-    own_a[r * HCP + kk] = g;
-    if (row0 + r < B) a.ws.ga2[(long long)(row0 + r) * H + k] = g;
-  });
-  __syncthreads();
-  scatter(own_a, ta2, H, 1, 0);                                   // linear_2 -> d a1
-  cluster.sync();
-  gather(1, 1, [&](int, int r, int kk, float s) {
-    const int k = n0 + kk;
-    const float g = a1[r * H + k] > 0.f ? s : 0.f;
-    own_a[r * HCP + kk] = g;
-    if (row0 + r < B) a.ws.ga1[(long long)(row0 + r) * H + k] = g;
-  });
-  __syncthreads();
-  scatter(own_a, ta1, H3, 0, 0);                                  // linear_1 -> d concat (slot = modality)
-  cluster.sync();
-  gather(0, 3, [&](int m, int r, int kk, float s) {
-    const int k = n0 + kk, col = m * H + k;
-    const float tot = g3h[r * H3 + col] + s * cat_factor(row0 + r, col);
-    const float g = hc[r * H3 + col] > 0.f ? tot : 0.f;
-    own_3[(m * FRB + r) * HCP + kk] = g;
-    if (row0 + r < B) a.ws.g3[(long long)(row0 + r) * H3 + col] = g;
-  });
-  __syncthreads();
-  for (int m = 0; m < 3; ++m) scatter(own_3 + m * FRB * HCP, t3 + m * HCP * H, H, 1, m);   // encoder layer 3 -> d h2
-  cluster.sync();
-  gather(1, 3, [&](int m, int r, int kk, float s) {
-    const int k = n0 + kk;
-    const float g = h2[(m * FRB + r) * H + k] > 0.f ? s : 0.f;
-    own_2[(m * FRB + r) * HCP + kk] = g;
-    if (row0 + r < B) a.ws.g2[((long long)m * B + row0 + r) * H + k] = g;
-  });
-  __syncthreads();
-  for (int m = 0; m < 3; ++m) scatter(own_2 + m * FRB * HCP, t2 + m * HCP * H, H, 0, m);   // encoder layer 2 -> d h1
-  cluster.sync();
-  gather(0, 3, [&](int m, int r, int kk, float s) {
-    const int k = n0 + kk;
-    const float g = h1[(m * FRB + r) * H + k] > 0.f ? s : 0.f;
-    if (row0 + r < B) a.ws.g1[((long long)m * B + row0 + r) * H + k] = g;
-  });
+#pragma unroll 1
+  for (int e = 0; e < 5; ++e) {
+    // exchange e: this CTA's pre-activation gradients `down` (slots of [FRB][HCP]) times its row slices `tileb` give
+    // partial input gradients for all K columns; column j of slot s goes to CTA j / HC; the owner adds the 8 partials in
+    // rank order, applies the ReLU mask of the activation it belongs to, keeps the result as its own `down` for the next
+    // exchange and writes it to global memory for the weight-gradient kernel.
+    const float *down, *tileb, *relu_act;
+    float *own_dst, *gdst;
+    int nsrc = 1, K = H, tile_ms = 0, nslot = 1, act_ss = 0, act_rs = H;
+    long long g_ss = 0, g_rs = H;
+    const int zone = e & 1;
+    if (e == 0) {         // attention_mlp.linear_3 -> d a2
+      down = own_a; tileb = ta3; relu_act = a2; own_dst = own_a; gdst = a.ws.ga2;
+    } else if (e == 1) {  // linear_2 -> d a1
+      down = own_a; tileb = ta2; relu_act = a1; own_dst = own_a; gdst = a.ws.ga1;
+    } else if (e == 2) {  // linear_1 -> d concat (slot = modality), plus the head's share, through the concat dropout
+      down = own_a; tileb = ta1; K = H3; nslot = 3; relu_act = hc; act_ss = H; act_rs = H3; own_dst = own_3; gdst = a.ws.g3;
+      g_ss = H; g_rs = H3;
+    } else if (e == 3) {  // encoder layer 3 -> d h2
+      down = own_3; tileb = t3; nsrc = 3; tile_ms = HCP * H; nslot = 3; relu_act = h2; act_ss = FRB * H; own_dst = own_2;
+      gdst = a.ws.g2; g_ss = (long long)B * H;
+    } else {              // encoder layer 2 -> d h1 (the input gradient of layer 1 is not needed)
+      down = own_2; tileb = t2; nsrc = 3; tile_ms = HCP * H; nslot = 3; relu_act = h1; act_ss = FRB * H; own_dst = nullptr;
+      gdst = a.ws.g1; g_ss = (long long)B * H;
+    }
+    __syncthreads();
+    float* zbase = rx + zone * (CL * 3 * FRB * HCP);
+#pragma unroll 1
+    for (int src = 0; src < nsrc; ++src) {
+      const float* dn = down + src * FRB * HCP;
+      const float* tl = tileb + src * tile_ms;
+      for (int k = tid; k < K; k += NT) {
+        float acc[FRB] = {0.f, 0.f, 0.f, 0.f};
+        for (int nl = 0; nl < nloc; ++nl) {
+          const float w = tl[nl * K + k];
+#pragma unroll
+          for (int r = 0; r < FRB; ++r) acc[r] = fmaf(dn[r * HCP + nl], w, acc[r]);
+        }
+        const int slot = src + k / H, j = k % H;
+        const int dest = j / HC, kk = j - dest * HC;
+        float* z = cluster.map_shared_rank(zbase, dest);
+#pragma unroll
+        for (int r = 0; r < FRB; ++r) z[((rank * 3 + slot) * FRB + r) * HCP + kk] = acc[r];
+      }
+    }
+    if (e == 0) FUS_TR(11);
+    cluster.sync();
+    if (e == 0) FUS_TR(12);
+    for (int i = tid; i < nslot * FRB * nloc; i += NT) {
+      const int kk = i % nloc, r = (i / nloc) % FRB, slot = i / (nloc * FRB);
+      float v = 0.f;
+#pragma unroll
+      for (int src = 0; src < CL; ++src) v += zbase[((src * 3 + slot) * FRB + r) * HCP + kk];
+      const int k = n0 + kk;
+      if (e == 2) v = g3h[r * H3 + slot * H + k] + v * cat_factor(row0 + r, slot * H + k);
+      const float g = relu_act[slot * act_ss + r * act_rs + k] > 0.f ? v : 0.f;
+      if (own_dst != nullptr) own_dst[(slot * FRB + r) * HCP + kk] = g;
+      if (row0 + r < B) gdst[slot * g_ss + (long long)(row0 + r) * g_rs + k] = g;
+    }
+  }
   FUS_TR(13);
   // zone 0 was last written before the barrier above and zone 1 two barriers ago: CTAs may retire independently
 }
@@ -1069,15 +1184,14 @@ int launch_rows_t(const RowArgs& a, cudaStream_t st) {
 // fast path: hidden <= 128 (a multiple of 4), feature widths multiples of 4, everything within 227 KB of shared memory
 bool fast_plan_for(const MerFusionDims& d, FastPlan* out) {
   const int in[3] = {d.audio_dim, d.text_dim, d.video_dim};
-  if (d.hidden > 128 || d.hidden % 4 != 0) return false;
+  if (d.hidden > 128 || d.hidden % 32 != 0 || d.out1 > 8) return false;  // slices of hidden / 8 columns move as 16-byte vectors
   for (int m = 0; m < 3; ++m)
     if (in[m] % 4 != 0) return false;
-  for (int kc1 = 384; kc1 >= 64; kc1 -= 64) {
-    const FastPlan p = make_fast_plan(d, kc1);
-    if ((size_t)p.total * 4 <= 227 * 1024) {
-      *out = p;
-      return true;
-    }
+  // layer-1 chunks hold 8 whole rows of W1[m] (one per warp: the accumulator slots rely on it)
+  const FastPlan p = make_fast_plan(d, 8);
+  if ((size_t)p.total * 4 <= 227 * 1024) {
+    *out = p;
+    return true;
   }
   return false;
 }

@@ -30,3 +30,4 @@ for B in (4, 32):
     lib.mer_debug_fusion_trace(None)
     t_ = buf.cpu().tolist()
     print(f"B={B}: " + "  ".join(f"{n}@{t_[i] - t_[0]}" for i, n in enumerate(NAMES) if t_[i]))
+    print("   head: " + "  ".join(f"{n}@{t_[16 + i] - t_[0]}" for i, n in enumerate(["att", "outputs", "loss grads", "d fused + datt"]) if t_[16 + i]))
