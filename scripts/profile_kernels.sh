@@ -11,11 +11,15 @@ out=gpurun_out
 mkdir -p "$out"
 # launch list of a window that contains at least one full step (cold-cache, serialised: shares, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 900 --csv --log-file "$out/${tag}_launches.csv" \
-    python bench.py --steps 1 --warmup 1 --cpu-clips 4 > "$out/${tag}_launches.log" 2>&1
-for spec in "gemm_kernel 20 4" "attention_f16_kernel 2 1" "attention_tc_kernel 2 1" "layernorm_kernel 8 1" \
-            "conv0_apply 0 1" "conv0_stats 0 1"; do
+    python bench.py --steps 1 --warmup 1 --cpu-clips 2 --no-extras > "$out/${tag}_launches.log" 2>&1
+# kernel regex, matching launches to skip, launches to capture, name of the report.  GEMM launch order inside a step:
+# [0] ViT patch embedding (TF32), [1..48] ViT layers (F16: qkv, out-proj, fc1, fc2 per layer), [49..54] HuBERT conv1-6
+# (BF16X3), [55] feature projection, [56] positional conv (F16), then the HuBERT and BERT layers (F16)
+for spec in "gemm_kernel 21 4 gemm_f16_vit_layer" "gemm_kernel 49 2 gemm_bf16x3_conv" "attention_f16_kernel 2 1 attention_f16" \
+            "attention_tc_kernel 2 1 attention_tc" "layernorm_kernel 8 1 layernorm" "conv0_apply 0 1 conv0_apply" \
+            "conv0_stats 0 1 conv0_stats" "fus_rows_fast_kernel 0 1 fus_rows" "fus_wgrad_kernel 0 1 fus_wgrad"; do
   set -- $spec
   ncu --set full --clock-control none --import-source on -k "regex:$1" -s "$2" -c "$3" -f \
-      -o "$out/${tag}_$1" python bench.py --steps 1 --warmup 1 --cpu-clips 4 > "$out/${tag}_$1.log" 2>&1
-  echo "$1: exit $?"
+      -o "$out/${tag}_$4" python bench.py --steps 1 --warmup 1 --cpu-clips 2 --no-extras > "$out/${tag}_$4.log" 2>&1
+  echo "$4: exit $?"
 done
