@@ -53,11 +53,11 @@ def attention():
 
 def encoders():
     from mertools_b200.encoders import BertEncoder, HubertEncoder, VitEncoder
-    sd = S.hubert_state_dict(seed=1, layers=2)
+    sd = S.hubert_state_dict(seed=1, layers=4)
     wav = (S.synth_waves(2, 16000, seed=2).astype(np.float64) / 32768.0).astype(np.float32)
     for prec in ("f16", "bf16x3"):
         HubertEncoder(sd, device=dev, stack_precision=prec).forward(torch.from_numpy(wav).to(dev))
-    BertEncoder(S.bert_state_dict(300, seed=2, layers=2), device=dev).forward([[2, 17, 250, 99, 3], [2, 5, 3]])
+    BertEncoder(S.bert_state_dict(300, seed=2, layers=4), device=dev).forward([[2, 17, 250, 99, 3], [2, 5, 3]])
     VitEncoder(S.vit_state_dict(seed=0, layers=2), device=dev).frame_features(torch.from_numpy(S.synth_frames(1, 2, seed=1)[0]).to(dev))
     torch.cuda.synchronize()
     print("encoders ok")
