@@ -56,8 +56,10 @@ enum { MER_EPI_GELU = 1, MER_EPI_ROUND_TF32 = 2, MER_EPI_SPLIT_BF16 = 4,
                                  fp32 output only, excludes the GELU flags */
        MER_EPI_OUT_F16 = 16,  /* out (and vt, if given) are IEEE fp16 arrays (round-to-nearest, saturating);
                                  ld_out / vt_ld in elements */
-       MER_ATT_QKV_F16 = 32   /* mer_attention only: qkv and vt are fp16 arrays (needs MER_EPI_OUT_F16, vt,
-                                 max_seqlen <= 249, vt_ld % 8 == 0) */ };
+       MER_ATT_QKV_F16 = 32   /* mer_attention only: qkv and vt are fp16 arrays (needs vt, vt_ld % 8 == 0, max_seqlen <=
+                                 505).  With MER_EPI_OUT_F16: attention_f16.cu up to 249 tokens, attention_f16_long.cu
+                                 beyond; with another ctx format (fp32, MER_EPI_ROUND_TF32, MER_EPI_SPLIT_BF16):
+                                 attention_f16_long.cu */ };
 /* Arithmetic mode of a GEMM.  TF32: operands are fp32 arrays (pre-rounded to tf32).  BF16X3: every
  * operand value x is stored as a bf16 pair (hi, lo), x = hi + lo to 2^-17; a row of K values (K % 32
  * == 0) occupies the bytes K fp32 values would, as 128-byte groups [32 x hi | 32 x lo]; three bf16

@@ -188,15 +188,22 @@ def round_tf32_(x):
     return x
 
 
-def attention(qkv, ctx, cu_seqlens, max_seqlen, heads, round_out=False, vt=None, f16_out=False):
-    """vt: optional V^T [heads*64, ld] (enables the tcgen05 kernel for max_seqlen <= 253).  fp16 qkv / vt /
-    ctx tensors select the all-fp16 kernel (max_seqlen <= 249)."""
+def attention(qkv, ctx, cu_seqlens, max_seqlen, heads, round_out=False, vt=None, f16_out=False, split_out=False):
+    """vt: optional V^T [heads*64, ld] (enables the tcgen05 kernel for max_seqlen <= 253).  fp16 qkv / vt select the
+    fp16-operand kernels (max_seqlen <= 505): an fp16 ctx tensor gives attention_f16.cu (<= 249 tokens) or
+    attention_f16_long.cu; an fp32 ctx tensor (plain, round_out = tf32-rounded, split_out = bf16 hi | lo rows) the
+    long-key kernel with that output format."""
     import torch
     if qkv.dtype == torch.float16:
-        assert vt is not None and vt.dtype == torch.float16 and ctx.dtype == torch.float16
+        assert vt is not None and vt.dtype == torch.float16
+        if ctx.dtype == torch.float16:
+            out_fl = MER_EPI_OUT_F16
+        else:
+            assert ctx.dtype == torch.float32
+            out_fl = MER_EPI_SPLIT_BF16 if split_out else (MER_EPI_ROUND_TF32 if round_out else 0)
         check(lib().mer_attention(ptr(qkv), ptr(vt), vt.shape[1], ptr(ctx), ptr(cu_seqlens),
                                   cu_seqlens.numel() - 1, qkv.shape[0], max_seqlen, heads,
-                                  MER_EPI_OUT_F16 | MER_ATT_QKV_F16, stream_ptr()))
+                                  out_fl | MER_ATT_QKV_F16, stream_ptr()))
         return ctx
     check(lib().mer_attention(ptr(qkv), ptr(vt), vt.shape[1] if vt is not None else 0, ptr(ctx),
                               ptr(cu_seqlens), cu_seqlens.numel() - 1, qkv.shape[0], max_seqlen, heads,

@@ -234,9 +234,13 @@ attention_kernel(const float* __restrict__ qkv, float* __restrict__ ctx,
 
 }  // namespace
 
-bool mer_attention_uses_tc(int max_seqlen) {
+bool mer_attention_legacy() {
   static const bool legacy = getenv("MER_ATTENTION_LEGACY") != nullptr;
-  return !legacy && max_seqlen <= 253;  // + up to 3 alignment keys must fit the 256-key S tile
+  return legacy;
+}
+
+bool mer_attention_uses_tc(int max_seqlen) {
+  return !mer_attention_legacy() && max_seqlen <= 253;  // + up to 3 alignment keys must fit the 256-key S tile
 }
 
 int mer_attention_launch(const float* qkv, const float* vt, long long vt_ld, float* ctx,
@@ -244,11 +248,15 @@ int mer_attention_launch(const float* qkv, const float* vt, long long vt_ld, flo
                          int flags, cudaStream_t stream) {
   MER_REQUIRE(qkv && ctx && cu_seqlens, "mer_attention: null operand");
   if (flags & MER_ATT_QKV_F16) {
-    MER_REQUIRE((flags & MER_EPI_OUT_F16) && vt && mer_attention_f16_supported(max_seqlen),
-                "mer_attention: fp16 inputs need MER_EPI_OUT_F16, V^T and sequences <= 249 tokens (max_seqlen %d)",
-                max_seqlen);
+    // fp16 q | k rows and V^T: attention_f16.cu (<= 249 tokens, fp16 ctx) or attention_f16_long.cu (<= 505 tokens, ctx in
+    // any operand format: the TF32 / BF16X3 stacks send their 254 .. 505-token rows here)
+    MER_REQUIRE(vt && mer_attention_f16_supported(max_seqlen),
+                "mer_attention: fp16 inputs need V^T and sequences <= 505 tokens (max_seqlen %d)", max_seqlen);
     if (tokens <= 0) return 0;
-    return mer_attention_f16_launch(qkv, vt, vt_ld, ctx, cu_seqlens, n_seq, tokens, heads, stream, max_seqlen);
+    const int out_mode = (flags & MER_EPI_OUT_F16) ? 3 : (flags & MER_EPI_SPLIT_BF16) ? 2 : ((flags & MER_EPI_ROUND_TF32) ? 1 : 0);
+    if (out_mode == 3)
+      return mer_attention_f16_launch(qkv, vt, vt_ld, ctx, cu_seqlens, n_seq, tokens, heads, stream, max_seqlen);
+    return mer_attention_f16_long_launch(qkv, vt, vt_ld, ctx, cu_seqlens, n_seq, tokens, heads, stream, max_seqlen, out_mode);
   }
   // sequences of up to 256 tokens (ViT 197, HuBERT 5 s = 249, most sentences): tcgen05 kernel,
   // which reads V^T (written by the QKV GEMM epilogue) instead of the V columns of qkv

@@ -949,7 +949,14 @@ extern "C" __attribute__((visibility("default"))) void mer_debug_attention_trace
   g_att_trace = device_buffer;
 }
 
-bool mer_attention_f16_supported(int max_seqlen) { return max_seqlen > 0 && max_seqlen <= 249; }
+// <= 249 tokens: this file; 250 .. 505: attention_f16_long.cu (MER_ATT_F16_LONG=0 sends those back to the fp32-operand
+// kernels, for A/B runs)
+bool mer_attention_f16_supported(int max_seqlen) {
+  if (max_seqlen <= 0 || mer_attention_legacy()) return false;
+  if (max_seqlen <= 249) return true;
+  const char* e = getenv("MER_ATT_F16_LONG");
+  return (e == nullptr || atoi(e) != 0) && mer_attention_f16_long_supported(max_seqlen);
+}
 
 // qkv16: fp16 [tokens, 3*heads*64] (V columns unused), vt16: fp16 [heads*64, vt_ld] with vt[d, token],
 // ctx16: fp16 [tokens, heads*64]
@@ -959,7 +966,9 @@ int mer_attention_f16_launch(const void* qkv16, const void* vt16, long long vt_l
   MER_REQUIRE(qkv16 && vt16 && ctx16 && cu_seqlens, "mer_attention_f16: null operand");
   MER_REQUIRE(vt_ld >= tokens && vt_ld % 8 == 0, "mer_attention_f16: V^T pitch %lld must be a multiple of 8 >= tokens",
               vt_ld);
-  if (max_seqlen <= 0 || max_seqlen > 249) max_seqlen = 249;
+  if (max_seqlen > 249)
+    return mer_attention_f16_long_launch(qkv16, vt16, vt_ld, ctx16, cu_seqlens, n_seq, tokens, heads, stream, max_seqlen, 3);
+  if (max_seqlen <= 0) max_seqlen = 249;
   // MER_ATT_F16_VER selects the kernel generation (see the header comments); read at every launch so that a test can
   // run all of them in one process.  VER 7 needs its shared-memory plan to fit (sequences up to ~230 tokens), else 6.
   const char* ver_env = getenv("MER_ATT_F16_VER");

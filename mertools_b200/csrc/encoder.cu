@@ -79,7 +79,13 @@ int mer_run_stack(const MerStackArgs& a, cudaStream_t stream) {
     const bool split = a.mode == MER_GEMM_BF16X3;
     // tcgen05 attention (sequences <= 256): the QKV GEMM writes V transposed into a.vt instead of
     // the V columns of qkv
-    float* vt = (a.vt && mer_attention_uses_tc(a.max_seqlen)) ? a.vt : nullptr;
+    // (254 .. 505 tokens: attention_f16_long.cu, which takes fp16 q | k | V^T whatever the stack's operand format)
+    const bool long_att = a.vt && !mer_attention_uses_tc(a.max_seqlen) && mer_attention_f16_supported(a.max_seqlen);
+    float* vt = (a.vt && (long_att || mer_attention_uses_tc(a.max_seqlen))) ? a.vt : nullptr;
+    // the TF32 / BF16X3 stacks: QKV epilogue and attention flags (q | k | v tf32-rounded fp32, or fp16 = the same 10-bit
+    // mantissa, for the long-key kernel)
+    const int qkv_fl = long_att ? MER_EPI_OUT_F16 : MER_EPI_ROUND_TF32;
+    const int att_in = long_att ? MER_ATT_QKV_F16 : 0;
     const int opnd = split ? MER_EPI_SPLIT_BF16 : MER_EPI_ROUND_TF32;
     if (a.pre_ln && a.mode == MER_GEMM_F16) {
       // same chain on fp16 operands: LN, the QKV GEMM (q | k rows and V^T), attention and FC1 write fp16
@@ -113,10 +119,10 @@ int mer_run_stack(const MerStackArgs& a, cudaStream_t stream) {
       // x = x + Wo * Attn(LN1(x));  x = x + W2 * GELU(W1 * LN2(x))
       MER_TRY(mer_layernorm_launch(a.x, w.ln1_g, w.ln1_b, split ? nullptr : a.xn, split ? a.xn : nullptr,
                                    nullptr, M, D, a.eps, MER_LN_ROUND_TF32, stream));
-      MER_TRY(linear(a.mode, a.xn, w.w_qkv, w.b_qkv, nullptr, a.qkv, M, DQKV, D, MER_EPI_ROUND_TF32, stream,
+      MER_TRY(linear(a.mode, a.xn, w.w_qkv, w.b_qkv, nullptr, a.qkv, M, DQKV, D, qkv_fl, stream,
                      vt, a.vt_ld, 2 * D));
       MER_TRY(mer_attention_launch(a.qkv, vt, a.vt_ld, a.xn, a.cu_seqlens, a.n_seq, M, a.max_seqlen, HEADS,
-                                   opnd, stream));
+                                   opnd | att_in, stream));
       MER_TRY(linear(a.mode, a.xn, w.w_o, w.b_o, a.x, a.x, M, D, D, 0, stream));
       MER_TRY(mer_layernorm_launch(a.x, w.ln2_g, w.ln2_b, split ? nullptr : a.xn, split ? a.xn : nullptr,
                                    nullptr, M, D, a.eps, MER_LN_ROUND_TF32, stream));
@@ -161,10 +167,10 @@ int mer_run_stack(const MerStackArgs& a, cudaStream_t stream) {
       // TF32: x itself is tf32-rounded and doubles as the GEMM operand.  BF16X3: x stays exact fp32
       // (residual) and xs carries its split copy (GEMM operand).
       const float* xop = split ? a.xs : a.x;
-      MER_TRY(linear(a.mode, xop, w.w_qkv, w.b_qkv, nullptr, a.qkv, M, DQKV, D, MER_EPI_ROUND_TF32, stream,
+      MER_TRY(linear(a.mode, xop, w.w_qkv, w.b_qkv, nullptr, a.qkv, M, DQKV, D, qkv_fl, stream,
                      vt, a.vt_ld, 2 * D));
       MER_TRY(mer_attention_launch(a.qkv, vt, a.vt_ld, a.xn, a.cu_seqlens, a.n_seq, M, a.max_seqlen, HEADS,
-                                   opnd, stream));
+                                   opnd | att_in, stream));
       // the pre-LN sum goes to the (now dead) qkv buffer: ctx in xn is still being read
       MER_TRY(linear(a.mode, a.xn, w.w_o, w.b_o, a.x, a.qkv, M, D, D, 0, stream));
       MER_TRY(mer_layernorm_launch(a.qkv, w.ln1_g, w.ln1_b, a.x, split ? a.xs : nullptr, nullptr, M, D,

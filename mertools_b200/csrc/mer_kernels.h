@@ -8,7 +8,7 @@
 // modes, MER_PROF_* below for the other kernels; work = algorithmic FLOPs or bytes of the launch.
 // begin returns a slot (or -1 when profiling is off); end records the closing event.
 enum { MER_PROF_ATT_F16 = 10, MER_PROF_ATT_TC = 11, MER_PROF_LAYERNORM = 12, MER_PROF_POSCONV = 13,
-       MER_PROF_CONV0 = 14 };
+       MER_PROF_CONV0 = 14, MER_PROF_ATT_LONG = 15 };
 int mer_prof_begin(int klass, double work, cudaStream_t stream);
 void mer_prof_end(int slot, cudaStream_t stream);
 void mer_prof_pause(int on);  // nest: launches of a composite op (timed as a whole) are not recorded themselves
@@ -46,8 +46,14 @@ int mer_attention_tc_launch(const float* qkv, const float* vt, long long vt_ld, 
                             const int* cu_seqlens, int n_seq, long long tokens, int heads, int flags,
                             cudaStream_t stream);
 
-// attention_f16.cu (tcgen05, fp16 q | k | v^T in, fp16 ctx out; max_seqlen <= 249)
+// attention_f16.cu (tcgen05, fp16 q | k | v^T in, fp16 ctx out; max_seqlen <= 249) and attention_f16_long.cu (250 .. 505:
+// audio rows of up to 10 s, CLIP L/14).  _supported: some fp16 kernel takes sequences of this length
 bool mer_attention_f16_supported(int max_seqlen);
+bool mer_attention_f16_long_supported(int max_seqlen);
+int mer_attention_f16_long_launch(const void* qkv16, const void* vt16, long long vt_ld, void* ctx16,
+                                  const int* cu_seqlens, int n_seq, long long tokens, int heads, cudaStream_t stream,
+                                  int max_seqlen, int out_mode);
+bool mer_attention_legacy();  // MER_ATTENTION_LEGACY set: only the mma.sync kernel of attention.cu (debug)
 int mer_attention_f16_launch(const void* qkv16, const void* vt16, long long vt_ld, void* ctx16,
                              const int* cu_seqlens, int n_seq, long long tokens, int heads,
                              cudaStream_t stream, int max_seqlen = 0);

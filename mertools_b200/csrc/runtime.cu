@@ -2,7 +2,9 @@
 // encoding through the driver entry point (resolved at run time so the library links without
 // libcuda and loads on a GPU-less build box), and the thin extern "C" wrappers of the kernel-level
 // entry points declared in include/mer_b200.h.
+#include <cuda_profiler_api.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -29,7 +31,55 @@ std::vector<ProfSlot> g_prof_pool;  // recycled event pairs
 
 void mer_prof_pause(int on) { g_prof_paused += on ? 1 : -1; }
 
+// ---- capture windows for `ncu --profile-from-start off` (scripts/profile_kernels.sh) ----
+// MER_CUPROF="klass:first:count,..." brackets launches [first, first + count) of a kernel class (the klass ids of
+// mer_prof_begin) with cudaProfilerStart / cudaProfilerStop, so that ONE profiled process captures a few launches of
+// every kernel of the step instead of one process per kernel.  Unset (the product): two integer compares per launch.
+namespace {
+struct CuprofWin { int klass, first, count, seen; };
+std::vector<CuprofWin> g_cuprof;
+int g_cuprof_state = 0;  // 0 = environment not parsed, 1 = no windows, 2 = windows present
+bool g_cuprof_open = false;
+
+void cuprof_parse() {
+  g_cuprof_state = 1;
+  const char* e = getenv("MER_CUPROF");
+  if (!e) return;
+  while (*e) {
+    CuprofWin w = {0, 0, 0, 0};
+    int used = 0;
+    if (sscanf(e, "%d:%d:%d%n", &w.klass, &w.first, &w.count, &used) == 3 && w.count > 0) g_cuprof.push_back(w);
+    e += used;
+    while (*e && *e != ',') ++e;
+    if (*e == ',') ++e;
+    if (used == 0 && !*e) break;
+  }
+  if (!g_cuprof.empty()) g_cuprof_state = 2;
+}
+
+void cuprof_begin(int klass) {
+  if (g_cuprof_state == 0) cuprof_parse();
+  if (g_cuprof_state != 2) return;
+  for (auto& w : g_cuprof) {
+    if (w.klass != klass) continue;
+    const int n = w.seen++;
+    if (n >= w.first && n < w.first + w.count && !g_cuprof_open) {
+      cudaProfilerStart();
+      g_cuprof_open = true;
+    }
+  }
+}
+
+void cuprof_end() {
+  if (g_cuprof_open) {
+    cudaProfilerStop();
+    g_cuprof_open = false;
+  }
+}
+}  // namespace
+
 int mer_prof_begin(int klass, double work, cudaStream_t stream) {
+  if (g_prof_paused == 0) cuprof_begin(klass);
   if (!g_prof_on || g_prof_paused > 0) return -1;
   ProfSlot slot;
   if (!g_prof_pool.empty()) {
@@ -46,6 +96,7 @@ int mer_prof_begin(int klass, double work, cudaStream_t stream) {
 }
 
 void mer_prof_end(int slot, cudaStream_t stream) {
+  if (g_prof_paused == 0) cuprof_end();
   if (slot >= 0 && slot < (int)g_prof.size()) cudaEventRecord(g_prof[slot].b, stream);
 }
 

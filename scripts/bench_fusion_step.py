@@ -14,7 +14,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def fusion_step_us(B, iters=200, dropout=0.3, hidden=128, device="cuda:0"):
+def fusion_step_us(B, iters=200, dropout=0.3, hidden=128, device="cuda:0", profile=False):
     from mertools_b200 import synthetic as S
     from mertools_b200.fusion import FusionNet
     net = FusionNet(hidden_dim=hidden, dropout=dropout, device=device, seed=7)
@@ -27,6 +27,11 @@ def fusion_step_us(B, iters=200, dropout=0.3, hidden=128, device="cuda:0"):
     key = next(iter(net._graphs))
     graph = net._graphs[key][0]
     torch.cuda.synchronize()
+    if profile:  # `ncu --profile-from-start off`: exactly one replay (fus_rows_fast_kernel + fus_wgrad_kernel) is captured
+        torch.cuda.cudart().cudaProfilerStart()
+        graph.replay()
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
@@ -63,9 +68,10 @@ if __name__ == "__main__":
     ap.add_argument("--batches", type=int, nargs="+", default=[32, 256])
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="bracket one graph replay with cudaProfilerStart / Stop")
     a = ap.parse_args()
     for B in a.batches:
-        r = fusion_step_us(B, a.iters)
+        r = fusion_step_us(B, a.iters, profile=a.profile)
         if not a.no_cpu:
             r["reference_cpu_step_us"] = round(reference_cpu_step_us(B), 1)
         print(json.dumps(r), flush=True)

@@ -1,25 +1,30 @@
 #!/usr/bin/env bash
-# ncu captures of the dominant kernels inside one bench step (one GPU; run under gpurun), as in round 1:
-#   bash scripts/profile_kernels.sh [tag]          -> gpurun_out/<tag>_<kernel>.ncu-rep + <tag>_launches.csv
-# Environment switches (MER_ATT_F16_VER=2 ...) are inherited, so a variant is profiled by exporting its switch.
-# Read the reports back in the build container:
-#   ncu -i gpurun_out/<tag>_attention_f16_kernel.ncu-rep --page raw --csv
-#   ncu -i ... --page source --csv --print-source sass        (per-instruction executed counts / stall samples)
+# ncu evidence of one bench step (one GPU; run under gpurun):   bash scripts/profile_kernels.sh [tag]
+#   gpurun_out/<tag>_launches.csv          launch list of `bench.py --steps 1 --warmup 1` (cold-cache, serialised: shares)
+#   gpurun_out/<tag>_gemm.json             ncu --set full summary of one ViT layer's four F16 GEMMs + two BF16X3 conv GEMMs
+#   gpurun_out/<tag>_kernels.{ncu-rep,json} attention_f16, LayerNorm, conv0 stats/apply, positional conv, long-key attention
+#   gpurun_out/<tag>_fusion.{ncu-rep,json}  the two kernels of one fusion training step (graph replay)
+# Three profiled processes instead of one per kernel: the capture windows are set with MER_CUPROF (runtime.cu).  The
+# GEMM report (source pages of 6 large kernels, ~40 MB) is summarised on the box and dropped: gpurun_out/ comes back only
+# below 64 MiB.  Environment switches (MER_ATT_F16_VER=...) are inherited.
 set -u
 tag=${1:-r2}
 out=gpurun_out
 mkdir -p "$out"
-# launch list of a window that contains at least one full step (cold-cache, serialised: shares, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 900 --csv --log-file "$out/${tag}_launches.csv" \
     python bench.py --steps 1 --warmup 1 --cpu-clips 2 --no-extras > "$out/${tag}_launches.log" 2>&1
-# kernel regex, matching launches to skip, launches to capture, name of the report.  GEMM launch order inside a step:
-# [0] ViT patch embedding (TF32), [1..48] ViT layers (F16: qkv, out-proj, fc1, fc2 per layer), [49..54] HuBERT conv1-6
-# (BF16X3), [55] feature projection, [56] positional conv (F16), then the HuBERT and BERT layers (F16)
-for spec in "gemm_kernel 21 4 gemm_f16_vit_layer" "gemm_kernel 49 2 gemm_bf16x3_conv" "attention_f16_kernel 2 1 attention_f16" \
-            "attention_tc_kernel 2 1 attention_tc" "layernorm_kernel 8 1 layernorm" "conv0_apply 0 1 conv0_apply" \
-            "conv0_stats 0 1 conv0_stats" "fus_rows_fast_kernel 0 1 fus_rows" "fus_wgrad_kernel 0 1 fus_wgrad"; do
-  set -- $spec
-  ncu --set full --clock-control none --import-source on -k "regex:$1" -s "$2" -c "$3" -f \
-      -o "$out/${tag}_$4" python bench.py --steps 1 --warmup 1 --cpu-clips 2 --no-extras > "$out/${tag}_$4.log" 2>&1
-  echo "$4: exit $?"
-done
+echo "launch list: exit $?"
+full="ncu --set full --clock-control none --import-source on --profile-from-start off -f"
+MER_CUPROF="2:21:4,1:0:2" $full -o "$out/${tag}_gemm" python scripts/profile_step.py > "$out/${tag}_gemm.log" 2>&1
+echo "gemm: exit $?"
+python scripts/ncu_hotspots.py "$out/${tag}_gemm.ncu-rep" > "$out/${tag}_gemm.json" 2>> "$out/${tag}_gemm.log" && rm -f "$out/${tag}_gemm.ncu-rep"
+MER_CUPROF="10:2:1,12:8:1,14:0:1,13:0:1,15:0:1" $full -o "$out/${tag}_kernels" python scripts/profile_step.py --long-audio \
+    > "$out/${tag}_kernels.log" 2>&1
+echo "kernels: exit $?"
+python scripts/ncu_hotspots.py "$out/${tag}_kernels.ncu-rep" > "$out/${tag}_kernels.json" 2>> "$out/${tag}_kernels.log"
+$full -o "$out/${tag}_fusion" python scripts/bench_fusion_step.py --no-cpu --batches 32 --iters 1 --profile \
+    > "$out/${tag}_fusion.log" 2>&1
+echo "fusion: exit $?"
+python scripts/ncu_hotspots.py "$out/${tag}_fusion.ncu-rep" > "$out/${tag}_fusion.json" 2>> "$out/${tag}_fusion.log"
+ls -la "$out" | grep "${tag}_"
+du -sh "$out"
