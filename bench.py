@@ -199,7 +199,7 @@ def run_ours(args):
     ms = ev[0].elapsed_time(ev[1])
     launches = int(L.lib().mer_launch_count() - l0 + models[3].graph_launches - g0)
     prof = {}
-    for name, mode in (("tf32", 0), ("bf16x3", 1), ("f16", 2), ("att_f16", 10), ("att_tc", 11), ("ln", 12),
+    for name, mode in (("tf32", 0), ("bf16x3", 1), ("f16", 2), ("f16_small", 3), ("att_f16", 10), ("att_tc", 11), ("ln", 12),
                        ("posconv", 13), ("conv0", 14)):
         t, f, n = C.c_double(), C.c_double(), C.c_int()
         L.lib().mer_profile_collect(mode, C.byref(t), C.byref(f), C.byref(n))
@@ -299,11 +299,15 @@ def run_ours(args):
         other = [e for e in (
             entry("bf16x3", "gemm_kernel<*, BF16X3> (3 bf16 MMAs per product; HuBERT conv1-6 + feature projection)", "tensor",
                   sus / 3.0, "TFLOP/s (useful)", 1e12),
-            entry("att_f16", "attention_f16_kernel (tcgen05 kind::f16; ViT, 197 tokens)", "tensor", sus, "TFLOP/s", 1e12),
+            entry("f16_small", "gemm_kernel<*, F16> on the HuBERT (63,744 rows) and BERT (8,192 rows) layers: 10 / 1.3 waves of "
+                  "tiles at N = 768", "tensor", sus, "TFLOP/s", 1e12),
+            entry("att_f16", "attention_f16_kernel (tcgen05 kind::f16; ViT 197, HuBERT 249, BERT 32 tokens)", "tensor", sus,
+                  "TFLOP/s", 1e12),
             entry("att_tc", "attention_tc_kernel (tcgen05 kind::tf32; HuBERT 249 tokens, BERT)", "tensor", sus / 2.0,
                   "TFLOP/s", 1e12),
             entry("ln", "layernorm_kernel (warp per row, 128-bit I/O)", "hbm", pk["hbm"], "GB/s", 1e9),
-            entry("conv0", "conv0_stats + conv0_apply (HuBERT conv0 + GroupNorm + GELU, two passes)", "hbm", pk["hbm"],
+            entry("conv0", "conv0 moments + coefficients + apply (HuBERT conv0 + GroupNorm + GELU; statistics from the "
+                  "waveform's tap moments, one pass over the output)", "hbm", pk["hbm"],
                   "GB/s", 1e9),
             entry("posconv", "HuBERT positional conv (grouped k=128) as a windowed block-diagonal F16 GEMM; algorithmic FLOPs "
                   "(the GEMM executes 6.67x as many)", "tensor", sus, "TFLOP/s", 1e12),
@@ -328,8 +332,8 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"kernel": ("gemm_kernel<256, F16, CTA pair, cta_group::2> (tcgen05 kind::f16; linear layers of the "
-                                    "ViT, HuBERT and BERT stacks + HuBERT positional conv)"
+            "roofline": {"kernel": ("gemm_kernel<256, F16, CTA pair, cta_group::2> (tcgen05 kind::f16; the 48 linear layers "
+                                    "of the ViT stack, 403,456 rows)"
                                     if use_f16 else
                                     "gemm_kernel<256, TF32, CTA pair, cta_group::2> (tcgen05 kind::tf32; ViT linear layers)"),
                          "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",

@@ -42,7 +42,8 @@ MER_API long long mer_launch_count(void);
 MER_API long long mer_gemm_variant_launches(int block_n, int mode, int cluster, int twosm);
 /* per-launch CUDA-event timing (roofline in bench.py): enable(1) starts a fresh recording, enable(0)
  * stops; collect sums duration / algorithmic work / launches of one kernel class since the last
- * enable(1).  Classes: MER_GEMM_* (work = 2*M*N*K flop), 10 = fp16 tcgen05 attention, 11 = TF32 tcgen05
+ * enable(1).  Classes: MER_GEMM_* (work = 2*M*N*K flop; MER_GEMM_F16 launches of fewer than 2^17 rows are
+ * class 3), 10 = fp16 tcgen05 attention (15 = its long-key form), 11 = TF32 tcgen05
  * attention (work = 4*S^2*64 flop per (sequence, head), S = tokens / n_seq), 12 = LayerNorm, 14 = HuBERT
  * conv0 (work = algorithmic HBM bytes), 13 = HuBERT positional conv (flop). */
 MER_API int mer_profile_enable(int on);

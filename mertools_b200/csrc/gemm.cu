@@ -612,8 +612,13 @@ int launch_gemm(const MerGemmDesc* g, cudaStream_t stream) {
   const long long tiles = groups * (g->N / BLOCK_N);
   int grid = (mer_num_sms() / CLUSTER) * CLUSTER;
   if (tiles * CLUSTER < grid) grid = (int)tiles * CLUSTER;
-  const int prof = mer_prof_begin(MODE, 2.0 * (double)g->rows_per_batch * g->batches * g->N *
-                                            (double)(g->K_inner * g->taps), stream);
+  // profile class: the GEMM mode; fp16 problems of fewer than 2^17 rows (the HuBERT / BERT layers: 63,744 / 8,192 rows
+  // at the bench shapes, against the ViT's 403,456) are kept apart as class 3 so that the dominant kernel's roofline
+  // is not an average over launches of very different sizes
+  const int klass = (MODE == MER_GEMM_F16 && (long long)g->rows_per_batch * g->batches < (1ll << 17)) ? MER_PROF_F16_SMALL
+                                                                                                        : MODE;
+  const int prof = mer_prof_begin(klass, 2.0 * (double)g->rows_per_batch * g->batches * g->N *
+                                             (double)(g->K_inner * g->taps), stream);
   {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

@@ -412,9 +412,10 @@ __device__ __forceinline__ void store_split4(void* row_base, int col, float4 v) 
       make_uint2(pack_bf16x2(v.x - hx, v.y - hy), pack_bf16x2(v.z - hz, v.w - hw));
 }
 __device__ __forceinline__ void store_split2(void* row_base, int col, float a, float b) {  // col % 2 == 0
-  const float ha = bf16_round(a), hb = bf16_round(b);
+  const uint32_t hp = pack_bf16x2(a, b);  // both hi halves in one conversion; as floats: the two 16-bit fields
+  const float ha = __uint_as_float(hp << 16), hb = __uint_as_float(hp & 0xffff0000u);
   uint16_t* o = reinterpret_cast<uint16_t*>(row_base) + split_index(col);
-  *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(ha, hb);
+  *reinterpret_cast<uint32_t*>(o) = hp;
   *reinterpret_cast<uint32_t*>(o + 32) = pack_bf16x2(a - ha, b - hb);
 }
 __device__ __forceinline__ void store_split1(void* row_base, int col, float v) {

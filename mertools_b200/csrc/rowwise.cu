@@ -87,6 +87,90 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
   }
 }
 
+// Round-2 form (default; MER_LN_VER=1 keeps the kernel above): the same arithmetic, row for row, with gamma / beta in
+// shared memory instead of 2 x 4 VEC registers per lane.  ncu of the first form at the ViT shape (profiles/
+// r1_layernorm_kernel_hotspots.json): 96 registers -> two blocks = 16 warps per SM, each alternating between a load
+// phase (3 KB in flight) and a reduce / store phase with nothing in flight: 0.69-0.72 of the HBM peak.  Here a warp
+// fits 64 registers at 768 columns (four blocks = 32 warps per SM) and requests its NEXT row before it reduces and stores the
+// current one, so loads stay in flight through the whole loop.
+template <int VEC>
+__global__ void __launch_bounds__(256, VEC <= 6 ? 4 : VEC <= 8 ? 3 : 2)
+layernorm2_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, float* __restrict__ y, void* __restrict__ ys,
+                  float* __restrict__ acc, long long rows, float eps, int flags) {
+  constexpr int DIM = 128 * VEC;
+  __shared__ float4 gs[32 * VEC], bs[32 * VEC];
+  for (int i = threadIdx.x; i < 32 * VEC; i += blockDim.x) {
+    gs[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+    bs[i] = __ldg(reinterpret_cast<const float4*>(beta) + i);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+  long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const bool y16 = (flags & MER_LN_OUT_F16) != 0;   // y is an fp16 row (the F16 GEMM operand)
+  const bool ys16 = (flags & MER_LN_SPLIT_F16) != 0;  // the second output is an fp16 row instead of a bf16 split row
+  float4 v[VEC];
+  {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * DIM);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) v[i] = xr[lane + 32 * i];
+  }
+  for (; row < rows; row += warps_total) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) * (1.0f / DIM);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / DIM) + eps);
+    float4* yr = (y && !y16) ? reinterpret_cast<float4*>(y + row * DIM) : nullptr;
+    uint2* yh = (y && y16) ? reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(y) + row * DIM) : nullptr;
+    float* ysr = (ys && !ys16) ? reinterpret_cast<float*>(ys) + row * DIM : nullptr;  // split row: DIM 4-byte slots
+    uint2* ysh = (ys && ys16) ? reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(ys) + row * DIM) : nullptr;
+    float4* ar = acc ? reinterpret_cast<float4*>(acc + row * DIM) : nullptr;
+    // (y == x is allowed: a warp has its whole row in registers before it writes; the NEXT row belongs to this warp too)
+    const long long nrow = row + warps_total;
+    const float4* xn = reinterpret_cast<const float4*>(x + (nrow < rows ? nrow : row) * DIM);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float4 g = gs[lane + 32 * i], b = bs[lane + 32 * i];
+      float4 o;
+      o.x = v[i].x * rstd * g.x + b.x;
+      o.y = v[i].y * rstd * g.y + b.y;
+      o.z = v[i].z * rstd * g.z + b.z;
+      o.w = v[i].w * rstd * g.w + b.w;
+      v[i] = xn[lane + 32 * i];  // the next row's slot i: in flight while this row is finished and stored
+      if (flags & MER_LN_GELU) {
+        o.x = gelu_erf_fast(o.x); o.y = gelu_erf_fast(o.y); o.z = gelu_erf_fast(o.z); o.w = gelu_erf_fast(o.w);
+      }
+      if (ar) {
+        if (flags & MER_LN_ACC_INIT) {
+          ar[lane + 32 * i] = o;
+        } else if (flags & MER_LN_ACC_ADD) {
+          float4 a = ar[lane + 32 * i];
+          a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+          ar[lane + 32 * i] = a;
+        }
+      }
+      if (ysr) store_split4(ysr, 4 * (lane + 32 * i), o);
+      if (ysh) ysh[lane + 32 * i] = make_uint2(pack_f16x2(o.x, o.y), pack_f16x2(o.z, o.w));
+      if (yh) yh[lane + 32 * i] = make_uint2(pack_f16x2(o.x, o.y), pack_f16x2(o.z, o.w));
+      if (yr) {
+        if (flags & MER_LN_ROUND_TF32) {
+          o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+        }
+        yr[lane + 32 * i] = o;
+      }
+    }
+  }
+}
+
 // fp32 [rows,K] -> split bf16 rows (128-byte groups of 32 hi | 32 lo), K % 32 == 0
 __global__ void split_bf16_kernel(const float* __restrict__ in, void* __restrict__ out, long long rows,
                                   int K) {
@@ -153,16 +237,19 @@ int mer_layernorm_launch(const float* x, const float* gamma, const float* beta, 
   const double out_b = (y ? ((flags & MER_LN_OUT_F16) ? 2.0 : 4.0) : 0.0) + (y_split ? 4.0 : 0.0) +
                        (acc ? ((flags & MER_LN_ACC_ADD) ? 8.0 : 4.0) : 0.0);
   const int prof = mer_prof_begin(MER_PROF_LAYERNORM, (double)rows * dim * (4.0 + out_b), stream);
-  if (dim == 768)
-    layernorm_kernel<6><<<(int)blocks, 256, 0, stream>>>(x, gamma, beta, y, y_split, acc, rows, eps, flags);
-  else if (dim == 1024)
-    layernorm_kernel<8><<<(int)blocks, 256, 0, stream>>>(x, gamma, beta, y, y_split, acc, rows, eps, flags);
-  else if (dim == 1280)  // whisper-large-v2
-    layernorm_kernel<10><<<(int)blocks, 256, 0, stream>>>(x, gamma, beta, y, y_split, acc, rows, eps, flags);
-  else if (dim == 1536)  // dinov2-giant
-    layernorm_kernel<12><<<(int)blocks, 256, 0, stream>>>(x, gamma, beta, y, y_split, acc, rows, eps, flags);
-  else
-    layernorm_kernel<4><<<(int)blocks, 256, 0, stream>>>(x, gamma, beta, y, y_split, acc, rows, eps, flags);
+  const char* ver = getenv("MER_LN_VER");  // read at every launch: tests run both forms in one process
+  const bool v1 = ver && atoi(ver) == 1;
+#define MER_LN_LAUNCH(VEC)                                                                                          \
+  do {                                                                                                              \
+    if (v1) layernorm_kernel<VEC><<<(int)blocks, 256, 0, stream>>>(x, gamma, beta, y, y_split, acc, rows, eps, flags);  \
+    else layernorm2_kernel<VEC><<<(int)blocks, 256, 0, stream>>>(x, gamma, beta, y, y_split, acc, rows, eps, flags);    \
+  } while (0)
+  if (dim == 768) MER_LN_LAUNCH(6);
+  else if (dim == 1024) MER_LN_LAUNCH(8);
+  else if (dim == 1280) MER_LN_LAUNCH(10);  // whisper-large-v2
+  else if (dim == 1536) MER_LN_LAUNCH(12);  // dinov2-giant
+  else MER_LN_LAUNCH(4);
+#undef MER_LN_LAUNCH
   mer_prof_end(prof, stream);
   MER_CUDA_CHECK(cudaGetLastError());
   mer_count_launches(1);

@@ -46,7 +46,7 @@ def sass(rep):
     secs, cur = [], None
     for row in csv.reader(io.StringIO(ncu(rep, "--page", "source", "--csv", "--print-source", "sass"))):
         if row and row[0] == "Kernel Name":
-            cur = {"hdr": None, "rows": []}
+            cur = {"hdr": None, "rows": [], "name": row[1] if len(row) > 1 else ""}
             secs.append(cur)
         elif cur is not None and cur["hdr"] is None:
             cur["hdr"] = row
@@ -76,7 +76,7 @@ def sass(rep):
                 reg = {"exec": e, "n": 1, "samples": s, "first": n, "last": n}
                 regions.append(reg)
         out.append({
-            "warp_instructions": tot_i, "stall_samples": tot_s,
+            "kernel": sec["name"][:100], "warp_instructions": tot_i, "stall_samples": tot_s,
             "opcodes_pct": {op: {"inst": round(v / tot_i * 100, 2), "samples": round(hs[op] / tot_s * 100, 2)}
                             for op, v in sorted(hi.items(), key=lambda kv: -kv[1])[:16]},
             "hot_regions": [dict(r, inst_share_pct=round(r["exec"] * r["n"] / tot_i * 100, 2))
@@ -87,10 +87,23 @@ def sass(rep):
 
 if __name__ == "__main__":
     rep = sys.argv[1]
-    ls, ss = launches(rep), sass(rep)
-    # the source page repeats every launch (one section per view); keep one section per launch
-    step = max(1, len(ss) // max(1, len(ls)))
-    for i, launch in enumerate(ls):
-        if i * step < len(ss):
-            launch["sass"] = ss[i * step]
-    json.dump({"report": rep, "launches": ls}, sys.stdout, indent=1)
+    ls = launches(rep)
+    try:  # reports captured without --import-source / the SourceCounters section have no source page
+        ss = sass(rep)
+    except Exception:  # noqa: BLE001
+        ss = []
+    # the source page may list a launch more than once (one section per view): drop consecutive repeats
+    uniq = []
+    for sec in ss:
+        if uniq and all(uniq[-1][k] == sec[k] for k in ("kernel", "warp_instructions", "stall_samples")):
+            continue
+        uniq.append(sec)
+    if len(uniq) == len(ls):
+        for launch, sec in zip(ls, uniq):
+            launch["sass"] = sec
+    else:
+        sys.stderr.write(f"source sections ({len(uniq)}) do not match launches ({len(ls)}): listed apart\n")
+    doc = {"report": rep, "launches": ls}
+    if len(uniq) != len(ls):
+        doc["sass_sections"] = uniq
+    json.dump(doc, sys.stdout, indent=1)
