@@ -237,7 +237,8 @@ attention_f16_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
     // The sequence bounds of the next item are loaded one item ahead (two independent loads, first touched later).
     const int t = warp == 1 ? 0 : 1;
     // these two warps have nothing else to do: spin on non-blocking probes (a try_wait that has gone to sleep reacted
-    // ~1k cycles late in the traces)
+    // ~1k cycles late in the traces).  A nanosleep back-off of 20 .. 160 ns between probes (to hand the issue slots to
+    // the softmax warps of the same scheduler) measured 0 .. -2 % (profiles/r2_ab_microbench.json): not kept.
     auto spin = [&](uint64_t* bar, uint32_t parity) {
       while (!mbar_test_wait(bar, parity)) {
       }

@@ -1083,10 +1083,9 @@ struct WArgs {
   const float* loss_terms; float inv_batch; float* loss_out;
 };
 
-__device__ __forceinline__ void adam_update(const WArgs& a, long long i, float grad, float t) {
-  // torch.optim.Adam (coupled L2), same operation order as fusion.cu:fus_adam_kernel
-  const float bc1 = 1.f - powf(a.beta1, t);
-  const float bc2_sqrt = sqrtf(1.f - powf(a.beta2, t));
+// torch.optim.Adam (coupled L2), same operation order as fusion.cu:fus_adam_kernel; bc1 / bc2_sqrt are the bias
+// corrections 1 - beta1^t and sqrt(1 - beta2^t) of this step (computed once per thread)
+__device__ __forceinline__ void adam_update(const WArgs& a, long long i, float grad, float bc1, float bc2_sqrt) {
   if (a.clip > 0.f) grad = fminf(fmaxf(grad, -a.clip), a.clip);
   const float pi = a.P[i];
   grad = fmaf(a.wd, pi, grad);
@@ -1098,31 +1097,51 @@ __device__ __forceinline__ void adam_update(const WArgs& a, long long i, float g
   a.P[i] = pi - (a.lr / bc1) * (mi / denom);
 }
 
+// VW outputs dW[n, k .. k + VW) per thread (VW = 4 when every K is a multiple of 4 and the activations are 16-byte
+// aligned: one 16-byte load of x per batch row instead of four scalar ones -- the kernel is load-issue bound; per
+// element the sum over the batch runs in the same order in both forms, so they agree bit for bit)
+template <int VW>
 __global__ void __launch_bounds__(NT) fus_wgrad_kernel(const __grid_constant__ WArgs a) {
   const int tid = threadIdx.x;
-  const float t = a.do_adam ? (float)(*a.step + 1) : 0.f;
+  float bc1 = 1.f, bc2_sqrt = 1.f;
+  if (a.do_adam) {
+    const float t = (float)(*a.step + 1);
+    bc1 = 1.f - powf(a.beta1, t);
+    bc2_sqrt = sqrtf(1.f - powf(a.beta2, t));
+  }
   int pi = 0;
 #pragma unroll
   for (int i = 1; i < 15; ++i)
     if ((int)blockIdx.x >= a.p[i].blk0) pi = i;
   const WProb& p = a.p[pi];
-  const long long e = (long long)(blockIdx.x - p.blk0) * NT + tid;
+  const long long e = ((long long)(blockIdx.x - p.blk0) * NT + tid) * VW;
   if (e < (long long)p.N * p.K) {
-    const int n = (int)(e / p.K), k = (int)(e % p.K);
-    float acc = 0.f, accb = 0.f;
+    const int n = (int)(e / p.K), k = (int)(e % p.K);  // K % VW == 0: the VW outputs share n
+    float acc[VW] = {}, accb = 0.f;
     const float* dy = p.dy + n;
     const float* x = p.x + k;
 #pragma unroll 8
     for (int b = 0; b < a.B; ++b) {
       const float g = dy[(long long)b * p.lddy];
       accb += g;
-      acc = fmaf(g, x[(long long)b * p.ldx], acc);
+      if (VW == 4) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + (long long)b * p.ldx);
+        acc[0] = fmaf(g, xv.x, acc[0]);
+        acc[1 % VW] = fmaf(g, xv.y, acc[1 % VW]);
+        acc[2 % VW] = fmaf(g, xv.z, acc[2 % VW]);
+        acc[3 % VW] = fmaf(g, xv.w, acc[3 % VW]);
+      } else {
+        acc[0] = fmaf(g, x[(long long)b * p.ldx], acc[0]);
+      }
     }
-    a.G[p.w_off + e] = acc;
-    if (a.do_adam) adam_update(a, p.w_off + e, acc, t);
+#pragma unroll
+    for (int j = 0; j < VW; ++j) {
+      a.G[p.w_off + e + j] = acc[j];
+      if (a.do_adam) adam_update(a, p.w_off + e + j, acc[j], bc1, bc2_sqrt);
+    }
     if (k == 0) {
       a.G[p.b_off + n] = accb;
-      if (a.do_adam) adam_update(a, p.b_off + n, accb, t);
+      if (a.do_adam) adam_update(a, p.b_off + n, accb, bc1, bc2_sqrt);
     }
   }
   if (blockIdx.x == 0 && tid == 0 && a.loss_out) {
@@ -1237,9 +1256,16 @@ int launch_wgrad(const MerFusionDims& d, const ULayout& L, const GWs& ws, const 
   const int H = d.hidden;
   const int in[3] = {d.audio_dim, d.text_dim, d.video_dim};
   int np = 0, blk = 0;
+  // four outputs per thread when every K is a multiple of 4 and every activation row starts on a 16-byte boundary
+  // (the workspace buffers do by construction; the inputs and `features` are the caller's)
+  bool vec = in[0] % 4 == 0 && in[1] % 4 == 0 && in[2] % 4 == 0 && (reinterpret_cast<uintptr_t>(features) & 15) == 0;
+  for (int m = 0; m < 3; ++m) vec = vec && (reinterpret_cast<uintptr_t>(drop ? ws.xd[m] : x[m]) & 15) == 0;
+  static const bool no_vec = getenv("MER_FUSION_WGRAD_SCALAR") != nullptr;  // A/B and bit-equality tests
+  if (no_vec) vec = false;
+  const int per_block = NT * (vec ? 4 : 1);
   auto add = [&](const float* dy, int lddy, const float* xin, int ldx, int N, int K, long long w_off, long long b_off) {
     w.p[np] = WProb{dy, lddy, xin, ldx, N, K, w_off, b_off, blk};
-    blk += (int)(((long long)N * K + NT - 1) / NT);
+    blk += (int)(((long long)N * K + per_block - 1) / per_block);
     ++np;
   };
   for (int m = 0; m < 3; ++m) {
@@ -1267,7 +1293,8 @@ int launch_wgrad(const MerFusionDims& d, const ULayout& L, const GWs& ws, const 
   w.loss_terms = ws.loss_terms;
   w.inv_batch = inv_batch;
   w.loss_out = loss_out;
-  fus_wgrad_kernel<<<blk, NT, 0, st>>>(w);
+  if (vec) fus_wgrad_kernel<4><<<blk, NT, 0, st>>>(w);
+  else fus_wgrad_kernel<1><<<blk, NT, 0, st>>>(w);
   MER_CUDA_CHECK(cudaGetLastError());
   mer_count_launches(1);
   return 0;

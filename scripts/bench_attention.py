@@ -71,6 +71,7 @@ if __name__ == "__main__":
     ap.add_argument("--tc-vers", type=int, nargs="*", default=[2])
     ap.add_argument("--poly", type=int, nargs="*", default=[None], help="MER_ATT_F16_POLY values to sweep")
     ap.add_argument("--n-seq", type=int, nargs="*", default=[2048], help="ViT sequences (37 = 3 items per SM, L2-resident)")
+    ap.add_argument("--only-f16", action="store_true", help="skip the long-key / legacy / TF32 kernels")
     a = ap.parse_args()
     for n in a.n_seq:
         for v in a.f16_vers:
@@ -80,6 +81,8 @@ if __name__ == "__main__":
                 r = run(torch.float16, n, 197, 12, "MER_ATT_F16_VER", v, a.iters)
                 r["poly"] = pl
                 print(json.dumps(r), flush=True)
+    if a.only_f16:
+        sys.exit(0)
     # attention_f16_long.cu: audio rows of 10 s (499 frames), 7 s (349), CLIP L/14 (257 tokens, 16 heads); beside them the
     # round-1 path for such rows (MER_ATT_F16_LONG=0 is read by the stacks, not here: the TF32-operand mma.sync kernel
     # is what an fp32 qkv without V^T gets)
