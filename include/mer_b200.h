@@ -43,7 +43,7 @@ MER_API long long mer_gemm_variant_launches(int block_n, int mode, int cluster, 
 /* per-launch CUDA-event timing (roofline in bench.py): enable(1) starts a fresh recording, enable(0)
  * stops; collect sums duration / algorithmic work / launches of one kernel class since the last
  * enable(1).  Classes: MER_GEMM_* (work = 2*M*N*K flop; MER_GEMM_F16 launches of fewer than 2^17 rows are
- * class 3), 10 = fp16 tcgen05 attention (15 = its long-key form), 11 = TF32 tcgen05
+ * class 3; 4 = HuBERT conv1 / conv2 as fp16 implicit GEMMs), 10 = fp16 tcgen05 attention (15 = its long-key form), 11 = TF32 tcgen05
  * attention (work = 4*S^2*64 flop per (sequence, head), S = tokens / n_seq), 12 = LayerNorm, 14 = HuBERT
  * conv0 (work = algorithmic HBM bytes), 13 = HuBERT positional conv (flop). */
 MER_API int mer_profile_enable(int on);
@@ -424,6 +424,12 @@ typedef struct MerHubertModel {
   const float* pos_layers_b[8];/* [hidden] */
   const float* ln_ones;        /* [hidden] ones / zeros: the affine of the affine-free LayerNorms */
   const float* ln_zeros;
+  /* ---- operand format of the first convolutions (group-norm feature encoder only; NULL = BF16X3 as conv3..6) ----
+   * conv_w_f16[0]: conv1's weights as fp16 [512, 3 * 512] ([out][tap][in]): conv0 then writes fp16 rows and conv1 runs
+   * as one MER_GEMM_F16 product instead of three bf16 MMAs; conv_w_f16[1] (needs [0]): the same for conv2 (conv1 then
+   * writes fp16 rows, conv2 split-bf16 rows for conv3).  conv1 + conv2 are 77 % of the conv stack's flops; emulated
+   * readout error with fp16 layers: 3.5e-4 against 3.2e-4 (profiles/r2_precision_conv_layers.json). */
+  const void* conv_w_f16[2];
 } MerHubertModel;
 
 /* per-row zero-mean / unit-variance (eps 1e-7) of HF Wav2Vec2FeatureExtractor(do_normalize=True)

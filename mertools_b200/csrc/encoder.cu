@@ -546,6 +546,10 @@ static int hubert_forward_impl(const MerHubertModel* m, const float* wave, int B
     MER_CUDA_CHECK(cudaMemcpyAsync(d_len, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
   }
 
+  // conv1 (and conv2) on fp16 operands when the model carries fp16 copies of their weights (group-norm family only):
+  // conv0 / conv1 then write fp16 rows [clip][frame][512] -- same strides in elements as the split rows in 4-byte slots
+  const bool f16_conv1 = !m->feat_norm_layer && m->conv_w_f16[0] != nullptr;
+  const bool f16_conv2 = f16_conv1 && m->conv_w_f16[1] != nullptr;
   const float* wsrc = wave;
   if (normalize) {
     MER_TRY(mer_wave_normalize_launch(wave, wave_n, B, L, L, L, stream, d_len));
@@ -557,7 +561,7 @@ static int hubert_forward_impl(const MerHubertModel* m, const float* wave, int B
                                        ping, (long long)p.Tpad[0] * 512, stream));
   } else {
     MER_TRY(mer_hubert_conv0_launch(wsrc, L, B, L, m->conv0_w, m->gn_g, m->gn_b, stats, ping,
-                                    (long long)p.Tpad[0] * 512, /*split_out=*/1, stream, d_t0));
+                                    (long long)p.Tpad[0] * 512, /*split_out=*/f16_conv1 ? 2 : 1, stream, d_t0));
   }
   // conv1..6 as implicit GEMMs over the time-major activations
   float* src = ping;
@@ -565,8 +569,10 @@ static int hubert_forward_impl(const MerHubertModel* m, const float* wave, int B
   for (int i = 1; i < 7; ++i) {
     MerGemmDesc g;
     memset(&g, 0, sizeof(g));
+    const bool in16 = (i == 1 && f16_conv1) || (i == 2 && f16_conv2);  // this conv's operands are fp16
+    const bool out16 = i == 1 && f16_conv2;                             // ... and so are the next one's
     g.A = src;
-    g.W = m->conv_w[i - 1];
+    g.W = in16 ? static_cast<const float*>(m->conv_w_f16[i - 1]) : m->conv_w[i - 1];
     g.rows_per_batch = p.T[i];
     g.a_rows_dim = p.Tpad[i - 1] / 2;
     g.batches = B;
@@ -581,7 +587,7 @@ static int hubert_forward_impl(const MerHubertModel* m, const float* wave, int B
     g.ep.out_bstride = (i == 6) ? p.T[6] : p.Tpad[i];  // conv6 output is packed [B*T, 512]
     g.ep.ld_out = 512;
     g.ep.split_off = 512;
-    g.mode = MER_GEMM_BF16X3;
+    g.mode = in16 ? MER_GEMM_F16 : MER_GEMM_BF16X3;
     if (m->feat_norm_layer) {
       // conv + bias -> fp32; LayerNorm(512) + GELU in place -> split rows (conv6: fp32, it feeds another LayerNorm)
       g.ep.bias = m->conv_b[i];
@@ -591,8 +597,17 @@ static int hubert_forward_impl(const MerHubertModel* m, const float* wave, int B
       MER_TRY(mer_layernorm_launch(dst, m->conv_ln_g[i], m->conv_ln_b[i], i == 6 ? dst : nullptr,
                                    i == 6 ? nullptr : dst, nullptr, rows, 512, 1e-5f, MER_LN_GELU, stream));
     } else {
-      g.ep.flags = MER_EPI_GELU | (i == 6 ? 0 : MER_EPI_SPLIT_BF16);  // conv6 feeds a LayerNorm: fp32
-      MER_TRY(mer_gemm_launch(&g, stream));
+      g.ep.flags = MER_EPI_GELU | (i == 6 ? 0 : out16 ? MER_EPI_OUT_F16 : MER_EPI_SPLIT_BF16);  // conv6 feeds a LayerNorm: fp32
+      if (in16) {  // timed as a class of its own (bench.py): not one of the ViT's linear layers
+        const int prof = mer_prof_begin(MER_PROF_CONV_F16, 2.0 * (double)B * p.T[i] * 512.0 * 512.0 * kHubK[i], stream);
+        mer_prof_pause(1);
+        const int rc = mer_gemm_launch(&g, stream);
+        mer_prof_pause(0);
+        mer_prof_end(prof, stream);
+        if (rc) return rc;
+      } else {
+        MER_TRY(mer_gemm_launch(&g, stream));
+      }
     }
     float* tmp = src;
     src = dst;

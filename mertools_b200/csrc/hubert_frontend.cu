@@ -13,6 +13,7 @@
 // The fp32 conv0 output (32.8 MB per 5 s clip) is never materialised un-normalised, and it is computed ONCE: the
 // waveform (320 KB per clip) is read three times (normalise, moments, apply).  Algorithmic traffic per clip:
 // 3 x 320 KB in + 15,999 x 512 x 4 B = 32.8 MB out.
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "mer_common.cuh"
@@ -187,7 +188,8 @@ conv0_apply_kernel(const float* __restrict__ wave, long long ld_wave, const floa
 #pragma unroll
     for (int k = 0; k < K0; ++k) y = fmaf(w[k], xs[t * S0 + k], y);
     const float v = gelu_erf_fast((y - mean) * g + bt);
-    if (split_out) store_split1(orow + (long long)t * C0, c, v);
+    if (split_out == 2) reinterpret_cast<__half*>(out)[((long long)b * out_bstride + (long long)(t0 + t) * C0) + c] = __float2half_rn(v);
+    else if (split_out) store_split1(orow + (long long)t * C0, c, v);
     else orow[(long long)t * C0 + c] = round_tf32(v);
   }
 }
@@ -196,17 +198,21 @@ conv0_apply_kernel(const float* __restrict__ wave, long long ld_wave, const floa
 // as a broadcast operand), FOUR frames per iteration sharing one window of 25 samples (six 16-byte shared-memory loads
 // and one scalar instead of 40 scalar loads: 5 t is a multiple of 4 floats when t is a multiple of 4), the packed GELU,
 // 4 + 4 byte split stores.  Per channel the conv arithmetic is the same sequence of fma.rn as the scalar kernel.
+// F16: the row is 512 fp16 values (the MER_GEMM_F16 operand: conv1 on fp16 operands); else a split-bf16 row
+template <bool F16>
 __device__ __forceinline__ void conv0_emit2(uint64_t y, uint64_t nmean2, uint64_t g2, uint64_t bt2, float* orow, int c) {
   float a0, a1, v0, v1;
   unpack2(fma2(add2(y, nmean2), g2, bt2), a0, a1);
   gelu_erf_fast2(a0, a1, v0, v1);
-  store_split2(orow, c, v0, v1);
+  if (F16) reinterpret_cast<uint32_t*>(orow)[c >> 1] = pack_f16x2(v0, v1);
+  else store_split2(orow, c, v0, v1);
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(C0 / 2)
 conv0_apply2_kernel(const float* __restrict__ wave, long long ld_wave, const float* __restrict__ w0,
                     const float* __restrict__ beta, const float2* __restrict__ coef, int T0,
-                    long long out_bstride /*floats*/, float* __restrict__ out /*split bf16 rows*/) {
+                    long long out_bstride /*elements*/, float* __restrict__ out /*split bf16 rows, or fp16 rows*/) {
   __shared__ __align__(16) float xs[TCHUNK * S0 + K0 + 2];
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * TCHUNK;
@@ -222,7 +228,9 @@ conv0_apply2_kernel(const float* __restrict__ wave, long long ld_wave, const flo
   const float4 mg = *reinterpret_cast<const float4*>(coef + (long long)b * C0 + c);  // (mean, g) of c and c + 1
   const uint64_t nmean2 = pack2(-mg.x, -mg.z), g2 = pack2(mg.y, mg.w);
   const uint64_t bt2 = pack2(__ldg(beta + c), __ldg(beta + c + 1));
-  float* orow = out + (long long)b * out_bstride + (long long)t0 * C0;
+  // a row is C0 4-byte slots (split) or C0 2-byte values (fp16): address it in floats either way
+  constexpr int RF = F16 ? C0 / 2 : C0;  // floats per row
+  float* orow = out + ((long long)b * out_bstride + (long long)t0 * C0) / (F16 ? 2 : 1);
   int t = 0;
   for (; t + 4 <= nt; t += 4) {
     uint64_t xp[4 * S0 + K0 - S0];  // 25 samples, each as a (v, v) pair
@@ -242,7 +250,7 @@ conv0_apply2_kernel(const float* __restrict__ wave, long long ld_wave, const flo
       uint64_t y = pack2(0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < K0; ++k) y = fma2(w[k], xp[f * S0 + k], y);
-      conv0_emit2(y, nmean2, g2, bt2, orow + (long long)(t + f) * C0, c);
+      conv0_emit2<F16>(y, nmean2, g2, bt2, orow + (long long)(t + f) * RF, c);
     }
   }
   for (; t < nt; ++t) {
@@ -252,7 +260,7 @@ conv0_apply2_kernel(const float* __restrict__ wave, long long ld_wave, const flo
       const float xv = xs[t * S0 + k];
       y = fma2(w[k], pack2(xv, xv), y);
     }
-    conv0_emit2(y, nmean2, g2, bt2, orow + (long long)t * C0, c);
+    conv0_emit2<F16>(y, nmean2, g2, bt2, orow + (long long)t * RF, c);
   }
 }
 
@@ -343,7 +351,8 @@ int mer_hubert_conv0_launch(const float* wave, long long ld_wave, int B, int L, 
   float2* coef = reinterpret_cast<float2*>(stats + (size_t)B * 128);
   MER_CUDA_CHECK(cudaMemsetAsync(mom, 0, (size_t)B * MOM_LD * sizeof(double), stream));
   // algorithmic bytes: the waveform in twice (moments, apply), the [T0, 512] operand (4 B per element) out once
-  const int prof = mer_prof_begin(MER_PROF_CONV0, (double)B * (2.0 * L * 4.0 + (double)T0 * C0 * 4.0), stream);
+  const int prof = mer_prof_begin(MER_PROF_CONV0, (double)B * (2.0 * L * 4.0 + (double)T0 * C0 * (split_out == 2 ? 2.0 : 4.0)),
+                                  stream);
   dim3 mgrid((T0 + MCHUNK - 1) / MCHUNK, B);
   if (t0s) conv0_moments_kernel<true><<<mgrid, MOM_THREADS, 0, stream>>>(wave, ld_wave, T0, mom, t0s);
   else conv0_moments_kernel<false><<<mgrid, MOM_THREADS, 0, stream>>>(wave, ld_wave, T0, mom, nullptr);
@@ -352,8 +361,10 @@ int mer_hubert_conv0_launch(const float* wave, long long ld_wave, int B, int L, 
   MER_CUDA_CHECK(cudaGetLastError());
   dim3 grid((T0 + TCHUNK - 1) / TCHUNK, B);
   const char* pk = getenv("MER_CONV0_PACKED");  // read at every launch: tests run both forms in one process
-  if (!(pk && atoi(pk) == 0) && split_out)  // default; MER_CONV0_PACKED=0: one channel per thread
-    conv0_apply2_kernel<<<grid, C0 / 2, 0, stream>>>(wave, ld_wave, w0, beta, coef, T0, out_bstride, out);
+  if (!(pk && atoi(pk) == 0) && split_out == 2)  // fp16 rows (conv1 on fp16 operands)
+    conv0_apply2_kernel<true><<<grid, C0 / 2, 0, stream>>>(wave, ld_wave, w0, beta, coef, T0, out_bstride, out);
+  else if (!(pk && atoi(pk) == 0) && split_out)  // default; MER_CONV0_PACKED=0: one channel per thread
+    conv0_apply2_kernel<false><<<grid, C0 / 2, 0, stream>>>(wave, ld_wave, w0, beta, coef, T0, out_bstride, out);
   else
     conv0_apply_kernel<<<grid, C0, 0, stream>>>(wave, ld_wave, w0, beta, coef, T0, out_bstride, split_out, out);
   mer_prof_end(prof, stream);

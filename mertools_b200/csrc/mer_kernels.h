@@ -7,7 +7,7 @@
 // runtime.cu — optional per-launch CUDA-event timing (bench.py roofline).  klass: MER_GEMM_* for the GEMM
 // modes, MER_PROF_* below for the other kernels; work = algorithmic FLOPs or bytes of the launch.
 // begin returns a slot (or -1 when profiling is off); end records the closing event.
-enum { MER_PROF_F16_SMALL = 3, MER_PROF_ATT_F16 = 10, MER_PROF_ATT_TC = 11, MER_PROF_LAYERNORM = 12, MER_PROF_POSCONV = 13,
+enum { MER_PROF_F16_SMALL = 3, MER_PROF_CONV_F16 = 4, MER_PROF_ATT_F16 = 10, MER_PROF_ATT_TC = 11, MER_PROF_LAYERNORM = 12, MER_PROF_POSCONV = 13,
        MER_PROF_CONV0 = 14, MER_PROF_ATT_LONG = 15 };
 int mer_prof_begin(int klass, double work, cudaStream_t stream);
 void mer_prof_end(int slot, cudaStream_t stream);

@@ -971,7 +971,8 @@ class MerHubertModel(C.Structure):
                 ("stable_layer_norm", C.c_int), ("conv_b", C.c_void_p * 7), ("conv_ln_g", C.c_void_p * 7),
                 ("conv_ln_b", C.c_void_p * 7), ("pos_window", C.c_int), ("layers_f16", C.POINTER(W.MerLayerWeights)),
                 ("n_pos_layers", C.c_int), ("pos_taps", C.c_int), ("pos_layers_w", C.c_void_p * 8),
-                ("pos_layers_b", C.c_void_p * 8), ("ln_ones", C.c_void_p), ("ln_zeros", C.c_void_p)]
+                ("pos_layers_b", C.c_void_p * 8), ("ln_ones", C.c_void_p), ("ln_zeros", C.c_void_p),
+                ("conv_w_f16", C.c_void_p * 2)]
 
 
 def block_diagonal_pos_conv_weight(wpos, block_n=256, window=320, group=48):
@@ -1019,7 +1020,8 @@ class HubertEncoder:
 
     Reference: MERBench/feature_extraction/audio/extract_audio_huggingface.py:18-36,93-110."""
 
-    def __init__(self, state_dict, device="cuda", ln_eps=1e-5, stable_layer_norm=None, stack_precision=None):
+    def __init__(self, state_dict, device="cuda", ln_eps=1e-5, stable_layer_norm=None, stack_precision=None,
+                 conv_precision=None):
         L.check(L.lib().mer_check_device())
         sd = W._np(state_dict)
         self.device = torch.device(device)
@@ -1110,6 +1112,21 @@ class HubertEncoder:
         if self.stack_precision == "f16":
             self.layers_f16 = W.pack_layers(sd, W.HUBERT_NAMES, self.n_layers, pk, f16=True)
             m.layers_f16 = self.layers_f16
+        # Operand format of conv1 / conv2 (77 % of the conv stack's flops), group-norm family with fp16 layers only:
+        # "f16" (default there) runs them as ONE fp16 MMA per product, conv3..6 and the feature projection stay BF16X3.
+        # Emulated readout error at 12 layers (4 checkpoints x clips): 3.5e-4 mean / 4.2e-4 max against 3.2e-4 / 3.7e-4
+        # with every conv on split operands; conv1..6 in fp16 would be 4.4e-4 / 5.1e-4
+        # (profiles/r2_precision_conv_layers.json).  MER_AUDIO_CONV_PRECISION=bf16x3 / conv_precision="bf16x3" opts out.
+        default_conv = "f16" if (self.stack_precision == "f16" and not ln_convs and not m.stable_layer_norm and
+                                 self.hidden == 768 and self.n_layers <= 12) else "bf16x3"  # the emulated configuration
+        self.conv_precision = conv_precision or _os.environ.get("MER_AUDIO_CONV_PRECISION", default_conv)
+        assert self.conv_precision in ("bf16x3", "f16"), self.conv_precision
+        if self.conv_precision == "f16":
+            assert not ln_convs, "fp16 conv1 / conv2 operands are implemented for the group-norm feature encoder"
+            for i in range(2):
+                w = sd[f"feature_extractor.conv_layers.{i + 1}.conv.weight"]
+                m.conv_w_f16[i] = pk.keep(np.ascontiguousarray(w.transpose(0, 2, 1)).reshape(512, 3 * 512),
+                                          f16=True).data_ptr()
         self.model = m
         self.ws = _Workspace(self.device)
         lib = L.lib()

@@ -135,7 +135,7 @@ class WavLmEncoder:
 
         from .. import _lib as L
         from ..encoders import HubertEncoder, MerHubertModel
-        self.front = HubertEncoder(state_dict, device=device)
+        self.front = HubertEncoder(state_dict, device=device, conv_precision="bf16x3")  # (verified with split convolutions)
         self.device, self.hidden, self.n_layers = self.front.device, self.front.hidden, self.front.n_layers
         self.net = WavLmNet(state_dict, _cuda_ops(device))
         assert self.net.stable == bool(self.front.model.stable_layer_norm)

@@ -102,6 +102,7 @@ def vit_gemms(rows=403456):
 
 
 def bench_gemm():
+    """The four GEMMs of a ViT layer, twice (the box drifts along its power cap: only neighbouring lines compare)."""
     gm = vit_gemms()
     for rep in range(2):
         for name, (fn, flops) in gm.items():

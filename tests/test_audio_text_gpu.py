@@ -29,6 +29,7 @@ def test_hubert_hidden_states_and_readout(cuda, layers, n_samples, batch, precis
     wav = (S.synth_waves(batch, n_samples, seed=21).astype(np.float64) / 32768.0).astype(np.float32)
     enc = HubertEncoder(sd, device=cuda, stack_precision=precision)
     assert enc.stack_precision == precision and HubertEncoder(sd, device=cuda).stack_precision == "f16"
+    assert enc.conv_precision == precision  # conv1 / conv2 follow the layers' operand format by default
     utt, frames, hidden = enc.forward(torch.from_numpy(wav).to(cuda), normalize=True,
                                       want_frames=True, return_hidden=True)
     torch.cuda.synchronize()

@@ -535,7 +535,7 @@ def test_ctypes_struct_layouts_match_the_header(tmp_path):
     from mertools_b200 import encoders as En
     if shutil.which("gcc") is None:
         pytest.skip("no C compiler")
-    probes = [("MerHubertModel", En.MerHubertModel, ["pos_window", "layers_f16", "n_pos_layers", "pos_layers_w", "ln_zeros"]),
+    probes = [("MerHubertModel", En.MerHubertModel, ["pos_window", "layers_f16", "n_pos_layers", "pos_layers_w", "ln_zeros", "conv_w_f16"]),
               ("MerCnnOp", En.MerCnnOp, ["relu", "ceil_mode", "p"]),
               ("MerCnnModel", En.MerCnnModel, ["ops", "scale", "mean", "feat_dim"]),
               ("MerVggishModel", En.MerVggishModel, ["fc_w", "fc_b"]),

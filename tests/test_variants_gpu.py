@@ -250,6 +250,18 @@ def test_hubert_packed_conv0_and_switches_keep_parity(cuda):
     for env, val in (("MER_CONV0_PACKED", "0"), ("MER_GELU_PACKED", "1"), ("MER_ATT_TC_VER", "1")):
         got = _with_env(env, val, run)
         assert float((got - base).abs().max()) / scale < 5e-5, env
+    # conv1 / conv2 on fp16 operands (the default next to fp16 layers): the fp16-row forms of the conv0 kernels (two
+    # channels per thread, and one with MER_CONV0_PACKED=0: an ulp apart before the fp16 rounding) agree, and the choice
+    # of conv operand format is independent of the layers' (here: split layers + fp16 conv1 / conv2) and stays inside the
+    # parity bar
+    assert enc.conv_precision == "bf16x3" and HubertEncoder(sd, device=cuda).conv_precision == "f16"
+    enc = HubertEncoder(sd, device=cuda, stack_precision="bf16x3", conv_precision="f16")
+    f16c = run()
+    assert float((f16c.reshape(ref.shape) - ref).abs().max()) / scale < 2e-3
+    err = float((f16c - base).abs().max()) / scale
+    print(f"fp16 conv1 / conv2 against split: {err:.2e}")
+    assert 0 < err < 1e-3
+    assert float((_with_env("MER_CONV0_PACKED", "0", run) - f16c).abs().max()) / scale < 2e-4
 
 
 @pytest.mark.parametrize("model_name,prefix,se", [("resnet50_ferplus_dag", "", False), ("senet50_ferplus_dag", "se_", True)])
