@@ -8,7 +8,9 @@ timed CPU reference, never as part of the product: ``mertools_b200/`` does not i
 (tests/test_host_logic.py enforces that) and has no CPU fallback.
 
 Pinning status: every restatement is checked against outputs of the unmodified reference code or of the
-third-party class the reference calls (tests/test_oracle.py, tests/test_golden.py), with one exception —
-``encoders.vggish_embeddings`` is PARITY UNPINNED: the reference graph needs TensorFlow / tf_slim, which are not
-installed, so it follows the definition file only (cross-checked against the torchvggish form of the network).
+third-party class the reference calls (tests/test_oracle.py, tests/test_golden.py).  One pin is weaker than the
+others: ``encoders.vggish_embeddings`` -- TensorFlow / tf_slim are not installed, so the unmodified reference graph
+definition and extractor (vggish_slim.py, extract_vggish_embedding.py) were run over a torch-backed stand-in for the
+TF calls they make (tests/golden/tf_slim_shim.py -> vggish_golden.npz): structure, variable names and extractor logic
+are the reference's, TensorFlow's float arithmetic is not exercised.
 """

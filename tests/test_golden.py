@@ -329,3 +329,27 @@ def test_frame_index_selection_and_cv2_path_match_load_video_from_npy_golden():
         assert list(x.shape) == list(g[f"shape{ci}"]), (readtype, x.shape)
         assert np.array_equal(x[:, :, ::16, ::16].astype(np.uint8), g[f"probe{ci}"]), readtype
         assert float(x.sum(dtype=np.float64)) == float(g[f"sum{ci}"][0]), readtype
+
+
+def test_vggish_oracle_matches_the_reference_graph_and_extractor_golden():
+    """tests/golden/make_golden_vggish.py ran the UNMODIFIED vggish_slim.define_vggish_slim / load_vggish_slim_checkpoint
+    and extract_vggish_embedding.extract (UTTERANCE: 0.5 s hop + mean, FRAME: 0.05 s hop; batches of 3 examples) over a
+    torch-backed stand-in for the TensorFlow / tf_slim calls they make (tests/golden/tf_slim_shim.py): the graph
+    structure, variable names and extractor logic are the reference's; the float arithmetic is torch's."""
+    g = np.load(os.path.join(G, "vggish_golden.npz"))
+    raw = S.vggish_state_dict(seed=8)
+    assert sorted(g["variable_names"].tolist()) == sorted(k + ":0" for k in raw)  # the graph's variables = the checkpoint names
+    sd = {k: torch.from_numpy(v) for k, v in raw.items()}
+    rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())  # noqa: E731
+    with torch.no_grad():
+        assert rel(E.vggish_embeddings(sd, torch.from_numpy(g["patches"])).numpy(), g["patch_embeddings"]) < 1e-5
+        for name, n, seed in zip(g["clip_names"], g["clip_samples"], g["clip_seeds"]):
+            w = S.synth_waves(1, int(n), seed=int(seed))[0].astype(np.int16)
+            for level, hop in (("UTTERANCE", 0.5), ("FRAME", 0.05)):
+                ex = P.waveform_to_examples(w / 32768.0, hop)
+                emb = E.vggish_embeddings(sd, torch.from_numpy(ex.astype(np.float32))).numpy()
+                if level == "UTTERANCE":      # extract_vggish_embedding.py:54-58
+                    emb = emb.squeeze()
+                    emb = emb.mean(axis=0) if emb.ndim != 1 else emb
+                ref = g[f"{name}_{level}"]
+                assert emb.shape == ref.shape and rel(emb, ref) < 1e-5, (name, level)

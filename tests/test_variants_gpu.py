@@ -186,6 +186,12 @@ def test_vggish_embeddings_match_oracle(cuda):
     ref = E.vggish_embeddings({k: torch.from_numpy(v) for k, v in sd.items()}, torch.from_numpy(x))
     assert got.shape == (5, 128)
     assert float((got - ref).abs().max() / ref.abs().max()) < 1e-3
+    # the same patches through the reference's own graph definition (tests/golden/make_golden_vggish.py)
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vggish_golden.npz"))
+    assert np.array_equal(g["patches"], x)
+    gold = torch.from_numpy(g["patch_embeddings"])
+    assert float((got - gold).abs().max() / gold.abs().max()) < 1e-3
 
 
 def test_vggish_extractor_files(cuda, tmp_path):
@@ -219,6 +225,20 @@ def test_vggish_extractor_files(cuda, tmp_path):
         ref = E.vggish_embeddings(tsd, torch.from_numpy(ex.astype(np.float32))).numpy()
         ref = ref.mean(0) if level == "UTTERANCE" else ref
         assert got.shape == ref.shape and np.abs(got - ref).max() / np.abs(ref).max() < 1e-3
+    # the clips of the golden: outputs of the UNMODIFIED reference extract() (graph definition + loop + save rules)
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vggish_golden.npz"))
+    paths = []
+    for name, n, seed in zip(g["clip_names"], g["clip_samples"], g["clip_seeds"]):
+        paths.append(str(tmp_path / f"{name}.wav"))
+        wavfile.write(paths[-1], 16000, S.synth_waves(1, int(n), seed=int(seed))[0].astype(np.int16))
+    for level in ("UTTERANCE", "FRAME"):
+        out = tmp_path / ("golden_" + level)
+        out.mkdir()
+        vggish.extract(paths, str(out), level, state_dict=sd, device="cuda:0")
+        for name in g["clip_names"]:
+            got, ref = np.load(out / f"{name}.npy"), g[f"{name}_{level}"]
+            assert got.shape == ref.shape and np.abs(got - ref).max() / np.abs(ref).max() < 1e-3, (name, level)
 
 
 def test_hubert_packed_conv0_and_switches_keep_parity(cuda):
