@@ -30,7 +30,7 @@ extern "C" {
 
 /* ---- library ------------------------------------------------------------------------- */
 MER_API const char* mer_last_error(void);
-MER_API int mer_abi_version(void); /* 3: model structs may only grow at the tail; zero-filled tails = the older behaviour */
+MER_API int mer_abi_version(void); /* 4: model structs may only grow at the tail; zero-filled tails = the older behaviour */
 /* 0 when the current device is compute capability 10.x, non-zero (and an error string) otherwise */
 MER_API int mer_check_device(void);
 

@@ -197,7 +197,7 @@ long long mer_launch_count(void) { return g_launches; }
 
 const char* mer_last_error(void) { return g_err; }
 
-int mer_abi_version(void) { return 3; }
+int mer_abi_version(void) { return 4; }
 
 int mer_check_device(void) {
   int dev = 0, major = 0, minor = 0;

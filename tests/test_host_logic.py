@@ -68,7 +68,7 @@ def test_shared_library_exports_every_declared_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(dll, n), f"missing export {n}"
-    assert dll.mer_abi_version() == 3
+    assert dll.mer_abi_version() == 4
     dll.mer_last_error.restype = ctypes.c_char_p
     assert isinstance(dll.mer_last_error(), bytes)
 
