@@ -69,6 +69,16 @@ class AudioExtractor:
         self._norm = L.declare("mer_wave_normalize", [C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                                       C.c_longlong, C.c_longlong, C.c_void_p])
 
+    def _staging(self, slot, rows, cols):
+        """View [rows, cols] of one of the two persistent pinned staging buffers (grown on demand)."""
+        if not hasattr(self, "_pinned"):
+            self._pinned = [None, None]
+        need = rows * cols
+        buf = self._pinned[slot]
+        if buf is None or buf.numel() < need:
+            buf = self._pinned[slot] = torch.zeros(max(need, self.max_samples, MAXLEN), dtype=torch.float32, pin_memory=True)
+        return buf[:need].view(rows, cols)
+
     def _run_rows(self, rows, normalize):
         """rows: CUDA fp32 [R, L] -> frames [R, T, D] (sum of the last four hidden states; D = 768 or 1024)."""
         outs = []
@@ -89,23 +99,45 @@ class AudioExtractor:
                 short.setdefault(len(w), []).append(i)
         if self.ragged and len(short) > 1:
             order = sorted((i for idxs in short.values() for i in idxs), key=lambda i: len(waves[i]))
-            s0 = 0
+            launches, s0 = [], 0
             while s0 < len(order):   # launches of consecutive (sorted) clips: rows * longest <= max_samples
                 e = s0 + 1
                 while (e < len(order) and e - s0 < self.max_rows
                        and (e - s0 + 1) * len(waves[order[e]]) <= self.max_samples):
                     e += 1
-                idxs = order[s0:e]
-                lens = [len(waves[i]) for i in idxs]
-                host = torch.zeros((len(idxs), max(lens)), dtype=torch.float32, pin_memory=True)
-                for r, i in enumerate(idxs):
-                    host[r, :lens[r]] = torch.from_numpy(np.asarray(waves[i]).astype(np.float32))
-                utt, frames = self.enc.forward_ragged(host.to(self.device, non_blocking=True), lens,
-                                                      normalize=self.do_normalize,
-                                                      want_frames=feature_level != "UTTERANCE")
-                for r, i in enumerate(idxs):
-                    res[i] = (utt[r] if feature_level == "UTTERANCE" else frames[r]).cpu().numpy()
+                launches.append(order[s0:e])
                 s0 = e
+            # Two persistent pinned staging buffers (a fresh pinned allocation per launch cost as much as the launch's
+            # device time) and a one-launch-deep pipeline: launch k is enqueued, the host fills the buffer of launch
+            # k + 1 while the GPU works, and only then are the results of launch k read back -- in ONE device-to-host
+            # copy per launch (round 2's first build synchronised once per clip).
+            want_frames = feature_level != "UTTERANCE"
+
+            def finish(p):
+                idxs, utt, frames = p
+                if want_frames:
+                    for r, i in enumerate(idxs):
+                        res[i] = frames[r].cpu().numpy()
+                else:
+                    u = utt.cpu().numpy()
+                    for r, i in enumerate(idxs):
+                        res[i] = u[r].copy()
+
+            pending = None
+            for k, idxs in enumerate(launches):
+                lens = [len(waves[i]) for i in idxs]
+                host = self._staging(k & 1, len(idxs), max(lens))
+                hn = host.numpy()            # shares the pinned memory; the assignment converts float64 -> float32 in place
+                for r, i in enumerate(idxs):
+                    hn[r, :lens[r]] = waves[i]
+                    hn[r, lens[r]:] = 0.0
+                utt, frames = self.enc.forward_ragged(host.to(self.device, non_blocking=True), lens,
+                                                      normalize=self.do_normalize, want_frames=want_frames)
+                if pending is not None:
+                    finish(pending)          # (synchronises: buffer k & 1 is free again two launches later)
+                pending = (idxs, utt, frames)
+            if pending is not None:
+                finish(pending)
             short = {}
         # clips <= 10 s: batch by identical length; normalisation fused on the device
         for n, idxs in short.items():
