@@ -1014,7 +1014,7 @@ class HubertEncoder:
     (hidden 1024, 16 heads, LayerNorm after every conv, conv biases, stable / pre-LN encoder: hubert-large,
     chinese-hubert-large, wav2vec2-large-lv60).  ``stable_layer_norm`` overrides the inference of
     ``config.do_stable_layer_norm`` from the feature extractor type (they coincide in every released checkpoint of
-    the extractor's model list).  Two more combinations are wired but have not run on a GPU yet: hidden 1024 on the
+    the extractor's model list).  Two more combinations (GPU-tested in tests/test_variants_gpu.py): hidden 1024 on the
     group-norm extractor with post-LN layers (wav2vec2-large-960h) and ``Data2VecAudioModel``
     (data2vec-audio-base-960h: LayerNorm convs without biases, a chain of positional convs, post-LN).
 

@@ -7,7 +7,7 @@ for ``whisper-base`` (d_model 512, 8 heads) and ``whisper-large-v2`` (1280, 20 h
 ``mer_layernorm``, ``mer_attention`` (encoder, 1500 frames), ``mer_small_attention`` (decoder) — through a small
 ``ops`` backend, so that the orchestration (weight packing, layer order, residuals, position tables) can be run against
 the reference golden with a torch backend on CPU (tests/test_host_logic.py); ``CudaOps`` is the product backend.
-Written after the round-1 GPU budget ran out: not yet run on a GPU.
+GPU parity test: tests/test_variants_gpu.py (green on a B200 since round 2).
 """
 from __future__ import annotations
 
