@@ -147,3 +147,39 @@ def test_rank_strided_batches_reassemble_in_reference_order_gloo():
     out = mgr.dict()
     mp.spawn(_dp_worker, args=(2, port, out), nprocs=2, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+def test_ragged_audio_launches_are_grouped_pipelined_and_restored_in_input_order():
+    """AudioExtractor.extract_waves, ragged branch, with the encoder stubbed (host logic only): sorted clips are cut into
+    launches of at most max_rows rows and max_samples padded samples, each row's tail is zeroed in the reused staging
+    buffer, launch k + 1 is staged before launch k is read back, and the results come back in input order."""
+    from mertools_b200.extract.audio import AudioExtractor
+
+    calls = []
+
+    class Enc:
+        device = torch.device("cpu")
+        hidden = 4
+
+        def forward_ragged(self, rows, lens, normalize=True, want_frames=False):
+            assert rows.shape == (len(lens), max(lens)) and normalize
+            for r, n in enumerate(lens):
+                assert float(rows[r, n:].abs().sum()) == 0.0          # stale samples of an earlier launch are gone
+            calls.append(list(lens))
+            utt = torch.stack([rows[r, :n].sum().repeat(4) for r, n in enumerate(lens)])      # a signature of the clip
+            frames = [rows[r, :n].reshape(-1, 1)[:3].repeat(1, 4) for r, n in enumerate(lens)] if want_frames else None
+            return utt, frames
+
+    ext = object.__new__(AudioExtractor)
+    ext.enc, ext.device, ext.max_rows, ext.ragged, ext.max_samples, ext.do_normalize = Enc(), torch.device("cpu"), 3, True, 40, True
+    rng = np.random.default_rng(0)
+    lens = [9, 3, 17, 5, 12, 20, 4, 8]
+    waves = [rng.standard_normal(n) for n in lens]
+    out = ext.extract_waves(waves, "UTTERANCE")
+    assert calls == [[3, 4, 5], [8, 9, 12], [17, 20]]                 # sorted; <= 3 rows; rows * longest <= 40
+    for w, o in zip(waves, out):
+        assert o.shape == (4,) and abs(float(o[0]) - float(np.float32(w.astype(np.float32).sum()))) < 1e-4
+    calls.clear()
+    out = ext.extract_waves(waves, "FRAME")
+    for w, o in zip(waves, out):
+        assert o.shape == (3, 4) and np.allclose(o[:, 0], w[:3].astype(np.float32))
