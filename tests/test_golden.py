@@ -353,3 +353,56 @@ def test_vggish_oracle_matches_the_reference_graph_and_extractor_golden():
                     emb = emb.mean(axis=0) if emb.ndim != 1 else emb
                 ref = g[f"{name}_{level}"]
                 assert emb.shape == ref.shape and rel(emb, ref) < 1e-5, (name, level)
+
+
+def test_tf_slim_stand_in_keeps_the_conventions_the_vggish_pin_relies_on():
+    """tests/golden/tf_slim_shim.py (the torch-backed stand-in that let the unmodified VGGish graph definition run):
+    variable naming under variable_scope / slim.repeat, arg_scope precedence (inner scope over outer, explicit argument
+    over both), SAME padding of stride-1 convolutions and of 2x2 / stride-2 pools on odd sizes, NHWC flatten order, and
+    feed-dict evaluation of a named tensor."""
+    import sys
+    import torch.nn.functional as F
+    sys.path.insert(0, G)
+    import tf_slim_shim as shim
+    saved = {k: sys.modules.get(k) for k in ("tensorflow", "tensorflow.compat", "tensorflow.compat.v1", "tf_slim")}
+    try:
+        tf, slim = shim.install(5, 7)
+        with tf.Graph().as_default(), tf.Session() as sess:
+            with slim.arg_scope([slim.conv2d, slim.fully_connected], activation_fn=tf.nn.relu), \
+                 slim.arg_scope([slim.conv2d], kernel_size=[3, 3], stride=1, padding="SAME"), \
+                 slim.arg_scope([slim.max_pool2d], kernel_size=[2, 2], stride=2, padding="SAME"), \
+                 tf.variable_scope("net"):
+                x = tf.placeholder(tf.float32, shape=(None, 5, 7), name="in")
+                y = tf.reshape(x, [-1, 5, 7, 1])
+                y = slim.repeat(y, 2, slim.conv2d, 4, scope="c")
+                y = slim.conv2d(y, 3, activation_fn=None, scope="lin")       # explicit argument beats the scope default
+                y = slim.max_pool2d(y, scope="p")                            # 5 x 7 -> 3 x 4 (SAME, odd sizes)
+                y = slim.fully_connected(slim.flatten(y), 2, scope="fc")
+                out = tf.identity(y, name="out")
+            names = sorted(v.name for v in tf.global_variables())
+            assert names == sorted(["net/c/c_1/weights:0", "net/c/c_1/biases:0", "net/c/c_2/weights:0", "net/c/c_2/biases:0",
+                                    "net/lin/weights:0", "net/lin/biases:0", "net/fc/weights:0", "net/fc/biases:0"])
+            rng = np.random.default_rng(0)
+            vals = {}
+            for v in tf.global_variables():
+                vals[v.name] = torch.from_numpy(rng.standard_normal(v.shape).astype(np.float32))
+                v.value = vals[v.name]
+            assert tuple(vals["net/fc/weights:0"].shape) == (3 * 4 * 3, 2)       # SAME pool of 5 x 7, 3 channels, NHWC
+            xin = rng.standard_normal((2, 5, 7)).astype(np.float32)
+            [got] = sess.run([sess.graph.get_tensor_by_name("net/out:0")],
+                             feed_dict={sess.graph.get_tensor_by_name("net/in:0"): xin})
+        # the same network written directly in torch (NCHW), TF conventions applied by hand
+        conv = lambda t, n: F.conv2d(t, vals[f"net/{n}/weights:0"].permute(3, 2, 0, 1), vals[f"net/{n}/biases:0"], padding=1)  # noqa: E731
+        t = torch.from_numpy(xin)[:, None]
+        t = torch.relu(conv(torch.relu(conv(t, "c/c_1")), "c/c_2"))
+        t = conv(t, "lin")                                                        # no activation
+        t = F.max_pool2d(F.pad(t, (0, 1, 0, 1), value=float("-inf")), 2, 2)       # SAME: the odd row / column pads at the end
+        t = t.permute(0, 2, 3, 1).reshape(2, -1)                                  # NHWC flatten
+        ref = torch.relu(t @ vals["net/fc/weights:0"] + vals["net/fc/biases:0"]).numpy()
+        assert got.shape == ref.shape == (2, 2) and np.abs(got - ref).max() < 1e-6 * np.abs(ref).max()
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
